@@ -1,0 +1,505 @@
+"""Opcode vocabulary: the hot-path subset of the reference's `prelude32` (src/prelude.rs, F = f32).
+
+Every function returns an `An` expression and cites the reference constructor it mirrors
+(file:line relative to /root/reference).  Names, argument order and argument meaning follow the
+reference; `pass` is spelled `pass_` (Python keyword).  Anything that needs a Rust closure
+(`envelope(|t| ..)`, `map`, `shape_fn`) cannot cross a C ABI and is intentionally absent;
+`adsr_live` is a closed-form opcode (src/adsr.rs:21-70).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .graph import (An, M_BRANCH, M_BUS, M_CHAIN, M_REDUCE, M_STACK, OP_ADD, OP_MUL, f32, multi)
+
+F = np.float32
+
+# SVF modes (src/svf.rs:26-221)
+LOWPASS, HIGHPASS, BANDPASS, NOTCH, PEAK, ALLPASS, BELL, LOWSHELF, HIGHSHELF = range(9)
+# global wavetables (src/wavetable.rs:493-623)
+SAW, SQUARE, TRIANGLE, ORGAN, SOFT_SAW, HAMMOND = range(6)
+
+
+def _frame(x):
+    return tuple(f32(v) for v in (x if isinstance(x, (tuple, list)) else (x,)))
+
+
+# ---- src/prelude.rs:189-235
+def constant(x):
+    v = _frame(x)
+    return An("constant", (v,), (), 0, len(v))
+
+
+dc = constant
+
+
+def zero():
+    return dc(0.0)
+
+
+def multizero(n):
+    return dc((0.0,) * n)
+
+
+# ---- src/prelude.rs:257-330
+def pass_():
+    return An("pass", (), (), 1, 1)
+
+
+def multipass(n):
+    return An("multipass", (n,), (), n, n)
+
+
+def sink():
+    return An("sink", (1,), (), 1, 0)
+
+
+def multisink(n):
+    return An("sink", (n,), (), n, 0)
+
+
+def reverse(n):
+    return An("reverse", (n,), (), n, n)
+
+
+# ---- src/prelude.rs:1675-1715
+def split(n):
+    return An("split", (n,), (), 1, n)
+
+
+def multisplit(m, n):
+    return An("multisplit", (m, n), (), m, m * n)
+
+
+def join(n):
+    return An("join", (n,), (), n, 1)
+
+
+def multijoin(m, n):
+    return An("multijoin", (m, n), (), m * n, m)
+
+
+# ---- src/prelude.rs:337-351
+def sine():
+    return An("sine", (), (), 1, 1)
+
+
+def sine_hz(f):
+    return constant(f) >> sine()
+
+
+# ---- src/prelude.rs:2003-2089 wavetable oscillators
+def _wave(kind):
+    return An("wavesynth", (kind, 1), (), 1, 1)
+
+
+def saw():
+    return _wave(SAW)
+
+
+def square():
+    return _wave(SQUARE)
+
+
+def triangle():
+    return _wave(TRIANGLE)
+
+
+def organ():
+    return _wave(ORGAN)
+
+
+def soft_saw():
+    return _wave(SOFT_SAW)
+
+
+def hammond():
+    return _wave(HAMMOND)
+
+
+def saw_hz(f):
+    return constant(f) >> saw()
+
+
+def square_hz(f):
+    return constant(f) >> square()
+
+
+def triangle_hz(f):
+    return constant(f) >> triangle()
+
+
+def organ_hz(f):
+    return constant(f) >> organ()
+
+
+def soft_saw_hz(f):
+    return constant(f) >> soft_saw()
+
+
+def hammond_hz(f):
+    return constant(f) >> hammond()
+
+
+# ---- src/prelude.rs:808-823
+def noise():
+    return An("noise", (), (), 0, 1)
+
+
+white = noise
+
+
+# ---- src/prelude.rs:2096-2560 Simper SVF family.  `x()` takes parameter inputs, `x_hz` is fixed, `x_q` fixes Q.
+def _svf(mode):
+    gain_in = mode >= BELL
+    return An("svf", (mode, 440.0, 1.0, 1.0), (), 4 if gain_in else 3, 1)
+
+
+def _svf_hz(mode, f, q, gain=1.0):
+    return An("fixed_svf", (mode, f32(f), f32(q), f32(gain)), (), 1, 1)
+
+
+def _svf_q(mode, q, gain=None):
+    n = An("svf", (mode, 440.0, f32(q), 1.0 if gain is None else f32(gain)), (), 3 if gain is None else 4, 1)
+    tail = dc(q) if gain is None else dc((q, gain))
+    return (multipass(2) | tail) >> n
+
+
+def lowpass():
+    return _svf(LOWPASS)
+
+
+def lowpass_hz(f, q):
+    return _svf_hz(LOWPASS, f, q)
+
+
+def lowpass_q(q):
+    return _svf_q(LOWPASS, q)
+
+
+def highpass():
+    return _svf(HIGHPASS)
+
+
+def highpass_hz(f, q):
+    return _svf_hz(HIGHPASS, f, q)
+
+
+def highpass_q(q):
+    return _svf_q(HIGHPASS, q)
+
+
+def bandpass():
+    return _svf(BANDPASS)
+
+
+def bandpass_hz(f, q):
+    return _svf_hz(BANDPASS, f, q)
+
+
+def bandpass_q(q):
+    return _svf_q(BANDPASS, q)
+
+
+def notch():
+    return _svf(NOTCH)
+
+
+def notch_hz(f, q):
+    return _svf_hz(NOTCH, f, q)
+
+
+def notch_q(q):
+    return _svf_q(NOTCH, q)
+
+
+def peak():
+    return _svf(PEAK)
+
+
+def peak_hz(f, q):
+    return _svf_hz(PEAK, f, q)
+
+
+def peak_q(q):
+    return _svf_q(PEAK, q)
+
+
+def allpass():
+    return _svf(ALLPASS)
+
+
+def allpass_hz(f, q):
+    return _svf_hz(ALLPASS, f, q)
+
+
+def allpass_q(q):
+    return _svf_q(ALLPASS, q)
+
+
+def bell():
+    return _svf(BELL)
+
+
+def bell_hz(f, q, gain):
+    return _svf_hz(BELL, f, q, gain)
+
+
+def bell_q(q, gain):
+    return _svf_q(BELL, q, gain)
+
+
+def lowshelf():
+    return _svf(LOWSHELF)
+
+
+def lowshelf_hz(f, q, gain):
+    return _svf_hz(LOWSHELF, f, q, gain)
+
+
+def lowshelf_q(q, gain):
+    return _svf_q(LOWSHELF, q, gain)
+
+
+def highshelf():
+    return _svf(HIGHSHELF)
+
+
+def highshelf_hz(f, q, gain):
+    return _svf_hz(HIGHSHELF, f, q, gain)
+
+
+def highshelf_q(q, gain):
+    return _svf_q(HIGHSHELF, q, gain)
+
+
+# ---- src/prelude.rs:441-548, src/prelude32.rs:2711-2713
+def biquad(a1, a2, b0, b1, b2):
+    return An("biquad", (f32(a1), f32(a2), f32(b0), f32(b1), f32(b2)), (), 1, 1)
+
+
+def biquad_bank():
+    return An("biquad_bank", (), (), 8, 8)
+
+
+def butterpass():
+    return An("butterpass", (440.0, 2), (), 2, 1)
+
+
+def butterpass_hz(f):
+    return An("butterpass", (f32(f), 1), (), 1, 1)
+
+
+def resonator():
+    return An("resonator", (440.0, 1.0, 3), (), 3, 1)
+
+
+def resonator_hz(center, q):
+    return An("resonator", (f32(center), f32(q), 1), (), 1, 1)
+
+
+# ---- src/prelude.rs:551-568
+def moog():
+    return An("moog", (1000.0, f32(0.1), 3), (), 3, 1)
+
+
+def moog_q(q):
+    return (multipass(2) | dc(q)) >> An("moog", (1000.0, f32(q), 3), (), 3, 1)
+
+
+def moog_hz(frequency, q):
+    return An("moog", (f32(frequency), f32(q), 1), (), 1, 1)
+
+
+# ---- src/prelude.rs:855-867
+def fir(weights):
+    w = _frame(weights)
+    return An("fir", (w,), (), 1, 1)
+
+
+def fir3_weights(gain):
+    alpha = (F(gain) + F(1.0)) / F(2.0)
+    beta = (F(1.0) - alpha) / F(2.0)
+    return (float(beta), float(alpha), float(beta))
+
+
+def fir3(gain):
+    return fir(fir3_weights(gain))
+
+
+# ---- src/prelude.rs:878-912
+def tick():
+    return An("tick", (1,), (), 1, 1)
+
+
+def multitick(n):
+    return An("tick", (n,), (), n, n)
+
+
+def delay(t):
+    return An("delay", (float(t),), (), 1, 1)
+
+
+# ---- src/prelude.rs:1102-1135
+def allnest_c(coefficient, x):
+    return An("allnest", (f32(coefficient), 1), (x,), 1, 1)
+
+
+def allnest(x):
+    return An("allnest", (0.0, 2), (x,), 2, 1)
+
+
+# ---- src/prelude.rs:1236-1256
+def panner():
+    return An("panner", (), (), 2, 2)
+
+
+def pan(p):
+    return An("pan", (f32(p),), (), 1, 2)
+
+
+# ---- src/prelude.rs:766-775 / src/adsr.rs:21-70
+def adsr_live(attack, decay, sustain, release):
+    return An("adsr_live", (f32(attack), f32(decay), f32(sustain), f32(release)), (), 1, 1)
+
+
+# ---- src/prelude.rs:1053-1085, 1336-1364
+def feedback(node):
+    return An("feedback", (0,), (node,), node.nin, node.nout)
+
+
+def fdn(node):
+    return An("feedback", (1,), (node,), node.nin, node.nout)
+
+
+# ---- src/prelude.rs:1370-1670 functional forms of the operators and the indexed multi-combinators
+def bus(x, y):
+    return x & y
+
+
+def stack(x, y):
+    return x | y
+
+
+def branch(x, y):
+    return x ^ y
+
+
+def pipe(x, y):
+    return x >> y
+
+
+def thru(x):
+    return ~x
+
+
+def product(x, y):
+    return x * y
+
+
+def sum(x, y):  # noqa: A001 (mirrors the reference name)
+    return x + y
+
+
+def busi(n, f):
+    return multi(M_BUS, 0, [f(i) for i in range(n)])
+
+
+def _frac(n, i):
+    return f32(i / (n - 1)) if n > 1 else 0.5
+
+
+def busf(n, f):
+    return multi(M_BUS, 0, [f(_frac(n, i)) for i in range(n)])
+
+
+def stacki(n, f):
+    return multi(M_STACK, 0, [f(i) for i in range(n)])
+
+
+def stackf(n, f):
+    return multi(M_STACK, 0, [f(_frac(n, i)) for i in range(n)])
+
+
+def branchi(n, f):
+    return multi(M_BRANCH, 0, [f(i) for i in range(n)])
+
+
+def branchf(n, f):
+    return multi(M_BRANCH, 0, [f(_frac(n, i)) for i in range(n)])
+
+
+def sumi(n, f):
+    return multi(M_REDUCE, OP_ADD, [f(i) for i in range(n)])
+
+
+def sumf(n, f):
+    return multi(M_REDUCE, OP_ADD, [f(_frac(n, i)) for i in range(n)])
+
+
+def pipei(n, f):
+    return multi(M_CHAIN, 0, [f(i) for i in range(n)])
+
+
+def pipef(n, f):
+    return multi(M_CHAIN, 0, [f(_frac(n, i)) for i in range(n)])
+
+
+# ---- f32 math used by the composites (src/math.rs:170-177, 430-437, 289-291)
+def lerp(a, b, t):
+    a, b, t = F(a), F(b), F(t)
+    return float(a * (F(1.0) - t) + b * t)
+
+
+def smooth9(x):
+    x = F(x)
+    x2 = x * x
+    return float(((((F(70) * x - F(315)) * x + F(540)) * x - F(420)) * x + F(126)) * x2 * x2 * x)
+
+
+def db_amp(db):
+    return math.exp((db / 20.0) * math.log(10.0))
+
+
+def xerp(a, b, t):
+    """f32 xerp (src/math.rs:236-238) as used for per-voice parameter draws."""
+    a, b, t = F(a), F(b), F(t)
+    la, lb = np.log(a), np.log(b)
+    return float(np.exp(la * (F(1.0) - t) + lb * t))
+
+
+REVERB_DELAYS = (
+    0.073904, 0.052918, 0.066238, 0.066387, 0.037783, 0.080073, 0.050961, 0.075900, 0.043646,
+    0.072095, 0.056194, 0.045961, 0.058934, 0.068016, 0.047529, 0.058156, 0.072972, 0.036084,
+    0.062715, 0.076377, 0.044339, 0.076725, 0.077884, 0.046126, 0.067741, 0.049800, 0.051709,
+    0.082923, 0.070121, 0.079315, 0.055039, 0.081859,
+)
+
+
+# ---- src/prelude.rs:1732-1762
+def reverb_stereo(room_size, time, damping):
+    a = F(math.pow(db_amp(-60.0), 0.03 * room_size / 10.0 / time))
+    w = fir3_weights(f32(1.0) - f32(damping))
+    weights = tuple(float(F(x) * a) for x in w)
+    line = stacki(32, lambda i: delay(REVERB_DELAYS[i] * room_size / 10.0) >> fir(weights))
+    reverb = fdn(line)
+    return (multisplit(2, 16) >> reverb
+            >> sumf(32, lambda x: pan(lerp(-1.0, 1.0, smooth9(x)))) * dc((1.0 / 16.0, 1.0 / 16.0)))
+
+
+# ---- src/prelude.rs:395-430
+def add(x):
+    v = _frame(x)
+    return multipass(len(v)) + dc(v) if len(v) > 1 else An("multipass", (1,), (), 1, 1) + dc(v)
+
+
+def sub(x):
+    v = _frame(x)
+    return An("multipass", (len(v),), (), len(v), len(v)) - dc(v)
+
+
+def mul(x):
+    v = _frame(x)
+    return An("multipass", (len(v),), (), len(v), len(v)) * dc(v)

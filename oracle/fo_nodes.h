@@ -1,0 +1,1289 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see fo_math.h header). CPU restatement of the *block*
+// (`process`) semantics of SamiPerttu/fundsp v0.23.0 for the hot path in SURVEY.md §8a.
+// Every class cites the reference file:line it follows. Buffers are [channel][64] f32
+// (src/buffer.rs:12-151: channel c, sample i at (c<<6)+i).
+#pragma once
+#include "fo_math.h"
+#include <algorithm>
+#include <cassert>
+#include <map>
+#include <memory>
+#include <utility>
+#include <vector>
+#include <xmmintrin.h>
+
+namespace fo {
+
+constexpr int B = MAX_BUFFER_SIZE;
+inline int simd_items(int n) { return (n + 7) >> 3; }   // src/lib.rs:76-79
+inline int full_simd_items(int n) { return n >> 3; }    // src/lib.rs:82-85
+
+// ---- src/setting.rs:14-62 Parameter / Address / Setting
+enum ParamKind { P_NULL = 0, P_CENTER, P_CENTER_Q, P_CENTER_Q_GAIN, P_VALUE, P_COEFFICIENT,
+                 P_BIQUAD, P_DELAY, P_TIME, P_ROUGHNESS, P_VARIABILITY, P_PAN,
+                 P_ATTACK_RELEASE, P_PHASE, P_SEED, P_INTERVAL };
+struct Address { int type; uint64_t value; };  // type 1 = Index, 2 = Node
+struct Setting {
+  int kind = P_NULL;
+  float v[5] = {0, 0, 0, 0, 0};
+  uint64_t seed = 0;
+  std::vector<Address> address;
+  Address direction() const { return address.empty() ? Address{0, 0} : address[0]; }
+  Setting peel() const { Setting s = *this; if (!s.address.empty()) s.address.erase(s.address.begin()); return s; }
+};
+
+// ---- src/audionode.rs:29-369 AudioNode / src/audiounit.rs:21-95 AudioUnit (merged: oracle is dynamic)
+struct Node {
+  virtual ~Node() {}
+  virtual int inputs() const = 0;
+  virtual int outputs() const = 0;
+  virtual uint64_t id() const = 0;
+  virtual void reset() {}
+  virtual void set_sample_rate(double) {}
+  virtual void tick(const float* in, float* out) = 0;
+  // src/audionode.rs:85-105 default process = per-sample tick.
+  virtual void process(int size, const float* in, float* out) {
+    float fi[256], fo_[256];
+    const int ni = inputs(), no = outputs();
+    for (int i = 0; i < size; i++) {
+      for (int c = 0; c < ni; c++) fi[c] = in[c * B + i];
+      tick(fi, fo_);
+      for (int c = 0; c < no; c++) out[c * B + i] = fo_[c];
+    }
+  }
+  // src/audionode.rs:110-126
+  void process_remainder(int size, const float* in, float* out) {
+    float fi[256], fo_[256];
+    const int ni = inputs(), no = outputs();
+    for (int i = size & ~7; i < size; i++) {
+      for (int c = 0; c < ni; c++) fi[c] = in[c * B + i];
+      tick(fi, fo_);
+      for (int c = 0; c < no; c++) out[c * B + i] = fo_[c];
+    }
+  }
+  virtual void set(const Setting&) {}
+  virtual void set_hash(uint64_t) {}
+  // src/audionode.rs:156-161
+  virtual AttoHash ping(bool probe, AttoHash hash) {
+    if (!probe) { set_hash(hash.state); if (ping_trace()) ping_trace()->push_back(hash.state); }
+    return hash.hash(id());
+  }
+  // test hook: records the hash handed to every leaf during a non-probe ping
+  static std::vector<uint64_t>*& ping_trace() { static std::vector<uint64_t>* t = nullptr; return t; }
+  virtual Node* clone() const = 0;
+  // src/audionode.rs:871-876 etc: constructor-time ping of composite nodes.
+  void ctor_ping() { AttoHash h = ping(true, AttoHash(id())); ping(false, h); }
+};
+typedef std::unique_ptr<Node> NodeP;
+#define FO_CLONE(T) Node* clone() const override { return new T(*this); }
+
+// deep-copying child pointer
+struct Child {
+  NodeP p;
+  Child() {}
+  explicit Child(Node* n) : p(n) {}
+  Child(const Child& o) : p(o.p ? o.p->clone() : nullptr) {}
+  Child& operator=(const Child& o) { if (this != &o) p.reset(o.p ? o.p->clone() : nullptr); return *this; }
+  Child(Child&& o) noexcept : p(std::move(o.p)) {}
+  Child& operator=(Child&& o) noexcept { p = std::move(o.p); return *this; }
+  Node* operator->() const { return p.get(); }
+};
+
+// ---- src/audionode.rs:374-402 MultiPass (ID 0), :404-433 Pass (ID 48)
+struct MultiPass : Node {
+  int n; bool single;
+  MultiPass(int n_, bool single_) : n(n_), single(single_) {}
+  int inputs() const override { return n; } int outputs() const override { return n; }
+  uint64_t id() const override { return single ? 48 : 0; }
+  void tick(const float* in, float* out) override { for (int c = 0; c < n; c++) out[c] = in[c]; }
+  void process(int size, const float* in, float* out) override {
+    for (int c = 0; c < n; c++) for (int i = 0; i < simd_items(size) * 8; i++) out[c * B + i] = in[c * B + i];
+  }
+  FO_CLONE(MultiPass)
+};
+// ---- src/audionode.rs:435-465 Sink (ID 1)
+struct Sink : Node {
+  int n; explicit Sink(int n_) : n(n_) {}
+  int inputs() const override { return n; } int outputs() const override { return 0; }
+  uint64_t id() const override { return 1; }
+  void tick(const float*, float*) override {}
+  void process(int, const float*, float*) override {}
+  FO_CLONE(Sink)
+};
+// ---- src/audionode.rs:467-523 Constant (ID 2)
+struct Constant : Node {
+  std::vector<float> v;
+  explicit Constant(std::vector<float> v_) : v(std::move(v_)) {}
+  int inputs() const override { return 0; } int outputs() const override { return (int)v.size(); }
+  uint64_t id() const override { return 2; }
+  void tick(const float*, float* out) override { for (size_t c = 0; c < v.size(); c++) out[c] = v[c]; }
+  void process(int size, const float*, float* out) override {
+    for (size_t c = 0; c < v.size(); c++) for (int i = 0; i < simd_items(size) * 8; i++) out[c * B + i] = v[c];
+  }
+  void set(const Setting& s) override { if (s.kind == P_VALUE) for (auto& x : v) x = s.v[0]; }
+  FO_CLONE(Constant)
+};
+// ---- src/audionode.rs:525-567 Split (ID 40), :569-613 MultiSplit (ID 38)
+struct MultiSplit : Node {
+  int m, n; bool single;
+  MultiSplit(int m_, int n_, bool single_) : m(m_), n(n_), single(single_) {}
+  int inputs() const override { return m; } int outputs() const override { return m * n; }
+  uint64_t id() const override { return single ? 40 : 38; }
+  void tick(const float* in, float* out) override { for (int c = 0; c < m * n; c++) out[c] = in[c % m]; }
+  void process(int size, const float* in, float* out) override {
+    for (int c = 0; c < m * n; c++) for (int i = 0; i < simd_items(size) * 8; i++) out[c * B + i] = in[(c % m) * B + i];
+  }
+  FO_CLONE(MultiSplit)
+};
+// ---- src/audionode.rs:615-663 Join (ID 41), :665-722 MultiJoin (ID 39).
+// NOTE: tick adds then divides; process scales by z = 1/N then adds (:642-659, :697-718).
+struct MultiJoin : Node {
+  int m, n; bool single;
+  MultiJoin(int m_, int n_, bool single_) : m(m_), n(n_), single(single_) {}
+  int inputs() const override { return m * n; } int outputs() const override { return m; }
+  uint64_t id() const override { return single ? 41 : 39; }
+  void tick(const float* in, float* out) override {
+    for (int j = 0; j < m; j++) {
+      float o = in[j];
+      for (int i = 1; i < n; i++) o += in[j + i * m];
+      out[j] = o / (float)(int64_t)n;
+    }
+  }
+  void process(int size, const float* in, float* out) override {
+    const float z = 1.0f / (float)(uint64_t)n;
+    const int len = simd_items(size) * 8;
+    for (int c = 0; c < m; c++) for (int i = 0; i < len; i++) out[c * B + i] = in[c * B + i] * z;
+    for (int c = m; c < m * n; c++) for (int i = 0; i < len; i++) out[(c % m) * B + i] += in[c * B + i] * z;
+  }
+  FO_CLONE(MultiJoin)
+};
+// ---- src/audionode.rs:2800-2837 Reverse (ID 45)
+struct Reverse : Node {
+  int n; explicit Reverse(int n_) : n(n_) {}
+  int inputs() const override { return n; } int outputs() const override { return n; }
+  uint64_t id() const override { return 45; }
+  void tick(const float* in, float* out) override { for (int c = 0; c < n; c++) out[c] = in[n - 1 - c]; }
+  FO_CLONE(Reverse)
+};
+
+// ---- src/audionode.rs:724-1027 Binop (ID 3): x -> temp, y -> out, out = op(temp, out)
+enum BinopKind { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2 };
+inline float binop(int k, float x, float y) { return k == OP_ADD ? x + y : k == OP_SUB ? x - y : x * y; }
+struct Binop : Node {
+  int kind; Child x, y; std::vector<float> buf;
+  Binop(int k, Node* x_, Node* y_) : kind(k), x(x_), y(y_) {
+    assert(x->outputs() == y->outputs());
+    buf.assign((size_t)x->outputs() * B, 0.0f);
+    ctor_ping();
+  }
+  int inputs() const override { return x->inputs() + y->inputs(); }
+  int outputs() const override { return x->outputs(); }
+  uint64_t id() const override { return 3; }
+  void reset() override { x->reset(); y->reset(); }
+  void set_sample_rate(double sr) override { x->set_sample_rate(sr); y->set_sample_rate(sr); }
+  void tick(const float* in, float* out) override {
+    float a[256], b[256];
+    x->tick(in, a); y->tick(in + x->inputs(), b);
+    for (int c = 0; c < outputs(); c++) out[c] = binop(kind, a[c], b[c]);
+  }
+  void process(int size, const float* in, float* out) override {
+    x->process(size, in, buf.data());
+    y->process(size, in + x->inputs() * B, out);
+    for (int c = 0; c < outputs(); c++)
+      for (int i = 0; i < simd_items(size) * 8; i++) out[c * B + i] = binop(kind, buf[c * B + i], out[c * B + i]);
+  }
+  void set(const Setting& s) override {
+    Address d = s.direction();
+    if (d.type == 1 && d.value == 0) x->set(s.peel()); else if (d.type == 1 && d.value == 1) y->set(s.peel());
+  }
+  AttoHash ping(bool probe, AttoHash h) override { return y->ping(probe, x->ping(probe, h.hash(id()))); }
+  FO_CLONE(Binop)
+};
+
+// ---- src/audionode.rs:1029-1326 Unop (ID 4) with FrameNeg / FrameAddScalar / FrameNegAddScalar / FrameMulScalar
+enum UnopKind { U_NEG = 0, U_ADD = 1, U_NEGADD = 2, U_MUL = 3 };
+inline float unop(int k, float s, float x) {
+  switch (k) { case U_NEG: return -x; case U_ADD: return x + s; case U_NEGADD: return -x + s; default: return x * s; }
+}
+struct Unop : Node {
+  int kind; float scalar; Child x;
+  Unop(int k, float s, Node* x_) : kind(k), scalar(s), x(x_) { ctor_ping(); }
+  int inputs() const override { return x->inputs(); } int outputs() const override { return x->outputs(); }
+  uint64_t id() const override { return 4; }
+  void reset() override { x->reset(); }
+  void set_sample_rate(double sr) override { x->set_sample_rate(sr); }
+  void tick(const float* in, float* out) override {
+    x->tick(in, out);
+    for (int c = 0; c < outputs(); c++) out[c] = unop(kind, scalar, out[c]);
+  }
+  void process(int size, const float* in, float* out) override {
+    x->process(size, in, out);
+    for (int c = 0; c < outputs(); c++) for (int i = 0; i < simd_items(size) * 8; i++) out[c * B + i] = unop(kind, scalar, out[c * B + i]);
+  }
+  void set(const Setting& s) override { x->set(s); }
+  AttoHash ping(bool probe, AttoHash h) override { return x->ping(probe, h.hash(id())); }
+  FO_CLONE(Unop)
+};
+
+// ---- src/audionode.rs:1370-1492 Pipe (ID 6)
+struct Pipe : Node {
+  Child x, y; std::vector<float> buf;
+  Pipe(Node* x_, Node* y_) : x(x_), y(y_) {
+    assert(x->outputs() == y->inputs());
+    buf.assign((size_t)std::max(1, x->outputs()) * B, 0.0f);
+    ctor_ping();
+  }
+  int inputs() const override { return x->inputs(); } int outputs() const override { return y->outputs(); }
+  uint64_t id() const override { return 6; }
+  void reset() override { x->reset(); y->reset(); }
+  void set_sample_rate(double sr) override { x->set_sample_rate(sr); y->set_sample_rate(sr); }
+  void tick(const float* in, float* out) override { float t[256]; x->tick(in, t); y->tick(t, out); }
+  void process(int size, const float* in, float* out) override {
+    x->process(size, in, buf.data());
+    y->process(size, buf.data(), out);
+  }
+  void set(const Setting& s) override {
+    Address d = s.direction();
+    if (d.type == 1 && d.value == 0) x->set(s.peel()); else if (d.type == 1 && d.value == 1) y->set(s.peel());
+  }
+  AttoHash ping(bool probe, AttoHash h) override { return y->ping(probe, x->ping(probe, h.hash(id()))); }
+  FO_CLONE(Pipe)
+};
+
+// ---- src/audionode.rs:1494-1649 Stack (ID 7), :1651-1792 Branch (ID 8), :1794-1946 Bus (ID 10)
+struct Stack : Node {
+  Child x, y;
+  Stack(Node* x_, Node* y_) : x(x_), y(y_) { ctor_ping(); }
+  int inputs() const override { return x->inputs() + y->inputs(); }
+  int outputs() const override { return x->outputs() + y->outputs(); }
+  uint64_t id() const override { return 7; }
+  void reset() override { x->reset(); y->reset(); }
+  void set_sample_rate(double sr) override { x->set_sample_rate(sr); y->set_sample_rate(sr); }
+  void tick(const float* in, float* out) override { x->tick(in, out); y->tick(in + x->inputs(), out + x->outputs()); }
+  void process(int size, const float* in, float* out) override {
+    x->process(size, in, out);
+    y->process(size, in + x->inputs() * B, out + x->outputs() * B);
+  }
+  void set(const Setting& s) override {
+    Address d = s.direction();
+    if (d.type == 1 && d.value == 0) x->set(s.peel()); else if (d.type == 1 && d.value == 1) y->set(s.peel());
+  }
+  AttoHash ping(bool probe, AttoHash h) override { return y->ping(probe, x->ping(probe, h.hash(id()))); }
+  FO_CLONE(Stack)
+};
+struct Branch : Node {
+  Child x, y;
+  Branch(Node* x_, Node* y_) : x(x_), y(y_) { assert(x->inputs() == y->inputs()); ctor_ping(); }
+  int inputs() const override { return x->inputs(); }
+  int outputs() const override { return x->outputs() + y->outputs(); }
+  uint64_t id() const override { return 8; }
+  void reset() override { x->reset(); y->reset(); }
+  void set_sample_rate(double sr) override { x->set_sample_rate(sr); y->set_sample_rate(sr); }
+  void tick(const float* in, float* out) override { x->tick(in, out); y->tick(in, out + x->outputs()); }
+  void process(int size, const float* in, float* out) override {
+    x->process(size, in, out);
+    y->process(size, in, out + x->outputs() * B);
+  }
+  void set(const Setting& s) override {
+    Address d = s.direction();
+    if (d.type == 1 && d.value == 0) x->set(s.peel()); else if (d.type == 1 && d.value == 1) y->set(s.peel());
+  }
+  AttoHash ping(bool probe, AttoHash h) override { return y->ping(probe, x->ping(probe, h.hash(id()))); }
+  FO_CLONE(Branch)
+};
+struct Bus : Node {
+  Child x, y; std::vector<float> buf;
+  Bus(Node* x_, Node* y_) : x(x_), y(y_) {
+    assert(x->inputs() == y->inputs() && x->outputs() == y->outputs());
+    buf.assign((size_t)x->outputs() * B, 0.0f);
+    ctor_ping();
+  }
+  int inputs() const override { return x->inputs(); } int outputs() const override { return x->outputs(); }
+  uint64_t id() const override { return 10; }
+  void reset() override { x->reset(); y->reset(); }
+  void set_sample_rate(double sr) override { x->set_sample_rate(sr); y->set_sample_rate(sr); }
+  void tick(const float* in, float* out) override {
+    float t[256]; x->tick(in, out); y->tick(in, t);
+    for (int c = 0; c < outputs(); c++) out[c] = out[c] + t[c];
+  }
+  void process(int size, const float* in, float* out) override {
+    x->process(size, in, out);
+    y->process(size, in, buf.data());
+    for (int c = 0; c < outputs(); c++) for (int i = 0; i < simd_items(size) * 8; i++) out[c * B + i] += buf[c * B + i];
+  }
+  void set(const Setting& s) override {
+    Address d = s.direction();
+    if (d.type == 1 && d.value == 0) x->set(s.peel()); else if (d.type == 1 && d.value == 1) y->set(s.peel());
+  }
+  AttoHash ping(bool probe, AttoHash h) override { return y->ping(probe, x->ping(probe, h.hash(id()))); }
+  FO_CLONE(Bus)
+};
+
+// ---- src/audionode.rs:1948-2061 Thru (ID 12): pass missing outputs through from inputs.
+struct Thru : Node {
+  Child x; std::vector<float> buf;
+  explicit Thru(Node* x_) : x(x_) { buf.assign((size_t)std::max(1, x->outputs()) * B, 0.0f); ctor_ping(); }
+  int inputs() const override { return x->inputs(); } int outputs() const override { return x->inputs(); }
+  uint64_t id() const override { return 12; }
+  void reset() override { x->reset(); }
+  void set_sample_rate(double sr) override { x->set_sample_rate(sr); }
+  void tick(const float* in, float* out) override {
+    float t[256]; x->tick(in, t);
+    for (int c = 0; c < inputs(); c++) out[c] = c < x->outputs() ? t[c] : in[c];
+  }
+  void process(int size, const float* in, float* out) override {
+    if (x->inputs() == 0) return;
+    if (x->outputs() <= x->inputs()) {
+      x->process(size, in, out);
+    } else {
+      x->process(size, in, buf.data());
+      for (int c = 0; c < inputs(); c++) for (int i = 0; i < simd_items(size) * 8; i++) out[c * B + i] = buf[c * B + i];
+    }
+    for (int c = x->outputs(); c < inputs(); c++) for (int i = 0; i < simd_items(size) * 8; i++) out[c * B + i] = in[c * B + i];
+  }
+  void set(const Setting& s) override { x->set(s); }
+  AttoHash ping(bool probe, AttoHash h) override { return x->ping(probe, h.hash(id())); }
+  FO_CLONE(Thru)
+};
+
+// ---- src/audionode.rs:2063-2200 MultiBus (28), :2202-2355 MultiStack (30), :2357-2530 Reduce (31),
+//      :2532-2660 MultiBranch (33), :2662-2800 Chain (32)
+enum MultiKind { M_BUS = 28, M_STACK = 30, M_REDUCE = 31, M_BRANCH = 33, M_CHAIN = 32 };
+struct Multi : Node {
+  int kind; int op; std::vector<Child> x; std::vector<float> buf, buf2;
+  Multi(int kind_, int op_, std::vector<Node*> nodes) : kind(kind_), op(op_) {
+    for (Node* n : nodes) x.emplace_back(n);
+    assert(!x.empty());
+    buf.assign((size_t)std::max(1, x[0]->outputs()) * B, 0.0f);
+    buf2 = buf;
+    ctor_ping();
+  }
+  int N() const { return (int)x.size(); }
+  int inputs() const override {
+    switch (kind) { case M_STACK: case M_REDUCE: return x[0]->inputs() * N(); default: return x[0]->inputs(); }
+  }
+  int outputs() const override {
+    switch (kind) { case M_STACK: case M_BRANCH: return x[0]->outputs() * N(); default: return x[0]->outputs(); }
+  }
+  uint64_t id() const override { return (uint64_t)kind; }
+  void reset() override { for (auto& c : x) c->reset(); }
+  void set_sample_rate(double sr) override { for (auto& c : x) c->set_sample_rate(sr); }
+  void tick(const float* in, float* out) override {
+    const int xi = x[0]->inputs(), xo = x[0]->outputs();
+    float t[256], u[256];
+    switch (kind) {
+      case M_BUS:
+        x[0]->tick(in, out);
+        for (int k = 1; k < N(); k++) { x[k]->tick(in, t); for (int c = 0; c < xo; c++) out[c] = out[c] + t[c]; }
+        break;
+      case M_STACK: for (int k = 0; k < N(); k++) x[k]->tick(in + k * xi, out + k * xo); break;
+      case M_BRANCH: for (int k = 0; k < N(); k++) x[k]->tick(in, out + k * xo); break;
+      case M_REDUCE:
+        x[0]->tick(in, out);
+        for (int k = 1; k < N(); k++) { x[k]->tick(in + k * xi, t); for (int c = 0; c < xo; c++) out[c] = binop(op, out[c], t[c]); }
+        break;
+      case M_CHAIN:
+        for (int c = 0; c < xi; c++) t[c] = in[c];
+        for (int k = 0; k < N(); k++) { x[k]->tick(t, u); for (int c = 0; c < xo; c++) t[c] = u[c]; }
+        for (int c = 0; c < xo; c++) out[c] = t[c];
+        break;
+    }
+  }
+  void process(int size, const float* in, float* out) override {
+    const int xi = x[0]->inputs(), xo = x[0]->outputs(), len = simd_items(size) * 8;
+    switch (kind) {
+      case M_BUS:  // :2124-2135
+        x[0]->process(size, in, out);
+        for (int k = 1; k < N(); k++) {
+          x[k]->process(size, in, buf.data());
+          for (int c = 0; c < xo; c++) for (int i = 0; i < len; i++) out[c * B + i] += buf[c * B + i];
+        }
+        break;
+      case M_STACK: for (int k = 0; k < N(); k++) x[k]->process(size, in + k * xi * B, out + k * xo * B); break;
+      case M_BRANCH: for (int k = 0; k < N(); k++) x[k]->process(size, in, out + k * xo * B); break;
+      case M_REDUCE:  // :2442-2463
+        x[0]->process(size, in, out);
+        for (int k = 1; k < N(); k++) {
+          x[k]->process(size, in + k * xi * B, buf.data());
+          for (int c = 0; c < xo; c++) for (int i = 0; i < len; i++) out[c * B + i] = binop(op, out[c * B + i], buf[c * B + i]);
+        }
+        break;
+      case M_CHAIN: {  // :2737-2751 ping-pong
+        if (N() == 1) { x[0]->process(size, in, out); break; }
+        x[0]->process(size, in, buf.data());
+        float* a = buf.data(); float* b = buf2.data();
+        for (int k = 1; k < N() - 1; k++) { x[k]->process(size, a, b); std::swap(a, b); }
+        x[N() - 1]->process(size, a, out);
+        break;
+      }
+    }
+  }
+  void set(const Setting& s) override {
+    Address d = s.direction();
+    if (d.type == 1 && d.value < x.size()) x[d.value]->set(s.peel());
+  }
+  AttoHash ping(bool probe, AttoHash h) override {
+    h = h.hash(id());
+    for (auto& c : x) h = c->ping(probe, h);
+    return h;
+  }
+  FO_CLONE(Multi)
+};
+
+// ---- src/noise.rs:170-234 Noise (ID 20)
+struct Noise : Node {
+  uint32_t state = 0; bool has_seed = false; uint64_t seed = 0; uint64_t hash = 0;
+  int inputs() const override { return 0; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 20; }
+  void reset() override { uint64_t h = has_seed ? seed : hash; state = (uint32_t)(h ^ (h >> 32)); }
+  void tick(const float*, float* out) override {
+    state += 1;
+    out[0] = (float)(hash32x(state) >> 8) * (2.0f / (float)((1 << 24) - 1)) - 1.0f;
+  }
+  void process(int size, const float*, float* out) override {  // :201-215
+    const float Z = 2.0f / (float)((1 << 24) - 1);
+    for (int i = 0; i < simd_items(size) * 8; i++) out[i] = (float)(hash32x(state + (uint32_t)i + 1u) >> 8) * Z - 1.0f;
+    state += (uint32_t)size;
+  }
+  void set(const Setting& s) override { if (s.kind == P_SEED) { has_seed = true; seed = s.seed; } }
+  void set_hash(uint64_t h) override { hash = h; reset(); }
+  FO_CLONE(Noise)
+};
+
+// ---- src/oscillator.rs:18-102 Sine<f32> (ID 21)
+struct Sine : Node {
+  float phase = 0, sample_duration = 0; uint64_t hash = 0; bool has_phase = false; float initial_phase = 0;
+  Sine() { reset(); set_sample_rate(DEFAULT_SR); }
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 21; }
+  void reset() override { phase = has_phase ? initial_phase : (float)rnd1(hash); }
+  void set_sample_rate(double sr) override { sample_duration = (float)(1.0 / sr); }
+  void tick(const float* in, float* out) override {  // :67-72 (libm::sinf, wrap per sample)
+    float p = phase;
+    phase += in[0] * sample_duration;
+    phase -= floorf(phase);
+    out[0] = sinf(p * 6.28318530717958647692f);
+  }
+  void process(int size, const float* in, float* out) override {  // :74-86 (wide sin, wrap once per block)
+    float p = phase;
+    for (int i = 0; i < full_simd_items(size); i++) {
+      for (int j = 0; j < 8; j++) {
+        float tmp = p;
+        p += in[(i << 3) + j] * sample_duration;
+        out[(i << 3) + j] = wide_sinf(tmp * 6.28318530717958647692f);
+      }
+    }
+    phase = p - floorf(p);
+    process_remainder(size, in, out);
+  }
+  void set(const Setting& s) override { if (s.kind == P_PHASE) { has_phase = true; initial_phase = s.v[0]; } }
+  void set_hash(uint64_t h) override { hash = h; reset(); }
+  FO_CLONE(Sine)
+};
+
+// ---- src/wavetable.rs:24-38 optimal4x44 (T = f32)
+inline float optimal4x44(float a0, float a1, float a2, float a3, float x) {
+  float z = x - (float)0.5;
+  float even1 = a2 + a1, odd1 = a2 - a1, even2 = a3 + a0, odd2 = a3 - a0;
+  float c0 = even1 * (float)0.4656725512077848 + even2 * (float)0.03432729708429672;
+  float c1 = odd1 * (float)0.5374383075356016 + odd2 * (float)0.1542946255730746;
+  float c2 = even1 * (float)-0.25194210134021744 + even2 * (float)0.2519474493593906;
+  float c3 = odd1 * (float)-0.46896069955075126 + odd2 * (float)0.15578800670302476;
+  float c4 = even1 * (float)0.00986988334359864 + even2 * (float)-0.00989340017126506;
+  return (((c4 * z + c3) * z + c2) * z + c1) * z + c0;
+}
+
+// ---- src/wavetable.rs:40-242 Wavetable. The inverse FFT (`microfft 0.6.0`, src/fft.rs:51-100, not
+// under /root/reference) is replaced by the exact inverse DFT evaluated in f64:
+//   x.im[n] * N = sum_k re_k sin(2 pi k n / N) + im_k cos(2 pi k n / N)   (parity unpinned ~1e-7 of peak)
+struct Wavetable {
+  std::vector<std::pair<float, std::vector<float>>> table;
+  static std::vector<float> make_wave(double pitch, double (*phase)(uint32_t), double (*amp)(double, uint32_t)) {
+    const double MAX_F = 22000.0, FADE_F = 20000.0;
+    size_t harmonics = (size_t)floor(MAX_F / pitch);
+    size_t target_len = 4 * harmonics;
+    size_t p2 = 1; while (p2 < target_len) p2 <<= 1;
+    size_t length = std::min<size_t>(std::max<size_t>(p2, 32), 8192);
+    std::vector<double> re(length, 0.0), im(length, 0.0);
+    for (size_t i = 1; i <= harmonics; i++) {
+      double f = pitch * (double)i;
+      double w = amp(pitch, (uint32_t)i);
+      w = w * smooth5d(clamp01d(delerpd(MAX_F, FADE_F, f)));
+      if (w > 0.0 && i < length) {
+        float r = (float)w, th = (float)(6.283185307179586 * phase((uint32_t)i));
+        re[i] = (double)(r * cosf(th));  // Complex32::from_polar
+        im[i] = (double)(r * sinf(th));
+      }
+    }
+    std::vector<double> sn(length), cs(length);
+    for (size_t n = 0; n < length; n++) { sn[n] = sin(6.283185307179586 * (double)n / (double)length); cs[n] = cos(6.283185307179586 * (double)n / (double)length); }
+    std::vector<float> out(length);
+    for (size_t n = 0; n < length; n++) {
+      double acc = 0.0;
+      for (size_t k = 1; k <= harmonics && k < length; k++) {
+        size_t a = (k * n) & (length - 1);
+        acc += re[k] * sn[a] + im[k] * cs[a];
+      }
+      out[n] = (float)acc;
+    }
+    return out;
+  }
+  Wavetable(double min_pitch, double max_pitch, double tables_per_octave, double (*phase)(uint32_t), double (*amp)(double, uint32_t)) {
+    double pitch = min_pitch;
+    double p_factor = pow(2.0, 1.0 / tables_per_octave);
+    float max_amplitude = 0.0f;
+    while (pitch <= max_pitch) {
+      std::vector<float> wave = make_wave(pitch, phase, amp);
+      for (float x : wave) max_amplitude = fmaxf(max_amplitude, fabsf(x));
+      table.emplace_back((float)pitch, std::move(wave));
+      pitch *= p_factor;
+    }
+    if (max_amplitude > 0.0f) {
+      float z = 1.0f / max_amplitude;
+      for (auto& t : table) for (float& x : t.second) x *= z;
+    }
+  }
+  float at(size_t i, float phase) const {  // :125-137
+    const std::vector<float>& t = table[i].second;
+    float p = (float)t.size() * phase;
+    size_t i1 = (size_t)p;
+    float w = p - (float)i1;
+    size_t mask = t.size() - 1;
+    size_t i0 = (i1 - 1) & mask; i1 &= mask;
+    size_t i2 = (i1 + 1) & mask, i3 = (i1 + 2) & mask;
+    return optimal4x44(t[i0], t[i1], t[i2], t[i3], w);
+  }
+  float at_simd_lane(size_t i, float phase) const {  // :139-155 (i32 lanes, fast_trunc_int)
+    const std::vector<float>& t = table[i].second;
+    float p = (float)t.size() * phase;
+    int32_t i1 = (int32_t)p;  // cvttps2dq: truncation toward zero
+    float w = p - (float)i1;
+    int32_t mask = (int32_t)t.size() - 1;
+    int32_t i0 = (i1 - 1) & mask; i1 &= mask;
+    int32_t i2 = (i1 + 1) & mask, i3 = (i2 + 1) & mask;
+    return optimal4x44(t[i0], t[i1], t[i2], t[i3], w);
+  }
+  size_t table_index(size_t hint, float frequency) const {  // :157-179
+    if (frequency >= table[hint].first && frequency <= table[hint + 1].first) return hint;
+    size_t i0 = 0, i1 = table.size() - 3;
+    while (i0 < i1) {
+      size_t i = (i0 + i1) >> 1;
+      if (table[i].first > frequency) i1 = i;
+      else if (table[i + 1].first > frequency) { i0 = i; break; }
+      else i0 = i + 1;
+    }
+    return i0;
+  }
+};
+
+inline double ph_saw(uint32_t i) { return (i & 1) == 1 ? 0.0 : 0.5; }
+inline double am_saw(double, uint32_t i) { return 1.0 / (double)i; }
+inline double ph_zero(uint32_t) { return 0.0; }
+inline double am_square(double, uint32_t i) { return (i & 1) == 1 ? 1.0 / (double)i : 0.0; }
+inline double ph_tri(uint32_t i) { return (i & 3) == 3 ? 0.5 : 0.0; }
+inline double am_tri(double, uint32_t i) { return (i & 1) == 1 ? 1.0 / (double)(i * i) : 0.0; }
+inline double ph_organ(uint32_t i) { return (i & 3) == 3 ? 0.5 : ((i & 1) == 1 ? 0.0 : 0.5); }
+inline double am_organ(double, uint32_t i) { uint32_t z = __builtin_ctz(i); uint32_t j = i >> z; return 1.0 / (double)(i + j * j * j); }
+inline double am_softsaw(double, uint32_t i) { return 1.0 / (double)(i * i); }
+inline double am_hammond(double, uint32_t i) {
+  uint32_t z = __builtin_ctz(i); uint32_t j = i >> z; double f = 1.0 / (double)((z + 1) * (z + 1));
+  if (i == 1 || i == 2 || i == 3) return 1.0;
+  if (j == 1 || j == 3) return f;
+  if (j == 9) return 0.2 * f;
+  return 0.0;
+}
+// ---- src/wavetable.rs:493-623 global tables: 0 saw, 1 square, 2 triangle, 3 organ, 4 soft_saw, 5 hammond
+inline const Wavetable& global_table(int kind) {
+  static std::unique_ptr<Wavetable> t[6];
+  if (!t[kind]) {
+    switch (kind) {
+      case 0: t[0].reset(new Wavetable(20.0, 20000.0, 4.0, ph_saw, am_saw)); break;
+      case 1: t[1].reset(new Wavetable(20.0, 20000.0, 4.0, ph_zero, am_square)); break;
+      case 2: t[2].reset(new Wavetable(20.0, 20000.0, 4.0, ph_tri, am_tri)); break;
+      case 3: t[3].reset(new Wavetable(20.0, 20000.0, 4.0, ph_organ, am_organ)); break;
+      case 4: t[4].reset(new Wavetable(20.0, 20000.0, 4.0, ph_organ, am_softsaw)); break;
+      default: t[5].reset(new Wavetable(20.0, 20000.0, 4.0, ph_zero, am_hammond)); break;
+    }
+  }
+  return *t[kind];
+}
+
+// ---- src/wavetable.rs:244-359 WaveSynth<N> (ID 34)
+struct WaveSynth : Node {
+  int kind, nout; float phase = 0; uint64_t hash = 0; bool has_phase = false; float initial_phase = 0;
+  size_t table_hint = 0; float sample_rate = (float)DEFAULT_SR; float sample_duration = 1.0f / (float)DEFAULT_SR;
+  WaveSynth(int kind_, int nout_) : kind(kind_), nout(nout_) {}
+  const Wavetable& tab() const { return global_table(kind); }
+  int inputs() const override { return 1; } int outputs() const override { return nout; }
+  uint64_t id() const override { return 34; }
+  void reset() override { phase = has_phase ? initial_phase : (float)rnd1(hash); }
+  void set_sample_rate(double sr) override { sample_rate = (float)sr; sample_duration = 1.0f / (float)sr; }
+  void set_hash(uint64_t h) override { hash = h; reset(); }
+  void tick(const float* in, float* out) override {  // :309-325
+    float frequency = in[0];
+    phase += frequency * sample_duration;
+    phase -= floorf(phase);
+    const Wavetable& t = tab();
+    size_t ti = t.table_index(table_hint, fabsf(frequency));
+    float w = clamp01f(delerpf(t.table[ti].first, t.table[ti + 1].first, fabsf(frequency)));
+    float o = (1.0f - w) * t.at(ti + 1, phase) + w * t.at(ti + 2, phase);
+    table_hint = ti;
+    out[0] = o; if (nout > 1) out[1] = phase;
+  }
+  void process(int size, const float* in, float* out) override {  // :327-348
+    float p = phase; size_t hint = table_hint; const Wavetable& t = tab();
+    for (int i = 0; i < full_simd_items(size); i++) {
+      float frequency = in[i << 3];
+      float ph[8];
+      for (int j = 0; j < 8; j++) { p += in[(i << 3) + j] * sample_duration; ph[j] = p; }
+      for (int j = 0; j < 8; j++) ph[j] = ph[j] - wide_floorf(ph[j]);
+      size_t ti = t.table_index(hint, fabsf(frequency));
+      float w = clamp01f(delerpf(t.table[ti].first, t.table[ti + 1].first, fabsf(frequency)));
+      for (int j = 0; j < 8; j++) {
+        out[(i << 3) + j] = (1.0f - w) * t.at_simd_lane(ti + 1, ph[j]) + w * t.at_simd_lane(ti + 2, ph[j]);
+        if (nout > 1) out[B + (i << 3) + j] = ph[j];
+      }
+      hint = ti;
+    }
+    phase = p - floorf(p);
+    table_hint = hint;
+    process_remainder(size, in, out);
+  }
+  void set(const Setting& s) override { if (s.kind == P_PHASE) { has_phase = true; initial_phase = s.v[0]; } }
+  FO_CLONE(WaveSynth)
+};
+
+// ---- src/svf.rs:16-221 SvfCoefs<f32>; modes 0 lowpass 1 highpass 2 bandpass 3 notch 4 peak 5 allpass 6 bell 7 lowshelf 8 highshelf
+struct SvfCoefs { float a1 = 0, a2 = 0, a3 = 0, m0 = 0, m1 = 0, m2 = 0; };
+inline SvfCoefs svf_coefs(int mode, float sr, float cutoff, float q, float gain) {
+  const float PI_F = (float)3.14159265358979323846;
+  SvfCoefs c; float g, k;
+  if (mode <= 5) {
+    g = tanf(PI_F * cutoff / sr); k = 1.0f / q;
+  } else if (mode == 6) {
+    float a = sqrtf(gain); g = tanf(PI_F * cutoff / sr); k = 1.0f / (q * a);
+    c.m0 = 1.0f; c.m1 = k * (a * a - 1.0f); c.m2 = 0.0f;
+  } else if (mode == 7) {
+    float a = sqrtf(gain); g = tanf(PI_F * cutoff / sr) / sqrtf(a); k = 1.0f / q;
+    c.m0 = 1.0f; c.m1 = k * (a - 1.0f); c.m2 = a * a - 1.0f;
+  } else {
+    float a = sqrtf(gain); g = tanf(PI_F * cutoff / sr) * sqrtf(a); k = 1.0f / q;
+    c.m0 = a * a; c.m1 = k * (1.0f - a) * a; c.m2 = 1.0f - a * a;
+  }
+  c.a1 = 1.0f / (1.0f + g * (g + k)); c.a2 = g * c.a1; c.a3 = g * c.a2;
+  switch (mode) {
+    case 0: c.m0 = 0.0f; c.m1 = 0.0f; c.m2 = 1.0f; break;
+    case 1: c.m0 = 1.0f; c.m1 = -k; c.m2 = -1.0f; break;
+    case 2: c.m0 = 0.0f; c.m1 = 1.0f; c.m2 = 0.0f; break;
+    case 3: c.m0 = 1.0f; c.m1 = -k; c.m2 = 0.0f; break;
+    case 4: c.m0 = 1.0f; c.m1 = -k; c.m2 = -2.0f; break;
+    case 5: c.m0 = 1.0f; c.m1 = -2.0f * k; c.m2 = 0.0f; break;
+    default: break;
+  }
+  return c;
+}
+// ---- src/svf.rs:744-855 Svf (ID 36, parameter inputs) and :857-1031 FixedSvf (ID 43)
+struct Svf : Node {
+  int mode; bool fixed; float sr, cutoff, q, gain; SvfCoefs c; float ic1eq = 0, ic2eq = 0;
+  Svf(int mode_, bool fixed_, float cutoff_, float q_, float gain_) : mode(mode_), fixed(fixed_), sr((float)DEFAULT_SR), cutoff(cutoff_), q(q_), gain(gain_) { update(); }
+  void update() { c = svf_coefs(mode, sr, cutoff, q, gain); }
+  int inputs() const override { return fixed ? 1 : (mode >= 6 ? 4 : 3); } int outputs() const override { return 1; }
+  uint64_t id() const override { return fixed ? 43 : 36; }
+  void reset() override { ic1eq = 0; ic2eq = 0; }
+  void set_sample_rate(double s) override { sr = (float)s; update(); }
+  void tick(const float* in, float* out) override {
+    if (!fixed) {  // update_inputs (svf.rs:305-312 etc.): recompute only on change
+      if (mode >= 6) { if (in[1] != cutoff || in[2] != q || in[3] != gain) { cutoff = in[1]; q = in[2]; gain = in[3]; update(); } }
+      else if (in[1] != cutoff || in[2] != q) { cutoff = in[1]; q = in[2]; update(); }
+    }
+    float v0 = in[0];
+    float v3 = v0 - ic2eq;
+    float v1 = c.a1 * ic1eq + c.a2 * v3;
+    float v2 = ic2eq + c.a2 * ic1eq + c.a3 * v3;
+    ic1eq = 2.0f * v1 - ic1eq;
+    ic2eq = 2.0f * v2 - ic2eq;
+    out[0] = c.m0 * v0 + c.m1 * v1 + c.m2 * v2;
+  }
+  void set(const Setting& s) override {
+    if (!fixed) return;
+    if (s.kind == P_CENTER) { cutoff = s.v[0]; update(); }
+    else if (s.kind == P_CENTER_Q) { cutoff = s.v[0]; q = s.v[1]; update(); }
+    else if (s.kind == P_CENTER_Q_GAIN) { cutoff = s.v[0]; q = s.v[1]; gain = s.v[2]; update(); }
+  }
+  FO_CLONE(Svf)
+};
+
+// ---- src/biquad.rs:17-116 BiquadCoefs<f32>
+struct BiquadCoefs { float a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0; };
+inline BiquadCoefs biquad_butter_lowpass(float sr, float cutoff) {
+  const float PI_F = 3.14159274101257324f, SQRT_2 = 1.41421354f;
+  float f = tanf(cutoff * PI_F / sr);
+  float a0r = 1.0f / (1.0f + SQRT_2 * f + f * f);
+  BiquadCoefs c; c.a1 = (2.0f * f * f - 2.0f) * a0r; c.a2 = (1.0f - SQRT_2 * f + f * f) * a0r;
+  c.b0 = f * f * a0r; c.b1 = 2.0f * c.b0; c.b2 = c.b0; return c;
+}
+inline BiquadCoefs biquad_resonator(float sr, float center, float q) {
+  const float PI_F = 3.14159274101257324f, TAU_F = 6.28318548202514648f;
+  float r = expf(-PI_F * center / (q * sr));
+  BiquadCoefs c; c.a1 = -2.0f * r * cosf(TAU_F * center / sr); c.a2 = r * r;
+  c.b0 = sqrtf(1.0f - r * r) * 0.5f; c.b1 = 0.0f; c.b2 = -c.b0; return c;
+}
+inline BiquadCoefs biquad_lowpass(float sr, float cutoff, float q) {
+  const float TAU_F = 6.28318548202514648f;
+  float omega = TAU_F * cutoff / sr;
+  float alpha = sinf(omega) / (2.0f * q);
+  float beta = cosf(omega);
+  float a0r = 1.0f / (1.0f + alpha);
+  BiquadCoefs c; c.a1 = -2.0f * beta * a0r; c.a2 = (1.0f - alpha) * a0r;
+  c.b1 = (1.0f - beta) * a0r; c.b0 = c.b1 * 0.5f; c.b2 = c.b0; return c;
+}
+inline BiquadCoefs biquad_highpass(float sr, float cutoff, float q) {
+  const float TAU_F = 6.28318548202514648f;
+  float omega = TAU_F * cutoff / sr;
+  float alpha = sinf(omega) / (2.0f * q);
+  float beta = cosf(omega);
+  float a0r = 1.0f / (1.0f + alpha);
+  BiquadCoefs c; c.a1 = -2.0f * beta * a0r; c.a2 = (1.0f - alpha) * a0r;
+  c.b0 = (1.0f + beta) * 0.5f * a0r; c.b1 = (-1.0f - beta) * a0r; c.b2 = c.b0; return c;
+}
+inline BiquadCoefs biquad_bell(float sr, float center, float q, float gain) {
+  const float TAU_F = 6.28318548202514648f;
+  float omega = TAU_F * center / sr;
+  float alpha = sinf(omega) / (2.0f * q);
+  float beta = cosf(omega);
+  float a = sqrtf(gain);
+  float a0r = 1.0f / (1.0f + alpha / a);
+  BiquadCoefs c; c.a1 = -2.0f * beta * a0r; c.a2 = (1.0f - alpha / a) * a0r;
+  c.b0 = (1.0f + alpha * a) * a0r; c.b1 = c.a1; c.b2 = (1.0f - alpha * a) * a0r; return c;
+}
+// ---- src/biquad.rs:130-218 Biquad<f32> (ID 15): DF1, evaluated left to right.
+struct Biquad : Node {
+  BiquadCoefs c; float x1 = 0, x2 = 0, y1 = 0, y2 = 0;
+  explicit Biquad(BiquadCoefs c_) : c(c_) {}
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 15; }
+  void reset() override { x1 = x2 = y1 = y2 = 0; }
+  void tick(const float* in, float* out) override {
+    float x0 = in[0];
+    float y0 = c.b0 * x0 + c.b1 * x1 + c.b2 * x2 - c.a1 * y1 - c.a2 * y2;
+    x2 = x1; x1 = x0; y2 = y1; y1 = y0; out[0] = y0;
+  }
+  void set(const Setting& s) override { if (s.kind == P_BIQUAD) { c.a1 = s.v[0]; c.a2 = s.v[1]; c.b0 = s.v[2]; c.b1 = s.v[3]; c.b2 = s.v[4]; } }
+  FO_CLONE(Biquad)
+};
+// ---- src/biquad.rs:220-299 ButterLowpass<f32,N> (ID 16), :301-382 Resonator<f32,N> (ID 17)
+struct ButterLowpass : Node {
+  int nin; Biquad bq; float sr, cutoff;
+  ButterLowpass(float cutoff_, int nin_) : nin(nin_), bq(BiquadCoefs()), sr((float)DEFAULT_SR), cutoff(0) { set_cutoff(cutoff_); }
+  void set_cutoff(float c) { bq.c = biquad_butter_lowpass(sr, c); cutoff = c; }
+  int inputs() const override { return nin; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 16; }
+  void reset() override { bq.reset(); }
+  void set_sample_rate(double s) override { sr = (float)s; bq.set_sample_rate(s); set_cutoff(cutoff); }
+  void tick(const float* in, float* out) override {
+    if (nin > 1) { float c = in[1]; if (c != cutoff) set_cutoff(c); }
+    bq.tick(in, out);
+  }
+  void set(const Setting& s) override { if (s.kind == P_CENTER) set_cutoff(s.v[0]); }
+  FO_CLONE(ButterLowpass)
+};
+struct Resonator : Node {
+  int nin; Biquad bq; float sr, center, q;
+  Resonator(float center_, float q_, int nin_) : nin(nin_), bq(BiquadCoefs()), sr((float)DEFAULT_SR), center(0), q(0) { set_center_q(center_, q_); }
+  void set_center_q(float c, float q_) { bq.c = biquad_resonator(sr, c, q_); center = c; q = q_; }
+  int inputs() const override { return nin; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 17; }
+  void reset() override { bq.reset(); }
+  void set_sample_rate(double s) override { sr = (float)s; set_center_q(center, q); }
+  void tick(const float* in, float* out) override {
+    if (nin >= 3) { float c = in[1], qq = in[2]; if (c != center || qq != q) set_center_q(c, qq); }
+    bq.tick(in, out);
+  }
+  void set(const Setting& s) override { if (s.kind == P_CENTER) set_center_q(s.v[0], q); else if (s.kind == P_CENTER_Q) set_center_q(s.v[0], s.v[1]); }
+  FO_CLONE(Resonator)
+};
+// ---- src/biquad_bank.rs:9-117 BiquadBank<f32x8> (ID 98): 8 lanes, one per channel.
+struct BiquadBank : Node {
+  BiquadCoefs c[8]; float x1[8] = {0}, x2[8] = {0}, y1[8] = {0}, y2[8] = {0};
+  int inputs() const override { return 8; } int outputs() const override { return 8; }
+  uint64_t id() const override { return 98; }
+  void reset() override { for (int l = 0; l < 8; l++) x1[l] = x2[l] = y1[l] = y2[l] = 0; }
+  void tick(const float* in, float* out) override {
+    for (int l = 0; l < 8; l++) {
+      float x0 = in[l];
+      float y0 = c[l].b0 * x0 + c[l].b1 * x1[l] + c[l].b2 * x2[l] - c[l].a1 * y1[l] - c[l].a2 * y2[l];
+      x2[l] = x1[l]; x1[l] = x0; y2[l] = y1[l]; y1[l] = y0; out[l] = y0;
+    }
+  }
+  void set(const Setting& s) override {
+    Address d = s.direction();
+    if (d.type == 1 && s.kind == P_BIQUAD && d.value < 8) { BiquadCoefs& k = c[d.value]; k.a1 = s.v[0]; k.a2 = s.v[1]; k.b0 = s.v[2]; k.b1 = s.v[3]; k.b2 = s.v[4]; }
+  }
+  FO_CLONE(BiquadBank)
+};
+
+// ---- src/moog.rs:11-117 Moog<f32, N> (ID 60)
+struct Moog : Node {
+  int nin; float q = 0, cutoff = 0, sr, rez = 0, p = 0, k = 0, s0 = 0, s1 = 0, s2 = 0, s3 = 0, px = 0, ps0 = 0, ps1 = 0, ps2 = 0;
+  Moog(float cutoff_, float q_, int nin_) : nin(nin_), sr((float)DEFAULT_SR) { set_cutoff_q(cutoff_, q_); }
+  void set_cutoff_q(float cutoff_, float q_) {  // :48-57
+    cutoff = cutoff_; q = q_;
+    float c = 2.0f * cutoff / sr;
+    p = c * (1.8f - 0.8f * c);
+    k = 2.0f * sinf(c * 3.14159274101257324f * 0.5f) - 1.0f;
+    float t1 = (1.0f - p) * 1.386249f;
+    float t2 = 12.0f + t1 * t1;
+    rez = q * (t2 + 6.0f * t1) / (t2 - 6.0f * t1);
+  }
+  int inputs() const override { return nin; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 60; }
+  void reset() override { s0 = s1 = s2 = s3 = px = ps0 = ps1 = ps2 = 0; }
+  void set_sample_rate(double s) override { sr = (float)s; set_cutoff_q(cutoff, q); }
+  void tick(const float* in, float* out) override {  // :81-100
+    if (nin > 1) set_cutoff_q(in[1], in[2]);
+    float x = -rez * s3 + in[0];
+    s0 = (x + px) * p - k * s0;
+    s1 = (s0 + ps0) * p - k * s1;
+    s2 = (s1 + ps1) * p - k * s2;
+    s3 = tanhf((s2 + ps2) * p - k * s3);
+    px = x; ps0 = s0; ps1 = s1; ps2 = s2;
+    out[0] = s3;
+  }
+  void set(const Setting& s) override { if (s.kind == P_CENTER) set_cutoff_q(s.v[0], q); else if (s.kind == P_CENTER_Q) set_cutoff_q(s.v[0], s.v[1]); }
+  FO_CLONE(Moog)
+};
+
+// ---- src/fir.rs:11-89 Fir<N> (ID 52)
+struct Fir : Node {
+  std::vector<float> w, v;
+  explicit Fir(std::vector<float> w_) : w(std::move(w_)), v(w.size(), 0.0f) {}
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 52; }
+  void reset() override { std::fill(v.begin(), v.end(), 0.0f); }
+  void tick(const float* in, float* out) override {
+    const size_t n = w.size();
+    for (size_t i = 0; i + 1 < n; i++) v[i] = v[i + 1];
+    v[n - 1] = in[0];
+    float o = 0.0f;
+    for (size_t i = 0; i < n; i++) o += w[i] * v[i];
+    out[0] = o;
+  }
+  FO_CLONE(Fir)
+};
+
+// ---- src/delay.rs:17-65 Tick<N> (ID 9)
+struct TickNode : Node {
+  std::vector<float> buf; explicit TickNode(int n) : buf(n, 0.0f) {}
+  int inputs() const override { return (int)buf.size(); } int outputs() const override { return (int)buf.size(); }
+  uint64_t id() const override { return 9; }
+  void reset() override { std::fill(buf.begin(), buf.end(), 0.0f); }
+  void tick(const float* in, float* out) override { for (size_t c = 0; c < buf.size(); c++) { float t = buf[c]; buf[c] = in[c]; out[c] = t; } }
+  FO_CLONE(TickNode)
+};
+// ---- src/delay.rs:67-139 Delay (ID 13)
+struct Delay : Node {
+  std::vector<float> buffer; size_t i = 0; double sample_rate = 0.0, time; size_t time_in_samples = 0;
+  explicit Delay(double t) : time(t) { assert(t >= 0.0); set_sample_rate(DEFAULT_SR); }
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 13; }
+  void reset() override { i = 0; std::fill(buffer.begin(), buffer.end(), 0.0f); }
+  void set_sample_rate(double sr) override {
+    if (sample_rate != sr) {
+      sample_rate = sr;
+      time_in_samples = (size_t)round(time * sr);
+      buffer.resize(time_in_samples + 1, 0.0f);
+      reset();
+    }
+  }
+  void tick(const float* in, float* out) override {
+    buffer[i] = in[0];
+    i += 1; if (i >= buffer.size()) i = 0;
+    out[0] = buffer[i];
+  }
+  FO_CLONE(Delay)
+};
+// ---- src/delay.rs:288-377 AllNest<N,X> (ID 83)
+struct AllNest : Node {
+  int nin; Child x; float eta, z = 0;
+  AllNest(float coefficient, Node* x_, int nin_) : nin(nin_), x(x_), eta(coefficient) {}
+  int inputs() const override { return nin; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 83; }
+  void reset() override { z = 0; x->reset(); }
+  void set_sample_rate(double sr) override { x->set_sample_rate(sr); }
+  void tick(const float* in, float* out) override {
+    if (nin > 1) eta = in[1];
+    float v = in[0] - eta * z;
+    float y = eta * v + z;
+    float o; x->tick(&v, &o); z = o;
+    out[0] = y;
+  }
+  void set(const Setting& s) override { if (s.kind == P_COEFFICIENT) eta = s.v[0]; }
+  AttoHash ping(bool probe, AttoHash h) override { return x->ping(probe, h.hash(id())); }
+  FO_CLONE(AllNest)
+};
+
+// ---- src/denormal.rs:5-21 prevent_denormals: _mm_setcsr(0x9fc0) = FTZ + DAZ, process-wide and sticky.
+inline bool& denormal_emulation_enabled() { static bool e = true; return e; }
+inline void prevent_denormals() { if (denormal_emulation_enabled()) _mm_setcsr(0x9fc0); }
+
+// ---- src/feedback.rs:17-66 FrameHadamard, :68-178 Feedback<N,X,U> (ID 11)
+inline void hadamard(float* v, int n) {
+  for (int h = 1; h < n; h *= 2)
+    for (int i = 0; i < n; i += h * 2)
+      for (int j = i; j < i + h; j++) { float x = v[j], y = v[j + h]; v[j] = x + y; v[j + h] = x - y; }
+  const float z = (float)(1.0 / sqrt((double)n));
+  for (int i = 0; i < n; i++) v[i] = v[i] * z;
+}
+struct Feedback : Node {
+  Child x; bool had; std::vector<float> value;
+  Feedback(Node* x_, bool hadamard_) : x(x_), had(hadamard_) {
+    assert(x->inputs() == x->outputs());
+    prevent_denormals();
+    value.assign(x->inputs(), 0.0f);
+    ctor_ping();
+  }
+  int inputs() const override { return x->inputs(); } int outputs() const override { return x->outputs(); }
+  uint64_t id() const override { return 11; }
+  void reset() override { x->reset(); std::fill(value.begin(), value.end(), 0.0f); }
+  void set_sample_rate(double sr) override { x->set_sample_rate(sr); }
+  void tick(const float* in, float* out) override {
+    const int n = inputs(); float t[256];
+    for (int c = 0; c < n; c++) t[c] = in[c] + value[c];
+    x->tick(t, out);
+    for (int c = 0; c < n; c++) value[c] = out[c];
+    if (had) hadamard(value.data(), n);
+  }
+  void process(int size, const float* in, float* out) override {  // :136-146: ticks the inner graph
+    const int n = inputs(); float t[256], o[256];
+    for (int i = 0; i < size; i++) {
+      for (int c = 0; c < n; c++) t[c] = in[c * B + i] + value[c];
+      x->tick(t, o);
+      for (int c = 0; c < n; c++) value[c] = o[c];
+      if (had) hadamard(value.data(), n);
+      for (int c = 0; c < n; c++) out[c * B + i] = o[c];
+    }
+  }
+  AttoHash ping(bool probe, AttoHash h) override { return x->ping(probe, h.hash(id())); }
+  FO_CLONE(Feedback)
+};
+
+// ---- src/pan.rs:12-91 Panner<N> (ID 49)
+inline void pan_weights(float value, float& l, float& r) {
+  float angle = (clamp11f(value) + 1.0f) * (3.14159274101257324f * 0.25f);
+  l = cosf(angle); r = sinf(angle);
+}
+struct Panner : Node {
+  int nin; float lw, rw;
+  Panner(float value, int nin_) : nin(nin_) { pan_weights(value, lw, rw); }
+  int inputs() const override { return nin; } int outputs() const override { return 2; }
+  uint64_t id() const override { return 49; }
+  void tick(const float* in, float* out) override {
+    if (nin > 1) pan_weights(in[1], lw, rw);
+    out[0] = lw * in[0]; out[1] = rw * in[0];
+  }
+  void process(int size, const float* in, float* out) override {
+    if (nin == 1) {
+      for (int i = 0; i < simd_items(size) * 8; i++) { out[i] = in[i] * lw; out[B + i] = in[i] * rw; }
+    } else {
+      for (int i = 0; i < size; i++) { pan_weights(in[B + i], lw, rw); out[i] = in[i] * lw; out[B + i] = in[i] * rw; }
+    }
+  }
+  void set(const Setting& s) override { if (s.kind == P_PAN) pan_weights(s.v[0], lw, rw); }
+  FO_CLONE(Panner)
+};
+
+// ---- src/envelope.rs:185-358 EnvelopeIn<f32, E, U1, f32> (ID 53) specialised to the closed-form
+// closure of src/adsr.rs:21-70 `adsr_live(attack, decay, sustain, release)`.
+struct AdsrLive : Node {
+  float attack, decay, sustain, release;
+  // closure state (adsr.rs:27-33): `attacked`, Shared attack_start (a) and release_start (b)
+  bool attacked = false; float attack_start = 0.0f, release_start = -1.0f;
+  // EnvelopeIn state
+  float t = 0, t_0 = 0, t_1 = 0; uint64_t t_hash = 0; float value_0 = 0, value_1 = 0, value = 0, value_d = 0;
+  float interval, sample_duration = 0; uint64_t hash = 0;
+  AdsrLive(float a, float d, float s, float r) : attack(a), decay(d), sustain(s), release(r), interval((float)0.002) {
+    set_sample_rate(DEFAULT_SR); reset();
+  }
+  static float ads(float attack, float decay, float sustain, float time) {
+    if (time < attack) return lerpf(0.0f, 1.0f, time / attack);
+    float decay_time = time - attack;
+    if (decay_time < decay) return lerpf(1.0f, sustain, decay_time / decay);
+    return sustain;
+  }
+  float envelope(float time, float control) {
+    if (release_start >= 0.0f && control > 0.0f) { attacked = true; attack_start = time; release_start = -1.0f; }
+    else if (release_start < 0.0f && control <= 0.0f) { release_start = time; }
+    if (!attacked) return 0.0f;
+    float ads_value = ads(attack, decay, sustain, time - attack_start);
+    if (release_start < 0.0f) return ads_value;
+    return ads_value * clamp01f(delerpf(release_start + release, release_start, time));
+  }
+  void next_segment(float input) {  // envelope.rs:238-263
+    if (t_0 == 0.0f && t_1 == 0.0f) { value_0 = envelope(t_0, input); }
+    else { t_0 = t_1; value_0 = value_1; }
+    float next_interval = lerpf(0.75f, 1.25f, (float)rnd1(t_hash)) * interval;
+    t_1 = t_0 + next_interval;
+    value_1 = envelope(t_1, input);
+    t_hash = t_hash * 6364136223846793005ull + 1ull;
+    float u = delerpf(t_0, t_1, t);
+    value = lerpf(value_0, value_1, u);
+    float samples = next_interval / sample_duration;
+    value_d = (value_1 - value_0) / samples;
+  }
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 53; }
+  void reset() override { t = 0; t_0 = 0; t_1 = 0; t_hash = hash; }
+  void set_sample_rate(double sr) override { sample_duration = (float)(1.0 / sr); }
+  void tick(const float* in, float* out) override {  // :297-305
+    if (t >= t_1) next_segment(in[0]);
+    out[0] = value; value += value_d; t += sample_duration;
+  }
+  void process(int size, const float* in, float* out) override {  // :307-341
+    if (size == 0) return;
+    if (t >= t_1) next_segment(in[0]);
+    int i = 0;
+    while (i < size) {
+      size_t segment_samples_left = (size_t)(int64_t)ceilf((t_1 - t) / sample_duration);
+      size_t loop_samples = std::min<size_t>((size_t)(size - i), segment_samples_left);
+      float v = value, delta = value_d;
+      for (size_t o = 0; o < loop_samples; o++) { out[i + o] = v; v += delta; }
+      value = v;
+      i += (int)loop_samples;
+      t += (float)(int64_t)loop_samples * sample_duration;
+      if (loop_samples == segment_samples_left && i < size) next_segment(in[i]);
+    }
+  }
+  void set(const Setting& s) override { if (s.kind == P_INTERVAL) interval = s.v[0]; }
+  void set_hash(uint64_t h) override { hash = h; t_hash = h; }
+  FO_CLONE(AdsrLive)
+};
+
+// ---- src/net.rs:73-146, 175-260, 556-820, 834-916, 1187-1286, 1383-1389; src/vertex.rs:16-122,162-170
+struct Port { int type; int node; int port; };  // type 0 Zero, 1 Global(port), 2 Local(node, port)
+struct Vertex {
+  Child unit; std::vector<Port> source; std::vector<float> input, output, tick_in, tick_out;
+  bool has_sv = false; int sv_node = 0, sv_port = 0; int unplugged = 0; bool ordered = false;
+};
+struct Net : Node {
+  int nin, nout; std::vector<Port> output_edge; std::vector<Vertex> vertex; std::vector<int> order; bool ordered = false;
+  float sample_rate = (float)DEFAULT_SR; bool cycle = false;
+  Net(int i, int o) : nin(i), nout(o) { output_edge.assign(o, Port{0, 0, 0}); }
+  int inputs() const override { return nin; } int outputs() const override { return nout; }
+  uint64_t id() const override { return 63; }
+  int push(Node* unit) {
+    unit->set_sample_rate((double)sample_rate);
+    Vertex v; v.unit = Child(unit);
+    v.source.assign(unit->inputs(), Port{0, 0, 0});
+    v.input.assign((size_t)std::max(1, unit->inputs()) * B, 0.0f);
+    v.output.assign((size_t)std::max(1, unit->outputs()) * B, 0.0f);
+    v.tick_in.assign(std::max(1, unit->inputs()), 0.0f); v.tick_out.assign(std::max(1, unit->outputs()), 0.0f);
+    vertex.push_back(std::move(v)); ordered = false;
+    return (int)vertex.size() - 1;
+  }
+  void connect(int s, int sp, int t, int tp) { assert(s != t); vertex[t].source[tp] = Port{2, s, sp}; ordered = false; }
+  void connect_input(int gi, int t, int tp) { vertex[t].source[tp] = Port{1, 0, gi}; ordered = false; }
+  void connect_output(int s, int sp, int go) { output_edge[go] = Port{2, s, sp}; ordered = false; }
+  void pass_through(int gi, int go) { output_edge[go] = Port{1, 0, gi}; ordered = false; }
+  void pipe_input(int t) {
+    for (int c = 0; c < vertex[t].unit->inputs(); c++) vertex[t].source[c] = nin > 0 ? Port{1, 0, c % nin} : Port{0, 0, 0};
+    ordered = false;
+  }
+  void pipe_output(int s) {
+    int no = vertex[s].unit->outputs();
+    for (int c = 0; c < nout; c++) output_edge[c] = no > 0 ? Port{2, s, c % no} : Port{0, 0, 0};
+    ordered = false;
+  }
+  void pipe_all(int s, int t) {
+    if (s == t) return;
+    int no = vertex[s].unit->outputs();
+    for (int c = 0; c < vertex[t].unit->inputs(); c++) vertex[t].source[c] = no > 0 ? Port{2, s, c % no} : Port{0, 0, 0};
+    ordered = false;
+  }
+  int chain(Node* unit) {  // :764-787
+    int ui = unit->inputs();
+    int idx = push(unit);
+    if (vertex.size() == 1) { if (nin > 0) pipe_input(idx); }
+    else for (int i = 0; i < ui; i++) vertex[idx].source[i] = nout > 0 ? output_edge[i % nout] : Port{0, 0, 0};
+    pipe_output(idx); ordered = false;
+    return idx;
+  }
+  static Net* wrap(Node* unit) {  // :925-935
+    Net* n = new Net(unit->inputs(), unit->outputs());
+    int id = n->push(unit);
+    if (n->nin > 0) n->pipe_input(id);
+    if (n->nout > 0) n->pipe_output(id);
+    return n;
+  }
+  void append_vertices(Net& o, int offset, int input_offset, bool global_to_output_edge) {
+    for (auto& v : o.vertex) vertex.push_back(v);
+    for (size_t node = offset; node < vertex.size(); node++)
+      for (auto& s : vertex[node].source) {
+        if (s.type == 2) s.node += offset;
+        else if (s.type == 1) { if (global_to_output_edge) s = output_edge[s.port]; else s.port += input_offset; }
+      }
+  }
+  // graph algebra (src/net.rs:1447-1832); each consumes both operands and returns a new net (net1 mutated).
+  static Net* bus(Net* n1, Net* n2) {
+    assert(n1->nin == n2->nin && n1->nout == n2->nout);
+    std::vector<Port> o1 = n1->output_edge, o2 = n2->output_edge;
+    int offset = (int)n1->vertex.size();
+    n1->append_vertices(*n2, offset, 0, false);
+    int add_offset = (int)n1->vertex.size();
+    for (int i = 0; i < n1->nout; i++) {
+      n1->push(new Binop(OP_ADD, new MultiPass(1, true), new MultiPass(1, true)));
+      n1->connect_output(add_offset + i, 0, i);
+    }
+    for (size_t i = 0; i < o1.size(); i++) {
+      if (o1[i].type == 2) n1->connect(o1[i].node, o1[i].port, add_offset + (int)i, 0);
+      else if (o1[i].type == 1) n1->connect_input(o1[i].port, add_offset + (int)i, 0);
+    }
+    for (size_t i = 0; i < o2.size(); i++) {
+      if (o2[i].type == 2) n1->connect(o2[i].node + offset, o2[i].port, add_offset + (int)i, 1);
+      else if (o2[i].type == 1) n1->connect_input(o2[i].port, add_offset + (int)i, 1);
+    }
+    n1->ordered = false; delete n2; return n1;
+  }
+  static Net* binary(Net* n1, Net* n2, int op) {
+    assert(n1->nout == n2->nout);
+    std::vector<Port> o1 = n1->output_edge, o2 = n2->output_edge;
+    int input_offset = n1->nin, offset = (int)n1->vertex.size();
+    n1->append_vertices(*n2, offset, input_offset, false);
+    n1->nin += n2->nin;
+    int add_offset = (int)n1->vertex.size();
+    for (int i = 0; i < n1->nout; i++) {
+      n1->push(new Binop(op, new MultiPass(1, true), new MultiPass(1, true)));
+      n1->connect_output(add_offset + i, 0, i);
+    }
+    for (size_t i = 0; i < o1.size(); i++) {
+      if (o1[i].type == 2) n1->connect(o1[i].node, o1[i].port, add_offset + (int)i, 0);
+      else if (o1[i].type == 1) n1->connect_input(o1[i].port, add_offset + (int)i, 0);
+    }
+    for (size_t i = 0; i < o2.size(); i++) {
+      if (o2[i].type == 2) n1->connect(o2[i].node + offset, o2[i].port, add_offset + (int)i, 1);
+      else if (o2[i].type == 1) n1->connect_input(o2[i].port + input_offset, add_offset + (int)i, 1);
+    }
+    n1->ordered = false; delete n2; return n1;
+  }
+  static Net* stack(Net* n1, Net* n2) {
+    int offset = (int)n1->vertex.size(), input_offset = n1->nin, output_offset = n1->nout;
+    n1->append_vertices(*n2, offset, input_offset, false);
+    for (auto e : n2->output_edge) {
+      if (e.type == 2) e.node += offset; else if (e.type == 1) e.port += input_offset;
+      n1->output_edge.push_back(e);
+    }
+    (void)output_offset;
+    n1->nin += n2->nin; n1->nout += n2->nout;
+    n1->ordered = false; delete n2; return n1;
+  }
+  static Net* branch(Net* n1, Net* n2) {
+    assert(n1->nin == n2->nin);
+    int offset = (int)n1->vertex.size();
+    n1->append_vertices(*n2, offset, 0, false);
+    for (auto e : n2->output_edge) { if (e.type == 2) e.node += offset; n1->output_edge.push_back(e); }
+    n1->nout += n2->nout;
+    n1->ordered = false; delete n2; return n1;
+  }
+  static Net* pipe(Net* n1, Net* n2) {
+    assert(n1->nout == n2->nin);
+    int offset = (int)n1->vertex.size();
+    n1->append_vertices(*n2, offset, 0, true);
+    std::vector<Port> oe1 = n1->output_edge;
+    n1->output_edge = n2->output_edge; n1->nout = n2->nout;
+    for (auto& e : n1->output_edge) {
+      if (e.type == 2) e.node += offset; else if (e.type == 1) e = oe1[e.port];
+    }
+    n1->ordered = false; delete n2; return n1;
+  }
+  // ---- ordering (:834-916)
+  void determine_order() {
+    for (auto& v : vertex) {  // vertex.rs:98-122 update_source_vertex
+      v.has_sv = false;
+      int ni = v.unit->inputs(); if (ni == 0) continue;
+      bool ok = true; int sn = 0, sp = 0;
+      for (int i = 0; i < ni && ok; i++) {
+        Port s = v.source[i];
+        if (s.type == 2) { if (i == 0) { sn = s.node; sp = s.port; } else if (sn != s.node || sp + i != s.port) ok = false; }
+        else ok = false;
+      }
+      if (ok) { v.has_sv = true; v.sv_node = sn; v.sv_port = sp; }
+    }
+    AttoHash h = ping(true, AttoHash(id())); ping(false, h);
+    order.clear();
+    for (auto& v : vertex) { v.unplugged = 0; v.ordered = false; }
+    for (auto& v : vertex) for (int c = 0; c < v.unit->inputs(); c++) if (v.source[c].type == 2) vertex[v.source[c].node].unplugged += 1;
+    for (size_t i = 0; i < vertex.size(); i++) {
+      if (vertex[i].ordered) continue;
+      if (vertex[i].unplugged == 0) { vertex[i].ordered = true; order.push_back((int)i); propagate((int)i); }
+    }
+    cycle = order.size() < vertex.size();
+    if (cycle) for (size_t i = 0; i < vertex.size(); i++) if (!vertex[i].ordered) order.push_back((int)i);
+    std::reverse(order.begin(), order.end());
+    ordered = true;
+  }
+  void propagate(int i) {  // explicit stack instead of recursion, same visiting order as :877-888
+    struct Fr { int node; int ch; };
+    std::vector<Fr> st; st.push_back({i, 0});
+    while (!st.empty()) {
+      Fr& f = st.back();
+      if (f.ch >= vertex[f.node].unit->inputs()) { st.pop_back(); continue; }
+      Port s = vertex[f.node].source[f.ch]; f.ch++;
+      if (s.type == 2) {
+        int j = s.node;
+        vertex[j].unplugged -= 1;
+        if (vertex[j].unplugged == 0) { vertex[j].ordered = true; order.push_back(j); st.push_back({j, 0}); }
+      }
+    }
+  }
+  void set_sample_rate(double sr) override {
+    float s = (float)sr;
+    if (sample_rate != s) { sample_rate = s; for (auto& v : vertex) v.unit->set_sample_rate((double)s); if (!ordered) determine_order(); }
+  }
+  void reset() override { for (auto& v : vertex) v.unit->reset(); if (!ordered) determine_order(); }
+  void tick(const float* in, float* out) override {
+    if (!ordered) determine_order();
+    for (int ni : order) {
+      Vertex& v = vertex[ni];
+      for (int c = 0; c < v.unit->inputs(); c++) {
+        Port s = v.source[c];
+        v.tick_in[c] = s.type == 0 ? 0.0f : s.type == 1 ? in[s.port] : vertex[s.node].tick_out[s.port];
+      }
+      v.unit->tick(v.tick_in.data(), v.tick_out.data());
+    }
+    for (int c = 0; c < nout; c++) {
+      Port s = output_edge[c];
+      out[c] = s.type == 0 ? 0.0f : s.type == 1 ? in[s.port] : vertex[s.node].tick_out[s.port];
+    }
+  }
+  void process(int size, const float* in, float* out) override {
+    if (!ordered) determine_order();
+    const int len = simd_items(size) * 8;
+    for (int ni : order) {
+      Vertex& v = vertex[ni];
+      if (v.has_sv) {
+        v.unit->process(size, vertex[v.sv_node].output.data() + v.sv_port * B, v.output.data());
+      } else {
+        for (int c = 0; c < v.unit->inputs(); c++) {
+          Port s = v.source[c];
+          for (int i = 0; i < len; i++) v.input[c * B + i] = s.type == 0 ? 0.0f : s.type == 1 ? in[s.port * B + i] : vertex[s.node].output[s.port * B + i];
+        }
+        v.unit->process(size, v.input.data(), v.output.data());
+      }
+    }
+    for (int c = 0; c < nout; c++) {
+      Port s = output_edge[c];
+      for (int i = 0; i < len; i++) out[c * B + i] = s.type == 0 ? 0.0f : s.type == 1 ? in[s.port * B + i] : vertex[s.node].output[s.port * B + i];
+    }
+  }
+  void set(const Setting& s) override {
+    Address d = s.direction();
+    if (d.type == 2 && d.value < vertex.size()) vertex[d.value].unit->set(s.peel());
+  }
+  AttoHash ping(bool probe, AttoHash h) override {
+    h = h.hash(id());
+    for (auto& v : vertex) h = v.unit->ping(probe, h);
+    return h;
+  }
+  FO_CLONE(Net)
+};
+
+}  // namespace fo

@@ -1,0 +1,208 @@
+"""ctypes binding of the CPU oracle (oracle/_build/libfundsp_oracle.so) — TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs import this module.
+`OracleBackend` lowers a `fundsp_b200.graph.An` expression onto the oracle's node classes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "oracle", "_build", "libfundsp_oracle.so")
+
+
+def build_oracle(force=False):
+    if force or not os.path.exists(SO):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build_oracle()
+        L = C.CDLL(SO)
+        P, F, D, I, U64, I64 = C.c_void_p, C.c_float, C.c_double, C.c_int, C.c_uint64, C.c_int64
+        FP = C.POINTER(C.c_float)
+        sig = {
+            "fo_about": (C.c_char_p, []),
+            "fo_rnd1": (D, [U64]), "fo_hash1": (U64, [U64]), "fo_attohash": (U64, [U64, U64]), "fo_hash32x": (C.c_uint32, [C.c_uint32]),
+            "fo_wide_sinf": (F, [F]), "fo_wide_floorf": (F, [F]), "fo_lerpf": (F, [F, F, F]), "fo_lerpd": (D, [D, D, D]),
+            "fo_delerpd": (D, [D, D, D]), "fo_xerpf": (F, [F, F, F]), "fo_xerpd": (D, [D, D, D]), "fo_db_amp": (D, [D]), "fo_smooth9f": (F, [F]),
+            "fo_set_denormal_emulation": (None, [I]), "fo_restore_denormals": (None, []),
+            "fo_wavetable_count": (I, [I]), "fo_wavetable_pitch": (F, [I, I]), "fo_wavetable_len": (I, [I, I]), "fo_wavetable_data": (FP, [I, I]),
+            "fo_constant": (P, [I, FP]), "fo_pass": (P, []), "fo_multipass": (P, [I]), "fo_sink": (P, [I]), "fo_split": (P, [I]),
+            "fo_multisplit": (P, [I, I]), "fo_join": (P, [I]), "fo_multijoin": (P, [I, I]), "fo_reverse": (P, [I]), "fo_sine": (P, []),
+            "fo_wavesynth": (P, [I, I]), "fo_noise": (P, []), "fo_fixed_svf": (P, [I, F, F, F]), "fo_svf": (P, [I, F, F, F]),
+            "fo_biquad": (P, [F, F, F, F, F]), "fo_biquad_bank": (P, []), "fo_butterpass": (P, [F, I]), "fo_resonator": (P, [F, F, I]),
+            "fo_moog": (P, [F, F, I]), "fo_fir": (P, [I, FP]), "fo_tick_node": (P, [I]), "fo_delay": (P, [D]), "fo_allnest": (P, [F, P, I]),
+            "fo_pan": (P, [F]), "fo_panner": (P, []), "fo_adsr_live": (P, [F, F, F, F]), "fo_biquad_coefs": (None, [I, F, F, F, F, FP]),
+            "fo_pipe": (P, [P, P]), "fo_stack": (P, [P, P]), "fo_branch": (P, [P, P]), "fo_bus": (P, [P, P]), "fo_thru": (P, [P]),
+            "fo_binop": (P, [I, P, P]), "fo_unop": (P, [I, F, P]), "fo_multi": (P, [I, I, I, C.POINTER(P)]), "fo_feedback": (P, [P, I]),
+            "fo_sine_hz": (P, [F]), "fo_wave_hz": (P, [I, F]), "fo_fir3": (P, [F]), "fo_moog_q": (P, [F]), "fo_reverb_stereo": (P, [D, D, D]),
+            "fo_phase": (None, [P, F]), "fo_seed": (None, [P, U64]), "fo_set": (None, [P, I, FP, I, U64, C.POINTER(I64), I]),
+            "fo_inputs": (I, [P]), "fo_outputs": (I, [P]), "fo_id": (U64, [P]), "fo_reset": (None, [P]), "fo_set_sample_rate": (None, [P, D]),
+            "fo_tick": (None, [P, FP, FP]), "fo_process": (None, [P, I, FP, FP]), "fo_ping": (U64, [P, I, U64]), "fo_set_hash": (None, [P, U64]),
+            "fo_clone": (P, [P]), "fo_leaf_hashes": (I, [P, C.POINTER(U64), I]), "fo_free": (None, [P]),
+            "fo_render_length": (I64, [D, D]), "fo_render": (None, [P, D, D, FP]), "fo_filter": (None, [P, D, FP, I64, I64, FP]),
+            "fo_process_many": (None, [P, I64, FP, FP]),
+            "fo_net_new": (P, [I, I]), "fo_net_wrap": (P, [P]), "fo_net_push": (I, [P, P]), "fo_net_chain": (I, [P, P]),
+            "fo_net_connect": (None, [P, I, I, I, I]), "fo_net_connect_input": (None, [P, I, I, I]), "fo_net_connect_output": (None, [P, I, I, I]),
+            "fo_net_pipe_input": (None, [P, I]), "fo_net_pipe_output": (None, [P, I]), "fo_net_pipe_all": (None, [P, I, I]),
+            "fo_net_pass_through": (None, [P, I, I]), "fo_net_size": (I, [P]), "fo_net_has_cycle": (I, [P]), "fo_net_order": (I, [P, C.POINTER(I)]),
+            "fo_net_combine": (P, [I, P, P]),
+            "fo_bank_render": (None, [C.POINTER(P), I64, D, I64, FP, FP, FP, I]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float)) if a is not None else None
+
+
+def _farr(v):
+    return (C.c_float * len(v))(*v)
+
+
+class OracleBackend:
+    """Lowers `An` expressions to oracle nodes (one `b_<op>` per primitive in fundsp_b200/graph.py)."""
+
+    def __init__(self):
+        self.L = lib()
+
+    def b_constant(self, v): return self.L.fo_constant(len(v), _farr(v))
+    def b_pass(self): return self.L.fo_pass()
+    def b_multipass(self, n): return self.L.fo_multipass(n)
+    def b_sink(self, n): return self.L.fo_sink(n)
+    def b_split(self, n): return self.L.fo_split(n)
+    def b_multisplit(self, m, n): return self.L.fo_multisplit(m, n)
+    def b_join(self, n): return self.L.fo_join(n)
+    def b_multijoin(self, m, n): return self.L.fo_multijoin(m, n)
+    def b_reverse(self, n): return self.L.fo_reverse(n)
+    def b_sine(self): return self.L.fo_sine()
+    def b_wavesynth(self, kind, nout): return self.L.fo_wavesynth(kind, nout)
+    def b_noise(self): return self.L.fo_noise()
+    def b_fixed_svf(self, mode, f, q, g): return self.L.fo_fixed_svf(mode, f, q, g)
+    def b_svf(self, mode, f, q, g): return self.L.fo_svf(mode, f, q, g)
+    def b_biquad(self, a1, a2, b0, b1, b2): return self.L.fo_biquad(a1, a2, b0, b1, b2)
+    def b_biquad_bank(self): return self.L.fo_biquad_bank()
+    def b_butterpass(self, f, nin): return self.L.fo_butterpass(f, nin)
+    def b_resonator(self, f, q, nin): return self.L.fo_resonator(f, q, nin)
+    def b_moog(self, f, q, nin): return self.L.fo_moog(f, q, nin)
+    def b_fir(self, w): return self.L.fo_fir(len(w), _farr(w))
+    def b_tick(self, n): return self.L.fo_tick_node(n)
+    def b_delay(self, t): return self.L.fo_delay(t)
+    def b_allnest(self, c, nin, x): return self.L.fo_allnest(c, x, nin)
+    def b_pan(self, p): return self.L.fo_pan(p)
+    def b_panner(self): return self.L.fo_panner()
+    def b_adsr_live(self, a, d, s, r): return self.L.fo_adsr_live(a, d, s, r)
+    def b_pipe(self, x, y): return self.L.fo_pipe(x, y)
+    def b_stack(self, x, y): return self.L.fo_stack(x, y)
+    def b_branch(self, x, y): return self.L.fo_branch(x, y)
+    def b_bus(self, x, y): return self.L.fo_bus(x, y)
+    def b_thru(self, x): return self.L.fo_thru(x)
+    def b_binop(self, op, x, y): return self.L.fo_binop(op, x, y)
+    def b_unop(self, kind, s, x): return self.L.fo_unop(kind, s, x)
+    def b_multi(self, kind, op, n, *nodes): return self.L.fo_multi(kind, op, n, (C.c_void_p * n)(*nodes))
+    def b_feedback(self, had, x): return self.L.fo_feedback(x, had)
+    def b_phase(self, p, x): self.L.fo_phase(x, p); return x
+    def b_seed(self, s, x): self.L.fo_seed(x, s); return x
+
+    def b_set(self, kind, values, seed, address, x):
+        addr = [v for pair in address for v in pair]
+        self.L.fo_set(x, kind, _farr(values), len(values), seed, (C.c_int64 * max(1, len(addr)))(*addr), len(address))
+        return x
+
+
+class OracleUnit:
+    """An oracle graph as an `AudioUnit`: render / filter / process / tick."""
+
+    def __init__(self, expr_or_handle):
+        self.L = lib()
+        self.h = expr_or_handle.lower(OracleBackend()) if hasattr(expr_or_handle, "lower") else expr_or_handle
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.fo_free(self.h)
+        except Exception:
+            pass
+
+    def take(self):
+        h, self.h = self.h, None
+        return h
+
+    def inputs(self): return self.L.fo_inputs(self.h)
+    def outputs(self): return self.L.fo_outputs(self.h)
+    def reset(self): self.L.fo_reset(self.h)
+    def set_sample_rate(self, sr): self.L.fo_set_sample_rate(self.h, sr)
+    def ping(self, probe, h): return self.L.fo_ping(self.h, 1 if probe else 0, h)
+
+    def leaf_hashes(self):
+        buf = (C.c_uint64 * 4096)()
+        n = self.L.fo_leaf_hashes(self.h, buf, 4096)
+        return [int(buf[i]) for i in range(n)]
+
+    def render(self, sr, duration):
+        n = self.L.fo_render_length(sr, duration)
+        out = np.zeros((self.outputs(), n), np.float32)
+        self.L.fo_render(self.h, sr, duration, _fp(out))
+        return out
+
+    def filter(self, sr, inp, total=None):
+        inp = np.ascontiguousarray(inp, np.float32).reshape(self.inputs(), -1)
+        total = inp.shape[1] if total is None else total
+        out = np.zeros((self.outputs(), total), np.float32)
+        self.L.fo_filter(self.h, sr, _fp(inp), inp.shape[1], total, _fp(out))
+        return out
+
+    def process_many(self, n, inp=None):
+        if inp is None:
+            inp = np.zeros((max(1, self.inputs()), n), np.float32)
+        inp = np.ascontiguousarray(inp, np.float32)
+        out = np.zeros((self.outputs(), n), np.float32)
+        self.L.fo_process_many(self.h, n, _fp(inp), _fp(out))
+        return out
+
+    def process(self, size, inp=None):
+        ib = np.zeros((max(1, self.inputs()), 64), np.float32)
+        if inp is not None:
+            ib[: self.inputs(), :size] = np.asarray(inp, np.float32).reshape(self.inputs(), -1)[:, :size]
+        ob = np.zeros((max(1, self.outputs()), 64), np.float32)
+        self.L.fo_process(self.h, size, _fp(ib), _fp(ob))
+        return ob[: self.outputs(), :size].copy()
+
+    def tick(self, frame=()):
+        fi = np.zeros(max(1, self.inputs()), np.float32)
+        fi[: len(frame)] = frame
+        fo = np.zeros(max(1, self.outputs()), np.float32)
+        self.L.fo_tick(self.h, _fp(fi), _fp(fo))
+        return fo[: self.outputs()].copy()
+
+
+def oracle_bank_render(exprs, sr, n, inp=None, per_voice=True, mix=False, threads=1):
+    """CPU 'bank' = a Vec of units + index-order sum. Returns (out[V,c,n] | None, mix[c,n] | None)."""
+    L = lib()
+    be = OracleBackend()
+    hs = [e.lower(be) for e in exprs]
+    V = len(hs)
+    no, ni = L.fo_outputs(hs[0]), L.fo_inputs(hs[0])
+    arr = (C.c_void_p * V)(*hs)
+    out = np.zeros((V, no, n), np.float32) if per_voice else None
+    mx = np.zeros((no, n), np.float32) if mix else None
+    ib = np.zeros((max(1, ni), n), np.float32) if inp is None else np.ascontiguousarray(inp, np.float32).reshape(max(1, ni), n)
+    L.fo_bank_render(arr, V, sr, n, _fp(ib), _fp(out), _fp(mx), threads)
+    for h in hs:
+        L.fo_free(h)
+    return out, mx

@@ -1,0 +1,366 @@
+"""CPU tests of the oracle against the reference's own pins:
+golden integer vectors, doctest known answers, analytic frequency responses (tests/test_flow.rs:18-80,
+tolerance 2e-4), allpass |H| = 1 (test_flow.rs:252-283), tick == process within 1e-4
+(tests/test_basic.rs:21-47), structural equivalences and pseudorandom-phase divergence
+(test_basic.rs:392-406, 520-612)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from fundsp_b200.graph import ArityError
+from fundsp_b200.prelude import *  # noqa: F401,F403
+from oracle import OracleUnit, lib, oracle_bank_render
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "int_vectors.json")))
+L = lib()
+
+
+# ---------------------------------------------------------------- integer paths: bit exact
+def test_golden_integer_paths():
+    for x, bits in GOLD["rnd1_bits"]:
+        assert L.fo_rnd1(x) == bits * 2.0 ** -53
+    for x, h in GOLD["hash1"]:
+        assert L.fo_hash1(x) == h
+    for s, d, h in GOLD["attohash"]:
+        assert L.fo_attohash(s, d) == h
+    for x, h in GOLD["hash32x"]:
+        assert L.fo_hash32x(x) == h
+
+
+def test_golden_leaf_hashes():
+    f, m = 440.0, 2.0
+    graphs = {
+        "sine_hz>>lowpass_hz": sine_hz(440.0) >> lowpass_hz(1000.0, 1.0),
+        "saw_hz>>lowpass_hz": saw_hz(110.0) >> lowpass_hz(1000.0, 1.0),
+        "white>>lowpass_hz": white() >> lowpass_hz(1000.0, 1.0),
+        "noise|noise": noise() | noise(),
+        "fm": sine_hz(f) * f * m + f >> sine(),
+    }
+    for k, g in graphs.items():
+        assert OracleUnit(g).leaf_hashes() == GOLD["leaf_hashes"][k], k
+
+
+def test_known_initial_sine_phase():
+    # Sine in `sine_hz(440) >> lowpass_hz(1000, 1)` gets hash 0x81b253a0d4def3fc -> phase 0.6899407
+    h = OracleUnit(sine_hz(440.0) >> lowpass_hz(1000.0, 1.0)).leaf_hashes()[1]
+    assert h == 0x81B253A0D4DEF3FC
+    assert np.float32(L.fo_rnd1(h)) == np.float32(0.6899407)
+
+
+# ---------------------------------------------------------------- doctest known answers
+def test_doctest_known_answers():
+    assert L.fo_lerpd(0.0, 5.0, 0.5) == 2.5 and L.fo_lerpd(0.0, 5.0, 1.0) == 5.0  # math.rs:184-188
+    assert L.fo_delerpd(2.0, 4.0, 3.0) == 0.5  # math.rs:212-215
+    assert 1.4125 < L.fo_db_amp(3.0) < 1.4126  # math.rs:285-287
+    assert OracleUnit(pass_()).tick([2.0])[0] == 2.0  # audionode.rs:77
+    assert OracleUnit(dc(2.0)).tick()[0] == 2.0  # audionode.rs:225
+    assert list(OracleUnit(dc((5.0, 6.0))).tick()) == [5.0, 6.0]  # audionode.rs:248
+    assert OracleUnit(add(1.0)).tick([1.0])[0] == 2.0  # audionode.rs:266
+    assert list(OracleUnit(add((2.0, 3.0))).tick([4.0, 5.0])) == [6.0, 8.0]  # audionode.rs:281
+    # net.rs:361-371
+    net = L.fo_net_new(1, 1)
+    L.fo_net_chain(net, add(1.0).lower(__import__("oracle").OracleBackend()))
+    L.fo_net_chain(net, add(2.0).lower(__import__("oracle").OracleBackend()))
+    u = OracleUnit(net)
+    assert L.fo_net_size(net) == 2 and u.tick([1.0])[0] == 4.0
+
+
+def test_arity_table():  # tests/test_basic.rs:616-658
+    io = lambda g: (g.inputs(), g.outputs())  # noqa: E731
+    assert io(pass_() ^ pass_()) == (1, 2)
+    assert io(mul(0.5) + mul(0.5)) == (2, 1)
+    assert io(sink() | zero()) == (1, 1)
+    assert io(sink() | zero() | pass_()) == (2, 2)
+    assert io(mul((0.0, 1.0))) == (2, 2)
+    assert io(~butterpass() >> ~butterpass() >> butterpass()) == (2, 1)
+    assert io(~resonator() >> resonator()) == (3, 1)
+    assert io(sine_hz(2.0) * 2.0 * 1.0 + 2.0 >> sine()) == (0, 1)
+    assert io((pass_() ^ mul(2.0)) >> sine() + sine()) == (1, 1)
+    assert io(sine() & mul(2.0) >> sine()) == (1, 1)
+    assert io(feedback(delay(0.5) * 0.5)) == (1, 1)
+    assert io(~zero()) == (0, 0)
+    assert io(-(-sink()) - 42.0 ^ sink() & -(-(-sink())) * 3.15) == (1, 0)
+    with pytest.raises(ArityError):
+        pass_() >> (pass_() | pass_())
+    for g in (pass_() ^ pass_(), mul(0.5) + mul(0.5), ~resonator() >> resonator(), sine() & mul(2.0) >> sine()):
+        u = OracleUnit(g)
+        assert (u.inputs(), u.outputs()) == io(g)
+
+
+# ---------------------------------------------------------------- analytic frequency responses
+def svf_response(mode, sr, fc, q, gain, f):
+    """Closed forms from src/svf.rs:315-322 ... :720-741 (f64)."""
+    g = math.tan(math.pi * fc / sr)
+    k = 1.0 / q
+    z = np.exp(1j * f * 2 * math.pi / sr)
+    den = (z - 1) ** 2 + g * g * (1 + z) ** 2 + g * k * (z * z - 1)
+    if mode == LOWPASS:
+        return g * g * (1 + z) ** 2 / den
+    if mode == HIGHPASS:
+        return (z - 1) ** 2 / den
+    if mode == BANDPASS:
+        return g * (z * z - 1) / den
+    if mode == NOTCH:
+        return ((z - 1) ** 2 + g * g * (1 + z) ** 2) / den
+    if mode == PEAK:
+        return -((1 + g + (g - 1) * z) * (-1 + g + z + g * z)) / den
+    if mode == ALLPASS:
+        return ((z - 1) ** 2 + g * g * (1 + z) ** 2 + g * (k - k * z * z)) / den
+    a = math.sqrt(gain)
+    if mode == BELL:
+        return (g * k * (z * z - 1) + a * (g * (1 + z) * ((a * a - 1) * k / a * (z - 1)) + ((z - 1) ** 2 + g * g * (1 + z) ** 2))) / (
+            g * k * (z * z - 1) + a * ((z - 1) ** 2 + g * g * (z + 1) ** 2))
+    sa = math.sqrt(a)
+    if mode == LOWSHELF:
+        return (a * (z - 1) ** 2 + g * g * a * a * (z + 1) ** 2 + sa * g * a * k * (z * z - 1)) / (
+            a * (z - 1) ** 2 + g * g * (1 + z) ** 2 + sa * g * k * (z * z - 1))
+    return (sa * g * (1 + z) * (-(a - 1) * a * k * (z - 1) + sa * g * (1 - a * a) * (1 + z))
+            + a * a * ((z - 1) ** 2 + a * g * g * (1 + z) ** 2 + sa * g * k * (z * z - 1))) / (
+        (z - 1) ** 2 + a * g * g * (1 + z) ** 2 + sa * g * k * (z * z - 1))
+
+
+def biquad_response(c, sr, f):  # src/biquad.rs:119-128
+    a1, a2, b0, b1, b2 = c
+    z1 = np.exp(-1j * 2 * math.pi * f / sr)
+    return (b0 + b1 * z1 + b2 * z1 * z1) / (1 + a1 * z1 + a2 * z1 * z1)
+
+
+def measure_response(unit, sr=44100.0, length=0x8000):
+    """tests/test_flow.rs:25-49: warm up with zeros, feed an impulse, FFT."""
+    unit.set_sample_rate(sr)
+    x = np.zeros((1, length // 2 + length), np.float32)
+    x[0, length // 2] = 1.0
+    y = unit.process_many(x.shape[1], x)[0, length // 2:]
+    return np.fft.rfft(y.astype(np.float64))
+
+
+def check_response(unit, analytic, sr=44100.0, length=0x8000):
+    spec = measure_response(unit, sr, length)
+    f = 10.0
+    while f <= 22000.0:
+        i = int(round(f * length / sr))
+        if i >= len(spec):
+            break
+        fi = i / length * sr
+        x, y = analytic(fi), spec[i]
+        tol = 2.0e-4 * max(1.0, abs(x), abs(y))  # test_flow.rs:18-23 is_equal_response
+        assert abs(x - y) <= tol, (fi, x, y)
+        f += 10.0 if f < 1000.0 else 100.0
+
+
+SR = 44100.0
+
+
+@pytest.mark.parametrize("mode,fc,q,gain", [
+    (BELL, 500.0, 1.0, 2.0), (LOWSHELF, 2000.0, 10.0, 5.0), (HIGHSHELF, 2000.0, 10.0, 5.0), (PEAK, 5000.0, 1.0, 1.0),
+    (ALLPASS, 500.0, 5.0, 1.0), (NOTCH, 1000.0, 1.0, 1.0), (LOWPASS, 50.0, 1.0, 1.0), (HIGHPASS, 5000.0, 1.0, 1.0),
+    (BANDPASS, 100.0, 1.0, 1.0)])
+def test_svf_responses(mode, fc, q, gain):  # test_flow.rs:85-94
+    from fundsp_b200.prelude import _svf_hz
+    check_response(OracleUnit(_svf_hz(mode, fc, q, gain)), lambda f: svf_response(mode, SR, fc, q, gain, f))
+
+
+def test_biquad_family_responses():  # test_flow.rs:103-110,158-166
+    c = np.zeros(5, np.float32)
+    cp = c.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_float))
+    L.fo_biquad_coefs(1, SR, 300.0, 20.0, 1.0, cp)
+    check_response(OracleUnit(resonator_hz(300.0, 20.0)), lambda f, c=c.copy(): biquad_response(c, SR, f))
+    for fc in (200.0, 1000.0):
+        L.fo_biquad_coefs(0, SR, fc, 1.0, 1.0, cp)
+        check_response(OracleUnit(butterpass_hz(fc)), lambda f, c=c.copy(): biquad_response(c, SR, f))
+    check_response(OracleUnit(biquad(0.1, 0.2, 0.3, 0.4, 0.5)), lambda f: biquad_response((0.1, 0.2, 0.3, 0.4, 0.5), SR, f))
+    # fir: test_flow.rs:158-160
+    w = (0.5, 0.3, 0.2)
+    check_response(OracleUnit(fir(w)), lambda f: __import__("builtins").sum(w[2 - i] * np.exp(-1j * 2 * math.pi * f / SR) ** i for i in range(3)))
+    # delays: test_flow.rs:98-100
+    check_response(OracleUnit(delay(0.0001) >> delay(0.0002)),
+                   lambda f: np.exp(-1j * 2 * math.pi * (round(0.0001 * SR) + round(0.0002 * SR)) * f / SR))
+    check_response(OracleUnit(pass_() & tick()), lambda f: 1 + np.exp(-1j * 2 * math.pi * f / SR))
+    # bus of SVFs: test_flow.rs:94
+    check_response(OracleUnit(highpass_hz(500.0, 1.0) & bandpass_hz(500.0, 2.0)),
+                   lambda f: svf_response(HIGHPASS, SR, 500.0, 1.0, 1.0, f) + svf_response(BANDPASS, SR, 500.0, 2.0, 1.0, f))
+
+
+def test_biquad_bank_lane_response():  # test_flow.rs:171-177
+    import ctypes
+    c = np.zeros(5, np.float32)
+    L.fo_biquad_coefs(2, SR, 1000.0, 2.0, 1.0, c.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+    g = (pass_() | multizero(7)) >> reverse(8) >> biquad_bank().set(6, c.tolist(), address=[(1, 7)]) >> (multisink(7) | pass_())
+    check_response(OracleUnit(g), lambda f: biquad_response(c, SR, f))
+
+
+def test_allpass_magnitude():  # test_flow.rs:252-283
+    for g in (allpass_hz(1000.0, 1.0), allpass_hz(100.0, 10.0), allpass_hz(10000.0, 0.5), tick(), delay(0.001), pass_()):
+        spec = measure_response(OracleUnit(g))
+        mag = np.abs(spec[1:-1])
+        assert np.all(np.abs(mag - 1.0) < 1.0e-5 * 20), float(np.abs(mag - 1).max())
+
+
+# ---------------------------------------------------------------- tick == process (test_basic.rs:21-47)
+def check_wave(g, n=441, sr=44100.0):
+    a = OracleUnit(g)
+    wave = a.render(sr, n / sr)
+    a.reset()
+    ticks = np.stack([a.tick() for _ in range(n)], axis=1)
+    assert wave.shape == ticks.shape
+    assert np.abs(wave - ticks).max() <= 1.0e-4, float(np.abs(wave - ticks).max())
+
+
+def test_tick_equals_process():
+    L.fo_set_denormal_emulation(0)
+    check_wave(noise().seed(1) * noise() | noise() + noise())
+    check_wave(noise() | sine_hz(440.0) & -noise())
+    check_wave(dc((110.0, 220.0)) >> multipass(2) >> -stackf(2, lambda f: (f - 0.5) * sine()))
+    check_wave(dc((110.0, 220.0, 440.0, 880.0)) >> multipass(4) >> (sink() | -sine().phase(0.0) | sink() | sine()))
+    check_wave(dc((880.0, 440.0)) >> pass_() - pass_() >> branchf(2, lambda f: (f - 0.5) * triangle()))
+    check_wave(dc((440.0, 880.0)) >> multisplit(2, 5) >> sumi(10, lambda i: saw() * 0.1) | saw_hz(220.0).phase(0.5) * 0.1)
+    check_wave(dc((440.0, 880.0)) >> multisplit(2, 3) >> multijoin(2, 3) >> (sine() | sine()))
+    check_wave((noise() >> split(16) >> join(16)) | (noise() >> split(11) >> join(11)))
+    check_wave((square_hz(110.0).phase(0.25) | dc(440.0)) >> pipei(4, lambda i: ~lowpass_q(1.0)) >> highpass_q(1.0)
+               | ((noise() | dc(880.0)) >> ~bandpass_q(1.0) >> notch_q(2.0)))
+    check_wave(noise() >> moog_hz(1500.0, 0.8) | noise() >> moog_hz(500.0, 0.4))
+    check_wave((noise() | dc((1000.0, 0.5))) >> moog() | (noise() | dc(800.0)) >> moog_q(0.3))
+    bq = biquad_bank().set(6, (0.0, 0.0, 0.2, 0.2, 0.2), address=[(1, 0)]).set(6, (0.2, 0.2, 0.1, 0.3, 0.5), address=[(1, 1)])
+    check_wave((noise() | noise() | multizero(6)) >> bq >> (pass_() | pass_() | multisink(6)))
+    check_wave((noise() | noise()) >> reverb_stereo(10.0, 5.0, 0.5))
+    check_wave(dc(1.0) >> adsr_live(0.001, 0.002, 0.5, 0.003) | dc(0.0) >> adsr_live(0.001, 0.002, 0.5, 0.003))
+    check_wave(organ_hz(330.0) | hammond_hz(220.0) * 0.5 & soft_saw_hz(55.0))
+    check_wave(noise() >> pan(0.3))
+    L.fo_restore_denormals()
+
+
+# ---------------------------------------------------------------- equivalences (test_basic.rs:392-406,520-529)
+def is_equal(a, b, n=200, seed=1):
+    ua, ub = OracleUnit(a), OracleUnit(b)
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-1, 1, (max(1, ua.inputs()), n)).astype(np.float32)
+    return np.array_equal(ua.process_many(n, x), ub.process_many(n, x))
+
+
+def test_structural_equivalences():
+    v, w, x, y, z = 1.0, -2.0, 3.0, -4.0, 5.0
+    assert is_equal((pass_() ^ mul(y)) >> add(z) + sub(x), add(z) & mul(y) >> sub(x))
+    assert is_equal((pass_() ^ mul(y) ^ add(w)) >> add(z) + sub(x) + mul(y), add(z) & mul(y) >> sub(x) & add(w) >> mul(y))
+    assert is_equal(tick() >> tick() >> tick(), delay(3.0 / 44100.0))
+    assert is_equal(tick() >> tick() >> tick() >> tick() >> tick(), delay(5.0 / 44100.0))
+    assert v == 1.0
+
+
+def outputs_diverge(g, n=64):
+    y = OracleUnit(g).render(44100.0, n / 44100.0)
+    for i in range(y.shape[0]):
+        for j in range(i + 1, y.shape[0]):
+            if np.array_equal(y[i], y[j]):
+                return False
+    return True
+
+
+def test_pseudorandom_phase_divergence():  # test_basic.rs:532-612
+    assert outputs_diverge(noise() | (~zero() >> noise()) | noise() | (~zero() >> noise()) | noise() | noise() | noise())
+    assert outputs_diverge(noise() ^ noise() ^ noise() & zero() ^ noise() ^ (noise() >> pass_()) ^ noise() ^ noise())
+    assert outputs_diverge((sine_hz(1.0) >> pass_()) | sine_hz(1.0) | (sine_hz(1.0) >> pass_() >> pass_()) | sine_hz(1.0) | sine_hz(1.0))
+    assert outputs_diverge(sine_hz(1.0) ^ sine_hz(1.0) ^ sine_hz(1.0) | sine_hz(1.0) | sine_hz(1.0))
+    assert outputs_diverge(sine_hz(1.0) - zero() | sine_hz(1.0) - zero())
+    assert outputs_diverge(noise() | noise())
+    assert outputs_diverge((dc(110.0) >> saw()) | (dc(110.0) >> saw()))
+    assert outputs_diverge((dc(110.0) >> square()) | (dc(110.0) >> triangle()) | (dc(110.0) >> square()))
+    # two structurally identical voices built separately are identical
+    a = OracleUnit(sine_hz(1.0)).render(44100.0, 0.01)
+    b = OracleUnit(sine_hz(1.0)).render(44100.0, 0.01)
+    assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------- composites, tables, block quirks
+def test_reverb_composite_matches_python_prelude():
+    L.fo_set_denormal_emulation(0)
+    a = OracleUnit(L.fo_reverb_stereo(10.0, 2.0, 0.5))
+    b = OracleUnit(reverb_stereo(10.0, 2.0, 0.5))
+    assert a.leaf_hashes() == b.leaf_hashes()
+    x = np.random.default_rng(0).uniform(-1, 1, (2, 4000)).astype(np.float32)
+    ya, yb = a.filter(48000.0, x), b.filter(48000.0, x)
+    assert np.array_equal(ya, yb) and np.abs(ya).max() > 1e-3
+    L.fo_restore_denormals()
+
+
+def test_wavetables():
+    n = L.fo_wavetable_count(0)
+    assert n == 40  # 20 * 2^(k/4) <= 20 kHz
+    total, peak = 0, 0.0
+    for i in range(n):
+        ln = L.fo_wavetable_len(0, i)
+        assert ln & (ln - 1) == 0 and 32 <= ln <= 8192
+        t = np.ctypeslib.as_array(L.fo_wavetable_data(0, i), (ln,))
+        total += ln
+        peak = max(peak, float(np.abs(t).max()))
+        assert abs(float(t.astype(np.float64).mean())) < 1e-6
+    assert total == 41024 and abs(peak - 1.0) < 1e-6
+    assert abs(L.fo_wavetable_pitch(0, 4) - 40.0) < 1e-4
+    # a 110 Hz saw has the harmonic series 1/k up to the band limit
+    y = OracleUnit(saw_hz(110.0)).render(44100.0, 1.0)[0].astype(np.float64)
+    spec = np.abs(np.fft.rfft(y))
+    assert all(abs(spec[110] / spec[110 * k] - k) < 1e-3 * k for k in (2, 3, 4, 5))
+
+
+def test_wide_sin_and_floor():
+    x = np.linspace(-200.0, 200.0, 20001).astype(np.float32)
+    y = np.array([L.fo_wide_sinf(float(v)) for v in x])
+    assert np.abs(y - np.sin(x.astype(np.float64))).max() < 4e-7
+    for v in (0.0, 0.25, 0.9999999, 1.0, 1.5, 7.99999, 27.3):
+        assert L.fo_wide_floorf(v) == math.floor(v)
+
+
+def test_block_path_quirks():
+    # Sine: block path keeps the phase unwrapped inside a block, tail samples go through tick (oscillator.rs:74-86)
+    a = OracleUnit(sine_hz(20000.0))
+    a.set_sample_rate(48000.0)
+    y = np.concatenate([a.process(61)[0], a.process(64)[0]])
+    b = OracleUnit(sine_hz(20000.0))
+    b.set_sample_rate(48000.0)
+    t = np.array([b.tick()[0] for _ in range(125)])
+    assert np.abs(y - t).max() < 1e-4 and not np.array_equal(y, t)
+    # size 0 is a no-op
+    assert a.process(0).shape == (1, 0)
+    # Join scales then adds in process (audionode.rs:642-659)
+    g = OracleUnit((dc(0.1) | dc(0.2) | dc(0.7)) >> join(3))
+    z = np.float32(1.0) / np.float32(3.0)
+    assert g.process(8)[0, 0] == (np.float32(0.1) * z + np.float32(0.2) * z) + np.float32(0.7) * z
+
+
+def test_net_equals_static_and_bus_tree():
+    import oracle as O
+    be = O.OracleBackend()
+    v = [sine_hz(110.0 * (i + 1)) >> lowpass_hz(1000.0, 1.0) >> pan(0.0) for i in range(4)]
+    nets = [L.fo_net_wrap(g.lower(be)) for g in v]
+    top = L.fo_net_combine(0, L.fo_net_combine(0, nets[0], nets[1]), L.fo_net_combine(0, nets[2], nets[3]))
+    u = OracleUnit(top)
+    assert L.fo_net_size(top) == 4 + 6 and L.fo_net_has_cycle(top) == 0
+    y = u.render(48000.0, 0.01)
+    assert y.shape == (2, 480) and np.abs(y).max() > 0.1
+    # cycle detection (test_basic.rs:355-362)
+    c = L.fo_net_new(2, 1)
+    i1 = L.fo_net_chain(c, join(2).lower(be))
+    i2 = L.fo_net_chain(c, pass_().lower(be))
+    assert L.fo_net_has_cycle(c) == 0
+    L.fo_net_connect(c, i2, 0, i1, 1)
+    assert L.fo_net_has_cycle(c) == 1
+    L.fo_free(c)
+    # Net == static graph for a chain (test_basic.rs:409-466)
+    n = L.fo_net_new(0, 2)
+    L.fo_net_chain(n, (noise() | noise()).lower(be))
+    L.fo_net_chain(n, (moog_hz(1500.0, 0.5) | moog_hz(1000.0, 0.6)).lower(be))
+    y1 = OracleUnit(n).render(44100.0, 0.01)
+    assert y1.shape == (2, 441) and np.isfinite(y1).all()
+
+
+def test_bank_render_mix_is_index_order_sum():
+    ex = [white().seed(i) >> lowpass_hz(500.0 + 100.0 * i, 1.0) for i in range(5)]
+    out, mix = oracle_bank_render(ex, 48000.0, 200, per_voice=True, mix=True, threads=1)
+    acc = out[0, 0].copy()
+    for i in range(1, 5):
+        acc = acc + out[i, 0]
+    assert np.array_equal(acc, mix[0])
+    out2, _ = oracle_bank_render(ex, 48000.0, 200, threads=3)
+    assert np.array_equal(out, out2)
