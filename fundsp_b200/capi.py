@@ -1,0 +1,176 @@
+"""ctypes binding of the C ABI (include/fundsp_b200.h) exported by fundsp_b200/libfundsp_b200.so.
+
+The library is hand-written CUDA for sm_100a plus its host runtime; there is no CPU fallback: if the
+shared object is missing or no CUDA device is usable the product path raises `FdspError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libfundsp_b200.so")
+HEADER = os.path.join(os.path.dirname(HERE), "include", "fundsp_b200.h")
+
+OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_ARITY, ERR_STATE = range(6)
+OUT_VOICES, OUT_MIX = 1, 2
+
+
+class FdspError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"fundsp_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+P, F, D, I, U32, U64, I64 = C.c_void_p, C.c_float, C.c_double, C.c_int, C.c_uint32, C.c_uint64, C.c_int64
+FP = C.POINTER(C.c_float)
+
+_SIG = {
+    "fdsp_version": (C.c_char_p, []), "fdsp_last_error": (C.c_char_p, []), "fdsp_device_count": (I, []),
+    "fdsp_constant": (P, [I, FP]), "fdsp_pass": (P, []), "fdsp_multipass": (P, [I]), "fdsp_sink": (P, [I]), "fdsp_split": (P, [I]),
+    "fdsp_multisplit": (P, [I, I]), "fdsp_join": (P, [I]), "fdsp_multijoin": (P, [I, I]), "fdsp_reverse": (P, [I]), "fdsp_sine": (P, []),
+    "fdsp_wavesynth": (P, [I, I]), "fdsp_noise": (P, []), "fdsp_fixed_svf": (P, [I, F, F, F]), "fdsp_svf": (P, [I, F, F, F]),
+    "fdsp_biquad": (P, [F, F, F, F, F]), "fdsp_biquad_bank": (P, []), "fdsp_butterpass": (P, [F, I]), "fdsp_resonator": (P, [F, F, I]),
+    "fdsp_moog": (P, [F, F, I]), "fdsp_fir": (P, [I, FP]), "fdsp_tick": (P, [I]), "fdsp_delay": (P, [D]), "fdsp_allnest": (P, [F, P, I]),
+    "fdsp_pan": (P, [F]), "fdsp_panner": (P, []), "fdsp_adsr_live": (P, [F, F, F, F]),
+    "fdsp_pipe": (P, [P, P]), "fdsp_stack": (P, [P, P]), "fdsp_branch": (P, [P, P]), "fdsp_bus": (P, [P, P]), "fdsp_thru": (P, [P]),
+    "fdsp_binop": (P, [I, P, P]), "fdsp_unop": (P, [I, F, P]), "fdsp_multi": (P, [I, I, I, C.POINTER(P)]), "fdsp_feedback": (P, [P, I]),
+    "fdsp_node_phase": (I, [P, F]), "fdsp_node_seed": (I, [P, U64]), "fdsp_node_set": (I, [P, I, FP, I, U64, C.POINTER(I64), I]),
+    "fdsp_node_inputs": (I, [P]), "fdsp_node_outputs": (I, [P]), "fdsp_node_id": (U64, [P]), "fdsp_node_ping": (U64, [P, I, U64]),
+    "fdsp_node_leaf_hashes": (I, [P, C.POINTER(U64), I]), "fdsp_node_signature": (I, [P, C.c_char_p, I]),
+    "fdsp_node_clone": (P, [P]), "fdsp_node_free": (None, [P]),
+    "fdsp_wavetable_count": (I, [I]), "fdsp_wavetable_info": (I, [I, I, FP, C.POINTER(I)]), "fdsp_wavetable_data": (FP, [I, I]),
+    "fdsp_bank_create": (I, [C.POINTER(P), U32, I, U32, C.POINTER(P)]), "fdsp_bank_destroy": (None, [P]), "fdsp_bank_clone": (I, [P, C.POINTER(P)]),
+    "fdsp_bank_voices": (U32, [P]), "fdsp_bank_inputs": (I, [P]), "fdsp_bank_voice_outputs": (I, [P]), "fdsp_bank_outputs": (I, [P]),
+    "fdsp_bank_set_sample_rate": (I, [P, D]), "fdsp_bank_reset": (I, [P]), "fdsp_bank_allocate": (I, [P, U64]),
+    "fdsp_bank_process": (I, [P, U32, FP, FP]), "fdsp_bank_render": (I, [P, U64, FP, FP, FP]),
+    "fdsp_bank_render_device": (I, [P, U64, P, U64, P, U64, P, U64]), "fdsp_bank_sync": (I, [P]), "fdsp_bank_stream": (P, [P]),
+    "fdsp_bank_num_classes": (I, [P]), "fdsp_bank_class_info": (I, [P, I, C.c_char_p, I, C.POINTER(U32), C.POINTER(U32), C.POINTER(U32), C.POINTER(U64)]),
+    "fdsp_bank_launch_count": (U64, [P]), "fdsp_bank_last_kernel_ms": (F, [P]),
+}
+
+
+def header_symbols():
+    """Every function name declared in include/fundsp_b200.h."""
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fdsp_[a-z0-9_]+)\s*\(", text)))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO):
+            raise FdspError(ERR_STATE, f"{SO} is missing: build it with `make -C fundsp_b200/csrc` (or __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(SO)
+        for name, (res, args) in _SIG.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(code):
+    if code != OK:
+        raise FdspError(code, lib().fdsp_last_error().decode())
+
+
+def _node(h, what):
+    if not h:
+        raise FdspError(ERR_ARITY, lib().fdsp_last_error().decode() or what)
+    return h
+
+
+def _farr(v):
+    return (C.c_float * len(v))(*v)
+
+
+class GpuBackend:
+    """Lowers `An` expressions to fdsp_node handles (one `b_<op>` per primitive in fundsp_b200/graph.py)."""
+
+    def __init__(self):
+        self.L = lib()
+
+    def b_constant(self, v): return _node(self.L.fdsp_constant(len(v), _farr(v)), "constant")
+    def b_pass(self): return _node(self.L.fdsp_pass(), "pass")
+    def b_multipass(self, n): return _node(self.L.fdsp_multipass(n), "multipass")
+    def b_sink(self, n): return _node(self.L.fdsp_sink(n), "sink")
+    def b_split(self, n): return _node(self.L.fdsp_split(n), "split")
+    def b_multisplit(self, m, n): return _node(self.L.fdsp_multisplit(m, n), "multisplit")
+    def b_join(self, n): return _node(self.L.fdsp_join(n), "join")
+    def b_multijoin(self, m, n): return _node(self.L.fdsp_multijoin(m, n), "multijoin")
+    def b_reverse(self, n): return _node(self.L.fdsp_reverse(n), "reverse")
+    def b_sine(self): return _node(self.L.fdsp_sine(), "sine")
+    def b_wavesynth(self, kind, nout): return _node(self.L.fdsp_wavesynth(kind, nout), "wavesynth")
+    def b_noise(self): return _node(self.L.fdsp_noise(), "noise")
+    def b_fixed_svf(self, mode, f, q, g): return _node(self.L.fdsp_fixed_svf(mode, f, q, g), "fixed_svf")
+    def b_svf(self, mode, f, q, g): return _node(self.L.fdsp_svf(mode, f, q, g), "svf")
+    def b_biquad(self, a1, a2, b0, b1, b2): return _node(self.L.fdsp_biquad(a1, a2, b0, b1, b2), "biquad")
+    def b_biquad_bank(self): return _node(self.L.fdsp_biquad_bank(), "biquad_bank")
+    def b_butterpass(self, f, nin): return _node(self.L.fdsp_butterpass(f, nin), "butterpass")
+    def b_resonator(self, f, q, nin): return _node(self.L.fdsp_resonator(f, q, nin), "resonator")
+    def b_moog(self, f, q, nin): return _node(self.L.fdsp_moog(f, q, nin), "moog")
+    def b_fir(self, w): return _node(self.L.fdsp_fir(len(w), _farr(w)), "fir")
+    def b_tick(self, n): return _node(self.L.fdsp_tick(n), "tick")
+    def b_delay(self, t): return _node(self.L.fdsp_delay(t), "delay")
+    def b_allnest(self, c, nin, x): return _node(self.L.fdsp_allnest(c, x, nin), "allnest")
+    def b_pan(self, p): return _node(self.L.fdsp_pan(p), "pan")
+    def b_panner(self): return _node(self.L.fdsp_panner(), "panner")
+    def b_adsr_live(self, a, d, s, r): return _node(self.L.fdsp_adsr_live(a, d, s, r), "adsr_live")
+    def b_pipe(self, x, y): return _node(self.L.fdsp_pipe(x, y), "pipe")
+    def b_stack(self, x, y): return _node(self.L.fdsp_stack(x, y), "stack")
+    def b_branch(self, x, y): return _node(self.L.fdsp_branch(x, y), "branch")
+    def b_bus(self, x, y): return _node(self.L.fdsp_bus(x, y), "bus")
+    def b_thru(self, x): return _node(self.L.fdsp_thru(x), "thru")
+    def b_binop(self, op, x, y): return _node(self.L.fdsp_binop(op, x, y), "binop")
+    def b_unop(self, kind, s, x): return _node(self.L.fdsp_unop(kind, s, x), "unop")
+    def b_multi(self, kind, op, n, *nodes): return _node(self.L.fdsp_multi(kind, op, n, (C.c_void_p * n)(*nodes)), "multi")
+    def b_feedback(self, had, x): return _node(self.L.fdsp_feedback(x, had), "feedback")
+
+    def b_phase(self, p, x):
+        check(self.L.fdsp_node_phase(x, p))
+        return x
+
+    def b_seed(self, s, x):
+        check(self.L.fdsp_node_seed(x, s))
+        return x
+
+    def b_set(self, kind, values, seed, address, x):
+        addr = [v for pair in address for v in pair]
+        check(self.L.fdsp_node_set(x, kind, _farr(values), len(values), seed, (C.c_int64 * max(1, len(addr)))(*addr), len(address)))
+        return x
+
+
+class NodeHandle:
+    """Owns an fdsp_node built from an `An` expression (host-side description; no GPU needed)."""
+
+    def __init__(self, expr):
+        self.L = lib()
+        self.h = expr.lower(GpuBackend())
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.fdsp_node_free(self.h)
+        except Exception:
+            pass
+
+    def take(self):
+        h, self.h = self.h, None
+        return h
+
+    def inputs(self): return self.L.fdsp_node_inputs(self.h)
+    def outputs(self): return self.L.fdsp_node_outputs(self.h)
+    def ping(self, probe, h): return self.L.fdsp_node_ping(self.h, 1 if probe else 0, h)
+
+    def leaf_hashes(self):
+        buf = (C.c_uint64 * 4096)()
+        n = self.L.fdsp_node_leaf_hashes(self.h, buf, 4096)
+        return [int(buf[i]) for i in range(n)]
+
+    def signature(self):
+        buf = C.create_string_buffer(1 << 16)
+        self.L.fdsp_node_signature(self.h, buf, len(buf))
+        return buf.value.decode()

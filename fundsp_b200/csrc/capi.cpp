@@ -1,0 +1,210 @@
+// fundsp_b200 C ABI (include/fundsp_b200.h): thin, exception-free shell over csrc/host.
+#include "../../include/fundsp_b200.h"
+
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "host/bank.h"
+
+using namespace fdsp::host;
+
+struct fdsp_node { HNode* n; };
+struct fdsp_bank { Bank b; };
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+fdsp_node* wrap(HNode* n, const char* what) {
+  if (!n) { g_err = std::string(what) + ": arity mismatch or invalid argument (the reference rejects this at compile time)"; return nullptr; }
+  return new (std::nothrow) fdsp_node{n};
+}
+HNode* take(fdsp_node* h) {  // consume a handle
+  if (!h) return nullptr;
+  HNode* n = h->n; delete h; return n;
+}
+int status(const std::string& e) {
+  if (e.empty()) return FDSP_OK;
+  int code = FDSP_ERR_CUDA;
+  if (e.find("no device program") != std::string::npos || e.find("no device lowering") != std::string::npos) code = FDSP_ERR_UNSUPPORTED;
+  else if (e.find("must") != std::string::npos || e.find("needs") != std::string::npos || e.find("no output buffer") != std::string::npos || e.find("no input buffer") != std::string::npos) code = FDSP_ERR_ARG;
+  return fail(code, e);
+}
+}  // namespace
+
+#define API extern "C" __attribute__((visibility("default")))
+
+API const char* fdsp_version(void) { return "fundsp_b200 0.1.0 (sm_100a; mirrors fundsp 0.23.0 hot path)"; }
+API const char* fdsp_last_error(void) { return g_err.c_str(); }
+API int fdsp_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
+
+API fdsp_node* fdsp_constant(int n, const float* v) { return (n < 1 || !v) ? wrap(nullptr, "constant") : wrap(mk_constant(n, v), "constant"); }
+API fdsp_node* fdsp_pass(void) { return wrap(mk_pass(), "pass"); }
+API fdsp_node* fdsp_multipass(int n) { return wrap(n < 0 ? nullptr : mk_multipass(n), "multipass"); }
+API fdsp_node* fdsp_sink(int n) { return wrap(n < 1 ? nullptr : mk_sink(n), "sink"); }
+API fdsp_node* fdsp_split(int n) { return wrap(n < 1 ? nullptr : mk_split(n), "split"); }
+API fdsp_node* fdsp_multisplit(int m, int n) { return wrap((m < 1 || n < 1) ? nullptr : mk_multisplit(m, n), "multisplit"); }
+API fdsp_node* fdsp_join(int n) { return wrap(n < 1 ? nullptr : mk_join(n), "join"); }
+API fdsp_node* fdsp_multijoin(int m, int n) { return wrap((m < 1 || n < 1) ? nullptr : mk_multijoin(m, n), "multijoin"); }
+API fdsp_node* fdsp_reverse(int n) { return wrap(n < 1 ? nullptr : mk_reverse(n), "reverse"); }
+API fdsp_node* fdsp_sine(void) { return wrap(mk_sine(), "sine"); }
+API fdsp_node* fdsp_wavesynth(int table, int outputs) { return wrap(mk_wavesynth(table, outputs), "wavesynth"); }
+API fdsp_node* fdsp_noise(void) { return wrap(mk_noise(), "noise"); }
+API fdsp_node* fdsp_fixed_svf(int mode, float c, float q, float g) { return wrap(mk_fixed_svf(mode, c, q, g), "fixed_svf"); }
+API fdsp_node* fdsp_svf(int mode, float c, float q, float g) { return wrap(mk_svf(mode, c, q, g), "svf"); }
+API fdsp_node* fdsp_biquad(float a1, float a2, float b0, float b1, float b2) { return wrap(mk_biquad(a1, a2, b0, b1, b2), "biquad"); }
+API fdsp_node* fdsp_biquad_bank(void) { return wrap(mk_biquad_bank(), "biquad_bank"); }
+API fdsp_node* fdsp_butterpass(float c, int nin) { return wrap((nin < 1 || nin > 2) ? nullptr : mk_butterpass(c, nin), "butterpass"); }
+API fdsp_node* fdsp_resonator(float c, float q, int nin) { return wrap((nin != 1 && nin != 3) ? nullptr : mk_resonator(c, q, nin), "resonator"); }
+API fdsp_node* fdsp_moog(float c, float q, int nin) { return wrap(mk_moog(c, q, nin), "moog"); }
+API fdsp_node* fdsp_fir(int n, const float* w) { return wrap((n < 1 || !w) ? nullptr : mk_fir(n, w), "fir"); }
+API fdsp_node* fdsp_tick(int n) { return wrap(n < 1 ? nullptr : mk_tick(n), "tick"); }
+API fdsp_node* fdsp_delay(double t) { return wrap(mk_delay(t), "delay"); }
+API fdsp_node* fdsp_allnest(float c, fdsp_node* x, int nin) { return wrap(mk_allnest(c, take(x), nin), "allnest"); }
+API fdsp_node* fdsp_pan(float v) { return wrap(mk_pan(v), "pan"); }
+API fdsp_node* fdsp_panner(void) { return wrap(mk_panner(), "panner"); }
+API fdsp_node* fdsp_adsr_live(float a, float d, float s, float r) { return wrap(mk_adsr_live(a, d, s, r), "adsr_live"); }
+API fdsp_node* fdsp_pipe(fdsp_node* x, fdsp_node* y) { return wrap(mk_pipe(take(x), take(y)), "pipe (>>)"); }
+API fdsp_node* fdsp_stack(fdsp_node* x, fdsp_node* y) { return wrap(mk_stack(take(x), take(y)), "stack (|)"); }
+API fdsp_node* fdsp_branch(fdsp_node* x, fdsp_node* y) { return wrap(mk_branch(take(x), take(y)), "branch (^)"); }
+API fdsp_node* fdsp_bus(fdsp_node* x, fdsp_node* y) { return wrap(mk_bus(take(x), take(y)), "bus (&)"); }
+API fdsp_node* fdsp_thru(fdsp_node* x) { return wrap(mk_thru(take(x)), "thru (!)"); }
+API fdsp_node* fdsp_binop(int op, fdsp_node* x, fdsp_node* y) { return wrap(mk_binop(op, take(x), take(y)), "binop"); }
+API fdsp_node* fdsp_unop(int kind, float s, fdsp_node* x) { return wrap(mk_unop(kind, s, take(x)), "unop"); }
+API fdsp_node* fdsp_multi(int kind, int op, int n, fdsp_node* const* nodes) {
+  if (n < 1 || !nodes) return wrap(nullptr, "multi");
+  std::vector<HNode*> v;
+  for (int i = 0; i < n; i++) v.push_back(take(nodes[i]));
+  return wrap(mk_multi(kind, op, n, v.data()), "multi");
+}
+API fdsp_node* fdsp_feedback(fdsp_node* x, int hadamard) { return wrap(mk_feedback(take(x), hadamard), "feedback"); }
+
+API int fdsp_node_phase(fdsp_node* h, float phase) {  // src/combinator.rs:263-268
+  if (!h) return fail(FDSP_ERR_ARG, "null node");
+  Setting s; s.kind = P_PHASE; s.v[0] = phase; s.address.push_back({1, 1});
+  h->n->set(s); h->n->reset();
+  return FDSP_OK;
+}
+API int fdsp_node_seed(fdsp_node* h, uint64_t seed) {  // src/combinator.rs:270-276
+  if (!h) return fail(FDSP_ERR_ARG, "null node");
+  Setting s; s.kind = P_SEED; s.seed = seed; s.address.push_back({1, 0});
+  h->n->set(s); h->n->reset();
+  return FDSP_OK;
+}
+API int fdsp_node_set(fdsp_node* h, int kind, const float* v, int nv, uint64_t seed, const int64_t* addr, int naddr) {
+  if (!h || nv < 0 || nv > 5 || naddr < 0 || naddr > 6) return fail(FDSP_ERR_ARG, "bad setting");
+  Setting s; s.kind = kind; s.seed = seed;
+  for (int i = 0; i < nv; i++) s.v[i] = v[i];
+  for (int i = 0; i < naddr; i++) s.address.push_back({(int)addr[2 * i], (uint64_t)addr[2 * i + 1]});
+  h->n->set(s);
+  return FDSP_OK;
+}
+API int fdsp_node_inputs(const fdsp_node* h) { return h ? h->n->inputs() : -1; }
+API int fdsp_node_outputs(const fdsp_node* h) { return h ? h->n->outputs() : -1; }
+API uint64_t fdsp_node_id(const fdsp_node* h) { return h ? h->n->id() : 0; }
+API uint64_t fdsp_node_ping(fdsp_node* h, int probe, uint64_t hash) { return h ? h->n->ping(probe != 0, AttoHash(hash)).state : 0; }
+API int fdsp_node_leaf_hashes(fdsp_node* h, uint64_t* out, int max) {
+  if (!h) return -1;
+  std::vector<uint64_t> t;
+  HNode::ping_trace() = &t;
+  AttoHash a = h->n->ping(true, AttoHash(h->n->id()));
+  h->n->ping(false, a);
+  HNode::ping_trace() = nullptr;
+  for (int i = 0; i < (int)t.size() && i < max; i++) out[i] = t[i];
+  return (int)t.size();
+}
+API int fdsp_node_signature(const fdsp_node* h, char* out, int max) {
+  if (!h || !out || max < 1) return -1;
+  std::string s; h->n->sig(s);
+  strncpy(out, s.c_str(), (size_t)max - 1); out[max - 1] = 0;
+  return (int)s.size();
+}
+API fdsp_node* fdsp_node_clone(const fdsp_node* h) { return h ? new (std::nothrow) fdsp_node{h->n->clone()} : nullptr; }
+API void fdsp_node_free(fdsp_node* h) { if (h) { delete h->n; delete h; } }
+
+API int fdsp_wavetable_count(int table) { return (table < 0 || table > 5) ? -1 : (int)global_wavetable(table).pitch.size(); }
+API int fdsp_wavetable_info(int table, int index, float* pitch, int* length) {
+  if (table < 0 || table > 5) return fail(FDSP_ERR_ARG, "bad table");
+  const WaveTableHost& t = global_wavetable(table);
+  if (index < 0 || index >= (int)t.pitch.size()) return fail(FDSP_ERR_ARG, "bad index");
+  if (pitch) *pitch = t.pitch[index];
+  if (length) *length = t.len[index];
+  return FDSP_OK;
+}
+API const float* fdsp_wavetable_data(int table, int index) {
+  if (table < 0 || table > 5) return nullptr;
+  const WaveTableHost& t = global_wavetable(table);
+  if (index < 0 || index >= (int)t.pitch.size()) return nullptr;
+  return t.data.data() + t.off[index];
+}
+
+API int fdsp_bank_create(fdsp_node* const* voices, uint32_t nvoices, int device, uint32_t out_mode, fdsp_bank** out) {
+  if (!voices || !out || nvoices == 0) return fail(FDSP_ERR_ARG, "bank_create: bad arguments");
+  std::vector<HNode*> v;
+  bool null_voice = false;
+  for (uint32_t i = 0; i < nvoices; i++) { if (!voices[i]) null_voice = true; v.push_back(take(voices[i])); }
+  if (null_voice) { for (HNode* n : v) delete n; return fail(FDSP_ERR_ARG, "bank_create: null voice"); }
+  fdsp_bank* b = new (std::nothrow) fdsp_bank();
+  if (!b) { for (HNode* n : v) delete n; return fail(FDSP_ERR_ARG, "out of memory"); }
+  std::string e = b->b.init(v, device, out_mode);
+  if (!e.empty()) { for (HNode* n : v) delete n; delete b; return status(e); }
+  *out = b;
+  return FDSP_OK;
+}
+API void fdsp_bank_destroy(fdsp_bank* b) { delete b; }
+API int fdsp_bank_clone(const fdsp_bank* b, fdsp_bank** out) {
+  if (!b || !out) return fail(FDSP_ERR_ARG, "null bank");
+  fdsp_bank* c = new (std::nothrow) fdsp_bank();
+  std::string e = b->b.clone_into(c->b);
+  if (!e.empty()) { delete c; return status(e); }
+  *out = c;
+  return FDSP_OK;
+}
+API uint32_t fdsp_bank_voices(const fdsp_bank* b) { return b ? b->b.V() : 0; }
+API int fdsp_bank_inputs(const fdsp_bank* b) { return b ? b->b.nin : -1; }
+API int fdsp_bank_voice_outputs(const fdsp_bank* b) { return b ? b->b.nout : -1; }
+API int fdsp_bank_outputs(const fdsp_bank* b) { return !b ? -1 : ((b->b.out_mode & 2u) ? b->b.nout : (int)(b->b.V() * (uint32_t)b->b.nout)); }
+API int fdsp_bank_set_sample_rate(fdsp_bank* b, double sr) { return b ? status(b->b.set_sample_rate(sr)) : fail(FDSP_ERR_ARG, "null bank"); }
+API int fdsp_bank_reset(fdsp_bank* b) { return b ? status(b->b.reset()) : fail(FDSP_ERR_ARG, "null bank"); }
+API int fdsp_bank_allocate(fdsp_bank* b, uint64_t max_n) {
+  if (!b) return fail(FDSP_ERR_ARG, "null bank");
+  uint32_t chunk = (uint32_t)std::min<uint64_t>(16384, std::max<uint64_t>(64, (max_n + 63) / 64 * 64));
+  return status(b->b.ensure_staging(chunk));
+}
+API int fdsp_bank_process(fdsp_bank* b, uint32_t size, const float* in, float* out) {
+  if (!b || !out) return fail(FDSP_ERR_ARG, "null bank or output");
+  return status(b->b.process(size, in, out));
+}
+API int fdsp_bank_render(fdsp_bank* b, uint64_t n, const float* in, float* out_voices, float* out_mix) {
+  if (!b) return fail(FDSP_ERR_ARG, "null bank");
+  return status(b->b.render_host(n, in, out_voices, out_mix));
+}
+API int fdsp_bank_render_device(fdsp_bank* b, uint64_t n, const float* in_dev, uint64_t in_stride, float* out_dev, uint64_t out_stride,
+                                float* mix_dev, uint64_t mix_stride) {
+  if (!b) return fail(FDSP_ERR_ARG, "null bank");
+  return status(b->b.render_device(n, in_dev, in_stride, out_dev, out_stride, mix_dev, mix_stride));
+}
+API int fdsp_bank_sync(fdsp_bank* b) {
+  if (!b) return fail(FDSP_ERR_ARG, "null bank");
+  cudaSetDevice(b->b.device);
+  cudaError_t e = cudaStreamSynchronize(b->b.stream);
+  if (e != cudaSuccess) return fail(FDSP_ERR_CUDA, cudaGetErrorString(e));
+  if (cudaEventElapsedTime(&b->b.last_ms, b->b.ev0, b->b.ev1) != cudaSuccess) b->b.last_ms = 0.0f;
+  return FDSP_OK;
+}
+API void* fdsp_bank_stream(fdsp_bank* b) { return b ? (void*)b->b.stream : nullptr; }
+API int fdsp_bank_num_classes(const fdsp_bank* b) { return b ? (int)b->b.classes.size() : -1; }
+API int fdsp_bank_class_info(const fdsp_bank* b, int cls, char* sig, int max, uint32_t* voices, uint32_t* state_words, uint32_t* param_words,
+                             uint64_t* delay_floats) {
+  if (!b || cls < 0 || cls >= (int)b->b.classes.size()) return fail(FDSP_ERR_ARG, "bad class index");
+  const VoiceClass& c = b->b.classes[cls];
+  if (sig && max > 0) { strncpy(sig, c.sig.c_str(), (size_t)max - 1); sig[max - 1] = 0; }
+  if (voices) *voices = c.V();
+  if (state_words) *state_words = (uint32_t)c.k->NS;
+  if (param_words) *param_words = (uint32_t)c.k->NP;
+  if (delay_floats) *delay_floats = c.dl_floats;
+  return FDSP_OK;
+}
+API uint64_t fdsp_bank_launch_count(const fdsp_bank* b) { return b ? b->b.launches : 0; }
+API float fdsp_bank_last_kernel_ms(const fdsp_bank* b) { return b ? b->b.last_ms : 0.0f; }

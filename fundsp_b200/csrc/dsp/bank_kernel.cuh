@@ -1,0 +1,125 @@
+// fundsp_b200 voice-bank kernel: one thread = one voice instance of the graph type G, V voices in
+// lockstep. Replaces the reference's per-voice `AudioUnit::process` recursion (src/audiounit.rs:393-395,
+// src/audionode.rs:85-105,1445-1449) driven by `Wave::render` (src/wave.rs:441-466).
+//
+// Launch shape: grid = ceil(V / NT) CTAs of NT threads; each thread keeps G::R (parameters + state) in
+// registers for all blocks of the launch and walks time in 64-sample blocks (8 SIMD groups of 8 + tail),
+// exactly the block structure the reference's `process` path exposes to the nodes.
+// Outputs: MODE bit 0 = per-voice rows out[(v*OUT+c)*stride + off + t] written as coalesced-by-row
+// 16-byte stores; MODE bit 1 = per-CTA index-order partial mix (shared-memory transpose + sequential
+// column sums), finished by mix_reduce_kernel in CTA order (deterministic).
+#pragma once
+#include "nodes.cuh"
+#include "bank_args.h"
+
+namespace fdsp {
+
+
+
+template <class G, int NT, int MODE>
+__global__ void __launch_bounds__(NT) bank_kernel(const BankArgs a) {
+  extern __shared__ float tile[];  // MODE&2: [OUT][64][NT+1]
+  const uint32_t tid = threadIdx.x;
+  const uint32_t v = blockIdx.x * NT + tid;
+  const bool active = v < a.V;
+  constexpr int IN = G::IN, OUT = G::OUT;
+  // big programs (e.g. the 32-line FDN in thread-per-voice form) are not unrolled over the 8-sample group
+  constexpr int UNROLL = (G::NS + G::NP > 96) ? 1 : 8;
+
+  typename G::R r;
+  Ctx c;
+  c.wt = a.wt; c.dl = a.dline; c.V = a.V; c.v = v; c.sr = a.sr; c.sd64 = a.sd64; c.sd32 = a.sd32;
+  if (active) {
+    Loader l{a.params, a.state, a.uniform, a.V, v, 0u, 0u, 0u, 0u};
+    G::load(r, l);
+  }
+  const bool vec_ok = ((a.out_stride | a.out_offset) & 3u) == 0u;
+
+  for (uint32_t t0 = 0; t0 < a.n; t0 += 64) {
+    const int nb = (a.n - t0) < 64u ? (int)(a.n - t0) : 64;
+    const int nfull = nb & ~7;
+    c.n = nb;
+    if (active) {
+      float* orow = (MODE & 1) ? a.out + (size_t)__ldg(a.row_map + v) * a.out_stride + a.out_offset + t0 : nullptr;
+      const float* irow = (IN > 0) ? a.in + a.in_offset + t0 : nullptr;
+      c.rem = false;
+      for (int g = 0; g < nfull; g += 8) {
+        float ob[OUT > 0 ? OUT : 1][8];
+#pragma unroll(UNROLL)
+        for (int j = 0; j < 8; j++) {
+          Fr<IN> in; Fr<OUT> o;
+#pragma unroll
+          for (int k = 0; k < IN; k++) in.v[k] = __ldg(irow + (size_t)k * a.in_stride + g + j);
+          c.i = g + j; c.first = (j == 0);
+          G::template step<false>(r, c, in, o);
+#pragma unroll
+          for (int k = 0; k < OUT; k++) {
+            ob[k][j] = o.v[k];
+            if (MODE & 2) tile[(k * 64 + g + j) * (NT + 1) + tid] = o.v[k];
+          }
+        }
+        if (MODE & 1) {
+#pragma unroll
+          for (int k = 0; k < OUT; k++) {
+            float* p = orow + (size_t)k * a.out_stride + g;
+            if (vec_ok) {
+              *reinterpret_cast<float4*>(p) = make_float4(ob[k][0], ob[k][1], ob[k][2], ob[k][3]);
+              *reinterpret_cast<float4*>(p + 4) = make_float4(ob[k][4], ob[k][5], ob[k][6], ob[k][7]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; j++) p[j] = ob[k][j];
+            }
+          }
+        }
+      }
+      G::end_simd(r);
+      c.rem = true; c.first = false;
+      for (int i = nfull; i < nb; i++) {
+        Fr<IN> in; Fr<OUT> o;
+#pragma unroll
+        for (int k = 0; k < IN; k++) in.v[k] = __ldg(irow + (size_t)k * a.in_stride + i);
+        c.i = i;
+        G::template step<false>(r, c, in, o);
+#pragma unroll
+        for (int k = 0; k < OUT; k++) {
+          if (MODE & 1) orow[(size_t)k * a.out_stride + i] = o.v[k];
+          if (MODE & 2) tile[(k * 64 + i) * (NT + 1) + tid] = o.v[k];
+        }
+      }
+    } else if (MODE & 2) {
+      for (int e = 0; e < OUT * 64; e++) tile[e * (NT + 1) + tid] = 0.0f;
+    }
+    if (MODE & 2) {
+      __syncthreads();
+      for (int e = tid; e < OUT * 64; e += NT) {
+        const int k = e >> 6, i = e & 63;
+        if (i < nb) {
+          const float* row = tile + e * (NT + 1);
+          float s = row[0];
+#pragma unroll 8
+          for (int q = 1; q < NT; q++) s += row[q];
+          a.partial[((size_t)blockIdx.x * OUT + k) * a.n + t0 + i] = s;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (active) {
+    Saver s{a.state, a.V, v, 0u};
+    G::save(r, s);
+  }
+}
+
+// Finishes the mix-down: mix[c][off + t] (+)= sum over CTAs in CTA order (deterministic).
+static __global__ void mix_reduce_kernel(const float* partial, uint32_t nparts, uint32_t outs, uint32_t n, float* mix,
+                                  uint32_t mix_stride, uint32_t mix_offset, int accumulate) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= outs * n) return;
+  const uint32_t c = e / n, t = e % n;
+  float s = partial[(size_t)c * n + t];
+  for (uint32_t b = 1; b < nparts; b++) s += partial[((size_t)b * outs + c) * n + t];
+  float* p = mix + (size_t)c * mix_stride + mix_offset + t;
+  *p = accumulate ? *p + s : s;
+}
+
+}  // namespace fdsp

@@ -1,0 +1,49 @@
+// Launcher template + registry entry macro shared by the ahead-of-time instance files (csrc/inst/*.cu).
+#pragma once
+#include "../host/registry.h"
+#include "bank_kernel.cuh"
+
+namespace fdsp {
+namespace host {
+
+constexpr int NT = 128;
+
+template <class G> cudaError_t launch_t(const BankArgs& a, int mode, cudaStream_t st) {
+  const unsigned grid = (a.V + NT - 1) / NT;
+  const size_t smem = (mode & 2) ? sizeof(float) * (size_t)G::OUT * 64 * (NT + 1) : 0;
+  cudaError_t e = cudaSuccess;
+  switch (mode & 3) {
+    case 1: bank_kernel<G, NT, 1><<<grid, NT, 0, st>>>(a); break;
+    case 2:
+      if (smem > 48 * 1024) e = cudaFuncSetAttribute(bank_kernel<G, NT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      bank_kernel<G, NT, 2><<<grid, NT, smem, st>>>(a);
+      break;
+    case 3:
+      if (smem > 48 * 1024) e = cudaFuncSetAttribute(bank_kernel<G, NT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      bank_kernel<G, NT, 3><<<grid, NT, smem, st>>>(a);
+      break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+inline int threads_t() { return NT; }
+
+#define FDSP_REG(...) \
+  {#__VA_ARGS__, __VA_ARGS__::IN, __VA_ARGS__::OUT, __VA_ARGS__::NP, __VA_ARGS__::NS, __VA_ARGS__::NU, &launch_t<__VA_ARGS__>, &threads_t}
+#define FDSP_INSTANCES(name, ...)                     \
+  extern const KernelEntry kInst_##name[] = {__VA_ARGS__}; \
+  extern const int kInst_##name##_n = (int)(sizeof(kInst_##name) / sizeof(kInst_##name[0]));
+
+// ---- shorthand for the config graphs (expanded to canonical type expressions by registry.cpp)
+typedef Pipe<Constant<1>, Sine> SineHz;
+typedef Pipe<Constant<1>, WaveSynth<0, 1>> SawHz;
+typedef Pipe<Unop<1, Unop<3, Unop<3, SineHz>>>, Sine> Fm;                       // sine_hz(f)*f*m+f >> sine()
+typedef Pipe<Pipe<MultiSplit<2, 16>, Feedback<1, Multi<30, 0, 32, Pipe<Delay, Fir<3>>>>>,
+             Binop<2, Multi<31, 0, 32, Panner<1>>, Constant<2>>> ReverbStereo;  // src/prelude.rs:1732-1762
+typedef Pipe<Binop<2, Pipe<Stack<SawHz, Constant<2>>, Moog<3>>, AdsrLive>, Panner<1>> SubtractiveDry;
+typedef Pipe<SubtractiveDry, Bus<MultiPass<2>, Unop<3, ReverbStereo>>> SubtractiveVoice;  // config 4
+
+}  // namespace host
+}  // namespace fdsp

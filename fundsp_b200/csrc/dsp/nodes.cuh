@@ -1,0 +1,599 @@
+// fundsp_b200 device node library: the leaf DSP nodes and structural combinators of the reference's
+// hot path as C++ templates that compose into ONE fused per-voice program.
+//
+// A graph type such as  Pipe<Pipe<Constant<1>,WaveSynth<0,1>>,FixedSvf>  is the device-side analogue of the
+// reference's monomorphised `An<Pipe<Pipe<Constant<U1>,WaveSynth<U1>>,FixedSvf<f32,LowpassMode>>>`.
+// One thread evaluates one voice: parameters and state live in registers (`R`), per-sample `step`
+// carries the recurrences, and the *block* semantics of the reference's `process` path (phase wrap once
+// per 64-block, table choice once per 8 samples, tail samples through `tick`, envelope run lengths) are
+// reproduced through the block context `Ctx` — see each node's reference citation.
+//
+// Word layout contract with the host lowering (csrc/host/lower.cpp): per-voice parameter words (P),
+// per-voice state words (S) and class-uniform words (U) are consumed in depth-first, left-to-right
+// order; `NP/NS/NU` are the totals the host checks against.
+#pragma once
+#include "math.cuh"
+#include "bank_args.h"
+
+namespace fdsp {
+
+
+
+template <int N> struct Fr { float v[N > 0 ? N : 1]; };
+
+// Block context. `first`: first lane of an 8-sample SIMD group; `rem`: sample belongs to the tail
+// (size & 7) that the reference runs through `tick` (src/audionode.rs:110-126); `i`/`n`: index / size of block.
+struct Ctx {
+  const WaveTableDev* wt;
+  float* dl;          // delay-line storage of this voice class, element (off + pos) * V + v
+  uint32_t V, v;
+  float sr;           // sample rate as f32
+  float sd64;         // (1.0f64 / sr) as f32   (src/oscillator.rs:62-64, src/envelope.rs:290-292)
+  float sd32;         // 1.0f32 / (sr as f32)   (src/wavetable.rs:299-302)
+  int i, n;
+  bool first, rem;
+};
+
+struct Loader {
+  const uint32_t* p; const uint32_t* s; const uint32_t* u; uint32_t V, v;
+  uint32_t pi, si, ui, dl;
+  FDSP_DEV uint32_t P() { return __ldg(p + (size_t)(pi++) * V + v); }
+  FDSP_DEV float Pf() { return __uint_as_float(P()); }
+  FDSP_DEV uint32_t S() { return s[(size_t)(si++) * V + v]; }
+  FDSP_DEV float Sf() { return __uint_as_float(S()); }
+  FDSP_DEV uint32_t U() { return __ldg(u + (ui++)); }
+  FDSP_DEV uint32_t D(uint32_t len) { uint32_t o = dl; dl += len; return o; }
+};
+struct Saver {
+  uint32_t* s; uint32_t V, v; uint32_t si;
+  FDSP_DEV void S(uint32_t w) { s[(size_t)(si++) * V + v] = w; }
+  FDSP_DEV void Sf(float f) { S(__float_as_uint(f)); }
+};
+
+#define FDSP_NODE(in_, out_, np_, ns_, nu_) \
+  static constexpr int IN = (in_), OUT = (out_), NP = (np_), NS = (ns_), NU = (nu_)
+
+struct Empty {};
+
+// ---------------------------------------------------------------- routing (src/audionode.rs:374-722,2800-2837)
+template <int N> struct Constant {  // ID 2
+  FDSP_NODE(0, N, N, 0, 0);
+  struct R { float v[N]; };
+  static FDSP_DEV void load(R& r, Loader& l) { for (int c = 0; c < N; c++) r.v[c] = l.Pf(); }
+  static FDSP_DEV void save(const R&, Saver&) {}
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx&, const Fr<0>&, Fr<N>& o) { for (int c = 0; c < N; c++) o.v[c] = r.v[c]; }
+  static FDSP_DEV void end_simd(R&) {}
+};
+template <int N> struct MultiPass {  // ID 0 (N-channel) / 48 (Pass)
+  FDSP_NODE(N, N, 0, 0, 0);
+  typedef Empty R;
+  static FDSP_DEV void load(R&, Loader&) {}
+  static FDSP_DEV void save(const R&, Saver&) {}
+  template <bool T> static FDSP_DEV void step(R&, const Ctx&, const Fr<N>& in, Fr<N>& o) { for (int c = 0; c < N; c++) o.v[c] = in.v[c]; }
+  static FDSP_DEV void end_simd(R&) {}
+};
+template <int N> struct Sink {  // ID 1
+  FDSP_NODE(N, 0, 0, 0, 0);
+  typedef Empty R;
+  static FDSP_DEV void load(R&, Loader&) {}
+  static FDSP_DEV void save(const R&, Saver&) {}
+  template <bool T> static FDSP_DEV void step(R&, const Ctx&, const Fr<N>&, Fr<0>&) {}
+  static FDSP_DEV void end_simd(R&) {}
+};
+template <int M, int N> struct MultiSplit {  // ID 40 / 38
+  FDSP_NODE(M, M * N, 0, 0, 0);
+  typedef Empty R;
+  static FDSP_DEV void load(R&, Loader&) {}
+  static FDSP_DEV void save(const R&, Saver&) {}
+  template <bool T> static FDSP_DEV void step(R&, const Ctx&, const Fr<M>& in, Fr<M * N>& o) { for (int c = 0; c < M * N; c++) o.v[c] = in.v[c % M]; }
+  static FDSP_DEV void end_simd(R&) {}
+};
+template <int M, int N> struct MultiJoin {  // ID 41 / 39: tick = add then divide; process = scale by 1/N then add
+  FDSP_NODE(M * N, M, 0, 0, 0);
+  typedef Empty R;
+  static FDSP_DEV void load(R&, Loader&) {}
+  static FDSP_DEV void save(const R&, Saver&) {}
+  template <bool T> static FDSP_DEV void step(R&, const Ctx&, const Fr<M * N>& in, Fr<M>& o) {
+    if (T) {
+      for (int j = 0; j < M; j++) { float a = in.v[j]; for (int k = 1; k < N; k++) a += in.v[j + k * M]; o.v[j] = a / (float)N; }
+    } else {
+      const float z = 1.0f / (float)N;
+      for (int j = 0; j < M; j++) o.v[j] = in.v[j] * z;
+      for (int c = M; c < M * N; c++) o.v[c % M] += in.v[c] * z;
+    }
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+template <int N> struct Reverse {  // ID 45
+  FDSP_NODE(N, N, 0, 0, 0);
+  typedef Empty R;
+  static FDSP_DEV void load(R&, Loader&) {}
+  static FDSP_DEV void save(const R&, Saver&) {}
+  template <bool T> static FDSP_DEV void step(R&, const Ctx&, const Fr<N>& in, Fr<N>& o) { for (int c = 0; c < N; c++) o.v[c] = in.v[N - 1 - c]; }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
+// ---------------------------------------------------------------- combinators (src/audionode.rs:724-2800)
+template <int K> FDSP_DEV float binop(float x, float y) { return K == 0 ? x + y : (K == 1 ? x - y : x * y); }
+
+template <int K, class X, class Y> struct Binop {  // ID 3: K 0 add, 1 sub, 2 mul
+  FDSP_NODE(X::IN + Y::IN, X::OUT, X::NP + Y::NP, X::NS + Y::NS, X::NU + Y::NU);
+  struct R { typename X::R x; typename Y::R y; };
+  static FDSP_DEV void load(R& r, Loader& l) { X::load(r.x, l); Y::load(r.y, l); }
+  static FDSP_DEV void save(const R& r, Saver& s) { X::save(r.x, s); Y::save(r.y, s); }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<IN>& in, Fr<OUT>& o) {
+    Fr<X::IN> xi; Fr<Y::IN> yi; Fr<X::OUT> a; Fr<Y::OUT> b;
+    for (int k = 0; k < X::IN; k++) xi.v[k] = in.v[k];
+    for (int k = 0; k < Y::IN; k++) yi.v[k] = in.v[X::IN + k];
+    X::template step<T>(r.x, c, xi, a); Y::template step<T>(r.y, c, yi, b);
+    for (int k = 0; k < OUT; k++) o.v[k] = binop<K>(a.v[k], b.v[k]);
+  }
+  static FDSP_DEV void end_simd(R& r) { X::end_simd(r.x); Y::end_simd(r.y); }
+};
+template <int K, class X> struct Unop {  // ID 4: K 0 neg, 1 +s, 2 -x+s, 3 *s
+  FDSP_NODE(X::IN, X::OUT, X::NP + (K == 0 ? 0 : 1), X::NS, X::NU);
+  struct R { float s; typename X::R x; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.s = (K == 0) ? 0.0f : l.Pf(); X::load(r.x, l); }
+  static FDSP_DEV void save(const R& r, Saver& s) { X::save(r.x, s); }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<IN>& in, Fr<OUT>& o) {
+    X::template step<T>(r.x, c, in, o);
+    for (int k = 0; k < OUT; k++) o.v[k] = K == 0 ? -o.v[k] : (K == 1 ? o.v[k] + r.s : (K == 2 ? -o.v[k] + r.s : o.v[k] * r.s));
+  }
+  static FDSP_DEV void end_simd(R& r) { X::end_simd(r.x); }
+};
+template <class X, class Y> struct Pipe {  // ID 6
+  FDSP_NODE(X::IN, Y::OUT, X::NP + Y::NP, X::NS + Y::NS, X::NU + Y::NU);
+  struct R { typename X::R x; typename Y::R y; };
+  static FDSP_DEV void load(R& r, Loader& l) { X::load(r.x, l); Y::load(r.y, l); }
+  static FDSP_DEV void save(const R& r, Saver& s) { X::save(r.x, s); Y::save(r.y, s); }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<IN>& in, Fr<OUT>& o) {
+    Fr<X::OUT> t; X::template step<T>(r.x, c, in, t); Y::template step<T>(r.y, c, t, o);
+  }
+  static FDSP_DEV void end_simd(R& r) { X::end_simd(r.x); Y::end_simd(r.y); }
+};
+template <class X, class Y> struct Stack {  // ID 7
+  FDSP_NODE(X::IN + Y::IN, X::OUT + Y::OUT, X::NP + Y::NP, X::NS + Y::NS, X::NU + Y::NU);
+  struct R { typename X::R x; typename Y::R y; };
+  static FDSP_DEV void load(R& r, Loader& l) { X::load(r.x, l); Y::load(r.y, l); }
+  static FDSP_DEV void save(const R& r, Saver& s) { X::save(r.x, s); Y::save(r.y, s); }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<IN>& in, Fr<OUT>& o) {
+    Fr<X::IN> xi; Fr<Y::IN> yi; Fr<X::OUT> a; Fr<Y::OUT> b;
+    for (int k = 0; k < X::IN; k++) xi.v[k] = in.v[k];
+    for (int k = 0; k < Y::IN; k++) yi.v[k] = in.v[X::IN + k];
+    X::template step<T>(r.x, c, xi, a); Y::template step<T>(r.y, c, yi, b);
+    for (int k = 0; k < X::OUT; k++) o.v[k] = a.v[k];
+    for (int k = 0; k < Y::OUT; k++) o.v[X::OUT + k] = b.v[k];
+  }
+  static FDSP_DEV void end_simd(R& r) { X::end_simd(r.x); Y::end_simd(r.y); }
+};
+template <class X, class Y> struct Branch {  // ID 8
+  FDSP_NODE(X::IN, X::OUT + Y::OUT, X::NP + Y::NP, X::NS + Y::NS, X::NU + Y::NU);
+  struct R { typename X::R x; typename Y::R y; };
+  static FDSP_DEV void load(R& r, Loader& l) { X::load(r.x, l); Y::load(r.y, l); }
+  static FDSP_DEV void save(const R& r, Saver& s) { X::save(r.x, s); Y::save(r.y, s); }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<IN>& in, Fr<OUT>& o) {
+    Fr<X::OUT> a; Fr<Y::OUT> b;
+    X::template step<T>(r.x, c, in, a); Y::template step<T>(r.y, c, in, b);
+    for (int k = 0; k < X::OUT; k++) o.v[k] = a.v[k];
+    for (int k = 0; k < Y::OUT; k++) o.v[X::OUT + k] = b.v[k];
+  }
+  static FDSP_DEV void end_simd(R& r) { X::end_simd(r.x); Y::end_simd(r.y); }
+};
+template <class X, class Y> struct Bus {  // ID 10
+  FDSP_NODE(X::IN, X::OUT, X::NP + Y::NP, X::NS + Y::NS, X::NU + Y::NU);
+  struct R { typename X::R x; typename Y::R y; };
+  static FDSP_DEV void load(R& r, Loader& l) { X::load(r.x, l); Y::load(r.y, l); }
+  static FDSP_DEV void save(const R& r, Saver& s) { X::save(r.x, s); Y::save(r.y, s); }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<IN>& in, Fr<OUT>& o) {
+    Fr<Y::OUT> b;
+    X::template step<T>(r.x, c, in, o); Y::template step<T>(r.y, c, in, b);
+    for (int k = 0; k < OUT; k++) o.v[k] = o.v[k] + b.v[k];
+  }
+  static FDSP_DEV void end_simd(R& r) { X::end_simd(r.x); Y::end_simd(r.y); }
+};
+template <class X> struct Thru {  // ID 12
+  FDSP_NODE(X::IN, X::IN, X::NP, X::NS, X::NU);
+  struct R { typename X::R x; };
+  static FDSP_DEV void load(R& r, Loader& l) { X::load(r.x, l); }
+  static FDSP_DEV void save(const R& r, Saver& s) { X::save(r.x, s); }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<IN>& in, Fr<OUT>& o) {
+    Fr<X::OUT> a; X::template step<T>(r.x, c, in, a);
+    for (int k = 0; k < IN; k++) o.v[k] = k < X::OUT ? a.v[k < X::OUT ? k : 0] : in.v[k];
+  }
+  static FDSP_DEV void end_simd(R& r) { X::end_simd(r.x); }
+};
+// Indexed combinators over N nodes of one type: KIND = reference node ID (28 bus, 30 stack, 31 reduce, 33 branch, 32 chain)
+template <int KIND, int OP, int N, class X> struct Multi {
+  static constexpr int IN = (KIND == 30 || KIND == 31) ? X::IN * N : X::IN;
+  static constexpr int OUT = (KIND == 30 || KIND == 33) ? X::OUT * N : X::OUT;
+  static constexpr int NP = X::NP * N, NS = X::NS * N, NU = X::NU * N;
+  struct R { typename X::R x[N]; };
+  static FDSP_DEV void load(R& r, Loader& l) {
+#pragma unroll
+    for (int k = 0; k < N; k++) X::load(r.x[k], l);
+  }
+  static FDSP_DEV void save(const R& r, Saver& s) {
+#pragma unroll
+    for (int k = 0; k < N; k++) X::save(r.x[k], s);
+  }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<IN>& in, Fr<OUT>& o) {
+    if (KIND == 32) {  // chain
+      Fr<X::IN> t; Fr<X::OUT> u;
+      for (int q = 0; q < X::IN; q++) t.v[q] = in.v[q];
+#pragma unroll
+      for (int k = 0; k < N; k++) { X::template step<T>(r.x[k], c, t, u); for (int q = 0; q < X::OUT && q < X::IN; q++) t.v[q] = u.v[q]; }
+      for (int q = 0; q < X::OUT; q++) o.v[q] = u.v[q];
+      return;
+    }
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      Fr<X::IN> xi; Fr<X::OUT> a;
+      for (int q = 0; q < X::IN; q++) xi.v[q] = in.v[((KIND == 30 || KIND == 31) ? k * X::IN : 0) + q];
+      X::template step<T>(r.x[k], c, xi, a);
+      for (int q = 0; q < X::OUT; q++) {
+        if (KIND == 30 || KIND == 33) o.v[k * X::OUT + q] = a.v[q];
+        else if (k == 0) o.v[q] = a.v[q];
+        else o.v[q] = (KIND == 28) ? o.v[q] + a.v[q] : binop<OP>(o.v[q], a.v[q]);
+      }
+    }
+  }
+  static FDSP_DEV void end_simd(R& r) {
+#pragma unroll
+    for (int k = 0; k < N; k++) X::end_simd(r.x[k]);
+  }
+};
+
+// ---------------------------------------------------------------- generators
+struct Noise {  // src/noise.rs:170-234, ID 20: counter-based white noise
+  FDSP_NODE(0, 1, 0, 1, 0);
+  struct R { uint32_t state; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.state = l.S(); }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.S(r.state); }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx&, const Fr<0>&, Fr<1>& o) {
+    r.state += 1u;
+    o.v[0] = (float)(hash32x(r.state) >> 8) * (2.0f / 16777215.0f) - 1.0f;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+struct Sine {  // src/oscillator.rs:18-102, ID 21
+  FDSP_NODE(1, 1, 0, 1, 0);
+  struct R { float phase; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.phase = l.Sf(); }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.phase); }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<1>& in, Fr<1>& o) {
+    float p = r.phase;
+    r.phase += in.v[0] * c.sd64;
+    if (T || c.rem) {  // tick path :67-72 (libm sinf, wrap every sample)
+      r.phase -= floorf(r.phase);
+      o.v[0] = sinf(p * TAU_F);
+    } else {           // block path :74-86 (wide sin, phase unwrapped inside the block)
+      o.v[0] = wide_sinf(p * TAU_F);
+    }
+  }
+  static FDSP_DEV void end_simd(R& r) { r.phase = r.phase - floorf(r.phase); }
+};
+template <int KIND, int NOUT> struct WaveSynth {  // src/wavetable.rs:244-359, ID 34
+  FDSP_NODE(1, NOUT, 0, 2, 0);
+  struct R { float phase; int hint; int ti; float w; const float* t1; const float* t2; int l1, l2; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.phase = l.Sf(); r.hint = (int)l.S(); r.ti = r.hint; r.w = 0.0f; r.t1 = r.t2 = nullptr; r.l1 = r.l2 = 32; }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.phase); s.S((uint32_t)r.hint); }
+  static FDSP_DEV int table_index(const WaveTableDev& t, int hint, float f) {  // :157-179
+    if (f >= __ldg(&t.pitch[hint]) && f <= __ldg(&t.pitch[hint + 1])) return hint;
+    int i0 = 0, i1 = t.n - 3;
+    while (i0 < i1) {
+      int i = (i0 + i1) >> 1;
+      if (__ldg(&t.pitch[i]) > f) i1 = i;
+      else if (__ldg(&t.pitch[i + 1]) > f) { i0 = i; break; }
+      else i0 = i + 1;
+    }
+    return i0;
+  }
+  static FDSP_DEV void select(R& r, const WaveTableDev& t, int hint, float freq) {  // read/read_simd :181-212
+    float f = fabsf(freq);
+    int ti = table_index(t, hint, f);
+    r.ti = ti;
+    r.w = clamp01f(delerpf(__ldg(&t.pitch[ti]), __ldg(&t.pitch[ti + 1]), f));
+    r.t1 = t.data + __ldg(&t.off[ti + 1]); r.l1 = __ldg(&t.len[ti + 1]);
+    r.t2 = t.data + __ldg(&t.off[ti + 2]); r.l2 = __ldg(&t.len[ti + 2]);
+  }
+  static FDSP_DEV float at(const float* t, int len, float phase) {  // :125-155 (i32 index math, truncation)
+    float p = (float)len * phase;
+    int i1 = (int)p;
+    float w = p - (float)i1;
+    int mask = len - 1;
+    int i0 = (i1 - 1) & mask; i1 &= mask;
+    int i2 = (i1 + 1) & mask, i3 = (i2 + 1) & mask;
+    return optimal4x44(__ldg(t + i0), __ldg(t + i1), __ldg(t + i2), __ldg(t + i3), w);
+  }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<1>& in, Fr<NOUT>& o) {
+    const WaveTableDev& t = c.wt[KIND];
+    float ph;
+    if (T || c.rem) {  // tick :309-325
+      r.phase += in.v[0] * c.sd32;
+      r.phase -= floorf(r.phase);
+      select(r, t, r.hint, in.v[0]);
+      r.hint = r.ti;
+      ph = r.phase;
+    } else {           // block :327-348: table from lane 0 of each 8-sample group, wide floor
+      if (c.first) select(r, t, r.ti, in.v[0]);
+      r.phase += in.v[0] * c.sd32;
+      ph = r.phase - wide_floorf(r.phase);
+    }
+    o.v[0] = (1.0f - r.w) * at(r.t1, r.l1, ph) + r.w * at(r.t2, r.l2, ph);
+    if (NOUT > 1) o.v[NOUT > 1 ? 1 : 0] = ph;
+  }
+  static FDSP_DEV void end_simd(R& r) { r.phase = r.phase - floorf(r.phase); r.hint = r.ti; }
+};
+
+// ---------------------------------------------------------------- filters
+struct FixedSvf {  // src/svf.rs:857-1031, ID 43 (coefficients computed on the host at set_sample_rate)
+  FDSP_NODE(1, 1, 6, 2, 0);
+  struct R { float a1, a2, a3, m0, m1, m2, ic1, ic2; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.a1 = l.Pf(); r.a2 = l.Pf(); r.a3 = l.Pf(); r.m0 = l.Pf(); r.m1 = l.Pf(); r.m2 = l.Pf(); r.ic1 = l.Sf(); r.ic2 = l.Sf(); }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.ic1); s.Sf(r.ic2); }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx&, const Fr<1>& in, Fr<1>& o) {  // :995-1006
+    float v0 = in.v[0];
+    float v3 = v0 - r.ic2;
+    float v1 = r.a1 * r.ic1 + r.a2 * v3;
+    float v2 = r.ic2 + r.a2 * r.ic1 + r.a3 * v3;
+    r.ic1 = 2.0f * v1 - r.ic1;
+    r.ic2 = 2.0f * v2 - r.ic2;
+    o.v[0] = r.m0 * v0 + r.m1 * v1 + r.m2 * v2;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+template <int MODE> struct Svf {  // src/svf.rs:744-855, ID 36 (audio-rate cutoff/Q[/gain] inputs; recompute on change)
+  static constexpr int NI = MODE >= 6 ? 4 : 3;
+  FDSP_NODE(NI, 1, 0, 11, 0);
+  struct R { float cutoff, q, gain; SvfCoefs k; float ic1, ic2; };
+  static FDSP_DEV void load(R& r, Loader& l) {
+    r.cutoff = l.Sf(); r.q = l.Sf(); r.gain = l.Sf();
+    r.k.a1 = l.Sf(); r.k.a2 = l.Sf(); r.k.a3 = l.Sf(); r.k.m0 = l.Sf(); r.k.m1 = l.Sf(); r.k.m2 = l.Sf();
+    r.ic1 = l.Sf(); r.ic2 = l.Sf();
+  }
+  static FDSP_DEV void save(const R& r, Saver& s) {
+    s.Sf(r.cutoff); s.Sf(r.q); s.Sf(r.gain);
+    s.Sf(r.k.a1); s.Sf(r.k.a2); s.Sf(r.k.a3); s.Sf(r.k.m0); s.Sf(r.k.m1); s.Sf(r.k.m2);
+    s.Sf(r.ic1); s.Sf(r.ic2);
+  }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<NI>& in, Fr<1>& o) {
+    bool ch = in.v[1] != r.cutoff || in.v[2] != r.q;
+    if (MODE >= 6) ch = ch || in.v[NI - 1] != r.gain;
+    if (ch) { r.cutoff = in.v[1]; r.q = in.v[2]; if (MODE >= 6) r.gain = in.v[NI - 1]; r.k = svf_coefs<MODE>(c.sr, r.cutoff, r.q, r.gain); }
+    float v0 = in.v[0];
+    float v3 = v0 - r.ic2;
+    float v1 = r.k.a1 * r.ic1 + r.k.a2 * v3;
+    float v2 = r.ic2 + r.k.a2 * r.ic1 + r.k.a3 * v3;
+    r.ic1 = 2.0f * v1 - r.ic1;
+    r.ic2 = 2.0f * v2 - r.ic2;
+    o.v[0] = r.k.m0 * v0 + r.k.m1 * v1 + r.k.m2 * v2;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+struct Biquad {  // src/biquad.rs:130-218, ID 15 (also the fixed ButterLowpass ID 16 / Resonator ID 17): DF1, left-to-right
+  FDSP_NODE(1, 1, 5, 4, 0);
+  struct R { float a1, a2, b0, b1, b2, x1, x2, y1, y2; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.a1 = l.Pf(); r.a2 = l.Pf(); r.b0 = l.Pf(); r.b1 = l.Pf(); r.b2 = l.Pf(); r.x1 = l.Sf(); r.x2 = l.Sf(); r.y1 = l.Sf(); r.y2 = l.Sf(); }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.x1); s.Sf(r.x2); s.Sf(r.y1); s.Sf(r.y2); }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx&, const Fr<1>& in, Fr<1>& o) {
+    float x0 = in.v[0];
+    float y0 = r.b0 * x0 + r.b1 * r.x1 + r.b2 * r.x2 - r.a1 * r.y1 - r.a2 * r.y2;
+    r.x2 = r.x1; r.x1 = x0; r.y2 = r.y1; r.y1 = y0;
+    o.v[0] = y0;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+struct BiquadBank {  // src/biquad_bank.rs:9-117, ID 98: 8 independent DF1 lanes, one per channel
+  FDSP_NODE(8, 8, 40, 32, 0);
+  struct R { Biquad::R b[8]; };
+  static FDSP_DEV void load(R& r, Loader& l) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) { r.b[k].a1 = l.Pf(); r.b[k].a2 = l.Pf(); r.b[k].b0 = l.Pf(); r.b[k].b1 = l.Pf(); r.b[k].b2 = l.Pf(); }
+#pragma unroll
+    for (int k = 0; k < 8; k++) { r.b[k].x1 = l.Sf(); r.b[k].x2 = l.Sf(); r.b[k].y1 = l.Sf(); r.b[k].y2 = l.Sf(); }
+  }
+  static FDSP_DEV void save(const R& r, Saver& s) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) { s.Sf(r.b[k].x1); s.Sf(r.b[k].x2); s.Sf(r.b[k].y1); s.Sf(r.b[k].y2); }
+  }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<8>& in, Fr<8>& o) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) { Fr<1> a, b; a.v[0] = in.v[k]; Biquad::step<T>(r.b[k], c, a, b); o.v[k] = b.v[0]; }
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+template <int NIN> struct Moog {  // src/moog.rs:11-117, ID 60
+  FDSP_NODE(NIN, 1, NIN == 1 ? 3 : 0, 8, 0);
+  struct R { float p, k, rez, s0, s1, s2, s3, px, ps0, ps1, ps2; };
+  static FDSP_DEV void load(R& r, Loader& l) {
+    if (NIN == 1) { r.p = l.Pf(); r.k = l.Pf(); r.rez = l.Pf(); } else { r.p = r.k = r.rez = 0.0f; }
+    r.s0 = l.Sf(); r.s1 = l.Sf(); r.s2 = l.Sf(); r.s3 = l.Sf(); r.px = l.Sf(); r.ps0 = l.Sf(); r.ps1 = l.Sf(); r.ps2 = l.Sf();
+  }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.s0); s.Sf(r.s1); s.Sf(r.s2); s.Sf(r.s3); s.Sf(r.px); s.Sf(r.ps0); s.Sf(r.ps1); s.Sf(r.ps2); }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<NIN>& in, Fr<1>& o) {
+    if (NIN > 1) {  // :48-57 set_cutoff_q, every sample (:83-85)
+      float cutoff = in.v[NIN > 1 ? 1 : 0], q = in.v[NIN > 2 ? 2 : 0];
+      float cc = 2.0f * cutoff / c.sr;
+      r.p = cc * (1.8f - 0.8f * cc);
+      r.k = 2.0f * sinf(cc * 3.14159274101257324f * 0.5f) - 1.0f;
+      float t1 = (1.0f - r.p) * 1.386249f;
+      float t2 = 12.0f + t1 * t1;
+      r.rez = q * (t2 + 6.0f * t1) / (t2 - 6.0f * t1);
+    }
+    float x = -r.rez * r.s3 + in.v[0];
+    r.s0 = (x + r.px) * r.p - r.k * r.s0;
+    r.s1 = (r.s0 + r.ps0) * r.p - r.k * r.s1;
+    r.s2 = (r.s1 + r.ps1) * r.p - r.k * r.s2;
+    r.s3 = tanhf((r.s2 + r.ps2) * r.p - r.k * r.s3);
+    r.px = x; r.ps0 = r.s0; r.ps1 = r.s1; r.ps2 = r.s2;
+    o.v[0] = r.s3;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+template <int N> struct Fir {  // src/fir.rs:11-89, ID 52: shift register, accumulate from 0.0 in index order
+  FDSP_NODE(1, 1, N, N, 0);
+  struct R { float w[N], v[N]; };
+  static FDSP_DEV void load(R& r, Loader& l) { for (int k = 0; k < N; k++) r.w[k] = l.Pf(); for (int k = 0; k < N; k++) r.v[k] = l.Sf(); }
+  static FDSP_DEV void save(const R& r, Saver& s) { for (int k = 0; k < N; k++) s.Sf(r.v[k]); }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx&, const Fr<1>& in, Fr<1>& o) {
+    for (int k = 0; k + 1 < N; k++) r.v[k] = r.v[k + 1];
+    r.v[N - 1] = in.v[0];
+    float a = 0.0f;
+    for (int k = 0; k < N; k++) a += r.w[k] * r.v[k];
+    o.v[0] = a;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
+// ---------------------------------------------------------------- delays / feedback
+template <int N> struct Tick {  // src/delay.rs:17-65, ID 9
+  FDSP_NODE(N, N, 0, N, 0);
+  struct R { float b[N]; };
+  static FDSP_DEV void load(R& r, Loader& l) { for (int k = 0; k < N; k++) r.b[k] = l.Sf(); }
+  static FDSP_DEV void save(const R& r, Saver& s) { for (int k = 0; k < N; k++) s.Sf(r.b[k]); }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx&, const Fr<N>& in, Fr<N>& o) { for (int k = 0; k < N; k++) { float t = r.b[k]; r.b[k] = in.v[k]; o.v[k] = t; } }
+  static FDSP_DEV void end_simd(R&) {}
+};
+struct Delay {  // src/delay.rs:67-139, ID 13: ring buffer of round(t*sr)+1 samples in HBM, element (off+pos)*V+v
+  FDSP_NODE(1, 1, 0, 1, 1);
+  struct R { uint32_t i, len, off; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.len = l.U(); r.off = l.D(r.len); r.i = l.S(); }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.S(r.i); }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<1>& in, Fr<1>& o) {
+    c.dl[(size_t)(r.off + r.i) * c.V + c.v] = in.v[0];
+    r.i += 1u; if (r.i >= r.len) r.i = 0u;
+    o.v[0] = c.dl[(size_t)(r.off + r.i) * c.V + c.v];
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+template <int NIN, class X> struct AllNest {  // src/delay.rs:288-377, ID 83
+  FDSP_NODE(NIN, 1, (NIN == 1 ? 1 : 0) + X::NP, 1 + (NIN > 1 ? 1 : 0) + X::NS, X::NU);
+  struct R { float eta, z; typename X::R x; };
+  static FDSP_DEV void load(R& r, Loader& l) { if (NIN == 1) { r.eta = l.Pf(); r.z = l.Sf(); } else { r.eta = l.Sf(); r.z = l.Sf(); } X::load(r.x, l); }
+  static FDSP_DEV void save(const R& r, Saver& s) { if (NIN > 1) s.Sf(r.eta); s.Sf(r.z); X::save(r.x, s); }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<NIN>& in, Fr<1>& o) {
+    if (NIN > 1) r.eta = in.v[NIN > 1 ? 1 : 0];
+    Fr<1> v, y;
+    v.v[0] = in.v[0] - r.eta * r.z;
+    float out = r.eta * v.v[0] + r.z;
+    X::template step<true>(r.x, c, v, y);  // default process = per-sample tick (no block path)
+    r.z = y.v[0];
+    o.v[0] = out;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+template <int N> FDSP_DEV void hadamard(float (&v)[N]) {  // src/feedback.rs:35-57
+#pragma unroll
+  for (int h = 1; h < N; h *= 2)
+#pragma unroll
+    for (int i = 0; i < N; i += h * 2)
+#pragma unroll
+      for (int j = i; j < i + h; j++) { float x = v[j], y = v[j + h]; v[j] = x + y; v[j + h] = x - y; }
+  const float z = (float)(1.0 / sqrt((double)N));
+#pragma unroll
+  for (int i = 0; i < N; i++) v[i] = v[i] * z;
+}
+template <int HAD, class X> struct Feedback {  // src/feedback.rs:68-178, ID 11: the enclosed graph runs its TICK semantics
+  static constexpr int N = X::IN;
+  FDSP_NODE(N, N, X::NP, N + X::NS, X::NU);
+  struct R { float value[N]; typename X::R x; };
+  static FDSP_DEV void load(R& r, Loader& l) { for (int k = 0; k < N; k++) r.value[k] = l.Sf(); X::load(r.x, l); }
+  static FDSP_DEV void save(const R& r, Saver& s) { for (int k = 0; k < N; k++) s.Sf(r.value[k]); X::save(r.x, s); }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<N>& in, Fr<N>& o) {
+    Fr<N> t;
+    for (int k = 0; k < N; k++) t.v[k] = in.v[k] + r.value[k];
+    X::template step<true>(r.x, c, t, o);
+    for (int k = 0; k < N; k++) r.value[k] = o.v[k];
+    if (HAD) hadamard<N>(r.value);
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
+// ---------------------------------------------------------------- panning / envelopes
+template <int NIN> struct Panner {  // src/pan.rs:19-91, ID 49
+  FDSP_NODE(NIN, 2, NIN == 1 ? 2 : 0, NIN == 1 ? 0 : 2, 0);
+  struct R { float lw, rw; };
+  static FDSP_DEV void load(R& r, Loader& l) { if (NIN == 1) { r.lw = l.Pf(); r.rw = l.Pf(); } else { r.lw = l.Sf(); r.rw = l.Sf(); } }
+  static FDSP_DEV void save(const R& r, Saver& s) { if (NIN > 1) { s.Sf(r.lw); s.Sf(r.rw); } }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx&, const Fr<NIN>& in, Fr<2>& o) {
+    if (NIN > 1) pan_weights(in.v[NIN > 1 ? 1 : 0], r.lw, r.rw);
+    o.v[0] = in.v[0] * r.lw; o.v[1] = in.v[0] * r.rw;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+struct AdsrLive {  // src/envelope.rs:185-358 EnvelopeIn<f32,_,U1,f32> (ID 53) + the closure of src/adsr.rs:21-70
+  FDSP_NODE(1, 1, 5, 15, 0);
+  struct R {
+    float attack, decay, sustain, release, interval;
+    uint32_t attacked; float attack_start, release_start;
+    float t, t0, t1; uint64_t t_hash; float v0, v1, value, delta;
+    uint32_t run, run_len, seg_end;  // block-path run bookkeeping (envelope.rs:315-340), see step()
+  };
+  static FDSP_DEV void load(R& r, Loader& l) {
+    r.attack = l.Pf(); r.decay = l.Pf(); r.sustain = l.Pf(); r.release = l.Pf(); r.interval = l.Pf();
+    r.attacked = l.S(); r.attack_start = l.Sf(); r.release_start = l.Sf();
+    r.t = l.Sf(); r.t0 = l.Sf(); r.t1 = l.Sf();
+    uint32_t lo = l.S(), hi = l.S(); r.t_hash = ((uint64_t)hi << 32) | lo;
+    r.v0 = l.Sf(); r.v1 = l.Sf(); r.value = l.Sf(); r.delta = l.Sf();
+    r.run = l.S(); r.run_len = l.S(); r.seg_end = l.S();
+  }
+  static FDSP_DEV void save(const R& r, Saver& s) {
+    s.S(r.attacked); s.Sf(r.attack_start); s.Sf(r.release_start);
+    s.Sf(r.t); s.Sf(r.t0); s.Sf(r.t1);
+    s.S((uint32_t)r.t_hash); s.S((uint32_t)(r.t_hash >> 32));
+    s.Sf(r.v0); s.Sf(r.v1); s.Sf(r.value); s.Sf(r.delta);
+    s.S(r.run); s.S(r.run_len); s.S(r.seg_end);
+  }
+  static FDSP_DEV float ads(const R& r, float time) {  // adsr.rs:59-70
+    if (time < r.attack) return lerpf(0.0f, 1.0f, time / r.attack);
+    float decay_time = time - r.attack;
+    if (decay_time < r.decay) return lerpf(1.0f, r.sustain, decay_time / r.decay);
+    return r.sustain;
+  }
+  static FDSP_DEV float envelope(R& r, float time, float control) {  // adsr.rs:34-56
+    if (r.release_start >= 0.0f && control > 0.0f) { r.attacked = 1u; r.attack_start = time; r.release_start = -1.0f; }
+    else if (r.release_start < 0.0f && control <= 0.0f) { r.release_start = time; }
+    if (!r.attacked) return 0.0f;
+    float a = ads(r, time - r.attack_start);
+    if (r.release_start < 0.0f) return a;
+    return a * clamp01f(delerpf(r.release_start + r.release, r.release_start, time));
+  }
+  static FDSP_DEV void next_segment(R& r, const Ctx& c, float input) {  // envelope.rs:238-263
+    if (r.t0 == 0.0f && r.t1 == 0.0f) { r.v0 = envelope(r, r.t0, input); }
+    else { r.t0 = r.t1; r.v0 = r.v1; }
+    float next_interval = lerpf(0.75f, 1.25f, (float)rnd1(r.t_hash)) * r.interval;
+    r.t1 = r.t0 + next_interval;
+    r.v1 = envelope(r, r.t1, input);
+    r.t_hash = r.t_hash * 6364136223846793005ull + 1ull;
+    float u = delerpf(r.t0, r.t1, r.t);
+    r.value = lerpf(r.v0, r.v1, u);
+    float samples = next_interval / c.sd64;
+    r.delta = (r.v1 - r.v0) / samples;
+  }
+  // plan the next run of the block path's while-loop (envelope.rs:321-339) starting at block index i
+  static FDSP_DEV void plan(R& r, const Ctx& c, float input) {
+    for (;;) {
+      unsigned long long left = (unsigned long long)(long long)ceilf((r.t1 - r.t) / c.sd64);
+      unsigned long long room = (unsigned long long)(c.n - c.i);
+      unsigned long long loop = left < room ? left : room;
+      if (loop == 0ull) { r.t += 0.0f * c.sd64; next_segment(r, c, input); continue; }
+      r.run = (uint32_t)loop; r.run_len = r.run; r.seg_end = (loop == left) ? 1u : 0u;
+      return;
+    }
+  }
+  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<1>& in, Fr<1>& o) {
+    if (T) {  // tick :297-305
+      if (r.t >= r.t1) next_segment(r, c, in.v[0]);
+      o.v[0] = r.value; r.value += r.delta; r.t += c.sd64;
+      return;
+    }
+    if (c.i == 0) { if (r.t >= r.t1) next_segment(r, c, in.v[0]); plan(r, c, in.v[0]); }
+    else if (r.run == 0u) { if (r.seg_end) next_segment(r, c, in.v[0]); plan(r, c, in.v[0]); }
+    o.v[0] = r.value; r.value += r.delta;
+    r.run -= 1u;
+    if (r.run == 0u) r.t += (float)r.run_len * c.sd64;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
+}  // namespace fdsp

@@ -1,0 +1,290 @@
+// fundsp_b200 bank runtime implementation — see bank.h.
+#include "bank.h"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+
+namespace fdsp {
+namespace host {
+
+namespace {
+constexpr uint32_t TIME_CHUNK = 16384;  // samples per launch (multiple of 64): bounds the partial-mix buffer
+
+std::string cuerr(const char* what, cudaError_t e) { return std::string(what) + ": " + cudaGetErrorString(e); }
+#define CU(call)                                          \
+  do {                                                    \
+    cudaError_t e_ = (call);                              \
+    if (e_ != cudaSuccess) return cuerr(#call, e_);       \
+  } while (0)
+
+template <class T> std::string dev_alloc(T** p, size_t count) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (count == 0) return "";
+  CU(cudaMalloc((void**)p, count * sizeof(T)));
+  return "";
+}
+}  // namespace
+
+Bank::~Bank() {
+  cudaSetDevice(device);
+  for (auto& c : classes) {
+    cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial);
+  }
+  for (float* p : d_wtdata) cudaFree(p);
+  cudaFree(d_wt); cudaFree(d_in); cudaFree(d_out); cudaFree(d_mix);
+  if (h_in) cudaFreeHost(h_in);
+  if (h_out) cudaFreeHost(h_out);
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+std::string Bank::init(std::vector<HNode*>& voices, int dev, uint32_t mode) {
+  device = dev; out_mode = mode;
+  for (HNode* v : voices) nodes.emplace_back(v);
+  voices.clear();
+  if (nodes.empty()) return "bank needs at least one voice";
+  if ((mode & 3u) == 0u) return "out_mode must include FDSP_OUT_VOICES and/or FDSP_OUT_MIX";
+  nin = nodes[0]->inputs(); nout = nodes[0]->outputs();
+  if (nout < 1) return "voices must have at least one output";
+  for (auto& n : nodes) if (n->inputs() != nin || n->outputs() != nout) return "all voices of a bank must agree on inputs() and outputs()";
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= dev) return "no usable CUDA device: fundsp_b200 has no CPU fallback";
+  CU(cudaSetDevice(device));
+  CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
+  return lower_and_upload(true);
+}
+
+std::string Bank::lower_and_upload(bool upload_state) {
+  CU(cudaSetDevice(device));
+  // 1. lower every voice, group into classes keyed by (type expression, uniform words)
+  struct Low { std::string key; Lowering l; std::string sig; };
+  std::vector<Low> lows(nodes.size());
+  std::map<std::string, int> index;
+  std::vector<VoiceClass> fresh;
+  for (size_t v = 0; v < nodes.size(); v++) {
+    Low& lo = lows[v];
+    nodes[v]->sig(lo.sig);
+    nodes[v]->lower(lo.l);
+    if (!lo.l.ok) return "voice " + std::to_string(v) + ": " + lo.l.why;
+    lo.key = lo.sig + "|";
+    lo.key.append((const char*)lo.l.U.data(), lo.l.U.size() * 4);
+    auto it = index.find(lo.key);
+    int ci;
+    if (it == index.end()) {
+      ci = (int)fresh.size(); index[lo.key] = ci;
+      VoiceClass c; c.sig = lo.sig; c.uniform = lo.l.U;
+      for (uint32_t d : lo.l.dlen) c.dl_floats += d;
+      c.k = find_kernel(lo.sig);
+      if (!c.k) return "no device program for graph class `" + lo.sig + "` (not in the AOT registry; JIT unavailable)";
+      if ((size_t)c.k->NP != lo.l.P.size() || (size_t)c.k->NS != lo.l.S.size() || (size_t)c.k->NU != lo.l.U.size() || c.k->IN != nin || c.k->OUT != nout)
+        return "internal: host lowering of `" + lo.sig + "` disagrees with the device word layout";
+      fresh.push_back(std::move(c));
+    } else ci = it->second;
+    fresh[ci].voices.push_back((uint32_t)v);
+  }
+  // 2. keep device buffers of classes that survive unchanged (same key order / sizes), else rebuild
+  const bool same_shape = classes.size() == fresh.size() && std::equal(classes.begin(), classes.end(), fresh.begin(), [](const VoiceClass& a, const VoiceClass& b) {
+                            return a.sig == b.sig && a.voices == b.voices && a.uniform == b.uniform; });
+  if (!same_shape) {
+    for (auto& c : classes) { cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); }
+    classes = std::move(fresh);
+    upload_state = true;
+  }
+  for (auto& c : classes) {
+    const uint32_t V = c.V(); const int NP = c.k->NP, NS = c.k->NS;
+    std::vector<uint32_t> P((size_t)NP * V), S((size_t)NS * V), rows(V);
+    for (uint32_t i = 0; i < V; i++) {
+      const Lowering& l = lows[c.voices[i]].l;
+      for (int k = 0; k < NP; k++) P[(size_t)k * V + i] = l.P[k];
+      for (int k = 0; k < NS; k++) S[(size_t)k * V + i] = l.S[k];
+      rows[i] = c.voices[i] * (uint32_t)nout;
+    }
+    c.state0 = S;
+    if (!same_shape) {
+      std::string e;
+      if (!(e = dev_alloc(&c.d_params, P.size())).empty()) return e;
+      if (!(e = dev_alloc(&c.d_state, S.size())).empty()) return e;
+      if (!(e = dev_alloc(&c.d_uniform, c.uniform.size())).empty()) return e;
+      if (!(e = dev_alloc(&c.d_rowmap, rows.size())).empty()) return e;
+      if (!(e = dev_alloc(&c.d_dline, (size_t)c.dl_floats * V)).empty()) return e;
+      CU(cudaMemcpy(c.d_rowmap, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice));
+      if (!c.uniform.empty()) CU(cudaMemcpy(c.d_uniform, c.uniform.data(), c.uniform.size() * 4, cudaMemcpyHostToDevice));
+    }
+    if (!P.empty()) CU(cudaMemcpy(c.d_params, P.data(), P.size() * 4, cudaMemcpyHostToDevice));
+    if (upload_state) {
+      if (!S.empty()) CU(cudaMemcpy(c.d_state, S.data(), S.size() * 4, cudaMemcpyHostToDevice));
+      if (c.dl_floats) CU(cudaMemset(c.d_dline, 0, (size_t)c.dl_floats * V * sizeof(float)));
+    }
+  }
+  // 3. wavetables used by any class
+  if (!d_wt) {
+    WaveTableDev h[6];
+    memset(h, 0, sizeof(h));
+    for (int kind = 0; kind < 6; kind++) {
+      bool used = false;
+      const std::string tag = "WaveSynth<" + std::to_string(kind) + ",";
+      for (auto& c : classes) used = used || c.sig.find(tag) != std::string::npos;
+      if (!used) continue;
+      const WaveTableHost& t = global_wavetable(kind);
+      h[kind].n = (int)t.pitch.size();
+      for (size_t i = 0; i < t.pitch.size() && i < 48; i++) { h[kind].pitch[i] = t.pitch[i]; h[kind].off[i] = t.off[i]; h[kind].len[i] = t.len[i]; }
+      std::string e = dev_alloc(&d_wtdata[kind], t.data.size());
+      if (!e.empty()) return e;
+      CU(cudaMemcpy(d_wtdata[kind], t.data.data(), t.data.size() * 4, cudaMemcpyHostToDevice));
+      h[kind].data = d_wtdata[kind];
+    }
+    std::string e = dev_alloc(&d_wt, 6);
+    if (!e.empty()) return e;
+    CU(cudaMemcpy(d_wt, h, sizeof(h), cudaMemcpyHostToDevice));
+  }
+  if (upload_state) dirty = false;
+  return "";
+}
+
+std::string Bank::set_sample_rate(double s) {  // AudioUnit::set_sample_rate
+  sr = s;
+  for (auto& n : nodes) n->set_sample_rate(s);
+  // Parameters always follow the new rate. State is re-initialised only while nothing has been rendered
+  // (or when delay lengths change, which resets the lines like src/delay.rs:105-113).
+  return lower_and_upload(!dirty);
+}
+
+std::string Bank::reset() {  // AudioUnit::reset: back to the construction-time state
+  CU(cudaSetDevice(device));
+  for (auto& c : classes) {
+    if (!c.state0.empty()) CU(cudaMemcpyAsync(c.d_state, c.state0.data(), c.state0.size() * 4, cudaMemcpyHostToDevice, stream));
+    if (c.dl_floats) CU(cudaMemsetAsync(c.d_dline, 0, (size_t)c.dl_floats * c.V() * sizeof(float), stream));
+  }
+  CU(cudaStreamSynchronize(stream));
+  dirty = false;
+  return "";
+}
+
+std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_stride, float* out_dev, uint64_t out_stride, float* mix_dev,
+                                uint64_t mix_stride) {
+  CU(cudaSetDevice(device));
+  if (nin > 0 && !in_dev) return "bank has inputs but no input buffer was given";
+  const bool want_v = (out_mode & 1u) && out_dev, want_m = (out_mode & 2u) && mix_dev;
+  if (!want_v && !want_m) return "no output buffer matches the bank's out_mode";
+  if (n == 0) return "";
+  const int mode = (want_v ? 1 : 0) | (want_m ? 2 : 0);
+  if (in_stride > 0xffffffffull || out_stride > 0xffffffffull || mix_stride > 0xffffffffull) return "stride too large";
+  CU(cudaEventRecord(ev0, stream));
+  for (uint64_t t0 = 0; t0 < n; t0 += TIME_CHUNK) {
+    const uint32_t len = (uint32_t)std::min<uint64_t>(TIME_CHUNK, n - t0);
+    bool first = true;
+    for (auto& c : classes) {
+      const uint32_t V = c.V();
+      const uint32_t grid = (V + (uint32_t)c.k->threads() - 1) / (uint32_t)c.k->threads();
+      if (want_m) {
+        const size_t need = (size_t)grid * nout * len;
+        if (c.partial_floats < need) { std::string e = dev_alloc(&c.d_partial, (size_t)grid * nout * TIME_CHUNK); if (!e.empty()) return e; c.partial_floats = (size_t)grid * nout * TIME_CHUNK; }
+      }
+      BankArgs a;
+      a.params = c.d_params; a.state = c.d_state; a.uniform = c.d_uniform; a.dline = c.d_dline; a.wt = d_wt;
+      a.in = in_dev; a.out = want_v ? out_dev : nullptr; a.partial = want_m ? c.d_partial : nullptr;
+      a.V = V; a.n = len;
+      a.in_stride = (uint32_t)in_stride; a.in_offset = (uint32_t)t0;
+      a.out_stride = (uint32_t)out_stride; a.out_offset = (uint32_t)t0;
+      a.row_map = c.d_rowmap;
+      a.sr = (float)sr; a.sd64 = (float)(1.0 / sr); a.sd32 = 1.0f / (float)sr;
+      if (t0 > 0xffffffffull - TIME_CHUNK) return "render too long for one call";
+      CU(c.k->launch(a, mode, stream));
+      launches++;
+      if (want_m) {
+        CU(launch_mix_reduce(c.d_partial, grid, (uint32_t)nout, len, mix_dev, (uint32_t)mix_stride, (uint32_t)t0, first ? 0 : 1, stream));
+        launches++;
+      }
+      first = false;
+    }
+  }
+  CU(cudaEventRecord(ev1, stream));
+  dirty = true;
+  return "";
+}
+
+std::string Bank::ensure_staging(uint32_t chunk) {
+  const size_t rows = (size_t)V() * nout;
+  std::string e;
+  if (nin > 0 && in_cap < (size_t)nin * chunk) { if (!(e = dev_alloc(&d_in, (size_t)nin * chunk)).empty()) return e; in_cap = (size_t)nin * chunk; }
+  if ((out_mode & 1u) && out_cap < rows * chunk) { if (!(e = dev_alloc(&d_out, rows * chunk)).empty()) return e; out_cap = rows * chunk; }
+  if ((out_mode & 2u) && mix_cap < (size_t)nout * chunk) { if (!(e = dev_alloc(&d_mix, (size_t)nout * chunk)).empty()) return e; mix_cap = (size_t)nout * chunk; }
+  stage_chunk = std::max(stage_chunk, chunk);
+  return "";
+}
+
+std::string Bank::render_host(uint64_t n, const float* in, float* out_voices, float* out_mix) {
+  CU(cudaSetDevice(device));
+  if (n == 0) return "";
+  const size_t rows = (size_t)V() * nout;
+  // chunk so that the per-voice staging buffer stays below ~512 MB
+  uint32_t chunk = TIME_CHUNK;
+  if ((out_mode & 1u) && out_voices) {
+    const uint64_t cap = (512ull << 20) / (rows * 4);
+    chunk = (uint32_t)std::max<uint64_t>(64, std::min<uint64_t>(TIME_CHUNK, cap / 64 * 64));
+  }
+  chunk = (uint32_t)std::min<uint64_t>(chunk, (n + 63) / 64 * 64);
+  std::string e = ensure_staging(chunk);
+  if (!e.empty()) return e;
+  for (uint64_t t0 = 0; t0 < n; t0 += chunk) {
+    const uint32_t len = (uint32_t)std::min<uint64_t>(chunk, n - t0);
+    if (nin > 0) {
+      if (!in) return "bank has inputs but no input buffer was given";
+      CU(cudaMemcpy2DAsync(d_in, (size_t)chunk * 4, in + t0, (size_t)n * 4, (size_t)len * 4, nin, cudaMemcpyHostToDevice, stream));
+    }
+    e = render_device(len, d_in, chunk, (out_voices ? d_out : nullptr), chunk, (out_mix ? d_mix : nullptr), chunk);
+    if (!e.empty()) return e;
+    if (out_voices && (out_mode & 1u)) CU(cudaMemcpy2DAsync(out_voices + t0, (size_t)n * 4, d_out, (size_t)chunk * 4, (size_t)len * 4, rows, cudaMemcpyDeviceToHost, stream));
+    if (out_mix && (out_mode & 2u)) CU(cudaMemcpy2DAsync(out_mix + t0, (size_t)n * 4, d_mix, (size_t)chunk * 4, (size_t)len * 4, nout, cudaMemcpyDeviceToHost, stream));
+  }
+  CU(cudaStreamSynchronize(stream));
+  return "";
+}
+
+std::string Bank::process(uint32_t size, const float* in, float* out) {  // AudioUnit::process (size <= 64)
+  if (size > 64) return "process: size must be <= 64 (MAX_BUFFER_SIZE)";
+  if (size == 0) return "";
+  CU(cudaSetDevice(device));
+  std::string e = ensure_staging(64);
+  if (!e.empty()) return e;
+  const bool mix = (out_mode & 2u) != 0;  // mix mode wins for the AudioUnit surface; voices mode returns V*c channels
+  const size_t rows = mix ? (size_t)nout : (size_t)V() * nout;
+  if (h_in_cap < (size_t)std::max(1, nin) * 64) { if (h_in) cudaFreeHost(h_in); CU(cudaMallocHost((void**)&h_in, (size_t)std::max(1, nin) * 64 * 4)); h_in_cap = (size_t)std::max(1, nin) * 64; }
+  if (h_out_cap < rows * 64) { if (h_out) cudaFreeHost(h_out); CU(cudaMallocHost((void**)&h_out, rows * 64 * 4)); h_out_cap = rows * 64; }
+  if (nin > 0) {
+    if (!in) return "bank has inputs but no input buffer was given";
+    memcpy(h_in, in, (size_t)nin * 64 * 4);
+    CU(cudaMemcpyAsync(d_in, h_in, (size_t)nin * 64 * 4, cudaMemcpyHostToDevice, stream));
+  }
+  e = render_device(size, d_in, 64, mix ? nullptr : d_out, 64, mix ? d_mix : nullptr, 64);
+  if (!e.empty()) return e;
+  CU(cudaMemcpyAsync(h_out, mix ? d_mix : d_out, rows * 64 * 4, cudaMemcpyDeviceToHost, stream));
+  CU(cudaStreamSynchronize(stream));
+  memcpy(out, h_out, rows * 64 * 4);
+  return "";
+}
+
+std::string Bank::clone_into(Bank& dst) const {
+  std::vector<HNode*> copies;
+  for (auto& n : nodes) copies.push_back(n->clone());
+  dst.sr = sr;
+  std::string e = dst.init(copies, device, out_mode);
+  if (!e.empty()) return e;
+  for (auto& n : dst.nodes) n->set_sample_rate(sr);
+  if (!(e = dst.lower_and_upload(true)).empty()) return e;
+  CU(cudaSetDevice(device));
+  CU(cudaStreamSynchronize(stream));
+  for (size_t i = 0; i < classes.size(); i++) {
+    const VoiceClass& s = classes[i]; VoiceClass& d = dst.classes[i];
+    if (!s.state0.empty()) CU(cudaMemcpy(d.d_state, s.d_state, s.state0.size() * 4, cudaMemcpyDeviceToDevice));
+    if (s.dl_floats) CU(cudaMemcpy(d.d_dline, s.d_dline, (size_t)s.dl_floats * s.V() * 4, cudaMemcpyDeviceToDevice));
+  }
+  dst.dirty = dirty;
+  return "";
+}
+
+}  // namespace host
+}  // namespace fdsp

@@ -1,0 +1,55 @@
+// fundsp_b200 bank runtime: V voices of one or more structural classes resident on one GPU.
+// Host mirror of "a Vec of V AudioUnits + mix" driven like Wave::render (reference src/wave.rs:441-466).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "graph.h"
+#include "registry.h"
+
+namespace fdsp {
+namespace host {
+
+struct VoiceClass {
+  std::string sig;
+  const KernelEntry* k = nullptr;
+  std::vector<uint32_t> voices;     // global voice indices, ascending
+  std::vector<uint32_t> uniform;    // class-uniform words (delay lengths ...)
+  uint64_t dl_floats = 0;           // delay-line floats per voice
+  std::vector<uint32_t> state0;     // initial state, SoA [NS][V]
+  uint32_t* d_params = nullptr; uint32_t* d_state = nullptr; uint32_t* d_uniform = nullptr; uint32_t* d_rowmap = nullptr;
+  float* d_dline = nullptr; float* d_partial = nullptr; size_t partial_floats = 0;
+  uint32_t V() const { return (uint32_t)voices.size(); }
+};
+
+struct Bank {
+  int device = 0; uint32_t out_mode = 0; int nin = 0, nout = 0;
+  double sr = DEFAULT_SR; bool dirty = false;
+  std::vector<std::unique_ptr<HNode>> nodes;
+  std::vector<VoiceClass> classes;
+  cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  WaveTableDev* d_wt = nullptr; float* d_wtdata[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // staging for host-buffer entry points
+  float *d_in = nullptr, *d_out = nullptr, *d_mix = nullptr; size_t in_cap = 0, out_cap = 0, mix_cap = 0; uint32_t stage_chunk = 0;
+  float *h_in = nullptr, *h_out = nullptr; size_t h_in_cap = 0, h_out_cap = 0;  // pinned, process() path
+  uint64_t launches = 0; float last_ms = 0.0f;
+
+  ~Bank();
+  uint32_t V() const { return (uint32_t)nodes.size(); }
+  std::string init(std::vector<HNode*>& voices, int device, uint32_t out_mode);  // returns "" or error text
+  std::string lower_and_upload(bool upload_state);
+  std::string set_sample_rate(double sr);
+  std::string reset();
+  std::string ensure_staging(uint32_t chunk);
+  std::string render_device(uint64_t n, const float* in_dev, uint64_t in_stride, float* out_dev, uint64_t out_stride, float* mix_dev,
+                            uint64_t mix_stride);
+  std::string render_host(uint64_t n, const float* in, float* out_voices, float* out_mix);
+  std::string process(uint32_t size, const float* in, float* out);
+  std::string clone_into(Bank& dst) const;
+};
+
+}  // namespace host
+}  // namespace fdsp

@@ -1,0 +1,419 @@
+// fundsp_b200 host graph implementation — see graph.h. Reference citations per class (paths relative to
+// the reference checkout). Coefficient formulas are evaluated in f32 with the host libm exactly where the
+// reference evaluates them (constructor / set_sample_rate / Setting), never per sample.
+#include "graph.h"
+
+#include <algorithm>
+#include <cassert>
+
+namespace fdsp {
+namespace host {
+
+std::vector<uint64_t>*& HNode::ping_trace() { static std::vector<uint64_t>* t = nullptr; return t; }
+
+AttoHash HNode::ping(bool probe, AttoHash hash) {  // src/audionode.rs:156-161
+  if (!probe) { set_hash(hash.state); if (ping_trace()) ping_trace()->push_back(hash.state); }
+  return hash.hash(id());
+}
+
+namespace {
+
+#define HCLONE(T) HNode* clone() const override { return new T(*this); }
+
+struct Kid {  // deep-copying owning pointer
+  std::unique_ptr<HNode> p;
+  Kid() {}
+  explicit Kid(HNode* n) : p(n) {}
+  Kid(const Kid& o) : p(o.p ? o.p->clone() : nullptr) {}
+  Kid(Kid&& o) noexcept : p(std::move(o.p)) {}
+  Kid& operator=(const Kid& o) { if (this != &o) p.reset(o.p ? o.p->clone() : nullptr); return *this; }
+  Kid& operator=(Kid&& o) noexcept { p = std::move(o.p); return *this; }
+  HNode* operator->() const { return p.get(); }
+};
+
+std::string I(int v) { return std::to_string(v); }
+
+// ---------------------------------------------------------------- routing leaves (src/audionode.rs:374-722,2800-2837)
+struct Routing : HNode {
+  enum K { PASS, MULTIPASS, SINK, SPLIT, MULTISPLIT, JOIN, MULTIJOIN, REVERSE } k; int m, n;
+  Routing(K k_, int m_, int n_) : k(k_), m(m_), n(n_) {}
+  int inputs() const override {
+    switch (k) { case PASS: return 1; case MULTIPASS: case SINK: case REVERSE: return n; case SPLIT: return 1; case MULTISPLIT: return m;
+      case JOIN: return n; default: return m * n; }
+  }
+  int outputs() const override {
+    switch (k) { case PASS: return 1; case MULTIPASS: case REVERSE: return n; case SINK: return 0; case SPLIT: return n; case MULTISPLIT: return m * n;
+      case JOIN: return 1; default: return m; }
+  }
+  uint64_t id() const override {
+    switch (k) { case PASS: return 48; case MULTIPASS: return 0; case SINK: return 1; case SPLIT: return 40; case MULTISPLIT: return 38;
+      case JOIN: return 41; case MULTIJOIN: return 39; default: return 45; }
+  }
+  void sig(std::string& o) const override {
+    switch (k) {
+      case PASS: o += "MultiPass<1>"; break; case MULTIPASS: o += "MultiPass<" + I(n) + ">"; break;
+      case SINK: o += "Sink<" + I(n) + ">"; break; case SPLIT: o += "MultiSplit<1," + I(n) + ">"; break;
+      case MULTISPLIT: o += "MultiSplit<" + I(m) + "," + I(n) + ">"; break; case JOIN: o += "MultiJoin<1," + I(n) + ">"; break;
+      case MULTIJOIN: o += "MultiJoin<" + I(m) + "," + I(n) + ">"; break; default: o += "Reverse<" + I(n) + ">"; break;
+    }
+  }
+  void lower(Lowering&) const override {}
+  HCLONE(Routing)
+};
+
+struct Constant : HNode {  // src/audionode.rs:467-523
+  std::vector<float> v;
+  explicit Constant(std::vector<float> v_) : v(std::move(v_)) {}
+  int inputs() const override { return 0; } int outputs() const override { return (int)v.size(); }
+  uint64_t id() const override { return 2; }
+  void set(const Setting& s) override { if (s.kind == P_VALUE) for (auto& x : v) x = s.v[0]; }
+  void sig(std::string& o) const override { o += "Constant<" + I((int)v.size()) + ">"; }
+  void lower(Lowering& l) const override { for (float x : v) l.p(x); }
+  HCLONE(Constant)
+};
+
+// ---------------------------------------------------------------- generators
+struct Noise : HNode {  // src/noise.rs:170-234
+  bool has_seed = false; uint64_t seed = 0, hash = 0;
+  int inputs() const override { return 0; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 20; }
+  void set(const Setting& s) override { if (s.kind == P_SEED) { has_seed = true; seed = s.seed; } }
+  void set_hash(uint64_t h) override { hash = h; }
+  void sig(std::string& o) const override { o += "Noise"; }
+  void lower(Lowering& l) const override { uint64_t h = has_seed ? seed : hash; l.su((uint32_t)(h ^ (h >> 32))); }
+  HCLONE(Noise)
+};
+struct Sine : HNode {  // src/oscillator.rs:18-102
+  uint64_t hash = 0; bool has_phase = false; float initial_phase = 0;
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 21; }
+  void set(const Setting& s) override { if (s.kind == P_PHASE) { has_phase = true; initial_phase = s.v[0]; } }
+  void set_hash(uint64_t h) override { hash = h; }
+  void sig(std::string& o) const override { o += "Sine"; }
+  void lower(Lowering& l) const override { l.s(has_phase ? initial_phase : (float)rnd1(hash)); }
+  HCLONE(Sine)
+};
+struct WaveSynth : HNode {  // src/wavetable.rs:244-359
+  int kind, nout; uint64_t hash = 0; bool has_phase = false; float initial_phase = 0;
+  WaveSynth(int k, int n) : kind(k), nout(n) {}
+  int inputs() const override { return 1; } int outputs() const override { return nout; }
+  uint64_t id() const override { return 34; }
+  void set(const Setting& s) override { if (s.kind == P_PHASE) { has_phase = true; initial_phase = s.v[0]; } }
+  void set_hash(uint64_t h) override { hash = h; }
+  void sig(std::string& o) const override { o += "WaveSynth<" + I(kind) + "," + I(nout) + ">"; }
+  void lower(Lowering& l) const override { l.s(has_phase ? initial_phase : (float)rnd1(hash)); l.su(0u); }
+  HCLONE(WaveSynth)
+};
+
+// ---------------------------------------------------------------- SVF (src/svf.rs)
+struct Coefs6 { float a1, a2, a3, m0, m1, m2; };
+Coefs6 svf_coefs(int mode, float sr, float cutoff, float q, float gain) {  // src/svf.rs:26-221
+  const float PI_F = (float)3.14159265358979323846;
+  Coefs6 c{0, 0, 0, 0, 0, 0}; float g, k;
+  if (mode <= 5) { g = tanf(PI_F * cutoff / sr); k = 1.0f / q; }
+  else if (mode == 6) { float a = sqrtf(gain); g = tanf(PI_F * cutoff / sr); k = 1.0f / (q * a); c.m0 = 1.0f; c.m1 = k * (a * a - 1.0f); c.m2 = 0.0f; }
+  else if (mode == 7) { float a = sqrtf(gain); g = tanf(PI_F * cutoff / sr) / sqrtf(a); k = 1.0f / q; c.m0 = 1.0f; c.m1 = k * (a - 1.0f); c.m2 = a * a - 1.0f; }
+  else { float a = sqrtf(gain); g = tanf(PI_F * cutoff / sr) * sqrtf(a); k = 1.0f / q; c.m0 = a * a; c.m1 = k * (1.0f - a) * a; c.m2 = 1.0f - a * a; }
+  c.a1 = 1.0f / (1.0f + g * (g + k)); c.a2 = g * c.a1; c.a3 = g * c.a2;
+  switch (mode) {
+    case 0: c.m0 = 0.0f; c.m1 = 0.0f; c.m2 = 1.0f; break;
+    case 1: c.m0 = 1.0f; c.m1 = -k; c.m2 = -1.0f; break;
+    case 2: c.m0 = 0.0f; c.m1 = 1.0f; c.m2 = 0.0f; break;
+    case 3: c.m0 = 1.0f; c.m1 = -k; c.m2 = 0.0f; break;
+    case 4: c.m0 = 1.0f; c.m1 = -k; c.m2 = -2.0f; break;
+    case 5: c.m0 = 1.0f; c.m1 = -2.0f * k; c.m2 = 0.0f; break;
+    default: break;
+  }
+  return c;
+}
+struct Svf : HNode {  // FixedSvf (ID 43, :857-1031) and Svf (ID 36, :744-855)
+  int mode; bool fixed; float sr, cutoff, q, gain;
+  Svf(int m, bool f, float c, float q_, float g) : mode(m), fixed(f), sr((float)DEFAULT_SR), cutoff(c), q(q_), gain(g) {}
+  int inputs() const override { return fixed ? 1 : (mode >= 6 ? 4 : 3); } int outputs() const override { return 1; }
+  uint64_t id() const override { return fixed ? 43 : 36; }
+  void set_sample_rate(double s) override { sr = (float)s; }
+  void set(const Setting& s) override {
+    if (!fixed) return;
+    if (s.kind == P_CENTER) cutoff = s.v[0];
+    else if (s.kind == P_CENTER_Q) { cutoff = s.v[0]; q = s.v[1]; }
+    else if (s.kind == P_CENTER_Q_GAIN) { cutoff = s.v[0]; q = s.v[1]; gain = s.v[2]; }
+  }
+  void sig(std::string& o) const override { if (fixed) o += "FixedSvf"; else o += "Svf<" + I(mode) + ">"; }
+  void lower(Lowering& l) const override {
+    Coefs6 c = svf_coefs(mode, sr, cutoff, q, gain);
+    if (fixed) { l.p(c.a1); l.p(c.a2); l.p(c.a3); l.p(c.m0); l.p(c.m1); l.p(c.m2); l.s(0.0f); l.s(0.0f); }
+    else { l.s(cutoff); l.s(q); l.s(gain); l.s(c.a1); l.s(c.a2); l.s(c.a3); l.s(c.m0); l.s(c.m1); l.s(c.m2); l.s(0.0f); l.s(0.0f); }
+  }
+  HCLONE(Svf)
+};
+
+// ---------------------------------------------------------------- biquads (src/biquad.rs, src/biquad_bank.rs)
+struct BqCoefs { float a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0; };
+BqCoefs bq_butter_lowpass(float sr, float cutoff) {  // src/biquad.rs:27-38
+  const float PI_F = 3.14159274101257324f, SQRT_2 = 1.41421354f;
+  float f = tanf(cutoff * PI_F / sr);
+  float a0r = 1.0f / (1.0f + SQRT_2 * f + f * f);
+  BqCoefs c; c.a1 = (2.0f * f * f - 2.0f) * a0r; c.a2 = (1.0f - SQRT_2 * f + f * f) * a0r;
+  c.b0 = f * f * a0r; c.b1 = 2.0f * c.b0; c.b2 = c.b0; return c;
+}
+BqCoefs bq_resonator(float sr, float center, float q) {  // src/biquad.rs:40-50
+  const float PI_F = 3.14159274101257324f, TAU_F = 6.28318548202514648f;
+  float r = expf(-PI_F * center / (q * sr));
+  BqCoefs c; c.a1 = -2.0f * r * cosf(TAU_F * center / sr); c.a2 = r * r;
+  c.b0 = sqrtf(1.0f - r * r) * 0.5f; c.b1 = 0.0f; c.b2 = -c.b0; return c;
+}
+struct Biquad : HNode {  // Biquad (ID 15), fixed ButterLowpass (ID 16), fixed Resonator (ID 17)
+  int kind;  // 0 arbitrary, 1 butterpass, 2 resonator
+  int nin; BqCoefs c; float sr, f, q;
+  Biquad(int kind_, int nin_, BqCoefs c_, float f_, float q_) : kind(kind_), nin(nin_), c(c_), sr((float)DEFAULT_SR), f(f_), q(q_) { update(); }
+  void update() { if (kind == 1) c = bq_butter_lowpass(sr, f); else if (kind == 2) c = bq_resonator(sr, f, q); }
+  int inputs() const override { return nin; } int outputs() const override { return 1; }
+  uint64_t id() const override { return kind == 0 ? 15 : (kind == 1 ? 16 : 17); }
+  void set_sample_rate(double s) override { sr = (float)s; update(); }
+  void set(const Setting& s) override {
+    if (kind == 0 && s.kind == P_BIQUAD) { c.a1 = s.v[0]; c.a2 = s.v[1]; c.b0 = s.v[2]; c.b1 = s.v[3]; c.b2 = s.v[4]; }
+    else if (kind == 1 && s.kind == P_CENTER) { f = s.v[0]; update(); }
+    else if (kind == 2 && s.kind == P_CENTER) { f = s.v[0]; update(); }
+    else if (kind == 2 && s.kind == P_CENTER_Q) { f = s.v[0]; q = s.v[1]; update(); }
+  }
+  void sig(std::string& o) const override { o += nin == 1 ? "Biquad" : "Unsupported"; }
+  void lower(Lowering& l) const override {
+    if (nin != 1) { l.fail("butterpass()/resonator() with audio-rate parameter inputs has no device lowering yet"); return; }
+    l.p(c.a1); l.p(c.a2); l.p(c.b0); l.p(c.b1); l.p(c.b2); for (int i = 0; i < 4; i++) l.s(0.0f);
+  }
+  HCLONE(Biquad)
+};
+struct BiquadBank : HNode {  // src/biquad_bank.rs:9-117
+  BqCoefs c[8];
+  int inputs() const override { return 8; } int outputs() const override { return 8; }
+  uint64_t id() const override { return 98; }
+  void set(const Setting& s) override {
+    Address d = s.direction();
+    if (d.type == 1 && s.kind == P_BIQUAD && d.value < 8) { BqCoefs& k = c[d.value]; k.a1 = s.v[0]; k.a2 = s.v[1]; k.b0 = s.v[2]; k.b1 = s.v[3]; k.b2 = s.v[4]; }
+  }
+  void sig(std::string& o) const override { o += "BiquadBank"; }
+  void lower(Lowering& l) const override {
+    for (int k = 0; k < 8; k++) { l.p(c[k].a1); l.p(c[k].a2); l.p(c[k].b0); l.p(c[k].b1); l.p(c[k].b2); }
+    for (int k = 0; k < 32; k++) l.s(0.0f);
+  }
+  HCLONE(BiquadBank)
+};
+
+// ---------------------------------------------------------------- Moog (src/moog.rs:11-117)
+struct Moog : HNode {
+  int nin; float cutoff, q, sr;
+  Moog(float c, float q_, int n) : nin(n), cutoff(c), q(q_), sr((float)DEFAULT_SR) {}
+  int inputs() const override { return nin; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 60; }
+  void set_sample_rate(double s) override { sr = (float)s; }
+  void set(const Setting& s) override { if (s.kind == P_CENTER) cutoff = s.v[0]; else if (s.kind == P_CENTER_Q) { cutoff = s.v[0]; q = s.v[1]; } }
+  void sig(std::string& o) const override { o += "Moog<" + I(nin) + ">"; }
+  void lower(Lowering& l) const override {
+    if (nin == 1) {  // :48-57
+      float c = 2.0f * cutoff / sr;
+      float p = c * (1.8f - 0.8f * c);
+      float k = 2.0f * sinf(c * 3.14159274101257324f * 0.5f) - 1.0f;
+      float t1 = (1.0f - p) * 1.386249f;
+      float t2 = 12.0f + t1 * t1;
+      float rez = q * (t2 + 6.0f * t1) / (t2 - 6.0f * t1);
+      l.p(p); l.p(k); l.p(rez);
+    }
+    for (int i = 0; i < 8; i++) l.s(0.0f);
+  }
+  HCLONE(Moog)
+};
+
+// ---------------------------------------------------------------- FIR / delays (src/fir.rs, src/delay.rs)
+struct Fir : HNode {
+  std::vector<float> w;
+  explicit Fir(std::vector<float> w_) : w(std::move(w_)) {}
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 52; }
+  void sig(std::string& o) const override { o += "Fir<" + I((int)w.size()) + ">"; }
+  void lower(Lowering& l) const override { for (float x : w) l.p(x); for (size_t i = 0; i < w.size(); i++) l.s(0.0f); }
+  HCLONE(Fir)
+};
+struct TickN : HNode {
+  int n; explicit TickN(int n_) : n(n_) {}
+  int inputs() const override { return n; } int outputs() const override { return n; }
+  uint64_t id() const override { return 9; }
+  void sig(std::string& o) const override { o += "Tick<" + I(n) + ">"; }
+  void lower(Lowering& l) const override { for (int i = 0; i < n; i++) l.s(0.0f); }
+  HCLONE(TickN)
+};
+struct Delay : HNode {  // src/delay.rs:67-139: length round(t*sr) + 1, class-uniform
+  double time, sr;
+  explicit Delay(double t) : time(t), sr(DEFAULT_SR) {}
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 13; }
+  void set_sample_rate(double s) override { sr = s; }
+  uint32_t len() const { return (uint32_t)((size_t)round(time * sr) + 1); }
+  // the length shapes the state, so it is part of the structural signature of the voice class
+  void sig(std::string& o) const override { o += "Delay"; }
+  void lower(Lowering& l) const override { l.U.push_back(len()); l.dlen.push_back(len()); l.su(0u); }
+  HCLONE(Delay)
+};
+struct AllNest : HNode {  // src/delay.rs:288-377
+  int nin; float eta; Kid x;
+  AllNest(float c, HNode* x_, int n) : nin(n), eta(c), x(x_) {}
+  int inputs() const override { return nin; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 83; }
+  void set_sample_rate(double s) override { x->set_sample_rate(s); }
+  void set(const Setting& s) override { if (s.kind == P_COEFFICIENT) eta = s.v[0]; }
+  AttoHash ping(bool probe, AttoHash h) override { return x->ping(probe, h.hash(id())); }
+  void sig(std::string& o) const override { o += "AllNest<" + I(nin) + ","; x->sig(o); o += ">"; }
+  void lower(Lowering& l) const override { if (nin == 1) { l.p(eta); l.s(0.0f); } else { l.s(eta); l.s(0.0f); } x->lower(l); }
+  HCLONE(AllNest)
+};
+
+// ---------------------------------------------------------------- pan / envelope (src/pan.rs, src/envelope.rs, src/adsr.rs)
+struct Panner : HNode {
+  int nin; float value;
+  Panner(float v, int n) : nin(n), value(v) {}
+  int inputs() const override { return nin; } int outputs() const override { return 2; }
+  uint64_t id() const override { return 49; }
+  void set(const Setting& s) override { if (s.kind == P_PAN) value = s.v[0]; }
+  void sig(std::string& o) const override { o += "Panner<" + I(nin) + ">"; }
+  void lower(Lowering& l) const override {  // src/pan.rs:14-17
+    float cl = fminf(fmaxf(value, -1.0f), 1.0f);
+    float angle = (cl + 1.0f) * (3.14159274101257324f * 0.25f);
+    float lw = cosf(angle), rw = sinf(angle);
+    if (nin == 1) { l.p(lw); l.p(rw); } else { l.s(lw); l.s(rw); }
+  }
+  HCLONE(Panner)
+};
+struct AdsrLive : HNode {
+  float a, d, s, r, interval; uint64_t hash = 0;
+  AdsrLive(float a_, float d_, float s_, float r_) : a(a_), d(d_), s(s_), r(r_), interval((float)0.002) {}
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 53; }
+  void set(const Setting& st) override { if (st.kind == P_INTERVAL) interval = st.v[0]; }
+  void set_hash(uint64_t h) override { hash = h; }
+  void sig(std::string& o) const override { o += "AdsrLive"; }
+  void lower(Lowering& l) const override {
+    l.p(a); l.p(d); l.p(s); l.p(r); l.p(interval);
+    l.su(0u); l.s(0.0f); l.s(-1.0f);              // attacked, attack_start, release_start (adsr.rs:27-33)
+    l.s(0.0f); l.s(0.0f); l.s(0.0f);              // t, t_0, t_1
+    l.su((uint32_t)hash); l.su((uint32_t)(hash >> 32));  // t_hash
+    l.s(0.0f); l.s(0.0f); l.s(0.0f); l.s(0.0f);   // value_0, value_1, value, value_d
+    l.su(0u); l.su(0u); l.su(0u);                 // run, run_len, seg_end
+  }
+  HCLONE(AdsrLive)
+};
+
+// ---------------------------------------------------------------- combinators (src/audionode.rs:724-2800)
+struct Binary : HNode {
+  enum K { PIPE = 6, STACK = 7, BRANCH = 8, BUS = 10, BINOP = 3 } k; int op; Kid x, y;
+  Binary(K k_, int op_, HNode* x_, HNode* y_) : k(k_), op(op_), x(x_), y(y_) { ctor_ping(); }
+  int inputs() const override { return (k == STACK || k == BINOP) ? x->inputs() + y->inputs() : x->inputs(); }
+  int outputs() const override { return k == PIPE ? y->outputs() : ((k == STACK || k == BRANCH) ? x->outputs() + y->outputs() : x->outputs()); }
+  uint64_t id() const override { return (uint64_t)k; }
+  void reset() override { x->reset(); y->reset(); }
+  void set_sample_rate(double s) override { x->set_sample_rate(s); y->set_sample_rate(s); }
+  void set(const Setting& s) override {
+    Address d = s.direction();
+    if (d.type == 1 && d.value == 0) x->set(s.peel()); else if (d.type == 1 && d.value == 1) y->set(s.peel());
+  }
+  AttoHash ping(bool probe, AttoHash h) override { return y->ping(probe, x->ping(probe, h.hash(id()))); }
+  void sig(std::string& o) const override {
+    switch (k) { case PIPE: o += "Pipe<"; break; case STACK: o += "Stack<"; break; case BRANCH: o += "Branch<"; break; case BUS: o += "Bus<"; break;
+      default: o += "Binop<" + I(op) + ","; }
+    x->sig(o); o += ","; y->sig(o); o += ">";
+  }
+  void lower(Lowering& l) const override { x->lower(l); y->lower(l); }
+  HCLONE(Binary)
+};
+struct Unary : HNode {
+  enum K { UNOP = 4, THRU = 12, FEEDBACK = 11 } k; int kind; float scalar; Kid x;
+  Unary(K k_, int kind_, float s, HNode* x_) : k(k_), kind(kind_), scalar(s), x(x_) { ctor_ping(); }
+  int inputs() const override { return x->inputs(); }
+  int outputs() const override { return k == THRU ? x->inputs() : x->outputs(); }
+  uint64_t id() const override { return (uint64_t)k; }
+  void reset() override { x->reset(); }
+  void set_sample_rate(double s) override { x->set_sample_rate(s); }
+  void set(const Setting& s) override { if (k != FEEDBACK) x->set(s); }
+  AttoHash ping(bool probe, AttoHash h) override { return x->ping(probe, h.hash(id())); }
+  void sig(std::string& o) const override {
+    if (k == UNOP) o += "Unop<" + I(kind) + ","; else if (k == THRU) o += "Thru<"; else o += "Feedback<" + I(kind) + ",";
+    x->sig(o); o += ">";
+  }
+  void lower(Lowering& l) const override {
+    if (k == UNOP && kind != 0) l.p(scalar);
+    if (k == FEEDBACK) for (int i = 0; i < x->inputs(); i++) l.s(0.0f);
+    x->lower(l);
+  }
+  HCLONE(Unary)
+};
+struct Multi : HNode {  // MultiBus 28, MultiStack 30, Reduce 31, MultiBranch 33, Chain 32
+  int kind, op; std::vector<Kid> x;
+  Multi(int kind_, int op_, int n, HNode** nodes) : kind(kind_), op(op_) { for (int i = 0; i < n; i++) x.emplace_back(nodes[i]); ctor_ping(); }
+  int N() const { return (int)x.size(); }
+  int inputs() const override { return (kind == 30 || kind == 31) ? x[0]->inputs() * N() : x[0]->inputs(); }
+  int outputs() const override { return (kind == 30 || kind == 33) ? x[0]->outputs() * N() : x[0]->outputs(); }
+  uint64_t id() const override { return (uint64_t)kind; }
+  void reset() override { for (auto& c : x) c->reset(); }
+  void set_sample_rate(double s) override { for (auto& c : x) c->set_sample_rate(s); }
+  void set(const Setting& s) override { Address d = s.direction(); if (d.type == 1 && d.value < x.size()) x[d.value]->set(s.peel()); }
+  AttoHash ping(bool probe, AttoHash h) override { h = h.hash(id()); for (auto& c : x) h = c->ping(probe, h); return h; }
+  void sig(std::string& o) const override {
+    // all children must share one structure (the reference enforces one type X by construction)
+    std::string first; x[0]->sig(first);
+    for (auto& c : x) { std::string s; c->sig(s); if (s != first) { o += "Unsupported"; return; } }
+    o += "Multi<" + I(kind) + "," + I(op) + "," + I(N()) + "," + first + ">";
+  }
+  void lower(Lowering& l) const override { for (auto& c : x) c->lower(l); }
+  HCLONE(Multi)
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------- builders
+HNode* mk_constant(int n, const float* v) { return new Constant(std::vector<float>(v, v + n)); }
+HNode* mk_pass() { return new Routing(Routing::PASS, 1, 1); }
+HNode* mk_multipass(int n) { return new Routing(Routing::MULTIPASS, 1, n); }
+HNode* mk_sink(int n) { return new Routing(Routing::SINK, 1, n); }
+HNode* mk_split(int n) { return new Routing(Routing::SPLIT, 1, n); }
+HNode* mk_multisplit(int m, int n) { return new Routing(Routing::MULTISPLIT, m, n); }
+HNode* mk_join(int n) { return new Routing(Routing::JOIN, 1, n); }
+HNode* mk_multijoin(int m, int n) { return new Routing(Routing::MULTIJOIN, m, n); }
+HNode* mk_reverse(int n) { return new Routing(Routing::REVERSE, 1, n); }
+HNode* mk_sine() { return new Sine(); }
+HNode* mk_wavesynth(int kind, int outputs) { return (kind < 0 || kind > 5 || outputs < 1 || outputs > 2) ? nullptr : new WaveSynth(kind, outputs); }
+HNode* mk_noise() { return new Noise(); }
+HNode* mk_fixed_svf(int mode, float cutoff, float q, float gain) { return (mode < 0 || mode > 8) ? nullptr : new Svf(mode, true, cutoff, q, gain); }
+HNode* mk_svf(int mode, float cutoff, float q, float gain) { return (mode < 0 || mode > 8) ? nullptr : new Svf(mode, false, cutoff, q, gain); }
+HNode* mk_biquad(float a1, float a2, float b0, float b1, float b2) { BqCoefs c; c.a1 = a1; c.a2 = a2; c.b0 = b0; c.b1 = b1; c.b2 = b2; return new Biquad(0, 1, c, 0, 0); }
+HNode* mk_biquad_bank() { return new BiquadBank(); }
+HNode* mk_butterpass(float cutoff, int nin) { return new Biquad(1, nin, BqCoefs(), cutoff, 0); }
+HNode* mk_resonator(float center, float q, int nin) { return new Biquad(2, nin, BqCoefs(), center, q); }
+HNode* mk_moog(float cutoff, float q, int nin) { return (nin != 1 && nin != 3) ? nullptr : new Moog(cutoff, q, nin); }
+HNode* mk_fir(int n, const float* w) { return n < 1 ? nullptr : new Fir(std::vector<float>(w, w + n)); }
+HNode* mk_tick(int n) { return new TickN(n); }
+HNode* mk_delay(double t) { return t < 0.0 ? nullptr : new Delay(t); }
+HNode* mk_allnest(float c, HNode* x, int nin) { if (!x || x->inputs() != 1 || x->outputs() != 1) { delete x; return nullptr; } return new AllNest(c, x, nin); }
+HNode* mk_pan(float value) { return new Panner(value, 1); }
+HNode* mk_panner() { return new Panner(0.0f, 2); }
+HNode* mk_adsr_live(float a, float d, float s, float r) { return new AdsrLive(a, d, s, r); }
+
+static HNode* bad2(HNode* x, HNode* y) { delete x; delete y; return nullptr; }
+HNode* mk_pipe(HNode* x, HNode* y) { if (!x || !y || x->outputs() != y->inputs()) return bad2(x, y); return new Binary(Binary::PIPE, 0, x, y); }
+HNode* mk_stack(HNode* x, HNode* y) { if (!x || !y) return bad2(x, y); return new Binary(Binary::STACK, 0, x, y); }
+HNode* mk_branch(HNode* x, HNode* y) { if (!x || !y || x->inputs() != y->inputs()) return bad2(x, y); return new Binary(Binary::BRANCH, 0, x, y); }
+HNode* mk_bus(HNode* x, HNode* y) { if (!x || !y || x->inputs() != y->inputs() || x->outputs() != y->outputs()) return bad2(x, y); return new Binary(Binary::BUS, 0, x, y); }
+HNode* mk_binop(int op, HNode* x, HNode* y) { if (!x || !y || op < 0 || op > 2 || x->outputs() != y->outputs()) return bad2(x, y); return new Binary(Binary::BINOP, op, x, y); }
+HNode* mk_thru(HNode* x) { if (!x) return nullptr; return new Unary(Unary::THRU, 0, 0.0f, x); }
+HNode* mk_unop(int kind, float scalar, HNode* x) { if (!x || kind < 0 || kind > 3) { delete x; return nullptr; } return new Unary(Unary::UNOP, kind, scalar, x); }
+HNode* mk_feedback(HNode* x, int hadamard) {
+  if (!x || x->inputs() != x->outputs() || (hadamard && (x->inputs() & (x->inputs() - 1)) != 0)) { delete x; return nullptr; }
+  return new Unary(Unary::FEEDBACK, hadamard ? 1 : 0, 0.0f, x);
+}
+HNode* mk_multi(int kind, int op, int n, HNode** nodes) {
+  bool ok = n > 0 && (kind == 28 || kind == 30 || kind == 31 || kind == 33 || kind == 32);
+  for (int i = 0; i < n && ok; i++) ok = nodes[i] && nodes[i]->inputs() == nodes[0]->inputs() && nodes[i]->outputs() == nodes[0]->outputs();
+  if (ok && kind == 32) ok = nodes[0]->inputs() == nodes[0]->outputs();
+  if (!ok) { for (int i = 0; i < n; i++) delete nodes[i]; return nullptr; }
+  return new Multi(kind, op, n, nodes);
+}
+
+}  // namespace host
+}  // namespace fdsp

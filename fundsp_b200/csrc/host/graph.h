@@ -1,0 +1,120 @@
+// fundsp_b200 host graph: construction-time mirror of the reference's AudioNode tree.
+//
+// The reference builds a typed tree of nodes (`An<X>`, src/combinator.rs:178) whose constructors thread a
+// deterministic hash through the tree (`ping`, src/audionode.rs:156-161 and every combinator `new`), apply
+// `Setting`s (src/setting.rs) and compute coefficients in `set_sample_rate`. This file keeps exactly that
+// construction-time behaviour on the host and *lowers* a tree to what the GPU needs:
+//   - a type expression (`sig`) naming the fused device program in csrc/dsp/nodes.cuh,
+//   - per-voice parameter words (P), per-voice initial state words (S), class-uniform words (U) and
+//     delay-line lengths, all in depth-first left-to-right order (the order Loader consumes them).
+// No audio is processed here; the product has no CPU DSP path.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace fdsp {
+namespace host {
+
+constexpr double DEFAULT_SR = 44100.0;  // src/lib.rs:42
+
+// ---- hashing (src/math.rs:569-576, 632-658)
+inline double rnd1(uint64_t x) {
+  x ^= 0x5555555555555555ull;
+  x *= 0x9e3779b97f4a7c15ull;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return (double)(x >> 11) * (1.0 / 9007199254740992.0);
+}
+struct AttoHash {
+  uint64_t state;
+  explicit AttoHash(uint64_t s = 0) : state(s) {}
+  AttoHash hash(uint64_t data) const { return AttoHash((((state << 5) | (state >> 59)) ^ data) * 0x517cc1b727220a95ull); }
+};
+
+// ---- settings (src/setting.rs:14-62); same numbering as the C ABI (include/fundsp_b200.h)
+enum ParamKind { P_NULL = 0, P_CENTER, P_CENTER_Q, P_CENTER_Q_GAIN, P_VALUE, P_COEFFICIENT, P_BIQUAD, P_DELAY, P_TIME,
+                 P_ROUGHNESS, P_VARIABILITY, P_PAN, P_ATTACK_RELEASE, P_PHASE, P_SEED, P_INTERVAL };
+struct Address { int type; uint64_t value; };  // 1 Index, 2 Node
+struct Setting {
+  int kind = P_NULL; float v[5] = {0, 0, 0, 0, 0}; uint64_t seed = 0; std::vector<Address> address;
+  Address direction() const { return address.empty() ? Address{0, 0} : address[0]; }
+  Setting peel() const { Setting s = *this; if (!s.address.empty()) s.address.erase(s.address.begin()); return s; }
+};
+
+inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+struct Lowering {
+  std::vector<uint32_t> P, S, U;   // words in DFS order
+  std::vector<uint32_t> dlen;      // delay-line lengths (floats per voice) in DFS order
+  bool ok = true; std::string why; // set when a node has no device lowering
+  void p(float f) { P.push_back(f2u(f)); }
+  void s(float f) { S.push_back(f2u(f)); }
+  void su(uint32_t u) { S.push_back(u); }
+  void fail(const std::string& w) { if (ok) { ok = false; why = w; } }
+};
+
+struct HNode {
+  virtual ~HNode() {}
+  virtual int inputs() const = 0;
+  virtual int outputs() const = 0;
+  virtual uint64_t id() const = 0;
+  virtual void reset() {}
+  virtual void set_sample_rate(double) {}
+  virtual void set(const Setting&) {}
+  virtual void set_hash(uint64_t) {}
+  virtual AttoHash ping(bool probe, AttoHash hash);
+  virtual HNode* clone() const = 0;
+  virtual void sig(std::string& out) const = 0;
+  virtual void lower(Lowering& l) const = 0;
+  void ctor_ping() { AttoHash h = ping(true, AttoHash(id())); ping(false, h); }
+  static std::vector<uint64_t>*& ping_trace();
+};
+
+// ---- builders (one per primitive; composites consume their children)
+HNode* mk_constant(int n, const float* v);
+HNode* mk_pass();
+HNode* mk_multipass(int n);
+HNode* mk_sink(int n);
+HNode* mk_split(int n);
+HNode* mk_multisplit(int m, int n);
+HNode* mk_join(int n);
+HNode* mk_multijoin(int m, int n);
+HNode* mk_reverse(int n);
+HNode* mk_sine();
+HNode* mk_wavesynth(int kind, int outputs);
+HNode* mk_noise();
+HNode* mk_fixed_svf(int mode, float cutoff, float q, float gain);
+HNode* mk_svf(int mode, float cutoff, float q, float gain);
+HNode* mk_biquad(float a1, float a2, float b0, float b1, float b2);
+HNode* mk_biquad_bank();
+HNode* mk_butterpass(float cutoff, int nin);
+HNode* mk_resonator(float center, float q, int nin);
+HNode* mk_moog(float cutoff, float q, int nin);
+HNode* mk_fir(int n, const float* w);
+HNode* mk_tick(int n);
+HNode* mk_delay(double t);
+HNode* mk_allnest(float coefficient, HNode* x, int nin);
+HNode* mk_pan(float value);
+HNode* mk_panner();
+HNode* mk_adsr_live(float a, float d, float s, float r);
+HNode* mk_pipe(HNode* x, HNode* y);
+HNode* mk_stack(HNode* x, HNode* y);
+HNode* mk_branch(HNode* x, HNode* y);
+HNode* mk_bus(HNode* x, HNode* y);
+HNode* mk_thru(HNode* x);
+HNode* mk_binop(int op, HNode* x, HNode* y);
+HNode* mk_unop(int kind, float scalar, HNode* x);
+HNode* mk_multi(int kind, int op, int n, HNode** nodes);
+HNode* mk_feedback(HNode* x, int hadamard);
+
+// ---- wavetables (src/wavetable.rs:40-123, 493-623): built once per waveform kind on the host
+struct WaveTableHost { std::vector<float> pitch; std::vector<int> off, len; std::vector<float> data; };
+const WaveTableHost& global_wavetable(int kind);
+
+}  // namespace host
+}  // namespace fdsp

@@ -1,0 +1,130 @@
+/* fundsp_b200 — C ABI of the B200-native voice-bank engine (libfundsp_b200.so).
+ *
+ * Drop-in boundary for the hot path of SamiPerttu/fundsp v0.23.0: the reference has no FFI; the seam is
+ * the Rust trait object `AudioUnit` (src/audiounit.rs:21-95). A Rust host keeps `AudioNode`/`AudioUnit`
+ * and the combinator operators (src/combinator.rs:289-488) and binds these entry points (see
+ * INTEGRATION.md for the `extern "C"` block and the `trait Lower` walk). Plain pointers and sizes only.
+ *
+ * Two layers:
+ *   1. fdsp_node_*  : construction-time mirror of the reference's graph (one call per primitive node or
+ *      combinator; same construction order => same deterministic `ping` hashes, src/audionode.rs:156-161).
+ *      Builders CONSUME their child handles (Rust move semantics). NULL is returned on an arity mismatch
+ *      (the reference rejects those at compile time) — see fdsp_last_error().
+ *   2. fdsp_bank_*  : V voice instances (a Vec of units + mix) evaluated in lockstep on
+ *      one GPU; `fdsp_bank_process` == `AudioUnit::process` (src/audiounit.rs:45), `fdsp_bank_render` ==
+ *      the `Wave::render` / `Wave::filter` loop (src/wave.rs:441-466, 518-565).
+ *
+ * Buffers: f32, channel-major. process(): `[channel][64]` like BufferRef/BufferMut (src/buffer.rs:12,156);
+ * render(): `[channel][n]`. Voice-major row order for per-voice outputs: row = voice * channels + channel.
+ * Errors: every int-returning call returns FDSP_OK or an error code and never throws; the reference's
+ * `process` has no error channel, so the Rust shim zero-fills its output on a non-zero status.
+ */
+#ifndef FUNDSP_B200_H
+#define FUNDSP_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fdsp_node fdsp_node;
+typedef struct fdsp_bank fdsp_bank;
+
+enum { FDSP_OK = 0, FDSP_ERR_ARG = 1, FDSP_ERR_CUDA = 2, FDSP_ERR_UNSUPPORTED = 3, FDSP_ERR_ARITY = 4, FDSP_ERR_STATE = 5 };
+/* Setting parameter kinds == src/setting.rs:14-31 */
+enum { FDSP_P_NULL = 0, FDSP_P_CENTER, FDSP_P_CENTER_Q, FDSP_P_CENTER_Q_GAIN, FDSP_P_VALUE, FDSP_P_COEFFICIENT, FDSP_P_BIQUAD,
+       FDSP_P_DELAY, FDSP_P_TIME, FDSP_P_ROUGHNESS, FDSP_P_VARIABILITY, FDSP_P_PAN, FDSP_P_ATTACK_RELEASE, FDSP_P_PHASE,
+       FDSP_P_SEED, FDSP_P_INTERVAL };
+/* output modes of a bank */
+enum { FDSP_OUT_VOICES = 1, FDSP_OUT_MIX = 2 };
+
+const char* fdsp_version(void);
+const char* fdsp_last_error(void);          /* thread-local, valid until the next failing call */
+int fdsp_device_count(void);                /* number of CUDA devices; 0 when no GPU/driver is usable */
+
+/* ---- graph construction. Leaves: src/prelude.rs constructors; IDs in comments are AudioNode::ID. */
+fdsp_node* fdsp_constant(int n, const float* values);          /* Constant<N>   ID 2  (dc / constant) */
+fdsp_node* fdsp_pass(void);                                    /* Pass          ID 48 */
+fdsp_node* fdsp_multipass(int n);                              /* MultiPass<N>  ID 0  */
+fdsp_node* fdsp_sink(int n);                                   /* Sink<N>       ID 1  */
+fdsp_node* fdsp_split(int n);                                  /* Split<N>      ID 40 */
+fdsp_node* fdsp_multisplit(int m, int n);                      /* MultiSplit    ID 38 */
+fdsp_node* fdsp_join(int n);                                   /* Join<N>       ID 41 */
+fdsp_node* fdsp_multijoin(int m, int n);                       /* MultiJoin     ID 39 */
+fdsp_node* fdsp_reverse(int n);                                /* Reverse<N>    ID 45 */
+fdsp_node* fdsp_sine(void);                                    /* Sine<f32>     ID 21 src/oscillator.rs:18 */
+fdsp_node* fdsp_wavesynth(int table, int outputs);             /* WaveSynth<N>  ID 34; table 0 saw 1 square 2 triangle 3 organ 4 soft_saw 5 hammond */
+fdsp_node* fdsp_noise(void);                                   /* Noise         ID 20 src/noise.rs:170 */
+fdsp_node* fdsp_fixed_svf(int mode, float cutoff, float q, float gain); /* FixedSvf ID 43; mode 0 lowpass 1 highpass 2 bandpass 3 notch 4 peak 5 allpass 6 bell 7 lowshelf 8 highshelf */
+fdsp_node* fdsp_svf(int mode, float cutoff, float q, float gain);       /* Svf ID 36 (audio, cutoff, q[, gain] inputs) */
+fdsp_node* fdsp_biquad(float a1, float a2, float b0, float b1, float b2); /* Biquad<f32> ID 15 */
+fdsp_node* fdsp_biquad_bank(void);                             /* BiquadBank<f32x8> ID 98 */
+fdsp_node* fdsp_butterpass(float cutoff, int inputs);          /* ButterLowpass ID 16 (inputs 1 = butterpass_hz) */
+fdsp_node* fdsp_resonator(float center, float q, int inputs);  /* Resonator     ID 17 (inputs 1 = resonator_hz) */
+fdsp_node* fdsp_moog(float cutoff, float q, int inputs);       /* Moog<f32,U1|U3> ID 60 */
+fdsp_node* fdsp_fir(int n, const float* weights);              /* Fir<N>        ID 52 */
+fdsp_node* fdsp_tick(int n);                                   /* Tick<N>       ID 9  */
+fdsp_node* fdsp_delay(double seconds);                         /* Delay         ID 13 */
+fdsp_node* fdsp_allnest(float coefficient, fdsp_node* x, int inputs); /* AllNest ID 83 */
+fdsp_node* fdsp_pan(float value);                              /* Panner<U1>    ID 49 */
+fdsp_node* fdsp_panner(void);                                  /* Panner<U2>    ID 49 */
+fdsp_node* fdsp_adsr_live(float attack, float decay, float sustain, float release); /* EnvelopeIn ID 53 + src/adsr.rs closure */
+/* combinators (src/combinator.rs:289-488; src/audionode.rs) */
+fdsp_node* fdsp_pipe(fdsp_node* x, fdsp_node* y);              /* x >> y  Pipe   ID 6  */
+fdsp_node* fdsp_stack(fdsp_node* x, fdsp_node* y);             /* x | y   Stack  ID 7  */
+fdsp_node* fdsp_branch(fdsp_node* x, fdsp_node* y);            /* x ^ y   Branch ID 8  */
+fdsp_node* fdsp_bus(fdsp_node* x, fdsp_node* y);               /* x & y   Bus    ID 10 */
+fdsp_node* fdsp_thru(fdsp_node* x);                            /* !x      Thru   ID 12 */
+fdsp_node* fdsp_binop(int op, fdsp_node* x, fdsp_node* y);     /* op 0 x+y, 1 x-y, 2 x*y   Binop ID 3 */
+fdsp_node* fdsp_unop(int kind, float scalar, fdsp_node* x);    /* kind 0 -x, 1 x+s, 2 s-x, 3 x*s   Unop ID 4 */
+fdsp_node* fdsp_multi(int kind, int op, int n, fdsp_node* const* nodes); /* kind 28 MultiBus, 30 MultiStack, 31 Reduce(op), 33 MultiBranch, 32 Chain */
+fdsp_node* fdsp_feedback(fdsp_node* x, int hadamard);          /* Feedback<N,X,FrameId|FrameHadamard> ID 11 */
+/* An<X> builder methods (src/combinator.rs:263-276) and generic Setting (src/setting.rs:52-211) */
+int fdsp_node_phase(fdsp_node* n, float phase);
+int fdsp_node_seed(fdsp_node* n, uint64_t seed);
+int fdsp_node_set(fdsp_node* n, int kind, const float* values, int nvalues, uint64_t seed, const int64_t* address_pairs, int naddress);
+int fdsp_node_inputs(const fdsp_node* n);
+int fdsp_node_outputs(const fdsp_node* n);
+uint64_t fdsp_node_id(const fdsp_node* n);
+uint64_t fdsp_node_ping(fdsp_node* n, int probe, uint64_t hash);            /* AudioNode::ping */
+int fdsp_node_leaf_hashes(fdsp_node* n, uint64_t* out, int max);            /* hashes handed to leaves by the constructor ping, in order */
+int fdsp_node_signature(const fdsp_node* n, char* out, int max);            /* device program type expression */
+fdsp_node* fdsp_node_clone(const fdsp_node* n);
+void fdsp_node_free(fdsp_node* n);
+/* wavetable introspection (host builder, src/wavetable.rs:82-123) */
+int fdsp_wavetable_count(int table);
+int fdsp_wavetable_info(int table, int index, float* pitch, int* length);
+const float* fdsp_wavetable_data(int table, int index);
+
+/* ---- voice banks */
+/* Takes ownership of `voices`. Voices may belong to several structural classes (dynamic Net of mixed
+ * graphs): each class becomes one fused kernel. All voices must agree on inputs() and outputs(). */
+int fdsp_bank_create(fdsp_node* const* voices, uint32_t nvoices, int device, uint32_t out_mode, fdsp_bank** out);
+void fdsp_bank_destroy(fdsp_bank* b);
+int fdsp_bank_clone(const fdsp_bank* b, fdsp_bank** out);                   /* deep copy incl. device state (dyn_clone) */
+uint32_t fdsp_bank_voices(const fdsp_bank* b);
+int fdsp_bank_inputs(const fdsp_bank* b);                                   /* shared (bus) input channels */
+int fdsp_bank_voice_outputs(const fdsp_bank* b);                            /* channels per voice */
+int fdsp_bank_outputs(const fdsp_bank* b);                                  /* AudioUnit::outputs(): mix: channels; voices: V*channels */
+int fdsp_bank_set_sample_rate(fdsp_bank* b, double sample_rate);            /* AudioUnit::set_sample_rate */
+int fdsp_bank_reset(fdsp_bank* b);                                          /* AudioUnit::reset */
+int fdsp_bank_allocate(fdsp_bank* b, uint64_t max_render_samples);          /* AudioUnit::allocate: later calls do not allocate */
+/* AudioUnit::process: size <= 64; host buffers in [inputs][64], out [outputs][64]; size 0 is a no-op */
+int fdsp_bank_process(fdsp_bank* b, uint32_t size, const float* in, float* out);
+/* Wave::render / Wave::filter: host buffers; in [inputs][n] or NULL; out_voices [V*channels][n] or NULL; out_mix [channels][n] or NULL */
+int fdsp_bank_render(fdsp_bank* b, uint64_t n, const float* in, float* out_voices, float* out_mix);
+/* same with device-resident buffers (strides in floats), asynchronous on the bank's stream */
+int fdsp_bank_render_device(fdsp_bank* b, uint64_t n, const float* in_dev, uint64_t in_stride, float* out_voices_dev, uint64_t voices_stride,
+                            float* out_mix_dev, uint64_t mix_stride);
+int fdsp_bank_sync(fdsp_bank* b);
+void* fdsp_bank_stream(fdsp_bank* b);                                       /* cudaStream_t the bank launches on */
+/* introspection */
+int fdsp_bank_num_classes(const fdsp_bank* b);
+int fdsp_bank_class_info(const fdsp_bank* b, int cls, char* signature, int max, uint32_t* voices, uint32_t* state_words, uint32_t* param_words, uint64_t* delay_floats);
+uint64_t fdsp_bank_launch_count(const fdsp_bank* b);                        /* kernels launched so far */
+float fdsp_bank_last_kernel_ms(const fdsp_bank* b);                         /* CUDA-event time of the voice kernels of the last render_device call */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

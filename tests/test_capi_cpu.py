@@ -1,0 +1,99 @@
+"""CPU tests of the product's host side (no GPU, no compute calls): the C-ABI library loads and exports
+every symbol include/fundsp_b200.h declares; its construction-time logic (ping hashes, settings, arity,
+type expressions, wavetables) agrees with the oracle."""
+import numpy as np
+import pytest
+
+from fundsp_b200 import capi, workloads
+from fundsp_b200.graph import ArityError
+from fundsp_b200.prelude import *  # noqa: F401,F403
+from oracle import OracleUnit, lib as olib
+
+L = capi.lib()
+
+
+def test_library_exports_every_declared_symbol():
+    syms = capi.header_symbols()
+    assert len(syms) >= 60
+    for s in syms:
+        assert hasattr(L, s), s
+    assert set(capi._SIG) == set(syms)
+    assert b"sm_100a" in L.fdsp_version()
+
+
+GRAPHS = [
+    lambda: sine_hz(440.0) >> lowpass_hz(1000.0, 1.0),
+    lambda: workloads.fm_voice(7),
+    lambda: workloads.noise_svf_voice(3),
+    lambda: workloads.saw_svf_voice(11),
+    lambda: workloads.biquad_bank_unit(2),
+    lambda: workloads.subtractive_voice(5),
+    lambda: workloads.net_voice(0), lambda: workloads.net_voice(1), lambda: workloads.net_voice(2), lambda: workloads.net_voice(3),
+    lambda: noise() | (~zero() >> noise()) | noise() & zero(),
+    lambda: (noise() | dc((1000.0, 0.5))) >> moog() | (noise() | dc(800.0)) >> moog_q(0.3),
+    lambda: dc((440.0, 880.0)) >> multisplit(2, 5) >> sumi(10, lambda i: saw() * 0.1) | saw_hz(220.0).phase(0.5) * 0.1,
+    lambda: (pass_() ^ mul(-4.0) ^ add(-2.0)) >> add(5.0) + sub(3.0) + mul(-4.0),
+    lambda: feedback(delay(0.5) * 0.5),
+    lambda: dc(1.0) >> adsr_live(0.001, 0.002, 0.5, 0.003),
+]
+
+
+@pytest.mark.parametrize("k", range(len(GRAPHS)))
+def test_host_ping_and_arity_match_oracle(k):
+    g = GRAPHS[k]()
+    n, o = capi.NodeHandle(g), OracleUnit(g)
+    assert (n.inputs(), n.outputs()) == (o.inputs(), o.outputs()) == (g.inputs(), g.outputs())
+    assert n.leaf_hashes() == o.leaf_hashes()
+    assert n.ping(True, 12345) == o.ping(True, 12345)
+
+
+def test_arity_errors_are_reported_not_crashes():
+    be = capi.GpuBackend()
+    a, b = be.b_pass(), be.b_stack(be.b_pass(), be.b_pass())
+    with pytest.raises(capi.FdspError) as e:
+        be.b_pipe(a, b)  # 1 output >> 2 inputs
+    assert e.value.code == capi.ERR_ARITY
+    with pytest.raises(ArityError):
+        pass_() >> (pass_() | pass_())
+    with pytest.raises(capi.FdspError):
+        be.b_wavesynth(9, 1)
+
+
+def test_config_graphs_have_aot_programs():
+    from ctypes import create_string_buffer
+    for name in workloads.WORKLOADS:
+        g = workloads.build(name, 1)[0]
+        sig = capi.NodeHandle(g).signature()
+        assert "Unsupported" not in sig, (name, sig)
+    assert capi.NodeHandle(workloads.saw_svf_voice(0)).signature() == "Pipe<Pipe<Constant<1>,WaveSynth<0,1>>,FixedSvf>"
+    assert capi.NodeHandle(workloads.fm_voice(0)).signature() == "Pipe<Unop<1,Unop<3,Unop<3,Pipe<Constant<1>,Sine>>>>,Sine>"
+    assert create_string_buffer(4) is not None
+
+
+def test_wavetables_match_oracle():
+    O = olib()
+    for kind in range(6):
+        n = L.fdsp_wavetable_count(kind)
+        assert n == O.fo_wavetable_count(kind) == 40
+        worst, differing, total = 0.0, 0, 0
+        for i in range(n):
+            pitch, ln = capi.C.c_float(), capi.C.c_int()
+            capi.check(L.fdsp_wavetable_info(kind, i, capi.C.byref(pitch), capi.C.byref(ln)))
+            assert pitch.value == O.fo_wavetable_pitch(kind, i) and ln.value == O.fo_wavetable_len(kind, i)
+            a = np.ctypeslib.as_array(L.fdsp_wavetable_data(kind, i), (ln.value,))
+            b = np.ctypeslib.as_array(O.fo_wavetable_data(kind, i), (ln.value,))
+            worst = max(worst, float(np.abs(a - b).max()))
+            differing += int((a != b).sum())
+            total += ln.value
+        # independent builders (radix-2 f64 inverse FFT vs direct f64 DFT): equal to f32 rounding
+        assert worst <= 2.4e-7, (kind, worst)
+        assert differing <= total // 50, (kind, differing, total)
+
+
+def test_bank_create_fails_loudly_without_gpu():
+    if L.fdsp_device_count() > 0:
+        pytest.skip("GPU present")
+    from fundsp_b200.bank import GpuBank
+    with pytest.raises(capi.FdspError) as e:
+        GpuBank([sine_hz(440.0) >> lowpass_hz(1000.0, 1.0)])
+    assert "no CPU fallback" in str(e.value)
