@@ -12,6 +12,7 @@ struct WaveTableDev {
   float pitch[48];
   int off[48];
   int len[48];
+  int total;          // floats in `data`
   const float* data;
 };
 

@@ -16,9 +16,31 @@ namespace fdsp {
 
 
 
-template <class G, int NT, int MODE>
+// ---- TMA (bulk async copy) + mbarrier primitives used to stage wavetables into shared memory
+FDSP_DEV uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+FDSP_DEV void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+FDSP_DEV void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+FDSP_DEV void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+FDSP_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+// TB: stage the wavetable data of kind WaveKind<G> in shared memory behind the mix tile (one TMA bulk copy per
+// 32 KB slice, single mbarrier), so the per-sample table taps become conflict-light LDS instead of divergent LDG.
+template <class G, int NT, int MODE, bool TB>
 __global__ void __launch_bounds__(NT) bank_kernel(const BankArgs a) {
-  extern __shared__ float tile[];  // MODE&2: [OUT][64][NT+1]
+  extern __shared__ __align__(16) float tile[];  // MODE&2: [OUT][64][NT+1]; TB: table data after it
   const uint32_t tid = threadIdx.x;
   const uint32_t v = blockIdx.x * NT + tid;
   const bool active = v < a.V;
@@ -27,7 +49,24 @@ __global__ void __launch_bounds__(NT) bank_kernel(const BankArgs a) {
   constexpr int UNROLL = (G::NS + G::NP > 96) ? 1 : 8;
 
   typename G::R r;
-  Ctx c;
+  CtxT<TB> c;
+  c.tsm = 0u; c.tsm_kind = -1;
+  if (TB) {
+    constexpr int KIND = WaveKind<G>::value >= 0 ? WaveKind<G>::value : 0;
+    __shared__ __align__(8) unsigned long long mbar;
+    float* tsm = tile + ((MODE & 2) ? G::OUT * 64 * (NT + 1) : 0);
+    const uint32_t bytes = (uint32_t)a.wt[KIND].total * 4u;
+    const uint32_t bar = smem_addr(&mbar);
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(bar, bytes);
+      const char* src = reinterpret_cast<const char*>(a.wt[KIND].data);
+      for (uint32_t o = 0; o < bytes; o += 32768u) bulk_g2s(smem_addr(tsm) + o, src + o, (bytes - o) < 32768u ? (bytes - o) : 32768u, bar);
+    }
+    mbar_wait(bar, 0);
+    c.tsm = smem_addr(tsm); c.tsm_kind = KIND;
+  }
   c.wt = a.wt; c.dl = a.dline; c.V = a.V; c.v = v; c.sr = a.sr; c.sd64 = a.sd64; c.sd32 = a.sd32;
   if (active) {
     Loader l{a.params, a.state, a.uniform, a.V, v, 0u, 0u, 0u, 0u};

@@ -8,30 +8,37 @@ namespace host {
 
 constexpr int NT = 128;
 
-template <class G> cudaError_t launch_t(const BankArgs& a, int mode, cudaStream_t st) {
-  const unsigned grid = (a.V + NT - 1) / NT;
-  const size_t smem = (mode & 2) ? sizeof(float) * (size_t)G::OUT * 64 * (NT + 1) : 0;
-  cudaError_t e = cudaSuccess;
-  switch (mode & 3) {
-    case 1: bank_kernel<G, NT, 1><<<grid, NT, 0, st>>>(a); break;
-    case 2:
-      if (smem > 48 * 1024) e = cudaFuncSetAttribute(bank_kernel<G, NT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      bank_kernel<G, NT, 2><<<grid, NT, smem, st>>>(a);
-      break;
-    case 3:
-      if (smem > 48 * 1024) e = cudaFuncSetAttribute(bank_kernel<G, NT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      bank_kernel<G, NT, 3><<<grid, NT, smem, st>>>(a);
-      break;
-    default: return cudaErrorInvalidValue;
+template <class G, int MODE, bool TB> cudaError_t launch_one(const BankArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(bank_kernel<G, NT, MODE, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
   }
+  bank_kernel<G, NT, MODE, TB><<<grid, NT, smem, st>>>(a);
   return cudaGetLastError();
 }
+template <class G, bool TB> cudaError_t launch_mode(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t st) {
+  const unsigned grid = (a.V + NT - 1) / NT;
+  const size_t smem = ((mode & 2) ? sizeof(float) * (size_t)G::OUT * 64 * (NT + 1) : 0) + (TB ? table_bytes : 0);
+  switch (mode & 3) {
+    case 1: return launch_one<G, 1, TB>(a, grid, smem, st);
+    case 2: return launch_one<G, 2, TB>(a, grid, smem, st);
+    case 3: return launch_one<G, 3, TB>(a, grid, smem, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+// table_bytes > 0 asks for the shared-memory wavetable variant (only meaningful when G reads a wavetable and it fits).
+template <class G> cudaError_t launch_t(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t st) {
+  if (WaveKind<G>::value >= 0 && table_bytes > 0) {
+    const size_t smem = ((mode & 2) ? sizeof(float) * (size_t)G::OUT * 64 * (NT + 1) : 0) + table_bytes;
+    if (smem <= 227 * 1024) return launch_mode<G, (WaveKind<G>::value >= 0)>(a, mode, table_bytes, st);
+  }
+  return launch_mode<G, false>(a, mode, 0, st);
+}
+template <class G> int wave_kind_t() { return WaveKind<G>::value; }
 inline int threads_t() { return NT; }
 
 #define FDSP_REG(...) \
-  {#__VA_ARGS__, __VA_ARGS__::IN, __VA_ARGS__::OUT, __VA_ARGS__::NP, __VA_ARGS__::NS, __VA_ARGS__::NU, &launch_t<__VA_ARGS__>, &threads_t}
+  {#__VA_ARGS__, __VA_ARGS__::IN, __VA_ARGS__::OUT, __VA_ARGS__::NP, __VA_ARGS__::NS, __VA_ARGS__::NU, &launch_t<__VA_ARGS__>, &threads_t, &wave_kind_t<__VA_ARGS__>}
 #define FDSP_INSTANCES(name, ...)                     \
   extern const KernelEntry kInst_##name[] = {__VA_ARGS__}; \
   extern const int kInst_##name##_n = (int)(sizeof(kInst_##name) / sizeof(kInst_##name[0]));

@@ -84,28 +84,4 @@ FDSP_DEV float optimal4x44(float a0, float a1, float a2, float a3, float x) {
   return (((c4 * z + c3) * z + c2) * z + c1) * z + c0;
 }
 
-// reference src/svf.rs:26-221 SvfCoefs<f32>; mode: 0 lowpass 1 highpass 2 bandpass 3 notch 4 peak 5 allpass 6 bell 7 lowshelf 8 highshelf
-struct SvfCoefs { float a1, a2, a3, m0, m1, m2; };
-template <int MODE> FDSP_DEV SvfCoefs svf_coefs(float sr, float cutoff, float q, float gain) {
-  SvfCoefs c; float g, k;
-  if (MODE <= 5) { g = tanf(PI_F * cutoff / sr); k = 1.0f / q; c.m0 = c.m1 = c.m2 = 0.0f; }
-  else if (MODE == 6) { float a = sqrtf(gain); g = tanf(PI_F * cutoff / sr); k = 1.0f / (q * a); c.m0 = 1.0f; c.m1 = k * (a * a - 1.0f); c.m2 = 0.0f; }
-  else if (MODE == 7) { float a = sqrtf(gain); g = tanf(PI_F * cutoff / sr) / sqrtf(a); k = 1.0f / q; c.m0 = 1.0f; c.m1 = k * (a - 1.0f); c.m2 = a * a - 1.0f; }
-  else { float a = sqrtf(gain); g = tanf(PI_F * cutoff / sr) * sqrtf(a); k = 1.0f / q; c.m0 = a * a; c.m1 = k * (1.0f - a) * a; c.m2 = 1.0f - a * a; }
-  c.a1 = 1.0f / (1.0f + g * (g + k)); c.a2 = g * c.a1; c.a3 = g * c.a2;
-  if (MODE == 0) { c.m0 = 0.0f; c.m1 = 0.0f; c.m2 = 1.0f; }
-  if (MODE == 1) { c.m0 = 1.0f; c.m1 = -k; c.m2 = -1.0f; }
-  if (MODE == 2) { c.m0 = 0.0f; c.m1 = 1.0f; c.m2 = 0.0f; }
-  if (MODE == 3) { c.m0 = 1.0f; c.m1 = -k; c.m2 = 0.0f; }
-  if (MODE == 4) { c.m0 = 1.0f; c.m1 = -k; c.m2 = -2.0f; }
-  if (MODE == 5) { c.m0 = 1.0f; c.m1 = -2.0f * k; c.m2 = 0.0f; }
-  return c;
-}
-
-// reference src/pan.rs:14-17
-FDSP_DEV void pan_weights(float value, float& l, float& r) {
-  float angle = (clamp11f(value) + 1.0f) * (3.14159274101257324f * 0.25f);
-  l = cosf(angle); r = sinf(angle);
-}
-
 }  // namespace fdsp

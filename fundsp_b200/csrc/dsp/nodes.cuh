@@ -12,7 +12,7 @@
 // per-voice state words (S) and class-uniform words (U) are consumed in depth-first, left-to-right
 // order; `NP/NS/NU` are the totals the host checks against.
 #pragma once
-#include "math.cuh"
+#include "libm.cuh"
 #include "bank_args.h"
 
 namespace fdsp {
@@ -23,8 +23,12 @@ template <int N> struct Fr { float v[N > 0 ? N : 1]; };
 
 // Block context. `first`: first lane of an 8-sample SIMD group; `rem`: sample belongs to the tail
 // (size & 7) that the reference runs through `tick` (src/audionode.rs:110-126); `i`/`n`: index / size of block.
-struct Ctx {
+// SM: the wavetables of one waveform kind are staged in shared memory (TMA bulk copy in the kernel prologue).
+template <bool SM> struct CtxT {
+  static constexpr bool SMEM_TABLES = SM;
   const WaveTableDev* wt;
+  uint32_t tsm;       // shared-space byte address of the staged table data (kind `tsm_kind`)
+  int tsm_kind;
   float* dl;          // delay-line storage of this voice class, element (off + pos) * V + v
   uint32_t V, v;
   float sr;           // sample rate as f32
@@ -33,6 +37,9 @@ struct Ctx {
   int i, n;
   bool first, rem;
 };
+typedef CtxT<false> Ctx;
+
+FDSP_DEV float lds_f32(uint32_t addr) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
 
 struct Loader {
   const uint32_t* p; const uint32_t* s; const uint32_t* u; uint32_t V, v;
@@ -61,7 +68,7 @@ template <int N> struct Constant {  // ID 2
   struct R { float v[N]; };
   static FDSP_DEV void load(R& r, Loader& l) { for (int c = 0; c < N; c++) r.v[c] = l.Pf(); }
   static FDSP_DEV void save(const R&, Saver&) {}
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx&, const Fr<0>&, Fr<N>& o) { for (int c = 0; c < N; c++) o.v[c] = r.v[c]; }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C&, const Fr<0>&, Fr<N>& o) { for (int c = 0; c < N; c++) o.v[c] = r.v[c]; }
   static FDSP_DEV void end_simd(R&) {}
 };
 template <int N> struct MultiPass {  // ID 0 (N-channel) / 48 (Pass)
@@ -69,7 +76,7 @@ template <int N> struct MultiPass {  // ID 0 (N-channel) / 48 (Pass)
   typedef Empty R;
   static FDSP_DEV void load(R&, Loader&) {}
   static FDSP_DEV void save(const R&, Saver&) {}
-  template <bool T> static FDSP_DEV void step(R&, const Ctx&, const Fr<N>& in, Fr<N>& o) { for (int c = 0; c < N; c++) o.v[c] = in.v[c]; }
+  template <bool T, class C> static FDSP_DEV void step(R&, const C&, const Fr<N>& in, Fr<N>& o) { for (int c = 0; c < N; c++) o.v[c] = in.v[c]; }
   static FDSP_DEV void end_simd(R&) {}
 };
 template <int N> struct Sink {  // ID 1
@@ -77,7 +84,7 @@ template <int N> struct Sink {  // ID 1
   typedef Empty R;
   static FDSP_DEV void load(R&, Loader&) {}
   static FDSP_DEV void save(const R&, Saver&) {}
-  template <bool T> static FDSP_DEV void step(R&, const Ctx&, const Fr<N>&, Fr<0>&) {}
+  template <bool T, class C> static FDSP_DEV void step(R&, const C&, const Fr<N>&, Fr<0>&) {}
   static FDSP_DEV void end_simd(R&) {}
 };
 template <int M, int N> struct MultiSplit {  // ID 40 / 38
@@ -85,7 +92,7 @@ template <int M, int N> struct MultiSplit {  // ID 40 / 38
   typedef Empty R;
   static FDSP_DEV void load(R&, Loader&) {}
   static FDSP_DEV void save(const R&, Saver&) {}
-  template <bool T> static FDSP_DEV void step(R&, const Ctx&, const Fr<M>& in, Fr<M * N>& o) { for (int c = 0; c < M * N; c++) o.v[c] = in.v[c % M]; }
+  template <bool T, class C> static FDSP_DEV void step(R&, const C&, const Fr<M>& in, Fr<M * N>& o) { for (int c = 0; c < M * N; c++) o.v[c] = in.v[c % M]; }
   static FDSP_DEV void end_simd(R&) {}
 };
 template <int M, int N> struct MultiJoin {  // ID 41 / 39: tick = add then divide; process = scale by 1/N then add
@@ -93,7 +100,7 @@ template <int M, int N> struct MultiJoin {  // ID 41 / 39: tick = add then divid
   typedef Empty R;
   static FDSP_DEV void load(R&, Loader&) {}
   static FDSP_DEV void save(const R&, Saver&) {}
-  template <bool T> static FDSP_DEV void step(R&, const Ctx&, const Fr<M * N>& in, Fr<M>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R&, const C&, const Fr<M * N>& in, Fr<M>& o) {
     if (T) {
       for (int j = 0; j < M; j++) { float a = in.v[j]; for (int k = 1; k < N; k++) a += in.v[j + k * M]; o.v[j] = a / (float)N; }
     } else {
@@ -109,7 +116,7 @@ template <int N> struct Reverse {  // ID 45
   typedef Empty R;
   static FDSP_DEV void load(R&, Loader&) {}
   static FDSP_DEV void save(const R&, Saver&) {}
-  template <bool T> static FDSP_DEV void step(R&, const Ctx&, const Fr<N>& in, Fr<N>& o) { for (int c = 0; c < N; c++) o.v[c] = in.v[N - 1 - c]; }
+  template <bool T, class C> static FDSP_DEV void step(R&, const C&, const Fr<N>& in, Fr<N>& o) { for (int c = 0; c < N; c++) o.v[c] = in.v[N - 1 - c]; }
   static FDSP_DEV void end_simd(R&) {}
 };
 
@@ -121,7 +128,7 @@ template <int K, class X, class Y> struct Binop {  // ID 3: K 0 add, 1 sub, 2 mu
   struct R { typename X::R x; typename Y::R y; };
   static FDSP_DEV void load(R& r, Loader& l) { X::load(r.x, l); Y::load(r.y, l); }
   static FDSP_DEV void save(const R& r, Saver& s) { X::save(r.x, s); Y::save(r.y, s); }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<IN>& in, Fr<OUT>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<IN>& in, Fr<OUT>& o) {
     Fr<X::IN> xi; Fr<Y::IN> yi; Fr<X::OUT> a; Fr<Y::OUT> b;
     for (int k = 0; k < X::IN; k++) xi.v[k] = in.v[k];
     for (int k = 0; k < Y::IN; k++) yi.v[k] = in.v[X::IN + k];
@@ -135,7 +142,7 @@ template <int K, class X> struct Unop {  // ID 4: K 0 neg, 1 +s, 2 -x+s, 3 *s
   struct R { float s; typename X::R x; };
   static FDSP_DEV void load(R& r, Loader& l) { r.s = (K == 0) ? 0.0f : l.Pf(); X::load(r.x, l); }
   static FDSP_DEV void save(const R& r, Saver& s) { X::save(r.x, s); }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<IN>& in, Fr<OUT>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<IN>& in, Fr<OUT>& o) {
     X::template step<T>(r.x, c, in, o);
     for (int k = 0; k < OUT; k++) o.v[k] = K == 0 ? -o.v[k] : (K == 1 ? o.v[k] + r.s : (K == 2 ? -o.v[k] + r.s : o.v[k] * r.s));
   }
@@ -146,7 +153,7 @@ template <class X, class Y> struct Pipe {  // ID 6
   struct R { typename X::R x; typename Y::R y; };
   static FDSP_DEV void load(R& r, Loader& l) { X::load(r.x, l); Y::load(r.y, l); }
   static FDSP_DEV void save(const R& r, Saver& s) { X::save(r.x, s); Y::save(r.y, s); }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<IN>& in, Fr<OUT>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<IN>& in, Fr<OUT>& o) {
     Fr<X::OUT> t; X::template step<T>(r.x, c, in, t); Y::template step<T>(r.y, c, t, o);
   }
   static FDSP_DEV void end_simd(R& r) { X::end_simd(r.x); Y::end_simd(r.y); }
@@ -156,7 +163,7 @@ template <class X, class Y> struct Stack {  // ID 7
   struct R { typename X::R x; typename Y::R y; };
   static FDSP_DEV void load(R& r, Loader& l) { X::load(r.x, l); Y::load(r.y, l); }
   static FDSP_DEV void save(const R& r, Saver& s) { X::save(r.x, s); Y::save(r.y, s); }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<IN>& in, Fr<OUT>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<IN>& in, Fr<OUT>& o) {
     Fr<X::IN> xi; Fr<Y::IN> yi; Fr<X::OUT> a; Fr<Y::OUT> b;
     for (int k = 0; k < X::IN; k++) xi.v[k] = in.v[k];
     for (int k = 0; k < Y::IN; k++) yi.v[k] = in.v[X::IN + k];
@@ -171,7 +178,7 @@ template <class X, class Y> struct Branch {  // ID 8
   struct R { typename X::R x; typename Y::R y; };
   static FDSP_DEV void load(R& r, Loader& l) { X::load(r.x, l); Y::load(r.y, l); }
   static FDSP_DEV void save(const R& r, Saver& s) { X::save(r.x, s); Y::save(r.y, s); }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<IN>& in, Fr<OUT>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<IN>& in, Fr<OUT>& o) {
     Fr<X::OUT> a; Fr<Y::OUT> b;
     X::template step<T>(r.x, c, in, a); Y::template step<T>(r.y, c, in, b);
     for (int k = 0; k < X::OUT; k++) o.v[k] = a.v[k];
@@ -184,7 +191,7 @@ template <class X, class Y> struct Bus {  // ID 10
   struct R { typename X::R x; typename Y::R y; };
   static FDSP_DEV void load(R& r, Loader& l) { X::load(r.x, l); Y::load(r.y, l); }
   static FDSP_DEV void save(const R& r, Saver& s) { X::save(r.x, s); Y::save(r.y, s); }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<IN>& in, Fr<OUT>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<IN>& in, Fr<OUT>& o) {
     Fr<Y::OUT> b;
     X::template step<T>(r.x, c, in, o); Y::template step<T>(r.y, c, in, b);
     for (int k = 0; k < OUT; k++) o.v[k] = o.v[k] + b.v[k];
@@ -196,7 +203,7 @@ template <class X> struct Thru {  // ID 12
   struct R { typename X::R x; };
   static FDSP_DEV void load(R& r, Loader& l) { X::load(r.x, l); }
   static FDSP_DEV void save(const R& r, Saver& s) { X::save(r.x, s); }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<IN>& in, Fr<OUT>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<IN>& in, Fr<OUT>& o) {
     Fr<X::OUT> a; X::template step<T>(r.x, c, in, a);
     for (int k = 0; k < IN; k++) o.v[k] = k < X::OUT ? a.v[k < X::OUT ? k : 0] : in.v[k];
   }
@@ -216,7 +223,7 @@ template <int KIND, int OP, int N, class X> struct Multi {
 #pragma unroll
     for (int k = 0; k < N; k++) X::save(r.x[k], s);
   }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<IN>& in, Fr<OUT>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<IN>& in, Fr<OUT>& o) {
     if (KIND == 32) {  // chain
       Fr<X::IN> t; Fr<X::OUT> u;
       for (int q = 0; q < X::IN; q++) t.v[q] = in.v[q];
@@ -249,7 +256,7 @@ struct Noise {  // src/noise.rs:170-234, ID 20: counter-based white noise
   struct R { uint32_t state; };
   static FDSP_DEV void load(R& r, Loader& l) { r.state = l.S(); }
   static FDSP_DEV void save(const R& r, Saver& s) { s.S(r.state); }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx&, const Fr<0>&, Fr<1>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C&, const Fr<0>&, Fr<1>& o) {
     r.state += 1u;
     o.v[0] = (float)(hash32x(r.state) >> 8) * (2.0f / 16777215.0f) - 1.0f;
   }
@@ -260,12 +267,12 @@ struct Sine {  // src/oscillator.rs:18-102, ID 21
   struct R { float phase; };
   static FDSP_DEV void load(R& r, Loader& l) { r.phase = l.Sf(); }
   static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.phase); }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<1>& in, Fr<1>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<1>& in, Fr<1>& o) {
     float p = r.phase;
     r.phase += in.v[0] * c.sd64;
     if (T || c.rem) {  // tick path :67-72 (libm sinf, wrap every sample)
       r.phase -= floorf(r.phase);
-      o.v[0] = sinf(p * TAU_F);
+      o.v[0] = m::sinf_(p * TAU_F);
     } else {           // block path :74-86 (wide sin, phase unwrapped inside the block)
       o.v[0] = wide_sinf(p * TAU_F);
     }
@@ -274,8 +281,8 @@ struct Sine {  // src/oscillator.rs:18-102, ID 21
 };
 template <int KIND, int NOUT> struct WaveSynth {  // src/wavetable.rs:244-359, ID 34
   FDSP_NODE(1, NOUT, 0, 2, 0);
-  struct R { float phase; int hint; int ti; float w; const float* t1; const float* t2; int l1, l2; };
-  static FDSP_DEV void load(R& r, Loader& l) { r.phase = l.Sf(); r.hint = (int)l.S(); r.ti = r.hint; r.w = 0.0f; r.t1 = r.t2 = nullptr; r.l1 = r.l2 = 32; }
+  struct R { float phase; int hint; int ti; float w; int o1, o2; int l1, l2; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.phase = l.Sf(); r.hint = (int)l.S(); r.ti = r.hint; r.w = 0.0f; r.o1 = r.o2 = 0; r.l1 = r.l2 = 32; }
   static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.phase); s.S((uint32_t)r.hint); }
   static FDSP_DEV int table_index(const WaveTableDev& t, int hint, float f) {  // :157-179
     if (f >= __ldg(&t.pitch[hint]) && f <= __ldg(&t.pitch[hint + 1])) return hint;
@@ -293,19 +300,23 @@ template <int KIND, int NOUT> struct WaveSynth {  // src/wavetable.rs:244-359, I
     int ti = table_index(t, hint, f);
     r.ti = ti;
     r.w = clamp01f(delerpf(__ldg(&t.pitch[ti]), __ldg(&t.pitch[ti + 1]), f));
-    r.t1 = t.data + __ldg(&t.off[ti + 1]); r.l1 = __ldg(&t.len[ti + 1]);
-    r.t2 = t.data + __ldg(&t.off[ti + 2]); r.l2 = __ldg(&t.len[ti + 2]);
+    r.o1 = __ldg(&t.off[ti + 1]); r.l1 = __ldg(&t.len[ti + 1]);
+    r.o2 = __ldg(&t.off[ti + 2]); r.l2 = __ldg(&t.len[ti + 2]);
   }
-  static FDSP_DEV float at(const float* t, int len, float phase) {  // :125-155 (i32 index math, truncation)
+  template <class C> static FDSP_DEV float tap(const C& c, const WaveTableDev& t, int idx) {
+    if (C::SMEM_TABLES) { if (c.tsm_kind == KIND) return lds_f32(c.tsm + 4u * (uint32_t)idx); }
+    return __ldg(t.data + idx);
+  }
+  template <class C> static FDSP_DEV float at(const C& c, const WaveTableDev& t, int off, int len, float phase) {  // :125-155 (i32 index math, truncation)
     float p = (float)len * phase;
     int i1 = (int)p;
     float w = p - (float)i1;
     int mask = len - 1;
     int i0 = (i1 - 1) & mask; i1 &= mask;
     int i2 = (i1 + 1) & mask, i3 = (i2 + 1) & mask;
-    return optimal4x44(__ldg(t + i0), __ldg(t + i1), __ldg(t + i2), __ldg(t + i3), w);
+    return optimal4x44(tap(c, t, off + i0), tap(c, t, off + i1), tap(c, t, off + i2), tap(c, t, off + i3), w);
   }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<1>& in, Fr<NOUT>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<1>& in, Fr<NOUT>& o) {
     const WaveTableDev& t = c.wt[KIND];
     float ph;
     if (T || c.rem) {  // tick :309-325
@@ -319,7 +330,7 @@ template <int KIND, int NOUT> struct WaveSynth {  // src/wavetable.rs:244-359, I
       r.phase += in.v[0] * c.sd32;
       ph = r.phase - wide_floorf(r.phase);
     }
-    o.v[0] = (1.0f - r.w) * at(r.t1, r.l1, ph) + r.w * at(r.t2, r.l2, ph);
+    o.v[0] = (1.0f - r.w) * at(c, t, r.o1, r.l1, ph) + r.w * at(c, t, r.o2, r.l2, ph);
     if (NOUT > 1) o.v[NOUT > 1 ? 1 : 0] = ph;
   }
   static FDSP_DEV void end_simd(R& r) { r.phase = r.phase - floorf(r.phase); r.hint = r.ti; }
@@ -331,7 +342,7 @@ struct FixedSvf {  // src/svf.rs:857-1031, ID 43 (coefficients computed on the h
   struct R { float a1, a2, a3, m0, m1, m2, ic1, ic2; };
   static FDSP_DEV void load(R& r, Loader& l) { r.a1 = l.Pf(); r.a2 = l.Pf(); r.a3 = l.Pf(); r.m0 = l.Pf(); r.m1 = l.Pf(); r.m2 = l.Pf(); r.ic1 = l.Sf(); r.ic2 = l.Sf(); }
   static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.ic1); s.Sf(r.ic2); }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx&, const Fr<1>& in, Fr<1>& o) {  // :995-1006
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C&, const Fr<1>& in, Fr<1>& o) {  // :995-1006
     float v0 = in.v[0];
     float v3 = v0 - r.ic2;
     float v1 = r.a1 * r.ic1 + r.a2 * v3;
@@ -356,7 +367,7 @@ template <int MODE> struct Svf {  // src/svf.rs:744-855, ID 36 (audio-rate cutof
     s.Sf(r.k.a1); s.Sf(r.k.a2); s.Sf(r.k.a3); s.Sf(r.k.m0); s.Sf(r.k.m1); s.Sf(r.k.m2);
     s.Sf(r.ic1); s.Sf(r.ic2);
   }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<NI>& in, Fr<1>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<NI>& in, Fr<1>& o) {
     bool ch = in.v[1] != r.cutoff || in.v[2] != r.q;
     if (MODE >= 6) ch = ch || in.v[NI - 1] != r.gain;
     if (ch) { r.cutoff = in.v[1]; r.q = in.v[2]; if (MODE >= 6) r.gain = in.v[NI - 1]; r.k = svf_coefs<MODE>(c.sr, r.cutoff, r.q, r.gain); }
@@ -375,7 +386,7 @@ struct Biquad {  // src/biquad.rs:130-218, ID 15 (also the fixed ButterLowpass I
   struct R { float a1, a2, b0, b1, b2, x1, x2, y1, y2; };
   static FDSP_DEV void load(R& r, Loader& l) { r.a1 = l.Pf(); r.a2 = l.Pf(); r.b0 = l.Pf(); r.b1 = l.Pf(); r.b2 = l.Pf(); r.x1 = l.Sf(); r.x2 = l.Sf(); r.y1 = l.Sf(); r.y2 = l.Sf(); }
   static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.x1); s.Sf(r.x2); s.Sf(r.y1); s.Sf(r.y2); }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx&, const Fr<1>& in, Fr<1>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C&, const Fr<1>& in, Fr<1>& o) {
     float x0 = in.v[0];
     float y0 = r.b0 * x0 + r.b1 * r.x1 + r.b2 * r.x2 - r.a1 * r.y1 - r.a2 * r.y2;
     r.x2 = r.x1; r.x1 = x0; r.y2 = r.y1; r.y1 = y0;
@@ -396,7 +407,7 @@ struct BiquadBank {  // src/biquad_bank.rs:9-117, ID 98: 8 independent DF1 lanes
 #pragma unroll
     for (int k = 0; k < 8; k++) { s.Sf(r.b[k].x1); s.Sf(r.b[k].x2); s.Sf(r.b[k].y1); s.Sf(r.b[k].y2); }
   }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<8>& in, Fr<8>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<8>& in, Fr<8>& o) {
 #pragma unroll
     for (int k = 0; k < 8; k++) { Fr<1> a, b; a.v[0] = in.v[k]; Biquad::step<T>(r.b[k], c, a, b); o.v[k] = b.v[0]; }
   }
@@ -404,27 +415,33 @@ struct BiquadBank {  // src/biquad_bank.rs:9-117, ID 98: 8 independent DF1 lanes
 };
 template <int NIN> struct Moog {  // src/moog.rs:11-117, ID 60
   FDSP_NODE(NIN, 1, NIN == 1 ? 3 : 0, 8, 0);
-  struct R { float p, k, rez, s0, s1, s2, s3, px, ps0, ps1, ps2; };
+  struct R { float p, k, rez, s0, s1, s2, s3, px, ps0, ps1, ps2; float cutoff, q; };
   static FDSP_DEV void load(R& r, Loader& l) {
     if (NIN == 1) { r.p = l.Pf(); r.k = l.Pf(); r.rez = l.Pf(); } else { r.p = r.k = r.rez = 0.0f; }
+    r.cutoff = r.q = __uint_as_float(0x7fc00000u);  // NaN: forces the first coefficient computation
     r.s0 = l.Sf(); r.s1 = l.Sf(); r.s2 = l.Sf(); r.s3 = l.Sf(); r.px = l.Sf(); r.ps0 = l.Sf(); r.ps1 = l.Sf(); r.ps2 = l.Sf();
   }
   static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.s0); s.Sf(r.s1); s.Sf(r.s2); s.Sf(r.s3); s.Sf(r.px); s.Sf(r.ps0); s.Sf(r.ps1); s.Sf(r.ps2); }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<NIN>& in, Fr<1>& o) {
-    if (NIN > 1) {  // :48-57 set_cutoff_q, every sample (:83-85)
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<NIN>& in, Fr<1>& o) {
+    if (NIN > 1) {
+      // :83-85 calls set_cutoff_q (:48-57) every sample; it is a pure function of (cutoff, q, sr), so it is
+      // re-evaluated only when an input actually changed (bit-identical result, no sin + divide per sample).
       float cutoff = in.v[NIN > 1 ? 1 : 0], q = in.v[NIN > 2 ? 2 : 0];
-      float cc = 2.0f * cutoff / c.sr;
-      r.p = cc * (1.8f - 0.8f * cc);
-      r.k = 2.0f * sinf(cc * 3.14159274101257324f * 0.5f) - 1.0f;
-      float t1 = (1.0f - r.p) * 1.386249f;
-      float t2 = 12.0f + t1 * t1;
-      r.rez = q * (t2 + 6.0f * t1) / (t2 - 6.0f * t1);
+      if (!(cutoff == r.cutoff && q == r.q)) {
+        r.cutoff = cutoff; r.q = q;
+        float cc = 2.0f * cutoff / c.sr;
+        r.p = cc * (1.8f - 0.8f * cc);
+        r.k = 2.0f * m::sinf_(cc * 3.14159274101257324f * 0.5f) - 1.0f;
+        float t1 = (1.0f - r.p) * 1.386249f;
+        float t2 = 12.0f + t1 * t1;
+        r.rez = q * (t2 + 6.0f * t1) / (t2 - 6.0f * t1);
+      }
     }
     float x = -r.rez * r.s3 + in.v[0];
     r.s0 = (x + r.px) * r.p - r.k * r.s0;
     r.s1 = (r.s0 + r.ps0) * r.p - r.k * r.s1;
     r.s2 = (r.s1 + r.ps1) * r.p - r.k * r.s2;
-    r.s3 = tanhf((r.s2 + r.ps2) * r.p - r.k * r.s3);
+    r.s3 = m::tanhf_((r.s2 + r.ps2) * r.p - r.k * r.s3);
     r.px = x; r.ps0 = r.s0; r.ps1 = r.s1; r.ps2 = r.s2;
     o.v[0] = r.s3;
   }
@@ -435,7 +452,7 @@ template <int N> struct Fir {  // src/fir.rs:11-89, ID 52: shift register, accum
   struct R { float w[N], v[N]; };
   static FDSP_DEV void load(R& r, Loader& l) { for (int k = 0; k < N; k++) r.w[k] = l.Pf(); for (int k = 0; k < N; k++) r.v[k] = l.Sf(); }
   static FDSP_DEV void save(const R& r, Saver& s) { for (int k = 0; k < N; k++) s.Sf(r.v[k]); }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx&, const Fr<1>& in, Fr<1>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C&, const Fr<1>& in, Fr<1>& o) {
     for (int k = 0; k + 1 < N; k++) r.v[k] = r.v[k + 1];
     r.v[N - 1] = in.v[0];
     float a = 0.0f;
@@ -451,7 +468,7 @@ template <int N> struct Tick {  // src/delay.rs:17-65, ID 9
   struct R { float b[N]; };
   static FDSP_DEV void load(R& r, Loader& l) { for (int k = 0; k < N; k++) r.b[k] = l.Sf(); }
   static FDSP_DEV void save(const R& r, Saver& s) { for (int k = 0; k < N; k++) s.Sf(r.b[k]); }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx&, const Fr<N>& in, Fr<N>& o) { for (int k = 0; k < N; k++) { float t = r.b[k]; r.b[k] = in.v[k]; o.v[k] = t; } }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C&, const Fr<N>& in, Fr<N>& o) { for (int k = 0; k < N; k++) { float t = r.b[k]; r.b[k] = in.v[k]; o.v[k] = t; } }
   static FDSP_DEV void end_simd(R&) {}
 };
 struct Delay {  // src/delay.rs:67-139, ID 13: ring buffer of round(t*sr)+1 samples in HBM, element (off+pos)*V+v
@@ -459,7 +476,7 @@ struct Delay {  // src/delay.rs:67-139, ID 13: ring buffer of round(t*sr)+1 samp
   struct R { uint32_t i, len, off; };
   static FDSP_DEV void load(R& r, Loader& l) { r.len = l.U(); r.off = l.D(r.len); r.i = l.S(); }
   static FDSP_DEV void save(const R& r, Saver& s) { s.S(r.i); }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<1>& in, Fr<1>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<1>& in, Fr<1>& o) {
     c.dl[(size_t)(r.off + r.i) * c.V + c.v] = in.v[0];
     r.i += 1u; if (r.i >= r.len) r.i = 0u;
     o.v[0] = c.dl[(size_t)(r.off + r.i) * c.V + c.v];
@@ -471,7 +488,7 @@ template <int NIN, class X> struct AllNest {  // src/delay.rs:288-377, ID 83
   struct R { float eta, z; typename X::R x; };
   static FDSP_DEV void load(R& r, Loader& l) { if (NIN == 1) { r.eta = l.Pf(); r.z = l.Sf(); } else { r.eta = l.Sf(); r.z = l.Sf(); } X::load(r.x, l); }
   static FDSP_DEV void save(const R& r, Saver& s) { if (NIN > 1) s.Sf(r.eta); s.Sf(r.z); X::save(r.x, s); }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<NIN>& in, Fr<1>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<NIN>& in, Fr<1>& o) {
     if (NIN > 1) r.eta = in.v[NIN > 1 ? 1 : 0];
     Fr<1> v, y;
     v.v[0] = in.v[0] - r.eta * r.z;
@@ -499,7 +516,7 @@ template <int HAD, class X> struct Feedback {  // src/feedback.rs:68-178, ID 11:
   struct R { float value[N]; typename X::R x; };
   static FDSP_DEV void load(R& r, Loader& l) { for (int k = 0; k < N; k++) r.value[k] = l.Sf(); X::load(r.x, l); }
   static FDSP_DEV void save(const R& r, Saver& s) { for (int k = 0; k < N; k++) s.Sf(r.value[k]); X::save(r.x, s); }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<N>& in, Fr<N>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<N>& in, Fr<N>& o) {
     Fr<N> t;
     for (int k = 0; k < N; k++) t.v[k] = in.v[k] + r.value[k];
     X::template step<true>(r.x, c, t, o);
@@ -515,7 +532,7 @@ template <int NIN> struct Panner {  // src/pan.rs:19-91, ID 49
   struct R { float lw, rw; };
   static FDSP_DEV void load(R& r, Loader& l) { if (NIN == 1) { r.lw = l.Pf(); r.rw = l.Pf(); } else { r.lw = l.Sf(); r.rw = l.Sf(); } }
   static FDSP_DEV void save(const R& r, Saver& s) { if (NIN > 1) { s.Sf(r.lw); s.Sf(r.rw); } }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx&, const Fr<NIN>& in, Fr<2>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C&, const Fr<NIN>& in, Fr<2>& o) {
     if (NIN > 1) pan_weights(in.v[NIN > 1 ? 1 : 0], r.lw, r.rw);
     o.v[0] = in.v[0] * r.lw; o.v[1] = in.v[0] * r.rw;
   }
@@ -558,7 +575,7 @@ struct AdsrLive {  // src/envelope.rs:185-358 EnvelopeIn<f32,_,U1,f32> (ID 53) +
     if (r.release_start < 0.0f) return a;
     return a * clamp01f(delerpf(r.release_start + r.release, r.release_start, time));
   }
-  static FDSP_DEV void next_segment(R& r, const Ctx& c, float input) {  // envelope.rs:238-263
+  template <class C> static FDSP_DEV void next_segment(R& r, const C& c, float input) {  // envelope.rs:238-263
     if (r.t0 == 0.0f && r.t1 == 0.0f) { r.v0 = envelope(r, r.t0, input); }
     else { r.t0 = r.t1; r.v0 = r.v1; }
     float next_interval = lerpf(0.75f, 1.25f, (float)rnd1(r.t_hash)) * r.interval;
@@ -571,7 +588,7 @@ struct AdsrLive {  // src/envelope.rs:185-358 EnvelopeIn<f32,_,U1,f32> (ID 53) +
     r.delta = (r.v1 - r.v0) / samples;
   }
   // plan the next run of the block path's while-loop (envelope.rs:321-339) starting at block index i
-  static FDSP_DEV void plan(R& r, const Ctx& c, float input) {
+  template <class C> static FDSP_DEV void plan(R& r, const C& c, float input) {
     for (;;) {
       unsigned long long left = (unsigned long long)(long long)ceilf((r.t1 - r.t) / c.sd64);
       unsigned long long room = (unsigned long long)(c.n - c.i);
@@ -581,7 +598,7 @@ struct AdsrLive {  // src/envelope.rs:185-358 EnvelopeIn<f32,_,U1,f32> (ID 53) +
       return;
     }
   }
-  template <bool T> static FDSP_DEV void step(R& r, const Ctx& c, const Fr<1>& in, Fr<1>& o) {
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<1>& in, Fr<1>& o) {
     if (T) {  // tick :297-305
       if (r.t >= r.t1) next_segment(r, c, in.v[0]);
       o.v[0] = r.value; r.value += r.delta; r.t += c.sd64;
@@ -595,5 +612,22 @@ struct AdsrLive {  // src/envelope.rs:185-358 EnvelopeIn<f32,_,U1,f32> (ID 53) +
   }
   static FDSP_DEV void end_simd(R&) {}
 };
+
+
+// ---------------------------------------------------------------- traits
+// First wavetable kind used by a graph type (-1: none): decides whether the kernel stages tables in shared memory.
+template <class G> struct WaveKind { static constexpr int value = -1; };
+template <int K, int N> struct WaveKind<WaveSynth<K, N>> { static constexpr int value = K; };
+template <class X, class Y> struct Wk2 { static constexpr int value = WaveKind<X>::value >= 0 ? WaveKind<X>::value : WaveKind<Y>::value; };
+template <int K, class X, class Y> struct WaveKind<Binop<K, X, Y>> : Wk2<X, Y> {};
+template <class X, class Y> struct WaveKind<Pipe<X, Y>> : Wk2<X, Y> {};
+template <class X, class Y> struct WaveKind<Stack<X, Y>> : Wk2<X, Y> {};
+template <class X, class Y> struct WaveKind<Branch<X, Y>> : Wk2<X, Y> {};
+template <class X, class Y> struct WaveKind<Bus<X, Y>> : Wk2<X, Y> {};
+template <int K, class X> struct WaveKind<Unop<K, X>> : WaveKind<X> {};
+template <class X> struct WaveKind<Thru<X>> : WaveKind<X> {};
+template <int KIND, int OP, int N, class X> struct WaveKind<Multi<KIND, OP, N, X>> : WaveKind<X> {};
+template <int NIN, class X> struct WaveKind<AllNest<NIN, X>> : WaveKind<X> {};
+template <int HAD, class X> struct WaveKind<Feedback<HAD, X>> : WaveKind<X> {};
 
 }  // namespace fdsp

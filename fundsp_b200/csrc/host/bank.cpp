@@ -129,7 +129,7 @@ std::string Bank::lower_and_upload(bool upload_state) {
       for (auto& c : classes) used = used || c.sig.find(tag) != std::string::npos;
       if (!used) continue;
       const WaveTableHost& t = global_wavetable(kind);
-      h[kind].n = (int)t.pitch.size();
+      h[kind].n = (int)t.pitch.size(); h[kind].total = (int)t.data.size();
       for (size_t i = 0; i < t.pitch.size() && i < 48; i++) { h[kind].pitch[i] = t.pitch[i]; h[kind].off[i] = t.off[i]; h[kind].len[i] = t.len[i]; }
       std::string e = dev_alloc(&d_wtdata[kind], t.data.size());
       if (!e.empty()) return e;
@@ -192,7 +192,12 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
       a.row_map = c.d_rowmap;
       a.sr = (float)sr; a.sd64 = (float)(1.0 / sr); a.sd32 = 1.0f / (float)sr;
       if (t0 > 0xffffffffull - TIME_CHUNK) return "render too long for one call";
-      CU(c.k->launch(a, mode, stream));
+      // long launches of wavetable programs stage the table set in shared memory (TMA bulk copy, ~160 KB per CTA);
+      // short ones (process()-sized) read the tables through L1/L2 instead
+      size_t table_bytes = 0;
+      const int wk = c.k->wave_kind();
+      if (wk >= 0 && len >= 1024) table_bytes = global_wavetable(wk).data.size() * sizeof(float);
+      CU(c.k->launch(a, mode, table_bytes, stream));
       launches++;
       if (want_m) {
         CU(launch_mix_reduce(c.d_partial, grid, (uint32_t)nout, len, mix_dev, (uint32_t)mix_stride, (uint32_t)t0, first ? 0 : 1, stream));

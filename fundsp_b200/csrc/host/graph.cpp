@@ -2,6 +2,7 @@
 // the reference checkout). Coefficient formulas are evaluated in f32 with the host libm exactly where the
 // reference evaluates them (constructor / set_sample_rate / Setting), never per sample.
 #include "graph.h"
+#include "../dsp/libm.cuh"
 
 #include <algorithm>
 #include <cassert>
@@ -106,25 +107,15 @@ struct WaveSynth : HNode {  // src/wavetable.rs:244-359
 };
 
 // ---------------------------------------------------------------- SVF (src/svf.rs)
-struct Coefs6 { float a1, a2, a3, m0, m1, m2; };
-Coefs6 svf_coefs(int mode, float sr, float cutoff, float q, float gain) {  // src/svf.rs:26-221
-  const float PI_F = (float)3.14159265358979323846;
-  Coefs6 c{0, 0, 0, 0, 0, 0}; float g, k;
-  if (mode <= 5) { g = tanf(PI_F * cutoff / sr); k = 1.0f / q; }
-  else if (mode == 6) { float a = sqrtf(gain); g = tanf(PI_F * cutoff / sr); k = 1.0f / (q * a); c.m0 = 1.0f; c.m1 = k * (a * a - 1.0f); c.m2 = 0.0f; }
-  else if (mode == 7) { float a = sqrtf(gain); g = tanf(PI_F * cutoff / sr) / sqrtf(a); k = 1.0f / q; c.m0 = 1.0f; c.m1 = k * (a - 1.0f); c.m2 = a * a - 1.0f; }
-  else { float a = sqrtf(gain); g = tanf(PI_F * cutoff / sr) * sqrtf(a); k = 1.0f / q; c.m0 = a * a; c.m1 = k * (1.0f - a) * a; c.m2 = 1.0f - a * a; }
-  c.a1 = 1.0f / (1.0f + g * (g + k)); c.a2 = g * c.a1; c.a3 = g * c.a2;
+typedef fdsp::SvfCoefs Coefs6;
+Coefs6 svf_coefs(int mode, float sr, float cutoff, float q, float gain) {  // src/svf.rs:26-221 (shared host/device code)
   switch (mode) {
-    case 0: c.m0 = 0.0f; c.m1 = 0.0f; c.m2 = 1.0f; break;
-    case 1: c.m0 = 1.0f; c.m1 = -k; c.m2 = -1.0f; break;
-    case 2: c.m0 = 0.0f; c.m1 = 1.0f; c.m2 = 0.0f; break;
-    case 3: c.m0 = 1.0f; c.m1 = -k; c.m2 = 0.0f; break;
-    case 4: c.m0 = 1.0f; c.m1 = -k; c.m2 = -2.0f; break;
-    case 5: c.m0 = 1.0f; c.m1 = -2.0f * k; c.m2 = 0.0f; break;
-    default: break;
+    case 0: return fdsp::svf_coefs<0>(sr, cutoff, q, gain); case 1: return fdsp::svf_coefs<1>(sr, cutoff, q, gain);
+    case 2: return fdsp::svf_coefs<2>(sr, cutoff, q, gain); case 3: return fdsp::svf_coefs<3>(sr, cutoff, q, gain);
+    case 4: return fdsp::svf_coefs<4>(sr, cutoff, q, gain); case 5: return fdsp::svf_coefs<5>(sr, cutoff, q, gain);
+    case 6: return fdsp::svf_coefs<6>(sr, cutoff, q, gain); case 7: return fdsp::svf_coefs<7>(sr, cutoff, q, gain);
+    default: return fdsp::svf_coefs<8>(sr, cutoff, q, gain);
   }
-  return c;
 }
 struct Svf : HNode {  // FixedSvf (ID 43, :857-1031) and Svf (ID 36, :744-855)
   int mode; bool fixed; float sr, cutoff, q, gain;
@@ -151,7 +142,7 @@ struct Svf : HNode {  // FixedSvf (ID 43, :857-1031) and Svf (ID 36, :744-855)
 struct BqCoefs { float a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0; };
 BqCoefs bq_butter_lowpass(float sr, float cutoff) {  // src/biquad.rs:27-38
   const float PI_F = 3.14159274101257324f, SQRT_2 = 1.41421354f;
-  float f = tanf(cutoff * PI_F / sr);
+  float f = fdsp::m::tanf_(cutoff * PI_F / sr);
   float a0r = 1.0f / (1.0f + SQRT_2 * f + f * f);
   BqCoefs c; c.a1 = (2.0f * f * f - 2.0f) * a0r; c.a2 = (1.0f - SQRT_2 * f + f * f) * a0r;
   c.b0 = f * f * a0r; c.b1 = 2.0f * c.b0; c.b2 = c.b0; return c;
@@ -159,7 +150,7 @@ BqCoefs bq_butter_lowpass(float sr, float cutoff) {  // src/biquad.rs:27-38
 BqCoefs bq_resonator(float sr, float center, float q) {  // src/biquad.rs:40-50
   const float PI_F = 3.14159274101257324f, TAU_F = 6.28318548202514648f;
   float r = expf(-PI_F * center / (q * sr));
-  BqCoefs c; c.a1 = -2.0f * r * cosf(TAU_F * center / sr); c.a2 = r * r;
+  BqCoefs c; c.a1 = -2.0f * r * fdsp::m::cosf_(TAU_F * center / sr); c.a2 = r * r;
   c.b0 = sqrtf(1.0f - r * r) * 0.5f; c.b1 = 0.0f; c.b2 = -c.b0; return c;
 }
 struct Biquad : HNode {  // Biquad (ID 15), fixed ButterLowpass (ID 16), fixed Resonator (ID 17)
@@ -212,7 +203,7 @@ struct Moog : HNode {
     if (nin == 1) {  // :48-57
       float c = 2.0f * cutoff / sr;
       float p = c * (1.8f - 0.8f * c);
-      float k = 2.0f * sinf(c * 3.14159274101257324f * 0.5f) - 1.0f;
+      float k = 2.0f * fdsp::m::sinf_(c * 3.14159274101257324f * 0.5f) - 1.0f;
       float t1 = (1.0f - p) * 1.386249f;
       float t2 = 12.0f + t1 * t1;
       float rez = q * (t2 + 6.0f * t1) / (t2 - 6.0f * t1);
@@ -275,9 +266,8 @@ struct Panner : HNode {
   void set(const Setting& s) override { if (s.kind == P_PAN) value = s.v[0]; }
   void sig(std::string& o) const override { o += "Panner<" + I(nin) + ">"; }
   void lower(Lowering& l) const override {  // src/pan.rs:14-17
-    float cl = fminf(fmaxf(value, -1.0f), 1.0f);
-    float angle = (cl + 1.0f) * (3.14159274101257324f * 0.25f);
-    float lw = cosf(angle), rw = sinf(angle);
+    float lw, rw;
+    fdsp::pan_weights(value, lw, rw);
     if (nin == 1) { l.p(lw); l.p(rw); } else { l.s(lw); l.s(rw); }
   }
   HCLONE(Panner)

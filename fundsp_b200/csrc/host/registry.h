@@ -13,8 +13,10 @@ struct KernelEntry {
   const char* sig;
   int IN, OUT, NP, NS, NU;
   // mode: FDSP_OUT_VOICES | FDSP_OUT_MIX bits
-  cudaError_t (*launch)(const BankArgs& a, int mode, cudaStream_t stream);
+  // table_bytes > 0: stage that many bytes of wavetable data in shared memory (long renders of wavetable graphs)
+  cudaError_t (*launch)(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t stream);
   int (*threads)();
+  int (*wave_kind)();  // first wavetable kind the program reads, -1 if none
 };
 
 const KernelEntry* find_kernel(const std::string& sig);

@@ -4,6 +4,7 @@
 // (src/buffer.rs:12-151: channel c, sample i at (c<<6)+i).
 #pragma once
 #include "fo_math.h"
+#include "fo_libm.h"
 #include <algorithm>
 #include <cassert>
 #include <map>
@@ -462,7 +463,7 @@ struct Sine : Node {
     float p = phase;
     phase += in[0] * sample_duration;
     phase -= floorf(phase);
-    out[0] = sinf(p * 6.28318530717958647692f);
+    out[0] = m::sinf_(p * 6.28318530717958647692f);
   }
   void process(int size, const float* in, float* out) override {  // :74-86 (wide sin, wrap once per block)
     float p = phase;
@@ -659,15 +660,15 @@ inline SvfCoefs svf_coefs(int mode, float sr, float cutoff, float q, float gain)
   const float PI_F = (float)3.14159265358979323846;
   SvfCoefs c; float g, k;
   if (mode <= 5) {
-    g = tanf(PI_F * cutoff / sr); k = 1.0f / q;
+    g = m::tanf_(PI_F * cutoff / sr); k = 1.0f / q;
   } else if (mode == 6) {
-    float a = sqrtf(gain); g = tanf(PI_F * cutoff / sr); k = 1.0f / (q * a);
+    float a = sqrtf(gain); g = m::tanf_(PI_F * cutoff / sr); k = 1.0f / (q * a);
     c.m0 = 1.0f; c.m1 = k * (a * a - 1.0f); c.m2 = 0.0f;
   } else if (mode == 7) {
-    float a = sqrtf(gain); g = tanf(PI_F * cutoff / sr) / sqrtf(a); k = 1.0f / q;
+    float a = sqrtf(gain); g = m::tanf_(PI_F * cutoff / sr) / sqrtf(a); k = 1.0f / q;
     c.m0 = 1.0f; c.m1 = k * (a - 1.0f); c.m2 = a * a - 1.0f;
   } else {
-    float a = sqrtf(gain); g = tanf(PI_F * cutoff / sr) * sqrtf(a); k = 1.0f / q;
+    float a = sqrtf(gain); g = m::tanf_(PI_F * cutoff / sr) * sqrtf(a); k = 1.0f / q;
     c.m0 = a * a; c.m1 = k * (1.0f - a) * a; c.m2 = 1.0f - a * a;
   }
   c.a1 = 1.0f / (1.0f + g * (g + k)); c.a2 = g * c.a1; c.a3 = g * c.a2;
@@ -717,7 +718,7 @@ struct Svf : Node {
 struct BiquadCoefs { float a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0; };
 inline BiquadCoefs biquad_butter_lowpass(float sr, float cutoff) {
   const float PI_F = 3.14159274101257324f, SQRT_2 = 1.41421354f;
-  float f = tanf(cutoff * PI_F / sr);
+  float f = m::tanf_(cutoff * PI_F / sr);
   float a0r = 1.0f / (1.0f + SQRT_2 * f + f * f);
   BiquadCoefs c; c.a1 = (2.0f * f * f - 2.0f) * a0r; c.a2 = (1.0f - SQRT_2 * f + f * f) * a0r;
   c.b0 = f * f * a0r; c.b1 = 2.0f * c.b0; c.b2 = c.b0; return c;
@@ -725,14 +726,14 @@ inline BiquadCoefs biquad_butter_lowpass(float sr, float cutoff) {
 inline BiquadCoefs biquad_resonator(float sr, float center, float q) {
   const float PI_F = 3.14159274101257324f, TAU_F = 6.28318548202514648f;
   float r = expf(-PI_F * center / (q * sr));
-  BiquadCoefs c; c.a1 = -2.0f * r * cosf(TAU_F * center / sr); c.a2 = r * r;
+  BiquadCoefs c; c.a1 = -2.0f * r * m::cosf_(TAU_F * center / sr); c.a2 = r * r;
   c.b0 = sqrtf(1.0f - r * r) * 0.5f; c.b1 = 0.0f; c.b2 = -c.b0; return c;
 }
 inline BiquadCoefs biquad_lowpass(float sr, float cutoff, float q) {
   const float TAU_F = 6.28318548202514648f;
   float omega = TAU_F * cutoff / sr;
-  float alpha = sinf(omega) / (2.0f * q);
-  float beta = cosf(omega);
+  float alpha = m::sinf_(omega) / (2.0f * q);
+  float beta = m::cosf_(omega);
   float a0r = 1.0f / (1.0f + alpha);
   BiquadCoefs c; c.a1 = -2.0f * beta * a0r; c.a2 = (1.0f - alpha) * a0r;
   c.b1 = (1.0f - beta) * a0r; c.b0 = c.b1 * 0.5f; c.b2 = c.b0; return c;
@@ -740,8 +741,8 @@ inline BiquadCoefs biquad_lowpass(float sr, float cutoff, float q) {
 inline BiquadCoefs biquad_highpass(float sr, float cutoff, float q) {
   const float TAU_F = 6.28318548202514648f;
   float omega = TAU_F * cutoff / sr;
-  float alpha = sinf(omega) / (2.0f * q);
-  float beta = cosf(omega);
+  float alpha = m::sinf_(omega) / (2.0f * q);
+  float beta = m::cosf_(omega);
   float a0r = 1.0f / (1.0f + alpha);
   BiquadCoefs c; c.a1 = -2.0f * beta * a0r; c.a2 = (1.0f - alpha) * a0r;
   c.b0 = (1.0f + beta) * 0.5f * a0r; c.b1 = (-1.0f - beta) * a0r; c.b2 = c.b0; return c;
@@ -749,8 +750,8 @@ inline BiquadCoefs biquad_highpass(float sr, float cutoff, float q) {
 inline BiquadCoefs biquad_bell(float sr, float center, float q, float gain) {
   const float TAU_F = 6.28318548202514648f;
   float omega = TAU_F * center / sr;
-  float alpha = sinf(omega) / (2.0f * q);
-  float beta = cosf(omega);
+  float alpha = m::sinf_(omega) / (2.0f * q);
+  float beta = m::cosf_(omega);
   float a = sqrtf(gain);
   float a0r = 1.0f / (1.0f + alpha / a);
   BiquadCoefs c; c.a1 = -2.0f * beta * a0r; c.a2 = (1.0f - alpha / a) * a0r;
@@ -830,7 +831,7 @@ struct Moog : Node {
     cutoff = cutoff_; q = q_;
     float c = 2.0f * cutoff / sr;
     p = c * (1.8f - 0.8f * c);
-    k = 2.0f * sinf(c * 3.14159274101257324f * 0.5f) - 1.0f;
+    k = 2.0f * m::sinf_(c * 3.14159274101257324f * 0.5f) - 1.0f;
     float t1 = (1.0f - p) * 1.386249f;
     float t2 = 12.0f + t1 * t1;
     rez = q * (t2 + 6.0f * t1) / (t2 - 6.0f * t1);
@@ -845,7 +846,7 @@ struct Moog : Node {
     s0 = (x + px) * p - k * s0;
     s1 = (s0 + ps0) * p - k * s1;
     s2 = (s1 + ps1) * p - k * s2;
-    s3 = tanhf((s2 + ps2) * p - k * s3);
+    s3 = m::tanhf_((s2 + ps2) * p - k * s3);
     px = x; ps0 = s0; ps1 = s1; ps2 = s2;
     out[0] = s3;
   }
@@ -970,7 +971,7 @@ struct Feedback : Node {
 // ---- src/pan.rs:12-91 Panner<N> (ID 49)
 inline void pan_weights(float value, float& l, float& r) {
   float angle = (clamp11f(value) + 1.0f) * (3.14159274101257324f * 0.25f);
-  l = cosf(angle); r = sinf(angle);
+  l = m::cosf_(angle); r = m::sinf_(angle);
 }
 struct Panner : Node {
   int nin; float lw, rw;
