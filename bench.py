@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py — headline throughput of the fundsp_b200 voice-bank hot path (contract in the task brief).
+
+A "step" renders `--seconds` of audio (48 kHz, block 64) for the workload's voice bank on every GPU and mixes
+it down to the voice's channel count — the `Wave::render` loop over "a Vec of V units + a sum" (SURVEY.md §3.6).
+  value   Msamples/s = voices x samples / time, whole job, device-resident result (CUDA events, max over ranks)
+  e2e     same metric through the public C-ABI call `fdsp_bank_render` with HOST buffers (D2H of the mix inside
+          the timed region; generators have no audio input, so h2d is 0 bytes unless the workload has a gate)
+  roofline / cpu_baseline / clocks / gpu_launches as the contract asks.
+`--impl reference` times the reference's CPU algorithm (the C++ oracle, all host threads) on the same config.
+Multi-GPU: one process per GPU (torchrun), voices sharded contiguously (weak scaling: V per GPU), the per-GPU
+stereo/mono partial mixes are summed with one NCCL reduce per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+SR = 48000.0
+METRIC = "Msamples/sec (f32) rendered across N voices"
+HEADLINE = {"saw_svf": 16384, "noise_svf": 16384, "fm": 4096, "biquad_bank": 2048, "subtractive_dry": 1024, "subtractive": 1024, "net": 65536}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="saw_svf", choices=sorted(HEADLINE))
+    ap.add_argument("--voices", type=int, default=None, help="voices per GPU (default: the BASELINE config size)")
+    ap.add_argument("--seconds", type=float, default=1.0, help="audio seconds rendered per step")
+    ap.add_argument("--per-voice", action="store_true", help="also materialise per-voice outputs in HBM (value only)")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, name in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def gate_for(workload, n):
+    from fundsp_b200 import workloads
+    return workloads.gate_signal(n) if workload.startswith("subtractive") else None
+
+
+def cpu_reference(workload, voices, n, threads, first=0):
+    """The reference's CPU algorithm for this path: V units, block-64 `process`, index-order mix (oracle, C++)."""
+    from fundsp_b200 import workloads
+    from oracle import oracle_bank_render
+    exprs = workloads.build(workload, voices, first)
+    _, mix = oracle_bank_render(exprs, SR, n, gate_for(workload, n), per_voice=False, mix=True, threads=threads)
+    return oracle_bank_render.last_seconds, mix  # steady state: graph construction excluded, like the GPU arm
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = int(round(a.seconds * SR))
+    V = a.voices or HEADLINE[a.workload]
+    cores = os.cpu_count() or 1
+    for _ in range(a.warmup):
+        cpu_reference(a.workload, V, min(n, 4800), cores)
+    ts = []
+    for _ in range(a.steps):
+        dt, _ = cpu_reference(a.workload, V, n, cores)
+        ts.append(dt)
+    t = sum(ts) / len(ts)
+    val = V * n / t / 1e6
+    sample = f"{V} voices x {n} samples per step (full workload), {cores} threads, voices sharded contiguously"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Msamples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a.workload, V), "voices_total": V, "sample_rate": SR, "block": 64, "seconds_per_step": a.seconds,
+                   "output": "index-order mix of all voices", "note": "C++ oracle restating the reference's block path (no Rust toolchain on the box)"},
+        "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_name(w, V):
+    names = {"saw_svf": f"{V}-voice saw_hz(f) >> lowpass_hz(fc,q) bank (north-star headline)", "noise_svf": f"{V}-voice white().seed(i) >> lowpass_hz(fc,q) bank (config 3a)",
+             "fm": f"{V}-voice FM bank sine_hz(f)*f*m+f >> sine() (config 2)", "biquad_bank": f"{V} x biquad_bank() = {8 * V} voices on white() (config 3b)",
+             "subtractive_dry": f"{V}-voice saw >> moog * adsr_live >> pan (config 4 without reverb)", "subtractive": f"{V}-voice subtractive + per-voice reverb_stereo (config 4)",
+             "net": f"{V}-voice dynamic Net, 4 classes (config 5)"}
+    return names[w]
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import numpy as np
+    import torch
+
+    from fundsp_b200 import workloads
+    from fundsp_b200.bank import GpuBank
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; fundsp_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    V = a.voices or HEADLINE[a.workload]
+    n = int(round(a.seconds * SR))
+    gate = gate_for(a.workload, n)
+
+    # ---- build this rank's shard: voices [rank*V, (rank+1)*V)
+    t_build = time.perf_counter()
+    bank = GpuBank(workloads.build(a.workload, V, first=rank * V), device=local, per_voice=a.per_voice, mix=True, sample_rate=SR)
+    bank.allocate(n)
+    t_build = time.perf_counter() - t_build
+    c = bank.voice_outputs()
+    mix = torch.zeros((c, n), device="cuda", dtype=torch.float32)
+    out = torch.empty((V * c, n), device="cuda", dtype=torch.float32) if a.per_voice else None
+    gin = torch.from_numpy(gate).cuda() if gate is not None else None
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    host_mix = torch.empty((c, n), dtype=torch.float32).pin_memory()
+    host_in = torch.from_numpy(gate).pin_memory() if gate is not None else None
+
+    def device_step():
+        bank.render_device(n, gin.data_ptr() if gin is not None else 0, n, out.data_ptr() if out is not None else 0, n, mix.data_ptr(), n, sync=True)
+        if dist is not None:
+            dist.reduce(mix, dst=0)
+
+    def e2e_step():
+        from fundsp_b200.capi import check
+        import ctypes as C
+        fp = C.POINTER(C.c_float)
+        check(bank.L.fdsp_bank_render(bank.h, n, C.cast(host_in.data_ptr(), fp) if host_in is not None else None, None, C.cast(host_mix.data_ptr(), fp)))
+        if dist is not None:
+            m = host_mix.cuda(non_blocking=True)
+            dist.reduce(m, dst=0)
+            if rank == 0:
+                host_mix.copy_(m)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(step_fn, steps):
+        """K steps, each bracketed by CUDA events on the current stream; L2 flushed between steps (untimed)."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        kern = []
+        barrier()
+        wall0 = time.perf_counter()
+        for e0, e1 in evs:
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            e0.record()
+            step_fn()
+            e1.record()
+            kern.append(bank.last_kernel_ms())
+        barrier()
+        wall = time.perf_counter() - wall0
+        ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+        return sum(ms) / len(ms), sum(kern) / len(kern), wall
+
+    for _ in range(max(3, a.warmup)):
+        device_step()
+        e2e_step()
+    launches0 = bank.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_step, ms_kernel, wall = timed(device_step, a.steps)
+    launches = bank.launch_count() - launches0
+    ms_e2e, _, _ = timed(e2e_step, a.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms_step, ms_e2e, ms_kernel], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, ms_e2e, ms_kernel = (float(x) for x in t.tolist())
+        ln = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ln)
+        launches = int(ln.item())
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    total = world * V * n
+    value = total / (ms_step * 1e-3) / 1e6
+    e2e = total / (ms_e2e * 1e-3) / 1e6
+    # ---- roofline of the dominant kernel (the fused voice program): algorithmic bytes per step / kernel time
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    cls = bank.classes()
+    state_b = sum(k["voices"] * (2 * k["state_words"] + k["param_words"]) * 4 for k in cls)
+    nlaunch_chunks = (n + 16383) // 16384
+    grid = sum((k["voices"] + 127) // 128 for k in cls)
+    bytes_step = state_b * nlaunch_chunks + grid * c * n * 4 * 2 + c * n * 4 + (V * c * n * 4 if a.per_voice else 0) + (n * 4 if gate is not None else 0)
+    bytes_step += sum(k["voices"] * 8 * n * (1 if k["delay_floats"] else 0) * 32 for k in cls)  # FDN: 32 lines x (4 B read + 4 B write) per sample
+    achieved = bytes_step / (ms_kernel * 1e-3) / 1e9
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic = prof.get(a.workload + ("+voices" if a.per_voice else ""))
+    except Exception:
+        pass
+    # ---- CPU baseline on this box's host cores (bounded sample of the same workload)
+    cores = os.cpu_count() or 1
+    ns = min(n, 24000)
+    cpu_reference(a.workload, min(V, 256), 480, cores)
+    dt, _ = cpu_reference(a.workload, V, ns, cores)
+    cpu_val = V * ns / dt / 1e6
+    line = {
+        "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a.workload, V), "voices_per_gpu": V, "voices_total": world * V, "sample_rate": SR, "block": 64,
+                   "seconds_per_step": a.seconds, "output": "mix-down to %d channel(s)%s" % (c, " + per-voice rows in HBM" if a.per_voice else ""),
+                   "parallelism": "voices sharded x%d, NCCL reduce of the mix" % world if world > 1 else "1 GPU", "l2": "flushed between timed steps (512 MB write)",
+                   "build_s": round(t_build, 3)},
+        "e2e": {"value": e2e, "unit": "Msamples/s", "h2d_bytes_per_step": int(n * 4 if gate is not None else 0), "d2h_bytes_per_step": int(c * n * 4),
+                "call": "fdsp_bank_render(host buffers)", "ms_per_step": ms_e2e},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "kernel": "fdsp::bank_kernel<...>", "kernel_ms_per_step": ms_kernel, "algorithmic_bytes_per_step": int(bytes_step),
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                     "note": "IIR voice programs are issue/latency bound, not HBM bound (DESIGN.md §Roofline); see profiles/ for issue-slot utilisation"},
+        "cpu_baseline": {"value": cpu_val, "unit": "Msamples/s", "cores": cores, "kind": "port",
+                         "sample": f"{V} voices x {ns} samples, oracle (C++ restatement of the reference block path), {cores} threads"},
+        "clocks": clocks,
+        "wall_s_timed_region": wall,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(NT) bank_kernel(const BankArgs a) {
   }
   const bool vec_ok = ((a.out_stride | a.out_offset) & 3u) == 0u;
 
+#pragma unroll 1
   for (uint32_t t0 = 0; t0 < a.n; t0 += 64) {
     const int nb = (a.n - t0) < 64u ? (int)(a.n - t0) : 64;
     const int nfull = nb & ~7;
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(NT) bank_kernel(const BankArgs a) {
       float* orow = (MODE & 1) ? a.out + (size_t)__ldg(a.row_map + v) * a.out_stride + a.out_offset + t0 : nullptr;
       const float* irow = (IN > 0) ? a.in + a.in_offset + t0 : nullptr;
       c.rem = false;
+#pragma unroll 1
       for (int g = 0; g < nfull; g += 8) {
         float ob[OUT > 0 ? OUT : 1][8];
 #pragma unroll(UNROLL)
@@ -113,6 +115,7 @@ __global__ void __launch_bounds__(NT) bank_kernel(const BankArgs a) {
       }
       G::end_simd(r);
       c.rem = true; c.first = false;
+#pragma unroll 1
       for (int i = nfull; i < nb; i++) {
         Fr<IN> in; Fr<OUT> o;
 #pragma unroll

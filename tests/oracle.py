@@ -202,7 +202,10 @@ def oracle_bank_render(exprs, sr, n, inp=None, per_voice=True, mix=False, thread
     out = np.zeros((V, no, n), np.float32) if per_voice else None
     mx = np.zeros((no, n), np.float32) if mix else None
     ib = np.zeros((max(1, ni), n), np.float32) if inp is None else np.ascontiguousarray(inp, np.float32).reshape(max(1, ni), n)
+    import time
+    t0 = time.perf_counter()
     L.fo_bank_render(arr, V, sr, n, _fp(ib), _fp(out), _fp(mx), threads)
+    oracle_bank_render.last_seconds = time.perf_counter() - t0  # render only (graph construction excluded)
     for h in hs:
         L.fo_free(h)
     return out, mx

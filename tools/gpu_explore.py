@@ -1,6 +1,6 @@
 """Scratch GPU exploration: error statistics + quick timings for every workload (run under gpurun)."""
 import sys, time, json
-sys.path.insert(0, "."); sys.path.insert(0, "tests")
+sys.path.insert(0, "."); sys.path.insert(0, "tests"); sys.path.insert(0, "..")
 import numpy as np
 from fundsp_b200 import workloads
 from fundsp_b200.bank import GpuBank
