@@ -202,16 +202,27 @@ def main():
         ms = [e0.elapsed_time(e1) for e0, e1 in evs]
         return sum(ms) / len(ms), sum(kern) / len(kern), wall
 
-    for _ in range(max(3, a.warmup)):
-        device_step()
-        e2e_step()
-    launches0 = bank.launch_count()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    t_w = time.perf_counter()
+    w = 0
+    while w < max(3, a.warmup) or (time.perf_counter() - t_w < 1.0 and w < 2000):  # >= W warm-up steps, >= 1 s under load for the clock samples
+        device_step()
+        e2e_step()
+        w += 1
+    launches0 = bank.launch_count()
     ms_step, ms_kernel, wall = timed(device_step, a.steps)
     launches = bank.launch_count() - launches0
     ms_e2e, _, _ = timed(e2e_step, a.steps)
+    # AudioUnit::process granularity: one C-ABI call per 64-sample block with host buffers (the Wave::render call pattern)
+    pb = 200
+    barrier()
+    t_p = time.perf_counter()
+    for _ in range(pb):
+        bank.process(64, gate[:, :64] if gate is not None else None)
+    t_p = time.perf_counter() - t_p
+    proc_val = world * V * 64 * pb / t_p / 1e6
     clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
         t = torch.tensor([ms_step, ms_e2e, ms_kernel], device="cuda", dtype=torch.float64)
@@ -262,7 +273,8 @@ def main():
                    "parallelism": "voices sharded x%d, NCCL reduce of the mix" % world if world > 1 else "1 GPU", "l2": "flushed between timed steps (512 MB write)",
                    "build_s": round(t_build, 3)},
         "e2e": {"value": e2e, "unit": "Msamples/s", "h2d_bytes_per_step": int(n * 4 if gate is not None else 0), "d2h_bytes_per_step": int(c * n * 4),
-                "call": "fdsp_bank_render(host buffers)", "ms_per_step": ms_e2e},
+                "call": "fdsp_bank_render(host buffers)", "ms_per_step": ms_e2e,
+                "process_granularity": {"value": proc_val, "unit": "Msamples/s", "us_per_call": t_p / pb * 1e6, "call": "fdsp_bank_process(64) per block, host buffers"}},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "fdsp::bank_kernel<...>", "kernel_ms_per_step": ms_kernel, "algorithmic_bytes_per_step": int(bytes_step),
