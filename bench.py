@@ -256,7 +256,8 @@ def main():
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        traffic = prof.get(a.workload + ("+voices" if a.per_voice else ""))
+        t = prof.get(a.workload + ("+voices" if a.per_voice else ""))
+        traffic = t["dram_bytes_per_launch"] * n / t["samples_per_launch"] if t else None  # ncu dram bytes of one 16384-sample launch, scaled to the step
     except Exception:
         pass
     # ---- CPU baseline on this box's host cores (bounded sample of the same workload)
