@@ -77,8 +77,9 @@ std::string Bank::lower_and_upload(bool upload_state) {
       ci = (int)fresh.size(); index[lo.key] = ci;
       VoiceClass c; c.sig = lo.sig; c.uniform = lo.l.U;
       for (uint32_t d : lo.l.dlen) c.dl_floats += d;
-      c.k = find_kernel(lo.sig);
-      if (!c.k) return "no device program for graph class `" + lo.sig + "` (not in the AOT registry; JIT unavailable)";
+      std::string jerr;
+      c.k = get_program(lo.sig, device, jerr);
+      if (!c.k) return "no device program for graph class `" + lo.sig + "`: " + jerr;
       if ((size_t)c.k->NP != lo.l.P.size() || (size_t)c.k->NS != lo.l.S.size() || (size_t)c.k->NU != lo.l.U.size() || c.k->IN != nin || c.k->OUT != nout)
         return "internal: host lowering of `" + lo.sig + "` disagrees with the device word layout";
       fresh.push_back(std::move(c));
@@ -178,7 +179,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
     bool first = true;
     for (auto& c : classes) {
       const uint32_t V = c.V();
-      const uint32_t grid = (V + (uint32_t)c.k->threads() - 1) / (uint32_t)c.k->threads();
+      const uint32_t grid = (V + (uint32_t)c.k->threads - 1) / (uint32_t)c.k->threads;
       if (want_m) {
         const size_t need = (size_t)grid * nout * len;
         if (c.partial_floats < need) { std::string e = dev_alloc(&c.d_partial, (size_t)grid * nout * TIME_CHUNK); if (!e.empty()) return e; c.partial_floats = (size_t)grid * nout * TIME_CHUNK; }
@@ -195,7 +196,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
       // long launches of wavetable programs stage the table set in shared memory (TMA bulk copy, ~160 KB per CTA);
       // short ones (process()-sized) read the tables through L1/L2 instead
       size_t table_bytes = 0;
-      const int wk = c.k->wave_kind();
+      const int wk = c.k->wave_kind;
       if (wk >= 0 && len >= 1024) table_bytes = global_wavetable(wk).data.size() * sizeof(float);
       CU(c.k->launch(a, mode, table_bytes, stream));
       launches++;

@@ -15,7 +15,7 @@ namespace host {
 
 struct VoiceClass {
   std::string sig;
-  const KernelEntry* k = nullptr;
+  std::shared_ptr<const Program> k;
   std::vector<uint32_t> voices;     // global voice indices, ascending
   std::vector<uint32_t> uniform;    // class-uniform words (delay lengths ...)
   uint64_t dl_floats = 0;           // delay-line floats per voice

@@ -1,0 +1,157 @@
+// fundsp_b200 NVRTC path: compile the fused voice program of a graph class that is not in the AOT tables.
+//
+// A class is named by a C++ type expression over the node templates of csrc/dsp/nodes.cuh (graph.h `sig`), so
+// "compiling a new graph" is instantiating `fdsp::bank_kernel<SIG, 128, MODE, TB>` from the SAME hand-written device
+// headers the AOT instances use (embedded in this library at build time, _build/jit_headers.inc). This is template
+// instantiation at run time, not tracing: the kernel body is the code in bank_kernel.cuh / nodes.cuh.
+// libnvrtc / libcuda are dlopen'ed on first use so the library loads on machines without them.
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "registry.h"
+
+#include "../_build/jit_headers.inc"  // kJitHeaderNames[], kJitHeaderSrc[], kJitHeaderCount
+
+namespace fdsp {
+namespace host {
+
+namespace {
+
+struct Api {
+  void* nvrtc = nullptr; void* cuda = nullptr; bool ok = false; std::string why;
+  nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*);
+  nvrtcResult (*DestroyProgram)(nvrtcProgram*);
+  nvrtcResult (*AddNameExpression)(nvrtcProgram, const char*);
+  nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*);
+  nvrtcResult (*GetLoweredName)(nvrtcProgram, const char*, const char**);
+  nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*);
+  nvrtcResult (*GetCUBIN)(nvrtcProgram, char*);
+  nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*);
+  nvrtcResult (*GetProgramLog)(nvrtcProgram, char*);
+  CUresult (*ModuleLoadData)(CUmodule*, const void*);
+  CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*);
+  CUresult (*ModuleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*);
+  CUresult (*MemcpyDtoH)(void*, CUdeviceptr, size_t);
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int);
+  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**);
+  CUresult (*GetErrorString)(CUresult, const char**);
+};
+
+template <class F> bool sym(void* lib, const char* name, F& f) { f = reinterpret_cast<F>(dlsym(lib, name)); return f != nullptr; }
+
+Api& api() {
+  static Api a;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    for (const char* n : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"})
+      if ((a.nvrtc = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;
+    for (const char* n : {"libcuda.so.1", "libcuda.so"})
+      if ((a.cuda = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;
+    if (!a.nvrtc) { a.why = "libnvrtc not found (JIT unavailable; only the ahead-of-time graph classes can run)"; return; }
+    if (!a.cuda) { a.why = "libcuda not found"; return; }
+    bool ok = sym(a.nvrtc, "nvrtcCreateProgram", a.CreateProgram) && sym(a.nvrtc, "nvrtcDestroyProgram", a.DestroyProgram) &&
+              sym(a.nvrtc, "nvrtcAddNameExpression", a.AddNameExpression) && sym(a.nvrtc, "nvrtcCompileProgram", a.CompileProgram) &&
+              sym(a.nvrtc, "nvrtcGetLoweredName", a.GetLoweredName) && sym(a.nvrtc, "nvrtcGetCUBINSize", a.GetCUBINSize) &&
+              sym(a.nvrtc, "nvrtcGetCUBIN", a.GetCUBIN) && sym(a.nvrtc, "nvrtcGetProgramLogSize", a.GetProgramLogSize) &&
+              sym(a.nvrtc, "nvrtcGetProgramLog", a.GetProgramLog) && sym(a.cuda, "cuModuleLoadData", a.ModuleLoadData) &&
+              sym(a.cuda, "cuModuleGetFunction", a.ModuleGetFunction) && sym(a.cuda, "cuModuleGetGlobal_v2", a.ModuleGetGlobal) &&
+              sym(a.cuda, "cuMemcpyDtoH_v2", a.MemcpyDtoH) && sym(a.cuda, "cuFuncSetAttribute", a.FuncSetAttribute) &&
+              sym(a.cuda, "cuLaunchKernel", a.LaunchKernel) && sym(a.cuda, "cuGetErrorString", a.GetErrorString);
+    if (!ok) { a.why = "missing NVRTC / driver symbols"; return; }
+    a.ok = true;
+  });
+  return a;
+}
+
+struct JitProgram : Program {
+  CUmodule mod = nullptr;
+  CUfunction fn[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};  // [mode-1][TB]
+  cudaError_t launch(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t st) const override {
+    const Api& A = api();
+    mode &= 3;
+    if (mode == 0) return cudaErrorInvalidValue;
+    const size_t tile = (mode & 2) ? sizeof(float) * (size_t)OUT * 64 * (threads + 1) : 0;
+    int tb = (wave_kind >= 0 && table_bytes > 0 && tile + table_bytes <= 227 * 1024) ? 1 : 0;
+    CUfunction f = fn[mode - 1][tb];
+    if (!f) return cudaErrorInvalidDeviceFunction;
+    const size_t smem = tile + (tb ? table_bytes : 0);
+    if (smem > 48 * 1024 && A.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    BankArgs args = a;
+    void* params[] = {&args};
+    const unsigned grid = (a.V + (unsigned)threads - 1) / (unsigned)threads;
+    CUresult r = A.LaunchKernel(f, grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)smem, (CUstream)st, params, nullptr);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorLaunchFailure;
+  }
+};
+
+std::mutex g_mu;
+std::map<std::string, std::shared_ptr<const Program>> g_cache;  // key: device:sig
+int g_compiled = 0;
+
+}  // namespace
+
+int jit_compiled_count() { return g_compiled; }
+
+std::shared_ptr<const Program> jit_program(const std::string& sig, int device, std::string& err) {
+  if (sig.find("Unsupported") != std::string::npos) { err = "the graph contains a node with no device lowering"; return nullptr; }
+  Api& A = api();
+  if (!A.ok) { err = A.why; return nullptr; }
+  std::lock_guard<std::mutex> lock(g_mu);
+  const std::string key = std::to_string(device) + ":" + sig;
+  auto it = g_cache.find(key);
+  if (it != g_cache.end()) return it->second;
+  cudaSetDevice(device);
+  cudaFree(nullptr);  // make sure the primary context exists and is current for the driver API calls below
+
+  std::string src = "#include \"dsp/bank_kernel.cuh\"\nnamespace fdsp { typedef " + sig + " JitG; }\n"
+                    "extern \"C\" __device__ int fdsp_jit_layout[6] = {fdsp::JitG::IN, fdsp::JitG::OUT, fdsp::JitG::NP, fdsp::JitG::NS, fdsp::JitG::NU, fdsp::WaveKind<fdsp::JitG>::value};\n";
+  nvrtcProgram prog;
+  if (A.CreateProgram(&prog, src.c_str(), "fdsp_jit.cu", kJitHeaderCount, kJitHeaderSrc, kJitHeaderNames) != NVRTC_SUCCESS) { err = "nvrtcCreateProgram failed"; return nullptr; }
+  std::vector<std::string> names;
+  for (int mode = 1; mode <= 3; mode++)
+    for (int tb = 0; tb < 2; tb++) {
+      names.push_back("fdsp::bank_kernel<fdsp::JitG, 128, " + std::to_string(mode) + ", " + (tb ? "true" : "false") + ">");
+      A.AddNameExpression(prog, names.back().c_str());
+    }
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-lineinfo", "-default-device"};
+  nvrtcResult rc = A.CompileProgram(prog, 5, opts);
+  if (rc != NVRTC_SUCCESS) {
+    size_t n = 0; A.GetProgramLogSize(prog, &n);
+    std::string log(n, '\0'); if (n) A.GetProgramLog(prog, &log[0]);
+    if (log.size() > 1500) log.resize(1500);
+    err = "NVRTC compile of `" + sig + "` failed: " + log;
+    A.DestroyProgram(&prog);
+    return nullptr;
+  }
+  size_t cn = 0; A.GetCUBINSize(prog, &cn);
+  std::vector<char> cubin(cn); A.GetCUBIN(prog, cubin.data());
+  auto p = std::make_shared<JitProgram>();
+  p->sig = sig; p->jit = true;
+  if (A.ModuleLoadData(&p->mod, cubin.data()) != CUDA_SUCCESS) { err = "cuModuleLoadData failed for the JIT cubin"; A.DestroyProgram(&prog); return nullptr; }
+  int k = 0;
+  for (int mode = 1; mode <= 3; mode++)
+    for (int tb = 0; tb < 2; tb++, k++) {
+      const char* low = nullptr;
+      if (A.GetLoweredName(prog, names[k].c_str(), &low) != NVRTC_SUCCESS || A.ModuleGetFunction(&p->fn[mode - 1][tb], p->mod, low) != CUDA_SUCCESS) {
+        err = "JIT kernel lookup failed"; A.DestroyProgram(&prog); return nullptr;
+      }
+    }
+  A.DestroyProgram(&prog);
+  CUdeviceptr d = 0; size_t bytes = 0; int lay[6] = {0, 0, 0, 0, 0, -1};
+  if (A.ModuleGetGlobal(&d, &bytes, p->mod, "fdsp_jit_layout") != CUDA_SUCCESS || bytes != sizeof(lay) || A.MemcpyDtoH(lay, d, sizeof(lay)) != CUDA_SUCCESS) {
+    err = "JIT layout readback failed"; return nullptr;
+  }
+  p->IN = lay[0]; p->OUT = lay[1]; p->NP = lay[2]; p->NS = lay[3]; p->NU = lay[4]; p->wave_kind = lay[5]; p->threads = 128;
+  g_compiled++;
+  g_cache[key] = p;
+  return p;
+}
+
+}  // namespace host
+}  // namespace fdsp

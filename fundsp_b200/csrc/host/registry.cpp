@@ -57,5 +57,21 @@ const KernelEntry* find_kernel(const std::string& sig) {
   return nullptr;
 }
 
+
+namespace {
+struct AotProgram : Program {
+  const KernelEntry* e;
+  explicit AotProgram(const KernelEntry* e_, const std::string& key) : e(e_) {
+    sig = key; IN = e->IN; OUT = e->OUT; NP = e->NP; NS = e->NS; NU = e->NU; threads = e->threads(); wave_kind = e->wave_kind();
+  }
+  cudaError_t launch(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t st) const override { return e->launch(a, mode, table_bytes, st); }
+};
+}  // namespace
+
+std::shared_ptr<const Program> get_program(const std::string& sig, int device, std::string& err) {
+  if (const KernelEntry* e = find_kernel(sig)) return std::make_shared<AotProgram>(e, sig);
+  return jit_program(sig, device, err);
+}
+
 }  // namespace host
 }  // namespace fdsp

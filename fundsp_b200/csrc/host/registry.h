@@ -1,7 +1,9 @@
-// Kernel registry: maps a device program type expression (graph.h `sig`) to its launcher.
+// Kernel programs: a fused voice program (device type expression, see graph.h `sig`) and how to launch it.
+// Two sources: the ahead-of-time instance tables (csrc/inst/*.cu) and the NVRTC path (jit.cpp).
 #pragma once
 #include <cuda_runtime.h>
 
+#include <memory>
 #include <string>
 
 #include "../dsp/bank_args.h"
@@ -9,21 +11,35 @@
 namespace fdsp {
 namespace host {
 
-struct KernelEntry {
+struct KernelEntry {  // AOT table row
   const char* sig;
   int IN, OUT, NP, NS, NU;
-  // mode: FDSP_OUT_VOICES | FDSP_OUT_MIX bits
   // table_bytes > 0: stage that many bytes of wavetable data in shared memory (long renders of wavetable graphs)
   cudaError_t (*launch)(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t stream);
   int (*threads)();
   int (*wave_kind)();  // first wavetable kind the program reads, -1 if none
 };
 
+struct Program {
+  std::string sig;
+  int IN = 0, OUT = 0, NP = 0, NS = 0, NU = 0, threads = 128, wave_kind = -1;
+  bool jit = false;
+  virtual ~Program() {}
+  // mode: FDSP_OUT_VOICES | FDSP_OUT_MIX bits
+  virtual cudaError_t launch(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t stream) const = 0;
+};
+
+// Returns the program for `sig` (AOT if listed, else NVRTC-compiled and cached); nullptr + `err` on failure.
+std::shared_ptr<const Program> get_program(const std::string& sig, int device, std::string& err);
 const KernelEntry* find_kernel(const std::string& sig);
 int registry_size();
 const KernelEntry* registry_at(int i);
+const char* registry_key(int i);
 cudaError_t launch_mix_reduce(const float* partial, uint32_t nparts, uint32_t outs, uint32_t n, float* mix, uint32_t mix_stride,
                               uint32_t mix_offset, int accumulate, cudaStream_t stream);
+// NVRTC path (jit.cpp)
+std::shared_ptr<const Program> jit_program(const std::string& sig, int device, std::string& err);
+int jit_compiled_count();
 
 }  // namespace host
 }  // namespace fdsp

@@ -1,0 +1,76 @@
+"""Structural coverage beyond the AOT config graphs: every §8a node family composed in ways the registry does not
+list, compiled at bank creation by the NVRTC path from the same device headers, checked bit-for-bit against the oracle."""
+import numpy as np
+import pytest
+
+from fundsp_b200.graph import An
+from fundsp_b200.prelude import *  # noqa: F401,F403
+from fundsp_b200.prelude import _svf_hz
+from oracle import lib as olib, oracle_bank_render
+
+pytestmark = pytest.mark.gpu
+SR = 48000.0
+
+
+def fv(i, k=0):  # deterministic per-voice variation
+    return ((i * 37 + k * 11) % 29) / 29.0
+
+
+CASES = {
+    "svf_var_lowpass_pan": lambda i: (noise().seed(i) | dc((300.0 + 4000.0 * fv(i), 0.5 + 4.0 * fv(i, 1)))) >> lowpass() >> pan(2.0 * fv(i, 2) - 1.0),
+    "svf_var_bell": lambda i: (noise().seed(i) | dc((300.0 + 4000.0 * fv(i), 0.7, 0.5 + 2.0 * fv(i, 1)))) >> bell(),
+    "svf_var_highshelf_mod": lambda i: (noise().seed(i) | (sine_hz(3.0 + i % 4) * 500.0 + 2000.0) | dc((1.0, 2.0))) >> highshelf(),
+    "svf_fixed_all_modes": lambda i: noise().seed(i) >> pipei(3, lambda k: _svf_hz((i + 3 * k) % 9, 400.0 + 900.0 * k + 50.0 * (i % 7), 0.8 + 0.3 * k, 1.5)),
+    "butter_resonator": lambda i: noise().seed(i) >> butterpass_hz(500.0 + 100.0 * (i % 9)) >> resonator_hz(800.0 + 40.0 * i, 5.0 + i % 3),
+    "ticks_bus": lambda i: noise().seed(i) >> (pass_() & tick() * 0.5 & (tick() >> tick()) * (0.1 + 0.01 * i)),
+    "feedback_delay": lambda i: noise().seed(i) >> feedback(delay(0.001) * (0.3 + 0.02 * (i % 10))),
+    "allnest_delay": lambda i: noise().seed(i) >> allnest_c(0.2 + 0.02 * (i % 20), delay(0.0013)) >> fir((0.25, 0.5, 0.25)),
+    "split_stacki_join": lambda i: noise().seed(i) >> split(4) >> stacki(4, lambda k: lowpass_hz(300.0 * (k + 1) + 10.0 * i, 1.0)) >> join(4),
+    "organ_hammond_bus": lambda i: organ_hz(110.0 + 7.0 * i) & 0.5 * hammond_hz(220.0 + 3.0 * i) & square_hz(55.0 + i) * 0.25 & triangle_hz(330.0 - i) & soft_saw_hz(82.0 + i),
+    "panner_audio_rate": lambda i: (noise().seed(i) | sine_hz(0.5 + 0.1 * (i % 5))) >> panner(),
+    "moog_var": lambda i: (noise().seed(i) | (sine_hz(2.0) * 400.0 + 1200.0 + 10.0 * i) | dc(0.2 + 0.02 * (i % 20))) >> moog(),
+    "moog_q_chain": lambda i: (noise().seed(i) | dc(900.0 + 25.0 * i)) >> moog_q(0.4) >> moog_hz(2000.0, 0.1 + 0.01 * (i % 30)),
+    "sumi_sines_ops": lambda i: 1.0 - (-(sumi(3, lambda k: sine_hz(110.0 * (k + 1) + i).phase(0.1 * k)) * 0.3) - 0.25) + 0.125,
+    "busi_branchi": lambda i: noise().seed(i) >> branchi(3, lambda k: lowpass_hz(200.0 * (k + 1) + i, 1.0)) >> (pass_() | sink() | pass_()) >> join(2),
+    "multisplit_multijoin_thru": lambda i: (noise().seed(i) | noise().seed(i + 1000)) >> multisplit(2, 3) >> multijoin(2, 3) >> ~(lowpass_hz(700.0 + i, 2.0)) >> reverse(2),
+    "wavesynth_phase_out": lambda i: dc(100.0 + 9.0 * i) >> An("wavesynth", (0, 2), (), 1, 2),
+    "product_fm_feedback": lambda i: (sine_hz(200.0 + i) * sine_hz(3.0 + 0.1 * i)) >> feedback(tick() * 0.25 >> lowpass_hz(2000.0, 0.7)),
+}
+GATED = {
+    "adsr_noise": lambda i: adsr_live(0.005 + 0.001 * (i % 5), 0.05, 0.5 + 0.01 * (i % 20), 0.1) * noise().seed(i) | ~zero() >> sine_hz(100.0 + i),
+}
+
+
+def run_case(mk, V, n, inp=None):
+    from fundsp_b200.bank import GpuBank
+    olib().fo_set_denormal_emulation(0)
+    b = GpuBank([mk(i) for i in range(V)], per_voice=True, sample_rate=SR)
+    g, _ = b.render_samples(n, inp)
+    o, _ = oracle_bank_render([mk(i) for i in range(V)], SR, n, inp, threads=4)
+    return b, g, o
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_jit_graph_matches_oracle(name):
+    b, g, o = run_case(CASES[name], 40, 2000 + 61)
+    assert g.shape == o.shape and np.isfinite(g).all() and np.abs(o).max() > 1e-4
+    bad = int((g != o).sum())
+    assert bad == 0, (name, bad, float(np.abs(g - o).max()), b.classes()[0]["signature"])
+
+
+def test_jit_gated_envelope():
+    n = 9600 + 7
+    gate = np.zeros((1, n), np.float32)
+    gate[0, 300:4000] = 1.0
+    gate[0, 6000:7000] = 0.7
+    b, g, o = run_case(GATED["adsr_noise"], 40, n, gate)
+    assert np.abs(o).max() > 0.1
+    assert np.array_equal(g, o), (int((g != o).sum()), float(np.abs(g - o).max()))
+
+
+def test_unsupported_graph_reports_error():
+    from fundsp_b200.bank import GpuBank
+    from fundsp_b200.capi import ERR_UNSUPPORTED, FdspError
+    with pytest.raises(FdspError) as e:
+        GpuBank([(noise() | dc(500.0)) >> butterpass()], per_voice=True)  # audio-rate butterpass has no device lowering
+    assert e.value.code == ERR_UNSUPPORTED
