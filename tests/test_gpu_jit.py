@@ -32,7 +32,7 @@ CASES = {
     "moog_q_chain": lambda i: (noise().seed(i) | dc(900.0 + 25.0 * i)) >> moog_q(0.4) >> moog_hz(2000.0, 0.1 + 0.01 * (i % 30)),
     "sumi_sines_ops": lambda i: 1.0 - (-(sumi(3, lambda k: sine_hz(110.0 * (k + 1) + i).phase(0.1 * k)) * 0.3) - 0.25) + 0.125,
     "busi_branchi": lambda i: noise().seed(i) >> branchi(3, lambda k: lowpass_hz(200.0 * (k + 1) + i, 1.0)) >> (pass_() | sink() | pass_()) >> join(2),
-    "multisplit_multijoin_thru": lambda i: (noise().seed(i) | noise().seed(i + 1000)) >> multisplit(2, 3) >> multijoin(2, 3) >> ~(lowpass_hz(700.0 + i, 2.0)) >> reverse(2),
+    "multisplit_multijoin_thru": lambda i: (noise().seed(i) | noise().seed(i + 1000)) >> multisplit(2, 3) >> multijoin(2, 3) >> ~(join(2) >> lowpass_hz(700.0 + i, 2.0)) >> reverse(2),
     "wavesynth_phase_out": lambda i: dc(100.0 + 9.0 * i) >> An("wavesynth", (0, 2), (), 1, 2),
     "product_fm_feedback": lambda i: (sine_hz(200.0 + i) * sine_hz(3.0 + 0.1 * i)) >> feedback(tick() * 0.25 >> lowpass_hz(2000.0, 0.7)),
 }
