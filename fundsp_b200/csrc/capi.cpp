@@ -201,9 +201,9 @@ API int fdsp_bank_class_info(const fdsp_bank* b, int cls, char* sig, int max, ui
   const VoiceClass& c = b->b.classes[cls];
   if (sig && max > 0) { strncpy(sig, c.sig.c_str(), (size_t)max - 1); sig[max - 1] = 0; }
   if (voices) *voices = c.V();
-  if (state_words) *state_words = (uint32_t)c.k->NS;
-  if (param_words) *param_words = (uint32_t)c.k->NP;
-  if (delay_floats) *delay_floats = c.dl_floats;
+  if (state_words) *state_words = c.ns;
+  if (param_words) *param_words = c.np;
+  if (delay_floats) *delay_floats = c.dl_floats + c.ring_floats;
   return FDSP_OK;
 }
 API uint64_t fdsp_bank_launch_count(const fdsp_bank* b) { return b ? b->b.launches : 0; }

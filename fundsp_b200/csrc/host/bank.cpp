@@ -1,7 +1,9 @@
 // fundsp_b200 bank runtime implementation — see bank.h.
 #include "bank.h"
+#include "../dsp/fdn_args.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -29,7 +31,7 @@ template <class T> std::string dev_alloc(T** p, size_t count) {
 Bank::~Bank() {
   cudaSetDevice(device);
   for (auto& c : classes) {
-    cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial);
+    cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows);
   }
   for (float* p : d_wtdata) cudaFree(p);
   cudaFree(d_wt); cudaFree(d_in); cudaFree(d_out); cudaFree(d_mix);
@@ -76,12 +78,39 @@ std::string Bank::lower_and_upload(bool upload_state) {
     if (it == index.end()) {
       ci = (int)fresh.size(); index[lo.key] = ci;
       VoiceClass c; c.sig = lo.sig; c.uniform = lo.l.U;
-      for (uint32_t d : lo.l.dlen) c.dl_floats += d;
-      std::string jerr;
-      c.k = get_program(lo.sig, device, jerr);
-      if (!c.k) return "no device program for graph class `" + lo.sig + "`: " + jerr;
-      if ((size_t)c.k->NP != lo.l.P.size() || (size_t)c.k->NS != lo.l.S.size() || (size_t)c.k->NU != lo.l.U.size() || c.k->IN != nin || c.k->OUT != nout)
-        return "internal: host lowering of `" + lo.sig + "` disagrees with the device word layout";
+      c.np = (uint32_t)lo.l.P.size(); c.ns = (uint32_t)lo.l.S.size(); c.nu = (uint32_t)lo.l.U.size();
+      std::string jerr, prog_sig = lo.sig;
+      // reverb_stereo tail -> warp-per-voice FDN kernel; the part in front of it (if any) stays a fused per-voice program
+      static const std::string REV = "Pipe<Pipe<MultiSplit<2,16>,Feedback<1,Multi<30,0,32,Pipe<Delay,Fir<3>>>>>,Binop<2,Multi<31,0,32,Panner<1>>,Constant<2>>>";
+      const std::string wet_tail = ",Bus<MultiPass<2>,Unop<3," + REV + ">>>", pipe_tail = "," + REV + ">";
+      auto ends_with = [](const std::string& s, const std::string& t) { return s.size() >= t.size() && s.compare(s.size() - t.size(), t.size(), t) == 0; };
+      bool wet = false;
+      const bool fdn_off = getenv("FDSP_DISABLE_FDN") != nullptr;  // A/B switch: run reverbs in the generic thread-per-voice form
+      if (fdn_off) {}
+      else if (lo.sig == REV && nin == 2) { c.fdn = true; prog_sig.clear(); }
+      else if (lo.sig.compare(0, 5, "Pipe<") == 0 && ends_with(lo.sig, wet_tail)) { c.fdn = true; wet = true; prog_sig = lo.sig.substr(5, lo.sig.size() - 5 - wet_tail.size()); }
+      else if (lo.sig.compare(0, 5, "Pipe<") == 0 && ends_with(lo.sig, pipe_tail)) { c.fdn = true; prog_sig = lo.sig.substr(5, lo.sig.size() - 5 - pipe_tail.size()); }
+      if (c.fdn) {
+        for (size_t k = lo.l.U.size() - 32; k < lo.l.U.size(); k++) if (lo.l.U[k] < 130u) c.fdn = false;  // prefetch distance needs rings >= 130 samples
+        if (!c.fdn) prog_sig = lo.sig;
+      }
+      if (c.fdn) {
+        c.p0 = c.np - 162; c.s0 = c.ns - 160; c.u0 = c.nu - 32;
+        c.scalar_row = wet ? (int)c.p0 - 1 : -1;
+        for (size_t k = 0; k < lo.l.dlen.size(); k++) (k + 32 >= lo.l.dlen.size() ? c.ring_floats : c.dl_floats) += lo.l.dlen[k];
+        if (!prog_sig.empty()) {
+          c.k = get_program(prog_sig, device, jerr);
+          if (!c.k) return "no device program for the dry stage `" + prog_sig + "`: " + jerr;
+          if ((uint32_t)c.k->NP != c.p0 - (wet ? 1u : 0u) || (uint32_t)c.k->NS != c.s0 || (uint32_t)c.k->NU != c.u0 || c.k->IN != nin || c.k->OUT != 2)
+            return "internal: dry-stage layout of `" + prog_sig + "` disagrees with the host lowering";
+        }
+      } else {
+        for (uint32_t d : lo.l.dlen) c.dl_floats += d;
+        c.k = get_program(lo.sig, device, jerr);
+        if (!c.k) return "no device program for graph class `" + lo.sig + "`: " + jerr;
+        if ((uint32_t)c.k->NP != c.np || (uint32_t)c.k->NS != c.ns || (uint32_t)c.k->NU != c.nu || c.k->IN != nin || c.k->OUT != nout)
+          return "internal: host lowering of `" + lo.sig + "` disagrees with the device word layout";
+      }
       fresh.push_back(std::move(c));
     } else ci = it->second;
     fresh[ci].voices.push_back((uint32_t)v);
@@ -90,12 +119,12 @@ std::string Bank::lower_and_upload(bool upload_state) {
   const bool same_shape = classes.size() == fresh.size() && std::equal(classes.begin(), classes.end(), fresh.begin(), [](const VoiceClass& a, const VoiceClass& b) {
                             return a.sig == b.sig && a.voices == b.voices && a.uniform == b.uniform; });
   if (!same_shape) {
-    for (auto& c : classes) { cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); }
+    for (auto& c : classes) { cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows); }
     classes = std::move(fresh);
     upload_state = true;
   }
   for (auto& c : classes) {
-    const uint32_t V = c.V(); const int NP = c.k->NP, NS = c.k->NS;
+    const uint32_t V = c.V(); const int NP = (int)c.np, NS = (int)c.ns;
     std::vector<uint32_t> P((size_t)NP * V), S((size_t)NS * V), rows(V);
     for (uint32_t i = 0; i < V; i++) {
       const Lowering& l = lows[c.voices[i]].l;
@@ -111,6 +140,16 @@ std::string Bank::lower_and_upload(bool upload_state) {
       if (!(e = dev_alloc(&c.d_uniform, c.uniform.size())).empty()) return e;
       if (!(e = dev_alloc(&c.d_rowmap, rows.size())).empty()) return e;
       if (!(e = dev_alloc(&c.d_dline, (size_t)c.dl_floats * V)).empty()) return e;
+      if (c.fdn) {
+        if (!(e = dev_alloc(&c.d_ring, (size_t)c.ring_floats * V)).empty()) return e;
+        if (c.k) {
+          if (!(e = dev_alloc(&c.d_dry, (size_t)V * 2 * TIME_CHUNK)).empty()) return e;
+          if (!(e = dev_alloc(&c.d_dryrows, V)).empty()) return e;
+          std::vector<uint32_t> id(V);
+          for (uint32_t i = 0; i < V; i++) id[i] = 2 * i;
+          CU(cudaMemcpy(c.d_dryrows, id.data(), V * 4, cudaMemcpyHostToDevice));
+        }
+      }
       CU(cudaMemcpy(c.d_rowmap, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice));
       if (!c.uniform.empty()) CU(cudaMemcpy(c.d_uniform, c.uniform.data(), c.uniform.size() * 4, cudaMemcpyHostToDevice));
     }
@@ -118,6 +157,7 @@ std::string Bank::lower_and_upload(bool upload_state) {
     if (upload_state) {
       if (!S.empty()) CU(cudaMemcpy(c.d_state, S.data(), S.size() * 4, cudaMemcpyHostToDevice));
       if (c.dl_floats) CU(cudaMemset(c.d_dline, 0, (size_t)c.dl_floats * V * sizeof(float)));
+      if (c.ring_floats) CU(cudaMemset(c.d_ring, 0, (size_t)c.ring_floats * V * sizeof(float)));
     }
   }
   // 3. wavetables used by any class
@@ -158,6 +198,7 @@ std::string Bank::reset() {  // AudioUnit::reset: back to the construction-time 
   for (auto& c : classes) {
     if (!c.state0.empty()) CU(cudaMemcpyAsync(c.d_state, c.state0.data(), c.state0.size() * 4, cudaMemcpyHostToDevice, stream));
     if (c.dl_floats) CU(cudaMemsetAsync(c.d_dline, 0, (size_t)c.dl_floats * c.V() * sizeof(float), stream));
+    if (c.ring_floats) CU(cudaMemsetAsync(c.d_ring, 0, (size_t)c.ring_floats * c.V() * sizeof(float), stream));
   }
   CU(cudaStreamSynchronize(stream));
   dirty = false;
@@ -179,7 +220,9 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
     bool first = true;
     for (auto& c : classes) {
       const uint32_t V = c.V();
-      const uint32_t grid = (V + (uint32_t)c.k->threads - 1) / (uint32_t)c.k->threads;
+      int fdn_warps = 1;
+      if (c.fdn) { fdn_warps = (int)((V + 147) / 148); if (fdn_warps > fdn_max_warps()) fdn_warps = fdn_max_warps(); if (fdn_warps < 1) fdn_warps = 1; }
+      const uint32_t grid = c.fdn ? (V + (uint32_t)fdn_warps - 1) / (uint32_t)fdn_warps : (V + (uint32_t)c.k->threads - 1) / (uint32_t)c.k->threads;
       if (want_m) {
         const size_t need = (size_t)grid * nout * len;
         if (c.partial_floats < need) { std::string e = dev_alloc(&c.d_partial, (size_t)grid * nout * TIME_CHUNK); if (!e.empty()) return e; c.partial_floats = (size_t)grid * nout * TIME_CHUNK; }
@@ -196,9 +239,27 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
       // long launches of wavetable programs stage the table set in shared memory (TMA bulk copy, ~160 KB per CTA);
       // short ones (process()-sized) read the tables through L1/L2 instead
       size_t table_bytes = 0;
-      const int wk = c.k->wave_kind;
+      const int wk = c.k ? c.k->wave_kind : -1;
       if (wk >= 0 && len >= 1024) table_bytes = global_wavetable(wk).data.size() * sizeof(float);
-      CU(c.k->launch(a, mode, table_bytes, stream));
+      if (c.fdn) {
+        FdnArgs f;
+        f.params = c.d_params; f.state = c.d_state; f.uniform = c.d_uniform; f.p0 = c.p0; f.s0 = c.s0; f.u0 = c.u0; f.scalar_row = c.scalar_row;
+        if (c.k) {  // stage 1: the fused dry program writes stereo rows [V][2][TIME_CHUNK]
+          BankArgs d = a;
+          d.out = c.d_dry; d.partial = nullptr; d.out_stride = TIME_CHUNK; d.out_offset = 0; d.row_map = c.d_dryrows;
+          CU(c.k->launch(d, 1, table_bytes, stream));
+          launches++;
+          f.dry = c.d_dry; f.dry_voice_stride = 2ull * TIME_CHUNK; f.dry_ch_stride = TIME_CHUNK; f.dry_offset = 0;
+        } else {    // reverb applied straight to the bank's stereo input
+          f.dry = in_dev; f.dry_voice_stride = 0; f.dry_ch_stride = (uint32_t)in_stride; f.dry_offset = (uint32_t)t0;
+        }
+        f.out = want_v ? out_dev : nullptr; f.row_map = c.d_rowmap; f.out_stride = (uint32_t)out_stride; f.out_offset = (uint32_t)t0;
+        f.partial = want_m ? c.d_partial : nullptr;
+        f.ring = c.d_ring; f.ring_voice_stride = c.ring_floats; f.V = V; f.n = len;
+        CU(launch_fdn(f, fdn_warps, stream));
+      } else {
+        CU(c.k->launch(a, mode, table_bytes, stream));
+      }
       launches++;
       if (want_m) {
         CU(launch_mix_reduce(c.d_partial, grid, (uint32_t)nout, len, mix_dev, (uint32_t)mix_stride, (uint32_t)t0, first ? 0 : 1, stream));
@@ -287,6 +348,7 @@ std::string Bank::clone_into(Bank& dst) const {
     const VoiceClass& s = classes[i]; VoiceClass& d = dst.classes[i];
     if (!s.state0.empty()) CU(cudaMemcpy(d.d_state, s.d_state, s.state0.size() * 4, cudaMemcpyDeviceToDevice));
     if (s.dl_floats) CU(cudaMemcpy(d.d_dline, s.d_dline, (size_t)s.dl_floats * s.V() * 4, cudaMemcpyDeviceToDevice));
+    if (s.ring_floats && s.d_ring && d.d_ring) CU(cudaMemcpy(d.d_ring, s.d_ring, (size_t)s.ring_floats * s.V() * 4, cudaMemcpyDeviceToDevice));
   }
   dst.dirty = dirty;
   return "";

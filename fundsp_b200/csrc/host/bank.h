@@ -18,7 +18,11 @@ struct VoiceClass {
   std::shared_ptr<const Program> k;
   std::vector<uint32_t> voices;     // global voice indices, ascending
   std::vector<uint32_t> uniform;    // class-uniform words (delay lengths ...)
-  uint64_t dl_floats = 0;           // delay-line floats per voice
+  uint64_t dl_floats = 0;           // delay-line floats per voice (thread-per-voice layout [pos][voice])
+  uint32_t np = 0, ns = 0, nu = 0;  // words per voice (whole graph)
+  // reverb_stereo tail handled by the warp-per-voice FDN kernel (dsp/fdn_kernel.cuh); `k` is then the dry-stage program (may be null)
+  bool fdn = false; int scalar_row = -1; uint32_t p0 = 0, s0 = 0, u0 = 0; uint64_t ring_floats = 0;
+  float* d_ring = nullptr; float* d_dry = nullptr; uint32_t* d_dryrows = nullptr;
   std::vector<uint32_t> state0;     // initial state, SoA [NS][V]
   uint32_t* d_params = nullptr; uint32_t* d_state = nullptr; uint32_t* d_uniform = nullptr; uint32_t* d_rowmap = nullptr;
   float* d_dline = nullptr; float* d_partial = nullptr; size_t partial_floats = 0;

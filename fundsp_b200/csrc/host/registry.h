@@ -8,6 +8,8 @@
 
 #include "../dsp/bank_args.h"
 
+namespace fdsp { struct FdnArgs; }
+
 namespace fdsp {
 namespace host {
 
@@ -37,6 +39,9 @@ const KernelEntry* registry_at(int i);
 const char* registry_key(int i);
 cudaError_t launch_mix_reduce(const float* partial, uint32_t nparts, uint32_t outs, uint32_t n, float* mix, uint32_t mix_stride,
                               uint32_t mix_offset, int accumulate, cudaStream_t stream);
+// warp-per-voice reverb_stereo kernel (inst/inst_fdn.cu)
+cudaError_t launch_fdn(const FdnArgs& a, int warps, cudaStream_t stream);
+int fdn_max_warps();
 // NVRTC path (jit.cpp)
 std::shared_ptr<const Program> jit_program(const std::string& sig, int device, std::string& err);
 int jit_compiled_count();

@@ -200,3 +200,51 @@ def test_full_size_headline_properties():
     assert rel_err(g[idx], o) <= 1e-5
     assert np.abs(mx - g.astype(np.float64).sum(axis=0)).max() <= 2e-6 * np.abs(g).sum(axis=0).max()
     assert np.isfinite(g).all() and np.abs(g).max() < 8.0
+
+
+# ---------------------------------------------------------------- warp-per-voice FDN kernel (reverb_stereo)
+def test_reverb_only_bank_on_stereo_bus_input():
+    """`reverb_stereo` applied to the bank's shared stereo input (one voice per room setting)."""
+    n = 6000 + 37
+    rng = np.random.default_rng(3)
+    x = (rng.uniform(-1, 1, (2, n)) * (np.arange(n) < 3000)).astype(np.float32)
+    mk = lambda i: reverb_stereo(10.0 + i, 1.0 + 0.5 * i, 0.3 + 0.1 * i)  # noqa: E731  (different delay lengths -> one class per voice)
+    b, g, _ = gpu_render([mk(i) for i in range(3)], n, x)
+    assert len(b.classes()) == 3
+    o, _ = oracle_bank_render([mk(i) for i in range(3)], SR, n, x)
+    assert np.array_equal(g, o) and np.abs(o).max() > 0.05
+
+
+def test_fdn_kernel_process_granularity_and_wet_only_pipe():
+    from fundsp_b200.bank import GpuBank
+    from oracle import OracleUnit
+    mk = lambda i: (noise().seed(i) >> pan(0.1 * i - 0.3)) >> reverb_stereo(12.0, 1.5, 0.4)  # noqa: E731  Pipe<X, Reverb>
+    V = 9
+    b = GpuBank([mk(i) for i in range(V)], per_voice=True, mix=True, sample_rate=SR)
+    units = [OracleUnit(mk(i)) for i in range(V)]
+    for u in units:
+        u.set_sample_rate(SR)
+    for s in (64, 64, 17, 64, 1, 0, 33, 64, 64, 64, 5):
+        g = b.process(s)
+        if s == 0:
+            continue
+        per_voice = np.stack([u.process(s) for u in units])  # [V, 2, s]
+        ref = per_voice.astype(np.float64).sum(axis=0)
+        assert g.shape == (2, s)
+        assert np.abs(g - ref).max() <= 1e-5 * max(1.0, np.abs(per_voice).sum(axis=0).max())
+
+
+def test_fdn_kernel_equals_generic_thread_per_voice_form():
+    """The specialised kernel and the generic lowering of the same graph must agree bit for bit."""
+    import os
+    import subprocess
+    import sys
+    code = ("import sys; sys.path[:0]=['.','tests']; import numpy as np; from fundsp_b200 import workloads; from fundsp_b200.bank import GpuBank;"
+            "b=GpuBank(workloads.build('subtractive',24),per_voice=True,sample_rate=48000.0); g,_=b.render_samples(4000+9, workloads.gate_signal(4009));"
+            "np.save(sys.argv[1], g); print(b.classes()[0]['signature'][:20])")
+    outs = []
+    for k, env in enumerate(({}, {"FDSP_DISABLE_FDN": "1"})):
+        path = f"/tmp/fdn_ab_{k}.npy"
+        subprocess.check_call([sys.executable, "-c", code, path], env={**os.environ, **env}, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        outs.append(np.load(path))
+    assert np.array_equal(outs[0], outs[1]) and np.abs(outs[0]).max() > 0.01
