@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(NT) bank_kernel(const BankArgs a) {
   const bool active = v < a.V;
   constexpr int IN = G::IN, OUT = G::OUT;
   // big programs (e.g. the 32-line FDN in thread-per-voice form) are not unrolled over the 8-sample group
-  constexpr int UNROLL = (G::NS + G::NP > 96) ? 1 : 8;
+  constexpr int UNROLL = Cost<G>::value <= 160 ? 8 : (Cost<G>::value <= 320 ? 4 : (Cost<G>::value <= 640 ? 2 : 1));
 
   typename G::R r;
   CtxT<TB> c;

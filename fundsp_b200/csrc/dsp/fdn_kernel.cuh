@@ -102,6 +102,9 @@ __global__ void __launch_bounds__(256) fdn_kernel(const FdnArgs a) {
   };
 
   const float hz = (float)(1.0 / sqrt(32.0));
+  uint32_t sgn[5];
+#pragma unroll
+  for (int s = 0; s < 5; s++) sgn[s] = (lane & (1 << s)) ? 0x80000000u : 0u;
   int cur = 0;
   prefetch(0, 0u, (int)(a.n < 64u ? a.n : 64u), 0u);
 #pragma unroll 1
@@ -117,21 +120,47 @@ __global__ void __launch_bounds__(256) fdn_kernel(const FdnArgs a) {
 #pragma unroll 1
       for (int h0 = 0; h0 < nb; h0 += 32) {
         const int hn = (nb - h0) < 32 ? (nb - h0) : 32;
-#pragma unroll 4
-        for (int tt = 0; tt < hn; tt++) {
+        int tt = 0;
+        // groups of 8 samples: all shared-memory reads first, then 8 interleaved Hadamard chains, then the stores
+        // (consecutive samples are independent: the feedback value only reaches the ring after >= 129 samples)
+#pragma unroll 1
+        for (; tt + 8 <= hn; tt += 8) {
+          float d[8], x[8], o[8], h[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) { d[u] = rb[h0 + tt + u]; x[u] = din[h0 + tt + u]; }
+#pragma unroll
+          for (int u = 0; u < 8; u++) { f0 = f1; f1 = f2; f2 = d[u]; o[u] = (w0 * f0 + w1 * f1) + w2 * f2; h[u] = o[u]; }
+#pragma unroll
+          for (int s = 0; s < 5; s++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              const float y = __shfl_xor_sync(0xffffffffu, h[u], 1 << s);
+              h[u] = y + __uint_as_float(__float_as_uint(h[u]) ^ sgn[s]);   // upper lane: partner - own; lower lane: own + partner
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            rb[h0 + tt + u] = x[u] + value;    // Feedback: x.tick(input + value); Delay stores it at ring[i]
+            value = h[u] * hz;
+            pbuf[(0 * 32 + lane) * FDN_PS + tt + u] = o[u] * lw;   // Panner<U1>::process: input * weight
+            pbuf[(1 * 32 + lane) * FDN_PS + tt + u] = o[u] * rw;
+          }
+        }
+#pragma unroll 1
+        for (; tt < hn; tt++) {
           const int t = h0 + tt;
           const float d = rb[t];                 // Delay output for this sample
-          rb[t] = din[t] + value;                // Feedback: x.tick(input + value); Delay stores it at ring[i]
+          rb[t] = din[t] + value;
           f0 = f1; f1 = f2; f2 = d;              // Fir<U3> shift register
           const float o = (w0 * f0 + w1 * f1) + w2 * f2;
           float h = o;                           // FrameHadamard<U32>
 #pragma unroll
-          for (int s = 1; s < 32; s <<= 1) {
-            const float y = __shfl_xor_sync(0xffffffffu, h, s);
-            h = (lane & s) ? (y - h) : (h + y);
+          for (int s = 0; s < 5; s++) {
+            const float y = __shfl_xor_sync(0xffffffffu, h, 1 << s);
+            h = y + __uint_as_float(__float_as_uint(h) ^ sgn[s]);
           }
           value = h * hz;
-          pbuf[(0 * 32 + lane) * FDN_PS + tt] = o * lw;   // Panner<U1>::process: input * weight
+          pbuf[(0 * 32 + lane) * FDN_PS + tt] = o * lw;
           pbuf[(1 * 32 + lane) * FDN_PS + tt] = o * rw;
         }
         __syncwarp();

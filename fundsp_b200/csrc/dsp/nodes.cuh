@@ -630,4 +630,30 @@ template <int KIND, int OP, int N, class X> struct WaveKind<Multi<KIND, OP, N, X
 template <int NIN, class X> struct WaveKind<AllNest<NIN, X>> : WaveKind<X> {};
 template <int HAD, class X> struct WaveKind<Feedback<HAD, X>> : WaveKind<X> {};
 
+
+// Rough per-sample instruction cost of a graph type: picks how far the 8-sample group is unrolled (big bodies
+// thrash the instruction cache when only one warp runs per scheduler).
+template <class G> struct Cost { static constexpr int value = 8; };
+template <int K, int N> struct Cost<WaveSynth<K, N>> { static constexpr int value = 100; };
+template <> struct Cost<Sine> { static constexpr int value = 40; };
+template <> struct Cost<Noise> { static constexpr int value = 16; };
+template <> struct Cost<FixedSvf> { static constexpr int value = 20; };
+template <int M> struct Cost<Svf<M>> { static constexpr int value = 60; };
+template <> struct Cost<Biquad> { static constexpr int value = 12; };
+template <> struct Cost<BiquadBank> { static constexpr int value = 96; };
+template <int N> struct Cost<Moog<N>> { static constexpr int value = 200; };
+template <> struct Cost<AdsrLive> { static constexpr int value = 60; };
+template <> struct Cost<Delay> { static constexpr int value = 12; };
+template <int N> struct Cost<Panner<N>> { static constexpr int value = N == 1 ? 2 : 80; };
+template <int K, class X, class Y> struct Cost<Binop<K, X, Y>> { static constexpr int value = Cost<X>::value + Cost<Y>::value + 1; };
+template <class X, class Y> struct Cost<Pipe<X, Y>> { static constexpr int value = Cost<X>::value + Cost<Y>::value; };
+template <class X, class Y> struct Cost<Stack<X, Y>> { static constexpr int value = Cost<X>::value + Cost<Y>::value; };
+template <class X, class Y> struct Cost<Branch<X, Y>> { static constexpr int value = Cost<X>::value + Cost<Y>::value; };
+template <class X, class Y> struct Cost<Bus<X, Y>> { static constexpr int value = Cost<X>::value + Cost<Y>::value + 1; };
+template <int K, class X> struct Cost<Unop<K, X>> { static constexpr int value = Cost<X>::value + 1; };
+template <class X> struct Cost<Thru<X>> { static constexpr int value = Cost<X>::value; };
+template <int KIND, int OP, int N, class X> struct Cost<Multi<KIND, OP, N, X>> { static constexpr int value = N * Cost<X>::value; };
+template <int NIN, class X> struct Cost<AllNest<NIN, X>> { static constexpr int value = Cost<X>::value + 6; };
+template <int HAD, class X> struct Cost<Feedback<HAD, X>> { static constexpr int value = Cost<X>::value + (HAD ? 6 * X::IN : X::IN); };
+
 }  // namespace fdsp
