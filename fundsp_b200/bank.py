@@ -35,6 +35,21 @@ class GpuBank:
         if sample_rate is not None:
             self.set_sample_rate(sample_rate)
 
+    @classmethod
+    def from_net(cls, net, device=0, per_voice=False, mix=True, sample_rate=None):
+        """Bank from a voice-separable `Net` (voice vertices + `Net::bus` adder trees): the mix-down follows the Net's own
+        association order bit for bit and voices get the phase hashes of `Net::ping`."""
+        self = object.__new__(cls)
+        self.L = capi.lib()
+        h = net.lower(GpuBackend())
+        mode = (OUT_VOICES if per_voice else 0) | (OUT_MIX if mix else 0)
+        out = C.c_void_p()
+        check(self.L.fdsp_bank_create_from_net(h, device, mode, C.byref(out)))
+        self.h, self.mode, self.device = out, mode, device
+        if sample_rate is not None:
+            self.set_sample_rate(sample_rate)
+        return self
+
     def __del__(self):
         try:
             if getattr(self, "h", None):

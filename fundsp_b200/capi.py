@@ -37,12 +37,14 @@ _SIG = {
     "fdsp_pan": (P, [F]), "fdsp_panner": (P, []), "fdsp_adsr_live": (P, [F, F, F, F]),
     "fdsp_pipe": (P, [P, P]), "fdsp_stack": (P, [P, P]), "fdsp_branch": (P, [P, P]), "fdsp_bus": (P, [P, P]), "fdsp_thru": (P, [P]),
     "fdsp_binop": (P, [I, P, P]), "fdsp_unop": (P, [I, F, P]), "fdsp_multi": (P, [I, I, I, C.POINTER(P)]), "fdsp_feedback": (P, [P, I]),
+    "fdsp_net_new": (P, [I, I]), "fdsp_net_push": (I, [P, P]), "fdsp_net_connect": (I, [P, I, I, I, I]), "fdsp_net_connect_input": (I, [P, I, I, I]),
+    "fdsp_net_connect_output": (I, [P, I, I, I]), "fdsp_net_pass_through": (I, [P, I, I]), "fdsp_net_size": (I, [P]),
     "fdsp_node_phase": (I, [P, F]), "fdsp_node_seed": (I, [P, U64]), "fdsp_node_set": (I, [P, I, FP, I, U64, C.POINTER(I64), I]),
     "fdsp_node_inputs": (I, [P]), "fdsp_node_outputs": (I, [P]), "fdsp_node_id": (U64, [P]), "fdsp_node_ping": (U64, [P, I, U64]),
     "fdsp_node_leaf_hashes": (I, [P, C.POINTER(U64), I]), "fdsp_node_signature": (I, [P, C.c_char_p, I]),
     "fdsp_node_clone": (P, [P]), "fdsp_node_free": (None, [P]),
     "fdsp_wavetable_count": (I, [I]), "fdsp_wavetable_info": (I, [I, I, FP, C.POINTER(I)]), "fdsp_wavetable_data": (FP, [I, I]),
-    "fdsp_bank_create": (I, [C.POINTER(P), U32, I, U32, C.POINTER(P)]), "fdsp_bank_destroy": (None, [P]), "fdsp_bank_clone": (I, [P, C.POINTER(P)]),
+    "fdsp_bank_create": (I, [C.POINTER(P), U32, I, U32, C.POINTER(P)]), "fdsp_bank_create_from_net": (I, [P, I, U32, C.POINTER(P)]), "fdsp_bank_destroy": (None, [P]), "fdsp_bank_clone": (I, [P, C.POINTER(P)]),
     "fdsp_bank_voices": (U32, [P]), "fdsp_bank_inputs": (I, [P]), "fdsp_bank_voice_outputs": (I, [P]), "fdsp_bank_outputs": (I, [P]),
     "fdsp_bank_set_sample_rate": (I, [P, D]), "fdsp_bank_reset": (I, [P]), "fdsp_bank_allocate": (I, [P, U64]),
     "fdsp_bank_process": (I, [P, U32, FP, FP]), "fdsp_bank_render": (I, [P, U64, FP, FP, FP]),
@@ -132,6 +134,20 @@ class GpuBackend:
     def b_phase(self, p, x):
         check(self.L.fdsp_node_phase(x, p))
         return x
+
+    # Net container (fundsp_b200/net.py)
+    def net_new(self, i, o): return _node(self.L.fdsp_net_new(i, o), "net_new")
+
+    def net_push(self, net, unit):
+        idx = self.L.fdsp_net_push(net, unit)
+        if idx < 0:
+            raise FdspError(ERR_ARG, "net_push failed")
+        return idx
+
+    def net_connect(self, net, s, sp, t, tp): check(self.L.fdsp_net_connect(net, s, sp, t, tp))
+    def net_connect_input(self, net, gi, t, tp): check(self.L.fdsp_net_connect_input(net, gi, t, tp))
+    def net_connect_output(self, net, s, sp, go): check(self.L.fdsp_net_connect_output(net, s, sp, go))
+    def net_pass_through(self, net, gi, go): check(self.L.fdsp_net_pass_through(net, gi, go))
 
     def b_seed(self, s, x):
         check(self.L.fdsp_node_seed(x, s))

@@ -80,6 +80,17 @@ API fdsp_node* fdsp_multi(int kind, int op, int n, fdsp_node* const* nodes) {
 }
 API fdsp_node* fdsp_feedback(fdsp_node* x, int hadamard) { return wrap(mk_feedback(take(x), hadamard), "feedback"); }
 
+API fdsp_node* fdsp_net_new(int inputs, int outputs) { return wrap(mk_net(inputs, outputs), "net_new"); }
+API int fdsp_net_push(fdsp_node* net, fdsp_node* unit) {
+  if (!net || !unit || !is_net(net->n)) { if (unit) fdsp_node_free(unit); return fail(FDSP_ERR_ARG, "net_push: bad arguments") * -1; }
+  return net_push(net->n, take(unit));
+}
+API int fdsp_net_connect(fdsp_node* net, int s, int sp, int d, int dp) { return (net && net_connect(net->n, s, sp, d, dp)) ? FDSP_OK : fail(FDSP_ERR_ARG, "net_connect: bad port"); }
+API int fdsp_net_connect_input(fdsp_node* net, int gi, int d, int dp) { return (net && net_connect_input(net->n, gi, d, dp)) ? FDSP_OK : fail(FDSP_ERR_ARG, "net_connect_input: bad port"); }
+API int fdsp_net_connect_output(fdsp_node* net, int s, int sp, int go) { return (net && net_connect_output(net->n, s, sp, go)) ? FDSP_OK : fail(FDSP_ERR_ARG, "net_connect_output: bad port"); }
+API int fdsp_net_pass_through(fdsp_node* net, int gi, int go) { return (net && net_pass_through(net->n, gi, go)) ? FDSP_OK : fail(FDSP_ERR_ARG, "net_pass_through: bad port"); }
+API int fdsp_net_size(const fdsp_node* net) { return net ? net_size(net->n) : -1; }
+
 API int fdsp_node_phase(fdsp_node* h, float phase) {  // src/combinator.rs:263-268
   if (!h) return fail(FDSP_ERR_ARG, "null node");
   Setting s; s.kind = P_PHASE; s.v[0] = phase; s.address.push_back({1, 1});
@@ -149,6 +160,20 @@ API int fdsp_bank_create(fdsp_node* const* voices, uint32_t nvoices, int device,
   if (!b) { for (HNode* n : v) delete n; return fail(FDSP_ERR_ARG, "out of memory"); }
   std::string e = b->b.init(v, device, out_mode);
   if (!e.empty()) { for (HNode* n : v) delete n; delete b; return status(e); }
+  *out = b;
+  return FDSP_OK;
+}
+API int fdsp_bank_create_from_net(fdsp_node* net, int device, uint32_t out_mode, fdsp_bank** out) {
+  if (!net || !out) return fail(FDSP_ERR_ARG, "bank_create_from_net: bad arguments");
+  std::vector<HNode*> v; std::string tree, err;
+  HNode* n = take(net);
+  const bool ok = net_extract_voices(n, v, tree, err);
+  delete n;
+  if (!ok) { for (HNode* x : v) delete x; return fail(FDSP_ERR_UNSUPPORTED, "no device lowering for this Net: " + err); }
+  fdsp_bank* b = new (std::nothrow) fdsp_bank();
+  b->b.tree_mix = tree == "pairwise" ? 1 : 2; b->b.net_rate = true;
+  std::string e = b->b.init(v, device, out_mode);
+  if (!e.empty()) { for (HNode* x : v) delete x; delete b; return status(e); }
   *out = b;
   return FDSP_OK;
 }

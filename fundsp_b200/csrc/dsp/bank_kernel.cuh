@@ -164,4 +164,44 @@ static __global__ void mix_reduce_kernel(const float* partial, uint32_t nparts, 
   *p = accumulate ? *p + s : s;
 }
 
+
+// Mix-down of per-voice rows in a FIXED association order, for parity with a reference `Net` whose outputs are adder
+// trees (src/net.rs:1693-1767 Net::bus adds one Binop<Add,Pass,Pass> vertex per output per call):
+//   pairwise = level-wise adjacent pairing with the odd element carried up (the balanced `Net::bus` tree),
+//   chain    = left fold in voice order (a left-leaning chain of `&`, or the index-order sum of a Sequencer).
+// One thread per (channel, sample); rows are read coalesced along time; the association is a binary-carry stack.
+static __global__ void tree_mix_kernel(const float* __restrict__ rows, uint32_t V, uint32_t outs, uint32_t row_stride, uint32_t row_offset, uint32_t n,
+                                       float* mix, uint32_t mix_stride, uint32_t mix_offset, int pairwise) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= outs * n) return;
+  const uint32_t ch = e / n, t = e - ch * n;
+  const float* p = rows + (size_t)ch * row_stride + row_offset + t;
+  const size_t vstep = (size_t)outs * row_stride;
+  float x;
+  if (pairwise) {
+    float st[32];
+    for (uint32_t v0 = 0; v0 < V; v0 += 8) {
+      float b[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) b[u] = (v0 + u < V) ? __ldg(p + (size_t)(v0 + u) * vstep) : 0.0f;
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        if (v0 + u < V) {
+          float y = b[u]; uint32_t q = v0 + u; int lvl = 0;
+          while (q & 1u) { y = st[lvl] + y; q >>= 1; lvl++; }
+          st[lvl] = y;
+        }
+      }
+    }
+    int lvl = 0; uint32_t q = V;
+    while (!(q & 1u)) { q >>= 1; lvl++; }
+    x = st[lvl]; q >>= 1; lvl++;
+    for (; q; q >>= 1, lvl++) if (q & 1u) x = st[lvl] + x;
+  } else {
+    x = __ldg(p);
+    for (uint32_t v = 1; v < V; v++) x += __ldg(p + (size_t)v * vstep);
+  }
+  mix[(size_t)ch * mix_stride + mix_offset + t] = x;
+}
+
 }  // namespace fdsp

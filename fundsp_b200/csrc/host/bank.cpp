@@ -34,7 +34,7 @@ Bank::~Bank() {
     cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows);
   }
   for (float* p : d_wtdata) cudaFree(p);
-  cudaFree(d_wt); cudaFree(d_in); cudaFree(d_out); cudaFree(d_mix);
+  cudaFree(d_wt); cudaFree(d_in); cudaFree(d_out); cudaFree(d_mix); cudaFree(d_rows);
   if (h_in) cudaFreeHost(h_in);
   if (h_out) cudaFreeHost(h_out);
   if (ev0) cudaEventDestroy(ev0);
@@ -187,7 +187,8 @@ std::string Bank::lower_and_upload(bool upload_state) {
 
 std::string Bank::set_sample_rate(double s) {  // AudioUnit::set_sample_rate
   sr = s;
-  for (auto& n : nodes) n->set_sample_rate(s);
+  const double unit_rate = net_rate ? (double)(float)s : s;
+  for (auto& n : nodes) n->set_sample_rate(unit_rate);
   // Parameters always follow the new rate. State is re-initialised only while nothing has been rendered
   // (or when delay lengths change, which resets the lines like src/delay.rs:105-113).
   return lower_and_upload(!dirty);
@@ -212,12 +213,24 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
   const bool want_v = (out_mode & 1u) && out_dev, want_m = (out_mode & 2u) && mix_dev;
   if (!want_v && !want_m) return "no output buffer matches the bank's out_mode";
   if (n == 0) return "";
-  const int mode = (want_v ? 1 : 0) | (want_m ? 2 : 0);
   if (in_stride > 0xffffffffull || out_stride > 0xffffffffull || mix_stride > 0xffffffffull) return "stride too large";
   CU(cudaEventRecord(ev0, stream));
-  for (uint64_t t0 = 0; t0 < n; t0 += TIME_CHUNK) {
-    const uint32_t len = (uint32_t)std::min<uint64_t>(TIME_CHUNK, n - t0);
+  // Net-ordered mix: the voice kernels materialise per-voice rows (user buffer, or an internal one) and tree_mix_kernel adds
+  // them in the Net's association order; the CTA-level partial mix is bypassed.
+  const bool tree = tree_mix != 0 && want_m;
+  const uint32_t CH = tree ? 4096u : TIME_CHUNK;
+  if (tree && !want_v) {
+    const size_t need = (size_t)V() * nout * CH;
+    if (rows_cap < need) { std::string e = dev_alloc(&d_rows, need); if (!e.empty()) return e; rows_cap = need; }
+  }
+  const bool save_want_v = want_v, save_want_m = want_m;
+  for (uint64_t t0 = 0; t0 < n; t0 += CH) {
+    const uint32_t len = (uint32_t)std::min<uint64_t>(CH, n - t0);
     bool first = true;
+    bool want_v = save_want_v, want_m = save_want_m;
+    float* out_dev_c = out_dev; uint64_t out_stride_c = out_stride; uint64_t out_t0 = t0;
+    if (tree) { want_m = false; if (!save_want_v) { want_v = true; out_dev_c = d_rows; out_stride_c = CH; out_t0 = 0; } }
+    const int mode = (want_v ? 1 : 0) | (want_m ? 2 : 0);
     for (auto& c : classes) {
       const uint32_t V = c.V();
       int fdn_warps = 1;
@@ -229,13 +242,14 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
       }
       BankArgs a;
       a.params = c.d_params; a.state = c.d_state; a.uniform = c.d_uniform; a.dline = c.d_dline; a.wt = d_wt;
-      a.in = in_dev; a.out = want_v ? out_dev : nullptr; a.partial = want_m ? c.d_partial : nullptr;
+      a.in = in_dev; a.out = want_v ? out_dev_c : nullptr; a.partial = want_m ? c.d_partial : nullptr;
       a.V = V; a.n = len;
       a.in_stride = (uint32_t)in_stride; a.in_offset = (uint32_t)t0;
-      a.out_stride = (uint32_t)out_stride; a.out_offset = (uint32_t)t0;
+      a.out_stride = (uint32_t)out_stride_c; a.out_offset = (uint32_t)out_t0;
       a.row_map = c.d_rowmap;
       a.sr = (float)sr; a.sd64 = (float)(1.0 / sr); a.sd32 = 1.0f / (float)sr;
       if (t0 > 0xffffffffull - TIME_CHUNK) return "render too long for one call";
+      if (c.fdn && len > TIME_CHUNK) return "internal: chunk";
       // long launches of wavetable programs stage the table set in shared memory (TMA bulk copy, ~160 KB per CTA);
       // short ones (process()-sized) read the tables through L1/L2 instead
       size_t table_bytes = 0;
@@ -253,7 +267,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
         } else {    // reverb applied straight to the bank's stereo input
           f.dry = in_dev; f.dry_voice_stride = 0; f.dry_ch_stride = (uint32_t)in_stride; f.dry_offset = (uint32_t)t0;
         }
-        f.out = want_v ? out_dev : nullptr; f.row_map = c.d_rowmap; f.out_stride = (uint32_t)out_stride; f.out_offset = (uint32_t)t0;
+        f.out = want_v ? out_dev_c : nullptr; f.row_map = c.d_rowmap; f.out_stride = (uint32_t)out_stride_c; f.out_offset = (uint32_t)out_t0;
         f.partial = want_m ? c.d_partial : nullptr;
         f.ring = c.d_ring; f.ring_voice_stride = c.ring_floats; f.V = V; f.n = len;
         CU(launch_fdn(f, fdn_warps, stream));
@@ -266,6 +280,10 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
         launches++;
       }
       first = false;
+    }
+    if (tree) {
+      CU(launch_tree_mix(out_dev_c, V(), (uint32_t)nout, (uint32_t)out_stride_c, (uint32_t)out_t0, len, mix_dev, (uint32_t)mix_stride, (uint32_t)t0, tree_mix == 1 ? 1 : 0, stream));
+      launches++;
     }
   }
   CU(cudaEventRecord(ev1, stream));
@@ -337,7 +355,7 @@ std::string Bank::process(uint32_t size, const float* in, float* out) {  // Audi
 std::string Bank::clone_into(Bank& dst) const {
   std::vector<HNode*> copies;
   for (auto& n : nodes) copies.push_back(n->clone());
-  dst.sr = sr;
+  dst.sr = sr; dst.tree_mix = tree_mix; dst.net_rate = net_rate;
   std::string e = dst.init(copies, device, out_mode);
   if (!e.empty()) return e;
   for (auto& n : dst.nodes) n->set_sample_rate(sr);

@@ -32,6 +32,9 @@ struct VoiceClass {
 struct Bank {
   int device = 0; uint32_t out_mode = 0; int nin = 0, nout = 0;
   double sr = DEFAULT_SR; bool dirty = false;
+  // voices extracted from a Net: mix in the Net's own association order (0 none, 1 pairwise tree, 2 left fold) and hand the
+  // units the Net's f32-rounded sample rate (src/net.rs:132,1323-1328)
+  int tree_mix = 0; bool net_rate = false; float* d_rows = nullptr; size_t rows_cap = 0;
   std::vector<std::unique_ptr<HNode>> nodes;
   std::vector<VoiceClass> classes;
   cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;

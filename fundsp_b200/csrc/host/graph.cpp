@@ -355,6 +355,120 @@ struct Multi : HNode {  // MultiBus 28, MultiStack 30, Reduce 31, MultiBranch 33
   HCLONE(Multi)
 };
 
+// ---------------------------------------------------------------- Net (src/net.rs, src/vertex.rs)
+struct NetPort { int type; int node; int port; };  // 0 Zero, 1 Global(port), 2 Local(node, port)
+struct HNet : HNode {
+  int nin, nout; float sr = (float)DEFAULT_SR;
+  struct Vx { Kid unit; std::vector<NetPort> src; };
+  std::vector<Vx> vx; std::vector<NetPort> out;
+  HNet(int i, int o) : nin(i), nout(o) { out.assign(o, NetPort{0, 0, 0}); }
+  int inputs() const override { return nin; } int outputs() const override { return nout; }
+  uint64_t id() const override { return 63; }
+  void reset() override { for (auto& v : vx) v.unit->reset(); }
+  void set_sample_rate(double s) override {  // src/net.rs:1322-1339: the rate is stored as f32
+    float f = (float)s;
+    if (sr != f) { sr = f; for (auto& v : vx) v.unit->set_sample_rate((double)f); }
+  }
+  void set(const Setting& s) override { Address d = s.direction(); if (d.type == 2 && d.value < vx.size()) vx[d.value].unit->set(s.peel()); }
+  AttoHash ping(bool probe, AttoHash h) override { h = h.hash(id()); for (auto& v : vx) h = v.unit->ping(probe, h); return h; }
+  void determine_order_ping() { AttoHash h = ping(true, AttoHash(id())); ping(false, h); }
+  void sig(std::string& o) const override { o += "Unsupported"; }
+  void lower(Lowering& l) const override { l.fail("a Net used as a node inside a voice has no device lowering yet (use fdsp_bank_create_from_net for voice-separable nets)"); }
+  HCLONE(HNet)
+};
+
+}  // namespace
+
+HNode* mk_net(int inputs, int outputs) { return (inputs < 0 || outputs < 0) ? nullptr : new HNet(inputs, outputs); }
+bool is_net(const HNode* n) { return dynamic_cast<const HNet*>(n) != nullptr; }
+int net_push(HNode* net, HNode* unit) {
+  HNet* n = dynamic_cast<HNet*>(net);
+  if (!n || !unit) { delete unit; return -1; }
+  unit->set_sample_rate((double)n->sr);
+  HNet::Vx v; v.unit = Kid(unit); v.src.assign(unit->inputs(), NetPort{0, 0, 0});
+  n->vx.push_back(std::move(v));
+  return (int)n->vx.size() - 1;
+}
+bool net_connect(HNode* net, int s, int sp, int d, int dp) {
+  HNet* n = dynamic_cast<HNet*>(net);
+  if (!n || s == d || s < 0 || d < 0 || s >= (int)n->vx.size() || d >= (int)n->vx.size() || sp < 0 || sp >= n->vx[s].unit->outputs() || dp < 0 || dp >= n->vx[d].unit->inputs()) return false;
+  n->vx[d].src[dp] = NetPort{2, s, sp};
+  return true;
+}
+bool net_connect_input(HNode* net, int gi, int d, int dp) {
+  HNet* n = dynamic_cast<HNet*>(net);
+  if (!n || gi < 0 || gi >= n->nin || d < 0 || d >= (int)n->vx.size() || dp < 0 || dp >= n->vx[d].unit->inputs()) return false;
+  n->vx[d].src[dp] = NetPort{1, 0, gi};
+  return true;
+}
+bool net_connect_output(HNode* net, int s, int sp, int go) {
+  HNet* n = dynamic_cast<HNet*>(net);
+  if (!n || go < 0 || go >= n->nout || s < 0 || s >= (int)n->vx.size() || sp < 0 || sp >= n->vx[s].unit->outputs()) return false;
+  n->out[go] = NetPort{2, s, sp};
+  return true;
+}
+bool net_pass_through(HNode* net, int gi, int go) {
+  HNet* n = dynamic_cast<HNet*>(net);
+  if (!n || gi < 0 || gi >= n->nin || go < 0 || go >= n->nout) return false;
+  n->out[go] = NetPort{1, 0, gi};
+  return true;
+}
+int net_size(const HNode* net) { const HNet* n = dynamic_cast<const HNet*>(net); return n ? (int)n->vx.size() : -1; }
+
+bool net_extract_voices(HNode* net, std::vector<HNode*>& voices, std::string& tree, std::string& err) {
+  HNet* n = dynamic_cast<HNet*>(net);
+  if (!n) { err = "not a Net"; return false; }
+  if (n->nout < 1) { err = "the Net has no outputs"; return false; }
+  n->determine_order_ping();
+  const int N = (int)n->vx.size();
+  std::vector<char> adder(N, 0);
+  for (int i = 0; i < N; i++) { std::string s; n->vx[i].unit->sig(s); adder[i] = (s == "Binop<0,MultiPass<1>,MultiPass<1>>"); }
+  // per output channel: expand the adder tree iteratively into (leaf sequence, shape string)
+  std::vector<int> leaves0; std::string shape0;
+  for (int c = 0; c < n->nout; c++) {
+    std::vector<int> leaves; std::string shape;
+    struct Fr { NetPort p; int stage; };
+    std::vector<Fr> st; st.push_back({n->out[c], 0});
+    while (!st.empty()) {
+      Fr f = st.back(); st.pop_back();
+      if (f.stage == 1) { shape.push_back(')'); continue; }
+      if (f.p.type != 2) { err = "a Net output is not driven by a vertex (zero/global pass-through outputs are not voice-separable)"; return false; }
+      if (adder[f.p.node]) {
+        shape.push_back('(');
+        st.push_back({NetPort{0, 0, 0}, 1});
+        st.push_back({n->vx[f.p.node].src[1], 0});
+        st.push_back({n->vx[f.p.node].src[0], 0});
+      } else {
+        if (f.p.port != c) { err = "voice output ports must map to the same global output channel"; return false; }
+        shape.push_back('v');
+        leaves.push_back(f.p.node);
+      }
+    }
+    if (c == 0) { leaves0 = leaves; shape0 = shape; }
+    else if (leaves != leaves0 || shape != shape0) { err = "the output channels of the Net use different mix trees"; return false; }
+  }
+  std::vector<char> used(N, 0);
+  for (int v : leaves0) {
+    if (used[v]) { err = "a voice vertex feeds the mix more than once"; return false; }
+    used[v] = 1;
+    HNode* u = n->vx[v].unit.p.get();
+    if (u->outputs() != n->nout) { err = "every voice vertex must have as many outputs as the Net"; return false; }
+    for (int k = 0; k < u->inputs(); k++) if (!(n->vx[v].src[k].type == 1 && n->vx[v].src[k].port == k)) { err = "voice inputs must be the Net's global inputs in order"; return false; }
+    if (u->inputs() != 0 && u->inputs() != n->nin) { err = "voice vertices must take all global inputs or none"; return false; }
+  }
+  for (int i = 0; i < N; i++) if (!used[i] && !adder[i]) { err = "the Net has vertices that are neither voices nor mix adders"; return false; }
+  // classify the shape: canonical level-wise adjacent pairing ("pairwise") or left fold ("chain")
+  const size_t V = leaves0.size();
+  auto pairwise = [&]() { std::vector<std::string> cur(V, "v"); while (cur.size() > 1) { std::vector<std::string> nx; for (size_t i = 0; i + 1 < cur.size(); i += 2) nx.push_back("(" + cur[i] + cur[i + 1] + ")"); if (cur.size() & 1) nx.push_back(cur.back()); cur.swap(nx); } return cur.empty() ? std::string() : cur[0]; };
+  auto chain = [&]() { std::string s = "v"; for (size_t i = 1; i < V; i++) s = "(" + s + "v)"; return s; };
+  if (V == 1 || shape0 == pairwise()) tree = "pairwise";
+  else if (shape0 == chain()) tree = "chain";
+  else { err = "the Net's mix tree is neither the level-wise pairwise tree nor a left fold"; return false; }
+  for (int v : leaves0) voices.push_back(n->vx[v].unit->clone());
+  return true;
+}
+
+namespace {
 }  // namespace
 
 // ---------------------------------------------------------------- builders

@@ -112,6 +112,21 @@ HNode* mk_unop(int kind, float scalar, HNode* x);
 HNode* mk_multi(int kind, int op, int n, HNode** nodes);
 HNode* mk_feedback(HNode* x, int hadamard);
 
+// ---- Net (src/net.rs:118-146): dynamic DAG of units. Vertex ids are indices (this mirror never removes vertices).
+HNode* mk_net(int inputs, int outputs);
+bool is_net(const HNode* n);
+int net_push(HNode* net, HNode* unit);                                 // Net::push (src/net.rs:204-213): sets the unit's sample rate
+bool net_connect(HNode* net, int src, int src_port, int dst, int dst_port);   // Net::connect
+bool net_connect_input(HNode* net, int global_in, int dst, int dst_port);     // Net::connect_input
+bool net_connect_output(HNode* net, int src, int src_port, int global_out);   // Net::connect_output
+bool net_pass_through(HNode* net, int global_in, int global_out);             // Net::pass_through
+int net_size(const HNode* net);
+// A voice-separable Net: every global output is an adder tree (Binop<Add,Pass,Pass> vertices, as built by Net::bus /
+// `&`) over the same sequence of voice vertices. Extracts the voices in leaf order; `tree` receives the canonical
+// description ("pairwise" when the tree is the level-wise adjacent pairing, "chain" for a left fold). Pings the net first
+// (Net::determine_order, src/net.rs:834-852) so the voices carry the hashes the reference would give them.
+bool net_extract_voices(HNode* net, std::vector<HNode*>& voices, std::string& tree, std::string& err);
+
 // ---- wavetables (src/wavetable.rs:40-123, 493-623): built once per waveform kind on the host
 struct WaveTableHost { std::vector<float> pitch; std::vector<int> off, len; std::vector<float> data; };
 const WaveTableHost& global_wavetable(int kind);

@@ -39,6 +39,8 @@ const KernelEntry* registry_at(int i);
 const char* registry_key(int i);
 cudaError_t launch_mix_reduce(const float* partial, uint32_t nparts, uint32_t outs, uint32_t n, float* mix, uint32_t mix_stride,
                               uint32_t mix_offset, int accumulate, cudaStream_t stream);
+cudaError_t launch_tree_mix(const float* rows, uint32_t V, uint32_t outs, uint32_t row_stride, uint32_t row_offset, uint32_t n, float* mix,
+                            uint32_t mix_stride, uint32_t mix_offset, int pairwise, cudaStream_t stream);
 // warp-per-voice reverb_stereo kernel (inst/inst_fdn.cu)
 cudaError_t launch_fdn(const FdnArgs& a, int warps, cudaStream_t stream);
 int fdn_max_warps();

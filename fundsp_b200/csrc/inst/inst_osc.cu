@@ -14,4 +14,11 @@ cudaError_t launch_mix_reduce(const float* partial, uint32_t nparts, uint32_t ou
   mix_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(partial, nparts, outs, n, mix, mix_stride, mix_offset, accumulate);
   return cudaGetLastError();
 }
+
+cudaError_t launch_tree_mix(const float* rows, uint32_t V, uint32_t outs, uint32_t row_stride, uint32_t row_offset, uint32_t n, float* mix,
+                            uint32_t mix_stride, uint32_t mix_offset, int pairwise, cudaStream_t st) {
+  const unsigned total = outs * n;
+  tree_mix_kernel<<<(total + 127) / 128, 128, 0, st>>>(rows, V, outs, row_stride, row_offset, n, mix, mix_stride, mix_offset, pairwise);
+  return cudaGetLastError();
+}
 }}

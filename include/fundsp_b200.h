@@ -79,6 +79,14 @@ fdsp_node* fdsp_binop(int op, fdsp_node* x, fdsp_node* y);     /* op 0 x+y, 1 x-
 fdsp_node* fdsp_unop(int kind, float scalar, fdsp_node* x);    /* kind 0 -x, 1 x+s, 2 s-x, 3 x*s   Unop ID 4 */
 fdsp_node* fdsp_multi(int kind, int op, int n, fdsp_node* const* nodes); /* kind 28 MultiBus, 30 MultiStack, 31 Reduce(op), 33 MultiBranch, 32 Chain */
 fdsp_node* fdsp_feedback(fdsp_node* x, int hadamard);          /* Feedback<N,X,FrameId|FrameHadamard> ID 11 */
+/* Net (src/net.rs:118-146, 204-213, 472-640): dynamic DAG of units; vertex ids are indices in push order */
+fdsp_node* fdsp_net_new(int inputs, int outputs);                 /* Net::new           ID 63 */
+int fdsp_net_push(fdsp_node* net, fdsp_node* unit);               /* Net::push -> vertex index (consumes unit), < 0 on error */
+int fdsp_net_connect(fdsp_node* net, int source, int source_port, int target, int target_port);   /* Net::connect */
+int fdsp_net_connect_input(fdsp_node* net, int global_input, int target, int target_port);        /* Net::connect_input */
+int fdsp_net_connect_output(fdsp_node* net, int source, int source_port, int global_output);      /* Net::connect_output */
+int fdsp_net_pass_through(fdsp_node* net, int global_input, int global_output);                   /* Net::pass_through */
+int fdsp_net_size(const fdsp_node* net);
 /* An<X> builder methods (src/combinator.rs:263-276) and generic Setting (src/setting.rs:52-211) */
 int fdsp_node_phase(fdsp_node* n, float phase);
 int fdsp_node_seed(fdsp_node* n, uint64_t seed);
@@ -100,6 +108,9 @@ const float* fdsp_wavetable_data(int table, int index);
 /* Takes ownership of `voices`. Voices may belong to several structural classes (dynamic Net of mixed
  * graphs): each class becomes one fused kernel. All voices must agree on inputs() and outputs(). */
 int fdsp_bank_create(fdsp_node* const* voices, uint32_t nvoices, int device, uint32_t out_mode, fdsp_bank** out);
+/* A voice-separable Net (voice vertices + the adder trees Net::bus builds) becomes a bank whose mix-down follows the
+ * Net's own association order bit for bit; voices get the hashes of Net::ping (src/net.rs:1383-1389). Consumes `net`. */
+int fdsp_bank_create_from_net(fdsp_node* net, int device, uint32_t out_mode, fdsp_bank** out);
 void fdsp_bank_destroy(fdsp_bank* b);
 int fdsp_bank_clone(const fdsp_bank* b, fdsp_bank** out);                   /* deep copy incl. device state (dyn_clone) */
 uint32_t fdsp_bank_voices(const fdsp_bank* b);

@@ -118,6 +118,13 @@ class OracleBackend:
     def b_feedback(self, had, x): return self.L.fo_feedback(x, had)
     def b_phase(self, p, x): self.L.fo_phase(x, p); return x
     def b_seed(self, s, x): self.L.fo_seed(x, s); return x
+    # Net container (fundsp_b200/net.py)
+    def net_new(self, i, o): return self.L.fo_net_new(i, o)
+    def net_push(self, net, unit): return self.L.fo_net_push(net, unit)
+    def net_connect(self, net, s, sp, t, tp): self.L.fo_net_connect(net, s, sp, t, tp)
+    def net_connect_input(self, net, gi, t, tp): self.L.fo_net_connect_input(net, gi, t, tp)
+    def net_connect_output(self, net, s, sp, go): self.L.fo_net_connect_output(net, s, sp, go)
+    def net_pass_through(self, net, gi, go): self.L.fo_net_pass_through(net, gi, go)
 
     def b_set(self, kind, values, seed, address, x):
         addr = [v for pair in address for v in pair]

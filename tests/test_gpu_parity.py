@@ -248,3 +248,39 @@ def test_fdn_kernel_equals_generic_thread_per_voice_form():
         subprocess.check_call([sys.executable, "-c", code, path], env={**os.environ, **env}, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
         outs.append(np.load(path))
     assert np.array_equal(outs[0], outs[1]) and np.abs(outs[0]).max() > 0.01
+
+
+# ---------------------------------------------------------------- dynamic Net (config 5): voices + Net::bus adder trees
+@pytest.mark.parametrize("V,n", [(64, 1500), (37, 700 + 13), (1, 200)])
+def test_net_of_voices_mix_is_bit_exact(V, n):
+    """The reference form of config 5: each voice `Net::wrap`ped and bussed as a balanced tree (one Pass+Pass adder per output
+    per `&`). The bank built from that Net must reproduce Net::ping's hashes and the tree's association order exactly."""
+    from fundsp_b200.bank import GpuBank
+    from fundsp_b200.net import voice_net
+    from oracle import OracleBackend, OracleUnit
+    olib().fo_set_denormal_emulation(0)
+    net = voice_net([workloads.net_voice(i) for i in range(V)])
+    ref = OracleUnit(net.lower(OracleBackend())).render(SR, n / SR)
+    b = GpuBank.from_net(voice_net([workloads.net_voice(i) for i in range(V)]), per_voice=True, mix=True, sample_rate=SR)
+    rows, mix = b.render_samples(n)
+    assert mix.shape == ref.shape == (2, n) and np.abs(ref).max() > 0.05
+    assert np.array_equal(mix, ref), (int((mix != ref).sum()), float(np.abs(mix - ref).max()))
+    assert len(b.classes()) == min(V, 4) and rows.shape == (V, 2, n)
+    # mix-only bank (internal row buffer) gives the same bits
+    b2 = GpuBank.from_net(voice_net([workloads.net_voice(i) for i in range(V)]), per_voice=False, mix=True, sample_rate=SR)
+    _, mix2 = b2.render_samples(n)
+    assert np.array_equal(mix2, ref)
+
+
+def test_net_left_fold_chain_mix_is_bit_exact():
+    from fundsp_b200.bank import GpuBank
+    from fundsp_b200.net import Net
+    from oracle import OracleBackend, OracleUnit
+    def build():
+        net = Net.wrap(workloads.net_voice(0))
+        for i in range(1, 9):
+            net = net & Net.wrap(workloads.net_voice(i))
+        return net
+    ref = OracleUnit(build().lower(OracleBackend())).render(SR, 0.02)
+    _, mix = GpuBank.from_net(build(), sample_rate=SR).render_samples(960)
+    assert np.array_equal(mix, ref)
