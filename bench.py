@@ -144,7 +144,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from datetime import timedelta
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=timedelta(seconds=180))
     V = a.voices or HEADLINE[a.workload]
     n = int(round(a.seconds * SR))
     gate = gate_for(a.workload, n)
@@ -205,12 +206,19 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    # >= W warm-up steps and about 1 s under load for the clock samples. The number of extra steps is decided by rank 0 and
+    # broadcast: every rank must issue the same number of collectives.
     t_w = time.perf_counter()
-    w = 0
-    while w < max(3, a.warmup) or (time.perf_counter() - t_w < 1.0 and w < 2000):  # >= W warm-up steps, >= 1 s under load for the clock samples
+    for _ in range(max(3, a.warmup)):
         device_step()
         e2e_step()
-        w += 1
+    per = (time.perf_counter() - t_w) / max(3, a.warmup)
+    extra = torch.tensor([min(500, max(0, int(1.0 / max(per, 1e-4))))], device="cuda", dtype=torch.int64)
+    if dist is not None:
+        dist.broadcast(extra, src=0)
+    for _ in range(int(extra.item())):
+        device_step()
+        e2e_step()
     launches0 = bank.launch_count()
     ms_step, ms_kernel, wall = timed(device_step, a.steps)
     launches = bank.launch_count() - launches0
