@@ -233,8 +233,14 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
     const int mode = (want_v ? 1 : 0) | (want_m ? 2 : 0);
     for (auto& c : classes) {
       const uint32_t V = c.V();
-      int fdn_warps = 1;
-      if (c.fdn) { fdn_warps = (int)((V + 147) / 148); if (fdn_warps > fdn_max_warps()) fdn_warps = fdn_max_warps(); if (fdn_warps < 1) fdn_warps = 1; }
+      int fdn_warps = 1, fdn_k = 0;   // fdn_warps: voices per CTA; fdn_k: warps per voice (0 = single-warp kernel)
+      if (c.fdn) {
+        const char* ks = getenv("FDSP_FDN_K");
+        fdn_k = ks ? atoi(ks) : 2;
+        if (fdn_k != 2 && fdn_k != 4) fdn_k = 0;
+        const int cap = fdn_k ? fdn_ts_max_vpb(fdn_k) : fdn_max_warps();
+        fdn_warps = (int)((V + 147) / 148); if (fdn_warps > cap) fdn_warps = cap; if (fdn_warps < 1) fdn_warps = 1;
+      }
       const uint32_t grid = c.fdn ? (V + (uint32_t)fdn_warps - 1) / (uint32_t)fdn_warps : (V + (uint32_t)c.k->threads - 1) / (uint32_t)c.k->threads;
       if (want_m) {
         const size_t need = (size_t)grid * nout * len;
@@ -270,7 +276,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
         f.out = want_v ? out_dev_c : nullptr; f.row_map = c.d_rowmap; f.out_stride = (uint32_t)out_stride_c; f.out_offset = (uint32_t)out_t0;
         f.partial = want_m ? c.d_partial : nullptr;
         f.ring = c.d_ring; f.ring_voice_stride = c.ring_floats; f.V = V; f.n = len;
-        CU(launch_fdn(f, fdn_warps, stream));
+        if (fdn_k) CU(launch_fdn_ts(f, fdn_k, fdn_warps, stream)); else CU(launch_fdn(f, fdn_warps, stream));
       } else {
         CU(c.k->launch(a, mode, table_bytes, stream));
       }

@@ -44,6 +44,8 @@ cudaError_t launch_tree_mix(const float* rows, uint32_t V, uint32_t outs, uint32
 // warp-per-voice reverb_stereo kernel (inst/inst_fdn.cu)
 cudaError_t launch_fdn(const FdnArgs& a, int warps, cudaStream_t stream);
 int fdn_max_warps();
+cudaError_t launch_fdn_ts(const FdnArgs& a, int K, int voices_per_cta, cudaStream_t stream);  // time-split form (K = 2 or 4 warps per voice)
+int fdn_ts_max_vpb(int K);
 // NVRTC path (jit.cpp)
 std::shared_ptr<const Program> jit_program(const std::string& sig, int device, std::string& err);
 int jit_compiled_count();
