@@ -1,0 +1,156 @@
+// fundsp_b200.hpp — header-only C++ host mirror of the reference's graph notation over the C ABI (fundsp_b200.h).
+//
+// The reference is Rust; where no Rust toolchain exists the host side above the C ABI is C++. This header gives C++
+// callers the same surface the reference gives Rust callers for this path:
+//   * `An` wraps a graph node like `An<X>` (src/combinator.rs:178) and overloads the same operators with the same
+//     meaning and precedence: `>>` Pipe, `|` Stack, `&` Bus, `^` Branch, `+ - *` Binop (or Unop with a float), unary `-`,
+//     and `!` Thru (src/combinator.rs:289-488); `.phase()` / `.seed()` as in src/combinator.rs:263-276.
+//   * the opcode constructors keep the prelude's names and argument order (src/prelude.rs): sine_hz, saw_hz, white,
+//     lowpass_hz, moog_hz, delay, pan, reverb-style building blocks, ...
+//   * `Bank` is the AudioUnit: process() == AudioUnit::process (src/audiounit.rs:45), render() == the Wave::render loop.
+// Nodes are move-only like Rust values: combining consumes the operands (use clone() to reuse a sub-graph).
+#pragma once
+#include <cstdint>
+#include <initializer_list>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "fundsp_b200.h"
+
+namespace fundsp_b200 {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+inline void check(int rc) { if (rc != FDSP_OK) throw Error(rc, fdsp_last_error()); }
+
+class An {
+  fdsp_node* h_;
+  static fdsp_node* need(fdsp_node* h) { if (!h) throw Error(FDSP_ERR_ARITY, fdsp_last_error()); return h; }
+
+ public:
+  explicit An(fdsp_node* h) : h_(need(h)) {}
+  An(An&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+  An& operator=(An&& o) noexcept { if (this != &o) { fdsp_node_free(h_); h_ = o.h_; o.h_ = nullptr; } return *this; }
+  An(const An&) = delete;
+  An& operator=(const An&) = delete;
+  ~An() { fdsp_node_free(h_); }
+  An clone() const { return An(fdsp_node_clone(h_)); }
+  fdsp_node* release() { fdsp_node* h = h_; h_ = nullptr; return h; }
+  const fdsp_node* get() const { return h_; }
+  int inputs() const { return fdsp_node_inputs(h_); }
+  int outputs() const { return fdsp_node_outputs(h_); }
+  An phase(float p) && { check(fdsp_node_phase(h_, p)); return std::move(*this); }
+  An seed(uint64_t s) && { check(fdsp_node_seed(h_, s)); return std::move(*this); }
+  std::string signature() const { std::string s(1 << 16, '\0'); int n = fdsp_node_signature(h_, &s[0], (int)s.size()); s.resize(n > 0 ? n : 0); return s; }
+};
+
+// ---- operators (src/combinator.rs:289-488)
+inline An operator>>(An x, An y) { return An(fdsp_pipe(x.release(), y.release())); }
+inline An operator|(An x, An y) { return An(fdsp_stack(x.release(), y.release())); }
+inline An operator&(An x, An y) { return An(fdsp_bus(x.release(), y.release())); }
+inline An operator^(An x, An y) { return An(fdsp_branch(x.release(), y.release())); }
+inline An operator!(An x) { return An(fdsp_thru(x.release())); }
+inline An operator-(An x) { return An(fdsp_unop(0, 0.0f, x.release())); }
+inline An operator+(An x, An y) { return An(fdsp_binop(0, x.release(), y.release())); }
+inline An operator-(An x, An y) { return An(fdsp_binop(1, x.release(), y.release())); }
+inline An operator*(An x, An y) { return An(fdsp_binop(2, x.release(), y.release())); }
+inline An operator+(An x, float y) { return An(fdsp_unop(1, y, x.release())); }
+inline An operator+(float y, An x) { return An(fdsp_unop(1, y, x.release())); }
+inline An operator-(An x, float y) { return An(fdsp_unop(1, -y, x.release())); }
+inline An operator-(float y, An x) { return An(fdsp_unop(2, y, x.release())); }
+inline An operator*(An x, float y) { return An(fdsp_unop(3, y, x.release())); }
+inline An operator*(float y, An x) { return An(fdsp_unop(3, y, x.release())); }
+
+// ---- opcodes (src/prelude.rs; F = f32)
+inline An constant(std::initializer_list<float> v) { return An(fdsp_constant((int)v.size(), v.begin())); }
+inline An dc(float x) { return constant({x}); }
+inline An dc(float x, float y) { return constant({x, y}); }
+inline An dc(float x, float y, float z) { return constant({x, y, z}); }
+inline An zero() { return dc(0.0f); }
+inline An pass() { return An(fdsp_pass()); }
+inline An multipass(int n) { return An(fdsp_multipass(n)); }
+inline An sink() { return An(fdsp_sink(1)); }
+inline An multisink(int n) { return An(fdsp_sink(n)); }
+inline An split(int n) { return An(fdsp_split(n)); }
+inline An multisplit(int m, int n) { return An(fdsp_multisplit(m, n)); }
+inline An join(int n) { return An(fdsp_join(n)); }
+inline An multijoin(int m, int n) { return An(fdsp_multijoin(m, n)); }
+inline An reverse(int n) { return An(fdsp_reverse(n)); }
+inline An sine() { return An(fdsp_sine()); }
+inline An sine_hz(float f) { return dc(f) >> sine(); }
+inline An saw() { return An(fdsp_wavesynth(0, 1)); }
+inline An square() { return An(fdsp_wavesynth(1, 1)); }
+inline An triangle() { return An(fdsp_wavesynth(2, 1)); }
+inline An organ() { return An(fdsp_wavesynth(3, 1)); }
+inline An soft_saw() { return An(fdsp_wavesynth(4, 1)); }
+inline An hammond() { return An(fdsp_wavesynth(5, 1)); }
+inline An saw_hz(float f) { return dc(f) >> saw(); }
+inline An square_hz(float f) { return dc(f) >> square(); }
+inline An triangle_hz(float f) { return dc(f) >> triangle(); }
+inline An noise() { return An(fdsp_noise()); }
+inline An white() { return An(fdsp_noise()); }
+inline An lowpass() { return An(fdsp_svf(0, 440.0f, 1.0f, 1.0f)); }
+inline An lowpass_hz(float f, float q) { return An(fdsp_fixed_svf(0, f, q, 1.0f)); }
+inline An highpass_hz(float f, float q) { return An(fdsp_fixed_svf(1, f, q, 1.0f)); }
+inline An bandpass_hz(float f, float q) { return An(fdsp_fixed_svf(2, f, q, 1.0f)); }
+inline An notch_hz(float f, float q) { return An(fdsp_fixed_svf(3, f, q, 1.0f)); }
+inline An peak_hz(float f, float q) { return An(fdsp_fixed_svf(4, f, q, 1.0f)); }
+inline An allpass_hz(float f, float q) { return An(fdsp_fixed_svf(5, f, q, 1.0f)); }
+inline An bell_hz(float f, float q, float gain) { return An(fdsp_fixed_svf(6, f, q, gain)); }
+inline An lowshelf_hz(float f, float q, float gain) { return An(fdsp_fixed_svf(7, f, q, gain)); }
+inline An highshelf_hz(float f, float q, float gain) { return An(fdsp_fixed_svf(8, f, q, gain)); }
+inline An biquad(float a1, float a2, float b0, float b1, float b2) { return An(fdsp_biquad(a1, a2, b0, b1, b2)); }
+inline An biquad_bank() { return An(fdsp_biquad_bank()); }
+inline An butterpass_hz(float f) { return An(fdsp_butterpass(f, 1)); }
+inline An resonator_hz(float center, float q) { return An(fdsp_resonator(center, q, 1)); }
+inline An moog() { return An(fdsp_moog(1000.0f, 0.1f, 3)); }
+inline An moog_hz(float f, float q) { return An(fdsp_moog(f, q, 1)); }
+inline An moog_q(float q) { return (multipass(2) | dc(q)) >> An(fdsp_moog(1000.0f, q, 3)); }
+inline An fir(std::initializer_list<float> w) { return An(fdsp_fir((int)w.size(), w.begin())); }
+inline An fir3(float gain) { float alpha = (gain + 1.0f) / 2.0f, beta = (1.0f - alpha) / 2.0f; return fir({beta, alpha, beta}); }
+inline An tick() { return An(fdsp_tick(1)); }
+inline An delay(double t) { return An(fdsp_delay(t)); }
+inline An pan(float p) { return An(fdsp_pan(p)); }
+inline An panner() { return An(fdsp_panner()); }
+inline An adsr_live(float a, float d, float s, float r) { return An(fdsp_adsr_live(a, d, s, r)); }
+inline An feedback(An x) { return An(fdsp_feedback(x.release(), 0)); }
+inline An fdn(An x) { return An(fdsp_feedback(x.release(), 1)); }
+template <class F> An stacki(int n, F f) { std::vector<fdsp_node*> v; for (int i = 0; i < n; i++) v.push_back(f(i).release()); return An(fdsp_multi(30, 0, n, v.data())); }
+template <class F> An busi(int n, F f) { std::vector<fdsp_node*> v; for (int i = 0; i < n; i++) v.push_back(f(i).release()); return An(fdsp_multi(28, 0, n, v.data())); }
+template <class F> An sumi(int n, F f) { std::vector<fdsp_node*> v; for (int i = 0; i < n; i++) v.push_back(f(i).release()); return An(fdsp_multi(31, 0, n, v.data())); }
+template <class F> An branchi(int n, F f) { std::vector<fdsp_node*> v; for (int i = 0; i < n; i++) v.push_back(f(i).release()); return An(fdsp_multi(33, 0, n, v.data())); }
+template <class F> An pipei(int n, F f) { std::vector<fdsp_node*> v; for (int i = 0; i < n; i++) v.push_back(f(i).release()); return An(fdsp_multi(32, 0, n, v.data())); }
+
+// ---- the voice bank as an AudioUnit
+class Bank {
+  fdsp_bank* b_ = nullptr;
+
+ public:
+  // consumes the voices; `mix`: sum the voices (outputs() == channels), else per-voice rows (outputs() == V * channels)
+  Bank(std::vector<An>& voices, int device = 0, bool per_voice = false, bool mix = true) {
+    std::vector<fdsp_node*> hs;
+    for (auto& v : voices) hs.push_back(v.release());
+    voices.clear();
+    check(fdsp_bank_create(hs.data(), (uint32_t)hs.size(), device, (per_voice ? FDSP_OUT_VOICES : 0) | (mix ? FDSP_OUT_MIX : 0), &b_));
+  }
+  Bank(const Bank&) = delete;
+  Bank& operator=(const Bank&) = delete;
+  ~Bank() { fdsp_bank_destroy(b_); }
+  int inputs() const { return fdsp_bank_inputs(b_); }
+  int outputs() const { return fdsp_bank_outputs(b_); }
+  uint32_t voices() const { return fdsp_bank_voices(b_); }
+  void set_sample_rate(double sr) { check(fdsp_bank_set_sample_rate(b_, sr)); }
+  void reset() { check(fdsp_bank_reset(b_)); }
+  void allocate(uint64_t max_samples = 64) { check(fdsp_bank_allocate(b_, max_samples)); }
+  // AudioUnit::process: buffers are [channel][64]
+  void process(uint32_t size, const float* input, float* output) { check(fdsp_bank_process(b_, size, input, output)); }
+  // Wave::render / Wave::filter: buffers are [channel][n]
+  void render(uint64_t n, const float* input, float* out_voices, float* out_mix) { check(fdsp_bank_render(b_, n, input, out_voices, out_mix)); }
+  fdsp_bank* get() { return b_; }
+};
+
+}  // namespace fundsp_b200

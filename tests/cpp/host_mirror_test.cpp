@@ -1,0 +1,36 @@
+// C++ host mirror smoke test (no GPU needed): graph expressions written like the reference's compile, get the
+// reference's arities, type expressions and ping hashes; arity errors surface as exceptions; a Bank fails loudly
+// without a CUDA device.
+#include <cstdio>
+#include <vector>
+
+#include "fundsp_b200.hpp"
+
+using namespace fundsp_b200;
+
+int main() {
+  An g = sine_hz(440.0f) >> lowpass_hz(1000.0f, 1.0f);
+  std::printf("sig %s\n", g.signature().c_str());
+  uint64_t h[8];
+  int n = fdsp_node_leaf_hashes(const_cast<fdsp_node*>(g.get()), h, 8);
+  for (int i = 0; i < n; i++) std::printf("hash %016llx\n", (unsigned long long)h[i]);
+  // FM voice (README.md:102) and a filtered-noise bus, exercising precedence: * before + before >> before & before ^ before |
+  float f = 220.0f, m = 2.0f;
+  An fm = sine_hz(f) * f * m + f >> sine();
+  std::printf("fm %d %d %s\n", fm.inputs(), fm.outputs(), fm.signature().c_str());
+  An bus = (noise().seed(7) >> lowpass_hz(500.0f, 1.0f) & noise() >> highpass_hz(2000.0f, 1.0f)) | !zero() >> white() * 0.5f;
+  std::printf("bus %d %d\n", bus.inputs(), bus.outputs());
+  An rev = stacki(4, [](int i) { return delay(0.01 * (i + 1)) >> fir3(0.5f); });
+  std::printf("stacki %d %d\n", rev.inputs(), rev.outputs());
+  try {
+    An bad = pass() >> (pass() | pass());
+    std::printf("arity NOT detected\n");
+    return 1;
+  } catch (const Error& e) { std::printf("arity error %d\n", e.code); }
+  if (fdsp_device_count() == 0) {
+    std::vector<An> voices;
+    voices.push_back(saw_hz(110.0f) >> lowpass_hz(800.0f, 2.0f));
+    try { Bank b(voices); std::printf("bank created without GPU?\n"); return 1; } catch (const Error& e) { std::printf("bank error: %s\n", e.what()); }
+  }
+  return 0;
+}

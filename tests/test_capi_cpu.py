@@ -141,3 +141,23 @@ def test_product_net_extraction_errors_and_hashes():
     h = voice_net([workloads.net_voice(i) for i in range(6)]).lower(be)
     assert L.fdsp_net_size(h) == 6 + 2 * 5
     L.fdsp_node_free(h)
+
+
+def test_cpp_host_mirror_compiles_and_matches_python_mirror(tmp_path):
+    """include/fundsp_b200.hpp: the reference's graph notation for C++ hosts (same operators / precedence / opcode names)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_mirror_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "host_mirror_test.cpp"),
+                           "-o", exe, "-L", os.path.join(root, "fundsp_b200"), "-lfundsp_b200", "-Wl,-rpath," + os.path.join(root, "fundsp_b200")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.splitlines()
+    n = capi.NodeHandle(sine_hz(440.0) >> lowpass_hz(1000.0, 1.0))
+    assert lines[0] == "sig " + n.signature()
+    assert [int(x.split()[1], 16) for x in lines if x.startswith("hash")] == n.leaf_hashes()
+    f, m = 220.0, 2.0
+    fm = capi.NodeHandle(sine_hz(f) * f * m + f >> sine())
+    assert f"fm 0 1 {fm.signature()}" in lines
+    assert "bus 0 2" in lines and "stacki 4 4" in lines and any(x.startswith("arity error") for x in lines)
