@@ -62,6 +62,11 @@ API fdsp_node* fdsp_fir(int n, const float* w) { return wrap((n < 1 || !w) ? nul
 API fdsp_node* fdsp_tick(int n) { return wrap(n < 1 ? nullptr : mk_tick(n), "tick"); }
 API fdsp_node* fdsp_delay(double t) { return wrap(mk_delay(t), "delay"); }
 API fdsp_node* fdsp_allnest(float c, fdsp_node* x, int nin) { return wrap(mk_allnest(c, take(x), nin), "allnest"); }
+API fdsp_node* fdsp_phase_osc(int kind) { return wrap(mk_phase_osc(kind), "phase_osc"); }
+API fdsp_node* fdsp_mls(int bits) { return wrap(mk_mls(bits), "mls"); }
+API fdsp_node* fdsp_impulse(int n) { return wrap(mk_impulse(n), "impulse"); }
+API fdsp_node* fdsp_tap(int ntaps, int linear, float mn, float mx) { return wrap(mk_tap(ntaps, linear, mn, mx), "tap"); }
+API fdsp_node* fdsp_feedback2(fdsp_node* x, fdsp_node* y, int hadamard) { return wrap(mk_feedback2(take(x), take(y), hadamard), "feedback2"); }
 API fdsp_node* fdsp_pan(float v) { return wrap(mk_pan(v), "pan"); }
 API fdsp_node* fdsp_panner(void) { return wrap(mk_panner(), "panner"); }
 API fdsp_node* fdsp_adsr_live(float a, float d, float s, float r) { return wrap(mk_adsr_live(a, d, s, r), "adsr_live"); }

@@ -462,6 +462,115 @@ template <int N> struct Fir {  // src/fir.rs:11-89, ID 52: shift register, accum
   static FDSP_DEV void end_simd(R&) {}
 };
 
+
+// ---------------------------------------------------------------- phase oscillators, MLS, impulse
+FDSP_DEV float polyblep(float t, float dt) {  // src/oscillator.rs:510-521
+  if (t < dt) { float z = t / dt; return z + z - z * z - 1.0f; }
+  else if (t > 1.0f - dt) { float z = (t - 1.0f) / dt; return z + z + z * z + 1.0f; }
+  return 0.0f;
+}
+template <int KIND> struct PhaseOsc {  // src/oscillator.rs:440-760: 0 Ramp (ID 94), 1 PolySaw (95), 2 PolySquare (96), 3 PolyPulse (97)
+  FDSP_NODE(KIND == 3 ? 2 : 1, 1, 0, 1, 0);
+  struct R { float phase; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.phase = l.Sf(); }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.phase); }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<IN>& in, Fr<1>& o) {
+    const float p = r.phase;
+    const float delta = in.v[0] * c.sd64;
+    r.phase += delta;
+    r.phase -= floorf(r.phase);
+    if (KIND == 0) { o.v[0] = p; return; }
+    if (KIND == 1) { o.v[0] = 2.0f * p - 1.0f - polyblep(p, delta); return; }
+    const float width = KIND == 2 ? 0.5f : in.v[IN - 1];
+    const float square = p < width ? 1.0f : -1.0f;
+    const float half = p - width;
+    o.v[0] = square + polyblep(p, delta) - polyblep(half - floorf(half), delta);
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+struct Mls {  // src/noise.rs:11-148, ID 19: params = feedback polynomial, length mask, n - 1
+  FDSP_NODE(0, 1, 3, 1, 0);
+  struct R { uint32_t poly, mask, shift, s; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.poly = l.P(); r.mask = l.P(); r.shift = l.P(); r.s = l.S(); }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.S(r.s); }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C&, const Fr<0>&, Fr<1>& o) {
+    const float value = (float)((r.s >> r.shift) & 1u);
+    const uint32_t parity = (uint32_t)__popc(r.poly & r.s) & 1u;
+    r.s = ((r.s << 1) | parity) & r.mask;
+    o.v[0] = value * 2.0f - 1.0f;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+template <int N> struct Impulse {  // src/audionode.rs:2839-2873, ID 81
+  FDSP_NODE(0, N, 0, 1, 0);
+  struct R { float value; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.value = l.Sf(); }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.value); }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C&, const Fr<0>&, Fr<N>& o) { for (int k = 0; k < N; k++) o.v[k] = r.value; r.value = 0.0f; }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
+// ---------------------------------------------------------------- interpolated taps (src/delay.rs:141-286, 379-505)
+FDSP_DEV float splinef(float y0, float y1, float y2, float y3, float x) {  // src/math.rs:327-333
+  return y1 + x * 0.5f * (y2 - y0 + x * (2.0f * y0 - 5.0f * y1 + 4.0f * y2 - y3 + x * (3.0f * (y1 - y2) + y3 - y0)));
+}
+template <int NT_, int LINEAR> struct Tap {  // Tap<N> ID 50 (Catmull-Rom) / TapLinear<N> ID 54; power-of-two ring in HBM
+  FDSP_NODE(NT_ + 1, 1, 2, 1, 1);
+  struct R { float lo, hi; uint32_t i, len, off; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.lo = l.Pf(); r.hi = l.Pf(); r.len = l.U(); r.off = l.D(r.len); r.i = l.S(); }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.S(r.i); }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<IN>& in, Fr<1>& o) {
+    const uint32_t mask = r.len - 1u;
+    float* b = c.dl + c.v;
+    const size_t V = c.V;
+    b[(size_t)(r.off + r.i) * V] = in.v[0];
+    float acc = 0.0f;
+#pragma unroll
+    for (int t = 1; t <= NT_; t++) {
+      const float tap = fminf(fmaxf(in.v[t], r.lo), r.hi) * c.sr;
+      const uint32_t tf = (uint32_t)tap;
+      const uint32_t i1 = (r.i - tf) & mask;
+      const float d = tap - (float)tf;
+      if (LINEAR) {
+        const uint32_t i2 = (i1 - 1u) & mask;
+        acc += lerpf(b[(size_t)(r.off + i1) * V], b[(size_t)(r.off + i2) * V], d);
+      } else {
+        const uint32_t i0 = (i1 + 1u) & mask, i2 = (i1 - 1u) & mask, i3 = (i1 - 2u) & mask;
+        acc += splinef(b[(size_t)(r.off + i0) * V], b[(size_t)(r.off + i1) * V], b[(size_t)(r.off + i2) * V], b[(size_t)(r.off + i3) * V], d);
+      }
+    }
+    r.i = (r.i + 1u) & mask;
+    o.v[0] = acc;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
+// ---------------------------------------------------------------- biquads with audio-rate parameters (src/biquad.rs:220-382)
+struct ButterLowpass2 {  // ButterLowpass<f32,U2>, ID 16: (audio, cutoff) -> 1, coefficients recomputed when the cutoff input changes
+  FDSP_NODE(2, 1, 0, 10, 0);
+  struct R { float cutoff; Biquad::R b; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.cutoff = l.Sf(); r.b.a1 = l.Sf(); r.b.a2 = l.Sf(); r.b.b0 = l.Sf(); r.b.b1 = l.Sf(); r.b.b2 = l.Sf(); r.b.x1 = l.Sf(); r.b.x2 = l.Sf(); r.b.y1 = l.Sf(); r.b.y2 = l.Sf(); }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.cutoff); s.Sf(r.b.a1); s.Sf(r.b.a2); s.Sf(r.b.b0); s.Sf(r.b.b1); s.Sf(r.b.b2); s.Sf(r.b.x1); s.Sf(r.b.x2); s.Sf(r.b.y1); s.Sf(r.b.y2); }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<2>& in, Fr<1>& o) {
+    if (in.v[1] != r.cutoff) { r.cutoff = in.v[1]; BqCoefs k = bq_butter_lowpass(c.sr, r.cutoff); r.b.a1 = k.a1; r.b.a2 = k.a2; r.b.b0 = k.b0; r.b.b1 = k.b1; r.b.b2 = k.b2; }
+    Fr<1> a; a.v[0] = in.v[0];
+    Biquad::step<T>(r.b, c, a, o);
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+struct Resonator3 {  // Resonator<f32,U3>, ID 17: (audio, center, q) -> 1
+  FDSP_NODE(3, 1, 0, 11, 0);
+  struct R { float center, q; Biquad::R b; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.center = l.Sf(); r.q = l.Sf(); r.b.a1 = l.Sf(); r.b.a2 = l.Sf(); r.b.b0 = l.Sf(); r.b.b1 = l.Sf(); r.b.b2 = l.Sf(); r.b.x1 = l.Sf(); r.b.x2 = l.Sf(); r.b.y1 = l.Sf(); r.b.y2 = l.Sf(); }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.center); s.Sf(r.q); s.Sf(r.b.a1); s.Sf(r.b.a2); s.Sf(r.b.b0); s.Sf(r.b.b1); s.Sf(r.b.b2); s.Sf(r.b.x1); s.Sf(r.b.x2); s.Sf(r.b.y1); s.Sf(r.b.y2); }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<3>& in, Fr<1>& o) {
+    if (in.v[1] != r.center || in.v[2] != r.q) { r.center = in.v[1]; r.q = in.v[2]; BqCoefs k = bq_resonator(c.sr, r.center, r.q); r.b.a1 = k.a1; r.b.a2 = k.a2; r.b.b0 = k.b0; r.b.b1 = k.b1; r.b.b2 = k.b2; }
+    Fr<1> a; a.v[0] = in.v[0];
+    Biquad::step<T>(r.b, c, a, o);
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
 // ---------------------------------------------------------------- delays / feedback
 template <int N> struct Tick {  // src/delay.rs:17-65, ID 9
   FDSP_NODE(N, N, 0, N, 0);
@@ -521,6 +630,24 @@ template <int HAD, class X> struct Feedback {  // src/feedback.rs:68-178, ID 11:
     for (int k = 0; k < N; k++) t.v[k] = in.v[k] + r.value[k];
     X::template step<true>(r.x, c, t, o);
     for (int k = 0; k < N; k++) r.value[k] = o.v[k];
+    if (HAD) hadamard<N>(r.value);
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
+
+template <int HAD, class X, class Y> struct Feedback2 {  // src/feedback.rs:180-314, ID 66: out = x(in + value); value = U(y(out))
+  static constexpr int N = X::IN;
+  FDSP_NODE(N, N, X::NP + Y::NP, N + X::NS + Y::NS, X::NU + Y::NU);
+  struct R { float value[N]; typename X::R x; typename Y::R y; };
+  static FDSP_DEV void load(R& r, Loader& l) { for (int k = 0; k < N; k++) r.value[k] = l.Sf(); X::load(r.x, l); Y::load(r.y, l); }
+  static FDSP_DEV void save(const R& r, Saver& s) { for (int k = 0; k < N; k++) s.Sf(r.value[k]); X::save(r.x, s); Y::save(r.y, s); }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<N>& in, Fr<N>& o) {
+    Fr<N> t, u;
+    for (int k = 0; k < N; k++) t.v[k] = in.v[k] + r.value[k];
+    X::template step<true>(r.x, c, t, o);
+    Y::template step<true>(r.y, c, o, u);
+    for (int k = 0; k < N; k++) r.value[k] = u.v[k];
     if (HAD) hadamard<N>(r.value);
   }
   static FDSP_DEV void end_simd(R&) {}
@@ -629,6 +756,7 @@ template <class X> struct WaveKind<Thru<X>> : WaveKind<X> {};
 template <int KIND, int OP, int N, class X> struct WaveKind<Multi<KIND, OP, N, X>> : WaveKind<X> {};
 template <int NIN, class X> struct WaveKind<AllNest<NIN, X>> : WaveKind<X> {};
 template <int HAD, class X> struct WaveKind<Feedback<HAD, X>> : WaveKind<X> {};
+template <int HAD, class X, class Y> struct WaveKind<Feedback2<HAD, X, Y>> : Wk2<X, Y> {};
 
 
 // Rough per-sample instruction cost of a graph type: picks how far the 8-sample group is unrolled (big bodies
@@ -654,6 +782,8 @@ template <int K, class X> struct Cost<Unop<K, X>> { static constexpr int value =
 template <class X> struct Cost<Thru<X>> { static constexpr int value = Cost<X>::value; };
 template <int KIND, int OP, int N, class X> struct Cost<Multi<KIND, OP, N, X>> { static constexpr int value = N * Cost<X>::value; };
 template <int NIN, class X> struct Cost<AllNest<NIN, X>> { static constexpr int value = Cost<X>::value + 6; };
+template <int HAD, class X, class Y> struct Cost<Feedback2<HAD, X, Y>> { static constexpr int value = Cost<X>::value + Cost<Y>::value + (HAD ? 6 * X::IN : X::IN); };
+template <int NT_, int LIN> struct Cost<Tap<NT_, LIN>> { static constexpr int value = 40 * NT_; };
 template <int HAD, class X> struct Cost<Feedback<HAD, X>> { static constexpr int value = Cost<X>::value + (HAD ? 6 * X::IN : X::IN); };
 
 }  // namespace fdsp

@@ -106,6 +106,66 @@ struct WaveSynth : HNode {  // src/wavetable.rs:244-359
   HCLONE(WaveSynth)
 };
 
+
+// ---------------------------------------------------------------- phase oscillators, MLS, impulse, taps
+struct PhaseOsc : HNode {  // src/oscillator.rs:440-760
+  int kind; uint64_t hash = 0; bool has_phase = false; float initial_phase = 0;
+  explicit PhaseOsc(int k) : kind(k) {}
+  int inputs() const override { return kind == 3 ? 2 : 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 94 + (uint64_t)kind; }
+  void set(const Setting& s) override { if (s.kind == P_PHASE) { has_phase = true; initial_phase = s.v[0]; } }
+  void set_hash(uint64_t h) override { hash = h; }
+  void sig(std::string& o) const override { o += "PhaseOsc<" + I(kind) + ">"; }
+  void lower(Lowering& l) const override { l.s(has_phase ? initial_phase : (float)rnd1(hash)); }
+  HCLONE(PhaseOsc)
+};
+const uint32_t kMlsPoly[31] = {
+    0b1, 0b11, 0b110, 0b1100, 0b10100, 0b110000, 0b1001000, 0b10111000, 0b100010000, 0b1001000000, 0b10100000000, 0b110010100000,
+    0b1101100000000, 0b11000010001000, 0b110000000000000, 0b1101000000001000, 0b10010000000000000, 0b100000010000000000,
+    0b1100011000000000000, 0b10010000000000000000, 0b101000000000000000000, 0b1100000000000000000000, 0b10000100000000000000000,
+    0b111000010000000000000000, 0b1001000000000000000000000, 0b10000000000000000000100011, 0b100000000000000000000010011,
+    0b1001000000000000000000000000, 0b10100000000000000000000000000, 0b100000000000000000000000101001, 0b1001000000000000000000000000000};
+struct Mls : HNode {  // src/noise.rs:11-148: unseeded until the first reset (set_hash / .seed())
+  uint32_t n, s; bool has_seed = false; uint64_t seed = 0, hash = 0;
+  explicit Mls(uint32_t n_) : n(n_), s((1u << n_) - 1u) {}
+  int inputs() const override { return 0; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 19; }
+  void reset() override { uint64_t h = has_seed ? seed : hash; s = 1u + (uint32_t)(h ^ (h >> 32)) % ((1u << n) - 1u); }
+  void set(const Setting& st) override { if (st.kind == P_SEED) { has_seed = true; seed = st.seed; } }
+  void set_hash(uint64_t h) override { hash = h; reset(); }
+  void sig(std::string& o) const override { o += "Mls"; }
+  void lower(Lowering& l) const override { l.P.push_back(kMlsPoly[n - 1]); l.P.push_back((1u << n) - 1u); l.P.push_back(n - 1); l.su(s); }
+  HCLONE(Mls)
+};
+struct ImpulseN : HNode {
+  int n; explicit ImpulseN(int n_) : n(n_) {}
+  int inputs() const override { return 0; } int outputs() const override { return n; }
+  uint64_t id() const override { return 81; }
+  void sig(std::string& o) const override { o += "Impulse<" + I(n) + ">"; }
+  void lower(Lowering& l) const override { l.s(1.0f); }
+  HCLONE(ImpulseN)
+};
+struct TapN : HNode {  // src/delay.rs:141-286 Tap / :379-505 TapLinear
+  int ntaps; bool linear; float min_delay, max_delay, sr = 0, lo = 0, hi = 0; uint32_t len = 1;
+  TapN(int n, bool lin, float mn, float mx) : ntaps(n), linear(lin), min_delay(mn), max_delay(mx) { set_sample_rate(DEFAULT_SR); }
+  int inputs() const override { return ntaps + 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return linear ? 54 : 50; }
+  void set_sample_rate(double s) override {
+    float f = (float)s;
+    if (sr != f) {
+      sr = f;
+      lo = linear ? min_delay : fmaxf(min_delay, 1.00001f / f);
+      hi = linear ? max_delay : fmaxf(max_delay, 1.00001f / f);
+      float bl = linear ? ceilf(max_delay * f) + 2.0f : ceilf(max_delay * f) + 3.0f + 8.0f;
+      size_t n = (size_t)bl, p2 = 1; while (p2 < n) p2 <<= 1;
+      len = (uint32_t)p2;
+    }
+  }
+  void sig(std::string& o) const override { o += "Tap<" + I(ntaps) + "," + I(linear ? 1 : 0) + ">"; }
+  void lower(Lowering& l) const override { l.p(lo); l.p(hi); l.U.push_back(len); l.dlen.push_back(len); l.su(0u); }
+  HCLONE(TapN)
+};
+
 // ---------------------------------------------------------------- SVF (src/svf.rs)
 typedef fdsp::SvfCoefs Coefs6;
 Coefs6 svf_coefs(int mode, float sr, float cutoff, float q, float gain) {  // src/svf.rs:26-221 (shared host/device code)
@@ -139,20 +199,9 @@ struct Svf : HNode {  // FixedSvf (ID 43, :857-1031) and Svf (ID 36, :744-855)
 };
 
 // ---------------------------------------------------------------- biquads (src/biquad.rs, src/biquad_bank.rs)
-struct BqCoefs { float a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0; };
-BqCoefs bq_butter_lowpass(float sr, float cutoff) {  // src/biquad.rs:27-38
-  const float PI_F = 3.14159274101257324f, SQRT_2 = 1.41421354f;
-  float f = fdsp::m::tanf_(cutoff * PI_F / sr);
-  float a0r = 1.0f / (1.0f + SQRT_2 * f + f * f);
-  BqCoefs c; c.a1 = (2.0f * f * f - 2.0f) * a0r; c.a2 = (1.0f - SQRT_2 * f + f * f) * a0r;
-  c.b0 = f * f * a0r; c.b1 = 2.0f * c.b0; c.b2 = c.b0; return c;
-}
-BqCoefs bq_resonator(float sr, float center, float q) {  // src/biquad.rs:40-50
-  const float PI_F = 3.14159274101257324f, TAU_F = 6.28318548202514648f;
-  float r = expf(-PI_F * center / (q * sr));
-  BqCoefs c; c.a1 = -2.0f * r * fdsp::m::cosf_(TAU_F * center / sr); c.a2 = r * r;
-  c.b0 = sqrtf(1.0f - r * r) * 0.5f; c.b1 = 0.0f; c.b2 = -c.b0; return c;
-}
+typedef fdsp::BqCoefs BqCoefs;
+BqCoefs bq_butter_lowpass(float sr, float cutoff) { return fdsp::bq_butter_lowpass(sr, cutoff); }   // src/biquad.rs:27-38
+BqCoefs bq_resonator(float sr, float center, float q) { return fdsp::bq_resonator(sr, center, q); }  // src/biquad.rs:40-50
 struct Biquad : HNode {  // Biquad (ID 15), fixed ButterLowpass (ID 16), fixed Resonator (ID 17)
   int kind;  // 0 arbitrary, 1 butterpass, 2 resonator
   int nin; BqCoefs c; float sr, f, q;
@@ -167,15 +216,16 @@ struct Biquad : HNode {  // Biquad (ID 15), fixed ButterLowpass (ID 16), fixed R
     else if (kind == 2 && s.kind == P_CENTER) { f = s.v[0]; update(); }
     else if (kind == 2 && s.kind == P_CENTER_Q) { f = s.v[0]; q = s.v[1]; update(); }
   }
-  void sig(std::string& o) const override { o += nin == 1 ? "Biquad" : "Unsupported"; }
+  void sig(std::string& o) const override { o += nin == 1 ? "Biquad" : (kind == 1 ? "ButterLowpass2" : "Resonator3"); }
   void lower(Lowering& l) const override {
-    if (nin != 1) { l.fail("butterpass()/resonator() with audio-rate parameter inputs has no device lowering yet"); return; }
-    l.p(c.a1); l.p(c.a2); l.p(c.b0); l.p(c.b1); l.p(c.b2); for (int i = 0; i < 4; i++) l.s(0.0f);
+    if (nin == 1) { l.p(c.a1); l.p(c.a2); l.p(c.b0); l.p(c.b1); l.p(c.b2); for (int i = 0; i < 4; i++) l.s(0.0f); return; }
+    l.s(f); if (kind == 2) l.s(q);   // audio-rate parameter inputs: the current cutoff / (center, q) and coefficients are state
+    l.s(c.a1); l.s(c.a2); l.s(c.b0); l.s(c.b1); l.s(c.b2); for (int i = 0; i < 4; i++) l.s(0.0f);
   }
   HCLONE(Biquad)
 };
 struct BiquadBank : HNode {  // src/biquad_bank.rs:9-117
-  BqCoefs c[8];
+  BqCoefs c[8] = {};
   int inputs() const override { return 8; } int outputs() const override { return 8; }
   uint64_t id() const override { return 98; }
   void set(const Setting& s) override {
@@ -334,6 +384,18 @@ struct Unary : HNode {
   }
   HCLONE(Unary)
 };
+struct Feedback2N : HNode {  // src/feedback.rs:180-314
+  int had; Kid x, y;
+  Feedback2N(HNode* x_, HNode* y_, int h) : had(h), x(x_), y(y_) { ctor_ping(); }
+  int inputs() const override { return x->inputs(); } int outputs() const override { return x->outputs(); }
+  uint64_t id() const override { return 66; }
+  void reset() override { x->reset(); y->reset(); }
+  void set_sample_rate(double s) override { x->set_sample_rate(s); y->set_sample_rate(s); }
+  AttoHash ping(bool probe, AttoHash h) override { return y->ping(probe, x->ping(probe, h.hash(id()))); }
+  void sig(std::string& o) const override { o += "Feedback2<" + I(had) + ","; x->sig(o); o += ","; y->sig(o); o += ">"; }
+  void lower(Lowering& l) const override { for (int i = 0; i < x->inputs(); i++) l.s(0.0f); x->lower(l); y->lower(l); }
+  HCLONE(Feedback2N)
+};
 struct Multi : HNode {  // MultiBus 28, MultiStack 30, Reduce 31, MultiBranch 33, Chain 32
   int kind, op; std::vector<Kid> x;
   Multi(int kind_, int op_, int n, HNode** nodes) : kind(kind_), op(op_) { for (int i = 0; i < n; i++) x.emplace_back(nodes[i]); ctor_ping(); }
@@ -486,15 +548,23 @@ HNode* mk_wavesynth(int kind, int outputs) { return (kind < 0 || kind > 5 || out
 HNode* mk_noise() { return new Noise(); }
 HNode* mk_fixed_svf(int mode, float cutoff, float q, float gain) { return (mode < 0 || mode > 8) ? nullptr : new Svf(mode, true, cutoff, q, gain); }
 HNode* mk_svf(int mode, float cutoff, float q, float gain) { return (mode < 0 || mode > 8) ? nullptr : new Svf(mode, false, cutoff, q, gain); }
-HNode* mk_biquad(float a1, float a2, float b0, float b1, float b2) { BqCoefs c; c.a1 = a1; c.a2 = a2; c.b0 = b0; c.b1 = b1; c.b2 = b2; return new Biquad(0, 1, c, 0, 0); }
+HNode* mk_biquad(float a1, float a2, float b0, float b1, float b2) { BqCoefs c{0, 0, 0, 0, 0}; c.a1 = a1; c.a2 = a2; c.b0 = b0; c.b1 = b1; c.b2 = b2; return new Biquad(0, 1, c, 0, 0); }
 HNode* mk_biquad_bank() { return new BiquadBank(); }
-HNode* mk_butterpass(float cutoff, int nin) { return new Biquad(1, nin, BqCoefs(), cutoff, 0); }
-HNode* mk_resonator(float center, float q, int nin) { return new Biquad(2, nin, BqCoefs(), center, q); }
+HNode* mk_butterpass(float cutoff, int nin) { return new Biquad(1, nin, BqCoefs{0, 0, 0, 0, 0}, cutoff, 0); }
+HNode* mk_resonator(float center, float q, int nin) { return new Biquad(2, nin, BqCoefs{0, 0, 0, 0, 0}, center, q); }
 HNode* mk_moog(float cutoff, float q, int nin) { return (nin != 1 && nin != 3) ? nullptr : new Moog(cutoff, q, nin); }
 HNode* mk_fir(int n, const float* w) { return n < 1 ? nullptr : new Fir(std::vector<float>(w, w + n)); }
 HNode* mk_tick(int n) { return new TickN(n); }
 HNode* mk_delay(double t) { return t < 0.0 ? nullptr : new Delay(t); }
 HNode* mk_allnest(float c, HNode* x, int nin) { if (!x || x->inputs() != 1 || x->outputs() != 1) { delete x; return nullptr; } return new AllNest(c, x, nin); }
+HNode* mk_phase_osc(int kind) { return (kind < 0 || kind > 3) ? nullptr : new PhaseOsc(kind); }
+HNode* mk_mls(int bits) { return (bits < 1 || bits > 31) ? nullptr : new Mls((uint32_t)bits); }
+HNode* mk_impulse(int n) { return n < 1 ? nullptr : new ImpulseN(n); }
+HNode* mk_tap(int ntaps, int linear, float mn, float mx) { return (ntaps < 1 || mn < 0.0f || mn > mx) ? nullptr : new TapN(ntaps, linear != 0, mn, mx); }
+HNode* mk_feedback2(HNode* x, HNode* y, int hadamard) {
+  if (!x || !y || x->inputs() != x->outputs() || y->inputs() != y->outputs() || x->inputs() != y->inputs() || (hadamard && (x->inputs() & (x->inputs() - 1)) != 0)) { delete x; delete y; return nullptr; }
+  return new Feedback2N(x, y, hadamard ? 1 : 0);
+}
 HNode* mk_pan(float value) { return new Panner(value, 1); }
 HNode* mk_panner() { return new Panner(0.0f, 2); }
 HNode* mk_adsr_live(float a, float d, float s, float r) { return new AdsrLive(a, d, s, r); }

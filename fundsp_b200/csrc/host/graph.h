@@ -99,6 +99,11 @@ HNode* mk_fir(int n, const float* w);
 HNode* mk_tick(int n);
 HNode* mk_delay(double t);
 HNode* mk_allnest(float coefficient, HNode* x, int nin);
+HNode* mk_phase_osc(int kind);                      // 0 ramp, 1 poly_saw, 2 poly_square, 3 poly_pulse
+HNode* mk_mls(int bits);
+HNode* mk_impulse(int n);
+HNode* mk_tap(int ntaps, int linear, float min_delay, float max_delay);
+HNode* mk_feedback2(HNode* x, HNode* y, int hadamard);
 HNode* mk_pan(float value);
 HNode* mk_panner();
 HNode* mk_adsr_live(float a, float d, float s, float r);

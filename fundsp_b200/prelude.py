@@ -503,3 +503,75 @@ def sub(x):
 def mul(x):
     v = _frame(x)
     return An("multipass", (len(v),), (), len(v), len(v)) * dc(v)
+
+
+# ---- src/prelude.rs:356-366, 3112-3156 phase oscillators
+def ramp():
+    return An("phase_osc", (0,), (), 1, 1)
+
+
+def ramp_hz(f):
+    return dc(f) >> ramp()
+
+
+def poly_saw():
+    return An("phase_osc", (1,), (), 1, 1)
+
+
+def poly_saw_hz(f):
+    return dc(f) >> poly_saw()
+
+
+def poly_square():
+    return An("phase_osc", (2,), (), 1, 1)
+
+
+def poly_square_hz(f):
+    return dc(f) >> poly_square()
+
+
+def poly_pulse():
+    return An("phase_osc", (3,), (), 2, 1)
+
+
+def poly_pulse_hz(f, width):
+    return dc((f, width)) >> poly_pulse()
+
+
+# ---- src/prelude.rs:783-797, 2860-2862
+def mls_bits(n):
+    return An("mls", (int(n),), (), 0, 1)
+
+
+def mls():
+    return mls_bits(29)
+
+
+def impulse(n=1):
+    return An("impulse", (n,), (), 0, n)
+
+
+# ---- src/prelude.rs:923-990 interpolated delay taps (delay times in seconds are audio-rate inputs)
+def tap(min_delay, max_delay):
+    return An("tap", (1, 0, f32(min_delay), f32(max_delay)), (), 2, 1)
+
+
+def multitap(n, min_delay, max_delay):
+    return An("tap", (n, 0, f32(min_delay), f32(max_delay)), (), n + 1, 1)
+
+
+def tap_linear(min_delay, max_delay):
+    return An("tap", (1, 1, f32(min_delay), f32(max_delay)), (), 2, 1)
+
+
+def multitap_linear(n, min_delay, max_delay):
+    return An("tap", (n, 1, f32(min_delay), f32(max_delay)), (), n + 1, 1)
+
+
+# ---- src/prelude.rs:1074-1085, 1353-1364
+def feedback2(node, loopback):
+    return An("feedback2", (0,), (node, loopback), node.nin, node.nout)
+
+
+def fdn2(node, loopback):
+    return An("feedback2", (1,), (node, loopback), node.nin, node.nout)

@@ -66,6 +66,11 @@ fdsp_node* fdsp_fir(int n, const float* weights);              /* Fir<N>        
 fdsp_node* fdsp_tick(int n);                                   /* Tick<N>       ID 9  */
 fdsp_node* fdsp_delay(double seconds);                         /* Delay         ID 13 */
 fdsp_node* fdsp_allnest(float coefficient, fdsp_node* x, int inputs); /* AllNest ID 83 */
+fdsp_node* fdsp_phase_osc(int kind);                           /* kind 0 Ramp ID 94, 1 PolySaw 95, 2 PolySquare 96, 3 PolyPulse 97 (src/oscillator.rs:440-760) */
+fdsp_node* fdsp_mls(int bits);                                 /* Mls           ID 19 src/noise.rs:100 */
+fdsp_node* fdsp_impulse(int n);                                /* Impulse<N>    ID 81 */
+fdsp_node* fdsp_tap(int taps, int linear, float min_delay, float max_delay); /* Tap<N> ID 50 / TapLinear<N> ID 54 */
+fdsp_node* fdsp_feedback2(fdsp_node* x, fdsp_node* y, int hadamard);         /* Feedback2 ID 66 (feedback2 / fdn2) */
 fdsp_node* fdsp_pan(float value);                              /* Panner<U1>    ID 49 */
 fdsp_node* fdsp_panner(void);                                  /* Panner<U2>    ID 49 */
 fdsp_node* fdsp_adsr_live(float attack, float decay, float sustain, float release); /* EnvelopeIn ID 53 + src/adsr.rs closure */

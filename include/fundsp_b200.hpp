@@ -114,6 +114,25 @@ inline An fir(std::initializer_list<float> w) { return An(fdsp_fir((int)w.size()
 inline An fir3(float gain) { float alpha = (gain + 1.0f) / 2.0f, beta = (1.0f - alpha) / 2.0f; return fir({beta, alpha, beta}); }
 inline An tick() { return An(fdsp_tick(1)); }
 inline An delay(double t) { return An(fdsp_delay(t)); }
+inline An ramp() { return An(fdsp_phase_osc(0)); }
+inline An ramp_hz(float f) { return dc(f) >> ramp(); }
+inline An poly_saw() { return An(fdsp_phase_osc(1)); }
+inline An poly_saw_hz(float f) { return dc(f) >> poly_saw(); }
+inline An poly_square() { return An(fdsp_phase_osc(2)); }
+inline An poly_square_hz(float f) { return dc(f) >> poly_square(); }
+inline An poly_pulse() { return An(fdsp_phase_osc(3)); }
+inline An poly_pulse_hz(float f, float width) { return dc(f, width) >> poly_pulse(); }
+inline An mls_bits(int n) { return An(fdsp_mls(n)); }
+inline An mls() { return mls_bits(29); }
+inline An impulse(int n = 1) { return An(fdsp_impulse(n)); }
+inline An tap(float min_delay, float max_delay) { return An(fdsp_tap(1, 0, min_delay, max_delay)); }
+inline An multitap(int n, float min_delay, float max_delay) { return An(fdsp_tap(n, 0, min_delay, max_delay)); }
+inline An tap_linear(float min_delay, float max_delay) { return An(fdsp_tap(1, 1, min_delay, max_delay)); }
+inline An multitap_linear(int n, float min_delay, float max_delay) { return An(fdsp_tap(n, 1, min_delay, max_delay)); }
+inline An butterpass() { return An(fdsp_butterpass(440.0f, 2)); }
+inline An resonator() { return An(fdsp_resonator(440.0f, 1.0f, 3)); }
+inline An feedback2(An x, An y) { return An(fdsp_feedback2(x.release(), y.release(), 0)); }
+inline An fdn2(An x, An y) { return An(fdsp_feedback2(x.release(), y.release(), 1)); }
 inline An pan(float p) { return An(fdsp_pan(p)); }
 inline An panner() { return An(fdsp_panner()); }
 inline An adsr_live(float a, float d, float s, float r) { return An(fdsp_adsr_live(a, d, s, r)); }

@@ -154,6 +154,34 @@ inline float expm1f_(float x) {  // s_expm1f.c
   if (k < 23) y = (x - e + (1.0f - uf)) * twopk; else y = (x - (e + uf) + 1.0f) * twopk;
   return y;
 }
+
+// e_expf.c (FreeBSD msun lineage, as ported by the Rust `libm` crate) + s_scalbnf.c
+inline float scalbnf_(float x, int n) {
+  float y = x;
+  if (n > 127) { y *= 0x1p127f; n -= 127; if (n > 127) { y *= 0x1p127f; n -= 127; if (n > 127) n = 127; } }
+  else if (n < -126) { y *= 0x1p-126f * 0x1p24f; n += 126 - 24; if (n < -126) { y *= 0x1p-126f * 0x1p24f; n += 126 - 24; if (n < -126) n = -126; } }
+  return y * fromb((uint32_t)(0x7f + n) << 23);
+}
+inline float expf_(float x) {
+  const float LN2_HI = 6.9314575195e-01f, LN2_LO = 1.4286067653e-06f, INV_LN2 = 1.4426950216e+00f, P1 = 1.6666625440e-1f, P2 = -2.7667332906e-3f;
+  uint32_t hx = fbits(x); const int sign = (int)(hx >> 31); hx &= 0x7fffffffu;
+  if (hx >= 0x42aeac50u) {                 // |x| >= 87.33655 or NaN
+    if (hx > 0x7f800000u) return x;
+    if (hx >= 0x42b17218u && !sign) { x *= 0x1p127f; return x; }
+    if (sign && hx >= 0x42cff1b5u) return 0.0f;
+  }
+  int k; float hi, lo;
+  if (hx > 0x3eb17218u) {                  // |x| > 0.5 ln2
+    if (hx > 0x3f851592u) k = (int)(INV_LN2 * x + (sign ? -0.5f : 0.5f)); else k = 1 - sign - sign;
+    const float kf = (float)k;
+    hi = x - kf * LN2_HI; lo = kf * LN2_LO; x = hi - lo;
+  } else if (hx > 0x39000000u) { k = 0; hi = x; lo = 0.0f; }
+  else return 1.0f + x;
+  const float xx = x * x;
+  const float c = x - xx * (P1 + xx * P2);
+  const float y = 1.0f + (x * c / (2.0f - c) - lo + hi);
+  return k == 0 ? y : scalbnf_(y, k);
+}
 inline float tanhf_(float x) {  // s_tanhf.c
   uint32_t w = fbits(x); int sign = (int)(w >> 31); w &= 0x7fffffffu;
   x = fromb(w);

@@ -725,7 +725,7 @@ inline BiquadCoefs biquad_butter_lowpass(float sr, float cutoff) {
 }
 inline BiquadCoefs biquad_resonator(float sr, float center, float q) {
   const float PI_F = 3.14159274101257324f, TAU_F = 6.28318548202514648f;
-  float r = expf(-PI_F * center / (q * sr));
+  float r = m::expf_(-PI_F * center / (q * sr));
   BiquadCoefs c; c.a1 = -2.0f * r * m::cosf_(TAU_F * center / sr); c.a2 = r * r;
   c.b0 = sqrtf(1.0f - r * r) * 0.5f; c.b1 = 0.0f; c.b2 = -c.b0; return c;
 }
@@ -966,6 +966,140 @@ struct Feedback : Node {
   }
   AttoHash ping(bool probe, AttoHash h) override { return x->ping(probe, h.hash(id())); }
   FO_CLONE(Feedback)
+};
+
+
+// ---- src/oscillator.rs:440-760 Ramp (ID 94), PolySaw (95), PolySquare (96), PolyPulse (97): phase oscillators, tick only
+inline float polyblep(float t, float dt) {  // :510-521
+  if (t < dt) { float z = t / dt; return z + z - z * z - 1.0f; }
+  else if (t > 1.0f - dt) { float z = (t - 1.0f) / dt; return z + z + z * z + 1.0f; }
+  return 0.0f;
+}
+struct PhaseOsc : Node {
+  int kind;  // 0 ramp, 1 poly_saw, 2 poly_square, 3 poly_pulse
+  float phase = 0, sample_duration = 0; uint64_t hash = 0; bool has_phase = false; float initial_phase = 0;
+  explicit PhaseOsc(int k) : kind(k) { reset(); set_sample_rate(DEFAULT_SR); }
+  int inputs() const override { return kind == 3 ? 2 : 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 94 + (uint64_t)kind; }
+  void reset() override { phase = has_phase ? initial_phase : (float)rnd1(hash); }
+  void set_sample_rate(double sr) override { sample_duration = (float)(1.0 / sr); }
+  void tick(const float* in, float* out) override {
+    float p = phase;
+    float delta = in[0] * sample_duration;
+    phase += delta;
+    phase -= floorf(phase);
+    if (kind == 0) { out[0] = p; return; }
+    if (kind == 1) { out[0] = 2.0f * p - 1.0f - polyblep(p, delta); return; }
+    float width = kind == 2 ? 0.5f : in[1];
+    float square = p < width ? 1.0f : -1.0f;
+    float half = p - width;
+    out[0] = square + polyblep(p, delta) - polyblep(half - floorf(half), delta);
+  }
+  void set(const Setting& s) override { if (s.kind == P_PHASE) { has_phase = true; initial_phase = s.v[0]; } }
+  void set_hash(uint64_t h) override { hash = h; reset(); }
+  FO_CLONE(PhaseOsc)
+};
+
+// ---- src/noise.rs:11-148 Mls (ID 19): maximum length sequence
+static const uint32_t MLS_POLY[31] = {
+    0b1, 0b11, 0b110, 0b1100, 0b10100, 0b110000, 0b1001000, 0b10111000, 0b100010000, 0b1001000000, 0b10100000000, 0b110010100000,
+    0b1101100000000, 0b11000010001000, 0b110000000000000, 0b1101000000001000, 0b10010000000000000, 0b100000010000000000,
+    0b1100011000000000000, 0b10010000000000000000, 0b101000000000000000000, 0b1100000000000000000000, 0b10000100000000000000000,
+    0b111000010000000000000000, 0b1001000000000000000000000, 0b10000000000000000000100011, 0b100000000000000000000010011,
+    0b1001000000000000000000000000, 0b10100000000000000000000000000, 0b100000000000000000000000101001, 0b1001000000000000000000000000000};
+struct Mls : Node {
+  uint32_t n, s; bool has_seed = false; uint64_t seed = 0, hash = 0;
+  explicit Mls(uint32_t n_) : n(n_), s((1u << n_) - 1u) {}
+  int inputs() const override { return 0; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 19; }
+  void reset() override { uint64_t h = has_seed ? seed : hash; uint32_t sd = (uint32_t)(h ^ (h >> 32)); s = 1u + sd % ((1u << n) - 1u); }
+  void tick(const float*, float* out) override {
+    float value = (float)((s >> (n - 1)) & 1u);
+    uint32_t fb = MLS_POLY[n - 1] & s;
+    uint32_t parity = (uint32_t)__builtin_popcount(fb) & 1u;
+    s = ((s << 1) | parity) & ((1u << n) - 1u);
+    out[0] = value * 2.0f - 1.0f;
+  }
+  void set(const Setting& st) override { if (st.kind == P_SEED) { has_seed = true; seed = st.seed; } }
+  void set_hash(uint64_t h) override { hash = h; reset(); }
+  FO_CLONE(Mls)
+};
+
+// ---- src/audionode.rs:2839-2873 Impulse<N> (ID 81)
+struct Impulse : Node {
+  int n; float value = 1.0f;
+  explicit Impulse(int n_) : n(n_) {}
+  int inputs() const override { return 0; } int outputs() const override { return n; }
+  uint64_t id() const override { return 81; }
+  void reset() override { value = 1.0f; }
+  void tick(const float*, float* out) override { for (int c = 0; c < n; c++) out[c] = value; value = 0.0f; }
+  FO_CLONE(Impulse)
+};
+
+// ---- src/math.rs:327-333 spline (Catmull-Rom), T = f32
+inline float splinef(float y0, float y1, float y2, float y3, float x) {
+  return y1 + x * 0.5f * (y2 - y0 + x * (2.0f * y0 - 5.0f * y1 + 4.0f * y2 - y3 + x * (3.0f * (y1 - y2) + y3 - y0)));
+}
+// ---- src/delay.rs:141-286 Tap<N> (ID 50) and :379-505 TapLinear<N> (ID 54). The block path (:238-279) writes the 8 inputs of a
+// SIMD group first and reads relative to each lane's own write position; since every tap is >= 1.00001 samples that equals the tick path.
+struct Tap : Node {
+  int ntaps; bool linear; std::vector<float> buffer; size_t i = 0; float sr = 0, min_delay, max_delay, min_c = 0, max_c = 0;
+  Tap(int ntaps_, bool linear_, float mn, float mx) : ntaps(ntaps_), linear(linear_), min_delay(mn), max_delay(mx) { assert(mn >= 0.0f && mn <= mx); set_sample_rate(DEFAULT_SR); }
+  int inputs() const override { return ntaps + 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return linear ? 54 : 50; }
+  void reset() override { i = 0; std::fill(buffer.begin(), buffer.end(), 0.0f); }
+  void set_sample_rate(double s) override {
+    float f = (float)s;
+    if (sr != f) {
+      sr = f;
+      min_c = fmaxf(min_delay, 1.00001f / f); max_c = fmaxf(max_delay, 1.00001f / f);
+      float bl = linear ? ceilf(max_delay * f) + 2.0f : ceilf(max_delay * f) + 3.0f + 8.0f;
+      size_t n = (size_t)bl, p2 = 1; while (p2 < n) p2 <<= 1;
+      buffer.assign(p2, 0.0f);
+      reset();
+    }
+  }
+  void tick(const float* in, float* out) override {
+    const size_t mask = buffer.size() - 1;
+    buffer[i] = in[0];
+    float o = 0.0f;
+    for (int t = 1; t <= ntaps; t++) {
+      float tap = (linear ? fminf(fmaxf(in[t], min_delay), max_delay) : fminf(fmaxf(in[t], min_c), max_c)) * sr;
+      size_t tf = (size_t)tap;
+      size_t i1 = (i - tf) & mask;
+      float d = tap - (float)tf;
+      if (linear) { size_t i2 = (i1 - 1) & mask; o += lerpf(buffer[i1], buffer[i2], d); }
+      else { size_t i0 = (i1 + 1) & mask, i2 = (i1 - 1) & mask, i3 = (i1 - 2) & mask; o += splinef(buffer[i0], buffer[i1], buffer[i2], buffer[i3], d); }
+    }
+    i = (i + 1) & mask;
+    out[0] = o;
+  }
+  FO_CLONE(Tap)
+};
+
+// ---- src/feedback.rs:180-314 Feedback2<N,X,Y,U> (ID 66): out = x(in + value); value = U(y(out))
+struct Feedback2 : Node {
+  Child x, y; bool had; std::vector<float> value;
+  Feedback2(Node* x_, Node* y_, bool hadamard_) : x(x_), y(y_), had(hadamard_) {
+    assert(x->inputs() == x->outputs() && y->inputs() == y->outputs() && x->inputs() == y->inputs());
+    prevent_denormals();
+    value.assign(x->inputs(), 0.0f);
+    ctor_ping();
+  }
+  int inputs() const override { return x->inputs(); } int outputs() const override { return x->outputs(); }
+  uint64_t id() const override { return 66; }
+  void reset() override { x->reset(); y->reset(); std::fill(value.begin(), value.end(), 0.0f); }
+  void set_sample_rate(double sr) override { x->set_sample_rate(sr); y->set_sample_rate(sr); }
+  void tick(const float* in, float* out) override {
+    const int n = inputs(); float t[256], u[256];
+    for (int c = 0; c < n; c++) t[c] = in[c] + value[c];
+    x->tick(t, out);
+    y->tick(out, u);
+    for (int c = 0; c < n; c++) value[c] = u[c];
+    if (had) hadamard(value.data(), n);
+  }
+  AttoHash ping(bool probe, AttoHash h) override { return y->ping(probe, x->ping(probe, h.hash(id()))); }
+  FO_CLONE(Feedback2)
 };
 
 // ---- src/pan.rs:12-91 Panner<N> (ID 49)

@@ -65,6 +65,11 @@ API Node* fo_allnest(float coefficient, Node* x, int nin) { return new AllNest(c
 API Node* fo_pan(float value) { return new Panner(value, 1); }
 API Node* fo_panner() { return new Panner(0.0f, 2); }
 API Node* fo_adsr_live(float a, float d, float s, float r) { return new AdsrLive(a, d, s, r); }
+API Node* fo_phase_osc(int kind) { return new PhaseOsc(kind); }   // 0 ramp, 1 poly_saw, 2 poly_square, 3 poly_pulse
+API Node* fo_mls(int bits) { return new Mls((uint32_t)bits); }
+API Node* fo_impulse(int n) { return new Impulse(n); }
+API Node* fo_tap(int ntaps, int linear, float min_delay, float max_delay) { return new Tap(ntaps, linear != 0, min_delay, max_delay); }
+API Node* fo_feedback2(Node* x, Node* y, int hadamard_) { return new Feedback2(x, y, hadamard_ != 0); }
 // BiquadCoefs constructors (src/biquad.rs:27-116), f32: kind 0 butter_lowpass, 1 resonator, 2 lowpass, 3 highpass, 4 bell
 API void fo_biquad_coefs(int kind, float sr, float f, float q, float gain, float* out5) {
   BiquadCoefs c;

@@ -35,6 +35,10 @@ GRAPHS = [
     lambda: (pass_() ^ mul(-4.0) ^ add(-2.0)) >> add(5.0) + sub(3.0) + mul(-4.0),
     lambda: feedback(delay(0.5) * 0.5),
     lambda: dc(1.0) >> adsr_live(0.001, 0.002, 0.5, 0.003),
+    lambda: poly_saw_hz(440.0) | poly_square_hz(220.0).phase(0.5) | poly_pulse_hz(110.0, 0.3) | ramp_hz(5.0),
+    lambda: mls() | mls_bits(10).seed(3) | (impulse(2) >> join(2)),
+    lambda: (noise() | sine_hz(0.5) * 0.004 + 0.005) >> tap(0.001, 0.01) | (noise() | dc((0.002, 0.007))) >> multitap_linear(2, 0.001, 0.01),
+    lambda: noise() >> feedback2(delay(0.002) * 0.5, lowpass_hz(2000.0, 1.0)) | (noise() | dc(800.0)) >> butterpass() | (noise() | dc((900.0, 8.0))) >> resonator(),
 ]
 
 

@@ -34,6 +34,15 @@ CASES = {
     "busi_branchi": lambda i: noise().seed(i) >> branchi(3, lambda k: lowpass_hz(200.0 * (k + 1) + i, 1.0)) >> (pass_() | sink() | pass_()) >> join(2),
     "multisplit_multijoin_thru": lambda i: (noise().seed(i) | noise().seed(i + 1000)) >> multisplit(2, 3) >> multijoin(2, 3) >> ~(join(2) >> lowpass_hz(700.0 + i, 2.0)) >> reverse(2),
     "wavesynth_phase_out": lambda i: dc(100.0 + 9.0 * i) >> An("wavesynth", (0, 2), (), 1, 2),
+    "polyblep_oscs": lambda i: poly_saw_hz(110.0 + 13.0 * i) * 0.5 & poly_square_hz(55.0 + 7.0 * i).phase(0.25) * 0.3 & poly_pulse_hz(220.0 + i, 0.1 + 0.02 * (i % 30)) * 0.2 & ramp_hz(3.0 + i),
+    "poly_pulse_modulated": lambda i: ((sine_hz(5.0) * 30.0 + 200.0 + 11.0 * i) | (sine_hz(0.5 + 0.1 * (i % 7)) * 0.4 + 0.5)) >> poly_pulse(),
+    "mls_impulse": lambda i: mls_bits(5 + i % 20) * 0.5 + mls().seed(i) * 0.25 + (impulse(1) >> lowpass_hz(500.0 + 10.0 * i, 4.0)),
+    "tap_spline_mod": lambda i: (noise().seed(i) | (sine_hz(0.7 + 0.1 * (i % 5)) * 0.004 + 0.005)) >> tap(0.0005, 0.01),
+    "multitap_linear": lambda i: (noise().seed(i) | dc((0.002 + 0.0001 * i, 0.007)) | (sine_hz(2.0) * 0.001 + 0.003)) >> multitap_linear(3, 0.001, 0.01),
+    "feedback2_delay_filter": lambda i: noise().seed(i) >> feedback2(delay(0.002) * (0.3 + 0.01 * (i % 30)), lowpass_hz(1500.0 + 20.0 * i, 1.0)),
+    "fdn2_pair": lambda i: (noise().seed(i) | noise().seed(i + 500)) >> fdn2(stacki(2, lambda k: delay(0.001 + 0.0004 * k) * 0.45), stacki(2, lambda k: fir3(0.4 + 0.01 * (i % 20)))),
+    "butterpass_audio_rate": lambda i: (noise().seed(i) | (sine_hz(1.0 + 0.2 * (i % 5)) * 300.0 + 900.0)) >> butterpass(),
+    "resonator_audio_rate": lambda i: (noise().seed(i) | (sine_hz(0.5) * 200.0 + 700.0 + 5.0 * i) | dc(20.0 + i)) >> resonator(),
     "product_fm_feedback": lambda i: (sine_hz(200.0 + i) * sine_hz(3.0 + 0.1 * i)) >> feedback(tick() * 0.25 >> lowpass_hz(2000.0, 0.7)),
 }
 GATED = {
@@ -72,5 +81,5 @@ def test_unsupported_graph_reports_error():
     from fundsp_b200.bank import GpuBank
     from fundsp_b200.capi import ERR_UNSUPPORTED, FdspError
     with pytest.raises(FdspError) as e:
-        GpuBank([(noise() | dc(500.0)) >> butterpass()], per_voice=True)  # audio-rate butterpass has no device lowering
+        GpuBank([busi(2, lambda k: noise() if k == 0 else sine_hz(440.0))], per_voice=True)  # busi needs one node type (MultiBus<N, X>)
     assert e.value.code == ERR_UNSUPPORTED

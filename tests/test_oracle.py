@@ -229,7 +229,59 @@ def test_tick_equals_process():
     check_wave(dc(1.0) >> adsr_live(0.001, 0.002, 0.5, 0.003) | dc(0.0) >> adsr_live(0.001, 0.002, 0.5, 0.003))
     check_wave(organ_hz(330.0) | hammond_hz(220.0) * 0.5 & soft_saw_hz(55.0))
     check_wave(noise() >> pan(0.3))
+    check_wave(noise().seed(1) * noise() | busi(4, lambda i: mls_bits(10 + i)))                        # test_basic.rs:171
+    check_wave(dc(440.0) >> ramp() | ramp_hz(-220.0).phase(0.5))                                       # test_basic.rs:235
+    check_wave(impulse(2))                                                                              # test_basic.rs:307
+    check_wave(poly_saw_hz(440.0) | poly_square_hz(4400.0))                                             # test_basic.rs:308
+    check_wave(poly_saw_hz(550.0).phase(0.75) | poly_square_hz(5500.0).phase(0.5))                      # test_basic.rs:309
+    check_wave(dc((660.0, 0.1)) >> poly_pulse().phase(0.75) | poly_pulse_hz(6600.0, 0.9).phase(0.9))    # test_basic.rs:311
+    lfo2 = (sine_hz(0.7) * 0.4 + 0.5) | (sine_hz(1.3) * 0.3 + 0.35)
+    check_wave((noise() | lfo2) >> multitap(2, 0.0, 1.0))                                               # test_basic.rs:347-349
+    check_wave((noise() | lfo2) >> multitap_linear(2, 0.0, 1.0))                                        # test_basic.rs:350-352
+    check_wave((mls() | dc(880.0)) >> ~butterpass() >> butterpass())                                    # test_basic.rs:199
+    check_wave((noise() | dc((440.0, 110.0))) >> resonator())
+    check_wave(noise() >> feedback2(delay(0.002) * 0.5, lowpass_hz(2000.0, 1.0)) | (noise() | noise()) >> fdn2(stacki(2, lambda i: delay(0.001 + 0.0005 * i) * 0.4), stacki(2, lambda i: fir3(0.5))))
     L.fo_restore_denormals()
+
+
+def test_mls_is_maximum_length():  # src/noise.rs:11-98: the sequence of an n-bit MLS repeats after exactly 2**n - 1 steps
+    for n in range(2, 15):
+        u = OracleUnit(mls_bits(n))
+        period = (1 << n) - 1
+        x = u.process_many(2 * period, None)[0]
+        assert set(np.unique(x)) == {-1.0, 1.0}
+        assert np.array_equal(x[:period], x[period:])
+        assert int((x[:period] > 0).sum()) == 1 << (n - 1)          # balance property: one more 1 than 0
+        ac = [float(np.dot(x[:period], np.roll(x[:period], k))) for k in (1, 2, 5)]
+        assert ac == [-1.0, -1.0, -1.0], (n, ac)                    # two-valued autocorrelation <=> maximal period
+
+
+def test_polyblep_oscillators_known_values():  # src/oscillator.rs:510-760
+    sr, f = 44100.0, 441.0
+    u = OracleUnit(poly_saw_hz(f).phase(0.0) | ramp_hz(f).phase(0.0) | poly_square_hz(f).phase(0.0) | poly_pulse_hz(f, 0.25).phase(0.0))
+    w = u.render(sr, 400 / sr)
+    ph = (np.arange(400) * 0.01) % 1.0
+    d = np.abs(w[1] - ph)
+    assert np.minimum(d, 1.0 - d).max() < 1e-4                       # Ramp outputs the phase itself (f32 accumulation)
+    mid = (ph > 0.02) & (ph < 0.97)
+    assert np.abs(w[0][mid] - (2.0 * ph[mid] - 1.0)).max() < 1e-4    # saw is naive away from the step
+    assert w[0][0] == 0.0                                            # and the BLEP residual centres the step
+    sq_mid = mid & (np.abs(ph - 0.5) > 0.02)
+    assert np.array_equal(w[2][sq_mid], np.where(ph[sq_mid] < 0.5, 1.0, -1.0).astype(np.float32))
+    pu_mid = mid & (np.abs(ph - 0.25) > 0.02)
+    assert np.array_equal(w[3][pu_mid], np.where(ph[pu_mid] < 0.25, 1.0, -1.0).astype(np.float32))
+    imp = OracleUnit(impulse(1)).process_many(70, None)[0]
+    assert imp[0] == 1.0 and not imp[1:].any()
+
+
+def test_tap_reads_exact_delay():  # src/delay.rs:141-286: an integer tap delay reproduces the input shifted by that many samples
+    sr = 44100.0
+    for mk in (tap, tap_linear):
+        u = OracleUnit((pass_() | dc(100.0 / sr)) >> mk(0.0, 0.01))
+        rng = np.random.default_rng(5)
+        x = rng.uniform(-1, 1, (1, 700)).astype(np.float32)
+        y = u.filter(sr, x)[0]
+        assert np.abs(y[100:] - x[0, :600]).max() < 1e-6 and not y[:98].any()
 
 
 # ---------------------------------------------------------------- equivalences (test_basic.rs:392-406,520-529)
