@@ -10,7 +10,7 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libfundsp_b200.so")
+SO = os.environ.get("FDSP_B200_LIB") or os.path.join(HERE, "libfundsp_b200.so")  # override: kernel build variants when tuning
 HEADER = os.path.join(os.path.dirname(HERE), "include", "fundsp_b200.h")
 
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_ARITY, ERR_STATE = range(6)

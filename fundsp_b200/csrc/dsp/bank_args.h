@@ -1,6 +1,7 @@
 // Plain-data kernel arguments shared by host (csrc/host) and device (csrc/dsp) code.
 #pragma once
 #ifndef __CUDACC_RTC__
+#include <cstddef>
 #include <cstdint>
 #endif
 
@@ -15,6 +16,16 @@ struct WaveTableDev {
   int total;          // floats in `data`
   const float* data;
 };
+
+// Depth (samples) of the CTA mix tile [OUT][TS][NT+1]: the tile is reduced and recycled every TS samples, so wide
+// voices keep a ~33 KB tile and the 164 KB wavetable set still fits beside it in shared memory.
+#ifdef __CUDACC__
+#define FDSP_HDC __host__ __device__
+#else
+#define FDSP_HDC
+#endif
+FDSP_HDC constexpr int mix_tile_samples(int outs) { return outs <= 1 ? 64 : (outs == 2 ? 32 : (outs <= 4 ? 16 : 8)); }
+FDSP_HDC constexpr size_t mix_tile_floats(int outs, int nt) { return (size_t)outs * (size_t)mix_tile_samples(outs) * (size_t)(nt + 1); }
 
 struct BankArgs {
   const uint32_t* params;   // [NP][V]

@@ -38,13 +38,21 @@ FDSP_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
 
 // TB: stage the wavetable data of kind WaveKind<G> in shared memory behind the mix tile (one TMA bulk copy per
 // 32 KB slice, single mbarrier), so the per-sample table taps become conflict-light LDS instead of divergent LDG.
+#ifndef FDSP_MIN_CTAS
+#define FDSP_MIN_CTAS 1   // one resident CTA per SM is all a bank needs: lets ptxas spend registers on overlapping the 8-sample group
+#endif
+#ifndef FDSP_NO_GROUP
+#define FDSP_NO_GROUP 0
+#endif
+
 template <class G, int NT, int MODE, bool TB>
-__global__ void __launch_bounds__(NT) bank_kernel(const BankArgs a) {
-  extern __shared__ __align__(16) float tile[];  // MODE&2: [OUT][64][NT+1]; TB: table data after it
+__global__ void __launch_bounds__(NT, FDSP_MIN_CTAS) bank_kernel(const BankArgs a) {
+  extern __shared__ __align__(16) float tile[];  // MODE&2: [OUT][TS][NT+1]; TB: table data after it
   const uint32_t tid = threadIdx.x;
   const uint32_t v = blockIdx.x * NT + tid;
   const bool active = v < a.V;
   constexpr int IN = G::IN, OUT = G::OUT;
+  constexpr int TS = (MODE & 2) ? mix_tile_samples(OUT) : 64;
   // big programs (e.g. the 32-line FDN in thread-per-voice form) are not unrolled over the 8-sample group
   constexpr int UNROLL = Cost<G>::value <= 160 ? 8 : (Cost<G>::value <= 320 ? 4 : (Cost<G>::value <= 640 ? 2 : 1));
 
@@ -54,7 +62,7 @@ __global__ void __launch_bounds__(NT) bank_kernel(const BankArgs a) {
   if (TB) {
     constexpr int KIND = WaveKind<G>::value >= 0 ? WaveKind<G>::value : 0;
     __shared__ __align__(8) unsigned long long mbar;
-    float* tsm = tile + ((MODE & 2) ? G::OUT * 64 * (NT + 1) : 0);
+    float* tsm = tile + ((MODE & 2) ? mix_tile_floats(OUT, NT) : 0);
     const uint32_t bytes = (uint32_t)a.wt[KIND].total * 4u;
     const uint32_t bar = smem_addr(&mbar);
     if (tid == 0) mbar_init(bar, 1);
@@ -71,6 +79,8 @@ __global__ void __launch_bounds__(NT) bank_kernel(const BankArgs a) {
   if (active) {
     Loader l{a.params, a.state, a.uniform, a.V, v, 0u, 0u, 0u, 0u};
     G::load(r, l);
+  } else if (MODE & 2) {
+    for (int e = 0; e < OUT * TS; e++) tile[e * (NT + 1) + tid] = 0.0f;  // columns of absent voices stay zero
   }
   const bool vec_ok = ((a.out_stride | a.out_offset) & 3u) == 0u;
 
@@ -79,71 +89,96 @@ __global__ void __launch_bounds__(NT) bank_kernel(const BankArgs a) {
     const int nb = (a.n - t0) < 64u ? (int)(a.n - t0) : 64;
     const int nfull = nb & ~7;
     c.n = nb;
-    if (active) {
-      float* orow = (MODE & 1) ? a.out + (size_t)__ldg(a.row_map + v) * a.out_stride + a.out_offset + t0 : nullptr;
-      const float* irow = (IN > 0) ? a.in + a.in_offset + t0 : nullptr;
-      c.rem = false;
+    float* orow = (active && (MODE & 1)) ? a.out + (size_t)__ldg(a.row_map + v) * a.out_stride + a.out_offset + t0 : nullptr;
+    const float* irow = (IN > 0) ? a.in + a.in_offset + t0 : nullptr;
 #pragma unroll 1
-      for (int g = 0; g < nfull; g += 8) {
-        float ob[OUT > 0 ? OUT : 1][8];
+    for (int s0 = 0; s0 < nb; s0 += TS) {   // one pass when there is no mix tile (TS = 64)
+      const int s1 = (s0 + TS) < nb ? (s0 + TS) : nb;
+      if (active) {
+        const int gend = s1 < nfull ? s1 : nfull;
+        c.rem = false;
+#pragma unroll 1
+        for (int g = s0; g < gend; g += 8) {
+          float ob[OUT > 0 ? OUT : 1][8];
+          if constexpr (UNROLL == 8 && !FDSP_NO_GROUP) {
+            // small programs: node by node over the 8-sample group (group_step), all intermediates in registers
+            Fr8<IN> in8; Fr8<OUT> o8;
+#pragma unroll
+            for (int k = 0; k < IN; k++) {
+#pragma unroll
+              for (int j = 0; j < 8; j++) in8.v[k][j] = __ldg(irow + (size_t)k * a.in_stride + g + j);
+            }
+            c.i = g; c.first = true;
+            group_step<G>(r, c, in8, o8);
+#pragma unroll
+            for (int k = 0; k < OUT; k++) {
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                ob[k][j] = o8.v[k][j];
+                if (MODE & 2) tile[(k * TS + (g - s0) + j) * (NT + 1) + tid] = o8.v[k][j];
+              }
+            }
+          } else {
 #pragma unroll(UNROLL)
-        for (int j = 0; j < 8; j++) {
-          Fr<IN> in; Fr<OUT> o;
+            for (int j = 0; j < 8; j++) {
+              Fr<IN> in; Fr<OUT> o;
 #pragma unroll
-          for (int k = 0; k < IN; k++) in.v[k] = __ldg(irow + (size_t)k * a.in_stride + g + j);
-          c.i = g + j; c.first = (j == 0);
-          G::template step<false>(r, c, in, o);
+              for (int k = 0; k < IN; k++) in.v[k] = __ldg(irow + (size_t)k * a.in_stride + g + j);
+              c.i = g + j; c.first = (j == 0);
+              G::template step<false>(r, c, in, o);
 #pragma unroll
-          for (int k = 0; k < OUT; k++) {
-            ob[k][j] = o.v[k];
-            if (MODE & 2) tile[(k * 64 + g + j) * (NT + 1) + tid] = o.v[k];
+              for (int k = 0; k < OUT; k++) {
+                ob[k][j] = o.v[k];
+                if (MODE & 2) tile[(k * TS + (g - s0) + j) * (NT + 1) + tid] = o.v[k];
+              }
+            }
+          }
+          if (MODE & 1) {
+#pragma unroll
+            for (int k = 0; k < OUT; k++) {
+              float* p = orow + (size_t)k * a.out_stride + g;
+              if (vec_ok) {
+                *reinterpret_cast<float4*>(p) = make_float4(ob[k][0], ob[k][1], ob[k][2], ob[k][3]);
+                *reinterpret_cast<float4*>(p + 4) = make_float4(ob[k][4], ob[k][5], ob[k][6], ob[k][7]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) p[j] = ob[k][j];
+              }
+            }
           }
         }
-        if (MODE & 1) {
+        if (s1 == nb) {  // end of the block: wrap up the SIMD part, then the (size & 7) tail through the tick path
+          G::end_simd(r);
+          c.rem = true; c.first = false;
+#pragma unroll 1
+          for (int i = nfull; i < nb; i++) {
+            Fr<IN> in; Fr<OUT> o;
 #pragma unroll
-          for (int k = 0; k < OUT; k++) {
-            float* p = orow + (size_t)k * a.out_stride + g;
-            if (vec_ok) {
-              *reinterpret_cast<float4*>(p) = make_float4(ob[k][0], ob[k][1], ob[k][2], ob[k][3]);
-              *reinterpret_cast<float4*>(p + 4) = make_float4(ob[k][4], ob[k][5], ob[k][6], ob[k][7]);
-            } else {
+            for (int k = 0; k < IN; k++) in.v[k] = __ldg(irow + (size_t)k * a.in_stride + i);
+            c.i = i;
+            G::template step<false>(r, c, in, o);
 #pragma unroll
-              for (int j = 0; j < 8; j++) p[j] = ob[k][j];
+            for (int k = 0; k < OUT; k++) {
+              if (MODE & 1) orow[(size_t)k * a.out_stride + i] = o.v[k];
+              if (MODE & 2) tile[(k * TS + (i - s0)) * (NT + 1) + tid] = o.v[k];
             }
           }
         }
       }
-      G::end_simd(r);
-      c.rem = true; c.first = false;
-#pragma unroll 1
-      for (int i = nfull; i < nb; i++) {
-        Fr<IN> in; Fr<OUT> o;
-#pragma unroll
-        for (int k = 0; k < IN; k++) in.v[k] = __ldg(irow + (size_t)k * a.in_stride + i);
-        c.i = i;
-        G::template step<false>(r, c, in, o);
-#pragma unroll
-        for (int k = 0; k < OUT; k++) {
-          if (MODE & 1) orow[(size_t)k * a.out_stride + i] = o.v[k];
-          if (MODE & 2) tile[(k * 64 + i) * (NT + 1) + tid] = o.v[k];
-        }
-      }
-    } else if (MODE & 2) {
-      for (int e = 0; e < OUT * 64; e++) tile[e * (NT + 1) + tid] = 0.0f;
-    }
-    if (MODE & 2) {
-      __syncthreads();
-      for (int e = tid; e < OUT * 64; e += NT) {
-        const int k = e >> 6, i = e & 63;
-        if (i < nb) {
-          const float* row = tile + e * (NT + 1);
-          float s = row[0];
+      if (MODE & 2) {
+        __syncthreads();
+        for (int e = tid; e < OUT * TS; e += NT) {
+          const int k = e / TS, i = e - k * TS;
+          if (s0 + i < s1) {
+            const float* row = tile + e * (NT + 1);
+            float s = row[0];
 #pragma unroll 8
-          for (int q = 1; q < NT; q++) s += row[q];
-          a.partial[((size_t)blockIdx.x * OUT + k) * a.n + t0 + i] = s;
+            for (int q = 1; q < NT; q++) s += row[q];
+            a.partial[((size_t)blockIdx.x * OUT + k) * a.n + t0 + s0 + i] = s;
+          }
         }
+        __syncthreads();
       }
-      __syncthreads();
     }
   }
   if (active) {

@@ -18,7 +18,7 @@ template <class G, int MODE, bool TB> cudaError_t launch_one(const BankArgs& a, 
 }
 template <class G, bool TB> cudaError_t launch_mode(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t st) {
   const unsigned grid = (a.V + NT - 1) / NT;
-  const size_t smem = ((mode & 2) ? sizeof(float) * (size_t)G::OUT * 64 * (NT + 1) : 0) + (TB ? table_bytes : 0);
+  const size_t smem = ((mode & 2) ? sizeof(float) * mix_tile_floats(G::OUT, NT) : 0) + (TB ? table_bytes : 0);
   switch (mode & 3) {
     case 1: return launch_one<G, 1, TB>(a, grid, smem, st);
     case 2: return launch_one<G, 2, TB>(a, grid, smem, st);
@@ -29,7 +29,7 @@ template <class G, bool TB> cudaError_t launch_mode(const BankArgs& a, int mode,
 // table_bytes > 0 asks for the shared-memory wavetable variant (only meaningful when G reads a wavetable and it fits).
 template <class G> cudaError_t launch_t(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t st) {
   if (WaveKind<G>::value >= 0 && table_bytes > 0) {
-    const size_t smem = ((mode & 2) ? sizeof(float) * (size_t)G::OUT * 64 * (NT + 1) : 0) + table_bytes;
+    const size_t smem = ((mode & 2) ? sizeof(float) * mix_tile_floats(G::OUT, NT) : 0) + table_bytes;
     if (smem <= 227 * 1024) return launch_mode<G, (WaveKind<G>::value >= 0)>(a, mode, table_bytes, st);
   }
   return launch_mode<G, false>(a, mode, 0, st);

@@ -84,4 +84,26 @@ FDSP_DEV float optimal4x44(float a0, float a1, float a2, float a3, float x) {
   return (((c4 * z + c3) * z + c2) * z + c1) * z + c0;
 }
 
+
+// ---- 8-lane forms of the two functions above: identical per-lane operation order, written lane-parallel so that the
+// eight independent evaluations overlap in one thread (the GPU counterpart of the reference's f32x8 arithmetic).
+#define FDSP_L8 _Pragma("unroll") for (int j = 0; j < 8; j++)
+FDSP_DEV void optimal4x44_8(const float* a0, const float* a1, const float* a2, const float* a3, const float* x, float* y) {
+  float z[8], e1[8], o1[8], e2[8], o2[8], c0[8], c1[8], c2[8], c3[8], c4[8];
+  FDSP_L8 z[j] = x[j] - 0.5f;
+  FDSP_L8 { e1[j] = a2[j] + a1[j]; o1[j] = a2[j] - a1[j]; e2[j] = a3[j] + a0[j]; o2[j] = a3[j] - a0[j]; }
+  FDSP_L8 c4[j] = e1[j] * (float)0.00986988334359864 + e2[j] * (float)-0.00989340017126506;
+  FDSP_L8 c3[j] = o1[j] * (float)-0.46896069955075126 + o2[j] * (float)0.15578800670302476;
+  FDSP_L8 c2[j] = e1[j] * (float)-0.25194210134021744 + e2[j] * (float)0.2519474493593906;
+  FDSP_L8 c1[j] = o1[j] * (float)0.5374383075356016 + o2[j] * (float)0.1542946255730746;
+  FDSP_L8 c0[j] = e1[j] * (float)0.4656725512077848 + e2[j] * (float)0.03432729708429672;
+  FDSP_L8 y[j] = c4[j] * z[j] + c3[j];
+  FDSP_L8 y[j] = y[j] * z[j] + c2[j];
+  FDSP_L8 y[j] = y[j] * z[j] + c1[j];
+  FDSP_L8 y[j] = y[j] * z[j] + c0[j];
+}
+FDSP_DEV void wide_sinf8(const float* v, float* out) {
+  FDSP_L8 out[j] = wide_sinf(v[j]);
+}
+
 }  // namespace fdsp

@@ -20,6 +20,9 @@ namespace fdsp {
 
 
 template <int N> struct Fr { float v[N > 0 ? N : 1]; };
+// Eight consecutive samples of N channels (channel-major): the device analogue of the reference's f32x8 lane group
+// (src/buffer.rs: channel c, sample i lives at slice[(c << 3) + (i >> 3)][i & 7]).
+template <int N> struct Fr8 { float v[N > 0 ? N : 1][8]; };
 
 // Block context. `first`: first lane of an 8-sample SIMD group; `rem`: sample belongs to the tail
 // (size & 7) that the reference runs through `tick` (src/audionode.rs:110-126); `i`/`n`: index / size of block.
@@ -61,6 +64,36 @@ struct Saver {
   static constexpr int IN = (in_), OUT = (out_), NP = (np_), NS = (ns_), NU = (nu_)
 
 struct Empty {};
+
+// ---------------------------------------------------------------- 8-sample group evaluation
+// The block path of the reference evaluates node by node over f32x8 groups, not sample by sample; nodes only interact
+// through their buffers, so evaluating X over 8 samples and then Y over the same 8 is exact. On the GPU this is what
+// gives one thread instruction-level parallelism: a voice is a serial recurrence, there are fewer voice-warps than
+// warp schedulers, so the 8 independent oscillator/table evaluations of a group have to overlap inside one thread.
+// A node opts in with `typedef void GroupStep;` + `step8`; everything else runs its per-sample `step` 8 times.
+template <class T> struct VoidT { typedef void type; };
+template <class Node, class = void> struct HasGroup { static constexpr bool value = false; };
+template <class Node> struct HasGroup<Node, typename VoidT<typename Node::GroupStep>::type> { static constexpr bool value = true; };
+
+template <class Node, class C> FDSP_DEV void group_step(typename Node::R& r, C& c, const Fr8<Node::IN>& in, Fr8<Node::OUT>& o) {
+  if constexpr (HasGroup<Node>::value) {
+    Node::step8(r, c, in, o);
+  } else {
+    const int base = c.i;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      Fr<Node::IN> a; Fr<Node::OUT> b;
+#pragma unroll
+      for (int k = 0; k < Node::IN; k++) a.v[k] = in.v[k][j];
+      c.i = base + j; c.first = (j == 0);
+      Node::template step<false>(r, c, a, b);
+#pragma unroll
+      for (int k = 0; k < Node::OUT; k++) o.v[k][j] = b.v[k];
+    }
+    c.i = base; c.first = true;
+  }
+}
+#define FDSP_G8 _Pragma("unroll") for (int j = 0; j < 8; j++)
 
 // ---------------------------------------------------------------- routing (src/audionode.rs:374-722,2800-2837)
 template <int N> struct Constant {  // ID 2
@@ -135,6 +168,14 @@ template <int K, class X, class Y> struct Binop {  // ID 3: K 0 add, 1 sub, 2 mu
     X::template step<T>(r.x, c, xi, a); Y::template step<T>(r.y, c, yi, b);
     for (int k = 0; k < OUT; k++) o.v[k] = binop<K>(a.v[k], b.v[k]);
   }
+  typedef void GroupStep;
+  template <class C> static FDSP_DEV void step8(R& r, C& c, const Fr8<IN>& in, Fr8<OUT>& o) {
+    Fr8<X::IN> xi; Fr8<Y::IN> yi; Fr8<Y::OUT> b;
+    for (int k = 0; k < X::IN; k++) FDSP_G8 xi.v[k][j] = in.v[k][j];
+    for (int k = 0; k < Y::IN; k++) FDSP_G8 yi.v[k][j] = in.v[X::IN + k][j];
+    group_step<X>(r.x, c, xi, o); group_step<Y>(r.y, c, yi, b);
+    for (int k = 0; k < OUT; k++) FDSP_G8 o.v[k][j] = binop<K>(o.v[k][j], b.v[k][j]);
+  }
   static FDSP_DEV void end_simd(R& r) { X::end_simd(r.x); Y::end_simd(r.y); }
 };
 template <int K, class X> struct Unop {  // ID 4: K 0 neg, 1 +s, 2 -x+s, 3 *s
@@ -146,6 +187,11 @@ template <int K, class X> struct Unop {  // ID 4: K 0 neg, 1 +s, 2 -x+s, 3 *s
     X::template step<T>(r.x, c, in, o);
     for (int k = 0; k < OUT; k++) o.v[k] = K == 0 ? -o.v[k] : (K == 1 ? o.v[k] + r.s : (K == 2 ? -o.v[k] + r.s : o.v[k] * r.s));
   }
+  typedef void GroupStep;
+  template <class C> static FDSP_DEV void step8(R& r, C& c, const Fr8<IN>& in, Fr8<OUT>& o) {
+    group_step<X>(r.x, c, in, o);
+    for (int k = 0; k < OUT; k++) FDSP_G8 o.v[k][j] = K == 0 ? -o.v[k][j] : (K == 1 ? o.v[k][j] + r.s : (K == 2 ? -o.v[k][j] + r.s : o.v[k][j] * r.s));
+  }
   static FDSP_DEV void end_simd(R& r) { X::end_simd(r.x); }
 };
 template <class X, class Y> struct Pipe {  // ID 6
@@ -155,6 +201,10 @@ template <class X, class Y> struct Pipe {  // ID 6
   static FDSP_DEV void save(const R& r, Saver& s) { X::save(r.x, s); Y::save(r.y, s); }
   template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<IN>& in, Fr<OUT>& o) {
     Fr<X::OUT> t; X::template step<T>(r.x, c, in, t); Y::template step<T>(r.y, c, t, o);
+  }
+  typedef void GroupStep;
+  template <class C> static FDSP_DEV void step8(R& r, C& c, const Fr8<IN>& in, Fr8<OUT>& o) {
+    Fr8<X::OUT> t; group_step<X>(r.x, c, in, t); group_step<Y>(r.y, c, t, o);
   }
   static FDSP_DEV void end_simd(R& r) { X::end_simd(r.x); Y::end_simd(r.y); }
 };
@@ -171,6 +221,15 @@ template <class X, class Y> struct Stack {  // ID 7
     for (int k = 0; k < X::OUT; k++) o.v[k] = a.v[k];
     for (int k = 0; k < Y::OUT; k++) o.v[X::OUT + k] = b.v[k];
   }
+  typedef void GroupStep;
+  template <class C> static FDSP_DEV void step8(R& r, C& c, const Fr8<IN>& in, Fr8<OUT>& o) {
+    Fr8<X::IN> xi; Fr8<Y::IN> yi; Fr8<X::OUT> a; Fr8<Y::OUT> b;
+    for (int k = 0; k < X::IN; k++) FDSP_G8 xi.v[k][j] = in.v[k][j];
+    for (int k = 0; k < Y::IN; k++) FDSP_G8 yi.v[k][j] = in.v[X::IN + k][j];
+    group_step<X>(r.x, c, xi, a); group_step<Y>(r.y, c, yi, b);
+    for (int k = 0; k < X::OUT; k++) FDSP_G8 o.v[k][j] = a.v[k][j];
+    for (int k = 0; k < Y::OUT; k++) FDSP_G8 o.v[X::OUT + k][j] = b.v[k][j];
+  }
   static FDSP_DEV void end_simd(R& r) { X::end_simd(r.x); Y::end_simd(r.y); }
 };
 template <class X, class Y> struct Branch {  // ID 8
@@ -184,6 +243,13 @@ template <class X, class Y> struct Branch {  // ID 8
     for (int k = 0; k < X::OUT; k++) o.v[k] = a.v[k];
     for (int k = 0; k < Y::OUT; k++) o.v[X::OUT + k] = b.v[k];
   }
+  typedef void GroupStep;
+  template <class C> static FDSP_DEV void step8(R& r, C& c, const Fr8<IN>& in, Fr8<OUT>& o) {
+    Fr8<X::OUT> a; Fr8<Y::OUT> b;
+    group_step<X>(r.x, c, in, a); group_step<Y>(r.y, c, in, b);
+    for (int k = 0; k < X::OUT; k++) FDSP_G8 o.v[k][j] = a.v[k][j];
+    for (int k = 0; k < Y::OUT; k++) FDSP_G8 o.v[X::OUT + k][j] = b.v[k][j];
+  }
   static FDSP_DEV void end_simd(R& r) { X::end_simd(r.x); Y::end_simd(r.y); }
 };
 template <class X, class Y> struct Bus {  // ID 10
@@ -196,6 +262,12 @@ template <class X, class Y> struct Bus {  // ID 10
     X::template step<T>(r.x, c, in, o); Y::template step<T>(r.y, c, in, b);
     for (int k = 0; k < OUT; k++) o.v[k] = o.v[k] + b.v[k];
   }
+  typedef void GroupStep;
+  template <class C> static FDSP_DEV void step8(R& r, C& c, const Fr8<IN>& in, Fr8<OUT>& o) {
+    Fr8<Y::OUT> b;
+    group_step<X>(r.x, c, in, o); group_step<Y>(r.y, c, in, b);
+    for (int k = 0; k < OUT; k++) FDSP_G8 o.v[k][j] = o.v[k][j] + b.v[k][j];
+  }
   static FDSP_DEV void end_simd(R& r) { X::end_simd(r.x); Y::end_simd(r.y); }
 };
 template <class X> struct Thru {  // ID 12
@@ -206,6 +278,11 @@ template <class X> struct Thru {  // ID 12
   template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<IN>& in, Fr<OUT>& o) {
     Fr<X::OUT> a; X::template step<T>(r.x, c, in, a);
     for (int k = 0; k < IN; k++) o.v[k] = k < X::OUT ? a.v[k < X::OUT ? k : 0] : in.v[k];
+  }
+  typedef void GroupStep;
+  template <class C> static FDSP_DEV void step8(R& r, C& c, const Fr8<IN>& in, Fr8<OUT>& o) {
+    Fr8<X::OUT> a; group_step<X>(r.x, c, in, a);
+    for (int k = 0; k < IN; k++) FDSP_G8 o.v[k][j] = k < X::OUT ? a.v[k < X::OUT ? k : 0][j] : in.v[k][j];
   }
   static FDSP_DEV void end_simd(R& r) { X::end_simd(r.x); }
 };
@@ -244,6 +321,30 @@ template <int KIND, int OP, int N, class X> struct Multi {
       }
     }
   }
+  typedef void GroupStep;
+  template <class C> static FDSP_DEV void step8(R& r, C& c, const Fr8<IN>& in, Fr8<OUT>& o) {
+    if (KIND == 32) {  // chain
+      Fr8<X::IN> t; Fr8<X::OUT> u;
+      for (int q = 0; q < X::IN; q++) FDSP_G8 t.v[q][j] = in.v[q][j];
+#pragma unroll
+      for (int k = 0; k < N; k++) { group_step<X>(r.x[k], c, t, u); for (int q = 0; q < X::OUT && q < X::IN; q++) FDSP_G8 t.v[q][j] = u.v[q][j]; }
+      for (int q = 0; q < X::OUT; q++) FDSP_G8 o.v[q][j] = u.v[q][j];
+      return;
+    }
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      Fr8<X::IN> xi; Fr8<X::OUT> a;
+      for (int q = 0; q < X::IN; q++) FDSP_G8 xi.v[q][j] = in.v[((KIND == 30 || KIND == 31) ? k * X::IN : 0) + q][j];
+      group_step<X>(r.x[k], c, xi, a);
+      for (int q = 0; q < X::OUT; q++) {
+        FDSP_G8 {
+          if (KIND == 30 || KIND == 33) o.v[k * X::OUT + q][j] = a.v[q][j];
+          else if (k == 0) o.v[q][j] = a.v[q][j];
+          else o.v[q][j] = (KIND == 28) ? o.v[q][j] + a.v[q][j] : binop<OP>(o.v[q][j], a.v[q][j]);
+        }
+      }
+    }
+  }
   static FDSP_DEV void end_simd(R& r) {
 #pragma unroll
     for (int k = 0; k < N; k++) X::end_simd(r.x[k]);
@@ -259,6 +360,13 @@ struct Noise {  // src/noise.rs:170-234, ID 20: counter-based white noise
   template <bool T, class C> static FDSP_DEV void step(R& r, const C&, const Fr<0>&, Fr<1>& o) {
     r.state += 1u;
     o.v[0] = (float)(hash32x(r.state) >> 8) * (2.0f / 16777215.0f) - 1.0f;
+  }
+  typedef void GroupStep;
+  template <class C> static FDSP_DEV void step8(R& r, C&, const Fr8<0>&, Fr8<1>& o) {
+    uint32_t h[8];
+    FDSP_G8 h[j] = hash32x(r.state + 1u + (uint32_t)j);
+    FDSP_G8 o.v[0][j] = (float)(h[j] >> 8) * (2.0f / 16777215.0f) - 1.0f;
+    r.state += 8u;
   }
   static FDSP_DEV void end_simd(R&) {}
 };
@@ -277,12 +385,18 @@ struct Sine {  // src/oscillator.rs:18-102, ID 21
       o.v[0] = wide_sinf(p * TAU_F);
     }
   }
+  typedef void GroupStep;
+  template <class C> static FDSP_DEV void step8(R& r, C& c, const Fr8<1>& in, Fr8<1>& o) {  // :74-86, 8 lanes at once
+    float p[8];
+    FDSP_G8 { p[j] = r.phase * TAU_F; r.phase += in.v[0][j] * c.sd64; }
+    wide_sinf8(p, o.v[0]);
+  }
   static FDSP_DEV void end_simd(R& r) { r.phase = r.phase - floorf(r.phase); }
 };
 template <int KIND, int NOUT> struct WaveSynth {  // src/wavetable.rs:244-359, ID 34
   FDSP_NODE(1, NOUT, 0, 2, 0);
-  struct R { float phase; int hint; int ti; float w; int o1, o2; int l1, l2; };
-  static FDSP_DEV void load(R& r, Loader& l) { r.phase = l.Sf(); r.hint = (int)l.S(); r.ti = r.hint; r.w = 0.0f; r.o1 = r.o2 = 0; r.l1 = r.l2 = 32; }
+  struct R { float phase; int hint; int ti; float w; int o1, o2; int l1, l2; float fsel; int hsel; };  // fsel/hsel: memo of the last select()
+  static FDSP_DEV void load(R& r, Loader& l) { r.phase = l.Sf(); r.hint = (int)l.S(); r.ti = r.hint; r.w = 0.0f; r.o1 = r.o2 = 0; r.l1 = r.l2 = 32; r.fsel = __int_as_float(0x7fc00000); r.hsel = -1; }
   static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.phase); s.S((uint32_t)r.hint); }
   static FDSP_DEV int table_index(const WaveTableDev& t, int hint, float f) {  // :157-179
     if (f >= __ldg(&t.pitch[hint]) && f <= __ldg(&t.pitch[hint + 1])) return hint;
@@ -297,6 +411,8 @@ template <int KIND, int NOUT> struct WaveSynth {  // src/wavetable.rs:244-359, I
   }
   static FDSP_DEV void select(R& r, const WaveTableDev& t, int hint, float freq) {  // read/read_simd :181-212
     float f = fabsf(freq);
+    if (f == r.fsel && hint == r.hsel) return;  // pure function of (hint, f): a constant-pitch voice looks the tables up once
+    r.fsel = f; r.hsel = hint;
     int ti = table_index(t, hint, f);
     r.ti = ti;
     r.w = clamp01f(delerpf(__ldg(&t.pitch[ti]), __ldg(&t.pitch[ti + 1]), f));
@@ -307,14 +423,13 @@ template <int KIND, int NOUT> struct WaveSynth {  // src/wavetable.rs:244-359, I
     if (C::SMEM_TABLES) { if (c.tsm_kind == KIND) return lds_f32(c.tsm + 4u * (uint32_t)idx); }
     return __ldg(t.data + idx);
   }
+  // Tables carry wrap-around guard samples (host device_wavetable): taps i1-1 .. i1+2 modulo len are consecutive floats.
   template <class C> static FDSP_DEV float at(const C& c, const WaveTableDev& t, int off, int len, float phase) {  // :125-155 (i32 index math, truncation)
     float p = (float)len * phase;
     int i1 = (int)p;
     float w = p - (float)i1;
-    int mask = len - 1;
-    int i0 = (i1 - 1) & mask; i1 &= mask;
-    int i2 = (i1 + 1) & mask, i3 = (i2 + 1) & mask;
-    return optimal4x44(tap(c, t, off + i0), tap(c, t, off + i1), tap(c, t, off + i2), tap(c, t, off + i3), w);
+    const int b = off + (i1 & (len - 1)) - 1;
+    return optimal4x44(tap(c, t, b), tap(c, t, b + 1), tap(c, t, b + 2), tap(c, t, b + 3), w);
   }
   template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<1>& in, Fr<NOUT>& o) {
     const WaveTableDev& t = c.wt[KIND];
@@ -332,6 +447,31 @@ template <int KIND, int NOUT> struct WaveSynth {  // src/wavetable.rs:244-359, I
     }
     o.v[0] = (1.0f - r.w) * at(c, t, r.o1, r.l1, ph) + r.w * at(c, t, r.o2, r.l2, ph);
     if (NOUT > 1) o.v[NOUT > 1 ? 1 : 0] = ph;
+  }
+  typedef void GroupStep;
+  template <class C> static FDSP_DEV void at8(const C& c, const WaveTableDev& t, int off, int len, const float* ph, float* y) {
+    float w[8], a0[8], a1[8], a2[8], a3[8];
+    const int mask = len - 1;
+    const float flen = (float)len;
+    FDSP_G8 {
+      const float p = flen * ph[j];
+      const int i1 = (int)p;
+      w[j] = p - (float)i1;
+      const int b = off + (i1 & mask) - 1;
+      a0[j] = tap(c, t, b); a1[j] = tap(c, t, b + 1); a2[j] = tap(c, t, b + 2); a3[j] = tap(c, t, b + 3);
+    }
+    optimal4x44_8(a0, a1, a2, a3, w, y);
+  }
+  template <class C> static FDSP_DEV void step8(R& r, C& c, const Fr8<1>& in, Fr8<NOUT>& o) {  // :327-348, one f32x8 group
+    const WaveTableDev& t = c.wt[KIND];
+    select(r, t, r.ti, in.v[0][0]);
+    float ph[8], a[8], b[8];
+    FDSP_G8 { r.phase += in.v[0][j] * c.sd32; ph[j] = r.phase - wide_floorf(r.phase); }
+    at8(c, t, r.o1, r.l1, ph, a);
+    at8(c, t, r.o2, r.l2, ph, b);
+    const float u = 1.0f - r.w;
+    FDSP_G8 o.v[0][j] = u * a[j] + r.w * b[j];
+    if (NOUT > 1) FDSP_G8 o.v[NOUT > 1 ? 1 : 0][j] = ph[j];
   }
   static FDSP_DEV void end_simd(R& r) { r.phase = r.phase - floorf(r.phase); r.hint = r.ti; }
 };

@@ -169,7 +169,7 @@ std::string Bank::lower_and_upload(bool upload_state) {
       const std::string tag = "WaveSynth<" + std::to_string(kind) + ",";
       for (auto& c : classes) used = used || c.sig.find(tag) != std::string::npos;
       if (!used) continue;
-      const WaveTableHost& t = global_wavetable(kind);
+      const WaveTableHost& t = device_wavetable(kind);
       h[kind].n = (int)t.pitch.size(); h[kind].total = (int)t.data.size();
       for (size_t i = 0; i < t.pitch.size() && i < 48; i++) { h[kind].pitch[i] = t.pitch[i]; h[kind].off[i] = t.off[i]; h[kind].len[i] = t.len[i]; }
       std::string e = dev_alloc(&d_wtdata[kind], t.data.size());
@@ -260,7 +260,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
       // short ones (process()-sized) read the tables through L1/L2 instead
       size_t table_bytes = 0;
       const int wk = c.k ? c.k->wave_kind : -1;
-      if (wk >= 0 && len >= 1024) table_bytes = global_wavetable(wk).data.size() * sizeof(float);
+      if (wk >= 0 && len >= 1024) table_bytes = device_wavetable(wk).data.size() * sizeof(float);
       if (c.fdn) {
         FdnArgs f;
         f.params = c.d_params; f.state = c.d_state; f.uniform = c.d_uniform; f.p0 = c.p0; f.s0 = c.s0; f.u0 = c.u0; f.scalar_row = c.scalar_row;

@@ -135,6 +135,7 @@ bool net_extract_voices(HNode* net, std::vector<HNode*>& voices, std::string& tr
 // ---- wavetables (src/wavetable.rs:40-123, 493-623): built once per waveform kind on the host
 struct WaveTableHost { std::vector<float> pitch; std::vector<int> off, len; std::vector<float> data; };
 const WaveTableHost& global_wavetable(int kind);
+const WaveTableHost& device_wavetable(int kind);   // same tables with wrap-around guard samples (the layout the kernels read)
 
 }  // namespace host
 }  // namespace fdsp

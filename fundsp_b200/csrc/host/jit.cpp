@@ -16,7 +16,7 @@
 
 #include "registry.h"
 
-#include "../_build/jit_headers.inc"  // kJitHeaderNames[], kJitHeaderSrc[], kJitHeaderCount
+#include "jit_headers.inc"  // kJitHeaderNames[], kJitHeaderSrc[], kJitHeaderCount
 
 namespace fdsp {
 namespace host {
@@ -76,7 +76,7 @@ struct JitProgram : Program {
     const Api& A = api();
     mode &= 3;
     if (mode == 0) return cudaErrorInvalidValue;
-    const size_t tile = (mode & 2) ? sizeof(float) * (size_t)OUT * 64 * (threads + 1) : 0;
+    const size_t tile = (mode & 2) ? sizeof(float) * mix_tile_floats(OUT, threads) : 0;
     int tb = (wave_kind >= 0 && table_bytes > 0 && tile + table_bytes <= 227 * 1024) ? 1 : 0;
     CUfunction f = fn[mode - 1][tb];
     if (!f) return cudaErrorInvalidDeviceFunction;

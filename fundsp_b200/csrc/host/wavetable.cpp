@@ -115,5 +115,29 @@ const WaveTableHost& global_wavetable(int kind) {
   return tables[kind];
 }
 
+// Device image of a wavetable set: each table is stored as [t[len-1]] t[0..len) [t[0] t[1]], so the four taps of the
+// cubic read (i1-1, i1, i1+1, i1+2, all modulo len; src/wavetable.rs:125-155) are four CONSECUTIVE floats and the kernel
+// needs one masked index per read instead of four. `off` points at t[0]; the total is padded to 16 bytes for TMA.
+const WaveTableHost& device_wavetable(int kind) {
+  static WaveTableHost tables[6];
+  static std::once_flag once[6];
+  std::call_once(once[kind], [kind]() {
+    const WaveTableHost& t = global_wavetable(kind);
+    WaveTableHost& d = tables[kind];
+    d.pitch = t.pitch; d.len = t.len;
+    for (size_t i = 0; i < t.off.size(); i++) {
+      const float* w = t.data.data() + t.off[i];
+      const int len = t.len[i];
+      d.data.push_back(w[len - 1]);
+      d.off.push_back((int)d.data.size());
+      d.data.insert(d.data.end(), w, w + len);
+      d.data.push_back(w[0]);
+      d.data.push_back(w[1 % len]);
+    }
+    while (d.data.size() & 3) d.data.push_back(0.0f);
+  });
+  return tables[kind];
+}
+
 }  // namespace host
 }  // namespace fdsp
