@@ -65,6 +65,13 @@ class GpuBank:
     def outputs(self): return self.L.fdsp_bank_outputs(self.h)
     def set_sample_rate(self, sr): check(self.L.fdsp_bank_set_sample_rate(self.h, float(sr)))
     def reset(self): check(self.L.fdsp_bank_reset(self.h))
+
+    def set(self, voice, kind, values=(), seed=0, address=()):
+        """AudioUnit::set on one voice: `kind` is a setting.rs Parameter index (capi.P_*), `address` = [(1, index) | (2, node_id), ...]."""
+        import ctypes as C
+        addr = [x for pair in address for x in pair]
+        vals = (C.c_float * max(1, len(values)))(*values)
+        check(self.L.fdsp_bank_set(self.h, voice, kind, vals, len(values), seed, (C.c_int64 * max(1, len(addr)))(*addr), len(address)))
     def allocate(self, max_samples=64): check(self.L.fdsp_bank_allocate(self.h, int(max_samples)))
 
     def clone(self):

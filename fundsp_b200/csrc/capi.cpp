@@ -196,6 +196,14 @@ API int fdsp_bank_inputs(const fdsp_bank* b) { return b ? b->b.nin : -1; }
 API int fdsp_bank_voice_outputs(const fdsp_bank* b) { return b ? b->b.nout : -1; }
 API int fdsp_bank_outputs(const fdsp_bank* b) { return !b ? -1 : ((b->b.out_mode & 2u) ? b->b.nout : (int)(b->b.V() * (uint32_t)b->b.nout)); }
 API int fdsp_bank_set_sample_rate(fdsp_bank* b, double sr) { return b ? status(b->b.set_sample_rate(sr)) : fail(FDSP_ERR_ARG, "null bank"); }
+API int fdsp_bank_set(fdsp_bank* b, uint32_t voice, int kind, const float* v, int nv, uint64_t seed, const int64_t* addr, int naddr) {
+  if (!b || nv < 0 || nv > 5 || naddr < 0 || naddr > 6) return fail(FDSP_ERR_ARG, "bad setting");
+  Setting s; s.kind = kind; s.seed = seed;
+  for (int i = 0; i < nv; i++) s.v[i] = v[i];
+  for (int i = 0; i < naddr; i++) s.address.push_back({(int)addr[2 * i], (uint64_t)addr[2 * i + 1]});
+  std::string e = b->b.set(voice, s);
+  return e.empty() ? FDSP_OK : fail(e.find("rebuild") != std::string::npos ? FDSP_ERR_UNSUPPORTED : FDSP_ERR_ARG, e);
+}
 API int fdsp_bank_reset(fdsp_bank* b) { return b ? status(b->b.reset()) : fail(FDSP_ERR_ARG, "null bank"); }
 API int fdsp_bank_allocate(fdsp_bank* b, uint64_t max_n) {
   if (!b) return fail(FDSP_ERR_ARG, "null bank");

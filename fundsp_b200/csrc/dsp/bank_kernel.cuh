@@ -166,16 +166,25 @@ __global__ void __launch_bounds__(NT, FDSP_MIN_CTAS) bank_kernel(const BankArgs 
         }
       }
       if (MODE & 2) {
+        // CTA partial mix: two threads per (channel, sample) row, each folding one half of the voice columns with four
+        // interleaved accumulators; fixed association ((a0+a1)+(a2+a3)) then low half + high half -> deterministic.
         __syncthreads();
-        for (int e = tid; e < OUT * TS; e += NT) {
+        constexpr int HALF = NT / 2, QN = HALF / 4, ROWS = OUT * TS;
+        const int h = (int)(tid & 1u);
+        // the odd thread starts QN columns further so that the 32 lanes of a warp (16 rows x 2 halves) hit 32 banks
+        const int c0 = h * HALF + (h * QN) % HALF, c1 = h * HALF + (QN + h * QN) % HALF, c2 = h * HALF + (2 * QN + h * QN) % HALF, c3 = h * HALF + (3 * QN + h * QN) % HALF;
+#pragma unroll 1
+        for (int eb = (int)(tid >> 5) * 16; eb < ROWS; eb += HALF) {   // warp-uniform trip count (full-mask shuffle below)
+          const int e = eb + (int)((tid & 31u) >> 1);
+          const bool ok = e < ROWS;
           const int k = e / TS, i = e - k * TS;
-          if (s0 + i < s1) {
-            const float* row = tile + e * (NT + 1);
-            float s = row[0];
-#pragma unroll 8
-            for (int q = 1; q < NT; q++) s += row[q];
-            a.partial[((size_t)blockIdx.x * OUT + k) * a.n + t0 + s0 + i] = s;
-          }
+          const float* row = tile + (ok ? e : 0) * (NT + 1);
+          float a0 = row[c0], a1 = row[c1], a2 = row[c2], a3 = row[c3];
+#pragma unroll
+          for (int q = 1; q < QN; q++) { a0 += row[c0 + q]; a1 += row[c1 + q]; a2 += row[c2 + q]; a3 += row[c3 + q]; }
+          const float s = (a0 + a1) + (a2 + a3);
+          const float other = __shfl_xor_sync(0xffffffffu, s, 1);
+          if (ok && h == 0 && s0 + i < s1) a.partial[((size_t)blockIdx.x * OUT + k) * a.n + t0 + s0 + i] = s + other;
         }
         __syncthreads();
       }

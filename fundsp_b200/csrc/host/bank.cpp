@@ -12,6 +12,7 @@ namespace host {
 
 namespace {
 constexpr uint32_t TIME_CHUNK = 16384;  // samples per launch (multiple of 64): bounds the partial-mix buffer
+constexpr uint32_t PIPE_CHUNK = 2048;   // sub-chunk of two-stage (dry program -> FDN reverb) classes: stage 1 of chunk k+1 overlaps stage 2 of chunk k
 
 std::string cuerr(const char* what, cudaError_t e) { return std::string(what) + ": " + cudaGetErrorString(e); }
 #define CU(call)                                          \
@@ -31,7 +32,7 @@ template <class T> std::string dev_alloc(T** p, size_t count) {
 Bank::~Bank() {
   cudaSetDevice(device);
   for (auto& c : classes) {
-    cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows);
+    cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows); cudaFree(c.d_dry2); cudaFree(c.d_partial2); for (int q = 0; q < 2; q++) { if (c.e_dry[q]) cudaEventDestroy(c.e_dry[q]); if (c.e_fdn[q]) cudaEventDestroy(c.e_fdn[q]); }
   }
   for (float* p : d_wtdata) cudaFree(p);
   cudaFree(d_wt); cudaFree(d_in); cudaFree(d_out); cudaFree(d_mix); cudaFree(d_rows);
@@ -54,7 +55,12 @@ std::string Bank::init(std::vector<HNode*>& voices, int dev, uint32_t mode) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= dev) return "no usable CUDA device: fundsp_b200 has no CPU fallback";
   CU(cudaSetDevice(device));
-  CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  // `stream` carries the latency-bound voice programs (few CTAs, long serial chains) and gets the highest priority, so that in
+  // the two-stage pipeline its CTAs are placed before the wide FDN kernel of the previous chunk (stream2) fills every SM.
+  int prio_lo = 0, prio_hi = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  CU(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_hi));
+  CU(cudaStreamCreateWithPriority(&stream2, cudaStreamNonBlocking, prio_lo));
   CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
   return lower_and_upload(true);
 }
@@ -119,7 +125,7 @@ std::string Bank::lower_and_upload(bool upload_state) {
   const bool same_shape = classes.size() == fresh.size() && std::equal(classes.begin(), classes.end(), fresh.begin(), [](const VoiceClass& a, const VoiceClass& b) {
                             return a.sig == b.sig && a.voices == b.voices && a.uniform == b.uniform; });
   if (!same_shape) {
-    for (auto& c : classes) { cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows); }
+    for (auto& c : classes) { cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows); cudaFree(c.d_dry2); cudaFree(c.d_partial2); for (int q = 0; q < 2; q++) { if (c.e_dry[q]) cudaEventDestroy(c.e_dry[q]); if (c.e_fdn[q]) cudaEventDestroy(c.e_fdn[q]); } }
     classes = std::move(fresh);
     upload_state = true;
   }
@@ -144,6 +150,8 @@ std::string Bank::lower_and_upload(bool upload_state) {
         if (!(e = dev_alloc(&c.d_ring, (size_t)c.ring_floats * V)).empty()) return e;
         if (c.k) {
           if (!(e = dev_alloc(&c.d_dry, (size_t)V * 2 * TIME_CHUNK)).empty()) return e;
+          if (!(e = dev_alloc(&c.d_dry2, (size_t)V * 2 * PIPE_CHUNK)).empty()) return e;
+          for (int q = 0; q < 2; q++) { CU(cudaEventCreateWithFlags(&c.e_dry[q], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c.e_fdn[q], cudaEventDisableTiming)); }
           if (!(e = dev_alloc(&c.d_dryrows, V)).empty()) return e;
           std::vector<uint32_t> id(V);
           for (uint32_t i = 0; i < V; i++) id[i] = 2 * i;
@@ -194,6 +202,29 @@ std::string Bank::set_sample_rate(double s) {  // AudioUnit::set_sample_rate
   return lower_and_upload(!dirty);
 }
 
+std::string Bank::set(uint32_t voice, const Setting& st) {  // AudioUnit::set (src/audiounit.rs:62, src/setting.rs) on a live bank
+  if (voice >= V()) return "set: voice index out of range";
+  CU(cudaSetDevice(device));
+  nodes[voice]->set(st);
+  Lowering l;
+  nodes[voice]->lower(l);
+  if (!l.ok) return l.why;
+  for (auto& c : classes) {
+    auto it = std::lower_bound(c.voices.begin(), c.voices.end(), voice);
+    if (it == c.voices.end() || *it != voice) continue;
+    const uint32_t i = (uint32_t)(it - c.voices.begin()), Vc = c.V();
+    if (l.U != c.uniform || l.P.size() != c.np || l.S.size() != c.ns)
+      return "set: the setting changes a class-uniform word (a delay length); rebuild the bank instead";
+    // parameters take effect at once (one strided column of the [NP][V] block); running state is left alone, the
+    // construction-time state (what reset() restores) follows the setting like the reference's stored phase/seed
+    if (c.np) CU(cudaMemcpy2DAsync(c.d_params + i, (size_t)Vc * 4, l.P.data(), 4, 4, c.np, cudaMemcpyHostToDevice, stream));
+    for (uint32_t k = 0; k < c.ns; k++) c.state0[(size_t)k * Vc + i] = l.S[k];
+    CU(cudaStreamSynchronize(stream));  // `l` is pageable and goes out of scope
+    return "";
+  }
+  return "internal: voice not found in any class";
+}
+
 std::string Bank::reset() {  // AudioUnit::reset: back to the construction-time state
   CU(cudaSetDevice(device));
   for (auto& c : classes) {
@@ -213,20 +244,41 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
   const bool want_v = (out_mode & 1u) && out_dev, want_m = (out_mode & 2u) && mix_dev;
   if (!want_v && !want_m) return "no output buffer matches the bank's out_mode";
   if (n == 0) return "";
+  const bool save_want_m_ = want_m;
   if (in_stride > 0xffffffffull || out_stride > 0xffffffffull || mix_stride > 0xffffffffull) return "stride too large";
   CU(cudaEventRecord(ev0, stream));
   // Net-ordered mix: the voice kernels materialise per-voice rows (user buffer, or an internal one) and tree_mix_kernel adds
   // them in the Net's association order; the CTA-level partial mix is bypassed.
   const bool tree = tree_mix != 0 && want_m;
-  const uint32_t CH = tree ? 4096u : TIME_CHUNK;
+  // two-stage classes (fused dry program + warp-per-voice FDN) run as a two-stream software pipeline over PIPE_CHUNK samples
+  bool pipelined = false;
+  if (!tree && !getenv("FDSP_NO_PIPELINE")) for (auto& c : classes) pipelined = pipelined || (c.fdn && c.k);
+  const uint32_t CH = tree ? 4096u : (pipelined ? PIPE_CHUNK : TIME_CHUNK);
+  struct Pending { VoiceClass* c; uint32_t grid, len; uint64_t t0; int buf; };
+  std::vector<Pending> pending;   // deferred CTA-partial reductions of pipelined classes (issued one chunk late, on `stream`)
+  auto flush_pending = [&](VoiceClass* only) -> std::string {
+    for (size_t q = 0; q < pending.size();) {
+      Pending& pd = pending[q];
+      if (only && pd.c != only) { q++; continue; }
+      CU(cudaStreamWaitEvent(stream, pd.c->e_fdn[pd.buf], 0));
+      if (save_want_m_) { CU(launch_mix_reduce(pd.buf ? pd.c->d_partial2 : pd.c->d_partial, pd.grid, (uint32_t)nout, pd.len, mix_dev, (uint32_t)mix_stride, (uint32_t)pd.t0, 1, stream)); launches++; }
+      pending.erase(pending.begin() + (long)q);
+    }
+    return "";
+  };
+  uint64_t chunk_index = 0;
   if (tree && !want_v) {
     const size_t need = (size_t)V() * nout * CH;
     if (rows_cap < need) { std::string e = dev_alloc(&d_rows, need); if (!e.empty()) return e; rows_cap = need; }
   }
   const bool save_want_v = want_v, save_want_m = want_m;
-  for (uint64_t t0 = 0; t0 < n; t0 += CH) {
+  for (uint64_t t0 = 0; t0 < n; t0 += CH, chunk_index++) {
     const uint32_t len = (uint32_t)std::min<uint64_t>(CH, n - t0);
     bool first = true;
+    if (pipelined && save_want_m) {  // every class accumulates into a zeroed mix region (reductions of pipelined classes arrive late)
+      CU(cudaMemset2DAsync(mix_dev + t0, (size_t)mix_stride * 4, 0, (size_t)len * 4, (size_t)nout, stream));
+      first = false;
+    }
     bool want_v = save_want_v, want_m = save_want_m;
     float* out_dev_c = out_dev; uint64_t out_stride_c = out_stride; uint64_t out_t0 = t0;
     if (tree) { want_m = false; if (!save_want_v) { want_v = true; out_dev_c = d_rows; out_stride_c = CH; out_t0 = 0; } }
@@ -245,6 +297,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
       if (want_m) {
         const size_t need = (size_t)grid * nout * len;
         if (c.partial_floats < need) { std::string e = dev_alloc(&c.d_partial, (size_t)grid * nout * TIME_CHUNK); if (!e.empty()) return e; c.partial_floats = (size_t)grid * nout * TIME_CHUNK; }
+        if (pipelined && c.fdn && c.k && c.partial2_floats < need) { std::string e = dev_alloc(&c.d_partial2, (size_t)grid * nout * PIPE_CHUNK); if (!e.empty()) return e; c.partial2_floats = (size_t)grid * nout * PIPE_CHUNK; }
       }
       BankArgs a;
       a.params = c.d_params; a.state = c.d_state; a.uniform = c.d_uniform; a.dline = c.d_dline; a.wt = d_wt;
@@ -264,6 +317,30 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
       if (c.fdn) {
         FdnArgs f;
         f.params = c.d_params; f.state = c.d_state; f.uniform = c.d_uniform; f.p0 = c.p0; f.s0 = c.s0; f.u0 = c.u0; f.scalar_row = c.scalar_row;
+        if (c.k && pipelined) {
+          // stage 1 of chunk k on `stream`, stage 2 on `stream2`; buffers alternate, chunk k-1's partial mix is reduced after
+          // stage 1 of chunk k has been queued so that the two stages of neighbouring chunks run side by side
+          const int buf = (int)(chunk_index & 1);
+          float* dry = buf ? c.d_dry2 : c.d_dry;
+          CU(cudaStreamWaitEvent(stream, c.e_fdn[buf], 0));   // FDN of chunk k-2 has consumed this dry buffer (no-op before the first record)
+          BankArgs d = a;
+          d.out = dry; d.partial = nullptr; d.out_stride = PIPE_CHUNK; d.out_offset = 0; d.row_map = c.d_dryrows;
+          CU(c.k->launch(d, 1, table_bytes, stream));
+          launches++;
+          CU(cudaEventRecord(c.e_dry[buf], stream));
+          std::string pe = flush_pending(&c);                  // reduce chunk k-1 of this class (waits for its FDN)
+          if (!pe.empty()) return pe;
+          f.dry = dry; f.dry_voice_stride = 2ull * PIPE_CHUNK; f.dry_ch_stride = PIPE_CHUNK; f.dry_offset = 0;
+          f.out = want_v ? out_dev_c : nullptr; f.row_map = c.d_rowmap; f.out_stride = (uint32_t)out_stride_c; f.out_offset = (uint32_t)out_t0;
+          f.partial = want_m ? (buf ? c.d_partial2 : c.d_partial) : nullptr;
+          f.ring = c.d_ring; f.ring_voice_stride = c.ring_floats; f.V = V; f.n = len;
+          CU(cudaStreamWaitEvent(stream2, c.e_dry[buf], 0));
+          if (fdn_k) CU(launch_fdn_ts(f, fdn_k, fdn_warps, stream2)); else CU(launch_fdn(f, fdn_warps, stream2));
+          launches++;
+          CU(cudaEventRecord(c.e_fdn[buf], stream2));
+          pending.push_back({&c, grid, len, t0, buf});
+          continue;
+        }
         if (c.k) {  // stage 1: the fused dry program writes stereo rows [V][2][TIME_CHUNK]
           BankArgs d = a;
           d.out = c.d_dry; d.partial = nullptr; d.out_stride = TIME_CHUNK; d.out_offset = 0; d.row_map = c.d_dryrows;
@@ -292,6 +369,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
       launches++;
     }
   }
+  { std::string pe = flush_pending(nullptr); if (!pe.empty()) return pe; }   // also joins stream2 back into `stream`
   CU(cudaEventRecord(ev1, stream));
   dirty = true;
   return "";

@@ -23,6 +23,9 @@ struct VoiceClass {
   // reverb_stereo tail handled by the warp-per-voice FDN kernel (dsp/fdn_kernel.cuh); `k` is then the dry-stage program (may be null)
   bool fdn = false; int scalar_row = -1; uint32_t p0 = 0, s0 = 0, u0 = 0; uint64_t ring_floats = 0;
   float* d_ring = nullptr; float* d_dry = nullptr; uint32_t* d_dryrows = nullptr;
+  // two-stage classes are software-pipelined over sub-chunks: dry stage of chunk k+1 (stream) runs beside the FDN of chunk k (stream2)
+  float* d_dry2 = nullptr; float* d_partial2 = nullptr; size_t partial2_floats = 0;
+  cudaEvent_t e_dry[2] = {nullptr, nullptr}, e_fdn[2] = {nullptr, nullptr};
   std::vector<uint32_t> state0;     // initial state, SoA [NS][V]
   uint32_t* d_params = nullptr; uint32_t* d_state = nullptr; uint32_t* d_uniform = nullptr; uint32_t* d_rowmap = nullptr;
   float* d_dline = nullptr; float* d_partial = nullptr; size_t partial_floats = 0;
@@ -37,7 +40,7 @@ struct Bank {
   int tree_mix = 0; bool net_rate = false; float* d_rows = nullptr; size_t rows_cap = 0;
   std::vector<std::unique_ptr<HNode>> nodes;
   std::vector<VoiceClass> classes;
-  cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   WaveTableDev* d_wt = nullptr; float* d_wtdata[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // staging for host-buffer entry points
   float *d_in = nullptr, *d_out = nullptr, *d_mix = nullptr; size_t in_cap = 0, out_cap = 0, mix_cap = 0; uint32_t stage_chunk = 0;
@@ -50,6 +53,7 @@ struct Bank {
   std::string lower_and_upload(bool upload_state);
   std::string set_sample_rate(double sr);
   std::string reset();
+  std::string set(uint32_t voice, const Setting& s);  // AudioUnit::set on one voice of a live bank (parameters only; state continues)
   std::string ensure_staging(uint32_t chunk);
   std::string render_device(uint64_t n, const float* in_dev, uint64_t in_stride, float* out_dev, uint64_t out_stride, float* mix_dev,
                             uint64_t mix_stride);

@@ -124,6 +124,9 @@ int fdsp_bank_voice_outputs(const fdsp_bank* b);                            /* c
 int fdsp_bank_outputs(const fdsp_bank* b);                                  /* AudioUnit::outputs(): mix: channels; voices: V*channels */
 int fdsp_bank_set_sample_rate(fdsp_bank* b, double sample_rate);            /* AudioUnit::set_sample_rate */
 int fdsp_bank_reset(fdsp_bank* b);                                          /* AudioUnit::reset */
+/* AudioUnit::set (src/audiounit.rs:62) on voice `voice` of a live bank: same encoding as fdsp_node_set. Parameters change at
+   once, running state continues; FDSP_ERR_UNSUPPORTED when the setting would change a delay length (rebuild the bank). */
+int fdsp_bank_set(fdsp_bank* b, uint32_t voice, int kind, const float* values, int nvalues, uint64_t seed, const int64_t* address_pairs, int naddress);
 int fdsp_bank_allocate(fdsp_bank* b, uint64_t max_render_samples);          /* AudioUnit::allocate: later calls do not allocate */
 /* AudioUnit::process: size <= 64; host buffers in [inputs][64], out [outputs][64]; size 0 is a no-op */
 int fdsp_bank_process(fdsp_bank* b, uint32_t size, const float* in, float* out);

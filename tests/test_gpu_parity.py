@@ -6,6 +6,8 @@ independently built wavetable enters the sample loop (tanh in Moog, sinf in tail
 differ by an f32 rounding), the bound is the north-star's 1e-5 relative f32:  |g - o| <= 1e-5 * max(|o|, floor)
 with floor = 1e-2 * peak(|o|) of that voice (relative error is undefined at zero crossings).
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -166,6 +168,37 @@ def test_reset_and_clone_and_continuation():
     r2, _ = b.render_samples(976)
     assert np.array_equal(np.concatenate([r1, r2], axis=-1), full)
     assert np.array_equal(a1, full[..., :1000])
+
+
+def test_set_on_live_bank_matches_oracle_units():
+    """AudioUnit::set (src/audiounit.rs:62) on single voices of a running bank: new coefficients, state continues."""
+    from fundsp_b200.bank import GpuBank
+    from oracle import OracleUnit
+    V, n1, n2 = 48, 1024, 1500
+    mk = lambda i: noise().seed(i) >> lowpass_hz(500.0 + 40.0 * i, 1.0 + 0.05 * i) >> highpass_hz(100.0, 0.7)
+    b = GpuBank([mk(i) for i in range(V)], per_voice=True, sample_rate=SR)
+    units = [OracleUnit(mk(i)) for i in range(V)]
+    olib().fo_set_denormal_emulation(0)
+    for u in units:
+        u.set_sample_rate(SR)
+    g1, _ = b.render_samples(n1)
+    o1 = np.stack([u.process_many(n1) for u in units])
+    CENTER_Q, LEFT, RIGHT = 2, (1, 0), (1, 1)          # Parameter::CenterQ; Address::Index(0|1) through Pipe<Pipe<Noise,Svf>,Svf>
+    for v in (0, 7, V - 1):
+        b.set(v, CENTER_Q, (2500.0 + v, 4.0), address=(LEFT, RIGHT))
+        units[v].L.fo_set(units[v].h, CENTER_Q, (C.c_float * 2)(2500.0 + v, 4.0), 2, 0, (C.c_int64 * 4)(1, 0, 1, 1), 2)
+    g2, _ = b.render_samples(n2)
+    o2 = np.stack([u.process_many(n2) for u in units])
+    assert np.array_equal(g1, o1)
+    assert np.array_equal(g2, o2)
+    b2 = GpuBank([mk(i) for i in range(V)], per_voice=True, sample_rate=SR)
+    b2.render_samples(n1)
+    h2, _ = b2.render_samples(n2)
+    changed = [v for v in range(V) if not np.array_equal(h2[v], g2[v])]
+    assert changed == [0, 7, V - 1]                    # only the addressed voices changed
+    b.reset()
+    g3, _ = b.render_samples(n1)
+    assert np.array_equal(g3[1:7], g1[1:7]) and not np.array_equal(g3[0], g1[0])   # reset keeps the new setting (reference: set is sticky)
 
 
 def test_set_sample_rate_recomputes_coefficients():
