@@ -262,10 +262,18 @@ def main():
     bytes_step += sum(k["voices"] * 8 * n * (1 if k["delay_floats"] else 0) * 32 for k in cls)  # FDN: 32 lines x (4 B read + 4 B write) per sample
     achieved = bytes_step / (ms_kernel * 1e-3) / 1e9
     traffic = None
+    issue = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
         t = prof.get(a.workload + ("+voices" if a.per_voice else ""))
         traffic = t["dram_bytes_per_launch"] * n / t["samples_per_launch"] if t else None  # ncu dram bytes of one 16384-sample launch, scaled to the step
+        if t and t.get("warp_inst_per_launch") and V == HEADLINE[a.workload]:
+            # what actually bounds a voice program: warp-instructions issued (ncu count of one 16384-sample launch, scaled to the
+            # step) against 148 SMs x 4 schedulers x 1 instruction per clock at the SM clock sampled during the timed region
+            winst = t["warp_inst_per_launch"] * n / t["samples_per_launch"]
+            mhz = float(clocks.get("sm_mhz") or 1965.0)
+            issue = {"warp_inst_per_step": winst, "achieved_ginst_s": winst / (ms_kernel * 1e-3) / 1e9, "peak_ginst_s": 592 * mhz * 1e6 / 1e9,
+                     "frac": winst / (ms_kernel * 1e-3) / (592 * mhz * 1e6), "source": "profiles/r01_traffic.json (smsp__inst_executed.sum of one launch)"}
     except Exception:
         pass
     # ---- CPU baseline on this box's host cores (bounded sample of the same workload)
@@ -287,7 +295,7 @@ def main():
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "fdsp::bank_kernel<...>", "kernel_ms_per_step": ms_kernel, "algorithmic_bytes_per_step": int(bytes_step),
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)", "issue": issue,
                      "note": "IIR voice programs are issue/latency bound, not HBM bound (DESIGN.md §Roofline); see profiles/ for issue-slot utilisation"},
         "cpu_baseline": {"value": cpu_val, "unit": "Msamples/s", "cores": cores, "kind": "port",
                          "sample": f"{V} voices x {ns} samples, oracle (C++ restatement of the reference block path), {cores} threads"},

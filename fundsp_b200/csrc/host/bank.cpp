@@ -3,6 +3,7 @@
 #include "../dsp/fdn_args.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -267,6 +268,10 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
     return "";
   };
   uint64_t chunk_index = 0;
+  // FDSP_PIPE_TRACE=1: print the device timeline of the two pipeline stages (diagnostic; synchronises)
+  const bool trace = pipelined && getenv("FDSP_PIPE_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tev;   // per chunk: dry start, dry end, fdn start, fdn end
+  auto tmark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
   if (tree && !want_v) {
     const size_t need = (size_t)V() * nout * CH;
     if (rows_cap < need) { std::string e = dev_alloc(&d_rows, need); if (!e.empty()) return e; rows_cap = need; }
@@ -325,8 +330,10 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
           CU(cudaStreamWaitEvent(stream, c.e_fdn[buf], 0));   // FDN of chunk k-2 has consumed this dry buffer (no-op before the first record)
           BankArgs d = a;
           d.out = dry; d.partial = nullptr; d.out_stride = PIPE_CHUNK; d.out_offset = 0; d.row_map = c.d_dryrows;
+          tmark(stream);
           CU(c.k->launch(d, 1, table_bytes, stream));
           launches++;
+          tmark(stream);
           CU(cudaEventRecord(c.e_dry[buf], stream));
           std::string pe = flush_pending(&c);                  // reduce chunk k-1 of this class (waits for its FDN)
           if (!pe.empty()) return pe;
@@ -335,8 +342,10 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
           f.partial = want_m ? (buf ? c.d_partial2 : c.d_partial) : nullptr;
           f.ring = c.d_ring; f.ring_voice_stride = c.ring_floats; f.V = V; f.n = len;
           CU(cudaStreamWaitEvent(stream2, c.e_dry[buf], 0));
+          tmark(stream2);
           if (fdn_k) CU(launch_fdn_ts(f, fdn_k, fdn_warps, stream2)); else CU(launch_fdn(f, fdn_warps, stream2));
           launches++;
+          tmark(stream2);
           CU(cudaEventRecord(c.e_fdn[buf], stream2));
           pending.push_back({&c, grid, len, t0, buf});
           continue;
@@ -371,6 +380,15 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
   }
   { std::string pe = flush_pending(nullptr); if (!pe.empty()) return pe; }   // also joins stream2 back into `stream`
   CU(cudaEventRecord(ev1, stream));
+  if (trace) {
+    CU(cudaStreamSynchronize(stream));
+    for (size_t q = 0; q + 3 < tev.size(); q += 4) {
+      float t[4];
+      for (int w = 0; w < 4; w++) cudaEventElapsedTime(&t[w], ev0, tev[q + w]);
+      fprintf(stderr, "[pipe] chunk %zu: dry %.3f..%.3f ms   fdn %.3f..%.3f ms\n", q / 4, t[0], t[1], t[2], t[3]);
+    }
+    for (auto e : tev) cudaEventDestroy(e);
+  }
   dirty = true;
   return "";
 }

@@ -20,9 +20,16 @@ def raw(rep):
 
 
 traffic = {}
+try:
+    traffic = json.load(open(os.path.join(OUT, f"{ROUND}_traffic.json")))   # keep entries whose .ncu-rep is no longer in gpurun_out/
+except Exception:
+    pass
 for rep in sorted(f for f in os.listdir(os.path.join(ROOT, "gpurun_out")) if f.startswith("full_") and f.endswith(".ncu-rep")):
     m = raw(os.path.join(ROOT, "gpurun_out", rep))
     name = rep[len("full_"):-len(".ncu-rep")]
+    for suffix in ("_r01e", "_r01"):
+        if name.endswith(suffix):
+            name = name[: -len(suffix)]
     lines = [f"# ncu --set full summary: {name} ({ROUND})", "", f"kernel: `{m.get('Kernel Name', ('?', ''))[0]}`", "", "| metric | value | unit |", "|---|---|---|"]
     for k in KEEP:
         if k in m:
@@ -35,6 +42,8 @@ for rep in sorted(f for f in os.listdir(os.path.join(ROOT, "gpurun_out")) if f.s
         return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
     key = {"saw_svf_mix": "saw_svf", "noise_svf_mix": "noise_svf", "saw_svf_voices": "saw_svf+voices"}.get(name, name)
     traffic[key] = {"dram_bytes_per_launch": tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum"), "samples_per_launch": 16384,
+                    "warp_inst_per_launch": float(m["smsp__inst_executed.sum"][0]) if "smsp__inst_executed.sum" in m else None,
+                    "issue_active_pct": float(m["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]) if "smsp__issue_active.avg.pct_of_peak_sustained_active" in m else None,
                     "note": "one 16384-sample launch of the fused voice kernel (bench steps are 3 such launches)"}
 json.dump(traffic, open(os.path.join(OUT, f"{ROUND}_traffic.json"), "w"), indent=1)
 
