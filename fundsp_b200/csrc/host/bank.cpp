@@ -296,7 +296,11 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
         fdn_k = ks ? atoi(ks) : 0;  // measured on B200 (1024 voices): single-warp form 2.15 ms, K=2 2.47 ms, K=4 2.49 ms per 16384 samples
         if (fdn_k != 2 && fdn_k != 4) fdn_k = 0;
         const int cap = fdn_k ? fdn_ts_max_vpb(fdn_k) : fdn_max_warps();
-        fdn_warps = (int)((V + 147) / 148); if (fdn_warps > cap) fdn_warps = cap; if (fdn_warps < 1) fdn_warps = 1;
+        // pipelined: leave SMs free for the CTAs of the dry stage of the next chunk (their shared-memory tables cannot share an SM
+        // with an FDN CTA), otherwise the two stages serialise on SM residency
+        uint32_t sms = 148;
+        if (pipelined && c.k) { const uint32_t dry_ctas = (V + (uint32_t)c.k->threads - 1) / (uint32_t)c.k->threads; sms = dry_ctas < 74 ? 148 - dry_ctas : 74; }
+        fdn_warps = (int)((V + sms - 1) / sms); if (fdn_warps > cap) fdn_warps = cap; if (fdn_warps < 1) fdn_warps = 1;
       }
       const uint32_t grid = c.fdn ? (V + (uint32_t)fdn_warps - 1) / (uint32_t)fdn_warps : (V + (uint32_t)c.k->threads - 1) / (uint32_t)c.k->threads;
       if (want_m) {
