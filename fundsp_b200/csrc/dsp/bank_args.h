@@ -27,6 +27,17 @@ struct WaveTableDev {
 FDSP_HDC constexpr int mix_tile_samples(int outs) { return outs <= 1 ? 64 : (outs == 2 ? 32 : (outs <= 4 ? 16 : 8)); }
 FDSP_HDC constexpr size_t mix_tile_floats(int outs, int nt) { return (size_t)outs * (size_t)mix_tile_samples(outs) * (size_t)(nt + 1); }
 
+// CTA shape of a class of V voices with NT threads per CTA: enough CTAs to cover the voices, rounded up to whole waves of the
+// 148 SMs once every CTA can still have a full warp, and the voices spread evenly over them (a bank is bound by per-SM
+// pipes and per-warp latency, so idle SMs are the first thing to use up).
+inline uint32_t bank_grid(uint32_t V, uint32_t nt, uint32_t* vpc) {
+  uint32_t grid = (V + nt - 1) / nt;
+  if (V >= 148u * 32u) grid = (grid + 147u) / 148u * 148u;
+  if (grid == 0) grid = 1;
+  *vpc = (V + grid - 1) / grid;
+  return (V + *vpc - 1) / *vpc;
+}
+
 struct BankArgs {
   const uint32_t* params;   // [NP][V]
   uint32_t* state;          // [NS][V]
@@ -37,6 +48,7 @@ struct BankArgs {
   float* out;               // per-voice output rows or null
   float* partial;           // [grid][OUT][n] per-CTA mix partials or null
   uint32_t V, n;
+  uint32_t vpc;             // voices per CTA (<= threads per CTA): CTA b runs voices [b*vpc, min(V, (b+1)*vpc)); 0 means NT
   uint32_t in_stride, in_offset;
   uint32_t out_stride, out_offset;  // row stride / first sample (multiples of 4 for the vector path)
   const uint32_t* row_map;          // class-local voice -> first output row (voice-major rows) inside `out`

@@ -44,17 +44,21 @@ FDSP_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
 #ifndef FDSP_NO_GROUP
 #define FDSP_NO_GROUP 0
 #endif
+#ifndef FDSP_GROUP_COST
+#define FDSP_GROUP_COST 160   // programs up to this static cost are evaluated 8 samples at a time, fully unrolled
+#endif
 
 template <class G, int NT, int MODE, bool TB>
 __global__ void __launch_bounds__(NT, FDSP_MIN_CTAS) bank_kernel(const BankArgs a) {
   extern __shared__ __align__(16) float tile[];  // MODE&2: [OUT][TS][NT+1]; TB: table data after it
   const uint32_t tid = threadIdx.x;
-  const uint32_t v = blockIdx.x * NT + tid;
-  const bool active = v < a.V;
+  const uint32_t vpc = a.vpc ? a.vpc : (uint32_t)NT;
+  const uint32_t v = blockIdx.x * vpc + tid;
+  const bool active = tid < vpc && v < a.V;
   constexpr int IN = G::IN, OUT = G::OUT;
   constexpr int TS = (MODE & 2) ? mix_tile_samples(OUT) : 64;
   // big programs (e.g. the 32-line FDN in thread-per-voice form) are not unrolled over the 8-sample group
-  constexpr int UNROLL = Cost<G>::value <= 160 ? 8 : (Cost<G>::value <= 320 ? 4 : (Cost<G>::value <= 640 ? 2 : 1));
+  constexpr int UNROLL = Cost<G>::value <= FDSP_GROUP_COST ? 8 : (Cost<G>::value <= 320 ? 4 : (Cost<G>::value <= 640 ? 2 : 1));
 
   typename G::R r;
   CtxT<TB> c;

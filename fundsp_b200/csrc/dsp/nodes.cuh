@@ -42,7 +42,15 @@ template <bool SM> struct CtxT {
 };
 typedef CtxT<false> Ctx;
 
-FDSP_DEV float lds_f32(uint32_t addr) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+#ifndef FDSP_LDS_VOLATILE
+#define FDSP_LDS_VOLATILE 0
+#endif
+FDSP_DEV float lds_f32(uint32_t addr) {
+  float v;
+  if (FDSP_LDS_VOLATILE) asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  else asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
 
 struct Loader {
   const uint32_t* p; const uint32_t* s; const uint32_t* u; uint32_t V, v;

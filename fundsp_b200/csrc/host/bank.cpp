@@ -238,6 +238,14 @@ std::string Bank::reset() {  // AudioUnit::reset: back to the construction-time 
   return "";
 }
 
+// Warp-specialised kernels (dsp/bank_kernel_ws.cuh) are built and parity-tested but OFF by default: measured on B200 they are
+// slower than the plain kernel (saw+SVF 16384 voices: 1.53 vs 1.45 ms, FM 4096: 1.03 vs 0.98 ms per 16384 samples) because the
+// wavetable gathers keep the shared-memory pipe ~65 % busy, which a second warp per scheduler cannot relieve. FDSP_WS=1 enables them.
+static bool use_ws(uint32_t) {
+  static const int forced = [] { const char* e = getenv("FDSP_WS"); return e ? atoi(e) : 0; }();
+  return forced != 0;
+}
+
 std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_stride, float* out_dev, uint64_t out_stride, float* mix_dev,
                                 uint64_t mix_stride) {
   CU(cudaSetDevice(device));
@@ -302,7 +310,11 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
         if (pipelined && c.k) { const uint32_t dry_ctas = (V + (uint32_t)c.k->threads - 1) / (uint32_t)c.k->threads; sms = dry_ctas < 74 ? 148 - dry_ctas : 74; }
         fdn_warps = (int)((V + sms - 1) / sms); if (fdn_warps > cap) fdn_warps = cap; if (fdn_warps < 1) fdn_warps = 1;
       }
-      const uint32_t grid = c.fdn ? (V + (uint32_t)fdn_warps - 1) / (uint32_t)fdn_warps : (V + (uint32_t)c.k->threads - 1) / (uint32_t)c.k->threads;
+      // voice programs: whole waves of CTAs with the voices spread evenly; the dry stage of a two-stage class stays compact
+      // (few CTAs) so that it leaves the other SMs to the FDN kernel it is pipelined with
+      uint32_t vpc = c.k ? (uint32_t)c.k->threads : 0u;
+      const uint32_t vgrid = !c.k ? 0u : (c.fdn || getenv("FDSP_NO_SPREAD") ? (V + vpc - 1) / vpc : bank_grid(V, (uint32_t)c.k->threads, &vpc));
+      const uint32_t grid = c.fdn ? (V + (uint32_t)fdn_warps - 1) / (uint32_t)fdn_warps : vgrid;
       if (want_m) {
         const size_t need = (size_t)grid * nout * len;
         if (c.partial_floats < need) { std::string e = dev_alloc(&c.d_partial, (size_t)grid * nout * TIME_CHUNK); if (!e.empty()) return e; c.partial_floats = (size_t)grid * nout * TIME_CHUNK; }
@@ -311,7 +323,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
       BankArgs a;
       a.params = c.d_params; a.state = c.d_state; a.uniform = c.d_uniform; a.dline = c.d_dline; a.wt = d_wt;
       a.in = in_dev; a.out = want_v ? out_dev_c : nullptr; a.partial = want_m ? c.d_partial : nullptr;
-      a.V = V; a.n = len;
+      a.V = V; a.n = len; a.vpc = vpc;
       a.in_stride = (uint32_t)in_stride; a.in_offset = (uint32_t)t0;
       a.out_stride = (uint32_t)out_stride_c; a.out_offset = (uint32_t)out_t0;
       a.row_map = c.d_rowmap;
@@ -368,7 +380,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
         f.ring = c.d_ring; f.ring_voice_stride = c.ring_floats; f.V = V; f.n = len;
         if (fdn_k) CU(launch_fdn_ts(f, fdn_k, fdn_warps, stream)); else CU(launch_fdn(f, fdn_warps, stream));
       } else {
-        CU(c.k->launch(a, mode, table_bytes, stream));
+        CU(c.k->launch(a, mode | (use_ws(V) ? 4 : 0), table_bytes, stream));
       }
       launches++;
       if (want_m) {

@@ -84,7 +84,7 @@ struct JitProgram : Program {
     if (smem > 48 * 1024 && A.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) != CUDA_SUCCESS) return cudaErrorInvalidValue;
     BankArgs args = a;
     void* params[] = {&args};
-    const unsigned grid = (a.V + (unsigned)threads - 1) / (unsigned)threads;
+    const unsigned vpc = a.vpc ? a.vpc : (unsigned)threads, grid = (a.V + vpc - 1) / vpc;
     CUresult r = A.LaunchKernel(f, grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)smem, (CUstream)st, params, nullptr);
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorLaunchFailure;
   }
