@@ -53,6 +53,12 @@ struct BankArgs {
   uint32_t out_stride, out_offset;  // row stride / first sample (multiples of 4 for the vector path)
   const uint32_t* row_map;          // class-local voice -> first output row (voice-major rows) inside `out`
   float sr, sd64, sd32;
+  // fused mix-down for short launches (process()-sized): when `ticket` is set, the last CTA to finish folds the per-CTA
+  // partials in CTA order into mix[c*mix_stride + mix_offset + t] itself (no mix_reduce_kernel launch)
+  uint32_t* ticket;
+  float* mix;
+  uint32_t mix_stride, mix_offset;
+  int mix_accumulate;
 };
 
 }  // namespace fdsp

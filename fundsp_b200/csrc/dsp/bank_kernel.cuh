@@ -198,6 +198,24 @@ __global__ void __launch_bounds__(NT, FDSP_MIN_CTAS) bank_kernel(const BankArgs 
     Saver s{a.state, a.V, v, 0u};
     G::save(r, s);
   }
+  if ((MODE & 2) && a.ticket) {   // fused finish of the mix-down: same CTA-order left fold as mix_reduce_kernel
+    __shared__ uint32_t s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1u) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      for (uint32_t e = tid; e < (uint32_t)OUT * a.n; e += NT) {
+        const uint32_t ch = e / a.n, t = e - ch * a.n;
+        float s = __ldcg(a.partial + (size_t)ch * a.n + t);
+        for (uint32_t b = 1; b < gridDim.x; b++) s += __ldcg(a.partial + ((size_t)b * OUT + ch) * a.n + t);
+        float* p = a.mix + (size_t)ch * a.mix_stride + a.mix_offset + t;
+        *p = a.mix_accumulate ? *p + s : s;
+      }
+      if (tid == 0) *a.ticket = 0u;
+    }
+  }
 }
 
 // Finishes the mix-down: mix[c][off + t] (+)= sum over CTAs in CTA order (deterministic).

@@ -41,6 +41,7 @@ Bank::~Bank() {
   if (h_out) cudaFreeHost(h_out);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
+  cudaFree(d_ticket);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -63,6 +64,7 @@ std::string Bank::init(std::vector<HNode*>& voices, int dev, uint32_t mode) {
   CU(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_hi));
   CU(cudaStreamCreateWithPriority(&stream2, cudaStreamNonBlocking, prio_lo));
   CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
+  CU(cudaMalloc((void**)&d_ticket, 4)); CU(cudaMemset(d_ticket, 0, 4));
   return lower_and_upload(true);
 }
 
@@ -255,7 +257,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
   if (n == 0) return "";
   const bool save_want_m_ = want_m;
   if (in_stride > 0xffffffffull || out_stride > 0xffffffffull || mix_stride > 0xffffffffull) return "stride too large";
-  CU(cudaEventRecord(ev0, stream));
+  if (timing) CU(cudaEventRecord(ev0, stream));
   // Net-ordered mix: the voice kernels materialise per-voice rows (user buffer, or an internal one) and tree_mix_kernel adds
   // them in the Net's association order; the CTA-level partial mix is bypassed.
   const bool tree = tree_mix != 0 && want_m;
@@ -328,13 +330,17 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
       a.out_stride = (uint32_t)out_stride_c; a.out_offset = (uint32_t)out_t0;
       a.row_map = c.d_rowmap;
       a.sr = (float)sr; a.sd64 = (float)(1.0 / sr); a.sd32 = 1.0f / (float)sr;
+      // process()-sized launches of plain voice programs finish their mix-down inside the kernel (one launch instead of two)
+      const bool fused_mix = want_m && !c.fdn && len <= 64 && !use_ws(V);
+      a.ticket = fused_mix ? d_ticket : nullptr; a.mix = mix_dev; a.mix_stride = (uint32_t)mix_stride; a.mix_offset = (uint32_t)t0; a.mix_accumulate = first ? 0 : 1;
       if (t0 > 0xffffffffull - TIME_CHUNK) return "render too long for one call";
       if (c.fdn && len > TIME_CHUNK) return "internal: chunk";
       // long launches of wavetable programs stage the table set in shared memory (TMA bulk copy, ~160 KB per CTA);
       // short ones (process()-sized) read the tables through L1/L2 instead
       size_t table_bytes = 0;
       const int wk = c.k ? c.k->wave_kind : -1;
-      if (wk >= 0 && len >= 1024) table_bytes = device_wavetable(wk).data.size() * sizeof(float);
+      static const uint32_t tb_min = [] { const char* e = getenv("FDSP_TB_MIN"); return e ? (uint32_t)atoi(e) : 32u; }();  // measured: at 64 samples the TMA-staged tables already win (35.0 vs 38.9 us per process call)
+      if (wk >= 0 && len >= tb_min) table_bytes = device_wavetable(wk).data.size() * sizeof(float);
       if (c.fdn) {
         FdnArgs f;
         f.params = c.d_params; f.state = c.d_state; f.uniform = c.d_uniform; f.p0 = c.p0; f.s0 = c.s0; f.u0 = c.u0; f.scalar_row = c.scalar_row;
@@ -383,7 +389,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
         CU(c.k->launch(a, mode | (use_ws(V) ? 4 : 0), table_bytes, stream));
       }
       launches++;
-      if (want_m) {
+      if (want_m && !fused_mix) {
         CU(launch_mix_reduce(c.d_partial, grid, (uint32_t)nout, len, mix_dev, (uint32_t)mix_stride, (uint32_t)t0, first ? 0 : 1, stream));
         launches++;
       }
@@ -395,7 +401,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
     }
   }
   { std::string pe = flush_pending(nullptr); if (!pe.empty()) return pe; }   // also joins stream2 back into `stream`
-  CU(cudaEventRecord(ev1, stream));
+  if (timing) CU(cudaEventRecord(ev1, stream));
   if (trace) {
     CU(cudaStreamSynchronize(stream));
     for (size_t q = 0; q + 3 < tev.size(); q += 4) {
@@ -456,15 +462,34 @@ std::string Bank::process(uint32_t size, const float* in, float* out) {  // Audi
   const bool mix = (out_mode & 2u) != 0;  // mix mode wins for the AudioUnit surface; voices mode returns V*c channels
   const size_t rows = mix ? (size_t)nout : (size_t)V() * nout;
   if (h_in_cap < (size_t)std::max(1, nin) * 64) { if (h_in) cudaFreeHost(h_in); CU(cudaMallocHost((void**)&h_in, (size_t)std::max(1, nin) * 64 * 4)); h_in_cap = (size_t)std::max(1, nin) * 64; }
-  if (h_out_cap < rows * 64) { if (h_out) cudaFreeHost(h_out); CU(cudaMallocHost((void**)&h_out, rows * 64 * 4)); h_out_cap = rows * 64; }
+  if (h_out_cap < rows * 64) {
+    if (h_out) cudaFreeHost(h_out);
+    CU(cudaHostAlloc((void**)&h_out, rows * 64 * 4, cudaHostAllocMapped));   // mapped: the mix is written straight into it by the GPU
+    CU(cudaHostGetDevicePointer((void**)&d_hout, h_out, 0));
+    h_out_cap = rows * 64;
+  }
   if (nin > 0) {
     if (!in) return "bank has inputs but no input buffer was given";
     memcpy(h_in, in, (size_t)nin * 64 * 4);
     CU(cudaMemcpyAsync(d_in, h_in, (size_t)nin * 64 * 4, cudaMemcpyHostToDevice, stream));
   }
-  e = render_device(size, d_in, 64, mix ? nullptr : d_out, 64, mix ? d_mix : nullptr, 64);
-  if (!e.empty()) return e;
-  CU(cudaMemcpyAsync(h_out, mix ? d_mix : d_out, rows * 64 * 4, cudaMemcpyDeviceToHost, stream));
+  struct NoTiming { bool& t; explicit NoTiming(bool& x) : t(x) { t = false; } ~NoTiming() { t = true; } } no_timing(timing);  // no event records on this path
+  bool two_stage = false;   // pipelined classes clear / accumulate the mix region on the device: keep that in device memory
+  for (auto& c : classes) two_stage = two_stage || (c.fdn && c.k);
+  if (mix && two_stage) {
+    e = render_device(size, d_in, 64, nullptr, 64, d_mix, 64);
+    if (!e.empty()) return e;
+    CU(cudaMemcpyAsync(h_out, d_mix, rows * 64 * 4, cudaMemcpyDeviceToHost, stream));
+  } else if (mix) {
+    // one block of mix is a few hundred bytes: mix_reduce_kernel stores it over PCIe into the mapped host buffer, which saves
+    // the separate device-to-host copy of the latency-critical process() path
+    e = render_device(size, d_in, 64, nullptr, 64, d_hout, 64);
+    if (!e.empty()) return e;
+  } else {
+    e = render_device(size, d_in, 64, d_out, 64, nullptr, 64);
+    if (!e.empty()) return e;
+    CU(cudaMemcpyAsync(h_out, d_out, rows * 64 * 4, cudaMemcpyDeviceToHost, stream));
+  }
   CU(cudaStreamSynchronize(stream));
   memcpy(out, h_out, rows * 64 * 4);
   return "";

@@ -44,8 +44,10 @@ struct Bank {
   WaveTableDev* d_wt = nullptr; float* d_wtdata[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // staging for host-buffer entry points
   float *d_in = nullptr, *d_out = nullptr, *d_mix = nullptr; size_t in_cap = 0, out_cap = 0, mix_cap = 0; uint32_t stage_chunk = 0;
-  float *h_in = nullptr, *h_out = nullptr; size_t h_in_cap = 0, h_out_cap = 0;  // pinned, process() path
+  float *h_in = nullptr, *h_out = nullptr, *d_hout = nullptr; size_t h_in_cap = 0, h_out_cap = 0;  // pinned (h_out also device-mapped), process() path
   uint64_t launches = 0; float last_ms = 0.0f;
+  uint32_t* d_ticket = nullptr;   // arrival counter of the fused mix-down (short launches)
+  bool timing = true;             // record ev0/ev1 around render_device (off on the process() path)
 
   ~Bank();
   uint32_t V() const { return (uint32_t)nodes.size(); }

@@ -40,7 +40,7 @@ for rep in sorted(f for f in os.listdir(os.path.join(ROOT, "gpurun_out")) if f.s
     def tobytes(key):
         v, u = m[key]
         return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-    key = {"saw_svf_mix": "saw_svf", "noise_svf_mix": "noise_svf", "saw_svf_voices": "saw_svf+voices"}.get(name, name)
+    key = {"saw_svf_mix": "saw_svf", "noise_svf_mix": "noise_svf", "saw_svf_voices": "saw_svf+voices", "fm_mix": "fm", "subdry": "subtractive_dry", "fdn": "subtractive"}.get(name, name)
     traffic[key] = {"dram_bytes_per_launch": tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum"), "samples_per_launch": 16384,
                     "warp_inst_per_launch": float(m["smsp__inst_executed.sum"][0]) if "smsp__inst_executed.sum" in m else None,
                     "issue_active_pct": float(m["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]) if "smsp__issue_active.avg.pct_of_peak_sustained_active" in m else None,
