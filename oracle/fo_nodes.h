@@ -9,6 +9,7 @@
 #include <cassert>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <utility>
 #include <vector>
 #include <xmmintrin.h>
@@ -596,7 +597,8 @@ inline double am_hammond(double, uint32_t i) {
 // ---- src/wavetable.rs:493-623 global tables: 0 saw, 1 square, 2 triangle, 3 organ, 4 soft_saw, 5 hammond
 inline const Wavetable& global_table(int kind) {
   static std::unique_ptr<Wavetable> t[6];
-  if (!t[kind]) {
+  static std::once_flag once[6];   // the bank renderer calls this from worker threads: build each table exactly once
+  std::call_once(once[kind], [kind]() {
     switch (kind) {
       case 0: t[0].reset(new Wavetable(20.0, 20000.0, 4.0, ph_saw, am_saw)); break;
       case 1: t[1].reset(new Wavetable(20.0, 20000.0, 4.0, ph_zero, am_square)); break;
@@ -605,7 +607,7 @@ inline const Wavetable& global_table(int kind) {
       case 4: t[4].reset(new Wavetable(20.0, 20000.0, 4.0, ph_organ, am_softsaw)); break;
       default: t[5].reset(new Wavetable(20.0, 20000.0, 4.0, ph_zero, am_hammond)); break;
     }
-  }
+  });
   return *t[kind];
 }
 
