@@ -636,6 +636,21 @@ template <int KIND> struct PhaseOsc {  // src/oscillator.rs:440-760: 0 Ramp (ID 
   }
   static FDSP_DEV void end_simd(R&) {}
 };
+template <int NIN> struct Dsf {  // src/oscillator.rs:104-208, ID 55: params = roughness (clamped), harmonic spacing
+  FDSP_NODE(NIN, 1, 2, 1, 0);
+  struct R { float roughness, spacing, phase; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.roughness = l.Pf(); r.spacing = l.Pf(); r.phase = l.Sf(); }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.phase); }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<NIN>& in, Fr<1>& o) {
+    if (NIN > 1) r.roughness = fminf(fmaxf(in.v[NIN > 1 ? 1 : 0], 0.0001f), 0.9999f);   // set_roughness :152-154 (sticky, like the reference field)
+    r.phase += in.v[0] * c.sd64;
+    r.phase -= floorf(r.phase);
+    const float n = floorf(22050.0f / in.v[0] / r.spacing);
+    const float f = r.phase * TAU_F, d = r.phase * TAU_F * r.spacing, q = r.roughness;
+    o.v[0] = (m::sinf_(f) - q * m::sinf_(f - d) - m::powf_(q, n + 1.0f) * (m::sinf_(f + (n + 1.0f) * d) - q * m::sinf_(f + n * d))) / (1.0f + q * q - 2.0f * q * m::cosf_(d));
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
 struct Mls {  // src/noise.rs:11-148, ID 19: params = feedback polynomial, length mask, n - 1
   FDSP_NODE(0, 1, 3, 1, 0);
   struct R { uint32_t poly, mask, shift, s; };
@@ -931,6 +946,7 @@ template <class X> struct Cost<Thru<X>> { static constexpr int value = Cost<X>::
 template <int KIND, int OP, int N, class X> struct Cost<Multi<KIND, OP, N, X>> { static constexpr int value = N * Cost<X>::value; };
 template <int NIN, class X> struct Cost<AllNest<NIN, X>> { static constexpr int value = Cost<X>::value + 6; };
 template <int HAD, class X, class Y> struct Cost<Feedback2<HAD, X, Y>> { static constexpr int value = Cost<X>::value + Cost<Y>::value + (HAD ? 6 * X::IN : X::IN); };
+template <int N> struct Cost<Dsf<N>> { static constexpr int value = 700; };
 template <int NT_, int LIN> struct Cost<Tap<NT_, LIN>> { static constexpr int value = 40 * NT_; };
 template <int HAD, class X> struct Cost<Feedback<HAD, X>> { static constexpr int value = Cost<X>::value + (HAD ? 6 * X::IN : X::IN); };
 

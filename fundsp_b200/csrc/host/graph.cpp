@@ -119,6 +119,21 @@ struct PhaseOsc : HNode {  // src/oscillator.rs:440-760
   void lower(Lowering& l) const override { l.s(has_phase ? initial_phase : (float)rnd1(hash)); }
   HCLONE(PhaseOsc)
 };
+struct DsfN : HNode {  // src/oscillator.rs:114-208
+  int nin; float spacing, roughness; uint64_t hash = 0; bool has_phase = false; float initial_phase = 0;
+  DsfN(int n, float sp, float r) : nin(n), spacing(sp) { set_roughness(r); }
+  void set_roughness(float r) { roughness = fminf(fmaxf(r, 0.0001f), 0.9999f); }
+  int inputs() const override { return nin; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 55; }
+  void set(const Setting& s) override {
+    if (s.kind == P_ROUGHNESS) set_roughness(s.v[0]);
+    else if (s.kind == P_PHASE) { has_phase = true; initial_phase = s.v[0]; }
+  }
+  void set_hash(uint64_t h) override { hash = h; }
+  void sig(std::string& o) const override { o += "Dsf<" + I(nin) + ">"; }
+  void lower(Lowering& l) const override { l.p(roughness); l.p(spacing); l.s(has_phase ? initial_phase : (float)rnd1(hash)); }
+  HCLONE(DsfN)
+};
 const uint32_t kMlsPoly[31] = {
     0b1, 0b11, 0b110, 0b1100, 0b10100, 0b110000, 0b1001000, 0b10111000, 0b100010000, 0b1001000000, 0b10100000000, 0b110010100000,
     0b1101100000000, 0b11000010001000, 0b110000000000000, 0b1101000000001000, 0b10010000000000000, 0b100000010000000000,
@@ -558,6 +573,7 @@ HNode* mk_tick(int n) { return new TickN(n); }
 HNode* mk_delay(double t) { return t < 0.0 ? nullptr : new Delay(t); }
 HNode* mk_allnest(float c, HNode* x, int nin) { if (!x || x->inputs() != 1 || x->outputs() != 1) { delete x; return nullptr; } return new AllNest(c, x, nin); }
 HNode* mk_phase_osc(int kind) { return (kind < 0 || kind > 3) ? nullptr : new PhaseOsc(kind); }
+HNode* mk_dsf(int inputs, float spacing, float roughness) { return (inputs < 1 || inputs > 2 || !(spacing > 0.0f)) ? nullptr : new DsfN(inputs, spacing, roughness); }
 HNode* mk_mls(int bits) { return (bits < 1 || bits > 31) ? nullptr : new Mls((uint32_t)bits); }
 HNode* mk_impulse(int n) { return n < 1 ? nullptr : new ImpulseN(n); }
 HNode* mk_tap(int ntaps, int linear, float mn, float mx) { return (ntaps < 1 || mn < 0.0f || mn > mx) ? nullptr : new TapN(ntaps, linear != 0, mn, mx); }

@@ -100,6 +100,7 @@ HNode* mk_tick(int n);
 HNode* mk_delay(double t);
 HNode* mk_allnest(float coefficient, HNode* x, int nin);
 HNode* mk_phase_osc(int kind);                      // 0 ramp, 1 poly_saw, 2 poly_square, 3 poly_pulse
+HNode* mk_dsf(int inputs, float harmonic_spacing, float roughness);
 HNode* mk_mls(int bits);
 HNode* mk_impulse(int n);
 HNode* mk_tap(int ntaps, int linear, float min_delay, float max_delay);

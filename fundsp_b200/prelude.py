@@ -575,3 +575,20 @@ def feedback2(node, loopback):
 
 def fdn2(node, loopback):
     return An("feedback2", (1,), (node, loopback), node.nin, node.nout)
+
+
+# ---- src/prelude.rs:1948-1978 discrete summation formula oscillators
+def dsf_saw():
+    return An("dsf", (2, 1.0, 0.5), (), 2, 1)
+
+
+def dsf_saw_r(roughness):
+    return An("dsf", (1, 1.0, f32(roughness)), (), 1, 1)
+
+
+def dsf_square():
+    return An("dsf", (2, 2.0, 0.5), (), 2, 1)
+
+
+def dsf_square_r(roughness):
+    return An("dsf", (1, 2.0, f32(roughness)), (), 1, 1)

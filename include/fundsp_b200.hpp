@@ -122,6 +122,10 @@ inline An poly_square() { return An(fdsp_phase_osc(2)); }
 inline An poly_square_hz(float f) { return dc(f) >> poly_square(); }
 inline An poly_pulse() { return An(fdsp_phase_osc(3)); }
 inline An poly_pulse_hz(float f, float width) { return dc(f, width) >> poly_pulse(); }
+inline An dsf_saw() { return An(fdsp_dsf(2, 1.0f, 0.5f)); }
+inline An dsf_saw_r(float roughness) { return An(fdsp_dsf(1, 1.0f, roughness)); }
+inline An dsf_square() { return An(fdsp_dsf(2, 2.0f, 0.5f)); }
+inline An dsf_square_r(float roughness) { return An(fdsp_dsf(1, 2.0f, roughness)); }
 inline An mls_bits(int n) { return An(fdsp_mls(n)); }
 inline An mls() { return mls_bits(29); }
 inline An impulse(int n = 1) { return An(fdsp_impulse(n)); }

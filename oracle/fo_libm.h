@@ -182,6 +182,139 @@ inline float expf_(float x) {
   const float y = 1.0f + (x * c / (2.0f - c) - lo + hi);
   return k == 0 ? y : scalbnf_(y, k);
 }
+// e_powf.c (FreeBSD msun lineage, as ported by the Rust `libm` crate, src/math/powf.rs): float-only arithmetic,
+// log2(x) in two pieces (t1 + t2), y*log2(x) split the same way, then 2**(p_h + p_l).
+inline float powf_(float x, float y) {
+  const float two24 = 16777216.0f, huge = 1.0e30f, tiny = 1.0e-30f;
+  const float L1 = 6.0000002384e-01f, L2 = 4.2857143283e-01f, L3 = 3.3333334327e-01f, L4 = 2.7272811532e-01f, L5 = 2.3066075146e-01f, L6 = 2.0697501302e-01f;
+  const float P1 = 1.6666667163e-01f, P2 = -2.7777778450e-03f, P3 = 6.6137559770e-05f, P4 = -1.6533901999e-06f, P5 = 4.1381369442e-08f;
+  const float lg2 = 6.9314718246e-01f, lg2_h = 6.93145752e-01f, lg2_l = 1.42860654e-06f, ovt = 4.2995665694e-08f;
+  const float cp = 9.6179670095e-01f, cp_h = 9.6191406250e-01f, cp_l = -1.1736857402e-04f;
+  const float ivln2 = 1.4426950216e+00f, ivln2_h = 1.4426879883e+00f, ivln2_l = 7.0526075433e-06f;
+  float z, ax, z_h, z_l, p_h, p_l, y1, t1, t2, r, s, sn, t, u, v, w;
+  int32_t i, j, k, yisint, n, is;
+  const int32_t hx = (int32_t)fbits(x), hy = (int32_t)fbits(y);
+  int32_t ix = hx & 0x7fffffff;
+  const int32_t iy = hy & 0x7fffffff;
+  if (iy == 0) return 1.0f;                    // x**0 = 1, even if x is NaN
+  if (hx == 0x3f800000) return 1.0f;           // 1**y = 1, even if y is NaN
+  if (ix > 0x7f800000 || iy > 0x7f800000) return x + y;
+  yisint = 0;                                   // 0: y not an integer, 1: odd, 2: even (only needed for x < 0)
+  if (hx < 0) {
+    if (iy >= 0x4b800000) yisint = 2;
+    else if (iy >= 0x3f800000) {
+      k = (iy >> 23) - 0x7f;
+      j = iy >> (23 - k);
+      if ((j << (23 - k)) == iy) yisint = 2 - (j & 1);
+    }
+  }
+  if (iy == 0x7f800000) {                       // y is +-inf
+    if (ix == 0x3f800000) return 1.0f;
+    else if (ix > 0x3f800000) return hy >= 0 ? y : 0.0f;
+    else return hy >= 0 ? 0.0f : -y;
+  }
+  if (iy == 0x3f800000) return hy >= 0 ? x : 1.0f / x;
+  if (hy == 0x40000000) return x * x;
+  if (hy == 0x3f000000 && hx >= 0) return sqrtf(x);
+  ax = fromb((uint32_t)ix);
+  if (ix == 0x7f800000 || ix == 0 || ix == 0x3f800000) {   // x is +-0, +-inf, +-1
+    z = ax;
+    if (hy < 0) z = 1.0f / z;
+    if (hx < 0) {
+      if (((ix - 0x3f800000) | yisint) == 0) z = (z - z) / (z - z);
+      else if (yisint == 1) z = -z;
+    }
+    return z;
+  }
+  sn = 1.0f;
+  if (hx < 0) {
+    if (yisint == 0) return (x - x) / (x - x);
+    if (yisint == 1) sn = -1.0f;
+  }
+  if (iy > 0x4d000000) {                        // |y| > 2**27
+    if (ix < 0x3f7ffff8) return hy < 0 ? sn * huge * huge : sn * tiny * tiny;
+    if (ix > 0x3f800007) return hy > 0 ? sn * huge * huge : sn * tiny * tiny;
+    t = ax - 1.0f;
+    w = (t * t) * (0.5f - t * (0.333333333333f - t * 0.25f));
+    u = ivln2_h * t;
+    v = t * ivln2_l - w * ivln2;
+    t1 = u + v;
+    t1 = fromb(fbits(t1) & 0xfffff000u);
+    t2 = v - (t1 - u);
+  } else {
+    float s2, s_h, s_l, t_h, t_l;
+    n = 0;
+    if (ix < 0x00800000) { ax *= two24; n -= 24; ix = (int32_t)fbits(ax); }
+    n += (ix >> 23) - 0x7f;
+    j = ix & 0x007fffff;
+    ix = j | 0x3f800000;
+    if (j <= 0x1cc471) k = 0;                   // |x| < sqrt(3/2)
+    else if (j < 0x5db3d7) k = 1;               // |x| < sqrt(3)
+    else { k = 0; n += 1; ix -= 0x00800000; }
+    ax = fromb((uint32_t)ix);
+    const float bpk = k ? 1.5f : 1.0f, dp_hk = k ? 5.84960938e-01f : 0.0f, dp_lk = k ? 1.56322085e-06f : 0.0f;
+    u = ax - bpk;
+    v = 1.0f / (ax + bpk);
+    s = u * v;
+    s_h = fromb(fbits(s) & 0xfffff000u);
+    is = (int32_t)((((uint32_t)ix >> 1) & 0xfffff000u) | 0x20000000u);
+    t_h = fromb((uint32_t)(is + 0x00400000 + (k << 21)));
+    t_l = ax - (t_h - bpk);
+    s_l = v * ((u - s_h * t_h) - s_h * t_l);
+    s2 = s * s;
+    r = s2 * s2 * (L1 + s2 * (L2 + s2 * (L3 + s2 * (L4 + s2 * (L5 + s2 * L6)))));
+    r += s_l * (s_h + s);
+    s2 = s_h * s_h;
+    t_h = 3.0f + s2 + r;
+    t_h = fromb(fbits(t_h) & 0xfffff000u);
+    t_l = r - ((t_h - 3.0f) - s2);
+    u = s_h * t_h;
+    v = s_l * t_h + t_l * s;
+    p_h = u + v;
+    p_h = fromb(fbits(p_h) & 0xfffff000u);
+    p_l = v - (p_h - u);
+    z_h = cp_h * p_h;
+    z_l = cp_l * p_h + p_l * cp + dp_lk;
+    t = (float)n;
+    t1 = (((z_h + z_l) + dp_hk) + t);
+    t1 = fromb(fbits(t1) & 0xfffff000u);
+    t2 = z_l - (((t1 - t) - dp_hk) - z_h);
+  }
+  y1 = fromb(fbits(y) & 0xfffff000u);
+  p_l = (y - y1) * t1 + y * t2;
+  p_h = y1 * t1;
+  z = p_l + p_h;
+  j = (int32_t)fbits(z);
+  if (j > 0x43000000) return sn * huge * huge;
+  else if (j == 0x43000000) { if (p_l + ovt > z - p_h) return sn * huge * huge; }
+  else if ((j & 0x7fffffff) > 0x43160000) return sn * tiny * tiny;
+  else if ((uint32_t)j == 0xc3160000u) { if (p_l <= z - p_h) return sn * tiny * tiny; }
+  i = j & 0x7fffffff;
+  k = (i >> 23) - 0x7f;
+  n = 0;
+  if (i > 0x3f000000) {                         // |z| > 0.5: n = [z + 0.5]
+    n = j + (0x00800000 >> (k + 1));
+    k = ((n & 0x7fffffff) >> 23) - 0x7f;
+    t = fromb((uint32_t)(n & ~(0x007fffff >> k)));
+    n = ((n & 0x007fffff) | 0x00800000) >> (23 - k);
+    if (j < 0) n = -n;
+    p_h -= t;
+  }
+  t = p_l + p_h;
+  t = fromb(fbits(t) & 0xffff8000u);
+  u = t * lg2_h;
+  v = (p_l - (t - p_h)) * lg2 + t * lg2_l;
+  z = u + v;
+  w = v - (z - u);
+  t = z * z;
+  t1 = z - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+  r = (z * t1) / (t1 - 2.0f) - (w + z * w);
+  z = 1.0f - (r - z);
+  j = (int32_t)fbits(z);
+  j += (int32_t)((uint32_t)n << 23);
+  if ((j >> 23) <= 0) z = scalbnf_(z, n); else z = fromb((uint32_t)j);
+  return sn * z;
+}
 inline float tanhf_(float x) {  // s_tanhf.c
   uint32_t w = fbits(x); int sign = (int)(w >> 31); w &= 0x7fffffffu;
   x = fromb(w);

@@ -1002,6 +1002,34 @@ struct PhaseOsc : Node {
   FO_CLONE(PhaseOsc)
 };
 
+// ---- src/oscillator.rs:104-208 Dsf<N> (ID 55): discrete summation formula oscillator (Moorer 1976), N = 1 or 2 inputs
+inline float dsf_formula(float f, float d, float r, float n) {  // :105-112, f32 instantiation: libm sinf / cosf / powf
+  return (m::sinf_(f) - r * m::sinf_(f - d) - m::powf_(r, n + 1.0f) * (m::sinf_(f + (n + 1.0f) * d) - r * m::sinf_(f + n * d))) / (1.0f + r * r - 2.0f * r * m::cosf_(d));
+}
+struct Dsf : Node {
+  int nin; float phase = 0, roughness, harmonic_spacing, sample_duration = 0; uint64_t hash = 0; bool has_phase = false; float initial_phase = 0;
+  Dsf(int nin_, float spacing, float rough) : nin(nin_), roughness(rough), harmonic_spacing(spacing) { reset(); set_sample_rate(DEFAULT_SR); set_roughness(rough); }
+  void set_roughness(float r) { roughness = fminf(fmaxf(r, 0.0001f), 0.9999f); }  // clamp(0.0001, 0.9999, r) = r.max(lo).min(hi)
+  int inputs() const override { return nin; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 55; }
+  void reset() override { phase = has_phase ? initial_phase : (float)rnd1(hash); }
+  void set_sample_rate(double sr) override { sample_duration = (float)(1.0 / sr); }
+  void tick(const float* in, float* out) override {  // :171-187
+    if (nin > 1) set_roughness(in[1]);
+    phase += in[0] * sample_duration;
+    phase -= floorf(phase);
+    const float n = floorf(22050.0f / in[0] / harmonic_spacing);
+    const float TAU_F = 6.28318548202514648f;   // f32::TAU
+    out[0] = dsf_formula(phase * TAU_F, phase * TAU_F * harmonic_spacing, roughness, n);
+  }
+  void set(const Setting& s) override {
+    if (s.kind == P_ROUGHNESS) set_roughness(s.v[0]);
+    else if (s.kind == P_PHASE) { has_phase = true; initial_phase = s.v[0]; }
+  }
+  void set_hash(uint64_t h) override { hash = h; reset(); }
+  FO_CLONE(Dsf)
+};
+
 // ---- src/noise.rs:11-148 Mls (ID 19): maximum length sequence
 static const uint32_t MLS_POLY[31] = {
     0b1, 0b11, 0b110, 0b1100, 0b10100, 0b110000, 0b1001000, 0b10111000, 0b100010000, 0b1001000000, 0b10100000000, 0b110010100000,

@@ -66,6 +66,21 @@ API Node* fo_pan(float value) { return new Panner(value, 1); }
 API Node* fo_panner() { return new Panner(0.0f, 2); }
 API Node* fo_adsr_live(float a, float d, float s, float r) { return new AdsrLive(a, d, s, r); }
 API Node* fo_phase_osc(int kind) { return new PhaseOsc(kind); }   // 0 ramp, 1 poly_saw, 2 poly_square, 3 poly_pulse
+// restated libm entry points, for the accuracy tests (fn: 0 sinf 1 cosf 2 tanf 3 tanhf 4 expm1f 5 expf 6 powf(x, y))
+API void fo_libm_eval(int fn, const float* x, const float* y, float* out, int64_t n) {
+  for (int64_t i = 0; i < n; i++) {
+    switch (fn) {
+      case 0: out[i] = m::sinf_(x[i]); break;
+      case 1: out[i] = m::cosf_(x[i]); break;
+      case 2: out[i] = m::tanf_(x[i]); break;
+      case 3: out[i] = m::tanhf_(x[i]); break;
+      case 4: out[i] = m::expm1f_(x[i]); break;
+      case 5: out[i] = m::expf_(x[i]); break;
+      default: out[i] = m::powf_(x[i], y[i]); break;
+    }
+  }
+}
+API Node* fo_dsf(int inputs, float harmonic_spacing, float roughness) { return new Dsf(inputs, harmonic_spacing, roughness); }
 API Node* fo_mls(int bits) { return new Mls((uint32_t)bits); }
 API Node* fo_impulse(int n) { return new Impulse(n); }
 API Node* fo_tap(int ntaps, int linear, float min_delay, float max_delay) { return new Tap(ntaps, linear != 0, min_delay, max_delay); }

@@ -1,6 +1,8 @@
 """CPU tests of the product's host side (no GPU, no compute calls): the C-ABI library loads and exports
 every symbol include/fundsp_b200.h declares; its construction-time logic (ping hashes, settings, arity,
 type expressions, wavetables) agrees with the oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -10,6 +12,7 @@ from fundsp_b200.prelude import *  # noqa: F401,F403
 from oracle import OracleUnit, lib as olib
 
 L = capi.lib()
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -38,6 +41,7 @@ GRAPHS = [
     lambda: poly_saw_hz(440.0) | poly_square_hz(220.0).phase(0.5) | poly_pulse_hz(110.0, 0.3) | ramp_hz(5.0),
     lambda: mls() | mls_bits(10).seed(3) | (impulse(2) >> join(2)),
     lambda: (noise() | sine_hz(0.5) * 0.004 + 0.005) >> tap(0.001, 0.01) | (noise() | dc((0.002, 0.007))) >> multitap_linear(2, 0.001, 0.01),
+    lambda: dc(220.0) >> dsf_saw_r(0.7) | (dc(110.0) | dc(0.4)) >> dsf_square() | dc(440.0) >> dsf_square_r(0.3).phase(0.25),
     lambda: noise() >> feedback2(delay(0.002) * 0.5, lowpass_hz(2000.0, 1.0)) | (noise() | dc(800.0)) >> butterpass() | (noise() | dc((900.0, 8.0))) >> resonator(),
 ]
 
@@ -165,3 +169,37 @@ def test_cpp_host_mirror_compiles_and_matches_python_mirror(tmp_path):
     fm = capi.NodeHandle(sine_hz(f) * f * m + f >> sine())
     assert f"fm 0 1 {fm.signature()}" in lines
     assert "bus 0 2" in lines and "stacki 4 4" in lines and any(x.startswith("arity error") for x in lines)
+
+
+# ---------------------------------------------------------------- the NVRTC translation unit compiles without a GPU
+def _nvrtc_available():
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            from cuda import nvrtc  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+JIT_SAMPLES = [
+    lambda: dc(220.0) >> dsf_saw_r(0.7),
+    lambda: (noise() | dc((0.002, 0.007))) >> multitap_linear(2, 0.001, 0.01),
+    lambda: noise() >> feedback2(delay(0.002) * 0.5, lowpass_hz(2000.0, 1.0)),
+    lambda: (noise() | dc((900.0, 8.0))) >> resonator() | mls() | poly_saw_hz(110.0),
+    lambda: (noise() | dc((1000.0, 0.5))) >> moog() >> pan(0.25),
+]
+
+
+@pytest.mark.skipif(not _nvrtc_available(), reason="cuda-python NVRTC bindings not importable")
+@pytest.mark.parametrize("k", range(len(JIT_SAMPLES)))
+def test_jit_translation_unit_compiles_for_sm100a(k):
+    """Same headers and options as csrc/host/jit.cpp (tools/nvrtc_check.py); compile only, nothing runs."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("nvrtc_check", os.path.join(ROOT, "tools", "nvrtc_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sig = capi.NodeHandle(JIT_SAMPLES[k]()).signature()
+    ok, log = mod.compile_sig(sig)
+    assert ok, (sig, log[:2000])

@@ -43,6 +43,8 @@ CASES = {
     "fdn2_pair": lambda i: (noise().seed(i) | noise().seed(i + 500)) >> fdn2(stacki(2, lambda k: delay(0.001 + 0.0004 * k) * 0.45), stacki(2, lambda k: fir3(0.4 + 0.01 * (i % 20)))),
     "butterpass_audio_rate": lambda i: (noise().seed(i) | (sine_hz(1.0 + 0.2 * (i % 5)) * 300.0 + 900.0)) >> butterpass(),
     "resonator_audio_rate": lambda i: (noise().seed(i) | (sine_hz(0.5) * 200.0 + 700.0 + 5.0 * i) | dc(20.0 + i)) >> resonator(),
+    "dsf_saw_fixed_roughness": lambda i: dc(55.0 + 9.0 * i) >> dsf_saw_r(0.3 + 0.015 * (i % 40)),
+    "dsf_square_modulated": lambda i: ((sine_hz(4.0) * 20.0 + 110.0 + 7.0 * i) | (sine_hz(0.3 + 0.05 * (i % 9)) * 0.45 + 0.5)) >> dsf_square(),
     "product_fm_feedback": lambda i: (sine_hz(200.0 + i) * sine_hz(3.0 + 0.1 * i)) >> feedback(tick() * 0.25 >> lowpass_hz(2000.0, 0.7)),
 }
 GATED = {

@@ -7,6 +7,8 @@ import json
 import math
 import os
 
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -15,6 +17,7 @@ from fundsp_b200.prelude import *  # noqa: F401,F403
 from oracle import OracleUnit, lib, oracle_bank_render
 
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "int_vectors.json")))
+FP = C.POINTER(C.c_float)
 L = lib()
 
 
@@ -242,6 +245,56 @@ def test_tick_equals_process():
     check_wave((noise() | dc((440.0, 110.0))) >> resonator())
     check_wave(noise() >> feedback2(delay(0.002) * 0.5, lowpass_hz(2000.0, 1.0)) | (noise() | noise()) >> fdn2(stacki(2, lambda i: delay(0.001 + 0.0005 * i) * 0.4), stacki(2, lambda i: fir3(0.5))))
     L.fo_restore_denormals()
+
+
+def test_restated_libm_accuracy():
+    """The musl/FreeBSD-lineage scalar functions restated in oracle/fo_libm.h (and, identically, in csrc/dsp/libm.cuh) against
+    float64 numpy: a wrong constant or branch shows up as errors of many ulp."""
+    rng = np.random.default_rng(11)
+    n = 400_000
+
+    def ulps(got, ref):
+        ref = ref.astype(np.float64)
+        e = np.floor(np.log2(np.maximum(np.abs(ref), 1e-300)))
+        u = np.exp2(np.maximum(e, -126.0) - 23.0)
+        ok = np.isfinite(ref) & (np.abs(ref) < 3.0e38) & np.isfinite(got)
+        return float((np.abs(got.astype(np.float64) - ref) / u)[ok].max())
+
+    def run(fn, x, y=None):
+        x = np.ascontiguousarray(x, np.float32)
+        y = np.ascontiguousarray(x if y is None else y, np.float32)
+        out = np.zeros_like(x)
+        L.fo_libm_eval(fn, x.ctypes.data_as(FP), y.ctypes.data_as(FP), out.ctypes.data_as(FP), x.size)
+        return out
+
+    xs = np.concatenate([rng.uniform(-20.0, 20.0, n), rng.uniform(-1e4, 1e4, n // 4), rng.uniform(-1e-3, 1e-3, n // 4)]).astype(np.float32)
+    x64 = xs.astype(np.float64)
+    assert ulps(run(0, xs), np.sin(x64)) <= 1.0
+    assert ulps(run(1, xs), np.cos(x64)) <= 1.0
+    tx = xs[np.abs(np.cos(x64)) > 1e-3]
+    assert ulps(run(2, tx), np.tan(tx.astype(np.float64))) <= 1.5
+    assert ulps(run(3, xs), np.tanh(x64)) <= 2.5
+    ex = rng.uniform(-80.0, 80.0, n).astype(np.float32)
+    assert ulps(run(4, ex), np.expm1(ex.astype(np.float64))) <= 1.0
+    assert ulps(run(5, ex), np.exp(ex.astype(np.float64))) <= 1.0
+    px = np.concatenate([rng.uniform(1e-4, 0.9999, n), rng.uniform(0.0, 50.0, n)]).astype(np.float32)
+    py = np.concatenate([np.floor(rng.uniform(1.0, 1200.0, n)), rng.uniform(-8.0, 8.0, n)]).astype(np.float32)
+    with np.errstate(over="ignore", under="ignore"):
+        ref = np.power(px.astype(np.float64), py.astype(np.float64))
+    keep = ref > 1.2e-38                                   # normal results (the subnormal tail rounds on a coarser grid)
+    assert ulps(run(6, px[keep], py[keep]), ref[keep]) <= 1.0
+    sp = run(6, np.float32([2, -2, -2, 0, np.inf, 0.5, 1, np.nan]), np.float32([10, 3, 2, -1, -1, np.inf, np.nan, 0]))
+    assert np.array_equal(sp, np.float32([1024, -8, 4, np.inf, 0, 0, 1, 1]))
+
+
+def test_dsf_spectrum_known_answer():  # src/oscillator.rs:104-112: sum over i of r**i * sin(f + i*d)
+    sr, f0 = 44100.0, 441.0
+    for mk, spacing in ((dsf_saw_r, 1), (dsf_square_r, 2)):
+        w = OracleUnit(dc(f0) >> mk(0.5).phase(0.0)).render(sr, 1.0)[0]
+        X = np.abs(np.fft.rfft(w)) / (len(w) / 2)
+        got = [float(X[int(round((1 + i * spacing) * f0))]) for i in range(6)]
+        assert np.allclose(got, [0.5 ** i for i in range(6)], atol=2e-4), got   # partial i sits at (1 + i*spacing)*f with amplitude r**i
+    check_wave(dc(330.0) >> dsf_saw_r(0.8) | (dc(220.0) | sine_hz(0.5) * 0.3 + 0.5) >> dsf_square())
 
 
 def test_mls_is_maximum_length():  # src/noise.rs:11-98: the sequence of an n-bit MLS repeats after exactly 2**n - 1 steps
