@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 #include <nvrtc.h>
 
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -69,16 +70,60 @@ Api& api() {
   return a;
 }
 
+// One NVRTC translation unit = the headers + `typedef <sig> JitG` + (optionally) one kernel instantiation. The layout TU
+// (no kernel) is compiled when the program is created; each (mode, TB) kernel variant is compiled on its first launch, so a
+// bank pays for the one variant it uses instead of all six.
+static bool compile_unit(const std::string& sig, const char* kernel_expr, std::vector<char>& cubin, std::string& lowered, std::string& err) {
+  Api& A = api();
+  std::string src = "#include \"dsp/bank_kernel.cuh\"\nnamespace fdsp { typedef " + sig + " JitG; }\n";
+  if (!kernel_expr)
+    src += "extern \"C\" __device__ int fdsp_jit_layout[6] = {fdsp::JitG::IN, fdsp::JitG::OUT, fdsp::JitG::NP, fdsp::JitG::NS, fdsp::JitG::NU, fdsp::WaveKind<fdsp::JitG>::value};\n";
+  nvrtcProgram prog;
+  if (A.CreateProgram(&prog, src.c_str(), "fdsp_jit.cu", kJitHeaderCount, kJitHeaderSrc, kJitHeaderNames) != NVRTC_SUCCESS) { err = "nvrtcCreateProgram failed"; return false; }
+  if (kernel_expr) A.AddNameExpression(prog, kernel_expr);
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-lineinfo", "-default-device"};
+  if (A.CompileProgram(prog, 5, opts) != NVRTC_SUCCESS) {
+    size_t n = 0; A.GetProgramLogSize(prog, &n);
+    std::string log(n, '\0'); if (n) A.GetProgramLog(prog, &log[0]);
+    if (log.size() > 1500) log.resize(1500);
+    err = "NVRTC compile of `" + sig + "` failed: " + log;
+    A.DestroyProgram(&prog);
+    return false;
+  }
+  if (kernel_expr) {
+    const char* low = nullptr;
+    if (A.GetLoweredName(prog, kernel_expr, &low) != NVRTC_SUCCESS || !low) { err = "JIT kernel name lookup failed"; A.DestroyProgram(&prog); return false; }
+    lowered = low;
+  }
+  size_t cn = 0; A.GetCUBINSize(prog, &cn);
+  cubin.resize(cn); A.GetCUBIN(prog, cubin.data());
+  A.DestroyProgram(&prog);
+  return true;
+}
+
 struct JitProgram : Program {
-  CUmodule mod = nullptr;
-  CUfunction fn[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};  // [mode-1][TB]
+  int device = 0;
+  mutable std::mutex mu;
+  mutable CUmodule mods[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  mutable CUfunction fn[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};  // [mode-1][TB]
+  CUfunction variant(int mode, int tb) const {
+    std::lock_guard<std::mutex> lock(mu);
+    if (fn[mode - 1][tb]) return fn[mode - 1][tb];
+    const Api& A = api();
+    const std::string expr = "fdsp::bank_kernel<fdsp::JitG, 128, " + std::to_string(mode) + ", " + (tb ? "true" : "false") + ">";
+    std::vector<char> cubin; std::string low, err;
+    if (!compile_unit(sig, expr.c_str(), cubin, low, err)) { fprintf(stderr, "fundsp_b200 JIT: %s\n", err.c_str()); return nullptr; }
+    if (A.ModuleLoadData(&mods[mode - 1][tb], cubin.data()) != CUDA_SUCCESS) return nullptr;
+    if (A.ModuleGetFunction(&fn[mode - 1][tb], mods[mode - 1][tb], low.c_str()) != CUDA_SUCCESS) { fn[mode - 1][tb] = nullptr; return nullptr; }
+    return fn[mode - 1][tb];
+  }
   cudaError_t launch(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t st) const override {
     const Api& A = api();
     mode &= 3;
     if (mode == 0) return cudaErrorInvalidValue;
     const size_t tile = (mode & 2) ? sizeof(float) * mix_tile_floats(OUT, threads) : 0;
     int tb = (wave_kind >= 0 && table_bytes > 0 && tile + table_bytes <= 227 * 1024) ? 1 : 0;
-    CUfunction f = fn[mode - 1][tb];
+    CUfunction f = variant(mode, tb);
     if (!f) return cudaErrorInvalidDeviceFunction;
     const size_t smem = tile + (tb ? table_bytes : 0);
     if (smem > 48 * 1024 && A.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) != CUDA_SUCCESS) return cudaErrorInvalidValue;
@@ -109,42 +154,14 @@ std::shared_ptr<const Program> jit_program(const std::string& sig, int device, s
   cudaSetDevice(device);
   cudaFree(nullptr);  // make sure the primary context exists and is current for the driver API calls below
 
-  std::string src = "#include \"dsp/bank_kernel.cuh\"\nnamespace fdsp { typedef " + sig + " JitG; }\n"
-                    "extern \"C\" __device__ int fdsp_jit_layout[6] = {fdsp::JitG::IN, fdsp::JitG::OUT, fdsp::JitG::NP, fdsp::JitG::NS, fdsp::JitG::NU, fdsp::WaveKind<fdsp::JitG>::value};\n";
-  nvrtcProgram prog;
-  if (A.CreateProgram(&prog, src.c_str(), "fdsp_jit.cu", kJitHeaderCount, kJitHeaderSrc, kJitHeaderNames) != NVRTC_SUCCESS) { err = "nvrtcCreateProgram failed"; return nullptr; }
-  std::vector<std::string> names;
-  for (int mode = 1; mode <= 3; mode++)
-    for (int tb = 0; tb < 2; tb++) {
-      names.push_back("fdsp::bank_kernel<fdsp::JitG, 128, " + std::to_string(mode) + ", " + (tb ? "true" : "false") + ">");
-      A.AddNameExpression(prog, names.back().c_str());
-    }
-  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-lineinfo", "-default-device"};
-  nvrtcResult rc = A.CompileProgram(prog, 5, opts);
-  if (rc != NVRTC_SUCCESS) {
-    size_t n = 0; A.GetProgramLogSize(prog, &n);
-    std::string log(n, '\0'); if (n) A.GetProgramLog(prog, &log[0]);
-    if (log.size() > 1500) log.resize(1500);
-    err = "NVRTC compile of `" + sig + "` failed: " + log;
-    A.DestroyProgram(&prog);
-    return nullptr;
-  }
-  size_t cn = 0; A.GetCUBINSize(prog, &cn);
-  std::vector<char> cubin(cn); A.GetCUBIN(prog, cubin.data());
+  std::vector<char> cubin; std::string low;
+  if (!compile_unit(sig, nullptr, cubin, low, err)) return nullptr;
   auto p = std::make_shared<JitProgram>();
-  p->sig = sig; p->jit = true;
-  if (A.ModuleLoadData(&p->mod, cubin.data()) != CUDA_SUCCESS) { err = "cuModuleLoadData failed for the JIT cubin"; A.DestroyProgram(&prog); return nullptr; }
-  int k = 0;
-  for (int mode = 1; mode <= 3; mode++)
-    for (int tb = 0; tb < 2; tb++, k++) {
-      const char* low = nullptr;
-      if (A.GetLoweredName(prog, names[k].c_str(), &low) != NVRTC_SUCCESS || A.ModuleGetFunction(&p->fn[mode - 1][tb], p->mod, low) != CUDA_SUCCESS) {
-        err = "JIT kernel lookup failed"; A.DestroyProgram(&prog); return nullptr;
-      }
-    }
-  A.DestroyProgram(&prog);
+  p->sig = sig; p->jit = true; p->device = device;
+  CUmodule lm = nullptr;
+  if (A.ModuleLoadData(&lm, cubin.data()) != CUDA_SUCCESS) { err = "cuModuleLoadData failed for the JIT layout unit"; return nullptr; }
   CUdeviceptr d = 0; size_t bytes = 0; int lay[6] = {0, 0, 0, 0, 0, -1};
-  if (A.ModuleGetGlobal(&d, &bytes, p->mod, "fdsp_jit_layout") != CUDA_SUCCESS || bytes != sizeof(lay) || A.MemcpyDtoH(lay, d, sizeof(lay)) != CUDA_SUCCESS) {
+  if (A.ModuleGetGlobal(&d, &bytes, lm, "fdsp_jit_layout") != CUDA_SUCCESS || bytes != sizeof(lay) || A.MemcpyDtoH(lay, d, sizeof(lay)) != CUDA_SUCCESS) {
     err = "JIT layout readback failed"; return nullptr;
   }
   p->IN = lay[0]; p->OUT = lay[1]; p->NP = lay[2]; p->NS = lay[3]; p->NU = lay[4]; p->wave_kind = lay[5]; p->threads = 128;
