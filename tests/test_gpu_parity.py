@@ -76,12 +76,12 @@ def test_net_voice_classes():
 
 def test_subtractive_dry_chain():
     n = 24000
-    check("subtractive_dry", 96, n, exact=False, inp=workloads.gate_signal(n))
+    check("subtractive_dry", 96, n, exact=True, inp=workloads.gate_signal(n))   # Moog tanh / sin through the restated musl libm: bit-exact
 
 
 def test_subtractive_with_fdn_reverb():
     n = 9600
-    check("subtractive", 33, n, exact=False, inp=workloads.gate_signal(n, SR) * 0 + np.concatenate(
+    check("subtractive", 33, n, exact=True, inp=workloads.gate_signal(n, SR) * 0 + np.concatenate(
         [np.zeros((1, 480), np.float32), np.ones((1, 4800), np.float32), np.zeros((1, n - 5280), np.float32)], axis=1))
 
 
