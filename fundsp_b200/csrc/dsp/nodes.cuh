@@ -816,6 +816,60 @@ template <int HAD, class X, class Y> struct Feedback2 {  // src/feedback.rs:180-
   static FDSP_DEV void end_simd(R&) {}
 };
 
+// ---------------------------------------------------------------- Reverb<F> (src/reverb.rs:139-279, ID 85: reverb3_stereo)
+// Allpass-loop stereo reverb: 4 pre-delay allpasses, then 8 blocks of (delay, 4 allpasses, loop filter, 4 allpasses, loop
+// filter) traversed in series; the last block's output is fed back. Tick-only in the reference, so every part runs `step<true>`.
+// Word order (host ReverbN::lower): a | feedback | pre[0..3] | per block: delay, ap0[0..3], f0, ap1[0..3], f1.
+template <class F> struct Reverb85 {
+  typedef AllNest<1, Delay> Sch;
+  static constexpr int IN = 2, OUT = 2;
+  static constexpr int NP = 1 + 68 * Sch::NP + 8 * Delay::NP + 16 * F::NP;
+  static constexpr int NS = 1 + 68 * Sch::NS + 8 * Delay::NS + 16 * F::NS;
+  static constexpr int NU = 68 * Sch::NU + 8 * Delay::NU + 16 * F::NU;
+  struct Blk { Delay::R delay; typename Sch::R a0[4]; typename F::R f0; typename Sch::R a1[4]; typename F::R f1; };
+  struct R { float a, feedback; typename Sch::R pre[4]; Blk b[8]; };
+  static FDSP_DEV void load(R& r, Loader& l) {
+    r.a = l.Pf(); r.feedback = l.Sf();
+    for (int k = 0; k < 4; k++) Sch::load(r.pre[k], l);
+    for (int i = 0; i < 8; i++) {
+      Delay::load(r.b[i].delay, l);
+      for (int k = 0; k < 4; k++) Sch::load(r.b[i].a0[k], l);
+      F::load(r.b[i].f0, l);
+      for (int k = 0; k < 4; k++) Sch::load(r.b[i].a1[k], l);
+      F::load(r.b[i].f1, l);
+    }
+  }
+  static FDSP_DEV void save(const R& r, Saver& s) {
+    s.Sf(r.feedback);
+    for (int k = 0; k < 4; k++) Sch::save(r.pre[k], s);
+    for (int i = 0; i < 8; i++) {
+      Delay::save(r.b[i].delay, s);
+      for (int k = 0; k < 4; k++) Sch::save(r.b[i].a0[k], s);
+      F::save(r.b[i].f0, s);
+      for (int k = 0; k < 4; k++) Sch::save(r.b[i].a1[k], s);
+      F::save(r.b[i].f1, s);
+    }
+  }
+  template <class N, class C> static FDSP_DEV float mono(typename N::R& r, const C& c, float x) { Fr<1> a, b; a.v[0] = x; N::template step<true>(r, c, a, b); return b.v[0]; }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<2>& in, Fr<2>& o) {  // :244-274
+    float v0 = r.feedback, o0 = 0.0f, o1 = 0.0f;
+    float in0 = mono<Sch>(r.pre[0], c, in.v[0] * 0.5f); in0 = mono<Sch>(r.pre[1], c, in0);
+    float in1 = mono<Sch>(r.pre[2], c, in.v[1] * 0.5f); in1 = mono<Sch>(r.pre[3], c, in1);
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) {
+      Blk& b = r.b[i];
+      v0 = mono<Delay>(b.delay, c, v0);
+      v0 = mono<Sch>(b.a0[0], c, r.a * v0 + in0); v0 = mono<Sch>(b.a0[1], c, v0); v0 = mono<Sch>(b.a0[2], c, v0); v0 = mono<Sch>(b.a0[3], c, v0);
+      v0 = mono<F>(b.f0, c, v0); o0 = v0;
+      v0 = mono<Sch>(b.a1[0], c, r.a * v0 + in1); v0 = mono<Sch>(b.a1[1], c, v0); v0 = mono<Sch>(b.a1[2], c, v0); v0 = mono<Sch>(b.a1[3], c, v0);
+      v0 = mono<F>(b.f1, c, v0); o1 = v0;
+    }
+    r.feedback = v0;
+    o.v[0] = o0; o.v[1] = o1;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
 // ---------------------------------------------------------------- panning / envelopes
 template <int NIN> struct Panner {  // src/pan.rs:19-91, ID 49
   FDSP_NODE(NIN, 2, NIN == 1 ? 2 : 0, NIN == 1 ? 0 : 2, 0);
@@ -946,6 +1000,8 @@ template <class X> struct Cost<Thru<X>> { static constexpr int value = Cost<X>::
 template <int KIND, int OP, int N, class X> struct Cost<Multi<KIND, OP, N, X>> { static constexpr int value = N * Cost<X>::value; };
 template <int NIN, class X> struct Cost<AllNest<NIN, X>> { static constexpr int value = Cost<X>::value + 6; };
 template <int HAD, class X, class Y> struct Cost<Feedback2<HAD, X, Y>> { static constexpr int value = Cost<X>::value + Cost<Y>::value + (HAD ? 6 * X::IN : X::IN); };
+template <class F> struct Cost<Reverb85<F>> { static constexpr int value = 1200 + 16 * Cost<F>::value; };
+template <class F> struct WaveKind<Reverb85<F>> : WaveKind<F> {};
 template <int N> struct Cost<Dsf<N>> { static constexpr int value = 700; };
 template <int NT_, int LIN> struct Cost<Tap<NT_, LIN>> { static constexpr int value = 40 * NT_; };
 template <int HAD, class X> struct Cost<Feedback<HAD, X>> { static constexpr int value = Cost<X>::value + (HAD ? 6 * X::IN : X::IN); };

@@ -30,6 +30,7 @@ struct Kid {  // deep-copying owning pointer
   Kid& operator=(const Kid& o) { if (this != &o) p.reset(o.p ? o.p->clone() : nullptr); return *this; }
   Kid& operator=(Kid&& o) noexcept { p = std::move(o.p); return *this; }
   HNode* operator->() const { return p.get(); }
+  HNode& operator*() const { return *p; }
 };
 
 std::string I(int v) { return std::to_string(v); }
@@ -322,6 +323,55 @@ struct AllNest : HNode {  // src/delay.rs:288-377
   HCLONE(AllNest)
 };
 
+// ---------------------------------------------------------------- Reverb<F> (src/reverb.rs:139-279) and Var (src/shared.rs:84-131)
+struct ReverbN : HNode {
+  struct Block { Kid delay, ap0[4], ap1[4], f0, f1; };
+  Kid pre[4]; Block block[8]; float a;
+  static HNode* schroeder(float coeff, int samples) { return new AllNest(coeff, new Delay((double)(samples - 1) / DEFAULT_SR), 1); }
+  ReverbN(double time, double diffusion, HNode* filter) {   // :156-206; the loop filter is cloned into its 16 positions as constructed
+    static const int ldelays[32] = {401, 421, 443, 463, 487, 503, 523, 547, 563, 587, 607, 619, 643, 661, 683, 701, 727, 743, 761, 787, 809, 823, 839, 863, 883, 907, 929, 947, 967, 983, 1009, 1021};
+    static const int rdelays[32] = {419, 433, 457, 479, 491, 509, 541, 557, 577, 593, 613, 631, 653, 673, 691, 719, 733, 757, 773, 797, 811, 829, 853, 877, 887, 911, 937, 953, 977, 997, 1013, 1033};
+    static const int delays[8] = {1087, 1091, 1093, 1097, 1103, 1109, 1117, 1123};
+    static const int predelay[4] = {245, 367, 263, 349};
+    const float coeff = (float)(0.5 * (1.0 - diffusion) + 0.9 * diffusion);
+    for (int i = 0; i < 8; i++) {
+      for (int j = 0; j < 4; j++) { block[i].ap0[j] = Kid(schroeder(coeff, ldelays[i + j * 8])); block[i].ap1[j] = Kid(schroeder(coeff, rdelays[i + j * 8])); }
+      block[i].delay = Kid(new Delay((double)delays[7 - i] / DEFAULT_SR));
+      block[i].f0 = Kid(filter->clone()); block[i].f1 = Kid(filter->clone());
+    }
+    a = (float)pow(exp((-60.0 / 20.0) * 2.302585092994046), 0.035 / time);   // pow(db_amp(-60.0), 0.035 / time) as f32 (src/math.rs:74-76,294-296)
+    for (int i = 0; i < 4; i++) pre[i] = Kid(schroeder(coeff, predelay[i]));
+    delete filter;
+  }
+  int inputs() const override { return 2; } int outputs() const override { return 2; }
+  uint64_t id() const override { return 85; }
+  template <class Fn> void each(Fn fn) { for (auto& b : block) { for (auto& x : b.ap0) fn(*x); for (auto& x : b.ap1) fn(*x); fn(*b.f0); fn(*b.f1); fn(*b.delay); } }
+  void reset() override { each([](HNode& n) { n.reset(); }); }
+  void set_sample_rate(double s) override { each([s](HNode& n) { n.set_sample_rate(s); }); }   // the pre-delays keep the default rate (:230-242)
+  void sig(std::string& o) const override { o += "Reverb85<"; block[0].f0->sig(o); o += ">"; }
+  void lower(Lowering& l) const override {
+    l.p(a); l.s(0.0f);
+    for (int i = 0; i < 4; i++) pre[i]->lower(l);
+    for (auto& b : block) {
+      b.delay->lower(l);
+      for (auto& x : b.ap0) x->lower(l);
+      b.f0->lower(l);
+      for (auto& x : b.ap1) x->lower(l);
+      b.f1->lower(l);
+    }
+  }
+  HCLONE(ReverbN)
+};
+struct VarN : HNode {  // the shared value is control-plane state: it enters as a parameter word and changes through Setting::value
+  float value; explicit VarN(float v) : value(v) {}
+  int inputs() const override { return 0; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 68; }
+  void set(const Setting& s) override { if (s.kind == P_VALUE) value = s.v[0]; }
+  void sig(std::string& o) const override { o += "Constant<1>"; }   // per block it is a constant (src/shared.rs:118-121)
+  void lower(Lowering& l) const override { l.p(value); }
+  HCLONE(VarN)
+};
+
 // ---------------------------------------------------------------- pan / envelope (src/pan.rs, src/envelope.rs, src/adsr.rs)
 struct Panner : HNode {
   int nin; float value;
@@ -573,6 +623,11 @@ HNode* mk_tick(int n) { return new TickN(n); }
 HNode* mk_delay(double t) { return t < 0.0 ? nullptr : new Delay(t); }
 HNode* mk_allnest(float c, HNode* x, int nin) { if (!x || x->inputs() != 1 || x->outputs() != 1) { delete x; return nullptr; } return new AllNest(c, x, nin); }
 HNode* mk_phase_osc(int kind) { return (kind < 0 || kind > 3) ? nullptr : new PhaseOsc(kind); }
+HNode* mk_reverb3(double time, double diffusion, HNode* filter) {
+  if (!filter || filter->inputs() != 1 || filter->outputs() != 1 || !(time > 0.0)) { delete filter; return nullptr; }
+  return new ReverbN(time, diffusion, filter);
+}
+HNode* mk_var(float value) { return new VarN(value); }
 HNode* mk_dsf(int inputs, float spacing, float roughness) { return (inputs < 1 || inputs > 2 || !(spacing > 0.0f)) ? nullptr : new DsfN(inputs, spacing, roughness); }
 HNode* mk_mls(int bits) { return (bits < 1 || bits > 31) ? nullptr : new Mls((uint32_t)bits); }
 HNode* mk_impulse(int n) { return n < 1 ? nullptr : new ImpulseN(n); }

@@ -12,7 +12,7 @@ import math
 
 import numpy as np
 
-from .graph import (An, M_BRANCH, M_BUS, M_CHAIN, M_REDUCE, M_STACK, OP_ADD, OP_MUL, f32, multi)
+from .graph import (An, ArityError, M_BRANCH, M_BUS, M_CHAIN, M_REDUCE, M_STACK, OP_ADD, OP_MUL, f32, multi)
 
 F = np.float32
 
@@ -592,3 +592,15 @@ def dsf_square():
 
 def dsf_square_r(roughness):
     return An("dsf", (1, 2.0, f32(roughness)), (), 1, 1)
+
+
+# ---- src/prelude.rs:1858-1864 allpass-loop stereo reverb with a user loop filter; src/shared.rs:84 shared control value
+def reverb3_stereo(time, diffusion, filt):
+    if (filt.nin, filt.nout) != (1, 1):
+        raise ArityError("reverb3_stereo: the loop filter must be 1 -> 1")
+    return An("reverb3", (float(time), float(diffusion)), (filt,), 2, 2)
+
+
+def var(value):
+    """var(&shared): here the shared value is changed through Setting value (kind 4) / GpuBank.set."""
+    return An("var", (f32(value),), (), 0, 1)

@@ -925,6 +925,68 @@ struct AllNest : Node {
   FO_CLONE(AllNest)
 };
 
+// ---- src/reverb.rs:139-279 Reverb<F> (ID 85): allpass-loop stereo reverb with a user loop filter (reverb3_stereo)
+struct Reverb85 : Node {
+  struct Block { std::unique_ptr<Node> delay, ap0[4], ap1[4], f0, f1; };
+  std::unique_ptr<Node> pre[4]; Block block[8]; float feedback = 0, a;
+  static Node* schroeder(float coeff, int samples) { return new AllNest(coeff, new Delay((double)(samples - 1) / DEFAULT_SR), 1); }
+  Reverb85(double time, double diffusion, Node* filter) {   // :156-206 (takes ownership of `filter`, clones it per loop position)
+    static const int ldelays[32] = {401, 421, 443, 463, 487, 503, 523, 547, 563, 587, 607, 619, 643, 661, 683, 701, 727, 743, 761, 787, 809, 823, 839, 863, 883, 907, 929, 947, 967, 983, 1009, 1021};
+    static const int rdelays[32] = {419, 433, 457, 479, 491, 509, 541, 557, 577, 593, 613, 631, 653, 673, 691, 719, 733, 757, 773, 797, 811, 829, 853, 877, 887, 911, 937, 953, 977, 997, 1013, 1033};
+    static const int delays[8] = {1087, 1091, 1093, 1097, 1103, 1109, 1117, 1123};
+    static const int predelay[4] = {245, 367, 263, 349};
+    const float coeff = (float)(0.5 * (1.0 - diffusion) + 0.9 * diffusion);   // lerp(0.5, 0.9, diffusion) = a*(1-t) + b*t
+    for (int i = 0; i < 8; i++) {
+      for (int j = 0; j < 4; j++) { block[i].ap0[j].reset(schroeder(coeff, ldelays[i + j * 8])); block[i].ap1[j].reset(schroeder(coeff, rdelays[i + j * 8])); }
+      block[i].delay.reset(new Delay((double)delays[7 - i] / DEFAULT_SR));
+      block[i].f0.reset(filter->clone()); block[i].f1.reset(filter->clone());
+    }
+    a = (float)pow(db_ampd(-60.0), 0.035 / time);                               // pow(db_amp(-60.0), 0.035 / time) as f32
+    for (int i = 0; i < 4; i++) pre[i].reset(schroeder(coeff, predelay[i]));
+    delete filter;
+  }
+  Reverb85(const Reverb85& o) : Node(o), feedback(o.feedback), a(o.a) {
+    for (int i = 0; i < 4; i++) pre[i].reset(o.pre[i]->clone());
+    for (int i = 0; i < 8; i++) {
+      for (int j = 0; j < 4; j++) { block[i].ap0[j].reset(o.block[i].ap0[j]->clone()); block[i].ap1[j].reset(o.block[i].ap1[j]->clone()); }
+      block[i].delay.reset(o.block[i].delay->clone()); block[i].f0.reset(o.block[i].f0->clone()); block[i].f1.reset(o.block[i].f1->clone());
+    }
+  }
+  int inputs() const override { return 2; } int outputs() const override { return 2; }
+  uint64_t id() const override { return 85; }
+  template <class Fn> void each(Fn fn) {
+    for (auto& b : block) { for (auto& x : b.ap0) fn(*x); for (auto& x : b.ap1) fn(*x); fn(*b.f0); fn(*b.f1); fn(*b.delay); }
+  }
+  void reset() override { each([](Node& n) { n.reset(); }); feedback = 0; }                        // :215-228 (the pre-delays are not reset)
+  void set_sample_rate(double sr) override { each([sr](Node& n) { n.set_sample_rate(sr); }); }    // :230-242 (nor re-rated)
+  static float mono(Node& n, float x) { float y; n.tick(&x, &y); return y; }
+  void tick(const float* in, float* out) override {  // :244-274
+    float v0 = feedback, o0 = 0, o1 = 0;
+    float in0 = mono(*pre[0], in[0] * 0.5f); in0 = mono(*pre[1], in0);
+    float in1 = mono(*pre[2], in[1] * 0.5f); in1 = mono(*pre[3], in1);
+    for (auto& b : block) {
+      v0 = mono(*b.delay, v0);
+      v0 = mono(*b.ap0[0], a * v0 + in0); v0 = mono(*b.ap0[1], v0); v0 = mono(*b.ap0[2], v0); v0 = mono(*b.ap0[3], v0);
+      v0 = mono(*b.f0, v0); o0 = v0;
+      v0 = mono(*b.ap1[0], a * v0 + in1); v0 = mono(*b.ap1[1], v0); v0 = mono(*b.ap1[2], v0); v0 = mono(*b.ap1[3], v0);
+      v0 = mono(*b.f1, v0); o1 = v0;
+    }
+    feedback = v0;
+    out[0] = o0; out[1] = o1;
+  }
+  Node* clone() const override { return new Reverb85(*this); }
+};
+// ---- src/shared.rs:84-131 Var (ID 68): outputs a shared control value, sampled once per block; here the value is a Setting
+struct Var : Node {
+  float value;
+  explicit Var(float v) : value(v) {}
+  int inputs() const override { return 0; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 68; }
+  void tick(const float*, float* out) override { out[0] = value; }
+  void set(const Setting& s) override { if (s.kind == P_VALUE) value = s.v[0]; }
+  FO_CLONE(Var)
+};
+
 // ---- src/denormal.rs:5-21 prevent_denormals: _mm_setcsr(0x9fc0) = FTZ + DAZ, process-wide and sticky.
 inline bool& denormal_emulation_enabled() { static bool e = true; return e; }
 inline void prevent_denormals() { if (denormal_emulation_enabled()) _mm_setcsr(0x9fc0); }

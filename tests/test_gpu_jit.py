@@ -45,6 +45,8 @@ CASES = {
     "resonator_audio_rate": lambda i: (noise().seed(i) | (sine_hz(0.5) * 200.0 + 700.0 + 5.0 * i) | dc(20.0 + i)) >> resonator(),
     "dsf_saw_fixed_roughness": lambda i: dc(55.0 + 9.0 * i) >> dsf_saw_r(0.3 + 0.015 * (i % 40)),
     "dsf_square_modulated": lambda i: ((sine_hz(4.0) * 20.0 + 110.0 + 7.0 * i) | (sine_hz(0.3 + 0.05 * (i % 9)) * 0.45 + 0.5)) >> dsf_square(),
+    "reverb3_lowpass_loop": lambda i: (noise().seed(i) | noise().seed(i + 100)) >> (multipass(2) & 0.25 * reverb3_stereo(1.0 + 0.1 * (i % 10), 0.3 + 0.01 * (i % 40), lowpass_hz(6000.0 + 50.0 * i, 0.7))),
+    "var_gain": lambda i: var(0.1 + 0.02 * i) * noise().seed(i) + var(0.5) * sine_hz(100.0 + i),
     "product_fm_feedback": lambda i: (sine_hz(200.0 + i) * sine_hz(3.0 + 0.1 * i)) >> feedback(tick() * 0.25 >> lowpass_hz(2000.0, 0.7)),
 }
 GATED = {

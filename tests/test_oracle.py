@@ -297,6 +297,29 @@ def test_dsf_spectrum_known_answer():  # src/oscillator.rs:104-112: sum over i o
     check_wave(dc(330.0) >> dsf_saw_r(0.8) | (dc(220.0) | sine_hz(0.5) * 0.3 + 0.5) >> dsf_square())
 
 
+def test_reverb3_and_var():  # src/reverb.rs:139-279, src/prelude.rs:1856 doc example, src/shared.rs:84-131
+    mk = lambda: (noise().seed(1) | noise().seed(2)) >> (multipass(2) & 0.25 * reverb3_stereo(2.0, 0.5, lowpass_hz(8000.0, 0.7)))
+    # tick == process on two FRESH units: Reverb::reset leaves the four pre-delay allpasses alone (src/reverb.rs:215-228), so the
+    # reset-then-tick pattern of check_wave would compare different states
+    blocks, ticks = OracleUnit(mk()), OracleUnit(mk())
+    wave = blocks.process_many(700)
+    tk = np.stack([ticks.tick() for _ in range(700)], axis=1)
+    assert np.abs(wave - tk).max() <= 1.0e-4 and np.abs(wave).max() > 0.1
+    # with an identity loop filter the structure is allpasses + delays + one gain a < 1: stable, and silent until the first tap
+    r = OracleUnit(impulse(2) >> reverb3_stereo(1.0, 0.5, pass_())).render(44100.0, 2.0)
+    first = int(np.argmax(np.abs(r).max(axis=0) > 0))
+    assert first == 0 and np.isfinite(r).all()     # every Schroeder allpass passes eta * x straight through
+    en = lambda a, b: 10.0 * np.log10(float((r[:, a:b] ** 2).mean()) + 1e-30)
+    assert en(2000, 6000) > en(42100, 46100) + 15.0 > en(84000, 88200) + 30.0     # monotone decay of the tail
+    # longer time = slower decay (a = db_amp(-60) ** (0.035 / time))
+    r4 = OracleUnit(impulse(2) >> reverb3_stereo(4.0, 0.5, pass_())).render(44100.0, 2.0)
+    assert (r4[:, 80000:] ** 2).mean() > 10.0 * (r[:, 80000:] ** 2).mean()
+    v = OracleUnit(var(0.25) * dc(2.0))
+    assert np.array_equal(v.process_many(70)[0], np.full(70, 0.5, np.float32))
+    v.L.fo_set(v.h, 4, (C.c_float * 1)(0.75), 1, 0, (C.c_int64 * 2)(1, 0), 1)   # Setting::value(0.75).left()
+    assert np.array_equal(v.process_many(70)[0], np.full(70, 1.5, np.float32))
+
+
 def test_mls_is_maximum_length():  # src/noise.rs:11-98: the sequence of an n-bit MLS repeats after exactly 2**n - 1 steps
     for n in range(2, 15):
         u = OracleUnit(mls_bits(n))
