@@ -816,6 +816,31 @@ template <int HAD, class X, class Y> struct Feedback2 {  // src/feedback.rs:180-
   static FDSP_DEV void end_simd(R&) {}
 };
 
+// ---------------------------------------------------------------- FeedbackUnit (src/feedback.rs:316-481, ID 79)
+// Feedback with an integrated delay of `samples` >= 1: a block no longer than the delay runs the inner graph's BLOCK path on
+// (input + output delayed by `samples`), a longer block ticks it. Per-channel power-of-two rings in HBM; uniform words:
+// samples, ring length. The rings never alias inside a block-mode block (the read position trails the write by >= size).
+template <class X> struct FeedbackUnit {
+  static constexpr int N = X::IN;
+  FDSP_NODE(N, N, X::NP, 1 + X::NS, 2 + X::NU);
+  struct R { uint32_t samples, len, off, index; bool block; typename X::R x; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.samples = l.U(); r.len = l.U(); r.off = l.D(r.len * (uint32_t)N); r.index = l.S(); r.block = false; X::load(r.x, l); }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.S(r.index); X::save(r.x, s); }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<N>& in, Fr<N>& o) {
+    const uint32_t mask = r.len - 1u;
+    const uint32_t ri = (r.index + r.len - r.samples) & mask;
+    Fr<N> t;
+#pragma unroll
+    for (int k = 0; k < N; k++) t.v[k] = in.v[k] + c.dl[(size_t)(r.off + (uint32_t)k * r.len + ri) * c.V + c.v];
+    r.block = !T && (uint32_t)c.n <= r.samples;
+    if (r.block) X::template step<false>(r.x, c, t, o); else X::template step<true>(r.x, c, t, o);
+#pragma unroll
+    for (int k = 0; k < N; k++) c.dl[(size_t)(r.off + (uint32_t)k * r.len + r.index) * c.V + c.v] = o.v[k];
+    r.index = (r.index + 1u) & mask;
+  }
+  static FDSP_DEV void end_simd(R& r) { if (r.block) X::end_simd(r.x); }
+};
+
 // ---------------------------------------------------------------- Reverb<F> (src/reverb.rs:139-279, ID 85: reverb3_stereo)
 // Allpass-loop stereo reverb: 4 pre-delay allpasses, then 8 blocks of (delay, 4 allpasses, loop filter, 4 allpasses, loop
 // filter) traversed in series; the last block's output is fed back. Tick-only in the reference, so every part runs `step<true>`.
@@ -1000,6 +1025,8 @@ template <class X> struct Cost<Thru<X>> { static constexpr int value = Cost<X>::
 template <int KIND, int OP, int N, class X> struct Cost<Multi<KIND, OP, N, X>> { static constexpr int value = N * Cost<X>::value; };
 template <int NIN, class X> struct Cost<AllNest<NIN, X>> { static constexpr int value = Cost<X>::value + 6; };
 template <int HAD, class X, class Y> struct Cost<Feedback2<HAD, X, Y>> { static constexpr int value = Cost<X>::value + Cost<Y>::value + (HAD ? 6 * X::IN : X::IN); };
+template <class X> struct WaveKind<FeedbackUnit<X>> : WaveKind<X> {};
+template <class X> struct Cost<FeedbackUnit<X>> { static constexpr int value = Cost<X>::value + 12 * X::IN; };
 template <class F> struct Cost<Reverb85<F>> { static constexpr int value = 1200 + 16 * Cost<F>::value; };
 template <class F> struct WaveKind<Reverb85<F>> : WaveKind<F> {};
 template <int N> struct Cost<Dsf<N>> { static constexpr int value = 700; };

@@ -362,6 +362,25 @@ struct ReverbN : HNode {
   }
   HCLONE(ReverbN)
 };
+struct FeedbackUnitN : HNode {  // src/feedback.rs:316-481
+  Kid x; double delay, sr = 0.0; uint32_t samples = 1, len = 1;
+  FeedbackUnitN(double d, HNode* x_) : x(x_), delay(d) { set_sample_rate(DEFAULT_SR); }
+  int inputs() const override { return x->inputs(); } int outputs() const override { return x->outputs(); }
+  uint64_t id() const override { return 79; }
+  void reset() override { x->reset(); }
+  void set_sample_rate(double s) override {
+    if (sr != s) {
+      sr = s;
+      x->set_sample_rate(s);
+      samples = (uint32_t)fmax(round(delay * s), 1.0);
+      len = 1; while (len < samples) len <<= 1;
+    }
+  }
+  AttoHash ping(bool probe, AttoHash h) override { return x->ping(probe, h.hash(id())); }
+  void sig(std::string& o) const override { o += "FeedbackUnit<"; x->sig(o); o += ">"; }
+  void lower(Lowering& l) const override { l.U.push_back(samples); l.U.push_back(len); l.dlen.push_back(len * (uint32_t)inputs()); l.su(0u); x->lower(l); }
+  HCLONE(FeedbackUnitN)
+};
 struct VarN : HNode {  // the shared value is control-plane state: it enters as a parameter word and changes through Setting::value
   float value; explicit VarN(float v) : value(v) {}
   int inputs() const override { return 0; } int outputs() const override { return 1; }
@@ -628,6 +647,10 @@ HNode* mk_reverb3(double time, double diffusion, HNode* filter) {
   return new ReverbN(time, diffusion, filter);
 }
 HNode* mk_var(float value) { return new VarN(value); }
+HNode* mk_feedback_unit(double delay, HNode* x) {
+  if (!x || x->inputs() != x->outputs() || x->inputs() < 1 || delay < 0.0) { delete x; return nullptr; }
+  return new FeedbackUnitN(delay, x);
+}
 HNode* mk_dsf(int inputs, float spacing, float roughness) { return (inputs < 1 || inputs > 2 || !(spacing > 0.0f)) ? nullptr : new DsfN(inputs, spacing, roughness); }
 HNode* mk_mls(int bits) { return (bits < 1 || bits > 31) ? nullptr : new Mls((uint32_t)bits); }
 HNode* mk_impulse(int n) { return n < 1 ? nullptr : new ImpulseN(n); }

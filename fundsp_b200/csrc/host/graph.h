@@ -101,7 +101,8 @@ HNode* mk_delay(double t);
 HNode* mk_allnest(float coefficient, HNode* x, int nin);
 HNode* mk_phase_osc(int kind);                      // 0 ramp, 1 poly_saw, 2 poly_square, 3 poly_pulse
 HNode* mk_reverb3(double time, double diffusion, HNode* filter);   // Reverb<F> ID 85; consumes `filter` (1 -> 1)
-HNode* mk_var(float value);                                          // Var ID 68
+HNode* mk_var(float value);
+HNode* mk_feedback_unit(double delay, HNode* x);                      // FeedbackUnit ID 79                                          // Var ID 68
 HNode* mk_dsf(int inputs, float harmonic_spacing, float roughness);
 HNode* mk_mls(int bits);
 HNode* mk_impulse(int n);

@@ -604,3 +604,10 @@ def reverb3_stereo(time, diffusion, filt):
 def var(value):
     """var(&shared): here the shared value is changed through Setting value (kind 4) / GpuBank.set."""
     return An("var", (f32(value),), (), 0, 1)
+
+
+def feedback_unit(delay, node):
+    """FeedbackUnit::new(delay, Box::new(node)) (src/feedback.rs:347): feedback loop with an integrated delay in seconds."""
+    if node.nin != node.nout:
+        raise ArityError("feedback_unit: the enclosed node must have as many outputs as inputs")
+    return An("feedback_unit", (float(delay),), (node,), node.nin, node.nout)

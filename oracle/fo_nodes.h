@@ -1032,6 +1032,67 @@ struct Feedback : Node {
   FO_CLONE(Feedback)
 };
 
+// ---- src/feedback.rs:316-481 FeedbackUnit (ID 79): feedback loop with an integrated delay of round(delay*sr) >= 1 samples.
+// Blocks no longer than the delay run the inner unit's BLOCK path on (input + delayed output); longer ones go sample by sample.
+struct FeedbackUnit : Node {
+  Child x; int channels; double sample_rate = 0.0, delay; size_t samples = 0, mask = 0, index = 0;
+  std::vector<std::vector<float>> feedback;
+  FeedbackUnit(double delay_, Node* x_) : x(x_), channels(x_->inputs()), delay(delay_) {
+    assert(x->inputs() == x->outputs());
+    prevent_denormals();
+    feedback.assign(channels, std::vector<float>());
+    set_sample_rate(DEFAULT_SR);
+  }
+  int inputs() const override { return channels; } int outputs() const override { return channels; }
+  uint64_t id() const override { return 79; }
+  size_t read_index(size_t d) const { return (index + mask + 1 - d) & mask; }
+  void reset() override { for (auto& f : feedback) std::fill(f.begin(), f.end(), 0.0f); x->reset(); index = 0; }
+  void set_sample_rate(double sr) override {
+    if (sample_rate != sr) {
+      sample_rate = sr;
+      x->set_sample_rate(sr);
+      samples = (size_t)fmax(round(delay * sr), 1.0);
+      size_t p2 = 1; while (p2 < samples) p2 <<= 1;
+      mask = p2 - 1;
+      for (auto& f : feedback) { std::fill(f.begin(), f.end(), 0.0f); f.resize(p2, 0.0f); }
+      index = 0;
+    }
+  }
+  void tick(const float* in, float* out) override {
+    float t[256];
+    const size_t ri = read_index(samples);
+    for (int c = 0; c < channels; c++) t[c] = in[c] + feedback[c][ri];
+    x->tick(t, out);
+    for (int c = 0; c < channels; c++) feedback[c][index] = out[c];
+    index = (index + 1) & mask;
+  }
+  void process(int size, const float* in, float* out) override {
+    if ((size_t)size <= samples) {
+      std::vector<float> buf((size_t)channels * B, 0.0f);
+      for (int c = 0; c < channels; c++) {
+        size_t ri = read_index(samples);
+        for (int i = 0; i < size; i++) { buf[c * B + i] = in[c * B + i] + feedback[c][ri]; ri = (ri + 1) & mask; }
+      }
+      x->process(size, buf.data(), out);
+      for (int c = 0; c < channels; c++) {
+        size_t wi = index;
+        for (int i = 0; i < size; i++) { feedback[c][wi] = out[c * B + i]; wi = (wi + 1) & mask; }
+      }
+    } else {
+      float t[256], o[256];
+      size_t ri = read_index(samples), wi = index;
+      for (int i = 0; i < size; i++) {
+        for (int c = 0; c < channels; c++) t[c] = in[c * B + i] + feedback[c][ri];
+        x->tick(t, o);
+        for (int c = 0; c < channels; c++) { out[c * B + i] = o[c]; feedback[c][wi] = o[c]; }
+        ri = (ri + 1) & mask; wi = (wi + 1) & mask;
+      }
+    }
+    index = (index + (size_t)size) & mask;
+  }
+  AttoHash ping(bool probe, AttoHash h) override { return x->ping(probe, h.hash(id())); }
+  FO_CLONE(FeedbackUnit)
+};
 
 // ---- src/oscillator.rs:440-760 Ramp (ID 94), PolySaw (95), PolySquare (96), PolyPulse (97): phase oscillators, tick only
 inline float polyblep(float t, float dt) {  // :510-521

@@ -47,6 +47,9 @@ CASES = {
     "dsf_square_modulated": lambda i: ((sine_hz(4.0) * 20.0 + 110.0 + 7.0 * i) | (sine_hz(0.3 + 0.05 * (i % 9)) * 0.45 + 0.5)) >> dsf_square(),
     "reverb3_lowpass_loop": lambda i: (noise().seed(i) | noise().seed(i + 100)) >> (multipass(2) & 0.25 * reverb3_stereo(1.0 + 0.1 * (i % 10), 0.3 + 0.01 * (i % 40), lowpass_hz(6000.0 + 50.0 * i, 0.7))),
     "var_gain": lambda i: var(0.1 + 0.02 * i) * noise().seed(i) + var(0.5) * sine_hz(100.0 + i),
+    "feedback_unit_block_mode": lambda i: noise().seed(i) >> feedback_unit(0.005 + 0.0001 * (i % 20), (0.4 + 0.005 * (i % 40)) * lowpass_hz(1000.0 + 30.0 * i, 1.0)),
+    "feedback_unit_tick_mode_sine": lambda i: noise().seed(i) >> feedback_unit(0.0005, 0.5 * (pass_() * sine_hz(3.0 + i))),
+    "feedback_unit_stereo": lambda i: (noise().seed(i) | sine_hz(220.0 + i)) >> feedback_unit(0.003, (0.3 * lowpass_hz(900.0 + 10.0 * i, 0.8)) | (0.3 * pass_())),
     "product_fm_feedback": lambda i: (sine_hz(200.0 + i) * sine_hz(3.0 + 0.1 * i)) >> feedback(tick() * 0.25 >> lowpass_hz(2000.0, 0.7)),
 }
 GATED = {

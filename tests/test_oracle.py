@@ -297,6 +297,18 @@ def test_dsf_spectrum_known_answer():  # src/oscillator.rs:104-112: sum over i o
     check_wave(dc(330.0) >> dsf_saw_r(0.8) | (dc(220.0) | sine_hz(0.5) * 0.3 + 0.5) >> dsf_square())
 
 
+def test_feedback_unit():  # tests/test_basic.rs:243-253 (FeedbackUnit inside check_wave), src/feedback.rs:316-481
+    mk = lambda: (noise() >> feedback_unit(0.01, 0.5 * lowpass_hz(1000.0, 1.0))) | (noise() >> feedback_unit(0.001, 0.5 * highpass_hz(1000.0, 1.0)))
+    check_wave(mk())
+    # with a pure gain inside, y[t] = x[t] * g + g * y[t - d]: an impulse comes back every d samples scaled by g
+    u = OracleUnit(impulse(1) >> feedback_unit(100.0 / 44100.0, 0.5 * pass_()))
+    y = u.process_many(450)[0]
+    assert np.array_equal(np.nonzero(y)[0], [0, 100, 200, 300, 400]) and np.allclose(y[[0, 100, 200, 300, 400]], [0.5, 0.25, 0.125, 0.0625, 0.03125])
+    # the minimum delay is one sample, also for delay = 0
+    y0 = OracleUnit(impulse(1) >> feedback_unit(0.0, 0.5 * pass_())).process_many(5)[0]
+    assert np.allclose(y0, [0.5, 0.25, 0.125, 0.0625, 0.03125])
+
+
 def test_reverb3_and_var():  # src/reverb.rs:139-279, src/prelude.rs:1856 doc example, src/shared.rs:84-131
     mk = lambda: (noise().seed(1) | noise().seed(2)) >> (multipass(2) & 0.25 * reverb3_stereo(2.0, 0.5, lowpass_hz(8000.0, 0.7)))
     # tick == process on two FRESH units: Reverb::reset leaves the four pre-delay allpasses alone (src/reverb.rs:215-228), so the
