@@ -816,6 +816,55 @@ template <int HAD, class X, class Y> struct Feedback2 {  // src/feedback.rs:180-
   static FDSP_DEV void end_simd(R&) {}
 };
 
+// ---------------------------------------------------------------- Convolver (src/convolve.rs:9-59, ID 100)
+// Direct-form linear convolution with an impulse response shared by the voice class (class-uniform words: K, ring length,
+// then h[0..K)); input history in a power-of-two HBM ring per voice. The block path produces 8 outputs per pass over the
+// window, so every history sample is loaded once per 8 outputs and meets a sliding register window of 8 coefficients.
+// The reference computes the same sum with a partitioned FFT (fft-convolver), so this node is tolerance-, not bit-checked;
+// FMA is therefore allowed here, and both paths accumulate in the same order (k ascending), so tick == process exactly.
+struct Convolver {
+  FDSP_NODE(1, 1, 0, 1, 2);   // NU counts the two header words; the K coefficient words follow them in the uniform block
+  struct R { uint32_t K, len, off, i; const uint32_t* h; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.K = l.U(); r.len = l.U(); r.h = l.u + l.ui; l.ui += r.K; r.off = l.D(r.len); r.i = l.S(); }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.S(r.i); }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<1>& in, Fr<1>& o) {
+    const uint32_t mask = r.len - 1u;
+    float* ring = c.dl + (size_t)r.off * c.V + c.v;
+    ring[(size_t)r.i * c.V] = in.v[0];
+    float acc = 0.0f;
+#pragma unroll 4
+    for (uint32_t k = 0; k < r.K; k++) acc = __fmaf_rn(__uint_as_float(__ldg(r.h + k)), ring[(size_t)((r.i - k) & mask) * c.V], acc);
+    r.i = (r.i + 1u) & mask;
+    o.v[0] = acc;
+  }
+  typedef void GroupStep;
+  template <class C> static FDSP_DEV void step8(R& r, C& c, const Fr8<1>& in, Fr8<1>& o) {
+    const uint32_t mask = r.len - 1u;
+    float* ring = c.dl + (size_t)r.off * c.V + c.v;
+#pragma unroll
+    for (int j = 0; j < 8; j++) ring[(size_t)((r.i + (uint32_t)j) & mask) * c.V] = in.v[0][j];
+    // window position m holds x[t0 + 7 - m]; it meets output j with coefficient k = j - 7 + m; hw[j] = h[j - 7 + m] slides with m
+    float acc[8], hw[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { acc[j] = 0.0f; hw[j] = 0.0f; }
+    hw[7] = __uint_as_float(__ldg(r.h));
+    const uint32_t last = r.i + 7u, M = r.K + 7u;
+#pragma unroll 2
+    for (uint32_t m = 0; m < M; m++) {
+      const float xv = ring[(size_t)((last - m) & mask) * c.V];
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[j] = __fmaf_rn(hw[j], xv, acc[j]);
+#pragma unroll
+      for (int j = 0; j < 7; j++) hw[j] = hw[j + 1];
+      hw[7] = (m + 1u < r.K) ? __uint_as_float(__ldg(r.h + m + 1u)) : 0.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) o.v[0][j] = acc[j];
+    r.i = (r.i + 8u) & mask;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
 // ---------------------------------------------------------------- FeedbackUnit (src/feedback.rs:316-481, ID 79)
 // Feedback with an integrated delay of `samples` >= 1: a block no longer than the delay runs the inner graph's BLOCK path on
 // (input + output delayed by `samples`), a longer block ticks it. Per-channel power-of-two rings in HBM; uniform words:
@@ -1025,6 +1074,7 @@ template <class X> struct Cost<Thru<X>> { static constexpr int value = Cost<X>::
 template <int KIND, int OP, int N, class X> struct Cost<Multi<KIND, OP, N, X>> { static constexpr int value = N * Cost<X>::value; };
 template <int NIN, class X> struct Cost<AllNest<NIN, X>> { static constexpr int value = Cost<X>::value + 6; };
 template <int HAD, class X, class Y> struct Cost<Feedback2<HAD, X, Y>> { static constexpr int value = Cost<X>::value + Cost<Y>::value + (HAD ? 6 * X::IN : X::IN); };
+template <> struct Cost<Convolver> { static constexpr int value = 48; };
 template <class X> struct WaveKind<FeedbackUnit<X>> : WaveKind<X> {};
 template <class X> struct Cost<FeedbackUnit<X>> { static constexpr int value = Cost<X>::value + 12 * X::IN; };
 template <class F> struct Cost<Reverb85<F>> { static constexpr int value = 1200 + 16 * Cost<F>::value; };

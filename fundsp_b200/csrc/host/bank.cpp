@@ -88,6 +88,7 @@ std::string Bank::lower_and_upload(bool upload_state) {
       ci = (int)fresh.size(); index[lo.key] = ci;
       VoiceClass c; c.sig = lo.sig; c.uniform = lo.l.U;
       c.np = (uint32_t)lo.l.P.size(); c.ns = (uint32_t)lo.l.S.size(); c.nu = (uint32_t)lo.l.U.size();
+      const uint32_t nu_static = c.nu - lo.l.extraU;   // what the device templates count (NU); the rest is variable-length uniform data
       std::string jerr, prog_sig = lo.sig;
       // reverb_stereo tail -> warp-per-voice FDN kernel; the part in front of it (if any) stays a fused per-voice program
       static const std::string REV = "Pipe<Pipe<MultiSplit<2,16>,Feedback<1,Multi<30,0,32,Pipe<Delay,Fir<3>>>>>,Binop<2,Multi<31,0,32,Panner<1>>,Constant<2>>>";
@@ -110,14 +111,14 @@ std::string Bank::lower_and_upload(bool upload_state) {
         if (!prog_sig.empty()) {
           c.k = get_program(prog_sig, device, jerr);
           if (!c.k) return "no device program for the dry stage `" + prog_sig + "`: " + jerr;
-          if ((uint32_t)c.k->NP != c.p0 - (wet ? 1u : 0u) || (uint32_t)c.k->NS != c.s0 || (uint32_t)c.k->NU != c.u0 || c.k->IN != nin || c.k->OUT != 2)
+          if ((uint32_t)c.k->NP != c.p0 - (wet ? 1u : 0u) || (uint32_t)c.k->NS != c.s0 || (uint32_t)c.k->NU != c.u0 - lo.l.extraU || c.k->IN != nin || c.k->OUT != 2)
             return "internal: dry-stage layout of `" + prog_sig + "` disagrees with the host lowering";
         }
       } else {
         for (uint32_t d : lo.l.dlen) c.dl_floats += d;
         c.k = get_program(lo.sig, device, jerr);
         if (!c.k) return "no device program for graph class `" + lo.sig + "`: " + jerr;
-        if ((uint32_t)c.k->NP != c.np || (uint32_t)c.k->NS != c.ns || (uint32_t)c.k->NU != c.nu || c.k->IN != nin || c.k->OUT != nout)
+        if ((uint32_t)c.k->NP != c.np || (uint32_t)c.k->NS != c.ns || (uint32_t)c.k->NU != nu_static || c.k->IN != nin || c.k->OUT != nout)
           return "internal: host lowering of `" + lo.sig + "` disagrees with the device word layout";
       }
       fresh.push_back(std::move(c));

@@ -381,6 +381,21 @@ struct FeedbackUnitN : HNode {  // src/feedback.rs:316-481
   void lower(Lowering& l) const override { l.U.push_back(samples); l.U.push_back(len); l.dlen.push_back(len * (uint32_t)inputs()); l.su(0u); x->lower(l); }
   HCLONE(FeedbackUnitN)
 };
+struct ConvolverN : HNode {  // src/convolve.rs:9-59: the impulse response is class-uniform data (voices with the same response share a class)
+  std::vector<float> h;
+  explicit ConvolverN(std::vector<float> r) : h(std::move(r)) { if (h.empty()) h.push_back(0.0f); }
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 100; }
+  void sig(std::string& o) const override { o += "Convolver"; }
+  void lower(Lowering& l) const override {
+    uint32_t len = 1; while (len < h.size() + 8) len <<= 1;   // the 8-sample block path looks K + 7 samples back
+    l.U.push_back((uint32_t)h.size()); l.U.push_back(len);
+    for (float x : h) l.U.push_back(f2u(x));
+    l.extraU += (uint32_t)h.size();
+    l.dlen.push_back(len); l.su(0u);
+  }
+  HCLONE(ConvolverN)
+};
 struct VarN : HNode {  // the shared value is control-plane state: it enters as a parameter word and changes through Setting::value
   float value; explicit VarN(float v) : value(v) {}
   int inputs() const override { return 0; } int outputs() const override { return 1; }
@@ -647,6 +662,7 @@ HNode* mk_reverb3(double time, double diffusion, HNode* filter) {
   return new ReverbN(time, diffusion, filter);
 }
 HNode* mk_var(float value) { return new VarN(value); }
+HNode* mk_convolve(const float* response, int n) { return (n < 1 || n > (1 << 20) || !response) ? nullptr : new ConvolverN(std::vector<float>(response, response + n)); }
 HNode* mk_feedback_unit(double delay, HNode* x) {
   if (!x || x->inputs() != x->outputs() || x->inputs() < 1 || delay < 0.0) { delete x; return nullptr; }
   return new FeedbackUnitN(delay, x);

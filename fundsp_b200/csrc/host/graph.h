@@ -51,6 +51,7 @@ inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 struct Lowering {
   std::vector<uint32_t> P, S, U;   // words in DFS order
   std::vector<uint32_t> dlen;      // delay-line lengths (floats per voice) in DFS order
+  uint32_t extraU = 0;             // uniform words beyond the nodes' static NU (e.g. a Convolver's impulse response)
   bool ok = true; std::string why; // set when a node has no device lowering
   void p(float f) { P.push_back(f2u(f)); }
   void s(float f) { S.push_back(f2u(f)); }
@@ -102,6 +103,7 @@ HNode* mk_allnest(float coefficient, HNode* x, int nin);
 HNode* mk_phase_osc(int kind);                      // 0 ramp, 1 poly_saw, 2 poly_square, 3 poly_pulse
 HNode* mk_reverb3(double time, double diffusion, HNode* filter);   // Reverb<F> ID 85; consumes `filter` (1 -> 1)
 HNode* mk_var(float value);
+HNode* mk_convolve(const float* response, int n);                     // Convolver ID 100
 HNode* mk_feedback_unit(double delay, HNode* x);                      // FeedbackUnit ID 79                                          // Var ID 68
 HNode* mk_dsf(int inputs, float harmonic_spacing, float roughness);
 HNode* mk_mls(int bits);

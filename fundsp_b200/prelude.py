@@ -611,3 +611,8 @@ def feedback_unit(delay, node):
     if node.nin != node.nout:
         raise ArityError("feedback_unit: the enclosed node must have as many outputs as inputs")
     return An("feedback_unit", (float(delay),), (node,), node.nin, node.nout)
+
+
+def convolve(response):
+    """convolve(&wave, channel) (src/prelude.rs:3158): `response` = the samples of that channel."""
+    return An("convolve", (tuple(f32(x) for x in response),), (), 1, 1)

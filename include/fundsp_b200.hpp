@@ -124,6 +124,7 @@ inline An poly_pulse() { return An(fdsp_phase_osc(3)); }
 inline An poly_pulse_hz(float f, float width) { return dc(f, width) >> poly_pulse(); }
 inline An reverb3_stereo(double time, double diffusion, An filter) { return An(fdsp_reverb3(time, diffusion, filter.release())); }
 inline An feedback_unit(double delay, An x) { return An(fdsp_feedback_unit(delay, x.release())); }
+inline An convolve(const std::vector<float>& response) { return An(fdsp_convolve(response.data(), (int)response.size())); }
 inline An var(float value) { return An(fdsp_var(value)); }
 inline An dsf_saw() { return An(fdsp_dsf(2, 1.0f, 0.5f)); }
 inline An dsf_saw_r(float roughness) { return An(fdsp_dsf(1, 1.0f, roughness)); }

@@ -976,6 +976,26 @@ struct Reverb85 : Node {
   }
   Node* clone() const override { return new Reverb85(*this); }
 };
+// ---- src/convolve.rs:9-59 Convolver (ID 100): y = x * h. The reference delegates to the un-vendored crate fft-convolver 0.3.0
+// (uniformly partitioned FFT overlap-add, block 64); what is restated here is the quantity that algorithm computes — the
+// linear convolution — accumulated in f64 and rounded once, which the FFT form matches to ~1e-6 of the signal scale.
+// Pin: tests/test_basic.rs:698-711 (impulse through [1, .75, .5, .25], tolerance 1e-4).
+struct Convolver : Node {
+  std::vector<float> h, hist; size_t i = 0;
+  explicit Convolver(std::vector<float> response) : h(std::move(response)) { if (h.empty()) h.push_back(0.0f); hist.assign(h.size(), 0.0f); }
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 100; }
+  void reset() override { std::fill(hist.begin(), hist.end(), 0.0f); i = 0; }
+  void tick(const float* in, float* out) override {
+    const size_t K = h.size();
+    hist[i] = in[0];
+    double acc = 0.0;
+    for (size_t k = 0; k < K; k++) acc += (double)h[k] * (double)hist[(i + K - k) % K];
+    i = (i + 1) % K;
+    out[0] = (float)acc;
+  }
+  FO_CLONE(Convolver)
+};
 // ---- src/shared.rs:84-131 Var (ID 68): outputs a shared control value, sampled once per block; here the value is a Setting
 struct Var : Node {
   float value;

@@ -43,6 +43,7 @@ GRAPHS = [
     lambda: (noise() | sine_hz(0.5) * 0.004 + 0.005) >> tap(0.001, 0.01) | (noise() | dc((0.002, 0.007))) >> multitap_linear(2, 0.001, 0.01),
     lambda: (noise() | noise()) >> (multipass(2) & 0.25 * reverb3_stereo(2.0, 0.5, lowpass_hz(8000.0, 0.7))) | var(0.5) * noise(),
     lambda: noise() >> feedback_unit(0.01, 0.5 * lowpass_hz(1000.0, 1.0)) | noise() >> feedback_unit(0.001, 0.5 * highpass_hz(1000.0, 1.0)),
+    lambda: noise() >> convolve([1.0, 0.9, 0.8]) | noise() >> convolve([0.5, 0.4, 0.3]),
     lambda: dc(220.0) >> dsf_saw_r(0.7) | (dc(110.0) | dc(0.4)) >> dsf_square() | dc(440.0) >> dsf_square_r(0.3).phase(0.25),
     lambda: noise() >> feedback2(delay(0.002) * 0.5, lowpass_hz(2000.0, 1.0)) | (noise() | dc(800.0)) >> butterpass() | (noise() | dc((900.0, 8.0))) >> resonator(),
 ]

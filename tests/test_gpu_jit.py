@@ -84,6 +84,25 @@ def test_jit_gated_envelope():
     assert np.array_equal(g, o), (int((g != o).sum()), float(np.abs(g - o).max()))
 
 
+@pytest.mark.parametrize("K", [1, 3, 64, 1000])
+def test_convolver_matches_linear_convolution(K):
+    """Convolver (src/convolve.rs): the reference computes y = x * h with a partitioned FFT (fft-convolver, not vendored), so the
+    bar is the tolerance of the path, 1e-5 of the output peak (the reference's own test, test_basic.rs:698-711, uses 1e-4)."""
+    rng = np.random.default_rng(K)
+    h = (rng.uniform(-1, 1, K) * np.exp(-np.arange(K) / max(1.0, K / 4.0))).astype(np.float32)
+    V, n = 48, 3000 + 61                       # ragged: the last block has 5 tail samples through the per-sample path
+    mk = lambda i: noise().seed(i) * (0.5 + 0.01 * i) >> convolve(h)
+    b, g, o = run_case(mk, V, n)
+    assert b.classes()[0]["voices"] == V       # one class: the impulse response is shared, class-uniform data
+    peak = float(np.abs(o).max())
+    assert peak > 0.1 and float(np.abs(g - o).max()) <= 1e-5 * peak, float(np.abs(g - o).max()) / peak
+    # state carries across calls and process()-sized launches agree with the long render
+    from fundsp_b200.bank import GpuBank
+    b2 = GpuBank([mk(i) for i in range(V)], per_voice=True, sample_rate=SR)
+    parts = [b2.render_samples(m)[0] for m in (64, 7, 1000, 61, n - 64 - 7 - 1000 - 61)]
+    assert np.array_equal(np.concatenate(parts, axis=-1), g)
+
+
 def test_unsupported_graph_reports_error():
     from fundsp_b200.bank import GpuBank
     from fundsp_b200.capi import ERR_UNSUPPORTED, FdspError

@@ -297,6 +297,19 @@ def test_dsf_spectrum_known_answer():  # src/oscillator.rs:104-112: sum over i o
     check_wave(dc(330.0) >> dsf_saw_r(0.8) | (dc(220.0) | sine_hz(0.5) * 0.3 + 0.5) >> dsf_square())
 
 
+def test_convolver():  # tests/test_basic.rs:698-711 (the reference's own pin, tolerance 1e-4) and :329-330 (check_wave)
+    u = OracleUnit(convolve([1.00, 0.75, 0.50, 0.25]))
+    got = [float(u.tick([x])[0]) for x in (0.0, 1.0, 0.0, 0.0, 0.0)]
+    assert np.allclose(got, [0.00, 1.00, 0.75, 0.50, 0.25], atol=1e-4)
+    check_wave(noise() >> convolve([1.0, 0.9, 0.8]) | noise().seed(5) >> convolve([0.5, 0.4, 0.3]))
+    rng = np.random.default_rng(3)
+    h = rng.uniform(-1, 1, 300).astype(np.float32)
+    x = rng.uniform(-1, 1, (1, 2000)).astype(np.float32)
+    y = OracleUnit(convolve(h)).filter(44100.0, x)[0]
+    ref = np.convolve(x[0].astype(np.float64), h.astype(np.float64))[:2000]
+    assert np.abs(y - ref).max() <= 1e-6 * np.abs(ref).max()
+
+
 def test_feedback_unit():  # tests/test_basic.rs:243-253 (FeedbackUnit inside check_wave), src/feedback.rs:316-481
     mk = lambda: (noise() >> feedback_unit(0.01, 0.5 * lowpass_hz(1000.0, 1.0))) | (noise() >> feedback_unit(0.001, 0.5 * highpass_hz(1000.0, 1.0)))
     check_wave(mk())
