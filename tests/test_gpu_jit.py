@@ -89,7 +89,8 @@ def test_convolver_matches_linear_convolution(K):
     """Convolver (src/convolve.rs): the reference computes y = x * h with a partitioned FFT (fft-convolver, not vendored), so the
     bar is the tolerance of the path, 1e-5 of the output peak (the reference's own test, test_basic.rs:698-711, uses 1e-4)."""
     rng = np.random.default_rng(K)
-    h = (rng.uniform(-1, 1, K) * np.exp(-np.arange(K) / max(1.0, K / 4.0))).astype(np.float32)
+    h = rng.uniform(-1, 1, K) * np.exp(-np.arange(K) / max(1.0, K / 4.0))
+    h = (h / np.abs(h).max()).astype(np.float32)
     V, n = 48, 3000 + 61                       # ragged: the last block has 5 tail samples through the per-sample path
     mk = lambda i: noise().seed(i) * (0.5 + 0.01 * i) >> convolve(h)
     b, g, o = run_case(mk, V, n)
