@@ -66,6 +66,7 @@ API fdsp_node* fdsp_phase_osc(int kind) { return wrap(mk_phase_osc(kind), "phase
 API fdsp_node* fdsp_reverb3(double time, double diffusion, fdsp_node* filter) { return wrap(mk_reverb3(time, diffusion, take(filter)), "reverb3"); }
 API fdsp_node* fdsp_feedback_unit(double delay, fdsp_node* x) { return wrap(mk_feedback_unit(delay, take(x)), "feedback_unit"); }
 API fdsp_node* fdsp_convolve(const float* response, int n) { return wrap(mk_convolve(response, n), "convolve"); }
+API fdsp_node* fdsp_onepole(int kind, float param, int inputs) { return wrap(mk_onepole(kind, param, inputs), "onepole"); }
 API fdsp_node* fdsp_var(float value) { return wrap(mk_var(value), "var"); }
 API fdsp_node* fdsp_dsf(int inputs, float spacing, float roughness) { return wrap(mk_dsf(inputs, spacing, roughness), "dsf"); }
 API fdsp_node* fdsp_mls(int bits) { return wrap(mk_mls(bits), "mls"); }

@@ -816,6 +816,53 @@ template <int HAD, class X, class Y> struct Feedback2 {  // src/feedback.rs:180-
   static FDSP_DEV void end_simd(R&) {}
 };
 
+// ---------------------------------------------------------------- one-pole family (src/filter.rs, F = f32)
+// KIND 0 Lowpole (ID 18), 1 Highpole (ID 47), 2 Allpole (ID 46), 3 DCBlock (ID 22); NIN = 2 adds the audio-rate parameter input
+// (cutoff: coefficient recomputed when it changes, :65-70 / :399-404; allpole delay: every sample, :315-317).
+template <int KIND, int NIN> struct OnePole {
+  FDSP_NODE(NIN, 1, NIN == 1 ? 1 : 0, (KIND == 0 ? 1 : 2) + (NIN > 1 ? 2 : 0), 0);
+  struct R { float coeff, param, x1, y1; };
+  static FDSP_DEV void load(R& r, Loader& l) {
+    if (NIN == 1) { r.coeff = l.Pf(); r.param = 0.0f; } else { r.param = l.Sf(); r.coeff = l.Sf(); }
+    r.x1 = (KIND == 0) ? 0.0f : l.Sf(); r.y1 = l.Sf();
+  }
+  static FDSP_DEV void save(const R& r, Saver& s) { if (NIN > 1) { s.Sf(r.param); s.Sf(r.coeff); } if (KIND != 0) s.Sf(r.x1); s.Sf(r.y1); }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<NIN>& in, Fr<1>& o) {
+    if (NIN > 1) {
+      const float p = in.v[NIN > 1 ? 1 : 0];
+      if (KIND == 2) r.coeff = (1.0f - p) / (1.0f + p);
+      else if (p != r.param) { r.param = p; r.coeff = m::expf_(-TAU_F * p / c.sr); }
+    }
+    const float x = in.v[0];
+    float y0;
+    if (KIND == 0) y0 = (1.0f - r.coeff) * x + r.coeff * r.y1;
+    else if (KIND == 1) y0 = r.coeff * (r.y1 + x - r.x1);
+    else if (KIND == 2) y0 = r.coeff * (x - r.y1) + r.x1;
+    else y0 = x - r.x1 + r.coeff * r.y1;
+    r.x1 = x; r.y1 = y0;
+    o.v[0] = y0;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+struct Pinkpass {  // src/filter.rs:178-262, ID 26 (Paul Kellett's pinking filter)
+  FDSP_NODE(1, 1, 0, 7, 0);
+  struct R { float b[7]; };
+  static FDSP_DEV void load(R& r, Loader& l) { for (int k = 0; k < 7; k++) r.b[k] = l.Sf(); }
+  static FDSP_DEV void save(const R& r, Saver& s) { for (int k = 0; k < 7; k++) s.Sf(r.b[k]); }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C&, const Fr<1>& in, Fr<1>& o) {
+    const float x = in.v[0];
+    r.b[0] = (float)0.99886 * r.b[0] + x * (float)0.0555179;
+    r.b[1] = (float)0.99332 * r.b[1] + x * (float)0.0750759;
+    r.b[2] = (float)0.96900 * r.b[2] + x * (float)0.1538520;
+    r.b[3] = (float)0.86650 * r.b[3] + x * (float)0.3104856;
+    r.b[4] = (float)0.55000 * r.b[4] + x * (float)0.5329522;
+    r.b[5] = (float)-0.7616 * r.b[5] - x * (float)0.0168980;
+    o.v[0] = (r.b[0] + r.b[1] + r.b[2] + r.b[3] + r.b[4] + r.b[5] + r.b[6] + x * (float)0.5362) * (float)0.115830421;
+    r.b[6] = x * (float)0.115926;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
 // ---------------------------------------------------------------- Convolver (src/convolve.rs:9-59, ID 100)
 // Direct-form linear convolution with an impulse response shared by the voice class (class-uniform words: K, ring length,
 // then h[0..K)); input history in a power-of-two HBM ring per voice. The block path produces 8 outputs per pass over the
@@ -1074,6 +1121,8 @@ template <class X> struct Cost<Thru<X>> { static constexpr int value = Cost<X>::
 template <int KIND, int OP, int N, class X> struct Cost<Multi<KIND, OP, N, X>> { static constexpr int value = N * Cost<X>::value; };
 template <int NIN, class X> struct Cost<AllNest<NIN, X>> { static constexpr int value = Cost<X>::value + 6; };
 template <int HAD, class X, class Y> struct Cost<Feedback2<HAD, X, Y>> { static constexpr int value = Cost<X>::value + Cost<Y>::value + (HAD ? 6 * X::IN : X::IN); };
+template <int K, int N> struct Cost<OnePole<K, N>> { static constexpr int value = N > 1 ? 40 : 8; };
+template <> struct Cost<Pinkpass> { static constexpr int value = 24; };
 template <> struct Cost<Convolver> { static constexpr int value = 48; };
 template <class X> struct WaveKind<FeedbackUnit<X>> : WaveKind<X> {};
 template <class X> struct Cost<FeedbackUnit<X>> { static constexpr int value = Cost<X>::value + 12 * X::IN; };

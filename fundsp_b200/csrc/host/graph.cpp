@@ -381,6 +381,32 @@ struct FeedbackUnitN : HNode {  // src/feedback.rs:316-481
   void lower(Lowering& l) const override { l.U.push_back(samples); l.U.push_back(len); l.dlen.push_back(len * (uint32_t)inputs()); l.su(0u); x->lower(l); }
   HCLONE(FeedbackUnitN)
 };
+struct OnePoleN : HNode {  // src/filter.rs: kind 0 Lowpole, 1 Highpole, 2 Allpole, 3 DCBlock, 4 Pinkpass (F = f32)
+  int kind, nin; float param, coeff = 0, sr = (float)DEFAULT_SR;
+  OnePoleN(int k, float p, int n) : kind(k), nin(n), param(p) { set_param(p); }
+  void set_param(float p) {
+    const float TAU = 6.28318548202514648f;
+    param = p;
+    if (kind == 0 || kind == 1) coeff = m::expf_(-TAU * p / sr);
+    else if (kind == 2) coeff = (1.0f - p) / (1.0f + p);
+    else if (kind == 3) coeff = 1.0f - TAU / sr * p;
+  }
+  int inputs() const override { return nin; } int outputs() const override { return 1; }
+  uint64_t id() const override { static const uint64_t ids[5] = {18, 47, 46, 22, 26}; return ids[kind]; }
+  void set_sample_rate(double s) override { sr = (float)s; if (kind != 2 && kind != 4) set_param(param); }
+  void set(const Setting& s) override {
+    if ((kind == 0 || kind == 1 || kind == 3) && s.kind == P_CENTER) set_param(s.v[0]);
+    else if (kind == 2 && s.kind == P_DELAY) set_param(s.v[0]);
+  }
+  void sig(std::string& o) const override { if (kind == 4) o += "Pinkpass"; else o += "OnePole<" + I(kind) + "," + I(nin) + ">"; }
+  void lower(Lowering& l) const override {
+    if (kind == 4) { for (int k = 0; k < 7; k++) l.s(0.0f); return; }
+    if (nin == 1) l.p(coeff); else { l.s(param); l.s(coeff); }
+    if (kind != 0) l.s(0.0f);
+    l.s(0.0f);
+  }
+  HCLONE(OnePoleN)
+};
 struct ConvolverN : HNode {  // src/convolve.rs:9-59: the impulse response is class-uniform data (voices with the same response share a class)
   std::vector<float> h;
   explicit ConvolverN(std::vector<float> r) : h(std::move(r)) { if (h.empty()) h.push_back(0.0f); }
@@ -662,6 +688,10 @@ HNode* mk_reverb3(double time, double diffusion, HNode* filter) {
   return new ReverbN(time, diffusion, filter);
 }
 HNode* mk_var(float value) { return new VarN(value); }
+HNode* mk_onepole(int kind, float param, int inputs) {
+  if (kind < 0 || kind > 4 || inputs < 1 || inputs > 2 || ((kind == 3 || kind == 4) && inputs != 1) || (kind == 2 && inputs == 1 && !(param > 0.0f))) return nullptr;
+  return new OnePoleN(kind, param, inputs);
+}
 HNode* mk_convolve(const float* response, int n) { return (n < 1 || n > (1 << 20) || !response) ? nullptr : new ConvolverN(std::vector<float>(response, response + n)); }
 HNode* mk_feedback_unit(double delay, HNode* x) {
   if (!x || x->inputs() != x->outputs() || x->inputs() < 1 || delay < 0.0) { delete x; return nullptr; }

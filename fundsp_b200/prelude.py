@@ -616,3 +616,48 @@ def feedback_unit(delay, node):
 def convolve(response):
     """convolve(&wave, channel) (src/prelude.rs:3158): `response` = the samples of that channel."""
     return An("convolve", (tuple(f32(x) for x in response),), (), 1, 1)
+
+
+# ---- src/prelude.rs:462-507, 1160-1175, 1306-1321 (prelude32: F = f32) one-pole filters, pink and brown noise
+def lowpole():
+    return An("onepole", (0, 440.0, 2), (), 2, 1)
+
+
+def lowpole_hz(cutoff):
+    return An("onepole", (0, f32(cutoff), 1), (), 1, 1)
+
+
+def highpole():
+    return An("onepole", (1, 440.0, 2), (), 2, 1)
+
+
+def highpole_hz(cutoff):
+    return An("onepole", (1, f32(cutoff), 1), (), 1, 1)
+
+
+def allpole():
+    return An("onepole", (2, 1.0, 2), (), 2, 1)
+
+
+def allpole_delay(delay_in_samples):
+    return An("onepole", (2, f32(delay_in_samples), 1), (), 1, 1)
+
+
+def dcblock_hz(cutoff):
+    return An("onepole", (3, f32(cutoff), 1), (), 1, 1)
+
+
+def dcblock():
+    return dcblock_hz(10.0)
+
+
+def pinkpass():
+    return An("onepole", (4, 0.0, 1), (), 1, 1)
+
+
+def pink():
+    return white() >> pinkpass()
+
+
+def brown():
+    return white() >> lowpole_hz(10.0) * dc(13.7)

@@ -125,6 +125,17 @@ inline An poly_pulse_hz(float f, float width) { return dc(f, width) >> poly_puls
 inline An reverb3_stereo(double time, double diffusion, An filter) { return An(fdsp_reverb3(time, diffusion, filter.release())); }
 inline An feedback_unit(double delay, An x) { return An(fdsp_feedback_unit(delay, x.release())); }
 inline An convolve(const std::vector<float>& response) { return An(fdsp_convolve(response.data(), (int)response.size())); }
+inline An lowpole() { return An(fdsp_onepole(0, 440.0f, 2)); }
+inline An lowpole_hz(float cutoff) { return An(fdsp_onepole(0, cutoff, 1)); }
+inline An highpole() { return An(fdsp_onepole(1, 440.0f, 2)); }
+inline An highpole_hz(float cutoff) { return An(fdsp_onepole(1, cutoff, 1)); }
+inline An allpole() { return An(fdsp_onepole(2, 1.0f, 2)); }
+inline An allpole_delay(float delay) { return An(fdsp_onepole(2, delay, 1)); }
+inline An dcblock_hz(float cutoff) { return An(fdsp_onepole(3, cutoff, 1)); }
+inline An dcblock() { return dcblock_hz(10.0f); }
+inline An pinkpass() { return An(fdsp_onepole(4, 0.0f, 1)); }
+inline An pink() { return white() >> pinkpass(); }
+inline An brown() { return white() >> lowpole_hz(10.0f) * dc(13.7f); }
 inline An var(float value) { return An(fdsp_var(value)); }
 inline An dsf_saw() { return An(fdsp_dsf(2, 1.0f, 0.5f)); }
 inline An dsf_saw_r(float roughness) { return An(fdsp_dsf(1, 1.0f, roughness)); }

@@ -976,6 +976,46 @@ struct Reverb85 : Node {
   }
   Node* clone() const override { return new Reverb85(*this); }
 };
+// ---- src/filter.rs (F = f32, the prelude32 instantiation): one-pole family
+// kind 0 Lowpole (ID 18, :19-99), 1 Highpole (ID 47, :353-430), 2 Allpole (ID 46, :269-350), 3 DCBlock (ID 22, :102-175), 4 Pinkpass (ID 26, :178-262)
+struct OnePole : Node {
+  int kind, nin; float param, coeff = 0, sr = (float)DEFAULT_SR, x1 = 0, y1 = 0, b[7] = {0, 0, 0, 0, 0, 0, 0};
+  OnePole(int kind_, float param_, int nin_) : kind(kind_), nin(nin_), param(param_) { set_param(param_); }
+  void set_param(float p) {
+    const float TAU = 6.28318548202514648f;
+    param = p;
+    if (kind == 0 || kind == 1) coeff = m::expf_(-TAU * p / sr);            // exp(-TAU * cutoff / sample_rate)
+    else if (kind == 2) coeff = (1.0f - p) / (1.0f + p);                    // eta
+    else if (kind == 3) coeff = 1.0f - TAU / sr * p;
+  }
+  int inputs() const override { return nin; } int outputs() const override { return 1; }
+  uint64_t id() const override { static const uint64_t ids[5] = {18, 47, 46, 22, 26}; return ids[kind]; }
+  void reset() override { x1 = y1 = 0; for (float& v : b) v = 0; }
+  void set_sample_rate(double s) override { sr = (float)s; if (kind != 2 && kind != 4) set_param(param); }
+  void tick(const float* in, float* out) override {
+    if (nin > 1) { if (kind == 2) set_param(in[1]); else if (in[1] != param) set_param(in[1]); }
+    const float x = in[0];
+    if (kind == 0) { y1 = (1.0f - coeff) * x + coeff * y1; out[0] = y1; }
+    else if (kind == 1) { float y0 = coeff * (y1 + x - x1); x1 = x; y1 = y0; out[0] = y0; }
+    else if (kind == 2) { float y0 = coeff * (x - y1) + x1; x1 = x; y1 = y0; out[0] = y0; }
+    else if (kind == 3) { float y0 = x - x1 + coeff * y1; x1 = x; y1 = y0; out[0] = y0; }
+    else {
+      b[0] = (float)0.99886 * b[0] + x * (float)0.0555179;
+      b[1] = (float)0.99332 * b[1] + x * (float)0.0750759;
+      b[2] = (float)0.96900 * b[2] + x * (float)0.1538520;
+      b[3] = (float)0.86650 * b[3] + x * (float)0.3104856;
+      b[4] = (float)0.55000 * b[4] + x * (float)0.5329522;
+      b[5] = (float)-0.7616 * b[5] - x * (float)0.0168980;
+      out[0] = (b[0] + b[1] + b[2] + b[3] + b[4] + b[5] + b[6] + x * (float)0.5362) * (float)0.115830421;
+      b[6] = x * (float)0.115926;
+    }
+  }
+  void set(const Setting& s) override {
+    if ((kind == 0 || kind == 1 || kind == 3) && s.kind == P_CENTER) set_param(s.v[0]);
+    else if (kind == 2 && s.kind == P_DELAY) set_param(s.v[0]);
+  }
+  FO_CLONE(OnePole)
+};
 // ---- src/convolve.rs:9-59 Convolver (ID 100): y = x * h. The reference delegates to the un-vendored crate fft-convolver 0.3.0
 // (uniformly partitioned FFT overlap-add, block 64); what is restated here is the quantity that algorithm computes — the
 // linear convolution — accumulated in f64 and rounded once, which the FFT form matches to ~1e-6 of the signal scale.

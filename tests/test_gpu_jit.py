@@ -50,6 +50,9 @@ CASES = {
     "feedback_unit_block_mode": lambda i: noise().seed(i) >> feedback_unit(0.005 + 0.0001 * (i % 20), (0.4 + 0.005 * (i % 40)) * lowpass_hz(1000.0 + 30.0 * i, 1.0)),
     "feedback_unit_tick_mode_sine": lambda i: noise().seed(i) >> feedback_unit(0.0005, 0.5 * (pass_() * sine_hz(3.0 + i))),
     "feedback_unit_stereo": lambda i: (noise().seed(i) | sine_hz(220.0 + i)) >> feedback_unit(0.003, (0.3 * lowpass_hz(900.0 + 10.0 * i, 0.8)) | (0.3 * pass_())),
+    "pink_brown_dcblock": lambda i: pink().seed(i) * 0.5 + brown().seed(i + 7) * 0.25 + (noise().seed(i + 9) >> dcblock_hz(20.0 + i) >> allpole_delay(0.2 + 0.03 * (i % 30))),
+    "onepoles_audio_rate": lambda i: (noise().seed(i) | (sine_hz(2.0) * 300.0 + 500.0 + 10.0 * i)) >> ~lowpole() >> highpole() | (noise().seed(i + 3) | (sine_hz(1.0 + 0.1 * (i % 7)) * 0.4 + 0.6)) >> allpole(),
+    "reverb3_lowpole_loop": lambda i: (noise().seed(i) | noise().seed(i + 100)) >> reverb3_stereo(2.0, 0.5, lowpole_hz(8000.0 - 40.0 * i)),
     "product_fm_feedback": lambda i: (sine_hz(200.0 + i) * sine_hz(3.0 + 0.1 * i)) >> feedback(tick() * 0.25 >> lowpass_hz(2000.0, 0.7)),
 }
 GATED = {

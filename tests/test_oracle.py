@@ -187,6 +187,36 @@ def test_biquad_family_responses():  # test_flow.rs:103-110,158-166
                    lambda f: svf_response(HIGHPASS, SR, 500.0, 1.0, 1.0, f) + svf_response(BANDPASS, SR, 500.0, 2.0, 1.0, f))
 
 
+def test_onepole_family_responses():  # test_flow.rs:95,101-105,114-115 against the closed forms of src/filter.rs `route`
+    z1 = lambda f: np.exp(-1j * 2 * math.pi * f / SR)
+    lowc = lambda fc: math.exp(-2 * math.pi * fc / SR)
+    for fc in (1000.0, 10000.0):
+        check_response(OracleUnit(lowpole_hz(fc)), lambda f, c=lowc(fc): (1 - c) / (1 - c * z1(f)))
+    check_response(OracleUnit(split(2) >> (lowpole_hz(100.0) + lowpole_hz(190.0))),
+                   lambda f: (1 - lowc(100.0)) / (1 - lowc(100.0) * z1(f)) + (1 - lowc(190.0)) / (1 - lowc(190.0) * z1(f)))
+    hp = lambda fc, f: lowc(fc) * (1 - z1(f)) / (1 - lowc(fc) * z1(f))
+    check_response(OracleUnit(highpole_hz(5000.0) & highpole_hz(500.0) & highpole_hz(2000.0)), lambda f: hp(5000.0, f) + hp(500.0, f) + hp(2000.0, f))
+    ap = lambda d, f: ((1 - d) / (1 + d) + z1(f)) / (1 + (1 - d) / (1 + d) * z1(f))
+    check_response(OracleUnit(allpole_delay(0.5) & allpole_delay(1.3) & allpole_delay(0.1)), lambda f: ap(0.5, f) + ap(1.3, f) + ap(0.1, f))
+    dcc = lambda fc: 1 - 2 * math.pi / SR * fc
+    check_response(OracleUnit(dcblock()), lambda f: (1 - z1(f)) / (1 - dcc(10.0) * z1(f)))
+    check_response(OracleUnit(dcblock_hz(100.0)), lambda f: (1 - z1(f)) / (1 - dcc(100.0) * z1(f)))
+
+    def pink_h(f):
+        z = z1(f)
+        return (0.0555179 / (1 - 0.99886 * z) + 0.0750759 / (1 - 0.99332 * z) + 0.1538520 / (1 - 0.96900 * z) + 0.3104856 / (1 - 0.86650 * z)
+                + 0.5329522 / (1 - 0.55000 * z) - 0.016898 / (1 + 0.7616 * z) + 0.115926 * z + 0.5362) * 0.115830421
+    check_response(OracleUnit(pinkpass() * dc(2.0)), lambda f: 2.0 * pink_h(f))
+    # tick == process: tests/test_basic.rs:172,198,202,335-336
+    L.fo_set_denormal_emulation(0)
+    check_wave(pink().seed(2) & noise() | sine_hz(440.0) & -noise())
+    check_wave((noise() | dc(440.0)) >> pipei(3, lambda i: ~lowpole()) >> lowpole())
+    check_wave((brown().seed(2) | dc(440.0)) >> pipei(4, lambda i: ~peak_q(1.0)) >> bell_q(1.0, 2.0))
+    check_wave(noise() >> (butterpass_hz(1000.0) ^ lowpole_hz(100.0)) | noise() >> (allpole_delay(0.5) ^ highpole_hz(500.0)))
+    check_wave((noise() | sine_hz(2.0) * 300.0 + 500.0) >> highpole() | (noise() | sine_hz(1.0) * 0.4 + 0.6) >> allpole())
+    L.fo_restore_denormals()
+
+
 def test_biquad_bank_lane_response():  # test_flow.rs:171-177
     import ctypes
     c = np.zeros(5, np.float32)
