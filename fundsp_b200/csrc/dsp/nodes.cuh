@@ -863,6 +863,30 @@ struct Pinkpass {  // src/filter.rs:178-262, ID 26 (Paul Kellett's pinking filte
   static FDSP_DEV void end_simd(R&) {}
 };
 
+// ---------------------------------------------------------------- Shaper<S> (src/shape.rs, ID 42)
+// KIND 0 Clip(h), 1 ClipTo(lo, hi), 2 Tanh(h), 3 Softsign(h), 4 Crush(levels), 5 SoftCrush(levels); the block path follows
+// Shape::simd (round-to-even, F32x::floor, |x|*h), tail and tick follow Shape::shape.
+FDSP_DEV float smooth9f(float x) { const float x2 = x * x; return ((((70.0f * x - 315.0f) * x + 540.0f) * x - 420.0f) * x + 126.0f) * x2 * x2 * x; }
+template <int KIND> struct Shaper {
+  FDSP_NODE(1, 1, 2, 0, 0);
+  struct R { float p0, p1; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.p0 = l.Pf(); r.p1 = l.Pf(); }
+  static FDSP_DEV void save(const R&, Saver&) {}
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<1>& in, Fr<1>& o) {
+    const float x = in.v[0];
+    const bool tick = T || c.rem;
+    float y;
+    if (KIND == 0) y = fminf(fmaxf(x * r.p0, -1.0f), 1.0f);
+    else if (KIND == 1) y = fminf(fmaxf(x, r.p0), r.p1);
+    else if (KIND == 2) y = m::tanhf_(x * r.p0);
+    else if (KIND == 3) y = tick ? (x * r.p0) / (1.0f + fabsf(x * r.p0)) : x * r.p0 / (1.0f + fabsf(x) * r.p0);
+    else if (KIND == 4) y = (tick ? roundf(x * r.p0) : wide_roundf(x * r.p0)) / r.p0;
+    else { const float v = x * r.p0, fl = tick ? floorf(v) : wide_floorf(v); y = (fl + smooth9f(v - fl)) / r.p0; }
+    o.v[0] = y;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
 // ---------------------------------------------------------------- Convolver (src/convolve.rs:9-59, ID 100)
 // Direct-form linear convolution with an impulse response shared by the voice class (class-uniform words: K, ring length,
 // then h[0..K)); input history in a power-of-two HBM ring per voice. The block path produces 8 outputs per pass over the
@@ -1123,6 +1147,7 @@ template <int NIN, class X> struct Cost<AllNest<NIN, X>> { static constexpr int 
 template <int HAD, class X, class Y> struct Cost<Feedback2<HAD, X, Y>> { static constexpr int value = Cost<X>::value + Cost<Y>::value + (HAD ? 6 * X::IN : X::IN); };
 template <int K, int N> struct Cost<OnePole<K, N>> { static constexpr int value = N > 1 ? 40 : 8; };
 template <> struct Cost<Pinkpass> { static constexpr int value = 24; };
+template <int K> struct Cost<Shaper<K>> { static constexpr int value = K == 2 ? 100 : 12; };
 template <> struct Cost<Convolver> { static constexpr int value = 48; };
 template <class X> struct WaveKind<FeedbackUnit<X>> : WaveKind<X> {};
 template <class X> struct Cost<FeedbackUnit<X>> { static constexpr int value = Cost<X>::value + 12 * X::IN; };

@@ -407,6 +407,15 @@ struct OnePoleN : HNode {  // src/filter.rs: kind 0 Lowpole, 1 Highpole, 2 Allpo
   }
   HCLONE(OnePoleN)
 };
+struct ShaperN : HNode {  // src/shape.rs:205-249
+  int kind; float p0, p1;
+  ShaperN(int k, float a, float b) : kind(k), p0(a), p1(b) {}
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 42; }
+  void sig(std::string& o) const override { o += "Shaper<" + I(kind) + ">"; }
+  void lower(Lowering& l) const override { l.p(p0); l.p(p1); }
+  HCLONE(ShaperN)
+};
 struct ConvolverN : HNode {  // src/convolve.rs:9-59: the impulse response is class-uniform data (voices with the same response share a class)
   std::vector<float> h;
   explicit ConvolverN(std::vector<float> r) : h(std::move(r)) { if (h.empty()) h.push_back(0.0f); }
@@ -688,6 +697,7 @@ HNode* mk_reverb3(double time, double diffusion, HNode* filter) {
   return new ReverbN(time, diffusion, filter);
 }
 HNode* mk_var(float value) { return new VarN(value); }
+HNode* mk_shaper(int kind, float p0, float p1) { return (kind < 0 || kind > 5) ? nullptr : new ShaperN(kind, p0, p1); }
 HNode* mk_onepole(int kind, float param, int inputs) {
   if (kind < 0 || kind > 4 || inputs < 1 || inputs > 2 || ((kind == 3 || kind == 4) && inputs != 1) || (kind == 2 && inputs == 1 && !(param > 0.0f))) return nullptr;
   return new OnePoleN(kind, param, inputs);

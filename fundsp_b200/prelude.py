@@ -661,3 +661,25 @@ def pink():
 
 def brown():
     return white() >> lowpole_hz(10.0) * dc(13.7)
+
+
+# ---- src/shape.rs + src/prelude.rs:1207-1223 waveshapers: shape(Tanh(1.5)), shape(Crush(16.0)), clip(), clip_to(lo, hi)
+def Clip(hardness=1.0): return ("shape", 0, f32(hardness), 0.0)
+def ClipTo(lo, hi): return ("shape", 1, f32(lo), f32(hi))
+def Tanh(hardness): return ("shape", 2, f32(hardness), 0.0)
+def Softsign(hardness): return ("shape", 3, f32(hardness), 0.0)
+def Crush(levels): return ("shape", 4, f32(levels), 0.0)
+def SoftCrush(levels): return ("shape", 5, f32(levels), 0.0)
+
+
+def shape(mode):
+    _, kind, p0, p1 = mode
+    return An("shaper", (kind, p0, p1), (), 1, 1)
+
+
+def clip():
+    return shape(Clip(1.0))
+
+
+def clip_to(lo, hi):
+    return shape(ClipTo(lo, hi))

@@ -136,6 +136,15 @@ inline An dcblock() { return dcblock_hz(10.0f); }
 inline An pinkpass() { return An(fdsp_onepole(4, 0.0f, 1)); }
 inline An pink() { return white() >> pinkpass(); }
 inline An brown() { return white() >> lowpole_hz(10.0f) * dc(13.7f); }
+inline An clip() { return An(fdsp_shaper(0, 1.0f, 0.0f)); }
+inline An clip_to(float lo, float hi) { return An(fdsp_shaper(1, lo, hi)); }
+struct Clip { float h; }; struct ClipTo { float lo, hi; }; struct Tanh { float h; }; struct Softsign { float h; }; struct Crush { float levels; }; struct SoftCrush { float levels; };
+inline An shape(Clip s) { return An(fdsp_shaper(0, s.h, 0.0f)); }
+inline An shape(ClipTo s) { return An(fdsp_shaper(1, s.lo, s.hi)); }
+inline An shape(Tanh s) { return An(fdsp_shaper(2, s.h, 0.0f)); }
+inline An shape(Softsign s) { return An(fdsp_shaper(3, s.h, 0.0f)); }
+inline An shape(Crush s) { return An(fdsp_shaper(4, s.levels, 0.0f)); }
+inline An shape(SoftCrush s) { return An(fdsp_shaper(5, s.levels, 0.0f)); }
 inline An var(float value) { return An(fdsp_var(value)); }
 inline An dsf_saw() { return An(fdsp_dsf(2, 1.0f, 0.5f)); }
 inline An dsf_saw_r(float roughness) { return An(fdsp_dsf(1, 1.0f, roughness)); }

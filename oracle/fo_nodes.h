@@ -1016,6 +1016,40 @@ struct OnePole : Node {
   }
   FO_CLONE(OnePole)
 };
+// ---- src/shape.rs Shaper<S> (ID 42): kind 0 Clip(h), 1 ClipTo(lo, hi), 2 Tanh(h), 3 Softsign(h), 4 Crush(levels), 5 SoftCrush(levels).
+// `tick` uses Shape::shape, the block path Shape::simd on f32x8 groups — they differ for Softsign (|x|*h vs |x*h|), Crush
+// (f32::round = half away from zero vs wide's round-to-even) and SoftCrush (libm floor vs F32x::floor, src/lib.rs:326-328).
+struct Shaper : Node {
+  int kind; float p0, p1;
+  Shaper(int k, float a, float b) : kind(k), p0(a), p1(b) {}
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 42; }
+  float shape(float x) const {
+    switch (kind) {
+      case 0: return fminf(fmaxf(x * p0, -1.0f), 1.0f);
+      case 1: return fminf(fmaxf(x, p0), p1);
+      case 2: return m::tanhf_(x * p0);
+      case 3: { float v = x * p0; return v / (1.0f + fabsf(v)); }
+      case 4: return roundf(x * p0) / p0;
+      default: { float v = x * p0, y = floorf(v); return (y + smooth9f(v - y)) / p0; }
+    }
+  }
+  float simd(float x) const {
+    switch (kind) {
+      case 3: return x * p0 / (1.0f + fabsf(x) * p0);
+      case 4: return wide_roundf(x * p0) / p0;
+      case 5: { float v = x * p0, y = wide_floorf(v); return (y + smooth9f(v - y)) / p0; }
+      default: return shape(x);
+    }
+  }
+  void tick(const float* in, float* out) override { out[0] = shape(in[0]); }
+  void process(int size, const float* in, float* out) override {  // :238-243
+    const int full = size & ~7;
+    for (int i = 0; i < full; i++) out[i] = simd(in[i]);
+    process_remainder(size, in, out);
+  }
+  FO_CLONE(Shaper)
+};
 // ---- src/convolve.rs:9-59 Convolver (ID 100): y = x * h. The reference delegates to the un-vendored crate fft-convolver 0.3.0
 // (uniformly partitioned FFT overlap-add, block 64); what is restated here is the quantity that algorithm computes — the
 // linear convolution — accumulated in f64 and rounded once, which the FFT form matches to ~1e-6 of the signal scale.

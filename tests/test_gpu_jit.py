@@ -53,6 +53,8 @@ CASES = {
     "pink_brown_dcblock": lambda i: pink().seed(i) * 0.5 + brown().seed(i + 7) * 0.25 + (noise().seed(i + 9) >> dcblock_hz(20.0 + i) >> allpole_delay(0.2 + 0.03 * (i % 30))),
     "onepoles_audio_rate": lambda i: (noise().seed(i) | (sine_hz(2.0) * 300.0 + 500.0 + 10.0 * i)) >> ~lowpole() >> highpole() | (noise().seed(i + 3) | (sine_hz(1.0 + 0.1 * (i % 7)) * 0.4 + 0.6)) >> allpole(),
     "reverb3_lowpole_loop": lambda i: (noise().seed(i) | noise().seed(i + 100)) >> reverb3_stereo(2.0, 0.5, lowpole_hz(8000.0 - 40.0 * i)),
+    "shapers": lambda i: noise().seed(i) * (0.5 + 0.05 * i) >> (shape(Tanh(1.0 + 0.1 * i)) & shape(Softsign(2.0)) & shape(Crush(4.0 + i)) & shape(SoftCrush(3.0 + i)) & clip() & clip_to(-0.3, 0.1 + 0.01 * i)),
+    "tanh_in_feedback": lambda i: noise().seed(i) >> feedback(delay(0.001 + 0.0001 * (i % 10)) >> shape(Tanh(1.2)) * 0.9),
     "product_fm_feedback": lambda i: (sine_hz(200.0 + i) * sine_hz(3.0 + 0.1 * i)) >> feedback(tick() * 0.25 >> lowpass_hz(2000.0, 0.7)),
 }
 GATED = {

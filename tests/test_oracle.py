@@ -327,6 +327,25 @@ def test_dsf_spectrum_known_answer():  # src/oscillator.rs:104-112: sum over i o
     check_wave(dc(330.0) >> dsf_saw_r(0.8) | (dc(220.0) | sine_hz(0.5) * 0.3 + 0.5) >> dsf_square())
 
 
+def test_shapers():  # src/shape.rs: Shape::shape (tick) and Shape::simd (block path)
+    x = np.float32([[-2.0, -0.75, -0.26, 0.0, 0.1, 0.26, 0.5, 0.75, 1.5, 3.0]])
+    f = lambda g: OracleUnit(g).filter(SR, x)[0]     # 10 samples: one SIMD group of 8 + 2 tail samples through `shape`
+    assert np.array_equal(f(clip()), np.clip(x[0], -1, 1))
+    assert np.array_equal(f(clip_to(-0.5, 0.25)), np.clip(x[0], -0.5, 0.25))
+    assert np.allclose(f(shape(Tanh(1.5))), np.tanh(1.5 * x[0].astype(np.float64)), atol=2e-7)
+    assert np.allclose(f(shape(Softsign(2.0))), 2 * x[0] / (1 + np.abs(2 * x[0])), atol=1e-7)
+    # Crush(2): block path rounds half to even (wide), the tail rounds half away from zero (f32::round)
+    y = f(shape(Crush(2.0)))
+    assert np.array_equal(y[:8], np.float32([-2.0, -1.0, -0.5, 0.0, 0.0, 0.5, 0.5, 1.0])) and np.array_equal(y[8:], np.float32([1.5, 3.0]))
+    ticks = OracleUnit(shape(Crush(2.0)))
+    assert [float(ticks.tick([v])[0]) for v in (-0.75, 0.75, 0.25)] == [-1.0, 1.0, 0.5]
+    sc = f(shape(SoftCrush(4.0)))
+    assert np.all(np.abs(sc - x[0]) <= 0.125 + 1e-6) and np.all(np.diff(sc) >= 0)     # monotone staircase with soft steps
+    L.fo_set_denormal_emulation(0)
+    check_wave(noise() >> shape(Tanh(2.0)) | noise().seed(3) >> shape(Softsign(3.0)) | noise().seed(4) >> shape(SoftCrush(7.0)) | noise().seed(5) >> clip_to(-0.3, 0.6))
+    L.fo_restore_denormals()
+
+
 def test_convolver():  # tests/test_basic.rs:698-711 (the reference's own pin, tolerance 1e-4) and :329-330 (check_wave)
     u = OracleUnit(convolve([1.00, 0.75, 0.50, 0.25]))
     got = [float(u.tick([x])[0]) for x in (0.0, 1.0, 0.0, 0.0, 0.0)]
