@@ -68,6 +68,7 @@ API fdsp_node* fdsp_feedback_unit(double delay, fdsp_node* x) { return wrap(mk_f
 API fdsp_node* fdsp_convolve(const float* response, int n) { return wrap(mk_convolve(response, n), "convolve"); }
 API fdsp_node* fdsp_onepole(int kind, float param, int inputs) { return wrap(mk_onepole(kind, param, inputs), "onepole"); }
 API fdsp_node* fdsp_shaper(int kind, float p0, float p1) { return wrap(mk_shaper(kind, p0, p1), "shaper"); }
+API fdsp_node* fdsp_follow(int asymmetric, float attack, float release) { return wrap(mk_follow(asymmetric, attack, release), "follow"); }
 API fdsp_node* fdsp_var(float value) { return wrap(mk_var(value), "var"); }
 API fdsp_node* fdsp_dsf(int inputs, float spacing, float roughness) { return wrap(mk_dsf(inputs, spacing, roughness), "dsf"); }
 API fdsp_node* fdsp_mls(int bits) { return wrap(mk_mls(bits), "mls"); }

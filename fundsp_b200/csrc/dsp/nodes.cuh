@@ -863,6 +863,27 @@ struct Pinkpass {  // src/filter.rs:178-262, ID 26 (Paul Kellett's pinking filte
   static FDSP_DEV void end_simd(R&) {}
 };
 
+// ---------------------------------------------------------------- Follow (ID 24) / AFollow (ID 29), src/follow.rs
+// Three one-pole smoothers in series; coefficients (host: halfway_coeff) are 1 for the very first sample after a reset.
+template <int ASYM> struct Follower {
+  FDSP_NODE(1, 1, 2, 5, 0);
+  struct R { float ac, rc, anow, rnow, v1, v2, v3; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.ac = l.Pf(); r.rc = l.Pf(); r.anow = l.Sf(); r.rnow = l.Sf(); r.v1 = l.Sf(); r.v2 = l.Sf(); r.v3 = l.Sf(); }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.anow); s.Sf(r.rnow); s.Sf(r.v1); s.Sf(r.v2); s.Sf(r.v3); }
+  static FDSP_DEV float pole2(float in, float cur, float a, float rr) { return cur + fmaxf(0.0f, in - cur) * a - fmaxf(0.0f, cur - in) * rr; }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C&, const Fr<1>& in, Fr<1>& o) {
+    if (ASYM) {
+      r.v1 = pole2(in.v[0], r.v1, r.anow, r.rnow); r.v2 = pole2(r.v1, r.v2, r.anow, r.rnow); r.v3 = pole2(r.v2, r.v3, r.anow, r.rnow);
+    } else {
+      const float k = 1.0f - r.anow;
+      r.v1 = r.anow * in.v[0] + k * r.v1; r.v2 = r.anow * r.v1 + k * r.v2; r.v3 = r.anow * r.v2 + k * r.v3;
+    }
+    r.anow = r.ac; r.rnow = r.rc;
+    o.v[0] = r.v3;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
 // ---------------------------------------------------------------- Shaper<S> (src/shape.rs, ID 42)
 // KIND 0 Clip(h), 1 ClipTo(lo, hi), 2 Tanh(h), 3 Softsign(h), 4 Crush(levels), 5 SoftCrush(levels); the block path follows
 // Shape::simd (round-to-even, F32x::floor, |x|*h), tail and tick follow Shape::shape.
@@ -1147,6 +1168,7 @@ template <int NIN, class X> struct Cost<AllNest<NIN, X>> { static constexpr int 
 template <int HAD, class X, class Y> struct Cost<Feedback2<HAD, X, Y>> { static constexpr int value = Cost<X>::value + Cost<Y>::value + (HAD ? 6 * X::IN : X::IN); };
 template <int K, int N> struct Cost<OnePole<K, N>> { static constexpr int value = N > 1 ? 40 : 8; };
 template <> struct Cost<Pinkpass> { static constexpr int value = 24; };
+template <int A> struct Cost<Follower<A>> { static constexpr int value = 16; };
 template <int K> struct Cost<Shaper<K>> { static constexpr int value = K == 2 ? 100 : 12; };
 template <> struct Cost<Convolver> { static constexpr int value = 48; };
 template <class X> struct WaveKind<FeedbackUnit<X>> : WaveKind<X> {};

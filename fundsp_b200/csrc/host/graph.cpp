@@ -407,6 +407,27 @@ struct OnePoleN : HNode {  // src/filter.rs: kind 0 Lowpole, 1 Highpole, 2 Allpo
   }
   HCLONE(OnePoleN)
 };
+static double halfway_coeff(double samples) {  // src/follow.rs:17-23
+  double r0 = log(fmax(1.0, samples)) - 0.861624594696583;
+  double r1 = 1.0 / (1.0 + exp(0.0 - r0));
+  double r2 = r1 * 1.13228543863477 - 0.1322853859;
+  return 1.0 - fmin(0.9999999, r2);
+}
+struct FollowerN : HNode {  // Follow ID 24 / AFollow ID 29
+  bool asym; float atime, rtime, acoeff = 0, rcoeff = 0, sr = 0;
+  FollowerN(bool as, float a, float r) : asym(as), atime(a), rtime(r) { set_sample_rate(DEFAULT_SR); }
+  void set_time(float a, float r) { atime = a; rtime = r; acoeff = (float)halfway_coeff((double)(atime * sr)); rcoeff = (float)halfway_coeff((double)(rtime * sr)); }
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return asym ? 29 : 24; }
+  void set_sample_rate(double s) override { sr = (float)s; set_time(atime, rtime); }
+  void set(const Setting& s) override {
+    if (!asym && s.kind == P_TIME) set_time(s.v[0], s.v[0]);
+    else if (asym && s.kind == P_ATTACK_RELEASE) set_time(s.v[0], s.v[1]);
+  }
+  void sig(std::string& o) const override { o += "Follower<" + I(asym ? 1 : 0) + ">"; }
+  void lower(Lowering& l) const override { l.p(acoeff); l.p(rcoeff); l.s(1.0f); l.s(1.0f); l.s(0.0f); l.s(0.0f); l.s(0.0f); }
+  HCLONE(FollowerN)
+};
 struct ShaperN : HNode {  // src/shape.rs:205-249
   int kind; float p0, p1;
   ShaperN(int k, float a, float b) : kind(k), p0(a), p1(b) {}
@@ -697,6 +718,7 @@ HNode* mk_reverb3(double time, double diffusion, HNode* filter) {
   return new ReverbN(time, diffusion, filter);
 }
 HNode* mk_var(float value) { return new VarN(value); }
+HNode* mk_follow(int asym, float attack, float release) { return new FollowerN(asym != 0, attack, asym ? release : attack); }
 HNode* mk_shaper(int kind, float p0, float p1) { return (kind < 0 || kind > 5) ? nullptr : new ShaperN(kind, p0, p1); }
 HNode* mk_onepole(int kind, float param, int inputs) {
   if (kind < 0 || kind > 4 || inputs < 1 || inputs > 2 || ((kind == 3 || kind == 4) && inputs != 1) || (kind == 2 && inputs == 1 && !(param > 0.0f))) return nullptr;

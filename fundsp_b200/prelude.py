@@ -683,3 +683,12 @@ def clip():
 
 def clip_to(lo, hi):
     return shape(ClipTo(lo, hi))
+
+
+# ---- src/prelude.rs:1264-1281 parameter smoothing
+def follow(response_time):
+    return An("follow", (0, f32(response_time), f32(response_time)), (), 1, 1)
+
+
+def afollow(attack_time, release_time):
+    return An("follow", (1, f32(attack_time), f32(release_time)), (), 1, 1)

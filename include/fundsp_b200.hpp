@@ -145,6 +145,8 @@ inline An shape(Tanh s) { return An(fdsp_shaper(2, s.h, 0.0f)); }
 inline An shape(Softsign s) { return An(fdsp_shaper(3, s.h, 0.0f)); }
 inline An shape(Crush s) { return An(fdsp_shaper(4, s.levels, 0.0f)); }
 inline An shape(SoftCrush s) { return An(fdsp_shaper(5, s.levels, 0.0f)); }
+inline An follow(float response_time) { return An(fdsp_follow(0, response_time, response_time)); }
+inline An afollow(float attack, float release) { return An(fdsp_follow(1, attack, release)); }
 inline An var(float value) { return An(fdsp_var(value)); }
 inline An dsf_saw() { return An(fdsp_dsf(2, 1.0f, 0.5f)); }
 inline An dsf_saw_r(float roughness) { return An(fdsp_dsf(1, 1.0f, roughness)); }

@@ -1016,6 +1016,43 @@ struct OnePole : Node {
   }
   FO_CLONE(OnePole)
 };
+// ---- src/follow.rs (F = f32): Follow (ID 24, :31-134) and AFollow (ID 29, :137-270): three one-pole smoothers in series
+inline double halfway_coeff(double samples) {  // :17-23
+  double r0 = log(fmax(1.0, samples)) - 0.861624594696583;
+  double r1 = 1.0 / (1.0 + exp(0.0 - r0));
+  double r2 = r1 * 1.13228543863477 - 0.1322853859;
+  return 1.0 - fmin(0.9999999, r2);
+}
+struct Follower : Node {
+  bool asym; float atime, rtime, acoeff = 0, rcoeff = 0, anow = 1, rnow = 1, v1 = 0, v2 = 0, v3 = 0, sr = 0;
+  Follower(bool asym_, float a, float r) : asym(asym_), atime(a), rtime(r) { reset(); set_sample_rate(DEFAULT_SR); }
+  void set_time(float a, float r) {
+    atime = a; rtime = r;
+    acoeff = (float)halfway_coeff((double)(atime * sr));
+    rcoeff = (float)halfway_coeff((double)(rtime * sr));
+    if (anow < 1.0f) { anow = acoeff; rnow = rcoeff; }
+  }
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return asym ? 29 : 24; }
+  void reset() override { v1 = v2 = v3 = 0; anow = rnow = 1.0f; }
+  void set_sample_rate(double s) override { sr = (float)s; set_time(atime, rtime); }
+  static float pole2(float in, float cur, float a, float r) { return cur + fmaxf(0.0f, in - cur) * a - fmaxf(0.0f, cur - in) * r; }
+  void tick(const float* in, float* out) override {
+    if (asym) {
+      v1 = pole2(in[0], v1, anow, rnow); v2 = pole2(v1, v2, anow, rnow); v3 = pole2(v2, v3, anow, rnow);
+    } else {
+      const float rc = 1.0f - anow;
+      v1 = anow * in[0] + rc * v1; v2 = anow * v1 + rc * v2; v3 = anow * v2 + rc * v3;
+    }
+    anow = acoeff; rnow = rcoeff;
+    out[0] = v3;
+  }
+  void set(const Setting& s) override {
+    if (!asym && s.kind == P_TIME) set_time(s.v[0], s.v[0]);
+    else if (asym && s.kind == P_ATTACK_RELEASE) set_time(s.v[0], s.v[1]);
+  }
+  FO_CLONE(Follower)
+};
 // ---- src/shape.rs Shaper<S> (ID 42): kind 0 Clip(h), 1 ClipTo(lo, hi), 2 Tanh(h), 3 Softsign(h), 4 Crush(levels), 5 SoftCrush(levels).
 // `tick` uses Shape::shape, the block path Shape::simd on f32x8 groups — they differ for Softsign (|x|*h vs |x*h|), Crush
 // (f32::round = half away from zero vs wide's round-to-even) and SoftCrush (libm floor vs F32x::floor, src/lib.rs:326-328).

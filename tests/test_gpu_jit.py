@@ -55,6 +55,7 @@ CASES = {
     "reverb3_lowpole_loop": lambda i: (noise().seed(i) | noise().seed(i + 100)) >> reverb3_stereo(2.0, 0.5, lowpole_hz(8000.0 - 40.0 * i)),
     "shapers": lambda i: noise().seed(i) * (0.5 + 0.05 * i) >> (shape(Tanh(1.0 + 0.1 * i)) & shape(Softsign(2.0)) & shape(Crush(4.0 + i)) & shape(SoftCrush(3.0 + i)) & clip() & clip_to(-0.3, 0.1 + 0.01 * i)),
     "tanh_in_feedback": lambda i: noise().seed(i) >> feedback(delay(0.001 + 0.0001 * (i % 10)) >> shape(Tanh(1.2)) * 0.9),
+    "followers": lambda i: (noise().seed(i) >> follow(0.0005 + 0.0001 * i)) * 4.0 + (square_hz(5.0 + i) >> afollow(0.001 + 0.0002 * (i % 9), 0.01 + 0.001 * (i % 13))),
     "product_fm_feedback": lambda i: (sine_hz(200.0 + i) * sine_hz(3.0 + 0.1 * i)) >> feedback(tick() * 0.25 >> lowpass_hz(2000.0, 0.7)),
 }
 GATED = {

@@ -327,6 +327,29 @@ def test_dsf_spectrum_known_answer():  # src/oscillator.rs:104-112: sum over i o
     check_wave(dc(330.0) >> dsf_saw_r(0.8) | (dc(220.0) | sine_hz(0.5) * 0.3 + 0.5) >> dsf_square())
 
 
+def test_follow_filters():  # test_flow.rs:96-97,102 and src/follow.rs
+    z1 = lambda f: np.exp(-1j * 2 * math.pi * f / SR)
+
+    def hc(samples):
+        r0 = math.log(max(1.0, samples)) - 0.861624594696583
+        r1 = 1.0 / (1.0 + math.exp(-r0))
+        return 1.0 - min(0.9999999, r1 * 1.13228543863477 - 0.1322853859)
+    for t in (0.0002, 0.001, 0.01):
+        c = 1.0 - float(np.float32(hc(float(np.float32(t) * np.float32(SR)))))
+        check_response(OracleUnit(follow(t)), lambda f, c=c: ((1 - c) / (1 - c * z1(f))) ** 3)
+    c = 1.0 - float(np.float32(hc(float(np.float32(0.001) * np.float32(SR)))))
+    check_response(OracleUnit(dcblock_hz(100.0) & follow(0.001)), lambda f: (1 - z1(f)) / (1 - (1 - 2 * math.pi / SR * 100.0) * z1(f)) + ((1 - c) / (1 - c * z1(f))) ** 3)
+    # halfway response: a step reaches 1/2 after `response_time` (0.5 % accuracy of the approximation, src/follow.rs:18)
+    step = np.concatenate([np.zeros(100, np.float32), np.ones(2000, np.float32)])[None, :]   # (the first sample after a reset is copied through)
+    y = OracleUnit(follow(0.01)).filter(SR, step)[0]
+    assert abs(int(np.argmax(y >= 0.5)) - 100 - 441) <= 4
+    # asymmetric: fast attack, slow release
+    x = np.concatenate([np.zeros(100, np.float32), np.ones(2000, np.float32), np.zeros(2000, np.float32)])[None, :]
+    ya = OracleUnit(afollow(0.001, 0.02)).filter(SR, x)[0]
+    assert abs(int(np.argmax(ya >= 0.5)) - 100 - 44) <= 2 and abs(int(np.argmax(ya[2100:] <= 0.5)) - 882) <= 8
+    check_wave(noise() >> follow(0.002) | noise().seed(2) >> afollow(0.001, 0.01))
+
+
 def test_shapers():  # src/shape.rs: Shape::shape (tick) and Shape::simd (block path)
     x = np.float32([[-2.0, -0.75, -0.26, 0.0, 0.1, 0.26, 0.5, 0.75, 1.5, 3.0]])
     f = lambda g: OracleUnit(g).filter(SR, x)[0]     # 10 samples: one SIMD group of 8 + 2 tail samples through `shape`
