@@ -935,20 +935,29 @@ struct Convolver {
     float* ring = c.dl + (size_t)r.off * c.V + c.v;
 #pragma unroll
     for (int j = 0; j < 8; j++) ring[(size_t)((r.i + (uint32_t)j) & mask) * c.V] = in.v[0][j];
-    // window position m holds x[t0 + 7 - m]; it meets output j with coefficient k = j - 7 + m; hw[j] = h[j - 7 + m] slides with m
-    float acc[8], hw[8];
+    // Window position m holds x[t0 + 7 - m] and meets output j with coefficient k = j - 7 + m. The window is walked 8 positions
+    // at a time: 8 independent ring loads in flight, then 64 FMAs against the 15 coefficients hw[t] = h[m0 - 7 + t] that
+    // this chunk can touch (7 carried over, 8 loaded). acc[j] still accumulates in ascending k, exactly like `step`.
+    float acc[8], hw[15];
 #pragma unroll
-    for (int j = 0; j < 8; j++) { acc[j] = 0.0f; hw[j] = 0.0f; }
-    hw[7] = __uint_as_float(__ldg(r.h));
+    for (int j = 0; j < 8; j++) acc[j] = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 15; t++) hw[t] = (t >= 7 && (uint32_t)(t - 7) < r.K) ? __uint_as_float(__ldg(r.h + (t - 7))) : 0.0f;
     const uint32_t last = r.i + 7u, M = r.K + 7u;
 #pragma unroll 2
-    for (uint32_t m = 0; m < M; m++) {
-      const float xv = ring[(size_t)((last - m) & mask) * c.V];
+    for (uint32_t m0 = 0; m0 < M; m0 += 8u) {
+      float xv[8];
 #pragma unroll
-      for (int j = 0; j < 8; j++) acc[j] = __fmaf_rn(hw[j], xv, acc[j]);
+      for (int q = 0; q < 8; q++) xv[q] = ring[(size_t)((last - m0 - (uint32_t)q) & mask) * c.V];
 #pragma unroll
-      for (int j = 0; j < 7; j++) hw[j] = hw[j + 1];
-      hw[7] = (m + 1u < r.K) ? __uint_as_float(__ldg(r.h + m + 1u)) : 0.0f;
+      for (int q = 0; q < 8; q++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = __fmaf_rn(hw[j + q], xv[q], acc[j]);
+      }
+#pragma unroll
+      for (int t = 0; t < 7; t++) hw[t] = hw[t + 8];
+#pragma unroll
+      for (int t = 7; t < 15; t++) { const uint32_t k = m0 + 1u + (uint32_t)t; hw[t] = k < r.K ? __uint_as_float(__ldg(r.h + k)) : 0.0f; }
     }
 #pragma unroll
     for (int j = 0; j < 8; j++) o.v[0][j] = acc[j];
