@@ -33,7 +33,7 @@ template <class T> std::string dev_alloc(T** p, size_t count) {
 Bank::~Bank() {
   cudaSetDevice(device);
   for (auto& c : classes) {
-    cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows); cudaFree(c.d_dry2); cudaFree(c.d_partial2); for (int q = 0; q < 2; q++) { if (c.e_dry[q]) cudaEventDestroy(c.e_dry[q]); if (c.e_fdn[q]) cudaEventDestroy(c.e_fdn[q]); }
+    cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows); cudaFree(c.d_dry2); cudaFree(c.d_partial2); for (int q = 0; q < 2; q++) { if (c.e_dry[q]) cudaEventDestroy(c.e_dry[q]); if (c.e_fdn[q]) cudaEventDestroy(c.e_fdn[q]); } if (c.cstream) cudaStreamDestroy(c.cstream); if (c.e_done) cudaEventDestroy(c.e_done);
   }
   for (float* p : d_wtdata) cudaFree(p);
   cudaFree(d_wt); cudaFree(d_in); cudaFree(d_out); cudaFree(d_mix); cudaFree(d_rows);
@@ -63,7 +63,7 @@ std::string Bank::init(std::vector<HNode*>& voices, int dev, uint32_t mode) {
   CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   CU(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_hi));
   CU(cudaStreamCreateWithPriority(&stream2, cudaStreamNonBlocking, prio_lo));
-  CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
+  CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1)); CU(cudaEventCreateWithFlags(&e_begin, cudaEventDisableTiming));
   CU(cudaMalloc((void**)&d_ticket, 4)); CU(cudaMemset(d_ticket, 0, 4));
   return lower_and_upload(true);
 }
@@ -129,7 +129,7 @@ std::string Bank::lower_and_upload(bool upload_state) {
   const bool same_shape = classes.size() == fresh.size() && std::equal(classes.begin(), classes.end(), fresh.begin(), [](const VoiceClass& a, const VoiceClass& b) {
                             return a.sig == b.sig && a.voices == b.voices && a.uniform == b.uniform; });
   if (!same_shape) {
-    for (auto& c : classes) { cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows); cudaFree(c.d_dry2); cudaFree(c.d_partial2); for (int q = 0; q < 2; q++) { if (c.e_dry[q]) cudaEventDestroy(c.e_dry[q]); if (c.e_fdn[q]) cudaEventDestroy(c.e_fdn[q]); } }
+    for (auto& c : classes) { cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows); cudaFree(c.d_dry2); cudaFree(c.d_partial2); for (int q = 0; q < 2; q++) { if (c.e_dry[q]) cudaEventDestroy(c.e_dry[q]); if (c.e_fdn[q]) cudaEventDestroy(c.e_fdn[q]); } if (c.cstream) cudaStreamDestroy(c.cstream); if (c.e_done) cudaEventDestroy(c.e_done); }
     classes = std::move(fresh);
     upload_state = true;
   }
@@ -299,8 +299,19 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
     float* out_dev_c = out_dev; uint64_t out_stride_c = out_stride; uint64_t out_t0 = t0;
     if (tree) { want_m = false; if (!save_want_v) { want_v = true; out_dev_c = d_rows; out_stride_c = CH; out_t0 = 0; } }
     const int mode = (want_v ? 1 : 0) | (want_m ? 2 : 0);
+    // several plain classes: launch the class kernels concurrently (own streams, forked from and joined back into `stream`); the
+    // partial mixes are still reduced on `stream` in class order, so the result does not depend on how the kernels overlap
+    bool concurrent = classes.size() > 1 && !pipelined && len > 64 && !getenv("FDSP_NO_CONCURRENT");
+    for (auto& c : classes) concurrent = concurrent && !c.fdn;
+    if (concurrent) CU(cudaEventRecord(e_begin, stream));
     for (auto& c : classes) {
       const uint32_t V = c.V();
+      cudaStream_t ks = stream;
+      if (concurrent) {
+        if (!c.cstream) { CU(cudaStreamCreateWithFlags(&c.cstream, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&c.e_done, cudaEventDisableTiming)); }
+        ks = c.cstream;
+        CU(cudaStreamWaitEvent(ks, e_begin, 0));
+      }
       int fdn_warps = 1, fdn_k = 0;   // fdn_warps: voices per CTA; fdn_k: warps per voice (0 = single-warp kernel)
       if (c.fdn) {
         const char* ks = getenv("FDSP_FDN_K");
@@ -387,14 +398,27 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
         f.ring = c.d_ring; f.ring_voice_stride = c.ring_floats; f.V = V; f.n = len;
         if (fdn_k) CU(launch_fdn_ts(f, fdn_k, fdn_warps, stream)); else CU(launch_fdn(f, fdn_warps, stream));
       } else {
-        CU(c.k->launch(a, mode | (use_ws(V) ? 4 : 0), table_bytes, stream));
+        CU(c.k->launch(a, mode | (use_ws(V) ? 4 : 0), table_bytes, ks));
       }
       launches++;
+      if (concurrent) { CU(cudaEventRecord(c.e_done, ks)); continue; }   // reduced below, after every class has been launched
       if (want_m && !fused_mix) {
         CU(launch_mix_reduce(c.d_partial, grid, (uint32_t)nout, len, mix_dev, (uint32_t)mix_stride, (uint32_t)t0, first ? 0 : 1, stream));
         launches++;
       }
       first = false;
+    }
+    if (concurrent) {
+      for (auto& c : classes) {
+        CU(cudaStreamWaitEvent(stream, c.e_done, 0));
+        if (want_m) {
+          uint32_t vpc = (uint32_t)c.k->threads;
+          const uint32_t grid = getenv("FDSP_NO_SPREAD") ? (c.V() + vpc - 1) / vpc : bank_grid(c.V(), (uint32_t)c.k->threads, &vpc);
+          CU(launch_mix_reduce(c.d_partial, grid, (uint32_t)nout, len, mix_dev, (uint32_t)mix_stride, (uint32_t)t0, first ? 0 : 1, stream));
+          launches++;
+        }
+        first = false;
+      }
     }
     if (tree) {
       CU(launch_tree_mix(out_dev_c, V(), (uint32_t)nout, (uint32_t)out_stride_c, (uint32_t)out_t0, len, mix_dev, (uint32_t)mix_stride, (uint32_t)t0, tree_mix == 1 ? 1 : 0, stream));

@@ -26,6 +26,9 @@ struct VoiceClass {
   // two-stage classes are software-pipelined over sub-chunks: dry stage of chunk k+1 (stream) runs beside the FDN of chunk k (stream2)
   float* d_dry2 = nullptr; float* d_partial2 = nullptr; size_t partial2_floats = 0;
   cudaEvent_t e_dry[2] = {nullptr, nullptr}, e_fdn[2] = {nullptr, nullptr};
+  // banks with several plain classes run the class kernels side by side, each on its own stream (one class alone leaves most
+  // warp schedulers with a single warp)
+  cudaStream_t cstream = nullptr; cudaEvent_t e_done = nullptr;
   std::vector<uint32_t> state0;     // initial state, SoA [NS][V]
   uint32_t* d_params = nullptr; uint32_t* d_state = nullptr; uint32_t* d_uniform = nullptr; uint32_t* d_rowmap = nullptr;
   float* d_dline = nullptr; float* d_partial = nullptr; size_t partial_floats = 0;
@@ -40,7 +43,7 @@ struct Bank {
   int tree_mix = 0; bool net_rate = false; float* d_rows = nullptr; size_t rows_cap = 0;
   std::vector<std::unique_ptr<HNode>> nodes;
   std::vector<VoiceClass> classes;
-  cudaStream_t stream = nullptr, stream2 = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr, e_begin = nullptr;
   WaveTableDev* d_wt = nullptr; float* d_wtdata[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // staging for host-buffer entry points
   float *d_in = nullptr, *d_out = nullptr, *d_mix = nullptr; size_t in_cap = 0, out_cap = 0, mix_cap = 0; uint32_t stage_chunk = 0;

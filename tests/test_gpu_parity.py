@@ -170,6 +170,26 @@ def test_reset_and_clone_and_continuation():
     assert np.array_equal(a1, full[..., :1000])
 
 
+def test_mixed_bank_two_stage_and_plain_classes():
+    """A bank holding a pipelined two-stage class (dry program + FDN kernel on a second stream) next to plain classes: per-voice
+    rows stay bit-exact and the mix (cleared, then accumulated by every class) equals the f64 sum of the rows."""
+    from fundsp_b200.bank import GpuBank
+    n = 6000 + 13
+    gate = workloads.gate_signal(n)
+    mk = lambda i: workloads.subtractive_voice(i) if i % 3 == 0 else ((pass_() * noise().seed(i) >> lowpass_hz(400.0 + 30.0 * i, 1.0) >> pan(0.1 * (i % 7) - 0.3)) if i % 3 == 1
+                                                                       else (pass_() * saw_hz(110.0 + 5.0 * i) >> pan(-0.5)))
+    V = 30
+    b = GpuBank([mk(i) for i in range(V)], per_voice=True, mix=True, sample_rate=SR)
+    assert len(b.classes()) == 3
+    rows, mix = b.render_samples(n, gate)
+    o, _ = oracle_bank_render([mk(i) for i in range(V)], SR, n, gate, threads=4)
+    assert np.array_equal(rows, o)
+    ref = rows.astype(np.float64).sum(axis=0)
+    assert np.abs(mix - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+    again, mix2 = GpuBank([mk(i) for i in range(V)], per_voice=True, mix=True, sample_rate=SR).render_samples(n, gate)
+    assert np.array_equal(mix, mix2)     # deterministic across runs (fixed accumulation order)
+
+
 def test_set_on_live_bank_matches_oracle_units():
     """AudioUnit::set (src/audiounit.rs:62) on single voices of a running bank: new coefficients, state continues."""
     from fundsp_b200.bank import GpuBank
