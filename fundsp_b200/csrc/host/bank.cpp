@@ -41,7 +41,9 @@ Bank::~Bank() {
   if (h_out) cudaFreeHost(h_out);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
+  if (e_begin) cudaEventDestroy(e_begin);
   cudaFree(d_ticket);
+  if (stream2) cudaStreamDestroy(stream2);
   if (stream) cudaStreamDestroy(stream);
 }
 
