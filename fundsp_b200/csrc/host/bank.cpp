@@ -100,6 +100,7 @@ std::string Bank::lower_and_upload(bool upload_state) {
       const bool fdn_off = getenv("FDSP_DISABLE_FDN") != nullptr;  // A/B switch: run reverbs in the generic thread-per-voice form
       if (fdn_off) {}
       else if (lo.sig == REV && nin == 2) { c.fdn = true; prog_sig.clear(); }
+      else if (lo.sig == "Bus<MultiPass<2>,Unop<3," + REV + ">>" && nin == 2) { c.fdn = true; wet = true; prog_sig.clear(); }   // dry + g * reverb on a stereo bus
       else if (lo.sig.compare(0, 5, "Pipe<") == 0 && ends_with(lo.sig, wet_tail)) { c.fdn = true; wet = true; prog_sig = lo.sig.substr(5, lo.sig.size() - 5 - wet_tail.size()); }
       else if (lo.sig.compare(0, 5, "Pipe<") == 0 && ends_with(lo.sig, pipe_tail)) { c.fdn = true; prog_sig = lo.sig.substr(5, lo.sig.size() - 5 - pipe_tail.size()); }
       if (c.fdn) {

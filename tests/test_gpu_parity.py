@@ -268,6 +268,20 @@ def test_reverb_only_bank_on_stereo_bus_input():
     assert np.array_equal(g, o) and np.abs(o).max() > 0.05
 
 
+def test_shared_bus_reverb_send_uses_the_fdn_kernel():
+    """`multipass() & g * reverb_stereo(..)` on a stereo bus (the shared-bus form of config 4, examples/keys.rs:164-181)."""
+    from fundsp_b200.bank import GpuBank
+    n = 4000 + 29
+    rng = np.random.default_rng(7)
+    x = rng.uniform(-0.5, 0.5, (2, n)).astype(np.float32)
+    mk = lambda i: multipass(2) & (0.2 + 0.05 * i) * reverb_stereo(10.0, 2.0, 0.5)
+    b = GpuBank([mk(i) for i in range(3)], per_voice=True, sample_rate=SR)
+    assert b.classes()[0]["delay_floats"] > 90000
+    g, _ = b.render_samples(n, x)
+    o, _ = oracle_bank_render([mk(i) for i in range(3)], SR, n, x, threads=3)
+    assert np.array_equal(g, o)
+
+
 def test_fdn_kernel_process_granularity_and_wet_only_pipe():
     from fundsp_b200.bank import GpuBank
     from oracle import OracleUnit
