@@ -64,6 +64,8 @@ class GpuBank:
     def voice_outputs(self): return self.L.fdsp_bank_voice_outputs(self.h)
     def outputs(self): return self.L.fdsp_bank_outputs(self.h)
     def set_sample_rate(self, sr): check(self.L.fdsp_bank_set_sample_rate(self.h, float(sr)))
+    def voice_of_vertex(self, vertex): return self.L.fdsp_bank_voice_of_vertex(self.h, int(vertex))
+
     def reset(self): check(self.L.fdsp_bank_reset(self.h))
 
     def set(self, voice, kind, values=(), seed=0, address=()):

@@ -178,17 +178,22 @@ API int fdsp_bank_create(fdsp_node* const* voices, uint32_t nvoices, int device,
 }
 API int fdsp_bank_create_from_net(fdsp_node* net, int device, uint32_t out_mode, fdsp_bank** out) {
   if (!net || !out) return fail(FDSP_ERR_ARG, "bank_create_from_net: bad arguments");
-  std::vector<HNode*> v; std::string tree, err;
+  std::vector<HNode*> v; std::string tree, err; std::vector<int> ids;
   HNode* n = take(net);
-  const bool ok = net_extract_voices(n, v, tree, err);
+  const bool ok = net_extract_voices(n, v, tree, err, &ids);
   delete n;
   if (!ok) { for (HNode* x : v) delete x; return fail(FDSP_ERR_UNSUPPORTED, "no device lowering for this Net: " + err); }
   fdsp_bank* b = new (std::nothrow) fdsp_bank();
-  b->b.tree_mix = tree == "pairwise" ? 1 : 2; b->b.net_rate = true;
+  b->b.tree_mix = tree == "pairwise" ? 1 : 2; b->b.net_rate = true; b->b.vertex_of_voice = ids;
   std::string e = b->b.init(v, device, out_mode);
   if (!e.empty()) { for (HNode* x : v) delete x; delete b; return status(e); }
   *out = b;
   return FDSP_OK;
+}
+API int fdsp_bank_voice_of_vertex(const fdsp_bank* b, int vertex) {
+  if (!b) return -1;
+  for (size_t i = 0; i < b->b.vertex_of_voice.size(); i++) if (b->b.vertex_of_voice[i] == vertex) return (int)i;
+  return -1;
 }
 API void fdsp_bank_destroy(fdsp_bank* b) { delete b; }
 API int fdsp_bank_clone(const fdsp_bank* b, fdsp_bank** out) {

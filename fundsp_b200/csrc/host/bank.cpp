@@ -526,7 +526,7 @@ std::string Bank::process(uint32_t size, const float* in, float* out) {  // Audi
 std::string Bank::clone_into(Bank& dst) const {
   std::vector<HNode*> copies;
   for (auto& n : nodes) copies.push_back(n->clone());
-  dst.sr = sr; dst.tree_mix = tree_mix; dst.net_rate = net_rate;
+  dst.sr = sr; dst.tree_mix = tree_mix; dst.net_rate = net_rate; dst.vertex_of_voice = vertex_of_voice;
   std::string e = dst.init(copies, device, out_mode);
   if (!e.empty()) return e;
   for (auto& n : dst.nodes) n->set_sample_rate(sr);

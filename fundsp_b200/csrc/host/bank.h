@@ -42,6 +42,7 @@ struct Bank {
   // units the Net's f32-rounded sample rate (src/net.rs:132,1323-1328)
   int tree_mix = 0; bool net_rate = false; float* d_rows = nullptr; size_t rows_cap = 0;
   std::vector<std::unique_ptr<HNode>> nodes;
+  std::vector<int> vertex_of_voice;   // banks made from a Net: the Net vertex (NodeId) behind each voice
   std::vector<VoiceClass> classes;
   cudaStream_t stream = nullptr, stream2 = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr, e_begin = nullptr;
   WaveTableDev* d_wt = nullptr; float* d_wtdata[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -632,7 +632,7 @@ bool net_pass_through(HNode* net, int gi, int go) {
 }
 int net_size(const HNode* net) { const HNet* n = dynamic_cast<const HNet*>(net); return n ? (int)n->vx.size() : -1; }
 
-bool net_extract_voices(HNode* net, std::vector<HNode*>& voices, std::string& tree, std::string& err) {
+bool net_extract_voices(HNode* net, std::vector<HNode*>& voices, std::string& tree, std::string& err, std::vector<int>* vertex_ids) {
   HNet* n = dynamic_cast<HNet*>(net);
   if (!n) { err = "not a Net"; return false; }
   if (n->nout < 1) { err = "the Net has no outputs"; return false; }
@@ -682,6 +682,7 @@ bool net_extract_voices(HNode* net, std::vector<HNode*>& voices, std::string& tr
   else if (shape0 == chain()) tree = "chain";
   else { err = "the Net's mix tree is neither the level-wise pairwise tree nor a left fold"; return false; }
   for (int v : leaves0) voices.push_back(n->vx[v].unit->clone());
+  if (vertex_ids) *vertex_ids = leaves0;   // voice i of the bank is vertex leaves0[i] of the Net (its NodeId in push order)
   return true;
 }
 

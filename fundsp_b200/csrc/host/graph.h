@@ -139,7 +139,7 @@ int net_size(const HNode* net);
 // `&`) over the same sequence of voice vertices. Extracts the voices in leaf order; `tree` receives the canonical
 // description ("pairwise" when the tree is the level-wise adjacent pairing, "chain" for a left fold). Pings the net first
 // (Net::determine_order, src/net.rs:834-852) so the voices carry the hashes the reference would give them.
-bool net_extract_voices(HNode* net, std::vector<HNode*>& voices, std::string& tree, std::string& err);
+bool net_extract_voices(HNode* net, std::vector<HNode*>& voices, std::string& tree, std::string& err, std::vector<int>* vertex_ids = nullptr);
 
 // ---- wavetables (src/wavetable.rs:40-123, 493-623): built once per waveform kind on the host
 struct WaveTableHost { std::vector<float> pitch; std::vector<int> off, len; std::vector<float> data; };

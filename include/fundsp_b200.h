@@ -124,6 +124,9 @@ int fdsp_bank_create(fdsp_node* const* voices, uint32_t nvoices, int device, uin
 /* A voice-separable Net (voice vertices + the adder trees Net::bus builds) becomes a bank whose mix-down follows the
  * Net's own association order bit for bit; voices get the hashes of Net::ping (src/net.rs:1383-1389). Consumes `net`. */
 int fdsp_bank_create_from_net(fdsp_node* net, int device, uint32_t out_mode, fdsp_bank** out);
+/* banks made from a Net: voice index of Net vertex `vertex` (the NodeId of Net::push), -1 if it is not a voice. With it
+   `net.set(setting.node(id))` (src/net.rs:1159-1169) becomes fdsp_bank_set(bank, fdsp_bank_voice_of_vertex(bank, id), ...) */
+int fdsp_bank_voice_of_vertex(const fdsp_bank* b, int vertex);
 void fdsp_bank_destroy(fdsp_bank* b);
 int fdsp_bank_clone(const fdsp_bank* b, fdsp_bank** out);                   /* deep copy incl. device state (dyn_clone) */
 uint32_t fdsp_bank_voices(const fdsp_bank* b);

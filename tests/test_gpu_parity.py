@@ -339,6 +339,32 @@ def test_net_of_voices_mix_is_bit_exact(V, n):
     assert np.array_equal(mix2, ref)
 
 
+def test_net_bank_setting_by_node_id():
+    """`net.set(Setting::center_q(..).node(id))` (src/net.rs:1159-1169) on a bank made from the Net: vertex id -> voice index."""
+    from fundsp_b200.bank import GpuBank
+    from fundsp_b200.net import Net
+    from oracle import OracleUnit
+    V, n = 6, 1500
+    mk = lambda i: noise().seed(i) >> lowpass_hz(300.0 + 100.0 * i, 1.0) >> pan(0.0)
+    net = Net.wrap(mk(0))
+    for i in range(1, V):
+        net = net & Net.wrap(mk(i))          # each `&` appends the new voice vertex and one adder vertex per output channel
+    ids = [0] + [1 + 3 * (i - 1) for i in range(1, V)]
+    b = GpuBank.from_net(net, per_voice=True, sample_rate=SR)
+    assert [b.voice_of_vertex(v) for v in ids] == list(range(V))
+    assert b.voice_of_vertex(2) == -1 and b.voice_of_vertex(3) == -1      # adder vertices are not voices
+    rows0, _ = b.render_samples(n)
+    b.set(b.voice_of_vertex(ids[3]), 2, (2500.0, 3.0), address=((1, 0), (1, 1)))   # CenterQ -> Pipe<Pipe<Noise,Svf>,Pan>: left, right
+    rows1, _ = b.render_samples(n)
+    olib().fo_set_denormal_emulation(0)
+    u = OracleUnit(mk(3)); u.set_sample_rate(SR)
+    o0 = u.process_many(n)
+    u.L.fo_set(u.h, 2, (C.c_float * 2)(2500.0, 3.0), 2, 0, (C.c_int64 * 4)(1, 0, 1, 1), 2)
+    o1 = u.process_many(n)
+    assert np.array_equal(rows0[3], o0) and np.array_equal(rows1[3], o1)
+    assert np.array_equal(rows1[2], np.concatenate([rows0[2], rows1[2]], axis=-1)[:, n:])  # other voices just continue
+
+
 def test_net_left_fold_chain_mix_is_bit_exact():
     from fundsp_b200.bank import GpuBank
     from fundsp_b200.net import Net
