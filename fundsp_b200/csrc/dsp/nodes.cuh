@@ -529,6 +529,41 @@ template <int MODE> struct Svf {  // src/svf.rs:744-855, ID 36 (audio-rate cutof
   }
   static FDSP_DEV void end_simd(R&) {}
 };
+struct Morph {  // src/svf.rs:1034-1111, ID 62: (peak SVF(audio, cutoff, q) + morph * audio) / 2
+  typedef Svf<4> F;
+  FDSP_NODE(4, 1, 0, F::NS, 0);
+  typedef F::R R;
+  static FDSP_DEV void load(R& r, Loader& l) { F::load(r, l); }
+  static FDSP_DEV void save(const R& r, Saver& s) { F::save(r, s); }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<4>& in, Fr<1>& o) {
+    Fr<3> a; Fr<1> y;
+    a.v[0] = in.v[0]; a.v[1] = in.v[1]; a.v[2] = in.v[2];
+    F::template step<T>(r, c, a, y);
+    o.v[0] = (y.v[0] + in.v[3] * in.v[0]) * 0.5f;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+template <int NIN> struct Rez {  // src/rez.rs, ID 75: params = bandpass (and f, fb when the cutoff / q are fixed)
+  FDSP_NODE(NIN, 1, NIN == 1 ? 3 : 1, NIN == 1 ? 2 : 6, 0);
+  struct R { float bandpass, f, fb, cutoff, q, buf0, buf1; };
+  static FDSP_DEV void load(R& r, Loader& l) {
+    r.bandpass = l.Pf();
+    if (NIN == 1) { r.f = l.Pf(); r.fb = l.Pf(); r.cutoff = r.q = 0.0f; } else { r.cutoff = l.Sf(); r.q = l.Sf(); r.f = l.Sf(); r.fb = l.Sf(); }
+    r.buf0 = l.Sf(); r.buf1 = l.Sf();
+  }
+  static FDSP_DEV void save(const R& r, Saver& s) { if (NIN > 1) { s.Sf(r.cutoff); s.Sf(r.q); s.Sf(r.f); s.Sf(r.fb); } s.Sf(r.buf0); s.Sf(r.buf1); }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<NIN>& in, Fr<1>& o) {
+    if (NIN > 1) {
+      const float cu = in.v[NIN > 1 ? 1 : 0], qq = in.v[NIN > 2 ? 2 : 0];
+      if (cu != r.cutoff || qq != r.q) { r.cutoff = cu; r.q = qq; r.f = 2.0f * m::sinf_(3.14159274101257324f * cu / c.sr); r.fb = qq + qq / (1.0f - r.f); }
+    }
+    const float hp = in.v[0] - r.buf0, bp = r.buf0 - r.buf1;
+    r.buf0 += r.f * (hp + r.fb * m::tanhf_(bp));
+    r.buf1 += r.f * (r.buf0 - r.buf1);
+    o.v[0] = r.buf1 - r.bandpass * r.buf0;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
 struct Biquad {  // src/biquad.rs:130-218, ID 15 (also the fixed ButterLowpass ID 16 / Resonator ID 17): DF1, left-to-right
   FDSP_NODE(1, 1, 5, 4, 0);
   struct R { float a1, a2, b0, b1, b2, x1, x2, y1, y2; };
@@ -1177,6 +1212,8 @@ template <int NIN, class X> struct Cost<AllNest<NIN, X>> { static constexpr int 
 template <int HAD, class X, class Y> struct Cost<Feedback2<HAD, X, Y>> { static constexpr int value = Cost<X>::value + Cost<Y>::value + (HAD ? 6 * X::IN : X::IN); };
 template <int K, int N> struct Cost<OnePole<K, N>> { static constexpr int value = N > 1 ? 40 : 8; };
 template <> struct Cost<Pinkpass> { static constexpr int value = 24; };
+template <> struct Cost<Morph> { static constexpr int value = 64; };
+template <int N> struct Cost<Rez<N>> { static constexpr int value = N > 1 ? 180 : 120; };
 template <int A> struct Cost<Follower<A>> { static constexpr int value = 16; };
 template <int K> struct Cost<Shaper<K>> { static constexpr int value = K == 2 ? 100 : 12; };
 template <> struct Cost<Convolver> { static constexpr int value = 48; };

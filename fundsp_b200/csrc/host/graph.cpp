@@ -214,6 +214,37 @@ struct Svf : HNode {  // FixedSvf (ID 43, :857-1031) and Svf (ID 36, :744-855)
   HCLONE(Svf)
 };
 
+struct MorphN : HNode {  // src/svf.rs:1034-1111
+  Svf filter;
+  MorphN(float cutoff, float q) : filter(4, false, cutoff, q, 0.0f) { ctor_ping(); }
+  int inputs() const override { return 4; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 62; }
+  void set_sample_rate(double s) override { filter.set_sample_rate(s); }
+  AttoHash ping(bool probe, AttoHash h) override { return filter.ping(probe, h).hash(id()); }
+  void sig(std::string& o) const override { o += "Morph"; }
+  void lower(Lowering& l) const override { filter.lower(l); }
+  HCLONE(MorphN)
+};
+struct RezN : HNode {  // src/rez.rs
+  int nin; float bandpass, cutoff, q, f = 1, fb = 1, sr = (float)DEFAULT_SR;
+  RezN(float bp, float c, float qq, int n) : nin(n), bandpass(bp), cutoff(c), q(qq) { update(); }
+  void update() { f = 2.0f * m::sinf_(3.14159274101257324f * cutoff / sr); fb = q + q / (1.0f - f); }
+  int inputs() const override { return nin; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 75; }
+  void set_sample_rate(double s) override { sr = (float)s; update(); }
+  void set(const Setting& s) override {
+    if (s.kind == P_CENTER) { cutoff = s.v[0]; update(); }
+    else if (s.kind == P_CENTER_Q) { cutoff = s.v[0]; q = s.v[1]; update(); }
+  }
+  void sig(std::string& o) const override { o += "Rez<" + I(nin) + ">"; }
+  void lower(Lowering& l) const override {
+    l.p(bandpass);
+    if (nin == 1) { l.p(f); l.p(fb); } else { l.s(cutoff); l.s(q); l.s(f); l.s(fb); }
+    l.s(0.0f); l.s(0.0f);
+  }
+  HCLONE(RezN)
+};
+
 // ---------------------------------------------------------------- biquads (src/biquad.rs, src/biquad_bank.rs)
 typedef fdsp::BqCoefs BqCoefs;
 BqCoefs bq_butter_lowpass(float sr, float cutoff) { return fdsp::bq_butter_lowpass(sr, cutoff); }   // src/biquad.rs:27-38
@@ -719,6 +750,8 @@ HNode* mk_reverb3(double time, double diffusion, HNode* filter) {
   return new ReverbN(time, diffusion, filter);
 }
 HNode* mk_var(float value) { return new VarN(value); }
+HNode* mk_morph(float cutoff, float q) { return new MorphN(cutoff, q); }
+HNode* mk_rez(float bandpass, float cutoff, float q, int inputs) { return (inputs != 1 && inputs != 3) ? nullptr : new RezN(bandpass, cutoff, q, inputs); }
 HNode* mk_follow(int asym, float attack, float release) { return new FollowerN(asym != 0, attack, asym ? release : attack); }
 HNode* mk_shaper(int kind, float p0, float p1) { return (kind < 0 || kind > 5) ? nullptr : new ShaperN(kind, p0, p1); }
 HNode* mk_onepole(int kind, float param, int inputs) {

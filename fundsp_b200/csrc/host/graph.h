@@ -103,6 +103,8 @@ HNode* mk_allnest(float coefficient, HNode* x, int nin);
 HNode* mk_phase_osc(int kind);                      // 0 ramp, 1 poly_saw, 2 poly_square, 3 poly_pulse
 HNode* mk_reverb3(double time, double diffusion, HNode* filter);   // Reverb<F> ID 85; consumes `filter` (1 -> 1)
 HNode* mk_var(float value);
+HNode* mk_morph(float cutoff, float q);                               // Morph ID 62
+HNode* mk_rez(float bandpass, float cutoff, float q, int inputs);    // Rez ID 75 (bandpass 0 lowrez / 1 bandrez)
 HNode* mk_follow(int asymmetric, float attack, float release);        // Follow ID 24 / AFollow ID 29
 HNode* mk_shaper(int kind, float p0, float p1);                       // Shaper ID 42: 0 Clip 1 ClipTo 2 Tanh 3 Softsign 4 Crush 5 SoftCrush
 HNode* mk_onepole(int kind, float param, int inputs);                  // 0 Lowpole 18, 1 Highpole 47, 2 Allpole 46, 3 DCBlock 22, 4 Pinkpass 26

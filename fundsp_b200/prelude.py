@@ -692,3 +692,36 @@ def follow(response_time):
 
 def afollow(attack_time, release_time):
     return An("follow", (1, f32(attack_time), f32(release_time)), (), 1, 1)
+
+
+# ---- src/prelude.rs:2559-2627 resonant two-pole (Rez) and morphing SVF
+def lowrez():
+    return An("rez", (0.0, 440.0, 1.0, 3), (), 3, 1)
+
+
+def lowrez_hz(cutoff, q):
+    return An("rez", (0.0, f32(cutoff), f32(q), 1), (), 1, 1)
+
+
+def lowrez_q(q):
+    return (multipass(2) | dc(f32(q))) >> lowrez()
+
+
+def bandrez():
+    return An("rez", (1.0, 440.0, 1.0, 3), (), 3, 1)
+
+
+def bandrez_hz(center, q):
+    return An("rez", (1.0, f32(center), f32(q), 1), (), 1, 1)
+
+
+def bandrez_q(q):
+    return (multipass(2) | dc(f32(q))) >> bandrez()
+
+
+def morph():
+    return An("morph", (440.0, 1.0), (), 4, 1)
+
+
+def morph_hz(f, q, m):
+    return (pass_() | dc((f32(f), f32(q), f32(m)))) >> An("morph", (f32(f), f32(q)), (), 4, 1)

@@ -147,6 +147,12 @@ inline An shape(Crush s) { return An(fdsp_shaper(4, s.levels, 0.0f)); }
 inline An shape(SoftCrush s) { return An(fdsp_shaper(5, s.levels, 0.0f)); }
 inline An follow(float response_time) { return An(fdsp_follow(0, response_time, response_time)); }
 inline An afollow(float attack, float release) { return An(fdsp_follow(1, attack, release)); }
+inline An morph() { return An(fdsp_morph(440.0f, 1.0f)); }
+inline An morph_hz(float f, float q, float m) { return (pass() | dc(f, q, m)) >> An(fdsp_morph(f, q)); }
+inline An lowrez() { return An(fdsp_rez(0.0f, 440.0f, 1.0f, 3)); }
+inline An lowrez_hz(float cutoff, float q) { return An(fdsp_rez(0.0f, cutoff, q, 1)); }
+inline An bandrez() { return An(fdsp_rez(1.0f, 440.0f, 1.0f, 3)); }
+inline An bandrez_hz(float center, float q) { return An(fdsp_rez(1.0f, center, q, 1)); }
 inline An var(float value) { return An(fdsp_var(value)); }
 inline An dsf_saw() { return An(fdsp_dsf(2, 1.0f, 0.5f)); }
 inline An dsf_saw_r(float roughness) { return An(fdsp_dsf(1, 1.0f, roughness)); }

@@ -716,6 +716,44 @@ struct Svf : Node {
   FO_CLONE(Svf)
 };
 
+// ---- src/svf.rs:1034-1111 Morph (ID 62): peak SVF morphing between lowpass, peak and highpass; inputs (audio, cutoff, q, morph)
+struct Morph : Node {
+  Svf filter;
+  Morph(float cutoff, float q) : filter(4 /* PeakMode */, false, cutoff, q, 0.0f) { ctor_ping(); }
+  int inputs() const override { return 4; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 62; }
+  void reset() override { filter.reset(); }
+  void set_sample_rate(double s) override { filter.set_sample_rate(s); }
+  void tick(const float* in, float* out) override { float y; filter.tick(in, &y); out[0] = (y + in[3] * in[0]) * 0.5f; }
+  AttoHash ping(bool probe, AttoHash h) override { return filter.ping(probe, h).hash(id()); }   // :1108-1110 (filter first, then the ID)
+  FO_CLONE(Morph)
+};
+// ---- src/rez.rs Rez<F, N> (ID 75, F = f32): Paul Kellett's resonant two-pole; bandpass = 0 lowrez, 1 bandrez
+struct Rez : Node {
+  int nin; float bandpass, cutoff, q, f = 1, fb = 1, sr = (float)DEFAULT_SR, buf0 = 0, buf1 = 0;
+  Rez(float bandpass_, float cutoff_, float q_, int nin_) : nin(nin_), bandpass(bandpass_), cutoff(cutoff_), q(q_) { set_cutoff_q(cutoff_, q_); }
+  void set_cutoff_q(float c, float qq) {
+    cutoff = c; f = 2.0f * m::sinf_(3.14159274101257324f * c / sr);
+    q = qq; fb = qq + qq / (1.0f - f);
+  }
+  int inputs() const override { return nin; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 75; }
+  void reset() override { buf0 = buf1 = 0; }
+  void set_sample_rate(double s) override { sr = (float)s; set_cutoff_q(cutoff, q); }
+  void tick(const float* in, float* out) override {
+    if (nin > 1 && (in[1] != cutoff || in[2] != q)) set_cutoff_q(in[1], in[2]);
+    const float hp = in[0] - buf0, bp = buf0 - buf1;
+    buf0 += f * (hp + fb * m::tanhf_(bp));
+    buf1 += f * (buf0 - buf1);
+    out[0] = buf1 - bandpass * buf0;
+  }
+  void set(const Setting& s) override {
+    if (s.kind == P_CENTER) set_cutoff_q(s.v[0], q);
+    else if (s.kind == P_CENTER_Q) set_cutoff_q(s.v[0], s.v[1]);
+  }
+  FO_CLONE(Rez)
+};
+
 // ---- src/biquad.rs:17-116 BiquadCoefs<f32>
 struct BiquadCoefs { float a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0; };
 inline BiquadCoefs biquad_butter_lowpass(float sr, float cutoff) {

@@ -86,6 +86,8 @@ API Node* fo_convolve(const float* response, int n) { return new Convolver(std::
 API Node* fo_onepole(int kind, float param, int inputs) { return new OnePole(kind, param, inputs); }   // 0 lowpole 1 highpole 2 allpole 3 dcblock 4 pinkpass
 API Node* fo_shaper(int kind, float p0, float p1) { return new Shaper(kind, p0, p1); }   // 0 clip 1 clip_to 2 tanh 3 softsign 4 crush 5 soft_crush
 API Node* fo_follow(int asymmetric, float attack, float release) { return new Follower(asymmetric != 0, attack, asymmetric ? release : attack); }
+API Node* fo_morph(float cutoff, float q) { return new Morph(cutoff, q); }
+API Node* fo_rez(float bandpass, float cutoff, float q, int inputs) { return new Rez(bandpass, cutoff, q, inputs); }
 API Node* fo_var(float value) { return new Var(value); }
 API Node* fo_dsf(int inputs, float harmonic_spacing, float roughness) { return new Dsf(inputs, harmonic_spacing, roughness); }
 API Node* fo_mls(int bits) { return new Mls((uint32_t)bits); }

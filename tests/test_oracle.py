@@ -327,6 +327,24 @@ def test_dsf_spectrum_known_answer():  # src/oscillator.rs:104-112: sum over i o
     check_wave(dc(330.0) >> dsf_saw_r(0.8) | (dc(220.0) | sine_hz(0.5) * 0.3 + 0.5) >> dsf_square())
 
 
+def test_rez_and_morph():  # tests/test_basic.rs:338-341 (check_wave_filter), src/rez.rs, src/svf.rs:1034-1111
+    L.fo_set_denormal_emulation(0)
+    check_wave((noise() | noise()) >> ((pass_() | dc((2000.0, 5.0, 0.8))) >> morph() | morph_hz(440.0, 1.0, 0.0)))
+    check_wave((noise() | noise()) >> (lowrez_hz(440.0, 0.5) | bandrez_hz(440.0, 0.5)))
+    check_wave((noise() | sine_hz(2.0) * 300.0 + 800.0) >> lowrez_q(0.3) | (noise() | dc((1200.0, 0.7))) >> bandrez())
+    L.fo_restore_denormals()
+    # morph = -1 / 0 / +1 turns the peak SVF (lowpass - highpass) into lowpass / peak / highpass: (peak + m * x) / 2 with x = lp + bp/q.. + hp
+    sr = 44100.0
+    for m, dc_gain, ny_gain in ((-1.0, 1.0, 0.0), (1.0, 0.0, 1.0)):
+        u = OracleUnit(morph_hz(1000.0, 1.0, m))
+        spec = measure_response(u, sr, 0x4000)
+        assert abs(abs(spec[1]) - dc_gain) < 2e-2 and abs(abs(spec[len(spec) - 2]) - ny_gain) < 2e-2, (m, abs(spec[1]), abs(spec[-2]))
+    # rez: the lowpass output passes DC with unit gain (buf1 follows the input), the bandpass output blocks it
+    ylo = OracleUnit(lowrez_hz(1000.0, 0.2)).filter(sr, np.ones((1, 4000), np.float32))[0]
+    ybp = OracleUnit(bandrez_hz(1000.0, 0.2)).filter(sr, np.ones((1, 4000), np.float32))[0]
+    assert abs(ylo[-1] - 1.0) < 1e-3 and abs(ybp[-1]) < 1e-3
+
+
 def test_follow_filters():  # test_flow.rs:96-97,102 and src/follow.rs
     z1 = lambda f: np.exp(-1j * 2 * math.pi * f / SR)
 
