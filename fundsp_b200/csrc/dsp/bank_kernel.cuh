@@ -45,7 +45,7 @@ FDSP_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
 #define FDSP_NO_GROUP 0
 #endif
 #ifndef FDSP_GROUP_COST
-#define FDSP_GROUP_COST 160   // programs up to this static cost are evaluated 8 samples at a time, fully unrolled
+#define FDSP_GROUP_COST 256   // programs whose group form unrolls to at most this many instructions per sample are evaluated 8 samples at a time
 #endif
 
 template <class G, int NT, int MODE, bool TB>
@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(NT, FDSP_MIN_CTAS) bank_kernel(const BankArgs 
   constexpr int IN = G::IN, OUT = G::OUT;
   constexpr int TS = (MODE & 2) ? mix_tile_samples(OUT) : 64;
   // big programs (e.g. the 32-line FDN in thread-per-voice form) are not unrolled over the 8-sample group
-  constexpr int UNROLL = Cost<G>::value <= FDSP_GROUP_COST ? 8 : (Cost<G>::value <= 320 ? 4 : (Cost<G>::value <= 640 ? 2 : 1));
+  constexpr bool GROUP = GroupPlan<G>::ok && GroupPlan<G>::code <= FDSP_GROUP_COST && !FDSP_NO_GROUP;
+  constexpr int UNROLL = GROUP ? 8 : (Cost<G>::value <= 160 ? 8 : (Cost<G>::value <= 320 ? 4 : (Cost<G>::value <= 640 ? 2 : 1)));
 
   typename G::R r;
   CtxT<TB> c;
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(NT, FDSP_MIN_CTAS) bank_kernel(const BankArgs 
 #pragma unroll 1
         for (int g = s0; g < gend; g += 8) {
           float ob[OUT > 0 ? OUT : 1][8];
-          if constexpr (UNROLL == 8 && !FDSP_NO_GROUP) {
+          if constexpr (GROUP) {
             // small programs: node by node over the 8-sample group (group_step), all intermediates in registers
             Fr8<IN> in8; Fr8<OUT> o8;
 #pragma unroll

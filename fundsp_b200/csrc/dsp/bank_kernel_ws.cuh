@@ -32,7 +32,7 @@ template <class P, class Q, class Y> struct PipeParts<Pipe<Pipe<P, Q>, Y>> {
 };
 template <class G> struct WsOk {
   typedef PipeParts<G> PP;
-  static constexpr bool value = PP::is_pipe && Cost<G>::value <= FDSP_GROUP_COST && Cost<typename PP::A>::value >= 24 && Cost<typename PP::B>::value >= 12 &&
+  static constexpr bool value = PP::is_pipe && GroupPlan<G>::ok && GroupPlan<G>::code <= FDSP_GROUP_COST && Cost<typename PP::A>::value >= 24 && Cost<typename PP::B>::value >= 12 &&
                                 PP::A::OUT >= 1 && PP::A::OUT <= 2;
 };
 __host__ __device__ constexpr int ws_hand_samples(int outs) { return mix_tile_samples(outs) < 16 ? mix_tile_samples(outs) : 16; }

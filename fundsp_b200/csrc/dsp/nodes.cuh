@@ -83,9 +83,46 @@ template <class T> struct VoidT { typedef void type; };
 template <class Node, class = void> struct HasGroup { static constexpr bool value = false; };
 template <class Node> struct HasGroup<Node, typename VoidT<typename Node::GroupStep>::type> { static constexpr bool value = true; };
 
+#ifndef FDSP_ROTATE_COST
+#define FDSP_ROTATE_COST 100   // leaves above this static cost are not unrolled over the group (their loop rotates the registers)
+#endif
+template <class G> struct Cost;   // static per-sample cost estimate of a program (defined with the traits below)
+
 template <class Node, class C> FDSP_DEV void group_step(typename Node::R& r, C& c, const Fr8<Node::IN>& in, Fr8<Node::OUT>& o) {
   if constexpr (HasGroup<Node>::value) {
     Node::step8(r, c, in, o);
+  } else if constexpr ((Cost<Node>::value > FDSP_ROTATE_COST)) {
+    // Heavy serial leaf (Moog, Rez, Dsf ...): unrolling it 8x only bloats the instruction stream, so its 8 steps run in a real
+    // loop. The group registers are ROTATED by one sample per iteration, which keeps every array index static (no local memory).
+    Fr8<Node::IN> ri = in;
+    Fr8<Node::OUT> ro;
+#pragma unroll
+    for (int k = 0; k < Node::OUT; k++) {
+#pragma unroll
+      for (int q = 0; q < 8; q++) ro.v[k][q] = 0.0f;
+    }
+    const int base = c.i;
+#pragma unroll 1
+    for (int j = 0; j < 8; j++) {
+      Fr<Node::IN> a; Fr<Node::OUT> b;
+#pragma unroll
+      for (int k = 0; k < Node::IN; k++) a.v[k] = ri.v[k][0];
+      c.i = base + j; c.first = (j == 0);
+      Node::template step<false>(r, c, a, b);
+#pragma unroll
+      for (int k = 0; k < Node::IN; k++) {
+#pragma unroll
+        for (int q = 0; q < 7; q++) ri.v[k][q] = ri.v[k][q + 1];
+      }
+#pragma unroll
+      for (int k = 0; k < Node::OUT; k++) {
+#pragma unroll
+        for (int q = 0; q < 7; q++) ro.v[k][q] = ro.v[k][q + 1];
+        ro.v[k][7] = b.v[k];
+      }
+    }
+    o = ro;
+    c.i = base; c.first = true;
   } else {
     const int base = c.i;
 #pragma unroll
@@ -1197,7 +1234,7 @@ template <int M> struct Cost<Svf<M>> { static constexpr int value = 60; };
 template <> struct Cost<Biquad> { static constexpr int value = 12; };
 template <> struct Cost<BiquadBank> { static constexpr int value = 96; };
 template <int N> struct Cost<Moog<N>> { static constexpr int value = 200; };
-template <> struct Cost<AdsrLive> { static constexpr int value = 60; };
+template <> struct Cost<AdsrLive> { static constexpr int value = 120; };
 template <> struct Cost<Delay> { static constexpr int value = 12; };
 template <int N> struct Cost<Panner<N>> { static constexpr int value = N == 1 ? 2 : 80; };
 template <int K, class X, class Y> struct Cost<Binop<K, X, Y>> { static constexpr int value = Cost<X>::value + Cost<Y>::value + 1; };
@@ -1224,5 +1261,23 @@ template <class F> struct WaveKind<Reverb85<F>> : WaveKind<F> {};
 template <int N> struct Cost<Dsf<N>> { static constexpr int value = 700; };
 template <int NT_, int LIN> struct Cost<Tap<NT_, LIN>> { static constexpr int value = 40 * NT_; };
 template <int HAD, class X> struct Cost<Feedback<HAD, X>> { static constexpr int value = Cost<X>::value + (HAD ? 6 * X::IN : X::IN); };
+
+
+// ---- group-evaluation plan: instructions the 8-sample group form of G unrolls to (per sample), and whether every heavy leaf is
+// narrow enough to rotate; the kernel uses the group form when ok && code <= FDSP_GROUP_COST
+template <class G> struct GroupPlan {
+  static constexpr bool heavy = !HasGroup<G>::value && Cost<G>::value > FDSP_ROTATE_COST;
+  static constexpr bool ok = !heavy || (G::IN + G::OUT <= 6);
+  static constexpr int code = heavy ? Cost<G>::value / 8 + 2 * (G::IN + G::OUT) : Cost<G>::value;
+};
+template <class X, class Y> struct Plan2 { static constexpr bool ok = GroupPlan<X>::ok && GroupPlan<Y>::ok; static constexpr int code = GroupPlan<X>::code + GroupPlan<Y>::code + 1; };
+template <int K, class X, class Y> struct GroupPlan<Binop<K, X, Y>> : Plan2<X, Y> {};
+template <class X, class Y> struct GroupPlan<Pipe<X, Y>> : Plan2<X, Y> {};
+template <class X, class Y> struct GroupPlan<Stack<X, Y>> : Plan2<X, Y> {};
+template <class X, class Y> struct GroupPlan<Branch<X, Y>> : Plan2<X, Y> {};
+template <class X, class Y> struct GroupPlan<Bus<X, Y>> : Plan2<X, Y> {};
+template <int K, class X> struct GroupPlan<Unop<K, X>> { static constexpr bool ok = GroupPlan<X>::ok; static constexpr int code = GroupPlan<X>::code + 1; };
+template <class X> struct GroupPlan<Thru<X>> : GroupPlan<X> {};
+template <int KIND, int OP, int N, class X> struct GroupPlan<Multi<KIND, OP, N, X>> { static constexpr bool ok = GroupPlan<X>::ok; static constexpr int code = N * GroupPlan<X>::code; };
 
 }  // namespace fdsp
