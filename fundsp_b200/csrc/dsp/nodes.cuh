@@ -723,6 +723,24 @@ template <int NIN> struct Dsf {  // src/oscillator.rs:104-208, ID 55: params = r
   }
   static FDSP_DEV void end_simd(R&) {}
 };
+template <int KIND> struct Chaos {  // src/oscillator.rs:318-438: KIND 0 Rossler (ID 73), 1 Lorenz (ID 74); input = frequency
+  FDSP_NODE(1, 1, 0, 3, 0);
+  struct R { float x, y, z; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.x = l.Sf(); r.y = l.Sf(); r.z = l.Sf(); }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.x); s.Sf(r.y); s.Sf(r.z); }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<1>& in, Fr<1>& o) {
+    if (KIND == 0) {
+      const float dx = -r.y - r.z, dy = r.x + 0.15f * r.y, dz = 0.2f + r.z * (r.x - 10.0f), dt = 2.91f * in.v[0] / c.sr;
+      r.x += dx * dt; r.y += dy * dt; r.z += dz * dt;
+      o.v[0] = r.x * 0.05757f;
+    } else {
+      const float dx = 10.0f * (r.y - r.x), dy = r.x * (28.0f - r.z) - r.y, dz = r.x * r.y - (8.0f / 3.0f) * r.z, dt = in.v[0] / c.sr;
+      r.x += dx * dt; r.y += dy * dt; r.z += dz * dt;
+      o.v[0] = r.x * 0.05107f;
+    }
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
 struct Mls {  // src/noise.rs:11-148, ID 19: params = feedback polynomial, length mask, n - 1
   FDSP_NODE(0, 1, 3, 1, 0);
   struct R { uint32_t poly, mask, shift, s; };
@@ -1249,6 +1267,7 @@ template <int NIN, class X> struct Cost<AllNest<NIN, X>> { static constexpr int 
 template <int HAD, class X, class Y> struct Cost<Feedback2<HAD, X, Y>> { static constexpr int value = Cost<X>::value + Cost<Y>::value + (HAD ? 6 * X::IN : X::IN); };
 template <int K, int N> struct Cost<OnePole<K, N>> { static constexpr int value = N > 1 ? 40 : 8; };
 template <> struct Cost<Pinkpass> { static constexpr int value = 24; };
+template <int K> struct Cost<Chaos<K>> { static constexpr int value = 32; };
 template <> struct Cost<Morph> { static constexpr int value = 64; };
 template <int N> struct Cost<Rez<N>> { static constexpr int value = N > 1 ? 180 : 120; };
 template <int A> struct Cost<Follower<A>> { static constexpr int value = 16; };

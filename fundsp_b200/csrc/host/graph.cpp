@@ -214,6 +214,16 @@ struct Svf : HNode {  // FixedSvf (ID 43, :857-1031) and Svf (ID 36, :744-855)
   HCLONE(Svf)
 };
 
+struct ChaosN : HNode {  // Rossler ID 73 / Lorenz ID 74 (src/oscillator.rs:318-438)
+  int kind; uint64_t hash = 0;
+  explicit ChaosN(int k) : kind(k) {}
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return kind == 0 ? 73 : 74; }
+  void set_hash(uint64_t h) override { hash = h; }
+  void sig(std::string& o) const override { o += "Chaos<" + I(kind) + ">"; }
+  void lower(Lowering& l) const override { const float t = (float)rnd1(hash); l.s(0.0f * (1.0f - t) + 1.0f * t); l.s(1.0f); l.s(1.0f); }
+  HCLONE(ChaosN)
+};
 struct MorphN : HNode {  // src/svf.rs:1034-1111
   Svf filter;
   MorphN(float cutoff, float q) : filter(4, false, cutoff, q, 0.0f) { ctor_ping(); }
@@ -750,6 +760,7 @@ HNode* mk_reverb3(double time, double diffusion, HNode* filter) {
   return new ReverbN(time, diffusion, filter);
 }
 HNode* mk_var(float value) { return new VarN(value); }
+HNode* mk_chaos(int kind) { return (kind < 0 || kind > 1) ? nullptr : new ChaosN(kind); }
 HNode* mk_morph(float cutoff, float q) { return new MorphN(cutoff, q); }
 HNode* mk_rez(float bandpass, float cutoff, float q, int inputs) { return (inputs != 1 && inputs != 3) ? nullptr : new RezN(bandpass, cutoff, q, inputs); }
 HNode* mk_follow(int asym, float attack, float release) { return new FollowerN(asym != 0, attack, asym ? release : attack); }

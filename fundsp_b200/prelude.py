@@ -725,3 +725,12 @@ def morph():
 
 def morph_hz(f, q, m):
     return (pass_() | dc((f32(f), f32(q), f32(m)))) >> An("morph", (f32(f), f32(q)), (), 4, 1)
+
+
+# ---- src/prelude.rs rossler() / lorenz(): chaotic oscillators, input = frequency
+def rossler():
+    return An("chaos", (0,), (), 1, 1)
+
+
+def lorenz():
+    return An("chaos", (1,), (), 1, 1)

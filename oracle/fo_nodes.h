@@ -1054,6 +1054,28 @@ struct OnePole : Node {
   }
   FO_CLONE(OnePole)
 };
+// ---- src/oscillator.rs:318-438 Rossler (ID 73) and Lorenz (ID 74) chaotic oscillators (explicit Euler, input = frequency)
+struct Chaos : Node {
+  int kind; float x = 0, y = 1, z = 1, sr = (float)DEFAULT_SR; uint64_t hash = 0;
+  explicit Chaos(int k) : kind(k) { reset(); }
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return kind == 0 ? 73 : 74; }
+  void reset() override { const float t = (float)rnd1(hash); x = 0.0f * (1.0f - t) + 1.0f * t; y = 1.0f; z = 1.0f; }
+  void set_sample_rate(double s) override { sr = (float)s; }
+  void tick(const float* in, float* out) override {
+    if (kind == 0) {
+      const float dx = -y - z, dy = x + 0.15f * y, dz = 0.2f + z * (x - 10.0f), dt = 2.91f * in[0] / sr;
+      x += dx * dt; y += dy * dt; z += dz * dt;
+      out[0] = x * 0.05757f;
+    } else {
+      const float dx = 10.0f * (y - x), dy = x * (28.0f - z) - y, dz = x * y - (8.0f / 3.0f) * z, dt = in[0] / sr;
+      x += dx * dt; y += dy * dt; z += dz * dt;
+      out[0] = x * 0.05107f;
+    }
+  }
+  void set_hash(uint64_t h) override { hash = h; reset(); }
+  FO_CLONE(Chaos)
+};
 // ---- src/follow.rs (F = f32): Follow (ID 24, :31-134) and AFollow (ID 29, :137-270): three one-pole smoothers in series
 inline double halfway_coeff(double samples) {  // :17-23
   double r0 = log(fmax(1.0, samples)) - 0.861624594696583;

@@ -327,6 +327,15 @@ def test_dsf_spectrum_known_answer():  # src/oscillator.rs:104-112: sum over i o
     check_wave(dc(330.0) >> dsf_saw_r(0.8) | (dc(220.0) | sine_hz(0.5) * 0.3 + 0.5) >> dsf_square())
 
 
+def test_chaotic_oscillators():  # src/oscillator.rs:318-438, tests/test_basic.rs (check_wave of lorenz / rossler)
+    check_wave(dc(220.0) >> lorenz() | dc(110.0) >> rossler())
+    for g in (dc(440.0) >> lorenz(), dc(440.0) >> rossler()):
+        y = OracleUnit(g).render(44100.0, 1.0)[0]
+        assert np.isfinite(y).all() and 0.2 < np.abs(y).max() < 1.5 and np.abs(y[-20000:]).std() > 0.05   # bounded, keeps moving
+    a, b = OracleUnit(dc(440.0) >> lorenz() | dc(440.0) >> lorenz()).render(44100.0, 0.5)
+    assert not np.array_equal(a, b)      # initial x comes from the node's own location hash
+
+
 def test_rez_and_morph():  # tests/test_basic.rs:338-341 (check_wave_filter), src/rez.rs, src/svf.rs:1034-1111
     L.fo_set_denormal_emulation(0)
     check_wave((noise() | noise()) >> ((pass_() | dc((2000.0, 5.0, 0.8))) >> morph() | morph_hz(440.0, 1.0, 0.0)))
