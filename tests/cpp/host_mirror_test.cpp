@@ -22,6 +22,14 @@ int main() {
   std::printf("bus %d %d\n", bus.inputs(), bus.outputs());
   An rev = stacki(4, [](int i) { return delay(0.01 * (i + 1)) >> fir3(0.5f); });
   std::printf("stacki %d %d\n", rev.inputs(), rev.outputs());
+  // the wider opcode set keeps the reference's names and argument order
+  An synth = (poly_saw_hz(110.0f) & 0.5f * (dc(55.0f) >> dsf_saw_r(0.6f))) >> lowrez_hz(900.0f, 0.4f) >> shape(Tanh{1.5f}) >> dcblock()
+             >> (pass() & 0.3f * feedback_unit(0.02, 0.5f * lowpole_hz(3000.0f))) >> pan(0.25f)
+             >> (multipass(2) & 0.25f * reverb3_stereo(2.0, 0.5, lowpole_hz(8000.0f)));
+  std::printf("synth %d %d %s\n", synth.inputs(), synth.outputs(), synth.signature().c_str());
+  An misc = pink() | brown() | (noise() >> convolve({1.0f, 0.5f, 0.25f})) | (dc(220.0f) >> lorenz()) | ((noise() | dc(800.0f, 1.0f, 0.5f)) >> morph())
+            | (noise() >> follow(0.01f)) | (var(0.5f) * mls()) | ((noise() | dc(0.004f)) >> tap(0.001f, 0.01f));
+  std::printf("misc %d %d\n", misc.inputs(), misc.outputs());
   try {
     An bad = pass() >> (pass() | pass());
     std::printf("arity NOT detected\n");

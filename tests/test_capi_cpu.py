@@ -177,6 +177,10 @@ def test_cpp_host_mirror_compiles_and_matches_python_mirror(tmp_path):
     fm = capi.NodeHandle(sine_hz(f) * f * m + f >> sine())
     assert f"fm 0 1 {fm.signature()}" in lines
     assert "bus 0 2" in lines and "stacki 4 4" in lines and any(x.startswith("arity error") for x in lines)
+    synth = capi.NodeHandle((poly_saw_hz(110.0) & 0.5 * (dc(55.0) >> dsf_saw_r(0.6))) >> lowrez_hz(900.0, 0.4) >> shape(Tanh(1.5)) >> dcblock()
+                            >> (pass_() & 0.3 * feedback_unit(0.02, 0.5 * lowpole_hz(3000.0))) >> pan(0.25)
+                            >> (multipass(2) & 0.25 * reverb3_stereo(2.0, 0.5, lowpole_hz(8000.0))))
+    assert f"synth 0 2 {synth.signature()}" in lines and "misc 0 8" in lines
 
 
 # ---------------------------------------------------------------- the NVRTC translation unit compiles without a GPU
