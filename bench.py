@@ -25,7 +25,14 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 SR = 48000.0
-METRIC = "Msamples/sec (f32) rendered across N voices"
+def _baseline_metric():
+    try:
+        return json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+    except Exception:
+        return "Msamples/sec (f32) rendered across N voices at 1/2/4/8 B200 vs host-CPU ref"
+
+
+METRIC = _baseline_metric()   # the metric string of BASELINE.json, verbatim
 HEADLINE = {"saw_svf": 16384, "noise_svf": 16384, "fm": 4096, "biquad_bank": 2048, "subtractive_dry": 1024, "subtractive": 1024, "net": 65536}
 
 
