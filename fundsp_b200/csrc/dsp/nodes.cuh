@@ -953,6 +953,37 @@ struct Pinkpass {  // src/filter.rs:178-262, ID 26 (Paul Kellett's pinking filte
   static FDSP_DEV void end_simd(R&) {}
 };
 
+// ---------------------------------------------------------------- Declick<f32> (src/dynamics.rs:245-315, ID 23)
+// smooth5 fade-in over the first `duration` seconds. The block path accumulates the fade phase inside the block and advances the
+// time by the whole block at once (process :287-307, which also covers the tail samples); tick recomputes the phase from t.
+FDSP_DEV float smooth5f(float x) { return ((x * 6.0f - 15.0f) * x + 10.0f) * x * x * x; }
+struct Declick {
+  FDSP_NODE(1, 1, 1, 1, 0);
+  struct R { float duration, t, phase, phase_d, end_time; int end_index; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.duration = l.Pf(); r.t = l.Sf(); r.phase = r.phase_d = r.end_time = 0.0f; r.end_index = 0; }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.t); }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<1>& in, Fr<1>& o) {
+    if (T) {
+      if (r.t < r.duration) { const float phase = (r.t - 0.0f) / (r.duration - 0.0f); o.v[0] = in.v[0] * smooth5f(phase); r.t += c.sd64; }
+      else o.v[0] = in.v[0];
+      return;
+    }
+    if (c.i == 0) {   // block start: plan the fade for this block
+      r.end_index = 0;
+      if (r.t < r.duration) {
+        r.phase = (r.t - 0.0f) / (r.duration - 0.0f);
+        r.phase_d = c.sd64 / r.duration;
+        r.end_time = r.t + (float)c.n * c.sd64;
+        r.end_index = r.duration < r.end_time ? (int)ceilf((r.duration - r.t) / c.sd64) : c.n;
+        r.t = r.end_time;
+      }
+    }
+    if (c.i < r.end_index) { o.v[0] = in.v[0] * smooth5f(r.phase); r.phase += r.phase_d; }
+    else o.v[0] = in.v[0];
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
 // ---------------------------------------------------------------- Follow (ID 24) / AFollow (ID 29), src/follow.rs
 // Three one-pole smoothers in series; coefficients (host: halfway_coeff) are 1 for the very first sample after a reset.
 template <int ASYM> struct Follower {
@@ -1267,6 +1298,7 @@ template <int NIN, class X> struct Cost<AllNest<NIN, X>> { static constexpr int 
 template <int HAD, class X, class Y> struct Cost<Feedback2<HAD, X, Y>> { static constexpr int value = Cost<X>::value + Cost<Y>::value + (HAD ? 6 * X::IN : X::IN); };
 template <int K, int N> struct Cost<OnePole<K, N>> { static constexpr int value = N > 1 ? 40 : 8; };
 template <> struct Cost<Pinkpass> { static constexpr int value = 24; };
+template <> struct Cost<Declick> { static constexpr int value = 24; };
 template <int K> struct Cost<Chaos<K>> { static constexpr int value = 32; };
 template <> struct Cost<Morph> { static constexpr int value = 64; };
 template <int N> struct Cost<Rez<N>> { static constexpr int value = N > 1 ? 180 : 120; };

@@ -214,6 +214,14 @@ struct Svf : HNode {  // FixedSvf (ID 43, :857-1031) and Svf (ID 36, :744-855)
   HCLONE(Svf)
 };
 
+struct DeclickN : HNode {  // src/dynamics.rs:245-315
+  float duration; explicit DeclickN(float d) : duration(d) {}
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 23; }
+  void sig(std::string& o) const override { o += "Declick"; }
+  void lower(Lowering& l) const override { l.p(duration); l.s(0.0f); }
+  HCLONE(DeclickN)
+};
 struct ChaosN : HNode {  // Rossler ID 73 / Lorenz ID 74 (src/oscillator.rs:318-438)
   int kind; uint64_t hash = 0;
   explicit ChaosN(int k) : kind(k) {}
@@ -760,6 +768,7 @@ HNode* mk_reverb3(double time, double diffusion, HNode* filter) {
   return new ReverbN(time, diffusion, filter);
 }
 HNode* mk_var(float value) { return new VarN(value); }
+HNode* mk_declick(float duration) { return new DeclickN(duration); }
 HNode* mk_chaos(int kind) { return (kind < 0 || kind > 1) ? nullptr : new ChaosN(kind); }
 HNode* mk_morph(float cutoff, float q) { return new MorphN(cutoff, q); }
 HNode* mk_rez(float bandpass, float cutoff, float q, int inputs) { return (inputs != 1 && inputs != 3) ? nullptr : new RezN(bandpass, cutoff, q, inputs); }

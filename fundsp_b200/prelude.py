@@ -734,3 +734,12 @@ def rossler():
 
 def lorenz():
     return An("chaos", (1,), (), 1, 1)
+
+
+# ---- src/prelude.rs:1180-1189
+def declick():
+    return An("declick", (f32(0.010),), (), 1, 1)
+
+
+def declick_s(t):
+    return An("declick", (f32(t),), (), 1, 1)

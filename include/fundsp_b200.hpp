@@ -155,6 +155,8 @@ inline An bandrez() { return An(fdsp_rez(1.0f, 440.0f, 1.0f, 3)); }
 inline An bandrez_hz(float center, float q) { return An(fdsp_rez(1.0f, center, q, 1)); }
 inline An rossler() { return An(fdsp_chaos(0)); }
 inline An lorenz() { return An(fdsp_chaos(1)); }
+inline An declick() { return An(fdsp_declick(0.010f)); }
+inline An declick_s(float t) { return An(fdsp_declick(t)); }
 inline An var(float value) { return An(fdsp_var(value)); }
 inline An dsf_saw() { return An(fdsp_dsf(2, 1.0f, 0.5f)); }
 inline An dsf_saw_r(float roughness) { return An(fdsp_dsf(1, 1.0f, roughness)); }

@@ -1076,6 +1076,32 @@ struct Chaos : Node {
   void set_hash(uint64_t h) override { hash = h; reset(); }
   FO_CLONE(Chaos)
 };
+// ---- src/dynamics.rs:245-315 Declick<f32> (ID 23): smooth5 fade-in over the first `duration` seconds
+inline float smooth5f(float x) { return ((x * 6.0f - 15.0f) * x + 10.0f) * x * x * x; }   // src/math.rs:418-420
+struct Declick : Node {
+  float t = 0, duration, sample_duration = 0;
+  explicit Declick(float d) : duration(d) { set_sample_rate(DEFAULT_SR); }
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 23; }
+  void reset() override { t = 0; }
+  void set_sample_rate(double sr) override { sample_duration = (float)(1.0 / sr); }
+  void tick(const float* in, float* out) override {
+    if (t < duration) { const float phase = (t - 0.0f) / (duration - 0.0f); const float value = smooth5f(phase); t += sample_duration; out[0] = in[0] * value; }
+    else out[0] = in[0];
+  }
+  void process(int size, const float* in, float* out) override {  // :287-307: the phase is accumulated inside the block, t jumps by the block
+    for (int i = 0; i < size; i++) out[i] = in[i];
+    if (t < duration) {
+      float phase = (t - 0.0f) / (duration - 0.0f);
+      const float phase_d = sample_duration / duration;
+      const float end_time = t + (float)size * sample_duration;
+      const int end_index = duration < end_time ? (int)ceilf((duration - t) / sample_duration) : size;
+      for (int i = 0; i < end_index && i < B; i++) { out[i] *= smooth5f(phase); phase += phase_d; }
+      t = end_time;
+    }
+  }
+  FO_CLONE(Declick)
+};
 // ---- src/follow.rs (F = f32): Follow (ID 24, :31-134) and AFollow (ID 29, :137-270): three one-pole smoothers in series
 inline double halfway_coeff(double samples) {  // :17-23
   double r0 = log(fmax(1.0, samples)) - 0.861624594696583;

@@ -58,6 +58,8 @@ CASES = {
     "followers": lambda i: (noise().seed(i) >> follow(0.0005 + 0.0001 * i)) * 4.0 + (square_hz(5.0 + i) >> afollow(0.001 + 0.0002 * (i % 9), 0.01 + 0.001 * (i % 13))),
     "rez_filters": lambda i: noise().seed(i) >> (lowrez_hz(300.0 + 40.0 * i, 0.2 + 0.01 * (i % 50)) & bandrez_hz(900.0 + 20.0 * i, 0.4)) | (noise().seed(i + 50) | (sine_hz(1.5) * 400.0 + 900.0) | dc(0.3 + 0.01 * (i % 30))) >> bandrez(),
     "morph_filter": lambda i: (noise().seed(i) | (sine_hz(0.7) * 500.0 + 1500.0) | dc(1.0 + 0.1 * (i % 20)) | (sine_hz(0.3 + 0.05 * (i % 11)) * 0.9)) >> morph() | noise().seed(i + 9) >> morph_hz(600.0 + 10.0 * i, 2.0, -0.5),
+    "declick": lambda i: noise().seed(i) >> declick_s(0.001 + 0.0005 * (i % 20)) | saw_hz(100.0 + i) >> declick(),
+    "declick_in_feedback": lambda i: noise().seed(i) >> feedback(delay(0.001) * 0.5 >> declick_s(0.003 + 0.0001 * i)),
     "lorenz_rossler": lambda i: dc(100.0 + 20.0 * i) >> lorenz() | (sine_hz(0.5) * 50.0 + 200.0 + i) >> rossler(),
     "product_fm_feedback": lambda i: (sine_hz(200.0 + i) * sine_hz(3.0 + 0.1 * i)) >> feedback(tick() * 0.25 >> lowpass_hz(2000.0, 0.7)),
 }

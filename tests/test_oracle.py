@@ -327,6 +327,13 @@ def test_dsf_spectrum_known_answer():  # src/oscillator.rs:104-112: sum over i o
     check_wave(dc(330.0) >> dsf_saw_r(0.8) | (dc(220.0) | sine_hz(0.5) * 0.3 + 0.5) >> dsf_square())
 
 
+def test_declick():  # src/dynamics.rs:245-315
+    check_wave(noise() >> declick() | dc(1.0) >> declick_s(0.002))
+    y = OracleUnit(dc(1.0) >> declick_s(0.005)).render(44100.0, 0.02)[0]
+    n = int(round(0.005 * 44100.0))
+    assert y[0] == 0.0 and np.all(np.diff(y[: n + 2]) >= -1e-6) and np.all(y[n + 2:] == 1.0) and abs(y[n // 2] - 0.5) < 0.03
+
+
 def test_chaotic_oscillators():  # src/oscillator.rs:318-438, tests/test_basic.rs (check_wave of lorenz / rossler)
     check_wave(dc(220.0) >> lorenz() | dc(110.0) >> rossler())
     for g in (dc(440.0) >> lorenz(), dc(440.0) >> rossler()):
