@@ -76,6 +76,28 @@ def test_arity_errors_are_reported_not_crashes():
         be.b_wavesynth(9, 1)
 
 
+def test_builder_argument_errors_return_null_with_a_message():
+    """Invalid constructor arguments (asserts / type errors in the reference) come back as NULL + fdsp_last_error, never a crash."""
+    be = capi.GpuBackend()
+    two_in = be.b_stack(be.b_pass(), be.b_pass())
+    bad = [
+        lambda: be.b_tap(1, 0, 0.02, 0.01),                 # min_delay > max_delay (src/delay.rs:164-165)
+        lambda: be.b_mls(0), lambda: be.b_mls(32),          # 1 <= n <= 31 (src/noise.rs:61)
+        lambda: be.b_onepole(7, 100.0, 1), lambda: be.b_onepole(3, 100.0, 2), lambda: be.b_onepole(2, 0.0, 1),   # allpole delay must be > 0
+        lambda: be.b_shaper(9, 1.0, 0.0), lambda: be.b_chaos(2), lambda: be.b_phase_osc(4), lambda: be.b_dsf(3, 1.0, 0.5),
+        lambda: be.b_convolve([]), lambda: be.b_rez(0.0, 440.0, 1.0, 2),
+        lambda: be.b_feedback_unit(0.01, be.b_stack(be.b_pass(), be.b_sink(1))),      # inputs != outputs (src/feedback.rs:349)
+        lambda: be.b_reverb3(2.0, 0.5, two_in),                                       # loop filter must be 1 -> 1
+        lambda: be.b_feedback2(0, be.b_pass(), be.b_stack(be.b_pass(), be.b_pass())), # X and Y arity differ
+        lambda: be.b_impulse(0),
+    ]
+    for k, f in enumerate(bad):
+        with pytest.raises(capi.FdspError) as e:
+            f()
+        assert e.value.code in (capi.ERR_ARITY, capi.ERR_ARG), k
+        assert len(str(e.value)) > 10
+
+
 def test_config_graphs_have_aot_programs():
     from ctypes import create_string_buffer
     for name in workloads.WORKLOADS:
