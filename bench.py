@@ -287,11 +287,14 @@ def main():
     except Exception:
         pass
     # ---- CPU baseline on this box's host cores (bounded sample of the same workload)
+    # (timed at N=1 only; multi-GPU runs carry the object with value null — the reference arm `--impl reference` covers every N)
     cores = os.cpu_count() or 1
     ns = min(n, 24000)
-    cpu_reference(a.workload, min(V, 256), 480, cores)
-    dt, _ = cpu_reference(a.workload, V, ns, cores)
-    cpu_val = V * ns / dt / 1e6
+    cpu_val = None
+    if world == 1:
+        cpu_reference(a.workload, min(V, 256), 480, cores)
+        dt, _ = cpu_reference(a.workload, V, ns, cores)
+        cpu_val = V * ns / dt / 1e6
     line = {
         "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -308,7 +311,8 @@ def main():
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)", "issue": issue,
                      "note": "IIR voice programs are issue/latency bound, not HBM bound (DESIGN.md §Roofline); see profiles/ for issue-slot utilisation"},
         "cpu_baseline": {"value": cpu_val, "unit": "Msamples/s", "cores": cores, "kind": "port",
-                         "sample": f"{V} voices x {ns} samples, oracle (C++ restatement of the reference block path), {cores} threads"},
+                         "sample": (f"{V} voices x {ns} samples, oracle (C++ restatement of the reference block path), {cores} threads" if world == 1
+                                    else "not timed at N > 1 (see the N=1 line and the --impl reference arm)")},
         "clocks": clocks,
         "wall_s_timed_region": wall,
     }
