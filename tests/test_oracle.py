@@ -451,6 +451,18 @@ def test_reverb3_and_var():  # src/reverb.rs:139-279, src/prelude.rs:1856 doc ex
     assert np.array_equal(v.process_many(70)[0], np.full(70, 1.5, np.float32))
 
 
+def test_more_reference_check_wave_lines():  # tests/test_basic.rs:170,187-190,199-209 restated with the wider node set
+    L.fo_set_denormal_emulation(0)
+    check_wave(noise() >> declick() | noise() + noise())                                                                 # :170
+    check_wave(dc((110.0, 220.0)) >> declick_s(0.1) + pass_() >> (saw() ^ dsf_square_r(0.9)))                             # :187
+    check_wave(dc((20.0, 40.0)) >> reverse(2) >> pass_() * pass_() >> (dsf_saw_r(0.999) ^ square() * 0.1))                # :188-190
+    check_wave((brown().seed(2) | dc(440.0)) >> pipei(4, lambda i: ~peak_q(1.0)) >> bell_q(1.0, 2.0)
+               | ((mls() | dc(880.0)) >> ~lowshelf_q(1.0, 0.5) >> highshelf_q(2.0, 2.0)))                                # :201-204
+    check_wave((square_hz(110.0).phase(0.25) | dc(440.0)) >> pipei(4, lambda i: ~lowpass_q(1.0)) >> highpass_q(1.0)
+               | ((mls() | dc(880.0)) >> ~bandpass_q(1.0) >> notch_q(2.0)))                                             # :205-210
+    L.fo_restore_denormals()
+
+
 def test_mls_is_maximum_length():  # src/noise.rs:11-98: the sequence of an n-bit MLS repeats after exactly 2**n - 1 steps
     for n in range(2, 15):
         u = OracleUnit(mls_bits(n))
@@ -612,6 +624,32 @@ def test_net_equals_static_and_bus_tree():
     L.fo_net_chain(n, (moog_hz(1500.0, 0.5) | moog_hz(1000.0, 0.6)).lower(be))
     y1 = OracleUnit(n).render(44100.0, 0.01)
     assert y1.shape == (2, 441) and np.isfinite(y1).all()
+
+
+def test_reference_net_check_wave_lines():  # tests/test_basic.rs:275-305,319-326: the Net scheduler itself, tick == process
+    from fundsp_b200.net import Net
+    L.fo_set_denormal_emulation(0)
+    net = Net(0, 2)
+    i = net.push(noise() >> moog_hz(1500.0, 0.8) | noise() >> moog_hz(500.0, 0.4))
+    net.connect_output(i, 0, 0); net.connect_output(i, 1, 1)
+    check_wave(net)                                                                    # :275-282
+    net = Net(0, 2)
+    net.chain(noise() | noise()); net.chain(moog_hz(1500.0, 0.5) | moog_hz(1000.0, 0.6)); net.chain(lowpole_hz(1000.0) | lowpole_hz(500.0))
+    check_wave(net)                                                                    # :284-289
+    static = (noise() | noise()) >> (moog_hz(1500.0, 0.5) | moog_hz(1000.0, 0.6)) >> (lowpole_hz(1000.0) | lowpole_hz(500.0))
+    assert OracleUnit(net).render(44100.0, 0.01).shape == OracleUnit(static).render(44100.0, 0.01).shape
+    net = Net(0, 2)
+    net.chain(noise()); net.chain(lowpole_hz(1000.0) ^ lowpole_hz(500.0)); net.chain(lowpole_hz(1000.0) | lowpole_hz(500.0))
+    check_wave(net)                                                                    # :291-296
+    net = Net.wrap(sine_hz(42.0))
+    net = net._copy() | net
+    net.chain(Net.wrap(reverb_stereo(10.0, 5.0, 0.5)))
+    check_wave(net)                                                                    # :298-303
+    dc42 = Net.wrap(dc(42.0))
+    dcs = dc42._copy() | dc42
+    filt = Net.wrap(lowpass_hz(1729.0, 1.0))
+    check_wave(dcs >> Net.wrap(reverb_stereo(40.0, 5.0, 1.0)) >> (filt._copy() | filt))  # :319-326
+    L.fo_restore_denormals()
 
 
 def test_bank_render_mix_is_index_order_sum():
