@@ -217,6 +217,50 @@ def test_onepole_family_responses():  # test_flow.rs:95,101-105,114-115 against 
     L.fo_restore_denormals()
 
 
+def test_composite_graph_responses():  # tests/test_flow.rs:107-155: combinators x filters against composed closed forms
+    import ctypes
+    z1 = lambda f: np.exp(-1j * 2 * math.pi * f / SR)
+
+    def bq(kind, fc, q=1.0):
+        c = np.zeros(5, np.float32)
+        L.fo_biquad_coefs(kind, SR, fc, q, 1.0, c.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+        return lambda f, c=c.copy(): biquad_response(c, SR, f)
+    butter = lambda fc: bq(0, fc)
+    reson = lambda fc, q: bq(1, fc, q)
+    svf = lambda mode, fc, q, gain=1.0: (lambda f: svf_response(mode, SR, fc, q, gain, f))
+    lowp = lambda fc: (lambda f, c=math.exp(-2 * math.pi * fc / SR): (1 - c) / (1 - c * z1(f)))
+    dly = lambda t: (lambda f, n=round(t * SR): z1(f) ** n)
+    check_response(OracleUnit(butterpass_hz(500.0) & bell_hz(2000.0, 10.0, 5.0)), lambda f: butter(500.0)(f) + svf(BELL, 2000.0, 10.0, 5.0)(f))          # :107
+    check_response(OracleUnit(butterpass_hz(6000.0) >> lowpass_hz(500.0, 3.0)), lambda f: butter(6000.0)(f) * svf(LOWPASS, 500.0, 3.0)(f))                 # :108
+    check_response(OracleUnit(pass_() * 0.25 & tick() * 0.5 & tick() >> tick() * 0.25), lambda f: 0.25 + 0.5 * z1(f) + 0.25 * z1(f) ** 2)                  # :110
+    check_response(OracleUnit(tick() & lowshelf_hz(500.0, 2.0, 0.1)), lambda f: z1(f) + svf(LOWSHELF, 500.0, 2.0, 0.1)(f))                                 # :111
+    check_response(OracleUnit((delay(0.001) ^ delay(0.002)) >> reverse(2) >> (delay(0.003) | delay(0.007)) >> join(2)),
+                   lambda f: 0.5 * (dly(0.002)(f) * dly(0.003)(f) + dly(0.001)(f) * dly(0.007)(f)))                                                         # :114-116
+    check_response(OracleUnit((butterpass_hz(15000.0) ^ allpass_hz(10000.0, 10.0)) >> lowpole_hz(500.0) + pass_()),
+                   lambda f: butter(15000.0)(f) * lowp(500.0)(f) + svf(ALLPASS, 10000.0, 10.0)(f))                                                         # :117-119
+    check_response(OracleUnit((resonator_hz(12000.0, 500.0) ^ lowpass_hz(3000.0, 0.5)) >> pass_() + highshelf_hz(3000.0, 0.5, 4.0)),
+                   lambda f: reson(12000.0, 500.0)(f) + svf(LOWPASS, 3000.0, 0.5)(f) * svf(HIGHSHELF, 3000.0, 0.5, 4.0)(f))                                 # :120-123
+    check_response(OracleUnit(split(32) >> multipass(32) >> join(32)), lambda f: 1.0 + 0.0 * f)                                                            # :124
+    check_response(OracleUnit(split(8) >> stacki(8, lambda i: resonator_hz(1000.0 + 1000.0 * i, 100.0 + 100.0 * i)) >> join(8)),
+                   lambda f: __import__("builtins").sum(reson(1000.0 + 1000.0 * i, 100.0 + 100.0 * i)(f) for i in range(8)) / 8.0)                       # :125-131
+    check_response(OracleUnit(pipei(4, lambda i: bell_hz(1000.0 + 1000.0 * i, float(i + 1), db_amp(float(i + 6))))),
+                   lambda f: np.prod([svf(BELL, 1000.0 + 1000.0 * i, float(i + 1), float(np.float32(db_amp(float(i + 6)))))(f) for i in range(4)], axis=0))   # :133-139
+    check_response(OracleUnit(split(5) >> stacki(5, lambda i: lowpole_hz(1000.0 + 1000.0 + i)) >> join(5)),
+                   lambda f: __import__("builtins").sum(lowp(2000.0 + i)(f) for i in range(5)) / 5.0)                                                       # :140-142
+    lw, rw = math.cos((0.5 + 1.0) * math.pi / 4), math.sin((0.5 + 1.0) * math.pi / 4)
+    check_response(OracleUnit(0.5 * pan(0.0) >> join(2)), lambda f: 0.5 * (math.cos(math.pi / 4) + math.sin(math.pi / 4)) / 2 + 0.0 * f)                 # :153
+    check_response(OracleUnit(pan(-1.0) * 0.5 >> multijoin(1, 2)), lambda f: 0.5 * (1.0 + 0.0) / 2 + 0.0 * f)                                               # :155
+    check_response(OracleUnit(fir((0.4, 0.3, 0.2, 0.1))), lambda f: 0.1 + 0.2 * z1(f) + 0.3 * z1(f) ** 2 + 0.4 * z1(f) ** 3)                               # :159
+    check_response(OracleUnit(morph_hz(1000.0, 1.0, 0.5)), lambda f: (svf(PEAK, 1000.0, 1.0)(f) + 0.5) * 0.5)                                              # :160
+    check_response(OracleUnit(morph_hz(2000.0, 2.0, -0.5)), lambda f: (svf(PEAK, 2000.0, 2.0)(f) - 0.5) * 0.5)                                             # :161
+    check_response(OracleUnit((pass_() | dc((500.0, 2.0, -1.0))) >> morph()), lambda f: (svf(PEAK, 500.0, 2.0)(f) - 1.0) * 0.5)                            # :163
+    check_response(OracleUnit(biquad(0.0, 0.17149, 0.29287, 0.58574, 0.29287)), lambda f: biquad_response((0.0, 0.17149, 0.29287, 0.58574, 0.29287), SR, f))  # :164
+    check_response(OracleUnit(biquad(0.033717, 0.171773, 1.059253, -0.035714, 0.181952)), lambda f: biquad_response((0.033717, 0.171773, 1.059253, -0.035714, 0.181952), SR, f))
+    from fundsp_b200.net import Net
+    net1 = Net(1, 1); net1.chain(lowpole_hz(1500.0))
+    check_response(OracleUnit(net1), lowp(1500.0))                                                                                                           # :176-178
+
+
 def test_biquad_bank_lane_response():  # test_flow.rs:171-177
     import ctypes
     c = np.zeros(5, np.float32)
