@@ -573,6 +573,29 @@ def outputs_diverge(g, n=64):
     return True
 
 
+def test_nodes_vs_networks():  # tests/test_basic.rs:409-466 (the parts that do not remove vertices)
+    from fundsp_b200.net import Net
+    pt = Net(2, 2); pt.pass_through(0, 0); pt.pass_through(1, 1)
+    assert is_equal(pass_() | pass_(), pt)
+    sw = Net(2, 2); sw.pass_through(0, 1); sw.pass_through(1, 0)
+    assert is_equal(reverse(2), sw)
+    mn = Net(2, 2)
+    id0 = mn.push(mul(2.0)); mn.push(sink()); mn.push(sine()); id1 = mn.push(mul(3.0))      # two idle vertices stay in the net
+    mn.connect_input(0, id0, 0); mn.connect_input(1, id1, 0); mn.connect_output(id0, 0, 0); mn.connect_output(id1, 0, 1)
+    assert is_equal(mul(2.0) | mul(3.0), mn)
+    an = Net(2, 2)
+    a0 = an.push(add((2.0, 3.0))); a1 = an.push(multipass(2))
+    an.pipe_input(a0); an.pipe_all(a0, a1); an.pipe_output(a1)
+    assert is_equal(add((2.0, 3.0)), an)
+    # Net operators against the static combinators (test_basic.rs:468-518 style)
+    x, y = lowpass_hz(800.0, 1.0), highpass_hz(300.0, 2.0)
+    assert is_equal(x >> y, Net.wrap(x) >> Net.wrap(y))
+    assert is_equal(x & y, Net.wrap(x) & Net.wrap(y))
+    assert is_equal(x ^ y, Net.wrap(x) ^ Net.wrap(y))
+    assert is_equal(x | y, Net.wrap(x) | Net.wrap(y))
+    assert is_equal(x + y, Net.wrap(x) + Net.wrap(y)) and is_equal(x * y, Net.wrap(x) * Net.wrap(y)) and is_equal(x - y, Net.wrap(x) - Net.wrap(y))
+
+
 def test_pseudorandom_phase_divergence():  # test_basic.rs:532-612
     assert outputs_diverge(noise() | (~zero() >> noise()) | noise() | (~zero() >> noise()) | noise() | noise() | noise())
     assert outputs_diverge(noise() ^ noise() ^ noise() & zero() ^ noise() ^ (noise() >> pass_()) ^ noise() ^ noise())
