@@ -561,7 +561,16 @@ def test_structural_equivalences():
     assert is_equal((pass_() ^ mul(y) ^ add(w)) >> add(z) + sub(x) + mul(y), add(z) & mul(y) >> sub(x) & add(w) >> mul(y))
     assert is_equal(tick() >> tick() >> tick(), delay(3.0 / 44100.0))
     assert is_equal(tick() >> tick() >> tick() >> tick() >> tick(), delay(5.0 / 44100.0))
-    assert v == 1.0
+    assert is_equal((pass_() ^ mul(y) ^ add(w) ^ sub(x)) >> add(z) + sub(x) + mul(y) + add(z), add(z) & mul(y) >> sub(x) & add(w) >> mul(y) & sub(x) >> add(z))   # :402-406
+    # multichannel constants vs. stacked constants (test_basic.rs:480-505)
+    assert is_equal(dc(w) | dc(x), constant((w, x)))
+    assert is_equal(dc(x) | dc(y) | dc(z), constant((x, y, z)))
+    assert is_equal(dc(x) | dc(y) | dc(z) | dc(w), constant((x, y, z, w)))
+    assert is_equal(dc(w) | dc(v) | dc(x) | dc(y) | dc(z), constant((w, v, x, y, z)))
+    assert is_equal(dc((w, x)) | dc((y, z, w)), constant((w, x, y, z, w)))
+    # sinks and zeros (test_basic.rs:507-517)
+    assert is_equal(sink() | sink() | zero() | zero(), zero() | zero() | sink() | sink())
+    assert is_equal(sink() | zero() | sink() | zero() | zero() | sink() | zero(), zero() | zero() | zero() | sink() | sink() | zero() | sink())
 
 
 def outputs_diverge(g, n=64):
