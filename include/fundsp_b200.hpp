@@ -204,6 +204,13 @@ class Bank {
   uint32_t voices() const { return fdsp_bank_voices(b_); }
   void set_sample_rate(double sr) { check(fdsp_bank_set_sample_rate(b_, sr)); }
   void reset() { check(fdsp_bank_reset(b_)); }
+  // AudioUnit::set on one voice: `kind` is the Parameter index of src/setting.rs (fundsp_b200.h), `address` = {type, value} pairs
+  // (type 1 Index, 2 Node) exactly as in fdsp_node_set; e.g. set(7, FDSP_P_CENTER_Q, {2500.f, 3.f}, {{1, 0}, {1, 1}})
+  void set(uint32_t voice, int kind, std::initializer_list<float> values, std::initializer_list<std::pair<int, int64_t>> address = {}, uint64_t seed = 0) {
+    std::vector<int64_t> a;
+    for (auto& p : address) { a.push_back(p.first); a.push_back(p.second); }
+    check(fdsp_bank_set(b_, voice, kind, values.begin(), (int)values.size(), seed, a.empty() ? nullptr : a.data(), (int)address.size()));
+  }
   void allocate(uint64_t max_samples = 64) { check(fdsp_bank_allocate(b_, max_samples)); }
   // AudioUnit::process: buffers are [channel][64]
   void process(uint32_t size, const float* input, float* output) { check(fdsp_bank_process(b_, size, input, output)); }
