@@ -43,7 +43,7 @@ _SIG = {
     "fdsp_node_phase": (I, [P, F]), "fdsp_node_seed": (I, [P, U64]), "fdsp_node_set": (I, [P, I, FP, I, U64, C.POINTER(I64), I]),
     "fdsp_node_inputs": (I, [P]), "fdsp_node_outputs": (I, [P]), "fdsp_node_id": (U64, [P]), "fdsp_node_ping": (U64, [P, I, U64]),
     "fdsp_node_leaf_hashes": (I, [P, C.POINTER(U64), I]), "fdsp_node_signature": (I, [P, C.c_char_p, I]),
-    "fdsp_node_clone": (P, [P]), "fdsp_node_free": (None, [P]),
+    "fdsp_node_lowering": (I, [P, C.POINTER(U32), I, C.POINTER(U32), I, C.POINTER(U32), I, C.POINTER(I), C.POINTER(I), C.POINTER(I)]), "fdsp_node_clone": (P, [P]), "fdsp_node_free": (None, [P]),
     "fdsp_wavetable_count": (I, [I]), "fdsp_wavetable_info": (I, [I, I, FP, C.POINTER(I)]), "fdsp_wavetable_data": (FP, [I, I]),
     "fdsp_bank_create": (I, [C.POINTER(P), U32, I, U32, C.POINTER(P)]), "fdsp_bank_create_from_net": (I, [P, I, U32, C.POINTER(P)]), "fdsp_bank_destroy": (None, [P]), "fdsp_bank_voice_of_vertex": (I, [P, I]), "fdsp_bank_clone": (I, [P, C.POINTER(P)]),
     "fdsp_bank_voices": (U32, [P]), "fdsp_bank_inputs": (I, [P]), "fdsp_bank_voice_outputs": (I, [P]), "fdsp_bank_outputs": (I, [P]),
@@ -130,6 +130,7 @@ class GpuBackend:
     def b_rez(self, bp, cutoff, q, nin): return _node(self.L.fdsp_rez(bp, cutoff, q, nin), "rez")
     def b_chaos(self, kind): return _node(self.L.fdsp_chaos(kind), "chaos")
     def b_declick(self, d): return _node(self.L.fdsp_declick(d), "declick")
+    def b_netnode(self, net): return net.lower(self)
     def b_var(self, value): return _node(self.L.fdsp_var(value), "var")
     def b_dsf(self, n, spacing, rough): return _node(self.L.fdsp_dsf(n, spacing, rough), "dsf")
     def b_mls(self, bits): return _node(self.L.fdsp_mls(bits), "mls")
@@ -203,6 +204,16 @@ class NodeHandle:
         buf = (C.c_uint64 * 4096)()
         n = self.L.fdsp_node_leaf_hashes(self.h, buf, 4096)
         return [int(buf[i]) for i in range(n)]
+
+    def lowering(self):
+        """(P, S, U) words of the device program, in load order (numpy uint32 arrays)."""
+        import numpy as np
+        n = [C.c_int(0), C.c_int(0), C.c_int(0)]
+        check(self.L.fdsp_node_lowering(self.h, None, 0, None, 0, None, 0, C.byref(n[0]), C.byref(n[1]), C.byref(n[2])))
+        arrs = [np.zeros(max(1, x.value), np.uint32) for x in n]
+        ptr = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint32))
+        check(self.L.fdsp_node_lowering(self.h, ptr(arrs[0]), len(arrs[0]), ptr(arrs[1]), len(arrs[1]), ptr(arrs[2]), len(arrs[2]), C.byref(n[0]), C.byref(n[1]), C.byref(n[2])))
+        return tuple(a[: x.value] for a, x in zip(arrs, n))
 
     def signature(self):
         buf = C.create_string_buffer(1 << 16)

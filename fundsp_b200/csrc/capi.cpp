@@ -148,6 +148,17 @@ API int fdsp_node_signature(const fdsp_node* h, char* out, int max) {
   strncpy(out, s.c_str(), (size_t)max - 1); out[max - 1] = 0;
   return (int)s.size();
 }
+API int fdsp_node_lowering(const fdsp_node* h, uint32_t* P, int maxp, uint32_t* S, int maxs, uint32_t* U, int maxu, int* np, int* ns, int* nu) {
+  if (!h || !np || !ns || !nu) return fail(FDSP_ERR_ARG, "node_lowering: bad arguments");
+  Lowering l;
+  h->n->lower(l);
+  if (!l.ok) return fail(FDSP_ERR_UNSUPPORTED, l.why);
+  *np = (int)l.P.size(); *ns = (int)l.S.size(); *nu = (int)l.U.size();
+  for (int i = 0; i < *np && i < maxp && P; i++) P[i] = l.P[i];
+  for (int i = 0; i < *ns && i < maxs && S; i++) S[i] = l.S[i];
+  for (int i = 0; i < *nu && i < maxu && U; i++) U[i] = l.U[i];
+  return FDSP_OK;
+}
 API fdsp_node* fdsp_node_clone(const fdsp_node* h) { return h ? new (std::nothrow) fdsp_node{h->n->clone()} : nullptr; }
 API void fdsp_node_free(fdsp_node* h) { if (h) { delete h->n; delete h; } }
 

@@ -11,6 +11,22 @@ typedef unsigned int uint32_t;
 typedef int int32_t;
 typedef unsigned long long uint64_t;
 typedef long long int64_t;
+#elif defined(FDSP_HOST_EMUL)
+// tests/cpp/device_emul.cpp compiles this node library for the host CPU (TEST INFRASTRUCTURE: lets the CPU-only test suite run
+// the device templates against the oracle; the product never defines FDSP_HOST_EMUL). Shims for the few intrinsics used.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#define __device__
+#define __host__
+#define __forceinline__ inline
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
+using std::isfinite;
 #else
 #include <cstdint>
 #include <cuda_runtime.h>

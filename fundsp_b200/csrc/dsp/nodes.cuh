@@ -46,10 +46,14 @@ typedef CtxT<false> Ctx;
 #define FDSP_LDS_VOLATILE 0
 #endif
 FDSP_DEV float lds_f32(uint32_t addr) {
+#ifdef FDSP_HOST_EMUL
+  (void)addr; return 0.0f;   // the host emulation never stages tables in shared memory
+#else
   float v;
   if (FDSP_LDS_VOLATILE) asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   else asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
+#endif
 }
 
 struct Loader {
@@ -1254,6 +1258,104 @@ struct AdsrLive {  // src/envelope.rs:185-358 EnvelopeIn<f32,_,U1,f32> (ID 53) +
 };
 
 
+// ---------------------------------------------------------------- Dag: a whole Net as ONE fused node (src/net.rs:118-146, 1224-1286)
+// The reference's Net is a dynamic DAG of boxed units processed vertex by vertex in dependency order, each vertex reading the
+// output buffers of its sources. Here the host emits the vertices in a dependency order and encodes every edge in the TYPE:
+//   Dag<NIN, NOUT, VList<Vx<Unit0, src...>, Vx<Unit1, src...>, ...>, Outs<src...>>
+// one `src` code per unit input / net output: (type << 24) | (vertex << 8) | port with type 0 = zero, 1 = global input `port`,
+// 2 = output `port` of an earlier vertex (vertex = position in the list). All vertex outputs of a group live in registers
+// (`buf`), so an arbitrary acyclic Net costs what the equivalent static combinator expression would. Block semantics hold
+// vertex by vertex (each runs its own group / tick form), exactly like Net::process calling `unit.process` per vertex.
+template <class U, int... S> struct Vx {
+  typedef U Unit;
+  static __host__ __device__ constexpr int src(int i) { constexpr int a[] = {S..., 0}; return a[i]; }
+};
+template <class... V> struct VList {};
+template <int... S> struct Outs { static __host__ __device__ constexpr int src(int i) { constexpr int a[] = {S..., 0}; return a[i]; } };
+template <class... V> struct DagState;
+template <> struct DagState<> {};
+template <class H, class... T> struct DagState<H, T...> { typename H::Unit::R head; DagState<T...> tail; };
+template <int NIN, int NOUT, class VL, class OS> struct Dag;
+template <int NIN, int NOUT, class... V, class OS> struct Dag<NIN, NOUT, VList<V...>, OS> {
+  static constexpr int IN = NIN, OUT = NOUT;
+  static constexpr int NP = (0 + ... + V::Unit::NP), NS = (0 + ... + V::Unit::NS), NU = (0 + ... + V::Unit::NU);
+  static constexpr int TOT = (0 + ... + V::Unit::OUT);
+  static constexpr int TB = TOT > 0 ? TOT : 1;
+  typedef DagState<V...> R;
+  static __host__ __device__ constexpr int offset(int k) { constexpr int outs[] = {V::Unit::OUT..., 0}; int o = 0; for (int i = 0; i < k; i++) o += outs[i]; return o; }
+
+  static FDSP_DEV void load_(DagState<>&, Loader&) {}
+  template <class H, class... T> static FDSP_DEV void load_(DagState<H, T...>& r, Loader& l) { H::Unit::load(r.head, l); load_(r.tail, l); }
+  static FDSP_DEV void save_(const DagState<>&, Saver&) {}
+  template <class H, class... T> static FDSP_DEV void save_(const DagState<H, T...>& r, Saver& s) { H::Unit::save(r.head, s); save_(r.tail, s); }
+  static FDSP_DEV void end_(DagState<>&) {}
+  template <class H, class... T> static FDSP_DEV void end_(DagState<H, T...>& r) { H::Unit::end_simd(r.head); end_(r.tail); }
+  static FDSP_DEV void load(R& r, Loader& l) { load_(r, l); }
+  static FDSP_DEV void save(const R& r, Saver& s) { save_(r, s); }
+  static FDSP_DEV void end_simd(R& r) { end_(r); }
+
+  // ---- 8-sample group form
+  template <int CODE> static FDSP_DEV void fetch8(const Fr8<NIN>& in, const float (&buf)[TB][8], float (&dst)[8]) {
+    constexpr int type = CODE >> 24, node = (CODE >> 8) & 0xffff, port = CODE & 0xff;
+    constexpr int row = type == 2 ? offset(node) + port : 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) dst[j] = type == 0 ? 0.0f : (type == 1 ? in.v[type == 1 ? port : 0][j] : buf[row][j]);
+  }
+  template <class H, int I> static FDSP_DEV void gather8(const Fr8<NIN>& in, const float (&buf)[TB][8], Fr8<H::Unit::IN>& a) {
+    if constexpr (I < H::Unit::IN) { fetch8<H::src(I)>(in, buf, a.v[I]); gather8<H, I + 1>(in, buf, a); }
+  }
+  template <int K, class C> static FDSP_DEV void run8(DagState<>&, C&, const Fr8<NIN>&, float (&)[TB][8]) {}
+  template <int K, class C, class H, class... T> static FDSP_DEV void run8(DagState<H, T...>& r, C& c, const Fr8<NIN>& in, float (&buf)[TB][8]) {
+    Fr8<H::Unit::IN> a; Fr8<H::Unit::OUT> b;
+    gather8<H, 0>(in, buf, a);
+    group_step<typename H::Unit>(r.head, c, a, b);
+    constexpr int base = offset(K);
+#pragma unroll
+    for (int q = 0; q < H::Unit::OUT; q++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) buf[base + q][j] = b.v[q][j];
+    }
+    run8<K + 1>(r.tail, c, in, buf);
+  }
+  template <int I> static FDSP_DEV void out8(const Fr8<NIN>& in, const float (&buf)[TB][8], Fr8<NOUT>& o) {
+    if constexpr (I < NOUT) { fetch8<OS::src(I)>(in, buf, o.v[I]); out8<I + 1>(in, buf, o); }
+  }
+  typedef void GroupStep;
+  template <class C> static FDSP_DEV void step8(R& r, C& c, const Fr8<NIN>& in, Fr8<NOUT>& o) {
+    float buf[TB][8];
+    run8<0>(r, c, in, buf);
+    out8<0>(in, buf, o);
+  }
+
+  // ---- per-sample form (tail samples, and Nets inside a Feedback: Net::tick, src/net.rs:1187-1222)
+  template <int CODE> static FDSP_DEV float fetch1(const Fr<NIN>& in, const float (&buf)[TB]) {
+    constexpr int type = CODE >> 24, node = (CODE >> 8) & 0xffff, port = CODE & 0xff;
+    constexpr int row = type == 2 ? offset(node) + port : 0;
+    return type == 0 ? 0.0f : (type == 1 ? in.v[type == 1 ? port : 0] : buf[row]);
+  }
+  template <class H, int I> static FDSP_DEV void gather1(const Fr<NIN>& in, const float (&buf)[TB], Fr<H::Unit::IN>& a) {
+    if constexpr (I < H::Unit::IN) { a.v[I] = fetch1<H::src(I)>(in, buf); gather1<H, I + 1>(in, buf, a); }
+  }
+  template <bool T, int K, class C> static FDSP_DEV void run1(DagState<>&, const C&, const Fr<NIN>&, float (&)[TB]) {}
+  template <bool T, int K, class C, class H, class... TT> static FDSP_DEV void run1(DagState<H, TT...>& r, const C& c, const Fr<NIN>& in, float (&buf)[TB]) {
+    Fr<H::Unit::IN> a; Fr<H::Unit::OUT> b;
+    gather1<H, 0>(in, buf, a);
+    H::Unit::template step<T>(r.head, c, a, b);
+    constexpr int base = offset(K);
+#pragma unroll
+    for (int q = 0; q < H::Unit::OUT; q++) buf[base + q] = b.v[q];
+    run1<T, K + 1>(r.tail, c, in, buf);
+  }
+  template <int I> static FDSP_DEV void out1(const Fr<NIN>& in, const float (&buf)[TB], Fr<NOUT>& o) {
+    if constexpr (I < NOUT) { o.v[I] = fetch1<OS::src(I)>(in, buf); out1<I + 1>(in, buf, o); }
+  }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<NIN>& in, Fr<NOUT>& o) {
+    float buf[TB];
+    run1<T, 0>(r, c, in, buf);
+    out1<0>(in, buf, o);
+  }
+};
+
 // ---------------------------------------------------------------- traits
 // First wavetable kind used by a graph type (-1: none): decides whether the kernel stages tables in shared memory.
 template <class G> struct WaveKind { static constexpr int value = -1; };
@@ -1314,6 +1416,12 @@ template <int NT_, int LIN> struct Cost<Tap<NT_, LIN>> { static constexpr int va
 template <int HAD, class X> struct Cost<Feedback<HAD, X>> { static constexpr int value = Cost<X>::value + (HAD ? 6 * X::IN : X::IN); };
 
 
+// ---- traits of a Dag: sums / first match over its vertices
+template <int... X> struct FirstNonNeg { static constexpr int value = -1; };
+template <int H, int... T> struct FirstNonNeg<H, T...> { static constexpr int value = H >= 0 ? H : FirstNonNeg<T...>::value; };
+template <int NIN, int NOUT, class... V, class OS> struct WaveKind<Dag<NIN, NOUT, VList<V...>, OS>> { static constexpr int value = FirstNonNeg<WaveKind<typename V::Unit>::value...>::value; };
+template <int NIN, int NOUT, class... V, class OS> struct Cost<Dag<NIN, NOUT, VList<V...>, OS>> { static constexpr int value = (2 + ... + Cost<typename V::Unit>::value); };
+
 // ---- group-evaluation plan: instructions the 8-sample group form of G unrolls to (per sample), and whether every heavy leaf is
 // narrow enough to rotate; the kernel uses the group form when ok && code <= FDSP_GROUP_COST
 template <class G> struct GroupPlan {
@@ -1330,5 +1438,10 @@ template <class X, class Y> struct GroupPlan<Bus<X, Y>> : Plan2<X, Y> {};
 template <int K, class X> struct GroupPlan<Unop<K, X>> { static constexpr bool ok = GroupPlan<X>::ok; static constexpr int code = GroupPlan<X>::code + 1; };
 template <class X> struct GroupPlan<Thru<X>> : GroupPlan<X> {};
 template <int KIND, int OP, int N, class X> struct GroupPlan<Multi<KIND, OP, N, X>> { static constexpr bool ok = GroupPlan<X>::ok; static constexpr int code = N * GroupPlan<X>::code; };
+
+template <int NIN, int NOUT, class... V, class OS> struct GroupPlan<Dag<NIN, NOUT, VList<V...>, OS>> {
+  static constexpr bool ok = (true && ... && GroupPlan<typename V::Unit>::ok);
+  static constexpr int code = (2 + ... + GroupPlan<typename V::Unit>::code);
+};
 
 }  // namespace fdsp

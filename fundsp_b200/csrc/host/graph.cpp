@@ -638,8 +638,58 @@ struct HNet : HNode {
   void set(const Setting& s) override { Address d = s.direction(); if (d.type == 2 && d.value < vx.size()) vx[d.value].unit->set(s.peel()); }
   AttoHash ping(bool probe, AttoHash h) override { h = h.hash(id()); for (auto& v : vx) h = v.unit->ping(probe, h); return h; }
   void determine_order_ping() { AttoHash h = ping(true, AttoHash(id())); ping(false, h); }
-  void sig(std::string& o) const override { o += "Unsupported"; }
-  void lower(Lowering& l) const override { l.fail("a Net used as a node inside a voice has no device lowering yet (use fdsp_bank_create_from_net for voice-separable nets)"); }
+  // Evaluation order exactly as Net::determine_order_in (src/net.rs:862-916): sinks first through `propagate`, then reversed.
+  // Returns false on a cycle (the reference would then read stale buffers; there is no device form for that).
+  bool order(std::vector<int>& ord) const {
+    const int N = (int)vx.size();
+    std::vector<int> unplugged(N, 0); std::vector<char> done(N, 0);
+    for (int i = 0; i < N; i++) for (auto& p : vx[i].src) if (p.type == 2) unplugged[p.node]++;
+    ord.clear();
+    std::vector<int> stack;
+    auto propagate = [&](int start) {   // iterative form of the recursive `propagate`
+      stack.push_back(start);
+      std::vector<size_t> chan(1, 0);
+      while (!stack.empty()) {
+        const int i = stack.back(); size_t& ch = chan.back();
+        if (ch >= vx[i].src.size()) { stack.pop_back(); chan.pop_back(); continue; }
+        const NetPort p = vx[i].src[ch++];
+        if (p.type == 2 && --unplugged[p.node] == 0) { done[p.node] = 1; ord.push_back(p.node); stack.push_back(p.node); chan.push_back(0); }
+      }
+    };
+    for (int i = 0; i < N; i++) { if (done[i]) continue; if (unplugged[i] == 0) { done[i] = 1; ord.push_back(i); propagate(i); } }
+    if ((int)ord.size() < N) return false;
+    std::reverse(ord.begin(), ord.end());
+    return true;
+  }
+  // A Net used as a node: one fused `Dag` program (csrc/dsp/nodes.cuh) with the edges encoded in the type expression.
+  void sig(std::string& o) const override {
+    std::vector<int> ord;
+    if (!order(ord) || vx.size() > 65535) { o += "Unsupported"; return; }
+    std::vector<int> pos(vx.size(), 0);
+    for (size_t k = 0; k < ord.size(); k++) pos[ord[k]] = (int)k;
+    auto code = [&](const NetPort& p) { return p.type == 0 ? 0 : (p.type == 1 ? ((1 << 24) | (p.port & 0xff)) : ((2 << 24) | (pos[p.node] << 8) | (p.port & 0xff))); };
+    o += "Dag<" + I(nin) + "," + I(nout) + ",VList<";
+    for (size_t k = 0; k < ord.size(); k++) {
+      const Vx& v = vx[ord[k]];
+      if (k) o += ",";
+      o += "Vx<"; v.unit->sig(o);
+      for (auto& p : v.src) o += "," + I(code(p));
+      o += ">";
+    }
+    o += ">,Outs<";
+    for (int c = 0; c < nout; c++) { if (c) o += ","; o += I(code(out[c])); }
+    o += ">>";
+  }
+  void lower(Lowering& l) const override {
+    std::vector<int> ord;
+    if (!order(ord)) { l.fail("the Net has a cycle (the reference would read stale buffers, src/net.rs:904-911); no device form"); return; }
+    if (vx.size() > 65535) { l.fail("Net too large to encode as one program"); return; }
+    // The first process()/tick() of a reference Net runs determine_order, which RE-PINGS the Net's own units from a fresh
+    // root hash (src/net.rs:839-842): whatever location hash an enclosing graph handed down at construction is replaced.
+    // Lowering happens after all construction, i.e. where the reference would be about to process for the first time.
+    const_cast<HNet*>(this)->determine_order_ping();
+    for (int v : ord) vx[v].unit->lower(l);
+  }
   HCLONE(HNet)
 };
 

@@ -173,6 +173,10 @@ class Net:
         return n
 
     # ---- lowering
+    def node(self):
+        """This Net as a graph node (an `An`), e.g. `noise() >> net.node()`: the reference's `An<Net>` / `Net` inside expressions."""
+        return An("netnode", (self,), (), self.inputs(), self.outputs())
+
     def lower(self, backend):
         h = backend.net_new(self.nin, self.nout)
         for unit, _ in self.vertex:

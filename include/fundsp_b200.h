@@ -114,6 +114,9 @@ uint64_t fdsp_node_id(const fdsp_node* n);
 uint64_t fdsp_node_ping(fdsp_node* n, int probe, uint64_t hash);            /* AudioNode::ping */
 int fdsp_node_leaf_hashes(fdsp_node* n, uint64_t* out, int max);            /* hashes handed to leaves by the constructor ping, in order */
 int fdsp_node_signature(const fdsp_node* n, char* out, int max);            /* device program type expression */
+/* the words the device program of this node consumes, in load order: per-voice parameters P, initial state S, class-uniform U
+   (host-only introspection; counts are returned even when the buffers are too small or NULL) */
+int fdsp_node_lowering(const fdsp_node* n, uint32_t* P, int maxp, uint32_t* S, int maxs, uint32_t* U, int maxu, int* np, int* ns, int* nu);
 fdsp_node* fdsp_node_clone(const fdsp_node* n);
 void fdsp_node_free(fdsp_node* n);
 /* wavetable introspection (host builder, src/wavetable.rs:82-123) */

@@ -116,6 +116,7 @@ class OracleBackend:
     def b_rez(self, bp, cutoff, q, nin): return self.L.fo_rez(bp, cutoff, q, nin)
     def b_chaos(self, kind): return self.L.fo_chaos(kind)
     def b_declick(self, d): return self.L.fo_declick(d)
+    def b_netnode(self, net): return net.lower(self)
     def b_var(self, value): return self.L.fo_var(value)
     def b_dsf(self, n, spacing, rough): return self.L.fo_dsf(n, spacing, rough)
     def b_mls(self, bits): return self.L.fo_mls(bits)

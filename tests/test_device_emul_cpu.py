@@ -1,0 +1,123 @@
+"""CPU-only check of the DEVICE node templates: tests/cpp/device_emul.cpp compiles csrc/dsp/nodes.cuh for the host and runs one
+voice of a graph's fused program through bank_kernel's block structure; the output must equal the oracle's bit for bit.
+This is how device-side logic (here: the Dag form of nested Nets, and a sample of ordinary graphs) is exercised without a GPU.
+The GPU tests remain the parity tests proper; nothing here is part of the product."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from fundsp_b200 import capi
+from fundsp_b200.net import Net
+from fundsp_b200.prelude import *  # noqa: F401,F403
+from oracle import OracleUnit, lib as olib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SR = 44100.0   # the construction-time default rate (src/lib.rs:42): node handles are lowered as constructed
+
+
+def emulate(g, n, x=None, tmp=None):
+    h = capi.NodeHandle(g)
+    sig = h.signature()
+    P, S, U = h.lowering()
+    nin = h.inputs()
+    exe = os.path.join(tmp, "emul")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-w", f"-DGRAPH={sig}", os.path.join(ROOT, "tests", "cpp", "device_emul.cpp"), "-o", exe])
+    blob = os.path.join(tmp, "in.bin"); outp = os.path.join(tmp, "out.bin")
+    with open(blob, "wb") as f:
+        f.write(struct.pack("<5I", len(P), len(S), len(U), nin, n))
+        f.write(struct.pack("<d", SR))
+        f.write(P.tobytes()); f.write(S.tobytes()); f.write(U.tobytes())
+        if nin:
+            f.write(np.ascontiguousarray(x, np.float32).tobytes())
+        kinds = [k for k in range(6) if f"WaveSynth<{k}," in sig]
+        f.write(struct.pack("<I", len(kinds)))
+        for k in kinds:
+            f.write(_table_blob(k))
+    r = subprocess.run([exe, blob, outp], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    return np.fromfile(outp, np.float32).reshape(h.outputs(), n), sig
+
+
+def _table_blob(kind):
+    """The wavetable set of one waveform in the layout the kernels read (csrc/host/wavetable.cpp device_wavetable): every table
+    stored as [t[len-1]] t[0..len) [t[0] t[1]], padded to a multiple of 4 floats; `off` points at t[0]."""
+    import ctypes as C
+    L = capi.lib()
+    n = L.fdsp_wavetable_count(kind)
+    pitch, off, length, data = [], [], [], []
+    for i in range(n):
+        p, ln = C.c_float(0), C.c_int(0)
+        L.fdsp_wavetable_info(kind, i, C.byref(p), C.byref(ln))
+        t = np.ctypeslib.as_array(L.fdsp_wavetable_data(kind, i), shape=(ln.value,)).astype(np.float32)
+        pitch.append(p.value); length.append(ln.value)
+        data.append(t[-1:]); off.append(__import__("builtins").sum(len(d) for d in data)); data += [t, t[:1], t[1 % ln.value: 1 % ln.value + 1]]
+    flat = np.concatenate(data).astype(np.float32)
+    flat = np.concatenate([flat, np.zeros((-len(flat)) % 4, np.float32)])
+    return (struct.pack("<3I", kind, n, len(flat)) + np.float32(pitch).tobytes() + np.int32(off).tobytes() + np.int32(length).tobytes() + flat.tobytes())
+
+
+def oracle(g, n, x=None):
+    olib().fo_set_denormal_emulation(0)
+    u = OracleUnit(g)
+    u.set_sample_rate(SR)
+    return u.process_many(n, x)
+
+
+def diamond_net():
+    net = Net(1, 2)
+    a = net.push(lowpass_hz(800.0, 1.0)); b = net.push(highpass_hz(300.0, 2.0)); c = net.push(pass_() + pass_())
+    net.connect_input(0, a, 0); net.connect_input(0, b, 0); net.connect(a, 0, c, 0); net.connect(b, 0, c, 1)
+    net.connect_output(c, 0, 0); net.connect_output(b, 0, 1)
+    return net
+
+
+def _chain_net():
+    net = Net(0, 2)
+    net.chain(noise().seed(11) | noise().seed(12)); net.chain(moog_hz(1500.0, 0.5) | moog_hz(1000.0, 0.6)); net.chain(lowpole_hz(1000.0) | lowpole_hz(500.0))
+    return net
+
+
+def _routing_net():
+    net = Net(2, 3)
+    v = net.push(mul(2.0))
+    net.connect_input(1, v, 0)
+    net.pass_through(0, 2); net.connect_output(v, 0, 0)      # output 1 stays unconnected (zero)
+    return net
+
+
+CASES = {
+    "plain_pipe": lambda: noise().seed(1) >> lowpass_hz(900.0, 1.5) >> shape(Tanh(1.2)) >> pan(0.2),
+    "dag_diamond": lambda: noise().seed(3) >> diamond_net().node(),
+    "dag_operators": lambda: ((Net.wrap(sine_hz(110.0)) | Net.wrap(noise().seed(5))) >> Net.wrap(lowpass_hz(500.0, 1.0) | pass_())).node() >> join(2),
+    "dag_chain_with_moog": lambda: _chain_net().node(),
+    "dag_in_feedback": lambda: noise().seed(9) >> feedback((Net.wrap(delay(0.001) * 0.5) >> Net.wrap(lowpole_hz(2000.0))).node()),
+    "dag_pass_through_and_zero": lambda: (noise().seed(2) | noise().seed(4)) >> _routing_net().node(),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_device_templates_on_host_match_oracle(name, tmp_path):
+    n = 64 * 3 + 61                         # three full blocks + a block with a 5-sample tick-path tail
+    g = CASES[name]()
+    want = oracle(CASES[name](), n)
+    got, sig = emulate(g, n, None, str(tmp_path))
+    assert ("Dag<" in sig) == name.startswith("dag"), sig
+    assert got.shape == want.shape and np.abs(want).max() > 1e-3
+    assert np.array_equal(got, want), (name, int((got != want).sum()), float(np.abs(got - want).max()))
+
+
+# ---- the whole JIT case list of the GPU suite, one voice each, on the host emulation (the GPU run checks 40 voices per case)
+import test_gpu_jit as _jit  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(_jit.CASES))
+def test_jit_case_on_host_emulation(name, tmp_path):
+    n = 64 * 2 + 61
+    mk = _jit.CASES[name]
+    want = oracle(mk(3), n)
+    got, _ = emulate(mk(3), n, None, str(tmp_path))
+    assert got.shape == want.shape
+    assert np.array_equal(got, want), (name, int((got != want).sum()), float(np.abs(got - want).max()))

@@ -16,6 +16,20 @@ def fv(i, k=0):  # deterministic per-voice variation
     return ((i * 37 + k * 11) % 29) / 29.0
 
 
+def _diamond(i):
+    from fundsp_b200.net import Net
+    net = Net(1, 2)
+    a = net.push(lowpass_hz(600.0 + 20.0 * i, 1.0)); b = net.push(highpass_hz(300.0, 2.0)); c = net.push(pass_() + pass_())
+    net.connect_input(0, a, 0); net.connect_input(0, b, 0); net.connect(a, 0, c, 0); net.connect(b, 0, c, 1)
+    net.connect_output(c, 0, 0); net.connect_output(b, 0, 1)
+    return net
+
+
+def _net_ops(i):
+    from fundsp_b200.net import Net
+    return (Net.wrap(sine_hz(110.0 + i)) | Net.wrap(noise().seed(i))) >> Net.wrap(lowpass_hz(500.0 + 10.0 * i, 1.0) | pass_())
+
+
 CASES = {
     "svf_var_lowpass_pan": lambda i: (noise().seed(i) | dc((300.0 + 4000.0 * fv(i), 0.5 + 4.0 * fv(i, 1)))) >> lowpass() >> pan(2.0 * fv(i, 2) - 1.0),
     "svf_var_bell": lambda i: (noise().seed(i) | dc((300.0 + 4000.0 * fv(i), 0.7, 0.5 + 2.0 * fv(i, 1)))) >> bell(),
@@ -61,6 +75,9 @@ CASES = {
     "declick": lambda i: noise().seed(i) >> declick_s(0.001 + 0.0005 * (i % 20)) | saw_hz(100.0 + i) >> declick(),
     "declick_in_feedback": lambda i: noise().seed(i) >> feedback(delay(0.001) * 0.5 >> declick_s(0.003 + 0.0001 * i)),
     "lorenz_rossler": lambda i: dc(100.0 + 20.0 * i) >> lorenz() | (sine_hz(0.5) * 50.0 + 200.0 + i) >> rossler(),
+    "dag_diamond_net": lambda i: noise().seed(i) >> _diamond(i).node(),
+    "dag_net_operators": lambda i: _net_ops(i).node() >> join(2),
+    "dag_net_in_feedback": lambda i: noise().seed(i) >> feedback((__import__("fundsp_b200.net", fromlist=["Net"]).Net.wrap(delay(0.001) * 0.5) >> __import__("fundsp_b200.net", fromlist=["Net"]).Net.wrap(lowpole_hz(1500.0 + 10.0 * i))).node()),
     "product_fm_feedback": lambda i: (sine_hz(200.0 + i) * sine_hz(3.0 + 0.1 * i)) >> feedback(tick() * 0.25 >> lowpass_hz(2000.0, 0.7)),
 }
 GATED = {
