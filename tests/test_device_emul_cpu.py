@@ -121,3 +121,30 @@ def test_jit_case_on_host_emulation(name, tmp_path):
     got, _ = emulate(mk(3), n, None, str(tmp_path))
     assert got.shape == want.shape
     assert np.array_equal(got, want), (name, int((got != want).sum()), float(np.abs(got - want).max()))
+
+
+# ---- the BASELINE configuration voices (AOT graph classes), incl. the gate-driven subtractive chain and the full voice with the
+# 32-line reverb in its generic thread-per-voice form
+from fundsp_b200 import workloads as _wl  # noqa: E402
+
+WORKLOAD_VOICES = {
+    "fm": lambda: _wl.fm_voice(5), "noise_svf": lambda: _wl.noise_svf_voice(5), "saw_svf": lambda: _wl.saw_svf_voice(5),
+    "biquad_bank": lambda: _wl.biquad_bank_unit(1), "net_a": lambda: _wl.net_voice(0), "net_b": lambda: _wl.net_voice(1),
+    "net_c": lambda: _wl.net_voice(2), "net_d": lambda: _wl.net_voice(3),
+    "subtractive_dry": lambda: _wl.subtractive_dry_voice(5), "subtractive": lambda: _wl.subtractive_voice(5),
+}
+
+
+@pytest.mark.parametrize("name", sorted(WORKLOAD_VOICES))
+def test_workload_voice_on_host_emulation(name, tmp_path):
+    n = 64 * 40 + 61 if name.startswith("subtractive") else 64 * 4 + 61
+    mk = WORKLOAD_VOICES[name]
+    nin = capi.NodeHandle(mk()).inputs()
+    x = None
+    if nin:
+        x = np.zeros((nin, n), np.float32)
+        x[0, 100:1500] = 1.0                     # gate: arms on the low -> high edge, releases inside the render
+    want = oracle(mk(), n, x)
+    got, _ = emulate(mk(), n, x, str(tmp_path))
+    assert np.abs(want).max() > 1e-3
+    assert np.array_equal(got, want), (name, int((got != want).sum()), float(np.abs(got - want).max()))
