@@ -73,6 +73,9 @@ API fdsp_node* fdsp_morph(float cutoff, float q) { return wrap(mk_morph(cutoff, 
 API fdsp_node* fdsp_rez(float bandpass, float cutoff, float q, int inputs) { return wrap(mk_rez(bandpass, cutoff, q, inputs), "rez"); }
 API fdsp_node* fdsp_chaos(int kind) { return wrap(mk_chaos(kind), "chaos"); }
 API fdsp_node* fdsp_declick(float duration) { return wrap(mk_declick(duration), "declick"); }
+API fdsp_node* fdsp_nl_biquad(int fb, int mode, int shape, float p0, float p1, int inputs, float center, float q, float gain) {
+  return wrap(mk_nl_biquad(fb, mode, shape, p0, p1, inputs, center, q, gain), "nl_biquad");
+}
 API fdsp_node* fdsp_var(float value) { return wrap(mk_var(value), "var"); }
 API fdsp_node* fdsp_dsf(int inputs, float spacing, float roughness) { return wrap(mk_dsf(inputs, spacing, roughness), "dsf"); }
 API fdsp_node* fdsp_mls(int bits) { return wrap(mk_mls(bits), "mls"); }

@@ -1013,6 +1013,53 @@ template <int ASYM> struct Follower {
 // KIND 0 Clip(h), 1 ClipTo(lo, hi), 2 Tanh(h), 3 Softsign(h), 4 Crush(levels), 5 SoftCrush(levels); the block path follows
 // Shape::simd (round-to-even, F32x::floor, |x|*h), tail and tick follow Shape::shape.
 FDSP_DEV float smooth9f(float x) { const float x2 = x * x; return ((((70.0f * x - 315.0f) * x + 540.0f) * x - 420.0f) * x + 126.0f) * x2 * x2 * x; }
+template <int KIND> FDSP_DEV float shape_tick(float p0, float p1, float x) {   // Shape::shape (src/shape.rs), per shape kind
+  if (KIND == 0) return fminf(fmaxf(x * p0, -1.0f), 1.0f);
+  if (KIND == 1) return fminf(fmaxf(x, p0), p1);
+  if (KIND == 2) return m::tanhf_(x * p0);
+  if (KIND == 3) return (x * p0) / (1.0f + fabsf(x * p0));
+  if (KIND == 4) return roundf(x * p0) / p0;
+  const float v = x * p0, fl = floorf(v);
+  return (fl + smooth9f(v - fl)) / p0;
+}
+// Nonlinear biquads (src/biquad.rs:494-920): transposed direct form II with a waveshaper in the loop.
+//   FB = 1: FbBiquad (ID 88) / FixedFbBiquad (ID 90): feedback is shape(y0);  FB = 0: DirtyBiquad (89) / FixedDirtyBiquad (91):
+//   both state updates are shaped. MODE 0 resonator, 1 lowpass, 2 highpass, 3 bell; SHAPE as in Shaper; NIN 1 = fixed coefficients,
+//   3 / 4 = audio-rate (center, q[, gain]) with the reference's change test squared(dc) + squared(dq) [+ squared(dg)] != 0.
+template <int FB, int MODE, int SHAPE, int NIN> struct NlBiquad {
+  FDSP_NODE(NIN, 1, 2 + (NIN == 1 ? 5 : 0), 2 + (NIN > 1 ? 8 : 0), 0);
+  struct R { float p0, p1; BqCoefs k; float center, q, gain, s1, s2; };
+  static FDSP_DEV void load(R& r, Loader& l) {
+    r.p0 = l.Pf(); r.p1 = l.Pf();
+    if (NIN == 1) { r.k.a1 = l.Pf(); r.k.a2 = l.Pf(); r.k.b0 = l.Pf(); r.k.b1 = l.Pf(); r.k.b2 = l.Pf(); r.center = r.q = r.gain = 0.0f; }
+    else { r.center = l.Sf(); r.q = l.Sf(); r.gain = l.Sf(); r.k.a1 = l.Sf(); r.k.a2 = l.Sf(); r.k.b0 = l.Sf(); r.k.b1 = l.Sf(); r.k.b2 = l.Sf(); }
+    r.s1 = l.Sf(); r.s2 = l.Sf();
+  }
+  static FDSP_DEV void save(const R& r, Saver& s) {
+    if (NIN > 1) { s.Sf(r.center); s.Sf(r.q); s.Sf(r.gain); s.Sf(r.k.a1); s.Sf(r.k.a2); s.Sf(r.k.b0); s.Sf(r.k.b1); s.Sf(r.k.b2); }
+    s.Sf(r.s1); s.Sf(r.s2);
+  }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<NIN>& in, Fr<1>& o) {
+    if (NIN > 1) {
+      const float ce = in.v[NIN > 1 ? 1 : 0], qq = in.v[NIN > 2 ? 2 : 0], gg = NIN > 3 ? in.v[NIN > 3 ? 3 : 0] : r.gain;
+      const float dc = ce - r.center, dq = qq - r.q, dg = gg - r.gain;
+      const float test = NIN > 3 ? dc * dc + dq * dq + dg * dg : dc * dc + dq * dq;
+      if (test != 0.0f) { r.center = ce; r.q = qq; r.gain = gg; r.k = bq_mode(MODE, c.sr, ce, qq, gg); }
+    }
+    const float x0 = in.v[0];
+    const float y0 = r.k.b0 * x0 + r.s1;
+    if (FB) {
+      const float fb = shape_tick<SHAPE>(r.p0, r.p1, y0);
+      r.s1 = r.s2 + r.k.b1 * x0 - fb * r.k.a1;
+      r.s2 = r.k.b2 * x0 - fb * r.k.a2;
+    } else {
+      r.s1 = shape_tick<SHAPE>(r.p0, r.p1, r.s2 + r.k.b1 * x0 - y0 * r.k.a1);
+      r.s2 = shape_tick<SHAPE>(r.p0, r.p1, r.k.b2 * x0 - y0 * r.k.a2);
+    }
+    o.v[0] = y0;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
 template <int KIND> struct Shaper {
   FDSP_NODE(1, 1, 2, 0, 0);
   struct R { float p0, p1; };
@@ -1405,6 +1452,7 @@ template <int K> struct Cost<Chaos<K>> { static constexpr int value = 32; };
 template <> struct Cost<Morph> { static constexpr int value = 64; };
 template <int N> struct Cost<Rez<N>> { static constexpr int value = N > 1 ? 180 : 120; };
 template <int A> struct Cost<Follower<A>> { static constexpr int value = 16; };
+template <int FB, int M, int S, int N> struct Cost<NlBiquad<FB, M, S, N>> { static constexpr int value = (S == 2 ? 120 : 30) * (FB ? 1 : 2) + (N > 1 ? 60 : 0); };
 template <int K> struct Cost<Shaper<K>> { static constexpr int value = K == 2 ? 100 : 12; };
 template <> struct Cost<Convolver> { static constexpr int value = 48; };
 template <class X> struct WaveKind<FeedbackUnit<X>> : WaveKind<X> {};

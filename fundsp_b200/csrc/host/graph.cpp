@@ -486,6 +486,31 @@ struct ShaperN : HNode {  // src/shape.rs:205-249
   void lower(Lowering& l) const override { l.p(p0); l.p(p1); }
   HCLONE(ShaperN)
 };
+struct NlBiquadN : HNode {  // src/biquad.rs:494-920
+  int fb, mode, shape, nin; float p0, p1, sr = (float)DEFAULT_SR, center = 440.0f, q = 1.0f, gain = 1.0f; BqCoefs c;
+  NlBiquadN(int fb_, int mode_, int shape_, float p0_, float p1_, int nin_, float ce, float qq, float gg) : fb(fb_), mode(mode_), shape(shape_), nin(nin_), p0(p0_), p1(p1_) {
+    update();
+    if (nin == 1) { center = ce; q = qq; gain = gg; update(); }
+  }
+  void update() { c = fdsp::bq_mode(mode, sr, center, q, gain); }
+  int inputs() const override { return nin; } int outputs() const override { return 1; }
+  uint64_t id() const override { return fb ? (nin == 1 ? 90 : 88) : (nin == 1 ? 91 : 89); }
+  void set_sample_rate(double s) override { sr = (float)s; update(); }
+  void set(const Setting& s) override {
+    if (nin != 1) return;
+    if (s.kind == P_CENTER) { center = s.v[0]; update(); }
+    else if (s.kind == P_CENTER_Q) { center = s.v[0]; q = s.v[1]; update(); }
+    else if (s.kind == P_CENTER_Q_GAIN) { center = s.v[0]; q = s.v[1]; gain = s.v[2]; update(); }
+  }
+  void sig(std::string& o) const override { o += "NlBiquad<" + I(fb) + "," + I(mode) + "," + I(shape) + "," + I(nin) + ">"; }
+  void lower(Lowering& l) const override {
+    l.p(p0); l.p(p1);
+    if (nin == 1) { l.p(c.a1); l.p(c.a2); l.p(c.b0); l.p(c.b1); l.p(c.b2); }
+    else { l.s(center); l.s(q); l.s(gain); l.s(c.a1); l.s(c.a2); l.s(c.b0); l.s(c.b1); l.s(c.b2); }
+    l.s(0.0f); l.s(0.0f);
+  }
+  HCLONE(NlBiquadN)
+};
 struct ConvolverN : HNode {  // src/convolve.rs:9-59: the impulse response is class-uniform data (voices with the same response share a class)
   std::vector<float> h;
   explicit ConvolverN(std::vector<float> r) : h(std::move(r)) { if (h.empty()) h.push_back(0.0f); }
@@ -818,6 +843,10 @@ HNode* mk_reverb3(double time, double diffusion, HNode* filter) {
   return new ReverbN(time, diffusion, filter);
 }
 HNode* mk_var(float value) { return new VarN(value); }
+HNode* mk_nl_biquad(int fb, int mode, int shape, float p0, float p1, int inputs, float center, float q, float gain) {
+  if (mode < 0 || mode > 3 || shape < 0 || shape > 5 || !(inputs == 1 || inputs == (mode == 3 ? 4 : 3))) return nullptr;
+  return new NlBiquadN(fb ? 1 : 0, mode, shape, p0, p1, inputs, center, q, gain);
+}
 HNode* mk_declick(float duration) { return new DeclickN(duration); }
 HNode* mk_chaos(int kind) { return (kind < 0 || kind > 1) ? nullptr : new ChaosN(kind); }
 HNode* mk_morph(float cutoff, float q) { return new MorphN(cutoff, q); }

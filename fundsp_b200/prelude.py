@@ -743,3 +743,27 @@ def declick():
 
 def declick_s(t):
     return An("declick", (f32(t),), (), 1, 1)
+
+
+# ---- src/prelude.rs:2900-3110 nonlinear biquads: d* = DirtyBiquad (shaped state), f* = FbBiquad (shaped feedback)
+def _nlb(fb, mode, shape_mode, nin, center=440.0, q=1.0, gain=1.0):
+    _, kind, p0, p1 = shape_mode
+    return An("nl_biquad", (fb, mode, kind, p0, p1, nin, f32(center), f32(q), f32(gain)), (), nin, 1)
+
+
+def dbell(s): return _nlb(0, 3, s, 4)
+def dbell_hz(s, center, q, gain): return _nlb(0, 3, s, 1, center, q, gain)
+def fbell(s): return _nlb(1, 3, s, 4)
+def fbell_hz(s, center, q, gain): return _nlb(1, 3, s, 1, center, q, gain)
+def dhighpass(s): return _nlb(0, 2, s, 3)
+def dhighpass_hz(s, cutoff, q): return _nlb(0, 2, s, 1, cutoff, q)
+def fhighpass(s): return _nlb(1, 2, s, 3)
+def fhighpass_hz(s, cutoff, q): return _nlb(1, 2, s, 1, cutoff, q)
+def dlowpass(s): return _nlb(0, 1, s, 3)
+def dlowpass_hz(s, cutoff, q): return _nlb(0, 1, s, 1, cutoff, q)
+def flowpass(s): return _nlb(1, 1, s, 3)
+def flowpass_hz(s, cutoff, q): return _nlb(1, 1, s, 1, cutoff, q)
+def dresonator(s): return _nlb(0, 0, s, 3)
+def dresonator_hz(s, center, q): return _nlb(0, 0, s, 1, center, q)
+def fresonator(s): return _nlb(1, 0, s, 3)
+def fresonator_hz(s, center, q): return _nlb(1, 0, s, 1, center, q)

@@ -1173,6 +1173,44 @@ struct Shaper : Node {
   }
   FO_CLONE(Shaper)
 };
+// ---- src/biquad.rs:494-920 nonlinear biquads (F = f32): FbBiquad (88) / FixedFbBiquad (90), DirtyBiquad (89) / FixedDirtyBiquad (91)
+// mode 0 resonator, 1 lowpass, 2 highpass, 3 bell; the waveshaper is one of the Shaper kinds, always through Shape::shape.
+struct NlBiquad : Node {
+  bool fb; int mode, nin; Shaper shaper; BiquadCoefs c; float sr = (float)DEFAULT_SR, center = 440.0f, q = 1.0f, gain = 1.0f, s1 = 0, s2 = 0;
+  NlBiquad(bool fb_, int mode_, int shape_kind, float p0, float p1, int nin_, float center_, float q_, float gain_)
+      : fb(fb_), mode(mode_), nin(nin_), shaper(shape_kind, p0, p1) {
+    update();                                   // new(): default parameters at the default rate
+    if (nin == 1) { center = center_; q = q_; gain = gain_; update(); }   // dbell_hz etc.: set_center_q[_gain] after construction
+  }
+  void update() {
+    switch (mode) { case 0: c = biquad_resonator(sr, center, q); break; case 1: c = biquad_lowpass(sr, center, q); break;
+      case 2: c = biquad_highpass(sr, center, q); break; default: c = biquad_bell(sr, center, q, gain); }
+  }
+  int inputs() const override { return nin; } int outputs() const override { return 1; }
+  uint64_t id() const override { return fb ? (nin == 1 ? 90 : 88) : (nin == 1 ? 91 : 89); }
+  void reset() override { s1 = s2 = 0; }
+  void set_sample_rate(double s) override { sr = (float)s; update(); }
+  void tick(const float* in, float* out) override {
+    if (nin == 3) {
+      const float dc = in[1] - center, dq = in[2] - q;
+      if (dc * dc + dq * dq != 0.0f) { center = in[1]; q = in[2]; update(); }
+    } else if (nin == 4) {
+      const float dc = in[1] - center, dq = in[2] - q, dg = in[3] - gain;
+      if (dc * dc + dq * dq + dg * dg != 0.0f) { center = in[1]; q = in[2]; gain = in[3]; update(); }
+    }
+    const float x0 = in[0], y0 = c.b0 * x0 + s1;
+    if (fb) { const float f = shaper.shape(y0); s1 = s2 + c.b1 * x0 - f * c.a1; s2 = c.b2 * x0 - f * c.a2; }
+    else { s1 = shaper.shape(s2 + c.b1 * x0 - y0 * c.a1); s2 = shaper.shape(c.b2 * x0 - y0 * c.a2); }
+    out[0] = y0;
+  }
+  void set(const Setting& s) override {
+    if (nin != 1) return;
+    if (s.kind == P_CENTER) { center = s.v[0]; update(); }
+    else if (s.kind == P_CENTER_Q) { center = s.v[0]; q = s.v[1]; update(); }
+    else if (s.kind == P_CENTER_Q_GAIN) { center = s.v[0]; q = s.v[1]; gain = s.v[2]; update(); }
+  }
+  FO_CLONE(NlBiquad)
+};
 // ---- src/convolve.rs:9-59 Convolver (ID 100): y = x * h. The reference delegates to the un-vendored crate fft-convolver 0.3.0
 // (uniformly partitioned FFT overlap-add, block 64); what is restated here is the quantity that algorithm computes — the
 // linear convolution — accumulated in f64 and rounded once, which the FFT form matches to ~1e-6 of the signal scale.

@@ -90,6 +90,9 @@ API Node* fo_morph(float cutoff, float q) { return new Morph(cutoff, q); }
 API Node* fo_rez(float bandpass, float cutoff, float q, int inputs) { return new Rez(bandpass, cutoff, q, inputs); }
 API Node* fo_chaos(int kind) { return new Chaos(kind); }   // 0 rossler, 1 lorenz
 API Node* fo_declick(float duration) { return new Declick(duration); }
+API Node* fo_nl_biquad(int fb, int mode, int shape_kind, float p0, float p1, int inputs, float center, float q, float gain) {
+  return new NlBiquad(fb != 0, mode, shape_kind, p0, p1, inputs, center, q, gain);
+}
 API Node* fo_var(float value) { return new Var(value); }
 API Node* fo_dsf(int inputs, float harmonic_spacing, float roughness) { return new Dsf(inputs, harmonic_spacing, roughness); }
 API Node* fo_mls(int bits) { return new Mls((uint32_t)bits); }

@@ -49,6 +49,7 @@ GRAPHS = [
     lambda: noise() >> follow(0.002) | noise() >> afollow(0.001, 0.01),
     lambda: (noise() | noise()) >> ((pass_() | dc((2000.0, 5.0, 0.8))) >> morph() | morph_hz(440.0, 1.0, 0.0)) | (noise() | noise()) >> (lowrez_hz(440.0, 0.5) | bandrez_hz(440.0, 0.5)) | (noise() | dc(900.0)) >> lowrez_q(0.3),
     lambda: noise() >> declick() >> declick_s(0.002),
+    lambda: noise() >> dbell_hz(Tanh(1.0), 1000.0, 10.0, 2.0) >> flowpass_hz(Clip(1.0), 2000.0, 2.0) | (noise() | dc((800.0, 3.0))) >> dresonator(Softsign(0.5)),
     lambda: dc(220.0) >> lorenz() | dc(110.0) >> rossler() | dc(330.0) >> lorenz(),
     lambda: dc(220.0) >> dsf_saw_r(0.7) | (dc(110.0) | dc(0.4)) >> dsf_square() | dc(440.0) >> dsf_square_r(0.3).phase(0.25),
     lambda: noise() >> feedback2(delay(0.002) * 0.5, lowpass_hz(2000.0, 1.0)) | (noise() | dc(800.0)) >> butterpass() | (noise() | dc((900.0, 8.0))) >> resonator(),

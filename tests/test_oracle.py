@@ -428,6 +428,26 @@ def test_follow_filters():  # test_flow.rs:96-97,102 and src/follow.rs
     check_wave(noise() >> follow(0.002) | noise().seed(2) >> afollow(0.001, 0.01))
 
 
+def test_nonlinear_biquads():  # tests/test_basic.rs:218-233 (the lines whose shapes do not need atan), src/biquad.rs:494-920
+    import ctypes
+    L.fo_set_denormal_emulation(0)
+    check_wave(noise() >> dbell_hz(Tanh(1.0), 1000.0, 10.0, 2.0) | noise().seed(2) >> dhighpass_hz(Softsign(1.0), 2000.0, 2.0))     # :218-221
+    check_wave(noise() >> dresonator_hz(Tanh(0.5), 1000.0, 10.0) | noise().seed(2) >> dlowpass_hz(Softsign(0.5), 2000.0, 2.0))     # :222-225
+    check_wave(noise() >> fbell_hz(Tanh(1.0), 500.0, 50.0, 0.5) | noise().seed(2) >> flowpass_hz(Clip(1.0), 2000.0, 2.0))           # :226-229 (Tanh for Atan)
+    check_wave(noise() >> fresonator_hz(Tanh(0.5), 500.0, 50.0) | noise().seed(2) >> fhighpass_hz(Softsign(0.2), 2000.0, 2.0))     # :230-233
+    check_wave((noise() | sine_hz(1.0) * 500.0 + 1500.0 | dc(2.0)) >> dlowpass(Tanh(1.0)) | (noise().seed(3) | dc((800.0, 3.0, 2.0))) >> fbell(Softsign(1.0)))
+    L.fo_restore_denormals()
+    # with a clipper that never engages the structure is a plain transposed-direct-form-II biquad: pins coefficients + recurrence
+    for mode, mk_d, mk_f, args in ((2, dlowpass_hz, flowpass_hz, (2000.0, 2.0)), (3, dhighpass_hz, fhighpass_hz, (3000.0, 1.0)), (1, dresonator_hz, fresonator_hz, (1200.0, 5.0))):
+        c = np.zeros(5, np.float32)
+        L.fo_biquad_coefs(mode, SR, args[0], args[1], 1.0, c.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+        for mk in (mk_d, mk_f):
+            check_response(OracleUnit(mk(ClipTo(-100.0, 100.0), *args)), lambda f, c=c.copy(): biquad_response(c, SR, f))
+    c = np.zeros(5, np.float32)
+    L.fo_biquad_coefs(4, SR, 1000.0, 2.0, 3.0, c.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+    check_response(OracleUnit(dbell_hz(ClipTo(-100.0, 100.0), 1000.0, 2.0, 3.0)), lambda f: biquad_response(c, SR, f))
+
+
 def test_shapers():  # src/shape.rs: Shape::shape (tick) and Shape::simd (block path)
     x = np.float32([[-2.0, -0.75, -0.26, 0.0, 0.1, 0.26, 0.5, 0.75, 1.5, 3.0]])
     f = lambda g: OracleUnit(g).filter(SR, x)[0]     # 10 samples: one SIMD group of 8 + 2 tail samples through `shape`
