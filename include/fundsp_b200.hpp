@@ -157,6 +157,31 @@ inline An rossler() { return An(fdsp_chaos(0)); }
 inline An lorenz() { return An(fdsp_chaos(1)); }
 inline An declick() { return An(fdsp_declick(0.010f)); }
 inline An declick_s(float t) { return An(fdsp_declick(t)); }
+/* nonlinear biquads (src/prelude.rs:2900-3110): d* = DirtyBiquad (shaped state), f* = FbBiquad (shaped feedback); the shape is any of the
+   Shaper structs above. The plain forms take (audio, center, q[, gain]) at audio rate. */
+struct ShapeMode { int kind; float p0, p1; };
+inline ShapeMode shape_mode(Clip s) { return {0, s.h, 0.0f}; }
+inline ShapeMode shape_mode(ClipTo s) { return {1, s.lo, s.hi}; }
+inline ShapeMode shape_mode(Tanh s) { return {2, s.h, 0.0f}; }
+inline ShapeMode shape_mode(Softsign s) { return {3, s.h, 0.0f}; }
+inline ShapeMode shape_mode(Crush s) { return {4, s.levels, 0.0f}; }
+inline ShapeMode shape_mode(SoftCrush s) { return {5, s.levels, 0.0f}; }
+inline An nl_biquad(int fb, int mode, ShapeMode m, int inputs, float center = 440.0f, float q = 1.0f, float gain = 1.0f) {
+    return An(fdsp_nl_biquad(fb, mode, m.kind, m.p0, m.p1, inputs, center, q, gain));
+}
+#define FDSP_NLB(NAME, FB, MODE, NIN)                                                                                   \
+    template <class S> inline An NAME(S s) { return nl_biquad(FB, MODE, shape_mode(s), NIN); }
+FDSP_NLB(dresonator, 0, 0, 3) FDSP_NLB(dlowpass, 0, 1, 3) FDSP_NLB(dhighpass, 0, 2, 3) FDSP_NLB(dbell, 0, 3, 4)
+FDSP_NLB(fresonator, 1, 0, 3) FDSP_NLB(flowpass, 1, 1, 3) FDSP_NLB(fhighpass, 1, 2, 3) FDSP_NLB(fbell, 1, 3, 4)
+#undef FDSP_NLB
+template <class S> inline An dresonator_hz(S s, float c, float q) { return nl_biquad(0, 0, shape_mode(s), 1, c, q); }
+template <class S> inline An dlowpass_hz(S s, float c, float q) { return nl_biquad(0, 1, shape_mode(s), 1, c, q); }
+template <class S> inline An dhighpass_hz(S s, float c, float q) { return nl_biquad(0, 2, shape_mode(s), 1, c, q); }
+template <class S> inline An dbell_hz(S s, float c, float q, float g) { return nl_biquad(0, 3, shape_mode(s), 1, c, q, g); }
+template <class S> inline An fresonator_hz(S s, float c, float q) { return nl_biquad(1, 0, shape_mode(s), 1, c, q); }
+template <class S> inline An flowpass_hz(S s, float c, float q) { return nl_biquad(1, 1, shape_mode(s), 1, c, q); }
+template <class S> inline An fhighpass_hz(S s, float c, float q) { return nl_biquad(1, 2, shape_mode(s), 1, c, q); }
+template <class S> inline An fbell_hz(S s, float c, float q, float g) { return nl_biquad(1, 3, shape_mode(s), 1, c, q, g); }
 inline An var(float value) { return An(fdsp_var(value)); }
 inline An dsf_saw() { return An(fdsp_dsf(2, 1.0f, 0.5f)); }
 inline An dsf_saw_r(float roughness) { return An(fdsp_dsf(1, 1.0f, roughness)); }

@@ -30,6 +30,8 @@ int main() {
   An misc = pink() | brown() | (noise() >> convolve({1.0f, 0.5f, 0.25f})) | (dc(220.0f) >> lorenz()) | ((noise() | dc(800.0f, 1.0f, 0.5f)) >> morph())
             | (noise() >> follow(0.01f)) | (var(0.5f) * mls()) | ((noise() | dc(0.004f)) >> tap(0.001f, 0.01f));
   std::printf("misc %d %d\n", misc.inputs(), misc.outputs());
+  An nlb = (noise() >> dlowpass_hz(Tanh{1.0f}, 1200.0f, 2.0f)) | ((noise() | dc(900.0f, 1.5f, 2.0f)) >> fbell(Softsign{0.8f})) | (noise() >> fresonator_hz(Clip{1.0f}, 700.0f, 4.0f));
+  std::printf("nlb %d %d %s\n", nlb.inputs(), nlb.outputs(), nlb.signature().c_str());
   try {
     An bad = pass() >> (pass() | pass());
     std::printf("arity NOT detected\n");

@@ -205,6 +205,8 @@ def test_cpp_host_mirror_compiles_and_matches_python_mirror(tmp_path):
                             >> (pass_() & 0.3 * feedback_unit(0.02, 0.5 * lowpole_hz(3000.0))) >> pan(0.25)
                             >> (multipass(2) & 0.25 * reverb3_stereo(2.0, 0.5, lowpole_hz(8000.0))))
     assert f"synth 0 2 {synth.signature()}" in lines and "misc 0 8" in lines
+    nlb = capi.NodeHandle((noise() >> dlowpass_hz(Tanh(1.0), 1200.0, 2.0)) | ((noise() | dc((900.0, 1.5, 2.0))) >> fbell(Softsign(0.8))) | (noise() >> fresonator_hz(Clip(1.0), 700.0, 4.0)))
+    assert f"nlb 0 3 {nlb.signature()}" in lines
 
 
 # ---------------------------------------------------------------- the NVRTC translation unit compiles without a GPU
