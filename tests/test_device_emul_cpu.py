@@ -113,10 +113,13 @@ def test_device_templates_on_host_match_oracle(name, tmp_path):
 import test_gpu_jit as _jit  # noqa: E402
 
 
-@pytest.mark.parametrize("name", sorted(_jit.CASES))
+_ALL = {**_jit.CASES, **_jit.WIDER}
+
+
+@pytest.mark.parametrize("name", sorted(_ALL))
 def test_jit_case_on_host_emulation(name, tmp_path):
     n = 64 * 2 + 61
-    mk = _jit.CASES[name]
+    mk = _ALL[name]
     want = oracle(mk(3), n)
     got, _ = emulate(mk(3), n, None, str(tmp_path))
     assert got.shape == want.shape

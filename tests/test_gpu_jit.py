@@ -75,13 +75,17 @@ CASES = {
     "declick": lambda i: noise().seed(i) >> declick_s(0.001 + 0.0005 * (i % 20)) | saw_hz(100.0 + i) >> declick(),
     "declick_in_feedback": lambda i: noise().seed(i) >> feedback(delay(0.001) * 0.5 >> declick_s(0.003 + 0.0001 * i)),
     "lorenz_rossler": lambda i: dc(100.0 + 20.0 * i) >> lorenz() | (sine_hz(0.5) * 50.0 + 200.0 + i) >> rossler(),
+    "product_fm_feedback": lambda i: (sine_hz(200.0 + i) * sine_hz(3.0 + 0.1 * i)) >> feedback(tick() * 0.25 >> lowpass_hz(2000.0, 0.7)),
+}
+# Cases added after the last GPU run of the round they were written in: tests/test_gpu_wider.py runs them AFTER the parity tests,
+# so that `pytest -x` reaches the BASELINE configurations first. (tests/test_device_emul_cpu.py runs them on the host emulation.)
+WIDER = {
     "dag_diamond_net": lambda i: noise().seed(i) >> _diamond(i).node(),
     "dag_net_operators": lambda i: _net_ops(i).node() >> join(2),
     "dag_net_in_feedback": lambda i: noise().seed(i) >> feedback((__import__("fundsp_b200.net", fromlist=["Net"]).Net.wrap(delay(0.001) * 0.5) >> __import__("fundsp_b200.net", fromlist=["Net"]).Net.wrap(lowpole_hz(1500.0 + 10.0 * i))).node()),
     "dirty_biquads": lambda i: noise().seed(i) >> (dbell_hz(Tanh(1.0), 800.0 + 30.0 * i, 10.0, 2.0) & dhighpass_hz(Softsign(1.0), 2000.0, 2.0) & dresonator_hz(Tanh(0.5), 1000.0 + 10.0 * i, 10.0) & dlowpass_hz(Crush(64.0), 1500.0, 2.0)),
     "feedback_biquads": lambda i: noise().seed(i) >> (fbell_hz(Tanh(1.0), 500.0 + 20.0 * i, 50.0, 0.5) & flowpass_hz(Clip(1.0), 2000.0, 2.0) & fresonator_hz(SoftCrush(32.0), 700.0, 20.0) & fhighpass_hz(Softsign(0.2), 2000.0 + 10.0 * i, 2.0)),
     "nl_biquads_audio_rate": lambda i: (noise().seed(i) | (sine_hz(1.0) * 500.0 + 1500.0 + 10.0 * i) | dc(2.0)) >> dlowpass(Tanh(1.0)) | (noise().seed(i + 3) | dc((800.0, 3.0, 2.0 + 0.05 * i))) >> fbell(Softsign(1.0)),
-    "product_fm_feedback": lambda i: (sine_hz(200.0 + i) * sine_hz(3.0 + 0.1 * i)) >> feedback(tick() * 0.25 >> lowpass_hz(2000.0, 0.7)),
 }
 GATED = {
     "adsr_noise": lambda i: adsr_live(0.005 + 0.001 * (i % 5), 0.05, 0.5 + 0.01 * (i % 20), 0.1) * noise().seed(i) | ~zero() >> sine_hz(100.0 + i),
