@@ -73,6 +73,10 @@ API fdsp_node* fdsp_morph(float cutoff, float q) { return wrap(mk_morph(cutoff, 
 API fdsp_node* fdsp_rez(float bandpass, float cutoff, float q, int inputs) { return wrap(mk_rez(bandpass, cutoff, q, inputs), "rez"); }
 API fdsp_node* fdsp_chaos(int kind) { return wrap(mk_chaos(kind), "chaos"); }
 API fdsp_node* fdsp_declick(float duration) { return wrap(mk_declick(duration), "declick"); }
+API fdsp_node* fdsp_phase_synth(int kind) { return wrap(mk_phase_synth(kind), "phase_synth"); }
+API fdsp_node* fdsp_pulse(void) { return wrap(mk_pulse(), "pulse"); }
+API fdsp_node* fdsp_mixer(int inputs, int outputs, const float* matrix) { return wrap(mk_mixer(inputs, outputs, matrix), "mixer"); }
+API fdsp_node* fdsp_rotate(float angle, float gain) { return wrap(mk_rotate(angle, gain), "rotate"); }
 API fdsp_node* fdsp_nl_biquad(int fb, int mode, int shape, float p0, float p1, int inputs, float center, float q, float gain) {
   return wrap(mk_nl_biquad(fb, mode, shape, p0, p1, inputs, center, q, gain), "nl_biquad");
 }

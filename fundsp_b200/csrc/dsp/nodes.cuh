@@ -525,6 +525,54 @@ template <int KIND, int NOUT> struct WaveSynth {  // src/wavetable.rs:244-359, I
   static FDSP_DEV void end_simd(R& r) { r.phase = r.phase - floorf(r.phase); r.hint = r.ti; }
 };
 
+// PhaseSynth (src/wavetable.rs:361-433, ID 35): table lookup driven by a phase input; the band is chosen from the phase increment.
+// The reference has no block override: every sample takes the scalar `read` (:181-195) on both paths.
+template <int KIND> struct PhaseSynth {
+  typedef WaveSynth<KIND, 1> W;
+  FDSP_NODE(1, 1, 0, 3, 0);
+  struct R { typename W::R w; float prev; int ready; };
+  static FDSP_DEV void load(R& r, Loader& l) {
+    r.prev = l.Sf(); r.ready = (int)l.S(); r.w.hint = (int)l.S();
+    r.w.phase = 0.0f; r.w.ti = r.w.hint; r.w.w = 0.0f; r.w.o1 = r.w.o2 = 0; r.w.l1 = r.w.l2 = 32; r.w.fsel = __int_as_float(0x7fc00000); r.w.hsel = -1;
+  }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.prev); s.S((uint32_t)r.ready); s.S((uint32_t)r.w.hint); }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<1>& in, Fr<1>& o) {
+    const WaveTableDev& t = c.wt[KIND];
+    const float phase = in.v[0] - floorf(in.v[0]);
+    float delta = 0.5f;   // first sample: pessimistically Nyquist
+    if (r.ready) delta = fminf(fabsf(phase - r.prev), fminf(fabsf(phase - 1.0f - r.prev), fabsf(phase + 1.0f - r.prev)));
+    r.ready = 1;
+    W::select(r.w, t, r.w.hint, delta * c.sr);
+    r.w.hint = r.w.ti;
+    r.prev = phase;
+    o.v[0] = (1.0f - r.w.w) * W::at(c, t, r.w.o1, r.w.l1, phase) + r.w.w * W::at(c, t, r.w.o2, r.w.l2, phase);
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
+// Mixer<M, N> (src/pan.rs:95-160, ID 84): constant N x M matrix, row i = weights of output i; tick only (0.0 + x0*y0 + x1*y1 ...).
+template <int M, int N> struct Mixer {
+  FDSP_NODE(M, N, M * N, 0, 0);
+  struct R { float m[N][M]; };
+  static FDSP_DEV void load(R& r, Loader& l) {
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+      for (int j = 0; j < M; j++) r.m[i][j] = l.Pf();
+  }
+  static FDSP_DEV void save(const R&, Saver&) {}
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C&, const Fr<M>& in, Fr<N>& o) {
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      float v = 0.0f;
+#pragma unroll
+      for (int j = 0; j < M; j++) v += in.v[j] * r.m[i][j];
+      o.v[i] = v;
+    }
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
 // ---------------------------------------------------------------- filters
 struct FixedSvf {  // src/svf.rs:857-1031, ID 43 (coefficients computed on the host at set_sample_rate)
   FDSP_NODE(1, 1, 6, 2, 0);
@@ -1407,6 +1455,7 @@ template <int NIN, int NOUT, class... V, class OS> struct Dag<NIN, NOUT, VList<V
 // First wavetable kind used by a graph type (-1: none): decides whether the kernel stages tables in shared memory.
 template <class G> struct WaveKind { static constexpr int value = -1; };
 template <int K, int N> struct WaveKind<WaveSynth<K, N>> { static constexpr int value = K; };
+template <int K> struct WaveKind<PhaseSynth<K>> { static constexpr int value = K; };
 template <class X, class Y> struct Wk2 { static constexpr int value = WaveKind<X>::value >= 0 ? WaveKind<X>::value : WaveKind<Y>::value; };
 template <int K, class X, class Y> struct WaveKind<Binop<K, X, Y>> : Wk2<X, Y> {};
 template <class X, class Y> struct WaveKind<Pipe<X, Y>> : Wk2<X, Y> {};
@@ -1425,6 +1474,8 @@ template <int HAD, class X, class Y> struct WaveKind<Feedback2<HAD, X, Y>> : Wk2
 // thrash the instruction cache when only one warp runs per scheduler).
 template <class G> struct Cost { static constexpr int value = 8; };
 template <int K, int N> struct Cost<WaveSynth<K, N>> { static constexpr int value = 100; };
+template <int K> struct Cost<PhaseSynth<K>> { static constexpr int value = 110; };
+template <int M, int N> struct Cost<Mixer<M, N>> { static constexpr int value = 2 * M * N; };
 template <> struct Cost<Sine> { static constexpr int value = 40; };
 template <> struct Cost<Noise> { static constexpr int value = 16; };
 template <> struct Cost<FixedSvf> { static constexpr int value = 20; };

@@ -181,8 +181,8 @@ std::string Bank::lower_and_upload(bool upload_state) {
     memset(h, 0, sizeof(h));
     for (int kind = 0; kind < 6; kind++) {
       bool used = false;
-      const std::string tag = "WaveSynth<" + std::to_string(kind) + ",";
-      for (auto& c : classes) used = used || c.sig.find(tag) != std::string::npos;
+      const std::string tag = "WaveSynth<" + std::to_string(kind) + ",", tag2 = "PhaseSynth<" + std::to_string(kind) + ">";
+      for (auto& c : classes) used = used || c.sig.find(tag) != std::string::npos || c.sig.find(tag2) != std::string::npos;
       if (!used) continue;
       const WaveTableHost& t = device_wavetable(kind);
       h[kind].n = (int)t.pitch.size(); h[kind].total = (int)t.data.size();

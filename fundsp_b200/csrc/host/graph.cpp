@@ -107,6 +107,23 @@ struct WaveSynth : HNode {  // src/wavetable.rs:244-359
   HCLONE(WaveSynth)
 };
 
+struct PhaseSynthN : HNode {  // src/wavetable.rs:361-433
+  int kind; explicit PhaseSynthN(int k) : kind(k) {}
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 35; }
+  void sig(std::string& o) const override { o += "PhaseSynth<" + I(kind) + ">"; }
+  void lower(Lowering& l) const override { l.s(0.0f); l.su(0u); l.su(0u); }   // previous phase, phase_ready, table hint
+  HCLONE(PhaseSynthN)
+};
+struct MixerN : HNode {  // src/pan.rs:95-160
+  int m, n; std::vector<float> w;   // w[i * m + j]: weight of input j in output i
+  MixerN(int m_, int n_, std::vector<float> w_) : m(m_), n(n_), w(std::move(w_)) {}
+  int inputs() const override { return m; } int outputs() const override { return n; }
+  uint64_t id() const override { return 84; }
+  void sig(std::string& o) const override { o += "Mixer<" + I(m) + "," + I(n) + ">"; }
+  void lower(Lowering& l) const override { for (float x : w) l.p(x); }
+  HCLONE(MixerN)
+};
 
 // ---------------------------------------------------------------- phase oscillators, MLS, impulse, taps
 struct PhaseOsc : HNode {  // src/oscillator.rs:440-760
@@ -592,6 +609,25 @@ struct Binary : HNode {
   void lower(Lowering& l) const override { x->lower(l); y->lower(l); }
   HCLONE(Binary)
 };
+struct PulseWaveN : HNode {  // src/wavetable.rs:439-491: (saw with phase output | width) >> (saw | phase + width >> saw at that phase) >> difference
+  Kid pulse;
+  PulseWaveN() {
+    HNode* a = new Binary(Binary::STACK, 0, new WaveSynth(0, 2), mk_pass());
+    HNode* b = new Binary(Binary::STACK, 0, mk_pass(), new Binary(Binary::PIPE, 0, new Binary(Binary::BINOP, 0, mk_pass(), mk_pass()), new PhaseSynthN(0)));
+    pulse = Kid(new Binary(Binary::PIPE, 0, new Binary(Binary::PIPE, 0, a, b), new Binary(Binary::BINOP, 1, mk_pass(), mk_pass())));
+  }
+  int inputs() const override { return 2; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 44; }
+  void reset() override { pulse->reset(); }
+  void set_sample_rate(double s) override { pulse->set_sample_rate(s); }
+  void set(const Setting& s) override {   // pulse.left_mut().left_mut().left_mut().set(setting): straight to the phase-output saw
+    Setting t = s; t.address.insert(t.address.begin(), {Address{1, 0}, Address{1, 0}, Address{1, 0}}); pulse->set(t);
+  }
+  AttoHash ping(bool probe, AttoHash h) override { return pulse->ping(probe, h).hash(id()); }
+  void sig(std::string& o) const override { pulse->sig(o); }
+  void lower(Lowering& l) const override { pulse->lower(l); }
+  HCLONE(PulseWaveN)
+};
 struct Unary : HNode {
   enum K { UNOP = 4, THRU = 12, FEEDBACK = 11 } k; int kind; float scalar; Kid x;
   Unary(K k_, int kind_, float s, HNode* x_) : k(k_), kind(kind_), scalar(s), x(x_) { ctor_ping(); }
@@ -843,6 +879,17 @@ HNode* mk_reverb3(double time, double diffusion, HNode* filter) {
   return new ReverbN(time, diffusion, filter);
 }
 HNode* mk_var(float value) { return new VarN(value); }
+HNode* mk_phase_synth(int kind) { return (kind < 0 || kind > 5) ? nullptr : new PhaseSynthN(kind); }
+HNode* mk_pulse() { return new PulseWaveN(); }
+HNode* mk_mixer(int inputs, int outputs, const float* matrix) {
+  if (inputs < 1 || outputs < 1 || inputs * outputs > 64 || !matrix) return nullptr;
+  return new MixerN(inputs, outputs, std::vector<float>(matrix, matrix + inputs * outputs));
+}
+HNode* mk_rotate(float angle, float gain) {   // src/prelude.rs:2876-2884 (f32 cos / sin of libm)
+  const float c = m::cosf_(angle), s = m::sinf_(angle);
+  const float w[4] = {c * gain, -s * gain, s * gain, c * gain};
+  return mk_mixer(2, 2, w);
+}
 HNode* mk_nl_biquad(int fb, int mode, int shape, float p0, float p1, int inputs, float center, float q, float gain) {
   if (mode < 0 || mode > 3 || shape < 0 || shape > 5 || !(inputs == 1 || inputs == (mode == 3 ? 4 : 3))) return nullptr;
   return new NlBiquadN(fb ? 1 : 0, mode, shape, p0, p1, inputs, center, q, gain);

@@ -104,6 +104,10 @@ HNode* mk_phase_osc(int kind);                      // 0 ramp, 1 poly_saw, 2 pol
 HNode* mk_reverb3(double time, double diffusion, HNode* filter);   // Reverb<F> ID 85; consumes `filter` (1 -> 1)
 HNode* mk_var(float value);
 HNode* mk_nl_biquad(int fb, int mode, int shape, float p0, float p1, int inputs, float center, float q, float gain);  // IDs 88-91
+HNode* mk_phase_synth(int kind);                                     // PhaseSynth ID 35
+HNode* mk_pulse();                                                   // PulseWave ID 44
+HNode* mk_mixer(int inputs, int outputs, const float* matrix);       // Mixer ID 84, matrix[output][input]
+HNode* mk_rotate(float angle, float gain);                           // rotate(): 2x2 Mixer
 HNode* mk_declick(float duration);                                   // Declick ID 23
 HNode* mk_chaos(int kind);                                           // 0 Rossler ID 73, 1 Lorenz ID 74
 HNode* mk_morph(float cutoff, float q);                               // Morph ID 62

@@ -12,7 +12,7 @@ import math
 
 import numpy as np
 
-from .graph import (An, ArityError, M_BRANCH, M_BUS, M_CHAIN, M_REDUCE, M_STACK, OP_ADD, OP_MUL, f32, multi)
+from .graph import (An, ArityError, _arity, M_BRANCH, M_BUS, M_CHAIN, M_REDUCE, M_STACK, OP_ADD, OP_MUL, f32, multi)
 
 F = np.float32
 
@@ -487,6 +487,51 @@ def reverb_stereo(room_size, time, damping):
     reverb = fdn(line)
     return (multisplit(2, 16) >> reverb
             >> sumf(32, lambda x: pan(lerp(-1.0, 1.0, smooth9(x)))) * dc((1.0 / 16.0, 1.0 / 16.0)))
+
+
+# ---- src/prelude.rs:1873-1946 reverb4_stereo: two 16-line Hadamard FDNs in series (delay times from the reference's optimiser run)
+REVERB4_DELAYS = (
+    0.059326634, 0.04778291, 0.06995449, 0.0393001, 0.041604012, 0.06215825, 0.052269846, 0.043227978,
+    0.06966107, 0.031615064, 0.068442, 0.037332155, 0.032944717, 0.034493037, 0.06787566, 0.038824916,
+    0.068260126, 0.068044715, 0.0688076, 0.066724524, 0.051293883, 0.06023173, 0.040897705, 0.031507637,
+    0.060309593, 0.049584292, 0.04532072, 0.056379095, 0.035180368, 0.041291796, 0.046129026, 0.05504605,
+)
+
+
+def reverb4_stereo_delays(delays, time):
+    _arity(len(delays) == 32, "reverb4_stereo_delays: 32 delay times")
+    d = [F(x) for x in delays]
+    a = F(math.pow(db_amp(-60.0), 0.03 * 10.0 / 10.0 / time))
+    w = (float(-a / F(4.0)), float(-a / F(2.0)), float(-a / F(4.0)))
+    line1 = stacki(16, lambda i: delay(float(d[i])) >> fir(w))
+    line2 = stacki(16, lambda i: delay(float(d[16 + i])) >> fir(w))
+    return (multisplit(2, 8) >> fdn(line1) >> multijoin(2, 8) >> multisplit(2, 8) >> fdn(line2)
+            >> sumf(16, lambda x: pan(lerp(-1.0, 1.0, smooth9(x)))) * dc((1.0 / 4.0, 1.0 / 4.0)))
+
+
+def reverb4_stereo(room_size, time):
+    k = np.maximum(F(room_size), F(15.0)) / F(10.0)   # "the delays sound like garbage below 15 meters"
+    return reverb4_stereo_delays([F(x) * k for x in REVERB4_DELAYS], time)
+
+
+# ---- src/prelude.rs:2606 pulse(), src/wavetable.rs:361 PhaseSynth, src/prelude.rs:2876 rotate(), src/pan.rs:95 Mixer
+def pulse():
+    return An("pulse", (), (), 2, 1)
+
+
+def phase_synth(kind):
+    return An("phase_synth", (kind,), (), 1, 1)
+
+
+def rotate(angle, gain):
+    return An("rotate", (f32(angle), f32(gain)), (), 2, 2)
+
+
+def mixer(matrix):
+    """matrix[i] = the weights of output i over the inputs (a Frame of Frames in the reference)."""
+    rows = [tuple(f32(x) for x in r) for r in matrix]
+    _arity(len(rows) > 0 and all(len(r) == len(rows[0]) and len(r) > 0 for r in rows), "mixer: ragged matrix")
+    return An("mixer", (len(rows[0]), len(rows), tuple(x for r in rows for x in r)), (), len(rows[0]), len(rows))
 
 
 # ---- src/prelude.rs:395-430

@@ -77,6 +77,10 @@ fdsp_node* fdsp_morph(float cutoff, float q);                  /* Morph ID 62 sr
 fdsp_node* fdsp_rez(float bandpass, float cutoff, float q, int inputs); /* Rez ID 75 src/rez.rs: bandpass 0 = lowrez, 1 = bandrez; inputs 1 or 3 (audio, cutoff, q) */
 fdsp_node* fdsp_chaos(int kind);                               /* kind 0 Rossler ID 73, 1 Lorenz ID 74 (src/oscillator.rs:318-438); input = frequency */
 fdsp_node* fdsp_declick(float duration);                       /* Declick ID 23 src/dynamics.rs:245: smooth fade-in over `duration` seconds */
+fdsp_node* fdsp_phase_synth(int kind);                         /* PhaseSynth ID 35 src/wavetable.rs:361: input = phase, table kind as fdsp_wavesynth */
+fdsp_node* fdsp_pulse(void);                                   /* PulseWave ID 44 src/wavetable.rs:439 (`pulse()`): inputs (frequency, width 0..1) */
+fdsp_node* fdsp_mixer(int inputs, int outputs, const float* matrix); /* Mixer<M,N> ID 84 src/pan.rs:95: matrix[output * inputs + input] */
+fdsp_node* fdsp_rotate(float angle, float gain);               /* `rotate(angle, gain)` src/prelude.rs:2876: the 2x2 Mixer of a stereo rotation */
 /* nonlinear biquads src/biquad.rs:494-920: fb 1 = FbBiquad 88 / FixedFbBiquad 90, 0 = DirtyBiquad 89 / FixedDirtyBiquad 91; mode 0 resonator,
    1 lowpass, 2 highpass, 3 bell; shape kind + (p0, p1) as in fdsp_shaper; inputs 1 = fixed (center, q, gain given), 3 (4 for bell) = audio rate */
 fdsp_node* fdsp_nl_biquad(int fb, int mode, int shape, float p0, float p1, int inputs, float center, float q, float gain);

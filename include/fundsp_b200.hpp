@@ -10,6 +10,7 @@
 //   * `Bank` is the AudioUnit: process() == AudioUnit::process (src/audiounit.rs:45), render() == the Wave::render loop.
 // Nodes are move-only like Rust values: combining consumes the operands (use clone() to reuse a sub-graph).
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <initializer_list>
 #include <stdexcept>
@@ -208,6 +209,41 @@ template <class F> An busi(int n, F f) { std::vector<fdsp_node*> v; for (int i =
 template <class F> An sumi(int n, F f) { std::vector<fdsp_node*> v; for (int i = 0; i < n; i++) v.push_back(f(i).release()); return An(fdsp_multi(31, 0, n, v.data())); }
 template <class F> An branchi(int n, F f) { std::vector<fdsp_node*> v; for (int i = 0; i < n; i++) v.push_back(f(i).release()); return An(fdsp_multi(33, 0, n, v.data())); }
 template <class F> An pipei(int n, F f) { std::vector<fdsp_node*> v; for (int i = 0; i < n; i++) v.push_back(f(i).release()); return An(fdsp_multi(32, 0, n, v.data())); }
+template <class F> An sumf(int n, F f) { std::vector<fdsp_node*> v; for (int i = 0; i < n; i++) v.push_back(f(n > 1 ? (float)((double)i / (double)(n - 1)) : 0.5f).release()); return An(fdsp_multi(31, 0, n, v.data())); }
+inline An pulse() { return An(fdsp_pulse()); }                                         // inputs (frequency, width)
+inline An phase_synth(int table) { return An(fdsp_phase_synth(table)); }               // An(PhaseSynth::new(table))
+inline An rotate(float angle, float gain) { return An(fdsp_rotate(angle, gain)); }
+inline An mixer(int inputs, int outputs, std::initializer_list<float> matrix) { return (int)matrix.size() == inputs * outputs ? An(fdsp_mixer(inputs, outputs, matrix.begin())) : An(nullptr); }
+
+// ---- src/math.rs helpers used by the reverbs, in the reference's precision
+inline float lerp(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+inline float smooth9(float x) { float x2 = x * x; return ((((70.0f * x - 315.0f) * x + 540.0f) * x - 420.0f) * x + 126.0f) * x2 * x2 * x; }
+inline double db_amp(double db) { return std::exp((db / 20.0) * std::log(10.0)); }
+// src/prelude.rs:1732-1762 and :1873-1946: the FDN reverbs as the reference composes them
+inline An reverb_stereo(double room_size, double time, float damping) {
+  static const double delays[32] = {0.073904, 0.052918, 0.066238, 0.066387, 0.037783, 0.080073, 0.050961, 0.075900, 0.043646, 0.072095, 0.056194,
+                                    0.045961, 0.058934, 0.068016, 0.047529, 0.058156, 0.072972, 0.036084, 0.062715, 0.076377, 0.044339, 0.076725,
+                                    0.077884, 0.046126, 0.067741, 0.049800, 0.051709, 0.082923, 0.070121, 0.079315, 0.055039, 0.081859};
+  const float a = (float)std::pow(db_amp(-60.0), 0.03 * room_size / 10.0 / time);
+  const float gain = 1.0f - damping, alpha = (gain + 1.0f) / 2.0f, beta = (1.0f - alpha) / 2.0f;
+  An line = stacki(32, [&](int i) { return delay(delays[i] * room_size / 10.0) >> fir({beta * a, alpha * a, beta * a}); });
+  return multisplit(2, 16) >> fdn(std::move(line)) >> sumf(32, [](float x) { return pan(lerp(-1.0f, 1.0f, smooth9(x))); }) * dc(1.0f / 16.0f, 1.0f / 16.0f);
+}
+inline An reverb4_stereo_delays(const float (&delays)[32], double time) {
+  const float a = (float)std::pow(db_amp(-60.0), 0.03 * 10.0 / 10.0 / time);
+  An line1 = stacki(16, [&](int i) { return delay((double)delays[i]) >> fir({-a / 4.0f, -a / 2.0f, -a / 4.0f}); });
+  An line2 = stacki(16, [&](int i) { return delay((double)delays[16 + i]) >> fir({-a / 4.0f, -a / 2.0f, -a / 4.0f}); });
+  return multisplit(2, 8) >> fdn(std::move(line1)) >> multijoin(2, 8) >> multisplit(2, 8) >> fdn(std::move(line2))
+         >> sumf(16, [](float x) { return pan(lerp(-1.0f, 1.0f, smooth9(x))); }) * dc(1.0f / 4.0f, 1.0f / 4.0f);
+}
+inline An reverb4_stereo(double room_size, double time) {
+  float d[32] = {0.059326634f, 0.04778291f, 0.06995449f, 0.0393001f, 0.041604012f, 0.06215825f, 0.052269846f, 0.043227978f, 0.06966107f, 0.031615064f, 0.068442f,
+                 0.037332155f, 0.032944717f, 0.034493037f, 0.06787566f, 0.038824916f, 0.068260126f, 0.068044715f, 0.0688076f, 0.066724524f, 0.051293883f, 0.06023173f,
+                 0.040897705f, 0.031507637f, 0.060309593f, 0.049584292f, 0.04532072f, 0.056379095f, 0.035180368f, 0.041291796f, 0.046129026f, 0.05504605f};
+  const float k = std::fmax((float)room_size, 15.0f) / 10.0f;
+  for (float& x : d) x *= k;
+  return reverb4_stereo_delays(d, time);
+}
 
 // ---- the voice bank as an AudioUnit
 class Bank {

@@ -656,6 +656,49 @@ struct WaveSynth : Node {
   FO_CLONE(WaveSynth)
 };
 
+// ---- src/wavetable.rs:361-433 PhaseSynth (ID 35): table lookup at an input phase; no block override (default process = tick)
+struct PhaseSynth : Node {
+  int kind; float phase = 0; bool phase_ready = false; size_t table_hint = 0; float sample_rate = (float)DEFAULT_SR;
+  explicit PhaseSynth(int k) : kind(k) {}
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 35; }
+  void reset() override { phase_ready = false; }
+  void set_sample_rate(double sr) override { sample_rate = (float)sr; }
+  void tick(const float* in, float* out) override {  // :400-428
+    float ph = in[0]; ph = ph - floorf(ph);
+    float delta;
+    if (phase_ready) delta = fminf(fabsf(ph - phase), fminf(fabsf(ph - 1.0f - phase), fabsf(ph + 1.0f - phase)));
+    else { phase_ready = true; delta = 0.5f; }
+    const Wavetable& t = global_table(kind);
+    const float frequency = delta * sample_rate;
+    size_t ti = t.table_index(table_hint, frequency);   // Wavetable::read :181-195
+    float w = clamp01f(delerpf(t.table[ti].first, t.table[ti + 1].first, frequency));
+    out[0] = (1.0f - w) * t.at(ti + 1, ph) + w * t.at(ti + 2, ph);
+    table_hint = ti; phase = ph;
+  }
+  FO_CLONE(PhaseSynth)
+};
+// ---- src/wavetable.rs:439-491 PulseWave (ID 44): difference of two saws, the second read at phase + width
+struct PulseWave : Node {
+  Child pulse;
+  PulseWave() {
+    Node* a = new Stack(new WaveSynth(0, 2), new MultiPass(1, true));
+    Node* b = new Stack(new MultiPass(1, true), new Pipe(new Binop(0, new MultiPass(1, true), new MultiPass(1, true)), new PhaseSynth(0)));
+    pulse = Child(new Pipe(new Pipe(a, b), new Binop(1, new MultiPass(1, true), new MultiPass(1, true))));
+  }
+  int inputs() const override { return 2; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 44; }
+  void reset() override { pulse->reset(); }
+  void set_sample_rate(double sr) override { pulse->set_sample_rate(sr); }
+  void tick(const float* in, float* out) override { pulse->tick(in, out); }
+  void process(int size, const float* in, float* out) override { pulse->process(size, in, out); }
+  void set(const Setting& s) override {   // :479-481 left_mut().left_mut().left_mut()
+    Setting t = s; t.address.insert(t.address.begin(), {Address{1, 0}, Address{1, 0}, Address{1, 0}}); pulse->set(t);
+  }
+  AttoHash ping(bool probe, AttoHash h) override { return pulse->ping(probe, h).hash(id()); }
+  FO_CLONE(PulseWave)
+};
+
 // ---- src/svf.rs:16-221 SvfCoefs<f32>; modes 0 lowpass 1 highpass 2 bandpass 3 notch 4 peak 5 allpass 6 bell 7 lowshelf 8 highshelf
 struct SvfCoefs { float a1 = 0, a2 = 0, a3 = 0, m0 = 0, m1 = 0, m2 = 0; };
 inline SvfCoefs svf_coefs(int mode, float sr, float cutoff, float q, float gain) {
@@ -1533,6 +1576,18 @@ struct Panner : Node {
   }
   void set(const Setting& s) override { if (s.kind == P_PAN) pan_weights(s.v[0], lw, rw); }
   FO_CLONE(Panner)
+};
+
+// ---- src/pan.rs:95-160 Mixer<M, N> (ID 84): constant matrix, tick only
+struct Mixer : Node {
+  int m, n; std::vector<float> w;
+  Mixer(int m_, int n_, const float* w_) : m(m_), n(n_), w(w_, w_ + (size_t)m_ * n_) {}
+  int inputs() const override { return m; } int outputs() const override { return n; }
+  uint64_t id() const override { return 84; }
+  void tick(const float* in, float* out) override {
+    for (int i = 0; i < n; i++) { float v = 0.0f; for (int j = 0; j < m; j++) v += in[j] * w[(size_t)i * m + j]; out[i] = v; }
+  }
+  FO_CLONE(Mixer)
 };
 
 // ---- src/envelope.rs:185-358 EnvelopeIn<f32, E, U1, f32> (ID 53) specialised to the closed-form

@@ -90,6 +90,14 @@ API Node* fo_morph(float cutoff, float q) { return new Morph(cutoff, q); }
 API Node* fo_rez(float bandpass, float cutoff, float q, int inputs) { return new Rez(bandpass, cutoff, q, inputs); }
 API Node* fo_chaos(int kind) { return new Chaos(kind); }   // 0 rossler, 1 lorenz
 API Node* fo_declick(float duration) { return new Declick(duration); }
+API Node* fo_phase_synth(int kind) { return new PhaseSynth(kind); }
+API Node* fo_pulse() { return new PulseWave(); }
+API Node* fo_mixer(int inputs, int outputs, const float* matrix) { return new Mixer(inputs, outputs, matrix); }
+API Node* fo_rotate(float angle, float gain) {   // src/prelude.rs:2876-2884
+  const float c = m::cosf_(angle), s = m::sinf_(angle);
+  const float w[4] = {c * gain, -s * gain, s * gain, c * gain};
+  return new Mixer(2, 2, w);
+}
 API Node* fo_nl_biquad(int fb, int mode, int shape_kind, float p0, float p1, int inputs, float center, float q, float gain) {
   return new NlBiquad(fb != 0, mode, shape_kind, p0, p1, inputs, center, q, gain);
 }

@@ -8,6 +8,18 @@
 
 using namespace fundsp_b200;
 
+// FNV-1a over the device program's parameter and state words: two builds of the same graph agree to the last bit of every coefficient
+static unsigned long long words_hash(const An& g) {
+  int np = 0, ns = 0, nu = 0;
+  fdsp_node_lowering(g.get(), nullptr, 0, nullptr, 0, nullptr, 0, &np, &ns, &nu);
+  std::vector<uint32_t> P(np + 1), S(ns + 1), U(nu + 1);
+  fdsp_node_lowering(g.get(), P.data(), np, S.data(), ns, U.data(), nu, &np, &ns, &nu);
+  unsigned long long h = 1469598103934665603ull;
+  for (int i = 0; i < np; i++) { h ^= P[i]; h *= 1099511628211ull; }
+  for (int i = 0; i < ns; i++) { h ^= S[i]; h *= 1099511628211ull; }
+  return h;
+}
+
 int main() {
   An g = sine_hz(440.0f) >> lowpass_hz(1000.0f, 1.0f);
   std::printf("sig %s\n", g.signature().c_str());
@@ -32,6 +44,11 @@ int main() {
   std::printf("misc %d %d\n", misc.inputs(), misc.outputs());
   An nlb = (noise() >> dlowpass_hz(Tanh{1.0f}, 1200.0f, 2.0f)) | ((noise() | dc(900.0f, 1.5f, 2.0f)) >> fbell(Softsign{0.8f})) | (noise() >> fresonator_hz(Clip{1.0f}, 700.0f, 4.0f));
   std::printf("nlb %d %d %s\n", nlb.inputs(), nlb.outputs(), nlb.signature().c_str());
+  An wide = ((dc(110.0f, 0.3f) >> pulse()) | (noise() >> phase_synth(2))) >> rotate(0.5f, 0.8f) >> mixer(2, 3, {0.5f, -0.25f, 0.125f, 1.0f, 1.0f, 1.0f});
+  std::printf("wide %d %d %s %016llx\n", wide.inputs(), wide.outputs(), wide.signature().c_str(), words_hash(wide));
+  An r1 = reverb_stereo(12.0, 2.5, 0.4f), r4 = reverb4_stereo(20.0, 3.0);
+  std::printf("reverb_stereo %s %016llx\n", r1.signature().c_str(), words_hash(r1));
+  std::printf("reverb4_stereo %s %016llx\n", r4.signature().c_str(), words_hash(r4));
   try {
     An bad = pass() >> (pass() | pass());
     std::printf("arity NOT detected\n");

@@ -32,7 +32,7 @@ def emulate(g, n, x=None, tmp=None):
         f.write(P.tobytes()); f.write(S.tobytes()); f.write(U.tobytes())
         if nin:
             f.write(np.ascontiguousarray(x, np.float32).tobytes())
-        kinds = [k for k in range(6) if f"WaveSynth<{k}," in sig]
+        kinds = [k for k in range(6) if f"WaveSynth<{k}," in sig or f"PhaseSynth<{k}>" in sig]   # as csrc/host/bank.cpp
         f.write(struct.pack("<I", len(kinds)))
         for k in kinds:
             f.write(_table_blob(k))

@@ -86,6 +86,10 @@ WIDER = {
     "dirty_biquads": lambda i: noise().seed(i) >> (dbell_hz(Tanh(1.0), 800.0 + 30.0 * i, 10.0, 2.0) & dhighpass_hz(Softsign(1.0), 2000.0, 2.0) & dresonator_hz(Tanh(0.5), 1000.0 + 10.0 * i, 10.0) & dlowpass_hz(Crush(64.0), 1500.0, 2.0)),
     "feedback_biquads": lambda i: noise().seed(i) >> (fbell_hz(Tanh(1.0), 500.0 + 20.0 * i, 50.0, 0.5) & flowpass_hz(Clip(1.0), 2000.0, 2.0) & fresonator_hz(SoftCrush(32.0), 700.0, 20.0) & fhighpass_hz(Softsign(0.2), 2000.0 + 10.0 * i, 2.0)),
     "nl_biquads_audio_rate": lambda i: (noise().seed(i) | (sine_hz(1.0) * 500.0 + 1500.0 + 10.0 * i) | dc(2.0)) >> dlowpass(Tanh(1.0)) | (noise().seed(i + 3) | dc((800.0, 3.0, 2.0 + 0.05 * i))) >> fbell(Softsign(1.0)),
+    "pulse_wave": lambda i: ((sine_hz(3.0 + i % 5) * 30.0 + 110.0 + 7.0 * i) | (sine_hz(0.7) * 0.4 + 0.5)) >> pulse() | dc((55.0 + i, 0.1 + 0.02 * (i % 40))) >> pulse().phase(0.25),
+    "phase_synth_tables": lambda i: ramp_hz(100.0 + 13.0 * i) >> (phase_synth(SQUARE) & phase_synth(ORGAN) * 0.5) | (sine_hz(50.0 + i) * 0.6) >> phase_synth(SOFT_SAW),
+    "rotate_mixer": lambda i: (noise().seed(i) | sine_hz(200.0 + i)) >> rotate(0.1 * i, 0.8) >> mixer([[0.5, -0.25], [0.125 * (i % 8), 1.0], [1.0, 1.0]]),
+    "reverb4_short_lines": lambda i: (noise().seed(i) | noise().seed(i + 100)) >> reverb4_stereo_delays([d * (0.15 + 0.002 * (i % 25)) for d in REVERB4_DELAYS], 1.0 + 0.05 * (i % 8)),
 }
 GATED = {
     "adsr_noise": lambda i: adsr_live(0.005 + 0.001 * (i % 5), 0.05, 0.5 + 0.01 * (i % 20), 0.1) * noise().seed(i) | ~zero() >> sine_hz(100.0 + i),

@@ -527,6 +527,58 @@ def test_more_reference_check_wave_lines():  # tests/test_basic.rs:170,187-190,1
     L.fo_restore_denormals()
 
 
+def test_pulse_rotate_mixer_reverb4():  # src/wavetable.rs:361-491, src/pan.rs:95-160, src/prelude.rs:1873-1946,2876
+    L.fo_set_denormal_emulation(0)
+    # tests/test_basic.rs:237: tick == process
+    check_wave(dc((110.0, 0.5)) >> pulse() * 0.2 >> delay(0.1))           # (check_wave_big: 441 samples)
+    check_wave(dc((110.0, 0.5)) >> pulse() * 0.2)
+    check_wave((sine_hz(3.0) * 30.0 + 220.0 | sine_hz(0.7) * 0.4 + 0.5) >> pulse())
+    assert outputs_diverge(dc((220.0, 0.3, 220.0, 0.3)) >> (pulse() | pulse()))   # test_basic.rs:606: two pulses draw different initial phases
+    # a pulse is the difference of two band-limited saws `width` apart: two levels 2A apart (A = the saws' slope
+    # amplitude), the duty cycle is the width, zero mean
+    sr, f = 44100.0, 110.25                                       # 400 samples per cycle
+    saw = OracleUnit(saw_hz(f).phase(0.0)).render(sr, 0.1)[0]
+    A = 2.0 * abs(float(saw[100 + 400]))                          # slope amplitude of the table (its peak 1.0 is the Gibbs overshoot)
+    assert 0.8 < A < 0.9
+    for w in (0.5, 0.25, 0.8):
+        y = OracleUnit(dc((f, w)) >> pulse()).render(sr, 1.0)[0]
+        a, b = np.median(y[y > np.median(y) + 0.5] if (y > np.median(y) + 0.5).any() else y), np.median(y[y < np.median(y) - 0.5] if (y < np.median(y) - 0.5).any() else y)
+        levels = sorted([float(a), float(b)])
+        assert abs((levels[1] - levels[0]) - 2.0 * A) < 0.05 and abs(y.mean()) < 0.01, (w, levels, y.mean())
+        frac_hi = float((y > 0.5 * (levels[0] + levels[1])).mean())
+        assert min(abs(frac_hi - w), abs(frac_hi - (1.0 - w))) < 0.01, (w, frac_hi)
+        assert abs(levels[1] - 2.0 * A * (1.0 - frac_hi)) < 0.05 and abs(levels[0] + 2.0 * A * frac_hi) < 0.05   # zero mean fixes both levels
+    # PhaseSynth driven by a ramp reproduces the free-running oscillator of the same table (past the first, Nyquist-band, sample)
+    a = OracleUnit(ramp_hz(441.0).phase(0.0) >> phase_synth(TRIANGLE)).render(sr, 2000 / sr)[0]
+    b = OracleUnit(triangle_hz(441.0).phase(0.0)).render(sr, 2000 / sr)[0]
+    assert min(np.abs(a[2:-2] - b[k:k + len(a) - 4]).max() for k in (1, 2, 3)) < 2e-3
+    # rotate (test_flow.rs:168-169): [[c g, -s g], [s g, c g]] with libm cos / sin in f32
+    x = np.random.default_rng(3).uniform(-1, 1, (2, 500)).astype(np.float32)
+    for ang, g in ((0.5, 1.0), (-0.1, 0.5)):
+        c, sn, g32 = np.float32(math.cos(np.float32(ang))), np.float32(math.sin(np.float32(ang))), np.float32(g)
+        y = OracleUnit(rotate(ang, g)).filter(sr, x)
+        want = np.stack([x[0] * (c * g32) + x[1] * (-sn * g32), x[0] * (sn * g32) + x[1] * (c * g32)])
+        assert np.abs(y - want).max() < 1e-6
+        u = OracleUnit(rotate(ang, g))
+        assert np.array_equal(y[:, :50], np.stack([u.tick(x[:, i]) for i in range(50)], axis=1))
+    y = OracleUnit(mixer([[0.5, -0.25, 1.0], [0.0, 2.0, 0.0]])).filter(sr, np.stack([x[0], x[1], x[0]]))
+    assert np.array_equal(y[1], x[1] * np.float32(2.0)) and np.abs(y[0] - (1.5 * x[0] - 0.25 * x[1])).max() < 1e-6
+    # reverb4_stereo: silent until the shortest path (two lines of about 31.5 ms x 1.5 at the 15 m floor) has passed, then an exponential tail
+    imp = np.zeros((2, int(sr * 4.6)), np.float32); imp[:, 0] = 1.0
+    y = OracleUnit(reverb4_stereo(10.0, 1.0)).filter(sr, imp)
+    first = int((0.031615064 + 0.031507637) * 1.5 * sr)          # the shortest line of each of the two FDNs in series
+    assert np.abs(y[:, :first - 3]).max() == 0.0 and np.abs(y[:, first - 3:first + 4]).max() > 0.0
+    # every trip round a line is scaled by a = 10**(-3 * 0.03 / time) (the loop FIR's gain at DC): with lines of 1.5 x 51.5 ms on
+    # average that is 60 * 0.03 / 0.0773 = 23 dB per second for each FDN; the cascade's t**2 envelope takes ~2.5 dB/s off between 3 and 4 s
+    e = (y.astype(np.float64) ** 2).sum(0)
+    mean_line = 1.5 * float(np.mean(REVERB4_DELAYS))
+    rate = 10.0 * np.log10(e[int(3.0 * sr):int(3.5 * sr)].sum() / e[int(4.0 * sr):int(4.5 * sr)].sum())
+    assert abs(rate - (60.0 * 0.03 / mean_line - 2.5)) < 4.0, (rate, 60.0 * 0.03 / mean_line)
+    assert np.array_equal(y[:, :3000], OracleUnit(reverb4_stereo(15.0, 1.0)).filter(sr, imp[:, :3000]))   # rooms below 15 m clamp
+    check_wave((noise() | noise().seed(3)) >> reverb4_stereo(20.0, 2.0), n=2205)
+    L.fo_restore_denormals()
+
+
 def test_mls_is_maximum_length():  # src/noise.rs:11-98: the sequence of an n-bit MLS repeats after exactly 2**n - 1 steps
     for n in range(2, 15):
         u = OracleUnit(mls_bits(n))
