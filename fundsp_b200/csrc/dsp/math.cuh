@@ -26,6 +26,8 @@ static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4);
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
+static inline double __longlong_as_double(long long x) { double d; memcpy(&d, &x, 8); return d; }
+static inline long long __double_as_longlong(double d) { long long x; memcpy(&x, &d, 8); return x; }
 using std::isfinite;
 #else
 #include <cstdint>

@@ -1211,6 +1211,78 @@ template <class X> struct FeedbackUnit {
   static FDSP_DEV void end_simd(R& r) { if (r.block) X::end_simd(r.x); }
 };
 
+// ---------------------------------------------------------------- MeterNode (ID 61, src/dynamics.rs:316-437), WavePlayer (ID 65,
+// src/wave.rs:739-797), Resample<X> (ID 69, src/resample.rs:210-300). All three are tick-only in the reference.
+template <int KIND> struct MeterNode {   // KIND 0 Sample, 1 Peak(timescale), 2 Rms(timescale); smoothing computed on the host in f64
+  FDSP_NODE(1, 1, 1, 1, 0);
+  struct R { float smoothing, state; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.smoothing = l.Pf(); r.state = l.Sf(); }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.Sf(r.state); }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C&, const Fr<1>& in, Fr<1>& o) {
+    const float v = in.v[0];
+    if (KIND == 0) { r.state = v; o.v[0] = v; }
+    else if (KIND == 1) { r.state = fmaxf(r.state * r.smoothing, fabsf(v)); o.v[0] = r.state; }
+    else { r.state = r.state * r.smoothing + (v * v) * (1.0f - r.smoothing); o.v[0] = sqrtf(r.state); }
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
+// The wave's samples are class-uniform data (voices playing the same wave share a class); the play region is per voice.
+struct WavePlayer {
+  FDSP_NODE(0, 1, 2, 1, 1);   // NU counts the length word; the samples follow it in the uniform block
+  struct R { uint32_t end, loop, index; const uint32_t* w; };
+  static FDSP_DEV void load(R& r, Loader& l) { const uint32_t n = l.U(); r.w = l.u + l.ui; l.ui += n; r.end = l.P(); r.loop = l.P(); r.index = l.S(); }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.S(r.index); }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C&, const Fr<0>&, Fr<1>& o) {
+    if (r.index < r.end) {
+      o.v[0] = __uint_as_float(__ldg(r.w + r.index));
+      r.index++;
+      if (r.index == r.end && r.loop != 0xffffffffu) r.index = r.loop;
+    } else o.v[0] = 0.0f;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
+// Variable-speed playback of a generator: the input is the speed (1 = original); the inner node is ticked as far as the cubic needs.
+// The 128-frame ring per channel lives in the class's delay-line storage. The read position is f64 like the reference's.
+template <class X> struct Resample {
+  static constexpr int NO = X::OUT;
+  FDSP_NODE(1, NO, X::NP, 3 + X::NS, X::NU);
+  struct R { double consumer; uint32_t producer, off; typename X::R x; };
+  static FDSP_DEV void load(R& r, Loader& l) {
+    const uint32_t lo = l.S(), hi = l.S();
+    r.consumer = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+    r.producer = l.S(); r.off = l.D(128u * (uint32_t)NO); X::load(r.x, l);
+  }
+  static FDSP_DEV void save(const R& r, Saver& s) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(r.consumer);
+    s.S((uint32_t)b); s.S((uint32_t)(b >> 32)); s.S(r.producer); X::save(r.x, s);
+  }
+  static FDSP_DEV float spline(float y0, float y1, float y2, float y3, float x) {   // src/math.rs:360-366, the reference's evaluation order
+    return y1 + x * 0.5f * (y2 - y0 + x * (2.0f * y0 - 5.0f * y1 + 4.0f * y2 - y3 + x * (3.0f * (y1 - y2) + y3 - y0)));
+  }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<1>& in, Fr<NO>& o) {
+    r.consumer += (double)fmaxf(0.0f, in.v[0]);
+    const double d = r.consumer - floor(r.consumer);
+    const uint32_t ci = (uint32_t)(unsigned long long)(r.consumer - d);
+    float* ring = c.dl + (size_t)r.off * c.V + c.v;
+    while (ci + 2u >= r.producer) {
+      Fr<0> none; Fr<NO> y;
+      X::template step<true>(r.x, c, none, y);
+#pragma unroll
+      for (int k = 0; k < NO; k++) ring[(size_t)((uint32_t)k * 128u + (r.producer & 0x7fu)) * c.V] = y.v[k];
+      r.producer++;
+    }
+    const float x = (float)d;
+#pragma unroll
+    for (int k = 0; k < NO; k++) {
+      const float* ch = ring + (size_t)((uint32_t)k * 128u) * c.V;
+      o.v[k] = spline(ch[(size_t)((ci + 0x7fu) & 0x7fu) * c.V], ch[(size_t)(ci & 0x7fu) * c.V], ch[(size_t)((ci + 1u) & 0x7fu) * c.V], ch[(size_t)((ci + 2u) & 0x7fu) * c.V], x);
+    }
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
 // ---------------------------------------------------------------- Reverb<F> (src/reverb.rs:139-279, ID 85: reverb3_stereo)
 // Allpass-loop stereo reverb: 4 pre-delay allpasses, then 8 blocks of (delay, 4 allpasses, loop filter, 4 allpasses, loop
 // filter) traversed in series; the last block's output is fed back. Tick-only in the reference, so every part runs `step<true>`.
@@ -1476,6 +1548,8 @@ template <class G> struct Cost { static constexpr int value = 8; };
 template <int K, int N> struct Cost<WaveSynth<K, N>> { static constexpr int value = 100; };
 template <int K> struct Cost<PhaseSynth<K>> { static constexpr int value = 110; };
 template <int M, int N> struct Cost<Mixer<M, N>> { static constexpr int value = 2 * M * N; };
+template <int K> struct Cost<MeterNode<K>> { static constexpr int value = 10; };
+template <> struct Cost<WavePlayer> { static constexpr int value = 12; };
 template <> struct Cost<Sine> { static constexpr int value = 40; };
 template <> struct Cost<Noise> { static constexpr int value = 16; };
 template <> struct Cost<FixedSvf> { static constexpr int value = 20; };
@@ -1506,6 +1580,8 @@ template <int A> struct Cost<Follower<A>> { static constexpr int value = 16; };
 template <int FB, int M, int S, int N> struct Cost<NlBiquad<FB, M, S, N>> { static constexpr int value = (S == 2 ? 120 : 30) * (FB ? 1 : 2) + (N > 1 ? 60 : 0); };
 template <int K> struct Cost<Shaper<K>> { static constexpr int value = K == 2 ? 100 : 12; };
 template <> struct Cost<Convolver> { static constexpr int value = 48; };
+template <class X> struct WaveKind<Resample<X>> : WaveKind<X> {};
+template <class X> struct Cost<Resample<X>> { static constexpr int value = 4 * Cost<X>::value + 120; };
 template <class X> struct WaveKind<FeedbackUnit<X>> : WaveKind<X> {};
 template <class X> struct Cost<FeedbackUnit<X>> { static constexpr int value = Cost<X>::value + 12 * X::IN; };
 template <class F> struct Cost<Reverb85<F>> { static constexpr int value = 1200 + 16 * Cost<F>::value; };

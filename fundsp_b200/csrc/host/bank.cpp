@@ -127,6 +127,7 @@ std::string Bank::lower_and_upload(bool upload_state) {
       fresh.push_back(std::move(c));
     } else ci = it->second;
     fresh[ci].voices.push_back((uint32_t)v);
+    std::string().swap(lo.key); std::vector<uint32_t>().swap(lo.l.U);   // the class keeps the uniform words (a sampler voice's may be a whole wave)
   }
   // 2. keep device buffers of classes that survive unchanged (same key order / sizes), else rebuild
   const bool same_shape = classes.size() == fresh.size() && std::equal(classes.begin(), classes.end(), fresh.begin(), [](const VoiceClass& a, const VoiceClass& b) {

@@ -4,6 +4,7 @@
 #include "graph.h"
 #include "../dsp/libm.cuh"
 
+#include <memory>
 #include <algorithm>
 #include <cassert>
 
@@ -543,6 +544,47 @@ struct ConvolverN : HNode {  // src/convolve.rs:9-59: the impulse response is cl
   }
   HCLONE(ConvolverN)
 };
+struct MeterN : HNode {  // MeterNode, src/dynamics.rs:316-437
+  int kind; double timescale, sr = DEFAULT_SR;
+  MeterN(int k, double t) : kind(k), timescale(t) {}
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 61; }
+  void set_sample_rate(double s) override { sr = s; }
+  void sig(std::string& o) const override { o += "MeterNode<" + I(kind) + ">"; }
+  void lower(Lowering& l) const override { l.p(kind == 0 ? 0.0f : (float)pow(0.5, 1.0 / (timescale * sr))); l.s(0.0f); }
+  HCLONE(MeterN)
+};
+struct WavePlayerN : HNode {  // src/wave.rs:739-797: the samples of one channel are class-uniform data; the play region is per voice
+  std::shared_ptr<const std::vector<float>> wave; uint32_t start, end, loop;   // loop 0xffffffff = none
+  WavePlayerN(std::shared_ptr<const std::vector<float>> w, uint32_t s, uint32_t e, uint32_t lp) : wave(std::move(w)), start(s), end(e), loop(lp) {}
+  int inputs() const override { return 0; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 65; }
+  void sig(std::string& o) const override { o += "WavePlayer"; }
+  void lower(Lowering& l) const override {
+    l.U.push_back((uint32_t)wave->size());
+    for (float x : *wave) l.U.push_back(f2u(x));
+    l.extraU += (uint32_t)wave->size();
+    l.P.push_back(end); l.P.push_back(loop); l.su(start);
+  }
+  HCLONE(WavePlayerN)
+};
+struct ResampleN : HNode {  // src/resample.rs:210-300
+  Kid x;
+  explicit ResampleN(HNode* x_) : x(x_) { AttoHash h = x->ping(true, AttoHash(69)); x->ping(false, h); }   // Resample::new pings the inner node directly (:228-232)
+  int inputs() const override { return 1; } int outputs() const override { return x->outputs(); }
+  uint64_t id() const override { return 69; }
+  void reset() override { x->reset(); }
+  void set_sample_rate(double s) override { x->set_sample_rate(s); }
+  AttoHash ping(bool probe, AttoHash h) override { return x->ping(probe, h.hash(id())); }
+  void sig(std::string& o) const override { o += "Resample<"; x->sig(o); o += ">"; }
+  void lower(Lowering& l) const override {
+    const double one = 1.0; uint64_t b; memcpy(&b, &one, 8);     // the read position starts at the second sample (:252-256)
+    l.su((uint32_t)b); l.su((uint32_t)(b >> 32)); l.su(0u);
+    l.dlen.push_back(128u * (uint32_t)x->outputs());
+    x->lower(l);
+  }
+  HCLONE(ResampleN)
+};
 struct VarN : HNode {  // the shared value is control-plane state: it enters as a parameter word and changes through Setting::value
   float value; explicit VarN(float v) : value(v) {}
   int inputs() const override { return 0; } int outputs() const override { return 1; }
@@ -879,6 +921,16 @@ HNode* mk_reverb3(double time, double diffusion, HNode* filter) {
   return new ReverbN(time, diffusion, filter);
 }
 HNode* mk_var(float value) { return new VarN(value); }
+HNode* mk_meter(int kind, double timescale) { return (kind < 0 || kind > 2 || (kind > 0 && !(timescale > 0.0))) ? nullptr : new MeterN(kind, timescale); }
+HNode* mk_playwave(const float* samples, uint64_t length, uint64_t start, uint64_t end, int64_t loop_point) {
+  if ((!samples && length) || length > (1ull << 28) || end > length || start > 0xfffffffeull || loop_point >= (int64_t)0xffffffffll) return nullptr;   // assert!(end_point <= wave.length())
+  auto w = std::make_shared<std::vector<float>>(samples, samples + length);
+  return new WavePlayerN(std::move(w), (uint32_t)start, (uint32_t)end, loop_point < 0 ? 0xffffffffu : (uint32_t)loop_point);
+}
+HNode* mk_resample(HNode* x) {
+  if (!x || x->inputs() != 0 || x->outputs() < 1) { delete x; return nullptr; }
+  return new ResampleN(x);
+}
 HNode* mk_phase_synth(int kind) { return (kind < 0 || kind > 5) ? nullptr : new PhaseSynthN(kind); }
 HNode* mk_pulse() { return new PulseWaveN(); }
 HNode* mk_mixer(int inputs, int outputs, const float* matrix) {

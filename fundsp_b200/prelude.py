@@ -534,6 +534,47 @@ def mixer(matrix):
     return An("mixer", (len(rows[0]), len(rows), tuple(x for r in rows for x in r)), (), len(rows[0]), len(rows))
 
 
+# ---- src/prelude.rs:299 meter(), src/dynamics.rs:316-326 Meter
+class Meter:
+    """Meter::Sample / Meter::Peak(timescale) / Meter::Rms(timescale)."""
+    Sample = (0, 0.0)
+
+    @staticmethod
+    def Peak(timescale): return (1, float(timescale))
+
+    @staticmethod
+    def Rms(timescale): return (2, float(timescale))
+
+
+def meter(m):
+    return An("meter", (int(m[0]), float(m[1])), (), 1, 1)
+
+
+# ---- src/prelude.rs:2631-2654 playwave / playwave_at: `wave` is a [channels, length] f32 array (Wave), src/prelude.rs:1034 resample
+def playwave_at(wave, channel, start_point, end_point, loop_point=None):
+    w = np.ascontiguousarray(np.atleast_2d(np.asarray(wave, np.float32))[channel])
+    _arity(0 <= start_point and end_point <= len(w), "playwave: end_point <= wave.length()")
+    return An("playwave", (_Samples(w), int(start_point), int(end_point), -1 if loop_point is None else int(loop_point)), (), 0, 1)
+
+
+def playwave(wave, channel, loop_point=None):
+    return playwave_at(wave, channel, 0, np.atleast_2d(np.asarray(wave)).shape[1], loop_point)
+
+
+class _Samples:
+    """A wave channel as an An argument (kept out of repr)."""
+    def __init__(self, a): self.a = a
+    def __len__(self): return len(self.a)
+    def __iter__(self): return iter(self.a)
+    def __array__(self, dtype=None, copy=None): return self.a if dtype is None else self.a.astype(dtype)
+    def __repr__(self): return f"<wave {len(self.a)}>"
+
+
+def resample(node):
+    _arity(node.nin == 0, "resample: the inner node must be a generator")
+    return An("resample", (), (node,), 1, node.nout)
+
+
 # ---- src/prelude.rs:395-430
 def add(x):
     v = _frame(x)

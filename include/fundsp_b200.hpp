@@ -214,6 +214,12 @@ inline An pulse() { return An(fdsp_pulse()); }                                  
 inline An phase_synth(int table) { return An(fdsp_phase_synth(table)); }               // An(PhaseSynth::new(table))
 inline An rotate(float angle, float gain) { return An(fdsp_rotate(angle, gain)); }
 inline An mixer(int inputs, int outputs, std::initializer_list<float> matrix) { return (int)matrix.size() == inputs * outputs ? An(fdsp_mixer(inputs, outputs, matrix.begin())) : An(nullptr); }
+struct Meter { int kind; double timescale; static Meter Sample() { return {0, 0.0}; } static Meter Peak(double t) { return {1, t}; } static Meter Rms(double t) { return {2, t}; } };
+inline An meter(Meter m) { return An(fdsp_meter(m.kind, m.timescale)); }
+// playwave(&wave, channel, loop): `samples` = wave.channel(channel); loop_point < 0 = None
+inline An playwave(const std::vector<float>& samples, long long loop_point = -1) { return An(fdsp_playwave(samples.data(), samples.size(), 0, samples.size(), loop_point)); }
+inline An playwave_at(const std::vector<float>& samples, size_t start, size_t end, long long loop_point = -1) { return An(fdsp_playwave(samples.data(), samples.size(), start, end, loop_point)); }
+inline An resample(An x) { return An(fdsp_resample(x.release())); }                    // input = speed
 
 // ---- src/math.rs helpers used by the reverbs, in the reference's precision
 inline float lerp(float a, float b, float t) { return a * (1.0f - t) + b * t; }

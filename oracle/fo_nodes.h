@@ -1590,6 +1590,72 @@ struct Mixer : Node {
   FO_CLONE(Mixer)
 };
 
+// ---- src/dynamics.rs:316-437 Meter / MeterState / MeterNode (ID 61); kind 0 Sample, 1 Peak(timescale), 2 Rms(timescale)
+struct MeterNode : Node {
+  int kind; double timescale; float smoothing = 0, state = 0;
+  MeterNode(int k, double t) : kind(k), timescale(t) { set_sample_rate(DEFAULT_SR); }
+  int inputs() const override { return 1; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 61; }
+  void reset() override { state = 0; }
+  void set_sample_rate(double sr) override { if (kind != 0) smoothing = (float)pow(0.5, 1.0 / (timescale * sr)); }
+  void tick(const float* in, float* out) override {
+    const float v = in[0];
+    if (kind == 0) { state = v; out[0] = state; }
+    else if (kind == 1) { state = fmaxf(state * smoothing, fabsf(v)); out[0] = state; }
+    else { state = state * smoothing + (v * v) * (1.0f - smoothing); out[0] = sqrtf(state); }
+  }
+  FO_CLONE(MeterNode)
+};
+// ---- src/wave.rs:739-797 WavePlayer (ID 65): plays one channel of a wave from start to end, optionally jumping to a loop point
+struct WavePlayer : Node {
+  std::shared_ptr<const std::vector<float>> wave; size_t index, start_point, end_point; bool has_loop; size_t loop_point;
+  WavePlayer(std::shared_ptr<const std::vector<float>> w, size_t s, size_t e, bool hl, size_t lp)
+      : wave(std::move(w)), index(s), start_point(s), end_point(e), has_loop(hl), loop_point(lp) { assert(end_point <= wave->size()); }
+  int inputs() const override { return 0; } int outputs() const override { return 1; }
+  uint64_t id() const override { return 65; }
+  void reset() override { index = start_point; }
+  void tick(const float*, float* out) override {
+    if (index < end_point) {
+      out[0] = (*wave)[index];
+      index += 1;
+      if (index == end_point && has_loop) index = loop_point;
+    } else out[0] = 0.0f;
+  }
+  FO_CLONE(WavePlayer)
+};
+// ---- src/resample.rs:210-300 Resample<X> (ID 69): cubic-interpolated variable-speed playback of a generator; input = speed
+struct Resample : Node {
+  Child x; std::vector<float> buffer; double consumer = 1.0; size_t producer = 0;
+  explicit Resample(Node* x_) : x(x_) {
+    assert(x->inputs() == 0);
+    x->set_sample_rate(DEFAULT_SR);
+    AttoHash h = x->ping(true, AttoHash(69)); x->ping(false, h);
+    buffer.assign((size_t)x->outputs() * 128, 0.0f);
+  }
+  int inputs() const override { return 1; } int outputs() const override { return x->outputs(); }
+  uint64_t id() const override { return 69; }
+  void reset() override { x->reset(); consumer = 1.0; producer = 0; }
+  void set_sample_rate(double sr) override { x->set_sample_rate(sr); }
+  void tick(const float* in, float* out) override {
+    consumer += (double)fmaxf(0.0f, in[0]);
+    const double d = consumer - floor(consumer);
+    const size_t ci = (size_t)(consumer - d);
+    const int no = x->outputs();
+    while (ci + 2 >= producer) {
+      float inner[256];
+      x->tick(nullptr, inner);
+      for (int c = 0; c < no; c++) buffer[(size_t)c * 128 + (producer & 0x7f)] = inner[c];
+      producer += 1;
+    }
+    for (int c = 0; c < no; c++) {
+      const float* b = &buffer[(size_t)c * 128];
+      out[c] = splinef(b[(ci + 0x7f) & 0x7f], b[ci & 0x7f], b[(ci + 1) & 0x7f], b[(ci + 2) & 0x7f], (float)d);
+    }
+  }
+  AttoHash ping(bool probe, AttoHash h) override { return x->ping(probe, h.hash(id())); }
+  FO_CLONE(Resample)
+};
+
 // ---- src/envelope.rs:185-358 EnvelopeIn<f32, E, U1, f32> (ID 53) specialised to the closed-form
 // closure of src/adsr.rs:21-70 `adsr_live(attack, decay, sustain, release)`.
 struct AdsrLive : Node {

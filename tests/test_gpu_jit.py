@@ -30,6 +30,8 @@ def _net_ops(i):
     return (Net.wrap(sine_hz(110.0 + i)) | Net.wrap(noise().seed(i))) >> Net.wrap(lowpass_hz(500.0 + 10.0 * i, 1.0) | pass_())
 
 
+_WAVE = np.random.default_rng(77).uniform(-1.0, 1.0, (2, 1500)).astype(np.float32)   # a two-channel `Wave` for the sampler cases
+
 CASES = {
     "svf_var_lowpass_pan": lambda i: (noise().seed(i) | dc((300.0 + 4000.0 * fv(i), 0.5 + 4.0 * fv(i, 1)))) >> lowpass() >> pan(2.0 * fv(i, 2) - 1.0),
     "svf_var_bell": lambda i: (noise().seed(i) | dc((300.0 + 4000.0 * fv(i), 0.7, 0.5 + 2.0 * fv(i, 1)))) >> bell(),
@@ -90,6 +92,9 @@ WIDER = {
     "phase_synth_tables": lambda i: ramp_hz(100.0 + 13.0 * i) >> (phase_synth(SQUARE) & phase_synth(ORGAN) * 0.5) | (sine_hz(50.0 + i) * 0.6) >> phase_synth(SOFT_SAW),
     "rotate_mixer": lambda i: (noise().seed(i) | sine_hz(200.0 + i)) >> rotate(0.1 * i, 0.8) >> mixer([[0.5, -0.25], [0.125 * (i % 8), 1.0], [1.0, 1.0]]),
     "reverb4_short_lines": lambda i: (noise().seed(i) | noise().seed(i + 100)) >> reverb4_stereo_delays([d * (0.15 + 0.002 * (i % 25)) for d in REVERB4_DELAYS], 1.0 + 0.05 * (i % 8)),
+    "meters": lambda i: noise().seed(i) * (0.2 + 0.02 * i) >> (meter(Meter.Sample) & meter(Meter.Peak(0.002 + 0.0005 * (i % 9))) & meter(Meter.Rms(0.001 + 0.0003 * (i % 7)))),
+    "sampler_regions": lambda i: playwave(_WAVE, i % 2, None if i % 3 else 100 + i) | playwave_at(_WAVE, 0, 10 + i, 400 + 7 * i, 50 + i) * 0.5,
+    "sampler_pitched": lambda i: (sine_hz(1.0 + 0.1 * i) * 0.3 + 0.5 + 0.04 * i) >> resample(playwave(_WAVE, 1, 0)) | dc(0.25 + 0.05 * (i % 30)) >> resample(saw_hz(110.0 + i) | noise().seed(i)),
 }
 GATED = {
     "adsr_noise": lambda i: adsr_live(0.005 + 0.001 * (i % 5), 0.05, 0.5 + 0.01 * (i % 20), 0.1) * noise().seed(i) | ~zero() >> sine_hz(100.0 + i),

@@ -579,6 +579,51 @@ def test_pulse_rotate_mixer_reverb4():  # src/wavetable.rs:361-491, src/pan.rs:9
     L.fo_restore_denormals()
 
 
+def test_meter_playwave_resample():  # src/dynamics.rs:316-437, src/wave.rs:739-797, src/resample.rs:210-300
+    sr = 44100.0
+    x = np.random.default_rng(5).uniform(-1, 1, (1, 3000)).astype(np.float32)
+    # Meter::Sample passes the signal through (test_dynamics.rs:53-60 compares it with the monitored value)
+    assert np.array_equal(OracleUnit(meter(Meter.Sample)).filter(sr, x), x)
+    # Meter::Peak: max(state * smoothing, |x|) with smoothing = 0.5 ** (1 / (timescale * sr)): a unit impulse halves in `timescale` seconds
+    imp = np.zeros((1, 9000), np.float32); imp[0, 10] = -1.0
+    y = OracleUnit(meter(Meter.Peak(0.1))).filter(sr, imp)[0]
+    assert y[9] == 0.0 and y[10] == 1.0 and abs(y[10 + 4410] - 0.5) < 1e-3 and np.all(np.diff(y[10:]) < 0)
+    yp = OracleUnit(meter(Meter.Peak(0.01))).filter(sr, x)[0]
+    assert np.all(yp >= np.abs(x[0])) and np.all(yp[1:] <= np.maximum(yp[:-1], np.abs(x[0, 1:])))
+    # Meter::Rms of a full-scale sine settles at 1 / sqrt(2)
+    yr = OracleUnit(sine_hz(1000.0) >> meter(Meter.Rms(0.01))).render(sr, 0.5)[0]
+    assert abs(yr[-2000:].mean() - 2.0 ** -0.5) < 2e-3
+    # WavePlayer: exact samples, silence after the end, loop jumps, play regions
+    w = np.random.default_rng(6).uniform(-1, 1, (2, 300)).astype(np.float32)
+    y = OracleUnit(playwave(w, 1)).render(sr, 500 / sr)[0]
+    assert np.array_equal(y[:300], w[1]) and not y[300:].any()
+    y = OracleUnit(playwave(w, 0, 100)).render(sr, 1000 / sr)[0]
+    assert np.array_equal(y, np.concatenate([w[0], np.tile(w[0, 100:], 4)])[:1000])
+    y = OracleUnit(playwave_at(w, 0, 50, 120, 60)).render(sr, 400 / sr)[0]
+    assert np.array_equal(y, np.concatenate([w[0, 50:120], np.tile(w[0, 60:120], 6)])[:400])
+    check_wave(playwave(w, 0, 0) | playwave_at(w, 1, 10, 40))
+    # Resample at speed 1: the read head starts one sample in and moves before it reads, so output n = inner sample n + 2 exactly
+    # (Catmull-Rom passes through its knots); at speed 1/2 the knots interleave with the cubic's midpoints (-a + 9b + 9c - d) / 16
+    src = OracleUnit(playwave(w, 0)).render(sr, 300 / sr)[0]
+    y = OracleUnit(dc(1.0) >> resample(playwave(w, 0))).render(sr, 200 / sr)[0]
+    assert np.array_equal(y, src[2:202])
+    y = OracleUnit(dc(0.5) >> resample(playwave(w, 0))).render(sr, 200 / sr)[0]
+    assert np.array_equal(y[1::2][:90], src[2:92])
+    mid = (-src[0:90] + 9.0 * src[1:91] + 9.0 * src[2:92] - src[3:93]) / 16.0
+    assert np.abs(y[0::2][:90] - mid).max() < 1e-6
+    # speed 2 reads every other sample; a negative speed is clamped to 0 and holds the value
+    y = OracleUnit(dc(2.0) >> resample(playwave(w, 0))).render(sr, 100 / sr)[0]
+    assert np.array_equal(y, src[3:203:2])
+    y = OracleUnit(dc(-1.0) >> resample(playwave(w, 0))).render(sr, 50 / sr)[0]
+    assert np.all(y == src[1])
+    # pitched sine: resampling a 440 Hz sine at speed 1.5 gives 660 Hz
+    y = OracleUnit(dc(1.5) >> resample(sine_hz(440.0))).render(sr, 1.0)[0]
+    spec = np.abs(np.fft.rfft(y * np.hanning(len(y))))
+    assert abs(int(np.argmax(spec)) - 660) <= 1
+    check_wave((sine_hz(2.0) * 0.5 + 1.0) >> resample(playwave(w, 0, 0)) | dc(0.37) >> resample(noise()))
+    assert outputs_diverge(dc(1.0) >> resample(noise()) | dc(1.0) >> resample(noise()))
+
+
 def test_mls_is_maximum_length():  # src/noise.rs:11-98: the sequence of an n-bit MLS repeats after exactly 2**n - 1 steps
     for n in range(2, 15):
         u = OracleUnit(mls_bits(n))
