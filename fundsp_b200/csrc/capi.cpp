@@ -73,6 +73,7 @@ API fdsp_node* fdsp_morph(float cutoff, float q) { return wrap(mk_morph(cutoff, 
 API fdsp_node* fdsp_rez(float bandpass, float cutoff, float q, int inputs) { return wrap(mk_rez(bandpass, cutoff, q, inputs), "rez"); }
 API fdsp_node* fdsp_chaos(int kind) { return wrap(mk_chaos(kind), "chaos"); }
 API fdsp_node* fdsp_declick(float duration) { return wrap(mk_declick(duration), "declick"); }
+API fdsp_node* fdsp_limiter(int channels, float attack, float release) { return wrap(mk_limiter(channels, attack, release), "limiter"); }
 API fdsp_node* fdsp_meter(int kind, double timescale) { return wrap(mk_meter(kind, timescale), "meter"); }
 API fdsp_node* fdsp_playwave(const float* samples, uint64_t length, uint64_t start, uint64_t end, int64_t loop_point) { return wrap(mk_playwave(samples, length, start, end, loop_point), "playwave"); }
 API fdsp_node* fdsp_resample(fdsp_node* x) { return wrap(mk_resample(take(x)), "resample"); }

@@ -1211,6 +1211,55 @@ template <class X> struct FeedbackUnit {
   static FDSP_DEV void end_simd(R& r) { if (r.block) X::end_simd(r.x); }
 };
 
+// ---------------------------------------------------------------- Limiter<N> (ID 25, src/dynamics.rs:56-243): look-ahead limiter.
+// A ring of L frames delays the audio; a binary max-tree over the last L amplitudes (ReduceBuffer, updated leaf-to-root per sample)
+// gives the window peak, which an asymmetric follower smooths into the gain. Ring and tree live in the class's delay-line storage:
+// every voice of a class has the same L and the same ring position, so all tree accesses of a warp are coalesced. Tick-only.
+template <int N> struct Limiter {
+  FDSP_NODE(N, N, 2, 7, 2);
+  struct R { float ac, rc, anow, rnow, v1, v2, v3; uint32_t L, leaf, off, index, filled; };
+  static FDSP_DEV void load(R& r, Loader& l) {
+    r.L = l.U(); r.leaf = l.U(); r.ac = l.Pf(); r.rc = l.Pf();
+    r.index = l.S(); r.filled = l.S(); r.anow = l.Sf(); r.rnow = l.Sf(); r.v1 = l.Sf(); r.v2 = l.Sf(); r.v3 = l.Sf();
+    r.off = l.D((uint32_t)N * r.L + r.leaf + r.L + (r.L & 1u));
+  }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.S(r.index); s.S(r.filled); s.Sf(r.anow); s.Sf(r.rnow); s.Sf(r.v1); s.Sf(r.v2); s.Sf(r.v3); }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<N>& in, Fr<N>& o) {
+    float* base = c.dl + (size_t)r.off * c.V + c.v;
+    float* tree = base + (size_t)((uint32_t)N * r.L) * c.V;
+    float amp = 0.0f;
+#pragma unroll
+    for (int k = 0; k < N; k++) amp = fmaxf(amp, fabsf(in.v[k]));
+    uint32_t i = r.leaf + r.index;
+    tree[(size_t)i * c.V] = amp;
+    float cur = amp;
+    while (i > 1u) {   // ReduceBuffer::set :106-114
+      cur = fmaxf(cur, tree[(size_t)(i ^ 1u) * c.V]);
+      i >>= 1;
+      tree[(size_t)i * c.V] = cur;
+    }
+    const float total = cur;   // = buffer[1]
+    if (r.filled < r.L) {      // filling the look-ahead: silence out
+#pragma unroll
+      for (int k = 0; k < N; k++) { base[(size_t)((uint32_t)k * r.L + r.index) * c.V] = in.v[k]; o.v[k] = 0.0f; }
+      r.filled++;
+      if (r.filled == r.L) { r.v1 = r.v2 = r.v3 = total; }   // start following from the buffer's peak
+    } else {
+      const float x = fmaxf(1.0f, total * 1.10f);            // leave some headroom
+      r.v1 = Follower<1>::pole2(x, r.v1, r.anow, r.rnow); r.v2 = Follower<1>::pole2(r.v1, r.v2, r.anow, r.rnow); r.v3 = Follower<1>::pole2(r.v2, r.v3, r.anow, r.rnow);
+      r.anow = r.ac; r.rnow = r.rc;
+      const float g = 1.0f / r.v3;
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        float* slot = base + (size_t)((uint32_t)k * r.L + r.index) * c.V;
+        o.v[k] = *slot * g; *slot = in.v[k];
+      }
+    }
+    r.index++; if (r.index >= r.L) r.index = 0u;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
 // ---------------------------------------------------------------- MeterNode (ID 61, src/dynamics.rs:316-437), WavePlayer (ID 65,
 // src/wave.rs:739-797), Resample<X> (ID 69, src/resample.rs:210-300). All three are tick-only in the reference.
 template <int KIND> struct MeterNode {   // KIND 0 Sample, 1 Peak(timescale), 2 Rms(timescale); smoothing computed on the host in f64
@@ -1550,6 +1599,7 @@ template <int K> struct Cost<PhaseSynth<K>> { static constexpr int value = 110; 
 template <int M, int N> struct Cost<Mixer<M, N>> { static constexpr int value = 2 * M * N; };
 template <int K> struct Cost<MeterNode<K>> { static constexpr int value = 10; };
 template <> struct Cost<WavePlayer> { static constexpr int value = 12; };
+template <int N> struct Cost<Limiter<N>> { static constexpr int value = 150; };
 template <> struct Cost<Sine> { static constexpr int value = 40; };
 template <> struct Cost<Noise> { static constexpr int value = 16; };
 template <> struct Cost<FixedSvf> { static constexpr int value = 20; };

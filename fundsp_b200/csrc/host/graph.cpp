@@ -495,6 +495,23 @@ struct FollowerN : HNode {  // Follow ID 24 / AFollow ID 29
   void lower(Lowering& l) const override { l.p(acoeff); l.p(rcoeff); l.s(1.0f); l.s(1.0f); l.s(0.0f); l.s(0.0f); l.s(0.0f); }
   HCLONE(FollowerN)
 };
+struct LimiterN : HNode {  // src/dynamics.rs:128-243
+  int n; double lookahead, sr = DEFAULT_SR; FollowerN follower;
+  LimiterN(int n_, float attack, float release) : n(n_), lookahead((double)attack), follower(true, attack * 0.4f, release * 0.4f) {}
+  uint32_t length() const { double r = round(sr * lookahead); return r < 1.0 ? 1u : (uint32_t)r; }   // max(1, round(sample_rate * lookahead) as usize)
+  int inputs() const override { return n; } int outputs() const override { return n; }
+  uint64_t id() const override { return 25; }
+  void set_sample_rate(double s) override { sr = s; follower.set_sample_rate(s); }
+  void sig(std::string& o) const override { o += "Limiter<" + I(n) + ">"; }
+  void lower(Lowering& l) const override {
+    const uint32_t L = length(); uint32_t leaf = 1; while (leaf < L) leaf <<= 1;   // usize::next_power_of_two
+    l.U.push_back(L); l.U.push_back(leaf);
+    l.p(follower.acoeff); l.p(follower.rcoeff);
+    l.su(0u); l.su(0u); l.s(1.0f); l.s(1.0f); l.s(0.0f); l.s(0.0f); l.s(0.0f);
+    l.dlen.push_back((uint32_t)n * L + leaf + L + (L & 1u));
+  }
+  HCLONE(LimiterN)
+};
 struct ShaperN : HNode {  // src/shape.rs:205-249
   int kind; float p0, p1;
   ShaperN(int k, float a, float b) : kind(k), p0(a), p1(b) {}
@@ -921,6 +938,10 @@ HNode* mk_reverb3(double time, double diffusion, HNode* filter) {
   return new ReverbN(time, diffusion, filter);
 }
 HNode* mk_var(float value) { return new VarN(value); }
+HNode* mk_limiter(int channels, float attack, float release) {
+  if (channels < 1 || channels > 8 || !(attack >= 0.0f) || !(release >= 0.0f) || attack > 10.0f) return nullptr;
+  return new LimiterN(channels, attack, release);
+}
 HNode* mk_meter(int kind, double timescale) { return (kind < 0 || kind > 2 || (kind > 0 && !(timescale > 0.0))) ? nullptr : new MeterN(kind, timescale); }
 HNode* mk_playwave(const float* samples, uint64_t length, uint64_t start, uint64_t end, int64_t loop_point) {
   if ((!samples && length) || length > (1ull << 28) || end > length || start > 0xfffffffeull || loop_point >= (int64_t)0xffffffffll) return nullptr;   // assert!(end_point <= wave.length())

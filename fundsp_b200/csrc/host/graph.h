@@ -111,6 +111,7 @@ HNode* mk_rotate(float angle, float gain);                           // rotate()
 HNode* mk_meter(int kind, double timescale);                         // MeterNode ID 61: kind 0 Sample, 1 Peak, 2 Rms
 HNode* mk_playwave(const float* samples, uint64_t length, uint64_t start, uint64_t end, int64_t loop_point);  // WavePlayer ID 65
 HNode* mk_resample(HNode* x);                                        // Resample<X> ID 69; consumes the generator
+HNode* mk_limiter(int channels, float attack, float release);       // Limiter<N> ID 25
 HNode* mk_declick(float duration);                                   // Declick ID 23
 HNode* mk_chaos(int kind);                                           // 0 Rossler ID 73, 1 Lorenz ID 74
 HNode* mk_morph(float cutoff, float q);                               // Morph ID 62

@@ -534,6 +534,15 @@ def mixer(matrix):
     return An("mixer", (len(rows[0]), len(rows), tuple(x for r in rows for x in r)), (), len(rows[0]), len(rows))
 
 
+# ---- src/prelude.rs:1288-1301 look-ahead limiters
+def limiter(attack_time, release_time):
+    return An("limiter", (1, f32(attack_time), f32(release_time)), (), 1, 1)
+
+
+def limiter_stereo(attack_time, release_time):
+    return An("limiter", (2, f32(attack_time), f32(release_time)), (), 2, 2)
+
+
 # ---- src/prelude.rs:299 meter(), src/dynamics.rs:316-326 Meter
 class Meter:
     """Meter::Sample / Meter::Peak(timescale) / Meter::Rms(timescale)."""

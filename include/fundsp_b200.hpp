@@ -219,6 +219,8 @@ inline An meter(Meter m) { return An(fdsp_meter(m.kind, m.timescale)); }
 // playwave(&wave, channel, loop): `samples` = wave.channel(channel); loop_point < 0 = None
 inline An playwave(const std::vector<float>& samples, long long loop_point = -1) { return An(fdsp_playwave(samples.data(), samples.size(), 0, samples.size(), loop_point)); }
 inline An playwave_at(const std::vector<float>& samples, size_t start, size_t end, long long loop_point = -1) { return An(fdsp_playwave(samples.data(), samples.size(), start, end, loop_point)); }
+inline An limiter(float attack_time, float release_time) { return An(fdsp_limiter(1, attack_time, release_time)); }
+inline An limiter_stereo(float attack_time, float release_time) { return An(fdsp_limiter(2, attack_time, release_time)); }
 inline An resample(An x) { return An(fdsp_resample(x.release())); }                    // input = speed
 
 // ---- src/math.rs helpers used by the reverbs, in the reference's precision

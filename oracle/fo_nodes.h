@@ -1164,6 +1164,7 @@ struct Follower : Node {
   int inputs() const override { return 1; } int outputs() const override { return 1; }
   uint64_t id() const override { return asym ? 29 : 24; }
   void reset() override { v1 = v2 = v3 = 0; anow = rnow = 1.0f; }
+  void set_value(float x) { v1 = v2 = v3 = x; }   // src/follow.rs:198-202
   void set_sample_rate(double s) override { sr = (float)s; set_time(atime, rtime); }
   static float pole2(float in, float cur, float a, float r) { return cur + fmaxf(0.0f, in - cur) * a - fmaxf(0.0f, cur - in) * r; }
   void tick(const float* in, float* out) override {
@@ -1590,6 +1591,49 @@ struct Mixer : Node {
   FO_CLONE(Mixer)
 };
 
+// ---- src/dynamics.rs:56-243 ReduceBuffer<f32, Maximum> + Limiter<N> (ID 25); the follower is AFollow<f32> (src/follow.rs:137-245)
+struct Limiter : Node {
+  int n; double lookahead, sample_rate; Follower follower;
+  std::vector<float> tree; size_t length = 0, leaf_offset = 0; std::vector<float> buffer; size_t filled = 0, index = 0;
+  void new_buffer() {
+    double r = round(sample_rate * lookahead);
+    length = r < 1.0 ? 1 : (size_t)r;
+    leaf_offset = 1; while (leaf_offset < length) leaf_offset <<= 1;
+    tree.assign(leaf_offset + length + (length & 1), 0.0f);
+  }
+  Limiter(int n_, float attack, float release) : n(n_), lookahead((double)attack), sample_rate(DEFAULT_SR), follower(true, attack * 0.4f, release * 0.4f) {
+    follower.set_sample_rate(sample_rate); new_buffer(); buffer.assign((size_t)n * length, 0.0f);
+  }
+  int inputs() const override { return n; } int outputs() const override { return n; }
+  uint64_t id() const override { return 25; }
+  void reset() override { set_sample_rate(sample_rate); }
+  void set_sample_rate(double sr) override {   // :185-195 (the follower is NOT reset: only its coefficients are recomputed)
+    index = 0; sample_rate = sr; new_buffer(); follower.set_sample_rate(sr);
+    buffer.assign((size_t)n * length, 0.0f); filled = 0;
+  }
+  void reduce_set(size_t idx, float value) {   // :106-114
+    size_t i = leaf_offset + idx;
+    tree[i] = value;
+    while (i > 1) { float reduced = fmaxf(tree[i], tree[i ^ 1]); i >>= 1; tree[i] = reduced; }
+  }
+  void tick(const float* in, float* out) override {   // :197-222
+    float amplitude = 0.0f;
+    for (int k = 0; k < n; k++) amplitude = fmaxf(amplitude, fabsf(in[k]));
+    reduce_set(index, amplitude);
+    if (filled < length) {
+      for (int k = 0; k < n; k++) { buffer[(size_t)k * length + filled] = in[k]; out[k] = 0.0f; }
+      filled++;
+      if (filled == length) follower.set_value(tree[1]);
+    } else {
+      float x = fmaxf(1.0f, tree[1] * 1.10f), y;
+      follower.tick(&x, &y);
+      const float limit = follower.v3, g = 1.0f / limit;
+      for (int k = 0; k < n; k++) { float* slot = &buffer[(size_t)k * length + index]; out[k] = *slot * g; *slot = in[k]; }
+    }
+    index += 1; if (index >= length) index = 0;
+  }
+  FO_CLONE(Limiter)
+};
 // ---- src/dynamics.rs:316-437 Meter / MeterState / MeterNode (ID 61); kind 0 Sample, 1 Peak(timescale), 2 Rms(timescale)
 struct MeterNode : Node {
   int kind; double timescale; float smoothing = 0, state = 0;

@@ -90,6 +90,7 @@ API Node* fo_morph(float cutoff, float q) { return new Morph(cutoff, q); }
 API Node* fo_rez(float bandpass, float cutoff, float q, int inputs) { return new Rez(bandpass, cutoff, q, inputs); }
 API Node* fo_chaos(int kind) { return new Chaos(kind); }   // 0 rossler, 1 lorenz
 API Node* fo_declick(float duration) { return new Declick(duration); }
+API Node* fo_limiter(int channels, float attack, float release) { return new Limiter(channels, attack, release); }
 API Node* fo_meter(int kind, double timescale) { return new MeterNode(kind, timescale); }
 API Node* fo_playwave(const float* samples, uint64_t length, uint64_t start, uint64_t end, int64_t loop_point) {
   auto w = std::make_shared<std::vector<float>>(samples, samples + length);

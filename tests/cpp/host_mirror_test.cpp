@@ -47,7 +47,7 @@ int main() {
   An wide = ((dc(110.0f, 0.3f) >> pulse()) | (noise() >> phase_synth(2))) >> rotate(0.5f, 0.8f) >> mixer(2, 3, {0.5f, -0.25f, 0.125f, 1.0f, 1.0f, 1.0f});
   std::printf("wide %d %d %s %016llx\n", wide.inputs(), wide.outputs(), wide.signature().c_str(), words_hash(wide));
   std::vector<float> wave(64); for (int i = 0; i < 64; i++) wave[i] = (float)i / 64.0f - 0.5f;
-  An smp = (dc(0.75f) >> resample(playwave(wave, 8))) | (playwave_at(wave, 4, 40) >> meter(Meter::Rms(0.05))) | (noise() >> meter(Meter::Peak(0.1)));
+  An smp = (dc(0.75f) >> resample(playwave(wave, 8))) | (playwave_at(wave, 4, 40) >> meter(Meter::Rms(0.05))) | (noise() >> meter(Meter::Peak(0.1)) >> limiter(0.003f, 0.02f));
   std::printf("smp %d %d %s %016llx\n", smp.inputs(), smp.outputs(), smp.signature().c_str(), words_hash(smp));
   An r1 = reverb_stereo(12.0, 2.5, 0.4f), r4 = reverb4_stereo(20.0, 3.0);
   std::printf("reverb_stereo %s %016llx\n", r1.signature().c_str(), words_hash(r1));

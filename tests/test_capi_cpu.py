@@ -53,6 +53,7 @@ GRAPHS = [
     lambda: dc(220.0) >> lorenz() | dc(110.0) >> rossler() | dc(330.0) >> lorenz(),
     lambda: dc((220.0, 0.3)) >> pulse() | dc((220.0, 0.3)) >> pulse().phase(0.5) | (ramp_hz(50.0) >> phase_synth(3) | noise()) >> rotate(0.3, 0.5) >> mixer([[1.0, 2.0]]),
     lambda: (noise() | noise()) >> reverb4_stereo(25.0, 2.0),
+    lambda: noise() >> limiter(0.005, 0.05) | (noise() | noise()) >> limiter_stereo(0.002, 0.02),
     lambda: dc(1.5) >> resample(noise() | sine_hz(440.0)) | dc(0.5) >> resample(playwave(np.linspace(-1, 1, 50, dtype=np.float32)[None, :], 0, 0)) | noise() >> meter(Meter.Rms(0.1)),
     lambda: dc(220.0) >> dsf_saw_r(0.7) | (dc(110.0) | dc(0.4)) >> dsf_square() | dc(440.0) >> dsf_square_r(0.3).phase(0.25),
     lambda: noise() >> feedback2(delay(0.002) * 0.5, lowpass_hz(2000.0, 1.0)) | (noise() | dc(800.0)) >> butterpass() | (noise() | dc((900.0, 8.0))) >> resonator(),
@@ -95,6 +96,7 @@ def test_builder_argument_errors_return_null_with_a_message():
         lambda: be.b_feedback2(0, be.b_pass(), be.b_stack(be.b_pass(), be.b_pass())), # X and Y arity differ
         lambda: be.b_impulse(0),
         lambda: be.b_meter(3, 0.1), lambda: be.b_meter(1, 0.0), lambda: be.b_playwave([0.0] * 8, 0, 9, -1), lambda: be.b_resample(be.b_pass()),   # end_point <= length; generator only
+        lambda: be.b_limiter(0, 0.01, 0.01), lambda: be.b_limiter(1, -1.0, 0.01),
         lambda: be.b_phase_synth(6), lambda: be.b_mixer(0, 2, [1.0]), lambda: be.b_mixer(9, 9, [0.0] * 81),      # tables 0..5; 1 <= M*N <= 64
     ]
     for k, f in enumerate(bad):
@@ -223,7 +225,7 @@ def test_cpp_host_mirror_compiles_and_matches_python_mirror(tmp_path):
     wide, wh = words_hash(((dc((110.0, 0.3)) >> pulse()) | (noise() >> phase_synth(2))) >> rotate(0.5, 0.8) >> mixer([[0.5, -0.25], [0.125, 1.0], [1.0, 1.0]]))
     assert f"wide 0 3 {wide.signature()} {wh}" in lines
     wv = (np.arange(64, dtype=np.float32) / np.float32(64.0) - np.float32(0.5))[None, :]
-    smp, sh = words_hash((dc(0.75) >> resample(playwave(wv, 0, 8))) | (playwave_at(wv, 0, 4, 40) >> meter(Meter.Rms(0.05))) | (noise() >> meter(Meter.Peak(0.1))))
+    smp, sh = words_hash((dc(0.75) >> resample(playwave(wv, 0, 8))) | (playwave_at(wv, 0, 4, 40) >> meter(Meter.Rms(0.05))) | (noise() >> meter(Meter.Peak(0.1)) >> limiter(0.003, 0.02)))
     assert f"smp 0 3 {smp.signature()} {sh}" in lines
     r1, h1 = words_hash(reverb_stereo(12.0, 2.5, 0.4))
     r4, h4 = words_hash(reverb4_stereo(20.0, 3.0))

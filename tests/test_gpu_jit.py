@@ -92,6 +92,7 @@ WIDER = {
     "phase_synth_tables": lambda i: ramp_hz(100.0 + 13.0 * i) >> (phase_synth(SQUARE) & phase_synth(ORGAN) * 0.5) | (sine_hz(50.0 + i) * 0.6) >> phase_synth(SOFT_SAW),
     "rotate_mixer": lambda i: (noise().seed(i) | sine_hz(200.0 + i)) >> rotate(0.1 * i, 0.8) >> mixer([[0.5, -0.25], [0.125 * (i % 8), 1.0], [1.0, 1.0]]),
     "reverb4_short_lines": lambda i: (noise().seed(i) | noise().seed(i + 100)) >> reverb4_stereo_delays([d * (0.15 + 0.002 * (i % 25)) for d in REVERB4_DELAYS], 1.0 + 0.05 * (i % 8)),
+    "limiters": lambda i: noise().seed(i) * (1.0 + 0.2 * i) >> limiter(0.001 + 0.0002 * (i % 5), 0.01) | (noise().seed(i + 50) * (sine_hz(3.0) * 2.0 + 2.5) | sine_hz(300.0 + i) * 4.0) >> limiter_stereo(0.0005, 0.003 + 0.001 * (i % 3)),
     "meters": lambda i: noise().seed(i) * (0.2 + 0.02 * i) >> (meter(Meter.Sample) & meter(Meter.Peak(0.002 + 0.0005 * (i % 9))) & meter(Meter.Rms(0.001 + 0.0003 * (i % 7)))),
     "sampler_regions": lambda i: playwave(_WAVE, i % 2, None if i % 3 else 100 + i) | playwave_at(_WAVE, 0, 10 + i, 400 + 7 * i, 50 + i) * 0.5,
     "sampler_pitched": lambda i: (sine_hz(1.0 + 0.1 * i) * 0.3 + 0.5 + 0.04 * i) >> resample(playwave(_WAVE, 1, 0)) | dc(0.25 + 0.05 * (i % 30)) >> resample(saw_hz(110.0 + i) | noise().seed(i)),

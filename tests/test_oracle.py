@@ -624,6 +624,38 @@ def test_meter_playwave_resample():  # src/dynamics.rs:316-437, src/wave.rs:739-
     assert outputs_diverge(dc(1.0) >> resample(noise()) | dc(1.0) >> resample(noise()))
 
 
+def test_limiter():  # tests/test_dynamics.rs:30-49 restated (seeded sizes instead of funutd's Rnd), src/dynamics.rs:56-243
+    rng = np.random.default_rng(11)
+    sr = 48000.0
+    for samples in [2, 3, 17, 100] + [int(round(2.0 * (20000.0 / 2.0) ** rng.uniform())) for _ in range(6)]:
+        u = OracleUnit(limiter(samples / sr, samples / sr))
+        u.set_sample_rate(sr)
+        edge = np.float32(math.exp((100.0 / 20.0) * math.log(10.0)))                     # a +100 dB edge: the hardest case
+        x = np.concatenate([np.zeros(samples, np.float32), np.full(samples + 1, edge, np.float32)])[None, :]
+        y = u.process_many(x.shape[1], x)[0]
+        assert np.all(y[samples:2 * samples] <= 1.0), samples
+        assert 0.90 <= y[2 * samples] <= 1.00, (samples, y[2 * samples])                   # headroom, but sufficient range
+    # below the threshold the limiter is a pure delay of round(sr * attack) samples with unit gain ... / 1.0 (the follower sits at 1)
+    x = np.random.default_rng(12).uniform(-0.5, 0.5, (1, 2000)).astype(np.float32)
+    y = OracleUnit(limiter(0.005, 0.05)).filter(44100.0, x)[0]
+    L = round(44100.0 * 0.005)
+    assert not y[:L].any() and np.array_equal(y[L:], x[0, :-L])
+    # stereo: both channels share the gain computed from the louder one
+    a = np.random.default_rng(13).uniform(-4, 4, (1, 4000)).astype(np.float32)
+    y2 = OracleUnit(limiter_stereo(0.002, 0.02)).filter(44100.0, np.concatenate([a, 0.25 * a]))
+    y1 = OracleUnit(limiter(0.002, 0.02)).filter(44100.0, a)
+    assert np.array_equal(y2[0], y1[0]) and np.abs(y2[1] - np.float32(0.25) * y1[0]).max() < 1e-6 and np.abs(y1).max() <= 1.0
+    # tick == process on fresh units. (After `reset()` the reference's limiter is NOT in its constructed state: Limiter::reset
+    # re-derives the follower's coefficients but neither clears its three poles nor re-arms its first-sample coefficient of 1
+    # (src/dynamics.rs:181-195, src/follow.rs:177-190), so the reference's own check_wave would not hold for it either.)
+    g = lambda: noise() * 3.0 >> limiter(0.002, 0.01) | (noise() | sine_hz(300.0) * 4.0) >> limiter_stereo(0.0005, 0.003) >> join(2)
+    wave = OracleUnit(g()).render(44100.0, 441 / 44100.0)
+    t = OracleUnit(g()); t.set_sample_rate(44100.0)
+    assert np.abs(wave - np.stack([t.tick() for _ in range(441)], axis=1)).max() <= 1e-4
+    u = OracleUnit(g()); first = u.render(44100.0, 0.01); u.reset()
+    assert np.abs(first - np.stack([u.tick() for _ in range(441)], axis=1)).max() > 1e-2
+
+
 def test_mls_is_maximum_length():  # src/noise.rs:11-98: the sequence of an n-bit MLS repeats after exactly 2**n - 1 steps
     for n in range(2, 15):
         u = OracleUnit(mls_bits(n))
