@@ -1,0 +1,77 @@
+"""`Sequencer`: host-side mirror of the reference's polyphony manager (src/sequencer.rs) — units scheduled with sample-accurate
+start and end times and fade envelopes, mixed into one output.
+
+Like `An` and `Net`, a `Sequencer` here is a description: the list of pushed events and edits, replayed onto a backend by
+`lower(backend)` (`sequencer_new / sequencer_push / sequencer_edit`). On the GPU every event is one voice of a bank: the voice's
+program is the event's graph wrapped in the device node `Event<X>`, which carries the reference's per-block scheduling arithmetic
+(f64 time, activation threshold, start / end index, fade phase) itself, so a sequence renders in long launches with no host
+involvement per block (fundsp_b200/bank.py `GpuBank.from_sequencer`).
+"""
+from __future__ import annotations
+
+from .graph import An, _arity
+
+
+class Fade:  # src/sequencer.rs:35-52
+    Power = 0
+    Smooth = 1
+
+
+class ReplayMode:  # src/sequencer.rs:219-229
+    All = (0, 0.0)
+    None_ = (1, 0.0)
+
+    @staticmethod
+    def Loop(t):
+        return (2, float(t))
+
+
+class Sequencer:
+    def __init__(self, inputs, outputs, mode=ReplayMode.None_):  # Sequencer::new (src/sequencer.rs:272-300)
+        self.nin, self.nout, self.mode = int(inputs), int(outputs), mode
+        self.events = []   # (start, end, fade_ease, fade_in, fade_out, unit, relative)
+        self.edits = []    # (event index, end_time, fade_out, relative), applied after the pushes in order
+        self.log = []      # pushes and edits in call order: ("push", event index) / ("edit", edit index)
+
+    def inputs(self):
+        return self.nin
+
+    def outputs(self):
+        return self.nout
+
+    def push(self, start_time, end_time, fade_ease, fade_in_time, fade_out_time, unit: An, _relative=False):  # :319-345
+        _arity(unit.inputs() == self.nin and unit.outputs() == self.nout, "sequencer.push: unit arity differs from the sequencer's")
+        duration = end_time - start_time
+        assert fade_in_time <= duration and fade_out_time <= duration
+        self.events.append((float(start_time), float(end_time), int(fade_ease), float(fade_in_time), float(fade_out_time), unit, _relative))
+        self.log.append(("push", len(self.events) - 1))
+        return len(self.events) - 1     # EventId
+
+    def push_relative(self, start_time, end_time, fade_ease, fade_in_time, fade_out_time, unit: An):  # :376-400 (time is 0 while describing)
+        return self.push(start_time, end_time, fade_ease, fade_in_time, fade_out_time, unit, _relative=True)
+
+    def push_duration(self, start_time, duration, fade_ease, fade_in_time, fade_out_time, unit: An):  # :420-437
+        return self.push(start_time, start_time + duration, fade_ease, fade_in_time, fade_out_time, unit)
+
+    def edit(self, event_id, end_time, fade_out_time, _relative=False):  # :441-483
+        self.edits.append((int(event_id), float(end_time), float(fade_out_time), _relative))
+        self.log.append(("edit", len(self.edits) - 1))
+
+    def edit_relative(self, event_id, end_time, fade_out_time):  # :486-528
+        self.edit(event_id, end_time, fade_out_time, _relative=True)
+
+    def node(self):
+        """This sequencer as a graph node (`Net::wrap(Box::new(sequencer))` / a boxed AudioUnit inside an expression)."""
+        return An("seqnode", (self,), (), self.nin, self.nout)
+
+    def lower(self, backend):
+        h = backend.sequencer_new(self.nin, self.nout, self.mode[0], self.mode[1])
+        ids = {}
+        for kind, k in self.log:
+            if kind == "push":
+                s, e, ease, fi, fo, unit, rel = self.events[k]
+                ids[k] = backend.sequencer_push(h, s, e, ease, fi, fo, unit.lower(backend), rel)
+            else:
+                ev, end, fo, rel = self.edits[k]
+                backend.sequencer_edit(h, ids[ev], end, fo, rel)
+        return h

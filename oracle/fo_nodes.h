@@ -1994,4 +1994,217 @@ struct Net : Node {
   FO_CLONE(Net)
 };
 
+// ---- src/sequencer.rs Sequencer (ID 64) without a backend: sample-accurate start / stop of units with fade envelopes.
+// Restated in full for ReplayMode::None / All / Loop(t), tick (:679-751) and process (:753-873), including the block-relative fade
+// indices applied to the unit's own buffer (:113-217) and BufferRef::span as written (src/buffer.rs:216-222: it copies input[start]
+// to every slot and only when length > start). std's BinaryHeap is restated from liballoc (push = sift_up with a strict compare,
+// pop = swap with the last, sift_down_to_bottom preferring the right child on ties, sift_up): ONLY the order in which events with
+// identical start times become active depends on it, i.e. the association order of their f32 sum.
+inline float sine_easef(float x) {   // src/math.rs:453-458, T = f32
+  x = x * (float)(3.141592653589793 * 0.5);
+  return 16.0f * x * ((float)3.141592653589793 - x) / ((float)(5.0 * 3.141592653589793 * 3.141592653589793) - 4.0f * x * ((float)3.141592653589793 - x));
+}
+inline double round_away(double x) { return round(x); }              // f64::round: half away from zero
+inline size_t as_usize(double x) { return x != x || x <= 0.0 ? 0 : (x >= 1.8446744073709552e19 ? SIZE_MAX : (size_t)x); }   // saturating `as usize`
+struct SeqEvent {
+  Child unit; double start_time, end_time, original_start_time, original_end_time; int fade_ease; double fade_in, fade_out; uint64_t id;
+};
+struct Sequencer : Node {
+  enum Mode { ALL = 0, NONE = 1, LOOP = 2 };
+  struct Edit { double end_time, fade_out; };
+  std::vector<SeqEvent> active, ready /* binary heap, earliest start at the root */, past;
+  std::map<uint64_t, size_t> active_map; std::map<uint64_t, Edit> edit_map;
+  double active_threshold = 0.0; int nin, nout; double time = 0.0, sample_rate = DEFAULT_SR, sample_duration = 1.0 / DEFAULT_SR;
+  std::vector<float> buffer, tick_buffer, input_buffer; int mode; double loop_arg, loop_point = 0.0; uint64_t next_id = 1;
+  Sequencer(int i, int o, int mode_, double loop_t) : nin(i), nout(o), mode(mode_), loop_arg(loop_t) {
+    buffer.assign((size_t)std::max(1, o) * B, 0.0f); tick_buffer.assign(std::max(1, o), 0.0f); input_buffer.assign((size_t)std::max(1, i) * B, 0.0f);
+    reset();
+  }
+  bool is_replay() const { return mode != NONE; } bool is_loop() const { return mode == LOOP; }
+  // BinaryHeap<Event> with Ord reversed on start_time (total_cmp): a <= b in heap order  <=>  a.start >= b.start
+  static bool heap_le(const SeqEvent& a, const SeqEvent& b) { return !(a.start_time < b.start_time); }
+  void heap_sift_up(size_t start, size_t pos) {
+    SeqEvent hole = std::move(ready[pos]);
+    while (pos > start) { size_t parent = (pos - 1) / 2; if (heap_le(hole, ready[parent])) break; ready[pos] = std::move(ready[parent]); pos = parent; }
+    ready[pos] = std::move(hole);
+  }
+  void heap_push(SeqEvent e) { ready.push_back(std::move(e)); heap_sift_up(0, ready.size() - 1); }
+  SeqEvent heap_pop() {
+    SeqEvent item = std::move(ready.back()); ready.pop_back();
+    if (!ready.empty()) {
+      std::swap(item, ready[0]);
+      const size_t end = ready.size(); size_t pos = 0;
+      SeqEvent hole = std::move(ready[0]);
+      size_t child = 1;
+      while (child <= (end >= 2 ? end - 2 : 0)) {   // end.saturating_sub(2)
+        if (heap_le(ready[child], ready[child + 1])) child += 1;
+        ready[pos] = std::move(ready[child]); pos = child; child = 2 * pos + 1;
+      }
+      if (child == end - 1) { ready[pos] = std::move(ready[child]); pos = child; }
+      ready[pos] = std::move(hole);
+      heap_sift_up(0, pos);
+    }
+    return item;
+  }
+  int inputs() const override { return nin; } int outputs() const override { return nout; }
+  uint64_t id() const override { return 64; }
+  uint64_t push(double start, double end, int ease, double fin, double fout, Node* unit) {   // :319-345
+    assert(unit->inputs() == nin && unit->outputs() == nout);
+    const double duration = end - start; assert(fin <= duration && fout <= duration); (void)duration;
+    unit->set_sample_rate(sample_rate);
+    SeqEvent e{Child(unit), start, end, start, end, ease, fin, fout, next_id++};
+    const uint64_t eid = e.id; push_event(std::move(e)); return eid;
+  }
+  void push_event(SeqEvent e) {   // :347-360
+    if (e.start_time < active_threshold) { active_map[e.id] = active.size(); active.push_back(std::move(e)); } else heap_push(std::move(e));
+  }
+  uint64_t push_relative(double start, double end, int ease, double fin, double fout, Node* unit) {   // :376-418
+    unit->set_sample_rate(sample_rate);
+    SeqEvent e{Child(unit), start + time, end + time, start, end, ease, fin, fout, next_id++};
+    e.original_start_time = start; e.original_end_time = end;   // Event::new ran before the shift (:392-400)
+    const uint64_t eid = e.id; push_event(std::move(e)); return eid;
+  }
+  void edit(uint64_t eid, double end_time, double fade_out) {   // :441-483
+    auto it = active_map.find(eid);
+    if (it != active_map.end()) {
+      SeqEvent& e = active[it->second];
+      e.original_end_time = end_time; e.end_time = end_time + e.start_time - e.original_start_time; e.fade_out = fade_out;
+    } else if (end_time < active_threshold) { if (is_replay()) edit_map[eid] = Edit{end_time, fade_out}; }
+    else edit_map[eid] = Edit{end_time, fade_out};
+  }
+  void edit_relative(uint64_t eid, double end_time, double fade_out) {   // :486-528
+    auto it = active_map.find(eid);
+    if (it != active_map.end()) {
+      SeqEvent& e = active[it->second];
+      e.end_time = time + end_time; e.original_end_time = e.end_time + e.original_start_time - e.start_time; e.fade_out = fade_out;
+    } else if (time + end_time < active_threshold) { if (is_replay()) edit_map[eid] = Edit{time + end_time, fade_out}; }
+    else edit_map[eid] = Edit{time + end_time, fade_out};
+  }
+  void ready_to_active(double next_end_time) {   // :531-553
+    active_threshold = next_end_time - sample_duration * 0.5;
+    while (!ready.empty() && ready[0].start_time < active_threshold) {
+      SeqEvent e = heap_pop();
+      active_map[e.id] = active.size();
+      auto ed = edit_map.find(e.id);
+      if (ed != edit_map.end()) { e.fade_out = ed->second.fade_out; e.end_time = ed->second.end_time; edit_map.erase(ed); }
+      active.push_back(std::move(e));
+    }
+  }
+  void end_of_event(size_t i) {   // :622-639
+    active_map.erase(active[i].id);
+    if (i + 1 < active.size()) active_map[active.back().id] = i;
+    SeqEvent e = std::move(active[i]);
+    if (i + 1 < active.size()) active[i] = std::move(active.back());
+    active.pop_back();
+    e.start_time = e.original_start_time; e.end_time = e.original_end_time;
+    if (is_replay()) e.unit->reset();
+    if (is_loop() && e.start_time >= time) heap_push(std::move(e)); else past.push_back(std::move(e));
+  }
+  void reset() override {   // :642-683
+    loop_point = is_loop() ? fmax(64.0 * sample_duration, round_away(loop_arg * sample_rate) / sample_rate) : INFINITY;
+    if (mode == NONE) { ready.clear(); past.clear(); active.clear(); edit_map.clear(); active_map.clear(); }
+    else {
+      if (is_loop()) { for (auto& e : active) { e.start_time -= loop_point; e.end_time -= loop_point; } }
+      else { while (!active.empty()) { SeqEvent e = std::move(active.back()); active.pop_back(); e.unit->reset(); heap_push(std::move(e)); } active_map.clear(); }
+      while (!past.empty()) { SeqEvent e = std::move(past.back()); past.pop_back(); heap_push(std::move(e)); }
+    }
+    time = 0.0; active_threshold = 0.0;
+  }
+  void set_sample_rate(double sr) override {   // :685-701
+    if (sample_rate != sr) {
+      sample_rate = sr; sample_duration = 1.0 / sr;
+      while (!ready.empty()) { SeqEvent e = heap_pop(); e.unit->set_sample_rate(sr); active.push_back(std::move(e)); }
+      for (auto& e : past) e.unit->set_sample_rate(sr);
+      for (auto& e : active) e.unit->set_sample_rate(sr);
+      reset();
+    }
+  }
+  static float ease(int kind, float x) { return kind == 0 ? sine_easef(x) : smooth5f(x); }   // Fade::Power = 0, Fade::Smooth = 1
+  void tick(const float* in, float* out) override {   // :704-766
+    if (!is_replay()) past.clear();
+    for (int c = 0; c < nout; c++) out[c] = 0.0f;
+    const double end_time = time + sample_duration;
+    ready_to_active(end_time);
+    size_t i = 0;
+    while (i < active.size()) {
+      if (active[i].end_time <= time + 0.5 * sample_duration) end_of_event(i);
+      else {
+        SeqEvent& e = active[i];
+        e.unit->tick(in, tick_buffer.data());
+        if (e.fade_in > 0.0) {
+          const float f = (float)((time - e.start_time) / ((e.start_time + e.fade_in) - e.start_time));
+          if (f < 1.0f) for (int c = 0; c < nout; c++) tick_buffer[c] *= ease(e.fade_ease, f);
+        }
+        if (e.fade_out > 0.0) {
+          const float f = (float)((time - (e.end_time - e.fade_out)) / (e.end_time - (e.end_time - e.fade_out)));
+          if (f > 0.0f) for (int c = 0; c < nout; c++) tick_buffer[c] *= ease(e.fade_ease, 1.0f - f);
+        }
+        for (int c = 0; c < nout; c++) out[c] += tick_buffer[c];
+        i += 1;
+      }
+    }
+    time = end_time;
+    if (time + 0.5 * sample_duration >= loop_point) reset();
+  }
+  void process(int size_, const float* in, float* out) override {   // :768-873
+    if (!is_replay()) past.clear();
+    if (size_ == 0) return;
+    const size_t size = (size_t)size_;
+    for (int c = 0; c < nout; c++) for (int j = 0; j < B; j++) out[c * B + j] = 0.0f;
+    const double end_time = fmin(time + sample_duration * (double)size, loop_point);
+    ready_to_active(end_time);
+    const size_t loop_size = is_loop() ? as_usize(round_away(fmax(0.0, loop_point - time) * sample_rate)) : size;
+    size_t i = 0;
+    while (i < active.size()) {
+      if (active[i].end_time <= time + 0.5 * sample_duration) { end_of_event(i); continue; }
+      SeqEvent& e = active[i];
+      const size_t start_index = e.start_time <= time ? 0 : as_usize(round_away((e.start_time - time) * sample_rate));
+      const size_t end_index = e.end_time >= end_time ? std::min(size, loop_size) : std::min(loop_size, as_usize(round_away((e.end_time - time) * sample_rate)));
+      if (end_index > start_index) {
+        const float* node_input = in;
+        if (start_index != 0) {   // input.span(start_index, end_index - start_index, &mut input_buffer) as written
+          for (int c = 0; c < nin; c++) for (size_t k = start_index; k < end_index - start_index; k++) input_buffer[c * B + (k - start_index)] = in[c * B + start_index];
+          node_input = input_buffer.data();
+        }
+        e.unit->process((int)(end_index - start_index), node_input, buffer.data());
+        {   // fade_in :113-160
+          const double fade_duration = e.fade_in, fade_start_time = e.start_time, fade_end_time = fade_start_time + fade_duration;
+          if (fade_duration > 0.0 && fade_end_time > time) {
+            const size_t fade_end_i = fade_end_time >= end_time ? end_index : as_usize(round_away((fade_end_time - time) / sample_duration));
+            const float fade_phase = (float)(((time + (double)start_index * sample_duration) - fade_start_time) / (fade_end_time - fade_start_time));
+            const float fade_d = (float)(sample_duration / fade_duration);
+            for (int c = 0; c < nout; c++) { float fade = fade_phase; for (size_t k = 0; k < fade_end_i; k++) { buffer[c * B + k] *= ease(e.fade_ease, fade); fade += fade_d; } }
+          }
+        }
+        {   // fade_out :162-217
+          const double fade_duration = e.fade_out, fade_end_time = e.end_time, fade_start_time = fade_end_time - fade_duration;
+          if (fade_duration > 0.0 && fade_start_time < end_time) {
+            const size_t fade_i = fade_start_time <= time ? 0 : as_usize(round_away((fade_start_time - time) / sample_duration));
+            const float fade_phase = (float)(((time + (double)fade_i * sample_duration) - fade_start_time) / (fade_end_time - fade_start_time));
+            const float fade_d = (float)(sample_duration / fade_duration);
+            for (int c = 0; c < nout; c++) { float fade = fade_phase; for (size_t k = fade_i; k < end_index; k++) { buffer[c * B + k] *= ease(e.fade_ease, 1.0f - fade); fade += fade_d; } }
+          }
+        }
+        for (int c = 0; c < nout; c++) for (size_t j = start_index; j < end_index; j++) out[c * B + j] += buffer[c * B + (j - start_index)];
+      }
+      i += 1;
+    }
+    time = end_time;
+    if (loop_size < size) {   // wrap around the loop point and render the rest of the block (:845-872)
+      reset();
+      // As written, both copy loops run `for j in loop_size - size..size`: with loop_size < size the start wraps (release builds; a
+      // debug build panics on the subtraction) and the ranges are empty, so the remainder is rendered from a zero input into a
+      // scratch buffer and the block's tail stays silent. Restated as written.
+      std::vector<float> lin((size_t)std::max(1, nin) * B, 0.0f), lout((size_t)std::max(1, nout) * B, 0.0f);
+      process((int)(size - loop_size), lin.data(), lout.data());
+    }
+  }
+  Node* clone() const override {
+    Sequencer* s = new Sequencer(nin, nout, mode, loop_arg);
+    s->active = active; s->ready = ready; s->past = past; s->active_map = active_map; s->edit_map = edit_map; s->active_threshold = active_threshold;
+    s->time = time; s->sample_rate = sample_rate; s->sample_duration = sample_duration; s->loop_point = loop_point; s->next_id = next_id;
+    return s;
+  }
+};
+
 }  // namespace fo

@@ -90,6 +90,13 @@ API Node* fo_morph(float cutoff, float q) { return new Morph(cutoff, q); }
 API Node* fo_rez(float bandpass, float cutoff, float q, int inputs) { return new Rez(bandpass, cutoff, q, inputs); }
 API Node* fo_chaos(int kind) { return new Chaos(kind); }   // 0 rossler, 1 lorenz
 API Node* fo_declick(float duration) { return new Declick(duration); }
+// Sequencer (src/sequencer.rs): mode 0 ReplayMode::All, 1 None, 2 Loop(loop_time); fade_ease 0 Fade::Power, 1 Fade::Smooth
+API Node* fo_sequencer(int inputs, int outputs, int mode, double loop_time) { return new Sequencer(inputs, outputs, mode, loop_time); }
+API uint64_t fo_sequencer_push(Node* s, double start, double end, int ease, double fade_in, double fade_out, Node* unit) { return static_cast<Sequencer*>(s)->push(start, end, ease, fade_in, fade_out, unit); }
+API uint64_t fo_sequencer_push_relative(Node* s, double start, double end, int ease, double fade_in, double fade_out, Node* unit) { return static_cast<Sequencer*>(s)->push_relative(start, end, ease, fade_in, fade_out, unit); }
+API void fo_sequencer_edit(Node* s, uint64_t id, double end_time, double fade_out) { static_cast<Sequencer*>(s)->edit(id, end_time, fade_out); }
+API void fo_sequencer_edit_relative(Node* s, uint64_t id, double end_time, double fade_out) { static_cast<Sequencer*>(s)->edit_relative(id, end_time, fade_out); }
+API double fo_sequencer_time(Node* s) { return static_cast<Sequencer*>(s)->time; }
 API Node* fo_limiter(int channels, float attack, float release) { return new Limiter(channels, attack, release); }
 API Node* fo_meter(int kind, double timescale) { return new MeterNode(kind, timescale); }
 API Node* fo_playwave(const float* samples, uint64_t length, uint64_t start, uint64_t end, int64_t loop_point) {

@@ -656,6 +656,86 @@ def test_limiter():  # tests/test_dynamics.rs:30-49 restated (seeded sizes inste
     assert np.abs(first - np.stack([u.tick() for _ in range(441)], axis=1)).max() > 1e-2
 
 
+def _seq_four():   # tests/test_basic.rs:255-273
+    from fundsp_b200.sequencer import Sequencer, Fade, ReplayMode
+    q = Sequencer(0, 2, ReplayMode.All)
+    q.push(0.1, 0.2, Fade.Smooth, 0.01, 0.0, noise() | sine_hz(220.0))
+    q.push(0.3, 0.4, Fade.Smooth, 0.09, 0.08, sine_hz(110.0) | noise())
+    q.push(0.25, 0.5, Fade.Power, 0.0, 0.01, mls() | noise())
+    q.push(0.6, 0.7, Fade.Power, 0.02, 0.03, noise() | mls())
+    return q
+
+
+def test_sequencer():  # src/sequencer.rs; tests/test_basic.rs:192-193,255-274,713-765; src/sequencer.rs:918-935 (module tests)
+    from fundsp_b200.sequencer import Sequencer, Fade, ReplayMode
+    L.fo_set_denormal_emulation(0)
+    sr = 44100.0
+    # an empty sequencer inside a graph (test_basic.rs:192-193) and the four-event sequence (:255-274): tick == process
+    check_wave((noise() | noise()) >> Sequencer(2, 2, ReplayMode.None_).node())
+    check_wave(_seq_four().node())
+    u = OracleUnit(_seq_four().node())
+    wave = u.render(sr, 0.75)
+    u.reset()                                                      # ReplayMode::All: reset replays every event
+    ticks = np.stack([u.tick() for _ in range(wave.shape[1])], axis=1)
+    assert np.abs(wave - ticks).max() <= 1e-4 and np.abs(wave).max() > 0.5
+    # silence outside the events, sound inside; event 0 starts at sample 4410 exactly
+    assert not wave[:, :4410].any() and wave[1, 4411] != 0.0 and not wave[:, int(0.2 * sr) + 1:int(0.25 * sr) - 1].any() and not wave[:, int(0.7 * sr) + 1:].any()
+    # test_sequencer_passthrough (:713-728): events with inputs, tick path
+    q = Sequencer(1, 1, ReplayMode.None_)
+    q.push(0.0, 1.0, Fade.Smooth, 0.0, 0.0, pass_())
+    q.push(1.0 / 44100.0, 1.0, Fade.Smooth, 0.0, 0.0, mul(2.0))
+    u = OracleUnit(q.node())
+    assert [float(u.tick([x])[0]) for x in (1.0, 2.0, 0.5)] == [1.0, 6.0, 1.5]
+    # test_sequencer_loop (:730-765)
+    q = Sequencer(0, 1, ReplayMode.Loop(79.0 / 44100.0))
+    q.push(12.0 / 44100.0, 89.0 / 44100.0, Fade.Smooth, 0.0, 0.0, dc(1.0))
+    u = OracleUnit(q.node())
+    got = [float(u.tick()[0]) for _ in range(12 + 77 + 2 + 77 + 2)]
+    assert got == [0.0] * 12 + [1.0] * 77 + [0.0] * 2 + [1.0] * 77 + [0.0] * 2
+    # reset_replays_events (src/sequencer.rs:918-935)
+    q = Sequencer(0, 1, ReplayMode.All); q.push(0.0, 1.0, Fade.Smooth, 0.0, 0.0, sine_hz(440.0))
+    u = OracleUnit(q.node()); first = u.tick(); u.reset()
+    assert np.array_equal(first, u.tick())
+    # known answers on the block path: dc events make the envelope itself visible.
+    q = Sequencer(0, 1, ReplayMode.None_)
+    q.push(100.0 / sr, 1100.0 / sr, Fade.Smooth, 200.0 / sr, 400.0 / sr, dc(1.0))
+    y = OracleUnit(q.node()).render(sr, 1300 / sr)[0]
+    assert not y[:100].any() and not y[1100:].any() and np.all(y[300:700] == 1.0)
+    s5 = lambda x: ((x * 6.0 - 15.0) * x + 10.0) * x ** 3
+    assert np.abs(y[100:300] - s5(np.arange(200) / 200.0)).max() < 1e-4                       # fade in: smooth5 over 200 samples
+    assert np.abs(y[700:1100] - s5(1.0 - np.arange(400) / 400.0)).max() < 1e-4               # fade out
+    q = Sequencer(0, 1, ReplayMode.None_)
+    q.push(37.0 / sr, 937.0 / sr, Fade.Power, 300.0 / sr, 300.0 / sr, dc(1.0))
+    y = OracleUnit(q.node()).render(sr, 1000 / sr)[0]
+    ph = np.arange(300) / 300.0
+    assert np.abs(y[37:337] - np.sin(ph * np.pi / 2)).max() < 2e-3 and np.abs(y[637:937] - np.cos(ph * np.pi / 2)).max() < 2e-3   # Bhaskara sine
+    # equal-power crossfade of two dc events: squares sum to one across the overlap
+    q = Sequencer(0, 2, ReplayMode.None_)
+    q.push(0.0, 1000.0 / sr, Fade.Power, 0.0, 500.0 / sr, dc((1.0, 0.0)))
+    q.push(500.0 / sr, 1500.0 / sr, Fade.Power, 500.0 / sr, 0.0, dc((0.0, 1.0)))
+    y = OracleUnit(q.node()).render(sr, 1500 / sr)
+    assert np.abs(y[0, 500:1000] ** 2 + y[1, 500:1000] ** 2 - 1.0).max() < 5e-3
+    # the sum of overlapping events equals the events rendered alone (same seeds: the same graph pushed at the same time)
+    mk = lambda: noise().seed(5) >> lowpass_hz(1200.0, 1.0)
+    q1 = Sequencer(0, 1, ReplayMode.None_); q1.push(0.01, 0.03, Fade.Smooth, 0.002, 0.004, mk())
+    q2 = Sequencer(0, 1, ReplayMode.None_); q2.push(0.02, 0.05, Fade.Smooth, 0.001, 0.001, sine_hz(300.0).phase(0.0))
+    q3 = Sequencer(0, 1, ReplayMode.None_); q3.push(0.01, 0.03, Fade.Smooth, 0.002, 0.004, mk()); q3.push(0.02, 0.05, Fade.Smooth, 0.001, 0.001, sine_hz(300.0).phase(0.0))
+    a, b, c = (OracleUnit(q.node()).render(sr, 0.06) for q in (q1, q2, q3))
+    assert np.array_equal(a + b, c)
+    # edit: shortening an event before it starts, and while it plays (the fade-out moves with the new end)
+    q = Sequencer(0, 1, ReplayMode.None_)
+    e = q.push(100.0 / sr, 2000.0 / sr, Fade.Smooth, 0.0, 0.0, dc(1.0))
+    q.edit(e, 600.0 / sr, 100.0 / sr)
+    y = OracleUnit(q.node()).render(sr, 800 / sr)[0]
+    assert np.all(y[100:500] == 1.0) and not y[600:].any() and np.abs(y[500:600] - s5(1.0 - np.arange(100) / 100.0)).max() < 1e-4
+    # a push that lands in the past of a running sequencer starts at once (:347-353)
+    h = L.fo_sequencer(0, 1, 1, 0.0); u = OracleUnit(h)
+    u.process_many(128)
+    L.fo_sequencer_push(h, 0.0, 1.0, 1, 0.0, 0.0, OracleUnit(dc(0.5)).take())
+    assert np.all(u.process_many(64)[0] == 0.5) and abs(L.fo_sequencer_time(h) - 192 / 44100.0) < 1e-12
+    L.fo_restore_denormals()
+
+
 def test_mls_is_maximum_length():  # src/noise.rs:11-98: the sequence of an n-bit MLS repeats after exactly 2**n - 1 steps
     for n in range(2, 15):
         u = OracleUnit(mls_bits(n))
