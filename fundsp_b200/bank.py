@@ -74,6 +74,31 @@ class GpuBank:
         addr = [x for pair in address for x in pair]
         vals = (C.c_float * max(1, len(values)))(*values)
         check(self.L.fdsp_bank_set(self.h, voice, kind, vals, len(values), seed, (C.c_int64 * max(1, len(addr)))(*addr), len(address)))
+
+    # ---- sequencer banks (voices built with fundsp_b200.sequencer.event): the mix output is Sequencer::process
+    @classmethod
+    def from_sequencer(cls, seq, device=0, per_voice=False, mix=True, sample_rate=None):
+        """One voice per pushed event (`Sequencer.voices()`), in push order."""
+        return cls(seq.voices(), device=device, per_voice=per_voice, mix=mix, sample_rate=sample_rate)
+
+    def time(self):
+        """Sequencer::time: seconds rendered since the last reset (the f64 clock every event voice keeps on the device)."""
+        return float(self.L.fdsp_bank_time(self.h))
+
+    def edit_event(self, voice, end_time, fade_out_time):
+        """Sequencer::edit on a live bank."""
+        check(self.L.fdsp_bank_edit_event(self.h, int(voice), float(end_time), float(fade_out_time)))
+
+    def push_event(self, ev):
+        """Sequencer::push on a running bank: `ev` (an `event(...)` expression) takes the slot of a finished event of the same
+        graph class; returns the voice index."""
+        v = C.c_uint32(0)
+        check(self.L.fdsp_bank_push_event(self.h, ev.lower(GpuBackend()), C.byref(v)))
+        return int(v.value)
+
+    def replace_voice(self, voice, unit):
+        check(self.L.fdsp_bank_replace_voice(self.h, int(voice), unit.lower(GpuBackend())))
+
     def allocate(self, max_samples=64): check(self.L.fdsp_bank_allocate(self.h, int(max_samples)))
 
     def clone(self):

@@ -73,6 +73,7 @@ API fdsp_node* fdsp_morph(float cutoff, float q) { return wrap(mk_morph(cutoff, 
 API fdsp_node* fdsp_rez(float bandpass, float cutoff, float q, int inputs) { return wrap(mk_rez(bandpass, cutoff, q, inputs), "rez"); }
 API fdsp_node* fdsp_chaos(int kind) { return wrap(mk_chaos(kind), "chaos"); }
 API fdsp_node* fdsp_declick(float duration) { return wrap(mk_declick(duration), "declick"); }
+API fdsp_node* fdsp_event(fdsp_node* x, double start, double end, int fade_ease, double fade_in, double fade_out) { return wrap(mk_event(take(x), start, end, fade_ease, fade_in, fade_out), "event"); }
 API fdsp_node* fdsp_limiter(int channels, float attack, float release) { return wrap(mk_limiter(channels, attack, release), "limiter"); }
 API fdsp_node* fdsp_meter(int kind, double timescale) { return wrap(mk_meter(kind, timescale), "meter"); }
 API fdsp_node* fdsp_playwave(const float* samples, uint64_t length, uint64_t start, uint64_t end, int64_t loop_point) { return wrap(mk_playwave(samples, length, start, end, loop_point), "playwave"); }
@@ -243,6 +244,27 @@ API int fdsp_bank_set(fdsp_bank* b, uint32_t voice, int kind, const float* v, in
   std::string e = b->b.set(voice, s);
   return e.empty() ? FDSP_OK : fail(e.find("rebuild") != std::string::npos ? FDSP_ERR_UNSUPPORTED : FDSP_ERR_ARG, e);
 }
+// ---- sequencer banks: voices made by fdsp_event
+API int fdsp_bank_edit_event(fdsp_bank* b, uint32_t voice, double end_time, double fade_out) {
+  if (!b) return fail(FDSP_ERR_ARG, "null bank");
+  std::string e = b->b.edit_event(voice, end_time, fade_out);
+  return e.empty() ? FDSP_OK : fail(FDSP_ERR_ARG, e);
+}
+API int fdsp_bank_replace_voice(fdsp_bank* b, uint32_t voice, fdsp_node* unit) {
+  if (!b) { fdsp_node_free(unit); return fail(FDSP_ERR_ARG, "null bank"); }
+  std::string e = b->b.replace_voice(voice, take(unit));
+  return e.empty() ? FDSP_OK : fail(e.find("rebuild") != std::string::npos || e.find("differs") != std::string::npos ? FDSP_ERR_UNSUPPORTED : FDSP_ERR_ARG, e);
+}
+API int fdsp_bank_push_event(fdsp_bank* b, fdsp_node* event, uint32_t* voice) {
+  if (!b || !event) { fdsp_node_free(event); return fail(FDSP_ERR_ARG, "null bank or event"); }
+  const int v = b->b.free_event_voice(event->n);
+  if (v < 0) { fdsp_node_free(event); return fail(FDSP_ERR_UNSUPPORTED, "no finished event of the same graph class is free: create the bank with spare (finished or far-future) events of this class, or rebuild it"); }
+  std::string e = b->b.replace_voice((uint32_t)v, take(event));
+  if (!e.empty()) return fail(FDSP_ERR_UNSUPPORTED, e);
+  if (voice) *voice = (uint32_t)v;
+  return FDSP_OK;
+}
+API double fdsp_bank_time(const fdsp_bank* b) { return b ? b->b.seq_time : 0.0; }
 API int fdsp_bank_reset(fdsp_bank* b) { return b ? status(b->b.reset()) : fail(FDSP_ERR_ARG, "null bank"); }
 API int fdsp_bank_allocate(fdsp_bank* b, uint64_t max_n) {
   if (!b) return fail(FDSP_ERR_ARG, "null bank");

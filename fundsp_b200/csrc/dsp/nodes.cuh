@@ -1211,6 +1211,103 @@ template <class X> struct FeedbackUnit {
   static FDSP_DEV void end_simd(R& r) { if (r.block) X::end_simd(r.x); }
 };
 
+// ---------------------------------------------------------------- Event<X>: ONE event of a Sequencer (src/sequencer.rs:768-843)
+// as a voice. The reference's per-block scheduling arithmetic runs here, per voice, at the start of every block, in f64 like the
+// reference: time += sample_duration * size; an event turns active when start_time < block_end - sample_duration / 2, ends when
+// end_time <= time + sample_duration / 2; inside a block the unit renders samples [start_index, end_index) with ITS OWN process()
+// of end_index - start_index samples (so its 8-sample groups and its tail are relative to start_index); fade-in / fade-out multiply
+// the unit's buffer from the block-relative indices of :113-217, the fade value advancing by f32 addition. Nothing here needs the
+// host per block, so a sequence renders in long launches. X is a generator (the span() of inputs is not reproduced).
+FDSP_DEV float sine_ease_f(float x) {   // src/math.rs:453-458, T = f32
+  const float pi = (float)3.141592653589793;
+  x = x * (float)(3.141592653589793 * 0.5);
+  return 16.0f * x * (pi - x) / ((float)(5.0 * 3.141592653589793 * 3.141592653589793) - 4.0f * x * (pi - x));
+}
+template <class X> struct Event {
+  static constexpr int NO = X::OUT;
+  FDSP_NODE(0, NO, 11 + X::NP, 3 + X::NS, X::NU);
+  struct R {
+    double sr, sd, start, end, fin, fout, time; int ease, status;   // status 0 ready, 1 active, 2 past
+    int s_idx, n_v, nfull_v, fi_end, fo_i, fo_end; float fi_cur, fi_d, fo_cur, fo_d; bool fi_on, fo_on;
+    typename X::R x;
+  };
+  static FDSP_DEV double ld64(Loader& l, bool state) {
+    const uint32_t lo = state ? l.S() : l.P(), hi = state ? l.S() : l.P();
+    return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+  }
+  static FDSP_DEV void load(R& r, Loader& l) {
+    r.sr = ld64(l, false); r.start = ld64(l, false); r.end = ld64(l, false); r.fin = ld64(l, false); r.fout = ld64(l, false); r.ease = (int)l.P();
+    r.sd = 1.0 / r.sr;
+    r.time = ld64(l, true); r.status = (int)l.S();
+    r.s_idx = r.n_v = r.nfull_v = r.fi_end = r.fo_i = r.fo_end = 0; r.fi_cur = r.fi_d = r.fo_cur = r.fo_d = 0.0f; r.fi_on = r.fo_on = false;
+    X::load(r.x, l);
+  }
+  static FDSP_DEV void save(const R& r, Saver& s) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(r.time);
+    s.S((uint32_t)b); s.S((uint32_t)(b >> 32)); s.S((uint32_t)r.status); X::save(r.x, s);
+  }
+  static FDSP_DEV int as_index(double x) { return x > 0.0 ? (x < 1.0e9 ? (int)x : 1000000000) : 0; }   // `as usize`, saturating
+  static FDSP_DEV void plan(R& r, int n) {   // Sequencer::process for this event, :768-843
+    const double end_blk = r.time + r.sd * (double)n;
+    if (r.status == 0 && r.start < end_blk - r.sd * 0.5) r.status = 1;                 // ready_to_active
+    r.n_v = 0; r.s_idx = 0; r.nfull_v = 0; r.fi_on = r.fo_on = false;
+    if (r.status == 1) {
+      if (r.end <= r.time + 0.5 * r.sd) r.status = 2;                                  // end_of_event
+      else {
+        const int s = r.start <= r.time ? 0 : as_index(round((r.start - r.time) * r.sr));
+        const int e0 = r.end >= end_blk ? n : as_index(round((r.end - r.time) * r.sr));
+        const int e = e0 < n ? e0 : n;
+        if (e > s) {
+          r.s_idx = s; r.n_v = e - s; r.nfull_v = (e - s) & ~7;
+          const double fe = r.start + r.fin;
+          if (r.fin > 0.0 && fe > r.time) {                                            // fade_in :113-160
+            r.fi_on = true;
+            r.fi_end = fe >= end_blk ? e : as_index(round((fe - r.time) / r.sd));
+            r.fi_cur = (float)(((r.time + (double)s * r.sd) - r.start) / (fe - r.start));
+            r.fi_d = (float)(r.sd / r.fin);
+          }
+          const double fs = r.end - r.fout;
+          if (r.fout > 0.0 && fs < end_blk) {                                          // fade_out :162-217
+            r.fo_on = true;
+            r.fo_i = fs <= r.time ? 0 : as_index(round((fs - r.time) / r.sd));
+            r.fo_cur = (float)(((r.time + (double)r.fo_i * r.sd) - fs) / (r.end - fs));
+            r.fo_d = (float)(r.sd / r.fout);
+            r.fo_end = e;
+          }
+        }
+      }
+    }
+    r.time = end_blk;
+  }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<0>& in, Fr<NO>& o) {
+    if (T) { X::template step<true>(r.x, c, in, o); return; }   // (an event is always the root of a voice: not reached)
+    if (c.i == 0) plan(r, c.n);
+    const int b = c.i - r.s_idx;
+    if (b >= 0 && b < r.n_v) {
+      C c2 = c;
+      c2.n = r.n_v; c2.i = b; c2.rem = b >= r.nfull_v; c2.first = !c2.rem && (b & 7) == 0;
+      if (b == r.nfull_v) X::end_simd(r.x);                       // the unit's own block: SIMD part done, tail through its tick path
+      X::template step<false>(r.x, c2, in, o);
+      if (b == r.n_v - 1 && r.nfull_v == r.n_v) X::end_simd(r.x); // no tail
+      float g = 1.0f; bool scaled = false;
+      if (r.fi_on && b < r.fi_end) { g = r.ease == 0 ? sine_ease_f(r.fi_cur) : smooth5f(r.fi_cur); r.fi_cur += r.fi_d; scaled = true; }
+      if (scaled) {
+#pragma unroll
+        for (int k = 0; k < NO; k++) o.v[k] *= g;
+      }
+      if (r.fo_on && b >= r.fo_i && b < r.fo_end) {
+        const float h = r.ease == 0 ? sine_ease_f(1.0f - r.fo_cur) : smooth5f(1.0f - r.fo_cur); r.fo_cur += r.fo_d;
+#pragma unroll
+        for (int k = 0; k < NO; k++) o.v[k] *= h;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NO; k++) o.v[k] = 0.0f;
+    }
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
 // ---------------------------------------------------------------- Limiter<N> (ID 25, src/dynamics.rs:56-243): look-ahead limiter.
 // A ring of L frames delays the audio; a binary max-tree over the last L amplitudes (ReduceBuffer, updated leaf-to-root per sample)
 // gives the window peak, which an asymmetric follower smooths into the gain. Ring and tree live in the class's delay-line storage:
@@ -1632,6 +1729,8 @@ template <int K> struct Cost<Shaper<K>> { static constexpr int value = K == 2 ? 
 template <> struct Cost<Convolver> { static constexpr int value = 48; };
 template <class X> struct WaveKind<Resample<X>> : WaveKind<X> {};
 template <class X> struct Cost<Resample<X>> { static constexpr int value = 4 * Cost<X>::value + 120; };
+template <class X> struct WaveKind<Event<X>> : WaveKind<X> {};
+template <class X> struct Cost<Event<X>> { static constexpr int value = Cost<X>::value + 110; };
 template <class X> struct WaveKind<FeedbackUnit<X>> : WaveKind<X> {};
 template <class X> struct Cost<FeedbackUnit<X>> { static constexpr int value = Cost<X>::value + 12 * X::IN; };
 template <class F> struct Cost<Reverb85<F>> { static constexpr int value = 1200 + 16 * Cost<F>::value; };

@@ -233,6 +233,75 @@ std::string Bank::set(uint32_t voice, const Setting& st) {  // AudioUnit::set (s
   return "internal: voice not found in any class";
 }
 
+void Bank::advance_clock(uint64_t n) {   // what every Event<X> voice does to its own clock (nodes.cuh Event::plan)
+  const double unit_rate = net_rate ? (double)(float)sr : sr, sd = 1.0 / unit_rate;
+  for (uint64_t t0 = 0; t0 < n; t0 += 64) seq_time = seq_time + sd * (double)std::min<uint64_t>(64, n - t0);
+}
+
+std::string Bank::upload_voice(uint32_t voice, const Lowering& l, bool with_state) {
+  for (auto& c : classes) {
+    auto it = std::lower_bound(c.voices.begin(), c.voices.end(), voice);
+    if (it == c.voices.end() || *it != voice) continue;
+    const uint32_t i = (uint32_t)(it - c.voices.begin()), Vc = c.V();
+    if (l.U != c.uniform || l.P.size() != c.np || l.S.size() != c.ns)
+      return "the voice does not fit its class: a class-uniform word (delay length, table, wave) or the word layout differs; rebuild the bank instead";
+    if (c.np) CU(cudaMemcpy2DAsync(c.d_params + i, (size_t)Vc * 4, l.P.data(), 4, 4, c.np, cudaMemcpyHostToDevice, stream));
+    for (uint32_t k = 0; k < c.ns; k++) c.state0[(size_t)k * Vc + i] = l.S[k];
+    if (with_state) {
+      if (c.fdn) return "voices of a two-stage (FDN reverb) class cannot be replaced in place";
+      if (c.ns) CU(cudaMemcpy2DAsync(c.d_state + i, (size_t)Vc * 4, l.S.data(), 4, 4, c.ns, cudaMemcpyHostToDevice, stream));
+      if (c.dl_floats) CU(cudaMemset2DAsync(c.d_dline + i, (size_t)Vc * 4, 0, 4, (size_t)c.dl_floats, stream));
+    }
+    CU(cudaStreamSynchronize(stream));  // `l` is pageable
+    return "";
+  }
+  return "internal: voice not found in any class";
+}
+
+std::string Bank::edit_event(uint32_t voice, double end_time, double fade_out) {
+  if (voice >= V()) return "edit: voice index out of range";
+  CU(cudaSetDevice(device));
+  if (!event_edit(nodes[voice].get(), end_time, fade_out)) return "edit: the voice is not a sequencer event";
+  Lowering l;
+  nodes[voice]->lower(l);
+  if (!l.ok) return l.why;
+  return upload_voice(voice, l, false);
+}
+
+std::string Bank::replace_voice(uint32_t voice, HNode* node) {
+  std::unique_ptr<HNode> n(node);
+  if (!n) return "replace: null node";
+  if (voice >= V()) return "replace: voice index out of range";
+  if (n->inputs() != nin || n->outputs() != nout) return "replace: the unit's arity differs from the bank's";
+  CU(cudaSetDevice(device));
+  std::string a, b;
+  n->sig(a); nodes[voice]->sig(b);
+  if (a != b) return "replace: the unit's graph differs from the voice's class `" + b + "`";
+  const double unit_rate = net_rate ? (double)(float)sr : sr;
+  n->set_sample_rate(unit_rate);
+  event_set_clock(n.get(), seq_time);   // an event pushed into a running sequencer counts from now
+  Lowering l;
+  n->lower(l);
+  if (!l.ok) return l.why;
+  std::string e = upload_voice(voice, l, true);
+  if (!e.empty()) return e;
+  nodes[voice] = std::move(n);
+  return "";
+}
+
+int Bank::free_event_voice(const HNode* like) const {
+  std::string want; like->sig(want);
+  const double unit_rate = net_rate ? (double)(float)sr : sr, sd = 1.0 / unit_rate;
+  for (uint32_t v = 0; v < V(); v++) {
+    double s0, e0;
+    if (!event_times(nodes[v].get(), &s0, &e0)) continue;
+    if (!(e0 <= seq_time + 0.5 * sd)) continue;   // Event::plan's end-of-event test at the start of the next block: nothing more to render
+    std::string sg; nodes[v]->sig(sg);
+    if (sg == want) return (int)v;
+  }
+  return -1;
+}
+
 std::string Bank::reset() {  // AudioUnit::reset: back to the construction-time state
   CU(cudaSetDevice(device));
   for (auto& c : classes) {
@@ -241,7 +310,7 @@ std::string Bank::reset() {  // AudioUnit::reset: back to the construction-time 
     if (c.ring_floats) CU(cudaMemsetAsync(c.d_ring, 0, (size_t)c.ring_floats * c.V() * sizeof(float), stream));
   }
   CU(cudaStreamSynchronize(stream));
-  dirty = false;
+  dirty = false; seq_time = 0.0;
   return "";
 }
 
@@ -440,7 +509,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
     }
     for (auto e : tev) cudaEventDestroy(e);
   }
-  dirty = true;
+  dirty = true; advance_clock(n);
   return "";
 }
 

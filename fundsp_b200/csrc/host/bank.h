@@ -59,6 +59,14 @@ struct Bank {
   std::string lower_and_upload(bool upload_state);
   std::string set_sample_rate(double sr);
   std::string reset();
+  // Sequencer banks (voices made by mk_event): the sequencer clock, replicated on the host with the device's own arithmetic
+  // (time += sample_duration * block for every 64-sample block and the tail), live edits and reuse of finished voices
+  double seq_time = 0.0;
+  void advance_clock(uint64_t n);
+  std::string upload_voice(uint32_t voice, const Lowering& l, bool with_state);
+  std::string edit_event(uint32_t voice, double end_time, double fade_out);   // Sequencer::edit
+  std::string replace_voice(uint32_t voice, HNode* node);                     // a new unit in the slot of a voice of the same class; consumes node
+  int free_event_voice(const HNode* like) const;                              // a finished event whose class matches `like`, or -1
   std::string set(uint32_t voice, const Setting& s);  // AudioUnit::set on one voice of a live bank (parameters only; state continues)
   std::string ensure_staging(uint32_t chunk);
   std::string render_device(uint64_t n, const float* in_dev, uint64_t in_stride, float* out_dev, uint64_t out_stride, float* mix_dev,

@@ -602,6 +602,25 @@ struct ResampleN : HNode {  // src/resample.rs:210-300
   }
   HCLONE(ResampleN)
 };
+struct EventN : HNode {  // one Sequencer event as a voice (src/sequencer.rs:55-92 Event, :768-843 process); device: nodes.cuh Event<X>
+  Kid x; double start, end, fade_in, fade_out, sr = DEFAULT_SR, time0 = 0.0; int ease; int status0 = 0;
+  EventN(HNode* x_, double s, double e, int ease_, double fi, double fo) : x(x_), start(s), end(e), fade_in(fi), fade_out(fo), ease(ease_) {}
+  int inputs() const override { return 0; } int outputs() const override { return x->outputs(); }
+  uint64_t id() const override { return 64; }
+  void reset() override { x->reset(); }
+  void set_sample_rate(double s) override { sr = s; x->set_sample_rate(s); }
+  void set(const Setting& s) override { x->set(s); }
+  AttoHash ping(bool probe, AttoHash h) override { return x->ping(probe, h); }   // the sequencer never pings its units (AudioUnit::ping default)
+  void sig(std::string& o) const override { o += "Event<"; x->sig(o); o += ">"; }
+  static void p64(Lowering& l, double v) { uint64_t b; memcpy(&b, &v, 8); l.P.push_back((uint32_t)b); l.P.push_back((uint32_t)(b >> 32)); }
+  void lower(Lowering& l) const override {
+    p64(l, sr); p64(l, start); p64(l, end); p64(l, fade_in); p64(l, fade_out); l.P.push_back((uint32_t)ease);
+    uint64_t tb; memcpy(&tb, &time0, 8);
+    l.su((uint32_t)tb); l.su((uint32_t)(tb >> 32)); l.su((uint32_t)status0);   // sequencer time at construction (0 unless pushed into a running bank), status ready
+    x->lower(l);
+  }
+  HCLONE(EventN)
+};
 struct VarN : HNode {  // the shared value is control-plane state: it enters as a parameter word and changes through Setting::value
   float value; explicit VarN(float v) : value(v) {}
   int inputs() const override { return 0; } int outputs() const override { return 1; }
@@ -938,6 +957,29 @@ HNode* mk_reverb3(double time, double diffusion, HNode* filter) {
   return new ReverbN(time, diffusion, filter);
 }
 HNode* mk_var(float value) { return new VarN(value); }
+bool event_edit(HNode* n, double end_time, double fade_out) {   // Sequencer::edit on an event (:441-483, no loop: start == original start)
+  EventN* e = dynamic_cast<EventN*>(n);
+  if (!e) return false;
+  e->end = end_time; e->fade_out = fade_out;
+  return true;
+}
+bool event_times(const HNode* n, double* start, double* end) {
+  const EventN* e = dynamic_cast<const EventN*>(n);
+  if (!e) return false;
+  *start = e->start; *end = e->end;
+  return true;
+}
+bool event_set_clock(HNode* n, double time) {
+  EventN* e = dynamic_cast<EventN*>(n);
+  if (!e) return false;
+  e->time0 = time;
+  return true;
+}
+HNode* mk_event(HNode* x, double start, double end, int fade_ease, double fade_in, double fade_out) {
+  // Sequencer::push asserts fade_in <= duration && fade_out <= duration (:329-330); the device event renders generators
+  if (!x || x->inputs() != 0 || x->outputs() < 1 || fade_ease < 0 || fade_ease > 1 || !(fade_in <= end - start) || !(fade_out <= end - start) || !(fade_in >= 0.0) || !(fade_out >= 0.0)) { delete x; return nullptr; }
+  return new EventN(x, start, end, fade_ease, fade_in, fade_out);
+}
 HNode* mk_limiter(int channels, float attack, float release) {
   if (channels < 1 || channels > 8 || !(attack >= 0.0f) || !(release >= 0.0f) || attack > 10.0f) return nullptr;
   return new LimiterN(channels, attack, release);

@@ -112,6 +112,10 @@ HNode* mk_meter(int kind, double timescale);                         // MeterNod
 HNode* mk_playwave(const float* samples, uint64_t length, uint64_t start, uint64_t end, int64_t loop_point);  // WavePlayer ID 65
 HNode* mk_resample(HNode* x);                                        // Resample<X> ID 69; consumes the generator
 HNode* mk_limiter(int channels, float attack, float release);       // Limiter<N> ID 25
+HNode* mk_event(HNode* x, double start, double end, int fade_ease, double fade_in, double fade_out);  // one Sequencer event (ID 64) as a voice; consumes x
+bool event_edit(HNode* n, double end_time, double fade_out);         // false when n is not an event
+bool event_times(const HNode* n, double* start, double* end);
+bool event_set_clock(HNode* n, double time);                         // the sequencer time the event's own clock starts from
 HNode* mk_declick(float duration);                                   // Declick ID 23
 HNode* mk_chaos(int kind);                                           // 0 Rossler ID 73, 1 Lorenz ID 74
 HNode* mk_morph(float cutoff, float q);                               // Morph ID 62

@@ -26,6 +26,12 @@ class ReplayMode:  # src/sequencer.rs:219-229
         return (2, float(t))
 
 
+def event(unit: An, start_time, end_time, fade_ease=Fade.Smooth, fade_in_time=0.0, fade_out_time=0.0):
+    """One sequencer event as a voice graph (what `Sequencer.voices()` is made of)."""
+    _arity(unit.inputs() == 0, "event: the GPU event renders generators (inputs == 0)")
+    return An("event", (float(start_time), float(end_time), int(fade_ease), float(fade_in_time), float(fade_out_time)), (unit,), 0, unit.outputs())
+
+
 class Sequencer:
     def __init__(self, inputs, outputs, mode=ReplayMode.None_):  # Sequencer::new (src/sequencer.rs:272-300)
         self.nin, self.nout, self.mode = int(inputs), int(outputs), mode
@@ -59,6 +65,17 @@ class Sequencer:
 
     def edit_relative(self, event_id, end_time, fade_out_time):  # :486-528
         self.edit(event_id, end_time, fade_out_time, _relative=True)
+
+    def voices(self):
+        """The events as voice graphs for a GPU bank (`GpuBank.from_sequencer`), in push order, with the edits recorded so far applied
+        the way the reference applies the edit of a not-yet-active event (its end time and fade-out are replaced, :531-553).
+        Generators only, ReplayMode::None or All (a bank reset replays everything, which is ReplayMode::All)."""
+        _arity(self.nin == 0, "Sequencer.voices: the GPU sequencer renders generators (inputs == 0)")
+        _arity(self.mode[0] != 2, "Sequencer.voices: ReplayMode::Loop is not lowered to the GPU")
+        ev = [list(e) for e in self.events]
+        for k, end, fo, rel in self.edits:
+            ev[k][1], ev[k][4] = end, fo     # time is 0 while describing: relative == absolute
+        return [event(u, s, e, ease, fi, fo) for s, e, ease, fi, fo, u, _ in ev]
 
     def node(self):
         """This sequencer as a graph node (`Net::wrap(Box::new(sequencer))` / a boxed AudioUnit inside an expression)."""

@@ -77,6 +77,10 @@ fdsp_node* fdsp_morph(float cutoff, float q);                  /* Morph ID 62 sr
 fdsp_node* fdsp_rez(float bandpass, float cutoff, float q, int inputs); /* Rez ID 75 src/rez.rs: bandpass 0 = lowrez, 1 = bandrez; inputs 1 or 3 (audio, cutoff, q) */
 fdsp_node* fdsp_chaos(int kind);                               /* kind 0 Rossler ID 73, 1 Lorenz ID 74 (src/oscillator.rs:318-438); input = frequency */
 fdsp_node* fdsp_declick(float duration);                       /* Declick ID 23 src/dynamics.rs:245: smooth fade-in over `duration` seconds */
+/* One event of a Sequencer (src/sequencer.rs:319-345 `push`) as a voice: the generator x sounds from start to end seconds (sample
+   accurate, the reference's rounding), with fade-in / fade-out of the given lengths; fade_ease 0 Fade::Power, 1 Fade::Smooth. A bank
+   of events IS the sequencer: its mix output is Sequencer::process. Consumes x. */
+fdsp_node* fdsp_event(fdsp_node* x, double start, double end, int fade_ease, double fade_in, double fade_out);
 fdsp_node* fdsp_limiter(int channels, float attack, float release); /* Limiter<N> ID 25 src/dynamics.rs:128 (`limiter`, `limiter_stereo`): look-ahead = attack seconds */
 fdsp_node* fdsp_meter(int kind, double timescale);             /* MeterNode ID 61 src/dynamics.rs:316: kind 0 Meter::Sample, 1 Peak(timescale), 2 Rms(timescale) */
 /* WavePlayer ID 65 src/wave.rs:739 (`playwave`, `playwave_at`): `samples` = wave.channel(ch) (copied); plays [start, end), then jumps to
@@ -154,6 +158,16 @@ int fdsp_bank_inputs(const fdsp_bank* b);                                   /* s
 int fdsp_bank_voice_outputs(const fdsp_bank* b);                            /* channels per voice */
 int fdsp_bank_outputs(const fdsp_bank* b);                                  /* AudioUnit::outputs(): mix: channels; voices: V*channels */
 int fdsp_bank_set_sample_rate(fdsp_bank* b, double sample_rate);            /* AudioUnit::set_sample_rate */
+/* Sequencer banks (voices made by fdsp_event; the bank's mix output is Sequencer::process, src/sequencer.rs:768-843).
+   fdsp_bank_edit_event = Sequencer::edit (:441-483): new end time and fade-out of one event, effective from the next block.
+   fdsp_bank_push_event = Sequencer::push on a running sequencer (:319-360): the event takes over the slot of a FINISHED event of the
+   same graph class (same type expression and class-uniform words) and starts its clock at the bank's current time; `*voice` receives
+   the slot. FDSP_ERR_UNSUPPORTED when no such slot is free. fdsp_bank_replace_voice puts any unit of the same class into a given
+   slot (fresh state). All three consume their node argument. fdsp_bank_time = Sequencer::time (seconds rendered since reset). */
+int fdsp_bank_edit_event(fdsp_bank* b, uint32_t voice, double end_time, double fade_out);
+int fdsp_bank_push_event(fdsp_bank* b, fdsp_node* event, uint32_t* voice);
+int fdsp_bank_replace_voice(fdsp_bank* b, uint32_t voice, fdsp_node* unit);
+double fdsp_bank_time(const fdsp_bank* b);
 int fdsp_bank_reset(fdsp_bank* b);                                          /* AudioUnit::reset */
 /* AudioUnit::set (src/audiounit.rs:62) on voice `voice` of a live bank: same encoding as fdsp_node_set. Parameters change at
    once, running state continues; FDSP_ERR_UNSUPPORTED when the setting would change a delay length (rebuild the bank). */

@@ -221,6 +221,11 @@ inline An playwave(const std::vector<float>& samples, long long loop_point = -1)
 inline An playwave_at(const std::vector<float>& samples, size_t start, size_t end, long long loop_point = -1) { return An(fdsp_playwave(samples.data(), samples.size(), start, end, loop_point)); }
 inline An limiter(float attack_time, float release_time) { return An(fdsp_limiter(1, attack_time, release_time)); }
 inline An limiter_stereo(float attack_time, float release_time) { return An(fdsp_limiter(2, attack_time, release_time)); }
+enum class Fade { Power = 0, Smooth = 1 };                                                 // src/sequencer.rs:35-52
+// one Sequencer event as a voice (Sequencer::push, src/sequencer.rs:319-345): a Bank of events is the sequencer
+inline An event(An unit, double start_time, double end_time, Fade ease = Fade::Smooth, double fade_in = 0.0, double fade_out = 0.0) {
+  return An(fdsp_event(unit.release(), start_time, end_time, (int)ease, fade_in, fade_out));
+}
 inline An resample(An x) { return An(fdsp_resample(x.release())); }                    // input = speed
 
 // ---- src/math.rs helpers used by the reverbs, in the reference's precision
@@ -281,6 +286,11 @@ class Bank {
     check(fdsp_bank_set(b_, voice, kind, values.begin(), (int)values.size(), seed, a.empty() ? nullptr : a.data(), (int)address.size()));
   }
   void allocate(uint64_t max_samples = 64) { check(fdsp_bank_allocate(b_, max_samples)); }
+  // sequencer banks: Sequencer::time / edit / push on a running bank (a pushed event reuses the slot of a finished event of its class)
+  double time() const { return fdsp_bank_time(b_); }
+  void edit_event(uint32_t voice, double end_time, double fade_out) { check(fdsp_bank_edit_event(b_, voice, end_time, fade_out)); }
+  uint32_t push_event(An ev) { uint32_t v = 0; check(fdsp_bank_push_event(b_, ev.release(), &v)); return v; }
+  void replace_voice(uint32_t voice, An unit) { check(fdsp_bank_replace_voice(b_, voice, unit.release())); }
   // AudioUnit::process: buffers are [channel][64]
   void process(uint32_t size, const float* input, float* output) { check(fdsp_bank_process(b_, size, input, output)); }
   // Wave::render / Wave::filter: buffers are [channel][n]

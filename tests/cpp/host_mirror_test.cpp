@@ -49,6 +49,8 @@ int main() {
   std::vector<float> wave(64); for (int i = 0; i < 64; i++) wave[i] = (float)i / 64.0f - 0.5f;
   An smp = (dc(0.75f) >> resample(playwave(wave, 8))) | (playwave_at(wave, 4, 40) >> meter(Meter::Rms(0.05))) | (noise() >> meter(Meter::Peak(0.1)) >> limiter(0.003f, 0.02f));
   std::printf("smp %d %d %s %016llx\n", smp.inputs(), smp.outputs(), smp.signature().c_str(), words_hash(smp));
+  An ev = event(saw_hz(220.0f) >> lowpass_hz(900.0f, 2.0f), 0.0125, 0.75, Fade::Power, 0.01, 0.2);
+  std::printf("event %d %d %s %016llx\n", ev.inputs(), ev.outputs(), ev.signature().c_str(), words_hash(ev));
   An r1 = reverb_stereo(12.0, 2.5, 0.4f), r4 = reverb4_stereo(20.0, 3.0);
   std::printf("reverb_stereo %s %016llx\n", r1.signature().c_str(), words_hash(r1));
   std::printf("reverb4_stereo %s %016llx\n", r4.signature().c_str(), words_hash(r4));

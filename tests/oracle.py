@@ -118,6 +118,10 @@ class OracleBackend:
     def b_rez(self, bp, cutoff, q, nin): return self.L.fo_rez(bp, cutoff, q, nin)
     def b_chaos(self, kind): return self.L.fo_chaos(kind)
     def b_declick(self, d): return self.L.fo_declick(d)
+    def b_event(self, start, end, ease, fi, fo, x):   # the checker for one event is a one-event Sequencer (ReplayMode::All)
+        h = self.L.fo_sequencer(0, self.L.fo_outputs(x), 0, 0.0)
+        self.L.fo_sequencer_push(h, start, end, ease, fi, fo, x)
+        return h
     def b_limiter(self, n, a, r): return self.L.fo_limiter(n, a, r)
     def b_meter(self, kind, timescale): return self.L.fo_meter(kind, timescale)
     def b_playwave(self, samples, start, end, loop): return self.L.fo_playwave(_farr(samples), len(samples), start, end, loop)

@@ -97,6 +97,7 @@ def test_builder_argument_errors_return_null_with_a_message():
         lambda: be.b_impulse(0),
         lambda: be.b_meter(3, 0.1), lambda: be.b_meter(1, 0.0), lambda: be.b_playwave([0.0] * 8, 0, 9, -1), lambda: be.b_resample(be.b_pass()),   # end_point <= length; generator only
         lambda: be.b_limiter(0, 0.01, 0.01), lambda: be.b_limiter(1, -1.0, 0.01),
+        lambda: be.b_event(0.0, 1.0, 1, 0.0, 0.0, be.b_pass()), lambda: be.b_event(0.0, 1.0, 1, 2.0, 0.0, be.b_noise()), lambda: be.b_event(0.0, 1.0, 3, 0.0, 0.0, be.b_noise()),   # generators only; fade <= duration
         lambda: be.b_phase_synth(6), lambda: be.b_mixer(0, 2, [1.0]), lambda: be.b_mixer(9, 9, [0.0] * 81),      # tables 0..5; 1 <= M*N <= 64
     ]
     for k, f in enumerate(bad):
@@ -227,6 +228,9 @@ def test_cpp_host_mirror_compiles_and_matches_python_mirror(tmp_path):
     wv = (np.arange(64, dtype=np.float32) / np.float32(64.0) - np.float32(0.5))[None, :]
     smp, sh = words_hash((dc(0.75) >> resample(playwave(wv, 0, 8))) | (playwave_at(wv, 0, 4, 40) >> meter(Meter.Rms(0.05))) | (noise() >> meter(Meter.Peak(0.1)) >> limiter(0.003, 0.02)))
     assert f"smp 0 3 {smp.signature()} {sh}" in lines
+    from fundsp_b200.sequencer import event, Fade
+    ev, eh = words_hash(event(saw_hz(220.0) >> lowpass_hz(900.0, 2.0), 0.0125, 0.75, Fade.Power, 0.01, 0.2))
+    assert f"event 0 1 {ev.signature()} {eh}" in lines
     r1, h1 = words_hash(reverb_stereo(12.0, 2.5, 0.4))
     r4, h4 = words_hash(reverb4_stereo(20.0, 3.0))
     assert f"reverb_stereo {r1.signature()} {h1}" in lines and f"reverb4_stereo {r4.signature()} {h4}" in lines   # every coefficient, bit for bit

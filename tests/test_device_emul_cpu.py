@@ -118,12 +118,14 @@ _ALL = {**_jit.CASES, **_jit.WIDER}
 
 @pytest.mark.parametrize("name", sorted(_ALL))
 def test_jit_case_on_host_emulation(name, tmp_path):
-    n = 64 * 2 + 61
+    n = 64 * 2 + 61 if not name.startswith("events") else 64 * 31 + 61   # events: long enough to start, fade and end
     mk = _ALL[name]
-    want = oracle(mk(3), n)
-    got, _ = emulate(mk(3), n, None, str(tmp_path))
+    vi = 4 if name.startswith("events") else 3
+    want = oracle(mk(vi), n)
+    got, _ = emulate(mk(vi), n, None, str(tmp_path))
     assert got.shape == want.shape
     assert np.array_equal(got, want), (name, int((got != want).sum()), float(np.abs(got - want).max()))
+    assert not name.startswith("events") or np.abs(want).max() > 1e-3
 
 
 # ---- the BASELINE configuration voices (AOT graph classes), incl. the gate-driven subtractive chain and the full voice with the

@@ -14,3 +14,92 @@ def test_wider_graph_matches_oracle(name):
     assert g.shape == o.shape and np.isfinite(g).all() and np.abs(o).max() > 1e-4
     bad = int((g != o).sum())
     assert bad == 0, (name, bad, float(np.abs(g - o).max()), b.classes()[0]["signature"])
+
+
+# ---------------------------------------------------------------- the sequencer as a bank of event voices (src/sequencer.rs)
+def _oracle_seq(seq, sr):
+    from oracle import OracleUnit
+    u = OracleUnit(seq.node())
+    u.set_sample_rate(sr)
+    return u
+
+
+def _close(g, o):
+    """Mix bar of DESIGN.md §4: the CTA-level sum associates differently from the sequencer's left fold over its active events."""
+    tol = 1e-5 * np.maximum(np.abs(o), 1e-2 * np.abs(o).max())
+    return bool(np.all(np.abs(g - o) <= tol))
+
+
+def test_sequencer_bank_matches_oracle_sequencer():
+    from fundsp_b200.bank import GpuBank
+    from fundsp_b200.prelude import noise, sine_hz, mls, saw_hz, lowpass_hz
+    from fundsp_b200.sequencer import Sequencer, Fade, ReplayMode
+    from oracle import lib as olib
+    olib().fo_set_denormal_emulation(0)
+    sr = 44100.0
+
+    def build():   # tests/test_basic.rs:255-273 plus a third overlapping voice that starts mid-block
+        q = Sequencer(0, 2, ReplayMode.All)
+        q.push(0.1, 0.2, Fade.Smooth, 0.01, 0.0, noise() | sine_hz(220.0))
+        q.push(0.3, 0.4, Fade.Smooth, 0.09, 0.08, sine_hz(110.0) | noise())
+        q.push(0.25, 0.5, Fade.Power, 0.0, 0.01, mls() | noise())
+        q.push(0.6, 0.7, Fade.Power, 0.02, 0.03, noise() | mls())
+        q.push(0.31234, 0.45678, Fade.Smooth, 0.02, 0.05, (saw_hz(220.0) >> lowpass_hz(1000.0, 1.0)) | sine_hz(330.0))
+        return q
+
+    n = int(0.75 * sr)
+    b = GpuBank.from_sequencer(build(), per_voice=True, mix=True, sample_rate=sr)
+    rows, mix = b.render_samples(n)
+    want = _oracle_seq(build(), sr).process_many(n)
+    assert np.abs(want).max() > 0.5 and _close(mix, want)
+    # where only one event sounds, the mix IS that event: bit-exact (x + 0.0)
+    solo = slice(int(0.1 * sr) + 2, int(0.2 * sr) - 2)
+    assert np.array_equal(mix[:, solo], want[:, solo]) and np.array_equal(rows[0][:, solo], want[:, solo])
+    assert abs(b.time() - n / sr) < 1e-9
+    # ReplayMode::All: reset replays every event
+    b.reset()
+    rows2, mix2 = b.render_samples(n)
+    assert np.array_equal(mix2, mix) and np.array_equal(rows2, rows)
+    # process()-sized calls (64, 61, 7, ...) walk the same blocks as the oracle's process calls
+    b.reset()
+    u = _oracle_seq(build(), sr)
+    sizes = [64, 61, 7, 64, 1, 33] * 60
+    for k, sz in enumerate(sizes):
+        got = b.process(sz)
+        exp = u.process(sz)
+        assert _close(got, exp), (k, sz)
+
+
+def test_sequencer_bank_live_edit_and_push():
+    from fundsp_b200.bank import GpuBank
+    from fundsp_b200.prelude import dc, sine_hz, saw_hz, lowpass_hz
+    from fundsp_b200.sequencer import Sequencer, Fade, ReplayMode, event
+    from oracle import OracleBackend, lib as olib
+    L = olib()
+    L.fo_set_denormal_emulation(0)
+    sr = 44100.0
+    voice = lambda f: saw_hz(f) >> lowpass_hz(4.0 * f, 1.0)
+    q = Sequencer(0, 1, ReplayMode.None_)
+    e0 = q.push(0.0, 10.0, Fade.Smooth, 0.001, 0.0, voice(110.0))          # a held note, released by a later edit
+    q.push(0.01, 0.02, Fade.Smooth, 0.001, 0.002, voice(220.0))             # a short note whose slot is reused
+    b = GpuBank.from_sequencer(q, per_voice=False, mix=True, sample_rate=sr)
+    u = _oracle_seq(q, sr)
+    be = OracleBackend()
+    n1 = 64 * 30                                                            # 43.5 ms in: the short note has ended
+    g1 = b.render_samples(n1)[1]; o1 = u.process_many(n1)
+    assert _close(g1, o1)
+    # release the held note: Sequencer::edit(id, end_time, fade_out) on both
+    t_end = b.time() + 0.02
+    b.edit_event(e0, t_end, 0.015)
+    L.fo_sequencer_edit(u.h, 1, t_end, 0.015)                               # oracle event ids count from 1 in push order
+    # note-on while running: the new event takes the finished note's slot and starts its clock at the bank's time
+    t0 = b.time() + 0.005
+    slot = b.push_event(event(voice(330.0), t0, t0 + 0.03, Fade.Smooth, 0.002, 0.004))
+    assert slot == 1
+    L.fo_sequencer_push(u.h, t0, t0 + 0.03, 1, 0.002, 0.004, voice(330.0).lower(be))
+    n2 = 64 * 40 + 17
+    g2 = b.render_samples(n2)[1]; o2 = u.process_many(n2)
+    assert np.abs(o2).max() > 0.1 and _close(g2, o2)
+    assert not g2[:, int((0.02 + 0.03 + 0.005) * sr):].any()                # everything has ended
+    with pytest.raises(Exception):                                           # no finished event of a different class to take over
+        b.push_event(event(dc(1.0), 1.0, 2.0))
