@@ -142,6 +142,7 @@ API int fdsp_node_set(fdsp_node* h, int kind, const float* v, int nv, uint64_t s
 }
 API int fdsp_node_inputs(const fdsp_node* h) { return h ? h->n->inputs() : -1; }
 API int fdsp_node_outputs(const fdsp_node* h) { return h ? h->n->outputs() : -1; }
+API int fdsp_node_set_sample_rate(fdsp_node* h, double sr) { if (!h || !(sr > 0.0)) return fail(FDSP_ERR_ARG, "bad sample rate"); h->n->set_sample_rate(sr); return FDSP_OK; }
 API uint64_t fdsp_node_id(const fdsp_node* h) { return h ? h->n->id() : 0; }
 API uint64_t fdsp_node_ping(fdsp_node* h, int probe, uint64_t hash) { return h ? h->n->ping(probe != 0, AttoHash(hash)).state : 0; }
 API int fdsp_node_leaf_hashes(fdsp_node* h, uint64_t* out, int max) {

@@ -130,6 +130,7 @@ int fdsp_node_outputs(const fdsp_node* n);
 uint64_t fdsp_node_id(const fdsp_node* n);
 uint64_t fdsp_node_ping(fdsp_node* n, int probe, uint64_t hash);            /* AudioNode::ping */
 int fdsp_node_leaf_hashes(fdsp_node* n, uint64_t* out, int max);            /* hashes handed to leaves by the constructor ping, in order */
+int fdsp_node_set_sample_rate(fdsp_node* n, double sample_rate);             /* AudioNode::set_sample_rate on a graph that is not in a bank yet */
 int fdsp_node_signature(const fdsp_node* n, char* out, int max);            /* device program type expression */
 /* the words the device program of this node consumes, in load order: per-voice parameters P, initial state S, class-uniform U
    (host-only introspection; counts are returned even when the buffers are too small or NULL) */

@@ -18,8 +18,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SR = 44100.0   # the construction-time default rate (src/lib.rs:42): node handles are lowered as constructed
 
 
-def emulate(g, n, x=None, tmp=None):
+def emulate(g, n, x=None, tmp=None, sr=SR):
     h = capi.NodeHandle(g)
+    if sr != SR:
+        h.set_sample_rate(sr)
     sig = h.signature()
     P, S, U = h.lowering()
     nin = h.inputs()
@@ -28,7 +30,7 @@ def emulate(g, n, x=None, tmp=None):
     blob = os.path.join(tmp, "in.bin"); outp = os.path.join(tmp, "out.bin")
     with open(blob, "wb") as f:
         f.write(struct.pack("<5I", len(P), len(S), len(U), nin, n))
-        f.write(struct.pack("<d", SR))
+        f.write(struct.pack("<d", sr))
         f.write(P.tobytes()); f.write(S.tobytes()); f.write(U.tobytes())
         if nin:
             f.write(np.ascontiguousarray(x, np.float32).tobytes())
@@ -59,10 +61,10 @@ def _table_blob(kind):
     return (struct.pack("<3I", kind, n, len(flat)) + np.float32(pitch).tobytes() + np.int32(off).tobytes() + np.int32(length).tobytes() + flat.tobytes())
 
 
-def oracle(g, n, x=None):
+def oracle(g, n, x=None, sr=SR):
     olib().fo_set_denormal_emulation(0)
     u = OracleUnit(g)
-    u.set_sample_rate(SR)
+    u.set_sample_rate(sr)
     return u.process_many(n, x)
 
 
@@ -153,3 +155,55 @@ def test_workload_voice_on_host_emulation(name, tmp_path):
     got, _ = emulate(mk(), n, x, str(tmp_path))
     assert np.abs(want).max() > 1e-3
     assert np.array_equal(got, want), (name, int((got != want).sum()), float(np.abs(got - want).max()))
+
+
+@pytest.mark.parametrize("name", sorted(_ALL))
+def test_every_voice_of_the_gpu_cases_builds(name):
+    """The GPU suite renders 40 voices per case: all of them must be constructible (arity and argument checks of the C ABI) and fall
+    into few classes; the GPU is not needed to find a case whose parameters run out of range at some voice index."""
+    sigs = set()
+    for i in range(40):
+        h = capi.NodeHandle(_ALL[name](i))
+        assert h.inputs() == 0 and h.outputs() >= 1
+        sigs.add(h.signature())
+    assert all("Unsupported" not in s for s in sigs) and len(sigs) <= 8, (name, len(sigs))
+
+
+@pytest.mark.parametrize("name", sorted(k for k in _ALL if k.startswith("events")))
+@pytest.mark.parametrize("vi", [0, 1, 7, 22, 39])
+def test_event_voices_at_the_gpu_suite_rate(name, vi, tmp_path):
+    """Event voices at 48 kHz (the rate of the GPU suite; the units and the sequencer clock are re-rated after construction) over the
+    GPU suite's length, several voice indices: start / end times on and off block boundaries, events that never start."""
+    n = 2000 + 61
+    want = oracle(_ALL[name](vi), n, sr=48000.0)
+    got, _ = emulate(_ALL[name](vi), n, None, str(tmp_path), sr=48000.0)
+    assert np.array_equal(got, want), (name, vi, int((got != want).sum()), float(np.abs(got - want).max()))
+
+
+def test_sequencer_event_voices_sum_to_the_oracle_sequencer(tmp_path):
+    """The GPU sequencer is a bank of event voices whose mix is Sequencer::process. Here every voice of the five-event sequence of
+    tests/test_gpu_wider.py runs on the host emulation and the rows are summed on the CPU: the sum must be the oracle Sequencer's
+    output (exactly where one event sounds, to rounding where several overlap)."""
+    from fundsp_b200.sequencer import Sequencer, Fade, ReplayMode
+    q = Sequencer(0, 2, ReplayMode.All)
+    q.push(0.1, 0.2, Fade.Smooth, 0.01, 0.0, noise() | sine_hz(220.0))
+    q.push(0.3, 0.4, Fade.Smooth, 0.09, 0.08, sine_hz(110.0) | noise())
+    q.push(0.25, 0.5, Fade.Power, 0.0, 0.01, mls() | noise())
+    q.push(0.6, 0.7, Fade.Power, 0.02, 0.03, noise() | mls())
+    q.push(0.31234, 0.45678, Fade.Smooth, 0.02, 0.05, (saw_hz(220.0) >> lowpass_hz(1000.0, 1.0)) | sine_hz(330.0))
+    n = int(0.75 * SR)
+    want = oracle(q.node(), n)
+    rows = []
+    for k, v in enumerate(q.voices()):
+        d = tmp_path / f"v{k}"; d.mkdir()
+        rows.append(emulate(v, n, None, str(d))[0])
+    total = np.sum(np.stack(rows).astype(np.float64), axis=0)
+    assert np.abs(want).max() > 0.5 and np.abs(total - want).max() <= 1e-6
+    solo = slice(int(0.1 * SR) + 2, int(0.2 * SR) - 2)
+    assert np.array_equal(rows[0][:, solo], want[:, solo])
+    # an edited event (recorded before the start) ends early with the new fade-out
+    q2 = Sequencer(0, 1, ReplayMode.None_)
+    e = q2.push(100.0 / SR, 2000.0 / SR, Fade.Smooth, 0.0, 0.0, dc(1.0))
+    q2.edit(e, 600.0 / SR, 100.0 / SR)
+    got = emulate(q2.voices()[0], 800, None, str(tmp_path))[0]
+    assert np.array_equal(got, oracle(q2.node(), 800)) and got[0, 300] == 1.0 and not got[0, 600:].any()
