@@ -172,6 +172,15 @@ API int fdsp_node_lowering(const fdsp_node* h, uint32_t* P, int maxp, uint32_t* 
   for (int i = 0; i < *nu && i < maxu && U; i++) U[i] = l.U[i];
   return FDSP_OK;
 }
+API int64_t fdsp_node_delay_floats(const fdsp_node* h) {   // floats of delay-line / ring storage the program of this node needs per voice
+  if (!h) return -1;
+  Lowering l;
+  h->n->lower(l);
+  if (!l.ok) return -1;
+  int64_t t = 0;
+  for (uint32_t d : l.dlen) t += d;
+  return t;
+}
 API fdsp_node* fdsp_node_clone(const fdsp_node* h) { return h ? new (std::nothrow) fdsp_node{h->n->clone()} : nullptr; }
 API void fdsp_node_free(fdsp_node* h) { if (h) { delete h->n; delete h; } }
 

@@ -135,6 +135,7 @@ int fdsp_node_signature(const fdsp_node* n, char* out, int max);            /* d
 /* the words the device program of this node consumes, in load order: per-voice parameters P, initial state S, class-uniform U
    (host-only introspection; counts are returned even when the buffers are too small or NULL) */
 int fdsp_node_lowering(const fdsp_node* n, uint32_t* P, int maxp, uint32_t* S, int maxs, uint32_t* U, int maxu, int* np, int* ns, int* nu);
+int64_t fdsp_node_delay_floats(const fdsp_node* n);                           /* per-voice delay-line storage (floats) of the device program; -1 on error */
 fdsp_node* fdsp_node_clone(const fdsp_node* n);
 void fdsp_node_free(fdsp_node* n);
 /* wavetable introspection (host builder, src/wavetable.rs:82-123) */

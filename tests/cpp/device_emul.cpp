@@ -57,6 +57,7 @@ int main(int argc, char** argv) {
   G::load(r, l);
   if (l.pi > np || l.si > ns || l.ui > nu) { fprintf(stderr, "word layout mismatch: consumed %u/%u/%u of %u/%u/%u\n", l.pi, l.si, l.ui, np, ns, nu); return 8; }
   std::vector<float> dline((size_t)l.dl + 1, 0.0f);
+  fprintf(stderr, "dl=%u\n", l.dl);   // the delay-line floats the device program claims (the host must allocate exactly this)
   c.dl = dline.data();
   constexpr int IN = G::IN, OUT = G::OUT;
   constexpr bool GROUP = GroupPlan<G>::ok && GroupPlan<G>::code <= 256;   // bank_kernel's FDSP_GROUP_COST

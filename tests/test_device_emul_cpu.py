@@ -40,6 +40,8 @@ def emulate(g, n, x=None, tmp=None, sr=SR):
             f.write(_table_blob(k))
     r = subprocess.run([exe, blob, outp], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stderr)
+    claimed = [int(x[3:]) for x in r.stderr.split() if x.startswith("dl=")]
+    assert claimed == [h.delay_floats()], ("delay-line storage: device program claims", claimed, "host allocates", h.delay_floats(), sig)
     return np.fromfile(outp, np.float32).reshape(h.outputs(), n), sig
 
 
