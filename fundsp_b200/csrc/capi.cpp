@@ -267,12 +267,8 @@ API int fdsp_bank_replace_voice(fdsp_bank* b, uint32_t voice, fdsp_node* unit) {
 }
 API int fdsp_bank_push_event(fdsp_bank* b, fdsp_node* event, uint32_t* voice) {
   if (!b || !event) { fdsp_node_free(event); return fail(FDSP_ERR_ARG, "null bank or event"); }
-  const int v = b->b.free_event_voice(event->n);
-  if (v < 0) { fdsp_node_free(event); return fail(FDSP_ERR_UNSUPPORTED, "no finished event of the same graph class is free: create the bank with spare (finished or far-future) events of this class, or rebuild it"); }
-  std::string e = b->b.replace_voice((uint32_t)v, take(event));
-  if (!e.empty()) return fail(FDSP_ERR_UNSUPPORTED, e);
-  if (voice) *voice = (uint32_t)v;
-  return FDSP_OK;
+  std::string e = b->b.push_event(take(event), voice);
+  return e.empty() ? FDSP_OK : fail(e.find("no finished event") != std::string::npos ? FDSP_ERR_UNSUPPORTED : FDSP_ERR_ARG, e);
 }
 API double fdsp_bank_time(const fdsp_bank* b) { return b ? b->b.seq_time : 0.0; }
 API int fdsp_bank_reset(fdsp_bank* b) { return b ? status(b->b.reset()) : fail(FDSP_ERR_ARG, "null bank"); }

@@ -289,17 +289,32 @@ std::string Bank::replace_voice(uint32_t voice, HNode* node) {
   return "";
 }
 
-int Bank::free_event_voice(const HNode* like) const {
-  std::string want; like->sig(want);
+std::string Bank::push_event(HNode* node, uint32_t* voice) {   // Sequencer::push on a running sequencer (src/sequencer.rs:319-360)
+  std::unique_ptr<HNode> n(node);
+  double s0, e0;
+  if (!n || !event_times(n.get(), &s0, &e0)) return "push: not a sequencer event (fdsp_event)";
+  if (n->inputs() != nin || n->outputs() != nout) return "push: the event's arity differs from the bank's";
+  CU(cudaSetDevice(device));
   const double unit_rate = net_rate ? (double)(float)sr : sr, sd = 1.0 / unit_rate;
-  for (uint32_t v = 0; v < V(); v++) {
-    double s0, e0;
-    if (!event_times(nodes[v].get(), &s0, &e0)) continue;
-    if (!(e0 <= seq_time + 0.5 * sd)) continue;   // Event::plan's end-of-event test at the start of the next block: nothing more to render
-    std::string sg; nodes[v]->sig(sg);
-    if (sg == want) return (int)v;
+  n->set_sample_rate(unit_rate);
+  event_set_clock(n.get(), seq_time);   // the event counts from now; a start time in the past makes it sound from the next block on
+  std::string want; n->sig(want);
+  Lowering l;
+  n->lower(l);
+  if (!l.ok) return l.why;
+  for (auto& c : classes) {
+    if (c.sig != want || c.uniform != l.U || c.fdn) continue;
+    for (uint32_t v : c.voices) {
+      if (!event_times(nodes[v].get(), &s0, &e0)) break;
+      if (!(e0 <= seq_time + 0.5 * sd)) continue;   // Event::plan's end-of-event test at the start of the next block: still sounding
+      std::string e = upload_voice(v, l, true);
+      if (!e.empty()) return e;
+      nodes[v] = std::move(n);
+      if (voice) *voice = v;
+      return "";
+    }
   }
-  return -1;
+  return "no finished event of the same graph class is free: create the bank with spare events of this class (finished, or ending at time 0), or rebuild it";
 }
 
 std::string Bank::reset() {  // AudioUnit::reset: back to the construction-time state

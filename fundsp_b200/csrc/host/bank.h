@@ -66,7 +66,7 @@ struct Bank {
   std::string upload_voice(uint32_t voice, const Lowering& l, bool with_state);
   std::string edit_event(uint32_t voice, double end_time, double fade_out);   // Sequencer::edit
   std::string replace_voice(uint32_t voice, HNode* node);                     // a new unit in the slot of a voice of the same class; consumes node
-  int free_event_voice(const HNode* like) const;                              // a finished event whose class matches `like`, or -1
+  std::string push_event(HNode* event, uint32_t* voice);                      // Sequencer::push on a running bank: takes the slot of a finished event of the same class; consumes event
   std::string set(uint32_t voice, const Setting& s);  // AudioUnit::set on one voice of a live bank (parameters only; state continues)
   std::string ensure_staging(uint32_t chunk);
   std::string render_device(uint64_t n, const float* in_dev, uint64_t in_stride, float* out_dev, uint64_t out_stride, float* mix_dev,

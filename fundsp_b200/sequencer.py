@@ -92,3 +92,86 @@ class Sequencer:
                 ev, end, fo, rel = self.edits[k]
                 backend.sequencer_edit(h, ids[ev], end, fo, rel)
         return h
+
+
+class GpuSequencer:
+    """`Sequencer::new(0, outputs, mode)` whose rendering side is a GPU bank (the role of `SequencerBackend`): the reference's calls
+    (`push`, `push_relative`, `push_duration`, `edit`, `edit_relative`, `time`, `reset`, `process`) with the reference's meaning.
+
+    Events pushed before the first render become the bank's voices. An event pushed while the sequencer runs takes over the voice
+    of a FINISHED event of the same graph class (`fdsp_bank_push_event`); `reserve(unit, count)` adds spare voices of a class up
+    front so that note-ons always find one (a spare is an event that ended at time 0)."""
+
+    def __init__(self, outputs, mode=ReplayMode.None_, device=0, sample_rate=44100.0):
+        _arity(mode[0] != 2, "GpuSequencer: ReplayMode::Loop is not lowered to the GPU")
+        self.nout, self.mode, self.device, self.sr = int(outputs), mode, device, float(sample_rate)
+        self.pending = []      # event expressions until the bank exists
+        self.bank = None
+        self.voice_of = {}     # EventId -> voice
+        self.next_id = 0
+
+    def inputs(self): return 0
+    def outputs(self): return self.nout
+
+    def time(self):
+        return self.bank.time() if self.bank is not None else 0.0
+
+    def reserve(self, unit: An, count):
+        assert self.bank is None, "reserve before the first render"
+        for _ in range(int(count)):
+            self.pending.append(event(unit, 0.0, 0.0))
+
+    def _push(self, start, end, ease, fade_in, fade_out, unit):
+        _arity(unit.inputs() == 0 and unit.outputs() == self.nout, "sequencer.push: unit arity differs from the sequencer's")
+        assert fade_in <= end - start and fade_out <= end - start
+        ev = event(unit, start, end, ease, fade_in, fade_out)
+        eid = self.next_id; self.next_id += 1
+        if self.bank is None:
+            self.pending.append(ev); self.voice_of[eid] = len(self.pending) - 1
+        else:
+            self.voice_of[eid] = self.bank.push_event(ev)
+        return eid
+
+    def push(self, start_time, end_time, fade_ease, fade_in_time, fade_out_time, unit: An):
+        return self._push(float(start_time), float(end_time), fade_ease, float(fade_in_time), float(fade_out_time), unit)
+
+    def push_relative(self, start_time, end_time, fade_ease, fade_in_time, fade_out_time, unit: An):
+        t = self.time()
+        return self._push(start_time + t, end_time + t, fade_ease, float(fade_in_time), float(fade_out_time), unit)
+
+    def push_duration(self, start_time, duration, fade_ease, fade_in_time, fade_out_time, unit: An):
+        return self.push(start_time, start_time + duration, fade_ease, fade_in_time, fade_out_time, unit)
+
+    def edit(self, event_id, end_time, fade_out_time):
+        v = self.voice_of[event_id]
+        if self.bank is None:
+            a = self.pending[v].args
+            self.pending[v] = An("event", (a[0], float(end_time), a[2], a[3], float(fade_out_time)), self.pending[v].kids, 0, self.nout)
+        else:
+            self.bank.edit_event(v, end_time, fade_out_time)
+
+    def edit_relative(self, event_id, end_time, fade_out_time):
+        self.edit(event_id, self.time() + end_time, fade_out_time)
+
+    def _ensure(self):
+        if self.bank is None:
+            from .bank import GpuBank
+            _arity(len(self.pending) > 0, "GpuSequencer: push or reserve at least one event before rendering")
+            self.bank = GpuBank(self.pending, device=self.device, per_voice=False, mix=True, sample_rate=self.sr)
+        return self.bank
+
+    def reset(self):
+        """ReplayMode::All: every event replays. ReplayMode::None: the sequencer is emptied (its voices stay as spares)."""
+        b = self._ensure()
+        b.reset()
+        if self.mode[0] == 1:
+            for v in range(b.voices()):
+                b.edit_event(v, 0.0, 0.0)
+            b.reset()          # the edited (ended) events are now the construction-time state as well
+            self.voice_of.clear()
+
+    def process(self, size):
+        return self._ensure().process(size)
+
+    def render(self, n):
+        return self._ensure().render_samples(int(n))[1]

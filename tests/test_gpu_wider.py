@@ -103,3 +103,31 @@ def test_sequencer_bank_live_edit_and_push():
     assert not g2[:, int((0.02 + 0.03 + 0.005) * sr):].any()                # everything has ended
     with pytest.raises(Exception):                                           # no finished event of a different class to take over
         b.push_event(event(dc(1.0), 1.0, 2.0))
+
+
+def test_gpu_sequencer_note_ons_while_running():
+    """An arpeggio played live: every 1024 samples a note-on (push_relative) with a short fade, eight reserved voices that the notes
+    cycle through as earlier notes finish; the oracle Sequencer receives the same calls at the same times."""
+    from fundsp_b200.prelude import saw_hz, lowpass_hz
+    from fundsp_b200.sequencer import GpuSequencer, Fade, ReplayMode
+    from oracle import OracleBackend, OracleUnit, lib as olib
+    L = olib()
+    L.fo_set_denormal_emulation(0)
+    sr = 44100.0
+    voice = lambda f: saw_hz(f) >> lowpass_hz(3.0 * f, 1.5)
+    g = GpuSequencer(1, ReplayMode.None_, sample_rate=sr)
+    g.reserve(voice(100.0), 8)
+    u = OracleUnit(L.fo_sequencer(0, 1, 1, 0.0))
+    be = OracleBackend()
+    got, want = [], []
+    for k in range(24):
+        f = 110.0 * 2.0 ** ((k * 7 % 12) / 12.0)
+        dur = 0.05 + 0.01 * (k % 5)                                   # up to four notes overlap
+        g.push_relative(0.003, 0.003 + dur, Fade.Smooth, 0.002, 0.01, voice(f))
+        L.fo_sequencer_push_relative(u.h, 0.003, 0.003 + dur, 1, 0.002, 0.01, voice(f).lower(be))
+        got.append(g.render(1024)); want.append(u.process_many(1024))
+        assert abs(g.time() - L.fo_sequencer_time(u.h)) < 1e-12
+    got, want = np.concatenate(got, axis=1), np.concatenate(want, axis=1)
+    assert np.abs(want).max() > 0.5 and _close(got, want)
+    g.reset()                                                         # ReplayMode::None: emptied
+    assert not g.render(2048).any()
