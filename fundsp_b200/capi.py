@@ -48,7 +48,7 @@ _SIG = {
     "fdsp_wavetable_count": (I, [I]), "fdsp_wavetable_info": (I, [I, I, FP, C.POINTER(I)]), "fdsp_wavetable_data": (FP, [I, I]),
     "fdsp_bank_create": (I, [C.POINTER(P), U32, I, U32, C.POINTER(P)]), "fdsp_bank_create_from_net": (I, [P, I, U32, C.POINTER(P)]), "fdsp_bank_destroy": (None, [P]), "fdsp_bank_voice_of_vertex": (I, [P, I]), "fdsp_bank_clone": (I, [P, C.POINTER(P)]),
     "fdsp_bank_voices": (U32, [P]), "fdsp_bank_inputs": (I, [P]), "fdsp_bank_voice_outputs": (I, [P]), "fdsp_bank_outputs": (I, [P]),
-    "fdsp_bank_set_sample_rate": (I, [P, D]), "fdsp_bank_reset": (I, [P]), "fdsp_bank_edit_event": (I, [P, U32, D, D]), "fdsp_bank_push_event": (I, [P, P, C.POINTER(U32)]), "fdsp_bank_replace_voice": (I, [P, U32, P]), "fdsp_bank_time": (D, [P]), "fdsp_bank_set": (I, [P, U32, I, FP, I, U64, C.POINTER(I64), I]), "fdsp_bank_allocate": (I, [P, U64]),
+    "fdsp_bank_set_sample_rate": (I, [P, D]), "fdsp_bank_reset": (I, [P]), "fdsp_wave_save": (I, [C.c_char_p, FP, U32, U64, U64, D, I]), "fdsp_wave_encode": (C.c_int64, [C.POINTER(C.c_uint8), U64, FP, U32, U64, U64, D, I]), "fdsp_wave_load": (I, [C.c_char_p, FP, U64, C.POINTER(U32), C.POINTER(U64), C.POINTER(D)]), "fdsp_bank_edit_event": (I, [P, U32, D, D]), "fdsp_bank_push_event": (I, [P, P, C.POINTER(U32)]), "fdsp_bank_replace_voice": (I, [P, U32, P]), "fdsp_bank_time": (D, [P]), "fdsp_bank_set": (I, [P, U32, I, FP, I, U64, C.POINTER(I64), I]), "fdsp_bank_allocate": (I, [P, U64]),
     "fdsp_bank_process": (I, [P, U32, FP, FP]), "fdsp_bank_render": (I, [P, U64, FP, FP, FP]),
     "fdsp_bank_render_device": (I, [P, U64, P, U64, P, U64, P, U64]), "fdsp_bank_sync": (I, [P]), "fdsp_bank_stream": (P, [P]),
     "fdsp_bank_num_classes": (I, [P]), "fdsp_bank_class_info": (I, [P, I, C.c_char_p, I, C.POINTER(U32), C.POINTER(U32), C.POINTER(U32), C.POINTER(U64)]),
@@ -238,3 +238,32 @@ class NodeHandle:
         buf = C.create_string_buffer(1 << 16)
         self.L.fdsp_node_signature(self.h, buf, len(buf))
         return buf.value.decode()
+
+
+# ---- Wave files (src/write.rs): planar [channels, n] f32 arrays <-> the reference's WAV bytes
+def save_wav(path, wave, sample_rate, bits=16):
+    """Wave::save_wav16 / save_wav32."""
+    w = np.ascontiguousarray(np.atleast_2d(np.asarray(wave, np.float32)))
+    check(lib().fdsp_wave_save(str(path).encode(), w.ctypes.data_as(FP), w.shape[0], w.shape[1], w.shape[1], float(sample_rate), int(bits)))
+
+
+def encode_wav(wave, sample_rate, bits=16):
+    """Wave::write_wav16 / write_wav32 into memory."""
+    w = np.ascontiguousarray(np.atleast_2d(np.asarray(wave, np.float32)))
+    L = lib()
+    n = L.fdsp_wave_encode(None, 0, w.ctypes.data_as(FP), w.shape[0], w.shape[1], w.shape[1], float(sample_rate), int(bits))
+    if n < 0:
+        check(ERR_ARG)
+    buf = (C.c_uint8 * n)()
+    L.fdsp_wave_encode(buf, n, w.ctypes.data_as(FP), w.shape[0], w.shape[1], w.shape[1], float(sample_rate), int(bits))
+    return bytes(buf)
+
+
+def load_wav(path):
+    """Returns (wave[channels, n], sample_rate)."""
+    L = lib()
+    ch, n, sr = U32(0), U64(0), D(0.0)
+    check(L.fdsp_wave_load(str(path).encode(), None, 0, C.byref(ch), C.byref(n), C.byref(sr)))
+    w = np.zeros((ch.value, n.value), np.float32)
+    check(L.fdsp_wave_load(str(path).encode(), w.ctypes.data_as(FP), w.size, C.byref(ch), C.byref(n), C.byref(sr)))
+    return w, sr.value

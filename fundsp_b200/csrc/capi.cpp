@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "host/bank.h"
+#include "host/wavfile.h"
 
 using namespace fdsp::host;
 
@@ -253,6 +254,26 @@ API int fdsp_bank_set(fdsp_bank* b, uint32_t voice, int kind, const float* v, in
   for (int i = 0; i < naddr; i++) s.address.push_back({(int)addr[2 * i], (uint64_t)addr[2 * i + 1]});
   std::string e = b->b.set(voice, s);
   return e.empty() ? FDSP_OK : fail(e.find("rebuild") != std::string::npos ? FDSP_ERR_UNSUPPORTED : FDSP_ERR_ARG, e);
+}
+// ---- WAV edge (src/write.rs): planar f32 [channels][stride] -> the reference's file bytes, and back
+API int fdsp_wave_save(const char* path, const float* planar, uint32_t channels, uint64_t length, uint64_t stride, double sample_rate, int bits) {
+  std::string e = wav_write(path, planar, channels, length, stride, sample_rate, bits);
+  return e.empty() ? FDSP_OK : fail(FDSP_ERR_ARG, e);
+}
+API int64_t fdsp_wave_encode(uint8_t* out, uint64_t max, const float* planar, uint32_t channels, uint64_t length, uint64_t stride, double sample_rate, int bits) {
+  std::vector<uint8_t> b;
+  std::string e = wav_encode(b, planar, channels, length, stride, sample_rate, bits);
+  if (!e.empty()) { fail(FDSP_ERR_ARG, e); return -1; }
+  if (out && max >= b.size()) memcpy(out, b.data(), b.size());
+  return (int64_t)b.size();
+}
+API int fdsp_wave_load(const char* path, float* planar, uint64_t max_floats, uint32_t* channels, uint64_t* length, double* sample_rate) {
+  if (!channels || !length || !sample_rate) return fail(FDSP_ERR_ARG, "wave_load: null output");
+  std::vector<float> p;
+  std::string e = wav_read(path, p, channels, length, sample_rate);
+  if (!e.empty()) return fail(FDSP_ERR_ARG, e);
+  if (planar && max_floats >= p.size()) memcpy(planar, p.data(), p.size() * 4);   // call once with planar = NULL to size the buffer
+  return FDSP_OK;
 }
 // ---- sequencer banks: voices made by fdsp_event
 API int fdsp_bank_edit_event(fdsp_bank* b, uint32_t voice, double end_time, double fade_out) {

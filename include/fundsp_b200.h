@@ -160,6 +160,13 @@ int fdsp_bank_inputs(const fdsp_bank* b);                                   /* s
 int fdsp_bank_voice_outputs(const fdsp_bank* b);                            /* channels per voice */
 int fdsp_bank_outputs(const fdsp_bank* b);                                  /* AudioUnit::outputs(): mix: channels; voices: V*channels */
 int fdsp_bank_set_sample_rate(fdsp_bank* b, double sample_rate);            /* AudioUnit::set_sample_rate */
+/* WAV edge (reference src/write.rs:24-116): `planar[c * stride + i]` -> Wave::write_wav16 (bits 16: round(clamp11(x) * 32767.49)) or
+   Wave::write_wav32 (bits 32: IEEE float) byte for byte — to a file, or into `out` (returns the byte count, also when out is NULL or
+   too small; -1 on error). fdsp_wave_load reads the two layouts back (16-bit samples / 32768); call it with planar = NULL to get the
+   sizes first. */
+int fdsp_wave_save(const char* path, const float* planar, uint32_t channels, uint64_t length, uint64_t stride, double sample_rate, int bits);
+int64_t fdsp_wave_encode(uint8_t* out, uint64_t max, const float* planar, uint32_t channels, uint64_t length, uint64_t stride, double sample_rate, int bits);
+int fdsp_wave_load(const char* path, float* planar, uint64_t max_floats, uint32_t* channels, uint64_t* length, double* sample_rate);
 /* Sequencer banks (voices made by fdsp_event; the bank's mix output is Sequencer::process, src/sequencer.rs:768-843).
    fdsp_bank_edit_event = Sequencer::edit (:441-483): new end time and fade-out of one event, effective from the next block.
    fdsp_bank_push_event = Sequencer::push on a running sequencer (:319-360): the event takes over the slot of a FINISHED event of the

@@ -261,3 +261,44 @@ def test_jit_translation_units_compile_for_sm100a():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "nvrtc_check.py")] + sigs, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
     assert r.stdout.count("ok   ") == len(sigs)
+
+
+def test_wav_files_match_the_reference_layout(tmp_path):
+    """Wave::write_wav16 / write_wav32 (src/write.rs:24-116) byte for byte: the expectation is built here with struct + numpy, and
+    Python's own `wave` module reads the 16-bit file back."""
+    import struct
+    import wave as pywave
+    rng = np.random.default_rng(9)
+    x = rng.uniform(-1.3, 1.3, (2, 1000)).astype(np.float32)
+    x[0, :6] = [0.0, 1.0, -1.0, 0.5, -0.5, 3.0e-5]
+    sr = 44100.0
+
+    def header(data_len, fmt, ch, rate):
+        sb = 2 if fmt == 1 else 4
+        return (b"RIFF" + struct.pack("<I", data_len + 36) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, fmt, ch, rate, rate * ch * sb, ch * sb, sb * 8)
+                + b"data" + struct.pack("<I", data_len))
+    # 16 bit: round(clamp11(x) * 32767.49) in f32, half away from zero
+    s = np.clip(x, np.float32(-1), np.float32(1)) * np.float32(32767.49)
+    q = (np.sign(s) * np.floor(np.abs(s) + np.float32(0.5))).astype(np.int16)        # f32 round-half-away (|s| + 0.5 is exact enough below 2**15: checked against np.round for non-ties)
+    nt = np.abs(np.abs(s) - np.floor(np.abs(s)) - 0.5) > 1e-3
+    assert np.array_equal(q[nt], np.round(s[nt]).astype(np.int16))
+    want16 = header(2 * 2 * 1000, 1, 2, 44100) + q.T.astype("<i2").tobytes()
+    got16 = capi.encode_wav(x, sr, 16)
+    assert got16 == want16
+    want32 = header(4 * 2 * 1000, 3, 2, 44100) + x.T.astype("<f4").tobytes()
+    assert capi.encode_wav(x, sr, 32) == want32
+    p16, p32 = tmp_path / "a16.wav", tmp_path / "a32.wav"
+    capi.save_wav(p16, x, sr, 16); capi.save_wav(p32, x, sr, 32)
+    assert p16.read_bytes() == want16 and p32.read_bytes() == want32
+    with pywave.open(str(p16), "rb") as f:
+        assert (f.getnchannels(), f.getsampwidth(), f.getframerate(), f.getnframes()) == (2, 2, 44100, 1000)
+        assert np.array_equal(np.frombuffer(f.readframes(1000), "<i2").reshape(1000, 2).T, q)
+    y32, r32 = capi.load_wav(p32)
+    assert r32 == 44100.0 and np.array_equal(y32, x)                                  # float files round-trip exactly
+    y16, _ = capi.load_wav(p16)
+    assert np.array_equal(y16, q.astype(np.float32) / np.float32(32768.0))
+    assert q[0, 0] == 0 and q[0, 1] == 32767 and q[0, 2] == -32767 and q[0, 5] == 1   # 3e-5 * 32767.49 = 0.98 -> 1
+    with pytest.raises(capi.FdspError):
+        capi.encode_wav(np.zeros((0, 10), np.float32), sr, 16)                       # assert!(self.channels() > 0)
+    with pytest.raises(capi.FdspError):
+        capi.load_wav(tmp_path / "missing.wav")
