@@ -1495,6 +1495,95 @@ template <int NIN> struct Panner {  // src/pan.rs:19-91, ID 49
   }
   static FDSP_DEV void end_simd(R&) {}
 };
+template <int T64> struct FSel { typedef float type; };
+template <> struct FSel<1> { typedef double type; };
+// Envelope<F, E, R> (src/envelope.rs:14-183, ID 14: `envelope`, `lfo`): a control signal sampled at jittered points ~interval apart
+// and interpolated linearly. The closure E lives on the host; its values at the sample points are data here. The points do not depend
+// on how the signal is processed (t_1 = t_0 + lerp(0.75, 1.25, rnd1(t_hash)) * interval, t_hash an LCG of the node's hash), so the
+// host evaluates the closure at exactly the points the reference would and lowers the K values per output as per-voice words; the
+// point arithmetic, interpolation and the block path's run logic (:131-157) are restated here. F = f32 or f64 (T64).
+template <int NO, int T64> struct EnvelopeTab {
+  typedef typename FSel<T64>::type F;
+  static constexpr int TW = T64 ? 2 : 1;   // words per time value
+  FDSP_NODE(0, NO, 2 * TW, 3 * TW + 3 + 4 * NO + 3, 1);   // NP counts interval and sample duration; the K * NO table words follow them (K is class-uniform)
+  struct R {
+    uint32_t K, k; const uint32_t* tab; uint32_t V;
+    F interval, sd, t, t0, t1; uint64_t t_hash;
+    float v0[NO], v1[NO], value[NO], delta[NO];
+    uint32_t run, run_len, seg_end;
+  };
+  static FDSP_DEV F ldF(Loader& l, bool state) {
+    if (T64) { const uint32_t lo = state ? l.S() : l.P(), hi = state ? l.S() : l.P(); return (F)__longlong_as_double((long long)(((unsigned long long)hi << 32) | lo)); }
+    return (F)(state ? l.Sf() : l.Pf());
+  }
+  static FDSP_DEV void stF(Saver& s, F x) {
+    if (T64) { const unsigned long long b = (unsigned long long)__double_as_longlong((double)x); s.S((uint32_t)b); s.S((uint32_t)(b >> 32)); }
+    else s.Sf((float)x);
+  }
+  static FDSP_DEV void load(R& r, Loader& l) {
+    r.K = l.U(); r.interval = ldF(l, false); r.sd = ldF(l, false);
+    r.tab = l.p + (size_t)l.pi * l.V + l.v; r.V = l.V; l.pi += r.K * (uint32_t)NO;
+    r.t = ldF(l, true); r.t0 = ldF(l, true); r.t1 = ldF(l, true);
+    const uint32_t lo = l.S(), hi = l.S(); r.t_hash = ((uint64_t)hi << 32) | lo;
+    r.k = l.S();
+#pragma unroll
+    for (int c = 0; c < NO; c++) { r.v0[c] = l.Sf(); r.v1[c] = l.Sf(); r.value[c] = l.Sf(); r.delta[c] = l.Sf(); }
+    r.run = l.S(); r.run_len = l.S(); r.seg_end = l.S();
+  }
+  static FDSP_DEV void save(const R& r, Saver& s) {
+    stF(s, r.t); stF(s, r.t0); stF(s, r.t1);
+    s.S((uint32_t)r.t_hash); s.S((uint32_t)(r.t_hash >> 32)); s.S(r.k);
+#pragma unroll
+    for (int c = 0; c < NO; c++) { s.Sf(r.v0[c]); s.Sf(r.v1[c]); s.Sf(r.value[c]); s.Sf(r.delta[c]); }
+    s.S(r.run); s.S(r.run_len); s.S(r.seg_end);
+  }
+  static FDSP_DEV void next_segment(R& r) {   // :63-82
+    r.t0 = r.t1;
+    const F w = (F)rnd1(r.t_hash);
+    const F next_interval = ((F)0.75f * ((F)1 - w) + (F)1.25f * w) * r.interval;
+    r.t1 = r.t0 + next_interval;
+    const uint32_t kk = r.k < r.K ? r.k : r.K - 1u;   // past the sampled horizon the last value holds
+    r.k += 1u;
+    r.t_hash = r.t_hash * 6364136223846793005ull + 1ull;
+    const float u = (float)((r.t - r.t0) / (r.t1 - r.t0));
+    const float samples = (float)(next_interval / r.sd);
+#pragma unroll
+    for (int c = 0; c < NO; c++) {
+      r.v0[c] = r.v1[c];
+      r.v1[c] = __uint_as_float(__ldg(r.tab + (size_t)(kk * (uint32_t)NO + (uint32_t)c) * r.V));
+      r.value[c] = r.v0[c] * (1.0f - u) + r.v1[c] * u;
+      r.delta[c] = (r.v1[c] - r.v0[c]) / samples;
+    }
+  }
+  static FDSP_DEV F ceilF(F x) { return T64 ? (F)ceil((double)x) : (F)ceilf((float)x); }
+  template <class C> static FDSP_DEV void plan(R& r, const C& c) {   // the while-loop of :135-156 from block index c.i
+    for (;;) {
+      const long long left = (long long)ceilF((r.t1 - r.t) / r.sd);
+      const long long room = (long long)(c.n - c.i);   // > 0: plan runs only with samples left in the block
+      const long long loop = left < room ? left : room;
+      if (loop <= 0) { next_segment(r); continue; }     // t == t_1 exactly: zero samples, loop_samples == segment_samples_left
+      r.run = (uint32_t)loop; r.run_len = r.run; r.seg_end = (loop == left) ? 1u : 0u;
+      return;
+    }
+  }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<0>&, Fr<NO>& o) {
+    if (T) {   // tick :117-126
+      if (r.t >= r.t1) next_segment(r);
+#pragma unroll
+      for (int k = 0; k < NO; k++) { o.v[k] = r.value[k]; r.value[k] += r.delta[k]; }
+      r.t += r.sd;
+      return;
+    }
+    if (c.i == 0) { if (r.t >= r.t1) next_segment(r); plan(r, c); }
+    else if (r.run == 0u) plan(r, c);
+#pragma unroll
+    for (int k = 0; k < NO; k++) { o.v[k] = r.value[k]; r.value[k] += r.delta[k]; }
+    r.run -= 1u;
+    if (r.run == 0u) { r.t += (F)(long long)r.run_len * r.sd; if (r.seg_end) next_segment(r); }
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
 struct AdsrLive {  // src/envelope.rs:185-358 EnvelopeIn<f32,_,U1,f32> (ID 53) + the closure of src/adsr.rs:21-70
   FDSP_NODE(1, 1, 5, 15, 0);
   struct R {
@@ -1697,6 +1786,7 @@ template <int M, int N> struct Cost<Mixer<M, N>> { static constexpr int value = 
 template <int K> struct Cost<MeterNode<K>> { static constexpr int value = 10; };
 template <> struct Cost<WavePlayer> { static constexpr int value = 12; };
 template <int N> struct Cost<Limiter<N>> { static constexpr int value = 150; };
+template <int N, int T> struct Cost<EnvelopeTab<N, T>> { static constexpr int value = 120; };
 template <> struct Cost<Sine> { static constexpr int value = 40; };
 template <> struct Cost<Noise> { static constexpr int value = 16; };
 template <> struct Cost<FixedSvf> { static constexpr int value = 20; };

@@ -114,14 +114,14 @@ std::string Bank::lower_and_upload(bool upload_state) {
         if (!prog_sig.empty()) {
           c.k = get_program(prog_sig, device, jerr);
           if (!c.k) return "no device program for the dry stage `" + prog_sig + "`: " + jerr;
-          if ((uint32_t)c.k->NP != c.p0 - (wet ? 1u : 0u) || (uint32_t)c.k->NS != c.s0 || (uint32_t)c.k->NU != c.u0 - lo.l.extraU || c.k->IN != nin || c.k->OUT != 2)
+          if ((uint32_t)c.k->NP != c.p0 - (wet ? 1u : 0u) - lo.l.extraP || (uint32_t)c.k->NS != c.s0 || (uint32_t)c.k->NU != c.u0 - lo.l.extraU || c.k->IN != nin || c.k->OUT != 2)
             return "internal: dry-stage layout of `" + prog_sig + "` disagrees with the host lowering";
         }
       } else {
         for (uint32_t d : lo.l.dlen) c.dl_floats += d;
         c.k = get_program(lo.sig, device, jerr);
         if (!c.k) return "no device program for graph class `" + lo.sig + "`: " + jerr;
-        if ((uint32_t)c.k->NP != c.np || (uint32_t)c.k->NS != c.ns || (uint32_t)c.k->NU != nu_static || c.k->IN != nin || c.k->OUT != nout)
+        if ((uint32_t)c.k->NP != c.np - lo.l.extraP || (uint32_t)c.k->NS != c.ns || (uint32_t)c.k->NU != nu_static || c.k->IN != nin || c.k->OUT != nout)
           return "internal: host lowering of `" + lo.sig + "` disagrees with the device word layout";
       }
       fresh.push_back(std::move(c));

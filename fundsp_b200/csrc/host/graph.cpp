@@ -621,6 +621,44 @@ struct EventN : HNode {  // one Sequencer event as a voice (src/sequencer.rs:55-
   }
   HCLONE(EventN)
 };
+struct EnvelopeN : HNode {  // src/envelope.rs:14-183: the closure is evaluated here, at the reference's sample points, when the graph is lowered
+  double interval; int nout, t64; EnvelopeFn fn; void* user; double horizon, sr = DEFAULT_SR; uint64_t hash = 0;
+  EnvelopeN(double iv, int n, int t64_, EnvelopeFn f, void* u, double hz) : interval(iv), nout(n), t64(t64_), fn(f), user(u), horizon(hz) {}
+  int inputs() const override { return 0; } int outputs() const override { return nout; }
+  uint64_t id() const override { return 14; }
+  void set_sample_rate(double s) override { sr = s; }
+  void set_hash(uint64_t h) override { hash = h; }
+  void set(const Setting& s) override { if (s.kind == P_INTERVAL) interval = (double)s.v[0]; }   // self.interval = F::from_f32(time)
+  void sig(std::string& o) const override { o += "EnvelopeTab<" + I(nout) + "," + I(t64 ? 1 : 0) + ">"; }
+  template <class F> void lower_as(Lowering& l) const {
+    auto pF = [&](F x) { if (sizeof(F) == 8) { double d = (double)x; uint64_t b; memcpy(&b, &d, 8); l.P.push_back((uint32_t)b); l.P.push_back((uint32_t)(b >> 32)); } else l.p((float)x); };
+    auto sF = [&](F x) { if (sizeof(F) == 8) { double d = (double)x; uint64_t b; memcpy(&b, &d, 8); l.su((uint32_t)b); l.su((uint32_t)(b >> 32)); } else l.s((float)x); };
+    const F iv = (F)interval, sd = (F)(1.0 / sr);
+    std::vector<double> out((size_t)nout);
+    std::vector<float> first((size_t)nout), tab;
+    fn(0.0, out.data(), user);                                             // reset(): value_0 = value_1 = E(0)
+    for (int c = 0; c < nout; c++) first[c] = (float)out[c];
+    F t0 = (F)0; uint64_t h = hash; uint32_t K = 0;
+    for (;;) {                                                             // next_segment :63-75, the points only
+      const F w = (F)rnd1(h);
+      const F t1 = t0 + ((F)0.75f * ((F)1 - w) + (F)1.25f * w) * iv;
+      fn((double)t1, out.data(), user);
+      for (int c = 0; c < nout; c++) tab.push_back((float)out[c]);
+      h = h * 6364136223846793005ull + 1ull; t0 = t1; K++;
+      if ((double)t1 > horizon || K >= (1u << 22)) break;
+    }
+    l.U.push_back(K);
+    pF(iv); pF(sd);
+    for (float x : tab) l.p(x);
+    l.extraP += K * (uint32_t)nout;
+    sF((F)0); sF((F)0); sF((F)0);
+    l.su((uint32_t)hash); l.su((uint32_t)(hash >> 32)); l.su(0u);
+    for (int c = 0; c < nout; c++) { l.s(first[c]); l.s(first[c]); l.s(0.0f); l.s(0.0f); }
+    l.su(0u); l.su(0u); l.su(0u);
+  }
+  void lower(Lowering& l) const override { if (t64) lower_as<double>(l); else lower_as<float>(l); }
+  HCLONE(EnvelopeN)
+};
 struct VarN : HNode {  // the shared value is control-plane state: it enters as a parameter word and changes through Setting::value
   float value; explicit VarN(float v) : value(v) {}
   int inputs() const override { return 0; } int outputs() const override { return 1; }
@@ -957,6 +995,10 @@ HNode* mk_reverb3(double time, double diffusion, HNode* filter) {
   return new ReverbN(time, diffusion, filter);
 }
 HNode* mk_var(float value) { return new VarN(value); }
+HNode* mk_envelope(double interval, int outputs, int time_f64, EnvelopeFn f, void* user, double horizon) {
+  if (!(interval > 0.0) || outputs < 1 || outputs > 8 || !f || !(horizon >= 0.0) || horizon / interval > 4.0e6) return nullptr;   // assert!(interval > F::zero())
+  return new EnvelopeN(time_f64 ? interval : (double)(float)interval, outputs, time_f64, f, user, horizon);
+}
 bool event_edit(HNode* n, double end_time, double fade_out) {   // Sequencer::edit on an event (:441-483, no loop: start == original start)
   EventN* e = dynamic_cast<EventN*>(n);
   if (!e) return false;

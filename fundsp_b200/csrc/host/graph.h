@@ -52,6 +52,7 @@ struct Lowering {
   std::vector<uint32_t> P, S, U;   // words in DFS order
   std::vector<uint32_t> dlen;      // delay-line lengths (floats per voice) in DFS order
   uint32_t extraU = 0;             // uniform words beyond the nodes' static NU (e.g. a Convolver's impulse response)
+  uint32_t extraP = 0;             // per-voice parameter words beyond the static NP (an envelope's sampled closure values)
   bool ok = true; std::string why; // set when a node has no device lowering
   void p(float f) { P.push_back(f2u(f)); }
   void s(float f) { S.push_back(f2u(f)); }
@@ -116,6 +117,10 @@ HNode* mk_event(HNode* x, double start, double end, int fade_ease, double fade_i
 bool event_edit(HNode* n, double end_time, double fade_out);         // false when n is not an event
 bool event_times(const HNode* n, double* start, double* end);
 bool event_set_clock(HNode* n, double time);                         // the sequencer time the event's own clock starts from
+// Envelope<F, E, R> (ID 14): `f(t, out[outputs], user)` is the closure E, evaluated ON THE HOST at the reference's sample points when the
+// graph is lowered (bank creation, sample-rate change, settings) for t <= horizon seconds; time_f64: F = f64 (else f32)
+typedef void (*EnvelopeFn)(double t, double* out, void* user);
+HNode* mk_envelope(double interval, int outputs, int time_f64, EnvelopeFn f, void* user, double horizon);
 HNode* mk_declick(float duration);                                   // Declick ID 23
 HNode* mk_chaos(int kind);                                           // 0 Rossler ID 73, 1 Lorenz ID 74
 HNode* mk_morph(float cutoff, float q);                               // Morph ID 62

@@ -534,6 +534,21 @@ def mixer(matrix):
     return An("mixer", (len(rows[0]), len(rows), tuple(x for r in rows for x in r)), (), len(rows[0]), len(rows))
 
 
+# ---- src/prelude.rs:580-612 envelope / lfo: control signals from a closure of time, sampled every ~2 ms and interpolated.
+# `f(t)` returns a float or a tuple (one value per output); `outputs` defaults to what f(0.0) returns. The closure runs on the HOST when
+# the graph is lowered, at the sample points the reference would use, up to `horizon` seconds (then the last value holds).
+# time64=True is `F = f64` (prelude64 / hacker); the default is the f32 time of hacker32.
+def envelope(f, outputs=None, horizon=10.0, time64=False, interval=0.002):
+    if outputs is None:
+        v = f(0.0)
+        outputs = len(v) if isinstance(v, (tuple, list)) else 1
+    return An("envelope", (float(interval) if time64 else f32(interval), int(outputs), 1 if time64 else 0, f, float(horizon)), (), 0, int(outputs))
+
+
+def lfo(f, outputs=None, horizon=10.0, time64=False):
+    return envelope(f, outputs, horizon, time64)
+
+
 # ---- src/prelude.rs:1288-1301 look-ahead limiters
 def limiter(attack_time, release_time):
     return An("limiter", (1, f32(attack_time), f32(release_time)), (), 1, 1)

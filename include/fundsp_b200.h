@@ -77,6 +77,12 @@ fdsp_node* fdsp_morph(float cutoff, float q);                  /* Morph ID 62 sr
 fdsp_node* fdsp_rez(float bandpass, float cutoff, float q, int inputs); /* Rez ID 75 src/rez.rs: bandpass 0 = lowrez, 1 = bandrez; inputs 1 or 3 (audio, cutoff, q) */
 fdsp_node* fdsp_chaos(int kind);                               /* kind 0 Rossler ID 73, 1 Lorenz ID 74 (src/oscillator.rs:318-438); input = frequency */
 fdsp_node* fdsp_declick(float duration);                       /* Declick ID 23 src/dynamics.rs:245: smooth fade-in over `duration` seconds */
+/* Envelope<F, E, R> ID 14 src/envelope.rs:14 (`envelope`, `lfo`; interval 0.002): the closure E crosses the ABI as a HOST callback. It is
+   called when the graph is lowered (bank creation, sample-rate change, settings) — never while rendering — at exactly the jittered sample
+   points the reference would evaluate it at (they depend only on the node's hash and the interval), for points up to `horizon` seconds;
+   later the last value holds. time_f64: F = f64, else f32 (t is then an f32 value). f and user must outlive the node and its bank. */
+typedef void (*fdsp_envelope_fn)(double t, double* out /* [outputs] */, void* user);
+fdsp_node* fdsp_envelope(double interval, int outputs, int time_f64, fdsp_envelope_fn f, void* user, double horizon);
 /* One event of a Sequencer (src/sequencer.rs:319-345 `push`) as a voice: the generator x sounds from start to end seconds (sample
    accurate, the reference's rounding), with fade-in / fade-out of the given lengths; fade_ease 0 Fade::Power, 1 Fade::Smooth. A bank
    of events IS the sequencer: its mix output is Sequencer::process. Consumes x. */

@@ -221,6 +221,10 @@ inline An playwave(const std::vector<float>& samples, long long loop_point = -1)
 inline An playwave_at(const std::vector<float>& samples, size_t start, size_t end, long long loop_point = -1) { return An(fdsp_playwave(samples.data(), samples.size(), start, end, loop_point)); }
 inline An limiter(float attack_time, float release_time) { return An(fdsp_limiter(1, attack_time, release_time)); }
 inline An limiter_stereo(float attack_time, float release_time) { return An(fdsp_limiter(2, attack_time, release_time)); }
+// envelope(|t| ...) / lfo(|t| ...) (src/prelude.rs:580-612): a capture-less lambda or function `void f(double t, double* out, void* user)`;
+// the closure runs on the host when the graph is lowered, at the reference's sample points, up to `horizon` seconds
+inline An envelope(fdsp_envelope_fn f, int outputs = 1, void* user = nullptr, double horizon = 10.0, bool time64 = false) { return An(fdsp_envelope(0.002, outputs, time64 ? 1 : 0, f, user, horizon)); }
+inline An lfo(fdsp_envelope_fn f, int outputs = 1, void* user = nullptr, double horizon = 10.0, bool time64 = false) { return envelope(f, outputs, user, horizon, time64); }
 enum class Fade { Power = 0, Smooth = 1 };                                                 // src/sequencer.rs:35-52
 // one Sequencer event as a voice (Sequencer::push, src/sequencer.rs:319-345): a Bank of events is the sequencer
 inline An event(An unit, double start_time, double end_time, Fade ease = Fade::Smooth, double fade_in = 0.0, double fade_out = 0.0) {

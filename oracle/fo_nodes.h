@@ -1634,6 +1634,54 @@ struct Limiter : Node {
   }
   FO_CLONE(Limiter)
 };
+// ---- src/envelope.rs:14-183 Envelope<F, E, R> (ID 14): the closure is a live callback here, exactly as in the reference
+typedef void (*EnvelopeFn)(double t, double* out, void* user);
+template <class F> struct Envelope : Node {
+  EnvelopeFn fn; void* user; int nout;
+  F t = 0, t_0 = 0, t_1 = 0, interval, sample_duration = 0; uint64_t t_hash = 0, hash = 0;
+  std::vector<float> value_0, value_1, value, value_d;
+  Envelope(F iv, int n, EnvelopeFn f, void* u) : fn(f), user(u), nout(n), interval(iv), value_0(n, 0.0f), value_1(n, 0.0f), value(n, 0.0f), value_d(n, 0.0f) {
+    set_sample_rate(DEFAULT_SR); reset();
+  }
+  void call(F at, std::vector<float>& into) { double o[16]; fn((double)at, o, user); for (int c = 0; c < nout; c++) into[c] = (float)o[c]; }
+  void next_segment() {   // :63-82
+    t_0 = t_1; value_0 = value_1;
+    const F w = (F)rnd1(t_hash);
+    const F next_interval = ((F)0.75f * ((F)1 - w) + (F)1.25f * w) * interval;
+    t_1 = t_0 + next_interval;
+    call(t_1, value_1);
+    t_hash = t_hash * 6364136223846793005ull + 1ull;
+    const F u = (t - t_0) / (t_1 - t_0);
+    const F samples = next_interval / sample_duration;
+    for (int c = 0; c < nout; c++) { value[c] = value_0[c] * (1.0f - (float)u) + value_1[c] * (float)u; value_d[c] = (value_1[c] - value_0[c]) / (float)samples; }
+  }
+  int inputs() const override { return 0; } int outputs() const override { return nout; }
+  uint64_t id() const override { return 14; }
+  void reset() override { t = 0; t_0 = 0; t_1 = 0; t_hash = hash; call(t_0, value_0); value_1 = value_0; }
+  void set_sample_rate(double sr) override { sample_duration = (F)(1.0 / sr); }
+  void tick(const float*, float* out) override {   // :117-126
+    if (t >= t_1) next_segment();
+    for (int c = 0; c < nout; c++) { out[c] = value[c]; value[c] += value_d[c]; }
+    t += sample_duration;
+  }
+  void process(int size_, const float*, float* out) override {   // :128-157
+    const size_t size = (size_t)size_;
+    if (t >= t_1) next_segment();
+    size_t i = 0;
+    while (i < size) {
+      const size_t left = (size_t)(long long)(sizeof(F) == 8 ? (double)ceil((double)((t_1 - t) / sample_duration)) : (double)ceilf((float)((t_1 - t) / sample_duration)));
+      const size_t loop = std::min(size - i, left);
+      for (int c = 0; c < nout; c++) { float v = value[c], d = value_d[c]; for (size_t o = 0; o < loop; o++) { out[c * B + i + o] = v; v += d; } value[c] = v; }
+      i += loop;
+      t += (F)(long long)loop * sample_duration;
+      if (loop == left) next_segment();
+    }
+  }
+  void set(const Setting& s) override { if (s.kind == P_INTERVAL) interval = (F)s.v[0]; }
+  void set_hash(uint64_t h) override { hash = h; t_hash = h; }
+  Node* clone() const override { return new Envelope<F>(*this); }
+};
+
 // ---- src/dynamics.rs:316-437 Meter / MeterState / MeterNode (ID 61); kind 0 Sample, 1 Peak(timescale), 2 Rms(timescale)
 struct MeterNode : Node {
   int kind; double timescale; float smoothing = 0, state = 0;

@@ -90,6 +90,10 @@ API Node* fo_morph(float cutoff, float q) { return new Morph(cutoff, q); }
 API Node* fo_rez(float bandpass, float cutoff, float q, int inputs) { return new Rez(bandpass, cutoff, q, inputs); }
 API Node* fo_chaos(int kind) { return new Chaos(kind); }   // 0 rossler, 1 lorenz
 API Node* fo_declick(float duration) { return new Declick(duration); }
+API Node* fo_envelope(double interval, int outputs, int time_f64, EnvelopeFn f, void* user) {
+  if (time_f64) return new Envelope<double>(interval, outputs, f, user);
+  return new Envelope<float>((float)interval, outputs, f, user);
+}
 // Sequencer (src/sequencer.rs): mode 0 ReplayMode::All, 1 None, 2 Loop(loop_time); fade_ease 0 Fade::Power, 1 Fade::Smooth
 API Node* fo_sequencer(int inputs, int outputs, int mode, double loop_time) { return new Sequencer(inputs, outputs, mode, loop_time); }
 API uint64_t fo_sequencer_push(Node* s, double start, double end, int ease, double fade_in, double fade_out, Node* unit) { return static_cast<Sequencer*>(s)->push(start, end, ease, fade_in, fade_out, unit); }

@@ -51,6 +51,8 @@ int main() {
   std::printf("smp %d %d %s %016llx\n", smp.inputs(), smp.outputs(), smp.signature().c_str(), words_hash(smp));
   An ev = event(saw_hz(220.0f) >> lowpass_hz(900.0f, 2.0f), 0.0125, 0.75, Fade::Power, 0.01, 0.2);
   std::printf("event %d %d %s %016llx\n", ev.inputs(), ev.outputs(), ev.signature().c_str(), words_hash(ev));
+  An vib = lfo([](double t, double* o, void*) { o[0] = 220.0 + 10.0 * t; }, 1, nullptr, 0.05) >> sine();
+  std::printf("vib %d %d %s\n", vib.inputs(), vib.outputs(), vib.signature().c_str());
   An r1 = reverb_stereo(12.0, 2.5, 0.4f), r4 = reverb4_stereo(20.0, 3.0);
   std::printf("reverb_stereo %s %016llx\n", r1.signature().c_str(), words_hash(r1));
   std::printf("reverb4_stereo %s %016llx\n", r4.signature().c_str(), words_hash(r4));

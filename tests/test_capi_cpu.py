@@ -53,6 +53,7 @@ GRAPHS = [
     lambda: dc(220.0) >> lorenz() | dc(110.0) >> rossler() | dc(330.0) >> lorenz(),
     lambda: dc((220.0, 0.3)) >> pulse() | dc((220.0, 0.3)) >> pulse().phase(0.5) | (ramp_hz(50.0) >> phase_synth(3) | noise()) >> rotate(0.3, 0.5) >> mixer([[1.0, 2.0]]),
     lambda: (noise() | noise()) >> reverb4_stereo(25.0, 2.0),
+    lambda: lfo(lambda t: 440.0 + t, horizon=0.05) >> sine() | envelope(lambda t: (t, 1.0 - t), horizon=0.05) >> (pass_() * pass_()) | lfo(lambda t: 1.0, horizon=0.02, time64=True) * noise(),
     lambda: noise() >> limiter(0.005, 0.05) | (noise() | noise()) >> limiter_stereo(0.002, 0.02),
     lambda: dc(1.5) >> resample(noise() | sine_hz(440.0)) | dc(0.5) >> resample(playwave(np.linspace(-1, 1, 50, dtype=np.float32)[None, :], 0, 0)) | noise() >> meter(Meter.Rms(0.1)),
     lambda: dc(220.0) >> dsf_saw_r(0.7) | (dc(110.0) | dc(0.4)) >> dsf_square() | dc(440.0) >> dsf_square_r(0.3).phase(0.25),
@@ -98,6 +99,7 @@ def test_builder_argument_errors_return_null_with_a_message():
         lambda: be.b_meter(3, 0.1), lambda: be.b_meter(1, 0.0), lambda: be.b_playwave([0.0] * 8, 0, 9, -1), lambda: be.b_resample(be.b_pass()),   # end_point <= length; generator only
         lambda: be.b_limiter(0, 0.01, 0.01), lambda: be.b_limiter(1, -1.0, 0.01),
         lambda: be.b_event(0.0, 1.0, 1, 0.0, 0.0, be.b_pass()), lambda: be.b_event(0.0, 1.0, 1, 2.0, 0.0, be.b_noise()), lambda: be.b_event(0.0, 1.0, 3, 0.0, 0.0, be.b_noise()),   # generators only; fade <= duration
+        lambda: be.b_envelope(0.0, 1, 0, lambda t: 0.0, 1.0), lambda: be.b_envelope(0.002, 0, 0, lambda t: 0.0, 1.0), lambda: be.b_envelope(1e-9, 1, 0, lambda t: 0.0, 10.0),   # interval > 0; 1..8 outputs; bounded table
         lambda: be.b_phase_synth(6), lambda: be.b_mixer(0, 2, [1.0]), lambda: be.b_mixer(9, 9, [0.0] * 81),      # tables 0..5; 1 <= M*N <= 64
     ]
     for k, f in enumerate(bad):
@@ -231,6 +233,7 @@ def test_cpp_host_mirror_compiles_and_matches_python_mirror(tmp_path):
     from fundsp_b200.sequencer import event, Fade
     ev, eh = words_hash(event(saw_hz(220.0) >> lowpass_hz(900.0, 2.0), 0.0125, 0.75, Fade.Power, 0.01, 0.2))
     assert f"event 0 1 {ev.signature()} {eh}" in lines
+    assert "vib 0 1 Pipe<EnvelopeTab<1,0>,Sine>" in lines
     r1, h1 = words_hash(reverb_stereo(12.0, 2.5, 0.4))
     r4, h4 = words_hash(reverb4_stereo(20.0, 3.0))
     assert f"reverb_stereo {r1.signature()} {h1}" in lines and f"reverb4_stereo {r4.signature()} {h4}" in lines   # every coefficient, bit for bit

@@ -1,5 +1,7 @@
 """Structural coverage beyond the AOT config graphs: every §8a node family composed in ways the registry does not
 list, compiled at bank creation by the NVRTC path from the same device headers, checked bit-for-bit against the oracle."""
+import math
+
 import numpy as np
 import pytest
 
@@ -97,6 +99,9 @@ WIDER = {
     "phase_synth_tables": lambda i: ramp_hz(100.0 + 13.0 * i) >> (phase_synth(SQUARE) & phase_synth(ORGAN) * 0.5) | (sine_hz(50.0 + i) * 0.6) >> phase_synth(SOFT_SAW),
     "rotate_mixer": lambda i: (noise().seed(i) | sine_hz(200.0 + i)) >> rotate(0.1 * i, 0.8) >> mixer([[0.5, -0.25], [0.125 * (i % 8), 1.0], [1.0, 1.0]]),
     "reverb4_short_lines": lambda i: (noise().seed(i) | noise().seed(i + 100)) >> reverb4_stereo_delays([d * (0.15 + 0.002 * (i % 25)) for d in REVERB4_DELAYS], 1.0 + 0.05 * (i % 8)),
+    # closures crossing the ABI as host callbacks (envelope / lfo): sampled on the host at the reference's points, interpolated on the device
+    "lfo_vibrato": lambda i: lfo(lambda t, i=i: 220.0 + 3.0 * i + (2.0 + 0.1 * i) * math.sin(2.0 * math.pi * (4.0 + 0.1 * i) * t), horizon=0.1) >> sine() | envelope(lambda t, i=i: math.exp(-t * (5.0 + i)), horizon=0.1) * noise().seed(i),
+    "envelope_two_outputs_f64": lambda i: envelope(lambda t, i=i: (min(1.0, t * (50.0 + i)), 300.0 + 100.0 * t), horizon=0.1, time64=True) >> (pass_() * (pass_() >> saw())),
     # sequencer events (src/sequencer.rs): per-voice start / end / fades; checked against one-event Sequencers of the oracle
     "events_saw_filter": lambda i: _ev(saw_hz(110.0 + 3.0 * i) >> lowpass_hz(900.0 + 20.0 * i, 2.0), (31.0 + 37.7 * i) / SR, (31.0 + 37.7 * i + 600.3 + 23.1 * i) / SR, 1, (40.5 + i) / SR, (200.0 + 5 * i) / SR),
     "events_power_fades_stereo": lambda i: _ev(sine_hz(300.0 + i) | noise().seed(i), (1.0 + 0.37 * i) * 64.0 / SR, ((1.0 + 0.37 * i) * 64.0 + 700.0 + 11.0 * i) / SR, 0, (100.0 + 3.3 * i) / SR, (300.0 + 2.1 * i) / SR),

@@ -736,6 +736,36 @@ def test_sequencer():  # src/sequencer.rs; tests/test_basic.rs:192-193,255-274,7
     L.fo_restore_denormals()
 
 
+def test_envelope_lfo():  # src/envelope.rs:14-183; tests/test_basic.rs:173-176,238,645
+    xerp = lambda a, b, t: math.exp(math.log(a) * (1.0 - t) + math.log(b) * t)
+    c01 = lambda t: min(1.0, max(0.0, t))
+    check_wave(lfo(lambda t: xerp(110.0, 220.0, c01(t))) >> sine() | (envelope(lambda t: xerp(220.0, 440.0, c01(t))) >> pass_() >> sine()) & mls())   # :173-176
+    check_wave(envelope(lambda t: math.exp(-t * 10.0)))                                                                  # :238
+    g = envelope(lambda t: math.exp(-t)) * noise()
+    assert (g.inputs(), g.outputs()) == (0, 1)                                                                           # :645
+    sr = 44100.0
+    # a linear closure is reproduced by linear interpolation: y[n] = n / sr to rounding, on both paths, f32 and f64 time
+    for t64 in (False, True):
+        y = OracleUnit(envelope(lambda t: t, time64=t64)).render(sr, 0.5)[0]
+        assert np.abs(y - np.arange(len(y)) / sr).max() < 2e-6
+    # the sample points are 0.75 .. 1.25 intervals apart: the knots of a piecewise-linear rendering of t**2 show them
+    y = OracleUnit(envelope(lambda t: t * t, interval=0.01)).render(sr, 1.0)[0].astype(np.float64)
+    dd = np.abs(np.diff(y, 2)) * sr * sr
+    knots = np.flatnonzero(dd > 100.0)                                    # slope changes by 2 * interval * (gap) at a knot
+    knots = knots[np.insert(np.diff(knots) > 3, 0, True)]
+    gaps = np.diff(knots) / sr
+    assert len(knots) > 80 and gaps.min() >= 0.0075 - 2 / sr and gaps.max() <= 0.0125 + 2 / sr and gaps.std() > 0.0005
+    # two envelopes in one graph draw different jitter (their hashes differ); the same graph built twice is identical
+    two = lambda: envelope(lambda t: t * t, interval=0.01) | envelope(lambda t: t * t, interval=0.01)
+    a, b = OracleUnit(two()).render(sr, 0.2), OracleUnit(two()).render(sr, 0.2)
+    assert np.array_equal(a, b) and not np.array_equal(a[0], a[1]) and np.abs(a[0] - a[1]).max() < 1e-4
+    # an lfo drives a parameter: vibrato depth shows up as the spread of instantaneous frequency
+    y = OracleUnit(lfo(lambda t: 440.0 + 40.0 * math.sin(2.0 * math.pi * 5.0 * t)) >> sine()).render(sr, 1.0)[0]
+    zc = np.flatnonzero((y[:-1] < 0) & (y[1:] >= 0))
+    f = sr / np.diff(zc)
+    assert 395.0 < f.min() < 410.0 and 470.0 < f.max() < 485.0
+
+
 def test_mls_is_maximum_length():  # src/noise.rs:11-98: the sequence of an n-bit MLS repeats after exactly 2**n - 1 steps
     for n in range(2, 15):
         u = OracleUnit(mls_bits(n))
