@@ -238,17 +238,18 @@ void Bank::advance_clock(uint64_t n) {   // what every Event<X> voice does to it
   for (uint64_t t0 = 0; t0 < n; t0 += 64) seq_time = seq_time + sd * (double)std::min<uint64_t>(64, n - t0);
 }
 
-std::string Bank::upload_voice(uint32_t voice, const Lowering& l, bool with_state) {
+// `l`: the words to run with. `reset_state`: the construction-time state that reset() restores (defaults to l.S).
+std::string Bank::upload_voice(uint32_t voice, const Lowering& l, bool with_state, const std::vector<uint32_t>* reset_state) {
   for (auto& c : classes) {
     auto it = std::lower_bound(c.voices.begin(), c.voices.end(), voice);
     if (it == c.voices.end() || *it != voice) continue;
     const uint32_t i = (uint32_t)(it - c.voices.begin()), Vc = c.V();
-    if (l.U != c.uniform || l.P.size() != c.np || l.S.size() != c.ns)
+    if (l.U != c.uniform || l.P.size() != c.np || l.S.size() != c.ns || (reset_state && reset_state->size() != c.ns))
       return "the voice does not fit its class: a class-uniform word (delay length, table, wave) or the word layout differs; rebuild the bank instead";
+    if (with_state && c.fdn) return "voices of a two-stage (FDN reverb) class cannot be replaced in place";
     if (c.np) CU(cudaMemcpy2DAsync(c.d_params + i, (size_t)Vc * 4, l.P.data(), 4, 4, c.np, cudaMemcpyHostToDevice, stream));
-    for (uint32_t k = 0; k < c.ns; k++) c.state0[(size_t)k * Vc + i] = l.S[k];
+    for (uint32_t k = 0; k < c.ns; k++) c.state0[(size_t)k * Vc + i] = reset_state ? (*reset_state)[k] : l.S[k];
     if (with_state) {
-      if (c.fdn) return "voices of a two-stage (FDN reverb) class cannot be replaced in place";
       if (c.ns) CU(cudaMemcpy2DAsync(c.d_state + i, (size_t)Vc * 4, l.S.data(), 4, 4, c.ns, cudaMemcpyHostToDevice, stream));
       if (c.dl_floats) CU(cudaMemset2DAsync(c.d_dline + i, (size_t)Vc * 4, 0, 4, (size_t)c.dl_floats, stream));
     }
@@ -279,11 +280,13 @@ std::string Bank::replace_voice(uint32_t voice, HNode* node) {
   if (a != b) return "replace: the unit's graph differs from the voice's class `" + b + "`";
   const double unit_rate = net_rate ? (double)(float)sr : sr;
   n->set_sample_rate(unit_rate);
-  event_set_clock(n.get(), seq_time);   // an event pushed into a running sequencer counts from now
-  Lowering l;
+  Lowering l0, l;
+  n->lower(l0);                                        // what reset() restores: the event's clock at 0, like every other voice
+  const bool ev = event_set_clock(n.get(), seq_time);  // an event put into a running sequencer counts from now
   n->lower(l);
+  if (ev) event_set_clock(n.get(), 0.0);
   if (!l.ok) return l.why;
-  std::string e = upload_voice(voice, l, true);
+  std::string e = upload_voice(voice, l, true, &l0.S);
   if (!e.empty()) return e;
   nodes[voice] = std::move(n);
   return "";
@@ -297,17 +300,19 @@ std::string Bank::push_event(HNode* node, uint32_t* voice) {   // Sequencer::pus
   CU(cudaSetDevice(device));
   const double unit_rate = net_rate ? (double)(float)sr : sr, sd = 1.0 / unit_rate;
   n->set_sample_rate(unit_rate);
-  event_set_clock(n.get(), seq_time);   // the event counts from now; a start time in the past makes it sound from the next block on
   std::string want; n->sig(want);
-  Lowering l;
+  Lowering l0, l;
+  n->lower(l0);                             // what reset() restores: the event's clock at 0 (ReplayMode::All replays it from the top)
+  event_set_clock(n.get(), seq_time);       // the event counts from now; a start time in the past makes it sound from the next block on
   n->lower(l);
+  event_set_clock(n.get(), 0.0);
   if (!l.ok) return l.why;
   for (auto& c : classes) {
     if (c.sig != want || c.uniform != l.U || c.fdn) continue;
     for (uint32_t v : c.voices) {
       if (!event_times(nodes[v].get(), &s0, &e0)) break;
       if (!(e0 <= seq_time + 0.5 * sd)) continue;   // Event::plan's end-of-event test at the start of the next block: still sounding
-      std::string e = upload_voice(v, l, true);
+      std::string e = upload_voice(v, l, true, &l0.S);
       if (!e.empty()) return e;
       nodes[v] = std::move(n);
       if (voice) *voice = v;
@@ -624,7 +629,7 @@ std::string Bank::clone_into(Bank& dst) const {
     if (s.dl_floats) CU(cudaMemcpy(d.d_dline, s.d_dline, (size_t)s.dl_floats * s.V() * 4, cudaMemcpyDeviceToDevice));
     if (s.ring_floats && s.d_ring && d.d_ring) CU(cudaMemcpy(d.d_ring, s.d_ring, (size_t)s.ring_floats * s.V() * 4, cudaMemcpyDeviceToDevice));
   }
-  dst.dirty = dirty;
+  dst.dirty = dirty; dst.seq_time = seq_time;
   return "";
 }
 

@@ -63,7 +63,7 @@ struct Bank {
   // (time += sample_duration * block for every 64-sample block and the tail), live edits and reuse of finished voices
   double seq_time = 0.0;
   void advance_clock(uint64_t n);
-  std::string upload_voice(uint32_t voice, const Lowering& l, bool with_state);
+  std::string upload_voice(uint32_t voice, const Lowering& l, bool with_state, const std::vector<uint32_t>* reset_state = nullptr);
   std::string edit_event(uint32_t voice, double end_time, double fade_out);   // Sequencer::edit
   std::string replace_voice(uint32_t voice, HNode* node);                     // a new unit in the slot of a voice of the same class; consumes node
   std::string push_event(HNode* event, uint32_t* voice);                      // Sequencer::push on a running bank: takes the slot of a finished event of the same class; consumes event
