@@ -549,6 +549,21 @@ def lfo(f, outputs=None, horizon=10.0, time64=False):
     return envelope(f, outputs, horizon, time64)
 
 
+# ---- src/prelude.rs:2719-2753 flanger / phaser: the delay (phase) closure is a closure of time, so it lowers like `lfo`
+def flanger(feedback_amount, minimum_delay, maximum_delay, delay_f, horizon=10.0):
+    return pass_() & feedback2((pass_() | lfo(lambda t: f32(delay_f(t)), 1, horizon)) >> tap(minimum_delay, maximum_delay), shape(Tanh(feedback_amount)))
+
+
+def phaser(feedback_amount, phase_f, horizon=10.0):
+    c01 = lambda x: min(1.0, max(0.0, f32(x)))
+    return pass_() & feedback((pass_() | lfo(lambda t: lerp(2.0, 20.0, c01(phase_f(t))), 1, horizon))
+                              >> pipei(10, lambda i: add((0.0, 0.1)) >> ~allpole()) >> (mul(feedback_amount) | sink()))
+
+
+def white():   # src/prelude.rs: white() is noise()
+    return noise()
+
+
 # ---- src/prelude.rs:1288-1301 look-ahead limiters
 def limiter(attack_time, release_time):
     return An("limiter", (1, f32(attack_time), f32(release_time)), (), 1, 1)

@@ -766,6 +766,24 @@ def test_envelope_lfo():  # src/envelope.rs:14-183; tests/test_basic.rs:173-176,
     assert 395.0 < f.min() < 410.0 and 470.0 < f.max() < 485.0
 
 
+def test_flanger_phaser():  # src/prelude.rs:2719-2753: compositions of lfo, tap, feedback2 / feedback, allpole
+    import math as m
+    check_wave(noise() >> flanger(0.5, 0.005, 0.010, lambda t: 0.0075 + 0.0025 * m.sin(2.0 * t)) | noise() >> phaser(0.5, lambda t: 0.5 + 0.5 * m.sin(3.0 * t)))
+    sr = 44100.0
+    # a flanger with a constant delay d and no feedback is a comb: dry + x[n - d], notches at odd multiples of 1 / (2 d)
+    d = 100.0 / sr
+    x = np.random.default_rng(4).uniform(-1, 1, (1, 1 << 15)).astype(np.float32)
+    y = OracleUnit(flanger(0.0, d, d, lambda t: d)).filter(sr, x)[0].astype(np.float64)
+    H = np.abs(np.fft.rfft(y * np.hanning(len(y)))[1:] / np.fft.rfft(x[0].astype(np.float64) * np.hanning(len(y)))[1:])
+    f = np.fft.rfftfreq(len(y), 1 / sr)[1:]
+    peak_bins = np.abs((f * d) % 1.0 - 0.0) < 0.02
+    notch_bins = np.abs((f * d) % 1.0 - 0.5) < 0.02
+    assert np.median(H[peak_bins]) > 1.8 and np.median(H[notch_bins]) < 0.25
+    # the phaser's ten first-order allpasses leave the magnitude of the wet path flat: with feedback 0 the output is the dry signal
+    y0 = OracleUnit(phaser(0.0, lambda t: 0.3)).filter(sr, x[:, :2000])
+    assert np.array_equal(y0, x[:, :2000])
+
+
 def test_mls_is_maximum_length():  # src/noise.rs:11-98: the sequence of an n-bit MLS repeats after exactly 2**n - 1 steps
     for n in range(2, 15):
         u = OracleUnit(mls_bits(n))
