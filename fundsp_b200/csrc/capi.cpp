@@ -256,6 +256,14 @@ API int fdsp_bank_set(fdsp_bank* b, uint32_t voice, int kind, const float* v, in
   std::string e = b->b.set(voice, s);
   return e.empty() ? FDSP_OK : fail(e.find("rebuild") != std::string::npos ? FDSP_ERR_UNSUPPORTED : FDSP_ERR_ARG, e);
 }
+// ---- JIT cache (csrc/host/jit.cpp): compiled units are kept on disk next to the library; a machine without a GPU can fill it
+API int fdsp_jit_precompile(const char* signature, int mode, int table_variant) {
+  if (!signature) return fail(FDSP_ERR_ARG, "null signature");
+  if (find_kernel(signature)) return FDSP_OK;   // ahead-of-time class: nothing to compile
+  std::string e = jit_precompile(signature, mode, table_variant);
+  return e.empty() ? FDSP_OK : fail(FDSP_ERR_UNSUPPORTED, e);
+}
+API void fdsp_jit_cache_stats(int* hits, int* nvrtc_runs) { jit_cache_stats(hits, nvrtc_runs); }
 // ---- WAV edge (src/write.rs): planar f32 [channels][stride] -> the reference's file bytes, and back
 API int fdsp_wave_save(const char* path, const float* planar, uint32_t channels, uint64_t length, uint64_t stride, double sample_rate, int bits) {
   std::string e = wav_write(path, planar, channels, length, stride, sample_rate, bits);

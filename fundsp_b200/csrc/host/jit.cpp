@@ -9,7 +9,11 @@
 #include <dlfcn.h>
 #include <nvrtc.h>
 
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -25,7 +29,8 @@ namespace host {
 namespace {
 
 struct Api {
-  void* nvrtc = nullptr; void* cuda = nullptr; bool ok = false; std::string why;
+  void* nvrtc = nullptr; void* cuda = nullptr; bool ok = false, ok_nvrtc = false; std::string why;
+  nvrtcResult (*Version)(int*, int*);
   nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*);
   nvrtcResult (*DestroyProgram)(nvrtcProgram*);
   nvrtcResult (*AddNameExpression)(nvrtcProgram, const char*);
@@ -55,12 +60,14 @@ Api& api() {
     for (const char* n : {"libcuda.so.1", "libcuda.so"})
       if ((a.cuda = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;
     if (!a.nvrtc) { a.why = "libnvrtc not found (JIT unavailable; only the ahead-of-time graph classes can run)"; return; }
+    a.ok_nvrtc = sym(a.nvrtc, "nvrtcCreateProgram", a.CreateProgram) && sym(a.nvrtc, "nvrtcDestroyProgram", a.DestroyProgram) &&
+                 sym(a.nvrtc, "nvrtcAddNameExpression", a.AddNameExpression) && sym(a.nvrtc, "nvrtcCompileProgram", a.CompileProgram) &&
+                 sym(a.nvrtc, "nvrtcGetLoweredName", a.GetLoweredName) && sym(a.nvrtc, "nvrtcGetCUBINSize", a.GetCUBINSize) &&
+                 sym(a.nvrtc, "nvrtcGetCUBIN", a.GetCUBIN) && sym(a.nvrtc, "nvrtcGetProgramLogSize", a.GetProgramLogSize) &&
+                 sym(a.nvrtc, "nvrtcGetProgramLog", a.GetProgramLog) && sym(a.nvrtc, "nvrtcVersion", a.Version);
+    if (!a.ok_nvrtc) { a.why = "missing NVRTC symbols"; return; }
     if (!a.cuda) { a.why = "libcuda not found"; return; }
-    bool ok = sym(a.nvrtc, "nvrtcCreateProgram", a.CreateProgram) && sym(a.nvrtc, "nvrtcDestroyProgram", a.DestroyProgram) &&
-              sym(a.nvrtc, "nvrtcAddNameExpression", a.AddNameExpression) && sym(a.nvrtc, "nvrtcCompileProgram", a.CompileProgram) &&
-              sym(a.nvrtc, "nvrtcGetLoweredName", a.GetLoweredName) && sym(a.nvrtc, "nvrtcGetCUBINSize", a.GetCUBINSize) &&
-              sym(a.nvrtc, "nvrtcGetCUBIN", a.GetCUBIN) && sym(a.nvrtc, "nvrtcGetProgramLogSize", a.GetProgramLogSize) &&
-              sym(a.nvrtc, "nvrtcGetProgramLog", a.GetProgramLog) && sym(a.cuda, "cuModuleLoadData", a.ModuleLoadData) &&
+    bool ok = sym(a.cuda, "cuModuleLoadData", a.ModuleLoadData) &&
               sym(a.cuda, "cuModuleGetFunction", a.ModuleGetFunction) && sym(a.cuda, "cuModuleGetGlobal_v2", a.ModuleGetGlobal) &&
               sym(a.cuda, "cuMemcpyDtoH_v2", a.MemcpyDtoH) && sym(a.cuda, "cuFuncSetAttribute", a.FuncSetAttribute) &&
               sym(a.cuda, "cuLaunchKernel", a.LaunchKernel) && sym(a.cuda, "cuGetErrorString", a.GetErrorString);
@@ -73,16 +80,73 @@ Api& api() {
 // One NVRTC translation unit = the headers + `typedef <sig> JitG` + (optionally) one kernel instantiation. The layout TU
 // (no kernel) is compiled when the program is created; each (mode, TB) kernel variant is compiled on its first launch, so a
 // bank pays for the one variant it uses instead of all six.
-static bool compile_unit(const std::string& sig, const char* kernel_expr, std::vector<char>& cubin, std::string& lowered, std::string& err) {
+// ---- on-disk cache of compiled units. Key: FNV-1a of (NVRTC version, options, embedded headers, unit source, kernel expression), so
+// an entry can only be hit by the identical compilation. Directory: $FDSP_JIT_CACHE, else jit_cache/ next to this library (it travels
+// with the in-tree build; tools/warm_jit_cache.py fills it on a machine without a GPU). FDSP_JIT_CACHE=off disables it.
+static const char* kJitOpts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-lineinfo", "-default-device"};
+static uint64_t fnv(uint64_t h, const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; } return h; }
+static std::string cache_dir() {
+  static const std::string dir = [] {
+    const char* e = getenv("FDSP_JIT_CACHE");
+    if (e && *e) return std::string(strcmp(e, "off") == 0 ? "" : e);
+    Dl_info info;
+    if (!dladdr((void*)&cache_dir, &info) || !info.dli_fname) return std::string();
+    std::string p(info.dli_fname);
+    const size_t k = p.rfind('/');
+    return (k == std::string::npos ? std::string(".") : p.substr(0, k)) + "/jit_cache";
+  }();
+  return dir;
+}
+static uint64_t unit_key(const std::string& src, const char* kernel_expr) {
+  static const uint64_t base = [] {
+    uint64_t h = 1469598103934665603ull;
+    int maj = 0, min = 0;
+    if (api().ok_nvrtc) api().Version(&maj, &min);
+    h = fnv(h, &maj, sizeof(maj)); h = fnv(h, &min, sizeof(min));
+    for (const char* o : kJitOpts) h = fnv(h, o, strlen(o) + 1);
+    for (int i = 0; i < kJitHeaderCount; i++) { h = fnv(h, kJitHeaderNames[i], strlen(kJitHeaderNames[i]) + 1); h = fnv(h, kJitHeaderSrc[i], strlen(kJitHeaderSrc[i]) + 1); }
+    return h;
+  }();
+  uint64_t h = fnv(base, src.data(), src.size() + 1);
+  if (kernel_expr) h = fnv(h, kernel_expr, strlen(kernel_expr) + 1);
+  return h;
+}
+static std::string cache_path(uint64_t key) { char b[32]; snprintf(b, sizeof(b), "/%016llx.fdspjit", (unsigned long long)key); return cache_dir() + b; }
+static bool cache_load(uint64_t key, std::vector<char>& cubin, std::string& lowered) {
+  if (cache_dir().empty()) return false;
+  FILE* f = fopen(cache_path(key).c_str(), "rb");
+  if (!f) return false;
+  uint32_t hdr[3] = {0, 0, 0};   // magic, lowered-name bytes, cubin bytes
+  bool ok = fread(hdr, 4, 3, f) == 3 && hdr[0] == 0x4a445346u && hdr[1] < (1u << 20) && hdr[2] > 0 && hdr[2] < (1u << 30);
+  if (ok) { lowered.resize(hdr[1]); cubin.resize(hdr[2]); ok = (hdr[1] == 0 || fread(&lowered[0], 1, hdr[1], f) == hdr[1]) && fread(cubin.data(), 1, hdr[2], f) == hdr[2]; }
+  fclose(f);
+  return ok;
+}
+static void cache_store(uint64_t key, const std::vector<char>& cubin, const std::string& lowered) {
+  if (cache_dir().empty() || cubin.empty()) return;
+  mkdir(cache_dir().c_str(), 0755);
+  const std::string path = cache_path(key), tmp = path + ".tmp" + std::to_string((long)getpid());
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  const uint32_t hdr[3] = {0x4a445346u, (uint32_t)lowered.size(), (uint32_t)cubin.size()};
+  const bool ok = fwrite(hdr, 4, 3, f) == 3 && fwrite(lowered.data(), 1, lowered.size(), f) == lowered.size() && fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+  if (fclose(f) != 0 || !ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+}
+static int g_cache_hits = 0, g_nvrtc_runs = 0;
+
+static bool compile_unit(const std::string& sig, const char* kernel_expr, std::vector<char>& cubin, std::string& lowered, std::string& err, bool use_cache = true) {
   Api& A = api();
+  if (!A.ok_nvrtc) { err = A.why; return false; }
   std::string src = "#include \"dsp/bank_kernel.cuh\"\nnamespace fdsp { typedef " + sig + " JitG; }\n";
   if (!kernel_expr)
     src += "extern \"C\" __device__ int fdsp_jit_layout[6] = {fdsp::JitG::IN, fdsp::JitG::OUT, fdsp::JitG::NP, fdsp::JitG::NS, fdsp::JitG::NU, fdsp::WaveKind<fdsp::JitG>::value};\n";
+  const uint64_t key = unit_key(src, kernel_expr);
+  if (use_cache && cache_load(key, cubin, lowered)) { g_cache_hits++; return true; }
+  g_nvrtc_runs++;
   nvrtcProgram prog;
   if (A.CreateProgram(&prog, src.c_str(), "fdsp_jit.cu", kJitHeaderCount, kJitHeaderSrc, kJitHeaderNames) != NVRTC_SUCCESS) { err = "nvrtcCreateProgram failed"; return false; }
   if (kernel_expr) A.AddNameExpression(prog, kernel_expr);
-  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-lineinfo", "-default-device"};
-  if (A.CompileProgram(prog, 5, opts) != NVRTC_SUCCESS) {
+  if (A.CompileProgram(prog, 5, kJitOpts) != NVRTC_SUCCESS) {
     size_t n = 0; A.GetProgramLogSize(prog, &n);
     std::string log(n, '\0'); if (n) A.GetProgramLog(prog, &log[0]);
     if (log.size() > 1500) log.resize(1500);
@@ -98,6 +162,7 @@ static bool compile_unit(const std::string& sig, const char* kernel_expr, std::v
   size_t cn = 0; A.GetCUBINSize(prog, &cn);
   cubin.resize(cn); A.GetCUBIN(prog, cubin.data());
   A.DestroyProgram(&prog);
+  cache_store(key, cubin, lowered);
   return true;
 }
 
@@ -113,7 +178,9 @@ struct JitProgram : Program {
     const std::string expr = "fdsp::bank_kernel<fdsp::JitG, 128, " + std::to_string(mode) + ", " + (tb ? "true" : "false") + ">";
     std::vector<char> cubin; std::string low, err;
     if (!compile_unit(sig, expr.c_str(), cubin, low, err)) { fprintf(stderr, "fundsp_b200 JIT: %s\n", err.c_str()); return nullptr; }
-    if (A.ModuleLoadData(&mods[mode - 1][tb], cubin.data()) != CUDA_SUCCESS) return nullptr;
+    if (A.ModuleLoadData(&mods[mode - 1][tb], cubin.data()) != CUDA_SUCCESS) {   // a damaged cache entry: compile afresh (which rewrites it)
+      if (!compile_unit(sig, expr.c_str(), cubin, low, err, false) || A.ModuleLoadData(&mods[mode - 1][tb], cubin.data()) != CUDA_SUCCESS) return nullptr;
+    }
     if (A.ModuleGetFunction(&fn[mode - 1][tb], mods[mode - 1][tb], low.c_str()) != CUDA_SUCCESS) { fn[mode - 1][tb] = nullptr; return nullptr; }
     return fn[mode - 1][tb];
   }
@@ -142,6 +209,18 @@ int g_compiled = 0;
 }  // namespace
 
 int jit_compiled_count() { return g_compiled; }
+void jit_cache_stats(int* hits, int* nvrtc_runs) { if (hits) *hits = g_cache_hits; if (nvrtc_runs) *nvrtc_runs = g_nvrtc_runs; }
+
+// Compile one unit of a graph class into the on-disk cache without touching a GPU (mode 0: the layout unit; 1..3: that kernel variant).
+std::string jit_precompile(const std::string& sig, int mode, int tb) {
+  if (sig.find("Unsupported") != std::string::npos) return "the graph contains a node with no device lowering";
+  if (mode < 0 || mode > 3) return "mode must be 0 (layout) or 1..3";
+  if (cache_dir().empty()) return "the JIT cache is disabled (FDSP_JIT_CACHE=off)";
+  std::vector<char> cubin; std::string low, err;
+  const std::string expr = "fdsp::bank_kernel<fdsp::JitG, 128, " + std::to_string(mode) + ", " + (tb ? "true" : "false") + ">";
+  if (!compile_unit(sig, mode == 0 ? nullptr : expr.c_str(), cubin, low, err)) return err;
+  return "";
+}
 
 std::shared_ptr<const Program> jit_program(const std::string& sig, int device, std::string& err) {
   if (sig.find("Unsupported") != std::string::npos) { err = "the graph contains a node with no device lowering"; return nullptr; }
@@ -159,7 +238,10 @@ std::shared_ptr<const Program> jit_program(const std::string& sig, int device, s
   auto p = std::make_shared<JitProgram>();
   p->sig = sig; p->jit = true; p->device = device;
   CUmodule lm = nullptr;
-  if (A.ModuleLoadData(&lm, cubin.data()) != CUDA_SUCCESS) { err = "cuModuleLoadData failed for the JIT layout unit"; return nullptr; }
+  if (A.ModuleLoadData(&lm, cubin.data()) != CUDA_SUCCESS) {
+    if (!compile_unit(sig, nullptr, cubin, low, err, false)) return nullptr;
+    if (A.ModuleLoadData(&lm, cubin.data()) != CUDA_SUCCESS) { err = "cuModuleLoadData failed for the JIT layout unit"; return nullptr; }
+  }
   CUdeviceptr d = 0; size_t bytes = 0; int lay[6] = {0, 0, 0, 0, 0, -1};
   if (A.ModuleGetGlobal(&d, &bytes, lm, "fdsp_jit_layout") != CUDA_SUCCESS || bytes != sizeof(lay) || A.MemcpyDtoH(lay, d, sizeof(lay)) != CUDA_SUCCESS) {
     err = "JIT layout readback failed"; return nullptr;

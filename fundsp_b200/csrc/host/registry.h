@@ -49,6 +49,8 @@ int fdn_ts_max_vpb(int K);
 // NVRTC path (jit.cpp)
 std::shared_ptr<const Program> jit_program(const std::string& sig, int device, std::string& err);
 int jit_compiled_count();
+void jit_cache_stats(int* hits, int* nvrtc_runs);                       // units served from the on-disk cache / compiled by NVRTC in this process
+std::string jit_precompile(const std::string& sig, int mode, int tb);   // fill the on-disk cache without a GPU (mode 0 = layout unit)
 
 }  // namespace host
 }  // namespace fdsp

@@ -166,6 +166,12 @@ int fdsp_bank_inputs(const fdsp_bank* b);                                   /* s
 int fdsp_bank_voice_outputs(const fdsp_bank* b);                            /* channels per voice */
 int fdsp_bank_outputs(const fdsp_bank* b);                                  /* AudioUnit::outputs(): mix: channels; voices: V*channels */
 int fdsp_bank_set_sample_rate(fdsp_bank* b, double sample_rate);            /* AudioUnit::set_sample_rate */
+/* Programs of graph classes outside the ahead-of-time table are compiled with NVRTC on first use and kept in an on-disk cache
+   ($FDSP_JIT_CACHE, default jit_cache/ next to the library; "off" disables it). fdsp_jit_precompile fills the cache WITHOUT a GPU:
+   `signature` is fdsp_node_signature's text, mode 0 the layout unit every class needs, 1..3 the kernel variant of FDSP_OUT_* with
+   (table_variant 1) or without the shared-memory wavetable stage. fdsp_jit_cache_stats: units served from disk / compiled in this process. */
+int fdsp_jit_precompile(const char* signature, int mode, int table_variant);
+void fdsp_jit_cache_stats(int* hits, int* nvrtc_runs);
 /* WAV edge (reference src/write.rs:24-116): `planar[c * stride + i]` -> Wave::write_wav16 (bits 16: round(clamp11(x) * 32767.49)) or
    Wave::write_wav32 (bits 32: IEEE float) byte for byte — to a file, or into `out` (returns the byte count, also when out is NULL or
    too small; -1 on error). fdsp_wave_load reads the two layouts back (16-bit samples / 32768); call it with planar = NULL to get the

@@ -306,3 +306,25 @@ def test_wav_files_match_the_reference_layout(tmp_path):
         capi.encode_wav(np.zeros((0, 10), np.float32), sr, 16)                       # assert!(self.channels() > 0)
     with pytest.raises(capi.FdspError):
         capi.load_wav(tmp_path / "missing.wav")
+
+
+def test_jit_disk_cache_fills_without_a_gpu(tmp_path):
+    """csrc/host/jit.cpp keeps compiled units on disk, keyed by the exact compilation; fdsp_jit_precompile fills the cache on a
+    machine without a GPU (tools/warm_jit_cache.py does it for the GPU suite's graph classes). Own process: the directory is read once."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from fundsp_b200 import capi\n"
+        "sig = 'Pipe<Noise,MeterNode<1>>'\n"
+        "capi.jit_precompile(sig, 0); capi.jit_precompile(sig, 1, 0); a = capi.jit_cache_stats()\n"
+        "capi.jit_precompile(sig, 0); capi.jit_precompile(sig, 1, 0); b = capi.jit_cache_stats()\n"
+        "capi.jit_precompile('Pipe<Pipe<Constant<1>,WaveSynth<0,1>>,FixedSvf>', 1, 1); c = capi.jit_cache_stats()\n"   # ahead-of-time class: nothing to do
+        "try:\n    capi.jit_precompile('Pipe<Noise,NoSuchNode>', 1, 0); bad = 'compiled'\nexcept capi.FdspError as e:\n    bad = 'error'\n"
+        "print(a, b, c, bad)\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, FDSP_JIT_CACHE=str(tmp_path / "cache"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip() == "{'hits': 0, 'nvrtc_runs': 2} {'hits': 2, 'nvrtc_runs': 2} {'hits': 2, 'nvrtc_runs': 2} error", r.stdout
+    files = sorted(os.listdir(tmp_path / "cache"))
+    assert len(files) == 2 and all(f.endswith(".fdspjit") for f in files)

@@ -17,6 +17,28 @@ def test_wider_graph_matches_oracle(name):
 
 
 # ---------------------------------------------------------------- the sequencer as a bank of event voices (src/sequencer.rs)
+def seq_five_events():   # tests/test_basic.rs:255-273 plus a fifth overlapping voice that starts mid-block
+    from fundsp_b200.prelude import noise, sine_hz, mls, saw_hz, lowpass_hz
+    from fundsp_b200.sequencer import Sequencer, Fade, ReplayMode
+    q = Sequencer(0, 2, ReplayMode.All)
+    q.push(0.1, 0.2, Fade.Smooth, 0.01, 0.0, noise() | sine_hz(220.0))
+    q.push(0.3, 0.4, Fade.Smooth, 0.09, 0.08, sine_hz(110.0) | noise())
+    q.push(0.25, 0.5, Fade.Power, 0.0, 0.01, mls() | noise())
+    q.push(0.6, 0.7, Fade.Power, 0.02, 0.03, noise() | mls())
+    q.push(0.31234, 0.45678, Fade.Smooth, 0.02, 0.05, (saw_hz(220.0) >> lowpass_hz(1000.0, 1.0)) | sine_hz(330.0))
+    return q
+
+
+def live_voice(f):
+    from fundsp_b200.prelude import saw_hz, lowpass_hz
+    return saw_hz(f) >> lowpass_hz(4.0 * f, 1.0)
+
+
+def arp_voice(f):
+    from fundsp_b200.prelude import saw_hz, lowpass_hz
+    return saw_hz(f) >> lowpass_hz(3.0 * f, 1.5)
+
+
 def _oracle_seq(seq, sr):
     from oracle import OracleUnit
     u = OracleUnit(seq.node())
@@ -38,14 +60,7 @@ def test_sequencer_bank_matches_oracle_sequencer():
     olib().fo_set_denormal_emulation(0)
     sr = 44100.0
 
-    def build():   # tests/test_basic.rs:255-273 plus a third overlapping voice that starts mid-block
-        q = Sequencer(0, 2, ReplayMode.All)
-        q.push(0.1, 0.2, Fade.Smooth, 0.01, 0.0, noise() | sine_hz(220.0))
-        q.push(0.3, 0.4, Fade.Smooth, 0.09, 0.08, sine_hz(110.0) | noise())
-        q.push(0.25, 0.5, Fade.Power, 0.0, 0.01, mls() | noise())
-        q.push(0.6, 0.7, Fade.Power, 0.02, 0.03, noise() | mls())
-        q.push(0.31234, 0.45678, Fade.Smooth, 0.02, 0.05, (saw_hz(220.0) >> lowpass_hz(1000.0, 1.0)) | sine_hz(330.0))
-        return q
+    build = seq_five_events
 
     n = int(0.75 * sr)
     b = GpuBank.from_sequencer(build(), per_voice=True, mix=True, sample_rate=sr)
@@ -78,7 +93,7 @@ def test_sequencer_bank_live_edit_and_push():
     L = olib()
     L.fo_set_denormal_emulation(0)
     sr = 44100.0
-    voice = lambda f: saw_hz(f) >> lowpass_hz(4.0 * f, 1.0)
+    voice = live_voice
     q = Sequencer(0, 1, ReplayMode.None_)
     e0 = q.push(0.0, 10.0, Fade.Smooth, 0.001, 0.0, voice(110.0))          # a held note, released by a later edit
     q.push(0.01, 0.02, Fade.Smooth, 0.001, 0.002, voice(220.0))             # a short note whose slot is reused
@@ -114,7 +129,7 @@ def test_gpu_sequencer_note_ons_while_running():
     L = olib()
     L.fo_set_denormal_emulation(0)
     sr = 44100.0
-    voice = lambda f: saw_hz(f) >> lowpass_hz(3.0 * f, 1.5)
+    voice = arp_voice
     g = GpuSequencer(1, ReplayMode.None_, sample_rate=sr)
     g.reserve(voice(100.0), 8)
     u = OracleUnit(L.fo_sequencer(0, 1, 1, 0.0))
