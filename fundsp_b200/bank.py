@@ -91,9 +91,15 @@ class GpuBank:
 
     def push_event(self, ev):
         """Sequencer::push on a running bank: `ev` (an `event(...)` expression) takes the slot of a finished event of the same
-        graph class; returns the voice index."""
+        graph class, or — when there is none — the bank grows by one voice (`add_voice`); returns the voice index."""
         v = C.c_uint32(0)
         check(self.L.fdsp_bank_push_event(self.h, ev.lower(GpuBackend()), C.byref(v)))
+        return int(v.value)
+
+    def add_voice(self, unit):
+        """Grow the bank by one voice (running state of the others preserved; O(bank state)); returns its index."""
+        v = C.c_uint32(0)
+        check(self.L.fdsp_bank_add_voice(self.h, unit.lower(GpuBackend()), C.byref(v)))
         return int(v.value)
 
     def replace_voice(self, voice, unit):

@@ -297,8 +297,17 @@ API int fdsp_bank_replace_voice(fdsp_bank* b, uint32_t voice, fdsp_node* unit) {
 }
 API int fdsp_bank_push_event(fdsp_bank* b, fdsp_node* event, uint32_t* voice) {
   if (!b || !event) { fdsp_node_free(event); return fail(FDSP_ERR_ARG, "null bank or event"); }
+  HNode* keep = event->n->clone();                   // push_event consumes its node; the slow path needs it again
   std::string e = b->b.push_event(take(event), voice);
-  return e.empty() ? FDSP_OK : fail(e.find("no finished event") != std::string::npos ? FDSP_ERR_UNSUPPORTED : FDSP_ERR_ARG, e);
+  if (e.empty()) { delete keep; return FDSP_OK; }
+  if (e.find("no finished event") == std::string::npos) { delete keep; return fail(FDSP_ERR_ARG, e); }
+  e = b->b.add_voice(keep, voice);                   // no free slot of this class: grow the bank (running state of the others preserved)
+  return e.empty() ? FDSP_OK : fail(e.find("rebuild") != std::string::npos ? FDSP_ERR_UNSUPPORTED : FDSP_ERR_ARG, e);
+}
+API int fdsp_bank_add_voice(fdsp_bank* b, fdsp_node* unit, uint32_t* voice) {
+  if (!b || !unit) { fdsp_node_free(unit); return fail(FDSP_ERR_ARG, "null bank or unit"); }
+  std::string e = b->b.add_voice(take(unit), voice);
+  return e.empty() ? FDSP_OK : fail(e.find("rebuild") != std::string::npos ? FDSP_ERR_UNSUPPORTED : FDSP_ERR_ARG, e);
 }
 API double fdsp_bank_time(const fdsp_bank* b) { return b ? b->b.seq_time : 0.0; }
 API int fdsp_bank_reset(fdsp_bank* b) { return b ? status(b->b.reset()) : fail(FDSP_ERR_ARG, "null bank"); }

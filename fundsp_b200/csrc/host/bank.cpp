@@ -176,26 +176,30 @@ std::string Bank::lower_and_upload(bool upload_state) {
       if (c.ring_floats) CU(cudaMemset(c.d_ring, 0, (size_t)c.ring_floats * V * sizeof(float)));
     }
   }
-  // 3. wavetables used by any class
-  if (!d_wt) {
-    WaveTableDev h[6];
-    memset(h, 0, sizeof(h));
+  // 3. wavetables used by any class (a class that arrives later — add_voice — may bring a waveform the bank has not loaded yet)
+  {
+    bool changed = false;
     for (int kind = 0; kind < 6; kind++) {
+      if (d_wtdata[kind]) continue;
       bool used = false;
       const std::string tag = "WaveSynth<" + std::to_string(kind) + ",", tag2 = "PhaseSynth<" + std::to_string(kind) + ">";
       for (auto& c : classes) used = used || c.sig.find(tag) != std::string::npos || c.sig.find(tag2) != std::string::npos;
       if (!used) continue;
       const WaveTableHost& t = device_wavetable(kind);
-      h[kind].n = (int)t.pitch.size(); h[kind].total = (int)t.data.size();
-      for (size_t i = 0; i < t.pitch.size() && i < 48; i++) { h[kind].pitch[i] = t.pitch[i]; h[kind].off[i] = t.off[i]; h[kind].len[i] = t.len[i]; }
+      h_wt[kind].n = (int)t.pitch.size(); h_wt[kind].total = (int)t.data.size();
+      for (size_t i = 0; i < t.pitch.size() && i < 48; i++) { h_wt[kind].pitch[i] = t.pitch[i]; h_wt[kind].off[i] = t.off[i]; h_wt[kind].len[i] = t.len[i]; }
       std::string e = dev_alloc(&d_wtdata[kind], t.data.size());
       if (!e.empty()) return e;
       CU(cudaMemcpy(d_wtdata[kind], t.data.data(), t.data.size() * 4, cudaMemcpyHostToDevice));
-      h[kind].data = d_wtdata[kind];
+      h_wt[kind].data = d_wtdata[kind];
+      changed = true;
     }
-    std::string e = dev_alloc(&d_wt, 6);
-    if (!e.empty()) return e;
-    CU(cudaMemcpy(d_wt, h, sizeof(h), cudaMemcpyHostToDevice));
+    if (!d_wt) {
+      std::string e = dev_alloc(&d_wt, 6);
+      if (!e.empty()) return e;
+      changed = true;
+    }
+    if (changed) CU(cudaMemcpy(d_wt, h_wt, sizeof(h_wt), cudaMemcpyHostToDevice));
   }
   if (upload_state) dirty = false;
   return "";
@@ -289,6 +293,69 @@ std::string Bank::replace_voice(uint32_t voice, HNode* node) {
   std::string e = upload_voice(voice, l, true, &l0.S);
   if (!e.empty()) return e;
   nodes[voice] = std::move(n);
+  return "";
+}
+
+// Grow a running bank by one voice without disturbing the others: the running state and delay lines of every voice are read back,
+// the classes are rebuilt with the new voice (it may found a new class: its program is compiled first, so a failure leaves the bank
+// untouched), and the saved columns are written into the new layout. O(bank state) — the slow path behind push_event.
+std::string Bank::add_voice(HNode* node, uint32_t* voice) {
+  std::unique_ptr<HNode> n(node);
+  if (!n) return "add: null node";
+  if (n->inputs() != nin || n->outputs() != nout) return "add: the unit's arity differs from the bank's";
+  if (tree_mix) return "add: a bank extracted from a Net mixes in the Net's order; rebuild it from the edited Net";
+  for (auto& c : classes) if (c.fdn) return "add: banks with a two-stage (FDN reverb) class cannot grow in place; rebuild the bank";
+  CU(cudaSetDevice(device));
+  const double unit_rate = net_rate ? (double)(float)sr : sr;
+  n->set_sample_rate(unit_rate);
+  Lowering l0, l;
+  n->lower(l0);
+  const bool ev = event_set_clock(n.get(), seq_time);
+  n->lower(l);
+  if (ev) event_set_clock(n.get(), 0.0);
+  if (!l.ok) return l.why;
+  { std::string sg, jerr; n->sig(sg); if (!get_program(sg, device, jerr)) return "add: no device program for `" + sg + "`: " + jerr; }
+  // 1. read back what is running
+  CU(cudaStreamSynchronize(stream));
+  struct Saved { std::string sig; std::vector<uint32_t> uniform, voices, S; std::vector<float> D; uint32_t ns; uint64_t dl; };
+  std::vector<Saved> saved;
+  for (auto& c : classes) {
+    Saved sv; sv.sig = c.sig; sv.uniform = c.uniform; sv.voices = c.voices; sv.ns = c.ns; sv.dl = c.dl_floats;
+    sv.S.resize((size_t)c.ns * c.V()); sv.D.resize((size_t)c.dl_floats * c.V());
+    if (!sv.S.empty()) CU(cudaMemcpy(sv.S.data(), c.d_state, sv.S.size() * 4, cudaMemcpyDeviceToHost));
+    if (!sv.D.empty()) CU(cudaMemcpy(sv.D.data(), c.d_dline, sv.D.size() * 4, cudaMemcpyDeviceToHost));
+    saved.push_back(std::move(sv));
+  }
+  const bool was_dirty = dirty; const double clock = seq_time;
+  // 2. rebuild with the new voice (fresh state everywhere)
+  nodes.push_back(std::move(n));
+  const uint32_t nv = V() - 1;
+  std::string e = lower_and_upload(true);
+  if (!e.empty()) { nodes.pop_back(); std::string e2 = lower_and_upload(true); return "add: " + e + (e2.empty() ? " (the bank was rebuilt without the voice; its running state is reset)" : " (and the bank could not be restored: " + e2 + ")"); }
+  // 3. put the saved columns back
+  for (auto& c : classes) {
+    const uint32_t Vc = c.V();
+    std::vector<uint32_t> S = c.state0;
+    std::vector<float> D((size_t)c.dl_floats * Vc, 0.0f);
+    for (uint32_t i = 0; i < Vc; i++) {
+      const uint32_t v = c.voices[i];
+      if (v == nv) { for (uint32_t k = 0; k < c.ns && k < l.S.size(); k++) S[(size_t)k * Vc + i] = l.S[k]; continue; }   // the newcomer: live state (an event's clock = now)
+      for (auto& sv : saved) {
+        auto it = std::lower_bound(sv.voices.begin(), sv.voices.end(), v);
+        if (it == sv.voices.end() || *it != v) continue;
+        if (sv.sig != c.sig || sv.ns != c.ns || sv.dl != c.dl_floats) return "internal: a voice changed class while the bank grew";
+        const uint32_t j = (uint32_t)(it - sv.voices.begin()), Vo = (uint32_t)sv.voices.size();
+        for (uint32_t k = 0; k < c.ns; k++) S[(size_t)k * Vc + i] = sv.S[(size_t)k * Vo + j];
+        for (uint64_t q = 0; q < c.dl_floats; q++) D[(size_t)q * Vc + i] = sv.D[(size_t)q * Vo + j];
+        break;
+      }
+    }
+    if (!S.empty()) CU(cudaMemcpyAsync(c.d_state, S.data(), S.size() * 4, cudaMemcpyHostToDevice, stream));
+    if (!D.empty()) CU(cudaMemcpyAsync(c.d_dline, D.data(), D.size() * 4, cudaMemcpyHostToDevice, stream));
+    CU(cudaStreamSynchronize(stream));
+  }
+  dirty = was_dirty; seq_time = clock;
+  if (voice) *voice = nv;
   return "";
 }
 

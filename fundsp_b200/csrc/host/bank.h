@@ -45,7 +45,7 @@ struct Bank {
   std::vector<int> vertex_of_voice;   // banks made from a Net: the Net vertex (NodeId) behind each voice
   std::vector<VoiceClass> classes;
   cudaStream_t stream = nullptr, stream2 = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr, e_begin = nullptr;
-  WaveTableDev* d_wt = nullptr; float* d_wtdata[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  WaveTableDev* d_wt = nullptr; float* d_wtdata[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; WaveTableDev h_wt[6] = {};   // h_wt: host copy of the table directory
   // staging for host-buffer entry points
   float *d_in = nullptr, *d_out = nullptr, *d_mix = nullptr; size_t in_cap = 0, out_cap = 0, mix_cap = 0; uint32_t stage_chunk = 0;
   float *h_in = nullptr, *h_out = nullptr, *d_hout = nullptr; size_t h_in_cap = 0, h_out_cap = 0;  // pinned (h_out also device-mapped), process() path
@@ -66,6 +66,7 @@ struct Bank {
   std::string upload_voice(uint32_t voice, const Lowering& l, bool with_state, const std::vector<uint32_t>* reset_state = nullptr);
   std::string edit_event(uint32_t voice, double end_time, double fade_out);   // Sequencer::edit
   std::string replace_voice(uint32_t voice, HNode* node);                     // a new unit in the slot of a voice of the same class; consumes node
+  std::string add_voice(HNode* unit, uint32_t* voice);                        // grow by one voice, running state of the others preserved; consumes unit
   std::string push_event(HNode* event, uint32_t* voice);                      // Sequencer::push on a running bank: takes the slot of a finished event of the same class; consumes event
   std::string set(uint32_t voice, const Setting& s);  // AudioUnit::set on one voice of a live bank (parameters only; state continues)
   std::string ensure_staging(uint32_t chunk);

@@ -183,11 +183,15 @@ int fdsp_wave_load(const char* path, float* planar, uint64_t max_floats, uint32_
    fdsp_bank_edit_event = Sequencer::edit (:441-483): new end time and fade-out of one event, effective from the next block.
    fdsp_bank_push_event = Sequencer::push on a running sequencer (:319-360): the event takes over the slot of a FINISHED event of the
    same graph class (same type expression and class-uniform words) and starts its clock at the bank's current time; `*voice` receives
-   the slot. FDSP_ERR_UNSUPPORTED when no such slot is free. fdsp_bank_replace_voice puts any unit of the same class into a given
-   slot (fresh state). All three consume their node argument. fdsp_bank_time = Sequencer::time (seconds rendered since reset). */
+   the slot. When no such slot is free the bank GROWS by one voice (fdsp_bank_add_voice: the running state and delay lines of all
+   voices are read back, the classes rebuilt — the newcomer may found a new class, compiled first — and the state written into the
+   new layout; O(bank state), not for the audio thread; banks with an FDN-reverb class or made from a Net cannot grow in place).
+   fdsp_bank_replace_voice puts any unit of the same class into a given slot (fresh state). All consume their node argument.
+   fdsp_bank_time = Sequencer::time (seconds rendered since reset). */
 int fdsp_bank_edit_event(fdsp_bank* b, uint32_t voice, double end_time, double fade_out);
 int fdsp_bank_push_event(fdsp_bank* b, fdsp_node* event, uint32_t* voice);
 int fdsp_bank_replace_voice(fdsp_bank* b, uint32_t voice, fdsp_node* unit);
+int fdsp_bank_add_voice(fdsp_bank* b, fdsp_node* unit, uint32_t* voice);
 double fdsp_bank_time(const fdsp_bank* b);
 int fdsp_bank_reset(fdsp_bank* b);                                          /* AudioUnit::reset */
 /* AudioUnit::set (src/audiounit.rs:62) on voice `voice` of a live bank: same encoding as fdsp_node_set. Parameters change at

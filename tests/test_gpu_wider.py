@@ -103,6 +103,13 @@ def test_sequencer_bank_live_edit_and_push():
     n1 = 64 * 30                                                            # 43.5 ms in: the short note has ended
     g1 = b.render_samples(n1)[1]; o1 = u.process_many(n1)
     assert _close(g1, o1)
+    # a note of a class the bank does not have yet: no slot to take over, the bank grows while the held note keeps sounding
+    ta = b.time() + 0.001
+    grown = b.push_event(event(sine_hz(500.0) * 0.5, ta, ta + 0.01, Fade.Power, 0.002, 0.002))
+    assert grown == 2 and b.voices() == 3 and len(b.classes()) == 2
+    L.fo_sequencer_push(u.h, ta, ta + 0.01, 0, 0.002, 0.002, (sine_hz(500.0) * 0.5).lower(be))
+    ga = b.render_samples(64 * 4)[1]; oa = u.process_many(64 * 4)
+    assert np.abs(oa).max() > 0.1 and _close(ga, oa)                       # the held note went on seamlessly, the newcomer started on time
     # release the held note: Sequencer::edit(id, end_time, fade_out) on both
     t_end = b.time() + 0.02
     b.edit_event(e0, t_end, 0.015)
@@ -115,9 +122,8 @@ def test_sequencer_bank_live_edit_and_push():
     n2 = 64 * 40 + 17
     g2 = b.render_samples(n2)[1]; o2 = u.process_many(n2)
     assert np.abs(o2).max() > 0.1 and _close(g2, o2)
-    assert not g2[:, int((0.02 + 0.03 + 0.005) * sr):].any()                # everything has ended
-    with pytest.raises(Exception):                                           # no finished event of a different class to take over
-        b.push_event(event(dc(1.0), 1.0, 2.0))
+    assert not g2[:, int((0.02 + 0.03 + 0.005) * sr):].any()                # everything has ended (times are relative to the start of g2)
+    assert b.push_event(event(voice(440.0), b.time() + 1.0, b.time() + 2.0)) in (0, 1)   # both saw voices have finished: a slot is reused
 
 
 def test_gpu_sequencer_note_ons_while_running():
