@@ -300,6 +300,7 @@ class Bank {
   void edit_event(uint32_t voice, double end_time, double fade_out) { check(fdsp_bank_edit_event(b_, voice, end_time, fade_out)); }
   uint32_t push_event(An ev) { uint32_t v = 0; check(fdsp_bank_push_event(b_, ev.release(), &v)); return v; }
   void replace_voice(uint32_t voice, An unit) { check(fdsp_bank_replace_voice(b_, voice, unit.release())); }
+  uint32_t add_voice(An unit) { uint32_t v = 0; check(fdsp_bank_add_voice(b_, unit.release(), &v)); return v; }   // grows the bank; the others keep their state
   // AudioUnit::process: buffers are [channel][64]
   void process(uint32_t size, const float* input, float* output) { check(fdsp_bank_process(b_, size, input, output)); }
   // Wave::render / Wave::filter: buffers are [channel][n]
