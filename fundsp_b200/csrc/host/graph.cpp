@@ -38,23 +38,23 @@ std::string I(int v) { return std::to_string(v); }
 
 // ---------------------------------------------------------------- routing leaves (src/audionode.rs:374-722,2800-2837)
 struct Routing : HNode {
-  enum K { PASS, MULTIPASS, SINK, SPLIT, MULTISPLIT, JOIN, MULTIJOIN, REVERSE } k; int m, n;
+  enum K { PASS, MULTIPASS, SINK, SPLIT, MULTISPLIT, JOIN, MULTIJOIN, REVERSE, MONITOR } k; int m, n;   // MONITOR: src/dynamics.rs:441 passes its input through (the Shared it feeds is host-side state)
   Routing(K k_, int m_, int n_) : k(k_), m(m_), n(n_) {}
   int inputs() const override {
-    switch (k) { case PASS: return 1; case MULTIPASS: case SINK: case REVERSE: return n; case SPLIT: return 1; case MULTISPLIT: return m;
+    switch (k) { case PASS: case MONITOR: return 1; case MULTIPASS: case SINK: case REVERSE: return n; case SPLIT: return 1; case MULTISPLIT: return m;
       case JOIN: return n; default: return m * n; }
   }
   int outputs() const override {
-    switch (k) { case PASS: return 1; case MULTIPASS: case REVERSE: return n; case SINK: return 0; case SPLIT: return n; case MULTISPLIT: return m * n;
+    switch (k) { case PASS: case MONITOR: return 1; case MULTIPASS: case REVERSE: return n; case SINK: return 0; case SPLIT: return n; case MULTISPLIT: return m * n;
       case JOIN: return 1; default: return m; }
   }
   uint64_t id() const override {
-    switch (k) { case PASS: return 48; case MULTIPASS: return 0; case SINK: return 1; case SPLIT: return 40; case MULTISPLIT: return 38;
+    switch (k) { case PASS: return 48; case MONITOR: return 56; case MULTIPASS: return 0; case SINK: return 1; case SPLIT: return 40; case MULTISPLIT: return 38;
       case JOIN: return 41; case MULTIJOIN: return 39; default: return 45; }
   }
   void sig(std::string& o) const override {
     switch (k) {
-      case PASS: o += "MultiPass<1>"; break; case MULTIPASS: o += "MultiPass<" + I(n) + ">"; break;
+      case PASS: case MONITOR: o += "MultiPass<1>"; break; case MULTIPASS: o += "MultiPass<" + I(n) + ">"; break;
       case SINK: o += "Sink<" + I(n) + ">"; break; case SPLIT: o += "MultiSplit<1," + I(n) + ">"; break;
       case MULTISPLIT: o += "MultiSplit<" + I(m) + "," + I(n) + ">"; break; case JOIN: o += "MultiJoin<1," + I(n) + ">"; break;
       case MULTIJOIN: o += "MultiJoin<" + I(m) + "," + I(n) + ">"; break; default: o += "Reverse<" + I(n) + ">"; break;
@@ -968,6 +968,7 @@ namespace {
 // ---------------------------------------------------------------- builders
 HNode* mk_constant(int n, const float* v) { return new Constant(std::vector<float>(v, v + n)); }
 HNode* mk_pass() { return new Routing(Routing::PASS, 1, 1); }
+HNode* mk_monitor() { return new Routing(Routing::MONITOR, 1, 1); }
 HNode* mk_multipass(int n) { return new Routing(Routing::MULTIPASS, 1, n); }
 HNode* mk_sink(int n) { return new Routing(Routing::SINK, 1, n); }
 HNode* mk_split(int n) { return new Routing(Routing::SPLIT, 1, n); }

@@ -80,6 +80,7 @@ struct HNode {
 // ---- builders (one per primitive; composites consume their children)
 HNode* mk_constant(int n, const float* v);
 HNode* mk_pass();
+HNode* mk_monitor();   // Monitor ID 56: pass-through in the audio path
 HNode* mk_multipass(int n);
 HNode* mk_sink(int n);
 HNode* mk_split(int n);

@@ -560,6 +560,14 @@ def phaser(feedback_amount, phase_f, horizon=10.0):
                               >> pipei(10, lambda i: add((0.0, 0.1)) >> ~allpole()) >> (mul(feedback_amount) | sink()))
 
 
+def unit(x):   # src/audiounit.rs:430-484 Unit<I, O>: a boxed AudioUnit as a node; transparent to ping, settings and processing
+    return x
+
+
+def monitor(shared=None, meter=None):   # src/dynamics.rs:441-520: the audio passes through; the Shared is host-side (use `meter` to read a level)
+    return An("monitor", (), (), 1, 1)
+
+
 def white():   # src/prelude.rs: white() is noise()
     return noise()
 

@@ -93,10 +93,10 @@ struct Child {
 
 // ---- src/audionode.rs:374-402 MultiPass (ID 0), :404-433 Pass (ID 48)
 struct MultiPass : Node {
-  int n; bool single;
-  MultiPass(int n_, bool single_) : n(n_), single(single_) {}
+  int n; bool single; uint64_t id_override = 0;   // Monitor (ID 56, src/dynamics.rs:441-520) is a pass in the audio path
+  MultiPass(int n_, bool single_, uint64_t id_ = 0) : n(n_), single(single_), id_override(id_) {}
   int inputs() const override { return n; } int outputs() const override { return n; }
-  uint64_t id() const override { return single ? 48 : 0; }
+  uint64_t id() const override { return id_override ? id_override : (single ? 48 : 0); }
   void tick(const float* in, float* out) override { for (int c = 0; c < n; c++) out[c] = in[c]; }
   void process(int size, const float* in, float* out) override {
     for (int c = 0; c < n; c++) for (int i = 0; i < simd_items(size) * 8; i++) out[c * B + i] = in[c * B + i];

@@ -53,6 +53,7 @@ GRAPHS = [
     lambda: dc(220.0) >> lorenz() | dc(110.0) >> rossler() | dc(330.0) >> lorenz(),
     lambda: dc((220.0, 0.3)) >> pulse() | dc((220.0, 0.3)) >> pulse().phase(0.5) | (ramp_hz(50.0) >> phase_synth(3) | noise()) >> rotate(0.3, 0.5) >> mixer([[1.0, 2.0]]),
     lambda: (noise() | noise()) >> reverb4_stereo(25.0, 2.0),
+    lambda: unit(noise() >> monitor() >> lowpass_hz(500.0, 1.0)) | noise() >> pass_() >> lowpass_hz(500.0, 1.0),     # Monitor hashes as ID 56, not as a Pass
     lambda: noise() >> flanger(0.5, 0.005, 0.010, lambda t: 0.0075, horizon=0.05) | noise() >> phaser(0.5, lambda t: 0.5, horizon=0.05) | white(),
     lambda: lfo(lambda t: 440.0 + t, horizon=0.05) >> sine() | envelope(lambda t: (t, 1.0 - t), horizon=0.05) >> (pass_() * pass_()) | lfo(lambda t: 1.0, horizon=0.02, time64=True) * noise(),
     lambda: noise() >> limiter(0.005, 0.05) | (noise() | noise()) >> limiter_stereo(0.002, 0.02),

@@ -766,6 +766,14 @@ def test_envelope_lfo():  # src/envelope.rs:14-183; tests/test_basic.rs:173-176,
     assert 395.0 < f.min() < 410.0 and 470.0 < f.max() < 485.0
 
 
+def test_monitor_and_unit_are_transparent():  # src/dynamics.rs:441-520 (test_flow.rs:159), src/audiounit.rs:430-484
+    x = np.random.default_rng(8).uniform(-1, 1, (1, 500)).astype(np.float32)
+    assert np.array_equal(OracleUnit(monitor()).filter(44100.0, x), x)
+    assert np.array_equal(OracleUnit(unit(monitor() >> mul(2.0))).filter(44100.0, x), x * np.float32(2.0))
+    # a Monitor is not a Pass to the phase hashes of the graph around it (ID 56 vs 48; a constructor's probe ping sees every node)
+    assert OracleUnit(monitor() >> sine()).leaf_hashes() != OracleUnit(pass_() >> sine()).leaf_hashes()
+
+
 def test_flanger_phaser():  # src/prelude.rs:2719-2753: compositions of lfo, tap, feedback2 / feedback, allpole
     import math as m
     check_wave(noise() >> flanger(0.5, 0.005, 0.010, lambda t: 0.0075 + 0.0025 * m.sin(2.0 * t)) | noise() >> phaser(0.5, lambda t: 0.5 + 0.5 * m.sin(3.0 * t)))
