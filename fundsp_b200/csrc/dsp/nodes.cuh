@@ -1308,6 +1308,115 @@ template <class X> struct Event {
   static FDSP_DEV void end_simd(R&) {}
 };
 
+// ---------------------------------------------------------------- Oversample<X> (Oversampler ID 51, src/oversample.rs): X at twice
+// the sample rate between two 43-tap minimum-phase halfband filters (24-tap polyphase interpolation, 48-tap decimation), the
+// reference's arithmetic as written: 8 lane accumulators per filter (`mul_add` = mul, add — the crate's non-FMA form), lanes summed
+// ((l0+l2)+(l1+l3)) low + high. The 128-sample rings of every input and output channel live in the class's delay-line storage. In a
+// block the inner program runs ITS block path twice over `size` inner samples (one per half of the outer block); with an odd size the
+// last outer sample is 0 and the inner program consumes one zero-input sample per half (see oracle/fo_nodes.h Oversampler).
+FDSP_DEV float os_tap(int k) {   // HALFBAND_MIN (:344-388); k is a compile-time constant wherever this is called
+  const float h[43] = {4.73552339e-02f, 1.81988040e-01f, 3.49148434e-01f, 3.92748135e-01f, 2.18230867e-01f, -5.31842843e-02f, -1.79186566e-01f, -7.34488007e-02f,
+                       8.94524103e-02f, 1.00868556e-01f, -2.08681451e-02f, -8.82510989e-02f, -2.07640777e-02f, 6.22587555e-02f, 4.07776255e-02f, -3.52258090e-02f,
+                       -4.57407870e-02f, 1.27033444e-02f, 4.14376136e-02f, 3.30799834e-03f, -3.24608206e-02f, -1.27856355e-02f, 2.21659033e-02f, 1.67803711e-02f,
+                       -1.27406974e-02f, -1.68177367e-02f, 5.35518220e-03f, 1.44761581e-02f, -3.70651781e-04f, -1.11140183e-02f, -2.40622311e-03f, 7.71596027e-03f,
+                       3.48227062e-03f, -4.86763558e-03f, -3.45536353e-03f, 2.79880054e-03f, 2.86736431e-03f, -1.48746153e-03f, -2.11827989e-03f, 7.72684113e-04f,
+                       1.44384114e-03f, -4.49807048e-04f, -9.41945265e-04f};
+  return h[k];
+}
+FDSP_DEV float os_reduce8(const float* a) { return ((a[0] + a[2]) + (a[1] + a[3])) + ((a[4] + a[6]) + (a[5] + a[7])); }
+template <class X> struct Oversample {
+  static constexpr int NI = X::IN, NO = X::OUT, NC = NI < NO ? NI : NO;
+  FDSP_NODE(NI, NO, X::NP, 2 + X::NS, X::NU);
+  struct R { uint32_t in_idx, out_idx, off; typename X::R x; };
+  static FDSP_DEV void load(R& r, Loader& l) { r.in_idx = l.S(); r.out_idx = l.S(); r.off = l.D(128u * (uint32_t)(NI + NO)); X::load(r.x, l); }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.S(r.in_idx); s.S(r.out_idx); X::save(r.x, s); }
+  template <class C> static FDSP_DEV float* ring(const R& r, const C& c, int channel) { return c.dl + (size_t)(r.off + (uint32_t)channel * 128u) * c.V + c.v; }
+  template <class C> static FDSP_DEV void interpolate(const float* rb, const C& c, uint32_t newest, float& even, float& odd) {   // :12-44
+    const uint32_t start = newest + (129u - 24u);
+    float ae[8], ao[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { ae[j] = 0.0f; ao[j] = 0.0f; }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int k = i * 8 + j;
+        const float sm = rb[(size_t)((start + (uint32_t)k) & 0x7fu) * c.V];
+        ae[j] = sm * (k < 2 ? 0.0f : os_tap(k < 2 ? 0 : 2 * (k - 2))) + ae[j];
+        ao[j] = sm * (k < 3 ? 0.0f : os_tap(k < 3 ? 0 : 2 * (k - 3) + 1)) + ao[j];
+      }
+    }
+    even = os_reduce8(ae) * 2.0f; odd = os_reduce8(ao) * 2.0f;
+  }
+  template <class C> static FDSP_DEV float decimate(const float* rb, const C& c, uint32_t last) {   // :46-66
+    const uint32_t start = last + (129u - 48u);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int k = i * 8 + j;
+        acc[j] = rb[(size_t)((start + (uint32_t)k) & 0x7fu) * c.V] * (k < 5 ? 0.0f : os_tap(k < 5 ? 0 : k - 5)) + acc[j];
+      }
+    }
+    return os_reduce8(acc);
+  }
+  template <class C> static FDSP_DEV void inner(R& r, const C& c, int idx, int n, const Fr<NI>& in, Fr<NO>& y) {   // one sample of X's own block of n samples
+    C c2 = c;
+    const int nfull = n & ~7;
+    c2.n = n; c2.i = idx; c2.rem = idx >= nfull; c2.first = !c2.rem && (idx & 7) == 0;
+    c2.sr = c.sr * 2.0f; c2.sd64 = c.sd64 * 0.5f; c2.sd32 = c.sd32 * 0.5f;   // X runs at twice the rate (exact: powers of two)
+    if (idx == nfull) X::end_simd(r.x);
+    X::template step<false>(r.x, c2, in, y);
+    if (idx == n - 1 && nfull == n) X::end_simd(r.x);
+  }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<NI>& in, Fr<NO>& o) {
+    Fr<NI> e, d; Fr<NO> y0, y1;
+    const bool live = T || c.i < 2 * (c.n / 2);
+    if (!live) {   // the odd tail sample of a block
+#pragma unroll
+      for (int k = 0; k < NO; k++) o.v[k] = 0.0f;
+      return;
+    }
+#pragma unroll
+    for (int k = 0; k < NI; k++) {
+      float* rb = ring(r, c, k);
+      rb[(size_t)r.in_idx * c.V] = in.v[k];
+      interpolate(rb, c, r.in_idx, e.v[k], d.v[k]);
+    }
+    r.in_idx = (r.in_idx + 1u) & 0x7fu;
+    if (T) {
+      C c2 = c; c2.sr = c.sr * 2.0f; c2.sd64 = c.sd64 * 0.5f; c2.sd32 = c.sd32 * 0.5f;
+      X::template step<true>(r.x, c2, e, y0); X::template step<true>(r.x, c2, d, y1);
+    }
+    else {
+      const int half = c.n / 2, local = c.i >= half ? c.i - half : c.i;
+      inner(r, c, 2 * local, c.n, e, y0);
+      inner(r, c, 2 * local + 1, c.n, d, y1);
+      if ((c.n & 1) && local == half - 1) {   // process(size) of an odd size: one inner sample more, fed from the zeroed buffer
+        Fr<NI> z; Fr<NO> drop;
+#pragma unroll
+        for (int k = 0; k < NI; k++) z.v[k] = 0.0f;
+        inner(r, c, c.n - 1, c.n, z, drop);
+      }
+    }
+    const uint32_t next = (r.out_idx + 1u) & 0x7fu;
+#pragma unroll
+    for (int k = 0; k < NO; k++) {
+      if (T || k < NC) {   // the block path decimates `Inputs` channels (:207)
+        float* rb = ring(r, c, NI + k);
+        rb[(size_t)r.out_idx * c.V] = y0.v[k];
+        rb[(size_t)next * c.V] = y1.v[k];
+        o.v[k] = decimate(rb, c, next);
+      } else o.v[k] = 0.0f;
+    }
+    r.out_idx = (r.out_idx + 2u) & 0x7fu;
+  }
+  static FDSP_DEV void end_simd(R&) {}
+};
+
 // ---------------------------------------------------------------- Limiter<N> (ID 25, src/dynamics.rs:56-243): look-ahead limiter.
 // A ring of L frames delays the audio; a binary max-tree over the last L amplitudes (ReduceBuffer, updated leaf-to-root per sample)
 // gives the window peak, which an asymmetric follower smooths into the gain. Ring and tree live in the class's delay-line storage:
@@ -1821,6 +1930,8 @@ template <class X> struct WaveKind<Resample<X>> : WaveKind<X> {};
 template <class X> struct Cost<Resample<X>> { static constexpr int value = 4 * Cost<X>::value + 120; };
 template <class X> struct WaveKind<Event<X>> : WaveKind<X> {};
 template <class X> struct Cost<Event<X>> { static constexpr int value = Cost<X>::value + 110; };
+template <class X> struct WaveKind<Oversample<X>> : WaveKind<X> {};
+template <class X> struct Cost<Oversample<X>> { static constexpr int value = 2 * Cost<X>::value + 150 * (X::IN + X::OUT) + 101; };
 template <class X> struct WaveKind<FeedbackUnit<X>> : WaveKind<X> {};
 template <class X> struct Cost<FeedbackUnit<X>> { static constexpr int value = Cost<X>::value + 12 * X::IN; };
 template <class F> struct Cost<Reverb85<F>> { static constexpr int value = 1200 + 16 * Cost<F>::value; };

@@ -659,6 +659,18 @@ struct EnvelopeN : HNode {  // src/envelope.rs:14-183: the closure is evaluated 
   void lower(Lowering& l) const override { if (t64) lower_as<double>(l); else lower_as<float>(l); }
   HCLONE(EnvelopeN)
 };
+struct OversampleN : HNode {  // src/oversample.rs:68-245
+  Kid x;
+  explicit OversampleN(HNode* x_) : x(x_) { x->set_sample_rate(DEFAULT_SR * 2.0); AttoHash h = x->ping(true, AttoHash(51)); x->ping(false, h); }   // Oversampler::new :85-97
+  int inputs() const override { return x->inputs(); } int outputs() const override { return x->outputs(); }
+  uint64_t id() const override { return 51; }
+  void reset() override { x->reset(); }
+  void set_sample_rate(double s) override { x->set_sample_rate(s * 2.0); }
+  AttoHash ping(bool probe, AttoHash h) override { return x->ping(probe, h.hash(id())); }
+  void sig(std::string& o) const override { o += "Oversample<"; x->sig(o); o += ">"; }
+  void lower(Lowering& l) const override { l.su(0u); l.su(0u); l.dlen.push_back(128u * (uint32_t)(x->inputs() + x->outputs())); x->lower(l); }
+  HCLONE(OversampleN)
+};
 struct VarN : HNode {  // the shared value is control-plane state: it enters as a parameter word and changes through Setting::value
   float value; explicit VarN(float v) : value(v) {}
   int inputs() const override { return 0; } int outputs() const override { return 1; }
@@ -996,6 +1008,10 @@ HNode* mk_reverb3(double time, double diffusion, HNode* filter) {
   return new ReverbN(time, diffusion, filter);
 }
 HNode* mk_var(float value) { return new VarN(value); }
+HNode* mk_oversample(HNode* x) {   // the block path decimates as many channels as X has inputs (:207): more inputs than outputs would index past the outputs
+  if (!x || x->outputs() < 1 || x->inputs() > x->outputs()) { delete x; return nullptr; }
+  return new OversampleN(x);
+}
 HNode* mk_envelope(double interval, int outputs, int time_f64, EnvelopeFn f, void* user, double horizon) {
   if (!(interval > 0.0) || outputs < 1 || outputs > 8 || !f || !(horizon >= 0.0) || horizon / interval > 4.0e6) return nullptr;   // assert!(interval > F::zero())
   return new EnvelopeN(time_f64 ? interval : (double)(float)interval, outputs, time_f64, f, user, horizon);

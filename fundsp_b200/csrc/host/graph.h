@@ -122,6 +122,7 @@ bool event_set_clock(HNode* n, double time);                         // the sequ
 // graph is lowered (bank creation, sample-rate change, settings) for t <= horizon seconds; time_f64: F = f64 (else f32)
 typedef void (*EnvelopeFn)(double t, double* out, void* user);
 HNode* mk_envelope(double interval, int outputs, int time_f64, EnvelopeFn f, void* user, double horizon);
+HNode* mk_oversample(HNode* x);                                      // Oversampler ID 51; consumes x
 HNode* mk_declick(float duration);                                   // Declick ID 23
 HNode* mk_chaos(int kind);                                           // 0 Rossler ID 73, 1 Lorenz ID 74
 HNode* mk_morph(float cutoff, float q);                               // Morph ID 62

@@ -568,6 +568,10 @@ def monitor(shared=None, meter=None):   # src/dynamics.rs:441-520: the audio pas
     return An("monitor", (), (), 1, 1)
 
 
+def oversample(node):   # src/prelude.rs:996-1005: run `node` at twice the sample rate between halfband filters
+    return An("oversample", (), (node,), node.nin, node.nout)
+
+
 def white():   # src/prelude.rs: white() is noise()
     return noise()
 

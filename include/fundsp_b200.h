@@ -77,6 +77,7 @@ fdsp_node* fdsp_morph(float cutoff, float q);                  /* Morph ID 62 sr
 fdsp_node* fdsp_rez(float bandpass, float cutoff, float q, int inputs); /* Rez ID 75 src/rez.rs: bandpass 0 = lowrez, 1 = bandrez; inputs 1 or 3 (audio, cutoff, q) */
 fdsp_node* fdsp_chaos(int kind);                               /* kind 0 Rossler ID 73, 1 Lorenz ID 74 (src/oscillator.rs:318-438); input = frequency */
 fdsp_node* fdsp_declick(float duration);                       /* Declick ID 23 src/dynamics.rs:245: smooth fade-in over `duration` seconds */
+fdsp_node* fdsp_oversample(fdsp_node* x);                      /* Oversampler<X> ID 51 src/oversample.rs (`oversample`): x at 2x the sample rate between 43-tap minimum-phase halfbands; consumes x (inputs <= outputs) */
 fdsp_node* fdsp_monitor(void);                                 /* Monitor ID 56 src/dynamics.rs:441 (`monitor(&shared, meter)`): the audio passes through; the Shared it feeds stays host-side (read the level with a `meter` voice output instead) */
 /* Envelope<F, E, R> ID 14 src/envelope.rs:14 (`envelope`, `lfo`; interval 0.002): the closure E crosses the ABI as a HOST callback. It is
    called when the graph is lowered (bank creation, sample-rate change, settings) — never while rendering — at exactly the jittered sample

@@ -235,6 +235,7 @@ enum class Fade { Power = 0, Smooth = 1 };                                      
 inline An event(An unit, double start_time, double end_time, Fade ease = Fade::Smooth, double fade_in = 0.0, double fade_out = 0.0) {
   return An(fdsp_event(unit.release(), start_time, end_time, (int)ease, fade_in, fade_out));
 }
+inline An oversample(An x) { return An(fdsp_oversample(x.release())); }                // x at twice the sample rate
 inline An resample(An x) { return An(fdsp_resample(x.release())); }                    // input = speed
 
 // ---- src/math.rs helpers used by the reverbs, in the reference's precision

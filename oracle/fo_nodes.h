@@ -1682,6 +1682,92 @@ template <class F> struct Envelope : Node {
   Node* clone() const override { return new Envelope<F>(*this); }
 };
 
+// ---- src/oversample.rs Oversampler<X> (ID 51): 2x oversampling around X with a 43-tap minimum-phase halfband (coefficients :344-388),
+// restated as written: the window ends at the newest sample and meets the taps in table order; decimation loops over the INPUT channel
+// count (:207); with an odd block size the last output sample is not written (0 here) and X processes one zero-input sample more per
+// half. `wide` without AVX/FMA (the default x86-64 build): mul_add = mul then add; reduce_add = ((l0+l2)+(l1+l3)) per f32x4, low half
+// + high half — the lane-sum association is restated from the crate's SSE path from memory (ulp-level parity unpinned, like libm).
+static const float kHalfbandMin[43] = {
+    4.73552339e-02f, 1.81988040e-01f, 3.49148434e-01f, 3.92748135e-01f, 2.18230867e-01f, -5.31842843e-02f, -1.79186566e-01f, -7.34488007e-02f,
+    8.94524103e-02f, 1.00868556e-01f, -2.08681451e-02f, -8.82510989e-02f, -2.07640777e-02f, 6.22587555e-02f, 4.07776255e-02f, -3.52258090e-02f,
+    -4.57407870e-02f, 1.27033444e-02f, 4.14376136e-02f, 3.30799834e-03f, -3.24608206e-02f, -1.27856355e-02f, 2.21659033e-02f, 1.67803711e-02f,
+    -1.27406974e-02f, -1.68177367e-02f, 5.35518220e-03f, 1.44761581e-02f, -3.70651781e-04f, -1.11140183e-02f, -2.40622311e-03f, 7.71596027e-03f,
+    3.48227062e-03f, -4.86763558e-03f, -3.45536353e-03f, 2.79880054e-03f, 2.86736431e-03f, -1.48746153e-03f, -2.11827989e-03f, 7.72684113e-04f,
+    1.44384114e-03f, -4.49807048e-04f, -9.41945265e-04f};
+inline float os_dec_coeff(int k) { return k < 5 ? 0.0f : kHalfbandMin[k - 5]; }                       // DECIMATING_COEFFS flattened, k = 0..47 (:395-457)
+inline float os_even_coeff(int k) { return k < 2 ? 0.0f : kHalfbandMin[2 * (k - 2)]; }               // INTERPOLATING_EVEN_COEFFS, k = 0..23 (:460-492)
+inline float os_odd_coeff(int k) { return k < 3 ? 0.0f : kHalfbandMin[2 * (k - 3) + 1]; }            // INTERPOLATING_ODD_COEFFS (:495-527)
+inline float os_reduce8(const float* a) { return ((a[0] + a[2]) + (a[1] + a[3])) + ((a[4] + a[6]) + (a[5] + a[7])); }
+inline void os_interpolate(const float* ring, size_t newest, float& even, float& odd) {                // :12-44
+  const size_t start = newest + (129 - 3 * 8);
+  float ae[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ao[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 8; j++) {
+    const float sm = ring[(start + (size_t)i * 8 + j) & 0x7f];
+    ae[j] = sm * os_even_coeff(i * 8 + j) + ae[j];
+    ao[j] = sm * os_odd_coeff(i * 8 + j) + ao[j];
+  }
+  even = os_reduce8(ae) * 2.0f; odd = os_reduce8(ao) * 2.0f;
+}
+inline float os_decimate(const float* ring, size_t last) {                                             // :46-66
+  const size_t start = last + (129 - (43 / 8 + 1) * 8);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 6; i++) for (int j = 0; j < 8; j++) acc[j] = ring[(start + (size_t)i * 8 + j) & 0x7f] * os_dec_coeff(i * 8 + j) + acc[j];
+  return os_reduce8(acc);
+}
+struct Oversampler : Node {
+  Child x; int nin, nout; std::vector<float> inv, outv, inner_in, inner_out; size_t input_rb_index = 0, output_rb_index = 0;
+  explicit Oversampler(Node* x_) : x(x_), nin(x_->inputs()), nout(x_->outputs()) {
+    x->set_sample_rate(DEFAULT_SR * 2.0);
+    AttoHash h = x->ping(true, AttoHash(51)); x->ping(false, h);
+    inv.assign((size_t)std::max(1, nin) * 128, 0.0f); outv.assign((size_t)std::max(1, nout) * 128, 0.0f);
+    inner_in.assign((size_t)std::max(1, nin) * B, 0.0f); inner_out.assign((size_t)std::max(1, nout) * B, 0.0f);
+  }
+  int inputs() const override { return nin; } int outputs() const override { return nout; }
+  uint64_t id() const override { return 51; }
+  void reset() override { x->reset(); std::fill(inv.begin(), inv.end(), 0.0f); std::fill(outv.begin(), outv.end(), 0.0f); }   // the ring positions keep running (:137-141)
+  void set_sample_rate(double sr) override { x->set_sample_rate(sr * 2.0); }
+  void tick(const float* in, float* out) override {   // :149-180
+    float a[64], b[64], y[64];
+    for (int c = 0; c < nin; c++) { inv[(size_t)c * 128 + input_rb_index] = in[c]; os_interpolate(&inv[(size_t)c * 128], input_rb_index, a[c], b[c]); }
+    input_rb_index = (input_rb_index + 1) & 0x7f;
+    x->tick(a, y);
+    for (int c = 0; c < nout; c++) outv[(size_t)c * 128 + output_rb_index] = y[c];
+    output_rb_index = (output_rb_index + 1) & 0x7f;
+    x->tick(b, y);
+    for (int c = 0; c < nout; c++) outv[(size_t)c * 128 + output_rb_index] = y[c];
+    for (int c = 0; c < nout; c++) out[c] = os_decimate(&outv[(size_t)c * 128], output_rb_index);
+    output_rb_index = (output_rb_index + 1) & 0x7f;
+  }
+  void process(int size, const float* in, float* out) override {   // :182-215
+    std::fill(inner_in.begin(), inner_in.end(), 0.0f); std::fill(inner_out.begin(), inner_out.end(), 0.0f);   // BufferArray::new() per call
+    if (size & 1) for (int c = 0; c < nout; c++) out[c * B + size - 1] = 0.0f;   // never written by the reference (see header)
+    for (int c = nin; c < nout; c++) for (int i = 0; i < size; i++) out[c * B + i] = 0.0f;   // channels beyond the input count: never written either
+    const int half = size / 2;
+    for (int offset : {0, half}) {
+      for (int i = 0; i < half; i++) {
+        for (int c = 0; c < nin; c++) {
+          inv[(size_t)c * 128 + input_rb_index] = in[c * B + i + offset];
+          os_interpolate(&inv[(size_t)c * 128], input_rb_index, inner_in[c * B + 2 * i], inner_in[c * B + 2 * i + 1]);
+        }
+        input_rb_index = (input_rb_index + 1) & 0x7f;
+      }
+      x->process(size, inner_in.data(), inner_out.data());
+      for (int i = 0; i < half; i++) {
+        for (int c = 0; c < nin && c < nout; c++) {   // `for channel in 0..Self::Inputs::USIZE` as written
+          outv[(size_t)c * 128 + output_rb_index] = inner_out[c * B + 2 * i];
+          const size_t next = (output_rb_index + 1) & 0x7f;
+          outv[(size_t)c * 128 + next] = inner_out[c * B + 2 * i + 1];
+          out[c * B + i + offset] = os_decimate(&outv[(size_t)c * 128], next);
+        }
+        output_rb_index = (output_rb_index + 2) & 0x7f;
+      }
+    }
+  }
+  void set(const Setting& s) override { (void)s; }
+  AttoHash ping(bool probe, AttoHash h) override { return x->ping(probe, h.hash(id())); }
+  FO_CLONE(Oversampler)
+};
+
 // ---- src/dynamics.rs:316-437 Meter / MeterState / MeterNode (ID 61); kind 0 Sample, 1 Peak(timescale), 2 Rms(timescale)
 struct MeterNode : Node {
   int kind; double timescale; float smoothing = 0, state = 0;

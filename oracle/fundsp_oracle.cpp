@@ -90,6 +90,7 @@ API Node* fo_morph(float cutoff, float q) { return new Morph(cutoff, q); }
 API Node* fo_rez(float bandpass, float cutoff, float q, int inputs) { return new Rez(bandpass, cutoff, q, inputs); }
 API Node* fo_chaos(int kind) { return new Chaos(kind); }   // 0 rossler, 1 lorenz
 API Node* fo_declick(float duration) { return new Declick(duration); }
+API Node* fo_oversample(Node* x) { return new Oversampler(x); }
 API Node* fo_monitor() { return new MultiPass(1, true, 56); }
 API Node* fo_envelope(double interval, int outputs, int time_f64, EnvelopeFn f, void* user) {
   if (time_f64) return new Envelope<double>(interval, outputs, f, user);

@@ -53,6 +53,7 @@ GRAPHS = [
     lambda: dc(220.0) >> lorenz() | dc(110.0) >> rossler() | dc(330.0) >> lorenz(),
     lambda: dc((220.0, 0.3)) >> pulse() | dc((220.0, 0.3)) >> pulse().phase(0.5) | (ramp_hz(50.0) >> phase_synth(3) | noise()) >> rotate(0.3, 0.5) >> mixer([[1.0, 2.0]]),
     lambda: (noise() | noise()) >> reverb4_stereo(25.0, 2.0),
+    lambda: noise() >> oversample(shape(Tanh(2.0)) >> lowpass_hz(5000.0, 1.0)) | oversample(saw_hz(110.0)) | noise() >> oversample(sine_hz(3.0) * pass_()),
     lambda: unit(noise() >> monitor() >> lowpass_hz(500.0, 1.0)) | noise() >> pass_() >> lowpass_hz(500.0, 1.0),     # Monitor hashes as ID 56, not as a Pass
     lambda: noise() >> flanger(0.5, 0.005, 0.010, lambda t: 0.0075, horizon=0.05) | noise() >> phaser(0.5, lambda t: 0.5, horizon=0.05) | white(),
     lambda: lfo(lambda t: 440.0 + t, horizon=0.05) >> sine() | envelope(lambda t: (t, 1.0 - t), horizon=0.05) >> (pass_() * pass_()) | lfo(lambda t: 1.0, horizon=0.02, time64=True) * noise(),
@@ -102,6 +103,7 @@ def test_builder_argument_errors_return_null_with_a_message():
         lambda: be.b_limiter(0, 0.01, 0.01), lambda: be.b_limiter(1, -1.0, 0.01),
         lambda: be.b_event(0.0, 1.0, 1, 0.0, 0.0, be.b_pass()), lambda: be.b_event(0.0, 1.0, 1, 2.0, 0.0, be.b_noise()), lambda: be.b_event(0.0, 1.0, 3, 0.0, 0.0, be.b_noise()),   # generators only; fade <= duration
         lambda: be.b_envelope(0.0, 1, 0, lambda t: 0.0, 1.0), lambda: be.b_envelope(0.002, 0, 0, lambda t: 0.0, 1.0), lambda: be.b_envelope(1e-9, 1, 0, lambda t: 0.0, 10.0),   # interval > 0; 1..8 outputs; bounded table
+        lambda: be.b_oversample(be.b_stack(be.b_pass(), be.b_sink(1))),   # more inputs than outputs
         lambda: be.b_phase_synth(6), lambda: be.b_mixer(0, 2, [1.0]), lambda: be.b_mixer(9, 9, [0.0] * 81),      # tables 0..5; 1 <= M*N <= 64
     ]
     for k, f in enumerate(bad):

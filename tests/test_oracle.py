@@ -774,6 +774,35 @@ def test_monitor_and_unit_are_transparent():  # src/dynamics.rs:441-520 (test_fl
     assert OracleUnit(monitor() >> sine()).leaf_hashes() != OracleUnit(pass_() >> sine()).leaf_hashes()
 
 
+def test_oversample():  # src/oversample.rs: 2x oversampling between 43-tap minimum-phase halfbands
+    sr = 44100.0
+    # transparent in the pass band: DC settles at 1, a 1 kHz and a 15 kHz sine keep their amplitude
+    y = OracleUnit(dc(1.0) >> oversample(pass_())).render(sr, 0.02)[0]
+    assert abs(y[-1] - 1.0) < 2e-3 and np.abs(y[200:] - 1.0).max() < 2e-3
+    for f, tol in ((1000.0, 0.01), (15000.0, 0.05)):
+        y = OracleUnit(sine_hz(f) >> oversample(pass_())).render(sr, 0.1)[0]
+        assert abs(np.abs(y[1000:]).max() - 1.0) < tol, (f, np.abs(y[1000:]).max())
+    # what it is for: the third harmonic of a hard-driven 8.5 kHz sine (25.5 kHz) folds to 18.6 kHz at 1x and is filtered out at 2x
+    n = 1 << 15
+    def level(g, f):
+        y = OracleUnit(g).render(sr, n / sr)[0].astype(np.float64)
+        sp = np.abs(np.fft.rfft(y * np.hanning(n)))
+        k = int(round(f * n / sr))
+        return 20.0 * np.log10(sp[k - 3:k + 4].max() / sp.max())
+    drive = lambda: sine_hz(8500.0) * 4.0
+    plain, over = level(drive() >> shape(Tanh(1.0)), 18600.0), level(drive() >> oversample(shape(Tanh(1.0))), 18600.0)
+    assert plain > -25.0 and over < plain - 25.0, (plain, over)
+    # the inner node runs at twice the rate: a one-pole at the same cutoff behaves the same inside and outside
+    a = OracleUnit(noise().seed(3) >> oversample(lowpole_hz(500.0))).render(sr, 0.2)[0]
+    b = OracleUnit(noise().seed(3) >> lowpole_hz(500.0)).render(sr, 0.2)[0]
+    assert abs(a[2000:].std() / b[2000:].std() - 1.0) < 0.05
+    # tick == process over whole even blocks (an odd block leaves its last sample unwritten in the reference: see the oracle header)
+    g = lambda: (noise().seed(1) | noise().seed(2)) >> oversample(lowpass_hz(3000.0, 1.0) | shape(Tanh(2.0)))
+    u = OracleUnit(g()); blocks = u.process_many(64 * 7)
+    t = OracleUnit(g()); ticks = np.stack([t.tick() for _ in range(64 * 7)], axis=1)
+    assert np.abs(blocks - ticks).max() <= 1e-4 and np.abs(blocks).max() > 0.1
+
+
 def test_flanger_phaser():  # src/prelude.rs:2719-2753: compositions of lfo, tap, feedback2 / feedback, allpole
     import math as m
     check_wave(noise() >> flanger(0.5, 0.005, 0.010, lambda t: 0.0075 + 0.0025 * m.sin(2.0 * t)) | noise() >> phaser(0.5, lambda t: 0.5 + 0.5 * m.sin(3.0 * t)))
