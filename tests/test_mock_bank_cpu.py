@@ -1,0 +1,62 @@
+"""The HOST runtime (csrc/host/bank.cpp, graph.cpp, capi.cpp: class building, word layout, launch sequencing, mix reduction, process()
+path, settings on a live bank, sequencer clock / edit / push / growth in place, clone, reset ...) exercised WITHOUT a GPU.
+
+tests/cpp/mock/ builds the host sources against a stand-in <cuda_runtime.h> ("device" memory is host memory, calls are synchronous) and
+replaces the kernels by the device node library compiled for the CPU (FDSP_HOST_EMUL), one small shared object per graph class walking
+every voice through bank_kernel's per-thread block structure. The whole GPU test-suite then runs against that library in a subprocess
+(FDSP_B200_LIB selects it there and only there). What this does NOT cover is the CUDA side proper — the CTA mix tile, TMA table
+staging, the warp-per-voice FDN kernel (reverbs run in the generic form here), stream concurrency — which the same tests check on a B200.
+The mock is test infrastructure: it is never built into, or loaded by, the product."""
+import hashlib
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "fundsp_b200", "csrc")
+MOCK = os.path.join(ROOT, "tests", "cpp", "mock")
+
+
+def _tree_hash():
+    h = hashlib.sha256()
+    files = [os.path.join(MOCK, f) for f in sorted(os.listdir(MOCK)) if f.endswith((".h", ".cpp"))]
+    for d in ("dsp", "host"):
+        files += [os.path.join(CSRC, d, f) for f in sorted(os.listdir(os.path.join(CSRC, d)))]
+    files += [os.path.join(CSRC, "capi.cpp"), os.path.join(ROOT, "include", "fundsp_b200.h")]
+    for f in files:
+        h.update(f.encode()); h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+@pytest.fixture(scope="module")
+def mock_env():
+    build = os.path.join(MOCK, "_build", _tree_hash())        # keyed by every source that goes into it: never stale
+    os.makedirs(build, exist_ok=True)
+    lib = os.path.join(build, "libfundsp_b200_mock.so")
+    if not os.path.exists(lib):
+        srcs = [os.path.join(CSRC, "host", f) for f in ("graph.cpp", "wavetable.cpp", "bank.cpp", "wavfile.cpp")] + [os.path.join(CSRC, "capi.cpp"), os.path.join(MOCK, "registry_mock.cpp")]
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-w", "-shared", "-fPIC", "-DFDSP_HOST_EMUL=1", "-I", MOCK, "-I", CSRC,
+                               "-x", "c++", *srcs, "-o", lib + ".tmp", "-ldl"])
+        os.replace(lib + ".tmp", lib)
+    return dict(os.environ, FDSP_B200_LIB=lib, FDSP_MOCK_ROOT=ROOT, FDSP_MOCK_CACHE=os.path.join(build, "classes"), FDSP_DISABLE_FDN="1")
+
+
+def test_gpu_suite_runs_on_the_mock_device(mock_env):
+    files = [os.path.join(ROOT, "tests", f) for f in ("test_gpu_jit.py", "test_gpu_parity.py", "test_gpu_wider.py")]
+    r = subprocess.run([sys.executable, "-m", "pytest", *files, "-m", "gpu", "-q", "-n", "8", "-p", "no:cacheprovider", "--tb=short"],
+                       capture_output=True, text=True, env=mock_env, cwd=ROOT, timeout=3000)
+    tail = r.stdout[-3000:]
+    assert r.returncode == 0, tail
+    assert " passed" in tail and "failed" not in tail and "error" not in tail.lower(), tail
+
+
+def test_product_library_is_not_the_mock():
+    """The mock is selected by FDSP_B200_LIB in the subprocess above only: the library the package loads by default is the CUDA build."""
+    from fundsp_b200 import capi
+    assert "FDSP_B200_LIB" not in os.environ or "mock" not in os.environ["FDSP_B200_LIB"]
+    path = capi.lib()._name
+    assert path.endswith("libfundsp_b200.so") and "mock" not in path
+    out = subprocess.run(["nm", "-D", "--undefined-only", path], capture_output=True, text=True).stdout
+    assert "fdsp_emul_launch" not in out and "g++" not in out
