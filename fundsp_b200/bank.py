@@ -96,6 +96,10 @@ class GpuBank:
         check(self.L.fdsp_bank_push_event(self.h, ev.lower(GpuBackend()), C.byref(v)))
         return int(v.value)
 
+    def slot_set(self, voice, fade_ease, fade_time, unit):
+        """Slot::set on a voice built with `slot(unit)`: crossfade to `unit` (same graph class) over fade_time seconds."""
+        check(self.L.fdsp_bank_slot_set(self.h, int(voice), int(fade_ease), float(fade_time), unit.lower(GpuBackend())))
+
     def add_voice(self, unit):
         """Grow the bank by one voice (running state of the others preserved; O(bank state)); returns its index."""
         v = C.c_uint32(0)

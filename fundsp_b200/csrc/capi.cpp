@@ -74,6 +74,7 @@ API fdsp_node* fdsp_morph(float cutoff, float q) { return wrap(mk_morph(cutoff, 
 API fdsp_node* fdsp_rez(float bandpass, float cutoff, float q, int inputs) { return wrap(mk_rez(bandpass, cutoff, q, inputs), "rez"); }
 API fdsp_node* fdsp_chaos(int kind) { return wrap(mk_chaos(kind), "chaos"); }
 API fdsp_node* fdsp_declick(float duration) { return wrap(mk_declick(duration), "declick"); }
+API fdsp_node* fdsp_slot(fdsp_node* unit) { return wrap(mk_slot(take(unit)), "slot"); }
 API fdsp_node* fdsp_oversample(fdsp_node* x) { return wrap(mk_oversample(take(x)), "oversample"); }
 API fdsp_node* fdsp_monitor(void) { return wrap(mk_monitor(), "monitor"); }
 API fdsp_node* fdsp_envelope(double interval, int outputs, int time_f64, fdsp_envelope_fn f, void* user, double horizon) { return wrap(mk_envelope(interval, outputs, time_f64, (EnvelopeFn)f, user, horizon), "envelope"); }
@@ -310,6 +311,11 @@ API int fdsp_bank_add_voice(fdsp_bank* b, fdsp_node* unit, uint32_t* voice) {
   if (!b || !unit) { fdsp_node_free(unit); return fail(FDSP_ERR_ARG, "null bank or unit"); }
   std::string e = b->b.add_voice(take(unit), voice);
   return e.empty() ? FDSP_OK : fail(e.find("rebuild") != std::string::npos ? FDSP_ERR_UNSUPPORTED : FDSP_ERR_ARG, e);
+}
+API int fdsp_bank_slot_set(fdsp_bank* b, uint32_t voice, int fade_ease, double fade_time, fdsp_node* unit) {
+  if (!b) { fdsp_node_free(unit); return fail(FDSP_ERR_ARG, "null bank"); }
+  std::string e = b->b.slot_set(voice, fade_ease, fade_time, take(unit));
+  return e.empty() ? FDSP_OK : fail(e.find("in progress") != std::string::npos || e.find("differs") != std::string::npos || e.find("rebuild") != std::string::npos ? FDSP_ERR_UNSUPPORTED : FDSP_ERR_ARG, e);
 }
 API double fdsp_bank_time(const fdsp_bank* b) { return b ? b->b.seq_time : 0.0; }
 API int fdsp_bank_reset(fdsp_bank* b) { return b ? status(b->b.reset()) : fail(FDSP_ERR_ARG, "null bank"); }

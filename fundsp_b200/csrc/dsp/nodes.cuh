@@ -1417,6 +1417,68 @@ template <class X> struct Oversample {
   static FDSP_DEV void end_simd(R&) {}
 };
 
+// ---------------------------------------------------------------- Slot<X> (SlotBackend ID 78, src/slot.rs): a voice whose unit can be
+// replaced by another unit OF THE SAME CLASS with a crossfade, without touching the program: two instances of X live in the voice, one
+// current, one next; the host writes the next instance's words and arms the fade (fdsp_bank_slot_set), the device runs both through
+// the block path, mixes them with the reference's per-block arithmetic (:205-262: phase_left, n, the fade advanced by f32 addition,
+// f64 phase) and swaps their roles when the fade is over. The root of a voice only.
+template <class X> struct Slot {
+  static constexpr int NI = X::IN, NO = X::OUT;
+  FDSP_NODE(NI, NO, 5 + 2 * X::NP, 4 + 2 * X::NS, 2 * X::NU);
+  struct R {
+    double sr, fade_time, fade_phase; int ease, which, has_next;
+    int n_f; float fade, fade_d; bool swap_at_end;
+    typename X::R u[2];
+  };
+  static FDSP_DEV double p64(Loader& l, bool state) {
+    const uint32_t lo = state ? l.S() : l.P(), hi = state ? l.S() : l.P();
+    return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+  }
+  static FDSP_DEV void load(R& r, Loader& l) {
+    r.sr = p64(l, false); r.fade_time = p64(l, false); r.ease = (int)l.P();
+    r.which = (int)l.S(); r.has_next = (int)l.S(); r.fade_phase = p64(l, true);
+    r.n_f = 0; r.fade = r.fade_d = 0.0f; r.swap_at_end = false;
+    X::load(r.u[0], l); X::load(r.u[1], l);
+  }
+  static FDSP_DEV void save(const R& r, Saver& s) {
+    s.S((uint32_t)r.which); s.S((uint32_t)r.has_next);
+    const unsigned long long b = (unsigned long long)__double_as_longlong(r.fade_phase);
+    s.S((uint32_t)b); s.S((uint32_t)(b >> 32));
+    X::save(r.u[0], s); X::save(r.u[1], s);
+  }
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<NI>& in, Fr<NO>& o) {
+    if (T) { if (r.which) X::template step<true>(r.u[1], c, in, o); else X::template step<true>(r.u[0], c, in, o); return; }   // (a slot is a root: not reached)
+    if (c.i == 0 && r.has_next) {   // the block's crossfade plan
+      const double span = r.fade_time * r.sr;
+      const double left = (1.0 - r.fade_phase) * span;
+      const int phase_left = left > 0.0 ? (left < 1.0e9 ? (int)left : 1000000000) : 0;
+      r.n_f = c.n < phase_left ? c.n : phase_left;
+      r.fade = (float)r.fade_phase; r.fade_d = (float)(1.0 / span);
+      r.swap_at_end = phase_left <= c.n;
+    }
+    Fr<NO> y;
+    if (r.which) X::template step<false>(r.u[1], c, in, o); else X::template step<false>(r.u[0], c, in, o);
+    if (r.has_next) {
+      if (r.which) X::template step<false>(r.u[0], c, in, y); else X::template step<false>(r.u[1], c, in, y);
+      if (c.i < r.n_f) {
+        const float e1 = r.ease == 0 ? sine_ease_f(1.0f - r.fade) : smooth5f(1.0f - r.fade);
+        const float e2 = r.ease == 0 ? sine_ease_f(r.fade) : smooth5f(r.fade);
+#pragma unroll
+        for (int k = 0; k < NO; k++) { const float a = o.v[k] * e1; o.v[k] = a + y.v[k] * e2; }
+        r.fade += r.fade_d;
+      } else {
+#pragma unroll
+        for (int k = 0; k < NO; k++) o.v[k] = y.v[k];
+      }
+      if (c.i == c.n - 1) {
+        r.fade_phase += (double)r.n_f / (r.fade_time * r.sr);
+        if (r.swap_at_end) { r.which ^= 1; r.has_next = 0; r.fade_phase = 0.0; }   // next_phase (no `latest`: the host refuses a set while fading)
+      }
+    }
+  }
+  static FDSP_DEV void end_simd(R& r) { X::end_simd(r.u[0]); X::end_simd(r.u[1]); }
+};
+
 // ---------------------------------------------------------------- Limiter<N> (ID 25, src/dynamics.rs:56-243): look-ahead limiter.
 // A ring of L frames delays the audio; a binary max-tree over the last L amplitudes (ReduceBuffer, updated leaf-to-root per sample)
 // gives the window peak, which an asymmetric follower smooths into the gain. Ring and tree live in the class's delay-line storage:
@@ -1932,6 +1994,8 @@ template <class X> struct WaveKind<Event<X>> : WaveKind<X> {};
 template <class X> struct Cost<Event<X>> { static constexpr int value = Cost<X>::value + 110; };
 template <class X> struct WaveKind<Oversample<X>> : WaveKind<X> {};
 template <class X> struct Cost<Oversample<X>> { static constexpr int value = 2 * Cost<X>::value + 150 * (X::IN + X::OUT) + 101; };
+template <class X> struct WaveKind<Slot<X>> : WaveKind<X> {};
+template <class X> struct Cost<Slot<X>> { static constexpr int value = 2 * Cost<X>::value + 101; };
 template <class X> struct WaveKind<FeedbackUnit<X>> : WaveKind<X> {};
 template <class X> struct Cost<FeedbackUnit<X>> { static constexpr int value = Cost<X>::value + 12 * X::IN; };
 template <class F> struct Cost<Reverb85<F>> { static constexpr int value = 1200 + 16 * Cost<F>::value; };

@@ -359,6 +359,44 @@ std::string Bank::add_voice(HNode* node, uint32_t* voice) {
   return "";
 }
 
+// Slot::set on a live bank (src/slot.rs:64-71,124-151): the unit goes into the idle instance of the voice's Slot<X> and the device
+// crossfades to it over fade_time seconds from the next block on. While a fade is running the reference parks a further update as
+// `latest`; here that call is refused (the caller retries after the fade).
+std::string Bank::slot_set(uint32_t voice, int ease, double fade_time, HNode* unit) {
+  std::unique_ptr<HNode> n(unit);
+  if (voice >= V()) return "slot: voice index out of range";
+  if (!n || ease < 0 || ease > 1 || !(fade_time > 0.0)) return "slot: needs a unit, fade 0 (Power) or 1 (Smooth) and a fade time > 0";
+  if (!is_slot(nodes[voice].get())) return "slot: the voice is not a slot (fdsp_slot)";
+  CU(cudaSetDevice(device));
+  for (auto& c : classes) {
+    auto it = std::lower_bound(c.voices.begin(), c.voices.end(), voice);
+    if (it == c.voices.end() || *it != voice) continue;
+    const uint32_t i = (uint32_t)(it - c.voices.begin()), Vc = c.V();
+    if (c.fdn || c.ns < 4 || ((c.ns - 4) & 1u) || (c.dl_floats & 1u)) return "slot: unexpected class layout";
+    CU(cudaStreamSynchronize(stream));
+    uint32_t head[2] = {0, 0};   // which, has_next of this voice
+    CU(cudaMemcpy2D(head, 4, c.d_state + i, (size_t)Vc * 4, 4, 2, cudaMemcpyDeviceToHost));
+    if (head[1]) return "slot: a crossfade is in progress on this voice; set again when it has finished";
+    const int inst = (int)(head[0] ^ 1u);
+    if (!slot_arm(nodes[voice].get(), n.release(), inst, ease, fade_time)) return "slot: the unit's graph class differs from the slot's (same type expression needed)";
+    Lowering l;
+    nodes[voice]->lower(l);
+    if (!l.ok) return l.why;
+    if (l.U != c.uniform || l.P.size() != c.np || l.S.size() != c.ns) return "slot: the unit changes a class-uniform word (delay length, table, wave); rebuild the bank instead";
+    const uint32_t xs = (c.ns - 4) / 2, s0 = 4 + (uint32_t)inst * xs;
+    const uint64_t xd = c.dl_floats / 2;
+    CU(cudaMemcpy2DAsync(c.d_params + i, (size_t)Vc * 4, l.P.data(), 4, 4, c.np, cudaMemcpyHostToDevice, stream));
+    if (xs) CU(cudaMemcpy2DAsync(c.d_state + (size_t)s0 * Vc + i, (size_t)Vc * 4, l.S.data() + s0, 4, 4, xs, cudaMemcpyHostToDevice, stream));
+    if (xd) CU(cudaMemset2DAsync(c.d_dline + (size_t)inst * xd * Vc + i, (size_t)Vc * 4, 0, 4, (size_t)xd, stream));
+    const uint32_t arm[3] = {1u, 0u, 0u};   // has_next = 1, fade_phase = 0.0
+    CU(cudaMemcpy2DAsync(c.d_state + (size_t)1 * Vc + i, (size_t)Vc * 4, arm, 4, 4, 3, cudaMemcpyHostToDevice, stream));
+    for (uint32_t k = 0; k < c.ns; k++) c.state0[(size_t)k * Vc + i] = l.S[k];   // reset() adopts the newest unit (:156-172)
+    CU(cudaStreamSynchronize(stream));
+    return "";
+  }
+  return "internal: voice not found in any class";
+}
+
 std::string Bank::push_event(HNode* node, uint32_t* voice) {   // Sequencer::push on a running sequencer (src/sequencer.rs:319-360)
   std::unique_ptr<HNode> n(node);
   double s0, e0;

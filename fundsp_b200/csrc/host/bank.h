@@ -67,6 +67,7 @@ struct Bank {
   std::string edit_event(uint32_t voice, double end_time, double fade_out);   // Sequencer::edit
   std::string replace_voice(uint32_t voice, HNode* node);                     // a new unit in the slot of a voice of the same class; consumes node
   std::string add_voice(HNode* unit, uint32_t* voice);                        // grow by one voice, running state of the others preserved; consumes unit
+  std::string slot_set(uint32_t voice, int ease, double fade_time, HNode* unit);   // Slot::set: crossfade the voice to a unit of the same class; consumes unit
   std::string push_event(HNode* event, uint32_t* voice);                      // Sequencer::push on a running bank: takes the slot of a finished event of the same class; consumes event
   std::string set(uint32_t voice, const Setting& s);  // AudioUnit::set on one voice of a live bank (parameters only; state continues)
   std::string ensure_staging(uint32_t chunk);

@@ -671,6 +671,23 @@ struct OversampleN : HNode {  // src/oversample.rs:68-245
   void lower(Lowering& l) const override { l.su(0u); l.su(0u); l.dlen.push_back(128u * (uint32_t)(x->inputs() + x->outputs())); x->lower(l); }
   HCLONE(OversampleN)
 };
+struct SlotN : HNode {  // src/slot.rs: two instances of one class in the voice (device: nodes.cuh Slot<X>); `newest` is what reset() adopts (:156-172)
+  Kid u[2]; int newest = 0, ease = 1; double fade_time = 0.0, sr = DEFAULT_SR;
+  explicit SlotN(HNode* x) { u[0] = Kid(x); u[1] = Kid(x->clone()); }
+  int inputs() const override { return u[0]->inputs(); } int outputs() const override { return u[0]->outputs(); }
+  uint64_t id() const override { return 78; }
+  void reset() override { u[0]->reset(); u[1]->reset(); }
+  void set_sample_rate(double s) override { sr = s; u[0]->set_sample_rate(s); u[1]->set_sample_rate(s); }
+  AttoHash ping(bool, AttoHash h) override { return h.hash(id()); }   // SlotBackend::ping hands its hash to set_hash of the boxed units, which reaches leaves only (:279-291)
+  void sig(std::string& o) const override { o += "Slot<"; u[0]->sig(o); o += ">"; }
+  static void p64(Lowering& l, double v) { uint64_t b; memcpy(&b, &v, 8); l.P.push_back((uint32_t)b); l.P.push_back((uint32_t)(b >> 32)); }
+  void lower(Lowering& l) const override {
+    p64(l, sr); p64(l, fade_time); l.P.push_back((uint32_t)ease);
+    l.su((uint32_t)newest); l.su(0u); l.su(0u); l.su(0u);   // which, has_next, fade_phase = 0.0
+    u[0]->lower(l); u[1]->lower(l);
+  }
+  HCLONE(SlotN)
+};
 struct VarN : HNode {  // the shared value is control-plane state: it enters as a parameter word and changes through Setting::value
   float value; explicit VarN(float v) : value(v) {}
   int inputs() const override { return 0; } int outputs() const override { return 1; }
@@ -1008,6 +1025,7 @@ HNode* mk_reverb3(double time, double diffusion, HNode* filter) {
   return new ReverbN(time, diffusion, filter);
 }
 HNode* mk_var(float value) { return new VarN(value); }
+HNode* mk_slot(HNode* x) { return x ? new SlotN(x) : nullptr; }
 HNode* mk_oversample(HNode* x) {   // the block path decimates as many channels as X has inputs (:207): more inputs than outputs would index past the outputs
   if (!x || x->outputs() < 1 || x->inputs() > x->outputs()) { delete x; return nullptr; }
   return new OversampleN(x);
@@ -1016,6 +1034,19 @@ HNode* mk_envelope(double interval, int outputs, int time_f64, EnvelopeFn f, voi
   if (!(interval > 0.0) || outputs < 1 || outputs > 8 || !f || !(horizon >= 0.0) || horizon / interval > 4.0e6) return nullptr;   // assert!(interval > F::zero())
   return new EnvelopeN(time_f64 ? interval : (double)(float)interval, outputs, time_f64, f, user, horizon);
 }
+// Slot::set (src/slot.rs:64-71) into instance `inst` of a slot voice: false when `n` is not a slot or the unit is of another class
+bool slot_arm(HNode* n, HNode* unit, int inst, int ease, double fade_time) {
+  SlotN* s = dynamic_cast<SlotN*>(n);
+  std::unique_ptr<HNode> keep(unit);
+  if (!s || !unit || inst < 0 || inst > 1) return false;
+  std::string a, b; unit->sig(a); s->u[0]->sig(b);
+  if (a != b || unit->inputs() != s->inputs() || unit->outputs() != s->outputs()) return false;
+  unit->set_sample_rate(s->sr);
+  s->u[inst] = Kid(keep.release());
+  s->newest = inst; s->ease = ease; s->fade_time = fade_time;
+  return true;
+}
+bool is_slot(const HNode* n) { return dynamic_cast<const SlotN*>(n) != nullptr; }
 bool event_edit(HNode* n, double end_time, double fade_out) {   // Sequencer::edit on an event (:441-483, no loop: start == original start)
   EventN* e = dynamic_cast<EventN*>(n);
   if (!e) return false;

@@ -123,6 +123,9 @@ bool event_set_clock(HNode* n, double time);                         // the sequ
 typedef void (*EnvelopeFn)(double t, double* out, void* user);
 HNode* mk_envelope(double interval, int outputs, int time_f64, EnvelopeFn f, void* user, double horizon);
 HNode* mk_oversample(HNode* x);                                      // Oversampler ID 51; consumes x
+HNode* mk_slot(HNode* x);                                            // SlotBackend ID 78: a replaceable unit; consumes x
+bool slot_arm(HNode* slot, HNode* unit, int instance, int ease, double fade_time);   // consumes unit
+bool is_slot(const HNode* n);
 HNode* mk_declick(float duration);                                   // Declick ID 23
 HNode* mk_chaos(int kind);                                           // 0 Rossler ID 73, 1 Lorenz ID 74
 HNode* mk_morph(float cutoff, float q);                               // Morph ID 62

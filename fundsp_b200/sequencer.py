@@ -32,6 +32,11 @@ def event(unit: An, start_time, end_time, fade_ease=Fade.Smooth, fade_in_time=0.
     return An("event", (float(start_time), float(end_time), int(fade_ease), float(fade_in_time), float(fade_out_time)), (unit,), 0, unit.outputs())
 
 
+def slot(unit: An):
+    """`Slot::new(unit)` as a voice graph: a unit that `GpuBank.slot_set` can replace with a crossfade (src/slot.rs)."""
+    return An("slot", (), (unit,), unit.inputs(), unit.outputs())
+
+
 class Sequencer:
     def __init__(self, inputs, outputs, mode=ReplayMode.None_):  # Sequencer::new (src/sequencer.rs:272-300)
         self.nin, self.nout, self.mode = int(inputs), int(outputs), mode

@@ -195,6 +195,13 @@ int fdsp_bank_push_event(fdsp_bank* b, fdsp_node* event, uint32_t* voice);
 int fdsp_bank_replace_voice(fdsp_bank* b, uint32_t voice, fdsp_node* unit);
 int fdsp_bank_add_voice(fdsp_bank* b, fdsp_node* unit, uint32_t* voice);
 double fdsp_bank_time(const fdsp_bank* b);
+/* Slot / SlotBackend (src/slot.rs): fdsp_slot(unit) is a voice whose unit can be replaced while the bank runs; fdsp_bank_slot_set is
+   Slot::set(fade, fade_time, unit): the voice crossfades to `unit` over fade_time seconds (fade 0 Power, 1 Smooth) with the reference's
+   block arithmetic. No new program is built: `unit` must be of the voice's graph class (same type expression and class-uniform words,
+   e.g. the same instrument with other parameters), else FDSP_ERR_UNSUPPORTED — as it is while a previous crossfade of that voice is
+   still running (the reference would park the update as `latest`). Both consume their node argument. */
+fdsp_node* fdsp_slot(fdsp_node* unit);
+int fdsp_bank_slot_set(fdsp_bank* b, uint32_t voice, int fade_ease, double fade_time, fdsp_node* unit);
 int fdsp_bank_reset(fdsp_bank* b);                                          /* AudioUnit::reset */
 /* AudioUnit::set (src/audiounit.rs:62) on voice `voice` of a live bank: same encoding as fdsp_node_set. Parameters change at
    once, running state continues; FDSP_ERR_UNSUPPORTED when the setting would change a delay length (rebuild the bank). */

@@ -231,6 +231,7 @@ inline An flanger(float feedback_amount, float minimum_delay, float maximum_dela
   return pass() & feedback2((pass() | lfo(delay_f, 1, user, horizon)) >> tap(minimum_delay, maximum_delay), shape(Tanh{feedback_amount}));
 }
 enum class Fade { Power = 0, Smooth = 1 };                                                 // src/sequencer.rs:35-52
+inline An slot(An unit) { return An(fdsp_slot(unit.release())); }                             // Slot::new: replaceable with a crossfade (Bank::slot_set)
 // one Sequencer event as a voice (Sequencer::push, src/sequencer.rs:319-345): a Bank of events is the sequencer
 inline An event(An unit, double start_time, double end_time, Fade ease = Fade::Smooth, double fade_in = 0.0, double fade_out = 0.0) {
   return An(fdsp_event(unit.release(), start_time, end_time, (int)ease, fade_in, fade_out));
@@ -301,6 +302,7 @@ class Bank {
   void edit_event(uint32_t voice, double end_time, double fade_out) { check(fdsp_bank_edit_event(b_, voice, end_time, fade_out)); }
   uint32_t push_event(An ev) { uint32_t v = 0; check(fdsp_bank_push_event(b_, ev.release(), &v)); return v; }
   void replace_voice(uint32_t voice, An unit) { check(fdsp_bank_replace_voice(b_, voice, unit.release())); }
+  void slot_set(uint32_t voice, Fade fade, double fade_time, An unit) { check(fdsp_bank_slot_set(b_, voice, (int)fade, fade_time, unit.release())); }   // Slot::set
   uint32_t add_voice(An unit) { uint32_t v = 0; check(fdsp_bank_add_voice(b_, unit.release(), &v)); return v; }   // grows the bank; the others keep their state
   // AudioUnit::process: buffers are [channel][64]
   void process(uint32_t size, const float* input, float* output) { check(fdsp_bank_process(b_, size, input, output)); }

@@ -2341,4 +2341,90 @@ struct Sequencer : Node {
   }
 };
 
+// ---- src/slot.rs Slot + SlotBackend (ID 78) merged: a unit that can be replaced with a crossfade. `set` queues an update that the
+// next tick / process picks up (handle_messages :124-142): the first becomes `next` and fades in over fade_time while `current` fades
+// out; one that arrives during a fade waits as `latest` (replacing an earlier one) and starts when the fade ends. Units are NOT re-rated
+// on arrival (only set_sample_rate touches them, :175-185).
+struct Slot : Node {
+  struct Update { int fade; double fade_time; Child unit; };
+  int nin, nout; double sample_rate = DEFAULT_SR;
+  Child current, next, latest; bool has_next = false, has_latest = false;
+  int fade = 1, latest_fade = 1; double fade_time = 0.0, fade_phase = 0.0, latest_fade_time = 0.0;
+  std::vector<Update> queue; std::vector<float> buffer, tick_buf;
+  explicit Slot(Node* unit) : nin(unit->inputs()), nout(unit->outputs()), current(unit) {
+    current->set_sample_rate(DEFAULT_SR);
+    buffer.assign((size_t)std::max(1, nout) * B, 0.0f); tick_buf.assign(std::max(1, nout), 0.0f);
+  }
+  void set(int fade_, double fade_time_, Node* unit) { assert(unit->inputs() == nin && unit->outputs() == nout); queue.push_back(Update{fade_, fade_time_, Child(unit)}); }
+  void handle_messages() {
+    for (auto& m : queue) {
+      if (!has_next) { next = std::move(m.unit); has_next = true; fade_phase = 0.0; fade_time = m.fade_time; fade = m.fade; }
+      else { latest = std::move(m.unit); has_latest = true; latest_fade = m.fade; latest_fade_time = m.fade_time; }
+    }
+    queue.clear();
+  }
+  void next_phase() {   // :143-151
+    current = std::move(next);
+    fade = latest_fade; fade_phase = 0.0; fade_time = latest_fade_time;
+    if (has_latest) { next = std::move(latest); has_next = true; has_latest = false; } else has_next = false;
+  }
+  int inputs() const override { return nin; } int outputs() const override { return nout; }
+  uint64_t id() const override { return 78; }
+  void reset() override {   // :156-172: adopt the latest configuration, then reset it
+    if (has_latest) { current = std::move(latest); has_latest = false; has_next = false; }
+    else if (has_next) { current = std::move(next); has_next = false; }
+    current->reset();
+  }
+  void set_sample_rate(double sr) override {
+    sample_rate = sr; current->set_sample_rate(sr);
+    if (has_next) next->set_sample_rate(sr);
+    if (has_latest) latest->set_sample_rate(sr);
+  }
+  static float ease(int kind, float x) { return kind == 0 ? sine_easef(x) : smooth5f(x); }
+  void tick(const float* in, float* out) override {   // :187-203
+    handle_messages();
+    current->tick(in, out);
+    if (has_next) {
+      const float f = (float)ease_d(fade, 1.0 - fade_phase);
+      for (int c = 0; c < nout; c++) out[c] *= f;
+      next->tick(in, tick_buf.data());
+      const float g = (float)ease_d(fade, fade_phase);
+      for (int c = 0; c < nout; c++) out[c] += tick_buf[c] * g;
+      fade_phase += 1.0 / (fade_time * sample_rate);
+      if (fade_phase >= 1.0) next_phase();
+    }
+  }
+  static double ease_d(int kind, double x) {   // Fade::at::<f64> on the tick path
+    if (kind == 1) return ((x * 6.0 - 15.0) * x + 10.0) * x * x * x;
+    const double PI = 3.141592653589793; x = x * (PI * 0.5);
+    return 16.0 * x * (PI - x) / (5.0 * PI * PI - 4.0 * x * (PI - x));
+  }
+  void process(int size_, const float* in, float* out) override {   // :205-262
+    handle_messages();
+    const size_t size = (size_t)size_;
+    current->process(size_, in, out);
+    if (has_next) {
+      const size_t phase_left = as_usize((1.0 - fade_phase) * fade_time * sample_rate);
+      const size_t n = std::min(size, phase_left);
+      const float fade_d = (float)(1.0 / (fade_time * sample_rate));
+      for (int c = 0; c < nout; c++) { float f = (float)fade_phase; for (size_t i = 0; i < n; i++) { out[c * B + i] *= ease(fade, 1.0f - f); f += fade_d; } }
+      next->process(size_, in, buffer.data());
+      for (int c = 0; c < nout; c++) {
+        float f = (float)fade_phase;
+        for (size_t i = 0; i < n; i++) { out[c * B + i] += buffer[c * B + i] * ease(fade, f); f += fade_d; }
+        for (size_t i = n; i < size; i++) out[c * B + i] = buffer[c * B + i];
+      }
+      fade_phase += (double)n / (fade_time * sample_rate);
+      if (phase_left <= size) next_phase();
+    }
+  }
+  AttoHash ping(bool probe, AttoHash h) override { (void)probe; return h.hash(id()); }   // set_hash on the boxed units reaches leaves only (:279-291)
+  Node* clone() const override {
+    Slot* s2 = new Slot(current->clone());
+    s2->sample_rate = sample_rate; s2->has_next = has_next; s2->has_latest = has_latest; if (has_next) s2->next = next; if (has_latest) s2->latest = latest;
+    s2->fade = fade; s2->latest_fade = latest_fade; s2->fade_time = fade_time; s2->fade_phase = fade_phase; s2->latest_fade_time = latest_fade_time; s2->queue = queue;
+    return s2;
+  }
+};
+
 }  // namespace fo

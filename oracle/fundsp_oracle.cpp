@@ -90,6 +90,8 @@ API Node* fo_morph(float cutoff, float q) { return new Morph(cutoff, q); }
 API Node* fo_rez(float bandpass, float cutoff, float q, int inputs) { return new Rez(bandpass, cutoff, q, inputs); }
 API Node* fo_chaos(int kind) { return new Chaos(kind); }   // 0 rossler, 1 lorenz
 API Node* fo_declick(float duration) { return new Declick(duration); }
+API Node* fo_slot(Node* unit) { return new Slot(unit); }
+API void fo_slot_set(Node* slot, int fade, double fade_time, Node* unit) { static_cast<Slot*>(slot)->set(fade, fade_time, unit); }
 API Node* fo_oversample(Node* x) { return new Oversampler(x); }
 API Node* fo_monitor() { return new MultiPass(1, true, 56); }
 API Node* fo_envelope(double interval, int outputs, int time_f64, EnvelopeFn f, void* user) {

@@ -43,7 +43,7 @@ def lib():
             "fo_wavesynth": (P, [I, I]), "fo_noise": (P, []), "fo_fixed_svf": (P, [I, F, F, F]), "fo_svf": (P, [I, F, F, F]),
             "fo_biquad": (P, [F, F, F, F, F]), "fo_biquad_bank": (P, []), "fo_butterpass": (P, [F, I]), "fo_resonator": (P, [F, F, I]),
             "fo_moog": (P, [F, F, I]), "fo_fir": (P, [I, FP]), "fo_tick_node": (P, [I]), "fo_delay": (P, [D]), "fo_allnest": (P, [F, P, I]),
-            "fo_phase_osc": (P, [I]), "fo_dsf": (P, [I, F, F]), "fo_reverb3": (P, [D, D, P]), "fo_var": (P, [F]), "fo_nl_biquad": (P, [I, I, I, F, F, I, F, F, F]), "fo_declick": (P, [F]), "fo_oversample": (P, [P]), "fo_monitor": (P, []), "fo_envelope": (P, [D, I, I, C.CFUNCTYPE(None, C.c_double, C.POINTER(C.c_double), C.c_void_p), P]), "fo_sequencer": (P, [I, I, I, D]), "fo_sequencer_push": (C.c_uint64, [P, D, D, I, D, D, P]), "fo_sequencer_push_relative": (C.c_uint64, [P, D, D, I, D, D, P]), "fo_sequencer_edit": (None, [P, C.c_uint64, D, D]), "fo_sequencer_edit_relative": (None, [P, C.c_uint64, D, D]), "fo_sequencer_time": (D, [P]), "fo_limiter": (P, [I, F, F]), "fo_meter": (P, [I, D]), "fo_playwave": (P, [C.POINTER(C.c_float), C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64]), "fo_resample": (P, [P]), "fo_phase_synth": (P, [I]), "fo_pulse": (P, []), "fo_mixer": (P, [I, I, C.POINTER(C.c_float)]), "fo_rotate": (P, [F, F]), "fo_chaos": (P, [I]), "fo_morph": (P, [F, F]), "fo_rez": (P, [F, F, F, I]), "fo_follow": (P, [I, F, F]), "fo_shaper": (P, [I, F, F]), "fo_onepole": (P, [I, F, I]), "fo_convolve": (P, [FP, I]), "fo_feedback_unit": (P, [D, P]), "fo_libm_eval": (None, [I, FP, FP, FP, C.c_int64]), "fo_mls": (P, [I]), "fo_impulse": (P, [I]), "fo_tap": (P, [I, I, F, F]), "fo_feedback2": (P, [P, P, I]),
+            "fo_phase_osc": (P, [I]), "fo_dsf": (P, [I, F, F]), "fo_reverb3": (P, [D, D, P]), "fo_var": (P, [F]), "fo_nl_biquad": (P, [I, I, I, F, F, I, F, F, F]), "fo_declick": (P, [F]), "fo_slot": (P, [P]), "fo_slot_set": (None, [P, I, D, P]), "fo_oversample": (P, [P]), "fo_monitor": (P, []), "fo_envelope": (P, [D, I, I, C.CFUNCTYPE(None, C.c_double, C.POINTER(C.c_double), C.c_void_p), P]), "fo_sequencer": (P, [I, I, I, D]), "fo_sequencer_push": (C.c_uint64, [P, D, D, I, D, D, P]), "fo_sequencer_push_relative": (C.c_uint64, [P, D, D, I, D, D, P]), "fo_sequencer_edit": (None, [P, C.c_uint64, D, D]), "fo_sequencer_edit_relative": (None, [P, C.c_uint64, D, D]), "fo_sequencer_time": (D, [P]), "fo_limiter": (P, [I, F, F]), "fo_meter": (P, [I, D]), "fo_playwave": (P, [C.POINTER(C.c_float), C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64]), "fo_resample": (P, [P]), "fo_phase_synth": (P, [I]), "fo_pulse": (P, []), "fo_mixer": (P, [I, I, C.POINTER(C.c_float)]), "fo_rotate": (P, [F, F]), "fo_chaos": (P, [I]), "fo_morph": (P, [F, F]), "fo_rez": (P, [F, F, F, I]), "fo_follow": (P, [I, F, F]), "fo_shaper": (P, [I, F, F]), "fo_onepole": (P, [I, F, I]), "fo_convolve": (P, [FP, I]), "fo_feedback_unit": (P, [D, P]), "fo_libm_eval": (None, [I, FP, FP, FP, C.c_int64]), "fo_mls": (P, [I]), "fo_impulse": (P, [I]), "fo_tap": (P, [I, I, F, F]), "fo_feedback2": (P, [P, P, I]),
             "fo_pan": (P, [F]), "fo_panner": (P, []), "fo_adsr_live": (P, [F, F, F, F]), "fo_biquad_coefs": (None, [I, F, F, F, F, FP]),
             "fo_pipe": (P, [P, P]), "fo_stack": (P, [P, P]), "fo_branch": (P, [P, P]), "fo_bus": (P, [P, P]), "fo_thru": (P, [P]),
             "fo_binop": (P, [I, P, P]), "fo_unop": (P, [I, F, P]), "fo_multi": (P, [I, I, I, C.POINTER(P)]), "fo_feedback": (P, [P, I]),
@@ -118,6 +118,7 @@ class OracleBackend:
     def b_rez(self, bp, cutoff, q, nin): return self.L.fo_rez(bp, cutoff, q, nin)
     def b_chaos(self, kind): return self.L.fo_chaos(kind)
     def b_declick(self, d): return self.L.fo_declick(d)
+    def b_slot(self, x): return self.L.fo_slot(x)
     def b_oversample(self, x): return self.L.fo_oversample(x)
     def b_monitor(self): return self.L.fo_monitor()
     def b_envelope(self, interval, nout, t64, fn, horizon):   # the oracle calls the closure live, like the reference (no horizon)

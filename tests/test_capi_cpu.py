@@ -53,6 +53,7 @@ GRAPHS = [
     lambda: dc(220.0) >> lorenz() | dc(110.0) >> rossler() | dc(330.0) >> lorenz(),
     lambda: dc((220.0, 0.3)) >> pulse() | dc((220.0, 0.3)) >> pulse().phase(0.5) | (ramp_hz(50.0) >> phase_synth(3) | noise()) >> rotate(0.3, 0.5) >> mixer([[1.0, 2.0]]),
     lambda: (noise() | noise()) >> reverb4_stereo(25.0, 2.0),
+    lambda: __import__('fundsp_b200.sequencer', fromlist=['slot']).slot(saw_hz(110.0) >> lowpass_hz(800.0, 1.0) | noise()),
     lambda: noise() >> oversample(shape(Tanh(2.0)) >> lowpass_hz(5000.0, 1.0)) | oversample(saw_hz(110.0)) | noise() >> oversample(sine_hz(3.0) * pass_()),
     lambda: unit(noise() >> monitor() >> lowpass_hz(500.0, 1.0)) | noise() >> pass_() >> lowpass_hz(500.0, 1.0),     # Monitor hashes as ID 56, not as a Pass
     lambda: noise() >> flanger(0.5, 0.005, 0.010, lambda t: 0.0075, horizon=0.05) | noise() >> phaser(0.5, lambda t: 0.5, horizon=0.05) | white(),

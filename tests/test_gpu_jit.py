@@ -99,6 +99,7 @@ WIDER = {
     "phase_synth_tables": lambda i: ramp_hz(100.0 + 13.0 * i) >> (phase_synth(SQUARE) & phase_synth(ORGAN) * 0.5) | (sine_hz(50.0 + i) * 0.6) >> phase_synth(SOFT_SAW),
     "rotate_mixer": lambda i: (noise().seed(i) | sine_hz(200.0 + i)) >> rotate(0.1 * i, 0.8) >> mixer([[0.5, -0.25], [0.125 * (i % 8), 1.0], [1.0, 1.0]]),
     "reverb4_short_lines": lambda i: (noise().seed(i) | noise().seed(i + 100)) >> reverb4_stereo_delays([d * (0.15 + 0.002 * (i % 25)) for d in REVERB4_DELAYS], 1.0 + 0.05 * (i % 8)),
+    "slot_voices": lambda i: __import__("fundsp_b200.sequencer", fromlist=["slot"]).slot((saw_hz(110.0 + 5.0 * i) >> lowpass_hz(800.0 + 30.0 * i, 1.0 + 0.05 * i)) | noise().seed(i) >> declick_s(0.003)),
     "oversampled_distortion": lambda i: (sine_hz(2000.0 + 150.0 * i) * (1.0 + 0.1 * i) | noise().seed(i)) >> oversample(shape(Tanh(1.0 + 0.05 * i)) | lowpass_hz(4000.0 + 100.0 * i, 1.0)),
     "oversampled_oscillator_mix": lambda i: noise().seed(i) * 0.01 >> oversample(pass_() + (saw_hz(300.0 + 20.0 * i) >> lowpole_hz(5000.0)) * 0.5 >> declick_s(0.002)),
     "flanger_phaser": lambda i: noise().seed(i) >> flanger(0.3 + 0.01 * (i % 40), 0.001, 0.004, lambda t, i=i: 0.0025 + 0.0015 * math.sin((20.0 + i) * t), horizon=0.1) | noise().seed(i + 7) >> phaser(0.2 + 0.01 * (i % 50), lambda t, i=i: 0.5 + 0.5 * math.sin((30.0 + i) * t), horizon=0.1),

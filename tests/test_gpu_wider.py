@@ -152,3 +152,43 @@ def test_gpu_sequencer_note_ons_while_running():
     assert np.abs(want).max() > 0.5 and _close(got, want)
     g.reset()                                                         # ReplayMode::None: emptied
     assert not g.render(2048).any()
+
+
+def test_slot_crossfades_to_a_new_unit():
+    """Slot / SlotBackend (src/slot.rs) as voices: units replaced with a crossfade while the bank runs, no new program built. Per-voice rows
+    are bit-exact against oracle Slots that receive the same `set` calls at the same times."""
+    from fundsp_b200.bank import GpuBank
+    from fundsp_b200.capi import FdspError
+    from fundsp_b200.prelude import saw_hz, lowpass_hz, sine_hz
+    from fundsp_b200.sequencer import slot, Fade
+    from oracle import OracleBackend, OracleUnit, lib as olib
+    L = olib()
+    L.fo_set_denormal_emulation(0)
+    sr = 44100.0                                   # (the reference does not re-rate a unit that arrives through Slot::set)
+    voice = lambda f, q=1.0: saw_hz(f) >> lowpass_hz(3.0 * f, q)
+    V = 6
+    b = GpuBank([slot(voice(110.0 * (k + 1))) for k in range(V)], per_voice=True, mix=False, sample_rate=sr)
+    us = [OracleUnit(slot(voice(110.0 * (k + 1)))) for k in range(V)]
+    be = OracleBackend()
+
+    def both(n):
+        g = b.render_samples(n)[0]
+        o = np.stack([u.process_many(n) for u in us])
+        assert np.array_equal(g, o), (int((g != o).sum()), float(np.abs(g - o).max()))
+        return g
+
+    both(64 * 5)
+    b.slot_set(2, Fade.Smooth, 0.01, voice(500.0, 2.0)); L.fo_slot_set(us[2].h, 1, 0.01, voice(500.0, 2.0).lower(be))
+    b.slot_set(4, Fade.Power, 0.003, voice(77.0)); L.fo_slot_set(us[4].h, 0, 0.003, voice(77.0).lower(be))
+    g = both(64 * 3 + 17)                          # mid-fade, ragged block
+    with pytest.raises(FdspError):
+        b.slot_set(2, Fade.Smooth, 0.01, voice(300.0))     # still fading: refused (the reference would park it as `latest`)
+    with pytest.raises(FdspError):
+        b.slot_set(1, Fade.Smooth, 0.01, sine_hz(300.0))   # another graph class
+    both(64 * 9)                                   # both fades have ended: the new units play alone
+    b.slot_set(2, Fade.Power, 0.002, voice(250.0)); L.fo_slot_set(us[2].h, 0, 0.002, voice(250.0).lower(be))   # the roles have swapped: the other instance takes it
+    both(64 * 4 + 5)
+    b.reset()                                      # reset adopts the newest units (:156-172)
+    for u in us:
+        u.reset()
+    assert np.abs(both(64 * 3)).max() > 0.1
