@@ -192,3 +192,36 @@ def test_slot_crossfades_to_a_new_unit():
     for u in us:
         u.reset()
     assert np.abs(both(64 * 3)).max() > 0.1
+
+
+def test_bank_grows_with_a_new_waveform_and_keeps_running_state():
+    """fdsp_bank_add_voice: voices with delay lines and filter state keep running bit for bit while the bank is rebuilt around them, and
+    a newcomer may bring a wavetable the bank had not loaded."""
+    from fundsp_b200.bank import GpuBank
+    from fundsp_b200.prelude import sine_hz, noise, feedback, delay, lowpass_hz, square_hz, organ_hz
+    from oracle import OracleUnit, lib as olib
+    olib().fo_set_denormal_emulation(0)
+    sr = 48000.0
+    echo = lambda i: noise().seed(i) * 0.3 >> lowpass_hz(900.0 + 100.0 * i, 1.0) >> feedback(delay(0.002 + 0.0005 * i) * 0.6)
+    voices = [sine_hz(200.0 + 10.0 * i) for i in range(3)] + [echo(i) for i in range(3)]
+    b = GpuBank(voices, per_voice=True, mix=False, sample_rate=sr)
+    us = [OracleUnit(v) for v in voices]
+    for u in us:
+        u.set_sample_rate(sr)
+
+    def both(n):
+        g = b.render_samples(n)[0]
+        o = np.stack([u.process_many(n) for u in us])
+        assert np.array_equal(g, o), (int((g != o).sum()), float(np.abs(g - o).max()))
+
+    both(64 * 7 + 3)
+    for newcomer in (square_hz(330.0) >> lowpass_hz(2000.0, 1.0), echo(7), organ_hz(150.0)):   # a new class with a table, an existing class, another table
+        v = b.add_voice(newcomer)
+        assert v == len(us) and b.voices() == len(us) + 1
+        u = OracleUnit(newcomer); u.set_sample_rate(sr); us.append(u)
+        both(64 * 5 + 11)
+    assert len(b.classes()) == 7                  # sine, four echo delay lengths (class-uniform words), square+filter, organ
+    b.reset()
+    for u in us:
+        u.reset()
+    both(64 * 4)
