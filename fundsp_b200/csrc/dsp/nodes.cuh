@@ -1229,6 +1229,7 @@ template <class X> struct Event {
   struct R {
     double sr, sd, start, end, fin, fout, time; int ease, status;   // status 0 ready, 1 active, 2 past
     int s_idx, n_v, nfull_v, fi_end, fo_i, fo_end; float fi_cur, fi_d, fo_cur, fo_d; bool fi_on, fo_on;
+    bool whole;   // this block: the event spans it entirely and no fade touches it -> X runs its own 8-sample group form (step8)
     typename X::R x;
   };
   static FDSP_DEV double ld64(Loader& l, bool state) {
@@ -1239,7 +1240,7 @@ template <class X> struct Event {
     r.sr = ld64(l, false); r.start = ld64(l, false); r.end = ld64(l, false); r.fin = ld64(l, false); r.fout = ld64(l, false); r.ease = (int)l.P();
     r.sd = 1.0 / r.sr;
     r.time = ld64(l, true); r.status = (int)l.S();
-    r.s_idx = r.n_v = r.nfull_v = r.fi_end = r.fo_i = r.fo_end = 0; r.fi_cur = r.fi_d = r.fo_cur = r.fo_d = 0.0f; r.fi_on = r.fo_on = false;
+    r.s_idx = r.n_v = r.nfull_v = r.fi_end = r.fo_i = r.fo_end = 0; r.fi_cur = r.fi_d = r.fo_cur = r.fo_d = 0.0f; r.fi_on = r.fo_on = false; r.whole = false;
     X::load(r.x, l);
   }
   static FDSP_DEV void save(const R& r, Saver& s) {
@@ -1250,7 +1251,7 @@ template <class X> struct Event {
   static FDSP_DEV void plan(R& r, int n) {   // Sequencer::process for this event, :768-843
     const double end_blk = r.time + r.sd * (double)n;
     if (r.status == 0 && r.start < end_blk - r.sd * 0.5) r.status = 1;                 // ready_to_active
-    r.n_v = 0; r.s_idx = 0; r.nfull_v = 0; r.fi_on = r.fo_on = false;
+    r.n_v = 0; r.s_idx = 0; r.nfull_v = 0; r.fi_on = r.fo_on = false; r.whole = false;
     if (r.status == 1) {
       if (r.end <= r.time + 0.5 * r.sd) r.status = 2;                                  // end_of_event
       else {
@@ -1277,18 +1278,22 @@ template <class X> struct Event {
         }
       }
     }
+    r.whole = r.n_v == n && !r.fi_on && !r.fo_on;
     r.time = end_blk;
   }
   template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<0>& in, Fr<NO>& o) {
     if (T) { X::template step<true>(r.x, c, in, o); return; }   // (an event is always the root of a voice: not reached)
     if (c.i == 0) plan(r, c.n);
+    step_planned(r, c, in, o);
+  }
+  template <class C> static FDSP_DEV void step_planned(R& r, const C& c, const Fr<0>& in, Fr<NO>& o) {
     const int b = c.i - r.s_idx;
     if (b >= 0 && b < r.n_v) {
       C c2 = c;
       c2.n = r.n_v; c2.i = b; c2.rem = b >= r.nfull_v; c2.first = !c2.rem && (b & 7) == 0;
-      if (b == r.nfull_v) X::end_simd(r.x);                       // the unit's own block: SIMD part done, tail through its tick path
-      X::template step<false>(r.x, c2, in, o);
-      if (b == r.n_v - 1 && r.nfull_v == r.n_v) X::end_simd(r.x); // no tail
+      if (b == r.nfull_v && !r.whole) X::end_simd(r.x);           // the unit's own block: SIMD part done, tail through its tick path
+      X::template step<false>(r.x, c2, in, o);                    // (a whole block: the kernel's end_simd call reaches X through end_simd below)
+      if (b == r.n_v - 1 && r.nfull_v == r.n_v && !r.whole) X::end_simd(r.x); // no tail
       float g = 1.0f; bool scaled = false;
       if (r.fi_on && b < r.fi_end) { g = r.ease == 0 ? sine_ease_f(r.fi_cur) : smooth5f(r.fi_cur); r.fi_cur += r.fi_d; scaled = true; }
       if (scaled) {
@@ -1305,7 +1310,38 @@ template <class X> struct Event {
       for (int k = 0; k < NO; k++) o.v[k] = 0.0f;
     }
   }
-  static FDSP_DEV void end_simd(R&) {}
+  // Steady state of a note — the block lies inside the event and outside its fades — is X's own group form at full speed; every
+  // other block (start, end, fades, silence) takes the per-sample path above. The plan is made by the block's first group.
+  typedef void GroupStep;
+  template <class C> static FDSP_DEV void step8(R& r, C& c, const Fr8<0>& in, Fr8<NO>& o) {
+    if (c.i == 0) plan(r, c.n);
+    if (r.whole) { group_step<X>(r.x, c, in, o); return; }
+    if (r.n_v == 0) {
+#pragma unroll
+      for (int k = 0; k < NO; k++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) o.v[k][j] = 0.0f;
+      }
+      return;
+    }
+    const int base = c.i;
+    const bool planned = true;
+    (void)planned;
+#pragma unroll 1
+    for (int j = 0; j < 8; j++) {
+      Fr<0> none; Fr<NO> y;
+      c.i = base + j; c.first = (j == 0);
+      step_planned(r, c, none, y);
+#pragma unroll
+      for (int k = 0; k < NO; k++) {
+#pragma unroll
+        for (int q = 0; q < 7; q++) o.v[k][q] = o.v[k][q + 1];
+        o.v[k][7] = y.v[k];
+      }
+    }
+    c.i = base; c.first = true;
+  }
+  static FDSP_DEV void end_simd(R& r) { if (r.whole) X::end_simd(r.x); }
 };
 
 // ---------------------------------------------------------------- Oversample<X> (Oversampler ID 51, src/oversample.rs): X at twice
@@ -2028,6 +2064,7 @@ template <int K, class X> struct GroupPlan<Unop<K, X>> { static constexpr bool o
 template <class X> struct GroupPlan<Thru<X>> : GroupPlan<X> {};
 template <int KIND, int OP, int N, class X> struct GroupPlan<Multi<KIND, OP, N, X>> { static constexpr bool ok = GroupPlan<X>::ok; static constexpr int code = N * GroupPlan<X>::code; };
 
+template <class X> struct GroupPlan<Event<X>> { static constexpr bool ok = GroupPlan<X>::ok; static constexpr int code = GroupPlan<X>::code + 24; };
 template <int NIN, int NOUT, class... V, class OS> struct GroupPlan<Dag<NIN, NOUT, VList<V...>, OS>> {
   static constexpr bool ok = (true && ... && GroupPlan<typename V::Unit>::ok);
   static constexpr int code = (2 + ... + GroupPlan<typename V::Unit>::code);
