@@ -1512,6 +1512,33 @@ template <class X> struct Slot {
       }
     }
   }
+  // No replacement pending: the current unit's own group form at full speed. A block with a fade runs both units per sample.
+  typedef void GroupStep;
+  template <class C> static FDSP_DEV void step8(R& r, C& c, const Fr8<NI>& in, Fr8<NO>& o) {
+    if (!r.has_next) { if (r.which) group_step<X>(r.u[1], c, in, o); else group_step<X>(r.u[0], c, in, o); return; }
+    const int base = c.i;
+    Fr8<NI> ri = in;
+#pragma unroll 1
+    for (int j = 0; j < 8; j++) {
+      Fr<NI> a; Fr<NO> y;
+#pragma unroll
+      for (int k = 0; k < NI; k++) a.v[k] = ri.v[k][0];
+      c.i = base + j; c.first = (j == 0);
+      step<false>(r, c, a, y);
+#pragma unroll
+      for (int k = 0; k < NI; k++) {
+#pragma unroll
+        for (int q = 0; q < 7; q++) ri.v[k][q] = ri.v[k][q + 1];
+      }
+#pragma unroll
+      for (int k = 0; k < NO; k++) {
+#pragma unroll
+        for (int q = 0; q < 7; q++) o.v[k][q] = o.v[k][q + 1];
+        o.v[k][7] = y.v[k];
+      }
+    }
+    c.i = base; c.first = true;
+  }
   static FDSP_DEV void end_simd(R& r) { X::end_simd(r.u[0]); X::end_simd(r.u[1]); }
 };
 
@@ -2064,6 +2091,7 @@ template <int K, class X> struct GroupPlan<Unop<K, X>> { static constexpr bool o
 template <class X> struct GroupPlan<Thru<X>> : GroupPlan<X> {};
 template <int KIND, int OP, int N, class X> struct GroupPlan<Multi<KIND, OP, N, X>> { static constexpr bool ok = GroupPlan<X>::ok; static constexpr int code = N * GroupPlan<X>::code; };
 
+template <class X> struct GroupPlan<Slot<X>> { static constexpr bool ok = GroupPlan<X>::ok; static constexpr int code = GroupPlan<X>::code + 16; };
 template <class X> struct GroupPlan<Event<X>> { static constexpr bool ok = GroupPlan<X>::ok; static constexpr int code = GroupPlan<X>::code + 24; };
 template <int NIN, int NOUT, class... V, class OS> struct GroupPlan<Dag<NIN, NOUT, VList<V...>, OS>> {
   static constexpr bool ok = (true && ... && GroupPlan<typename V::Unit>::ok);
