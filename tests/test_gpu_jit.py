@@ -109,6 +109,7 @@ WIDER = {
     # sequencer events (src/sequencer.rs): per-voice start / end / fades; checked against one-event Sequencers of the oracle
     "events_saw_filter": lambda i: _ev(saw_hz(110.0 + 3.0 * i) >> lowpass_hz(900.0 + 20.0 * i, 2.0), (31.0 + 37.7 * i) / SR, (31.0 + 37.7 * i + 600.3 + 23.1 * i) / SR, 1, (40.5 + i) / SR, (200.0 + 5 * i) / SR),
     "events_power_fades_stereo": lambda i: _ev(sine_hz(300.0 + i) | noise().seed(i), (1.0 + 0.37 * i) * 64.0 / SR, ((1.0 + 0.37 * i) * 64.0 + 700.0 + 11.0 * i) / SR, 0, (100.0 + 3.3 * i) / SR, (300.0 + 2.1 * i) / SR),
+    "events_moog_program": lambda i: _ev(saw_hz(80.0 + 4.0 * i) >> moog_hz(700.0 + 30.0 * i, 0.5) >> pan(0.02 * i - 0.4), (17.0 + 9.3 * i) / SR, (17.0 + 9.3 * i + 900.0) / SR, i % 2, (50.0 + i) / SR, (250.0 + 3 * i) / SR),
     "events_short_and_late": lambda i: _ev(organ_hz(200.0 + 5.0 * i) >> declick_s(0.002), (i * 50.25) / SR, (i * 50.25 + 1.0 + 9.0 * (i % 13)) / SR, i % 2, 0.0, 0.0) if i % 3 else _ev(organ_hz(200.0 + 5.0 * i) >> declick_s(0.002), 5000.0 / SR, 6000.0 / SR, 1, 0.0, 0.0),
     "limiters": lambda i: noise().seed(i) * (1.0 + 0.2 * i) >> limiter(0.001 + 0.0004 * (i % 2), 0.01) | (noise().seed(i + 50) * (sine_hz(3.0) * 2.0 + 2.5) | sine_hz(300.0 + i) * 4.0) >> limiter_stereo(0.0005, 0.003 + 0.001 * (i % 3)),
     "meters": lambda i: noise().seed(i) * (0.2 + 0.02 * i) >> (meter(Meter.Sample) & meter(Meter.Peak(0.002 + 0.0005 * (i % 9))) & meter(Meter.Rms(0.001 + 0.0003 * (i % 7)))),
