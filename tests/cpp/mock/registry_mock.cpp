@@ -44,7 +44,8 @@ std::shared_ptr<const Program> get_program(const std::string& sig, int, std::str
   const std::string so = std::string(dir) + name;
   if (access(so.c_str(), R_OK) != 0) {
     const std::string tmp = so + ".tmp" + std::to_string((long)getpid());
-    const std::string cmd = "g++ -std=c++17 -O1 -ffp-contract=off -w -shared -fPIC '-DGRAPH=" + sig + "' -I '" + root + "/fundsp_b200/csrc' '" + root +
+    const char* extra = getenv("FDSP_MOCK_CXXFLAGS");   // e.g. -fsanitize=address -g for a sanitizer run of the whole suite
+    const std::string cmd = std::string("g++ -std=c++17 -O1 -ffp-contract=off -w -shared -fPIC ") + (extra ? extra : "") + " '-DGRAPH=" + sig + "' -I '" + root + "/fundsp_b200/csrc' '" + root +
                             "/tests/cpp/mock/emul_module.cpp' -o '" + tmp + "' 2> '" + so + ".log' && mv '" + tmp + "' '" + so + "'";
     if (system(cmd.c_str()) != 0) { err = "mock registry: g++ failed for `" + sig + "` (see " + so + ".log)"; return nullptr; }
   }
