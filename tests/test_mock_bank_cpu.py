@@ -37,6 +37,10 @@ SAN = os.environ.get("FDSP_MOCK_SANITIZE", "")   # "address" or "undefined": bui
 def mock_env():
     build = os.path.join(MOCK, "_build", _tree_hash() + ("_" + SAN if SAN else ""))        # keyed by every source that goes into it: never stale
     os.makedirs(build, exist_ok=True)
+    for d in os.listdir(os.path.dirname(build)):            # builds of older sources are never used again
+        if not d.startswith(_tree_hash()):
+            import shutil
+            shutil.rmtree(os.path.join(os.path.dirname(build), d), ignore_errors=True)
     lib = os.path.join(build, "libfundsp_b200_mock.so")
     if not os.path.exists(lib):
         srcs = [os.path.join(CSRC, "host", f) for f in ("graph.cpp", "wavetable.cpp", "bank.cpp", "wavfile.cpp")] + [os.path.join(CSRC, "capi.cpp"), os.path.join(MOCK, "registry_mock.cpp")]
