@@ -126,6 +126,14 @@ def net_voice(i):
     return g >> pan(p)
 
 
+# ---- the headline voices as sequencer events (src/sequencer.rs): notes that start within the first half second and are held, so the
+# steps after the first measure the steady state of Event<X> (the block plan + X's own group form) against the plain `saw_svf` bank
+def saw_svf_event_voice(i):
+    from .sequencer import event, Fade
+    start = 0.5 * u(i, 4)
+    return event(saw_svf_voice(i), start, start + 1.0e6, Fade.Smooth, 0.005, 0.0)
+
+
 WORKLOADS = {
     # name: (voice builder, default voices, inputs)
     "fm": (fm_voice, 4096),
@@ -135,6 +143,7 @@ WORKLOADS = {
     "subtractive_dry": (subtractive_dry_voice, 1024),
     "subtractive": (subtractive_voice, 1024),
     "net": (net_voice, 65536),
+    "saw_svf_events": (saw_svf_event_voice, 16384),
 }
 
 

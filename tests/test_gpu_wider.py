@@ -225,3 +225,21 @@ def test_bank_grows_with_a_new_waveform_and_keeps_running_state():
     for u in us:
         u.reset()
     both(64 * 4)
+
+
+def test_event_workload_of_the_bench_matches_oracle():
+    """`bench.py --workload saw_svf_events`: the headline voices as held sequencer events (start within 0.5 s, fade-in 5 ms)."""
+    from fundsp_b200 import workloads
+    from fundsp_b200.bank import GpuBank
+    from oracle import lib as olib, oracle_bank_render
+    olib().fo_set_denormal_emulation(0)
+    V, n, sr = 64, 28800, 48000.0
+    b = GpuBank(workloads.build("saw_svf_events", V), per_voice=True, mix=True, sample_rate=sr)
+    rows, mix = b.render_samples(n)
+    ref, _ = oracle_bank_render(workloads.build("saw_svf_events", V), sr, n, threads=4)
+    assert np.array_equal(rows, ref) and np.abs(ref[:, :, -64:]).max(axis=(1, 2)).min() > 0.0     # every note has started and is held
+    assert _close(mix, ref.astype(np.float64).sum(0).astype(np.float32))
+    rows2, _ = b.render_samples(4800)                 # steady state: every block is a whole block of every event
+    ref2 = np.stack([r for r in rows2])               # (shape check only; continuity against the oracle below)
+    o = oracle_bank_render(workloads.build("saw_svf_events", V), sr, n + 4800, threads=4)[0][:, :, n:]
+    assert np.array_equal(ref2, o)

@@ -10,3 +10,4 @@ tail -15 gpurun_out/pytest_gpu.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
 timeout 300 python bench.py > gpurun_out/bench_line.json 2> gpurun_out/bench_err.log; tail -c 600 gpurun_out/bench_line.json
 timeout 200 python tools/prof_sequencer.py > gpurun_out/sequencer.log 2>&1; tail -5 gpurun_out/sequencer.log
+timeout 300 python bench.py --workload saw_svf_events > gpurun_out/bench_events.json 2>> gpurun_out/bench_err.log; tail -c 400 gpurun_out/bench_events.json
