@@ -39,8 +39,13 @@ def jobs():
     from fundsp_b200.sequencer import event
     for mk in (W.live_voice, W.arp_voice):
         add(capi.NodeHandle(event(mk(100.0), 0.0, 1.0)).signature(), (2,))
-    from fundsp_b200.prelude import dc
+    from fundsp_b200.prelude import dc, sine_hz
     add(capi.NodeHandle(event(dc(1.0), 1.0, 2.0)).signature(), (2,))
+    add(capi.NodeHandle(event(sine_hz(500.0) * 0.5, 0.0, 1.0)).signature(), (2,))
+    from fundsp_b200 import workloads
+    from fundsp_b200.sequencer import slot
+    add(capi.NodeHandle(workloads.build("saw_svf_events", 1)[0]).signature(), (2, 3))      # bench --workload saw_svf_events and its parity test
+    add(capi.NodeHandle(slot(W.arp_voice(100.0))).signature(), (1,))                        # test_slot_crossfades_to_a_new_unit
     return sorted(out)
 
 
