@@ -13,7 +13,11 @@ extern "C" void fdsp_emul_layout(int* lay) {
   lay[0] = G::IN; lay[1] = G::OUT; lay[2] = G::NP; lay[3] = G::NS; lay[4] = G::NU; lay[5] = WaveKind<G>::value;
 }
 
-extern "C" int fdsp_emul_launch(const BankArgs* ap, int mode) {
+// per_voice_in != null: voice v reads its OWN input rows per_voice_in + v * voice_stride (+ k * a.in_stride + a.in_offset + t) instead of the
+// shared bank input — how the mock runs the reverb stage of a two-stage class on the dry rows of the voices (registry_mock.cpp launch_fdn)
+extern "C" int fdsp_emul_launch_ex(const BankArgs* ap, int mode, const float* per_voice_in, uint64_t voice_stride);
+extern "C" int fdsp_emul_launch(const BankArgs* ap, int mode) { return fdsp_emul_launch_ex(ap, mode, nullptr, 0); }
+extern "C" int fdsp_emul_launch_ex(const BankArgs* ap, int mode, const float* per_voice_in, uint64_t voice_stride) {
   const BankArgs& a = *ap;
   constexpr int IN = G::IN, OUT = G::OUT;
   constexpr bool GROUP = GroupPlan<G>::ok && GroupPlan<G>::code <= 256;   // bank_kernel's FDSP_GROUP_COST
@@ -35,7 +39,7 @@ extern "C" int fdsp_emul_launch(const BankArgs* ap, int mode) {
     for (uint32_t t0 = 0; t0 < a.n; t0 += 64) {
       const int nb = (a.n - t0) < 64u ? (int)(a.n - t0) : 64;
       const int nfull = nb & ~7;
-      const float* irow = (IN > 0) ? a.in + a.in_offset + t0 : nullptr;
+      const float* irow = (IN > 0) ? (per_voice_in ? per_voice_in + (size_t)v * voice_stride : a.in) + a.in_offset + t0 : nullptr;
       c.n = nb; c.rem = false;
       for (int g = 0; g < nfull; g += 8) {
         if (GROUP) {

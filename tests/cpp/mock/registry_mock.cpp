@@ -9,6 +9,8 @@
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#include <vector>
+#include <cstring>
 
 #include "host/registry.h"
 #include "dsp/fdn_args.h"
@@ -19,8 +21,9 @@ namespace host {
 namespace {
 typedef void (*LayoutFn)(int*);
 typedef int (*LaunchFn)(const BankArgs*, int);
+typedef int (*LaunchExFn)(const BankArgs*, int, const float*, uint64_t);
 struct MockProgram : Program {
-  LaunchFn fn = nullptr;
+  LaunchFn fn = nullptr; LaunchExFn fn_ex = nullptr;
   cudaError_t launch(const BankArgs& a, int mode, size_t, cudaStream_t) const override {
     mode &= 3;
     return (mode && fn && fn(&a, mode) == 0) ? cudaSuccess : cudaErrorLaunchFailure;
@@ -54,7 +57,8 @@ std::shared_ptr<const Program> get_program(const std::string& sig, int, std::str
   LayoutFn lay = (LayoutFn)dlsym(h, "fdsp_emul_layout");
   auto p = std::make_shared<MockProgram>();
   p->fn = (LaunchFn)dlsym(h, "fdsp_emul_launch");
-  if (!lay || !p->fn) { err = "mock registry: missing symbols"; return nullptr; }
+  p->fn_ex = (LaunchExFn)dlsym(h, "fdsp_emul_launch_ex");
+  if (!lay || !p->fn || !p->fn_ex) { err = "mock registry: missing symbols"; return nullptr; }
   int L[6]; lay(L);
   p->sig = sig; p->jit = true; p->IN = L[0]; p->OUT = L[1]; p->NP = L[2]; p->NS = L[3]; p->NU = L[4]; p->wave_kind = L[5]; p->threads = 128;
   g_cache[sig] = p;
@@ -93,11 +97,43 @@ cudaError_t launch_tree_mix(const float* rows, uint32_t V, uint32_t outs, uint32
     }
   return cudaSuccess;
 }
-// the warp-per-voice FDN kernel has no emulation: the mock runs reverbs in the generic thread-per-voice form (FDSP_DISABLE_FDN=1)
-cudaError_t launch_fdn(const FdnArgs&, int, cudaStream_t) { return cudaErrorLaunchFailure; }
+// The warp-per-voice FDN kernel (dsp/fdn_kernel.cuh) computes `reverb_stereo` exactly like the generic thread-per-voice program (the GPU
+// tests compare the two bit for bit), so the mock runs that generic program on the kernel's argument block: the last words of the
+// class are the reverb's words, the rings are its delay lines, the input is each voice's dry stereo rows. This puts the HOST side of the
+// two-stage classes (dry buffers, chunk pipeline, deferred reductions, wet gain row) under the CPU suite.
+static const char* kRevSig = "Pipe<Pipe<MultiSplit<2,16>,Feedback<1,Multi<30,0,32,Pipe<Delay,Fir<3>>>>>,Binop<2,Multi<31,0,32,Panner<1>>,Constant<2>>>";
+cudaError_t launch_fdn(const FdnArgs& f, int warps, cudaStream_t) {
+  std::string err;
+  auto prog = std::dynamic_pointer_cast<const MockProgram>(get_program(kRevSig, 0, err));
+  if (!prog || warps < 1) return cudaErrorLaunchFailure;
+  const uint32_t V = f.V, n = f.n, grid = (V + (uint32_t)warps - 1) / (uint32_t)warps;
+  std::vector<float> rev((size_t)V * 2 * n, 0.0f);
+  std::vector<uint32_t> rows(V);
+  for (uint32_t v = 0; v < V; v++) rows[v] = 2 * v;
+  BankArgs a; memset(&a, 0, sizeof(a));
+  a.params = f.params + (size_t)f.p0 * V; a.state = f.state + (size_t)f.s0 * V; a.uniform = f.uniform + f.u0;
+  a.dline = f.ring; a.wt = nullptr; a.out = rev.data(); a.V = V; a.n = n; a.vpc = 0;
+  a.in = f.dry; a.in_stride = f.dry_ch_stride; a.in_offset = f.dry_offset; a.out_stride = n; a.out_offset = 0; a.row_map = rows.data();
+  a.sr = 0.0f; a.sd64 = 0.0f; a.sd32 = 0.0f;   // (the reverb's nodes do not read the rate: delay lengths are class-uniform words)
+  if (prog->fn_ex(&a, 1, f.dry_voice_stride ? f.dry : nullptr, f.dry_voice_stride) != 0) return cudaErrorLaunchFailure;
+  if (f.partial) for (size_t e = 0; e < (size_t)grid * 2 * n; e++) f.partial[e] = 0.0f;
+  for (uint32_t v = 0; v < V; v++)
+    for (uint32_t ch = 0; ch < 2; ch++)
+      for (uint32_t t = 0; t < n; t++) {
+        float y = rev[((size_t)2 * v + ch) * n + t];
+        if (f.scalar_row >= 0) {   // Bus<MultiPass<2>, Unop<3, Reverb>>: dry + reverb * g
+          float g; memcpy(&g, f.params + (size_t)f.scalar_row * V + v, 4);
+          const float dry = f.dry[(size_t)v * f.dry_voice_stride + (size_t)ch * f.dry_ch_stride + f.dry_offset + t];
+          y = dry + y * g;
+        }
+        if (f.out) f.out[(size_t)(f.row_map[v] + ch) * f.out_stride + f.out_offset + t] = y;
+        if (f.partial) f.partial[((size_t)(v / (uint32_t)warps) * 2 + ch) * n + t] += y;
+      }
+  return cudaSuccess;
+}
 int fdn_max_warps() { return 8; }
-cudaError_t launch_fdn_ts(const FdnArgs&, int, int, cudaStream_t) { return cudaErrorLaunchFailure; }
-int fdn_ts_max_vpb(int) { return 1; }
+cudaError_t launch_fdn_ts(const FdnArgs& f, int, int vpb, cudaStream_t s) { return launch_fdn(f, vpb, s); }
+int fdn_ts_max_vpb(int) { return 4; }
 std::shared_ptr<const Program> jit_program(const std::string& sig, int device, std::string& err) { return get_program(sig, device, err); }
 int jit_compiled_count() { return (int)g_cache.size(); }
 void jit_cache_stats(int* hits, int* runs) { if (hits) *hits = 0; if (runs) *runs = 0; }

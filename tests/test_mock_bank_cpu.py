@@ -5,7 +5,8 @@ tests/cpp/mock/ builds the host sources against a stand-in <cuda_runtime.h> ("de
 replaces the kernels by the device node library compiled for the CPU (FDSP_HOST_EMUL), one small shared object per graph class walking
 every voice through bank_kernel's per-thread block structure. The whole GPU test-suite then runs against that library in a subprocess
 (FDSP_B200_LIB selects it there and only there). What this does NOT cover is the CUDA side proper — the CTA mix tile, TMA table
-staging, the warp-per-voice FDN kernel (reverbs run in the generic form here), stream concurrency — which the same tests check on a B200.
+staging, the warp-per-voice FDN kernel itself (the mock runs the equivalent generic reverb program on its argument block, so the host side of
+the two-stage classes IS covered), stream concurrency — which the same tests check on a B200.
 The mock is test infrastructure: it is never built into, or loaded by, the product."""
 import hashlib
 import os
@@ -48,7 +49,7 @@ def mock_env():
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-w", "-shared", "-fPIC", "-DFDSP_HOST_EMUL=1", *san, "-I", MOCK, "-I", CSRC,
                                "-x", "c++", *srcs, "-o", lib + ".tmp", "-ldl"])
         os.replace(lib + ".tmp", lib)
-    env = dict(os.environ, FDSP_B200_LIB=lib, FDSP_MOCK_ROOT=ROOT, FDSP_MOCK_CACHE=os.path.join(build, "classes"), FDSP_DISABLE_FDN="1")
+    env = dict(os.environ, FDSP_B200_LIB=lib, FDSP_MOCK_ROOT=ROOT, FDSP_MOCK_CACHE=os.path.join(build, "classes"))
     if SAN:   # every "device" buffer is a host allocation here, so the sanitizer sees each out-of-bounds word the GPU would silently read or write
         rt = subprocess.check_output(["gcc", "-print-file-name=lib" + ("asan" if SAN == "address" else "ubsan") + ".so"], text=True).strip()
         env.update(LD_PRELOAD=rt, ASAN_OPTIONS="detect_leaks=0", UBSAN_OPTIONS="halt_on_error=1",
