@@ -239,7 +239,6 @@ def test_event_workload_of_the_bench_matches_oracle():
     ref, _ = oracle_bank_render(workloads.build("saw_svf_events", V), sr, n, threads=4)
     assert np.array_equal(rows, ref) and np.abs(ref[:, :, -64:]).max(axis=(1, 2)).min() > 0.0     # every note has started and is held
     assert _close(mix, ref.astype(np.float64).sum(0).astype(np.float32))
-    rows2, _ = b.render_samples(4800)                 # steady state: every block is a whole block of every event
-    ref2 = np.stack([r for r in rows2])               # (shape check only; continuity against the oracle below)
-    o = oracle_bank_render(workloads.build("saw_svf_events", V), sr, n + 4800, threads=4)[0][:, :, n:]
-    assert np.array_equal(ref2, o)
+    rows2, _ = b.render_samples(4800)                 # steady state: every block is a whole block of every event (X's own group form)
+    cont = oracle_bank_render(workloads.build("saw_svf_events", V), sr, n + 4800, threads=4)[0][:, :, n:]
+    assert np.array_equal(rows2, cont)
