@@ -132,7 +132,8 @@ def workload_name(w, V):
     names = {"saw_svf": f"{V}-voice saw_hz(f) >> lowpass_hz(fc,q) bank (north-star headline)", "noise_svf": f"{V}-voice white().seed(i) >> lowpass_hz(fc,q) bank (config 3a)",
              "fm": f"{V}-voice FM bank sine_hz(f)*f*m+f >> sine() (config 2)", "biquad_bank": f"{V} x biquad_bank() = {8 * V} voices on white() (config 3b)",
              "subtractive_dry": f"{V}-voice saw >> moog * adsr_live >> pan (config 4 without reverb)", "subtractive": f"{V}-voice subtractive + per-voice reverb_stereo (config 4)",
-             "net": f"{V}-voice dynamic Net, 4 classes (config 5)"}
+             "net": f"{V}-voice dynamic Net, 4 classes (config 5)",
+             "saw_svf_events": f"{V} held sequencer events of saw_hz(f) >> lowpass_hz(fc,q) (the headline voices behind Sequencer::push; not a BASELINE config)"}
     return names[w]
 
 
