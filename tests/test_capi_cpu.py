@@ -332,3 +332,15 @@ def test_jit_disk_cache_fills_without_a_gpu(tmp_path):
     assert r.stdout.strip() == "{'hits': 0, 'nvrtc_runs': 2} {'hits': 2, 'nvrtc_runs': 2} {'hits': 2, 'nvrtc_runs': 2} error", r.stdout
     files = sorted(os.listdir(tmp_path / "cache"))
     assert len(files) == 2 and all(f.endswith(".fdspjit") for f in files)
+
+
+def test_bench_tables_cover_every_workload():
+    """bench.py --workload choices, its names and the workload builders stay in step (no GPU needed to find a missing key)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert set(bench.HEADLINE) == set(workloads.WORKLOADS)
+    for w, v in bench.HEADLINE.items():
+        assert str(v) in bench.workload_name(w, v) and workloads.WORKLOADS[w][1] == v
+        assert bench.gate_for(w, 64) is None or bench.gate_for(w, 64).shape == (1, 64)
