@@ -133,8 +133,10 @@ class GpuSequencer:
         eid = self.next_id; self.next_id += 1
         if self.bank is None:
             self.pending.append(ev); self.voice_of[eid] = len(self.pending) - 1
+        elif self.mode[0] == 1:
+            self.voice_of[eid] = self.bank.push_event(ev)      # ReplayMode::None drops finished events: their voices are free to take over
         else:
-            self.voice_of[eid] = self.bank.push_event(ev)
+            self.voice_of[eid] = self.bank.add_voice(ev)       # ReplayMode::All replays every event after a reset: nothing may be overwritten
         return eid
 
     def push(self, start_time, end_time, fade_ease, fade_in_time, fade_out_time, unit: An):

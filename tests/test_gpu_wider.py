@@ -242,3 +242,27 @@ def test_event_workload_of_the_bench_matches_oracle():
     rows2, _ = b.render_samples(4800)                 # steady state: every block is a whole block of every event (X's own group form)
     cont = oracle_bank_render(workloads.build("saw_svf_events", V), sr, n + 4800, threads=4)[0][:, :, n:]
     assert np.array_equal(rows2, cont)
+
+
+def test_gpu_sequencer_replay_all_keeps_every_event():
+    """ReplayMode::All: events pushed while running are added (never written over a finished one), so a reset replays all of them."""
+    from fundsp_b200.sequencer import GpuSequencer, Fade, ReplayMode
+    from oracle import OracleBackend, OracleUnit, lib as olib
+    L = olib()
+    L.fo_set_denormal_emulation(0)
+    sr = 44100.0
+    g = GpuSequencer(1, ReplayMode.All, sample_rate=sr)
+    u = OracleUnit(L.fo_sequencer(0, 1, 0, 0.0))
+    be = OracleBackend()
+    def push(start, end, f):
+        g.push(start, end, Fade.Smooth, 0.002, 0.004, arp_voice(f))
+        L.fo_sequencer_push(u.h, start, end, 1, 0.002, 0.004, arp_voice(f).lower(be))
+    push(0.0, 0.02, 220.0)
+    a = g.render(64 * 20); b = u.process_many(64 * 20)             # the first note has ended
+    assert _close(a, b) and np.abs(b).max() > 0.1
+    push(g.time() + 0.001, g.time() + 0.02, 330.0)                  # a second note, pushed into the running sequencer
+    a = g.render(64 * 20); b = u.process_many(64 * 20)
+    assert _close(a, b) and np.abs(b).max() > 0.1 and g.bank.voices() == 2
+    g.reset(); u.reset()                                            # both notes replay
+    a = g.render(64 * 45); b = u.process_many(64 * 45)
+    assert _close(a, b) and np.abs(b[:, :64 * 20]).max() > 0.1 and np.abs(b[:, 64 * 21:]).max() > 0.1
