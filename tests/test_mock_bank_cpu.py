@@ -75,6 +75,16 @@ def test_sharded_bank_on_the_mock_device(mock_env):
     assert r.returncode == 0 and r.stdout.count(": ok") == 3 and "MISMATCH" not in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
 
 
+def test_gpu_box_scripts_run_on_the_mock_device(mock_env):
+    """The scripts of the first GPU call of a round (tools/gpu_first_call.sh) are dry-run here at toy sizes, so GPU minutes are not
+    spent finding a typo: smoke() and the sequencer timing script."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "prof_sequencer.py"), "--voices", "24", "--samples", "2048"],
+                       capture_output=True, text=True, env=mock_env, cwd=ROOT, timeout=900)
+    assert r.returncode == 0 and "sequencer bank" in r.stdout and "per push_event" in r.stdout, (r.stdout[-800:], r.stderr[-1500:])
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], capture_output=True, text=True, env=mock_env, cwd=ROOT, timeout=900)
+    assert r.returncode == 0 and "smoke ok" in r.stdout, (r.stdout[-800:], r.stderr[-1500:])
+
+
 def test_product_library_is_not_the_mock():
     """The mock is selected by FDSP_B200_LIB in the subprocess above only: the library the package loads by default is the CUDA build."""
     from fundsp_b200 import capi
