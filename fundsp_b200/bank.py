@@ -164,7 +164,8 @@ class GpuBank:
             sig = C.create_string_buffer(1 << 16)
             v, s, p, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint64()
             check(self.L.fdsp_bank_class_info(self.h, i, sig, len(sig), C.byref(v), C.byref(s), C.byref(p), C.byref(d)))
-            out.append(dict(signature=sig.value.decode(), voices=v.value, state_words=s.value, param_words=p.value, delay_floats=d.value))
+            out.append(dict(signature=sig.value.decode(), voices=v.value, state_words=s.value, param_words=p.value, delay_floats=d.value,
+                            stages=self.L.fdsp_bank_class_stages(self.h, i)))
         return out
 
 

@@ -263,7 +263,7 @@ API int fdsp_bank_set(fdsp_bank* b, uint32_t voice, int kind, const float* v, in
 API int fdsp_jit_precompile(const char* signature, int mode, int table_variant) {
   if (!signature) return fail(FDSP_ERR_ARG, "null signature");
   if (find_kernel(signature)) return FDSP_OK;   // ahead-of-time class: nothing to compile
-  std::string e = jit_precompile(signature, mode, table_variant);
+  std::string e = jit_precompile(signature, mode, table_variant & 1, table_variant >> 8);   // bits 8..: width (32 / 128) of the stage-pipelined kernel, 0 = plain
   return e.empty() ? FDSP_OK : fail(FDSP_ERR_UNSUPPORTED, e);
 }
 API void fdsp_jit_cache_stats(int* hits, int* nvrtc_runs) { jit_cache_stats(hits, nvrtc_runs); }
@@ -357,6 +357,11 @@ API int fdsp_bank_class_info(const fdsp_bank* b, int cls, char* sig, int max, ui
   if (param_words) *param_words = c.np;
   if (delay_floats) *delay_floats = c.dl_floats + c.ring_floats;
   return FDSP_OK;
+}
+API int fdsp_bank_class_stages(const fdsp_bank* b, int cls) {
+  if (!b || cls < 0 || cls >= (int)b->b.classes.size()) return -1;
+  const VoiceClass& c = b->b.classes[cls];
+  return c.k ? c.k->stages : 1;
 }
 API uint64_t fdsp_bank_launch_count(const fdsp_bank* b) { return b ? b->b.launches : 0; }
 API float fdsp_bank_last_kernel_ms(const fdsp_bank* b) { return b ? b->b.last_ms : 0.0f; }

@@ -6,6 +6,14 @@
 
 namespace fdsp {
 
+// physical ring length of a delay line of `len` samples: a multiple of 64 floats, so block-aligned slices are 16-byte aligned and a
+// block never straddles the end (the kernel and the host's allocation both use this)
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+constexpr uint32_t fdn_ring_phys(uint32_t len) { return (len + 63u) & ~63u; }
+constexpr uint32_t FDN_MIN_RING = 193;   // shortest delay line the kernel takes (prefetch distance 2 blocks + the block itself)
+
 struct FdnArgs {
   const uint32_t* params; uint32_t* state; const uint32_t* uniform;
   uint32_t p0, s0, u0;

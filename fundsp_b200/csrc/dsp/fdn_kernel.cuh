@@ -2,16 +2,27 @@
 // feedback delay network  multisplit<2,16> >> fdn<32>(stacki<32>(delay >> fir3)) >> sumf<32>(pan) * dc((1/16,1/16)).
 //
 // The reference ticks the whole inner graph per sample (src/feedback.rs:136-146): 32 x (Delay::tick src/delay.rs:116-124
-// + Fir<U3>::tick src/fir.rs:57-70) + one 32-point Hadamard (src/feedback.rs:35-57). Here ONE WARP evaluates one voice:
-//   lane l   = delay line l (its FIR shift register, feedback value, pan weights, ring index live in registers)
-//   Hadamard = 5 butterfly stages of __shfl_xor (upper lane computes partner - own, exactly the reference's x - y)
-//   delay lines live in HBM, voice-major [voice][line][ring]; per 64-sample block the warp stages the 32 x 64 ring
-//   slice it will read into shared memory with coalesced cp.async (double buffered, next block prefetched while the
-//   current one is computed: the shortest line is >= 130 samples) and writes the 32 x 64 new samples back with
-//   coalesced stores. This is the one HBM-bound program of the path: 32 lines x (4 B read + 4 B write) per voice-sample.
-//   The output `Reduce` (sum of 32 pans, left fold in index order, src/audionode.rs:2442-2463) is done from a shared
-//   transpose so the sum order — and therefore every bit — matches the reference.
-// The wet/dry composition around it,  dry >> (multipass::<U2>() & s * reverb_stereo(..)), is applied in the epilogue.
+// + Fir<U3>::tick src/fir.rs:57-70) + one 32-point Hadamard (src/feedback.rs:35-57). This is the one HBM-bound program of
+// the path: 32 lines x (4 B read + 4 B write) per voice-sample, and the kernel is organised around moving those bytes.
+//
+// ONE WARP = one voice, and inside a 64-sample block the warp works TIME-parallel (round 2; round 1 had lane = delay line):
+// every delay is >= 192 samples, so what the network writes in a block cannot reach what it reads in the same block — the
+// 64 samples of a block are independent given the ring contents. Hence
+//   * lane t evaluates samples t and t + 32 of the block with ALL 32 lines in its registers: the three FIR taps per line are
+//     three neighbouring shared-memory words, the 32-point Hadamard is the reference's in-place butterfly (h = 1, 2, 4, 8, 16;
+//     a[j], a[j+h] = x + y, x - y) on a register array — no shuffles —, the output `Reduce` (sum of 32 pans, src/audionode.rs:
+//     2442-2463) is the same left fold in line order in two registers;
+//   * the ring slice a block reads (32 lines x 64 samples, contiguous per line) arrives by TMA: one `cp.async.bulk` per line
+//     (two when it wraps) issued by lane l for line l, three blocks in flight per warp, completion on one mbarrier per stage;
+//   * the 64 new samples per line are produced in place in the same shared-memory rows and leave by one `cp.async.bulk`
+//     shared->global per line.
+// Ring storage (private to this kernel; the host only sizes, clears and copies it): voice-major [voice][line][ring], each
+// line's ring padded to a multiple of 64 floats (`fdn_ring_phys`) so that block-aligned slices are 16-byte aligned and a
+// block never straddles the end. The state word of a line holds its WRITE position w; the sample written at w is read
+// L - 1 steps later (Delay::tick writes buffer[i], then returns buffer[i + 1], length L).
+// After a ragged block (process(size) with size % 4 != 0) positions lose their 16-byte alignment: reads are still TMA (an
+// aligned superset + a per-line shift), writes fall back to per-lane stores until the positions re-align.
+// The wet/dry composition around the reverb,  dry >> (multipass::<U2>() & s * reverb_stereo(..)), is applied in the epilogue.
 // Word layout of the reverb inside the class arrays (DFS order, see csrc/host/graph.cpp):
 //   P: 32 x Fir weights(3) | 32 x Panner(lw, rw) | Constant<2>          (162 words, first row p0)
 //   S: Feedback value[32] | 32 x (Delay idx, Fir v[3])                   (160 words, first row s0)
@@ -22,15 +33,27 @@
 
 namespace fdsp {
 
+constexpr int FDN_NST = 3;                      // ring-slice stages per warp (prefetch distance 2 blocks)
+constexpr int FDN_RS = 72;                      // row stride (floats): 4 lead + 3 shift + 64 samples, 16-byte multiple
+constexpr int FDN_ROWS = 32 * FDN_RS;           // one stage
+// per warp: stages | dbuf [NST][2][64] | wtab [32][4] (w0 w1 w2 lw) | tb2 [NST][32][2] (rw, row offset) | vcarry [32] | obuf [2][64] | mbarriers
+constexpr int FDN_WARP_FLOATS = FDN_NST * FDN_ROWS + FDN_NST * 128 + 128 + FDN_NST * 64 + 32 + 128 + 2 * FDN_NST + 2;
 
-
-constexpr int FDN_RS = 65;                 // padded row stride (floats): bank = (line + t) % 32, conflict-free both ways
-constexpr int FDN_PS = 33;
-constexpr int FDN_WARP_FLOATS = 2 * 32 * FDN_RS + 2 * 32 * FDN_PS + 2 * 2 * 64 + 2 * 64 + 3 * 32;  // rbuf x2, pbuf, dbuf x2, obuf, line tables
-
-FDSP_DEV void cp_async4(uint32_t smem, const float* g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem), "l"(g) : "memory"); }
-FDSP_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> FDSP_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+FDSP_DEV uint32_t fdn_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+FDSP_DEV void fdn_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+FDSP_DEV void fdn_mbar_expect(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+FDSP_DEV void fdn_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tFW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra FD_%=;\n\tbra FW_%=;\n\tFD_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+FDSP_DEV void fdn_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+FDSP_DEV void fdn_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+FDSP_DEV void fdn_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> FDSP_DEV void fdn_bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+FDSP_DEV void fdn_fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // blockDim.x = 32 * W (W voices per CTA), dynamic smem = W * FDN_WARP_FLOATS * 4 bytes
 __global__ void __launch_bounds__(256) fdn_kernel(const FdnArgs a) {
@@ -39,140 +62,124 @@ __global__ void __launch_bounds__(256) fdn_kernel(const FdnArgs a) {
   const uint32_t v = blockIdx.x * W + warp;
   const bool active = v < a.V;
   float* sm = fdn_smem + (size_t)warp * FDN_WARP_FLOATS;
-  float* rbuf = sm;                                  // [2][32][65] ring slices read this / next block; reused for the new samples
-  float* pbuf = rbuf + 2 * 32 * FDN_RS;              // [2][32][33] pan products of a 32-sample half block
-  float* dbuf = pbuf + 2 * 32 * FDN_PS;              // [2][2][64] stereo input of this / next block
-  float* obuf = dbuf + 2 * 2 * 64;                   // [2][64] final output of this block (for the CTA mix)
-  uint32_t* tlen = reinterpret_cast<uint32_t*>(obuf + 2 * 64);  // [32] ring length, [32] ring offset, [32] ring index
-  uint32_t* toff = tlen + 32;
-  uint32_t* tidx = toff + 32;
+  float* rbuf = sm;                                   // [NST][32][RS] ring slices; new samples are produced in place (slots 0..63 of a row)
+  float* dbuf = rbuf + FDN_NST * FDN_ROWS;            // [NST][2][64] stereo input of the blocks in flight
+  float4* wtab = reinterpret_cast<float4*>(dbuf + FDN_NST * 128);   // [32] (w0, w1, w2, lw)
+  float2* tb2 = reinterpret_cast<float2*>(reinterpret_cast<float*>(wtab) + 128);   // [NST][32] (rw, float offset of d[0] of the line inside the stage)
+  float* vcarry = reinterpret_cast<float*>(tb2) + FDN_NST * 64;      // [32] Feedback value entering the next block
+  float* obuf = vcarry + 32;                          // [2][64] final output of this block (for the CTA mix)
+  const uint32_t bar0 = fdn_smem_addr(obuf + 128);    // NST mbarriers (8 bytes each)
 
-  float w0 = 0, w1 = 0, w2 = 0, lw = 0, rw = 0, c0 = 0, c1 = 0, scalar = 1.0f, value = 0, f0 = 0, f1 = 0, f2 = 0;
-  uint32_t idx = 0, len = 1, off = 0;
+  // ---- lane = line bookkeeping: ring geometry, write position, FIR shift register
+  float f0 = 0, f1 = 0, f2 = 0, c0 = 0, c1 = 0, scalar = 1.0f;
+  uint32_t idx = 0, len = 193, lp = 256, off = 0;
   float* ring = nullptr;
+  if (lane == 0) { for (int s = 0; s < FDN_NST; s++) fdn_mbar_init(bar0 + 8u * s, 32); }
   if (active) {
     const uint32_t V = a.V;
     auto P = [&](uint32_t row) { return __uint_as_float(__ldg(a.params + (size_t)row * V + v)); };
     auto S = [&](uint32_t row) { return a.state[(size_t)row * V + v]; };
-    w0 = P(a.p0 + 3 * lane); w1 = P(a.p0 + 3 * lane + 1); w2 = P(a.p0 + 3 * lane + 2);
-    lw = P(a.p0 + 96 + 2 * lane); rw = P(a.p0 + 96 + 2 * lane + 1);
+    wtab[lane] = make_float4(P(a.p0 + 3 * lane), P(a.p0 + 3 * lane + 1), P(a.p0 + 3 * lane + 2), P(a.p0 + 96 + 2 * lane));
+    const float rw = P(a.p0 + 96 + 2 * lane + 1);
+    for (int s = 0; s < FDN_NST; s++) tb2[s * 32 + lane] = make_float2(rw, 0.0f);
     c0 = P(a.p0 + 160); c1 = P(a.p0 + 161);
     if (a.scalar_row >= 0) scalar = P((uint32_t)a.scalar_row);
-    value = __uint_as_float(S(a.s0 + lane));
+    vcarry[lane] = __uint_as_float(S(a.s0 + lane));
     idx = S(a.s0 + 32 + 4 * lane);
     f0 = __uint_as_float(S(a.s0 + 32 + 4 * lane + 1)); f1 = __uint_as_float(S(a.s0 + 32 + 4 * lane + 2)); f2 = __uint_as_float(S(a.s0 + 32 + 4 * lane + 3));
     len = __ldg(a.uniform + a.u0 + lane);
-    uint32_t incl = len;  // inclusive scan over lanes -> ring offset of each line
+    lp = fdn_ring_phys(len);
+    uint32_t incl = lp;  // inclusive scan over lanes -> ring offset of each line
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
-    off = incl - len;
-    ring = a.ring + (size_t)v * a.ring_voice_stride;
-    tlen[lane] = len; toff[lane] = off; tidx[lane] = idx;
+    off = incl - lp;
+    ring = a.ring + (size_t)v * a.ring_voice_stride + off;
   }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncwarp();
-  const uint32_t rb0 = (uint32_t)__cvta_generic_to_shared(rbuf), db0 = (uint32_t)__cvta_generic_to_shared(dbuf);
   const float* dry = active ? a.dry + (size_t)v * a.dry_voice_stride + a.dry_offset : nullptr;
+  const uint32_t rb0 = fdn_smem_addr(rbuf);
 
-  // stage the ring slice + stereo input a block will read: lanes sweep time, lines are looped (coalesced 128 B rows)
-  auto prefetch = [&](int buf, uint32_t t0, int nb, uint32_t adv) {
-    if (active && nb > 0) {
-#pragma unroll 4
-      for (int l = 0; l < 32; l++) {
-        const uint32_t L = tlen[l], base = toff[l], i0 = tidx[l] + adv;   // ring index at the start of that block
+  // lane l fetches the slice line l reads in the block that starts `adv` samples after the current write position: an aligned
+  // superset lands at float 4 of the row, d[t] of the block is row[4 + sh + t]
+  auto prefetch = [&](int st, uint32_t t0, int nb, uint32_t adv) {
+    if (!active || nb <= 0) return;
+    uint32_t rs = idx + adv + lp - (len - 1u);             // read start = write position - (L - 1)
+    rs -= (rs >= lp) ? lp : 0u; rs -= (rs >= lp) ? lp : 0u;
+    const uint32_t sh = rs & 3u, ra = rs - sh;
+    const uint32_t cnt = (sh + (uint32_t)nb + 3u) & ~3u;    // floats, multiple of 4
+    const uint32_t bar = bar0 + 8u * (uint32_t)st;
+    const uint32_t dst = rb0 + 4u * (uint32_t)(st * FDN_ROWS + lane * FDN_RS + 4);
+    tb2[st * 32 + lane].y = __int_as_float(lane * FDN_RS + 4 + (int)sh);
+    fdn_mbar_expect(bar, cnt * 4u);
+    const uint32_t first = (ra + cnt <= lp) ? cnt : lp - ra;
+    fdn_g2s(dst, ring + ra, first * 4u, bar);
+    if (first < cnt) fdn_g2s(dst + first * 4u, ring, (cnt - first) * 4u, bar);
+    // stereo input of that block (lanes sweep time; any alignment)
+    float* db = dbuf + st * 128;
 #pragma unroll
-        for (int q = 0; q < 2; q++) {
-          const int t = lane + 32 * q;
-          if (t < nb) {
-            uint32_t pos = i0 + 1u + (uint32_t)t;           // Delay::tick reads buffer[i + 1] after writing buffer[i]
-            pos -= (pos >= L) ? L : 0u; pos -= (pos >= L) ? L : 0u;
-            cp_async4(rb0 + 4u * (uint32_t)((buf * 32 + l) * FDN_RS + t), ring + base + pos);
-          }
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 2; q++) {
-        const int t = lane + 32 * q;
-        if (t < nb) {
-          cp_async4(db0 + 4u * (uint32_t)((buf * 2 + 0) * 64 + t), dry + t0 + t);
-          cp_async4(db0 + 4u * (uint32_t)((buf * 2 + 1) * 64 + t), dry + a.dry_ch_stride + t0 + t);
-        }
-      }
+    for (int q = 0; q < 2; q++) {
+      const int t = lane + 32 * q;
+      if (t < nb) { db[t] = __ldg(dry + t0 + t); db[64 + t] = __ldg(dry + a.dry_ch_stride + t0 + t); }
     }
-    cp_async_commit();
   };
 
   const float hz = (float)(1.0 / sqrt(32.0));
-  uint32_t sgn[5];
-#pragma unroll
-  for (int s = 0; s < 5; s++) sgn[s] = (lane & (1 << s)) ? 0x80000000u : 0u;
-  int cur = 0;
-  prefetch(0, 0u, (int)(a.n < 64u ? a.n : 64u), 0u);
+  const uint32_t nblk = (a.n + 63u) / 64u;
+  auto blen = [&](uint32_t b) { return b < nblk ? (int)((a.n - b * 64u) < 64u ? (a.n - b * 64u) : 64u) : 0; };
+  prefetch(0, 0u, blen(0), 0u);
+  prefetch(1, 64u, blen(1), 64u);
 #pragma unroll 1
-  for (uint32_t t0 = 0; t0 < a.n; t0 += 64) {
-    const int nb = (a.n - t0) < 64u ? (int)(a.n - t0) : 64;
-    const uint32_t rest = a.n - t0 - (uint32_t)nb;
-    prefetch(cur ^ 1, t0 + (uint32_t)nb, (int)(rest < 64u ? rest : 64u), (uint32_t)nb);
-    cp_async_wait<1>();
-    __syncwarp();
+  for (uint32_t b = 0; b < nblk; b++) {
+    const int st = (int)(b % FDN_NST);
+    const uint32_t t0 = b * 64u;
+    const int nb = blen(b);
     if (active) {
-      float* rb = rbuf + (cur * 32 + lane) * FDN_RS;
-      const float* din = dbuf + (cur * 2 + (lane & 1)) * 64;   // MultiSplit<2,16>: channel c reads input c % 2
+      fdn_mbar_wait(bar0 + 8u * (uint32_t)st, (b / FDN_NST) & 1u);
+      float* rst = rbuf + st * FDN_ROWS;
+      const float* db = dbuf + st * 128;
+      {  // lane = line: FIR history in front of d[0], and the first new sample (input + the Feedback value carried over)
+        const int ro = __float_as_int(tb2[st * 32 + lane].y);
+        rst[ro - 2] = f1; rst[ro - 1] = f2;
+        rst[lane * FDN_RS] = db[(lane & 1) * 64] + vcarry[lane];   // MultiSplit<2,16>: line l reads input channel l % 2
+      }
+      __syncwarp();
+      const float2* t2 = tb2 + st * 32;
 #pragma unroll 1
       for (int h0 = 0; h0 < nb; h0 += 32) {
-        const int hn = (nb - h0) < 32 ? (nb - h0) : 32;
-        int tt = 0;
-        // groups of 8 samples: all shared-memory reads first, then 8 interleaved Hadamard chains, then the stores
-        // (consecutive samples are independent: the feedback value only reaches the ring after >= 129 samples)
-#pragma unroll 1
-        for (; tt + 8 <= hn; tt += 8) {
-          float d[8], x[8], o[8], h[8];
+        const int t = h0 + lane;
+        const bool ok = t < nb;
+        const int tc = ok ? t : 0;
+        float av[32], sl = 0.0f, sr = 0.0f;
 #pragma unroll
-          for (int u = 0; u < 8; u++) { d[u] = rb[h0 + tt + u]; x[u] = din[h0 + tt + u]; }
+        for (int l = 0; l < 32; l++) {
+          const float4 wv = wtab[l];
+          const float2 q = t2[l];
+          const float* row = rst + __float_as_int(q.y) + tc;
+          const float o = (wv.x * row[-2] + wv.y * row[-1]) + wv.z * row[0];     // Fir<U3>: accumulate in tap order from the oldest
+          av[l] = o;
+          if (l == 0) { sl = o * wv.w; sr = o * q.x; } else { sl += o * wv.w; sr += o * q.x; }   // Reduce<U32, Panner, FrameAdd>: left fold
+        }
+        // FrameHadamard<U32> (src/feedback.rs:35-57): in-place butterflies h = 1, 2, 4, 8, 16, then * (1 / sqrt(32)) as f32
 #pragma unroll
-          for (int u = 0; u < 8; u++) { f0 = f1; f1 = f2; f2 = d[u]; o[u] = (w0 * f0 + w1 * f1) + w2 * f2; h[u] = o[u]; }
+        for (int h = 1; h < 32; h <<= 1) {
 #pragma unroll
-          for (int s = 0; s < 5; s++) {
+          for (int i = 0; i < 32; i += 2 * h) {
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-              const float y = __shfl_xor_sync(0xffffffffu, h[u], 1 << s);
-              h[u] = y + __uint_as_float(__float_as_uint(h[u]) ^ sgn[s]);   // upper lane: partner - own; lower lane: own + partner
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 8; u++) {
-            rb[h0 + tt + u] = x[u] + value;    // Feedback: x.tick(input + value); Delay stores it at ring[i]
-            value = h[u] * hz;
-            pbuf[(0 * 32 + lane) * FDN_PS + tt + u] = o[u] * lw;   // Panner<U1>::process: input * weight
-            pbuf[(1 * 32 + lane) * FDN_PS + tt + u] = o[u] * rw;
+            for (int j = i; j < i + h; j++) { const float x = av[j], y = av[j + h]; av[j] = x + y; av[j + h] = x - y; }
           }
         }
-#pragma unroll 1
-        for (; tt < hn; tt++) {
-          const int t = h0 + tt;
-          const float d = rb[t];                 // Delay output for this sample
-          rb[t] = din[t] + value;
-          f0 = f1; f1 = f2; f2 = d;              // Fir<U3> shift register
-          const float o = (w0 * f0 + w1 * f1) + w2 * f2;
-          float h = o;                           // FrameHadamard<U32>
+        const float x0n = db[tc + 1 < 64 ? tc + 1 : 63], x1n = db[64 + (tc + 1 < 64 ? tc + 1 : 63)];   // input of sample t + 1
+        sl = sl * c0; sr = sr * c1;
+        if (a.scalar_row >= 0) { sl = db[tc] + sl * scalar; sr = db[64 + tc] + sr * scalar; }
+        __syncwarp();   // every lane has read its taps of this half: the rows may now take the new samples (slots <= h0 + 32 < first tap of the next half)
+        if (ok) {
+          if (t + 1 < nb) {
 #pragma unroll
-          for (int s = 0; s < 5; s++) {
-            const float y = __shfl_xor_sync(0xffffffffu, h, 1 << s);
-            h = y + __uint_as_float(__float_as_uint(h) ^ sgn[s]);
-          }
-          value = h * hz;
-          pbuf[(0 * 32 + lane) * FDN_PS + tt] = o * lw;
-          pbuf[(1 * 32 + lane) * FDN_PS + tt] = o * rw;
-        }
-        __syncwarp();
-        if (lane < hn) {                         // Reduce<U32, Panner, FrameAdd>: left fold in channel order, then * dc, * s, + dry
-          const int t = h0 + lane;
-          float sl = pbuf[(0 * 32 + 0) * FDN_PS + lane], sr = pbuf[(1 * 32 + 0) * FDN_PS + lane];
+            for (int l = 0; l < 32; l++) rst[l * FDN_RS + t + 1] = ((l & 1) ? x1n : x0n) + av[l] * hz;   // Feedback: x.tick(input + value); Delay stores it
+          } else {
 #pragma unroll
-          for (int l = 1; l < 32; l++) { sl += pbuf[(0 * 32 + l) * FDN_PS + lane]; sr += pbuf[(1 * 32 + l) * FDN_PS + lane]; }
-          sl = sl * c0; sr = sr * c1;
-          if (a.scalar_row >= 0) {
-            sl = dbuf[(cur * 2 + 0) * 64 + t] + sl * scalar;
-            sr = dbuf[(cur * 2 + 1) * 64 + t] + sr * scalar;
+            for (int l = 0; l < 32; l++) vcarry[l] = av[l] * hz;    // enters the first sample of the next block
           }
           obuf[t] = sl; obuf[64 + t] = sr;
           if (a.out) {
@@ -180,45 +187,64 @@ __global__ void __launch_bounds__(256) fdn_kernel(const FdnArgs a) {
             orow[0] = sl; orow[a.out_stride] = sr;
           }
         }
-        __syncwarp();
       }
-      // write the 32 x nb new samples back to the rings (coalesced rows) and advance the ring indices
-#pragma unroll 4
-      for (int l = 0; l < 32; l++) {
-        const uint32_t L = tlen[l], base = toff[l], i0 = tidx[l];
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-          const int t = lane + 32 * q;
-          if (t < nb) {
-            uint32_t pos = i0 + (uint32_t)t;
-            pos -= (pos >= L) ? L : 0u;
-            ring[base + pos] = rbuf[(cur * 32 + l) * FDN_RS + t];
-          }
-        }
+      // lane = line again: FIR history for the next block, then the new samples of the line go back to its ring
+      {
+        const int ro = __float_as_int(tb2[st * 32 + lane].y);
+        if (nb >= 3) { f0 = rst[ro + nb - 3]; f1 = rst[ro + nb - 2]; f2 = rst[ro + nb - 1]; }
+        else { for (int i = 0; i < nb; i++) { f0 = f1; f1 = f2; f2 = rst[ro + i]; } }
       }
       __syncwarp();
-      idx += (uint32_t)nb; idx -= (idx >= len) ? len : 0u;
-      tidx[lane] = idx;
-    } else {
-      if (a.partial) { for (int t = lane; t < 128; t += 32) obuf[t] = 0.0f; }
+      const bool bulk_ok = __all_sync(0xffffffffu, ((idx | (uint32_t)nb) & 3u) == 0u);
+      if (bulk_ok) {
+        fdn_fence_async();   // the rows were written through the generic proxy
+        const uint32_t src = rb0 + 4u * (uint32_t)(st * FDN_ROWS + lane * FDN_RS);
+        const uint32_t first = (idx + (uint32_t)nb <= lp) ? (uint32_t)nb : lp - idx;
+        fdn_s2g(ring + idx, src, first * 4u);
+        if (first < (uint32_t)nb) fdn_s2g(ring, src + first * 4u, ((uint32_t)nb - first) * 4u);
+        fdn_bulk_commit();
+      } else {
+        // ragged positions: lanes sweep time, lines are looped (coalesced rows); lane-invariant ring geometry through shuffles
+#pragma unroll 1
+        for (int l = 0; l < 32; l++) {
+          const uint32_t il = __shfl_sync(0xffffffffu, idx, l), ll = __shfl_sync(0xffffffffu, lp, l), ol = __shfl_sync(0xffffffffu, off, l);
+          float* rl = a.ring + (size_t)v * a.ring_voice_stride + ol;
+#pragma unroll
+          for (int q = 0; q < 2; q++) {
+            const int t = lane + 32 * q;
+            if (t < nb) { uint32_t pos = il + (uint32_t)t; pos -= (pos >= ll) ? ll : 0u; rl[pos] = rst[l * FDN_RS + t]; }
+          }
+        }
+        __threadfence();
+        fdn_fence_async();   // later TMA reads of these samples go through the async proxy
+        fdn_bulk_commit();   // (an empty group keeps the wait below uniform)
+      }
+      idx += (uint32_t)nb; idx -= (idx >= lp) ? lp : 0u;
+      // the stage of block b - 1 is refilled for block b + 2: its own store (one group back) must have completed — both because the
+      // rows are overwritten and because a short ring may read what that store wrote
+      fdn_bulk_wait<1>();
+      __syncwarp();
+      prefetch((int)((b + 2) % FDN_NST), t0 + 128u, blen(b + 2), 64u);
+    } else if (a.partial) {
+      for (int t = lane; t < 128; t += 32) obuf[t] = 0.0f;
     }
     if (a.partial) {   // CTA mix in warp (= voice) order, deterministic
       __syncthreads();
       for (int e = threadIdx.x; e < 2 * nb; e += blockDim.x) {
         const int ch = e / nb, t = e - ch * nb;
-        float s = fdn_smem[(size_t)0 * FDN_WARP_FLOATS + (obuf - sm) + ch * 64 + t];
-        for (int w = 1; w < W; w++) s += fdn_smem[(size_t)w * FDN_WARP_FLOATS + (obuf - sm) + ch * 64 + t];
+        const size_t ob = (size_t)(obuf - sm);
+        float s = fdn_smem[ob + ch * 64 + t];
+        for (int w = 1; w < W; w++) s += fdn_smem[(size_t)w * FDN_WARP_FLOATS + ob + ch * 64 + t];
         a.partial[((size_t)blockIdx.x * 2 + ch) * a.n + t0 + t] = s;
       }
       __syncthreads();
     }
-    __syncwarp();
-    cur ^= 1;
   }
-  cp_async_wait<0>();
+  fdn_bulk_wait<0>();
   if (active) {
     const uint32_t V = a.V;
-    a.state[(size_t)(a.s0 + lane) * V + v] = __float_as_uint(value);
+    __syncwarp();
+    a.state[(size_t)(a.s0 + lane) * V + v] = __float_as_uint(vcarry[lane]);
     a.state[(size_t)(a.s0 + 32 + 4 * lane) * V + v] = idx;
     a.state[(size_t)(a.s0 + 32 + 4 * lane + 1) * V + v] = __float_as_uint(f0);
     a.state[(size_t)(a.s0 + 32 + 4 * lane + 2) * V + v] = __float_as_uint(f1);

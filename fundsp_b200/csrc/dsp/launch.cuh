@@ -2,7 +2,7 @@
 #pragma once
 #include "../host/registry.h"
 #include "bank_kernel.cuh"
-#include "bank_kernel_ws.cuh"
+#include "bank_kernel_st.cuh"
 
 namespace fdsp {
 namespace host {
@@ -27,37 +27,40 @@ template <class G, bool TB> cudaError_t launch_mode(const BankArgs& a, int mode,
     default: return cudaErrorInvalidValue;
   }
 }
-// warp-specialised variant (bank_kernel_ws.cuh): 2*NT threads per CTA, stage A and stage B of the top-level Pipe in different warps
-template <class G, int MODE, bool TB> cudaError_t launch_ws_one(const BankArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(bank_kernel_ws<G, NT, MODE, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+// stage-pipelined variant (bank_kernel_st.cuh): K * NTV threads per CTA, the stages of StagePlan<G> in different warps
+template <class G, int NTV, int MODE, bool TB> cudaError_t launch_st_one(const BankArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
+  if constexpr (StagePlan<G>::K >= 2) {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(bank_kernel_st<G, NTV, MODE, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    bank_kernel_st<G, NTV, MODE, TB><<<grid, StagePlan<G>::K * NTV, smem, st>>>(a);
+    return cudaGetLastError();
+  } else {
+    return cudaErrorInvalidValue;
   }
-  bank_kernel_ws<G, NT, MODE, TB><<<grid, 2 * NT, smem, st>>>(a);
-  return cudaGetLastError();
 }
-template <class G, bool TB> cudaError_t launch_ws_mode(const BankArgs& a, int mode, size_t smem, cudaStream_t st) {
-  const unsigned vpc = a.vpc ? a.vpc : (unsigned)NT, grid = (a.V + vpc - 1) / vpc;
+template <class G, int NTV, bool TB> cudaError_t launch_st_mode(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t st) {
+  const unsigned vpc = a.vpc ? a.vpc : (unsigned)NTV, grid = (a.V + vpc - 1) / vpc;
+  const bool mix = (mode & 2) != 0;
+  const size_t smem = (mix ? sizeof(float) * mix_tile_floats(G::OUT, NTV) : 0) + sizeof(float) * st_hand_floats<G>(NTV, mix) + (TB ? table_bytes : 0);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
   switch (mode & 3) {
-    case 1: return launch_ws_one<G, 1, TB>(a, grid, smem, st);
-    case 2: return launch_ws_one<G, 2, TB>(a, grid, smem, st);
-    case 3: return launch_ws_one<G, 3, TB>(a, grid, smem, st);
+    case 1: return launch_st_one<G, NTV, 1, TB>(a, grid, smem, st);
+    case 2: return launch_st_one<G, NTV, 2, TB>(a, grid, smem, st);
+    case 3: return launch_st_one<G, NTV, 3, TB>(a, grid, smem, st);
     default: return cudaErrorInvalidValue;
   }
 }
+// stage width: 32 voices per CTA when the launch asks for at most 32 (a.vpc), else 128
+template <class G> cudaError_t launch_st_t(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t st) {
+  constexpr bool WT = WaveKind<G>::value >= 0;
+  const bool tb = WT && table_bytes > 0;
+  if (a.vpc && a.vpc <= 32u) return tb ? launch_st_mode<G, 32, WT>(a, mode, table_bytes, st) : launch_st_mode<G, 32, false>(a, mode, 0, st);
+  return tb ? launch_st_mode<G, 128, WT>(a, mode, table_bytes, st) : launch_st_mode<G, 128, false>(a, mode, 0, st);
+}
 // table_bytes > 0 asks for the shared-memory wavetable variant (only meaningful when G reads a wavetable and it fits).
-// mode bit 2 (value 4) asks for the warp-specialised kernel where the graph has one and its shared memory fits.
 template <class G> cudaError_t launch_t(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t st) {
-  if constexpr (WsOk<G>::value) {
-    if (mode & 4) {
-      typedef typename PipeParts<G>::A A;
-      const bool mix = (mode & 2) != 0;
-      const size_t base = (mix ? sizeof(float) * mix_tile_floats(G::OUT, NT) : 0) + sizeof(float) * ws_hand_floats(A::OUT, G::OUT, NT, mix);
-      const bool want_tb = WaveKind<G>::value >= 0 && table_bytes > 0;
-      if (want_tb && base + table_bytes <= 227 * 1024) return launch_ws_mode<G, (WaveKind<G>::value >= 0)>(a, mode, base + table_bytes, st);
-      if (!want_tb && base <= 227 * 1024) return launch_ws_mode<G, false>(a, mode, base, st);
-    }
-  }
   if (WaveKind<G>::value >= 0 && table_bytes > 0) {
     const size_t smem = ((mode & 2) ? sizeof(float) * mix_tile_floats(G::OUT, NT) : 0) + table_bytes;
     if (smem <= 227 * 1024) return launch_mode<G, (WaveKind<G>::value >= 0)>(a, mode, table_bytes, st);
@@ -67,8 +70,13 @@ template <class G> cudaError_t launch_t(const BankArgs& a, int mode, size_t tabl
 template <class G> int wave_kind_t() { return WaveKind<G>::value; }
 inline int threads_t() { return NT; }
 
+template <class G> int stages_t() { return StagePlan<G>::K; }
 #define FDSP_REG(...) \
-  {#__VA_ARGS__, __VA_ARGS__::IN, __VA_ARGS__::OUT, __VA_ARGS__::NP, __VA_ARGS__::NS, __VA_ARGS__::NU, &launch_t<__VA_ARGS__>, &threads_t, &wave_kind_t<__VA_ARGS__>}
+  {#__VA_ARGS__, __VA_ARGS__::IN, __VA_ARGS__::OUT, __VA_ARGS__::NP, __VA_ARGS__::NS, __VA_ARGS__::NU, &launch_t<__VA_ARGS__>, &threads_t, &wave_kind_t<__VA_ARGS__>, 1, nullptr}
+// the same, plus the stage-pipelined kernels of the graph (bank_kernel_st.cuh; only graphs with a heavy leaf have any)
+#define FDSP_REG_ST(...) \
+  {#__VA_ARGS__, __VA_ARGS__::IN, __VA_ARGS__::OUT, __VA_ARGS__::NP, __VA_ARGS__::NS, __VA_ARGS__::NU, &launch_t<__VA_ARGS__>, &threads_t, &wave_kind_t<__VA_ARGS__>, \
+   StagePlan<__VA_ARGS__>::K, &launch_st_t<__VA_ARGS__>}
 #define FDSP_INSTANCES(name, ...)                     \
   extern const KernelEntry kInst_##name[] = {__VA_ARGS__}; \
   extern const int kInst_##name##_n = (int)(sizeof(kInst_##name) / sizeof(kInst_##name[0]));

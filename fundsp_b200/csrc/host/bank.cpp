@@ -13,7 +13,12 @@ namespace host {
 
 namespace {
 constexpr uint32_t TIME_CHUNK = 16384;  // samples per launch (multiple of 64): bounds the partial-mix buffer
-constexpr uint32_t PIPE_CHUNK = 2048;   // sub-chunk of two-stage (dry program -> FDN reverb) classes: stage 1 of chunk k+1 overlaps stage 2 of chunk k
+// sub-chunk of two-stage (dry program -> FDN reverb) classes: stage 1 of chunk k+1 overlaps stage 2 of chunk k (FDSP_PIPE_CHUNK: tuning)
+static uint32_t pipe_chunk() {
+  static const uint32_t v = [] { const char* e = getenv("FDSP_PIPE_CHUNK"); uint32_t x = e ? (uint32_t)atoi(e) : 2048u; x = x / 64u * 64u; return x < 256u ? 256u : (x > TIME_CHUNK ? TIME_CHUNK : x); }();
+  return v;
+}
+#define PIPE_CHUNK pipe_chunk()
 
 std::string cuerr(const char* what, cudaError_t e) { return std::string(what) + ": " + cudaGetErrorString(e); }
 #define CU(call)                                          \
@@ -104,13 +109,13 @@ std::string Bank::lower_and_upload(bool upload_state) {
       else if (lo.sig.compare(0, 5, "Pipe<") == 0 && ends_with(lo.sig, wet_tail)) { c.fdn = true; wet = true; prog_sig = lo.sig.substr(5, lo.sig.size() - 5 - wet_tail.size()); }
       else if (lo.sig.compare(0, 5, "Pipe<") == 0 && ends_with(lo.sig, pipe_tail)) { c.fdn = true; prog_sig = lo.sig.substr(5, lo.sig.size() - 5 - pipe_tail.size()); }
       if (c.fdn) {
-        for (size_t k = lo.l.U.size() - 32; k < lo.l.U.size(); k++) if (lo.l.U[k] < 130u) c.fdn = false;  // prefetch distance needs rings >= 130 samples
+        for (size_t k = lo.l.U.size() - 32; k < lo.l.U.size(); k++) if (lo.l.U[k] < FDN_MIN_RING) c.fdn = false;  // the kernel's prefetch distance needs every delay >= 192 samples
         if (!c.fdn) prog_sig = lo.sig;
       }
       if (c.fdn) {
         c.p0 = c.np - 162; c.s0 = c.ns - 160; c.u0 = c.nu - 32;
         c.scalar_row = wet ? (int)c.p0 - 1 : -1;
-        for (size_t k = 0; k < lo.l.dlen.size(); k++) (k + 32 >= lo.l.dlen.size() ? c.ring_floats : c.dl_floats) += lo.l.dlen[k];
+        for (size_t k = 0; k < lo.l.dlen.size(); k++) { if (k + 32 >= lo.l.dlen.size()) c.ring_floats += fdn_ring_phys(lo.l.dlen[k]); else c.dl_floats += lo.l.dlen[k]; }
         if (!prog_sig.empty()) {
           c.k = get_program(prog_sig, device, jerr);
           if (!c.k) return "no device program for the dry stage `" + prog_sig + "`: " + jerr;
@@ -439,12 +444,28 @@ std::string Bank::reset() {  // AudioUnit::reset: back to the construction-time 
   return "";
 }
 
-// Warp-specialised kernels (dsp/bank_kernel_ws.cuh) are built and parity-tested but OFF by default: measured on B200 they are
-// slower than the plain kernel (saw+SVF 16384 voices: 1.53 vs 1.45 ms, FM 4096: 1.03 vs 0.98 ms per 16384 samples) because the
-// wavetable gathers keep the shared-memory pipe ~65 % busy, which a second warp per scheduler cannot relieve. FDSP_WS=1 enables them.
-static bool use_ws(uint32_t) {
-  static const int forced = [] { const char* e = getenv("FDSP_WS"); return e ? atoi(e) : 0; }();
-  return forced != 0;
+// long launches of wavetable programs stage the table set in shared memory (TMA bulk copy, ~160 KB per CTA); short ones
+// (process()-sized) read the tables through L1/L2 instead
+static size_t table_bytes_of(const VoiceClass& c, uint32_t len) {
+  const int wk = c.k ? c.k->wave_kind : -1;
+  static const uint32_t tb_min = [] { const char* e = getenv("FDSP_TB_MIN"); return e ? (uint32_t)atoi(e) : 32u; }();  // measured: at 64 samples the TMA-staged tables already win (35.0 vs 38.9 us per process call)
+  return (wk >= 0 && len >= tb_min) ? device_wavetable(wk).data.size() * sizeof(float) : 0;
+}
+// Stage-pipelined kernels (dsp/bank_kernel_st.cuh): programs with a heavy serial leaf (Moog ...) run their stages in different warps.
+// Used for launches long enough to fill the pipeline; FDSP_STAGED=0 switches them off (A/B), FDSP_STAGED_MAXV bounds the class size.
+static bool use_staged(const Program* k, uint32_t V, uint32_t len) {
+  const char* e = getenv("FDSP_STAGED");            // read per call: the tests toggle it inside one process
+  const char* m = getenv("FDSP_STAGED_MAXV");
+  const int on = e ? atoi(e) : 1;
+  const uint32_t maxv = m ? (uint32_t)atoi(m) : 0xffffffffu;
+  return on != 0 && k && k->stages >= 2 && len >= 256u && V <= maxv;
+}
+// CTA shape of a stage-pipelined class: 32 voices per CTA while that still leaves SMs free, else 128 with the voices spread evenly
+// (FDSP_STAGED_W=128 forces the wide shape: lets the tests reach it with few voices)
+static uint32_t staged_grid(uint32_t V, uint32_t* vpc) {
+  const char* w = getenv("FDSP_STAGED_W");
+  if (V <= 148u * 32u && !(w && atoi(w) == 128)) { *vpc = 32u; return (V + 31u) / 32u; }
+  return bank_grid(V, 128u, vpc);
 }
 
 std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_stride, float* out_dev, uint64_t out_stride, float* mix_dev,
@@ -510,22 +531,21 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
         ks = c.cstream;
         CU(cudaStreamWaitEvent(ks, e_begin, 0));
       }
-      int fdn_warps = 1, fdn_k = 0;   // fdn_warps: voices per CTA; fdn_k: warps per voice (0 = single-warp kernel)
+      const bool staged = use_staged(c.k.get(), V, len);
+      int fdn_warps = 1;   // voices (= warps) per CTA of the FDN kernel
       if (c.fdn) {
-        const char* ks = getenv("FDSP_FDN_K");
-        fdn_k = ks ? atoi(ks) : 0;  // measured on B200 (1024 voices): single-warp form 2.15 ms, K=2 2.47 ms, K=4 2.49 ms per 16384 samples
-        if (fdn_k != 2 && fdn_k != 4) fdn_k = 0;
-        const int cap = fdn_k ? fdn_ts_max_vpb(fdn_k) : fdn_max_warps();
+        const int cap = fdn_max_warps();
         // pipelined: leave SMs free for the CTAs of the dry stage of the next chunk (their shared-memory tables cannot share an SM
         // with an FDN CTA), otherwise the two stages serialise on SM residency
         uint32_t sms = 148;
-        if (pipelined && c.k) { const uint32_t dry_ctas = (V + (uint32_t)c.k->threads - 1) / (uint32_t)c.k->threads; sms = dry_ctas < 74 ? 148 - dry_ctas : 74; }
+        if (pipelined && c.k) { uint32_t dv = 0; const uint32_t dry_ctas = staged ? staged_grid(V, &dv) : (V + (uint32_t)c.k->threads - 1) / (uint32_t)c.k->threads; sms = dry_ctas < 74 ? 148 - dry_ctas : 74; }
         fdn_warps = (int)((V + sms - 1) / sms); if (fdn_warps > cap) fdn_warps = cap; if (fdn_warps < 1) fdn_warps = 1;
       }
       // voice programs: whole waves of CTAs with the voices spread evenly; the dry stage of a two-stage class stays compact
       // (few CTAs) so that it leaves the other SMs to the FDN kernel it is pipelined with
       uint32_t vpc = c.k ? (uint32_t)c.k->threads : 0u;
-      const uint32_t vgrid = !c.k ? 0u : (c.fdn || getenv("FDSP_NO_SPREAD") ? (V + vpc - 1) / vpc : bank_grid(V, (uint32_t)c.k->threads, &vpc));
+      const uint32_t vgrid = !c.k ? 0u : (staged ? staged_grid(V, &vpc) : (c.fdn || getenv("FDSP_NO_SPREAD") ? (V + vpc - 1) / vpc : bank_grid(V, (uint32_t)c.k->threads, &vpc)));
+      auto launch_voice = [&](const BankArgs& args, int md, cudaStream_t st) { return staged ? c.k->launch_staged(args, md, table_bytes_of(c, len), st) : c.k->launch(args, md, table_bytes_of(c, len), st); };
       const uint32_t grid = c.fdn ? (V + (uint32_t)fdn_warps - 1) / (uint32_t)fdn_warps : vgrid;
       if (want_m) {
         const size_t need = (size_t)grid * nout * len;
@@ -541,16 +561,12 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
       a.row_map = c.d_rowmap;
       a.sr = (float)sr; a.sd64 = (float)(1.0 / sr); a.sd32 = 1.0f / (float)sr;
       // process()-sized launches of plain voice programs finish their mix-down inside the kernel (one launch instead of two)
-      const bool fused_mix = want_m && !c.fdn && len <= 64 && !use_ws(V);
+      const bool fused_mix = want_m && !c.fdn && len <= 64;
       a.ticket = fused_mix ? d_ticket : nullptr; a.mix = mix_dev; a.mix_stride = (uint32_t)mix_stride; a.mix_offset = (uint32_t)t0; a.mix_accumulate = first ? 0 : 1;
       if (t0 > 0xffffffffull - TIME_CHUNK) return "render too long for one call";
       if (c.fdn && len > TIME_CHUNK) return "internal: chunk";
       // long launches of wavetable programs stage the table set in shared memory (TMA bulk copy, ~160 KB per CTA);
       // short ones (process()-sized) read the tables through L1/L2 instead
-      size_t table_bytes = 0;
-      const int wk = c.k ? c.k->wave_kind : -1;
-      static const uint32_t tb_min = [] { const char* e = getenv("FDSP_TB_MIN"); return e ? (uint32_t)atoi(e) : 32u; }();  // measured: at 64 samples the TMA-staged tables already win (35.0 vs 38.9 us per process call)
-      if (wk >= 0 && len >= tb_min) table_bytes = device_wavetable(wk).data.size() * sizeof(float);
       if (c.fdn) {
         FdnArgs f;
         f.params = c.d_params; f.state = c.d_state; f.uniform = c.d_uniform; f.p0 = c.p0; f.s0 = c.s0; f.u0 = c.u0; f.scalar_row = c.scalar_row;
@@ -563,7 +579,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
           BankArgs d = a;
           d.out = dry; d.partial = nullptr; d.out_stride = PIPE_CHUNK; d.out_offset = 0; d.row_map = c.d_dryrows;
           tmark(stream);
-          CU(c.k->launch(d, 1, table_bytes, stream));
+          CU(launch_voice(d, 1, stream));
           launches++;
           tmark(stream);
           CU(cudaEventRecord(c.e_dry[buf], stream));
@@ -575,7 +591,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
           f.ring = c.d_ring; f.ring_voice_stride = c.ring_floats; f.V = V; f.n = len;
           CU(cudaStreamWaitEvent(stream2, c.e_dry[buf], 0));
           tmark(stream2);
-          if (fdn_k) CU(launch_fdn_ts(f, fdn_k, fdn_warps, stream2)); else CU(launch_fdn(f, fdn_warps, stream2));
+          CU(launch_fdn(f, fdn_warps, stream2));
           launches++;
           tmark(stream2);
           CU(cudaEventRecord(c.e_fdn[buf], stream2));
@@ -585,7 +601,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
         if (c.k) {  // stage 1: the fused dry program writes stereo rows [V][2][TIME_CHUNK]
           BankArgs d = a;
           d.out = c.d_dry; d.partial = nullptr; d.out_stride = TIME_CHUNK; d.out_offset = 0; d.row_map = c.d_dryrows;
-          CU(c.k->launch(d, 1, table_bytes, stream));
+          CU(launch_voice(d, 1, stream));
           launches++;
           f.dry = c.d_dry; f.dry_voice_stride = 2ull * TIME_CHUNK; f.dry_ch_stride = TIME_CHUNK; f.dry_offset = 0;
         } else {    // reverb applied straight to the bank's stereo input
@@ -594,9 +610,9 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
         f.out = want_v ? out_dev_c : nullptr; f.row_map = c.d_rowmap; f.out_stride = (uint32_t)out_stride_c; f.out_offset = (uint32_t)out_t0;
         f.partial = want_m ? c.d_partial : nullptr;
         f.ring = c.d_ring; f.ring_voice_stride = c.ring_floats; f.V = V; f.n = len;
-        if (fdn_k) CU(launch_fdn_ts(f, fdn_k, fdn_warps, stream)); else CU(launch_fdn(f, fdn_warps, stream));
+        CU(launch_fdn(f, fdn_warps, stream));
       } else {
-        CU(c.k->launch(a, mode | (use_ws(V) ? 4 : 0), table_bytes, ks));
+        CU(launch_voice(a, mode, ks));
       }
       launches++;
       if (concurrent) { CU(cudaEventRecord(c.e_done, ks)); continue; }   // reduced below, after every class has been launched
@@ -611,7 +627,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
         CU(cudaStreamWaitEvent(stream, c.e_done, 0));
         if (want_m) {
           uint32_t vpc = (uint32_t)c.k->threads;
-          const uint32_t grid = getenv("FDSP_NO_SPREAD") ? (c.V() + vpc - 1) / vpc : bank_grid(c.V(), (uint32_t)c.k->threads, &vpc);
+          const uint32_t grid = use_staged(c.k.get(), c.V(), len) ? staged_grid(c.V(), &vpc) : (getenv("FDSP_NO_SPREAD") ? (c.V() + vpc - 1) / vpc : bank_grid(c.V(), (uint32_t)c.k->threads, &vpc));
           CU(launch_mix_reduce(c.d_partial, grid, (uint32_t)nout, len, mix_dev, (uint32_t)mix_stride, (uint32_t)t0, first ? 0 : 1, stream));
           launches++;
         }

@@ -137,9 +137,10 @@ static int g_cache_hits = 0, g_nvrtc_runs = 0;
 static bool compile_unit(const std::string& sig, const char* kernel_expr, std::vector<char>& cubin, std::string& lowered, std::string& err, bool use_cache = true) {
   Api& A = api();
   if (!A.ok_nvrtc) { err = A.why; return false; }
-  std::string src = "#include \"dsp/bank_kernel.cuh\"\nnamespace fdsp { typedef " + sig + " JitG; }\n";
+  std::string src = "#include \"dsp/bank_kernel_st.cuh\"\nnamespace fdsp { typedef " + sig + " JitG; }\n";
   if (!kernel_expr)
-    src += "extern \"C\" __device__ int fdsp_jit_layout[6] = {fdsp::JitG::IN, fdsp::JitG::OUT, fdsp::JitG::NP, fdsp::JitG::NS, fdsp::JitG::NU, fdsp::WaveKind<fdsp::JitG>::value};\n";
+    src += "extern \"C\" __device__ int fdsp_jit_layout[8] = {fdsp::JitG::IN, fdsp::JitG::OUT, fdsp::JitG::NP, fdsp::JitG::NS, fdsp::JitG::NU, fdsp::WaveKind<fdsp::JitG>::value, "
+           "fdsp::StagePlan<fdsp::JitG>::K, fdsp::MidSum<fdsp::StagePlan<fdsp::JitG>::stages>::value};\n";
   const uint64_t key = unit_key(src, kernel_expr);
   if (use_cache && cache_load(key, cubin, lowered)) { g_cache_hits++; return true; }
   g_nvrtc_runs++;
@@ -166,23 +167,51 @@ static bool compile_unit(const std::string& sig, const char* kernel_expr, std::v
   return true;
 }
 
+// width 0: the plain kernel (128 threads); 32 / 128: the stage-pipelined kernel with that many voices per CTA
+static std::string kernel_expr_of(int mode, int tb, int width) {
+  const std::string tail = std::to_string(mode) + ", " + (tb ? "true" : "false") + ">";
+  return width ? "fdsp::bank_kernel_st<fdsp::JitG, " + std::to_string(width) + ", " + tail : "fdsp::bank_kernel<fdsp::JitG, 128, " + tail;
+}
+
 struct JitProgram : Program {
-  int device = 0;
+  int device = 0, mid_sum = 0;   // mid_sum: channels crossing the stage boundaries (sizes the hand-off rings)
   mutable std::mutex mu;
-  mutable CUmodule mods[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
-  mutable CUfunction fn[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};  // [mode-1][TB]
-  CUfunction variant(int mode, int tb) const {
+  mutable CUmodule mods[3][3][2] = {};
+  mutable CUfunction fn[3][3][2] = {};  // [0 plain | 1 staged x32 | 2 staged x128][mode-1][TB]
+  CUfunction variant(int mode, int tb, int width = 0) const {
     std::lock_guard<std::mutex> lock(mu);
-    if (fn[mode - 1][tb]) return fn[mode - 1][tb];
+    const int wi = width == 0 ? 0 : (width == 32 ? 1 : 2);
+    CUfunction& f = fn[wi][mode - 1][tb]; CUmodule& m = mods[wi][mode - 1][tb];
+    if (f) return f;
     const Api& A = api();
-    const std::string expr = "fdsp::bank_kernel<fdsp::JitG, 128, " + std::to_string(mode) + ", " + (tb ? "true" : "false") + ">";
+    const std::string expr = kernel_expr_of(mode, tb, width);
     std::vector<char> cubin; std::string low, err;
     if (!compile_unit(sig, expr.c_str(), cubin, low, err)) { fprintf(stderr, "fundsp_b200 JIT: %s\n", err.c_str()); return nullptr; }
-    if (A.ModuleLoadData(&mods[mode - 1][tb], cubin.data()) != CUDA_SUCCESS) {   // a damaged cache entry: compile afresh (which rewrites it)
-      if (!compile_unit(sig, expr.c_str(), cubin, low, err, false) || A.ModuleLoadData(&mods[mode - 1][tb], cubin.data()) != CUDA_SUCCESS) return nullptr;
+    if (A.ModuleLoadData(&m, cubin.data()) != CUDA_SUCCESS) {   // a damaged cache entry: compile afresh (which rewrites it)
+      if (!compile_unit(sig, expr.c_str(), cubin, low, err, false) || A.ModuleLoadData(&m, cubin.data()) != CUDA_SUCCESS) return nullptr;
     }
-    if (A.ModuleGetFunction(&fn[mode - 1][tb], mods[mode - 1][tb], low.c_str()) != CUDA_SUCCESS) { fn[mode - 1][tb] = nullptr; return nullptr; }
-    return fn[mode - 1][tb];
+    if (A.ModuleGetFunction(&f, m, low.c_str()) != CUDA_SUCCESS) { f = nullptr; return nullptr; }
+    return f;
+  }
+  cudaError_t launch_staged(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t st) const override {
+    const Api& A = api();
+    mode &= 3;
+    if (mode == 0 || stages < 2) return cudaErrorInvalidValue;
+    const int width = (a.vpc && a.vpc <= 32u) ? 32 : 128;
+    const bool mix = (mode & 2) != 0;
+    const int hs = mix && mix_tile_samples(OUT) < 16 ? mix_tile_samples(OUT) : 16;   // st_hand_samples
+    const size_t base = (mix ? sizeof(float) * mix_tile_floats(OUT, width) : 0) + sizeof(float) * 2 /*ST_NSLOT*/ * (size_t)mid_sum * hs * width;
+    const int tb = (wave_kind >= 0 && table_bytes > 0 && base + table_bytes <= 227 * 1024) ? 1 : 0;
+    const size_t smem = base + (tb ? table_bytes : 0);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    CUfunction f = variant(mode, tb, width);
+    if (!f) return cudaErrorInvalidDeviceFunction;
+    if (smem > 48 * 1024 && A.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    BankArgs args = a;
+    void* params[] = {&args};
+    const unsigned vpc = a.vpc ? a.vpc : (unsigned)width, grid = (a.V + vpc - 1) / vpc;
+    CUresult r = A.LaunchKernel(f, grid, 1, 1, (unsigned)(stages * width), 1, 1, (unsigned)smem, (CUstream)st, params, nullptr);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorLaunchFailure;
   }
   cudaError_t launch(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t st) const override {
     const Api& A = api();
@@ -212,12 +241,13 @@ int jit_compiled_count() { return g_compiled; }
 void jit_cache_stats(int* hits, int* nvrtc_runs) { if (hits) *hits = g_cache_hits; if (nvrtc_runs) *nvrtc_runs = g_nvrtc_runs; }
 
 // Compile one unit of a graph class into the on-disk cache without touching a GPU (mode 0: the layout unit; 1..3: that kernel variant).
-std::string jit_precompile(const std::string& sig, int mode, int tb) {
+std::string jit_precompile(const std::string& sig, int mode, int tb, int staged_width) {
   if (sig.find("Unsupported") != std::string::npos) return "the graph contains a node with no device lowering";
   if (mode < 0 || mode > 3) return "mode must be 0 (layout) or 1..3";
   if (cache_dir().empty()) return "the JIT cache is disabled (FDSP_JIT_CACHE=off)";
   std::vector<char> cubin; std::string low, err;
-  const std::string expr = "fdsp::bank_kernel<fdsp::JitG, 128, " + std::to_string(mode) + ", " + (tb ? "true" : "false") + ">";
+  if (staged_width != 0 && staged_width != 32 && staged_width != 128) return "staged width must be 0, 32 or 128";
+  const std::string expr = kernel_expr_of(mode, tb, staged_width);
   if (!compile_unit(sig, mode == 0 ? nullptr : expr.c_str(), cubin, low, err)) return err;
   return "";
 }
@@ -242,11 +272,11 @@ std::shared_ptr<const Program> jit_program(const std::string& sig, int device, s
     if (!compile_unit(sig, nullptr, cubin, low, err, false)) return nullptr;
     if (A.ModuleLoadData(&lm, cubin.data()) != CUDA_SUCCESS) { err = "cuModuleLoadData failed for the JIT layout unit"; return nullptr; }
   }
-  CUdeviceptr d = 0; size_t bytes = 0; int lay[6] = {0, 0, 0, 0, 0, -1};
+  CUdeviceptr d = 0; size_t bytes = 0; int lay[8] = {0, 0, 0, 0, 0, -1, 1, 0};
   if (A.ModuleGetGlobal(&d, &bytes, lm, "fdsp_jit_layout") != CUDA_SUCCESS || bytes != sizeof(lay) || A.MemcpyDtoH(lay, d, sizeof(lay)) != CUDA_SUCCESS) {
     err = "JIT layout readback failed"; return nullptr;
   }
-  p->IN = lay[0]; p->OUT = lay[1]; p->NP = lay[2]; p->NS = lay[3]; p->NU = lay[4]; p->wave_kind = lay[5]; p->threads = 128;
+  p->IN = lay[0]; p->OUT = lay[1]; p->NP = lay[2]; p->NS = lay[3]; p->NU = lay[4]; p->wave_kind = lay[5]; p->threads = 128; p->stages = lay[6]; p->mid_sum = lay[7];
   g_compiled++;
   g_cache[key] = p;
   return p;

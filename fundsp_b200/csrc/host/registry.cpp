@@ -63,8 +63,12 @@ struct AotProgram : Program {
   const KernelEntry* e;
   explicit AotProgram(const KernelEntry* e_, const std::string& key) : e(e_) {
     sig = key; IN = e->IN; OUT = e->OUT; NP = e->NP; NS = e->NS; NU = e->NU; threads = e->threads(); wave_kind = e->wave_kind();
+    stages = e->launch_st ? e->stages : 1;
   }
   cudaError_t launch(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t st) const override { return e->launch(a, mode, table_bytes, st); }
+  cudaError_t launch_staged(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t st) const override {
+    return e->launch_st ? e->launch_st(a, mode, table_bytes, st) : cudaErrorInvalidValue;
+  }
 };
 }  // namespace
 

@@ -20,15 +20,20 @@ struct KernelEntry {  // AOT table row
   cudaError_t (*launch)(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t stream);
   int (*threads)();
   int (*wave_kind)();  // first wavetable kind the program reads, -1 if none
+  int stages;          // stages of the stage-pipelined form (dsp/bank_kernel_st.cuh); 1 = none built
+  cudaError_t (*launch_st)(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t stream);
 };
 
 struct Program {
   std::string sig;
   int IN = 0, OUT = 0, NP = 0, NS = 0, NU = 0, threads = 128, wave_kind = -1;
   bool jit = false;
+  int stages = 1;      // >= 2: launch_staged runs the program as a pipeline of that many warp stages per voice (dsp/bank_kernel_st.cuh)
   virtual ~Program() {}
   // mode: FDSP_OUT_VOICES | FDSP_OUT_MIX bits
   virtual cudaError_t launch(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t stream) const = 0;
+  // a.vpc <= 32 selects the 32-voice CTA shape, else 128 voices per CTA; same word layout as `launch` (the two can alternate)
+  virtual cudaError_t launch_staged(const BankArgs&, int, size_t, cudaStream_t) const { return cudaErrorInvalidValue; }
 };
 
 // Returns the program for `sig` (AOT if listed, else NVRTC-compiled and cached); nullptr + `err` on failure.
@@ -44,13 +49,11 @@ cudaError_t launch_tree_mix(const float* rows, uint32_t V, uint32_t outs, uint32
 // warp-per-voice reverb_stereo kernel (inst/inst_fdn.cu)
 cudaError_t launch_fdn(const FdnArgs& a, int warps, cudaStream_t stream);
 int fdn_max_warps();
-cudaError_t launch_fdn_ts(const FdnArgs& a, int K, int voices_per_cta, cudaStream_t stream);  // time-split form (K = 2 or 4 warps per voice)
-int fdn_ts_max_vpb(int K);
 // NVRTC path (jit.cpp)
 std::shared_ptr<const Program> jit_program(const std::string& sig, int device, std::string& err);
 int jit_compiled_count();
 void jit_cache_stats(int* hits, int* nvrtc_runs);                       // units served from the on-disk cache / compiled by NVRTC in this process
-std::string jit_precompile(const std::string& sig, int mode, int tb);   // fill the on-disk cache without a GPU (mode 0 = layout unit)
+std::string jit_precompile(const std::string& sig, int mode, int tb, int staged_width = 0);   // fill the on-disk cache without a GPU (mode 0 = layout unit; staged_width 32 / 128 = that stage-pipelined kernel)
 
 }  // namespace host
 }  // namespace fdsp

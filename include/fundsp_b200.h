@@ -219,6 +219,7 @@ void* fdsp_bank_stream(fdsp_bank* b);                                       /* c
 /* introspection */
 int fdsp_bank_num_classes(const fdsp_bank* b);
 int fdsp_bank_class_info(const fdsp_bank* b, int cls, char* signature, int max, uint32_t* voices, uint32_t* state_words, uint32_t* param_words, uint64_t* delay_floats);
+int fdsp_bank_class_stages(const fdsp_bank* b, int cls);                    /* warp stages of the class's stage-pipelined kernel (csrc/dsp/bank_kernel_st.cuh); 1 = it has none */
 uint64_t fdsp_bank_launch_count(const fdsp_bank* b);                        /* kernels launched so far */
 float fdsp_bank_last_kernel_ms(const fdsp_bank* b);                         /* CUDA-event time of the voice kernels of the last render_device call */
 

@@ -15,9 +15,72 @@
 #include <vector>
 
 #include "../../fundsp_b200/csrc/dsp/nodes.cuh"
+#ifdef STAGED
+#include "../../fundsp_b200/csrc/dsp/stage_plan.cuh"
+#endif
 
 using namespace fdsp;
 typedef GRAPH G;
+
+#ifdef STAGED
+// -DSTAGED: the stages of StagePlan<G> (dsp/stage_plan.cuh, what bank_kernel_st runs in different warps) evaluated BACK TO BACK per 64-sample
+// block through [channel][64] buffers, each stage with its own registers loaded from its own span of the word arrays.
+template <int I> struct StageEmul {
+  typedef typename StagePlan<G>::stages STG;
+  static constexpr int K = StagePlan<G>::K;
+  typedef typename ChainAt<(I < K ? I : 0), STG>::type S;
+  template <int J> static void skip(Loader& l) { if constexpr (J < I) { typename ChainAt<J, STG>::type::R sk; ChainAt<J, STG>::type::load(sk, l); skip<J + 1>(l); } }
+  static void block(typename S::R& r, CtxT<false> c, int nb, const float* in /*[IN][64]*/, float* out /*[OUT][64]*/) {
+    constexpr int IN = S::IN, OUT = S::OUT;
+    constexpr bool GROUP = GroupPlan<S>::ok && GroupPlan<S>::code <= 256;
+    const int nfull = nb & ~7;
+    c.n = nb; c.rem = false;
+    for (int g = 0; g < nfull; g += 8) {
+      if (GROUP) {
+        Fr8<IN> in8; Fr8<OUT> o8;
+        for (int k = 0; k < IN; k++) for (int j = 0; j < 8; j++) in8.v[k][j] = in[k * 64 + g + j];
+        c.i = g; c.first = true;
+        group_step<S>(r, c, in8, o8);
+        for (int k = 0; k < OUT; k++) for (int j = 0; j < 8; j++) out[k * 64 + g + j] = o8.v[k][j];
+      } else {
+        for (int j = 0; j < 8; j++) {
+          Fr<IN> a; Fr<OUT> b;
+          for (int k = 0; k < IN; k++) a.v[k] = in[k * 64 + g + j];
+          c.i = g + j; c.first = (j == 0);
+          S::template step<false>(r, c, a, b);
+          for (int k = 0; k < OUT; k++) out[k * 64 + g + j] = b.v[k];
+        }
+      }
+    }
+    S::end_simd(r);
+    c.rem = true; c.first = false;
+    for (int i = nfull; i < nb; i++) {
+      Fr<IN> a; Fr<OUT> b;
+      for (int k = 0; k < IN; k++) a.v[k] = in[k * 64 + i];
+      c.i = i;
+      S::template step<false>(r, c, a, b);
+      for (int k = 0; k < OUT; k++) out[k * 64 + i] = b.v[k];
+    }
+  }
+};
+template <int I> struct StageRegs { typename StageEmul<I>::S::R r; StageRegs<I + 1> next; };
+template <> struct StageRegs<StagePlan<G>::K> {};
+template <int I> static void staged_load(StageRegs<I>& regs, const uint32_t* P, const uint32_t* S, const uint32_t* U, uint32_t& dl) {
+  if constexpr (I < StagePlan<G>::K) {
+    Loader l{P, S, U, 1u, 0u, 0u, 0u, 0u, 0u};
+    StageEmul<I>::template skip<0>(l);
+    StageEmul<I>::S::load(regs.r, l);
+    dl = l.dl;
+    staged_load<I + 1>(regs.next, P, S, U, dl);
+  }
+}
+template <int I> static void staged_block(StageRegs<I>& regs, const CtxT<false>& c, int nb, float* a, float* b) {
+  if constexpr (I < StagePlan<G>::K) {
+    StageEmul<I>::block(regs.r, c, nb, a, b);
+    staged_block<I + 1>(regs.next, c, nb, b, a);   // ping-pong: the output of stage I is the input of stage I + 1
+  }
+}
+#endif
 
 int main(int argc, char** argv) {
   if (argc < 3) return 2;
@@ -49,6 +112,34 @@ int main(int argc, char** argv) {
   }
   fclose(f);
 
+#ifdef STAGED
+  {
+    static_assert(StagePlan<G>::K >= 2, "the graph has no stage plan (no heavy leaf on its spine)");
+    fprintf(stderr, "stages=%d\n", StagePlan<G>::K);
+    CtxT<false> c;
+    c.wt = wt; c.tsm = 0u; c.tsm_kind = -1; c.V = 1; c.v = 0;
+    c.sr = (float)sr; c.sd64 = (float)(1.0 / sr); c.sd32 = 1.0f / (float)sr;
+    StageRegs<0> regs; uint32_t dl = 0;
+    staged_load<0>(regs, P.data(), S.data(), U.data(), dl);
+    std::vector<float> dline((size_t)dl + 1, 0.0f);
+    fprintf(stderr, "dl=%u\n", dl);
+    c.dl = dline.data();
+    constexpr int CH = 64;   // widest boundary the ping-pong buffers hold
+    std::vector<float> bufa(CH * 64), bufb(CH * 64);
+    for (uint32_t t0 = 0; t0 < n; t0 += 64) {
+      const int nb = (n - t0) < 64u ? (int)(n - t0) : 64;
+      for (uint32_t k = 0; k < nin; k++) for (int i = 0; i < nb; i++) bufa[k * 64 + i] = in[(size_t)k * n + t0 + i];
+      staged_block<0>(regs, c, nb, bufa.data(), bufb.data());
+      const float* res = (StagePlan<G>::K & 1) ? bufb.data() : bufa.data();
+      for (int k = 0; k < G::OUT; k++) for (int i = 0; i < nb; i++) out[(size_t)k * n + t0 + i] = res[k * 64 + i];
+    }
+    FILE* o = fopen(argv[2], "wb");
+    if (!o) return 9;
+    fwrite(out.data(), 4, (size_t)G::OUT * n, o);
+    fclose(o);
+    return 0;
+  }
+#endif
   typename G::R r;
   CtxT<false> c;
   c.wt = wt; c.tsm = 0u; c.tsm_kind = -1; c.V = 1; c.v = 0;

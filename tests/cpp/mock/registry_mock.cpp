@@ -132,12 +132,10 @@ cudaError_t launch_fdn(const FdnArgs& f, int warps, cudaStream_t) {
   return cudaSuccess;
 }
 int fdn_max_warps() { return 8; }
-cudaError_t launch_fdn_ts(const FdnArgs& f, int, int vpb, cudaStream_t s) { return launch_fdn(f, vpb, s); }
-int fdn_ts_max_vpb(int) { return 4; }
 std::shared_ptr<const Program> jit_program(const std::string& sig, int device, std::string& err) { return get_program(sig, device, err); }
 int jit_compiled_count() { return (int)g_cache.size(); }
 void jit_cache_stats(int* hits, int* runs) { if (hits) *hits = 0; if (runs) *runs = 0; }
-std::string jit_precompile(const std::string&, int, int) { return "mock registry: no NVRTC"; }
+std::string jit_precompile(const std::string&, int, int, int) { return "mock registry: no NVRTC"; }
 
 }  // namespace host
 }  // namespace fdsp

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SR = 44100.0   # the construction-time default rate (src/lib.rs:42): node handles are lowered as constructed
 
 
-def emulate(g, n, x=None, tmp=None, sr=SR):
+def emulate(g, n, x=None, tmp=None, sr=SR, staged=False):
     h = capi.NodeHandle(g)
     if sr != SR:
         h.set_sample_rate(sr)
@@ -26,7 +26,8 @@ def emulate(g, n, x=None, tmp=None, sr=SR):
     P, S, U = h.lowering()
     nin = h.inputs()
     exe = os.path.join(tmp, "emul")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-w", f"-DGRAPH={sig}", os.path.join(ROOT, "tests", "cpp", "device_emul.cpp"), "-o", exe])
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-w", f"-DGRAPH={sig}"] + (["-DSTAGED=1"] if staged else []) +
+                          [os.path.join(ROOT, "tests", "cpp", "device_emul.cpp"), "-o", exe])
     blob = os.path.join(tmp, "in.bin"); outp = os.path.join(tmp, "out.bin")
     with open(blob, "wb") as f:
         f.write(struct.pack("<5I", len(P), len(S), len(U), nin, n))
@@ -40,6 +41,8 @@ def emulate(g, n, x=None, tmp=None, sr=SR):
             f.write(_table_blob(k))
     r = subprocess.run([exe, blob, outp], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stderr)
+    if staged:
+        emulate.stages = [int(x[7:]) for x in r.stderr.split() if x.startswith("stages=")][0]
     claimed = [int(x[3:]) for x in r.stderr.split() if x.startswith("dl=")]
     assert claimed == [h.delay_floats()], ("delay-line storage: device program claims", claimed, "host allocates", h.delay_floats(), sig)
     return np.fromfile(outp, np.float32).reshape(h.outputs(), n), sig
@@ -209,3 +212,32 @@ def test_sequencer_event_voices_sum_to_the_oracle_sequencer(tmp_path):
     q2.edit(e, 600.0 / SR, 100.0 / SR)
     got = emulate(q2.voices()[0], 800, None, str(tmp_path))[0]
     assert np.array_equal(got, oracle(q2.node(), 800)) and got[0, 300] == 1.0 and not got[0, 600:].any()
+
+
+# ---- stage plans (csrc/dsp/stage_plan.cuh): the cut of a program into the warp stages of bank_kernel_st must keep every bit and the
+# word layout. The emulation runs the stages of StagePlan<G> back to back per block, each from its own span of the word arrays.
+STAGED = {
+    # name: (graph, expected stages)
+    "subtractive_dry": (lambda: _wl.subtractive_dry_voice(5), 3),                    # [saw | dc(fc,q) | gate] -> [Moog<3> | gate] -> [x ADSR >> pan]
+    "net_b_saw_moog_pan": (lambda: _wl.net_voice(1), 2),                             # [saw] -> [Moog<1> >> pan]  (the pan is absorbed by the heavy stage)
+    "moog_in_stack": (lambda: ((noise().seed(3) >> moog_hz(900.0, 0.4)) | sine_hz(220.0)) >> join(2), 2),   # noise (tiny) is absorbed into the Moog stage; [sine | join] behind it
+    "two_moogs_in_series": (lambda: noise().seed(5) >> moog_hz(2000.0, 0.3) >> lowpass_hz(700.0, 1.0) >> moog_hz(500.0, 0.6) >> pan(-0.3), 3),
+    "delay_in_front_of_moog": (lambda: noise().seed(8) >> delay(0.002) >> moog_hz(1500.0, 0.5) >> (pass_() & delay(0.001)), 3),   # delay-line cursors across stages
+    "audio_rate_moog_sum": (lambda: ((noise().seed(2) | (sine_hz(3.0) * 400.0 + 900.0) | dc(0.5)) >> moog()) + sine_hz(50.0), 3),
+}
+
+
+@pytest.mark.parametrize("name", sorted(STAGED))
+def test_stage_plan_keeps_every_bit(name, tmp_path):
+    mk, k = STAGED[name]
+    n = 64 * 30 + 61
+    nin = capi.NodeHandle(mk()).inputs()
+    x = None
+    if nin:
+        x = np.zeros((nin, n), np.float32)
+        x[0, 100:1200] = 1.0
+    want = oracle(mk(), n, x)
+    got, sig = emulate(mk(), n, x, str(tmp_path), staged=True)
+    assert emulate.stages == k, (sig, emulate.stages)
+    assert np.abs(want).max() > 1e-3
+    assert np.array_equal(got, want), (name, int((got != want).sum()), float(np.abs(got - want).max()))

@@ -255,6 +255,39 @@ def test_full_size_headline_properties():
     assert np.isfinite(g).all() and np.abs(g).max() < 8.0
 
 
+# ---------------------------------------------------------------- stage-pipelined kernels (csrc/dsp/bank_kernel_st.cuh)
+@pytest.mark.parametrize("width", [32, 128])
+@pytest.mark.parametrize("name,V", [("subtractive_dry", 70), ("net", 4 * 45)])
+def test_stage_pipelined_kernels_equal_plain_kernels_and_oracle(name, V, width, monkeypatch):
+    """Programs with a Moog run their stages in different warps (saw | Moog | ADSR, pan). Rows must equal the plain kernel's and the
+    oracle's bit for bit (same per-node code on the same 8-sample groups), at both CTA shapes, with a ragged last block, a partly
+    filled last CTA, per-voice rows and the CTA mix; state saved by one form continues in the other."""
+    from fundsp_b200.bank import GpuBank
+    olib().fo_set_denormal_emulation(0)
+    n = 64 * 21 + 61
+    inp = workloads.gate_signal(2 * n)[:, :n] if name.startswith("subtractive") else None
+    monkeypatch.setenv("FDSP_STAGED_W", str(width))
+    monkeypatch.setenv("FDSP_STAGED", "1")
+    b = GpuBank(workloads.build(name, V), per_voice=True, mix=True, sample_rate=SR)
+    rows, mix = b.render_samples(n, inp)
+    import os
+    assert "mock" in os.environ.get("FDSP_B200_LIB", "") or any(c["stages"] >= 2 for c in b.classes()), b.classes()   # (the CPU mock device has no staged form)
+    o, _ = oracle_bank_render(workloads.build(name, V), SR, n, inp, threads=4)
+    assert np.abs(o).max() > 1e-3
+    assert np.array_equal(rows, o), (int((rows != o).sum()), float(np.abs(rows - o).max()))
+    monkeypatch.setenv("FDSP_STAGED", "0")
+    p = GpuBank(workloads.build(name, V), per_voice=True, mix=True, sample_rate=SR)
+    rows0, mix0 = p.render_samples(n, inp)
+    assert np.array_equal(rows0, rows)
+    assert np.abs(mix - rows.astype(np.float64).sum(axis=0)).max() <= 1e-5 * max(1.0, np.abs(rows).sum(axis=0).max())
+    # continuation: the staged bank goes on with the plain kernel, the plain bank with the staged one
+    inp2 = np.zeros((1, n), np.float32) if inp is not None else None
+    a2, _ = b.render_samples(n, inp2)
+    monkeypatch.setenv("FDSP_STAGED", "1")
+    b2, _ = p.render_samples(n, inp2)
+    assert np.array_equal(a2, b2) and np.abs(a2).max() > 1e-4
+
+
 # ---------------------------------------------------------------- warp-per-voice FDN kernel (reverb_stereo)
 def test_reverb_only_bank_on_stereo_bus_input():
     """`reverb_stereo` applied to the bank's shared stereo input (one voice per room setting)."""

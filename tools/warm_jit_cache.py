@@ -16,6 +16,12 @@ def has_table(sig):
     return "WaveSynth<" in sig or "PhaseSynth<" in sig
 
 
+def has_heavy(sig):
+    """Leaves that csrc/dsp/stage_plan.cuh gives a warp of their own (IsHeavyLeaf); when they sit on the Pipe spine the bank launches the staged kernel."""
+    import re
+    return "Moog<" in sig or "Dsf<" in sig or re.search(r"NlBiquad<\d+,\d+,2,", sig) is not None
+
+
 def jobs():
     from fundsp_b200 import capi
     import test_gpu_jit as J
@@ -29,6 +35,8 @@ def jobs():
                 out[(sig, m, tb)] = True
             if has_table(sig) and m == 1:
                 out[(sig, 1, 1)] = True
+            if has_heavy(sig):   # the stage-pipelined kernel of the class (32 voices per CTA: what a 40-voice test bank launches), if it has one
+                out[(sig, m, (1 if has_table(sig) else 0) | (32 << 8))] = True
 
     for table in (J.CASES, J.WIDER, J.GATED):
         for name, mk in table.items():
