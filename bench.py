@@ -85,6 +85,41 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_cores():
+    """Threads the CPU arms may really use: the affinity mask capped by the cgroup CPU quota (os.cpu_count() reports the machine,
+    not the lease — round 1's two boxes both said 128 and differed 5x)."""
+    import math
+    aff = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    eff = max(1, min(aff, int(math.ceil(quota)))) if quota else max(1, aff)
+    return eff, {"affinity": aff, "cgroup_quota": quota, "os_cpu_count": os.cpu_count()}
+
+
+def native_oracle():
+    """The timed CPU arm runs the oracle built for THIS host (-march=native, as BASELINE.md §3 states); the parity tests keep the
+    portable x86-64-v3 build. Built once per box next to the portable one; falls back to it if the compiler is missing."""
+    so = os.path.join(ROOT, "oracle", "_build", "libfundsp_oracle_native.so")
+    try:
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "native"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+        if os.path.exists(so):
+            os.environ["FDSP_ORACLE_SO"] = so
+            return "g++ -O3 -march=native -ffp-contract=off"
+    except Exception:
+        pass
+    return "g++ -O3 -march=x86-64-v3 -ffp-contract=off (native build unavailable)"
+
+
 def gate_for(workload, n):
     from fundsp_b200 import workloads
     return workloads.gate_signal(n) if workload.startswith("subtractive") else None
@@ -106,8 +141,10 @@ def run_reference(a):
     n = int(round(a.seconds * SR))
     Vg = a.voices or HEADLINE[a.workload]
     V = Vg * max(1, a.gpus)          # the same whole-job configuration our arm runs at --gpus N (weak scaling: V per GPU)
-    cores = os.cpu_count() or 1
-    # bounded sample of the step: at most ~1.5e9 voice-samples per step so that K steps end within minutes on the host cores
+    build = native_oracle()
+    cores, core_info = host_cores()
+    # the whole step at N = 1 (and whenever it is at most ~1.5e9 voice-samples); beyond that a bounded sample of the step so that K
+    # steps end within minutes on the host cores — the sample is stated, `ms_per_step` is what was measured, not an extrapolation
     ns = n if V * n <= 1.5e9 else max(64, int(1.5e9 / V) // 64 * 64)
     for _ in range(a.warmup):
         cpu_reference(a.workload, V, min(ns, 4800), cores)
@@ -117,13 +154,19 @@ def run_reference(a):
         ts.append(dt)
     t = sum(ts) / len(ts)
     val = V * ns / t / 1e6
-    sample = f"{V} voices x {ns} of {n} samples per step, {cores} threads, voices sharded contiguously over the threads"
+    v1 = min(V, 64)
+    cpu_reference(a.workload, v1, 480, 1)
+    dt1, _ = cpu_reference(a.workload, v1, min(ns, 24000), 1)
+    per_core = v1 * min(ns, 24000) / dt1 / 1e6
+    sample = (f"{V} voices x {ns} of {n} samples per step ({'the whole step' if ns == n else 'bounded sample'}), {cores} threads "
+              f"(affinity {core_info['affinity']}, cgroup quota {core_info['cgroup_quota']}, os.cpu_count {core_info['os_cpu_count']}), voices sharded contiguously over the threads; {build}")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Msamples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": t * 1e3 * (n / ns), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a.workload, Vg), "voices_per_gpu": Vg, "voices_total": V, "sample_rate": SR, "block": 64, "seconds_per_step": a.seconds,
                    "output": "index-order mix of all voices", "note": "C++ oracle restating the reference's block path (no Rust toolchain on the box)"},
-        "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample, "single_core": per_core,
+                         "samples_per_step_timed": ns, "samples_per_step_config": n},
         "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -153,10 +196,15 @@ def main():
         raise SystemExit("bench.py: no CUDA device; fundsp_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dist = None
+    group = None
     if world > 1:
         import torch.distributed as dist
         from datetime import timedelta
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=timedelta(seconds=180))
+        # the mix-down collective itself runs below the C ABI (fdsp_group_*: NCCL gather over NVLink + rank-order fold on the bank's
+        # stream); torch.distributed only carries the 128-byte id, the barriers and the max-over-ranks of the timings
+        from fundsp_b200.parallel import BankGroup
+        group = BankGroup.from_torch_distributed(local)
     V = a.voices or HEADLINE[a.workload]
     n = int(round(a.seconds * SR))
     gate = gate_for(a.workload, n)
@@ -175,20 +223,20 @@ def main():
     host_in = torch.from_numpy(gate).pin_memory() if gate is not None else None
 
     def device_step():
-        bank.render_device(n, gin.data_ptr() if gin is not None else 0, n, out.data_ptr() if out is not None else 0, n, mix.data_ptr(), n, sync=True)
-        if dist is not None:
-            dist.reduce(mix, dst=0)
+        bank.render_device(n, gin.data_ptr() if gin is not None else 0, n, out.data_ptr() if out is not None else 0, n, mix.data_ptr(), n, sync=False)
+        if group is not None:
+            group.reduce_device(bank, n, mix.data_ptr(), n, 0)      # fdsp_bank_reduce_device, on the bank's stream
+        bank.sync()
 
     def e2e_step():
         from fundsp_b200.capi import check
         import ctypes as C
         fp = C.POINTER(C.c_float)
-        check(bank.L.fdsp_bank_render(bank.h, n, C.cast(host_in.data_ptr(), fp) if host_in is not None else None, None, C.cast(host_mix.data_ptr(), fp)))
-        if dist is not None:
-            m = host_mix.cuda(non_blocking=True)
-            dist.reduce(m, dst=0)
-            if rank == 0:
-                host_mix.copy_(m)
+        hin = C.cast(host_in.data_ptr(), fp) if host_in is not None else None
+        if group is None:
+            check(bank.L.fdsp_bank_render(bank.h, n, hin, None, C.cast(host_mix.data_ptr(), fp)))
+        else:   # one call per rank: render the shard, reduce the device mix over NVLink, ONE D2H on the root
+            check(bank.L.fdsp_bank_render_reduced(bank.h, group.h, n, hin, C.cast(host_mix.data_ptr(), fp) if rank == 0 else None, 0))
 
     def barrier():
         torch.cuda.synchronize()
@@ -289,30 +337,34 @@ def main():
         pass
     # ---- CPU baseline on this box's host cores (bounded sample of the same workload)
     # (timed at N=1 only; multi-GPU runs carry the object with value null — the reference arm `--impl reference` covers every N)
-    cores = os.cpu_count() or 1
+    cores, core_info = host_cores()
     ns = min(n, 24000)
-    cpu_val = None
+    cpu_val = per_core = None
+    build = ""
     if world == 1:
+        build = native_oracle()
         cpu_reference(a.workload, min(V, 256), 480, cores)
         dt, _ = cpu_reference(a.workload, V, ns, cores)
         cpu_val = V * ns / dt / 1e6
+        dt1, _ = cpu_reference(a.workload, min(V, 64), ns, 1)
+        per_core = min(V, 64) * ns / dt1 / 1e6
     line = {
         "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a.workload, V), "voices_per_gpu": V, "voices_total": world * V, "sample_rate": SR, "block": 64,
                    "seconds_per_step": a.seconds, "output": "mix-down to %d channel(s)%s" % (c, " + per-voice rows in HBM" if a.per_voice else ""),
-                   "parallelism": "voices sharded x%d, NCCL reduce of the mix" % world if world > 1 else "1 GPU", "l2": "flushed between timed steps (512 MB write)",
+                   "parallelism": "voices sharded x%d, one mix-down per step below the C ABI (NCCL send/recv gather over NVLink + rank-order fold)" % world if world > 1 else "1 GPU", "l2": "flushed between timed steps (512 MB write)",
                    "build_s": round(t_build, 3)},
         "e2e": {"value": e2e, "unit": "Msamples/s", "h2d_bytes_per_step": int(n * 4 if gate is not None else 0), "d2h_bytes_per_step": int(c * n * 4),
-                "call": "fdsp_bank_render(host buffers)", "ms_per_step": ms_e2e,
+                "call": "fdsp_bank_render(host buffers)" if world == 1 else "fdsp_bank_render_reduced(host buffers; D2H of the reduced mix on the root)", "ms_per_step": ms_e2e,
                 "process_granularity": {"value": proc_val, "unit": "Msamples/s", "us_per_call": t_p / pb * 1e6, "call": "fdsp_bank_process(64) per block, host buffers"}},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "fdsp::bank_kernel<...>", "kernel_ms_per_step": ms_kernel, "algorithmic_bytes_per_step": int(bytes_step),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)", "issue": issue,
                      "note": "IIR voice programs are issue/latency bound, not HBM bound (DESIGN.md §Roofline); see profiles/ for issue-slot utilisation"},
-        "cpu_baseline": {"value": cpu_val, "unit": "Msamples/s", "cores": cores, "kind": "port",
-                         "sample": (f"{V} voices x {ns} samples, oracle (C++ restatement of the reference block path), {cores} threads" if world == 1
+        "cpu_baseline": {"value": cpu_val, "unit": "Msamples/s", "cores": cores, "kind": "port", "single_core": per_core, "core_info": core_info,
+                         "sample": (f"{V} voices x {ns} samples, oracle (C++ restatement of the reference block path; {build}), {cores} threads" if world == 1
                                     else "not timed at N > 1 (see the N=1 line and the --impl reference arm)")},
         "clocks": clocks,
         "wall_s_timed_region": wall,

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "host/bank.h"
+#include "host/group.h"
 #include "host/wavfile.h"
 
 using namespace fdsp::host;
@@ -336,6 +337,33 @@ API int fdsp_bank_render_device(fdsp_bank* b, uint64_t n, const float* in_dev, u
                                 float* mix_dev, uint64_t mix_stride) {
   if (!b) return fail(FDSP_ERR_ARG, "null bank");
   return status(b->b.render_device(n, in_dev, in_stride, out_dev, out_stride, mix_dev, mix_stride));
+}
+// ---- multi-GPU mix-down (host/group.h)
+struct fdsp_group { fdsp::host::Group* g; };
+API int fdsp_group_unique_id(void* id, uint64_t bytes) {
+  if (!id || bytes < 128) return fail(FDSP_ERR_ARG, "the id buffer must hold 128 bytes");
+  return status(fdsp::host::group_unique_id(id));
+}
+API int fdsp_group_create(int nranks, int rank, const void* id, int device, fdsp_group** out) {
+  if (!out) return fail(FDSP_ERR_ARG, "null out pointer");
+  fdsp::host::Group* g = nullptr;
+  std::string e = fdsp::host::group_create(nranks, rank, id, device, &g);
+  if (!e.empty()) return status(e);
+  fdsp_group* h = new (std::nothrow) fdsp_group();
+  if (!h) { delete g; return fail(FDSP_ERR_STATE, "out of memory"); }
+  h->g = g; *out = h;
+  return FDSP_OK;
+}
+API void fdsp_group_destroy(fdsp_group* g) { if (g) { delete g->g; delete g; } }
+API int fdsp_group_rank(const fdsp_group* g) { return g ? g->g->rank : -1; }
+API int fdsp_group_size(const fdsp_group* g) { return g ? g->g->nranks : -1; }
+API int fdsp_bank_render_reduced(fdsp_bank* b, fdsp_group* g, uint64_t n, const float* in, float* out_mix, int root) {
+  if (!b || !g) return fail(FDSP_ERR_ARG, "null bank or group");
+  return status(fdsp::host::group_render_host(b->b, *g->g, n, in, out_mix, root));
+}
+API int fdsp_bank_reduce_device(fdsp_bank* b, fdsp_group* g, uint64_t n, float* mix_dev, uint64_t mix_stride, int root) {
+  if (!b || !g) return fail(FDSP_ERR_ARG, "null bank or group");
+  return status(fdsp::host::group_reduce_device(b->b, *g->g, n, mix_dev, mix_stride, root));
 }
 API int fdsp_bank_sync(fdsp_bank* b) {
   if (!b) return fail(FDSP_ERR_ARG, "null bank");

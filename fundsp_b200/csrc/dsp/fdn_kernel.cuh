@@ -12,16 +12,19 @@
 //     three neighbouring shared-memory words, the 32-point Hadamard is the reference's in-place butterfly (h = 1, 2, 4, 8, 16;
 //     a[j], a[j+h] = x + y, x - y) on a register array — no shuffles —, the output `Reduce` (sum of 32 pans, src/audionode.rs:
 //     2442-2463) is the same left fold in line order in two registers;
-//   * the ring slice a block reads (32 lines x 64 samples, contiguous per line) arrives by TMA: one `cp.async.bulk` per line
-//     (two when it wraps) issued by lane l for line l, three blocks in flight per warp, completion on one mbarrier per stage;
-//   * the 64 new samples per line are produced in place in the same shared-memory rows and leave by one `cp.async.bulk`
-//     shared->global per line.
+//   * the ring slice a block reads (32 lines x 64 samples, contiguous per line) is staged with 16-byte `cp.async.cg` (LDGSTS.128:
+//     17 warp-instructions per block, lanes cover (line, 16-byte chunk) pairs), three blocks in flight per warp;
+//   * the 64 new samples per line are produced in place in the same shared-memory rows and go back with 16-byte stores.
+//   (A first round-2 version moved every line's slice with its own `cp.async.bulk` — 64..96 TMA operations of 256 bytes per block
+//   and warp. It was bit-exact and no faster than round 1: 2.1 ms per 16384 samples, because the TMA unit serves about one
+//   operation per ~46 cycles per SM regardless of size, and 7 warps x 96 operations x 46 cycles is the whole block time. Bulk
+//   copies pay from about 1 KB up; a delay line hands out 256 contiguous bytes per block.)
 // Ring storage (private to this kernel; the host only sizes, clears and copies it): voice-major [voice][line][ring], each
 // line's ring padded to a multiple of 64 floats (`fdn_ring_phys`) so that block-aligned slices are 16-byte aligned and a
-// block never straddles the end. The state word of a line holds its WRITE position w; the sample written at w is read
+// block of new samples never straddles the end. The state word of a line holds its WRITE position w; the sample written at w is read
 // L - 1 steps later (Delay::tick writes buffer[i], then returns buffer[i + 1], length L).
-// After a ragged block (process(size) with size % 4 != 0) positions lose their 16-byte alignment: reads are still TMA (an
-// aligned superset + a per-line shift), writes fall back to per-lane stores until the positions re-align.
+// Reads always fetch a 16-byte aligned superset of the slice (per-line shift 0..3 floats). After a ragged block (process(size)
+// with size % 4 != 0) write positions lose their 16-byte alignment and the write-back falls back to 4-byte stores.
 // The wet/dry composition around the reverb,  dry >> (multipass::<U2>() & s * reverb_stereo(..)), is applied in the epilogue.
 // Word layout of the reverb inside the class arrays (DFS order, see csrc/host/graph.cpp):
 //   P: 32 x Fir weights(3) | 32 x Panner(lw, rw) | Constant<2>          (162 words, first row p0)
@@ -36,24 +39,14 @@ namespace fdsp {
 constexpr int FDN_NST = 3;                      // ring-slice stages per warp (prefetch distance 2 blocks)
 constexpr int FDN_RS = 72;                      // row stride (floats): 4 lead + 3 shift + 64 samples, 16-byte multiple
 constexpr int FDN_ROWS = 32 * FDN_RS;           // one stage
-// per warp: stages | dbuf [NST][2][64] | wtab [32][4] (w0 w1 w2 lw) | tb2 [NST][32][2] (rw, row offset) | vcarry [32] | obuf [2][64] | mbarriers
-constexpr int FDN_WARP_FLOATS = FDN_NST * FDN_ROWS + FDN_NST * 128 + 128 + FDN_NST * 64 + 32 + 128 + 2 * FDN_NST + 2;
+// per warp: stages | dbuf [NST][2][64] | wtab [32][4] (w0 w1 w2 lw) | tb2 [NST][32][2] (rw, row offset) | vcarry [32] | obuf [2][64] | geo [32][4] (idx, len, lp, off)
+constexpr int FDN_WARP_FLOATS = FDN_NST * FDN_ROWS + FDN_NST * 128 + 128 + FDN_NST * 64 + 32 + 128 + 128;
 
 FDSP_DEV uint32_t fdn_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-FDSP_DEV void fdn_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-FDSP_DEV void fdn_mbar_expect(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
-FDSP_DEV void fdn_mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile("{\n\t.reg .pred p;\n\tFW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra FD_%=;\n\tbra FW_%=;\n\tFD_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-FDSP_DEV void fdn_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-FDSP_DEV void fdn_s2g(void* dst, uint32_t src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-FDSP_DEV void fdn_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> FDSP_DEV void fdn_bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
-FDSP_DEV void fdn_fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+FDSP_DEV void fdn_cp16(uint32_t dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+FDSP_DEV void fdn_cp4(uint32_t dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); }
+FDSP_DEV void fdn_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> FDSP_DEV void fdn_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // blockDim.x = 32 * W (W voices per CTA), dynamic smem = W * FDN_WARP_FLOATS * 4 bytes
 __global__ void __launch_bounds__(256) fdn_kernel(const FdnArgs a) {
@@ -68,13 +61,11 @@ __global__ void __launch_bounds__(256) fdn_kernel(const FdnArgs a) {
   float2* tb2 = reinterpret_cast<float2*>(reinterpret_cast<float*>(wtab) + 128);   // [NST][32] (rw, float offset of d[0] of the line inside the stage)
   float* vcarry = reinterpret_cast<float*>(tb2) + FDN_NST * 64;      // [32] Feedback value entering the next block
   float* obuf = vcarry + 32;                          // [2][64] final output of this block (for the CTA mix)
-  const uint32_t bar0 = fdn_smem_addr(obuf + 128);    // NST mbarriers (8 bytes each)
+  uint4* geo = reinterpret_cast<uint4*>(obuf + 128);  // [32] (write position, length, physical length, ring offset) of every line, for the lanes that sweep (line, chunk)
 
   // ---- lane = line bookkeeping: ring geometry, write position, FIR shift register
   float f0 = 0, f1 = 0, f2 = 0, c0 = 0, c1 = 0, scalar = 1.0f;
   uint32_t idx = 0, len = 193, lp = 256, off = 0;
-  float* ring = nullptr;
-  if (lane == 0) { for (int s = 0; s < FDN_NST; s++) fdn_mbar_init(bar0 + 8u * s, 32); }
   if (active) {
     const uint32_t V = a.V;
     auto P = [&](uint32_t row) { return __uint_as_float(__ldg(a.params + (size_t)row * V + v)); };
@@ -93,35 +84,41 @@ __global__ void __launch_bounds__(256) fdn_kernel(const FdnArgs a) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
     off = incl - lp;
-    ring = a.ring + (size_t)v * a.ring_voice_stride + off;
+    geo[lane] = make_uint4(idx, len, lp, off);
   }
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncwarp();
+  float* const vring = active ? a.ring + (size_t)v * a.ring_voice_stride : nullptr;
   const float* dry = active ? a.dry + (size_t)v * a.dry_voice_stride + a.dry_offset : nullptr;
   const uint32_t rb0 = fdn_smem_addr(rbuf);
 
-  // lane l fetches the slice line l reads in the block that starts `adv` samples after the current write position: an aligned
-  // superset lands at float 4 of the row, d[t] of the block is row[4 + sh + t]
+  // stage the slices of the block that starts `adv` samples after the current write positions: per line an aligned superset of
+  // 17 x 16 bytes lands at float 4 of the row (d[t] of the block is row[4 + sh + t]); lanes sweep (line, chunk), 17 passes
+  const uint32_t db0 = fdn_smem_addr(dbuf);
   auto prefetch = [&](int st, uint32_t t0, int nb, uint32_t adv) {
-    if (!active || nb <= 0) return;
-    uint32_t rs = idx + adv + lp - (len - 1u);             // read start = write position - (L - 1)
-    rs -= (rs >= lp) ? lp : 0u; rs -= (rs >= lp) ? lp : 0u;
-    const uint32_t sh = rs & 3u, ra = rs - sh;
-    const uint32_t cnt = (sh + (uint32_t)nb + 3u) & ~3u;    // floats, multiple of 4
-    const uint32_t bar = bar0 + 8u * (uint32_t)st;
-    const uint32_t dst = rb0 + 4u * (uint32_t)(st * FDN_ROWS + lane * FDN_RS + 4);
-    tb2[st * 32 + lane].y = __int_as_float(lane * FDN_RS + 4 + (int)sh);
-    fdn_mbar_expect(bar, cnt * 4u);
-    const uint32_t first = (ra + cnt <= lp) ? cnt : lp - ra;
-    fdn_g2s(dst, ring + ra, first * 4u, bar);
-    if (first < cnt) fdn_g2s(dst + first * 4u, ring, (cnt - first) * 4u, bar);
-    // stereo input of that block (lanes sweep time; any alignment)
-    float* db = dbuf + st * 128;
+    if (active && nb > 0) {
+      const uint32_t nch = ((uint32_t)nb + 3u + 3u) >> 2;    // 16-byte chunks that cover shift + nb floats for any shift (17 for a full block)
+#pragma unroll 1
+      for (uint32_t e = (uint32_t)lane; e < 32u * nch; e += 32u) {
+        const uint32_t l = e / nch, k = e - l * nch;
+        const uint4 g = geo[l];                               // (idx, len, lp, off)
+        uint32_t rs = g.x + adv + g.z - (g.y - 1u);           // read start = write position - (L - 1)
+        rs -= (rs >= g.z) ? g.z : 0u; rs -= (rs >= g.z) ? g.z : 0u;
+        uint32_t pos = (rs & ~3u) + 4u * k;
+        pos -= (pos >= g.z) ? g.z : 0u;                       // lp is a multiple of 4: a chunk never straddles the end
+        fdn_cp16(rb0 + 4u * (uint32_t)(st * FDN_ROWS + (int)l * FDN_RS + 4 + 4 * (int)k), vring + g.w + pos);
+        if (k == 0) tb2[st * 32 + l].y = __int_as_float((int)l * FDN_RS + 4 + (int)(rs & 3u));
+      }
+      // stereo input of that block (lanes sweep time; any alignment)
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-      const int t = lane + 32 * q;
-      if (t < nb) { db[t] = __ldg(dry + t0 + t); db[64 + t] = __ldg(dry + a.dry_ch_stride + t0 + t); }
+      for (int q = 0; q < 2; q++) {
+        const int t = lane + 32 * q;
+        if (t < nb) {
+          fdn_cp4(db0 + 4u * (uint32_t)(st * 128 + t), dry + t0 + t);
+          fdn_cp4(db0 + 4u * (uint32_t)(st * 128 + 64 + t), dry + a.dry_ch_stride + t0 + t);
+        }
+      }
     }
+    fdn_cp_commit();   // one group per call, empty or not: the wait below counts groups
   };
 
   const float hz = (float)(1.0 / sqrt(32.0));
@@ -134,8 +131,9 @@ __global__ void __launch_bounds__(256) fdn_kernel(const FdnArgs a) {
     const int st = (int)(b % FDN_NST);
     const uint32_t t0 = b * 64u;
     const int nb = blen(b);
+    fdn_cp_wait<1>();   // all but the newest group: block b has landed (this lane's copies; the __syncwarp below publishes the others')
+    __syncwarp();
     if (active) {
-      fdn_mbar_wait(bar0 + 8u * (uint32_t)st, (b / FDN_NST) & 1u);
       float* rst = rbuf + st * FDN_ROWS;
       const float* db = dbuf + st * 128;
       {  // lane = line: FIR history in front of d[0], and the first new sample (input + the Feedback value carried over)
@@ -195,35 +193,35 @@ __global__ void __launch_bounds__(256) fdn_kernel(const FdnArgs a) {
         else { for (int i = 0; i < nb; i++) { f0 = f1; f1 = f2; f2 = rst[ro + i]; } }
       }
       __syncwarp();
-      const bool bulk_ok = __all_sync(0xffffffffu, ((idx | (uint32_t)nb) & 3u) == 0u);
-      if (bulk_ok) {
-        fdn_fence_async();   // the rows were written through the generic proxy
-        const uint32_t src = rb0 + 4u * (uint32_t)(st * FDN_ROWS + lane * FDN_RS);
-        const uint32_t first = (idx + (uint32_t)nb <= lp) ? (uint32_t)nb : lp - idx;
-        fdn_s2g(ring + idx, src, first * 4u);
-        if (first < (uint32_t)nb) fdn_s2g(ring, src + first * 4u, ((uint32_t)nb - first) * 4u);
-        fdn_bulk_commit();
+      const bool vec_ok = __all_sync(0xffffffffu, ((idx | (uint32_t)nb) & 3u) == 0u);
+      if (vec_ok) {
+        // 16-byte stores: lanes sweep (line, chunk of 4 samples); a chunk never straddles the ring end (positions and lp are multiples of 4)
+        const uint32_t nch = (uint32_t)nb >> 2;
+#pragma unroll 4
+        for (uint32_t e = (uint32_t)lane; e < 32u * nch; e += 32u) {
+          const uint32_t l = e / nch, k = e - l * nch;
+          const uint4 g = geo[l];
+          uint32_t pos = g.x + 4u * k; pos -= (pos >= g.z) ? g.z : 0u;
+          *reinterpret_cast<float4*>(vring + g.w + pos) = *reinterpret_cast<const float4*>(rst + l * FDN_RS + 4 * k);
+        }
       } else {
-        // ragged positions: lanes sweep time, lines are looped (coalesced rows); lane-invariant ring geometry through shuffles
+        // ragged positions: lanes sweep time, lines are looped (coalesced rows)
 #pragma unroll 1
         for (int l = 0; l < 32; l++) {
-          const uint32_t il = __shfl_sync(0xffffffffu, idx, l), ll = __shfl_sync(0xffffffffu, lp, l), ol = __shfl_sync(0xffffffffu, off, l);
-          float* rl = a.ring + (size_t)v * a.ring_voice_stride + ol;
+          const uint4 g = geo[l];
 #pragma unroll
           for (int q = 0; q < 2; q++) {
             const int t = lane + 32 * q;
-            if (t < nb) { uint32_t pos = il + (uint32_t)t; pos -= (pos >= ll) ? ll : 0u; rl[pos] = rst[l * FDN_RS + t]; }
+            if (t < nb) { uint32_t pos = g.x + (uint32_t)t; pos -= (pos >= g.z) ? g.z : 0u; vring[g.w + pos] = rst[l * FDN_RS + t]; }
           }
         }
-        __threadfence();
-        fdn_fence_async();   // later TMA reads of these samples go through the async proxy
-        fdn_bulk_commit();   // (an empty group keeps the wait below uniform)
       }
+      __syncwarp();   // geo is read by every lane above and advanced by its owner below
       idx += (uint32_t)nb; idx -= (idx >= lp) ? lp : 0u;
-      // the stage of block b - 1 is refilled for block b + 2: its own store (one group back) must have completed — both because the
-      // rows are overwritten and because a short ring may read what that store wrote
-      fdn_bulk_wait<1>();
+      geo[lane].x = idx;
       __syncwarp();
+      // the stage of block b - 1 is refilled for block b + 2 (its rows were stored one iteration ago, in program order before this point);
+      // what block b + 2 reads was written at least one whole block ago (every delay >= 192): plain program order through L2 makes it visible
       prefetch((int)((b + 2) % FDN_NST), t0 + 128u, blen(b + 2), 64u);
     } else if (a.partial) {
       for (int t = lane; t < 128; t += 32) obuf[t] = 0.0f;
@@ -240,7 +238,7 @@ __global__ void __launch_bounds__(256) fdn_kernel(const FdnArgs a) {
       __syncthreads();
     }
   }
-  fdn_bulk_wait<0>();
+  fdn_cp_wait<0>();
   if (active) {
     const uint32_t V = a.V;
     __syncwarp();

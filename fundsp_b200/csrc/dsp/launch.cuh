@@ -55,8 +55,13 @@ template <class G, int NTV, bool TB> cudaError_t launch_st_mode(const BankArgs& 
 // stage width: 32 voices per CTA when the launch asks for at most 32 (a.vpc), else 128
 template <class G> cudaError_t launch_st_t(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t st) {
   constexpr bool WT = WaveKind<G>::value >= 0;
-  const bool tb = WT && table_bytes > 0;
-  if (a.vpc && a.vpc <= 32u) return tb ? launch_st_mode<G, 32, WT>(a, mode, table_bytes, st) : launch_st_mode<G, 32, false>(a, mode, 0, st);
+  const bool narrow = a.vpc && a.vpc <= 32u;
+  const bool mix = (mode & 2) != 0;
+  const int ntv = narrow ? 32 : 128;
+  // tables in shared memory only when they fit beside the mix tile and the hand-off rings (else they are read through L1 / L2)
+  const size_t base = (mix ? sizeof(float) * mix_tile_floats(G::OUT, ntv) : 0) + sizeof(float) * st_hand_floats<G>(ntv, mix);
+  const bool tb = WT && table_bytes > 0 && base + table_bytes <= 227 * 1024;
+  if (narrow) return tb ? launch_st_mode<G, 32, WT>(a, mode, table_bytes, st) : launch_st_mode<G, 32, false>(a, mode, 0, st);
   return tb ? launch_st_mode<G, 128, WT>(a, mode, table_bytes, st) : launch_st_mode<G, 128, false>(a, mode, 0, st);
 }
 // table_bytes > 0 asks for the shared-memory wavetable variant (only meaningful when G reads a wavetable and it fits).

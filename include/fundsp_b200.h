@@ -215,6 +215,24 @@ int fdsp_bank_render(fdsp_bank* b, uint64_t n, const float* in, float* out_voice
 int fdsp_bank_render_device(fdsp_bank* b, uint64_t n, const float* in_dev, uint64_t in_stride, float* out_voices_dev, uint64_t voices_stride,
                             float* out_mix_dev, uint64_t mix_stride);
 int fdsp_bank_sync(fdsp_bank* b);
+/* ---- multi-GPU mix-down (csrc/host/group.h). Voices shard across ranks: one bank per GPU (one process per GPU, or
+   several banks in one process), no data-path collective — the ONE exchange step is the sum of the per-GPU partial mixes. It runs
+   below this ABI over NCCL / NVLink on the bank's own stream, so `render_reduced` is to a sharded bank what `Wave::render` of
+   "a Vec of units + a sum" (reference src/wave.rs:441-466) is to one: the root rank receives the finished mix.
+   Default association: the partials are gathered on the root and added in RANK ORDER ((p0 + p1) + p2) + ..., independent of NCCL's
+   algorithm choice (FDSP_GROUP_REDUCE=nccl: plain ncclReduce). The 128-byte unique id comes from rank 0 and is handed to the other
+   ranks by the host (a file, a socket, MPI, torch.distributed ...), like ncclGetUniqueId / ncclCommInitRank. */
+typedef struct fdsp_group fdsp_group;
+int fdsp_group_unique_id(void* id, uint64_t bytes);                          /* bytes >= 128 */
+int fdsp_group_create(int nranks, int rank, const void* id, int device, fdsp_group** out);   /* collective: every rank calls it */
+void fdsp_group_destroy(fdsp_group* g);
+int fdsp_group_rank(const fdsp_group* g);
+int fdsp_group_size(const fdsp_group* g);
+/* renders `samples` of this rank's bank (FDSP_OUT_MIX) and reduces; out_mix [channels][samples] (host) is written on `root` only */
+int fdsp_bank_render_reduced(fdsp_bank* b, fdsp_group* g, uint64_t samples, const float* in, float* out_mix, int root);
+/* device form: mix_dev [channels][mix_stride] holds this rank's partial (e.g. from fdsp_bank_render_device) and, on the root, the sum
+   afterwards; enqueued on the bank's stream */
+int fdsp_bank_reduce_device(fdsp_bank* b, fdsp_group* g, uint64_t samples, float* mix_dev, uint64_t mix_stride, int root);
 void* fdsp_bank_stream(fdsp_bank* b);                                       /* cudaStream_t the bank launches on */
 /* introspection */
 int fdsp_bank_num_classes(const fdsp_bank* b);

@@ -20,7 +20,7 @@ from fundsp_b200.sequencer import event  # noqa: E402
 
 early_events = lambda i: event(workloads.saw_svf_voice(i), (i % 7) * 0.0011, 1.0e6, 1, 0.003, 0.0)   # noqa: E731  (sequencer events that start within the render)
 for name, fn in (("saw_svf", workloads.saw_svf_voice), ("saw_svf_events", early_events), ("fm", workloads.fm_voice)):
-    sb = ShardedBank(fn, total, sample_rate=48000.0)
+    sb = ShardedBank(fn, total, device=0, sample_rate=48000.0)   # the mock has one "device"; on a GPU box the default is LOCAL_RANK
     mix = sb.render_mix(n)
     if dist.get_rank() == 0:
         from oracle import oracle_bank_render

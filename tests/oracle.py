@@ -28,7 +28,7 @@ def lib():
     global _lib
     if _lib is None:
         build_oracle()
-        L = C.CDLL(SO)
+        L = C.CDLL(os.environ.get("FDSP_ORACLE_SO") or SO)   # FDSP_ORACLE_SO: bench.py's -march=native build for the TIMED CPU arm only
         P, F, D, I, U64, I64 = C.c_void_p, C.c_float, C.c_double, C.c_int, C.c_uint64, C.c_int64
         FP = C.POINTER(C.c_float)
         sig = {

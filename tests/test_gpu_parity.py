@@ -255,6 +255,42 @@ def test_full_size_headline_properties():
     assert np.isfinite(g).all() and np.abs(g).max() < 8.0
 
 
+# Every BASELINE configuration at ITS OWN size (class layout, CTA spreading of bank_grid, the concurrent class streams of the 4-class Net
+# bank, the stage-pipelined Moog classes, 1024 FDN voices in one wave): per-voice rows of a strided sample of voices against the oracle.
+FULL = {
+    # name: (voices, samples, voice stride, exact)
+    "fm": (4096, 64 * 20, 173, True),                  # full blocks only: the wide-sin block path
+    "noise_svf": (16384, 64 * 12 + 5, 701, True),
+    "biquad_bank": (2048, 64 * 12 + 5, 97, True),
+    "subtractive": (1024, 4800 + 7, 53, True),         # 1024 voices: stage-pipelined dry program -> FDN kernel, two-stream pipeline
+    "net": (65536, 64 * 10, 2731, False),              # 4 classes x 16384 on concurrent streams; odd stride: every class is sampled
+}
+
+
+@pytest.mark.parametrize("name", sorted(FULL))
+def test_full_size_config_sampled_voices(name):
+    import os
+    from fundsp_b200.bank import GpuBank
+    if "mock" in os.environ.get("FDSP_B200_LIB", ""):
+        pytest.skip("BASELINE-size banks are for the GPU (the CPU mock device walks every voice serially)")
+    olib().fo_set_denormal_emulation(0)
+    V, n, stride, exact = FULL[name]
+    inp = workloads.gate_signal(n) if name == "subtractive" else None
+    b = GpuBank(workloads.build(name, V), per_voice=True, mix=True, sample_rate=SR)
+    g, mx = b.render_samples(n, inp)
+    idx = list(range(0, V, stride)) + [V - 1]
+    fn = workloads.WORKLOADS[name][0]
+    o, _ = oracle_bank_render([fn(i) for i in idx], SR, n, inp, threads=4)
+    assert np.abs(o).max() > 1e-3 and np.isfinite(g).all()
+    if exact:
+        assert np.array_equal(g[idx], o), (name, int((g[idx] != o).sum()), float(np.abs(g[idx] - o).max()))
+    else:
+        assert rel_err(g[idx], o) <= 1e-5, (name, rel_err(g[idx], o))
+    # the mix of ALL voices against the f64 sum of the rows: sqrt(V) * eps * sum|x|
+    ref = g.astype(np.float64).sum(axis=0)
+    assert np.abs(mx - ref).max() <= 4.0 * np.sqrt(V) * 2.0 ** -24 * np.abs(g).astype(np.float64).sum(axis=0).max() + 1e-7
+
+
 # ---------------------------------------------------------------- stage-pipelined kernels (csrc/dsp/bank_kernel_st.cuh)
 @pytest.mark.parametrize("width", [32, 128])
 @pytest.mark.parametrize("name,V", [("subtractive_dry", 70), ("net", 4 * 45)])

@@ -44,7 +44,7 @@ def mock_env():
             shutil.rmtree(os.path.join(os.path.dirname(build), d), ignore_errors=True)
     lib = os.path.join(build, "libfundsp_b200_mock.so")
     if not os.path.exists(lib):
-        srcs = [os.path.join(CSRC, "host", f) for f in ("graph.cpp", "wavetable.cpp", "bank.cpp", "wavfile.cpp")] + [os.path.join(CSRC, "capi.cpp"), os.path.join(MOCK, "registry_mock.cpp")]
+        srcs = [os.path.join(CSRC, "host", f) for f in ("graph.cpp", "wavetable.cpp", "bank.cpp", "group.cpp", "wavfile.cpp")] + [os.path.join(CSRC, "capi.cpp"), os.path.join(MOCK, "registry_mock.cpp")]
         san = ["-fsanitize=" + SAN, "-g", "-fno-omit-frame-pointer"] if SAN else []
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-w", "-shared", "-fPIC", "-DFDSP_HOST_EMUL=1", *san, "-I", MOCK, "-I", CSRC,
                                "-x", "c++", *srcs, "-o", lib + ".tmp", "-ldl"])
