@@ -21,7 +21,7 @@ struct FdnArgs {
   const float* dry;          // stereo input rows: dry[v * dry_voice_stride + ch * dry_ch_stride + dry_offset + t]
   uint64_t dry_voice_stride; uint32_t dry_ch_stride, dry_offset;
   float* out; const uint32_t* row_map; uint32_t out_stride, out_offset;  // per-voice rows (2 per voice) or null
-  float* partial;            // [grid][2][n] CTA partial mixes or null
+  float* partial;            // [V][2][n] per-voice rows of the mix-down (mix_reduce_kernel adds them in voice order) or null
   float* ring; uint64_t ring_voice_stride;
   uint32_t V, n;
 };

@@ -36,11 +36,11 @@
 
 namespace fdsp {
 
-constexpr int FDN_NST = 3;                      // ring-slice stages per warp (prefetch distance 2 blocks)
+constexpr int FDN_NST = 2;                      // ring-slice stages per warp: block b + 1 is fetched while block b is computed (a block takes ~6 us, HBM ~1 us)
 constexpr int FDN_RS = 72;                      // row stride (floats): 4 lead + 3 shift + 64 samples, 16-byte multiple
 constexpr int FDN_ROWS = 32 * FDN_RS;           // one stage
-// per warp: stages | dbuf [NST][2][64] | wtab [32][4] (w0 w1 w2 lw) | tb2 [NST][32][2] (rw, row offset) | vcarry [32] | obuf [2][64] | geo [32][4] (idx, len, lp, off)
-constexpr int FDN_WARP_FLOATS = FDN_NST * FDN_ROWS + FDN_NST * 128 + 128 + FDN_NST * 64 + 32 + 128 + 128;
+// per warp: stages | dbuf [NST][2][64] | wtab [32][4] (w0 w1 w2 lw) | tb2 [NST][32][2] (rw, row offset) | vcarry [32] | geo [32][4] (idx, len, lp, off)
+constexpr int FDN_WARP_FLOATS = FDN_NST * FDN_ROWS + FDN_NST * 128 + 128 + FDN_NST * 64 + 32 + 128;
 
 FDSP_DEV uint32_t fdn_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 FDSP_DEV void fdn_cp16(uint32_t dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
@@ -49,7 +49,7 @@ FDSP_DEV void fdn_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memor
 template <int N> FDSP_DEV void fdn_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // blockDim.x = 32 * W (W voices per CTA), dynamic smem = W * FDN_WARP_FLOATS * 4 bytes
-__global__ void __launch_bounds__(256) fdn_kernel(const FdnArgs a) {
+__global__ void __launch_bounds__(320) fdn_kernel(const FdnArgs a) {
   extern __shared__ __align__(16) float fdn_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
   const uint32_t v = blockIdx.x * W + warp;
@@ -60,8 +60,7 @@ __global__ void __launch_bounds__(256) fdn_kernel(const FdnArgs a) {
   float4* wtab = reinterpret_cast<float4*>(dbuf + FDN_NST * 128);   // [32] (w0, w1, w2, lw)
   float2* tb2 = reinterpret_cast<float2*>(reinterpret_cast<float*>(wtab) + 128);   // [NST][32] (rw, float offset of d[0] of the line inside the stage)
   float* vcarry = reinterpret_cast<float*>(tb2) + FDN_NST * 64;      // [32] Feedback value entering the next block
-  float* obuf = vcarry + 32;                          // [2][64] final output of this block (for the CTA mix)
-  uint4* geo = reinterpret_cast<uint4*>(obuf + 128);  // [32] (write position, length, physical length, ring offset) of every line, for the lanes that sweep (line, chunk)
+  uint4* geo = reinterpret_cast<uint4*>(vcarry + 32);  // [32] (write position, length, physical length, ring offset) of every line, for the lanes that sweep (line, chunk)
 
   // ---- lane = line bookkeeping: ring geometry, write position, FIR shift register
   float f0 = 0, f1 = 0, f2 = 0, c0 = 0, c1 = 0, scalar = 1.0f;
@@ -96,17 +95,27 @@ __global__ void __launch_bounds__(256) fdn_kernel(const FdnArgs a) {
   const uint32_t db0 = fdn_smem_addr(dbuf);
   auto prefetch = [&](int st, uint32_t t0, int nb, uint32_t adv) {
     if (active && nb > 0) {
+      // half a warp per line: lanes 0-15 fetch chunks 0..15 of line 2i, lanes 16-31 those of line 2i + 1 (256 contiguous bytes each);
+      // the 17th chunk of every line (needed whenever the slice starts off a 16-byte boundary) goes in one extra pass, lane = line
       const uint32_t nch = ((uint32_t)nb + 3u + 3u) >> 2;    // 16-byte chunks that cover shift + nb floats for any shift (17 for a full block)
-#pragma unroll 1
-      for (uint32_t e = (uint32_t)lane; e < 32u * nch; e += 32u) {
-        const uint32_t l = e / nch, k = e - l * nch;
+      const uint32_t hl = (uint32_t)lane >> 4, k = (uint32_t)lane & 15u;
+#pragma unroll 4
+      for (uint32_t i = 0; i < 16u; i++) {
+        const uint32_t l = 2u * i + hl;
         const uint4 g = geo[l];                               // (idx, len, lp, off)
         uint32_t rs = g.x + adv + g.z - (g.y - 1u);           // read start = write position - (L - 1)
         rs -= (rs >= g.z) ? g.z : 0u; rs -= (rs >= g.z) ? g.z : 0u;
         uint32_t pos = (rs & ~3u) + 4u * k;
         pos -= (pos >= g.z) ? g.z : 0u;                       // lp is a multiple of 4: a chunk never straddles the end
-        fdn_cp16(rb0 + 4u * (uint32_t)(st * FDN_ROWS + (int)l * FDN_RS + 4 + 4 * (int)k), vring + g.w + pos);
-        if (k == 0) tb2[st * 32 + l].y = __int_as_float((int)l * FDN_RS + 4 + (int)(rs & 3u));
+        if (k < nch) fdn_cp16(rb0 + 4u * (uint32_t)(st * FDN_ROWS + (int)l * FDN_RS + 4 + 4 * (int)k), vring + g.w + pos);
+      }
+      {
+        uint32_t rs = idx + adv + lp - (len - 1u);            // lane = line: this lane's own registers
+        rs -= (rs >= lp) ? lp : 0u; rs -= (rs >= lp) ? lp : 0u;
+        uint32_t pos = (rs & ~3u) + 64u;
+        pos -= (pos >= lp) ? lp : 0u;
+        if (nch > 16u) fdn_cp16(rb0 + 4u * (uint32_t)(st * FDN_ROWS + lane * FDN_RS + 4 + 64), vring + off + pos);
+        tb2[st * 32 + lane].y = __int_as_float(lane * FDN_RS + 4 + (int)(rs & 3u));
       }
       // stereo input of that block (lanes sweep time; any alignment)
 #pragma unroll
@@ -125,12 +134,14 @@ __global__ void __launch_bounds__(256) fdn_kernel(const FdnArgs a) {
   const uint32_t nblk = (a.n + 63u) / 64u;
   auto blen = [&](uint32_t b) { return b < nblk ? (int)((a.n - b * 64u) < 64u ? (a.n - b * 64u) : 64u) : 0; };
   prefetch(0, 0u, blen(0), 0u);
-  prefetch(1, 64u, blen(1), 64u);
 #pragma unroll 1
   for (uint32_t b = 0; b < nblk; b++) {
     const int st = (int)(b % FDN_NST);
     const uint32_t t0 = b * 64u;
     const int nb = blen(b);
+    // the other stage held block b - 1: its rows went back to the rings before the __syncwarp that ended the last iteration. What block
+    // b + 1 reads was written at least a whole block ago (every delay >= 192 samples), in program order before this point.
+    prefetch((int)((b + 1) % FDN_NST), t0 + 64u, blen(b + 1), (uint32_t)nb);
     fdn_cp_wait<1>();   // all but the newest group: block b has landed (this lane's copies; the __syncwarp below publishes the others')
     __syncwarp();
     if (active) {
@@ -179,7 +190,9 @@ __global__ void __launch_bounds__(256) fdn_kernel(const FdnArgs a) {
 #pragma unroll
             for (int l = 0; l < 32; l++) vcarry[l] = av[l] * hz;    // enters the first sample of the next block
           }
-          obuf[t] = sl; obuf[64 + t] = sr;
+          if (a.partial) {   // per-voice rows of the mix-down [V][2][n]: mix_reduce_kernel adds them in voice order
+            a.partial[((size_t)v * 2) * a.n + t0 + t] = sl; a.partial[((size_t)v * 2 + 1) * a.n + t0 + t] = sr;
+          }
           if (a.out) {
             float* orow = a.out + (size_t)__ldg(a.row_map + v) * a.out_stride + a.out_offset + t0 + t;
             orow[0] = sl; orow[a.out_stride] = sr;
@@ -196,13 +209,14 @@ __global__ void __launch_bounds__(256) fdn_kernel(const FdnArgs a) {
       const bool vec_ok = __all_sync(0xffffffffu, ((idx | (uint32_t)nb) & 3u) == 0u);
       if (vec_ok) {
         // 16-byte stores: lanes sweep (line, chunk of 4 samples); a chunk never straddles the ring end (positions and lp are multiples of 4)
-        const uint32_t nch = (uint32_t)nb >> 2;
+        const uint32_t nch = (uint32_t)nb >> 2;                  // <= 16: half a warp per line, as in the prefetch
+        const uint32_t hl = (uint32_t)lane >> 4, k = (uint32_t)lane & 15u;
 #pragma unroll 4
-        for (uint32_t e = (uint32_t)lane; e < 32u * nch; e += 32u) {
-          const uint32_t l = e / nch, k = e - l * nch;
+        for (uint32_t i = 0; i < 16u; i++) {
+          const uint32_t l = 2u * i + hl;
           const uint4 g = geo[l];
           uint32_t pos = g.x + 4u * k; pos -= (pos >= g.z) ? g.z : 0u;
-          *reinterpret_cast<float4*>(vring + g.w + pos) = *reinterpret_cast<const float4*>(rst + l * FDN_RS + 4 * k);
+          if (k < nch) *reinterpret_cast<float4*>(vring + g.w + pos) = *reinterpret_cast<const float4*>(rst + l * FDN_RS + 4 * k);
         }
       } else {
         // ragged positions: lanes sweep time, lines are looped (coalesced rows)
@@ -220,22 +234,6 @@ __global__ void __launch_bounds__(256) fdn_kernel(const FdnArgs a) {
       idx += (uint32_t)nb; idx -= (idx >= lp) ? lp : 0u;
       geo[lane].x = idx;
       __syncwarp();
-      // the stage of block b - 1 is refilled for block b + 2 (its rows were stored one iteration ago, in program order before this point);
-      // what block b + 2 reads was written at least one whole block ago (every delay >= 192): plain program order through L2 makes it visible
-      prefetch((int)((b + 2) % FDN_NST), t0 + 128u, blen(b + 2), 64u);
-    } else if (a.partial) {
-      for (int t = lane; t < 128; t += 32) obuf[t] = 0.0f;
-    }
-    if (a.partial) {   // CTA mix in warp (= voice) order, deterministic
-      __syncthreads();
-      for (int e = threadIdx.x; e < 2 * nb; e += blockDim.x) {
-        const int ch = e / nb, t = e - ch * nb;
-        const size_t ob = (size_t)(obuf - sm);
-        float s = fdn_smem[ob + ch * 64 + t];
-        for (int w = 1; w < W; w++) s += fdn_smem[(size_t)w * FDN_WARP_FLOATS + ob + ch * 64 + t];
-        a.partial[((size_t)blockIdx.x * 2 + ch) * a.n + t0 + t] = s;
-      }
-      __syncthreads();
     }
   }
   fdn_cp_wait<0>();

@@ -35,10 +35,25 @@ template <class T> std::string dev_alloc(T** p, size_t count) {
 }
 }  // namespace
 
+// `Pipe<X, Convolver>` with a response long enough for 128-wide tiles goes to the tensor-core form (FDSP_TC_CONV=0: direct form only;
+// FDSP_TC_MINK: shortest response, default 32 taps). One output channel, and not on the CPU mock device.
+static bool tc_conv_wanted(const std::string& sig, const Lowering& l, int nout) {
+#ifdef FDSP_HOST_EMUL
+  (void)sig; (void)l; (void)nout; return false;
+#else
+  static const std::string CT = ",Convolver>";
+  const char* e = getenv("FDSP_TC_CONV"); const char* m = getenv("FDSP_TC_MINK");
+  if (e && atoi(e) == 0) return false;
+  const uint32_t mink = m ? (uint32_t)atoi(m) : 32u;
+  return nout == 1 && sig.compare(0, 5, "Pipe<") == 0 && sig.size() > 5 + CT.size() && sig.compare(sig.size() - CT.size(), CT.size(), CT) == 0 && l.conv_K >= mink &&
+         l.conv_off + 2u + l.conv_K == l.U.size();
+#endif
+}
+
 Bank::~Bank() {
   cudaSetDevice(device);
   for (auto& c : classes) {
-    cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows); cudaFree(c.d_dry2); cudaFree(c.d_partial2); for (int q = 0; q < 2; q++) { if (c.e_dry[q]) cudaEventDestroy(c.e_dry[q]); if (c.e_fdn[q]) cudaEventDestroy(c.e_fdn[q]); } if (c.cstream) cudaStreamDestroy(c.cstream); if (c.e_done) cudaEventDestroy(c.e_done);
+    cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows); cudaFree(c.d_dry2); cudaFree(c.d_partial2); cudaFree(c.d_cx); cudaFree(c.d_cxl); cudaFree(c.d_th); cudaFree(c.d_tl); cudaFree(c.d_crows); for (int q = 0; q < 2; q++) { if (c.e_dry[q]) cudaEventDestroy(c.e_dry[q]); if (c.e_fdn[q]) cudaEventDestroy(c.e_fdn[q]); } if (c.cstream) cudaStreamDestroy(c.cstream); if (c.e_done) cudaEventDestroy(c.e_done);
   }
   for (float* p : d_wtdata) cudaFree(p);
   cudaFree(d_wt); cudaFree(d_in); cudaFree(d_out); cudaFree(d_mix); cudaFree(d_rows);
@@ -122,6 +137,19 @@ std::string Bank::lower_and_upload(bool upload_state) {
           if ((uint32_t)c.k->NP != c.p0 - (wet ? 1u : 0u) - lo.l.extraP || (uint32_t)c.k->NS != c.s0 || (uint32_t)c.k->NU != c.u0 - lo.l.extraU || c.k->IN != nin || c.k->OUT != 2)
             return "internal: dry-stage layout of `" + prog_sig + "` disagrees with the host lowering";
         }
+      } else if (tc_conv_wanted(lo.sig, lo.l, nout)) {
+        // `X >> convolve(h)`: X stays a fused per-voice program that writes its rows, the tap contraction runs on tensor cores. The
+        // Convolver's own words (ring index, history ring) stay in the layout and are simply not used by this form.
+        static const std::string CT = ",Convolver>";
+        const std::string xsig = lo.sig.substr(5, lo.sig.size() - 5 - CT.size());
+        for (uint32_t d : lo.l.dlen) c.dl_floats += d;
+        c.k = get_program(xsig, device, jerr);
+        if (!c.k) return "no device program for `" + xsig + "` (in front of the convolver): " + jerr;
+        if ((uint32_t)c.k->NP != c.np - lo.l.extraP || (uint32_t)c.k->NS + 1u != c.ns || (uint32_t)c.k->NU + 2u != nu_static || c.k->IN != nin || c.k->OUT != 1)
+          return "internal: layout of `" + xsig + "` in front of the convolver disagrees with the host lowering";
+        c.conv = true; c.conv_K = lo.l.conv_K; c.conv_off = lo.l.conv_off;
+        c.conv_H = (c.conv_K - 1u + 31u) / 32u * 32u; if (c.conv_H == 0) c.conv_H = 32;
+        c.conv_J = conv_tc_toeplitz_cols(c.conv_K); c.conv_stride = c.conv_H + TIME_CHUNK;
       } else {
         for (uint32_t d : lo.l.dlen) c.dl_floats += d;
         c.k = get_program(lo.sig, device, jerr);
@@ -134,11 +162,19 @@ std::string Bank::lower_and_upload(bool upload_state) {
     fresh[ci].voices.push_back((uint32_t)v);
     std::string().swap(lo.key); std::vector<uint32_t>().swap(lo.l.U);   // the class keeps the uniform words (a sampler voice's may be a whole wave)
   }
+  if (fresh.size() > 1) {   // the tensor-core convolver form is for one-class banks (its mix-down is the voice-order fold of its own rows)
+    for (auto& c : fresh) if (c.conv) {
+      std::string jerr;
+      c.conv = false;
+      c.k = get_program(c.sig, device, jerr);
+      if (!c.k) return "no device program for graph class `" + c.sig + "`: " + jerr;
+    }
+  }
   // 2. keep device buffers of classes that survive unchanged (same key order / sizes), else rebuild
   const bool same_shape = classes.size() == fresh.size() && std::equal(classes.begin(), classes.end(), fresh.begin(), [](const VoiceClass& a, const VoiceClass& b) {
                             return a.sig == b.sig && a.voices == b.voices && a.uniform == b.uniform; });
   if (!same_shape) {
-    for (auto& c : classes) { cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows); cudaFree(c.d_dry2); cudaFree(c.d_partial2); for (int q = 0; q < 2; q++) { if (c.e_dry[q]) cudaEventDestroy(c.e_dry[q]); if (c.e_fdn[q]) cudaEventDestroy(c.e_fdn[q]); } if (c.cstream) cudaStreamDestroy(c.cstream); if (c.e_done) cudaEventDestroy(c.e_done); }
+    for (auto& c : classes) { cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows); cudaFree(c.d_dry2); cudaFree(c.d_partial2); cudaFree(c.d_cx); cudaFree(c.d_cxl); cudaFree(c.d_th); cudaFree(c.d_tl); cudaFree(c.d_crows); for (int q = 0; q < 2; q++) { if (c.e_dry[q]) cudaEventDestroy(c.e_dry[q]); if (c.e_fdn[q]) cudaEventDestroy(c.e_fdn[q]); } if (c.cstream) cudaStreamDestroy(c.cstream); if (c.e_done) cudaEventDestroy(c.e_done); }
     classes = std::move(fresh);
     upload_state = true;
   }
@@ -171,6 +207,17 @@ std::string Bank::lower_and_upload(bool upload_state) {
           CU(cudaMemcpy(c.d_dryrows, id.data(), V * 4, cudaMemcpyHostToDevice));
         }
       }
+      if (c.conv) {
+        if (!(e = dev_alloc(&c.d_cx, (size_t)V * c.conv_stride)).empty()) return e;
+        if (!(e = dev_alloc(&c.d_cxl, (size_t)V * c.conv_stride)).empty()) return e;
+        if (!(e = dev_alloc(&c.d_th, (size_t)128 * c.conv_J)).empty()) return e;
+        if (!(e = dev_alloc(&c.d_tl, (size_t)128 * c.conv_J)).empty()) return e;
+        if (!(e = dev_alloc(&c.d_dryrows, V)).empty()) return e;
+        std::vector<uint32_t> id(V);
+        for (uint32_t i = 0; i < V; i++) id[i] = i;
+        CU(cudaMemcpy(c.d_dryrows, id.data(), V * 4, cudaMemcpyHostToDevice));
+        CU(conv_tc_make_maps(c.d_cx, c.d_cxl, V, c.conv_stride, c.d_th, c.d_tl, c.conv_J, &c.conv_maps));
+      }
       CU(cudaMemcpy(c.d_rowmap, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice));
       if (!c.uniform.empty()) CU(cudaMemcpy(c.d_uniform, c.uniform.data(), c.uniform.size() * 4, cudaMemcpyHostToDevice));
     }
@@ -179,6 +226,11 @@ std::string Bank::lower_and_upload(bool upload_state) {
       if (!S.empty()) CU(cudaMemcpy(c.d_state, S.data(), S.size() * 4, cudaMemcpyHostToDevice));
       if (c.dl_floats) CU(cudaMemset(c.d_dline, 0, (size_t)c.dl_floats * V * sizeof(float)));
       if (c.ring_floats) CU(cudaMemset(c.d_ring, 0, (size_t)c.ring_floats * V * sizeof(float)));
+      if (c.conv) {
+        CU(cudaMemset(c.d_cx, 0, (size_t)V * c.conv_stride * sizeof(float))); CU(cudaMemset(c.d_cxl, 0, (size_t)V * c.conv_stride * sizeof(float)));
+        CU(launch_conv_toeplitz(reinterpret_cast<const float*>(c.d_uniform + c.conv_off + 2), c.conv_K, c.d_th, c.d_tl, c.conv_J, stream));
+        CU(cudaStreamSynchronize(stream));
+      }
     }
   }
   // 3. wavetables used by any class (a class that arrives later — add_voice — may bring a waveform the bank has not loaded yet)
@@ -438,6 +490,7 @@ std::string Bank::reset() {  // AudioUnit::reset: back to the construction-time 
     if (!c.state0.empty()) CU(cudaMemcpyAsync(c.d_state, c.state0.data(), c.state0.size() * 4, cudaMemcpyHostToDevice, stream));
     if (c.dl_floats) CU(cudaMemsetAsync(c.d_dline, 0, (size_t)c.dl_floats * c.V() * sizeof(float), stream));
     if (c.ring_floats) CU(cudaMemsetAsync(c.d_ring, 0, (size_t)c.ring_floats * c.V() * sizeof(float), stream));
+    if (c.conv) { CU(cudaMemsetAsync(c.d_cx, 0, (size_t)c.V() * c.conv_stride * sizeof(float), stream)); CU(cudaMemsetAsync(c.d_cxl, 0, (size_t)c.V() * c.conv_stride * sizeof(float), stream)); }
   }
   CU(cudaStreamSynchronize(stream));
   dirty = false; seq_time = 0.0;
@@ -498,6 +551,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
     return "";
   };
   uint64_t chunk_index = 0;
+  bool joined = true;
   // FDSP_PIPE_TRACE=1: print the device timeline of the two pipeline stages (diagnostic; synchronises)
   const bool trace = pipelined && getenv("FDSP_PIPE_TRACE") != nullptr;
   std::vector<cudaEvent_t> tev;   // per chunk: dry start, dry end, fdn start, fdn end
@@ -507,13 +561,13 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
     if (rows_cap < need) { std::string e = dev_alloc(&d_rows, need); if (!e.empty()) return e; rows_cap = need; }
   }
   const bool save_want_v = want_v, save_want_m = want_m;
+  // pipelined banks accumulate into a zeroed mix: cleared once for the whole call, so that nothing sits between the dry-stage launches of
+  // consecutive chunks on `stream` (a gap there lets the wide FDN kernel of the previous chunk take every SM first)
+  if (pipelined && save_want_m) CU(cudaMemset2DAsync(mix_dev, (size_t)mix_stride * 4, 0, (size_t)n * 4, (size_t)nout, stream));
   for (uint64_t t0 = 0; t0 < n; t0 += CH, chunk_index++) {
     const uint32_t len = (uint32_t)std::min<uint64_t>(CH, n - t0);
     bool first = true;
-    if (pipelined && save_want_m) {  // every class accumulates into a zeroed mix region (reductions of pipelined classes arrive late)
-      CU(cudaMemset2DAsync(mix_dev + t0, (size_t)mix_stride * 4, 0, (size_t)len * 4, (size_t)nout, stream));
-      first = false;
-    }
+    if (pipelined && save_want_m) first = false;   // every class accumulates into the mix region zeroed above (reductions of pipelined classes arrive late)
     bool want_v = save_want_v, want_m = save_want_m;
     float* out_dev_c = out_dev; uint64_t out_stride_c = out_stride; uint64_t out_t0 = t0;
     if (tree) { want_m = false; if (!save_want_v) { want_v = true; out_dev_c = d_rows; out_stride_c = CH; out_t0 = 0; } }
@@ -546,7 +600,28 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
       uint32_t vpc = c.k ? (uint32_t)c.k->threads : 0u;
       const uint32_t vgrid = !c.k ? 0u : (staged ? staged_grid(V, &vpc) : (c.fdn || getenv("FDSP_NO_SPREAD") ? (V + vpc - 1) / vpc : bank_grid(V, (uint32_t)c.k->threads, &vpc)));
       auto launch_voice = [&](const BankArgs& args, int md, cudaStream_t st) { return staged ? c.k->launch_staged(args, md, table_bytes_of(c, len), st) : c.k->launch(args, md, table_bytes_of(c, len), st); };
-      const uint32_t grid = c.fdn ? (V + (uint32_t)fdn_warps - 1) / (uint32_t)fdn_warps : vgrid;
+      const uint32_t grid = c.fdn ? V : vgrid;   // rows of the partial-mix buffer: one per CTA of a voice program, one per VOICE of the FDN kernel (its warps never meet)
+      if (c.conv) {
+        // stage 1: the program in front of the convolver writes its rows behind the history columns; then x_lo, the Toeplitz GEMM tiles
+        // (rows straight into the caller's buffer, or an internal one), the history shift, and the voice-order fold of the rows
+        BankArgs d;
+        d.params = c.d_params; d.state = c.d_state; d.uniform = c.d_uniform; d.dline = c.d_dline; d.wt = d_wt; d.in = in_dev; d.partial = nullptr;
+        d.out = c.d_cx; d.V = V; d.n = len; d.vpc = vpc; d.in_stride = (uint32_t)in_stride; d.in_offset = (uint32_t)t0; d.out_stride = c.conv_stride; d.out_offset = c.conv_H;
+        d.row_map = c.d_dryrows; d.sr = (float)sr; d.sd64 = (float)(1.0 / sr); d.sd32 = 1.0f / (float)sr; d.ticket = nullptr; d.mix = nullptr; d.mix_stride = 0; d.mix_offset = 0; d.mix_accumulate = 0;
+        CU(launch_voice(d, 1, stream));
+        CU(launch_conv_split(c.d_cx, c.d_cxl, V, c.conv_stride, c.conv_H, len, stream));
+        float* y = want_v ? out_dev_c : nullptr; uint32_t ys = (uint32_t)out_stride_c, yo = (uint32_t)out_t0;
+        if (!y) {
+          if (c.crows_cap < (size_t)V * TIME_CHUNK) { std::string e = dev_alloc(&c.d_crows, (size_t)V * TIME_CHUNK); if (!e.empty()) return e; c.crows_cap = (size_t)V * TIME_CHUNK; }
+          y = c.d_crows; ys = TIME_CHUNK; yo = 0;
+        }
+        CU(launch_conv_tc(c.conv_maps, y, ys, yo, c.d_dryrows, V, len, c.conv_K, c.conv_H, stream));
+        CU(launch_conv_history(c.d_cx, c.d_cxl, V, c.conv_stride, c.conv_H, len, stream));
+        launches += 4;
+        if (want_m) { CU(launch_tree_mix(y, V, 1u, ys, yo, len, mix_dev, (uint32_t)mix_stride, (uint32_t)t0, 0, stream)); launches++; }
+        first = false;
+        continue;
+      }
       if (want_m) {
         const size_t need = (size_t)grid * nout * len;
         if (c.partial_floats < need) { std::string e = dev_alloc(&c.d_partial, (size_t)grid * nout * TIME_CHUNK); if (!e.empty()) return e; c.partial_floats = (size_t)grid * nout * TIME_CHUNK; }
@@ -583,8 +658,11 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
           launches++;
           tmark(stream);
           CU(cudaEventRecord(c.e_dry[buf], stream));
-          std::string pe = flush_pending(&c);                  // reduce chunk k-1 of this class (waits for its FDN)
-          if (!pe.empty()) return pe;
+          // A bank of this one class keeps `stream` for the dry stage alone — chunk k + 1 follows chunk k with nothing in between, so it
+          // holds its SMs before the wide FDN kernel of chunk k floods the rest — and reduces on stream2 behind the FDN kernel. With other
+          // classes in the bank every reduction stays on `stream` (they accumulate into the same mix region), one chunk late.
+          const bool solo = classes.size() == 1;
+          if (!solo) { std::string pe = flush_pending(&c); if (!pe.empty()) return pe; }   // reduce chunk k-1 of this class (waits for its FDN)
           f.dry = dry; f.dry_voice_stride = 2ull * PIPE_CHUNK; f.dry_ch_stride = PIPE_CHUNK; f.dry_offset = 0;
           f.out = want_v ? out_dev_c : nullptr; f.row_map = c.d_rowmap; f.out_stride = (uint32_t)out_stride_c; f.out_offset = (uint32_t)out_t0;
           f.partial = want_m ? (buf ? c.d_partial2 : c.d_partial) : nullptr;
@@ -595,7 +673,12 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
           launches++;
           tmark(stream2);
           CU(cudaEventRecord(c.e_fdn[buf], stream2));
-          pending.push_back({&c, grid, len, t0, buf});
+          if (!solo) pending.push_back({&c, grid, len, t0, buf});
+          else if (want_m) {
+            CU(launch_mix_reduce(buf ? c.d_partial2 : c.d_partial, grid, (uint32_t)nout, len, mix_dev, (uint32_t)mix_stride, (uint32_t)t0, 1, stream2));
+            launches++;
+            joined = false;
+          }
           continue;
         }
         if (c.k) {  // stage 1: the fused dry program writes stereo rows [V][2][TIME_CHUNK]
@@ -640,6 +723,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
     }
   }
   { std::string pe = flush_pending(nullptr); if (!pe.empty()) return pe; }   // also joins stream2 back into `stream`
+  if (!joined) { CU(cudaEventRecord(e_begin, stream2)); CU(cudaStreamWaitEvent(stream, e_begin, 0)); }   // solo two-stage class: its reductions ran on stream2
   if (timing) CU(cudaEventRecord(ev1, stream));
   if (trace) {
     CU(cudaStreamSynchronize(stream));
@@ -749,6 +833,7 @@ std::string Bank::clone_into(Bank& dst) const {
     if (!s.state0.empty()) CU(cudaMemcpy(d.d_state, s.d_state, s.state0.size() * 4, cudaMemcpyDeviceToDevice));
     if (s.dl_floats) CU(cudaMemcpy(d.d_dline, s.d_dline, (size_t)s.dl_floats * s.V() * 4, cudaMemcpyDeviceToDevice));
     if (s.ring_floats && s.d_ring && d.d_ring) CU(cudaMemcpy(d.d_ring, s.d_ring, (size_t)s.ring_floats * s.V() * 4, cudaMemcpyDeviceToDevice));
+    if (s.conv && d.conv) { CU(cudaMemcpy(d.d_cx, s.d_cx, (size_t)s.V() * s.conv_stride * 4, cudaMemcpyDeviceToDevice)); CU(cudaMemcpy(d.d_cxl, s.d_cxl, (size_t)s.V() * s.conv_stride * 4, cudaMemcpyDeviceToDevice)); }
   }
   dst.dirty = dirty; dst.seq_time = seq_time;
   return "";

@@ -23,6 +23,11 @@ struct VoiceClass {
   // reverb_stereo tail handled by the warp-per-voice FDN kernel (dsp/fdn_kernel.cuh); `k` is then the dry-stage program (may be null)
   bool fdn = false; int scalar_row = -1; uint32_t p0 = 0, s0 = 0, u0 = 0; uint64_t ring_floats = 0;
   float* d_ring = nullptr; float* d_dry = nullptr; uint32_t* d_dryrows = nullptr;
+  // `... >> convolve(h)` tail on tensor cores (dsp/conv_tc_kernel.cuh): `k` is then the program in front of the Convolver; its output rows
+  // live in d_cx [V][conv_H + chunk] (history columns in front), d_cxl = their TF32 remainders, d_th / d_tl = Toeplitz(h) hi / lo
+  bool conv = false; uint32_t conv_K = 0, conv_H = 0, conv_J = 0, conv_stride = 0, conv_off = 0;
+  float *d_cx = nullptr, *d_cxl = nullptr, *d_th = nullptr, *d_tl = nullptr, *d_crows = nullptr; size_t crows_cap = 0;
+  ConvTcMaps conv_maps;
   // two-stage classes are software-pipelined over sub-chunks: dry stage of chunk k+1 (stream) runs beside the FDN of chunk k (stream2)
   float* d_dry2 = nullptr; float* d_partial2 = nullptr; size_t partial2_floats = 0;
   cudaEvent_t e_dry[2] = {nullptr, nullptr}, e_fdn[2] = {nullptr, nullptr};

@@ -554,6 +554,7 @@ struct ConvolverN : HNode {  // src/convolve.rs:9-59: the impulse response is cl
   void sig(std::string& o) const override { o += "Convolver"; }
   void lower(Lowering& l) const override {
     uint32_t len = 1; while (len < h.size() + 8) len <<= 1;   // the 8-sample block path looks K + 7 samples back
+    l.conv_K = (uint32_t)h.size(); l.conv_off = (uint32_t)l.U.size();
     l.U.push_back((uint32_t)h.size()); l.U.push_back(len);
     for (float x : h) l.U.push_back(f2u(x));
     l.extraU += (uint32_t)h.size();

@@ -53,6 +53,7 @@ struct Lowering {
   std::vector<uint32_t> dlen;      // delay-line lengths (floats per voice) in DFS order
   uint32_t extraU = 0;             // uniform words beyond the nodes' static NU (e.g. a Convolver's impulse response)
   uint32_t extraP = 0;             // per-voice parameter words beyond the static NP (an envelope's sampled closure values)
+  uint32_t conv_K = 0, conv_off = 0;   // last Convolver lowered: taps, and the index of its header (K, ring length, then K coefficient words) in U
   bool ok = true; std::string why; // set when a node has no device lowering
   void p(float f) { P.push_back(f2u(f)); }
   void s(float f) { S.push_back(f2u(f)); }

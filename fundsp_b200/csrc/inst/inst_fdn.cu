@@ -14,5 +14,5 @@ cudaError_t launch_fdn(const FdnArgs& a, int warps, cudaStream_t st) {
   fdn_kernel<<<grid, 32 * warps, smem, st>>>(a);
   return cudaGetLastError();
 }
-int fdn_max_warps() { return (int)((227 * 1024) / (FDN_WARP_FLOATS * sizeof(float))) < 8 ? (int)((227 * 1024) / (FDN_WARP_FLOATS * sizeof(float))) : 8; }
+int fdn_max_warps() { const int m = (int)((227 * 1024) / (FDN_WARP_FLOATS * sizeof(float))); return m < 10 ? m : 10; }   // __launch_bounds__(320)
 }}

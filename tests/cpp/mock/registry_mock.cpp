@@ -106,7 +106,7 @@ cudaError_t launch_fdn(const FdnArgs& f, int warps, cudaStream_t) {
   std::string err;
   auto prog = std::dynamic_pointer_cast<const MockProgram>(get_program(kRevSig, 0, err));
   if (!prog || warps < 1) return cudaErrorLaunchFailure;
-  const uint32_t V = f.V, n = f.n, grid = (V + (uint32_t)warps - 1) / (uint32_t)warps;
+  const uint32_t V = f.V, n = f.n, grid = V;   // the kernel writes one partial-mix row pair per voice
   std::vector<float> rev((size_t)V * 2 * n, 0.0f);
   std::vector<uint32_t> rows(V);
   for (uint32_t v = 0; v < V; v++) rows[v] = 2 * v;
@@ -127,11 +127,18 @@ cudaError_t launch_fdn(const FdnArgs& f, int warps, cudaStream_t) {
           y = dry + y * g;
         }
         if (f.out) f.out[(size_t)(f.row_map[v] + ch) * f.out_stride + f.out_offset + t] = y;
-        if (f.partial) f.partial[((size_t)(v / (uint32_t)warps) * 2 + ch) * n + t] += y;
+        if (f.partial) f.partial[((size_t)v * 2 + ch) * n + t] += y;
       }
   return cudaSuccess;
 }
 int fdn_max_warps() { return 8; }
+// the tensor-core convolver form is never selected on the mock (bank.cpp tc_conv_wanted); the symbols only have to link
+cudaError_t conv_tc_make_maps(float*, float*, uint32_t, uint32_t, float*, float*, uint32_t, ConvTcMaps*) { return cudaErrorInvalidValue; }
+cudaError_t launch_conv_tc(const ConvTcMaps&, float*, uint32_t, uint32_t, const uint32_t*, uint32_t, uint32_t, uint32_t, uint32_t, cudaStream_t) { return cudaErrorInvalidValue; }
+cudaError_t launch_conv_split(const float*, float*, uint32_t, uint32_t, uint32_t, uint32_t, cudaStream_t) { return cudaErrorInvalidValue; }
+cudaError_t launch_conv_history(float*, float*, uint32_t, uint32_t, uint32_t, uint32_t, cudaStream_t) { return cudaErrorInvalidValue; }
+cudaError_t launch_conv_toeplitz(const float*, uint32_t, float*, float*, uint32_t, cudaStream_t) { return cudaErrorInvalidValue; }
+uint32_t conv_tc_toeplitz_cols(uint32_t) { return 0; }
 std::shared_ptr<const Program> jit_program(const std::string& sig, int device, std::string& err) { return get_program(sig, device, err); }
 int jit_compiled_count() { return (int)g_cache.size(); }
 void jit_cache_stats(int* hits, int* runs) { if (hits) *hits = 0; if (runs) *runs = 0; }
