@@ -33,7 +33,7 @@ def _baseline_metric():
 
 
 METRIC = _baseline_metric()   # the metric string of BASELINE.json, verbatim
-HEADLINE = {"saw_svf_events": 16384, "saw_svf": 16384, "noise_svf": 16384, "fm": 4096, "biquad_bank": 2048, "subtractive_dry": 1024, "subtractive": 1024, "net": 65536}
+HEADLINE = {"conv": 16384, "saw_svf_events": 16384, "saw_svf": 16384, "noise_svf": 16384, "fm": 4096, "biquad_bank": 2048, "subtractive_dry": 1024, "subtractive": 1024, "net": 65536}
 
 
 def parse():
@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--voices", type=int, default=None, help="voices per GPU (default: the BASELINE config size)")
     ap.add_argument("--seconds", type=float, default=1.0, help="audio seconds rendered per step")
     ap.add_argument("--per-voice", action="store_true", help="also materialise per-voice outputs in HBM (value only)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --voices per GPU (default); strong: the config's voices split over the GPUs")
     return ap.parse_args()
 
 
@@ -140,7 +141,9 @@ def run_reference(a):
         return
     n = int(round(a.seconds * SR))
     Vg = a.voices or HEADLINE[a.workload]
-    V = Vg * max(1, a.gpus)          # the same whole-job configuration our arm runs at --gpus N (weak scaling: V per GPU)
+    V = Vg * max(1, a.gpus) if a.scaling == "weak" else Vg   # the same whole-job configuration our arm runs at --gpus N
+    if a.workload == "conv":
+        Vg = V = min(V, 256)         # (a 1000-tap direct form on the CPU: a bounded number of voices stands for the bank)
     build = native_oracle()
     cores, core_info = host_cores()
     # the whole step at N = 1 (and whenever it is at most ~1.5e9 voice-samples); beyond that a bounded sample of the step so that K
@@ -162,7 +165,7 @@ def run_reference(a):
               f"(affinity {core_info['affinity']}, cgroup quota {core_info['cgroup_quota']}, os.cpu_count {core_info['os_cpu_count']}), voices sharded contiguously over the threads; {build}")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Msamples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a.workload, Vg), "voices_per_gpu": Vg, "voices_total": V, "sample_rate": SR, "block": 64, "seconds_per_step": a.seconds,
                    "output": "index-order mix of all voices", "note": "C++ oracle restating the reference's block path (no Rust toolchain on the box)"},
         "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample, "single_core": per_core,
@@ -176,6 +179,7 @@ def workload_name(w, V):
              "fm": f"{V}-voice FM bank sine_hz(f)*f*m+f >> sine() (config 2)", "biquad_bank": f"{V} x biquad_bank() = {8 * V} voices on white() (config 3b)",
              "subtractive_dry": f"{V}-voice saw >> moog * adsr_live >> pan (config 4 without reverb)", "subtractive": f"{V}-voice subtractive + per-voice reverb_stereo (config 4)",
              "net": f"{V}-voice dynamic Net, 4 classes (config 5)",
+             "conv": f"{V}-voice white().seed(i) >> convolve(h), one shared 1000-tap response (the dense tap contraction; not a BASELINE config)",
              "saw_svf_events": f"{V} held sequencer events of saw_hz(f) >> lowpass_hz(fc,q) (the headline voices behind Sequencer::push; not a BASELINE config)"}
     return names[w]
 
@@ -206,6 +210,10 @@ def main():
         from fundsp_b200.parallel import BankGroup
         group = BankGroup.from_torch_distributed(local)
     V = a.voices or HEADLINE[a.workload]
+    if a.scaling == "strong":
+        if V % world:
+            raise SystemExit(f"--scaling strong: {V} voices do not split evenly over {world} GPUs")
+        V //= world                       # the configuration's voices split over the GPUs: total work fixed
     n = int(round(a.seconds * SR))
     gate = gate_for(a.workload, n)
 
@@ -350,8 +358,8 @@ def main():
         per_core = min(V, 64) * ns / dt1 / 1e6
     line = {
         "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a.workload, V), "voices_per_gpu": V, "voices_total": world * V, "sample_rate": SR, "block": 64,
+        "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a.workload, V * (world if a.scaling == "strong" else 1)), "voices_per_gpu": V, "voices_total": world * V, "sample_rate": SR, "block": 64,
                    "seconds_per_step": a.seconds, "output": "mix-down to %d channel(s)%s" % (c, " + per-voice rows in HBM" if a.per_voice else ""),
                    "parallelism": "voices sharded x%d, one mix-down per step below the C ABI (NCCL send/recv gather over NVLink + rank-order fold)" % world if world > 1 else "1 GPU", "l2": "flushed between timed steps (512 MB write)",
                    "build_s": round(t_build, 3)},

@@ -20,7 +20,9 @@ thread_local std::string g_err;
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 fdsp_node* wrap(HNode* n, const char* what) {
   if (!n) { g_err = std::string(what) + ": arity mismatch or invalid argument (the reference rejects this at compile time)"; return nullptr; }
-  return new (std::nothrow) fdsp_node{n};
+  fdsp_node* h = new (std::nothrow) fdsp_node{n};
+  if (!h) { delete n; g_err = std::string(what) + ": out of memory"; }
+  return h;
 }
 HNode* take(fdsp_node* h) {  // consume a handle
   if (!h) return nullptr;
@@ -139,7 +141,7 @@ API int fdsp_node_seed(fdsp_node* h, uint64_t seed) {  // src/combinator.rs:270-
   return FDSP_OK;
 }
 API int fdsp_node_set(fdsp_node* h, int kind, const float* v, int nv, uint64_t seed, const int64_t* addr, int naddr) {
-  if (!h || nv < 0 || nv > 5 || naddr < 0 || naddr > 6) return fail(FDSP_ERR_ARG, "bad setting");
+  if (!h || nv < 0 || nv > 5 || naddr < 0 || naddr > 6 || (nv > 0 && !v) || (naddr > 0 && !addr)) return fail(FDSP_ERR_ARG, "bad setting");
   Setting s; s.kind = kind; s.seed = seed;
   for (int i = 0; i < nv; i++) s.v[i] = v[i];
   for (int i = 0; i < naddr; i++) s.address.push_back({(int)addr[2 * i], (uint64_t)addr[2 * i + 1]});
@@ -227,6 +229,7 @@ API int fdsp_bank_create_from_net(fdsp_node* net, int device, uint32_t out_mode,
   delete n;
   if (!ok) { for (HNode* x : v) delete x; return fail(FDSP_ERR_UNSUPPORTED, "no device lowering for this Net: " + err); }
   fdsp_bank* b = new (std::nothrow) fdsp_bank();
+  if (!b) { for (HNode* x : v) delete x; return fail(FDSP_ERR_STATE, "out of memory"); }
   b->b.tree_mix = tree == "pairwise" ? 1 : 2; b->b.net_rate = true; b->b.vertex_of_voice = ids;
   std::string e = b->b.init(v, device, out_mode);
   if (!e.empty()) { for (HNode* x : v) delete x; delete b; return status(e); }
@@ -242,6 +245,7 @@ API void fdsp_bank_destroy(fdsp_bank* b) { delete b; }
 API int fdsp_bank_clone(const fdsp_bank* b, fdsp_bank** out) {
   if (!b || !out) return fail(FDSP_ERR_ARG, "null bank");
   fdsp_bank* c = new (std::nothrow) fdsp_bank();
+  if (!c) return fail(FDSP_ERR_STATE, "out of memory");
   std::string e = b->b.clone_into(c->b);
   if (!e.empty()) { delete c; return status(e); }
   *out = c;
@@ -253,7 +257,7 @@ API int fdsp_bank_voice_outputs(const fdsp_bank* b) { return b ? b->b.nout : -1;
 API int fdsp_bank_outputs(const fdsp_bank* b) { return !b ? -1 : ((b->b.out_mode & 2u) ? b->b.nout : (int)(b->b.V() * (uint32_t)b->b.nout)); }
 API int fdsp_bank_set_sample_rate(fdsp_bank* b, double sr) { return b ? status(b->b.set_sample_rate(sr)) : fail(FDSP_ERR_ARG, "null bank"); }
 API int fdsp_bank_set(fdsp_bank* b, uint32_t voice, int kind, const float* v, int nv, uint64_t seed, const int64_t* addr, int naddr) {
-  if (!b || nv < 0 || nv > 5 || naddr < 0 || naddr > 6) return fail(FDSP_ERR_ARG, "bad setting");
+  if (!b || nv < 0 || nv > 5 || naddr < 0 || naddr > 6 || (nv > 0 && !v) || (naddr > 0 && !addr)) return fail(FDSP_ERR_ARG, "bad setting");
   Setting s; s.kind = kind; s.seed = seed;
   for (int i = 0; i < nv; i++) s.v[i] = v[i];
   for (int i = 0; i < naddr; i++) s.address.push_back({(int)addr[2 * i], (uint64_t)addr[2 * i + 1]});

@@ -3,7 +3,7 @@
 // Toeplitz matrix of h — the one place on this path where tensor cores apply (north-star: "tensor cores are used only on the dense
 // FIR/convolve tap contraction as a batched GEMM").
 //
-//     Y[v, t0 + n] = sum_j X[v, t0 - (K-1) + j] * T[j, n],     T[j, n] = h[K - 1 + n - j]  (0 outside the band),  j < N + K - 1
+//     Y[v, t0 + n] = sum_j X[v, t0 - P + j] * T[j, n],     T[j, n] = h[P + n - j]  (0 outside the band),  j < N + P,  P = K - 1 rounded up to 4
 //
 //   M = 128 voices per CTA tile, N = 128 output samples, contraction over the N + K - 1 input samples the tile can see, in chunks
 //   of 32 floats (one 128-byte swizzle row). Flops per tile = 2 * 128 * 128 * (127 + K)  (2 * V * 64 * (63 + K) per
@@ -66,7 +66,9 @@ __device__ __forceinline__ void ctc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// grid = (time tiles, voice tiles); block = 192
+// grid = (time tiles, voice tiles); block = 192. STEP < 4 builds bring-up probes (tests/cpp/conv_tc_probe.cu): 1 = TMEM allocation only,
+// 2 = + TMA pipeline, 3 = + MMA issue, 4 = the kernel.
+template <int STEP = 4>
 __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant__ CUtensorMap mxl,
                                                          const __grid_constant__ CUtensorMap mt, const __grid_constant__ CUtensorMap mtl, const ConvTcArgs a) {
   extern __shared__ uint8_t ctc_raw[];
@@ -78,7 +80,8 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   const uint32_t tmem_slot = bars + 8u * (2 * CTC_STAGES + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t t0 = blockIdx.x * CTC_N, v0 = blockIdx.y * CTC_M;
-  const int nchunk = (int)((CTC_N + a.K - 1u + CTC_KC - 1u) / CTC_KC);         // contraction chunks of 32 input samples
+  const uint32_t P = (a.K - 1u + 3u) & ~3u;                                    // look-back padded to 4 samples: every window starts 16-byte aligned
+  const int nchunk = (int)((CTC_N + P + CTC_KC - 1u) / CTC_KC);                // contraction chunks of 32 input samples
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < CTC_STAGES; s++) { ctc_mbar_init(full_bar(s), 1); ctc_mbar_init(empty_bar(s), 1); }
@@ -96,11 +99,12 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
 
   if (warp == 0) {
-    if (lane == 0) {   // ---- TMA producer
-      const int col0 = (int)(a.H - (a.K - 1u) + t0);                           // window start inside the X rows
+    if (lane == 0 && STEP >= 2) {   // ---- TMA producer
+      const int col0 = (int)(a.H - P + t0);                                    // window start inside the X rows
       for (int c = 0; c < nchunk; c++) {
         const int s = c % CTC_STAGES, use = c / CTC_STAGES;
-        if (use > 0) ctc_mbar_wait(empty_bar(s), (uint32_t)(use - 1) & 1u);
+        if (use > 0 && STEP >= 3) ctc_mbar_wait(empty_bar(s), (uint32_t)(use - 1) & 1u);
+        if (STEP == 2 && c >= CTC_STAGES) break;
         const uint32_t st = base + (uint32_t)s * CTC_STAGE_BYTES;
         ctc_mbar_expect(full_bar(s), CTC_STAGE_BYTES);
         ctc_tma_2d(st, &mx, col0 + c * CTC_KC, (int)v0, full_bar(s));
@@ -110,13 +114,15 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {   // ---- MMA issue: per 8-wide k-step  acc += xh*hl + xl*hh + xh*hh
+    if (lane == 0 && STEP >= 2) {   // ---- MMA issue: per 8-wide k-step  acc += xh*hl + xl*hh + xh*hh
       for (int c = 0; c < nchunk; c++) {
+        if (STEP == 2 && c >= CTC_STAGES) break;
         const int s = c % CTC_STAGES, use = c / CTC_STAGES;
         ctc_mbar_wait(full_bar(s), (uint32_t)use & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = base + (uint32_t)s * CTC_STAGE_BYTES;
         const uint64_t dxh = ctc_desc(st), dxl = ctc_desc(st + CTC_TILE_A), dth = ctc_desc(st + 2 * CTC_TILE_A), dtl = ctc_desc(st + 2 * CTC_TILE_A + CTC_TILE_B);
+        if (STEP >= 3)
 #pragma unroll
         for (int k = 0; k < CTC_KC / 8; k++) {
           const uint64_t adv = (uint64_t)((k * 32) >> 4);                      // 8 floats = 32 bytes further inside the swizzle row
@@ -124,11 +130,11 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
           ctc_mma(tmem, dxl + adv, dth + adv, 1u);
           ctc_mma(tmem, dxh + adv, dth + adv, 1u);
         }
-        ctc_commit(empty_bar(s));                                              // the stage is free once these MMAs have read it
+        if (STEP >= 3) ctc_commit(empty_bar(s));                               // the stage is free once these MMAs have read it
       }
-      ctc_commit(accum_bar);                                                   // accumulator complete
+      if (STEP >= 3) ctc_commit(accum_bar);                                    // accumulator complete
     }
-  } else {
+  } else if (STEP >= 4) {
     // ---- epilogue: warp w owns TMEM lanes 32 * (w % 4) .. +31 = voices of the tile; 4 x 32 columns each
     ctc_mbar_wait(accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -165,7 +171,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
 }
 
 // xl = x - (x with the low 13 mantissa bits cleared), over the new columns of every X row
-__global__ void conv_split_lo_kernel(const float* __restrict__ x, float* __restrict__ xl, uint32_t V, uint32_t row_stride, uint32_t col0, uint32_t n) {
+static __global__ void conv_split_lo_kernel(const float* __restrict__ x, float* __restrict__ xl, uint32_t V, uint32_t row_stride, uint32_t col0, uint32_t n) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
   if (t >= n || v >= V) return;
   const size_t e = (size_t)v * row_stride + col0 + t;
@@ -174,18 +180,19 @@ __global__ void conv_split_lo_kernel(const float* __restrict__ x, float* __restr
 }
 // the last H samples of every row (columns [n, n + H)) move to the front (columns [0, H)): history for the next chunk. One CTA per
 // (row, array); the row's H values go through shared memory because source and destination overlap when n < H.
-__global__ void conv_history_kernel(float* x, float* xl, uint32_t row_stride, uint32_t H, uint32_t n) {
+static __global__ void conv_history_kernel(float* x, float* xl, uint32_t row_stride, uint32_t H, uint32_t n) {
   extern __shared__ float hs[];
   float* row = (blockIdx.y ? xl : x) + (size_t)blockIdx.x * row_stride;
   for (uint32_t i = threadIdx.x; i < H; i += blockDim.x) hs[i] = row[n + i];
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < H; i += blockDim.x) row[i] = hs[i];
 }
-// T[n][j] = h[K - 1 + n - j] inside the band, 0 outside; hi = the f32 itself, lo = h - tf32(h). Rows n < 128, J columns (multiple of 32).
-__global__ void conv_toeplitz_kernel(const float* __restrict__ h, uint32_t K, float* th, float* tl, uint32_t J) {
+// T[n][j] = h[P + n - j] inside the band, 0 outside (P = K - 1 rounded up to 4: window column j is input sample t0 - P + j); hi = the f32
+// itself, lo = h - tf32(h). Rows n < 128, J columns (multiple of 32).
+static __global__ void conv_toeplitz_kernel(const float* __restrict__ h, uint32_t K, float* th, float* tl, uint32_t J) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.y;
   if (j >= J) return;
-  const int k = (int)K - 1 + (int)n - (int)j;
+  const int k = (int)((K - 1u + 3u) & ~3u) + (int)n - (int)j;
   const float f = (k >= 0 && k < (int)K) ? h[k] : 0.0f;
   th[(size_t)n * J + j] = f;
   tl[(size_t)n * J + j] = f - __uint_as_float(__float_as_uint(f) & 0xffffe000u);

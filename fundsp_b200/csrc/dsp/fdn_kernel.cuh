@@ -154,6 +154,59 @@ __global__ void __launch_bounds__(320) fdn_kernel(const FdnArgs a) {
       }
       __syncwarp();
       const float2* t2 = tb2 + st * 32;
+      if (nb == 64) {
+        // full block: lane t evaluates samples t and t + 32 in ONE pass — the per-line weights are loaded once for both, and two independent
+        // chains per lane keep the FP32 pipe fed. All taps of the block are read before any new sample is stored.
+        float a0[32], a1[32], sl0 = 0.0f, sr0 = 0.0f, sl1 = 0.0f, sr1 = 0.0f;
+#pragma unroll
+        for (int l = 0; l < 32; l++) {
+          const float4 wv = wtab[l];
+          const float2 q = t2[l];
+          const float* row = rst + __float_as_int(q.y) + lane;
+          const float o0 = (wv.x * row[-2] + wv.y * row[-1]) + wv.z * row[0];      // Fir<U3>: accumulate in tap order from the oldest
+          const float o1 = (wv.x * row[30] + wv.y * row[31]) + wv.z * row[32];
+          a0[l] = o0; a1[l] = o1;
+          if (l == 0) { sl0 = o0 * wv.w; sr0 = o0 * q.x; sl1 = o1 * wv.w; sr1 = o1 * q.x; }   // Reduce<U32, Panner, FrameAdd>: left fold
+          else { sl0 += o0 * wv.w; sr0 += o0 * q.x; sl1 += o1 * wv.w; sr1 += o1 * q.x; }
+        }
+        // FrameHadamard<U32> (src/feedback.rs:35-57): in-place butterflies h = 1, 2, 4, 8, 16, then * (1 / sqrt(32)) as f32
+#pragma unroll
+        for (int h = 1; h < 32; h <<= 1) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2 * h) {
+#pragma unroll
+            for (int j = i; j < i + h; j++) {
+              const float x0 = a0[j], y0 = a0[j + h]; a0[j] = x0 + y0; a0[j + h] = x0 - y0;
+              const float x1 = a1[j], y1 = a1[j + h]; a1[j] = x1 + y1; a1[j + h] = x1 - y1;
+            }
+          }
+        }
+        const float xa0 = db[lane + 1], xb0 = db[64 + lane + 1];                                      // input of sample t + 1
+        const float xa1 = db[lane + 33 < 64 ? lane + 33 : 63], xb1 = db[64 + (lane + 33 < 64 ? lane + 33 : 63)];
+        sl0 = sl0 * c0; sr0 = sr0 * c1; sl1 = sl1 * c0; sr1 = sr1 * c1;
+        if (a.scalar_row >= 0) {
+          sl0 = db[lane] + sl0 * scalar; sr0 = db[64 + lane] + sr0 * scalar;
+          sl1 = db[lane + 32] + sl1 * scalar; sr1 = db[64 + lane + 32] + sr1 * scalar;
+        }
+        __syncwarp();   // every lane has read its taps: the rows may now take the new samples
+#pragma unroll
+        for (int l = 0; l < 32; l++) rst[l * FDN_RS + lane + 1] = ((l & 1) ? xb0 : xa0) + a0[l] * hz;   // Feedback: x.tick(input + value); Delay stores it
+        if (lane < 31) {
+#pragma unroll
+          for (int l = 0; l < 32; l++) rst[l * FDN_RS + lane + 33] = ((l & 1) ? xb1 : xa1) + a1[l] * hz;
+        } else {
+#pragma unroll
+          for (int l = 0; l < 32; l++) vcarry[l] = a1[l] * hz;    // enters the first sample of the next block
+        }
+        if (a.partial) {   // per-voice rows of the mix-down [V][2][n]: mix_reduce_kernel adds them in voice order
+          float* pr = a.partial + ((size_t)v * 2) * a.n + t0 + lane;
+          pr[0] = sl0; pr[32] = sl1; pr[a.n] = sr0; pr[a.n + 32] = sr1;
+        }
+        if (a.out) {
+          float* orow = a.out + (size_t)__ldg(a.row_map + v) * a.out_stride + a.out_offset + t0 + lane;
+          orow[0] = sl0; orow[32] = sl1; orow[a.out_stride] = sr0; orow[a.out_stride + 32] = sr1;
+        }
+      } else {
 #pragma unroll 1
       for (int h0 = 0; h0 < nb; h0 += 32) {
         const int t = h0 + lane;
@@ -198,6 +251,7 @@ __global__ void __launch_bounds__(320) fdn_kernel(const FdnArgs a) {
             orow[0] = sl; orow[a.out_stride] = sr;
           }
         }
+      }
       }
       // lane = line again: FIR history for the next block, then the new samples of the line go back to its ring
       {

@@ -274,9 +274,12 @@ std::string Bank::set_sample_rate(double s) {  // AudioUnit::set_sample_rate
 std::string Bank::set(uint32_t voice, const Setting& st) {  // AudioUnit::set (src/audiounit.rs:62, src/setting.rs) on a live bank
   if (voice >= V()) return "set: voice index out of range";
   CU(cudaSetDevice(device));
-  nodes[voice]->set(st);
+  // the setting is tried on a COPY of the voice's host graph: a refused setting (one that would change a class-uniform word) leaves
+  // both the host graph and the device untouched; the copy replaces the original only after the upload
+  std::unique_ptr<HNode> trial(nodes[voice]->clone());
+  trial->set(st);
   Lowering l;
-  nodes[voice]->lower(l);
+  trial->lower(l);
   if (!l.ok) return l.why;
   for (auto& c : classes) {
     auto it = std::lower_bound(c.voices.begin(), c.voices.end(), voice);
@@ -287,8 +290,9 @@ std::string Bank::set(uint32_t voice, const Setting& st) {  // AudioUnit::set (s
     // parameters take effect at once (one strided column of the [NP][V] block); running state is left alone, the
     // construction-time state (what reset() restores) follows the setting like the reference's stored phase/seed
     if (c.np) CU(cudaMemcpy2DAsync(c.d_params + i, (size_t)Vc * 4, l.P.data(), 4, 4, c.np, cudaMemcpyHostToDevice, stream));
-    for (uint32_t k = 0; k < c.ns; k++) c.state0[(size_t)k * Vc + i] = l.S[k];
     CU(cudaStreamSynchronize(stream));  // `l` is pageable and goes out of scope
+    for (uint32_t k = 0; k < c.ns; k++) c.state0[(size_t)k * Vc + i] = l.S[k];
+    nodes[voice] = std::move(trial);
     return "";
   }
   return "internal: voice not found in any class";
@@ -435,9 +439,11 @@ std::string Bank::slot_set(uint32_t voice, int ease, double fade_time, HNode* un
     CU(cudaMemcpy2D(head, 4, c.d_state + i, (size_t)Vc * 4, 4, 2, cudaMemcpyDeviceToHost));
     if (head[1]) return "slot: a crossfade is in progress on this voice; set again when it has finished";
     const int inst = (int)(head[0] ^ 1u);
-    if (!slot_arm(nodes[voice].get(), n.release(), inst, ease, fade_time)) return "slot: the unit's graph class differs from the slot's (same type expression needed)";
+    // arm a COPY of the voice's host slot: a refused unit leaves the host graph as it was (it replaces the original after the upload)
+    std::unique_ptr<HNode> trial(nodes[voice]->clone());
+    if (!slot_arm(trial.get(), n.release(), inst, ease, fade_time)) return "slot: the unit's graph class differs from the slot's (same type expression needed)";
     Lowering l;
-    nodes[voice]->lower(l);
+    trial->lower(l);
     if (!l.ok) return l.why;
     if (l.U != c.uniform || l.P.size() != c.np || l.S.size() != c.ns) return "slot: the unit changes a class-uniform word (delay length, table, wave); rebuild the bank instead";
     const uint32_t xs = (c.ns - 4) / 2, s0 = 4 + (uint32_t)inst * xs;
@@ -447,8 +453,9 @@ std::string Bank::slot_set(uint32_t voice, int ease, double fade_time, HNode* un
     if (xd) CU(cudaMemset2DAsync(c.d_dline + (size_t)inst * xd * Vc + i, (size_t)Vc * 4, 0, 4, (size_t)xd, stream));
     const uint32_t arm[3] = {1u, 0u, 0u};   // has_next = 1, fade_phase = 0.0
     CU(cudaMemcpy2DAsync(c.d_state + (size_t)1 * Vc + i, (size_t)Vc * 4, arm, 4, 4, 3, cudaMemcpyHostToDevice, stream));
-    for (uint32_t k = 0; k < c.ns; k++) c.state0[(size_t)k * Vc + i] = l.S[k];   // reset() adopts the newest unit (:156-172)
     CU(cudaStreamSynchronize(stream));
+    for (uint32_t k = 0; k < c.ns; k++) c.state0[(size_t)k * Vc + i] = l.S[k];   // reset() adopts the newest unit (:156-172)
+    nodes[voice] = std::move(trial);
     return "";
   }
   return "internal: voice not found in any class";

@@ -42,14 +42,14 @@ cudaError_t launch_conv_tc(const ConvTcMaps& maps, float* y, uint32_t y_stride, 
                            cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CTC_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, CTC_SMEM);
     if (e != cudaSuccess) return e;
     attr = true;
   }
   const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(maps.m);
   ConvTcArgs a{y, y_stride, y_offset, row_map, V, n, K, H};
   dim3 grid((n + CTC_N - 1) / CTC_N, (V + CTC_M - 1) / CTC_M);
-  conv_tc_kernel<<<grid, 192, CTC_SMEM, st>>>(m[0], m[1], m[2], m[3], a);
+  conv_tc_kernel<4><<<grid, 192, CTC_SMEM, st>>>(m[0], m[1], m[2], m[3], a);
   return cudaGetLastError();
 }
 cudaError_t launch_conv_split(const float* x, float* xl, uint32_t V, uint32_t row_stride, uint32_t col0, uint32_t n, cudaStream_t st) {
@@ -66,5 +66,5 @@ cudaError_t launch_conv_toeplitz(const float* h, uint32_t K, float* th, float* t
   conv_toeplitz_kernel<<<dim3((J + 255) / 256, CTC_N), 256, 0, st>>>(h, K, th, tl, J);
   return cudaGetLastError();
 }
-uint32_t conv_tc_toeplitz_cols(uint32_t K) { return (CTC_N + K - 1u + CTC_KC - 1u) / CTC_KC * CTC_KC; }
+uint32_t conv_tc_toeplitz_cols(uint32_t K) { return (CTC_N + ((K - 1u + 3u) & ~3u) + CTC_KC - 1u) / CTC_KC * CTC_KC; }
 }}

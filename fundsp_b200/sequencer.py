@@ -134,7 +134,12 @@ class GpuSequencer:
         if self.bank is None:
             self.pending.append(ev); self.voice_of[eid] = len(self.pending) - 1
         elif self.mode[0] == 1:
-            self.voice_of[eid] = self.bank.push_event(ev)      # ReplayMode::None drops finished events: their voices are free to take over
+            v = self.bank.push_event(ev)                       # ReplayMode::None drops finished events: their voices are free to take over
+            # the finished event that owned this voice is gone for good: its id must not reach the new tenant (the reference ignores
+            # edits of past events in this mode, src/sequencer.rs:466-476)
+            for old in [k for k, w in self.voice_of.items() if w == v]:
+                del self.voice_of[old]
+            self.voice_of[eid] = v
         else:
             self.voice_of[eid] = self.bank.add_voice(ev)       # ReplayMode::All replays every event after a reset: nothing may be overwritten
         return eid
@@ -150,7 +155,9 @@ class GpuSequencer:
         return self.push(start_time, start_time + duration, fade_ease, fade_in_time, fade_out_time, unit)
 
     def edit(self, event_id, end_time, fade_out_time):
-        v = self.voice_of[event_id]
+        v = self.voice_of.get(event_id)
+        if v is None:
+            return             # an unknown or past event: a no-op, like the reference's edit
         if self.bank is None:
             a = self.pending[v].args
             self.pending[v] = An("event", (a[0], float(end_time), a[2], a[3], float(fade_out_time)), self.pending[v].kids, 0, self.nout)

@@ -134,6 +134,25 @@ def saw_svf_event_voice(i):
     return event(saw_svf_voice(i), start, start + 1.0e6, Fade.Smooth, 0.005, 0.0)
 
 
+# ---- the dense tap contraction (north-star: tensor cores "only on the dense FIR/convolve tap contraction"): every voice convolves its own
+# noise with ONE shared K-tap response (class-uniform data), src/convolve.rs:9-59
+def conv_response(K=1000):
+    import numpy as np
+    k = np.arange(K)
+    h = np.array([2.0 * rnd1(1_000_003 + int(j)) - 1.0 for j in k]) * np.exp(-k / (K / 4.0))
+    return (h / np.abs(h).max()).astype(np.float32)
+
+
+_CONV_H = {}
+
+
+def conv_voice(i, K=1000):
+    from .prelude import convolve
+    if K not in _CONV_H:
+        _CONV_H[K] = conv_response(K)
+    return white().seed(i) * f32(lerp(0.25, 1.0, u(i, 0))) >> convolve(_CONV_H[K])
+
+
 WORKLOADS = {
     # name: (voice builder, default voices, inputs)
     "fm": (fm_voice, 4096),
@@ -144,6 +163,7 @@ WORKLOADS = {
     "subtractive": (subtractive_voice, 1024),
     "net": (net_voice, 65536),
     "saw_svf_events": (saw_svf_event_voice, 16384),
+    "conv": (conv_voice, 16384),
 }
 
 

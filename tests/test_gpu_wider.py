@@ -154,6 +154,32 @@ def test_gpu_sequencer_note_ons_while_running():
     assert not g.render(2048).any()
 
 
+def test_gpu_sequencer_late_edit_of_a_finished_event_is_ignored():
+    """A note-off that arrives after its note has ended — and after another note has taken over the voice — must not touch the new note
+    (the reference ignores edits of past events in ReplayMode::None, src/sequencer.rs:466-476)."""
+    from fundsp_b200.sequencer import GpuSequencer, Fade, ReplayMode
+    from oracle import OracleBackend, OracleUnit, lib as olib
+    L = olib()
+    L.fo_set_denormal_emulation(0)
+    sr = 44100.0
+    g = GpuSequencer(1, ReplayMode.None_, sample_rate=sr)
+    g.reserve(arp_voice(100.0), 1)                                    # ONE voice: the second note must reuse it
+    u = OracleUnit(L.fo_sequencer(0, 1, 1, 0.0))
+    be = OracleBackend()
+    a = g.push_relative(0.0, 0.01, Fade.Smooth, 0.001, 0.001, arp_voice(220.0))
+    ua = L.fo_sequencer_push_relative(u.h, 0.0, 0.01, 1, 0.001, 0.001, arp_voice(220.0).lower(be))
+    got, want = [g.render(1024)], [u.process_many(1024)]             # the first note (441 samples) has ended
+    b = g.push_relative(0.0, 0.05, Fade.Smooth, 0.001, 0.001, arp_voice(330.0))
+    L.fo_sequencer_push_relative(u.h, 0.0, 0.05, 1, 0.001, 0.001, arp_voice(330.0).lower(be))
+    assert g.voice_of[b] == 0 and a not in g.voice_of                 # the finished note's id no longer maps to the voice
+    g.edit_relative(a, 0.0, 0.0)                                      # late note-off of the first note
+    L.fo_sequencer_edit_relative(u.h, ua, 0.0, 0.0)
+    got.append(g.render(4096)); want.append(u.process_many(4096))
+    got, want = np.concatenate(got, axis=1), np.concatenate(want, axis=1)
+    assert np.abs(want[:, 1024:3000]).max() > 0.1 and _close(got, want)    # the second note sounds in full
+    g.edit(12345, 0.0, 0.0)                                           # an id that never existed: no-op
+
+
 def test_slot_crossfades_to_a_new_unit():
     """Slot / SlotBackend (src/slot.rs) as voices: units replaced with a crossfade while the bank runs, no new program built. Per-voice rows
     are bit-exact against oracle Slots that receive the same `set` calls at the same times."""
