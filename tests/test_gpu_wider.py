@@ -166,9 +166,10 @@ def test_gpu_sequencer_late_edit_of_a_finished_event_is_ignored():
     g.reserve(arp_voice(100.0), 1)                                    # ONE voice: the second note must reuse it
     u = OracleUnit(L.fo_sequencer(0, 1, 1, 0.0))
     be = OracleBackend()
+    got, want = [g.render(64)], [u.process_many(64)]                 # the sequencer runs: from here on a push takes over a finished voice
     a = g.push_relative(0.0, 0.01, Fade.Smooth, 0.001, 0.001, arp_voice(220.0))
     ua = L.fo_sequencer_push_relative(u.h, 0.0, 0.01, 1, 0.001, 0.001, arp_voice(220.0).lower(be))
-    got, want = [g.render(1024)], [u.process_many(1024)]             # the first note (441 samples) has ended
+    got.append(g.render(1024)); want.append(u.process_many(1024))    # the first note (441 samples) has ended
     b = g.push_relative(0.0, 0.05, Fade.Smooth, 0.001, 0.001, arp_voice(330.0))
     L.fo_sequencer_push_relative(u.h, 0.0, 0.05, 1, 0.001, 0.001, arp_voice(330.0).lower(be))
     assert g.voice_of[b] == 0 and a not in g.voice_of                 # the finished note's id no longer maps to the voice
@@ -176,7 +177,7 @@ def test_gpu_sequencer_late_edit_of_a_finished_event_is_ignored():
     L.fo_sequencer_edit_relative(u.h, ua, 0.0, 0.0)
     got.append(g.render(4096)); want.append(u.process_many(4096))
     got, want = np.concatenate(got, axis=1), np.concatenate(want, axis=1)
-    assert np.abs(want[:, 1024:3000]).max() > 0.1 and _close(got, want)    # the second note sounds in full
+    assert np.abs(want[:, 1088:3000]).max() > 0.1 and _close(got, want)    # the second note sounds in full
     g.edit(12345, 0.0, 0.0)                                           # an id that never existed: no-op
 
 
