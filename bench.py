@@ -255,7 +255,7 @@ def main():
     def timed(step_fn, steps):
         """K steps, each bracketed by CUDA events on the current stream; L2 flushed between steps (untimed)."""
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        kern = []
+        kern, dom = [], []
         barrier()
         wall0 = time.perf_counter()
         for e0, e1 in evs:
@@ -265,9 +265,11 @@ def main():
             step_fn()
             e1.record()
             kern.append(bank.last_kernel_ms())
+            dom.append(bank.last_dominant_ms())
         barrier()
         wall = time.perf_counter() - wall0
         ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+        timed.dominant_ms = sum(dom) / len(dom)
         return sum(ms) / len(ms), sum(kern) / len(kern), wall
 
     sampler = ClockSampler(local)
@@ -288,6 +290,7 @@ def main():
         e2e_step()
     launches0 = bank.launch_count()
     ms_step, ms_kernel, wall = timed(device_step, a.steps)
+    ms_dom = timed.dominant_ms      # the dominant kernel alone (CUDA events on the stream it is launched on, inside the bank)
     launches = bank.launch_count() - launches0
     ms_e2e, _, _ = timed(e2e_step, a.steps)
     # AudioUnit::process granularity: one C-ABI call per 64-sample block with host buffers (the Wave::render call pattern)
@@ -300,9 +303,9 @@ def main():
     proc_val = world * V * 64 * pb / t_p / 1e6
     clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
-        t = torch.tensor([ms_step, ms_e2e, ms_kernel], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms_step, ms_e2e, ms_kernel, ms_dom], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step, ms_e2e, ms_kernel = (float(x) for x in t.tolist())
+        ms_step, ms_e2e, ms_kernel, ms_dom = (float(x) for x in t.tolist())
         ln = torch.tensor([launches], device="cuda", dtype=torch.int64)
         dist.all_reduce(ln)
         launches = int(ln.item())
@@ -326,21 +329,40 @@ def main():
     nlaunch_chunks = (n + 16383) // 16384
     grid = sum((k["voices"] + 127) // 128 for k in cls)
     bytes_step = state_b * nlaunch_chunks + grid * c * n * 4 * 2 + c * n * 4 + (V * c * n * 4 if a.per_voice else 0) + (n * 4 if gate is not None else 0)
-    bytes_step += sum(k["voices"] * 8 * n * (1 if k["delay_floats"] else 0) * 32 for k in cls)  # FDN: 32 lines x (4 B read + 4 B write) per sample
-    achieved = bytes_step / (ms_kernel * 1e-3) / 1e9
+    kernel_name, bound, unit, roof_extra = "fdsp::bank_kernel<...>", "hbm", "GB/s", {}
+    if a.workload == "subtractive":
+        # the HBM-bound kernel of the path: per voice-sample 32 lines x (4 B read + 4 B write) + 2 x 4 B dry in + 2 x 4 B mix-row out
+        kernel_name = "fdsp::fdn_kernel<2>"
+        bytes_step = V * n * (32 * 8 + 8 + 8)
+        roof_extra = {"dry_stage": "the stage-pipelined voice program (Moog ladder in its own warp) runs beside it on the other stream and is the longer of the two: "
+                                   "kernel_ms_all_per_step - kernel_ms_per_step is what it adds"}
+    if a.workload == "conv":
+        # the tensor-core tiles: issued = 3 (3xTF32) x 2 x V(padded to 128) x n(padded to 128 per 16384-chunk) x (128 + P, padded to 32) flops
+        kernel_name, bound, unit = "fdsp::conv_tc_kernel<4>", "tensor", "TFLOP/s"
+        K = 1000
+        J = (128 + ((K - 1 + 3) // 4 * 4) + 31) // 32 * 32
+        npad = sum(((min(16384, n - t0) + 127) // 128) * 128 for t0 in range(0, n, 16384))
+        flops = 3 * 2.0 * ((V + 127) // 128 * 128) * npad * J
+        peak = float(peaks.get("bf16_tflops", 1720.0)) / 2.0
+        achieved = flops / (ms_dom * 1e-3) / 1e12
+        roof_extra = {"useful_tflops": 2.0 * V * n * K / (ms_dom * 1e-3) / 1e12, "issued_flops_per_step": flops,
+                      "peak_note": "TF32 dense = half of the measured BF16 dense rate of MEASURED_PEAKS.json (bf16_tflops / 2)"}
+    else:
+        achieved = bytes_step / (ms_dom * 1e-3) / 1e9
     traffic = None
     issue = None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         t = prof.get(a.workload + ("+voices" if a.per_voice else ""))
-        traffic = t["dram_bytes_per_launch"] * n / t["samples_per_launch"] if t else None  # ncu dram bytes of one 16384-sample launch, scaled to the step
-        if t and t.get("warp_inst_per_launch") and V == HEADLINE[a.workload]:
+        # ncu dram bytes of one 16384-sample launch of the dominant kernel, scaled to the step
+        traffic = t["dram_bytes_per_launch"] * n / t["samples_per_launch"] if t else None
+        if t and t.get("warp_inst_per_launch") and V == HEADLINE[a.workload] and bound == "hbm":
             # what actually bounds a voice program: warp-instructions issued (ncu count of one 16384-sample launch, scaled to the
             # step) against 148 SMs x 4 schedulers x 1 instruction per clock at the SM clock sampled during the timed region
             winst = t["warp_inst_per_launch"] * n / t["samples_per_launch"]
             mhz = float(clocks.get("sm_mhz") or 1965.0)
-            issue = {"warp_inst_per_step": winst, "achieved_ginst_s": winst / (ms_kernel * 1e-3) / 1e9, "peak_ginst_s": 592 * mhz * 1e6 / 1e9,
-                     "frac": winst / (ms_kernel * 1e-3) / (592 * mhz * 1e6), "source": "profiles/r01_traffic.json (smsp__inst_executed.sum of one launch)"}
+            issue = {"warp_inst_per_step": winst, "achieved_ginst_s": winst / (ms_dom * 1e-3) / 1e9, "peak_ginst_s": 592 * mhz * 1e6 / 1e9,
+                     "frac": winst / (ms_dom * 1e-3) / (592 * mhz * 1e6), "source": "profiles/r02_traffic.json (smsp__inst_executed.sum of one launch)"}
     except Exception:
         pass
     # ---- CPU baseline on this box's host cores (bounded sample of the same workload)
@@ -349,13 +371,16 @@ def main():
     ns = min(n, 24000)
     cpu_val = per_core = None
     build = ""
+    Vc = V
     if world == 1:
         build = native_oracle()
-        cpu_reference(a.workload, min(V, 256), 480, cores)
-        dt, _ = cpu_reference(a.workload, V, ns, cores)
-        cpu_val = V * ns / dt / 1e6
-        dt1, _ = cpu_reference(a.workload, min(V, 64), ns, 1)
-        per_core = min(V, 64) * ns / dt1 / 1e6
+        if a.workload == "conv":
+            Vc, ns = min(V, 2 * cores), 4800       # (1000 taps in the direct form on the CPU: a small sample stands for the bank)
+        cpu_reference(a.workload, min(Vc, 256), 480, cores)
+        dt, _ = cpu_reference(a.workload, Vc, ns, cores)
+        cpu_val = Vc * ns / dt / 1e6
+        dt1, _ = cpu_reference(a.workload, min(Vc, 64), ns, 1)
+        per_core = min(Vc, 64) * ns / dt1 / 1e6
     line = {
         "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -367,12 +392,12 @@ def main():
                 "call": "fdsp_bank_render(host buffers)" if world == 1 else "fdsp_bank_render_reduced(host buffers; D2H of the reduced mix on the root)", "ms_per_step": ms_e2e,
                 "process_granularity": {"value": proc_val, "unit": "Msamples/s", "us_per_call": t_p / pb * 1e6, "call": "fdsp_bank_process(64) per block, host buffers"}},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "fdsp::bank_kernel<...>", "kernel_ms_per_step": ms_kernel, "algorithmic_bytes_per_step": int(bytes_step),
+        "roofline": {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, "traffic": traffic,
+                     "kernel": kernel_name, "kernel_ms_per_step": ms_dom, "kernel_ms_all_per_step": ms_kernel, "algorithmic_bytes_per_step": int(bytes_step), **roof_extra,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)", "issue": issue,
                      "note": "IIR voice programs are issue/latency bound, not HBM bound (DESIGN.md §Roofline); see profiles/ for issue-slot utilisation"},
         "cpu_baseline": {"value": cpu_val, "unit": "Msamples/s", "cores": cores, "kind": "port", "single_core": per_core, "core_info": core_info,
-                         "sample": (f"{V} voices x {ns} samples, oracle (C++ restatement of the reference block path; {build}), {cores} threads" if world == 1
+                         "sample": (f"{Vc} voices x {ns} samples, oracle (C++ restatement of the reference block path; {build}), {cores} threads" if world == 1
                                     else "not timed at N > 1 (see the N=1 line and the --impl reference arm)")},
         "clocks": clocks,
         "wall_s_timed_region": wall,

@@ -157,6 +157,7 @@ class GpuBank:
     def stream(self): return self.L.fdsp_bank_stream(self.h)
     def launch_count(self): return int(self.L.fdsp_bank_launch_count(self.h))
     def last_kernel_ms(self): return float(self.L.fdsp_bank_last_kernel_ms(self.h))
+    def last_dominant_ms(self): return float(self.L.fdsp_bank_last_dominant_ms(self.h))
 
     def classes(self):
         out = []

@@ -68,7 +68,7 @@ _SIG = {
     "fdsp_bank_process": (I, [P, U32, FP, FP]), "fdsp_bank_render": (I, [P, U64, FP, FP, FP]),
     "fdsp_bank_render_device": (I, [P, U64, P, U64, P, U64, P, U64]), "fdsp_bank_sync": (I, [P]), "fdsp_bank_stream": (P, [P]),
     "fdsp_bank_num_classes": (I, [P]), "fdsp_bank_class_info": (I, [P, I, C.c_char_p, I, C.POINTER(U32), C.POINTER(U32), C.POINTER(U32), C.POINTER(U64)]),
-    "fdsp_bank_launch_count": (U64, [P]), "fdsp_bank_last_kernel_ms": (F, [P]),
+    "fdsp_bank_launch_count": (U64, [P]), "fdsp_bank_last_kernel_ms": (F, [P]), "fdsp_bank_last_dominant_ms": (F, [P]),
 }
 
 

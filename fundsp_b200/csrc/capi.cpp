@@ -375,6 +375,8 @@ API int fdsp_bank_sync(fdsp_bank* b) {
   cudaError_t e = cudaStreamSynchronize(b->b.stream);
   if (e != cudaSuccess) return fail(FDSP_ERR_CUDA, cudaGetErrorString(e));
   if (cudaEventElapsedTime(&b->b.last_ms, b->b.ev0, b->b.ev1) != cudaSuccess) b->b.last_ms = 0.0f;
+  b->b.last_dom_ms = 0.0f;
+  for (size_t i = 0; i + 1 < b->b.dom_n; i += 2) { float t = 0.0f; if (cudaEventElapsedTime(&t, b->b.dom_ev[i], b->b.dom_ev[i + 1]) == cudaSuccess) b->b.last_dom_ms += t; }
   return FDSP_OK;
 }
 API void* fdsp_bank_stream(fdsp_bank* b) { return b ? (void*)b->b.stream : nullptr; }
@@ -397,3 +399,4 @@ API int fdsp_bank_class_stages(const fdsp_bank* b, int cls) {
 }
 API uint64_t fdsp_bank_launch_count(const fdsp_bank* b) { return b ? b->b.launches : 0; }
 API float fdsp_bank_last_kernel_ms(const fdsp_bank* b) { return b ? b->b.last_ms : 0.0f; }
+API float fdsp_bank_last_dominant_ms(const fdsp_bank* b) { return b ? b->b.last_dom_ms : 0.0f; }

@@ -12,8 +12,12 @@
 // Precision: TF32 keeps 10 mantissa bits, the bar is 1e-5 of the output peak, so the product is taken in the 3xTF32 split
 //     x = xh + xl,  h = hh + hl   (xh = x with the low 13 mantissa bits cleared — what the tensor core reads anyway —, xl = x - xh exactly)
 //     x * h  ~  xh*hl + xl*hh + xh*hh        (the dropped xl*hl is <= 2^-20 |x h|)
-// as three `tcgen05.mma.kind::tf32` into the same FP32 accumulator in TMEM per 8-wide k-step. A "hi" operand is simply the f32
-// array itself; only the "lo" arrays are materialised (conv_split_lo_kernel, conv_toeplitz_kernel).
+// as three `tcgen05.mma.kind::tf32` per 8-wide k-step. A "hi" operand is simply the f32 array itself; only the "lo" arrays are
+// materialised (conv_split_lo_kernel, conv_toeplitz_kernel).
+// Accumulation: the tensor core rounds the FP32 accumulator at every MMA, and a 4096-tap response is 1560 MMAs in a row — measured,
+// one accumulator gave 1.3e-5 of the peak at K = 4096 (error growing with K). So the sum is spread over FOUR accumulators in TMEM
+// (all 512 columns): the xh*hh products of chunks c = 0, 1, 2 (mod 3) in three of them — a third of the sequential roundings each —
+// and both cross terms, 2^-11 smaller, in the fourth, where their roundings do not count; the epilogue adds the four in FP32.
 //
 // Kernel (one output tile per CTA, 192 threads): warp 0 = TMA producer (4 `cp.async.bulk.tensor.2d` per stage: X, Xlo, T, Tlo tiles,
 // 128-byte swizzle, 3-stage ring of 64 KB, full/empty mbarriers), warp 1 = TMEM allocation + MMA issue (one elected lane; smem
@@ -88,8 +92,8 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     ctc_mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM: 128 lanes x 128 columns of FP32 accumulators
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(CTC_N) : "memory");
+  if (warp == 1) {   // TMEM: 128 lanes x 4 accumulators of 128 FP32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(4 * CTC_N) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -126,9 +130,9 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
 #pragma unroll
         for (int k = 0; k < CTC_KC / 8; k++) {
           const uint64_t adv = (uint64_t)((k * 32) >> 4);                      // 8 floats = 32 bytes further inside the swizzle row
-          ctc_mma(tmem, dxh + adv, dtl + adv, (c | k) != 0 ? 1u : 0u);
-          ctc_mma(tmem, dxl + adv, dth + adv, 1u);
-          ctc_mma(tmem, dxh + adv, dth + adv, 1u);
+          ctc_mma(tmem + (uint32_t)((c % 3) * CTC_N), dxh + adv, dth + adv, (c >= 3 || k != 0) ? 1u : 0u);   // xh*hh: accumulator c mod 3
+          ctc_mma(tmem + 3u * CTC_N, dxh + adv, dtl + adv, (c | k) != 0 ? 1u : 0u);                            // cross terms: the fourth
+          ctc_mma(tmem + 3u * CTC_N, dxl + adv, dth + adv, 1u);
         }
         if (STEP >= 3) ctc_commit(empty_bar(s));                               // the stage is free once these MMAs have read it
       }
@@ -146,13 +150,21 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
 #pragma unroll 1
     for (int cb = 0; cb < CTC_N; cb += 32) {
       uint32_t r[32];
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cb;
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
-                     "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
-                     "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                   : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float acc[32];
+#pragma unroll 1
+      for (int part = 0; part < 4; part++) {   // ((a0 + a1) + a2) + cross
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * CTC_N + cb);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+                       "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+                       "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; j++) acc[j] = part == 0 ? __uint_as_float(r[j]) : acc[j] + __uint_as_float(r[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j++) r[j] = __float_as_uint(acc[j]);
       if (rok) {
         const uint32_t left = a.n > t0 + (uint32_t)cb ? a.n - t0 - (uint32_t)cb : 0u;   // valid samples from this column on
         if (vec_ok && left >= 32u) {
@@ -167,7 +179,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(CTC_N) : "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(4 * CTC_N) : "memory");
 }
 
 // xl = x - (x with the low 13 mantissa bits cleared), over the new columns of every X row

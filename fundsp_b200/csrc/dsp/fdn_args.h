@@ -24,6 +24,7 @@ struct FdnArgs {
   float* partial;            // [V][2][n] per-voice rows of the mix-down (mix_reduce_kernel adds them in voice order) or null
   float* ring; uint64_t ring_voice_stride;
   uint32_t V, n;
+  uint32_t flags;            // diagnostics (FDSP_FDN_FLAGS): bit 0 = one sample per lane and pass, bit 1 = three-stage form
 };
 
 }  // namespace fdsp

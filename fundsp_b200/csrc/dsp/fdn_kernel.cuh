@@ -36,11 +36,12 @@
 
 namespace fdsp {
 
-constexpr int FDN_NST = 2;                      // ring-slice stages per warp: block b + 1 is fetched while block b is computed (a block takes ~6 us, HBM ~1 us)
+constexpr int FDN_NST_DEFAULT = 2;                      // ring-slice stages per warp: block b + 1 is fetched while block b is computed (a block takes ~6 us, HBM ~1 us)
 constexpr int FDN_RS = 72;                      // row stride (floats): 4 lead + 3 shift + 64 samples, 16-byte multiple
 constexpr int FDN_ROWS = 32 * FDN_RS;           // one stage
+__host__ __device__ constexpr int fdn_warp_floats(int nst) { return nst * FDN_ROWS + nst * 128 + 128 + nst * 64 + 32 + 128; }
 // per warp: stages | dbuf [NST][2][64] | wtab [32][4] (w0 w1 w2 lw) | tb2 [NST][32][2] (rw, row offset) | vcarry [32] | geo [32][4] (idx, len, lp, off)
-constexpr int FDN_WARP_FLOATS = FDN_NST * FDN_ROWS + FDN_NST * 128 + 128 + FDN_NST * 64 + 32 + 128;
+constexpr int FDN_WARP_FLOATS = fdn_warp_floats(FDN_NST_DEFAULT);
 
 FDSP_DEV uint32_t fdn_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 FDSP_DEV void fdn_cp16(uint32_t dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
@@ -49,7 +50,9 @@ FDSP_DEV void fdn_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memor
 template <int N> FDSP_DEV void fdn_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // blockDim.x = 32 * W (W voices per CTA), dynamic smem = W * FDN_WARP_FLOATS * 4 bytes
+template <int FDN_NST>
 __global__ void __launch_bounds__(320) fdn_kernel(const FdnArgs a) {
+  constexpr int FDN_WARP_FLOATS = fdn_warp_floats(FDN_NST);
   extern __shared__ __align__(16) float fdn_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
   const uint32_t v = blockIdx.x * W + warp;
@@ -134,6 +137,7 @@ __global__ void __launch_bounds__(320) fdn_kernel(const FdnArgs a) {
   const uint32_t nblk = (a.n + 63u) / 64u;
   auto blen = [&](uint32_t b) { return b < nblk ? (int)((a.n - b * 64u) < 64u ? (a.n - b * 64u) : 64u) : 0; };
   prefetch(0, 0u, blen(0), 0u);
+  if (FDN_NST == 3) prefetch(1, 64u, blen(1), 64u);
 #pragma unroll 1
   for (uint32_t b = 0; b < nblk; b++) {
     const int st = (int)(b % FDN_NST);
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(320) fdn_kernel(const FdnArgs a) {
     const int nb = blen(b);
     // the other stage held block b - 1: its rows went back to the rings before the __syncwarp that ended the last iteration. What block
     // b + 1 reads was written at least a whole block ago (every delay >= 192 samples), in program order before this point.
-    prefetch((int)((b + 1) % FDN_NST), t0 + 64u, blen(b + 1), (uint32_t)nb);
+    if (FDN_NST == 2) prefetch((int)((b + 1) % FDN_NST), t0 + 64u, blen(b + 1), (uint32_t)nb);
     fdn_cp_wait<1>();   // all but the newest group: block b has landed (this lane's copies; the __syncwarp below publishes the others')
     __syncwarp();
     if (active) {
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(320) fdn_kernel(const FdnArgs a) {
       }
       __syncwarp();
       const float2* t2 = tb2 + st * 32;
-      if (nb == 64) {
+      if (nb == 64 && !(a.flags & 1u)) {
         // full block: lane t evaluates samples t and t + 32 in ONE pass — the per-line weights are loaded once for both, and two independent
         // chains per lane keep the FP32 pipe fed. All taps of the block are read before any new sample is stored.
         float a0[32], a1[32], sl0 = 0.0f, sr0 = 0.0f, sl1 = 0.0f, sr1 = 0.0f;
@@ -289,6 +293,7 @@ __global__ void __launch_bounds__(320) fdn_kernel(const FdnArgs a) {
       geo[lane].x = idx;
       __syncwarp();
     }
+    if (FDN_NST == 3) prefetch((int)((b + 2) % FDN_NST), t0 + 128u, blen(b + 2), 64u);   // (diagnostic three-stage form: distance 2, issued after the block)
   }
   fdn_cp_wait<0>();
   if (active) {

@@ -59,6 +59,7 @@ Bank::~Bank() {
   cudaFree(d_wt); cudaFree(d_in); cudaFree(d_out); cudaFree(d_mix); cudaFree(d_rows);
   if (h_in) cudaFreeHost(h_in);
   if (h_out) cudaFreeHost(h_out);
+  for (cudaEvent_t e : dom_ev) cudaEventDestroy(e);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   if (e_begin) cudaEventDestroy(e_begin);
@@ -528,6 +529,13 @@ static uint32_t staged_grid(uint32_t V, uint32_t* vpc) {
   return bank_grid(V, 128u, vpc);
 }
 
+std::string Bank::dom_mark(cudaStream_t st) {   // called in pairs: begin, end
+  if (!timing) return "";
+  if (dom_n == dom_ev.size()) { cudaEvent_t e; CU(cudaEventCreate(&e)); dom_ev.push_back(e); }
+  CU(cudaEventRecord(dom_ev[dom_n++], st));
+  return "";
+}
+
 std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_stride, float* out_dev, uint64_t out_stride, float* mix_dev,
                                 uint64_t mix_stride) {
   CU(cudaSetDevice(device));
@@ -537,7 +545,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
   if (n == 0) return "";
   const bool save_want_m_ = want_m;
   if (in_stride > 0xffffffffull || out_stride > 0xffffffffull || mix_stride > 0xffffffffull) return "stride too large";
-  if (timing) CU(cudaEventRecord(ev0, stream));
+  if (timing) { CU(cudaEventRecord(ev0, stream)); dom_n = 0; }
   // Net-ordered mix: the voice kernels materialise per-voice rows (user buffer, or an internal one) and tree_mix_kernel adds
   // them in the Net's association order; the CTA-level partial mix is bypassed.
   const bool tree = tree_mix != 0 && want_m;
@@ -622,7 +630,9 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
           if (c.crows_cap < (size_t)V * TIME_CHUNK) { std::string e = dev_alloc(&c.d_crows, (size_t)V * TIME_CHUNK); if (!e.empty()) return e; c.crows_cap = (size_t)V * TIME_CHUNK; }
           y = c.d_crows; ys = TIME_CHUNK; yo = 0;
         }
+        { std::string de = dom_mark(stream); if (!de.empty()) return de; }
         CU(launch_conv_tc(c.conv_maps, y, ys, yo, c.d_dryrows, V, len, c.conv_K, c.conv_H, stream));
+        { std::string de = dom_mark(stream); if (!de.empty()) return de; }
         CU(launch_conv_history(c.d_cx, c.d_cxl, V, c.conv_stride, c.conv_H, len, stream));
         launches += 4;
         if (want_m) { CU(launch_tree_mix(y, V, 1u, ys, yo, len, mix_dev, (uint32_t)mix_stride, (uint32_t)t0, 0, stream)); launches++; }
@@ -676,15 +686,16 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
           f.ring = c.d_ring; f.ring_voice_stride = c.ring_floats; f.V = V; f.n = len;
           CU(cudaStreamWaitEvent(stream2, c.e_dry[buf], 0));
           tmark(stream2);
+          { std::string de = dom_mark(stream2); if (!de.empty()) return de; }
           CU(launch_fdn(f, fdn_warps, stream2));
+          { std::string de = dom_mark(stream2); if (!de.empty()) return de; }
           launches++;
           tmark(stream2);
           CU(cudaEventRecord(c.e_fdn[buf], stream2));
           if (!solo) pending.push_back({&c, grid, len, t0, buf});
-          else if (want_m) {
-            CU(launch_mix_reduce(buf ? c.d_partial2 : c.d_partial, grid, (uint32_t)nout, len, mix_dev, (uint32_t)mix_stride, (uint32_t)t0, 1, stream2));
-            launches++;
-            joined = false;
+          else {
+            if (want_m) { CU(launch_mix_reduce(buf ? c.d_partial2 : c.d_partial, grid, (uint32_t)nout, len, mix_dev, (uint32_t)mix_stride, (uint32_t)t0, 1, stream2)); launches++; }
+            joined = false;   // stream2 carries work `stream` has not waited for (rows written by the FDN kernel, the reduction): joined after the loop
           }
           continue;
         }
@@ -700,9 +711,13 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
         f.out = want_v ? out_dev_c : nullptr; f.row_map = c.d_rowmap; f.out_stride = (uint32_t)out_stride_c; f.out_offset = (uint32_t)out_t0;
         f.partial = want_m ? c.d_partial : nullptr;
         f.ring = c.d_ring; f.ring_voice_stride = c.ring_floats; f.V = V; f.n = len;
+        { std::string de = dom_mark(stream); if (!de.empty()) return de; }
         CU(launch_fdn(f, fdn_warps, stream));
+        { std::string de = dom_mark(stream); if (!de.empty()) return de; }
       } else {
+        { std::string de = dom_mark(ks); if (!de.empty()) return de; }
         CU(launch_voice(a, mode, ks));
+        { std::string de = dom_mark(ks); if (!de.empty()) return de; }
       }
       launches++;
       if (concurrent) { CU(cudaEventRecord(c.e_done, ks)); continue; }   // reduced below, after every class has been launched

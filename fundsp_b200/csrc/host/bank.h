@@ -57,6 +57,10 @@ struct Bank {
   uint64_t launches = 0; float last_ms = 0.0f;
   uint32_t* d_ticket = nullptr;   // arrival counter of the fused mix-down (short launches)
   bool timing = true;             // record ev0/ev1 around render_device (off on the process() path)
+  // event pairs around the DOMINANT kernel of every chunk (the voice program; the FDN kernel of a two-stage class; the tensor-core tiles of
+  // a convolver class), on the stream it is launched on: bench.py's roofline divides by this, not by the whole render
+  std::vector<cudaEvent_t> dom_ev; size_t dom_n = 0; float last_dom_ms = 0.0f;
+  std::string dom_mark(cudaStream_t st);
 
   ~Bank();
   uint32_t V() const { return (uint32_t)nodes.size(); }

@@ -240,6 +240,7 @@ int fdsp_bank_class_info(const fdsp_bank* b, int cls, char* signature, int max, 
 int fdsp_bank_class_stages(const fdsp_bank* b, int cls);                    /* warp stages of the class's stage-pipelined kernel (csrc/dsp/bank_kernel_st.cuh); 1 = it has none */
 uint64_t fdsp_bank_launch_count(const fdsp_bank* b);                        /* kernels launched so far */
 float fdsp_bank_last_kernel_ms(const fdsp_bank* b);                         /* CUDA-event time of the voice kernels of the last render_device call */
+float fdsp_bank_last_dominant_ms(const fdsp_bank* b);                       /* of that, the dominant kernel alone (voice program | FDN kernel | tensor-core tiles), summed over chunks and classes */
 
 #ifdef __cplusplus
 }

@@ -211,7 +211,7 @@ def test_tensor_core_convolver(K, monkeypatch):
     if "mock" not in os.environ.get("FDSP_B200_LIB", ""):
         monkeypatch.setenv("FDSP_TC_CONV", "0")
         d, _ = GpuBank([mk(i) for i in range(V)], per_voice=True, mix=True, sample_rate=SR).render_samples(2000)
-        assert float(np.abs(d - g[..., :2000]).max()) <= 4e-6 * peak
+        assert float(np.abs(d - g[..., :2000]).max()) <= 1e-5 * peak
 
 
 def oracle_rows(expr, n):

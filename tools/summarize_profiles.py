@@ -24,9 +24,10 @@ try:
     traffic = json.load(open(os.path.join(OUT, f"{ROUND}_traffic.json")))   # keep entries whose .ncu-rep is no longer in gpurun_out/
 except Exception:
     pass
-for rep in sorted(f for f in os.listdir(os.path.join(ROOT, "gpurun_out")) if f.startswith("full_") and f.endswith(".ncu-rep")):
+PREFIX = "full_" if ROUND == "r01" else f"{ROUND}_full_"
+for rep in sorted(f for f in os.listdir(os.path.join(ROOT, "gpurun_out")) if f.startswith(PREFIX) and f.endswith(".ncu-rep")):
     m = raw(os.path.join(ROOT, "gpurun_out", rep))
-    name = rep[len("full_"):-len(".ncu-rep")]
+    name = rep[len(PREFIX):-len(".ncu-rep")]
     for suffix in ("_r01e", "_r01"):
         if name.endswith(suffix):
             name = name[: -len(suffix)]
@@ -40,7 +41,8 @@ for rep in sorted(f for f in os.listdir(os.path.join(ROOT, "gpurun_out")) if f.s
     def tobytes(key):
         v, u = m[key]
         return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-    key = {"saw_svf_mix": "saw_svf", "noise_svf_mix": "noise_svf", "saw_svf_voices": "saw_svf+voices", "fm_mix": "fm", "subdry": "subtractive_dry", "fdn": "subtractive"}.get(name, name)
+    key = {"saw_svf_mix": "saw_svf", "noise_svf_mix": "noise_svf", "saw_svf_voices": "saw_svf+voices", "fm_mix": "fm", "subdry": "subtractive_dry", "subdry_st": "subtractive_dry",
+           "fdn": "subtractive", "conv_tc": "conv", "net_mix": "net"}.get(name, name)
     traffic[key] = {"dram_bytes_per_launch": tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum"), "samples_per_launch": 16384,
                     "warp_inst_per_launch": float(m["smsp__inst_executed.sum"][0]) if "smsp__inst_executed.sum" in m else None,
                     "issue_active_pct": float(m["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]) if "smsp__issue_active.avg.pct_of_peak_sustained_active" in m else None,
@@ -48,7 +50,7 @@ for rep in sorted(f for f in os.listdir(os.path.join(ROOT, "gpurun_out")) if f.s
 json.dump(traffic, open(os.path.join(OUT, f"{ROUND}_traffic.json"), "w"), indent=1)
 
 # launch list of the bench command: per-kernel totals and shares
-src = os.path.join(ROOT, "gpurun_out", "launches_bench.csv")
+src = os.path.join(ROOT, "gpurun_out", "launches_bench.csv" if ROUND == "r01" else f"{ROUND}_launches_bench.csv")
 if os.path.exists(src):
     rows = [r for r in csv.reader(open(src)) if len(r) > 10]
     hdr = rows[0]
