@@ -50,7 +50,12 @@ template <class G, int NT, int MODE, bool TB, int I> struct StRun {
     if constexpr (J < I) { typename ChainAt<J, STG>::type::R skip; ChainAt<J, STG>::type::load(skip, l); skip_to<J + 1>(l); }
   }
 
-  static FDSP_DEV void run(const BankArgs& a, float* tile, float* hand, uint32_t bar0, CtxT<TB>& c, uint32_t lt, uint32_t v, bool active) {
+  static FDSP_DEV void run(const BankArgs& a, float* tile, float* hand, uint32_t bar0, CtxT<TB>& c0, uint32_t lt, uint32_t v, bool active) {
+    // a stage built around a heavy leaf is one serial chain per lane: its 8 steps of a group are unrolled outright (static register indices, the
+    // group's inputs loaded up front) instead of the rotating loop the one-warp-does-everything kernel uses to keep its instruction stream small
+    CtxT<TB, SpineHeavy<S>::value> c;
+    c.wt = c0.wt; c.tsm = c0.tsm; c.tsm_kind = c0.tsm_kind; c.dl = c0.dl; c.V = c0.V; c.v = c0.v; c.sr = c0.sr; c.sd64 = c0.sd64; c.sd32 = c0.sd32;
+    c.i = 0; c.n = 0; c.first = false; c.rem = false;
     const uint32_t w = lt >> 5, lane = lt & 31u;
     constexpr int MIDI = FIRST ? 1 : IN, MIDO = LAST ? 1 : OUT;
     // barriers: index 1 + ((b * NW + w) * NSLOT + slot) * 2 (+1 = empty)

@@ -27,8 +27,9 @@ template <int N> struct Fr8 { float v[N > 0 ? N : 1][8]; };
 // Block context. `first`: first lane of an 8-sample SIMD group; `rem`: sample belongs to the tail
 // (size & 7) that the reference runs through `tick` (src/audionode.rs:110-126); `i`/`n`: index / size of block.
 // SM: the wavetables of one waveform kind are staged in shared memory (TMA bulk copy in the kernel prologue).
-template <bool SM> struct CtxT {
+template <bool SM, bool UH = false> struct CtxT {
   static constexpr bool SMEM_TABLES = SM;
+  static constexpr bool UNROLL_HEAVY = UH;   // heavy serial leaves run their 8 steps fully unrolled (the stage-pipelined kernel gives them a warp of their own)
   const WaveTableDev* wt;
   uint32_t tsm;       // shared-space byte address of the staged table data (kind `tsm_kind`)
   int tsm_kind;
@@ -95,7 +96,7 @@ template <class G> struct Cost;   // static per-sample cost estimate of a progra
 template <class Node, class C> FDSP_DEV void group_step(typename Node::R& r, C& c, const Fr8<Node::IN>& in, Fr8<Node::OUT>& o) {
   if constexpr (HasGroup<Node>::value) {
     Node::step8(r, c, in, o);
-  } else if constexpr ((Cost<Node>::value > FDSP_ROTATE_COST)) {
+  } else if constexpr ((Cost<Node>::value > FDSP_ROTATE_COST) && !C::UNROLL_HEAVY) {
     // Heavy serial leaf (Moog, Rez, Dsf ...): unrolling it 8x only bloats the instruction stream, so its 8 steps run in a real
     // loop. The group registers are ROTATED by one sample per iteration, which keeps every array index static (no local memory).
     Fr8<Node::IN> ri = in;
