@@ -513,12 +513,15 @@ static size_t table_bytes_of(const VoiceClass& c, uint32_t len) {
   return (wk >= 0 && len >= tb_min) ? device_wavetable(wk).data.size() * sizeof(float) : 0;
 }
 // Stage-pipelined kernels (dsp/bank_kernel_st.cuh): programs with a heavy serial leaf (Moog ...) run their stages in different warps.
-// Used for launches long enough to fill the pipeline; FDSP_STAGED=0 switches them off (A/B), FDSP_STAGED_MAXV bounds the class size.
+// Used for launches long enough to fill the pipeline and for classes too small to give every warp scheduler a voice-warp of its own
+// (V <= 148 SMs x 32: measured on B200, the 1024-voice config-4 dry program 6.93 -> 4.60 ms per 16384 samples staged, the 16384-voice
+// saw >> moog >> pan class of config 5 6.35 -> 10.75 ms: with a warp per scheduler already, stages only add hand-off work).
+// FDSP_STAGED=0 switches them off (A/B), FDSP_STAGED_MAXV moves the class-size bound.
 static bool use_staged(const Program* k, uint32_t V, uint32_t len) {
   const char* e = getenv("FDSP_STAGED");            // read per call: the tests toggle it inside one process
   const char* m = getenv("FDSP_STAGED_MAXV");
   const int on = e ? atoi(e) : 1;
-  const uint32_t maxv = m ? (uint32_t)atoi(m) : 0xffffffffu;
+  const uint32_t maxv = m ? (uint32_t)atoi(m) : 148u * 32u;
   return on != 0 && k && k->stages >= 2 && len >= 256u && V <= maxv;
 }
 // CTA shape of a stage-pipelined class: 32 voices per CTA while that still leaves SMs free, else 128 with the voices spread evenly
