@@ -372,6 +372,7 @@ API int fdsp_bank_reduce_device(fdsp_bank* b, fdsp_group* g, uint64_t n, float* 
 API int fdsp_bank_sync(fdsp_bank* b) {
   if (!b) return fail(FDSP_ERR_ARG, "null bank");
   cudaSetDevice(b->b.device);
+  { std::string re = b->b.rt_stop(); if (!re.empty()) return status(re); }
   cudaError_t e = cudaStreamSynchronize(b->b.stream);
   if (e != cudaSuccess) return fail(FDSP_ERR_CUDA, cudaGetErrorString(e));
   if (cudaEventElapsedTime(&b->b.last_ms, b->b.ev0, b->b.ev1) != cudaSuccess) b->b.last_ms = 0.0f;

@@ -3,6 +3,7 @@
 #include "../host/registry.h"
 #include "bank_kernel.cuh"
 #include "bank_kernel_st.cuh"
+#include "bank_kernel_rt.cuh"
 
 namespace fdsp {
 namespace host {
@@ -72,16 +73,31 @@ template <class G> cudaError_t launch_t(const BankArgs& a, int mode, size_t tabl
   }
   return launch_mode<G, false>(a, mode, 0, st);
 }
+// resident process() kernel (bank_kernel_rt.cuh): one launch serves 64-sample blocks on a doorbell until it is told to leave
+template <class G, bool TB> cudaError_t launch_rt_one(const BankArgs& a, const RtArgs& rt, size_t smem, cudaStream_t st) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(bank_kernel_rt<G, NT, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const unsigned vpc = a.vpc ? a.vpc : (unsigned)NT, grid = (a.V + vpc - 1) / vpc;
+  bank_kernel_rt<G, NT, TB><<<grid, NT, smem, st>>>(a, rt);
+  return cudaGetLastError();
+}
+template <class G> cudaError_t launch_rt_t(const BankArgs& a, const RtArgs& rt, size_t table_bytes, cudaStream_t st) {
+  const size_t tile = sizeof(float) * mix_tile_floats(G::OUT, NT);
+  if (WaveKind<G>::value >= 0 && table_bytes > 0 && tile + table_bytes <= 227 * 1024) return launch_rt_one<G, (WaveKind<G>::value >= 0)>(a, rt, tile + table_bytes, st);
+  return launch_rt_one<G, false>(a, rt, tile, st);
+}
 template <class G> int wave_kind_t() { return WaveKind<G>::value; }
 inline int threads_t() { return NT; }
 
 template <class G> int stages_t() { return StagePlan<G>::K; }
 #define FDSP_REG(...) \
-  {#__VA_ARGS__, __VA_ARGS__::IN, __VA_ARGS__::OUT, __VA_ARGS__::NP, __VA_ARGS__::NS, __VA_ARGS__::NU, &launch_t<__VA_ARGS__>, &threads_t, &wave_kind_t<__VA_ARGS__>, 1, nullptr}
+  {#__VA_ARGS__, __VA_ARGS__::IN, __VA_ARGS__::OUT, __VA_ARGS__::NP, __VA_ARGS__::NS, __VA_ARGS__::NU, &launch_t<__VA_ARGS__>, &threads_t, &wave_kind_t<__VA_ARGS__>, 1, nullptr, &launch_rt_t<__VA_ARGS__>}
 // the same, plus the stage-pipelined kernels of the graph (bank_kernel_st.cuh; only graphs with a heavy leaf have any)
 #define FDSP_REG_ST(...) \
   {#__VA_ARGS__, __VA_ARGS__::IN, __VA_ARGS__::OUT, __VA_ARGS__::NP, __VA_ARGS__::NS, __VA_ARGS__::NU, &launch_t<__VA_ARGS__>, &threads_t, &wave_kind_t<__VA_ARGS__>, \
-   StagePlan<__VA_ARGS__>::K, &launch_st_t<__VA_ARGS__>}
+   StagePlan<__VA_ARGS__>::K, &launch_st_t<__VA_ARGS__>, &launch_rt_t<__VA_ARGS__>}
 #define FDSP_INSTANCES(name, ...)                     \
   extern const KernelEntry kInst_##name[] = {__VA_ARGS__}; \
   extern const int kInst_##name##_n = (int)(sizeof(kInst_##name) / sizeof(kInst_##name[0]));

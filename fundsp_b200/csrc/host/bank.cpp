@@ -3,6 +3,7 @@
 #include "../dsp/fdn_args.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -52,6 +53,9 @@ static bool tc_conv_wanted(const std::string& sig, const Lowering& l, int nout) 
 
 Bank::~Bank() {
   cudaSetDevice(device);
+  rt_stop();
+  if (rt_ctl) cudaFreeHost(rt_ctl);
+  cudaFree(d_rt_relay); cudaFree(d_rt_partial);
   for (auto& c : classes) {
     cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows); cudaFree(c.d_dry2); cudaFree(c.d_partial2); cudaFree(c.d_cx); cudaFree(c.d_cxl); cudaFree(c.d_th); cudaFree(c.d_tl); cudaFree(c.d_crows); for (int q = 0; q < 2; q++) { if (c.e_dry[q]) cudaEventDestroy(c.e_dry[q]); if (c.e_fdn[q]) cudaEventDestroy(c.e_fdn[q]); } if (c.cstream) cudaStreamDestroy(c.cstream); if (c.e_done) cudaEventDestroy(c.e_done);
   }
@@ -93,6 +97,7 @@ std::string Bank::init(std::vector<HNode*>& voices, int dev, uint32_t mode) {
 
 std::string Bank::lower_and_upload(bool upload_state) {
   CU(cudaSetDevice(device));
+  { std::string re = rt_stop(); if (!re.empty()) return re; } process_streak = 0;
   // 1. lower every voice, group into classes keyed by (type expression, uniform words)
   struct Low { std::string key; Lowering l; std::string sig; };
   std::vector<Low> lows(nodes.size());
@@ -275,6 +280,7 @@ std::string Bank::set_sample_rate(double s) {  // AudioUnit::set_sample_rate
 std::string Bank::set(uint32_t voice, const Setting& st) {  // AudioUnit::set (src/audiounit.rs:62, src/setting.rs) on a live bank
   if (voice >= V()) return "set: voice index out of range";
   CU(cudaSetDevice(device));
+  { std::string re = rt_stop(); if (!re.empty()) return re; } process_streak = 0;
   // the setting is tried on a COPY of the voice's host graph: a refused setting (one that would change a class-uniform word) leaves
   // both the host graph and the device untouched; the copy replaces the original only after the upload
   std::unique_ptr<HNode> trial(nodes[voice]->clone());
@@ -306,6 +312,7 @@ void Bank::advance_clock(uint64_t n) {   // what every Event<X> voice does to it
 
 // `l`: the words to run with. `reset_state`: the construction-time state that reset() restores (defaults to l.S).
 std::string Bank::upload_voice(uint32_t voice, const Lowering& l, bool with_state, const std::vector<uint32_t>* reset_state) {
+  { std::string re = rt_stop(); if (!re.empty()) return re; } process_streak = 0;
   for (auto& c : classes) {
     auto it = std::lower_bound(c.voices.begin(), c.voices.end(), voice);
     if (it == c.voices.end() || *it != voice) continue;
@@ -368,6 +375,7 @@ std::string Bank::add_voice(HNode* node, uint32_t* voice) {
   if (tree_mix) return "add: a bank extracted from a Net mixes in the Net's order; rebuild it from the edited Net";
   for (auto& c : classes) if (c.fdn) return "add: banks with a two-stage (FDN reverb) class cannot grow in place; rebuild the bank";
   CU(cudaSetDevice(device));
+  { std::string re = rt_stop(); if (!re.empty()) return re; } process_streak = 0;
   const double unit_rate = net_rate ? (double)(float)sr : sr;
   n->set_sample_rate(unit_rate);
   Lowering l0, l;
@@ -430,6 +438,7 @@ std::string Bank::slot_set(uint32_t voice, int ease, double fade_time, HNode* un
   if (!n || ease < 0 || ease > 1 || !(fade_time > 0.0)) return "slot: needs a unit, fade 0 (Power) or 1 (Smooth) and a fade time > 0";
   if (!is_slot(nodes[voice].get())) return "slot: the voice is not a slot (fdsp_slot)";
   CU(cudaSetDevice(device));
+  { std::string re = rt_stop(); if (!re.empty()) return re; } process_streak = 0;
   for (auto& c : classes) {
     auto it = std::lower_bound(c.voices.begin(), c.voices.end(), voice);
     if (it == c.voices.end() || *it != voice) continue;
@@ -494,6 +503,7 @@ std::string Bank::push_event(HNode* node, uint32_t* voice) {   // Sequencer::pus
 
 std::string Bank::reset() {  // AudioUnit::reset: back to the construction-time state
   CU(cudaSetDevice(device));
+  { std::string re = rt_stop(); if (!re.empty()) return re; } process_streak = 0;
   for (auto& c : classes) {
     if (!c.state0.empty()) CU(cudaMemcpyAsync(c.d_state, c.state0.data(), c.state0.size() * 4, cudaMemcpyHostToDevice, stream));
     if (c.dl_floats) CU(cudaMemsetAsync(c.d_dline, 0, (size_t)c.dl_floats * c.V() * sizeof(float), stream));
@@ -532,6 +542,84 @@ static uint32_t staged_grid(uint32_t V, uint32_t* vpc) {
   return bank_grid(V, 128u, vpc);
 }
 
+// ---- resident process() kernel
+std::string Bank::rt_stop() {
+  if (!rt_running) return "";
+  rt_ctl->doorbell = RT_QUIT;
+  __sync_synchronize();
+  rt_running = false;
+  CU(cudaStreamSynchronize(stream));   // the kernel has saved the state words
+  return "";
+}
+// One block through the resident kernel. `served` = false: the form does not apply (or the kernel had just left): the caller takes the
+// one-launch-per-block path, which continues from the saved state.
+std::string Bank::rt_process(uint32_t size, const float* in, float* out, bool* served) {
+  *served = false;
+#ifdef FDSP_HOST_EMUL
+  (void)size; (void)in; (void)out; return "";
+#else
+  const char* rte = getenv("FDSP_RT");          // read per call: the tests toggle it inside one process
+  const int on = rte ? atoi(rte) : 1;
+  if (!on) { process_streak = 0; return ""; }
+  if (classes.size() != 1 || !(out_mode & 2u) || tree_mix || nout > 8 || nin > 8) return "";
+  VoiceClass& c = classes[0];
+  if (c.fdn || c.conv || !c.k || !c.k->has_rt) return "";
+  uint32_t vpc = (uint32_t)c.k->threads;
+  const uint32_t grid = bank_grid(c.V(), (uint32_t)c.k->threads, &vpc);
+  if (grid > 148u) return "";                       // every CTA must be resident at once
+  if (++process_streak < 3u && !rt_running) return "";   // a bank that is driven block by block: the third process() call in a row starts the kernel
+  if (!rt_ctl) {
+    CU(cudaHostAlloc((void**)&rt_ctl, sizeof(RtCtl), cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer((void**)&rt_ctl_dev, rt_ctl, 0));
+    CU(cudaMalloc((void**)&d_rt_relay, 16));
+  }
+  if (rt_partial_cap < (size_t)grid * nout * 64) { cudaFree(d_rt_partial); d_rt_partial = nullptr; CU(cudaMalloc((void**)&d_rt_partial, (size_t)grid * nout * 64 * 4)); rt_partial_cap = (size_t)grid * nout * 64; }
+  if (!rt_running) {
+    const uint32_t first = ++rt_seq; if (rt_seq >= 0xfffffff0u) rt_seq = 1;
+    memset((void*)rt_ctl, 0, sizeof(RtCtl));
+    rt_ctl->doorbell = first - 1u; rt_ctl->done = first - 1u;
+    const uint32_t relay[4] = {first - 1u, 0u, 0u, 0u};
+    CU(cudaMemcpyAsync(d_rt_relay, relay, 16, cudaMemcpyHostToDevice, stream));
+    CU(cudaMemsetAsync(d_ticket, 0, 4, stream));
+    BankArgs a;
+    a.params = c.d_params; a.state = c.d_state; a.uniform = c.d_uniform; a.dline = c.d_dline; a.wt = d_wt; a.in = nullptr; a.out = nullptr; a.partial = d_rt_partial;
+    a.V = c.V(); a.n = 64; a.vpc = vpc; a.in_stride = 0; a.in_offset = 0; a.out_stride = 0; a.out_offset = 0; a.row_map = c.d_rowmap;
+    a.sr = (float)sr; a.sd64 = (float)(1.0 / sr); a.sd32 = 1.0f / (float)sr; a.ticket = d_ticket; a.mix = nullptr; a.mix_stride = 0; a.mix_offset = 0; a.mix_accumulate = 0;
+    RtArgs rt{rt_ctl_dev, d_rt_relay, first};
+    CU(cudaStreamSynchronize(stream));   // the relay words are in place (pageable source)
+    CU(c.k->launch_rt(a, rt, table_bytes_of(c, 64), stream));
+    launches++;
+    rt_running = true;
+    rt_seq = first - 1u;
+  }
+  const uint32_t seq = ++rt_seq;
+  if (nin > 0) { if (!in) return "bank has inputs but no input buffer was given"; memcpy((void*)rt_ctl->in, in, (size_t)nin * 64 * 4); }
+  rt_ctl->size = size;
+  __sync_synchronize();
+  rt_ctl->doorbell = seq;
+  const auto t_ring = std::chrono::steady_clock::now();
+  for (uint64_t spins = 0;; spins++) {
+    const uint32_t d = rt_ctl->done;
+    if (d == seq) break;
+    if (d == RT_EXITED) {                 // the kernel left (idle) just before the doorbell rang: not served, state saved
+      rt_running = false; rt_seq--;
+      CU(cudaStreamSynchronize(stream));
+      return "";
+    }
+    if ((spins & 0xfffu) == 0xfffu && std::chrono::steady_clock::now() - t_ring > std::chrono::seconds(5)) {
+      rt_ctl->doorbell = RT_QUIT; rt_running = false;
+      return "process: the resident kernel does not answer (are all its CTAs resident? another kernel may hold the GPU)";
+    }
+    __builtin_ia32_pause();
+  }
+  __sync_synchronize();
+  memcpy(out, (const void*)rt_ctl->out, (size_t)nout * 64 * 4);
+  dirty = true; advance_clock(size);
+  *served = true;
+  return "";
+#endif
+}
+
 std::string Bank::dom_mark(cudaStream_t st) {   // called in pairs: begin, end
   if (!timing) return "";
   if (dom_n == dom_ev.size()) { cudaEvent_t e; CU(cudaEventCreate(&e)); dom_ev.push_back(e); }
@@ -542,6 +630,8 @@ std::string Bank::dom_mark(cudaStream_t st) {   // called in pairs: begin, end
 std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_stride, float* out_dev, uint64_t out_stride, float* mix_dev,
                                 uint64_t mix_stride) {
   CU(cudaSetDevice(device));
+  { std::string re = rt_stop(); if (!re.empty()) return re; }
+  if (!in_process) process_streak = 0;
   if (nin > 0 && !in_dev) return "bank has inputs but no input buffer was given";
   const bool want_v = (out_mode & 1u) && out_dev, want_m = (out_mode & 2u) && mix_dev;
   if (!want_v && !want_m) return "no output buffer matches the bank's out_mode";
@@ -805,6 +895,15 @@ std::string Bank::process(uint32_t size, const float* in, float* out) {  // Audi
   if (size > 64) return "process: size must be <= 64 (MAX_BUFFER_SIZE)";
   if (size == 0) return "";
   CU(cudaSetDevice(device));
+  {
+    bool served = false;
+    std::string re = rt_process(size, in, out, &served);
+    if (!re.empty() || served) return re;
+    const uint32_t keep = process_streak;
+    re = rt_stop();                        // (no-op unless the resident kernel has just been declared unusable)
+    if (!re.empty()) return re;
+    process_streak = keep;
+  }
   std::string e = ensure_staging(64);
   if (!e.empty()) return e;
   const bool mix = (out_mode & 2u) != 0;  // mix mode wins for the AudioUnit surface; voices mode returns V*c channels
@@ -822,6 +921,7 @@ std::string Bank::process(uint32_t size, const float* in, float* out) {  // Audi
     CU(cudaMemcpyAsync(d_in, h_in, (size_t)nin * 64 * 4, cudaMemcpyHostToDevice, stream));
   }
   struct NoTiming { bool& t; explicit NoTiming(bool& x) : t(x) { t = false; } ~NoTiming() { t = true; } } no_timing(timing);  // no event records on this path
+  struct InProcess { bool& f; explicit InProcess(bool& x) : f(x) { f = true; } ~InProcess() { f = false; } } in_proc(in_process);
   bool two_stage = false;   // pipelined classes clear / accumulate the mix region on the device: keep that in device memory
   for (auto& c : classes) two_stage = two_stage || (c.fdn && c.k);
   if (mix && two_stage) {
@@ -844,6 +944,7 @@ std::string Bank::process(uint32_t size, const float* in, float* out) {  // Audi
 }
 
 std::string Bank::clone_into(Bank& dst) const {
+  { std::string re = const_cast<Bank*>(this)->rt_stop(); if (!re.empty()) return re; }
   std::vector<HNode*> copies;
   for (auto& n : nodes) copies.push_back(n->clone());
   dst.sr = sr; dst.tree_mix = tree_mix; dst.net_rate = net_rate; dst.vertex_of_voice = vertex_of_voice;

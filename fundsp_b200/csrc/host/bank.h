@@ -9,6 +9,7 @@
 
 #include "graph.h"
 #include "registry.h"
+#include "../dsp/rt_args.h"
 
 namespace fdsp {
 namespace host {
@@ -62,6 +63,12 @@ struct Bank {
   std::vector<cudaEvent_t> dom_ev; size_t dom_n = 0; float last_dom_ms = 0.0f;
   std::string dom_mark(cudaStream_t st);
 
+  // resident process() kernel (dsp/bank_kernel_rt.cuh): a single-class bank that is driven block by block keeps one kernel on the GPU
+  // and rings a doorbell per block; every other call on the bank stops it first (state words are saved on the way out)
+  RtCtl* rt_ctl = nullptr; RtCtl* rt_ctl_dev = nullptr; uint32_t* d_rt_relay = nullptr; float* d_rt_partial = nullptr; size_t rt_partial_cap = 0;
+  bool rt_running = false, in_process = false; uint32_t rt_seq = 1; uint32_t process_streak = 0;
+  std::string rt_stop();
+  std::string rt_process(uint32_t size, const float* in, float* out, bool* served);
   ~Bank();
   uint32_t V() const { return (uint32_t)nodes.size(); }
   std::string init(std::vector<HNode*>& voices, int device, uint32_t out_mode);  // returns "" or error text

@@ -132,7 +132,9 @@ std::string group_reduce_device(Bank& b, Group& g, uint64_t n, float* mix_dev, u
   }
   NC(N.GroupStart());
   if (g.rank == root) {
-    for (int r = 0; r < g.nranks; r++) if (r != root) NC(N.Recv(g.d_gather + (size_t)r * plane, plane, kNcclFloat32, r, (ncclComm_t)g.comm, b.stream));
+    // one receive per channel row: NCCL pairs sends and receives in order, and their counts must agree (the sender's rows may be strided)
+    for (int r = 0; r < g.nranks; r++) if (r != root)
+      for (uint32_t c = 0; c < ch; c++) NC(N.Recv(g.d_gather + (size_t)r * plane + (size_t)c * n, n, kNcclFloat32, r, (ncclComm_t)g.comm, b.stream));
   } else {
     // rows of a strided mix buffer go one by one (the receiver's plane is dense [channel][n])
     for (uint32_t c = 0; c < ch; c++) NC(N.Send(mix_dev + c * mix_stride, n, kNcclFloat32, root, (ncclComm_t)g.comm, b.stream));

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "registry.h"
+#include "../dsp/rt_args.h"
 
 #include "jit_headers.inc"  // kJitHeaderNames[], kJitHeaderSrc[], kJitHeaderCount
 
@@ -137,7 +138,7 @@ static int g_cache_hits = 0, g_nvrtc_runs = 0;
 static bool compile_unit(const std::string& sig, const char* kernel_expr, std::vector<char>& cubin, std::string& lowered, std::string& err, bool use_cache = true) {
   Api& A = api();
   if (!A.ok_nvrtc) { err = A.why; return false; }
-  std::string src = "#include \"dsp/bank_kernel_st.cuh\"\nnamespace fdsp { typedef " + sig + " JitG; }\n";
+  std::string src = "#include \"dsp/bank_kernel_st.cuh\"\n#include \"dsp/bank_kernel_rt.cuh\"\nnamespace fdsp { typedef " + sig + " JitG; }\n";
   if (!kernel_expr)
     src += "extern \"C\" __device__ int fdsp_jit_layout[8] = {fdsp::JitG::IN, fdsp::JitG::OUT, fdsp::JitG::NP, fdsp::JitG::NS, fdsp::JitG::NU, fdsp::WaveKind<fdsp::JitG>::value, "
            "fdsp::StagePlan<fdsp::JitG>::K, fdsp::MidSum<fdsp::StagePlan<fdsp::JitG>::stages>::value};\n";
@@ -167,8 +168,9 @@ static bool compile_unit(const std::string& sig, const char* kernel_expr, std::v
   return true;
 }
 
-// width 0: the plain kernel (128 threads); 32 / 128: the stage-pipelined kernel with that many voices per CTA
+// width 0: the plain kernel (128 threads); 32 / 128: the stage-pipelined kernel with that many voices per CTA; -1: the resident process() kernel
 static std::string kernel_expr_of(int mode, int tb, int width) {
+  if (width < 0) return std::string("fdsp::bank_kernel_rt<fdsp::JitG, 128, ") + (tb ? "true" : "false") + ">";
   const std::string tail = std::to_string(mode) + ", " + (tb ? "true" : "false") + ">";
   return width ? "fdsp::bank_kernel_st<fdsp::JitG, " + std::to_string(width) + ", " + tail : "fdsp::bank_kernel<fdsp::JitG, 128, " + tail;
 }
@@ -176,11 +178,11 @@ static std::string kernel_expr_of(int mode, int tb, int width) {
 struct JitProgram : Program {
   int device = 0, mid_sum = 0;   // mid_sum: channels crossing the stage boundaries (sizes the hand-off rings)
   mutable std::mutex mu;
-  mutable CUmodule mods[3][3][2] = {};
-  mutable CUfunction fn[3][3][2] = {};  // [0 plain | 1 staged x32 | 2 staged x128][mode-1][TB]
+  mutable CUmodule mods[4][3][2] = {};
+  mutable CUfunction fn[4][3][2] = {};  // [0 plain | 1 staged x32 | 2 staged x128 | 3 resident][mode-1][TB]
   CUfunction variant(int mode, int tb, int width = 0) const {
     std::lock_guard<std::mutex> lock(mu);
-    const int wi = width == 0 ? 0 : (width == 32 ? 1 : 2);
+    const int wi = width < 0 ? 3 : (width == 0 ? 0 : (width == 32 ? 1 : 2));
     CUfunction& f = fn[wi][mode - 1][tb]; CUmodule& m = mods[wi][mode - 1][tb];
     if (f) return f;
     const Api& A = api();
@@ -192,6 +194,20 @@ struct JitProgram : Program {
     }
     if (A.ModuleGetFunction(&f, m, low.c_str()) != CUDA_SUCCESS) { f = nullptr; return nullptr; }
     return f;
+  }
+  cudaError_t launch_rt(const BankArgs& a, const RtArgs& rt, size_t table_bytes, cudaStream_t st) const override {
+    const Api& A = api();
+    const size_t tile = sizeof(float) * mix_tile_floats(OUT, threads);
+    const int tb = (wave_kind >= 0 && table_bytes > 0 && tile + table_bytes <= 227 * 1024) ? 1 : 0;
+    CUfunction f = variant(2, tb, -1);
+    if (!f) return cudaErrorInvalidDeviceFunction;
+    const size_t smem = tile + (tb ? table_bytes : 0);
+    if (smem > 48 * 1024 && A.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    BankArgs args = a; RtArgs r = rt;
+    void* params[] = {&args, &r};
+    const unsigned vpc = a.vpc ? a.vpc : (unsigned)threads, grid = (a.V + vpc - 1) / vpc;
+    CUresult rc = A.LaunchKernel(f, grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)smem, (CUstream)st, params, nullptr);
+    return rc == CUDA_SUCCESS ? cudaSuccess : cudaErrorLaunchFailure;
   }
   cudaError_t launch_staged(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t st) const override {
     const Api& A = api();
@@ -246,7 +262,8 @@ std::string jit_precompile(const std::string& sig, int mode, int tb, int staged_
   if (mode < 0 || mode > 3) return "mode must be 0 (layout) or 1..3";
   if (cache_dir().empty()) return "the JIT cache is disabled (FDSP_JIT_CACHE=off)";
   std::vector<char> cubin; std::string low, err;
-  if (staged_width != 0 && staged_width != 32 && staged_width != 128) return "staged width must be 0, 32 or 128";
+  if (staged_width != 0 && staged_width != 32 && staged_width != 128 && staged_width != 255) return "staged width must be 0, 32, 128 or 255 (the resident process() kernel)";
+  if (staged_width == 255) staged_width = -1;
   const std::string expr = kernel_expr_of(mode, tb, staged_width);
   if (!compile_unit(sig, mode == 0 ? nullptr : expr.c_str(), cubin, low, err)) return err;
   return "";
@@ -276,7 +293,7 @@ std::shared_ptr<const Program> jit_program(const std::string& sig, int device, s
   if (A.ModuleGetGlobal(&d, &bytes, lm, "fdsp_jit_layout") != CUDA_SUCCESS || bytes != sizeof(lay) || A.MemcpyDtoH(lay, d, sizeof(lay)) != CUDA_SUCCESS) {
     err = "JIT layout readback failed"; return nullptr;
   }
-  p->IN = lay[0]; p->OUT = lay[1]; p->NP = lay[2]; p->NS = lay[3]; p->NU = lay[4]; p->wave_kind = lay[5]; p->threads = 128; p->stages = lay[6]; p->mid_sum = lay[7];
+  p->IN = lay[0]; p->OUT = lay[1]; p->NP = lay[2]; p->NS = lay[3]; p->NU = lay[4]; p->wave_kind = lay[5]; p->threads = 128; p->stages = lay[6]; p->mid_sum = lay[7]; p->has_rt = true;
   g_compiled++;
   g_cache[key] = p;
   return p;

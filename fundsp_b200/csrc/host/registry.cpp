@@ -1,5 +1,6 @@
 // Kernel registry lookup: collects the ahead-of-time instance tables (csrc/inst/*.cu).
 #include "registry.h"
+#include "../dsp/rt_args.h"
 
 #include <vector>
 
@@ -64,10 +65,14 @@ struct AotProgram : Program {
   explicit AotProgram(const KernelEntry* e_, const std::string& key) : e(e_) {
     sig = key; IN = e->IN; OUT = e->OUT; NP = e->NP; NS = e->NS; NU = e->NU; threads = e->threads(); wave_kind = e->wave_kind();
     stages = e->launch_st ? e->stages : 1;
+    has_rt = e->launch_rt != nullptr;
   }
   cudaError_t launch(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t st) const override { return e->launch(a, mode, table_bytes, st); }
   cudaError_t launch_staged(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t st) const override {
     return e->launch_st ? e->launch_st(a, mode, table_bytes, st) : cudaErrorInvalidValue;
+  }
+  cudaError_t launch_rt(const BankArgs& a, const RtArgs& rt, size_t table_bytes, cudaStream_t st) const override {
+    return e->launch_rt ? e->launch_rt(a, rt, table_bytes, st) : cudaErrorInvalidValue;
   }
 };
 }  // namespace

@@ -8,7 +8,7 @@
 
 #include "../dsp/bank_args.h"
 
-namespace fdsp { struct FdnArgs; }
+namespace fdsp { struct FdnArgs; struct RtArgs; }
 
 namespace fdsp {
 namespace host {
@@ -22,6 +22,7 @@ struct KernelEntry {  // AOT table row
   int (*wave_kind)();  // first wavetable kind the program reads, -1 if none
   int stages;          // stages of the stage-pipelined form (dsp/bank_kernel_st.cuh); 1 = none built
   cudaError_t (*launch_st)(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t stream);
+  cudaError_t (*launch_rt)(const BankArgs& a, const RtArgs& rt, size_t table_bytes, cudaStream_t stream);   // resident process() kernel
 };
 
 struct Program {
@@ -34,6 +35,9 @@ struct Program {
   virtual cudaError_t launch(const BankArgs& a, int mode, size_t table_bytes, cudaStream_t stream) const = 0;
   // a.vpc <= 32 selects the 32-voice CTA shape, else 128 voices per CTA; same word layout as `launch` (the two can alternate)
   virtual cudaError_t launch_staged(const BankArgs&, int, size_t, cudaStream_t) const { return cudaErrorInvalidValue; }
+  // the resident process() kernel (dsp/bank_kernel_rt.cuh): serves 64-sample blocks on a doorbell until told to leave; mix mode only
+  virtual cudaError_t launch_rt(const BankArgs&, const RtArgs&, size_t, cudaStream_t) const { return cudaErrorInvalidValue; }
+  bool has_rt = false;
 };
 
 // Returns the program for `sig` (AOT if listed, else NVRTC-compiled and cached); nullptr + `err` on failure.

@@ -23,7 +23,7 @@ def test_sharded_banks_reduce_to_the_oracle_mix():
     world = 2 if n < 4 else 4
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1", "--master-port", str(port),
-                        os.path.join(ROOT, "tests", "_gpu_group_worker.py")], capture_output=True, text=True, cwd=ROOT, timeout=900)
+                        os.path.join(ROOT, "tests", "_gpu_group_worker.py")], capture_output=True, text=True, cwd=ROOT, timeout=200)
     assert r.returncode == 0 and r.stdout.count("rank-order ok") == 3 and "MISMATCH" not in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
 
 

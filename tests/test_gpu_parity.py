@@ -117,6 +117,30 @@ def test_process_granularity_equals_render_and_oracle_blocks():
                 assert np.abs(g - o).max() <= 2e-6, (name, s, float(np.abs(g - o).max()))
 
 
+@pytest.mark.parametrize("name,V", [("saw_svf", 300), ("noise_svf", 5000), ("fm", 130)])
+def test_resident_process_kernel_equals_launch_per_block(name, V, monkeypatch):
+    """A mix-mode bank that is driven block by block keeps ONE kernel resident and rings a doorbell per block (csrc/dsp/bank_kernel_rt.cuh).
+    Same blocks, same CTA mix, same fold: the mixes must equal the one-launch-per-block path bit for bit, through ragged sizes, across a
+    render() in the middle (which stops the resident kernel: its state words must be saved and picked up), reset and clone."""
+    from fundsp_b200.bank import GpuBank
+    sizes = [64, 64, 64, 61, 8, 7, 1, 64, 0, 33, 64, 17, 64, 64]
+    def run(rt):
+        monkeypatch.setenv("FDSP_RT", rt)
+        b = GpuBank(workloads.build(name, V), per_voice=False, mix=True, sample_rate=SR)
+        out = [b.process(s) for s in sizes if s]
+        _, mid = b.render_samples(200)                  # any other call stops the resident kernel first
+        out += [mid] + [b.process(s) for s in (64, 64, 64, 64, 5)]
+        c = b.clone()
+        out += [b.process(64), c.process(64)]
+        b.reset()
+        out += [b.process(s) for s in (64, 64, 64, 64)]
+        return out
+    a, r = run("1"), run("0")
+    assert len(a) == len(r) and all(np.array_equal(x, y) for x, y in zip(a, r)), [i for i, (x, y) in enumerate(zip(a, r)) if not np.array_equal(x, y)]
+    assert np.abs(np.concatenate(a, axis=-1)).max() > 0.1
+    assert np.array_equal(a[-6], a[-5])                 # the clone continues exactly like the original
+
+
 def test_ragged_length_and_time_chunking():
     n = 16384 * 2 + 64 * 3 + 5  # crosses the kernel's time chunk and ends in a ragged block
     check("noise_svf", 130, n, exact=True)

@@ -4,8 +4,8 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/mg8_gpus.txt
 one() { local name=$1 n=$2; shift 2
-  if [ "$n" = 1 ]; then timeout 400 python bench.py --gpus 1 --steps 5 --warmup 3 "$@" > gpurun_out/mg8_${name}_n$n.json 2> gpurun_out/mg8_${name}_n$n.err
-  else timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 500)) bench.py --gpus $n --steps 5 --warmup 3 "$@" > gpurun_out/mg8_${name}_n$n.json 2> gpurun_out/mg8_${name}_n$n.err; fi
+  if [ "$n" = 1 ]; then timeout 150 python bench.py --gpus 1 --steps 5 --warmup 3 "$@" > gpurun_out/mg8_${name}_n$n.json 2> gpurun_out/mg8_${name}_n$n.err
+  else timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 500)) bench.py --gpus $n --steps 5 --warmup 3 "$@" > gpurun_out/mg8_${name}_n$n.json 2> gpurun_out/mg8_${name}_n$n.err; fi
   python - <<PY
 import json
 try:
