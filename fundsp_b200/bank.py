@@ -107,7 +107,12 @@ class GpuBank:
         return int(v.value)
 
     def replace_voice(self, voice, unit):
+        """`Net::replace`: any unit of the bank's arity in the voice's place (fresh state); another graph class regroups the classes around it."""
         check(self.L.fdsp_bank_replace_voice(self.h, int(voice), unit.lower(GpuBackend())))
+
+    def remove_voice(self, voice):
+        """`Net::remove`: the voice carries silence from now on (its place in the mix order stays)."""
+        check(self.L.fdsp_bank_remove_voice(self.h, int(voice)))
 
     def allocate(self, max_samples=64): check(self.L.fdsp_bank_allocate(self.h, int(max_samples)))
 

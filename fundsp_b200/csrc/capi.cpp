@@ -303,6 +303,11 @@ API int fdsp_bank_replace_voice(fdsp_bank* b, uint32_t voice, fdsp_node* unit) {
   std::string e = b->b.replace_voice(voice, take(unit));
   return e.empty() ? FDSP_OK : fail(e.find("rebuild") != std::string::npos || e.find("differs") != std::string::npos ? FDSP_ERR_UNSUPPORTED : FDSP_ERR_ARG, e);
 }
+API int fdsp_bank_remove_voice(fdsp_bank* b, uint32_t voice) {
+  if (!b) return fail(FDSP_ERR_ARG, "null bank");
+  std::string e = b->b.remove_voice(voice);
+  return e.empty() ? FDSP_OK : fail(e.find("rebuild") != std::string::npos ? FDSP_ERR_UNSUPPORTED : FDSP_ERR_ARG, e);
+}
 API int fdsp_bank_push_event(fdsp_bank* b, fdsp_node* event, uint32_t* voice) {
   if (!b || !event) { fdsp_node_free(event); return fail(FDSP_ERR_ARG, "null bank or event"); }
   HNode* keep = event->n->clone();                   // push_event consumes its node; the slow path needs it again

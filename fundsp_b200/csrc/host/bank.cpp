@@ -350,7 +350,9 @@ std::string Bank::replace_voice(uint32_t voice, HNode* node) {
   CU(cudaSetDevice(device));
   std::string a, b;
   n->sig(a); nodes[voice]->sig(b);
-  if (a != b) return "replace: the unit's graph differs from the voice's class `" + b + "`";
+  // another graph class (Net::replace takes any unit of the same arity, src/net.rs:460-470): the voice moves to the class of its new graph —
+  // the classes are regrouped around it, every other voice keeps its running state (the slow path, like add_voice)
+  if (a != b) return regroup(n.release(), (int)voice, nullptr);
   const double unit_rate = net_rate ? (double)(float)sr : sr;
   n->set_sample_rate(unit_rate);
   Lowering l0, l;
@@ -368,12 +370,27 @@ std::string Bank::replace_voice(uint32_t voice, HNode* node) {
 // Grow a running bank by one voice without disturbing the others: the running state and delay lines of every voice are read back,
 // the classes are rebuilt with the new voice (it may found a new class: its program is compiled first, so a failure leaves the bank
 // untouched), and the saved columns are written into the new layout. O(bank state) — the slow path behind push_event.
-std::string Bank::add_voice(HNode* node, uint32_t* voice) {
+std::string Bank::add_voice(HNode* node, uint32_t* voice) { return regroup(node, -1, voice); }
+
+// Net::remove on a bank made from a Net (src/net.rs:351-404: "connections from the unit are replaced with zeros"): the voice's place in the
+// mix keeps its position and carries silence from now on.
+std::string Bank::remove_voice(uint32_t voice) {
+  if (voice >= V()) return "remove: voice index out of range";
+  std::vector<float> z((size_t)nout, 0.0f);
+  HNode* silent = mk_constant(nout, z.data());
+  if (nin > 0) silent = mk_pipe(mk_sink(nin), silent);
+  if (!silent) return "remove: could not build the silent unit";
+  return replace_voice(voice, silent);
+}
+
+// `at` < 0: append the unit as a new voice (add_voice); else put it in place of voice `at` (replace_voice across classes).
+std::string Bank::regroup(HNode* node, int at, uint32_t* voice) {
   std::unique_ptr<HNode> n(node);
-  if (!n) return "add: null node";
-  if (n->inputs() != nin || n->outputs() != nout) return "add: the unit's arity differs from the bank's";
-  if (tree_mix) return "add: a bank extracted from a Net mixes in the Net's order; rebuild it from the edited Net";
-  for (auto& c : classes) if (c.fdn) return "add: banks with a two-stage (FDN reverb) class cannot grow in place; rebuild the bank";
+  const char* what = at < 0 ? "add" : "replace";
+  if (!n) return std::string(what) + ": null node";
+  if (n->inputs() != nin || n->outputs() != nout) return std::string(what) + ": the unit's arity differs from the bank's";
+  if (tree_mix && at < 0) return "add: a bank extracted from a Net mixes in the Net's order; rebuild it from the edited Net";
+  for (auto& c : classes) if (c.fdn || c.conv) return std::string(what) + ": banks with a two-stage class (FDN reverb, tensor-core convolver) cannot be regrouped in place; rebuild the bank";
   CU(cudaSetDevice(device));
   { std::string re = rt_stop(); if (!re.empty()) return re; } process_streak = 0;
   const double unit_rate = net_rate ? (double)(float)sr : sr;
@@ -384,7 +401,7 @@ std::string Bank::add_voice(HNode* node, uint32_t* voice) {
   n->lower(l);
   if (ev) event_set_clock(n.get(), 0.0);
   if (!l.ok) return l.why;
-  { std::string sg, jerr; n->sig(sg); if (!get_program(sg, device, jerr)) return "add: no device program for `" + sg + "`: " + jerr; }
+  { std::string sg, jerr; n->sig(sg); if (!get_program(sg, device, jerr)) return std::string(what) + ": no device program for `" + sg + "`: " + jerr; }
   // 1. read back what is running
   CU(cudaStreamSynchronize(stream));
   struct Saved { std::string sig; std::vector<uint32_t> uniform, voices, S; std::vector<float> D; uint32_t ns; uint64_t dl; };
@@ -398,10 +415,15 @@ std::string Bank::add_voice(HNode* node, uint32_t* voice) {
   }
   const bool was_dirty = dirty; const double clock = seq_time;
   // 2. rebuild with the new voice (fresh state everywhere)
-  nodes.push_back(std::move(n));
-  const uint32_t nv = V() - 1;
+  uint32_t nv;
+  if (at < 0) { nodes.push_back(std::move(n)); nv = V() - 1; }
+  else { nv = (uint32_t)at; std::swap(nodes[nv], n); }        // `n` now holds the unit that leaves
   std::string e = lower_and_upload(true);
-  if (!e.empty()) { nodes.pop_back(); std::string e2 = lower_and_upload(true); return "add: " + e + (e2.empty() ? " (the bank was rebuilt without the voice; its running state is reset)" : " (and the bank could not be restored: " + e2 + ")"); }
+  if (!e.empty()) {
+    if (at < 0) nodes.pop_back(); else std::swap(nodes[nv], n);
+    std::string e2 = lower_and_upload(true);
+    return std::string(what) + ": " + e + (e2.empty() ? " (the bank was rebuilt as it was; its running state is reset)" : " (and the bank could not be restored: " + e2 + ")");
+  }
   // 3. put the saved columns back
   for (auto& c : classes) {
     const uint32_t Vc = c.V();
@@ -409,7 +431,10 @@ std::string Bank::add_voice(HNode* node, uint32_t* voice) {
     std::vector<float> D((size_t)c.dl_floats * Vc, 0.0f);
     for (uint32_t i = 0; i < Vc; i++) {
       const uint32_t v = c.voices[i];
-      if (v == nv) { for (uint32_t k = 0; k < c.ns && k < l.S.size(); k++) S[(size_t)k * Vc + i] = l.S[k]; continue; }   // the newcomer: live state (an event's clock = now)
+      if (v == nv) {   // the newcomer: live state (an event's clock = now); what reset() restores is its construction-time state
+        for (uint32_t k = 0; k < c.ns && k < l.S.size(); k++) { S[(size_t)k * Vc + i] = l.S[k]; c.state0[(size_t)k * Vc + i] = l0.S[k]; }
+        continue;
+      }
       for (auto& sv : saved) {
         auto it = std::lower_bound(sv.voices.begin(), sv.voices.end(), v);
         if (it == sv.voices.end() || *it != v) continue;

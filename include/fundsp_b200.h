@@ -188,12 +188,17 @@ int fdsp_wave_load(const char* path, float* planar, uint64_t max_floats, uint32_
    the slot. When no such slot is free the bank GROWS by one voice (fdsp_bank_add_voice: the running state and delay lines of all
    voices are read back, the classes rebuilt — the newcomer may found a new class, compiled first — and the state written into the
    new layout; O(bank state), not for the audio thread; banks with an FDN-reverb class or made from a Net cannot grow in place).
-   fdsp_bank_replace_voice puts any unit of the same class into a given slot (fresh state). All consume their node argument.
+   fdsp_bank_replace_voice = Net::replace (src/net.rs:460-470) / a new unit in a voice's place, fresh state: any unit of the bank's arity. A unit
+   of the voice's own graph class is written into its slot; a unit of another class moves the voice to that class (compiled first if new) —
+   the classes are regrouped around it, every other voice keeps its running state and, in a bank made from a Net, the voice keeps its
+   place in the Net's mix order. fdsp_bank_remove_voice = Net::remove (:351-404, connections replaced with zeros): the voice carries
+   silence from now on. Both are the slow path (O(bank state)), like add_voice. All consume their node argument.
    fdsp_bank_time = Sequencer::time (seconds rendered since reset). */
 int fdsp_bank_edit_event(fdsp_bank* b, uint32_t voice, double end_time, double fade_out);
 int fdsp_bank_push_event(fdsp_bank* b, fdsp_node* event, uint32_t* voice);
 int fdsp_bank_replace_voice(fdsp_bank* b, uint32_t voice, fdsp_node* unit);
 int fdsp_bank_add_voice(fdsp_bank* b, fdsp_node* unit, uint32_t* voice);
+int fdsp_bank_remove_voice(fdsp_bank* b, uint32_t voice);
 double fdsp_bank_time(const fdsp_bank* b);
 /* Slot / SlotBackend (src/slot.rs): fdsp_slot(unit) is a voice whose unit can be replaced while the bank runs; fdsp_bank_slot_set is
    Slot::set(fade, fade_time, unit): the voice crossfades to `unit` over fade_time seconds (fade 0 Power, 1 Smooth) with the reference's

@@ -293,3 +293,40 @@ def test_gpu_sequencer_replay_all_keeps_every_event():
     g.reset(); u.reset()                                            # both notes replay
     a = g.render(64 * 45); b = u.process_many(64 * 45)
     assert _close(a, b) and np.abs(b[:, :64 * 20]).max() > 0.1 and np.abs(b[:, 64 * 21:]).max() > 0.1
+
+
+def test_net_bank_replace_and_remove_vertices_across_classes():
+    """Net::replace / Net::remove (src/net.rs:351-404,460-470) on a RUNNING bank made from a Net: a vertex gets a unit of ANOTHER graph class
+    (the voice moves to that class — compiled on the spot if new — while every other voice keeps its running state and the mix keeps the Net's
+    association order), another vertex is removed (its connections carry zeros). Rows against an unedited twin bank and fresh oracle units."""
+    from fundsp_b200 import workloads
+    from fundsp_b200.bank import GpuBank
+    from fundsp_b200.net import voice_net
+    from fundsp_b200.prelude import moog_hz, pan, noise, lowpass_hz
+    from oracle import OracleUnit, lib as olib
+    olib().fo_set_denormal_emulation(0)
+    SR = 48000.0
+    V, n1, n2 = 21, 1000 + 7, 1500
+    mk = lambda: voice_net([workloads.net_voice(i) for i in range(V)])
+    b = GpuBank.from_net(mk(), per_voice=True, mix=True, sample_rate=SR)
+    twin = GpuBank.from_net(mk(), per_voice=True, mix=True, sample_rate=SR)
+    b.render_samples(n1); twin.render_samples(n1)
+    newcomer = lambda: noise().seed(77) >> lowpass_hz(700.0, 2.0) >> moog_hz(900.0, 0.3) >> pan(0.25)     # a class the bank does not have yet
+    b.replace_voice(4, newcomer())
+    b.replace_voice(9, workloads.net_voice(2))                                  # an existing class (voice 9 was class B)
+    b.remove_voice(13)           # (fdsp_bank_voice_of_vertex maps a NodeId to the voice index, see test_net_bank_setting_by_node_id)
+    assert len(b.classes()) >= 5
+    rows, mix = b.render_samples(n2)
+    want, _ = twin.render_samples(n2)
+    changed = [v for v in range(V) if not np.array_equal(rows[v], want[v])]
+    assert changed == [4, 9, 13], changed                                   # every other voice just continues
+    assert not rows[13].any()
+    for v, g in ((4, newcomer()), (9, workloads.net_voice(2))):
+        u = OracleUnit(g); u.set_sample_rate(float(np.float32(SR)))          # (a Net hands its units the f32-rounded rate)
+        assert np.array_equal(rows[v], u.process_many(n2)), v
+    ref = rows.astype(np.float64).sum(axis=0)
+    assert np.abs(mix - ref).max() <= 1e-5 * max(1.0, np.abs(rows).sum(axis=0).max())
+    b.reset()                                                               # reset keeps the edited net
+    r2, _ = b.render_samples(200)
+    u = OracleUnit(newcomer()); u.set_sample_rate(float(np.float32(SR)))
+    assert not r2[13].any() and np.array_equal(r2[4], u.process_many(200))
