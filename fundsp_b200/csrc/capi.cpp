@@ -28,12 +28,14 @@ HNode* take(fdsp_node* h) {  // consume a handle
   if (!h) return nullptr;
   HNode* n = h->n; delete h; return n;
 }
-int status(const std::string& e) {
+// Runtime messages carry their status as a leading tag (csrc/host/bank.h): "#U " unsupported, "#A " argument, "#N " no free slot.
+char tag_of(const std::string& e) { return e.size() > 3 && e[0] == '#' && e[2] == ' ' ? e[1] : 0; }
+int status(const std::string& e, int untagged = FDSP_ERR_CUDA) {
   if (e.empty()) return FDSP_OK;
-  int code = FDSP_ERR_CUDA;
-  if (e.find("no device program") != std::string::npos || e.find("no device lowering") != std::string::npos) code = FDSP_ERR_UNSUPPORTED;
-  else if (e.find("must") != std::string::npos || e.find("needs") != std::string::npos || e.find("no output buffer") != std::string::npos || e.find("no input buffer") != std::string::npos) code = FDSP_ERR_ARG;
-  return fail(code, e);
+  const char t = tag_of(e);
+  if (t == 'U') return fail(FDSP_ERR_UNSUPPORTED, e.substr(3));
+  if (t == 'A' || t == 'N') return fail(FDSP_ERR_ARG, e.substr(3));
+  return fail(e.find("no device lowering") != std::string::npos ? FDSP_ERR_UNSUPPORTED : untagged, e);
 }
 }  // namespace
 
@@ -262,7 +264,7 @@ API int fdsp_bank_set(fdsp_bank* b, uint32_t voice, int kind, const float* v, in
   for (int i = 0; i < nv; i++) s.v[i] = v[i];
   for (int i = 0; i < naddr; i++) s.address.push_back({(int)addr[2 * i], (uint64_t)addr[2 * i + 1]});
   std::string e = b->b.set(voice, s);
-  return e.empty() ? FDSP_OK : fail(e.find("rebuild") != std::string::npos ? FDSP_ERR_UNSUPPORTED : FDSP_ERR_ARG, e);
+  return status(e, FDSP_ERR_ARG);
 }
 // ---- JIT cache (csrc/host/jit.cpp): compiled units are kept on disk next to the library; a machine without a GPU can fill it
 API int fdsp_jit_precompile(const char* signature, int mode, int table_variant) {
@@ -296,36 +298,36 @@ API int fdsp_wave_load(const char* path, float* planar, uint64_t max_floats, uin
 API int fdsp_bank_edit_event(fdsp_bank* b, uint32_t voice, double end_time, double fade_out) {
   if (!b) return fail(FDSP_ERR_ARG, "null bank");
   std::string e = b->b.edit_event(voice, end_time, fade_out);
-  return e.empty() ? FDSP_OK : fail(FDSP_ERR_ARG, e);
+  return status(e, FDSP_ERR_ARG);
 }
 API int fdsp_bank_replace_voice(fdsp_bank* b, uint32_t voice, fdsp_node* unit) {
   if (!b) { fdsp_node_free(unit); return fail(FDSP_ERR_ARG, "null bank"); }
   std::string e = b->b.replace_voice(voice, take(unit));
-  return e.empty() ? FDSP_OK : fail(e.find("rebuild") != std::string::npos || e.find("differs") != std::string::npos ? FDSP_ERR_UNSUPPORTED : FDSP_ERR_ARG, e);
+  return status(e, FDSP_ERR_ARG);
 }
 API int fdsp_bank_remove_voice(fdsp_bank* b, uint32_t voice) {
   if (!b) return fail(FDSP_ERR_ARG, "null bank");
   std::string e = b->b.remove_voice(voice);
-  return e.empty() ? FDSP_OK : fail(e.find("rebuild") != std::string::npos ? FDSP_ERR_UNSUPPORTED : FDSP_ERR_ARG, e);
+  return status(e, FDSP_ERR_ARG);
 }
 API int fdsp_bank_push_event(fdsp_bank* b, fdsp_node* event, uint32_t* voice) {
   if (!b || !event) { fdsp_node_free(event); return fail(FDSP_ERR_ARG, "null bank or event"); }
   HNode* keep = event->n->clone();                   // push_event consumes its node; the slow path needs it again
   std::string e = b->b.push_event(take(event), voice);
   if (e.empty()) { delete keep; return FDSP_OK; }
-  if (e.find("no finished event") == std::string::npos) { delete keep; return fail(FDSP_ERR_ARG, e); }
+  if (tag_of(e) != 'N') { delete keep; return status(e, FDSP_ERR_ARG); }   // anything but "no finished event of this class is free"
   e = b->b.add_voice(keep, voice);                   // no free slot of this class: grow the bank (running state of the others preserved)
-  return e.empty() ? FDSP_OK : fail(e.find("rebuild") != std::string::npos ? FDSP_ERR_UNSUPPORTED : FDSP_ERR_ARG, e);
+  return status(e, FDSP_ERR_ARG);
 }
 API int fdsp_bank_add_voice(fdsp_bank* b, fdsp_node* unit, uint32_t* voice) {
   if (!b || !unit) { fdsp_node_free(unit); return fail(FDSP_ERR_ARG, "null bank or unit"); }
   std::string e = b->b.add_voice(take(unit), voice);
-  return e.empty() ? FDSP_OK : fail(e.find("rebuild") != std::string::npos ? FDSP_ERR_UNSUPPORTED : FDSP_ERR_ARG, e);
+  return status(e, FDSP_ERR_ARG);
 }
 API int fdsp_bank_slot_set(fdsp_bank* b, uint32_t voice, int fade_ease, double fade_time, fdsp_node* unit) {
   if (!b) { fdsp_node_free(unit); return fail(FDSP_ERR_ARG, "null bank"); }
   std::string e = b->b.slot_set(voice, fade_ease, fade_time, take(unit));
-  return e.empty() ? FDSP_OK : fail(e.find("in progress") != std::string::npos || e.find("differs") != std::string::npos || e.find("rebuild") != std::string::npos ? FDSP_ERR_UNSUPPORTED : FDSP_ERR_ARG, e);
+  return status(e, FDSP_ERR_ARG);
 }
 API double fdsp_bank_time(const fdsp_bank* b) { return b ? b->b.seq_time : 0.0; }
 API int fdsp_bank_reset(fdsp_bank* b) { return b ? status(b->b.reset()) : fail(FDSP_ERR_ARG, "null bank"); }

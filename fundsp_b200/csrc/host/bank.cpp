@@ -76,11 +76,11 @@ std::string Bank::init(std::vector<HNode*>& voices, int dev, uint32_t mode) {
   device = dev; out_mode = mode;
   for (HNode* v : voices) nodes.emplace_back(v);
   voices.clear();
-  if (nodes.empty()) return "bank needs at least one voice";
-  if ((mode & 3u) == 0u) return "out_mode must include FDSP_OUT_VOICES and/or FDSP_OUT_MIX";
+  if (nodes.empty()) return "#A bank needs at least one voice";
+  if ((mode & 3u) == 0u) return "#A out_mode must include FDSP_OUT_VOICES and/or FDSP_OUT_MIX";
   nin = nodes[0]->inputs(); nout = nodes[0]->outputs();
-  if (nout < 1) return "voices must have at least one output";
-  for (auto& n : nodes) if (n->inputs() != nin || n->outputs() != nout) return "all voices of a bank must agree on inputs() and outputs()";
+  if (nout < 1) return "#A voices must have at least one output";
+  for (auto& n : nodes) if (n->inputs() != nin || n->outputs() != nout) return "#A all voices of a bank must agree on inputs() and outputs()";
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= dev) return "no usable CUDA device: fundsp_b200 has no CPU fallback";
   CU(cudaSetDevice(device));
@@ -107,7 +107,7 @@ std::string Bank::lower_and_upload(bool upload_state) {
     Low& lo = lows[v];
     nodes[v]->sig(lo.sig);
     nodes[v]->lower(lo.l);
-    if (!lo.l.ok) return "voice " + std::to_string(v) + ": " + lo.l.why;
+    if (!lo.l.ok) return "#U voice " + std::to_string(v) + ": " + lo.l.why;
     lo.key = lo.sig + "|";
     lo.key.append((const char*)lo.l.U.data(), lo.l.U.size() * 4);
     auto it = index.find(lo.key);
@@ -139,7 +139,7 @@ std::string Bank::lower_and_upload(bool upload_state) {
         for (size_t k = 0; k < lo.l.dlen.size(); k++) { if (k + 32 >= lo.l.dlen.size()) c.ring_floats += fdn_ring_phys(lo.l.dlen[k]); else c.dl_floats += lo.l.dlen[k]; }
         if (!prog_sig.empty()) {
           c.k = get_program(prog_sig, device, jerr);
-          if (!c.k) return "no device program for the dry stage `" + prog_sig + "`: " + jerr;
+          if (!c.k) return "#U no device program for the dry stage `" + prog_sig + "`: " + jerr;
           if ((uint32_t)c.k->NP != c.p0 - (wet ? 1u : 0u) - lo.l.extraP || (uint32_t)c.k->NS != c.s0 || (uint32_t)c.k->NU != c.u0 - lo.l.extraU || c.k->IN != nin || c.k->OUT != 2)
             return "internal: dry-stage layout of `" + prog_sig + "` disagrees with the host lowering";
         }
@@ -150,7 +150,7 @@ std::string Bank::lower_and_upload(bool upload_state) {
         const std::string xsig = lo.sig.substr(5, lo.sig.size() - 5 - CT.size());
         for (uint32_t d : lo.l.dlen) c.dl_floats += d;
         c.k = get_program(xsig, device, jerr);
-        if (!c.k) return "no device program for `" + xsig + "` (in front of the convolver): " + jerr;
+        if (!c.k) return "#U no device program for `" + xsig + "` (in front of the convolver): " + jerr;
         if ((uint32_t)c.k->NP != c.np - lo.l.extraP || (uint32_t)c.k->NS + 1u != c.ns || (uint32_t)c.k->NU + 2u != nu_static || c.k->IN != nin || c.k->OUT != 1)
           return "internal: layout of `" + xsig + "` in front of the convolver disagrees with the host lowering";
         c.conv = true; c.conv_K = lo.l.conv_K; c.conv_off = lo.l.conv_off;
@@ -159,7 +159,7 @@ std::string Bank::lower_and_upload(bool upload_state) {
       } else {
         for (uint32_t d : lo.l.dlen) c.dl_floats += d;
         c.k = get_program(lo.sig, device, jerr);
-        if (!c.k) return "no device program for graph class `" + lo.sig + "`: " + jerr;
+        if (!c.k) return "#U no device program for graph class `" + lo.sig + "`: " + jerr;
         if ((uint32_t)c.k->NP != c.np - lo.l.extraP || (uint32_t)c.k->NS != c.ns || (uint32_t)c.k->NU != nu_static || c.k->IN != nin || c.k->OUT != nout)
           return "internal: host lowering of `" + lo.sig + "` disagrees with the device word layout";
       }
@@ -173,7 +173,7 @@ std::string Bank::lower_and_upload(bool upload_state) {
       std::string jerr;
       c.conv = false;
       c.k = get_program(c.sig, device, jerr);
-      if (!c.k) return "no device program for graph class `" + c.sig + "`: " + jerr;
+      if (!c.k) return "#U no device program for graph class `" + c.sig + "`: " + jerr;
     }
   }
   // 2. keep device buffers of classes that survive unchanged (same key order / sizes), else rebuild
@@ -278,7 +278,7 @@ std::string Bank::set_sample_rate(double s) {  // AudioUnit::set_sample_rate
 }
 
 std::string Bank::set(uint32_t voice, const Setting& st) {  // AudioUnit::set (src/audiounit.rs:62, src/setting.rs) on a live bank
-  if (voice >= V()) return "set: voice index out of range";
+  if (voice >= V()) return "#A set: voice index out of range";
   CU(cudaSetDevice(device));
   { std::string re = rt_stop(); if (!re.empty()) return re; } process_streak = 0;
   // the setting is tried on a COPY of the voice's host graph: a refused setting (one that would change a class-uniform word) leaves
@@ -287,13 +287,13 @@ std::string Bank::set(uint32_t voice, const Setting& st) {  // AudioUnit::set (s
   trial->set(st);
   Lowering l;
   trial->lower(l);
-  if (!l.ok) return l.why;
+  if (!l.ok) return "#U " + l.why;
   for (auto& c : classes) {
     auto it = std::lower_bound(c.voices.begin(), c.voices.end(), voice);
     if (it == c.voices.end() || *it != voice) continue;
     const uint32_t i = (uint32_t)(it - c.voices.begin()), Vc = c.V();
     if (l.U != c.uniform || l.P.size() != c.np || l.S.size() != c.ns)
-      return "set: the setting changes a class-uniform word (a delay length); rebuild the bank instead";
+      return "#U set: the setting changes a class-uniform word (a delay length); rebuild the bank instead";
     // parameters take effect at once (one strided column of the [NP][V] block); running state is left alone, the
     // construction-time state (what reset() restores) follows the setting like the reference's stored phase/seed
     if (c.np) CU(cudaMemcpy2DAsync(c.d_params + i, (size_t)Vc * 4, l.P.data(), 4, 4, c.np, cudaMemcpyHostToDevice, stream));
@@ -318,8 +318,8 @@ std::string Bank::upload_voice(uint32_t voice, const Lowering& l, bool with_stat
     if (it == c.voices.end() || *it != voice) continue;
     const uint32_t i = (uint32_t)(it - c.voices.begin()), Vc = c.V();
     if (l.U != c.uniform || l.P.size() != c.np || l.S.size() != c.ns || (reset_state && reset_state->size() != c.ns))
-      return "the voice does not fit its class: a class-uniform word (delay length, table, wave) or the word layout differs; rebuild the bank instead";
-    if (with_state && c.fdn) return "voices of a two-stage (FDN reverb) class cannot be replaced in place";
+      return "#U the voice does not fit its class: a class-uniform word (delay length, table, wave) or the word layout differs; rebuild the bank instead";
+    if (with_state && c.fdn) return "#U voices of a two-stage (FDN reverb) class cannot be replaced in place";
     if (c.np) CU(cudaMemcpy2DAsync(c.d_params + i, (size_t)Vc * 4, l.P.data(), 4, 4, c.np, cudaMemcpyHostToDevice, stream));
     for (uint32_t k = 0; k < c.ns; k++) c.state0[(size_t)k * Vc + i] = reset_state ? (*reset_state)[k] : l.S[k];
     if (with_state) {
@@ -333,20 +333,20 @@ std::string Bank::upload_voice(uint32_t voice, const Lowering& l, bool with_stat
 }
 
 std::string Bank::edit_event(uint32_t voice, double end_time, double fade_out) {
-  if (voice >= V()) return "edit: voice index out of range";
+  if (voice >= V()) return "#A edit: voice index out of range";
   CU(cudaSetDevice(device));
-  if (!event_edit(nodes[voice].get(), end_time, fade_out)) return "edit: the voice is not a sequencer event";
+  if (!event_edit(nodes[voice].get(), end_time, fade_out)) return "#A edit: the voice is not a sequencer event";
   Lowering l;
   nodes[voice]->lower(l);
-  if (!l.ok) return l.why;
+  if (!l.ok) return "#U " + l.why;
   return upload_voice(voice, l, false);
 }
 
 std::string Bank::replace_voice(uint32_t voice, HNode* node) {
   std::unique_ptr<HNode> n(node);
-  if (!n) return "replace: null node";
-  if (voice >= V()) return "replace: voice index out of range";
-  if (n->inputs() != nin || n->outputs() != nout) return "replace: the unit's arity differs from the bank's";
+  if (!n) return "#A replace: null node";
+  if (voice >= V()) return "#A replace: voice index out of range";
+  if (n->inputs() != nin || n->outputs() != nout) return "#U replace: the unit's arity differs from the bank's";
   CU(cudaSetDevice(device));
   std::string a, b;
   n->sig(a); nodes[voice]->sig(b);
@@ -360,7 +360,7 @@ std::string Bank::replace_voice(uint32_t voice, HNode* node) {
   const bool ev = event_set_clock(n.get(), seq_time);  // an event put into a running sequencer counts from now
   n->lower(l);
   if (ev) event_set_clock(n.get(), 0.0);
-  if (!l.ok) return l.why;
+  if (!l.ok) return "#U " + l.why;
   std::string e = upload_voice(voice, l, true, &l0.S);
   if (!e.empty()) return e;
   nodes[voice] = std::move(n);
@@ -375,7 +375,7 @@ std::string Bank::add_voice(HNode* node, uint32_t* voice) { return regroup(node,
 // Net::remove on a bank made from a Net (src/net.rs:351-404: "connections from the unit are replaced with zeros"): the voice's place in the
 // mix keeps its position and carries silence from now on.
 std::string Bank::remove_voice(uint32_t voice) {
-  if (voice >= V()) return "remove: voice index out of range";
+  if (voice >= V()) return "#A remove: voice index out of range";
   std::vector<float> z((size_t)nout, 0.0f);
   HNode* silent = mk_constant(nout, z.data());
   if (nin > 0) silent = mk_pipe(mk_sink(nin), silent);
@@ -387,10 +387,10 @@ std::string Bank::remove_voice(uint32_t voice) {
 std::string Bank::regroup(HNode* node, int at, uint32_t* voice) {
   std::unique_ptr<HNode> n(node);
   const char* what = at < 0 ? "add" : "replace";
-  if (!n) return std::string(what) + ": null node";
-  if (n->inputs() != nin || n->outputs() != nout) return std::string(what) + ": the unit's arity differs from the bank's";
-  if (tree_mix && at < 0) return "add: a bank extracted from a Net mixes in the Net's order; rebuild it from the edited Net";
-  for (auto& c : classes) if (c.fdn || c.conv) return std::string(what) + ": banks with a two-stage class (FDN reverb, tensor-core convolver) cannot be regrouped in place; rebuild the bank";
+  if (!n) return std::string("#A ") + what + ": null node";
+  if (n->inputs() != nin || n->outputs() != nout) return std::string("#U ") + what + ": the unit's arity differs from the bank's";
+  if (tree_mix && at < 0) return "#U add: a bank extracted from a Net mixes in the Net's order; rebuild it from the edited Net";
+  for (auto& c : classes) if (c.fdn || c.conv) return std::string("#U ") + what + ": banks with a two-stage class (FDN reverb, tensor-core convolver) cannot be regrouped in place; rebuild the bank";
   CU(cudaSetDevice(device));
   { std::string re = rt_stop(); if (!re.empty()) return re; } process_streak = 0;
   const double unit_rate = net_rate ? (double)(float)sr : sr;
@@ -400,8 +400,8 @@ std::string Bank::regroup(HNode* node, int at, uint32_t* voice) {
   const bool ev = event_set_clock(n.get(), seq_time);
   n->lower(l);
   if (ev) event_set_clock(n.get(), 0.0);
-  if (!l.ok) return l.why;
-  { std::string sg, jerr; n->sig(sg); if (!get_program(sg, device, jerr)) return std::string(what) + ": no device program for `" + sg + "`: " + jerr; }
+  if (!l.ok) return "#U " + l.why;
+  { std::string sg, jerr; n->sig(sg); if (!get_program(sg, device, jerr)) return std::string("#U ") + what + ": no device program for `" + sg + "`: " + jerr; }
   // 1. read back what is running
   CU(cudaStreamSynchronize(stream));
   struct Saved { std::string sig; std::vector<uint32_t> uniform, voices, S; std::vector<float> D; uint32_t ns; uint64_t dl; };
@@ -459,9 +459,9 @@ std::string Bank::regroup(HNode* node, int at, uint32_t* voice) {
 // `latest`; here that call is refused (the caller retries after the fade).
 std::string Bank::slot_set(uint32_t voice, int ease, double fade_time, HNode* unit) {
   std::unique_ptr<HNode> n(unit);
-  if (voice >= V()) return "slot: voice index out of range";
-  if (!n || ease < 0 || ease > 1 || !(fade_time > 0.0)) return "slot: needs a unit, fade 0 (Power) or 1 (Smooth) and a fade time > 0";
-  if (!is_slot(nodes[voice].get())) return "slot: the voice is not a slot (fdsp_slot)";
+  if (voice >= V()) return "#A slot: voice index out of range";
+  if (!n || ease < 0 || ease > 1 || !(fade_time > 0.0)) return "#A slot: needs a unit, fade 0 (Power) or 1 (Smooth) and a fade time > 0";
+  if (!is_slot(nodes[voice].get())) return "#A slot: the voice is not a slot (fdsp_slot)";
   CU(cudaSetDevice(device));
   { std::string re = rt_stop(); if (!re.empty()) return re; } process_streak = 0;
   for (auto& c : classes) {
@@ -472,15 +472,15 @@ std::string Bank::slot_set(uint32_t voice, int ease, double fade_time, HNode* un
     CU(cudaStreamSynchronize(stream));
     uint32_t head[2] = {0, 0};   // which, has_next of this voice
     CU(cudaMemcpy2D(head, 4, c.d_state + i, (size_t)Vc * 4, 4, 2, cudaMemcpyDeviceToHost));
-    if (head[1]) return "slot: a crossfade is in progress on this voice; set again when it has finished";
+    if (head[1]) return "#U slot: a crossfade is in progress on this voice; set again when it has finished";
     const int inst = (int)(head[0] ^ 1u);
     // arm a COPY of the voice's host slot: a refused unit leaves the host graph as it was (it replaces the original after the upload)
     std::unique_ptr<HNode> trial(nodes[voice]->clone());
-    if (!slot_arm(trial.get(), n.release(), inst, ease, fade_time)) return "slot: the unit's graph class differs from the slot's (same type expression needed)";
+    if (!slot_arm(trial.get(), n.release(), inst, ease, fade_time)) return "#U slot: the unit's graph class differs from the slot's (same type expression needed)";
     Lowering l;
     trial->lower(l);
-    if (!l.ok) return l.why;
-    if (l.U != c.uniform || l.P.size() != c.np || l.S.size() != c.ns) return "slot: the unit changes a class-uniform word (delay length, table, wave); rebuild the bank instead";
+    if (!l.ok) return "#U " + l.why;
+    if (l.U != c.uniform || l.P.size() != c.np || l.S.size() != c.ns) return "#U slot: the unit changes a class-uniform word (delay length, table, wave); rebuild the bank instead";
     const uint32_t xs = (c.ns - 4) / 2, s0 = 4 + (uint32_t)inst * xs;
     const uint64_t xd = c.dl_floats / 2;
     CU(cudaMemcpy2DAsync(c.d_params + i, (size_t)Vc * 4, l.P.data(), 4, 4, c.np, cudaMemcpyHostToDevice, stream));
@@ -499,8 +499,8 @@ std::string Bank::slot_set(uint32_t voice, int ease, double fade_time, HNode* un
 std::string Bank::push_event(HNode* node, uint32_t* voice) {   // Sequencer::push on a running sequencer (src/sequencer.rs:319-360)
   std::unique_ptr<HNode> n(node);
   double s0, e0;
-  if (!n || !event_times(n.get(), &s0, &e0)) return "push: not a sequencer event (fdsp_event)";
-  if (n->inputs() != nin || n->outputs() != nout) return "push: the event's arity differs from the bank's";
+  if (!n || !event_times(n.get(), &s0, &e0)) return "#A push: not a sequencer event (fdsp_event)";
+  if (n->inputs() != nin || n->outputs() != nout) return "#U push: the event's arity differs from the bank's";
   CU(cudaSetDevice(device));
   const double unit_rate = net_rate ? (double)(float)sr : sr, sd = 1.0 / unit_rate;
   n->set_sample_rate(unit_rate);
@@ -510,7 +510,7 @@ std::string Bank::push_event(HNode* node, uint32_t* voice) {   // Sequencer::pus
   event_set_clock(n.get(), seq_time);       // the event counts from now; a start time in the past makes it sound from the next block on
   n->lower(l);
   event_set_clock(n.get(), 0.0);
-  if (!l.ok) return l.why;
+  if (!l.ok) return "#U " + l.why;
   for (auto& c : classes) {
     if (c.sig != want || c.uniform != l.U || c.fdn) continue;
     for (uint32_t v : c.voices) {
@@ -523,7 +523,7 @@ std::string Bank::push_event(HNode* node, uint32_t* voice) {   // Sequencer::pus
       return "";
     }
   }
-  return "no finished event of the same graph class is free: create the bank with spare events of this class (finished, or ending at time 0), or rebuild it";
+  return "#N no finished event of the same graph class is free: create the bank with spare events of this class (finished, or ending at time 0), or rebuild it";
 }
 
 std::string Bank::reset() {  // AudioUnit::reset: back to the construction-time state
@@ -618,7 +618,7 @@ std::string Bank::rt_process(uint32_t size, const float* in, float* out, bool* s
     rt_seq = first - 1u;
   }
   const uint32_t seq = ++rt_seq;
-  if (nin > 0) { if (!in) return "bank has inputs but no input buffer was given"; memcpy((void*)rt_ctl->in, in, (size_t)nin * 64 * 4); }
+  if (nin > 0) { if (!in) return "#A bank has inputs but no input buffer was given"; memcpy((void*)rt_ctl->in, in, (size_t)nin * 64 * 4); }
   rt_ctl->size = size;
   __sync_synchronize();
   rt_ctl->doorbell = seq;
@@ -657,12 +657,12 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
   CU(cudaSetDevice(device));
   { std::string re = rt_stop(); if (!re.empty()) return re; }
   if (!in_process) process_streak = 0;
-  if (nin > 0 && !in_dev) return "bank has inputs but no input buffer was given";
+  if (nin > 0 && !in_dev) return "#A bank has inputs but no input buffer was given";
   const bool want_v = (out_mode & 1u) && out_dev, want_m = (out_mode & 2u) && mix_dev;
-  if (!want_v && !want_m) return "no output buffer matches the bank's out_mode";
+  if (!want_v && !want_m) return "#A no output buffer matches the bank's out_mode";
   if (n == 0) return "";
   const bool save_want_m_ = want_m;
-  if (in_stride > 0xffffffffull || out_stride > 0xffffffffull || mix_stride > 0xffffffffull) return "stride too large";
+  if (in_stride > 0xffffffffull || out_stride > 0xffffffffull || mix_stride > 0xffffffffull) return "#A stride too large";
   if (timing) { CU(cudaEventRecord(ev0, stream)); dom_n = 0; }
   // Net-ordered mix: the voice kernels materialise per-voice rows (user buffer, or an internal one) and tree_mix_kernel adds
   // them in the Net's association order; the CTA-level partial mix is bypassed.
@@ -773,7 +773,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
       // process()-sized launches of plain voice programs finish their mix-down inside the kernel (one launch instead of two)
       const bool fused_mix = want_m && !c.fdn && len <= 64;
       a.ticket = fused_mix ? d_ticket : nullptr; a.mix = mix_dev; a.mix_stride = (uint32_t)mix_stride; a.mix_offset = (uint32_t)t0; a.mix_accumulate = first ? 0 : 1;
-      if (t0 > 0xffffffffull - TIME_CHUNK) return "render too long for one call";
+      if (t0 > 0xffffffffull - TIME_CHUNK) return "#A render too long for one call";
       if (c.fdn && len > TIME_CHUNK) return "internal: chunk";
       // long launches of wavetable programs stage the table set in shared memory (TMA bulk copy, ~160 KB per CTA);
       // short ones (process()-sized) read the tables through L1/L2 instead
@@ -904,7 +904,7 @@ std::string Bank::render_host(uint64_t n, const float* in, float* out_voices, fl
   for (uint64_t t0 = 0; t0 < n; t0 += chunk) {
     const uint32_t len = (uint32_t)std::min<uint64_t>(chunk, n - t0);
     if (nin > 0) {
-      if (!in) return "bank has inputs but no input buffer was given";
+      if (!in) return "#A bank has inputs but no input buffer was given";
       CU(cudaMemcpy2DAsync(d_in, (size_t)chunk * 4, in + t0, (size_t)n * 4, (size_t)len * 4, nin, cudaMemcpyHostToDevice, stream));
     }
     e = render_device(len, d_in, chunk, (out_voices ? d_out : nullptr), chunk, (out_mix ? d_mix : nullptr), chunk);
@@ -917,7 +917,7 @@ std::string Bank::render_host(uint64_t n, const float* in, float* out_voices, fl
 }
 
 std::string Bank::process(uint32_t size, const float* in, float* out) {  // AudioUnit::process (size <= 64)
-  if (size > 64) return "process: size must be <= 64 (MAX_BUFFER_SIZE)";
+  if (size > 64) return "#A process: size must be <= 64 (MAX_BUFFER_SIZE)";
   if (size == 0) return "";
   CU(cudaSetDevice(device));
   {
@@ -941,7 +941,7 @@ std::string Bank::process(uint32_t size, const float* in, float* out) {  // Audi
     h_out_cap = rows * 64;
   }
   if (nin > 0) {
-    if (!in) return "bank has inputs but no input buffer was given";
+    if (!in) return "#A bank has inputs but no input buffer was given";
     memcpy(h_in, in, (size_t)nin * 64 * 4);
     CU(cudaMemcpyAsync(d_in, h_in, (size_t)nin * 64 * 4, cudaMemcpyHostToDevice, stream));
   }

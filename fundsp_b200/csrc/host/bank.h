@@ -14,6 +14,9 @@
 namespace fdsp {
 namespace host {
 
+// Error convention of the runtime: "" = ok, otherwise the message, which may start with a status tag that csrc/capi.cpp turns into the
+// ABI's code and strips: "#U " unsupported (FDSP_ERR_UNSUPPORTED), "#A " bad argument (FDSP_ERR_ARG), "#N " no free slot (push_event falls
+// back to growing the bank). Untagged messages are device / driver failures (FDSP_ERR_CUDA). Codes never depend on the wording.
 struct VoiceClass {
   std::string sig;
   std::shared_ptr<const Program> k;
