@@ -237,8 +237,35 @@ static __global__ void mix_reduce_kernel(const float* partial, uint32_t nparts, 
 //   pairwise = level-wise adjacent pairing with the odd element carried up (the balanced `Net::bus` tree),
 //   chain    = left fold in voice order (a left-leaning chain of `&`, or the index-order sum of a Sequencer).
 // One thread per (channel, sample); rows are read coalesced along time; the association is a binary-carry stack.
+// Level 1 of the balanced tree for big banks: the subtree sum of every COMPLETE block of 2^LB consecutive voices, one thread per (block,
+// channel, sample). A complete aligned block is a whole subtree of the level-wise pairing, so its sum does not depend on the rest of the bank;
+// tree_mix_kernel then pushes the block sums at level LB of its carry stack (exactly what pushing the block's voices one by one would have left
+// there) and goes on with the tail voices. Same association, every bit — with V / 2^LB times the parallelism over the voices.
+template <int LB>
+static __global__ void tree_mix_block_kernel(const float* __restrict__ rows, uint32_t outs, uint32_t row_stride, uint32_t row_offset, uint32_t n, float* __restrict__ partial) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x, blk = blockIdx.y;
+  if (e >= outs * n) return;
+  const uint32_t ch = e / n, t = e - ch * n;
+  const size_t vstep = (size_t)outs * row_stride;
+  const float* p = rows + (size_t)ch * row_stride + row_offset + t + (size_t)blk * ((size_t)1 << LB) * vstep;
+  float st[LB + 1];
+  for (uint32_t v0 = 0; v0 < (1u << LB); v0 += 8) {
+    float b[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) b[u] = __ldg(p + (size_t)(v0 + u) * vstep);
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      float y = b[u]; uint32_t q = v0 + u; int lvl = 0;
+      while (q & 1u) { y = st[lvl] + y; q >>= 1; lvl++; }
+      st[lvl] = y;
+    }
+  }
+  partial[((size_t)blk * outs + ch) * n + t] = st[LB];
+}
+
 static __global__ void tree_mix_kernel(const float* __restrict__ rows, uint32_t V, uint32_t outs, uint32_t row_stride, uint32_t row_offset, uint32_t n,
-                                       float* mix, uint32_t mix_stride, uint32_t mix_offset, int pairwise) {
+                                       float* mix, uint32_t mix_stride, uint32_t mix_offset, int pairwise, const float* __restrict__ partial = nullptr,
+                                       uint32_t nfull = 0, int lb = 0) {
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= outs * n) return;
   const uint32_t ch = e / n, t = e - ch * n;
@@ -247,7 +274,13 @@ static __global__ void tree_mix_kernel(const float* __restrict__ rows, uint32_t 
   float x;
   if (pairwise) {
     float st[32];
-    for (uint32_t v0 = 0; v0 < V; v0 += 8) {
+    // complete blocks of 2^lb voices arrive as their subtree sums (tree_mix_block_kernel): pushed at level lb with the block index as the carry pattern
+    for (uint32_t bk = 0; bk < nfull; bk++) {
+      float y = __ldg(partial + ((size_t)bk * outs + ch) * n + t); uint32_t q = bk; int lvl = lb;
+      while (q & 1u) { y = st[lvl] + y; q >>= 1; lvl++; }
+      st[lvl] = y;
+    }
+    for (uint32_t v0 = nfull << lb; v0 < V; v0 += 8) {
       float b[8];
 #pragma unroll
       for (int u = 0; u < 8; u++) b[u] = (v0 + u < V) ? __ldg(p + (size_t)(v0 + u) * vstep) : 0.0f;

@@ -60,7 +60,7 @@ Bank::~Bank() {
     cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows); cudaFree(c.d_dry2); cudaFree(c.d_partial2); cudaFree(c.d_cx); cudaFree(c.d_cxl); cudaFree(c.d_th); cudaFree(c.d_tl); cudaFree(c.d_crows); for (int q = 0; q < 2; q++) { if (c.e_dry[q]) cudaEventDestroy(c.e_dry[q]); if (c.e_fdn[q]) cudaEventDestroy(c.e_fdn[q]); } if (c.cstream) cudaStreamDestroy(c.cstream); if (c.e_done) cudaEventDestroy(c.e_done);
   }
   for (float* p : d_wtdata) cudaFree(p);
-  cudaFree(d_wt); cudaFree(d_in); cudaFree(d_out); cudaFree(d_mix); cudaFree(d_rows);
+  cudaFree(d_wt); cudaFree(d_in); cudaFree(d_out); cudaFree(d_mix); cudaFree(d_rows); cudaFree(d_treepart);
   if (h_in) cudaFreeHost(h_in);
   if (h_out) cudaFreeHost(h_out);
   for (cudaEvent_t e : dom_ev) cudaEventDestroy(e);
@@ -858,8 +858,10 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
       }
     }
     if (tree) {
-      CU(launch_tree_mix(out_dev_c, V(), (uint32_t)nout, (uint32_t)out_stride_c, (uint32_t)out_t0, len, mix_dev, (uint32_t)mix_stride, (uint32_t)t0, tree_mix == 1 ? 1 : 0, stream));
-      launches++;
+      const size_t sc = tree_mix == 1 ? tree_mix_scratch_floats(V(), (uint32_t)nout, CH) : 0;   // balanced tree of a big bank: subtree sums first
+      if (sc > treepart_cap) { std::string e = dev_alloc(&d_treepart, sc); if (!e.empty()) return e; treepart_cap = sc; }
+      CU(launch_tree_mix(out_dev_c, V(), (uint32_t)nout, (uint32_t)out_stride_c, (uint32_t)out_t0, len, mix_dev, (uint32_t)mix_stride, (uint32_t)t0, tree_mix == 1 ? 1 : 0, stream, sc ? d_treepart : nullptr));
+      launches += sc ? 2 : 1;
     }
   }
   { std::string pe = flush_pending(nullptr); if (!pe.empty()) return pe; }   // also joins stream2 back into `stream`

@@ -49,7 +49,7 @@ struct Bank {
   double sr = DEFAULT_SR; bool dirty = false;
   // voices extracted from a Net: mix in the Net's own association order (0 none, 1 pairwise tree, 2 left fold) and hand the
   // units the Net's f32-rounded sample rate (src/net.rs:132,1323-1328)
-  int tree_mix = 0; bool net_rate = false; float* d_rows = nullptr; size_t rows_cap = 0;
+  int tree_mix = 0; bool net_rate = false; float* d_rows = nullptr; size_t rows_cap = 0; float* d_treepart = nullptr; size_t treepart_cap = 0;
   std::vector<std::unique_ptr<HNode>> nodes;
   std::vector<int> vertex_of_voice;   // banks made from a Net: the Net vertex (NodeId) behind each voice
   std::vector<VoiceClass> classes;

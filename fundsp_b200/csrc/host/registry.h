@@ -48,8 +48,10 @@ const KernelEntry* registry_at(int i);
 const char* registry_key(int i);
 cudaError_t launch_mix_reduce(const float* partial, uint32_t nparts, uint32_t outs, uint32_t n, float* mix, uint32_t mix_stride,
                               uint32_t mix_offset, int accumulate, cudaStream_t stream);
+// `scratch` (tree_mix_scratch_floats(V, outs, n) floats, or null): lets a big balanced tree reduce its 256-voice subtrees in parallel first
 cudaError_t launch_tree_mix(const float* rows, uint32_t V, uint32_t outs, uint32_t row_stride, uint32_t row_offset, uint32_t n, float* mix,
-                            uint32_t mix_stride, uint32_t mix_offset, int pairwise, cudaStream_t stream);
+                            uint32_t mix_stride, uint32_t mix_offset, int pairwise, cudaStream_t stream, float* scratch = nullptr);
+size_t tree_mix_scratch_floats(uint32_t V, uint32_t outs, uint32_t n);
 // warp-per-voice reverb_stereo kernel (inst/inst_fdn.cu)
 cudaError_t launch_fdn(const FdnArgs& a, int warps, cudaStream_t stream);
 int fdn_max_warps();

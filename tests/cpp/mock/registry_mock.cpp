@@ -79,7 +79,7 @@ cudaError_t launch_mix_reduce(const float* partial, uint32_t nparts, uint32_t ou
     }
   return cudaSuccess;
 }
-cudaError_t launch_tree_mix(const float* rows, uint32_t V, uint32_t outs, uint32_t row_stride, uint32_t row_offset, uint32_t n, float* mix, uint32_t mix_stride, uint32_t mix_offset, int pairwise, cudaStream_t) {
+cudaError_t launch_tree_mix(const float* rows, uint32_t V, uint32_t outs, uint32_t row_stride, uint32_t row_offset, uint32_t n, float* mix, uint32_t mix_stride, uint32_t mix_offset, int pairwise, cudaStream_t, float*) {
   for (uint32_t ch = 0; ch < outs; ch++)
     for (uint32_t t = 0; t < n; t++) {   // tree_mix_kernel: the binary-carry stack of the balanced tree, or the left fold
       const float* p = rows + (size_t)ch * row_stride + row_offset + t;
@@ -131,6 +131,7 @@ cudaError_t launch_fdn(const FdnArgs& f, int warps, cudaStream_t) {
       }
   return cudaSuccess;
 }
+size_t tree_mix_scratch_floats(uint32_t, uint32_t, uint32_t) { return 0; }
 int fdn_max_warps() { return 8; }
 // the tensor-core convolver form is never selected on the mock (bank.cpp tc_conv_wanted); the symbols only have to link
 cudaError_t conv_tc_make_maps(float*, float*, uint32_t, uint32_t, float*, float*, uint32_t, ConvTcMaps*) { return cudaErrorInvalidValue; }

@@ -411,7 +411,7 @@ def test_fdn_kernel_equals_generic_thread_per_voice_form():
 
 
 # ---------------------------------------------------------------- dynamic Net (config 5): voices + Net::bus adder trees
-@pytest.mark.parametrize("V,n", [(64, 1500), (37, 700 + 13), (1, 200)])
+@pytest.mark.parametrize("V,n", [(64, 1500), (37, 700 + 13), (1, 200), (1300, 300)])   # 1300: above 1024 voices the balanced tree reduces its 256-voice subtrees first
 def test_net_of_voices_mix_is_bit_exact(V, n):
     """The reference form of config 5: each voice `Net::wrap`ped and bussed as a balanced tree (one Pass+Pass adder per output
     per `&`). The bank built from that Net must reproduce Net::ping's hashes and the tree's association order exactly."""
