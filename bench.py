@@ -291,6 +291,8 @@ def main():
     launches0 = bank.launch_count()
     ms_step, ms_kernel, wall = timed(device_step, a.steps)
     ms_dom = timed.dominant_ms      # the dominant kernel alone (CUDA events on the stream it is launched on, inside the bank)
+    if not ms_dom > 0.0:            # FDSP_NO_DOM=1 (the A/B switch of those event records): fall back on the whole device region
+        ms_dom = ms_kernel
     launches = bank.launch_count() - launches0
     ms_e2e, _, _ = timed(e2e_step, a.steps)
     # AudioUnit::process granularity: one C-ABI call per 64-sample block with host buffers (the Wave::render call pattern)

@@ -3,6 +3,7 @@
 
 #include <cstring>
 #include <new>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -383,8 +384,18 @@ API int fdsp_bank_sync(fdsp_bank* b) {
   cudaError_t e = cudaStreamSynchronize(b->b.stream);
   if (e != cudaSuccess) return fail(FDSP_ERR_CUDA, cudaGetErrorString(e));
   if (cudaEventElapsedTime(&b->b.last_ms, b->b.ev0, b->b.ev1) != cudaSuccess) b->b.last_ms = 0.0f;
+  // time covered by the voice kernels: the union of their [begin, end] intervals measured from ev0 (classes of a multi-class bank run on
+  // concurrent streams, so a plain sum of the durations would exceed the step)
   b->b.last_dom_ms = 0.0f;
-  for (size_t i = 0; i + 1 < b->b.dom_n; i += 2) { float t = 0.0f; if (cudaEventElapsedTime(&t, b->b.dom_ev[i], b->b.dom_ev[i + 1]) == cudaSuccess) b->b.last_dom_ms += t; }
+  std::vector<std::pair<float, float>> iv;
+  for (size_t i = 0; i + 1 < b->b.dom_n; i += 2) {
+    float t0 = 0.0f, t1 = 0.0f;
+    if (cudaEventElapsedTime(&t0, b->b.ev0, b->b.dom_ev[i]) == cudaSuccess && cudaEventElapsedTime(&t1, b->b.ev0, b->b.dom_ev[i + 1]) == cudaSuccess && t1 > t0)
+      iv.emplace_back(t0, t1);
+  }
+  std::sort(iv.begin(), iv.end());
+  float hi = -1.0f;
+  for (auto& q : iv) { if (q.second <= hi) continue; b->b.last_dom_ms += q.second - std::max(q.first, hi); hi = q.second; }
   return FDSP_OK;
 }
 API void* fdsp_bank_stream(fdsp_bank* b) { return b ? (void*)b->b.stream : nullptr; }
