@@ -85,6 +85,7 @@ API fdsp_node* fdsp_oversample(fdsp_node* x) { return wrap(mk_oversample(take(x)
 API fdsp_node* fdsp_monitor(void) { return wrap(mk_monitor(), "monitor"); }
 API fdsp_node* fdsp_envelope(double interval, int outputs, int time_f64, fdsp_envelope_fn f, void* user, double horizon) { return wrap(mk_envelope(interval, outputs, time_f64, (EnvelopeFn)f, user, horizon), "envelope"); }
 API fdsp_node* fdsp_event(fdsp_node* x, double start, double end, int fade_ease, double fade_in, double fade_out) { return wrap(mk_event(take(x), start, end, fade_ease, fade_in, fade_out), "event"); }
+API fdsp_node* fdsp_event_loop(fdsp_node* x, double start, double end, int fade_ease, double fade_in, double fade_out, double loop_seconds) { return wrap(mk_event_loop(take(x), start, end, fade_ease, fade_in, fade_out, loop_seconds), "event_loop"); }
 API fdsp_node* fdsp_limiter(int channels, float attack, float release) { return wrap(mk_limiter(channels, attack, release), "limiter"); }
 API fdsp_node* fdsp_meter(int kind, double timescale) { return wrap(mk_meter(kind, timescale), "meter"); }
 API fdsp_node* fdsp_playwave(const float* samples, uint64_t length, uint64_t start, uint64_t end, int64_t loop_point) { return wrap(mk_playwave(samples, length, start, end, loop_point), "playwave"); }

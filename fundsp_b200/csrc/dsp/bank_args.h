@@ -59,6 +59,10 @@ struct BankArgs {
   float* mix;
   uint32_t mix_stride, mix_offset;
   int mix_accumulate;
+  // reset image of the class's state words [NS][V] and delay-line floats per voice: what Event<X> of a looping sequencer needs to reset its unit
+  // on the device (null / 0 when the class has no such voices)
+  const uint32_t* state0;
+  uint32_t dl_floats;
 };
 
 }  // namespace fdsp

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(NT, FDSP_MIN_CTAS) bank_kernel_rt(const BankAr
     c.tsm = smem_addr(tsm); c.tsm_kind = KIND;
   }
   c.wt = a.wt; c.dl = a.dline; c.V = a.V; c.v = v; c.sr = a.sr; c.sd64 = a.sd64; c.sd32 = a.sd32;
+  c.rp = a.params; c.rs0 = a.state0; c.ru = a.uniform; c.dl_total = a.dl_floats;
   if (active) {
     Loader l{a.params, a.state, a.uniform, a.V, v, 0u, 0u, 0u, 0u};
     G::load(r, l);

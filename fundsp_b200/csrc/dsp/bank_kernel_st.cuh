@@ -55,6 +55,7 @@ template <class G, int NT, int MODE, bool TB, int I> struct StRun {
     // group's inputs loaded up front) instead of the rotating loop the one-warp-does-everything kernel uses to keep its instruction stream small
     CtxT<TB, SpineHeavy<S>::value> c;
     c.wt = c0.wt; c.tsm = c0.tsm; c.tsm_kind = c0.tsm_kind; c.dl = c0.dl; c.V = c0.V; c.v = c0.v; c.sr = c0.sr; c.sd64 = c0.sd64; c.sd32 = c0.sd32;
+    c.rp = c0.rp; c.rs0 = c0.rs0; c.ru = c0.ru; c.dl_total = c0.dl_total;
     c.i = 0; c.n = 0; c.first = false; c.rem = false;
     const uint32_t w = lt >> 5, lane = lt & 31u;
     constexpr int MIDI = FIRST ? 1 : IN, MIDO = LAST ? 1 : OUT;
@@ -253,6 +254,7 @@ __global__ void __launch_bounds__(StagePlan<G>::K * NT, 1) bank_kernel_st(const 
     c.tsm = smem_addr(tsm); c.tsm_kind = KIND;
   }
   c.wt = a.wt; c.dl = a.dline; c.V = a.V; c.v = v; c.sr = a.sr; c.sd64 = a.sd64; c.sd32 = a.sd32;
+  c.rp = a.params; c.rs0 = a.state0; c.ru = a.uniform; c.dl_total = a.dl_floats;
   st_dispatch<G, NT, MODE, TB, 0>(stage, a, tile, hand, bar0, c, lt, v, active);
 }
 

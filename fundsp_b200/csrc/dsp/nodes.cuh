@@ -35,6 +35,9 @@ template <bool SM, bool UH = false> struct CtxT {
   int tsm_kind;
   float* dl;          // delay-line storage of this voice class, element (off + pos) * V + v
   uint32_t V, v;
+  // what a node needs to put a sub-program back into its construction-time state on the device (Event<X> in a looping sequencer): the class's
+  // parameter / reset-image / uniform words and the delay-line floats per voice
+  const uint32_t* rp; const uint32_t* rs0; const uint32_t* ru; uint32_t dl_total;
   float sr;           // sample rate as f32
   float sd64;         // (1.0f64 / sr) as f32   (src/oscillator.rs:62-64, src/envelope.rs:290-292)
   float sd32;         // 1.0f32 / (sr as f32)   (src/wavetable.rs:299-302)
@@ -1226,65 +1229,102 @@ FDSP_DEV float sine_ease_f(float x) {   // src/math.rs:453-458, T = f32
 }
 template <class X> struct Event {
   static constexpr int NO = X::OUT;
-  FDSP_NODE(0, NO, 11 + X::NP, 3 + X::NS, X::NU);
+  static constexpr int NPE = 13, NSE = 7;   // the event's own parameter / state words, in front of X's
+  static constexpr int NOSPLIT = 1 << 30;
+  FDSP_NODE(0, NO, NPE + X::NP, NSE + X::NS, X::NU);
   struct R {
     double sr, sd, start, end, fin, fout, time; int ease, status;   // status 0 ready, 1 active, 2 past
+    // ReplayMode::Loop (src/sequencer.rs:219-229): lp = loop point in seconds (+inf: no loop); cs / ce = the event's CURRENT start / end, which a
+    // wrap shifts back by lp while the event is sounding and the end of the event restores to start / end (the original times, :622-639)
+    double lp, cs, ce;
     int s_idx, n_v, nfull_v, fi_end, fo_i, fo_end; float fi_cur, fi_d, fo_cur, fo_d; bool fi_on, fo_on;
     bool whole;   // this block: the event spans it entirely and no fade touches it -> X runs its own 8-sample group form (step8)
+    int split;    // loop: index inside this block at which the sequencer wraps (NOSPLIT: it does not)
+    bool silent;  // the rest of a block after the wrap is rendered into a scratch buffer by the reference (:845-872 as written): state advances, output stays 0
     typename X::R x;
   };
   static FDSP_DEV double ld64(Loader& l, bool state) {
     const uint32_t lo = state ? l.S() : l.P(), hi = state ? l.S() : l.P();
     return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
   }
+  static FDSP_DEV void st64(Saver& s, double v) { const unsigned long long b = (unsigned long long)__double_as_longlong(v); s.S((uint32_t)b); s.S((uint32_t)(b >> 32)); }
+  static FDSP_DEV bool looped(const R& r) { return r.lp < 1.0e300; }
   static FDSP_DEV void load(R& r, Loader& l) {
     r.sr = ld64(l, false); r.start = ld64(l, false); r.end = ld64(l, false); r.fin = ld64(l, false); r.fout = ld64(l, false); r.ease = (int)l.P();
+    r.lp = ld64(l, false);
     r.sd = 1.0 / r.sr;
-    r.time = ld64(l, true); r.status = (int)l.S();
+    r.time = ld64(l, true); r.status = (int)l.S(); r.cs = ld64(l, true); r.ce = ld64(l, true);
     r.s_idx = r.n_v = r.nfull_v = r.fi_end = r.fo_i = r.fo_end = 0; r.fi_cur = r.fi_d = r.fo_cur = r.fo_d = 0.0f; r.fi_on = r.fo_on = false; r.whole = false;
+    r.split = NOSPLIT; r.silent = false;
     X::load(r.x, l);
   }
   static FDSP_DEV void save(const R& r, Saver& s) {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(r.time);
-    s.S((uint32_t)b); s.S((uint32_t)(b >> 32)); s.S((uint32_t)r.status); X::save(r.x, s);
+    st64(s, r.time); s.S((uint32_t)r.status); st64(s, r.cs); st64(s, r.ce); X::save(r.x, s);
   }
   static FDSP_DEV int as_index(double x) { return x > 0.0 ? (x < 1.0e9 ? (int)x : 1000000000) : 0; }   // `as usize`, saturating
-  static FDSP_DEV void plan(R& r, int n) {   // Sequencer::process for this event, :768-843
-    const double end_blk = r.time + r.sd * (double)n;
-    if (r.status == 0 && r.start < end_blk - r.sd * 0.5) r.status = 1;                 // ready_to_active
-    r.n_v = 0; r.s_idx = 0; r.nfull_v = 0; r.fi_on = r.fo_on = false; r.whole = false;
+  // `unit.reset()` of a finished event in a replaying sequencer (:631-633): X back to its construction-time words (the class's reset image),
+  // its delay lines cleared. Only looping events get here on the device (ReplayMode::All resets the whole bank from the host).
+  template <class C> static FDSP_DEV void reset_x(R& r, const C& c) {
+    Loader l{c.rp, c.rs0, c.ru, c.V, c.v, (uint32_t)NPE, (uint32_t)NSE, 0u, 0u};
+    X::load(r.x, l);
+    for (uint32_t k = 0; k < c.dl_total; k++) c.dl[(size_t)k * c.V + c.v] = 0.0f;
+  }
+  // Sequencer::process (:768-843) for this event over `n` samples that begin at index `off` of the kernel's block
+  template <class C> static FDSP_DEV void plan(R& r, const C& c, int n, int off, bool silent) {
+    const bool lo = looped(r);
+    const double end_blk = lo ? fmin(r.time + r.sd * (double)n, r.lp) : r.time + r.sd * (double)n;
+    if (r.status == 0 && (lo ? r.cs : r.start) < end_blk - r.sd * 0.5) r.status = 1;    // ready_to_active
+    const int loop_size = lo ? as_index(round(fmax(0.0, r.lp - r.time) * r.sr)) : n;
+    r.n_v = 0; r.s_idx = off; r.nfull_v = 0; r.fi_on = r.fo_on = false; r.whole = false; r.silent = silent;
     if (r.status == 1) {
-      if (r.end <= r.time + 0.5 * r.sd) r.status = 2;                                  // end_of_event
-      else {
-        const int s = r.start <= r.time ? 0 : as_index(round((r.start - r.time) * r.sr));
-        const int e0 = r.end >= end_blk ? n : as_index(round((r.end - r.time) * r.sr));
-        const int e = e0 < n ? e0 : n;
+      const double st = lo ? r.cs : r.start, en = lo ? r.ce : r.end;
+      if (en <= r.time + 0.5 * r.sd) {                                                  // end_of_event
+        if (lo) { r.cs = r.start; r.ce = r.end; reset_x(r, c); r.status = r.cs >= r.time ? 0 : 2; }
+        else r.status = 2;
+      } else {
+        const int s = st <= r.time ? 0 : as_index(round((st - r.time) * r.sr));
+        const int lim = n < loop_size ? n : loop_size;
+        const int e0 = en >= end_blk ? lim : as_index(round((en - r.time) * r.sr));
+        const int e = en >= end_blk ? lim : (e0 < loop_size ? e0 : loop_size);
         if (e > s) {
-          r.s_idx = s; r.n_v = e - s; r.nfull_v = (e - s) & ~7;
-          const double fe = r.start + r.fin;
+          r.s_idx = off + s; r.n_v = e - s; r.nfull_v = (e - s) & ~7;
+          const double fe = st + r.fin;
           if (r.fin > 0.0 && fe > r.time) {                                            // fade_in :113-160
             r.fi_on = true;
             r.fi_end = fe >= end_blk ? e : as_index(round((fe - r.time) / r.sd));
-            r.fi_cur = (float)(((r.time + (double)s * r.sd) - r.start) / (fe - r.start));
+            r.fi_cur = (float)(((r.time + (double)s * r.sd) - st) / (fe - st));
             r.fi_d = (float)(r.sd / r.fin);
           }
-          const double fs = r.end - r.fout;
+          const double fs = en - r.fout;
           if (r.fout > 0.0 && fs < end_blk) {                                          // fade_out :162-217
             r.fo_on = true;
             r.fo_i = fs <= r.time ? 0 : as_index(round((fs - r.time) / r.sd));
-            r.fo_cur = (float)(((r.time + (double)r.fo_i * r.sd) - fs) / (r.end - fs));
+            r.fo_cur = (float)(((r.time + (double)r.fo_i * r.sd) - fs) / (en - fs));
             r.fo_d = (float)(r.sd / r.fout);
             r.fo_end = e;
           }
         }
       }
     }
-    r.whole = r.n_v == n && !r.fi_on && !r.fo_on;
+    r.whole = r.n_v == n && off == 0 && !silent && !r.fi_on && !r.fo_on;
     r.time = end_blk;
+    r.split = loop_size < n ? off + loop_size : NOSPLIT;
+  }
+  // first sample of a kernel block: plan it; the sample at which the loop wraps: Sequencer::reset in loop mode (:642-683 — sounding events
+  // move back by the loop period, past events become ready again, time restarts) and the plan of the rest of the block, which the reference
+  // renders into a scratch buffer (a loop is at least 64 samples, so a block wraps at most once)
+  template <class C> static FDSP_DEV void at_sample(R& r, const C& c) {
+    if (c.i == 0) plan(r, c, c.n, 0, false);
+    if (c.i == r.split) {
+      const int off = r.split;
+      if (r.status == 1) { r.cs -= r.lp; r.ce -= r.lp; } else if (r.status == 2) r.status = 0;
+      r.time = 0.0;
+      plan(r, c, c.n - off, off, true);
+    }
   }
   template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<0>& in, Fr<NO>& o) {
     if (T) { X::template step<true>(r.x, c, in, o); return; }   // (an event is always the root of a voice: not reached)
-    if (c.i == 0) plan(r, c.n);
+    at_sample(r, c);
     step_planned(r, c, in, o);
   }
   template <class C> static FDSP_DEV void step_planned(R& r, const C& c, const Fr<0>& in, Fr<NO>& o) {
@@ -1306,6 +1346,10 @@ template <class X> struct Event {
 #pragma unroll
         for (int k = 0; k < NO; k++) o.v[k] *= h;
       }
+      if (r.silent) {
+#pragma unroll
+        for (int k = 0; k < NO; k++) o.v[k] = 0.0f;
+      }
     } else {
 #pragma unroll
       for (int k = 0; k < NO; k++) o.v[k] = 0.0f;
@@ -1315,9 +1359,9 @@ template <class X> struct Event {
   // other block (start, end, fades, silence) takes the per-sample path above. The plan is made by the block's first group.
   typedef void GroupStep;
   template <class C> static FDSP_DEV void step8(R& r, C& c, const Fr8<0>& in, Fr8<NO>& o) {
-    if (c.i == 0) plan(r, c.n);
+    at_sample(r, c);
     if (r.whole) { group_step<X>(r.x, c, in, o); return; }
-    if (r.n_v == 0) {
+    if (r.n_v == 0 && r.split == NOSPLIT) {
 #pragma unroll
       for (int k = 0; k < NO; k++) {
 #pragma unroll
@@ -1332,6 +1376,7 @@ template <class X> struct Event {
     for (int j = 0; j < 8; j++) {
       Fr<0> none; Fr<NO> y;
       c.i = base + j; c.first = (j == 0);
+      if (j > 0 && c.i == r.split) at_sample(r, c);
       step_planned(r, c, none, y);
 #pragma unroll
       for (int k = 0; k < NO; k++) {

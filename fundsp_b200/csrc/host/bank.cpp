@@ -3,6 +3,8 @@
 #include "../dsp/fdn_args.h"
 
 #include <algorithm>
+#include <cmath>
+#include <limits>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -57,7 +59,7 @@ Bank::~Bank() {
   if (rt_ctl) cudaFreeHost(rt_ctl);
   cudaFree(d_rt_relay); cudaFree(d_rt_partial);
   for (auto& c : classes) {
-    cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows); cudaFree(c.d_dry2); cudaFree(c.d_partial2); cudaFree(c.d_cx); cudaFree(c.d_cxl); cudaFree(c.d_th); cudaFree(c.d_tl); cudaFree(c.d_crows); for (int q = 0; q < 2; q++) { if (c.e_dry[q]) cudaEventDestroy(c.e_dry[q]); if (c.e_fdn[q]) cudaEventDestroy(c.e_fdn[q]); } if (c.cstream) cudaStreamDestroy(c.cstream); if (c.e_done) cudaEventDestroy(c.e_done);
+    cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_state0); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows); cudaFree(c.d_dry2); cudaFree(c.d_partial2); cudaFree(c.d_cx); cudaFree(c.d_cxl); cudaFree(c.d_th); cudaFree(c.d_tl); cudaFree(c.d_crows); for (int q = 0; q < 2; q++) { if (c.e_dry[q]) cudaEventDestroy(c.e_dry[q]); if (c.e_fdn[q]) cudaEventDestroy(c.e_fdn[q]); } if (c.cstream) cudaStreamDestroy(c.cstream); if (c.e_done) cudaEventDestroy(c.e_done);
   }
   for (float* p : d_wtdata) cudaFree(p);
   cudaFree(d_wt); cudaFree(d_in); cudaFree(d_out); cudaFree(d_mix); cudaFree(d_rows); cudaFree(d_treepart);
@@ -98,6 +100,13 @@ std::string Bank::init(std::vector<HNode*>& voices, int dev, uint32_t mode) {
 std::string Bank::lower_and_upload(bool upload_state) {
   CU(cudaSetDevice(device));
   { std::string re = rt_stop(); if (!re.empty()) return re; } process_streak = 0;
+  // a looping sequencer (ReplayMode::Loop): every event of the bank carries the sequencer's loop period
+  {
+    double la = 0.0; bool any = false; size_t events = 0;
+    for (auto& n : nodes) { double t = 0.0; if (!event_loop(n.get(), &t)) continue; events++; if (!any) { la = t; any = true; } else if (t != la) return "#U the events of one bank belong to one sequencer: their loop periods differ"; }
+    if (la > 0.0 && events != nodes.size()) return "#U a looping sequencer bank holds events only";
+    loop_arg = la;
+  }
   // 1. lower every voice, group into classes keyed by (type expression, uniform words)
   struct Low { std::string key; Lowering l; std::string sig; };
   std::vector<Low> lows(nodes.size());
@@ -180,7 +189,7 @@ std::string Bank::lower_and_upload(bool upload_state) {
   const bool same_shape = classes.size() == fresh.size() && std::equal(classes.begin(), classes.end(), fresh.begin(), [](const VoiceClass& a, const VoiceClass& b) {
                             return a.sig == b.sig && a.voices == b.voices && a.uniform == b.uniform; });
   if (!same_shape) {
-    for (auto& c : classes) { cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows); cudaFree(c.d_dry2); cudaFree(c.d_partial2); cudaFree(c.d_cx); cudaFree(c.d_cxl); cudaFree(c.d_th); cudaFree(c.d_tl); cudaFree(c.d_crows); for (int q = 0; q < 2; q++) { if (c.e_dry[q]) cudaEventDestroy(c.e_dry[q]); if (c.e_fdn[q]) cudaEventDestroy(c.e_fdn[q]); } if (c.cstream) cudaStreamDestroy(c.cstream); if (c.e_done) cudaEventDestroy(c.e_done); }
+    for (auto& c : classes) { cudaFree(c.d_params); cudaFree(c.d_state); cudaFree(c.d_state0); cudaFree(c.d_uniform); cudaFree(c.d_rowmap); cudaFree(c.d_dline); cudaFree(c.d_partial); cudaFree(c.d_ring); cudaFree(c.d_dry); cudaFree(c.d_dryrows); cudaFree(c.d_dry2); cudaFree(c.d_partial2); cudaFree(c.d_cx); cudaFree(c.d_cxl); cudaFree(c.d_th); cudaFree(c.d_tl); cudaFree(c.d_crows); for (int q = 0; q < 2; q++) { if (c.e_dry[q]) cudaEventDestroy(c.e_dry[q]); if (c.e_fdn[q]) cudaEventDestroy(c.e_fdn[q]); } if (c.cstream) cudaStreamDestroy(c.cstream); if (c.e_done) cudaEventDestroy(c.e_done); }
     classes = std::move(fresh);
     upload_state = true;
   }
@@ -193,7 +202,7 @@ std::string Bank::lower_and_upload(bool upload_state) {
       for (int k = 0; k < NS; k++) S[(size_t)k * V + i] = l.S[k];
       rows[i] = c.voices[i] * (uint32_t)nout;
     }
-    c.state0 = S;
+    c.state0 = S; c.state0_stale = true;
     if (!same_shape) {
       std::string e;
       if (!(e = dev_alloc(&c.d_params, P.size())).empty()) return e;
@@ -299,15 +308,36 @@ std::string Bank::set(uint32_t voice, const Setting& st) {  // AudioUnit::set (s
     if (c.np) CU(cudaMemcpy2DAsync(c.d_params + i, (size_t)Vc * 4, l.P.data(), 4, 4, c.np, cudaMemcpyHostToDevice, stream));
     CU(cudaStreamSynchronize(stream));  // `l` is pageable and goes out of scope
     for (uint32_t k = 0; k < c.ns; k++) c.state0[(size_t)k * Vc + i] = l.S[k];
+    c.state0_stale = true;
     nodes[voice] = std::move(trial);
     return "";
   }
   return "internal: voice not found in any class";
 }
 
-void Bank::advance_clock(uint64_t n) {   // what every Event<X> voice does to its own clock (nodes.cuh Event::plan)
-  const double unit_rate = net_rate ? (double)(float)sr : sr, sd = 1.0 / unit_rate;
-  for (uint64_t t0 = 0; t0 < n; t0 += 64) seq_time = seq_time + sd * (double)std::min<uint64_t>(64, n - t0);
+double Bank::loop_point() const {
+  if (!(loop_arg > 0.0)) return std::numeric_limits<double>::infinity();
+  const double unit_rate = net_rate ? (double)(float)sr : sr;
+  return std::max(64.0 * (1.0 / unit_rate), std::round(loop_arg * unit_rate) / unit_rate);
+}
+void Bank::advance_clock(uint64_t n) {   // what every Event<X> voice does to its own clock (nodes.cuh Event::plan / at_sample)
+  const double unit_rate = net_rate ? (double)(float)sr : sr, sd = 1.0 / unit_rate, lp = loop_point();
+  for (uint64_t t0 = 0; t0 < n; t0 += 64) {
+    const uint64_t size = std::min<uint64_t>(64, n - t0);
+    if (!(loop_arg > 0.0)) { seq_time = seq_time + sd * (double)size; continue; }
+    const double x = std::round(std::max(0.0, lp - seq_time) * unit_rate);
+    const uint64_t loop_size = x > 0.0 ? (uint64_t)x : 0;
+    seq_time = std::min(seq_time + sd * (double)size, lp);
+    if (loop_size < size) seq_time = std::min(0.0 + sd * (double)(size - loop_size), lp);   // wrapped: the rest of the block counts from 0
+  }
+}
+std::string Bank::state0_to_device(VoiceClass& c, const uint32_t** out) {
+  *out = nullptr;
+  if (!(loop_arg > 0.0) || c.state0.empty() || c.sig.compare(0, 6, "Event<") != 0) return "";
+  if (!c.d_state0) { std::string e = dev_alloc(&c.d_state0, c.state0.size()); if (!e.empty()) return e; c.state0_stale = true; }
+  if (c.state0_stale) { CU(cudaMemcpy(c.d_state0, c.state0.data(), c.state0.size() * 4, cudaMemcpyHostToDevice)); c.state0_stale = false; }
+  *out = c.d_state0;
+  return "";
 }
 
 // `l`: the words to run with. `reset_state`: the construction-time state that reset() restores (defaults to l.S).
@@ -322,6 +352,7 @@ std::string Bank::upload_voice(uint32_t voice, const Lowering& l, bool with_stat
     if (with_state && c.fdn) return "#U voices of a two-stage (FDN reverb) class cannot be replaced in place";
     if (c.np) CU(cudaMemcpy2DAsync(c.d_params + i, (size_t)Vc * 4, l.P.data(), 4, 4, c.np, cudaMemcpyHostToDevice, stream));
     for (uint32_t k = 0; k < c.ns; k++) c.state0[(size_t)k * Vc + i] = reset_state ? (*reset_state)[k] : l.S[k];
+    c.state0_stale = true;
     if (with_state) {
       if (c.ns) CU(cudaMemcpy2DAsync(c.d_state + i, (size_t)Vc * 4, l.S.data(), 4, 4, c.ns, cudaMemcpyHostToDevice, stream));
       if (c.dl_floats) CU(cudaMemset2DAsync(c.d_dline + i, (size_t)Vc * 4, 0, 4, (size_t)c.dl_floats, stream));
@@ -335,6 +366,7 @@ std::string Bank::upload_voice(uint32_t voice, const Lowering& l, bool with_stat
 std::string Bank::edit_event(uint32_t voice, double end_time, double fade_out) {
   if (voice >= V()) return "#A edit: voice index out of range";
   CU(cudaSetDevice(device));
+  if (loop_arg > 0.0) return "#U edit: events of a looping sequencer are not edited on the device (their current times live in the state words)";
   if (!event_edit(nodes[voice].get(), end_time, fade_out)) return "#A edit: the voice is not a sequencer event";
   Lowering l;
   nodes[voice]->lower(l);
@@ -433,6 +465,7 @@ std::string Bank::regroup(HNode* node, int at, uint32_t* voice) {
       const uint32_t v = c.voices[i];
       if (v == nv) {   // the newcomer: live state (an event's clock = now); what reset() restores is its construction-time state
         for (uint32_t k = 0; k < c.ns && k < l.S.size(); k++) { S[(size_t)k * Vc + i] = l.S[k]; c.state0[(size_t)k * Vc + i] = l0.S[k]; }
+        c.state0_stale = true;
         continue;
       }
       for (auto& sv : saved) {
@@ -490,6 +523,7 @@ std::string Bank::slot_set(uint32_t voice, int ease, double fade_time, HNode* un
     CU(cudaMemcpy2DAsync(c.d_state + (size_t)1 * Vc + i, (size_t)Vc * 4, arm, 4, 4, 3, cudaMemcpyHostToDevice, stream));
     CU(cudaStreamSynchronize(stream));
     for (uint32_t k = 0; k < c.ns; k++) c.state0[(size_t)k * Vc + i] = l.S[k];   // reset() adopts the newest unit (:156-172)
+    c.state0_stale = true;
     nodes[voice] = std::move(trial);
     return "";
   }
@@ -500,6 +534,7 @@ std::string Bank::push_event(HNode* node, uint32_t* voice) {   // Sequencer::pus
   std::unique_ptr<HNode> n(node);
   double s0, e0;
   if (!n || !event_times(n.get(), &s0, &e0)) return "#A push: not a sequencer event (fdsp_event)";
+  if (loop_arg > 0.0) return "#U push: a looping sequencer bank takes its events before the first render";
   if (n->inputs() != nin || n->outputs() != nout) return "#U push: the event's arity differs from the bank's";
   CU(cudaSetDevice(device));
   const double unit_rate = net_rate ? (double)(float)sr : sr, sd = 1.0 / unit_rate;
@@ -607,6 +642,7 @@ std::string Bank::rt_process(uint32_t size, const float* in, float* out, bool* s
     CU(cudaMemcpyAsync(d_rt_relay, relay, 16, cudaMemcpyHostToDevice, stream));
     CU(cudaMemsetAsync(d_ticket, 0, 4, stream));
     BankArgs a;
+    { std::string se = state0_to_device(c, &a.state0); if (!se.empty()) return se; } a.dl_floats = (uint32_t)c.dl_floats;
     a.params = c.d_params; a.state = c.d_state; a.uniform = c.d_uniform; a.dline = c.d_dline; a.wt = d_wt; a.in = nullptr; a.out = nullptr; a.partial = d_rt_partial;
     a.V = c.V(); a.n = 64; a.vpc = vpc; a.in_stride = 0; a.in_offset = 0; a.out_stride = 0; a.out_offset = 0; a.row_map = c.d_rowmap;
     a.sr = (float)sr; a.sd64 = (float)(1.0 / sr); a.sd32 = 1.0f / (float)sr; a.ticket = d_ticket; a.mix = nullptr; a.mix_stride = 0; a.mix_offset = 0; a.mix_accumulate = 0;
@@ -711,11 +747,26 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
     bool concurrent = classes.size() > 1 && !pipelined && len > 64 && !getenv("FDSP_NO_CONCURRENT");
     for (auto& c : classes) concurrent = concurrent && !c.fdn;
     if (concurrent) CU(cudaEventRecord(e_begin, stream));
-    for (auto& c : classes) {
+    // Launch order of concurrent classes: the class with the longest dependency chain per sample (a heavy serial leaf on its spine, which
+    // is what StagePlan reports as stages > 1) goes first, on a stream of the highest priority. Its CTAs carry the wavetables (~190 KB of
+    // shared memory): if CTAs of two light classes reach an SM first they do not fit beside them and the critical class starts late by a
+    // light class's whole run. (Measured on B200, config 5: 7.45 ms per 16 384-sample chunk inside a 3-chunk render against 6.35 alone.)
+    // The partial mixes are reduced below in class order whatever the launch order.
+    std::vector<size_t> order(classes.size());
+    for (size_t q = 0; q < order.size(); q++) order[q] = q;
+    if (concurrent && !getenv("FDSP_NO_HEAVY_FIRST"))
+      std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return (classes[x].k && classes[x].k->stages > 1) > (classes[y].k && classes[y].k->stages > 1); });
+    for (size_t oi = 0; oi < order.size(); oi++) {
+      auto& c = classes[order[oi]];
       const uint32_t V = c.V();
       cudaStream_t ks = stream;
       if (concurrent) {
-        if (!c.cstream) { CU(cudaStreamCreateWithFlags(&c.cstream, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&c.e_done, cudaEventDisableTiming)); }
+        if (!c.cstream) {
+          int lo = 0, hi = 0;
+          CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = greatest priority (numerically lowest)
+          CU(cudaStreamCreateWithPriority(&c.cstream, cudaStreamNonBlocking, (c.k && c.k->stages > 1) ? hi : lo));
+          CU(cudaEventCreateWithFlags(&c.e_done, cudaEventDisableTiming));
+        }
         ks = c.cstream;
         CU(cudaStreamWaitEvent(ks, e_begin, 0));
       }
@@ -764,6 +815,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
         if (pipelined && c.fdn && c.k && c.partial2_floats < need) { std::string e = dev_alloc(&c.d_partial2, (size_t)grid * nout * PIPE_CHUNK); if (!e.empty()) return e; c.partial2_floats = (size_t)grid * nout * PIPE_CHUNK; }
       }
       BankArgs a;
+      { std::string se = state0_to_device(c, &a.state0); if (!se.empty()) return se; } a.dl_floats = (uint32_t)c.dl_floats;
       a.params = c.d_params; a.state = c.d_state; a.uniform = c.d_uniform; a.dline = c.d_dline; a.wt = d_wt;
       a.in = in_dev; a.out = want_v ? out_dev_c : nullptr; a.partial = want_m ? c.d_partial : nullptr;
       a.V = V; a.n = len; a.vpc = vpc;

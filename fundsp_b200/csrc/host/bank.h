@@ -39,6 +39,8 @@ struct VoiceClass {
   // warp schedulers with a single warp)
   cudaStream_t cstream = nullptr; cudaEvent_t e_done = nullptr;
   std::vector<uint32_t> state0;     // initial state, SoA [NS][V]
+  // looping sequencer banks: the reset image also lives on the device (Event<X> resets its unit from it when the event ends, src/sequencer.rs:631-633)
+  uint32_t* d_state0 = nullptr; bool state0_stale = true;
   uint32_t* d_params = nullptr; uint32_t* d_state = nullptr; uint32_t* d_uniform = nullptr; uint32_t* d_rowmap = nullptr;
   float* d_dline = nullptr; float* d_partial = nullptr; size_t partial_floats = 0;
   uint32_t V() const { return (uint32_t)voices.size(); }
@@ -81,7 +83,10 @@ struct Bank {
   // Sequencer banks (voices made by mk_event): the sequencer clock, replicated on the host with the device's own arithmetic
   // (time += sample_duration * block for every 64-sample block and the tail), live edits and reuse of finished voices
   double seq_time = 0.0;
+  double loop_arg = 0.0;              // ReplayMode::Loop(t) of the sequencer the events came from (0: no loop); every event of the bank carries the same t
+  double loop_point() const;          // Sequencer::reset :644-650: max(64 samples, t rounded to a sample), +inf without a loop
   void advance_clock(uint64_t n);
+  std::string state0_to_device(VoiceClass& c, const uint32_t** out);   // (re)uploads the reset image of an event class of a looping bank
   std::string upload_voice(uint32_t voice, const Lowering& l, bool with_state, const std::vector<uint32_t>* reset_state = nullptr);
   std::string edit_event(uint32_t voice, double end_time, double fade_out);   // Sequencer::edit
   std::string replace_voice(uint32_t voice, HNode* node);                     // a new unit in the slot of a voice of the same class; consumes node

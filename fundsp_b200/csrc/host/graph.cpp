@@ -4,6 +4,8 @@
 #include "graph.h"
 #include "../dsp/libm.cuh"
 
+#include <cmath>
+#include <limits>
 #include <memory>
 #include <algorithm>
 #include <cassert>
@@ -605,19 +607,36 @@ struct ResampleN : HNode {  // src/resample.rs:210-300
 };
 struct EventN : HNode {  // one Sequencer event as a voice (src/sequencer.rs:55-92 Event, :768-843 process); device: nodes.cuh Event<X>
   Kid x; double start, end, fade_in, fade_out, sr = DEFAULT_SR, time0 = 0.0; int ease; int status0 = 0;
+  double loop_arg = 0.0;   // ReplayMode::Loop(t) of the sequencer this event belongs to (0: none)
+  double cs = 0.0, ce = 0.0; bool shifted = false;   // current start / end after re-rating shifts (see set_sample_rate); valid when shifted
   EventN(HNode* x_, double s, double e, int ease_, double fi, double fo) : x(x_), start(s), end(e), fade_in(fi), fade_out(fo), ease(ease_) {}
   int inputs() const override { return 0; } int outputs() const override { return x->outputs(); }
   uint64_t id() const override { return 64; }
   void reset() override { x->reset(); }
-  void set_sample_rate(double s) override { sr = s; x->set_sample_rate(s); }
+  static double loop_point_at(double loop_arg, double rate) { return std::max(64.0 * (1.0 / rate), std::round(loop_arg * rate) / rate); }   // Sequencer::reset :644-650
+  // Sequencer::set_sample_rate (:685-701) as written: on a CHANGE of rate every ready event is moved to `active`, then reset() runs — which in
+  // loop mode moves every active event back by the (new) loop point and leaves it active. An event pushed at the default rate and then re-rated
+  // therefore plays its first period shifted: already over (it ends at once, is reset and starts again at its own time) or — when it straddles
+  // the loop point — with its tail at the very beginning. Restated so that a re-rated looping bank equals a re-rated reference sequencer.
+  void set_sample_rate(double s) override {
+    if (loop_arg > 0.0 && s != sr) { if (!shifted) { cs = start; ce = end; shifted = true; } const double lp = loop_point_at(loop_arg, s); cs -= lp; ce -= lp; }
+    sr = s; x->set_sample_rate(s);
+  }
   void set(const Setting& s) override { x->set(s); }
   AttoHash ping(bool probe, AttoHash h) override { return x->ping(probe, h); }   // the sequencer never pings its units (AudioUnit::ping default)
   void sig(std::string& o) const override { o += "Event<"; x->sig(o); o += ">"; }
   static void p64(Lowering& l, double v) { uint64_t b; memcpy(&b, &v, 8); l.P.push_back((uint32_t)b); l.P.push_back((uint32_t)(b >> 32)); }
   void lower(Lowering& l) const override {
     p64(l, sr); p64(l, start); p64(l, end); p64(l, fade_in); p64(l, fade_out); l.P.push_back((uint32_t)ease);
+    // loop point as Sequencer::reset computes it (:644-650): at least 64 samples, rounded to the nearest sample; +inf when the sequencer does not loop
+    const double sd = 1.0 / sr;
+    (void)sd;
+    p64(l, loop_arg > 0.0 ? loop_point_at(loop_arg, sr) : std::numeric_limits<double>::infinity());
     uint64_t tb; memcpy(&tb, &time0, 8);
-    l.su((uint32_t)tb); l.su((uint32_t)(tb >> 32)); l.su((uint32_t)status0);   // sequencer time at construction (0 unless pushed into a running bank), status ready
+    l.su((uint32_t)tb); l.su((uint32_t)(tb >> 32)); l.su((uint32_t)(shifted ? 1 : status0));   // sequencer time at construction (0 unless pushed into a running bank), status ready (re-rated loop event: active)
+    const double cs0 = shifted ? cs : start, ce0 = shifted ? ce : end;
+    uint64_t sb, eb; memcpy(&sb, &cs0, 8); memcpy(&eb, &ce0, 8);
+    l.su((uint32_t)sb); l.su((uint32_t)(sb >> 32)); l.su((uint32_t)eb); l.su((uint32_t)(eb >> 32));   // current start / end (a loop wrap moves them while the event sounds)
     x->lower(l);
   }
   HCLONE(EventN)
@@ -1059,6 +1078,18 @@ bool event_times(const HNode* n, double* start, double* end) {
   if (!e) return false;
   *start = e->start; *end = e->end;
   return true;
+}
+bool event_loop(const HNode* n, double* loop_seconds) {
+  const EventN* e = dynamic_cast<const EventN*>(n);
+  if (!e) return false;
+  *loop_seconds = e->loop_arg;
+  return true;
+}
+HNode* mk_event_loop(HNode* x, double start, double end, int fade_ease, double fade_in, double fade_out, double loop_seconds) {
+  if (!(loop_seconds >= 0.0) || std::isinf(loop_seconds)) { delete x; return nullptr; }
+  HNode* n = mk_event(x, start, end, fade_ease, fade_in, fade_out);
+  if (n) static_cast<EventN*>(n)->loop_arg = loop_seconds;
+  return n;
 }
 bool event_set_clock(HNode* n, double time) {
   EventN* e = dynamic_cast<EventN*>(n);

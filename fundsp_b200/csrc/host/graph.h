@@ -118,6 +118,8 @@ HNode* mk_limiter(int channels, float attack, float release);       // Limiter<N
 HNode* mk_event(HNode* x, double start, double end, int fade_ease, double fade_in, double fade_out);  // one Sequencer event (ID 64) as a voice; consumes x
 bool event_edit(HNode* n, double end_time, double fade_out);         // false when n is not an event
 bool event_times(const HNode* n, double* start, double* end);
+HNode* mk_event_loop(HNode* x, double start, double end, int fade_ease, double fade_in, double fade_out, double loop_seconds);  // an event of a ReplayMode::Loop(loop_seconds) sequencer
+bool event_loop(const HNode* n, double* loop_seconds);               // false when n is not an event; 0 = the event's sequencer does not loop
 bool event_set_clock(HNode* n, double time);                         // the sequencer time the event's own clock starts from
 // Envelope<F, E, R> (ID 14): `f(t, out[outputs], user)` is the closure E, evaluated ON THE HOST at the reference's sample points when the
 // graph is lowered (bank creation, sample-rate change, settings) for t <= horizon seconds; time_f64: F = f64 (else f32)

@@ -26,9 +26,11 @@ class ReplayMode:  # src/sequencer.rs:219-229
         return (2, float(t))
 
 
-def event(unit: An, start_time, end_time, fade_ease=Fade.Smooth, fade_in_time=0.0, fade_out_time=0.0):
-    """One sequencer event as a voice graph (what `Sequencer.voices()` is made of)."""
+def event(unit: An, start_time, end_time, fade_ease=Fade.Smooth, fade_in_time=0.0, fade_out_time=0.0, loop=0.0):
+    """One sequencer event as a voice graph (what `Sequencer.voices()` is made of). `loop`: the period of a `ReplayMode::Loop(loop)` sequencer."""
     _arity(unit.inputs() == 0, "event: the GPU event renders generators (inputs == 0)")
+    if loop:
+        return An("event_loop", (float(start_time), float(end_time), int(fade_ease), float(fade_in_time), float(fade_out_time), float(loop)), (unit,), 0, unit.outputs())
     return An("event", (float(start_time), float(end_time), int(fade_ease), float(fade_in_time), float(fade_out_time)), (unit,), 0, unit.outputs())
 
 
@@ -74,13 +76,17 @@ class Sequencer:
     def voices(self):
         """The events as voice graphs for a GPU bank (`GpuBank.from_sequencer`), in push order, with the edits recorded so far applied
         the way the reference applies the edit of a not-yet-active event (its end time and fade-out are replaced, :531-553).
-        Generators only, ReplayMode::None or All (a bank reset replays everything, which is ReplayMode::All)."""
+        Generators only. ReplayMode::None or All: a bank reset replays everything, which is ReplayMode::All. ReplayMode::Loop(t): every
+        event carries the loop period and wraps on the device (`Event<X>` in nodes.cuh); an edit recorded before the first render changes
+        the event's end for the first pass only in the reference (it sets `end_time`, not `original_end_time`, :531-553), which the
+        device event does not model: edits of a looping sequencer are refused."""
         _arity(self.nin == 0, "Sequencer.voices: the GPU sequencer renders generators (inputs == 0)")
-        _arity(self.mode[0] != 2, "Sequencer.voices: ReplayMode::Loop is not lowered to the GPU")
+        loop = self.mode[1] if self.mode[0] == 2 else 0.0
+        _arity(not (loop and self.edits), "Sequencer.voices: edits of a ReplayMode::Loop sequencer are not lowered to the GPU")
         ev = [list(e) for e in self.events]
         for k, end, fo, rel in self.edits:
             ev[k][1], ev[k][4] = end, fo     # time is 0 while describing: relative == absolute
-        return [event(u, s, e, ease, fi, fo) for s, e, ease, fi, fo, u, _ in ev]
+        return [event(u, s, e, ease, fi, fo, loop=loop) for s, e, ease, fi, fo, u, _ in ev]
 
     def node(self):
         """This sequencer as a graph node (`Net::wrap(Box::new(sequencer))` / a boxed AudioUnit inside an expression)."""
@@ -108,8 +114,8 @@ class GpuSequencer:
     front so that note-ons always find one (a spare is an event that ended at time 0)."""
 
     def __init__(self, outputs, mode=ReplayMode.None_, device=0, sample_rate=44100.0):
-        _arity(mode[0] != 2, "GpuSequencer: ReplayMode::Loop is not lowered to the GPU")
         self.nout, self.mode, self.device, self.sr = int(outputs), mode, device, float(sample_rate)
+        self.loop = float(mode[1]) if mode[0] == 2 else 0.0     # ReplayMode::Loop(t): events pushed before the first render loop on the device
         self.pending = []      # event expressions until the bank exists
         self.bank = None
         self.voice_of = {}     # EventId -> voice
@@ -129,7 +135,8 @@ class GpuSequencer:
     def _push(self, start, end, ease, fade_in, fade_out, unit):
         _arity(unit.inputs() == 0 and unit.outputs() == self.nout, "sequencer.push: unit arity differs from the sequencer's")
         assert fade_in <= end - start and fade_out <= end - start
-        ev = event(unit, start, end, ease, fade_in, fade_out)
+        _arity(not (self.loop and self.bank is not None), "GpuSequencer: a looping sequencer takes its events before the first render")
+        ev = event(unit, start, end, ease, fade_in, fade_out, loop=self.loop)
         eid = self.next_id; self.next_id += 1
         if self.bank is None:
             self.pending.append(ev); self.voice_of[eid] = len(self.pending) - 1
@@ -155,6 +162,7 @@ class GpuSequencer:
         return self.push(start_time, start_time + duration, fade_ease, fade_in_time, fade_out_time, unit)
 
     def edit(self, event_id, end_time, fade_out_time):
+        _arity(not self.loop, "GpuSequencer: edits of a ReplayMode::Loop sequencer are not lowered to the GPU")
         v = self.voice_of.get(event_id)
         if v is None:
             return             # an unknown or past event: a no-op, like the reference's edit

@@ -89,6 +89,12 @@ fdsp_node* fdsp_envelope(double interval, int outputs, int time_f64, fdsp_envelo
    accurate, the reference's rounding), with fade-in / fade-out of the given lengths; fade_ease 0 Fade::Power, 1 Fade::Smooth. A bank
    of events IS the sequencer: its mix output is Sequencer::process. Consumes x. */
 fdsp_node* fdsp_event(fdsp_node* x, double start, double end, int fade_ease, double fade_in, double fade_out);
+/* The same for a sequencer made with ReplayMode::Loop(loop_seconds) (src/sequencer.rs:219-229; loop_seconds == 0: fdsp_event): the event
+   keeps the sequencer's loop point (>= 64 samples, rounded to a sample, :644-650) and replays every period — an event that straddles the
+   loop point continues into the next period shifted by it, a finished one is reset (its unit back to its construction state, :622-639)
+   and starts again. All voices of a looping bank are events with the same loop_seconds, pushed before the first render; the block path
+   is the reference's AS WRITTEN: the samples of a 64-block behind the wrap are rendered but not delivered (:845-872). */
+fdsp_node* fdsp_event_loop(fdsp_node* x, double start, double end, int fade_ease, double fade_in, double fade_out, double loop_seconds);
 fdsp_node* fdsp_limiter(int channels, float attack, float release); /* Limiter<N> ID 25 src/dynamics.rs:128 (`limiter`, `limiter_stereo`): look-ahead = attack seconds */
 fdsp_node* fdsp_meter(int kind, double timescale);             /* MeterNode ID 61 src/dynamics.rs:316: kind 0 Meter::Sample, 1 Peak(timescale), 2 Rms(timescale) */
 /* WavePlayer ID 65 src/wave.rs:739 (`playwave`, `playwave_at`): `samples` = wave.channel(ch) (copied); plays [start, end), then jumps to

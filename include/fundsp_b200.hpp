@@ -236,6 +236,10 @@ inline An slot(An unit) { return An(fdsp_slot(unit.release())); }               
 inline An event(An unit, double start_time, double end_time, Fade ease = Fade::Smooth, double fade_in = 0.0, double fade_out = 0.0) {
   return An(fdsp_event(unit.release(), start_time, end_time, (int)ease, fade_in, fade_out));
 }
+// an event of a `Sequencer::new(0, outputs, ReplayMode::Loop(loop_seconds))` (src/sequencer.rs:219-229)
+inline An event_loop(An unit, double start_time, double end_time, double loop_seconds, Fade ease = Fade::Smooth, double fade_in = 0.0, double fade_out = 0.0) {
+  return An(fdsp_event_loop(unit.release(), start_time, end_time, (int)ease, fade_in, fade_out, loop_seconds));
+}
 inline An oversample(An x) { return An(fdsp_oversample(x.release())); }                // x at twice the sample rate
 inline An resample(An x) { return An(fdsp_resample(x.release())); }                    // input = speed
 

@@ -119,6 +119,7 @@ int main(int argc, char** argv) {
     CtxT<false> c;
     c.wt = wt; c.tsm = 0u; c.tsm_kind = -1; c.V = 1; c.v = 0;
     c.sr = (float)sr; c.sd64 = (float)(1.0 / sr); c.sd32 = 1.0f / (float)sr;
+    c.rp = P.data(); c.rs0 = S.data(); c.ru = U.data(); c.dl_total = 0u;
     StageRegs<0> regs; uint32_t dl = 0;
     staged_load<0>(regs, P.data(), S.data(), U.data(), dl);
     std::vector<float> dline((size_t)dl + 1, 0.0f);
@@ -144,12 +145,14 @@ int main(int argc, char** argv) {
   CtxT<false> c;
   c.wt = wt; c.tsm = 0u; c.tsm_kind = -1; c.V = 1; c.v = 0;
   c.sr = (float)sr; c.sd64 = (float)(1.0 / sr); c.sd32 = 1.0f / (float)sr;
+  const std::vector<uint32_t> S0 = S;   // the reset image (Event<X> of a looping sequencer resets its unit from it)
+  c.rp = P.data(); c.rs0 = S0.data(); c.ru = U.data(); c.dl_total = 0u;
   Loader l{P.data(), S.data(), U.data(), 1u, 0u, 0u, 0u, 0u, 0u};
   G::load(r, l);
   if (l.pi > np || l.si > ns || l.ui > nu) { fprintf(stderr, "word layout mismatch: consumed %u/%u/%u of %u/%u/%u\n", l.pi, l.si, l.ui, np, ns, nu); return 8; }
   std::vector<float> dline((size_t)l.dl + 1, 0.0f);
   fprintf(stderr, "dl=%u\n", l.dl);   // the delay-line floats the device program claims (the host must allocate exactly this)
-  c.dl = dline.data();
+  c.dl = dline.data(); c.dl_total = l.dl;
   constexpr int IN = G::IN, OUT = G::OUT;
   constexpr bool GROUP = GroupPlan<G>::ok && GroupPlan<G>::code <= 256;   // bank_kernel's FDSP_GROUP_COST
   for (uint32_t t0 = 0; t0 < n; t0 += 64) {

@@ -29,6 +29,7 @@ extern "C" int fdsp_emul_launch_ex(const BankArgs* ap, int mode, const float* pe
     typename G::R r;
     CtxT<false> c;
     c.wt = a.wt; c.tsm = 0u; c.tsm_kind = -1; c.dl = a.dline; c.V = a.V; c.v = v; c.sr = a.sr; c.sd64 = a.sd64; c.sd32 = a.sd32;
+    c.rp = a.params; c.rs0 = a.state0; c.ru = a.uniform; c.dl_total = a.dl_floats;
     Loader l{a.params, a.state, a.uniform, a.V, v, 0u, 0u, 0u, 0u};
     G::load(r, l);
     const uint32_t b = v / vpc;

@@ -128,6 +128,10 @@ class OracleBackend:
         h = self.L.fo_sequencer(0, self.L.fo_outputs(x), 0, 0.0)
         self.L.fo_sequencer_push(h, start, end, ease, fi, fo, x)
         return h
+    def b_event_loop(self, start, end, ease, fi, fo, loop, x):   # ... of a ReplayMode::Loop(loop) sequencer (mode 2)
+        h = self.L.fo_sequencer(0, self.L.fo_outputs(x), 2, loop)
+        self.L.fo_sequencer_push(h, start, end, ease, fi, fo, x)
+        return h
     def b_limiter(self, n, a, r): return self.L.fo_limiter(n, a, r)
     def b_meter(self, kind, timescale): return self.L.fo_meter(kind, timescale)
     def b_playwave(self, samples, start, end, loop): return self.L.fo_playwave(_farr(samples), len(samples), start, end, loop)

@@ -34,9 +34,9 @@ def _net_ops(i):
 
 _WAVE = np.random.default_rng(77).uniform(-1.0, 1.0, (2, 1500)).astype(np.float32)   # a two-channel `Wave` for the sampler cases
 
-def _ev(unit, start, end, ease, fade_in, fade_out):
+def _ev(unit, start, end, ease, fade_in, fade_out, loop=0.0):
     from fundsp_b200.sequencer import event
-    return event(unit, start, end, ease, fade_in, fade_out)
+    return event(unit, start, end, ease, fade_in, fade_out, loop=loop)
 
 
 CASES = {
@@ -110,6 +110,10 @@ WIDER = {
     "events_saw_filter": lambda i: _ev(saw_hz(110.0 + 3.0 * i) >> lowpass_hz(900.0 + 20.0 * i, 2.0), (31.0 + 37.7 * i) / SR, (31.0 + 37.7 * i + 600.3 + 23.1 * i) / SR, 1, (40.5 + i) / SR, (200.0 + 5 * i) / SR),
     "events_power_fades_stereo": lambda i: _ev(sine_hz(300.0 + i) | noise().seed(i), (1.0 + 0.37 * i) * 64.0 / SR, ((1.0 + 0.37 * i) * 64.0 + 700.0 + 11.0 * i) / SR, 0, (100.0 + 3.3 * i) / SR, (300.0 + 2.1 * i) / SR),
     "events_moog_program": lambda i: _ev(saw_hz(80.0 + 4.0 * i) >> moog_hz(700.0 + 30.0 * i, 0.5) >> pan(0.02 * i - 0.4), (17.0 + 9.3 * i) / SR, (17.0 + 9.3 * i + 900.0) / SR, i % 2, (50.0 + i) / SR, (250.0 + 3 * i) / SR),
+    # events of a ReplayMode::Loop(777.25 / SR) sequencer: notes that end and restart every period (unit reset on the device, delay line cleared), notes that
+    # straddle the loop point, notes longer than a period; the silent block tails behind each wrap are the reference's (src/sequencer.rs:845-872 as written)
+    "events_looping": lambda i: _ev(saw_hz(90.0 + 5.0 * i) >> (pass_() & delay(0.0005 + 0.00001 * i)) >> moog_hz(900.0 + 25.0 * i, 0.4), (13.0 + 17.3 * i) / SR,
+                                    (13.0 + 17.3 * i + 300.0 + 19.7 * i) / SR, i % 2, (20.5 + i) / SR, (60.0 + 2 * i) / SR, loop=777.25 / SR),
     "events_short_and_late": lambda i: _ev(organ_hz(200.0 + 5.0 * i) >> declick_s(0.002), (i * 50.25) / SR, (i * 50.25 + 1.0 + 9.0 * (i % 13)) / SR, i % 2, 0.0, 0.0) if i % 3 else _ev(organ_hz(200.0 + 5.0 * i) >> declick_s(0.002), 5000.0 / SR, 6000.0 / SR, 1, 0.0, 0.0),
     "limiters": lambda i: noise().seed(i) * (1.0 + 0.2 * i) >> limiter(0.001 + 0.0004 * (i % 2), 0.01) | (noise().seed(i + 50) * (sine_hz(3.0) * 2.0 + 2.5) | sine_hz(300.0 + i) * 4.0) >> limiter_stereo(0.0005, 0.003 + 0.001 * (i % 3)),
     "meters": lambda i: noise().seed(i) * (0.2 + 0.02 * i) >> (meter(Meter.Sample) & meter(Meter.Peak(0.002 + 0.0005 * (i % 9))) & meter(Meter.Rms(0.001 + 0.0003 * (i % 7)))),

@@ -85,6 +85,62 @@ def test_sequencer_bank_matches_oracle_sequencer():
         assert _close(got, exp), (k, sz)
 
 
+def seq_loop_events(loop_samples, sr):
+    """A `Sequencer::new(0, 1, ReplayMode::Loop(t))`: the event of the reference's own loop test scaled to the period (tests/test_basic.rs:730-765: it
+    straddles the loop point and continues into the next period), notes that end and start again every period (their units are reset), a unit with
+    delay lines, fades of both kinds, an event that starts at 0 and one that outlasts a whole period."""
+    from fundsp_b200.prelude import dc, noise, sine_hz, saw_hz, moog_hz, lowpass_hz, delay, pass_
+    from fundsp_b200.sequencer import Sequencer, Fade, ReplayMode
+    T = loop_samples / sr
+    q = Sequencer(0, 1, ReplayMode.Loop(T))
+    q.push(12.0 / 79.0 * T, 89.0 / 79.0 * T, Fade.Smooth, 0.0, 0.0, dc(0.25))
+    q.push(0.10 * T, 0.45 * T, Fade.Smooth, 0.05 * T, 0.10 * T, sine_hz(440.0))
+    q.push(0.30 * T, 0.80 * T, Fade.Power, 0.02 * T, 0.03 * T, noise().seed(3) >> (pass_() & delay(0.0007)) >> lowpass_hz(900.0, 1.0))
+    q.push(0.0, 0.20 * T, Fade.Smooth, 0.0, 0.05 * T, saw_hz(300.0) >> moog_hz(1200.0, 0.4))
+    q.push(0.60 * T, 1.90 * T, Fade.Power, 0.10 * T, 0.20 * T, sine_hz(660.0) * 0.5)
+    return q
+
+
+@pytest.mark.parametrize("loop_samples,sr", [(79, 44100.0), (600, 44100.0), (1024, 44100.0), (3001, 44100.0), (600, 48000.0), (1024, 48000.0)])
+def test_looping_sequencer_bank_matches_oracle_sequencer(loop_samples, sr):
+    """ReplayMode::Loop on the device (`Event<X>` wraps its own clock, shifts a sounding event by the period, resets the unit of a finished one
+    from the class's reset image): per-voice rows bit-exact against one-event oracle Sequencers of the same mode, the mix against the
+    whole oracle Sequencer, over many periods in one launch and through process()-sized calls. The block path is the reference's as written
+    (src/sequencer.rs:845-872: the samples of a 64-block behind the wrap are rendered into a scratch buffer and never delivered)."""
+    from fundsp_b200.bank import GpuBank
+    from oracle import OracleUnit, lib as olib
+    olib().fo_set_denormal_emulation(0)
+    # sr = 44100 is the construction-time rate. At 48 kHz the sequencer is RE-RATED after its events were pushed, which the reference turns into
+    # a shift of every event by one loop period for the first pass (Sequencer::set_sample_rate :685-701 moves the ready events to `active`, then
+    # reset() in loop mode moves active events back by the loop point): restated by the host lowering (graph.cpp EventN::set_sample_rate).
+    n = max(64 * 40 + 37, int(3.3 * loop_samples))
+    q = seq_loop_events(loop_samples, sr)
+    b = GpuBank.from_sequencer(q, per_voice=True, mix=True, sample_rate=sr)
+    rows, mix = b.render_samples(n)
+    for v, ev in enumerate(seq_loop_events(loop_samples, sr).voices()):
+        u = OracleUnit(ev); u.set_sample_rate(sr)
+        want_v = u.process_many(n)
+        assert np.abs(want_v).max() > 1e-3, v
+        assert np.array_equal(rows[v], want_v), (loop_samples, v, int((rows[v] != want_v).sum()), float(np.abs(rows[v] - want_v).max()))
+    u = _oracle_seq(seq_loop_events(loop_samples, sr), sr)
+    want = u.process_many(n)
+    assert _close(mix, want)
+    assert abs(b.time() - olib().fo_sequencer_time(u.h)) < 1e-12, (b.time(), olib().fo_sequencer_time(u.h))
+    # more than one period must actually have been played: the second period carries sound
+    assert np.abs(want[:, loop_samples + 64:2 * loop_samples]).max() > 1e-3
+    # process()-sized calls: blocks that wrap in the middle, at their first sample, not at all
+    b2 = GpuBank.from_sequencer(seq_loop_events(loop_samples, sr), per_voice=False, mix=True, sample_rate=sr)
+    u2 = _oracle_seq(seq_loop_events(loop_samples, sr), sr)
+    for k, sz in enumerate([64, 61, 7, 64, 1, 33, 64, 64] * 12):
+        got, exp = b2.process(sz), u2.process(sz)
+        assert _close(got, exp), (loop_samples, k, sz)
+    assert abs(b2.time() - olib().fo_sequencer_time(u2.h)) < 1e-12
+    # edits and pushes into a running looping bank are refused, not mis-rendered
+    from fundsp_b200.capi import FdspError
+    with pytest.raises(FdspError):
+        b.edit_event(0, 0.001, 0.0)
+
+
 def test_sequencer_bank_live_edit_and_push():
     from fundsp_b200.bank import GpuBank
     from fundsp_b200.prelude import dc, sine_hz, saw_hz, lowpass_hz

@@ -44,6 +44,8 @@ def jobs():
                 add(capi.NodeHandle(mk(i)).signature(), (1,))
     for v in W.seq_five_events().voices():
         add(capi.NodeHandle(v).signature(), (2, 3))
+    for v in W.seq_loop_events(600, 44100.0).voices():                                       # test_looping_sequencer_bank_matches_oracle_sequencer (rows + mix, mix alone)
+        add(capi.NodeHandle(v).signature(), (2, 3))
     from fundsp_b200.sequencer import event
     for mk in (W.live_voice, W.arp_voice):
         add(capi.NodeHandle(event(mk(100.0), 0.0, 1.0)).signature(), (2,))
