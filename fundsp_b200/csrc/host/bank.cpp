@@ -3,6 +3,7 @@
 #include "../dsp/fdn_args.h"
 
 #include <algorithm>
+#include <mutex>
 #include <cmath>
 #include <limits>
 #include <chrono>
@@ -53,9 +54,14 @@ static bool tc_conv_wanted(const std::string& sig, const Lowering& l, int nout) 
 #endif
 }
 
+namespace {
+std::mutex g_rt_mu;          // registry of the bank that owns each device's resident process() kernel (see rt_stop)
+Bank* g_rt_owner[64] = {};
+}
 Bank::~Bank() {
   cudaSetDevice(device);
   rt_stop();
+  if (device >= 0 && device < 64) { std::lock_guard<std::mutex> lock(g_rt_mu); if (g_rt_owner[device] == this) g_rt_owner[device] = nullptr; }
   if (rt_ctl) cudaFreeHost(rt_ctl);
   cudaFree(d_rt_relay); cudaFree(d_rt_partial);
   for (auto& c : classes) {
@@ -603,11 +609,19 @@ static uint32_t staged_grid(uint32_t V, uint32_t* vpc) {
 }
 
 // ---- resident process() kernel
+// A resident kernel holds a CTA (and, with staged wavetables, nearly all shared memory) on every SM: anything else launched on the device
+// would sit behind it until its idle time-out. So at most one bank per device keeps one, and every entry point of EVERY bank of that
+// device — they all begin with rt_stop() — first asks the owner to leave. (Banks of one device are driven from one thread at a time,
+// like the units of the reference's audio thread; the registry itself is locked.)
 std::string Bank::rt_stop() {
+  Bank* other = nullptr;
+  if (device >= 0 && device < 64) { std::lock_guard<std::mutex> lock(g_rt_mu); other = g_rt_owner[device]; if (other == this || (other && !other->rt_running)) other = nullptr; }
+  if (other) { std::string e = other->rt_stop(); if (!e.empty()) return e; }
   if (!rt_running) return "";
   rt_ctl->doorbell = RT_QUIT;
   __sync_synchronize();
   rt_running = false;
+  if (device >= 0 && device < 64) { std::lock_guard<std::mutex> lock(g_rt_mu); if (g_rt_owner[device] == this) g_rt_owner[device] = nullptr; }
   CU(cudaStreamSynchronize(stream));   // the kernel has saved the state words
   return "";
 }
@@ -628,6 +642,7 @@ std::string Bank::rt_process(uint32_t size, const float* in, float* out, bool* s
   const uint32_t grid = bank_grid(c.V(), (uint32_t)c.k->threads, &vpc);
   if (grid > 148u) return "";                       // every CTA must be resident at once
   if (++process_streak < 3u && !rt_running) return "";   // a bank that is driven block by block: the third process() call in a row starts the kernel
+  if (!rt_running) { std::string re = rt_stop(); if (!re.empty()) return re; }   // (another bank of this device may own the resident slot)
   if (!rt_ctl) {
     CU(cudaHostAlloc((void**)&rt_ctl, sizeof(RtCtl), cudaHostAllocMapped));
     CU(cudaHostGetDevicePointer((void**)&rt_ctl_dev, rt_ctl, 0));
@@ -651,6 +666,7 @@ std::string Bank::rt_process(uint32_t size, const float* in, float* out, bool* s
     CU(c.k->launch_rt(a, rt, table_bytes_of(c, 64), stream));
     launches++;
     rt_running = true;
+    if (device >= 0 && device < 64) { std::lock_guard<std::mutex> lock(g_rt_mu); g_rt_owner[device] = this; }
     rt_seq = first - 1u;
   }
   const uint32_t seq = ++rt_seq;

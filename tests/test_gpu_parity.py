@@ -141,6 +141,29 @@ def test_resident_process_kernel_equals_launch_per_block(name, V, monkeypatch):
     assert np.array_equal(a[-6], a[-5])                 # the clone continues exactly like the original
 
 
+def test_two_banks_share_the_resident_slot(monkeypatch):
+    """A resident process() kernel occupies every SM; a second bank of the device (or any other launch) must not sit behind it until its
+    idle time-out. Two banks driven alternately, three blocks each, hand the slot over (every entry point of a bank first asks the owner of
+    the device's resident kernel to leave): same mixes as the launch-per-block path, and no second-long stalls."""
+    import time
+    from fundsp_b200.bank import GpuBank
+    def run(rt):
+        monkeypatch.setenv("FDSP_RT", rt)
+        a = GpuBank(workloads.build("saw_svf", 600), per_voice=False, mix=True, sample_rate=SR)
+        b = GpuBank(workloads.build("saw_svf", 500, first=600), per_voice=False, mix=True, sample_rate=SR)
+        a.process(64); b.process(64)                        # (first launches: module load, table upload)
+        t = time.perf_counter()
+        out = []
+        for _ in range(6):
+            out += [a.process(64) for _ in range(4)] + [b.process(64) for _ in range(4)]
+        _, tail = b.render_samples(300)                       # a render of one bank while the OTHER may hold the slot
+        out += [a.process(33), tail]
+        return out, time.perf_counter() - t
+    (x, tx), (y, ty) = run("1"), run("0")
+    assert all(np.array_equal(p, q) for p, q in zip(x, y))
+    assert tx < 1.0, (tx, ty)                                 # 12 hand-overs: an idle time-out alone is about a second
+
+
 def test_ragged_length_and_time_chunking():
     n = 16384 * 2 + 64 * 3 + 5  # crosses the kernel's time chunk and ends in a ragged block
     check("noise_svf", 130, n, exact=True)
