@@ -15,6 +15,7 @@ template <class G, int MODE, bool TB> cudaError_t launch_one(const BankArgs& a, 
     cudaError_t e = cudaFuncSetAttribute(bank_kernel<G, NT, MODE, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
+  if (launch_carveout() >= 0) cudaFuncSetAttribute(bank_kernel<G, NT, MODE, TB>, cudaFuncAttributePreferredSharedMemoryCarveout, launch_carveout());
   bank_kernel<G, NT, MODE, TB><<<grid, NT, smem, st>>>(a);
   return cudaGetLastError();
 }

@@ -763,26 +763,21 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
     bool concurrent = classes.size() > 1 && !pipelined && len > 64 && !getenv("FDSP_NO_CONCURRENT");
     for (auto& c : classes) concurrent = concurrent && !c.fdn;
     if (concurrent) CU(cudaEventRecord(e_begin, stream));
-    // Launch order of concurrent classes: the class with the longest dependency chain per sample (a heavy serial leaf on its spine, which
-    // is what StagePlan reports as stages > 1) goes first, on a stream of the highest priority. Its CTAs carry the wavetables (~190 KB of
-    // shared memory): if CTAs of two light classes reach an SM first they do not fit beside them and the critical class starts late by a
-    // light class's whole run. (Measured on B200, config 5: 7.45 ms per 16 384-sample chunk inside a 3-chunk render against 6.35 alone.)
-    // The partial mixes are reduced below in class order whatever the launch order.
+    // (Launching the class with the longest dependency chain first, on a high-priority stream, was measured on B200 and is WORSE for config 5:
+    // 26.4 ms per step against 22.9 in class order — its CTAs hold ~195 KB of shared memory, so every light class then waits for all of it.
+    // FDSP_HEAVY_FIRST=1 keeps that order for experiments; FDSP_CARVEOUT=<percent> makes every class kernel ask for the same carve-out.)
     std::vector<size_t> order(classes.size());
     for (size_t q = 0; q < order.size(); q++) order[q] = q;
-    if (concurrent && !getenv("FDSP_NO_HEAVY_FIRST"))
+    if (concurrent && getenv("FDSP_HEAVY_FIRST"))
       std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return (classes[x].k && classes[x].k->stages > 1) > (classes[y].k && classes[y].k->stages > 1); });
+    struct CarveGuard { int saved; CarveGuard() : saved(launch_carveout()) {} ~CarveGuard() { launch_carveout() = saved; } } carve_guard;
+    if (concurrent) { const char* cv = getenv("FDSP_CARVEOUT"); if (cv) launch_carveout() = atoi(cv); }
     for (size_t oi = 0; oi < order.size(); oi++) {
       auto& c = classes[order[oi]];
       const uint32_t V = c.V();
       cudaStream_t ks = stream;
       if (concurrent) {
-        if (!c.cstream) {
-          int lo = 0, hi = 0;
-          CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = greatest priority (numerically lowest)
-          CU(cudaStreamCreateWithPriority(&c.cstream, cudaStreamNonBlocking, (c.k && c.k->stages > 1) ? hi : lo));
-          CU(cudaEventCreateWithFlags(&c.e_done, cudaEventDisableTiming));
-        }
+        if (!c.cstream) { CU(cudaStreamCreateWithFlags(&c.cstream, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&c.e_done, cudaEventDisableTiming)); }
         ks = c.cstream;
         CU(cudaStreamWaitEvent(ks, e_begin, 0));
       }

@@ -203,6 +203,7 @@ struct JitProgram : Program {
     if (!f) return cudaErrorInvalidDeviceFunction;
     const size_t smem = tile + (tb ? table_bytes : 0);
     if (smem > 48 * 1024 && A.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    if (launch_carveout() >= 0) A.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, launch_carveout());
     BankArgs args = a; RtArgs r = rt;
     void* params[] = {&args, &r};
     const unsigned vpc = a.vpc ? a.vpc : (unsigned)threads, grid = (a.V + vpc - 1) / vpc;
@@ -223,6 +224,7 @@ struct JitProgram : Program {
     CUfunction f = variant(mode, tb, width);
     if (!f) return cudaErrorInvalidDeviceFunction;
     if (smem > 48 * 1024 && A.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    if (launch_carveout() >= 0) A.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, launch_carveout());
     BankArgs args = a;
     void* params[] = {&args};
     const unsigned vpc = a.vpc ? a.vpc : (unsigned)width, grid = (a.V + vpc - 1) / vpc;
@@ -239,6 +241,7 @@ struct JitProgram : Program {
     if (!f) return cudaErrorInvalidDeviceFunction;
     const size_t smem = tile + (tb ? table_bytes : 0);
     if (smem > 48 * 1024 && A.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    if (launch_carveout() >= 0) A.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, launch_carveout());
     BankArgs args = a;
     void* params[] = {&args};
     const unsigned vpc = a.vpc ? a.vpc : (unsigned)threads, grid = (a.V + vpc - 1) / vpc;

@@ -13,6 +13,12 @@ namespace fdsp { struct FdnArgs; struct RtArgs; }
 namespace fdsp {
 namespace host {
 
+// Preferred shared-memory carve-out (percent of the SM's unified L1 / shared memory) that the voice-kernel launchers apply to the kernel they
+// launch; -1 = leave the driver's choice. The concurrent classes of a multi-class bank set it to the maximum, so that a class whose CTAs
+// stage the wavetables (~195 KB) and the light classes beside it agree on ONE configuration and can share an SM (kernels that ask for
+// different carve-outs are not co-resident). Set and read by the thread that drives the bank.
+inline int& launch_carveout() { static thread_local int v = -1; return v; }
+
 struct KernelEntry {  // AOT table row
   const char* sig;
   int IN, OUT, NP, NS, NU;
