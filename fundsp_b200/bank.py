@@ -110,6 +110,10 @@ class GpuBank:
         """`Net::replace`: any unit of the bank's arity in the voice's place (fresh state); another graph class regroups the classes around it."""
         check(self.L.fdsp_bank_replace_voice(self.h, int(voice), unit.lower(GpuBackend())))
 
+    def crossfade_voice(self, voice, fade_ease, fade_time, unit):
+        """`Net::crossfade`: the voice fades to `unit` (any graph class of the bank's arity) over fade_time seconds, Fade.Power (0) or Fade.Smooth (1)."""
+        check(self.L.fdsp_bank_crossfade_voice(self.h, int(voice), int(fade_ease), float(fade_time), unit.lower(GpuBackend())))
+
     def remove_voice(self, voice):
         """`Net::remove`: the voice carries silence from now on (its place in the mix order stays)."""
         check(self.L.fdsp_bank_remove_voice(self.h, int(voice)))

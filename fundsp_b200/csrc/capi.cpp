@@ -307,6 +307,11 @@ API int fdsp_bank_replace_voice(fdsp_bank* b, uint32_t voice, fdsp_node* unit) {
   std::string e = b->b.replace_voice(voice, take(unit));
   return status(e, FDSP_ERR_ARG);
 }
+API int fdsp_bank_crossfade_voice(fdsp_bank* b, uint32_t voice, int fade_ease, float fade_time, fdsp_node* unit) {
+  if (!b) { fdsp_node_free(unit); return fail(FDSP_ERR_ARG, "null bank"); }
+  std::string e = b->b.crossfade_voice(voice, fade_ease, fade_time, take(unit));
+  return status(e, FDSP_ERR_ARG);
+}
 API int fdsp_bank_remove_voice(fdsp_bank* b, uint32_t voice) {
   if (!b) return fail(FDSP_ERR_ARG, "null bank");
   std::string e = b->b.remove_voice(voice);

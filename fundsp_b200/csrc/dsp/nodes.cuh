@@ -1588,6 +1588,84 @@ template <class X> struct Slot {
   static FDSP_DEV void end_simd(R& r) { X::end_simd(r.u[0]); X::end_simd(r.u[1]); }
 };
 
+// ---------------------------------------------------------------- Xfade<X, Y>: a Net vertex that crossfades from its unit X to a unit Y
+// of ANY graph class (Net::crossfade, src/net.rs:480-504; the arithmetic of src/vertex.rs:138-229, all in f32: fade_phase, fade_time and the
+// Net's f32 sample rate). While the fade runs both programs are evaluated (each through its own block path, like `unit.process` and
+// `next.process`); afterwards the voice is Y alone (`next_phase`). The host builds this class around a RUNNING voice: X's state words and
+// delay lines are carried over from the voice's old class (csrc/host/bank.cpp crossfade_voice).
+template <class X, class Y> struct Xfade {
+  static constexpr int NI = X::IN, NO = X::OUT;
+  static_assert(X::IN == Y::IN && X::OUT == Y::OUT, "Net::crossfade: the replacement has the arity of the unit it replaces");
+  FDSP_NODE(NI, NO, 3 + X::NP + Y::NP, 2 + X::NS + Y::NS, X::NU + Y::NU);
+  struct R {
+    float sr, fade_time, fade_phase; int ease, done;
+    int n_f; float fade, fade_d; bool swap_at_end;
+    typename X::R x; typename Y::R y;
+  };
+  static FDSP_DEV void load(R& r, Loader& l) {
+    r.sr = l.Pf(); r.fade_time = l.Pf(); r.ease = (int)l.P();
+    r.done = (int)l.S(); r.fade_phase = l.Sf();
+    r.n_f = 0; r.fade = r.fade_d = 0.0f; r.swap_at_end = false;
+    X::load(r.x, l); Y::load(r.y, l);
+  }
+  static FDSP_DEV void save(const R& r, Saver& s) { s.S((uint32_t)r.done); s.Sf(r.fade_phase); X::save(r.x, s); Y::save(r.y, s); }
+  static FDSP_DEV float at(int ease, float x) { return ease == 0 ? sine_ease_f(x) : smooth5f(x); }   // Fade::at (src/sequencer.rs:48-55)
+  template <bool T, class C> static FDSP_DEV void step(R& r, const C& c, const Fr<NI>& in, Fr<NO>& o) {
+    if (T) { if (r.done) Y::template step<true>(r.y, c, in, o); else X::template step<true>(r.x, c, in, o); return; }   // (a vertex of a voice bank is a root: not reached)
+    if (r.done) { Y::template step<false>(r.y, c, in, o); return; }
+    if (c.i == 0) {   // the block's plan, vertex.rs:173-176
+      const float left = (1.0f - r.fade_phase) * r.fade_time * r.sr;
+      const int phase_left = left > 0.0f ? (left < 1.0e9f ? (int)left : 1000000000) : 0;   // `as usize`, saturating
+      r.n_f = c.n < phase_left ? c.n : phase_left;
+      r.fade = r.fade_phase; r.fade_d = 1.0f / (r.fade_time * r.sr);
+      r.swap_at_end = phase_left <= c.n;
+    }
+    Fr<NO> y;
+    X::template step<false>(r.x, c, in, o);
+    Y::template step<false>(r.y, c, in, y);
+    if (c.i < r.n_f) {   // x *= at(1 - fade); x += y * at(fade): two passes over the block in the reference, the same f32 fade sequence in both
+      const float e1 = at(r.ease, 1.0f - r.fade), e2 = at(r.ease, r.fade);
+#pragma unroll
+      for (int k = 0; k < NO; k++) { const float a = o.v[k] * e1; o.v[k] = a + y.v[k] * e2; }
+      r.fade += r.fade_d;
+    } else {
+#pragma unroll
+      for (int k = 0; k < NO; k++) o.v[k] = y.v[k];
+    }
+    if (c.i == c.n - 1) {
+      r.fade_phase += (float)r.n_f / (r.fade_time * r.sr);
+      if (r.swap_at_end) { r.done = 1; r.fade_phase = 0.0f; }   // next_phase: the vertex's unit is Y from the next block on
+    }
+  }
+  typedef void GroupStep;
+  template <class C> static FDSP_DEV void step8(R& r, C& c, const Fr8<NI>& in, Fr8<NO>& o) {
+    if (r.done) { group_step<Y>(r.y, c, in, o); return; }
+    const int base = c.i;
+    Fr8<NI> ri = in;
+#pragma unroll 1
+    for (int j = 0; j < 8; j++) {
+      Fr<NI> a; Fr<NO> y;
+#pragma unroll
+      for (int k = 0; k < NI; k++) a.v[k] = ri.v[k][0];
+      c.i = base + j; c.first = (j == 0);
+      step<false>(r, c, a, y);
+#pragma unroll
+      for (int k = 0; k < NI; k++) {
+#pragma unroll
+        for (int q = 0; q < 7; q++) ri.v[k][q] = ri.v[k][q + 1];
+      }
+#pragma unroll
+      for (int k = 0; k < NO; k++) {
+#pragma unroll
+        for (int q = 0; q < 7; q++) o.v[k][q] = o.v[k][q + 1];
+        o.v[k][7] = y.v[k];
+      }
+    }
+    c.i = base; c.first = true;
+  }
+  static FDSP_DEV void end_simd(R& r) { X::end_simd(r.x); Y::end_simd(r.y); }
+};
+
 // ---------------------------------------------------------------- Limiter<N> (ID 25, src/dynamics.rs:56-243): look-ahead limiter.
 // A ring of L frames delays the audio; a binary max-tree over the last L amplitudes (ReduceBuffer, updated leaf-to-root per sample)
 // gives the window peak, which an asymmetric follower smooths into the gain. Ring and tree live in the class's delay-line storage:
@@ -2105,6 +2183,8 @@ template <class X> struct WaveKind<Oversample<X>> : WaveKind<X> {};
 template <class X> struct Cost<Oversample<X>> { static constexpr int value = 2 * Cost<X>::value + 150 * (X::IN + X::OUT) + 101; };
 template <class X> struct WaveKind<Slot<X>> : WaveKind<X> {};
 template <class X> struct Cost<Slot<X>> { static constexpr int value = 2 * Cost<X>::value + 101; };
+template <class X, class Y> struct WaveKind<Xfade<X, Y>> { static constexpr int value = WaveKind<X>::value >= 0 ? WaveKind<X>::value : WaveKind<Y>::value; };
+template <class X, class Y> struct Cost<Xfade<X, Y>> { static constexpr int value = Cost<X>::value + Cost<Y>::value + 101; };
 template <class X> struct WaveKind<FeedbackUnit<X>> : WaveKind<X> {};
 template <class X> struct Cost<FeedbackUnit<X>> { static constexpr int value = Cost<X>::value + 12 * X::IN; };
 template <class F> struct Cost<Reverb85<F>> { static constexpr int value = 1200 + 16 * Cost<F>::value; };
@@ -2138,6 +2218,7 @@ template <class X> struct GroupPlan<Thru<X>> : GroupPlan<X> {};
 template <int KIND, int OP, int N, class X> struct GroupPlan<Multi<KIND, OP, N, X>> { static constexpr bool ok = GroupPlan<X>::ok; static constexpr int code = N * GroupPlan<X>::code; };
 
 template <class X> struct GroupPlan<Slot<X>> { static constexpr bool ok = GroupPlan<X>::ok; static constexpr int code = GroupPlan<X>::code + 16; };
+template <class X, class Y> struct GroupPlan<Xfade<X, Y>> { static constexpr bool ok = GroupPlan<X>::ok && GroupPlan<Y>::ok; static constexpr int code = GroupPlan<X>::code + GroupPlan<Y>::code + 16; };
 template <class X> struct GroupPlan<Event<X>> { static constexpr bool ok = GroupPlan<X>::ok; static constexpr int code = GroupPlan<X>::code + 24; };
 template <int NIN, int NOUT, class... V, class OS> struct GroupPlan<Dag<NIN, NOUT, VList<V...>, OS>> {
   static constexpr bool ok = (true && ... && GroupPlan<typename V::Unit>::ok);

@@ -92,6 +92,7 @@ std::string Bank::init(std::vector<HNode*>& voices, int dev, uint32_t mode) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= dev) return "no usable CUDA device: fundsp_b200 has no CPU fallback";
   CU(cudaSetDevice(device));
+  { std::string re = rt_stop(); if (!re.empty()) return re; }   // (another bank's resident process() kernel would make the allocations below wait for its idle time-out)
   // `stream` carries the latency-bound voice programs (few CTAs, long serial chains) and gets the highest priority, so that in
   // the two-stage pipeline its CTAs are placed before the wide FDN kernel of the previous chunk (stream2) fills every SM.
   int prio_lo = 0, prio_hi = 0;
@@ -422,7 +423,7 @@ std::string Bank::remove_voice(uint32_t voice) {
 }
 
 // `at` < 0: append the unit as a new voice (add_voice); else put it in place of voice `at` (replace_voice across classes).
-std::string Bank::regroup(HNode* node, int at, uint32_t* voice) {
+std::string Bank::regroup(HNode* node, int at, uint32_t* voice, const Carry* carry) {
   std::unique_ptr<HNode> n(node);
   const char* what = at < 0 ? "add" : "replace";
   if (!n) return std::string("#A ") + what + ": null node";
@@ -434,10 +435,12 @@ std::string Bank::regroup(HNode* node, int at, uint32_t* voice) {
   const double unit_rate = net_rate ? (double)(float)sr : sr;
   n->set_sample_rate(unit_rate);
   Lowering l0, l;
-  n->lower(l0);
+  n->lower(l0);                                      // (a crossfading vertex lowers as ARRIVED: a bank reset leaves it at its second unit)
+  const bool xf = xfade_set_done(n.get(), false);   // ... and starts its life fading
   const bool ev = event_set_clock(n.get(), seq_time);
   n->lower(l);
   if (ev) event_set_clock(n.get(), 0.0);
+  if (xf) xfade_set_done(n.get(), true);
   if (!l.ok) return "#U " + l.why;
   { std::string sg, jerr; n->sig(sg); if (!get_program(sg, device, jerr)) return std::string("#U ") + what + ": no device program for `" + sg + "`: " + jerr; }
   // 1. read back what is running
@@ -472,6 +475,17 @@ std::string Bank::regroup(HNode* node, int at, uint32_t* voice) {
       if (v == nv) {   // the newcomer: live state (an event's clock = now); what reset() restores is its construction-time state
         for (uint32_t k = 0; k < c.ns && k < l.S.size(); k++) { S[(size_t)k * Vc + i] = l.S[k]; c.state0[(size_t)k * Vc + i] = l0.S[k]; }
         c.state0_stale = true;
+        if (carry) {   // a unit that keeps RUNNING inside the newcomer (the fading-out side of a crossfade): its words and delay lines move over
+          for (auto& sv : saved) {
+            auto it = std::lower_bound(sv.voices.begin(), sv.voices.end(), v);
+            if (it == sv.voices.end() || *it != v) continue;
+            const uint32_t j = (uint32_t)(it - sv.voices.begin()), Vo = (uint32_t)sv.voices.size();
+            if (carry->src_s + carry->ns > sv.ns || carry->dst_s + carry->ns > c.ns || carry->src_d + carry->nd > sv.dl || carry->dst_d + carry->nd > c.dl_floats) return "internal: crossfade carry out of range";
+            for (uint32_t k = 0; k < carry->ns; k++) S[(size_t)(carry->dst_s + k) * Vc + i] = sv.S[(size_t)(carry->src_s + k) * Vo + j];
+            for (uint64_t q = 0; q < carry->nd; q++) D[(size_t)(carry->dst_d + q) * Vc + i] = sv.D[(size_t)(carry->src_d + q) * Vo + j];
+            break;
+          }
+        }
         continue;
       }
       for (auto& sv : saved) {
@@ -491,6 +505,45 @@ std::string Bank::regroup(HNode* node, int at, uint32_t* voice) {
   dirty = was_dirty; seq_time = clock;
   if (voice) *voice = nv;
   return "";
+}
+
+// Net::crossfade (src/net.rs:480-504) on a running bank: the voice becomes a vertex that fades from its unit to `unit` — of ANY graph class —
+// over fade_time seconds (device: nodes.cuh Xfade<X, Y>, the arithmetic of src/vertex.rs:138-229) and is `unit` alone afterwards. The voice moves
+// to the class Xfade<old, new> (compiled first if new); the old unit keeps running inside it: its state words and delay lines are carried over.
+// A voice that has finished an earlier crossfade continues from its faded-in unit; while a fade is running the reference parks a further
+// edit as `latest` — here that call is refused (the caller retries after the fade).
+std::string Bank::crossfade_voice(uint32_t voice, int ease, float fade_time, HNode* unit) {
+  std::unique_ptr<HNode> n(unit);
+  if (voice >= V()) return "#A crossfade: voice index out of range";
+  if (!n || ease < 0 || ease > 1 || !(fade_time > 0.0f)) return "#A crossfade: needs a unit, fade 0 (Power) or 1 (Smooth) and a fade time > 0";
+  if (n->inputs() != nin || n->outputs() != nout) return "#U crossfade: the unit's arity differs from the bank's";
+  CU(cudaSetDevice(device));
+  { std::string re = rt_stop(); if (!re.empty()) return re; } process_streak = 0;
+  const HNode* cur = nodes[voice].get();
+  Carry carry{0, 0, 0, 0, 0, 0};
+  auto count = [](const HNode* h, uint32_t* ns, uint64_t* nd) { Lowering q; h->lower(q); *ns = (uint32_t)q.S.size(); *nd = 0; for (uint32_t d : q.dlen) *nd += d; return q.ok; };
+  std::unique_ptr<HNode> old;
+  if (const HNode* y = xfade_unit(cur, 1)) {   // the vertex crossfaded before: it must have arrived at its second unit
+    for (auto& c : classes) {
+      auto it = std::lower_bound(c.voices.begin(), c.voices.end(), voice);
+      if (it == c.voices.end() || *it != voice) continue;
+      CU(cudaStreamSynchronize(stream));
+      uint32_t done = 0;
+      CU(cudaMemcpy(&done, c.d_state + (size_t)(it - c.voices.begin()), 4, cudaMemcpyDeviceToHost));   // state word 0 of Xfade: done
+      if (!done) return "#U crossfade: a crossfade is in progress on this voice; call again when it has finished";
+    }
+    uint32_t xs = 0; uint64_t xd = 0;
+    if (!count(xfade_unit(cur, 0), &xs, &xd) || !count(y, &carry.ns, &carry.nd)) return "internal: crossfade: lowering failed";
+    carry.src_s = 2u + xs; carry.src_d = xd;
+    old.reset(y->clone());
+  } else {
+    if (!count(cur, &carry.ns, &carry.nd)) return "internal: crossfade: lowering failed";
+    old.reset(cur->clone());
+  }
+  carry.dst_s = 2u; carry.dst_d = 0;      // Xfade<X, Y>: its own two state words, then X's, then Y's; X's delay lines first
+  HNode* x = mk_xfade(old.release(), n.release(), ease, fade_time);
+  if (!x) return "#A crossfade: the units do not fit one vertex";
+  return regroup(x, (int)voice, nullptr, &carry);
 }
 
 // Slot::set on a live bank (src/slot.rs:64-71,124-151): the unit goes into the idle instance of the voice's Slot<X> and the device
@@ -771,7 +824,9 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
     if (concurrent && getenv("FDSP_HEAVY_FIRST"))
       std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return (classes[x].k && classes[x].k->stages > 1) > (classes[y].k && classes[y].k->stages > 1); });
     struct CarveGuard { int saved; CarveGuard() : saved(launch_carveout()) {} ~CarveGuard() { launch_carveout() = saved; } } carve_guard;
-    if (concurrent) { const char* cv = getenv("FDSP_CARVEOUT"); if (cv) launch_carveout() = atoi(cv); }
+    // Concurrent classes ask for ONE carve-out, the maximum: the class that stages the wavetables (~195 KB per CTA) needs it anyway, and kernels
+    // that prefer different L1 / shared-memory splits do not share an SM. Measured on B200, config 5 (bench step, 3 chunks): 22.87 -> 18.72 ms.
+    if (concurrent) { const char* cv = getenv("FDSP_CARVEOUT"); launch_carveout() = cv ? atoi(cv) : 100; }
     for (size_t oi = 0; oi < order.size(); oi++) {
       auto& c = classes[order[oi]];
       const uint32_t V = c.V();
@@ -945,6 +1000,7 @@ std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_str
 }
 
 std::string Bank::ensure_staging(uint32_t chunk) {
+  { std::string re = rt_stop(); if (!re.empty()) return re; }   // allocations synchronise with the device: no resident kernel may be waiting on its doorbell
   const size_t rows = (size_t)V() * nout;
   std::string e;
   if (nin > 0 && in_cap < (size_t)nin * chunk) { if (!(e = dev_alloc(&d_in, (size_t)nin * chunk)).empty()) return e; in_cap = (size_t)nin * chunk; }
@@ -956,6 +1012,7 @@ std::string Bank::ensure_staging(uint32_t chunk) {
 
 std::string Bank::render_host(uint64_t n, const float* in, float* out_voices, float* out_mix) {
   CU(cudaSetDevice(device));
+  { std::string re = rt_stop(); if (!re.empty()) return re; }
   if (n == 0) return "";
   const size_t rows = (size_t)V() * nout;
   // chunk so that the per-voice staging buffer stays below ~512 MB

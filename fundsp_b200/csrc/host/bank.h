@@ -90,7 +90,9 @@ struct Bank {
   std::string upload_voice(uint32_t voice, const Lowering& l, bool with_state, const std::vector<uint32_t>* reset_state = nullptr);
   std::string edit_event(uint32_t voice, double end_time, double fade_out);   // Sequencer::edit
   std::string replace_voice(uint32_t voice, HNode* node);                     // a new unit in the slot of a voice of the same class; consumes node
-  std::string regroup(HNode* unit, int at, uint32_t* voice);                  // classes rebuilt around one new / replaced voice, running state of the others kept
+  struct Carry { uint32_t src_s, dst_s, ns; uint64_t src_d, dst_d, nd; };    // state words / delay-line floats of the OLD voice that move into the new one
+  std::string regroup(HNode* unit, int at, uint32_t* voice, const Carry* carry = nullptr);   // classes rebuilt around one new / replaced voice, running state of the others kept
+  std::string crossfade_voice(uint32_t voice, int ease, float fade_time, HNode* unit);   // Net::crossfade: fade the voice to a unit of any class; consumes unit
   std::string remove_voice(uint32_t voice);                                   // Net::remove: the voice carries silence from now on
   std::string add_voice(HNode* unit, uint32_t* voice);                        // grow by one voice, running state of the others preserved; consumes unit
   std::string slot_set(uint32_t voice, int ease, double fade_time, HNode* unit);   // Slot::set: crossfade the voice to a unit of the same class; consumes unit

@@ -708,6 +708,25 @@ struct SlotN : HNode {  // src/slot.rs: two instances of one class in the voice 
   }
   HCLONE(SlotN)
 };
+struct XfadeN : HNode {  // a Net vertex fading from unit x to unit y of any class (Net::crossfade, src/net.rs:480-504); device: nodes.cuh Xfade<X, Y>
+  Kid x, y; int ease; float fade_time; double sr = DEFAULT_SR;
+  bool done = true;   // what lower() writes: the RESET image has the vertex at its second unit (the fade is an edit of a running net); the bank lowers the live words with done = false
+  XfadeN(HNode* x_, HNode* y_, int ease_, float ft) : x(x_), y(y_), ease(ease_), fade_time(ft) {}
+  int inputs() const override { return y->inputs(); } int outputs() const override { return y->outputs(); }
+  uint64_t id() const override { return y->id(); }
+  void reset() override { x->reset(); y->reset(); }
+  void set_sample_rate(double s) override { sr = s; x->set_sample_rate(s); y->set_sample_rate(s); }
+  void set(const Setting& s) override { y->set(s); }                                   // settings address the vertex's newest unit
+  AttoHash ping(bool probe, AttoHash h) override { return y->ping(probe, h); }
+  void sig(std::string& o) const override { o += "Xfade<"; x->sig(o); o += ","; y->sig(o); o += ">"; }
+  void lower(Lowering& l) const override {
+    const float srf = (float)sr;                                                        // the Net's rate is f32 (src/net.rs:132)
+    uint32_t w; memcpy(&w, &srf, 4); l.P.push_back(w); memcpy(&w, &fade_time, 4); l.P.push_back(w); l.P.push_back((uint32_t)ease);
+    l.su(done ? 1u : 0u); l.su(0u);                                                     // done, fade_phase = 0.0f
+    x->lower(l); y->lower(l);
+  }
+  HCLONE(XfadeN)
+};
 struct VarN : HNode {  // the shared value is control-plane state: it enters as a parameter word and changes through Setting::value
   float value; explicit VarN(float v) : value(v) {}
   int inputs() const override { return 0; } int outputs() const override { return 1; }
@@ -1067,6 +1086,13 @@ bool slot_arm(HNode* n, HNode* unit, int inst, int ease, double fade_time) {
   return true;
 }
 bool is_slot(const HNode* n) { return dynamic_cast<const SlotN*>(n) != nullptr; }
+HNode* mk_xfade(HNode* x, HNode* y, int ease, float fade_time) {
+  if (!x || !y || x->inputs() != y->inputs() || x->outputs() != y->outputs() || ease < 0 || ease > 1 || !(fade_time > 0.0f)) { delete x; delete y; return nullptr; }
+  return new XfadeN(x, y, ease, fade_time);
+}
+// the two units of a crossfading vertex (null when n is not one); `newest` = the unit the vertex is (or will be) left with
+bool xfade_set_done(HNode* n, bool done) { XfadeN* q = dynamic_cast<XfadeN*>(n); if (!q) return false; q->done = done; return true; }
+const HNode* xfade_unit(const HNode* n, int which) { const XfadeN* q = dynamic_cast<const XfadeN*>(n); return q ? (which ? q->y.p.get() : q->x.p.get()) : nullptr; }
 bool event_edit(HNode* n, double end_time, double fade_out) {   // Sequencer::edit on an event (:441-483, no loop: start == original start)
   EventN* e = dynamic_cast<EventN*>(n);
   if (!e) return false;

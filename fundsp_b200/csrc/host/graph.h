@@ -126,6 +126,9 @@ bool event_set_clock(HNode* n, double time);                         // the sequ
 typedef void (*EnvelopeFn)(double t, double* out, void* user);
 HNode* mk_envelope(double interval, int outputs, int time_f64, EnvelopeFn f, void* user, double horizon);
 HNode* mk_oversample(HNode* x);                                      // Oversampler ID 51; consumes x
+HNode* mk_xfade(HNode* x, HNode* y, int ease, float fade_time);        // a Net vertex fading from x to y (Net::crossfade); consumes both
+bool xfade_set_done(HNode* n, bool done);                            // lower the vertex as already arrived at its second unit (what a bank reset restores)
+const HNode* xfade_unit(const HNode* n, int which);                  // 0: the unit being faded out, 1: the unit being faded in; null when n is not a crossfading vertex
 HNode* mk_slot(HNode* x);                                            // SlotBackend ID 78: a replaceable unit; consumes x
 bool slot_arm(HNode* slot, HNode* unit, int instance, int ease, double fade_time);   // consumes unit
 bool is_slot(const HNode* n);

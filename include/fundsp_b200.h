@@ -203,6 +203,12 @@ int fdsp_wave_load(const char* path, float* planar, uint64_t max_floats, uint32_
 int fdsp_bank_edit_event(fdsp_bank* b, uint32_t voice, double end_time, double fade_out);
 int fdsp_bank_push_event(fdsp_bank* b, fdsp_node* event, uint32_t* voice);
 int fdsp_bank_replace_voice(fdsp_bank* b, uint32_t voice, fdsp_node* unit);
+/* Net::crossfade (src/net.rs:480-504): the voice fades from its unit to `unit` — any graph class of the bank's arity — over fade_time seconds
+   with the curve fade_ease (0 Fade::Power, 1 Fade::Smooth), the reference's f32 vertex arithmetic (src/vertex.rs:138-229), and is `unit` alone
+   afterwards. Both programs run in the voice while the fade lasts (class Xfade<old, new>, compiled first if new; the old unit's running state
+   and delay lines are carried into it; slow path like replace_voice). A further crossfade of the same voice is accepted once the running one
+   has finished (FDSP_ERR_UNSUPPORTED until then: the reference would park it as `latest`). A bank reset leaves the voice at `unit`. Consumes unit. */
+int fdsp_bank_crossfade_voice(fdsp_bank* b, uint32_t voice, int fade_ease, float fade_time, fdsp_node* unit);
 int fdsp_bank_add_voice(fdsp_bank* b, fdsp_node* unit, uint32_t* voice);
 int fdsp_bank_remove_voice(fdsp_bank* b, uint32_t voice);
 double fdsp_bank_time(const fdsp_bank* b);

@@ -1902,9 +1902,58 @@ struct AdsrLive : Node {
 
 // ---- src/net.rs:73-146, 175-260, 556-820, 834-916, 1187-1286, 1383-1389; src/vertex.rs:16-122,162-170
 struct Port { int type; int node; int port; };  // type 0 Zero, 1 Global(port), 2 Local(node, port)
+inline float sine_easef(float x);   // (src/math.rs:453-458, defined with the sequencer below)
+inline float fade_atf(int fade, float x) { return fade == 0 ? sine_easef(x) : smooth5f(x); }   // Fade::at (src/sequencer.rs:48-55), 0 Power, 1 Smooth
 struct Vertex {
   Child unit; std::vector<Port> source; std::vector<float> input, output, tick_in, tick_out;
   bool has_sv = false; int sv_node = 0, sv_port = 0; int unplugged = 0; bool ordered = false;
+  // Net::crossfade (src/net.rs:480-504) / src/vertex.rs:35-39,124-245: the unit we are fading into, the one queued behind it, all in f32
+  Child next, latest; bool has_next = false, has_latest = false; int next_fade = 1, latest_fade = 1; float next_fade_time = 0.0f, latest_fade_time = 0.0f;
+  float fade_phase = 0.0f; std::vector<float> output_tmp, tick_out_tmp;
+  int outs() const { return unit->outputs(); }
+  void enqueue(Node* u, int fade, float fade_time) {   // vertex.rs:232-245
+    if (has_next) { latest = Child(u); has_latest = true; latest_fade = fade; latest_fade_time = fade_time; }   // replaces a queued unit
+    else { next = Child(u); has_next = true; next_fade = fade; next_fade_time = fade_time; fade_phase = 0.0f; }
+  }
+  void next_phase() {   // vertex.rs:124-135: the faded-in unit becomes the unit; the queued one (if any) starts fading in
+    unit = std::move(next);
+    next_fade = latest_fade; fade_phase = 0.0f; next_fade_time = latest_fade_time;
+    next = std::move(latest); has_next = has_latest; has_latest = false;
+  }
+  void tick(float sample_rate) {   // vertex.rs:138-160
+    unit->tick(tick_in.data(), tick_out.data());
+    if (has_next) {
+      const int no = outs();
+      if ((int)tick_out_tmp.size() < std::max(1, no)) tick_out_tmp.assign(std::max(1, no), 0.0f);
+      float f = fade_atf(next_fade, 1.0f - fade_phase);
+      for (int c = 0; c < no; c++) tick_out[c] *= f;
+      next->tick(tick_in.data(), tick_out_tmp.data());
+      f = fade_atf(next_fade, fade_phase);
+      for (int c = 0; c < no; c++) tick_out[c] += tick_out_tmp[c] * f;
+      fade_phase += 1.0f / (next_fade_time * sample_rate);
+      if (fade_phase >= 1.0f) next_phase();
+    }
+  }
+  void process(int size, const float* in, float sample_rate) {   // vertex.rs:163-229
+    unit->process(size, in, output.data());
+    if (has_next) {
+      const int no = outs();
+      if (output_tmp.size() < (size_t)std::max(1, no) * B) output_tmp.assign((size_t)std::max(1, no) * B, 0.0f);
+      const float pl = (1.0f - fade_phase) * next_fade_time * sample_rate;
+      const size_t phase_left = pl != pl || pl <= 0.0f ? 0 : (pl >= 1.8446744073709552e19f ? SIZE_MAX : (size_t)pl);   // `as usize`
+      const int n = (int)std::min<size_t>((size_t)size, phase_left);
+      const float fade_d = 1.0f / (next_fade_time * sample_rate);
+      for (int c = 0; c < no; c++) { float fade = fade_phase; for (int i = 0; i < n; i++) { output[c * B + i] *= fade_atf(next_fade, 1.0f - fade); fade += fade_d; } }
+      next->process(size, in, output_tmp.data());
+      for (int c = 0; c < no; c++) {
+        float fade = fade_phase;
+        for (int i = 0; i < n; i++) { output[c * B + i] += output_tmp[c * B + i] * fade_atf(next_fade, fade); fade += fade_d; }
+        for (int i = n; i < size; i++) output[c * B + i] = output_tmp[c * B + i];
+      }
+      fade_phase += (float)n / (next_fade_time * sample_rate);
+      if (phase_left <= (size_t)size) next_phase();   // "We don't start fading in the latest unit until the next block."
+    }
+  }
 };
 struct Net : Node {
   int nin, nout; std::vector<Port> output_edge; std::vector<Vertex> vertex; std::vector<int> order; bool ordered = false;
@@ -1921,6 +1970,11 @@ struct Net : Node {
     v.tick_in.assign(std::max(1, unit->inputs()), 0.0f); v.tick_out.assign(std::max(1, unit->outputs()), 0.0f);
     vertex.push_back(std::move(v)); ordered = false;
     return (int)vertex.size() - 1;
+  }
+  void crossfade(int node, int fade, float fade_time, Node* unit) {   // src/net.rs:480-504 (no backend: enqueued at once)
+    assert(unit->inputs() == vertex[node].unit->inputs() && unit->outputs() == vertex[node].unit->outputs());
+    unit->set_sample_rate((double)sample_rate);
+    vertex[node].enqueue(unit, fade, fade_time);
   }
   void connect(int s, int sp, int t, int tp) { assert(s != t); vertex[t].source[tp] = Port{2, s, sp}; ordered = false; }
   void connect_input(int gi, int t, int tp) { vertex[t].source[tp] = Port{1, 0, gi}; ordered = false; }
@@ -2089,7 +2143,7 @@ struct Net : Node {
         Port s = v.source[c];
         v.tick_in[c] = s.type == 0 ? 0.0f : s.type == 1 ? in[s.port] : vertex[s.node].tick_out[s.port];
       }
-      v.unit->tick(v.tick_in.data(), v.tick_out.data());
+      v.tick(sample_rate);
     }
     for (int c = 0; c < nout; c++) {
       Port s = output_edge[c];
@@ -2102,13 +2156,13 @@ struct Net : Node {
     for (int ni : order) {
       Vertex& v = vertex[ni];
       if (v.has_sv) {
-        v.unit->process(size, vertex[v.sv_node].output.data() + v.sv_port * B, v.output.data());
+        v.process(size, vertex[v.sv_node].output.data() + v.sv_port * B, sample_rate);
       } else {
         for (int c = 0; c < v.unit->inputs(); c++) {
           Port s = v.source[c];
           for (int i = 0; i < len; i++) v.input[c * B + i] = s.type == 0 ? 0.0f : s.type == 1 ? in[s.port * B + i] : vertex[s.node].output[s.port * B + i];
         }
-        v.unit->process(size, v.input.data(), v.output.data());
+        v.process(size, v.input.data(), sample_rate);
       }
     }
     for (int c = 0; c < nout; c++) {

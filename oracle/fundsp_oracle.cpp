@@ -279,6 +279,7 @@ API void fo_net_pipe_input(Node* net, int t) { static_cast<Net*>(net)->pipe_inpu
 API void fo_net_pipe_output(Node* net, int s) { static_cast<Net*>(net)->pipe_output(s); }
 API void fo_net_pipe_all(Node* net, int s, int t) { static_cast<Net*>(net)->pipe_all(s, t); }
 API void fo_net_pass_through(Node* net, int gi, int go) { static_cast<Net*>(net)->pass_through(gi, go); }
+API void fo_net_crossfade(Node* net, int node, int fade, float fade_time, Node* unit) { static_cast<Net*>(net)->crossfade(node, fade, fade_time, unit); }   // Net::crossfade (src/net.rs:480-504)
 API int fo_net_size(Node* net) { return (int)static_cast<Net*>(net)->vertex.size(); }
 API int fo_net_has_cycle(Node* net) { Net* n = static_cast<Net*>(net); if (!n->ordered) n->determine_order(); return n->cycle ? 1 : 0; }
 API int fo_net_order(Node* net, int* out) { Net* n = static_cast<Net*>(net); if (!n->ordered) n->determine_order(); for (size_t i = 0; i < n->order.size(); i++) out[i] = n->order[i]; return (int)n->order.size(); }

@@ -58,7 +58,7 @@ def lib():
             "fo_net_connect": (None, [P, I, I, I, I]), "fo_net_connect_input": (None, [P, I, I, I]), "fo_net_connect_output": (None, [P, I, I, I]),
             "fo_net_pipe_input": (None, [P, I]), "fo_net_pipe_output": (None, [P, I]), "fo_net_pipe_all": (None, [P, I, I]),
             "fo_net_pass_through": (None, [P, I, I]), "fo_net_size": (I, [P]), "fo_net_has_cycle": (I, [P]), "fo_net_order": (I, [P, C.POINTER(I)]),
-            "fo_net_combine": (P, [I, P, P]),
+            "fo_net_combine": (P, [I, P, P]), "fo_net_crossfade": (None, [P, I, I, F, P]),
             "fo_bank_render": (None, [C.POINTER(P), I64, D, I64, FP, FP, FP, I]),
         }
         for name, (res, args) in sig.items():

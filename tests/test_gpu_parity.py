@@ -161,7 +161,7 @@ def test_two_banks_share_the_resident_slot(monkeypatch):
         return out, time.perf_counter() - t
     (x, tx), (y, ty) = run("1"), run("0")
     assert all(np.array_equal(p, q) for p, q in zip(x, y))
-    assert tx < 3.0, (tx, ty)                                 # 12 hand-overs: an idle time-out is about a second each
+    assert tx < 0.5, (tx, ty)                                 # 12 hand-overs and a render: one idle time-out alone is about a second
 
 
 def test_ragged_length_and_time_chunking():

@@ -386,3 +386,57 @@ def test_net_bank_replace_and_remove_vertices_across_classes():
     r2, _ = b.render_samples(200)
     u = OracleUnit(newcomer()); u.set_sample_rate(float(np.float32(SR)))
     assert not r2[13].any() and np.array_equal(r2[4], u.process_many(200))
+
+
+def test_net_bank_crossfades_vertices_across_classes():
+    """Net::crossfade (src/net.rs:480-504, src/vertex.rs:138-229) on a RUNNING bank made from a Net: a vertex fades to a unit of ANOTHER graph class
+    (device: Xfade<X, Y>; the old unit keeps running inside the new class with its state and delay lines carried over), with both curves, fades
+    that end inside a block, process()-sized calls during the fade, a second crossfade of a vertex that has arrived, and the refusal of one that
+    has not. The mix equals the oracle Net that receives the same `crossfade` calls bit for bit (it is summed in the Net's own order)."""
+    from fundsp_b200 import workloads
+    from fundsp_b200.bank import GpuBank
+    from fundsp_b200.capi import FdspError
+    from fundsp_b200.net import voice_net
+    from fundsp_b200.prelude import moog_hz, pan, noise, lowpass_hz, saw_hz, delay, pass_
+    from fundsp_b200.sequencer import Fade
+    from oracle import OracleBackend, OracleUnit, lib as olib
+    L = olib(); L.fo_set_denormal_emulation(0)
+    SR = 48000.0
+    V = 13
+    mk = lambda: voice_net([workloads.net_voice(i) for i in range(V)])
+    b = GpuBank.from_net(mk(), per_voice=True, mix=True, sample_rate=SR)
+    twin = GpuBank.from_net(mk(), per_voice=True, mix=True, sample_rate=SR)
+    u = OracleUnit(mk().node()); u.set_sample_rate(SR)
+    be = OracleBackend()
+    vertex_of = {b.voice_of_vertex(x): x for x in range(mk().size()) if b.voice_of_vertex(x) >= 0}
+    assert sorted(vertex_of) == list(range(V))
+
+    def both(n):
+        rows, mix = b.render_samples(n)
+        want = u.process_many(n)
+        assert np.array_equal(mix, want), (n, int((mix != want).sum()), float(np.abs(mix - want).max()))
+        return rows
+
+    both(1000 + 7); twin.render_samples(1000 + 7)
+    new_a = lambda: noise().seed(77) >> (pass_() & delay(0.0004)) >> lowpass_hz(700.0, 2.0) >> moog_hz(900.0, 0.3) >> pan(0.25)   # a class the bank does not have
+    new_c = lambda: workloads.net_voice(2 + 4 * 5)                                                                                  # a class it has (noise >> bandpass >> pan)
+    b.crossfade_voice(4, Fade.Smooth, 0.01, new_a());   L.fo_net_crossfade(u.h, vertex_of[4], Fade.Smooth, 0.01, new_a().lower(be))
+    b.crossfade_voice(9, Fade.Power, 0.0333, new_c());  L.fo_net_crossfade(u.h, vertex_of[9], Fade.Power, 0.0333, new_c().lower(be))
+    assert any("Xfade<" in c["signature"] for c in b.classes())
+    rows = both(300)                                                      # inside both fades
+    want_rows, _ = twin.render_samples(300)
+    changed = [v for v in range(V) if not np.array_equal(rows[v], want_rows[v])]
+    assert changed == [4, 9], changed                                    # every other voice just continues
+    with pytest.raises(FdspError):
+        b.crossfade_voice(4, Fade.Smooth, 0.01, new_c())                 # (the reference would park it as `latest`)
+    for sz in (64, 61, 7, 64, 64, 33, 64):                                # the 480-sample fade of voice 4 ends inside one of these blocks
+        got, exp = b.process(sz), u.process(sz)
+        assert np.array_equal(got, exp), sz
+    both(64 * 30 + 5)                                                     # past the end of the second fade (1598 samples)
+    # a vertex that has arrived fades again, from the unit it arrived at
+    b.crossfade_voice(4, Fade.Power, 0.004, workloads.net_voice(1)); L.fo_net_crossfade(u.h, vertex_of[4], Fade.Power, 0.004, workloads.net_voice(1).lower(be))
+    both(500)
+    # reset: the edited net, every vertex at its newest unit
+    b.reset(); u.reset()
+    r2 = both(300)
+    assert np.abs(r2[4]).max() > 1e-3

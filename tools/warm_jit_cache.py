@@ -54,6 +54,12 @@ def jobs():
     add(capi.NodeHandle(event(sine_hz(500.0) * 0.5, 0.0, 1.0)).signature(), (2,))
     from fundsp_b200 import workloads
     from fundsp_b200.sequencer import slot
+    # test_net_bank_crossfades_vertices_across_classes: the classes Xfade<old, new> the bank builds around the crossfading voices
+    from fundsp_b200.prelude import noise, pass_, delay, lowpass_hz, moog_hz, pan
+    sg = lambda g: capi.NodeHandle(g).signature()
+    new_a = noise().seed(77) >> (pass_() & delay(0.0004)) >> lowpass_hz(700.0, 2.0) >> moog_hz(900.0, 0.3) >> pan(0.25)
+    for x, y in ((workloads.net_voice(4), new_a), (workloads.net_voice(9), workloads.net_voice(22)), (new_a, workloads.net_voice(1))):
+        add("Xfade<" + sg(x) + "," + sg(y) + ">", (1,))
     add(capi.NodeHandle(workloads.build("saw_svf_events", 1)[0]).signature(), (2, 3))      # bench --workload saw_svf_events and its parity test
     add(capi.NodeHandle(slot(W.arp_voice(100.0))).signature(), (1,))                        # test_slot_crossfades_to_a_new_unit
     return sorted(out)
