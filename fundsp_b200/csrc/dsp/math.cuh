@@ -37,6 +37,12 @@ using std::isfinite;
 namespace fdsp {
 
 #define FDSP_DEV __device__ __forceinline__
+// cold paths that must NOT be inlined into a sample loop (coefficient recomputation behind an "input changed" test): one copy, out of line
+#ifdef FDSP_HOST_EMUL
+#define FDSP_COLD static inline
+#else
+#define FDSP_COLD static __device__ __noinline__
+#endif
 
 constexpr float TAU_F = 6.28318530717958647692f;  // f32::TAU
 constexpr float PI_F = 3.14159265358979323846f;   // f32::PI

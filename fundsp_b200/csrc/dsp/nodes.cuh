@@ -90,6 +90,9 @@ struct Empty {};
 template <class T> struct VoidT { typedef void type; };
 template <class Node, class = void> struct HasGroup { static constexpr bool value = false; };
 template <class Node> struct HasGroup<Node, typename VoidT<typename Node::GroupStep>::type> { static constexpr bool value = true; };
+// `typedef void SteadyGroup;` + `steady8` / `step8_steady`: a heavy leaf whose per-sample "input changed" test can be decided for the whole group
+template <class Node, class = void> struct HasSteady { static constexpr bool value = false; };
+template <class Node> struct HasSteady<Node, typename VoidT<typename Node::SteadyGroup>::type> { static constexpr bool value = true; };
 
 #ifndef FDSP_ROTATE_COST
 #define FDSP_ROTATE_COST 100   // leaves above this static cost are not unrolled over the group (their loop rotates the registers)
@@ -132,6 +135,9 @@ template <class Node, class C> FDSP_DEV void group_step(typename Node::R& r, C& 
     o = ro;
     c.i = base; c.first = true;
   } else {
+    if constexpr (HasSteady<Node>::value && C::UNROLL_HEAVY) {
+      if (Node::steady8(r, in)) { Node::step8_steady(r, in, o); return; }
+    }
     const int base = c.i;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -689,6 +695,20 @@ struct BiquadBank {  // src/biquad_bank.rs:9-117, ID 98: 8 independent DF1 lanes
   }
   static FDSP_DEV void end_simd(R&) {}
 };
+// Moog::set_cutoff_q (src/moog.rs:48-57). Out of line: the audio-rate form tests per sample whether (cutoff, q) changed, and an inlined
+// sinf + division behind that test put ~400 cold instructions between every two samples of the unrolled ladder (73 KB per 8-sample group:
+// instruction-fetch stalls on the recurrence's critical path).
+struct MoogCoefs { float p, k, rez; };
+FDSP_COLD MoogCoefs moog_coefs(float cutoff, float q, float sr) {
+  MoogCoefs o;
+  const float cc = 2.0f * cutoff / sr;
+  o.p = cc * (1.8f - 0.8f * cc);
+  o.k = 2.0f * m::sinf_(cc * 3.14159274101257324f * 0.5f) - 1.0f;
+  const float t1 = (1.0f - o.p) * 1.386249f;
+  const float t2 = 12.0f + t1 * t1;
+  o.rez = q * (t2 + 6.0f * t1) / (t2 - 6.0f * t1);
+  return o;
+}
 template <int NIN> struct Moog {  // src/moog.rs:11-117, ID 60
   FDSP_NODE(NIN, 1, NIN == 1 ? 3 : 0, 8, 0);
   struct R { float p, k, rez, s0, s1, s2, s3, px, ps0, ps1, ps2; float cutoff, q; };
@@ -705,21 +725,35 @@ template <int NIN> struct Moog {  // src/moog.rs:11-117, ID 60
       float cutoff = in.v[NIN > 1 ? 1 : 0], q = in.v[NIN > 2 ? 2 : 0];
       if (!(cutoff == r.cutoff && q == r.q)) {
         r.cutoff = cutoff; r.q = q;
-        float cc = 2.0f * cutoff / c.sr;
-        r.p = cc * (1.8f - 0.8f * cc);
-        r.k = 2.0f * m::sinf_(cc * 3.14159274101257324f * 0.5f) - 1.0f;
-        float t1 = (1.0f - r.p) * 1.386249f;
-        float t2 = 12.0f + t1 * t1;
-        r.rez = q * (t2 + 6.0f * t1) / (t2 - 6.0f * t1);
+        const MoogCoefs m = moog_coefs(cutoff, q, c.sr);
+        r.p = m.p; r.k = m.k; r.rez = m.rez;
       }
     }
-    float x = -r.rez * r.s3 + in.v[0];
+    o.v[0] = ladder(r, in.v[0]);
+  }
+  static FDSP_DEV float ladder(R& r, float in0) {   // :87-98
+    float x = -r.rez * r.s3 + in0;
     r.s0 = (x + r.px) * r.p - r.k * r.s0;
     r.s1 = (r.s0 + r.ps0) * r.p - r.k * r.s1;
     r.s2 = (r.s1 + r.ps1) * r.p - r.k * r.s2;
     r.s3 = m::tanhf_((r.s2 + r.ps2) * r.p - r.k * r.s3);
     r.px = x; r.ps0 = r.s0; r.ps1 = r.s1; r.ps2 = r.s2;
-    o.v[0] = r.s3;
+    return r.s3;
+  }
+  // Steady group (group_step, fully unrolled form): when none of the 8 samples changes (cutoff, q) — the normal case — the ladder runs its 8
+  // steps as straight-line code, without the "did an input change" test and its branch / reconvergence point between every two samples.
+  typedef void SteadyGroup;
+  static FDSP_DEV bool steady8(const R& r, const Fr8<NIN>& in) {
+    bool same = true;
+    if (NIN > 1) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) same = same && in.v[NIN > 1 ? 1 : 0][j] == r.cutoff && in.v[NIN > 2 ? 2 : 0][j] == r.q;
+    }
+    return same;
+  }
+  static FDSP_DEV void step8_steady(R& r, const Fr8<NIN>& in, Fr8<1>& o) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) o.v[0][j] = ladder(r, in.v[0][j]);
   }
   static FDSP_DEV void end_simd(R&) {}
 };

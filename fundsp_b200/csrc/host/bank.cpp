@@ -179,6 +179,14 @@ std::string Bank::lower_and_upload(bool upload_state) {
         if ((uint32_t)c.k->NP != c.np - lo.l.extraP || (uint32_t)c.k->NS != c.ns || (uint32_t)c.k->NU != nu_static || c.k->IN != nin || c.k->OUT != nout)
           return "internal: host lowering of `" + lo.sig + "` disagrees with the device word layout";
       }
+      {   // reset exemptions of this graph class, in the class's own word / delay-line coordinates
+        for (auto& r : lo.l.keepS) if (r.second > r.first) c.keep_s.emplace_back(r.first, r.second);
+        std::vector<uint64_t> doff(lo.l.dlen.size() + 1, 0);
+        const size_t nd_lines = c.fdn ? lo.l.dlen.size() - 32 : lo.l.dlen.size();   // the last 32 lines of an FDN class live in its rings
+        for (size_t k = 0; k < lo.l.dlen.size(); k++) doff[k + 1] = doff[k] + (k < nd_lines ? lo.l.dlen[k] : 0u);
+        for (auto& r : lo.l.keepD) if (r.second > r.first && r.second <= nd_lines) c.keep_d.emplace_back(doff[r.first], doff[r.second]);
+        std::sort(c.keep_s.begin(), c.keep_s.end()); std::sort(c.keep_d.begin(), c.keep_d.end());
+      }
       fresh.push_back(std::move(c));
     } else ci = it->second;
     fresh[ci].voices.push_back((uint32_t)v);
@@ -624,8 +632,14 @@ std::string Bank::reset() {  // AudioUnit::reset: back to the construction-time 
   CU(cudaSetDevice(device));
   { std::string re = rt_stop(); if (!re.empty()) return re; } process_streak = 0;
   for (auto& c : classes) {
-    if (!c.state0.empty()) CU(cudaMemcpyAsync(c.d_state, c.state0.data(), c.state0.size() * 4, cudaMemcpyHostToDevice, stream));
-    if (c.dl_floats) CU(cudaMemsetAsync(c.d_dline, 0, (size_t)c.dl_floats * c.V() * sizeof(float), stream));
+    // everything goes back to its construction-time value EXCEPT what the reference's reset leaves alone (keep_s / keep_d)
+    const size_t Vc = c.V();
+    { uint64_t at = 0;
+      auto span = [&](uint64_t a, uint64_t b) -> cudaError_t { return b > a ? cudaMemcpyAsync(c.d_state + a * Vc, c.state0.data() + a * Vc, (size_t)(b - a) * Vc * 4, cudaMemcpyHostToDevice, stream) : cudaSuccess; };
+      if (!c.state0.empty()) { for (auto& k : c.keep_s) { CU(span(at, k.first)); at = std::max(at, k.second); } CU(span(at, c.ns)); } }
+    { uint64_t at = 0;
+      auto span = [&](uint64_t a, uint64_t b) -> cudaError_t { return b > a ? cudaMemsetAsync(c.d_dline + a * Vc, 0, (size_t)(b - a) * Vc * sizeof(float), stream) : cudaSuccess; };
+      if (c.dl_floats) { for (auto& k : c.keep_d) { CU(span(at, k.first)); at = std::max(at, k.second); } CU(span(at, c.dl_floats)); } }
     if (c.ring_floats) CU(cudaMemsetAsync(c.d_ring, 0, (size_t)c.ring_floats * c.V() * sizeof(float), stream));
     if (c.conv) { CU(cudaMemsetAsync(c.d_cx, 0, (size_t)c.V() * c.conv_stride * sizeof(float), stream)); CU(cudaMemsetAsync(c.d_cxl, 0, (size_t)c.V() * c.conv_stride * sizeof(float), stream)); }
   }

@@ -39,6 +39,8 @@ struct VoiceClass {
   // warp schedulers with a single warp)
   cudaStream_t cstream = nullptr; cudaEvent_t e_done = nullptr;
   std::vector<uint32_t> state0;     // initial state, SoA [NS][V]
+  // what AudioUnit::reset leaves alone (Lowering::keepS / keepD): state word ranges and delay-line float ranges (per voice), ascending
+  std::vector<std::pair<uint64_t, uint64_t>> keep_s, keep_d;
   // looping sequencer banks: the reset image also lives on the device (Event<X> resets its unit from it when the event ends, src/sequencer.rs:631-633)
   uint32_t* d_state0 = nullptr; bool state0_stale = true;
   uint32_t* d_params = nullptr; uint32_t* d_state = nullptr; uint32_t* d_uniform = nullptr; uint32_t* d_rowmap = nullptr;

@@ -420,7 +420,9 @@ struct ReverbN : HNode {
   void sig(std::string& o) const override { o += "Reverb85<"; block[0].f0->sig(o); o += ">"; }
   void lower(Lowering& l) const override {
     l.p(a); l.s(0.0f);
+    const uint32_t s0 = (uint32_t)l.S.size(), d0 = (uint32_t)l.dlen.size();
     for (int i = 0; i < 4; i++) pre[i]->lower(l);
+    l.keepS.emplace_back(s0, (uint32_t)l.S.size()); l.keepD.emplace_back(d0, (uint32_t)l.dlen.size());   // Reverb::reset leaves `pre` alone (:215-228)
     for (auto& b : block) {
       b.delay->lower(l);
       for (auto& x : b.ap0) x->lower(l);
@@ -509,7 +511,10 @@ struct LimiterN : HNode {  // src/dynamics.rs:128-243
     const uint32_t L = length(); uint32_t leaf = 1; while (leaf < L) leaf <<= 1;   // usize::next_power_of_two
     l.U.push_back(L); l.U.push_back(leaf);
     l.p(follower.acoeff); l.p(follower.rcoeff);
-    l.su(0u); l.su(0u); l.s(1.0f); l.s(1.0f); l.s(0.0f); l.s(0.0f); l.s(0.0f);
+    l.su(0u); l.su(0u);
+    const uint32_t s0 = (uint32_t)l.S.size();
+    l.s(1.0f); l.s(1.0f); l.s(0.0f); l.s(0.0f); l.s(0.0f);
+    l.keepS.emplace_back(s0, (uint32_t)l.S.size());   // Limiter::reset = set_sample_rate: index, reducer and buffer are cleared, the follower keeps its state (:181-195)
     l.dlen.push_back((uint32_t)n * L + leaf + L + (L & 1u));
   }
   HCLONE(LimiterN)

@@ -54,6 +54,9 @@ struct Lowering {
   uint32_t extraU = 0;             // uniform words beyond the nodes' static NU (e.g. a Convolver's impulse response)
   uint32_t extraP = 0;             // per-voice parameter words beyond the static NP (an envelope's sampled closure values)
   uint32_t conv_K = 0, conv_off = 0;   // last Convolver lowered: taps, and the index of its header (K, ring length, then K coefficient words) in U
+  // [begin, end) of state words / of `dlen` entries that AudioUnit::reset leaves ALONE where the reference's reset does (Reverb::reset keeps
+  // its pre-delay allpasses, src/reverb.rs:215-228; Limiter::reset keeps its follower, src/dynamics.rs:181-195): Bank::reset skips them
+  std::vector<std::pair<uint32_t, uint32_t>> keepS, keepD;
   bool ok = true; std::string why; // set when a node has no device lowering
   void p(float f) { P.push_back(f2u(f)); }
   void s(float f) { S.push_back(f2u(f)); }

@@ -30,8 +30,12 @@ template <int I> struct StageEmul {
   static constexpr int K = StagePlan<G>::K;
   typedef typename ChainAt<(I < K ? I : 0), STG>::type S;
   template <int J> static void skip(Loader& l) { if constexpr (J < I) { typename ChainAt<J, STG>::type::R sk; ChainAt<J, STG>::type::load(sk, l); skip<J + 1>(l); } }
-  static void block(typename S::R& r, CtxT<false> c, int nb, const float* in /*[IN][64]*/, float* out /*[OUT][64]*/) {
+  static void block(typename S::R& r, CtxT<false> c0, int nb, const float* in /*[IN][64]*/, float* out /*[OUT][64]*/) {
     constexpr int IN = S::IN, OUT = S::OUT;
+    // like bank_kernel_st: a stage built around a heavy leaf runs the leaf's 8 steps fully unrolled (and takes its steady-group path)
+    CtxT<false, SpineHeavy<S>::value> c;
+    c.wt = c0.wt; c.tsm = c0.tsm; c.tsm_kind = c0.tsm_kind; c.dl = c0.dl; c.V = c0.V; c.v = c0.v; c.sr = c0.sr; c.sd64 = c0.sd64; c.sd32 = c0.sd32;
+    c.rp = c0.rp; c.rs0 = c0.rs0; c.ru = c0.ru; c.dl_total = c0.dl_total; c.i = 0; c.n = 0; c.first = false; c.rem = false;
     constexpr bool GROUP = GroupPlan<S>::ok && GroupPlan<S>::code <= 256;
     const int nfull = nb & ~7;
     c.n = nb; c.rem = false;

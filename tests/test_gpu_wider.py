@@ -440,3 +440,31 @@ def test_net_bank_crossfades_vertices_across_classes():
     b.reset(); u.reset()
     r2 = both(300)
     assert np.abs(r2[4]).max() > 1e-3
+
+
+# ---------------------------------------------------------------- AudioUnit::reset where the reference's reset is NOT "back to the constructed state"
+@pytest.mark.parametrize("name", ["reverb3_lowpass_loop", "limiters"])
+def test_bank_reset_leaves_alone_what_the_reference_reset_leaves_alone(name):
+    """Reverb::reset (src/reverb.rs:215-228) resets its eight loop blocks and the feedback sample but NOT its four pre-delay allpasses;
+    Limiter::reset (src/dynamics.rs:181-195) is set_sample_rate: index, reducer and buffer are cleared, the follower keeps its state.
+    `fdsp_bank_reset` follows both (Lowering::keepS / keepD): render, reset, render equals the oracle units doing the same, bit for bit — and
+    the second render differs from the first (something did survive the reset) for the reverb."""
+    from fundsp_b200.bank import GpuBank
+    from oracle import OracleUnit, lib as olib
+    from test_gpu_jit import CASES, SR
+    mk = {**CASES, **WIDER}[name]
+    olib().fo_set_denormal_emulation(0)
+    V, n1, n2 = 12, 1500 + 37, 900
+    b = GpuBank([mk(i) for i in range(V)], per_voice=True, sample_rate=SR)
+    g1, _ = b.render_samples(n1)
+    b.reset()
+    g2, _ = b.render_samples(n2)
+    for v in (0, 5, V - 1):
+        u = OracleUnit(mk(v)); u.set_sample_rate(SR)
+        o1 = u.process_many(n1)
+        u.reset()
+        o2 = u.process_many(n2)
+        assert np.array_equal(g1[v], o1), (name, v, "before the reset")
+        assert np.array_equal(g2[v], o2), (name, v, "after the reset", int((g2[v] != o2).sum()))
+    if name.startswith("reverb3"):
+        assert not np.array_equal(g2, g1[..., :n2])   # the pre-delay allpasses were still ringing
