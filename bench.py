@@ -146,6 +146,8 @@ def run_reference(a):
         Vg = V = min(V, 256)         # (a 1000-tap direct form on the CPU: a bounded number of voices stands for the bank)
     build = native_oracle()
     cores, core_info = host_cores()
+    from fundsp_b200 import capi, workloads
+    channels = capi.NodeHandle(workloads.build(a.workload, 1)[0]).outputs()   # host-side graph: no GPU involved
     # the whole step at N = 1 (and whenever it is at most ~1.5e9 voice-samples); beyond that a bounded sample of the step so that K
     # steps end within minutes on the host cores — the sample is stated, `ms_per_step` is what was measured, not an extrapolation
     ns = n if V * n <= 1.5e9 else max(64, int(1.5e9 / V) // 64 * 64)
@@ -166,12 +168,23 @@ def run_reference(a):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Msamples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a.workload, Vg), "voices_per_gpu": Vg, "voices_total": V, "sample_rate": SR, "block": 64, "seconds_per_step": a.seconds,
-                   "output": "index-order mix of all voices", "note": "C++ oracle restating the reference's block path (no Rust toolchain on the box)"},
+        "config": job_config(a, max(1, a.gpus), channels),
+        "note": "the reference's CPU algorithm for this path: C++ oracle restating the block path (no Rust toolchain on the box), index-order mix of all voices, host cores only"
+                + ("; the 1000-tap direct form is timed on %d voices standing for the bank" % V if a.workload == "conv" else ""),
         "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample, "single_core": per_core,
                          "samples_per_step_timed": ns, "samples_per_step_config": n},
         "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def job_config(a, world, channels):
+    """The configuration both arms print — identical keys and values for `bench.py` and `bench.py --impl reference` at the same flags."""
+    V0 = a.voices or HEADLINE[a.workload]
+    per, total = (V0 // world, V0) if a.scaling == "strong" else (V0, V0 * world)
+    return {"workload": workload_name(a.workload, V0), "voices_per_gpu": per, "voices_total": total, "sample_rate": SR, "block": 64, "seconds_per_step": a.seconds,
+            "output": "mix-down to %d channel(s)%s" % (channels, " + per-voice rows in HBM" if a.per_voice else ""),
+            "parallelism": "voices sharded x%d, one mix-down per step below the C ABI (NCCL send/recv gather over NVLink + rank-order fold)" % world if world > 1 else "1 GPU",
+            "l2": "flushed between timed steps (512 MB write)"}
 
 
 def workload_name(w, V):
@@ -386,10 +399,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a.workload, V * (world if a.scaling == "strong" else 1)), "voices_per_gpu": V, "voices_total": world * V, "sample_rate": SR, "block": 64,
-                   "seconds_per_step": a.seconds, "output": "mix-down to %d channel(s)%s" % (c, " + per-voice rows in HBM" if a.per_voice else ""),
-                   "parallelism": "voices sharded x%d, one mix-down per step below the C ABI (NCCL send/recv gather over NVLink + rank-order fold)" % world if world > 1 else "1 GPU", "l2": "flushed between timed steps (512 MB write)",
-                   "build_s": round(t_build, 3)},
+        "config": job_config(a, world, c), "build_s": round(t_build, 3),
         "e2e": {"value": e2e, "unit": "Msamples/s", "h2d_bytes_per_step": int(n * 4 if gate is not None else 0), "d2h_bytes_per_step": int(c * n * 4),
                 "call": "fdsp_bank_render(host buffers)" if world == 1 else "fdsp_bank_render_reduced(host buffers; D2H of the reduced mix on the root)", "ms_per_step": ms_e2e,
                 "process_granularity": {"value": proc_val, "unit": "Msamples/s", "us_per_call": t_p / pb * 1e6, "call": "fdsp_bank_process(64) per block, host buffers"}},
