@@ -399,6 +399,7 @@ std::string Bank::replace_voice(uint32_t voice, HNode* node) {
   n->sig(a); nodes[voice]->sig(b);
   // another graph class (Net::replace takes any unit of the same arity, src/net.rs:460-470): the voice moves to the class of its new graph —
   // the classes are regrouped around it, every other voice keeps its running state (the slow path, like add_voice)
+  slot_latest.erase(voice); xfade_latest.erase(voice);   // (a parked update belongs to the unit that leaves)
   if (a != b) return regroup(n.release(), (int)voice, nullptr);
   const double unit_rate = net_rate ? (double)(float)sr : sr;
   n->set_sample_rate(unit_rate);
@@ -519,7 +520,7 @@ std::string Bank::regroup(HNode* node, int at, uint32_t* voice, const Carry* car
 // over fade_time seconds (device: nodes.cuh Xfade<X, Y>, the arithmetic of src/vertex.rs:138-229) and is `unit` alone afterwards. The voice moves
 // to the class Xfade<old, new> (compiled first if new); the old unit keeps running inside it: its state words and delay lines are carried over.
 // A voice that has finished an earlier crossfade continues from its faded-in unit; while a fade is running the reference parks a further
-// edit as `latest` — here that call is refused (the caller retries after the fade).
+// edit as `latest`: so does the bank (bank.h `xfade_latest`, `slot_service`).
 std::string Bank::crossfade_voice(uint32_t voice, int ease, float fade_time, HNode* unit) {
   std::unique_ptr<HNode> n(unit);
   if (voice >= V()) return "#A crossfade: voice index out of range";
@@ -538,8 +539,22 @@ std::string Bank::crossfade_voice(uint32_t voice, int ease, float fade_time, HNo
       CU(cudaStreamSynchronize(stream));
       uint32_t done = 0;
       CU(cudaMemcpy(&done, c.d_state + (size_t)(it - c.voices.begin()), 4, cudaMemcpyDeviceToHost));   // state word 0 of Xfade: done
-      if (!done) return "#U crossfade: a crossfade is in progress on this voice; call again when it has finished";
+      if (!done) {
+        // Vertex::enqueue with `next` occupied: the edit waits as `latest`, a newer one replaces it (src/vertex.rs:203-218). Its program — the
+        // class Xfade<second unit, new unit> the voice will move to — is compiled now, so that a unit without a device program is refused here
+        std::unique_ptr<HNode> probe(mk_xfade(y->clone(), n->clone(), ease, fade_time));
+        std::string sg, jerr;
+        if (!probe) return "#A crossfade: the units do not fit one vertex";
+        probe->set_sample_rate(net_rate ? (double)(float)sr : sr);
+        { Lowering q; probe->lower(q); if (!q.ok) return "#U " + q.why; }
+        probe->sig(sg);
+        if (!get_program(sg, device, jerr)) return "#U crossfade: no device program for `" + sg + "`: " + jerr;
+        SlotLatest& w = xfade_latest[voice];
+        w.unit = std::move(n); w.ease = ease; w.fade_time = (double)fade_time;
+        return "";
+      }
     }
+    xfade_latest.erase(voice);
     uint32_t xs = 0; uint64_t xd = 0;
     if (!count(xfade_unit(cur, 0), &xs, &xd) || !count(y, &carry.ns, &carry.nd)) return "internal: crossfade: lowering failed";
     carry.src_s = 2u + xs; carry.src_d = xd;
@@ -555,13 +570,17 @@ std::string Bank::crossfade_voice(uint32_t voice, int ease, float fade_time, HNo
 }
 
 // Slot::set on a live bank (src/slot.rs:64-71,124-151): the unit goes into the idle instance of the voice's Slot<X> and the device
-// crossfades to it over fade_time seconds from the next block on. While a fade is running the reference parks a further update as
-// `latest`; here that call is refused (the caller retries after the fade).
+// crossfades to it over fade_time seconds from the next block on. While a fade is running the update is parked as `latest` (see bank.h).
 std::string Bank::slot_set(uint32_t voice, int ease, double fade_time, HNode* unit) {
   std::unique_ptr<HNode> n(unit);
   if (voice >= V()) return "#A slot: voice index out of range";
   if (!n || ease < 0 || ease > 1 || !(fade_time > 0.0)) return "#A slot: needs a unit, fade 0 (Power) or 1 (Smooth) and a fade time > 0";
   if (!is_slot(nodes[voice].get())) return "#A slot: the voice is not a slot (fdsp_slot)";
+  return slot_arm_now(voice, ease, fade_time, n.release(), false);
+}
+
+std::string Bank::slot_arm_now(uint32_t voice, int ease, double fade_time, HNode* unit, bool force) {
+  std::unique_ptr<HNode> n(unit);
   CU(cudaSetDevice(device));
   { std::string re = rt_stop(); if (!re.empty()) return re; } process_streak = 0;
   for (auto& c : classes) {
@@ -572,15 +591,22 @@ std::string Bank::slot_set(uint32_t voice, int ease, double fade_time, HNode* un
     CU(cudaStreamSynchronize(stream));
     uint32_t head[2] = {0, 0};   // which, has_next of this voice
     CU(cudaMemcpy2D(head, 4, c.d_state + i, (size_t)Vc * 4, 4, 2, cudaMemcpyDeviceToHost));
-    if (head[1]) return "#U slot: a crossfade is in progress on this voice; set again when it has finished";
+    const bool fading = head[1] != 0 && !force;
     const int inst = (int)(head[0] ^ 1u);
     // arm a COPY of the voice's host slot: a refused unit leaves the host graph as it was (it replaces the original after the upload)
     std::unique_ptr<HNode> trial(nodes[voice]->clone());
+    std::unique_ptr<HNode> parked(fading ? n->clone() : nullptr);   // a parked unit is checked now (with a copy), armed later
     if (!slot_arm(trial.get(), n.release(), inst, ease, fade_time)) return "#U slot: the unit's graph class differs from the slot's (same type expression needed)";
     Lowering l;
     trial->lower(l);
     if (!l.ok) return "#U " + l.why;
     if (l.U != c.uniform || l.P.size() != c.np || l.S.size() != c.ns) return "#U slot: the unit changes a class-uniform word (delay length, table, wave); rebuild the bank instead";
+    if (fading) {   // SlotBackend::handle_messages with `next` occupied: the update waits as `latest`, a newer one takes its place (:142-150)
+      SlotLatest& w = slot_latest[voice];
+      w.unit = std::move(parked); w.ease = ease; w.fade_time = fade_time;
+      return "";
+    }
+    slot_latest.erase(voice);
     const uint32_t xs = (c.ns - 4) / 2, s0 = 4 + (uint32_t)inst * xs;
     const uint64_t xd = c.dl_floats / 2;
     CU(cudaMemcpy2DAsync(c.d_params + i, (size_t)Vc * 4, l.P.data(), 4, 4, c.np, cudaMemcpyHostToDevice, stream));
@@ -595,6 +621,93 @@ std::string Bank::slot_set(uint32_t voice, int ease, double fade_time, HNode* un
     return "";
   }
   return "internal: voice not found in any class";
+}
+
+// Before a launch of n samples: a parked unit whose fade has ended is armed now (it starts fading with this launch's first block, the block
+// after the one in which `next_phase` ran, src/slot.rs:163-172, src/vertex.rs:124-136); for the fades that are still running, the block in
+// which each ends is found by replaying the device's per-block arithmetic (nodes.cuh Slot<X>::step in f64, Xfade<X, Y>::step in f32:
+// phase_left, n_f, fade_phase += n_f / (fade_time sr)) from the voice's fade_phase word.
+std::string Bank::slot_service(uint64_t n, uint64_t* cut) {
+  *cut = n;
+  auto locate = [&](uint32_t voice, VoiceClass** pc, uint32_t* pi) {
+    for (auto& c : classes) {
+      auto vi = std::lower_bound(c.voices.begin(), c.voices.end(), voice);
+      if (vi != c.voices.end() && *vi == voice) { *pc = &c; *pi = (uint32_t)(vi - c.voices.begin()); return true; }
+    }
+    return false;
+  };
+  // 1. arm what is ready. Arming a vertex regroups the classes, so the scan starts over after every arm.
+  for (bool again = true; again;) {
+    again = false;
+    CU(cudaStreamSynchronize(stream));
+    for (auto it = slot_latest.begin(); it != slot_latest.end(); ++it) {
+      VoiceClass* c = nullptr; uint32_t i = 0;
+      if (!locate(it->first, &c, &i) || !is_slot(nodes[it->first].get())) { slot_latest.erase(it); again = true; break; }
+      uint32_t has_next = 0;
+      CU(cudaMemcpy(&has_next, c->d_state + (size_t)1 * c->V() + i, 4, cudaMemcpyDeviceToHost));
+      if (has_next) continue;
+      const uint32_t voice = it->first;
+      SlotLatest w = std::move(it->second);
+      slot_latest.erase(it);
+      std::string e = slot_arm_now(voice, w.ease, w.fade_time, w.unit.release(), false);
+      if (!e.empty()) return e;
+      again = true; break;
+    }
+    if (again) continue;
+    for (auto it = xfade_latest.begin(); it != xfade_latest.end(); ++it) {
+      VoiceClass* c = nullptr; uint32_t i = 0;
+      if (!locate(it->first, &c, &i) || !xfade_unit(nodes[it->first].get(), 1)) { xfade_latest.erase(it); again = true; break; }
+      uint32_t done = 0;
+      CU(cudaMemcpy(&done, c->d_state + i, 4, cudaMemcpyDeviceToHost));
+      if (!done) continue;
+      const uint32_t voice = it->first;
+      SlotLatest w = std::move(it->second);
+      xfade_latest.erase(it);
+      std::string e = crossfade_voice(voice, w.ease, (float)w.fade_time, w.unit.release());
+      if (!e.empty()) return e;
+      again = true; break;
+    }
+  }
+  // 2. where do the running fades with a parked unit end?
+  auto consider = [&](uint64_t t_end) { if (t_end < *cut) *cut = t_end; };
+  for (auto& kv : slot_latest) {
+    VoiceClass* c = nullptr; uint32_t i = 0;
+    if (!locate(kv.first, &c, &i)) continue;
+    uint32_t w[2] = {0, 0};
+    CU(cudaMemcpy2D(w, 4, c->d_state + (size_t)2 * c->V() + i, (size_t)c->V() * 4, 4, 2, cudaMemcpyDeviceToHost));   // fade_phase (f64)
+    double fade_time = 0.0, rate = 0.0;
+    if (!slot_fade(nodes[kv.first].get(), &fade_time, &rate)) return "internal: a parked slot update on a voice that is not a slot";
+    const uint64_t bits = ((uint64_t)w[1] << 32) | w[0];
+    double phase; memcpy(&phase, &bits, 8);
+    for (uint64_t t = 0; t < n;) {
+      const int nb = (int)std::min<uint64_t>(64, n - t);
+      const double span = fade_time * rate;
+      const double left = (1.0 - phase) * span;
+      const int phase_left = left > 0.0 ? (left < 1.0e9 ? (int)left : 1000000000) : 0;
+      const int n_f = nb < phase_left ? nb : phase_left;
+      phase += (double)n_f / (fade_time * rate);
+      t += (uint64_t)nb;
+      if (phase_left <= nb) { consider(t); break; }
+    }
+  }
+  for (auto& kv : xfade_latest) {
+    VoiceClass* c = nullptr; uint32_t i = 0;
+    if (!locate(kv.first, &c, &i)) continue;
+    float phase = 0.0f;
+    CU(cudaMemcpy(&phase, c->d_state + (size_t)1 * c->V() + i, 4, cudaMemcpyDeviceToHost));   // fade_phase (f32)
+    float fade_time = 0.0f, rate = 0.0f;
+    if (!xfade_fade(nodes[kv.first].get(), &fade_time, &rate)) return "internal: a parked crossfade on a voice that is not a crossfading vertex";
+    for (uint64_t t = 0; t < n;) {
+      const int nb = (int)std::min<uint64_t>(64, n - t);
+      const float left = (1.0f - phase) * fade_time * rate;
+      const int phase_left = left > 0.0f ? (left < 1.0e9f ? (int)left : 1000000000) : 0;
+      const int n_f = nb < phase_left ? nb : phase_left;
+      phase += (float)n_f / (fade_time * rate);
+      t += (uint64_t)nb;
+      if (phase_left <= nb) { consider(t); break; }
+    }
+  }
+  return "";
 }
 
 std::string Bank::push_event(HNode* node, uint32_t* voice) {   // Sequencer::push on a running sequencer (src/sequencer.rs:319-360)
@@ -631,6 +744,14 @@ std::string Bank::push_event(HNode* node, uint32_t* voice) {   // Sequencer::pus
 std::string Bank::reset() {  // AudioUnit::reset: back to the construction-time state
   CU(cudaSetDevice(device));
   { std::string re = rt_stop(); if (!re.empty()) return re; } process_streak = 0;
+  while (!slot_latest.empty()) {   // SlotBackend::reset adopts the LATEST configuration (src/slot.rs:156-172): arm it (its words become the voice's reset image)
+    auto it = slot_latest.begin();
+    const uint32_t voice = it->first;
+    SlotLatest w = std::move(it->second);
+    slot_latest.erase(it);
+    std::string e = slot_arm_now(voice, w.ease, w.fade_time, w.unit.release(), true);
+    if (!e.empty()) return e;
+  }
   for (auto& c : classes) {
     // everything goes back to its construction-time value EXCEPT what the reference's reset leaves alone (keep_s / keep_d)
     const size_t Vc = c.V();
@@ -702,6 +823,7 @@ std::string Bank::rt_process(uint32_t size, const float* in, float* out, bool* s
   const char* rte = getenv("FDSP_RT");          // read per call: the tests toggle it inside one process
   const int on = rte ? atoi(rte) : 1;
   if (!on) { process_streak = 0; return ""; }
+  if (has_parked()) { process_streak = 0; return ""; }   // parked Slot / crossfade updates are armed between launches (render_device)
   if (classes.size() != 1 || !(out_mode & 2u) || tree_mix || nout > 8 || nin > 8) return "";
   VoiceClass& c = classes[0];
   if (c.fdn || c.conv || !c.k || !c.k->has_rt) return "";
@@ -774,6 +896,25 @@ std::string Bank::dom_mark(cudaStream_t st) {   // called in pairs: begin, end
 
 std::string Bank::render_device(uint64_t n, const float* in_dev, uint64_t in_stride, float* out_dev, uint64_t out_stride, float* mix_dev,
                                 uint64_t mix_stride) {
+  if (!has_parked()) return render_device_run(n, in_dev, in_stride, out_dev, out_stride, mix_dev, mix_stride);
+  // parked Slot updates: the launch is cut behind the block in which a running fade ends, the parked unit is armed, the rest follows
+  CU(cudaSetDevice(device));
+  { std::string re = rt_stop(); if (!re.empty()) return re; }
+  uint64_t done = 0;
+  do {
+    uint64_t cut = n - done;
+    std::string e = slot_service(n - done, &cut);
+    if (!e.empty()) return e;
+    if (cut == 0) break;
+    e = render_device_run(cut, in_dev ? in_dev + done : nullptr, in_stride, out_dev ? out_dev + done : nullptr, out_stride, mix_dev ? mix_dev + done : nullptr, mix_stride);
+    if (!e.empty()) return e;
+    done += cut;
+  } while (done < n);
+  return "";
+}
+
+std::string Bank::render_device_run(uint64_t n, const float* in_dev, uint64_t in_stride, float* out_dev, uint64_t out_stride, float* mix_dev,
+                                    uint64_t mix_stride) {
   CU(cudaSetDevice(device));
   { std::string re = rt_stop(); if (!re.empty()) return re; }
   if (!in_process) process_streak = 0;
@@ -1124,6 +1265,8 @@ std::string Bank::clone_into(Bank& dst) const {
     if (s.conv && d.conv) { CU(cudaMemcpy(d.d_cx, s.d_cx, (size_t)s.V() * s.conv_stride * 4, cudaMemcpyDeviceToDevice)); CU(cudaMemcpy(d.d_cxl, s.d_cxl, (size_t)s.V() * s.conv_stride * 4, cudaMemcpyDeviceToDevice)); }
   }
   dst.dirty = dirty; dst.seq_time = seq_time;
+  for (auto& kv : slot_latest) { SlotLatest& w = dst.slot_latest[kv.first]; w.unit.reset(kv.second.unit->clone()); w.ease = kv.second.ease; w.fade_time = kv.second.fade_time; }
+  for (auto& kv : xfade_latest) { SlotLatest& w = dst.xfade_latest[kv.first]; w.unit.reset(kv.second.unit->clone()); w.ease = kv.second.ease; w.fade_time = kv.second.fade_time; }
   return "";
 }
 

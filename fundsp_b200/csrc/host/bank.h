@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -98,6 +99,17 @@ struct Bank {
   std::string remove_voice(uint32_t voice);                                   // Net::remove: the voice carries silence from now on
   std::string add_voice(HNode* unit, uint32_t* voice);                        // grow by one voice, running state of the others preserved; consumes unit
   std::string slot_set(uint32_t voice, int ease, double fade_time, HNode* unit);   // Slot::set: crossfade the voice to a unit of the same class; consumes unit
+  // Slot::set while the voice is still fading: the reference parks the update as `latest` (a newer one replaces it) and starts fading to it in the
+  // block after the running fade has ended (src/slot.rs:136-161). The bank does the same: the unit waits here, `slot_service` finds the block in
+  // which the device's fade ends (the device's own f64 arithmetic, replayed from the voice's fade_phase word), render_device cuts the launch
+  // behind that block and arms the waiting unit into the instance that has just gone idle.
+  struct SlotLatest { std::unique_ptr<HNode> unit; int ease; double fade_time; };
+  std::map<uint32_t, SlotLatest> slot_latest;
+  std::map<uint32_t, SlotLatest> xfade_latest;   // the same for Net::crossfade on a vertex that is still fading (`latest` of src/vertex.rs:124-136, :181-245)
+  bool has_parked() const { return !slot_latest.empty() || !xfade_latest.empty(); }
+  std::string slot_arm_now(uint32_t voice, int ease, double fade_time, HNode* unit, bool force);   // consumes unit; force: also while a fade is running (reset adopts `latest`)
+  std::string slot_service(uint64_t n, uint64_t* cut);   // arms parked units whose fade is over; *cut = samples (<= n) after which the first running fade with a parked unit ends
+  std::string render_device_run(uint64_t n, const float* in_dev, uint64_t in_stride, float* out_dev, uint64_t out_stride, float* mix_dev, uint64_t mix_stride);
   std::string push_event(HNode* event, uint32_t* voice);                      // Sequencer::push on a running bank: takes the slot of a finished event of the same class; consumes event
   std::string set(uint32_t voice, const Setting& s);  // AudioUnit::set on one voice of a live bank (parameters only; state continues)
   std::string ensure_staging(uint32_t chunk);

@@ -1091,12 +1091,14 @@ bool slot_arm(HNode* n, HNode* unit, int inst, int ease, double fade_time) {
   return true;
 }
 bool is_slot(const HNode* n) { return dynamic_cast<const SlotN*>(n) != nullptr; }
+bool slot_fade(const HNode* n, double* fade_time, double* sr) { const SlotN* s = dynamic_cast<const SlotN*>(n); if (!s) return false; *fade_time = s->fade_time; *sr = s->sr; return true; }
 HNode* mk_xfade(HNode* x, HNode* y, int ease, float fade_time) {
   if (!x || !y || x->inputs() != y->inputs() || x->outputs() != y->outputs() || ease < 0 || ease > 1 || !(fade_time > 0.0f)) { delete x; delete y; return nullptr; }
   return new XfadeN(x, y, ease, fade_time);
 }
 // the two units of a crossfading vertex (null when n is not one); `newest` = the unit the vertex is (or will be) left with
 bool xfade_set_done(HNode* n, bool done) { XfadeN* q = dynamic_cast<XfadeN*>(n); if (!q) return false; q->done = done; return true; }
+bool xfade_fade(const HNode* n, float* fade_time, float* sr) { const XfadeN* q = dynamic_cast<const XfadeN*>(n); if (!q) return false; *fade_time = q->fade_time; *sr = (float)q->sr; return true; }
 const HNode* xfade_unit(const HNode* n, int which) { const XfadeN* q = dynamic_cast<const XfadeN*>(n); return q ? (which ? q->y.p.get() : q->x.p.get()) : nullptr; }
 bool event_edit(HNode* n, double end_time, double fade_out) {   // Sequencer::edit on an event (:441-483, no loop: start == original start)
   EventN* e = dynamic_cast<EventN*>(n);

@@ -131,10 +131,12 @@ HNode* mk_envelope(double interval, int outputs, int time_f64, EnvelopeFn f, voi
 HNode* mk_oversample(HNode* x);                                      // Oversampler ID 51; consumes x
 HNode* mk_xfade(HNode* x, HNode* y, int ease, float fade_time);        // a Net vertex fading from x to y (Net::crossfade); consumes both
 bool xfade_set_done(HNode* n, bool done);                            // lower the vertex as already arrived at its second unit (what a bank reset restores)
+bool xfade_fade(const HNode* n, float* fade_time, float* sr);                              // the f32 fade time and rate the vertex's crossfade runs with
 const HNode* xfade_unit(const HNode* n, int which);                  // 0: the unit being faded out, 1: the unit being faded in; null when n is not a crossfading vertex
 HNode* mk_slot(HNode* x);                                            // SlotBackend ID 78: a replaceable unit; consumes x
 bool slot_arm(HNode* slot, HNode* unit, int instance, int ease, double fade_time);   // consumes unit
 bool is_slot(const HNode* n);
+bool slot_fade(const HNode* slot, double* fade_time, double* sr);                      // the fade time and rate the slot's crossfade runs with (its parameter words)
 HNode* mk_declick(float duration);                                   // Declick ID 23
 HNode* mk_chaos(int kind);                                           // 0 Rossler ID 73, 1 Lorenz ID 74
 HNode* mk_morph(float cutoff, float q);                               // Morph ID 62

@@ -118,10 +118,19 @@ std::string group_reduce_device(Bank& b, Group& g, uint64_t n, float* mix_dev, u
   CU(cudaSetDevice(b.device));
   const uint32_t ch = (uint32_t)b.nout;
   if (n > 0xffffffffull / std::max(1u, ch)) return "reduce: too many samples for one call";
+  // an NCCL group that was started is always ended, also when a call inside it fails (an open group would swallow every later NCCL call)
+  struct GroupScope {
+    Nccl& N; bool open = false;
+    explicit GroupScope(Nccl& n) : N(n) {}
+    int start() { const int rc = N.GroupStart(); open = rc == 0; return rc; }
+    int end() { open = false; return N.GroupEnd(); }
+    ~GroupScope() { if (open) N.GroupEnd(); }
+  };
   if (g.nccl_reduce) {
-    NC(N.GroupStart());
+    GroupScope gs(N);
+    NC(gs.start());
     for (uint32_t c = 0; c < ch; c++) NC(N.Reduce(mix_dev + c * mix_stride, mix_dev + c * mix_stride, n, kNcclFloat32, kNcclSum, root, (ncclComm_t)g.comm, b.stream));
-    NC(N.GroupEnd());
+    NC(gs.end());
     return "";
   }
   const size_t plane = (size_t)ch * n;
@@ -130,7 +139,8 @@ std::string group_reduce_device(Bank& b, Group& g, uint64_t n, float* mix_dev, u
     CU(cudaMalloc((void**)&g.d_gather, plane * g.nranks * sizeof(float)));
     g.gather_cap = plane * g.nranks;
   }
-  NC(N.GroupStart());
+  GroupScope gs(N);
+  NC(gs.start());
   if (g.rank == root) {
     // one receive per channel row: NCCL pairs sends and receives in order, and their counts must agree (the sender's rows may be strided)
     for (int r = 0; r < g.nranks; r++) if (r != root)
@@ -139,7 +149,7 @@ std::string group_reduce_device(Bank& b, Group& g, uint64_t n, float* mix_dev, u
     // rows of a strided mix buffer go one by one (the receiver's plane is dense [channel][n])
     for (uint32_t c = 0; c < ch; c++) NC(N.Send(mix_dev + c * mix_stride, n, kNcclFloat32, root, (ncclComm_t)g.comm, b.stream));
   }
-  NC(N.GroupEnd());
+  NC(gs.end());
   if (g.rank == root) {
     const uint32_t total = ch * (uint32_t)n;
     rank_fold_kernel<<<(total + 255) / 256, 256, 0, b.stream>>>(mix_dev, (uint32_t)mix_stride, g.d_gather, (uint32_t)g.nranks, (uint32_t)root, ch, (uint32_t)n);

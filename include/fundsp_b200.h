@@ -206,8 +206,9 @@ int fdsp_bank_replace_voice(fdsp_bank* b, uint32_t voice, fdsp_node* unit);
 /* Net::crossfade (src/net.rs:480-504): the voice fades from its unit to `unit` — any graph class of the bank's arity — over fade_time seconds
    with the curve fade_ease (0 Fade::Power, 1 Fade::Smooth), the reference's f32 vertex arithmetic (src/vertex.rs:138-229), and is `unit` alone
    afterwards. Both programs run in the voice while the fade lasts (class Xfade<old, new>, compiled first if new; the old unit's running state
-   and delay lines are carried into it; slow path like replace_voice). A further crossfade of the same voice is accepted once the running one
-   has finished (FDSP_ERR_UNSUPPORTED until then: the reference would park it as `latest`). A bank reset leaves the voice at `unit`. Consumes unit. */
+   and delay lines are carried into it; slow path like replace_voice). A further crossfade of a voice that is still fading waits as the vertex's
+   `latest` edit (a newer one replaces it) and starts in the block after the running fade has ended, like src/vertex.rs:124-136,203-218: the bank
+   finds that block and cuts its launch there. A bank reset leaves the voice at `unit`. Consumes unit. */
 int fdsp_bank_crossfade_voice(fdsp_bank* b, uint32_t voice, int fade_ease, float fade_time, fdsp_node* unit);
 int fdsp_bank_add_voice(fdsp_bank* b, fdsp_node* unit, uint32_t* voice);
 int fdsp_bank_remove_voice(fdsp_bank* b, uint32_t voice);
@@ -215,8 +216,9 @@ double fdsp_bank_time(const fdsp_bank* b);
 /* Slot / SlotBackend (src/slot.rs): fdsp_slot(unit) is a voice whose unit can be replaced while the bank runs; fdsp_bank_slot_set is
    Slot::set(fade, fade_time, unit): the voice crossfades to `unit` over fade_time seconds (fade 0 Power, 1 Smooth) with the reference's
    block arithmetic. No new program is built: `unit` must be of the voice's graph class (same type expression and class-uniform words,
-   e.g. the same instrument with other parameters), else FDSP_ERR_UNSUPPORTED — as it is while a previous crossfade of that voice is
-   still running (the reference would park the update as `latest`). Both consume their node argument. */
+   e.g. the same instrument with other parameters), else FDSP_ERR_UNSUPPORTED. A set while a previous crossfade of that voice is still
+   running waits as `latest` (a newer one replaces it) and starts in the block after the running fade has ended; a reset adopts it
+   (src/slot.rs:136-172). Both consume their node argument. */
 fdsp_node* fdsp_slot(fdsp_node* unit);
 int fdsp_bank_slot_set(fdsp_bank* b, uint32_t voice, int fade_ease, double fade_time, fdsp_node* unit);
 int fdsp_bank_reset(fdsp_bank* b);                                          /* AudioUnit::reset */

@@ -264,17 +264,33 @@ def test_slot_crossfades_to_a_new_unit():
     b.slot_set(2, Fade.Smooth, 0.01, voice(500.0, 2.0)); L.fo_slot_set(us[2].h, 1, 0.01, voice(500.0, 2.0).lower(be))
     b.slot_set(4, Fade.Power, 0.003, voice(77.0)); L.fo_slot_set(us[4].h, 0, 0.003, voice(77.0).lower(be))
     g = both(64 * 3 + 17)                          # mid-fade, ragged block
-    with pytest.raises(FdspError):
-        b.slot_set(2, Fade.Smooth, 0.01, voice(300.0))     # still fading: refused (the reference would park it as `latest`)
+    # a set while the voice is still fading is parked as `latest` (src/slot.rs:142-150), a newer one replaces it, and the voice starts fading to it
+    # in the block after its running fade has ended: the bank cuts the launch there (the fade of voice 2 ends inside the next render)
+    b.slot_set(2, Fade.Smooth, 0.01, voice(300.0)); L.fo_slot_set(us[2].h, 1, 0.01, voice(300.0).lower(be))
+    b.slot_set(2, Fade.Power, 0.004, voice(333.0, 3.0)); L.fo_slot_set(us[2].h, 0, 0.004, voice(333.0, 3.0).lower(be))   # replaces the parked one
     with pytest.raises(FdspError):
         b.slot_set(1, Fade.Smooth, 0.01, sine_hz(300.0))   # another graph class
-    both(64 * 9)                                   # both fades have ended: the new units play alone
+    with pytest.raises(FdspError):
+        b.slot_set(2, Fade.Smooth, 0.01, sine_hz(300.0))   # ... also refused at once when it would only be parked
+    both(64 * 9)                                   # first fades end; voice 2 goes on to its parked unit
+    both(64 * 2 + 9); both(31); both(64 * 6)       # (ragged calls across the second fade)
     b.slot_set(2, Fade.Power, 0.002, voice(250.0)); L.fo_slot_set(us[2].h, 0, 0.002, voice(250.0).lower(be))   # the roles have swapped: the other instance takes it
     both(64 * 4 + 5)
-    b.reset()                                      # reset adopts the newest units (:156-172)
+    # reset with an update parked behind a running fade adopts the parked (latest) unit (:156-172)
+    b.slot_set(3, Fade.Smooth, 0.02, voice(90.0)); L.fo_slot_set(us[3].h, 1, 0.02, voice(90.0).lower(be))
+    both(64 * 2)
+    b.slot_set(3, Fade.Smooth, 0.02, voice(700.0, 4.0)); L.fo_slot_set(us[3].h, 1, 0.02, voice(700.0, 4.0).lower(be))   # parked
+    both(64)
+    b.reset()                                      # reset adopts the newest units
     for u in us:
         u.reset()
     assert np.abs(both(64 * 3)).max() > 0.1
+    # process()-sized calls with an update parked: armed between two calls
+    b.slot_set(0, Fade.Power, 0.003, voice(123.0)); L.fo_slot_set(us[0].h, 0, 0.003, voice(123.0).lower(be))
+    both(64)
+    b.slot_set(0, Fade.Smooth, 0.002, voice(456.0)); L.fo_slot_set(us[0].h, 1, 0.002, voice(456.0).lower(be))   # parked
+    for size in (64, 64, 61, 64, 7, 64, 64, 64):
+        both(size)
 
 
 def test_bank_grows_with_a_new_waveform_and_keeps_running_state():
@@ -391,8 +407,8 @@ def test_net_bank_replace_and_remove_vertices_across_classes():
 def test_net_bank_crossfades_vertices_across_classes():
     """Net::crossfade (src/net.rs:480-504, src/vertex.rs:138-229) on a RUNNING bank made from a Net: a vertex fades to a unit of ANOTHER graph class
     (device: Xfade<X, Y>; the old unit keeps running inside the new class with its state and delay lines carried over), with both curves, fades
-    that end inside a block, process()-sized calls during the fade, a second crossfade of a vertex that has arrived, and the refusal of one that
-    has not. The mix equals the oracle Net that receives the same `crossfade` calls bit for bit (it is summed in the Net's own order)."""
+    that end inside a block, process()-sized calls during the fade, a second crossfade of a vertex that has arrived, and crossfades parked behind a
+    running one (`latest`). The mix equals the oracle Net that receives the same `crossfade` calls bit for bit (it is summed in the Net's own order)."""
     from fundsp_b200 import workloads
     from fundsp_b200.bank import GpuBank
     from fundsp_b200.capi import FdspError
@@ -427,8 +443,10 @@ def test_net_bank_crossfades_vertices_across_classes():
     want_rows, _ = twin.render_samples(300)
     changed = [v for v in range(V) if not np.array_equal(rows[v], want_rows[v])]
     assert changed == [4, 9], changed                                    # every other voice just continues
-    with pytest.raises(FdspError):
-        b.crossfade_voice(4, Fade.Smooth, 0.01, new_c())                 # (the reference would park it as `latest`)
+    # a crossfade of a vertex that is still fading waits as `latest` (src/vertex.rs:203-218; a newer one replaces it) and starts in the block after
+    # the running fade has ended: the bank finds that block, cuts its launch there and moves the voice to the class Xfade<new_a, new_c>
+    b.crossfade_voice(4, Fade.Power, 0.5, workloads.net_voice(3)); L.fo_net_crossfade(u.h, vertex_of[4], Fade.Power, 0.5, workloads.net_voice(3).lower(be))
+    b.crossfade_voice(4, Fade.Smooth, 0.01, new_c()); L.fo_net_crossfade(u.h, vertex_of[4], Fade.Smooth, 0.01, new_c().lower(be))   # replaces the parked one
     for sz in (64, 61, 7, 64, 64, 33, 64):                                # the 480-sample fade of voice 4 ends inside one of these blocks
         got, exp = b.process(sz), u.process(sz)
         assert np.array_equal(got, exp), sz
@@ -436,6 +454,11 @@ def test_net_bank_crossfades_vertices_across_classes():
     # a vertex that has arrived fades again, from the unit it arrived at
     b.crossfade_voice(4, Fade.Power, 0.004, workloads.net_voice(1)); L.fo_net_crossfade(u.h, vertex_of[4], Fade.Power, 0.004, workloads.net_voice(1).lower(be))
     both(500)
+    # a parked crossfade whose turn comes in the MIDDLE of a long render: the launch is cut behind the block in which the running fade ends
+    b.crossfade_voice(9, Fade.Smooth, 0.005, workloads.net_voice(0)); L.fo_net_crossfade(u.h, vertex_of[9], Fade.Smooth, 0.005, workloads.net_voice(0).lower(be))
+    both(64)
+    b.crossfade_voice(9, Fade.Power, 0.003, new_a()); L.fo_net_crossfade(u.h, vertex_of[9], Fade.Power, 0.003, new_a().lower(be))   # parked: 176 samples of the first fade are left
+    both(64 * 20 + 3)
     # reset: the edited net, every vertex at its newest unit
     b.reset(); u.reset()
     r2 = both(300)
