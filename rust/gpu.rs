@@ -8,7 +8,12 @@
 //!   Moog::cutoff_q() -> (f32, f32)                  (moog.rs:20-34)        Fir::weights() -> &[f32]                  (fir.rs:15)
 //!   Delay::length_seconds() -> f64                  (delay.rs:69)          Panner::<U1>::pan_value() -> f32          (pan.rs:19)
 //!   Unop scalar: FrameAddScalar / FrameMulScalar / FrameNegAddScalar ::scalar() (audionode.rs:1114,1155,1197)
-//! Everything else goes through the public API (`Pipe::left()/right()`, `Constant::value()`, `AudioNode::ID`, ...).
+//!   Resonator::center_q() -> (f32, f32)             (biquad.rs:310-318)    ButterLowpass::cutoff() -> f32            (biquad.rs:227-232)
+//!   AllNest::coefficient() / inner() -> &X          (delay.rs:294-302)     Tap / TapLinear::delay_range() -> (f32, f32) (delay.rs:148-160,386)
+//!   Dsf::spacing_roughness() -> (f32, f32)          (oscillator.rs:120)    Mls::bits() -> u32                        (noise.rs:101)
+//!   Feedback::inner() / Feedback2::inner_pair()     (feedback.rs:71,183)   Reverb::time_diffusion_filter()           (reverb.rs:154-162)
+//!   MultiBus / MultiStack / Reduce / MultiBranch / Chain ::nodes() -> &[X]  (audionode.rs:2065-2673)
+//! Everything else goes through the public API (`Pipe::left()/right()`, `Constant::value()`, `Svf::cutoff()/q()/gain()`, `Biquad::coefs()`, `AudioNode::ID`, ...).
 #![allow(clippy::missing_safety_doc)]
 use crate::audionode::*;
 use crate::audiounit::AudioUnit;
@@ -58,6 +63,46 @@ extern "C" {
     fn fdsp_unop(kind: c_int, scalar: f32, x: *mut FdspNode) -> *mut FdspNode;
     fn fdsp_multi(kind: c_int, op: c_int, n: c_int, nodes: *const *mut FdspNode) -> *mut FdspNode;
     fn fdsp_feedback(x: *mut FdspNode, hadamard: c_int) -> *mut FdspNode;
+    // the rest of SURVEY.md §8(a): routing, audio-rate filters, oscillators, delays, feedback forms, reverb, envelopes, Net
+    fn fdsp_split(n: c_int) -> *mut FdspNode;
+    fn fdsp_join(n: c_int) -> *mut FdspNode;
+    fn fdsp_reverse(n: c_int) -> *mut FdspNode;
+    fn fdsp_impulse(n: c_int) -> *mut FdspNode;
+    fn fdsp_svf(mode: c_int, cutoff: f32, q: f32, gain: f32) -> *mut FdspNode;
+    fn fdsp_biquad(a1: f32, a2: f32, b0: f32, b1: f32, b2: f32) -> *mut FdspNode;
+    fn fdsp_biquad_bank() -> *mut FdspNode;
+    fn fdsp_butterpass(cutoff: f32, inputs: c_int) -> *mut FdspNode;
+    fn fdsp_resonator(center: f32, q: f32, inputs: c_int) -> *mut FdspNode;
+    fn fdsp_tick(n: c_int) -> *mut FdspNode;
+    fn fdsp_allnest(coefficient: f32, x: *mut FdspNode, inputs: c_int) -> *mut FdspNode;
+    fn fdsp_phase_osc(kind: c_int) -> *mut FdspNode;
+    fn fdsp_dsf(inputs: c_int, harmonic_spacing: f32, roughness: f32) -> *mut FdspNode;
+    fn fdsp_mls(bits: c_int) -> *mut FdspNode;
+    fn fdsp_tap(taps: c_int, linear: c_int, min_delay: f32, max_delay: f32) -> *mut FdspNode;
+    fn fdsp_feedback2(x: *mut FdspNode, y: *mut FdspNode, hadamard: c_int) -> *mut FdspNode;
+    fn fdsp_feedback_unit(delay: f64, x: *mut FdspNode) -> *mut FdspNode;
+    fn fdsp_reverb3(time: f64, diffusion: f64, filter: *mut FdspNode) -> *mut FdspNode;
+    fn fdsp_panner() -> *mut FdspNode;
+    fn fdsp_var(value: f32) -> *mut FdspNode;
+    fn fdsp_net_new(inputs: c_int, outputs: c_int) -> *mut FdspNode;
+    fn fdsp_net_push(net: *mut FdspNode, unit: *mut FdspNode) -> c_int;
+    fn fdsp_net_connect(net: *mut FdspNode, source: c_int, source_port: c_int, target: c_int, target_port: c_int) -> c_int;
+    fn fdsp_net_connect_input(net: *mut FdspNode, global_input: c_int, target: c_int, target_port: c_int) -> c_int;
+    fn fdsp_net_connect_output(net: *mut FdspNode, source: c_int, source_port: c_int, global_output: c_int) -> c_int;
+    fn fdsp_net_pass_through(net: *mut FdspNode, global_input: c_int, global_output: c_int) -> c_int;
+    fn fdsp_bank_create_from_net(net: *mut FdspNode, device: c_int, out_mode: u32, out: *mut *mut FdspBank) -> c_int;
+    fn fdsp_bank_voice_of_vertex(b: *const FdspBank, vertex: c_int) -> c_int;
+    // live edits of a running bank (Net::replace / remove / crossfade, Slot::set, Sequencer::push / edit)
+    fn fdsp_bank_replace_voice(b: *mut FdspBank, voice: u32, unit: *mut FdspNode) -> c_int;
+    fn fdsp_bank_remove_voice(b: *mut FdspBank, voice: u32) -> c_int;
+    fn fdsp_bank_crossfade_voice(b: *mut FdspBank, voice: u32, fade_ease: c_int, fade_time: f32, unit: *mut FdspNode) -> c_int;
+    fn fdsp_slot(unit: *mut FdspNode) -> *mut FdspNode;
+    fn fdsp_bank_slot_set(b: *mut FdspBank, voice: u32, fade_ease: c_int, fade_time: f64, unit: *mut FdspNode) -> c_int;
+    fn fdsp_event(x: *mut FdspNode, start: f64, end: f64, fade_ease: c_int, fade_in: f64, fade_out: f64) -> *mut FdspNode;
+    fn fdsp_event_loop(x: *mut FdspNode, start: f64, end: f64, fade_ease: c_int, fade_in: f64, fade_out: f64, loop_seconds: f64) -> *mut FdspNode;
+    fn fdsp_bank_push_event(b: *mut FdspBank, event: *mut FdspNode, voice: *mut u32) -> c_int;
+    fn fdsp_bank_edit_event(b: *mut FdspBank, voice: u32, end_time: f64, fade_out: f64) -> c_int;
+    fn fdsp_bank_time(b: *const FdspBank) -> f64;
     fn fdsp_node_phase(n: *mut FdspNode, phase: f32) -> c_int;
     fn fdsp_node_seed(n: *mut FdspNode, seed: u64) -> c_int;
     fn fdsp_node_free(n: *mut FdspNode);
@@ -176,6 +221,70 @@ impl Lower for crate::pan::Panner<U1> { unsafe fn lower(&self) -> *mut FdspNode 
 impl Lower for crate::convolve::Convolver {
     unsafe fn lower(&self) -> *mut FdspNode { let h = self.response(); fdsp_convolve(h.as_ptr(), h.len() as c_int) }                     // convolve.rs:9
 }
+// ---- the rest of SURVEY.md §8(a). Type parameters as in v0.23.0; `F = f32` is the prelude32 instantiation the hot path uses.
+impl<N: Size<f32>> Lower for Split<N> { unsafe fn lower(&self) -> *mut FdspNode { fdsp_split(N::I32) } }                               // audionode.rs:527
+impl<N: Size<f32>> Lower for Join<N> { unsafe fn lower(&self) -> *mut FdspNode { fdsp_join(N::I32) } }                                 // audionode.rs:617
+impl<M: Size<f32>, N: Size<f32>> Lower for MultiSplit<M, N> { unsafe fn lower(&self) -> *mut FdspNode { fdsp_multisplit(M::I32, N::I32) } }   // :571
+impl<M: Size<f32>, N: Size<f32>> Lower for MultiJoin<M, N> { unsafe fn lower(&self) -> *mut FdspNode { fdsp_multijoin(M::I32, N::I32) } }     // :668
+impl<N: Size<f32>> Lower for Reverse<N> { unsafe fn lower(&self) -> *mut FdspNode { fdsp_reverse(N::I32) } }                           // audionode.rs:2808
+impl<N: Size<f32>> Lower for Impulse<N> { unsafe fn lower(&self) -> *mut FdspNode { fdsp_impulse(N::I32) } }                           // audionode.rs:2841
+/// Svf<f32, M> with audio-rate cutoff / Q (/ gain) inputs (svf.rs:748): the initial parameters are public accessors.
+impl<M: crate::svf::SvfMode<f32> + SvfModeIndex> Lower for crate::svf::Svf<f32, M> {
+    unsafe fn lower(&self) -> *mut FdspNode { fdsp_svf(M::INDEX, self.cutoff(), self.q(), self.gain()) }
+}
+impl Lower for crate::biquad::Biquad<f32> {
+    unsafe fn lower(&self) -> *mut FdspNode { let c = self.coefs(); fdsp_biquad(c.a1, c.a2, c.b0, c.b1, c.b2) }                        // biquad.rs:136-165
+}
+impl Lower for crate::biquad_bank::BiquadBank<wide::f32x8> { unsafe fn lower(&self) -> *mut FdspNode { fdsp_biquad_bank() } }          // biquad_bank.rs:14; lanes are set with Setting::biquad(..).index(l)
+impl<N: Size<f32>> Lower for crate::biquad::ButterLowpass<f32, N> { unsafe fn lower(&self) -> *mut FdspNode { fdsp_butterpass(self.cutoff(), N::I32) } }   // N = U1 fixed, U2 audio-rate cutoff
+impl<N: Size<f32>> Lower for crate::biquad::Resonator<f32, N> {
+    unsafe fn lower(&self) -> *mut FdspNode { let (c, q) = self.center_q(); fdsp_resonator(c, q, N::I32) }                              // N = U1 fixed, U3 audio-rate center / Q
+}
+impl<N: Size<f32>> Lower for crate::delay::Tick<N> { unsafe fn lower(&self) -> *mut FdspNode { fdsp_tick(N::I32) } }                    // delay.rs:19
+impl<N: Size<f32>, X: AudioNode<Inputs = U1, Outputs = U1> + Lower> Lower for crate::delay::AllNest<N, X> {
+    unsafe fn lower(&self) -> *mut FdspNode { fdsp_allnest(self.coefficient(), self.inner().lower(), N::I32) }                          // delay.rs:294 (N = U2: audio-rate coefficient)
+}
+impl<N> Lower for crate::delay::Tap<N> where N: Size<f32> + core::ops::Add<U1>, <N as core::ops::Add<U1>>::Output: Size<f32> {
+    unsafe fn lower(&self) -> *mut FdspNode { let (lo, hi) = self.delay_range(); fdsp_tap(N::I32, 0, lo, hi) }                          // delay.rs:148 (cubic taps)
+}
+impl<N> Lower for crate::delay::TapLinear<N> where N: Size<f32> + core::ops::Add<U1>, <N as core::ops::Add<U1>>::Output: Size<f32> {
+    unsafe fn lower(&self) -> *mut FdspNode { let (lo, hi) = self.delay_range(); fdsp_tap(N::I32, 1, lo, hi) }                          // delay.rs:386
+}
+impl Lower for crate::oscillator::Ramp<f32> { unsafe fn lower(&self) -> *mut FdspNode { fdsp_phase_osc(0) } }                           // oscillator.rs:441
+impl Lower for crate::oscillator::PolySaw<f32> { unsafe fn lower(&self) -> *mut FdspNode { fdsp_phase_osc(1) } }                        // :529
+impl Lower for crate::oscillator::PolySquare<f32> { unsafe fn lower(&self) -> *mut FdspNode { fdsp_phase_osc(2) } }                     // :605
+impl Lower for crate::oscillator::PolyPulse<f32> { unsafe fn lower(&self) -> *mut FdspNode { fdsp_phase_osc(3) } }                      // :688
+impl<N: Size<f32>> Lower for crate::oscillator::Dsf<N> {
+    unsafe fn lower(&self) -> *mut FdspNode { let (h, r) = self.spacing_roughness(); fdsp_dsf(N::I32, h, r) }                           // oscillator.rs:120 (N = U1 fixed, U2 audio-rate roughness)
+}
+impl Lower for crate::noise::Mls { unsafe fn lower(&self) -> *mut FdspNode { fdsp_mls(self.bits() as c_int) } }                          // noise.rs:101
+impl Lower for crate::pan::Panner<U2> { unsafe fn lower(&self) -> *mut FdspNode { fdsp_panner() } }                                     // pan.rs:19 (audio-rate pan)
+/// Feedback<N, X, FrameId | FrameHadamard> (feedback.rs:71) and Feedback2 (:183): the frame operator is a type, the C ABI takes a flag.
+pub trait FeedbackFrame { const HADAMARD: c_int; }
+impl<N: Size<f32>> FeedbackFrame for FrameId<N> { const HADAMARD: c_int = 0; }
+impl<N: Size<f32>> FeedbackFrame for crate::feedback::FrameHadamard<N> { const HADAMARD: c_int = 1; }
+impl<N, X, U> Lower for crate::feedback::Feedback<N, X, U> where N: Size<f32>, X: AudioNode<Inputs = N, Outputs = N> + Lower, U: FrameUnop<N> + FeedbackFrame {
+    unsafe fn lower(&self) -> *mut FdspNode { fdsp_feedback(self.inner().lower(), U::HADAMARD) }
+}
+impl<N, X, Y, U> Lower for crate::feedback::Feedback2<N, X, Y, U>
+where N: Size<f32>, X: AudioNode<Inputs = N, Outputs = N> + Lower, Y: AudioNode<Inputs = N, Outputs = N> + Lower, U: FrameUnop<N> + FeedbackFrame {
+    unsafe fn lower(&self) -> *mut FdspNode { let (x, y) = self.inner_pair(); fdsp_feedback2(x.lower(), y.lower(), U::HADAMARD) }
+}
+impl<F: AudioNode<Inputs = U1, Outputs = U1> + Lower> Lower for crate::reverb::Reverb<F> {
+    unsafe fn lower(&self) -> *mut FdspNode { let (t, d, f) = self.time_diffusion_filter(); fdsp_reverb3(t, d, f.lower()) }               // reverb.rs:154 (reverb3_stereo)
+}
+impl Lower for crate::shared::Var { unsafe fn lower(&self) -> *mut FdspNode { fdsp_var(self.value()) } }                                 // shared.rs:85; later changes: Setting::value through AudioUnit::set
+/// The N-ary combinators hold their units in a Frame<X, N> (audionode.rs:2065-2673); kind codes are the nodes' IDs.
+macro_rules! lower_multi { ($t:ident, $kind:expr, $op:expr) => {
+    impl<N: Size<f32> + Size<X>, X: AudioNode + Lower> Lower for $t<N, X> {
+        unsafe fn lower(&self) -> *mut FdspNode { let hs: Vec<*mut FdspNode> = self.nodes().iter().map(|x| x.lower()).collect(); fdsp_multi($kind, $op, hs.len() as c_int, hs.as_ptr()) }
+    }
+} }
+lower_multi!(MultiBus, 28, 0); lower_multi!(MultiStack, 30, 0); lower_multi!(MultiBranch, 33, 0); lower_multi!(Chain, 32, 0);
+impl<N: Size<f32> + Size<X>, X: AudioNode + Lower, B: FrameBinop<X::Outputs> + BinopCode> Lower for Reduce<N, X, B> {
+    unsafe fn lower(&self) -> *mut FdspNode { let hs: Vec<*mut FdspNode> = self.nodes().iter().map(|x| x.lower()).collect(); fdsp_multi(31, B::OP, hs.len() as c_int, hs.as_ptr()) }
+}
+
 /// `adsr_live(a, d, s, r)` is `EnvelopeIn` with the closure of adsr.rs:21-70: closures do not cross a C ABI, the closed form does.
 pub struct AdsrLive { pub attack: f32, pub decay: f32, pub sustain: f32, pub release: f32 }
 impl Lower for AdsrLive { unsafe fn lower(&self) -> *mut FdspNode { fdsp_adsr_live(self.attack, self.decay, self.sustain, self.release) } }
@@ -207,6 +316,53 @@ impl GpuBank {
     }
     pub fn failed(&self) -> bool { self.failed }
 }
+/// Live edits keep the reference's names (INTEGRATION.md "A dynamic Net", "A Sequencer as one bank"); `voice` = `voice_of_vertex(NodeId)` for banks made from a Net.
+impl GpuBank {
+    /// A voice-separable `Net` handed over vertex by vertex (`NetBuilder` below) becomes a bank that mixes in the Net's own order.
+    pub unsafe fn from_net_handle(net: *mut FdspNode, device: i32, mix: bool) -> Result<Self, String> {
+        let mut b: *mut FdspBank = core::ptr::null_mut();
+        check(fdsp_bank_create_from_net(net, device, if mix { FDSP_OUT_MIX } else { FDSP_OUT_VOICES }, &mut b))?;
+        Ok(GpuBank { h: b, inputs: fdsp_bank_inputs(b) as usize, outputs: fdsp_bank_outputs(b) as usize, failed: false })
+    }
+    pub fn voice_of_vertex(&self, vertex: usize) -> Option<u32> { let v = unsafe { fdsp_bank_voice_of_vertex(self.h, vertex as c_int) }; if v < 0 { None } else { Some(v as u32) } }
+    pub fn replace<X: AudioNode + Lower>(&mut self, voice: u32, unit: &An<X>) -> Result<(), String> { check(unsafe { fdsp_bank_replace_voice(self.h, voice, unit.lower()) }) }   // Net::replace (net.rs:460)
+    pub fn remove(&mut self, voice: u32) -> Result<(), String> { check(unsafe { fdsp_bank_remove_voice(self.h, voice) }) }                                                       // Net::remove (net.rs:351)
+    pub fn crossfade<X: AudioNode + Lower>(&mut self, voice: u32, fade: crate::sequencer::Fade, fade_time: f32, unit: &An<X>) -> Result<(), String> {                             // Net::crossfade (net.rs:480)
+        check(unsafe { fdsp_bank_crossfade_voice(self.h, voice, fade as c_int, fade_time, unit.lower()) })
+    }
+    pub fn slot_set<X: AudioNode + Lower>(&mut self, voice: u32, fade: crate::sequencer::Fade, fade_time: f64, unit: &An<X>) -> Result<(), String> {                              // Slot::set (slot.rs:64)
+        check(unsafe { fdsp_bank_slot_set(self.h, voice, fade as c_int, fade_time, unit.lower()) })
+    }
+    pub fn time(&self) -> f64 { unsafe { fdsp_bank_time(self.h) } }
+}
+/// `Slot::new(unit)` as a voice graph (slot.rs:33): lower the unit, wrap the handle.
+pub struct SlotVoice<X>(pub An<X>);
+impl<X: AudioNode + Lower> Lower for SlotVoice<X> { unsafe fn lower(&self) -> *mut FdspNode { fdsp_slot(self.0.lower()) } }
+/// One Sequencer event as a voice (sequencer.rs:319-345); `loop_seconds` > 0 for a ReplayMode::Loop sequencer.
+pub struct EventVoice<X> { pub unit: An<X>, pub start: f64, pub end: f64, pub fade: crate::sequencer::Fade, pub fade_in: f64, pub fade_out: f64, pub loop_seconds: f64 }
+impl<X: AudioNode + Lower> Lower for EventVoice<X> {
+    unsafe fn lower(&self) -> *mut FdspNode {
+        if self.loop_seconds > 0.0 { fdsp_event_loop(self.unit.lower(), self.start, self.end, self.fade.clone() as c_int, self.fade_in, self.fade_out, self.loop_seconds) }
+        else { fdsp_event(self.unit.lower(), self.start, self.end, self.fade.clone() as c_int, self.fade_in, self.fade_out) }
+    }
+}
+/// Mirror of the Net construction calls (net.rs:204-213,320-345,520-640): vertex ids are the indices `Net::push` hands out.
+pub struct NetBuilder { h: *mut FdspNode }
+impl NetBuilder {
+    pub fn new(inputs: usize, outputs: usize) -> Self { NetBuilder { h: unsafe { fdsp_net_new(inputs as c_int, outputs as c_int) } } }
+    pub fn push<X: AudioNode + Lower>(&mut self, unit: &An<X>) -> Result<usize, String> { let v = unsafe { fdsp_net_push(self.h, unit.lower()) }; if v < 0 { Err(last_error()) } else { Ok(v as usize) } }
+    pub fn connect(&mut self, source: usize, source_port: usize, target: usize, target_port: usize) -> Result<(), String> { check(unsafe { fdsp_net_connect(self.h, source as c_int, source_port as c_int, target as c_int, target_port as c_int) }) }
+    pub fn connect_input(&mut self, global_input: usize, target: usize, target_port: usize) -> Result<(), String> { check(unsafe { fdsp_net_connect_input(self.h, global_input as c_int, target as c_int, target_port as c_int) }) }
+    pub fn connect_output(&mut self, source: usize, source_port: usize, global_output: usize) -> Result<(), String> { check(unsafe { fdsp_net_connect_output(self.h, source as c_int, source_port as c_int, global_output as c_int) }) }
+    pub fn pass_through(&mut self, global_input: usize, global_output: usize) -> Result<(), String> { check(unsafe { fdsp_net_pass_through(self.h, global_input as c_int, global_output as c_int) }) }
+    /// The finished Net as a bank (consumes the handle) ...
+    pub fn into_bank(self, device: i32, mix: bool) -> Result<GpuBank, String> { let h = self.h; core::mem::forget(self); unsafe { GpuBank::from_net_handle(h, device, mix) } }
+    /// ... or as a node of a larger voice expression: any acyclic Net lowers to one fused program.
+    pub fn into_node(self) -> NetNode { let h = self.h; core::mem::forget(self); NetNode(h) }
+}
+impl Drop for NetBuilder { fn drop(&mut self) { if !self.h.is_null() { unsafe { fdsp_node_free(self.h) } } } }
+pub struct NetNode(*mut FdspNode);
+
 impl AudioUnit for GpuBank {
     fn inputs(&self) -> usize { self.inputs }
     fn outputs(&self) -> usize { self.outputs }
